@@ -1,0 +1,288 @@
+/*
+ * pfrx.h -- C ABI of the B200-native operator-split chemistry step.
+ *
+ * This is the drop-in boundary for ONE path of PFLOTRAN (as carried by
+ * fmyuan/pflotran-elm-interface): the per-cell reaction step behind the OS
+ * cell loop
+ *     PMCSubsurfaceOSRTStepDT   src/pflotran/pmc_subsurface_osrt.F90:346-383
+ *       -> RStep                src/pflotran/reaction.F90:3564
+ *         -> RReact             src/pflotran/reaction.F90:3742
+ * Host Fortran reaches it through ISO_C_BINDING; every
+ * signature below uses only plain pointers, sizes and POD structs.
+ *
+ * Conventions
+ *   - all reals are IEEE binary64, all indices int32, species ids are 0-BASED
+ *     (the reference is 1-based; the binding subtracts 1 when it flattens
+ *     reaction_rt_type);
+ *   - ragged stoichiometry tables are CSR: ptr[n+1], id[nnz], stoich[nnz]
+ *     (the reference stores id(0:max,n)/stoich(max,n); reaction_aux.F90:171-196);
+ *   - per-cell state is "cell-major SoA": field f, component k, cell c lives at
+ *     f[k*ld + c] with ld = pfrx_state.ld >= ncell.  A thread-per-cell kernel
+ *     then reads consecutive doubles from consecutive lanes;
+ *   - return value 0 = success, >0 = error class (PFRX_E_*); nothing aborts
+ *     the process (the reference's `stop` in RStep, reaction.F90:3669, becomes
+ *     a per-cell ierror).
+ */
+#ifndef PFRX_H
+#define PFRX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFRX_ABI_VERSION 1
+
+/* error classes */
+#define PFRX_OK 0
+#define PFRX_E_INVALID 1   /* bad argument / unsupported configuration      */
+#define PFRX_E_CUDA 2      /* CUDA runtime error (see pfrx_last_error())     */
+#define PFRX_E_NOTBOUND 3  /* rstep before bind_state                        */
+#define PFRX_E_NCCL 4      /* NCCL missing or failed                         */
+#define PFRX_E_LIMIT 5     /* problem exceeds a compiled-in size limit       */
+
+/* reaction_aux.F90:33-38 */
+#define PFRX_ACT_COEF_FREQUENCY_OFF 0
+#define PFRX_ACT_COEF_FREQUENCY_TIMESTEP 1
+#define PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER 2
+#define PFRX_ACT_COEF_ALGORITHM_LAG 3
+#define PFRX_ACT_COEF_ALGORITHM_NEWTON 4
+
+/* reaction_surf_complex_aux.F90: surface types */
+#define PFRX_NULL_SURFACE 0
+#define PFRX_ROCK_SURFACE 1
+#define PFRX_MINERAL_SURFACE 2
+
+/* compiled-in limits of the CUDA path (oracle has none beyond memory) */
+#define PFRX_MAX_NCOMP 32
+#define PFRX_MAX_PREFACTORS 10      /* reaction_mineral.F90:688 */
+#define PFRX_MAX_PREFACTOR_SPECIES 5
+
+/*
+ * Flattened, read-only reaction description: the subset of
+ *   reaction_rt_type            reaction_aux.F90:123-311
+ *   mineral_type                reaction_mineral_aux.F90:82-138
+ *   surface_complexation_type   reaction_surf_complex_aux.F90:68-128
+ *   reaction_sandbox_clm_cn_type reaction_sandbox_clm_cn.F90:22-42
+ * that RStep and its callees read.  pfrx_create() copies everything; the
+ * caller keeps ownership of the arrays.
+ */
+typedef struct pfrx_config {
+  int32_t abi_version;           /* = PFRX_ABI_VERSION */
+
+  /* ---- sizes: ncomp = naqcomp + nimcomp, offset_immobile = naqcomp -------- */
+  int32_t naqcomp;
+  int32_t nimcomp;               /* reaction%immobile%nimmobile */
+
+  /* ---- flags / tolerances (defaults: reaction_aux.F90:371-556) ------------ */
+  int32_t use_full_geochemistry; /* 0 => RStep early-outs, reaction.F90:3604  */
+  int32_t use_log_formulation;
+  int32_t use_total_as_guess;
+  int32_t use_isothermal;        /* 0 => logK(T) per cell, reaction.F90:5976  */
+  int32_t act_coef_update_frequency;
+  int32_t act_coef_update_algorithm;
+  int32_t use_activity_h2o;
+  int32_t h2o_aq_id;             /* species_idx%h2o_aq_id, -1 if none         */
+  int32_t maximum_reaction_iterations;   /* 20 */
+  int32_t maximum_reaction_cuts;         /* 10 */
+  double max_dlnC_rreact;                /* 5   */
+  double max_relative_change_tolerance;  /* 1e-6 */
+  double max_residual_tolerance;         /* 1e-12 */
+  double max_rel_residual_tolerance;     /* 1e-8 */
+  double rt_min_saturation;              /* 1e-40, reactive_transport_aux.F90:19 */
+  double debyeA, debyeB, debyeBdot;      /* reaction_database.F90:931-1023 */
+
+  /* ---- primary aqueous species ------------------------------------------- */
+  const double *primary_spec_Z;          /* [naqcomp] */
+  const double *primary_spec_a0;         /* [naqcomp] */
+
+  /* ---- secondary aqueous complexes (RTotalAqueous, reaction.F90:4665) ---- */
+  int32_t neqcplx;
+  const int32_t *eqcplx_ptr;             /* [neqcplx+1] */
+  const int32_t *eqcplx_specid;          /* [nnz] primary ids */
+  const double *eqcplx_stoich;           /* [nnz] */
+  const double *eqcplx_h2ostoich;        /* [neqcplx]; 0 when eqcplxh2oid==0 */
+  const double *eqcplx_logK;             /* [neqcplx] at the reference T     */
+  const double *eqcplx_logKcoef;         /* [5*neqcplx] or NULL (isothermal) */
+  const double *eqcplx_Z;                /* [neqcplx] */
+  const double *eqcplx_a0;               /* [neqcplx] */
+
+  /* ---- kinetic minerals (RKineticMineral, reaction_mineral.F90:647) ------ */
+  int32_t nkinmnrl;
+  const int32_t *kinmnrl_ptr;            /* [nkinmnrl+1] */
+  const int32_t *kinmnrl_specid;         /* [nnz] primary ids */
+  const double *kinmnrl_stoich;          /* [nnz] */
+  const double *kinmnrl_h2ostoich;       /* [nkinmnrl] */
+  const double *kinmnrl_logK;            /* [nkinmnrl] */
+  const double *kinmnrl_logKcoef;        /* [5*nkinmnrl] or NULL */
+  const double *kinmnrl_molar_vol;       /* [nkinmnrl] m^3/mol */
+  const double *kinmnrl_rate_constant;   /* [nkinmnrl] mol/m^2/s */
+  const double *kinmnrl_activation_energy; /* [nkinmnrl] J/mol, 0 = none */
+  const double *kinmnrl_affinity_threshold; /* [nkinmnrl] */
+  const double *kinmnrl_rate_limiter;    /* [nkinmnrl] */
+  const int32_t *kinmnrl_irreversible;   /* [nkinmnrl] */
+  /* optional arrays: NULL reproduces the reference's `.not.associated(...)` */
+  const double *kinmnrl_Temkin_const;    /* [nkinmnrl] or NULL */
+  const double *kinmnrl_min_scale_factor;/* [nkinmnrl] or NULL */
+  const double *kinmnrl_affinity_power;  /* [nkinmnrl] or NULL */
+  /* prefactors (reaction_mineral.F90:838-890); all NULL when unused.
+   * Dense like the reference: pref index p < PFRX_MAX_PREFACTORS, species
+   * slot s < PFRX_MAX_PREFACTOR_SPECIES, layout [(m*MAXP + p)*MAXS + s].     */
+  const int32_t *kinmnrl_num_prefactors; /* [nkinmnrl] or NULL */
+  const int32_t *kinmnrl_pref_nspec;     /* [nkinmnrl*MAXP] */
+  const int32_t *kinmnrl_prefactor_id;   /* >=0 primary id; <0 => -(icplx+1) */
+  const double *kinmnrl_pref_alpha;
+  const double *kinmnrl_pref_beta;
+  const double *kinmnrl_pref_atten_coef;
+  const double *kinmnrl_pref_rate;       /* [nkinmnrl*MAXP] */
+  const double *kinmnrl_pref_activation_energy; /* [nkinmnrl*MAXP] */
+
+  /* ---- surface complexation (reaction_surf_complex.F90:446-900) ---------- */
+  int32_t nsrfcplxrxn;
+  int32_t nsrfcplx;
+  const int32_t *srfcplxrxn_ptr;         /* [nsrfcplxrxn+1] -> complex ids   */
+  const int32_t *srfcplxrxn_to_complex;  /* [.] */
+  const int32_t *srfcplxrxn_surf_type;   /* [nsrfcplxrxn] PFRX_*_SURFACE     */
+  const int32_t *srfcplxrxn_to_surf;     /* [nsrfcplxrxn] kinetic-mineral id */
+  const double *srfcplxrxn_site_density; /* [nsrfcplxrxn] */
+  const int32_t *srfcplxrxn_stoich_flag; /* [nsrfcplxrxn] 1 => inner Newton  */
+  const int32_t *srfcplx_ptr;            /* [nsrfcplx+1] */
+  const int32_t *srfcplx_specid;
+  const double *srfcplx_stoich;
+  const double *srfcplx_h2ostoich;       /* [nsrfcplx] */
+  const double *srfcplx_free_site_stoich;/* [nsrfcplx] */
+  const double *srfcplx_logK;            /* [nsrfcplx] */
+  const double *srfcplx_logKcoef;        /* [5*nsrfcplx] or NULL */
+  int32_t neqsrfcplxrxn;
+  const int32_t *eqsrfcplxrxn_to_srfcplxrxn;   /* [neqsrfcplxrxn] */
+  int32_t nkinmrsrfcplxrxn;
+  const int32_t *kinmrsrfcplxrxn_to_srfcplxrxn;/* [nkinmrsrfcplxrxn] */
+  const int32_t *kinmr_rate_ptr;         /* [nkinmrsrfcplxrxn+1] */
+  const double *kinmr_rate;              /* [.] 1/s */
+  const double *kinmr_frac;              /* [.] */
+
+  /* ---- CLM-CN reaction sandbox (reaction_sandbox_clm_cn.F90:468-787) ----- */
+  int32_t clmcn_nrxn;                    /* 0 => sandbox absent */
+  int32_t clmcn_npool;
+  int32_t clmcn_C_species_id;            /* immobile ids, 0-based */
+  int32_t clmcn_N_species_id;
+  const double *clmcn_CN_ratio;          /* [npool] mol C/mol N; <0 => litter */
+  const int32_t *clmcn_pool_nspec;       /* [npool] 1 (SOM) or 2 (litter C,N) */
+  const int32_t *clmcn_pool_C_id;        /* [npool] immobile id of C or SOM   */
+  const int32_t *clmcn_pool_N_id;        /* [npool] immobile id of N, -1 SOM  */
+  const int32_t *clmcn_upstream_pool_id; /* [nrxn] */
+  const int32_t *clmcn_downstream_pool_id; /* [nrxn], -1 => none */
+  const double *clmcn_rate_constant;     /* [nrxn] 1/s */
+  const double *clmcn_respiration_fraction; /* [nrxn] */
+  const double *clmcn_inhibition_constant;  /* [nrxn] */
+} pfrx_config;
+
+/*
+ * Per-cell state views (cell-major SoA).  Device pointers for
+ * pfrx_bind_state(), host pointers for pfrx_rstep_host().  A pointer may be
+ * NULL when its count is zero.  "in" = read, "io" = read and updated in place.
+ *   reactive_transport_auxvar_type  reactive_transport_aux.F90:21-74
+ *   global_auxvar_type              global_aux.F90:11-35
+ *   material_auxvar_type            material_aux.F90:53-77
+ */
+typedef struct pfrx_state {
+  int64_t ld;                  /* leading dimension (>= ncell) of every field */
+  /* rt_auxvar */
+  double *total;               /* io [naqcomp]  mol/L; in: transported total* */
+  double *pri_molal;           /* io [naqcomp]  mol/kg; in: Newton guess      */
+  double *immobile;            /* io [nimcomp]  mol/m^3                       */
+  double *pri_act_coef;        /* io [naqcomp]                                */
+  double *sec_act_coef;        /* io [neqcplx]                                */
+  double *sec_molal;           /* io [neqcplx]                                */
+  double *ln_act_h2o;          /* io [1]                                      */
+  double *mnrl_volfrac;        /* io [nkinmnrl]                               */
+  double *mnrl_area;           /* in [nkinmnrl] m^2/m^3                       */
+  double *mnrl_rate;           /* io [nkinmnrl] mol/m^3/s                     */
+  double *srfcplxrxn_free_site_conc; /* io [nsrfcplxrxn]                      */
+  double *eqsrfcplx_conc;      /* io [nsrfcplx]                               */
+  double *total_sorb_eq;       /* io [naqcomp]                                */
+  double *kinmr_total_sorb;    /* io [sum_r naqcomp*(nrate_r+1)]: rxn r, rate
+                                  slot q (0 = equilibrium target), comp i at
+                                  row  naqcomp*(kinmr_rate_ptr[r]+r+q) + i    */
+  /* global_auxvar / material_auxvar */
+  const double *den_kg;        /* in [1] kg/m^3 */
+  const double *sat;           /* in [1] liquid saturation */
+  const double *temp;          /* in [1] deg C */
+  const double *porosity;      /* in [1] */
+  const double *volume;        /* in [1] m^3 */
+  const double *soil_particle_density; /* in [1] or NULL */
+  const int32_t *imat;         /* in [1] or NULL; <=0 => inactive, skipped
+                                  (pmc_subsurface_osrt.F90:351)               */
+  /* per-cell results of RStep (reaction.F90:3564-3566) */
+  int32_t *num_sub_steps;
+  int32_t *num_iterations;
+  int32_t *num_kinetic_state_updates;
+  int32_t *ierror;
+} pfrx_state;
+
+/* Shard-level result: what the OS coupler accumulates after the cell loop
+ * (pmc_subsurface_osrt.F90:364-388) plus the flags the north star asks for. */
+typedef struct pfrx_step_result {
+  int64_t ncell_active;        /* cells with imat > 0                        */
+  int64_t sum_newton_iterations;
+  int32_t max_newton_iterations;
+  int32_t max_num_kinetic_state_updates;
+  int32_t rstep_error;         /* max over cells of ierror                   */
+  int32_t max_sub_steps;
+  int64_t num_cut_cells;       /* cells that needed >= 1 reaction-dt cut     */
+  int64_t first_failed_cell;   /* lowest failing local cell index, or -1     */
+} pfrx_step_result;
+
+typedef struct pfrx_handle pfrx_handle;
+
+/* library identification; safe to call without a GPU */
+int pfrx_abi_version(void);
+const char *pfrx_last_error(void);
+
+/* Replaces nothing in the reference: flattening of reaction_rt_type is done by
+ * the binding.  `device` is the CUDA ordinal this handle is tied to. */
+int pfrx_create(const pfrx_config *cfg, int device, pfrx_handle **out);
+void pfrx_destroy(pfrx_handle *h);
+
+/* Bind device-resident SoA state of `ncell` cells (zero-copy: the kernels
+ * update these arrays in place).  Replaces the rt_auxvars(ghosted_id) /
+ * global_auxvars / material_auxvars lookups at pmc_subsurface_osrt.F90:349-363. */
+int pfrx_bind_state(pfrx_handle *h, int64_t ncell, const pfrx_state *dev);
+
+/* The cell loop pmc_subsurface_osrt.F90:349-378: RStep on every bound cell over
+ * tran_dt.  Asynchronous variant enqueues on the handle's stream;
+ * pfrx_rstep_finish() synchronises and returns the shard summary.           */
+int pfrx_rstep_async(pfrx_handle *h, double tran_dt);
+int pfrx_rstep_finish(pfrx_handle *h, pfrx_step_result *out);
+int pfrx_rstep(pfrx_handle *h, double tran_dt, pfrx_step_result *out);
+
+/* Same step for HOST-resident SoA state (what a Fortran caller has after its
+ * AoS->SoA pack): H2D of every `in`/`io` field, kernel, D2H of every `io`
+ * field and the per-cell results, through pinned staging owned by the handle. */
+int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *host,
+                    double tran_dt, pfrx_step_result *out);
+
+/* Multi-GPU: one rank per GPU, cells sharded by ownership range, no halo.
+ * pfrx_allreduce() replaces MPI_Allreduce(rstep_error,MAX)+MPI_Barrier at
+ * pmc_subsurface_osrt.F90:381-383 (MAX of error / iteration / update counts,
+ * SUM of iterations and cell counts) with one NCCL call over NVLink.
+ * The 128-byte id comes from rank 0 (pfrx_comm_unique_id) and is distributed
+ * by the host (MPI_Bcast in the Fortran caller).                            */
+int pfrx_comm_unique_id(void *id128);
+int pfrx_comm_init(pfrx_handle *h, int nranks, int rank, const void *id128);
+int pfrx_allreduce(pfrx_handle *h, pfrx_step_result *inout);
+
+/* stream the handle launches on (cudaStream_t), for callers that time with
+ * CUDA events or chain their own work behind the step */
+void *pfrx_stream(pfrx_handle *h);
+/* number of kernel launches issued by this handle so far */
+int64_t pfrx_launch_count(pfrx_handle *h);
+/* bytes of state read+written per cell-solve by the bound configuration
+ * (the algorithmic HBM traffic of SURVEY.md section 8(d))                    */
+int64_t pfrx_bytes_per_cell(pfrx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFRX_H */

@@ -1,0 +1,1497 @@
+/*
+ * pfrx_oracle.c -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * A plain-C restatement of the reference's operator-split chemistry step, in
+ * the reference's operation order, used only by tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs as the checker and the
+ * CPU baseline.  Nothing under pflotran_elm_interface_b200/ may call it.
+ *
+ * Parity status: the residual/Jacobian functions (RTotalAqueous,
+ * RActivityCoefficients, RKineticMineral, surface complexation, CLM_CN_React)
+ * are pinned against the reference's GIRT batch golds (tests/golden/, see
+ * tests/test_oracle_golden.py).  RStep/RReact themselves (sub-stepping, OS
+ * convergence tests, iteration counts) are "parity unpinned by reference
+ * tests; pinned by source restatement" -- SURVEY.md section 0.2: the fork's
+ * RSolve skips back-substitution on this call path, so its *_os golds encode
+ * a no-op.  This oracle back-substitutes (the evident intended algorithm);
+ * PFRX_ORACLE_REF_BUG_COMPAT=1 reproduces the no-op for harness self-checks.
+ *
+ * The reference cannot be compiled in this image (no Fortran compiler, PETSc
+ * or MPI), so there is no oracle/_ref; DESIGN.md records that.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
+ * Every function cites the reference file:line it follows; paths are relative
+ * to src/pflotran/ of the reference.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/pfrx.h"
+
+/* pflotran_constants.F90:84-92 (truncated on purpose, as in the reference) */
+#define LOG_TO_LN 2.30258509299
+#define IDEAL_GAS_CONSTANT 8.31446
+#define MAX_DOUBLE 1.e20
+
+static int g_ref_bug_compat = 0;
+
+/* ------------------------------------------------------------------------ */
+/* one cell, gathered from the SoA views (the role of rt_auxvar +             */
+/* global_auxvar + material_auxvar)                                           */
+typedef struct {
+  int naq, nim, n, ncplx, nkin, nsrfrxn, nsrfcplx, nmrrows;
+  double *total, *pri_molal, *immobile, *pri_act_coef, *sec_act_coef;
+  double *sec_molal, *mnrl_volfrac, *mnrl_area, *mnrl_rate;
+  double *free_site, *eqsrfcplx_conc, *total_sorb_eq, *dtotal_sorb_eq;
+  double *kinmr_total_sorb;
+  double *dtotal;      /* dtotal(i,j) at [i + j*naq] */
+  double ln_act_h2o;
+  double den_kg, sat, temp, porosity, volume, soil_particle_density;
+  /* per-cell copies of the temperature dependent tables
+   * (the reference overwrites the shared ones, reaction.F90:6003-6031) */
+  double *eqcplx_logK, *kinmnrl_logK, *srfcplx_logK;
+  /* scratch */
+  double *buf;
+  int option_ierror;
+} cell_t;
+
+static int mr_rows(const pfrx_config *cfg) {
+  int nmr = cfg->nkinmrsrfcplxrxn;
+  if (nmr <= 0) return 0;
+  return cfg->naqcomp * (cfg->kinmr_rate_ptr[nmr] + nmr);
+}
+
+static size_t cell_doubles(const pfrx_config *cfg) {
+  size_t naq = cfg->naqcomp, nim = cfg->nimcomp, nc = cfg->neqcplx;
+  size_t nk = cfg->nkinmnrl, nr = cfg->nsrfcplxrxn, ns = cfg->nsrfcplx;
+  return 4 * naq + nim + 3 * nc + 4 * nk + nr + 2 * ns + naq + 2 * naq * naq +
+         mr_rows(cfg) + 64;
+}
+
+static void cell_init(cell_t *c, const pfrx_config *cfg) {
+  memset(c, 0, sizeof(*c));
+  c->naq = cfg->naqcomp;
+  c->nim = cfg->nimcomp;
+  c->n = c->naq + c->nim;
+  c->ncplx = cfg->neqcplx;
+  c->nkin = cfg->nkinmnrl;
+  c->nsrfrxn = cfg->nsrfcplxrxn;
+  c->nsrfcplx = cfg->nsrfcplx;
+  c->nmrrows = mr_rows(cfg);
+  c->buf = (double *)calloc(cell_doubles(cfg), sizeof(double));
+  double *p = c->buf;
+#define TAKE(field, cnt) \
+  c->field = p;          \
+  p += (cnt)
+  TAKE(total, c->naq);
+  TAKE(pri_molal, c->naq);
+  TAKE(immobile, c->nim);
+  TAKE(pri_act_coef, c->naq);
+  TAKE(sec_act_coef, c->ncplx);
+  TAKE(sec_molal, c->ncplx);
+  TAKE(mnrl_volfrac, c->nkin);
+  TAKE(mnrl_area, c->nkin);
+  TAKE(mnrl_rate, c->nkin);
+  TAKE(free_site, c->nsrfrxn);
+  TAKE(eqsrfcplx_conc, c->nsrfcplx);
+  TAKE(total_sorb_eq, c->naq);
+  TAKE(dtotal_sorb_eq, c->naq * c->naq);
+  TAKE(kinmr_total_sorb, c->nmrrows);
+  TAKE(dtotal, c->naq * c->naq);
+  TAKE(eqcplx_logK, c->ncplx);
+  TAKE(kinmnrl_logK, c->nkin);
+  TAKE(srfcplx_logK, c->nsrfcplx);
+#undef TAKE
+  if (c->ncplx) memcpy(c->eqcplx_logK, cfg->eqcplx_logK, sizeof(double) * c->ncplx);
+  if (c->nkin) memcpy(c->kinmnrl_logK, cfg->kinmnrl_logK, sizeof(double) * c->nkin);
+  if (c->nsrfcplx) memcpy(c->srfcplx_logK, cfg->srfcplx_logK, sizeof(double) * c->nsrfcplx);
+}
+
+static void cell_free(cell_t *c) { free(c->buf); }
+
+#define LD(arr, k) ((arr)[(int64_t)(k) * st->ld + ic])
+
+static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
+                        int64_t ic) {
+  int k;
+  (void)cfg;
+  for (k = 0; k < c->naq; k++) {
+    c->total[k] = LD(st->total, k);
+    c->pri_molal[k] = LD(st->pri_molal, k);
+    c->pri_act_coef[k] = LD(st->pri_act_coef, k);
+    if (st->total_sorb_eq) c->total_sorb_eq[k] = LD(st->total_sorb_eq, k);
+  }
+  for (k = 0; k < c->nim; k++) c->immobile[k] = LD(st->immobile, k);
+  for (k = 0; k < c->ncplx; k++) {
+    c->sec_act_coef[k] = LD(st->sec_act_coef, k);
+    c->sec_molal[k] = LD(st->sec_molal, k);
+  }
+  c->ln_act_h2o = st->ln_act_h2o ? LD(st->ln_act_h2o, 0) : 0.0;
+  for (k = 0; k < c->nkin; k++) {
+    c->mnrl_volfrac[k] = LD(st->mnrl_volfrac, k);
+    c->mnrl_area[k] = LD(st->mnrl_area, k);
+    c->mnrl_rate[k] = LD(st->mnrl_rate, k);
+  }
+  for (k = 0; k < c->nsrfrxn; k++) c->free_site[k] = LD(st->srfcplxrxn_free_site_conc, k);
+  for (k = 0; k < c->nsrfcplx; k++)
+    c->eqsrfcplx_conc[k] = st->eqsrfcplx_conc ? LD(st->eqsrfcplx_conc, k) : 0.0;
+  for (k = 0; k < c->nmrrows; k++) c->kinmr_total_sorb[k] = LD(st->kinmr_total_sorb, k);
+  c->den_kg = LD(st->den_kg, 0);
+  c->sat = LD(st->sat, 0);
+  c->temp = LD(st->temp, 0);
+  c->porosity = LD(st->porosity, 0);
+  c->volume = LD(st->volume, 0);
+  c->soil_particle_density = st->soil_particle_density ? LD(st->soil_particle_density, 0) : 0.0;
+  c->option_ierror = 0;
+}
+
+static void cell_scatter(const cell_t *c, const pfrx_state *st, int64_t ic) {
+  int k;
+  for (k = 0; k < c->naq; k++) {
+    LD(st->total, k) = c->total[k];
+    LD(st->pri_molal, k) = c->pri_molal[k];
+    LD(st->pri_act_coef, k) = c->pri_act_coef[k];
+    if (st->total_sorb_eq) LD(st->total_sorb_eq, k) = c->total_sorb_eq[k];
+  }
+  for (k = 0; k < c->nim; k++) LD(st->immobile, k) = c->immobile[k];
+  for (k = 0; k < c->ncplx; k++) {
+    LD(st->sec_act_coef, k) = c->sec_act_coef[k];
+    LD(st->sec_molal, k) = c->sec_molal[k];
+  }
+  if (st->ln_act_h2o) LD(st->ln_act_h2o, 0) = c->ln_act_h2o;
+  for (k = 0; k < c->nkin; k++) {
+    LD(st->mnrl_volfrac, k) = c->mnrl_volfrac[k];
+    LD(st->mnrl_rate, k) = c->mnrl_rate[k];
+  }
+  for (k = 0; k < c->nsrfrxn; k++) LD(st->srfcplxrxn_free_site_conc, k) = c->free_site[k];
+  if (st->eqsrfcplx_conc)
+    for (k = 0; k < c->nsrfcplx; k++) LD(st->eqsrfcplx_conc, k) = c->eqsrfcplx_conc[k];
+  for (k = 0; k < c->nmrrows; k++) LD(st->kinmr_total_sorb, k) = c->kinmr_total_sorb[k];
+}
+
+/* ------------------------------------------------------------------------ */
+/* utility.F90:597-688  LUDecomposition1 (NR ludcmp, Crout, implicit scaling) */
+static int lu_decomposition(double *A, int N, int *indx) {
+  const double tiny = 1.0e-20;
+  double VV[PFRX_MAX_NCOMP * 4];
+  double *vv = VV, *heap = NULL;
+  int i, j, k, imax = 0;
+  double aamax, sum, dum;
+  if (N > PFRX_MAX_NCOMP * 4) vv = heap = (double *)malloc(sizeof(double) * N);
+#define a(i, j) A[(i) + (size_t)(j) * N]
+  for (i = 0; i < N; i++) {
+    aamax = 0.0;
+    for (j = 0; j < N; j++)
+      if (fabs(a(i, j)) > aamax) aamax = fabs(a(i, j));
+    if (aamax <= 0.0) {
+      free(heap);
+      return 1; /* singular row, stop_on_error = false */
+    }
+    vv[i] = 1. / aamax;
+  }
+  for (j = 0; j < N; j++) {
+    for (i = 0; i < j; i++) {
+      sum = a(i, j);
+      for (k = 0; k < i; k++) sum = sum - a(i, k) * a(k, j);
+      a(i, j) = sum;
+    }
+    aamax = 0;
+    imax = j;
+    for (i = j; i < N; i++) {
+      sum = a(i, j);
+      for (k = 0; k < j; k++) sum = sum - a(i, k) * a(k, j);
+      a(i, j) = sum;
+      dum = vv[i] * fabs(sum);
+      if (dum >= aamax) {
+        imax = i;
+        aamax = dum;
+      }
+    }
+    if (j != imax) {
+      for (k = 0; k < N; k++) {
+        dum = a(imax, k);
+        a(imax, k) = a(j, k);
+        a(j, k) = dum;
+      }
+      vv[imax] = vv[j];
+    }
+    indx[j] = imax;
+    if (a(j, j) == 0.0) a(j, j) = tiny;
+    if (j != N - 1) {
+      dum = 1.0 / a(j, j);
+      for (i = j + 1; i < N; i++) a(i, j) = a(i, j) * dum;
+    }
+  }
+  free(heap);
+  return 0;
+}
+
+/* utility.F90:692-735  LUBackSubstitution (NR lubksb) */
+static void lu_back_substitution(const double *A, int N, const int *indx, double *B) {
+  int i, j, ii = -1, ll;
+  double sum;
+  for (i = 0; i < N; i++) {
+    ll = indx[i];
+    sum = B[ll];
+    B[ll] = B[i];
+    if (ii != -1) {
+      for (j = ii; j <= i - 1; j++) sum = sum - a(i, j) * B[j];
+    } else if (sum != 0.0) {
+      ii = i;
+    }
+    B[i] = sum;
+  }
+  for (i = N - 1; i >= 0; i--) {
+    sum = B[i];
+    if (i < N - 1)
+      for (j = i + 1; j < N; j++) sum = sum - a(i, j) * B[j];
+    B[i] = sum / a(i, i);
+  }
+}
+#undef a
+
+/* reaction_aux.F90:1285-1312  ReactionInterpolateLogK */
+static void interpolate_logK(const double *coefs, double *logKs, double temp, int n) {
+  double temp_kelvin = temp + 273.15;
+  int i;
+  for (i = 0; i < n; i++) {
+    const double *c = coefs + 5 * i;
+    logKs[i] = c[0] * log(temp_kelvin) + c[1] + c[2] * temp_kelvin + c[3] / temp_kelvin +
+               c[4] / (temp_kelvin * temp_kelvin);
+  }
+}
+
+/* reaction.F90:5976-6067  RUpdateTempDependentCoefs (non-hpt branch) */
+static void update_temp_dependent_coefs(cell_t *c, const pfrx_config *cfg) {
+  if (cfg->eqcplx_logKcoef) interpolate_logK(cfg->eqcplx_logKcoef, c->eqcplx_logK, c->temp, c->ncplx);
+  if (cfg->kinmnrl_logKcoef) interpolate_logK(cfg->kinmnrl_logKcoef, c->kinmnrl_logK, c->temp, c->nkin);
+  if (cfg->srfcplx_logKcoef) interpolate_logK(cfg->srfcplx_logKcoef, c->srfcplx_logK, c->temp, c->nsrfcplx);
+}
+
+/* ------------------------------------------------------------------------ */
+/* reaction.F90:4368-4614  RActivityCoefficients */
+static void r_activity_coefficients(cell_t *c, const pfrx_config *cfg) {
+  int icplx, icomp, it, j, jcomp, i;
+  double I, sqrt_I, II, f, fpri, didi, dcdi = 0, den, dgamdi, lnQK, sum;
+  double sum_pri_molal = 0.0, sum_sec_molal;
+  const double *Z = cfg->primary_spec_Z, *a0 = cfg->primary_spec_a0;
+  const double *cZ = cfg->eqcplx_Z, *ca0 = cfg->eqcplx_a0;
+
+  if (cfg->use_activity_h2o) {
+    sum_pri_molal = 0.0;
+    for (j = 0; j < c->naq; j++)
+      if (j != cfg->h2o_aq_id) sum_pri_molal = sum_pri_molal + c->pri_molal[j];
+  }
+
+  if (cfg->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON) {
+    double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+    for (j = 0; j < c->naq; j++) {
+      ln_conc[j] = log(c->pri_molal[j]);
+      ln_act[j] = ln_conc[j] + log(c->pri_act_coef[j]);
+    }
+    fpri = 0.0;
+    for (j = 0; j < c->naq; j++) fpri = fpri + c->pri_molal[j] * Z[j] * Z[j];
+    it = 0;
+    II = 0;
+    for (;;) {
+      it = it + 1;
+      if (it > 50) {
+        /* reference poisons with NaN and never leaves the loop
+         * (reaction.F90:4421-4431); we flag the error and leave */
+        for (j = 0; j < c->naq; j++) {
+          c->pri_molal[j] = NAN;
+          c->pri_act_coef[j] = NAN;
+        }
+        for (j = 0; j < c->ncplx; j++) c->sec_act_coef[j] = NAN;
+        c->option_ierror = 1;
+        return;
+      }
+      I = fpri;
+      for (icplx = 0; icplx < c->ncplx; icplx++)
+        I = I + c->sec_molal[icplx] * cZ[icplx] * cZ[icplx];
+      I = 0.5 * I;
+      f = I;
+      if (fabs(I - II) < 1.e-6 * I) break;
+
+      if (c->ncplx > 0) {
+        didi = 0.0;
+        sqrt_I = sqrt(I);
+        for (icplx = 0; icplx < c->ncplx; icplx++) {
+          if (fabs(cZ[icplx]) > 0.0) {
+            double t = 1.0 + cfg->debyeB * ca0[icplx] * sqrt_I;
+            sum = 0.5 * cfg->debyeA * cZ[icplx] * cZ[icplx] / (sqrt_I * (t * t)) - cfg->debyeBdot;
+            for (i = cfg->eqcplx_ptr[icplx]; i < cfg->eqcplx_ptr[icplx + 1]; i++) {
+              j = cfg->eqcplx_specid[i];
+              if (fabs(Z[j]) > 0.0) {
+                double tj = 1.0 + cfg->debyeB * a0[j] * sqrt_I;
+                dgamdi = -0.5 * cfg->debyeA * (Z[j] * Z[j]) / (sqrt_I * (tj * tj)) + cfg->debyeBdot;
+                sum = sum + cfg->eqcplx_stoich[i] * dgamdi;
+              }
+            }
+            dcdi = c->sec_molal[icplx] * LOG_TO_LN * sum;
+            didi = didi + 0.5 * cZ[icplx] * cZ[icplx] * dcdi;
+          }
+        }
+        den = 1.0 - didi;
+        if (fabs(den) > 0.0)
+          II = (f - I * didi) / den;
+        else
+          II = f;
+      } else {
+        II = f;
+      }
+      if (II < 0.0) {
+        for (j = 0; j < c->naq; j++) {
+          c->pri_molal[j] = NAN;
+          c->pri_act_coef[j] = NAN;
+        }
+        for (j = 0; j < c->ncplx; j++) c->sec_act_coef[j] = NAN;
+        c->option_ierror = 1;
+        return;
+      }
+      I = II;
+      sqrt_I = sqrt(I);
+      for (icomp = 0; icomp < c->naq; icomp++) {
+        if (fabs(Z[icomp]) > 0.0)
+          c->pri_act_coef[icomp] =
+              exp((-Z[icomp] * Z[icomp] * sqrt_I * cfg->debyeA / (1.0 + a0[icomp] * cfg->debyeB * sqrt_I) +
+                   cfg->debyeBdot * I) *
+                  LOG_TO_LN);
+        else
+          c->pri_act_coef[icomp] = 1.0;
+      }
+      sum_sec_molal = 0.0;
+      for (icplx = 0; icplx < c->ncplx; icplx++) {
+        if (fabs(cZ[icplx]) > 0.0)
+          c->sec_act_coef[icplx] =
+              exp((-cZ[icplx] * cZ[icplx] * sqrt_I * cfg->debyeA / (1.0 + ca0[icplx] * cfg->debyeB * sqrt_I) +
+                   cfg->debyeBdot * I) *
+                  LOG_TO_LN);
+        else
+          c->sec_act_coef[icplx] = 1.0;
+        lnQK = -c->eqcplx_logK[icplx] * LOG_TO_LN;
+        if (cfg->eqcplx_h2ostoich[icplx] != 0.0) lnQK = lnQK + cfg->eqcplx_h2ostoich[icplx] * c->ln_act_h2o;
+        for (i = cfg->eqcplx_ptr[icplx]; i < cfg->eqcplx_ptr[icplx + 1]; i++) {
+          jcomp = cfg->eqcplx_specid[i];
+          lnQK = lnQK + cfg->eqcplx_stoich[i] * ln_act[jcomp];
+        }
+        c->sec_molal[icplx] = exp(lnQK) / c->sec_act_coef[icplx];
+        sum_sec_molal = sum_sec_molal + c->sec_molal[icplx];
+      }
+      if (cfg->use_activity_h2o) {
+        c->ln_act_h2o = 1.0 - 0.017 * (sum_pri_molal + sum_sec_molal);
+        if (c->ln_act_h2o > 0.0)
+          c->ln_act_h2o = log(c->ln_act_h2o);
+        else
+          c->ln_act_h2o = 0.0;
+      }
+    }
+  } else {
+    /* LAG algorithm, reaction.F90:4553-4612 */
+    I = 0.0;
+    for (icomp = 0; icomp < c->naq; icomp++) I = I + c->pri_molal[icomp] * Z[icomp] * Z[icomp];
+    for (icplx = 0; icplx < c->ncplx; icplx++) I = I + c->sec_molal[icplx] * cZ[icplx] * cZ[icplx];
+    I = 0.5 * I;
+    sqrt_I = sqrt(I);
+    for (icomp = 0; icomp < c->naq; icomp++) {
+      if (fabs(Z[icomp]) > 1.e-10)
+        c->pri_act_coef[icomp] =
+            exp((-Z[icomp] * Z[icomp] * sqrt_I * cfg->debyeA / (1.0 + a0[icomp] * cfg->debyeB * sqrt_I) +
+                 cfg->debyeBdot * I) *
+                LOG_TO_LN);
+      else
+        c->pri_act_coef[icomp] = 1.0;
+    }
+    sum_sec_molal = 0.0;
+    for (icplx = 0; icplx < c->ncplx; icplx++) {
+      if (fabs(cZ[icplx]) > 1.e-10)
+        c->sec_act_coef[icplx] =
+            exp((-cZ[icplx] * cZ[icplx] * sqrt_I * cfg->debyeA / (1.0 + ca0[icplx] * cfg->debyeB * sqrt_I) +
+                 cfg->debyeBdot * I) *
+                LOG_TO_LN);
+      else
+        c->sec_act_coef[icplx] = 1.0;
+      sum_sec_molal = sum_sec_molal + c->sec_molal[icplx];
+    }
+    if (cfg->use_activity_h2o) {
+      c->ln_act_h2o = 1.0 - 0.017 * (sum_pri_molal + sum_sec_molal);
+      if (c->ln_act_h2o > 0.0)
+        c->ln_act_h2o = log(c->ln_act_h2o);
+      else
+        c->ln_act_h2o = 0.0;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* reaction.F90:4665-4759  RTotalAqueous */
+static void r_total_aqueous(cell_t *c, const pfrx_config *cfg) {
+  int i, j, icplx, icomp, jcomp, naq = c->naq;
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  double lnQK, tempreal, den_kg_per_L;
+
+  den_kg_per_L = c->den_kg * 1.0 * 1.e-3; /* xmass = 1 */
+  for (i = 0; i < naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+    c->total[i] = c->pri_molal[i];
+  }
+  for (i = 0; i < naq * naq; i++) c->dtotal[i] = 0.0;
+  for (i = 0; i < naq; i++) c->dtotal[i + i * naq] = 1.0;
+
+  for (icplx = 0; icplx < c->ncplx; icplx++) {
+    int p0 = cfg->eqcplx_ptr[icplx], p1 = cfg->eqcplx_ptr[icplx + 1];
+    lnQK = -c->eqcplx_logK[icplx] * LOG_TO_LN;
+    if (cfg->eqcplx_h2ostoich[icplx] != 0.0) lnQK = lnQK + cfg->eqcplx_h2ostoich[icplx] * c->ln_act_h2o;
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->eqcplx_specid[i];
+      lnQK = lnQK + cfg->eqcplx_stoich[i] * ln_act[icomp];
+    }
+    c->sec_molal[icplx] = exp(lnQK) / c->sec_act_coef[icplx];
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->eqcplx_specid[i];
+      c->total[icomp] = c->total[icomp] + cfg->eqcplx_stoich[i] * c->sec_molal[icplx];
+    }
+    for (j = p0; j < p1; j++) {
+      jcomp = cfg->eqcplx_specid[j];
+      tempreal = cfg->eqcplx_stoich[j] * exp(lnQK - ln_conc[jcomp]) / c->sec_act_coef[icplx];
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->eqcplx_specid[i];
+        c->dtotal[icomp + jcomp * naq] = c->dtotal[icomp + jcomp * naq] + cfg->eqcplx_stoich[i] * tempreal;
+      }
+    }
+  }
+  for (i = 0; i < naq; i++) c->total[i] = c->total[i] * den_kg_per_L;
+  for (i = 0; i < naq * naq; i++) c->dtotal[i] = c->dtotal[i] * den_kg_per_L;
+}
+
+/* reaction_surf_complex.F90:641-900  RTotalSorbEqSurfCplx1
+ * srfcplx_out may be NULL (the multirate caller passes a null pointer). */
+static void r_total_sorb_eq_surf_cplx1(cell_t *c, const pfrx_config *cfg, int irxn,
+                                       double *external_free_site_conc, double *srfcplx_out,
+                                       double *external_total_sorb, double *external_dtotal_sorb) {
+  int i, j, k, icplx, icomp, jcomp, naq = c->naq;
+  double srfcplx_conc[256];
+  double dSx_dmi[PFRX_MAX_NCOMP * 4];
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  double nui_Si_over_Sx, ln_free_site, lnQK, tempreal, total;
+  const double tol = 1.e-12;
+  int one_more, num_iterations;
+  double res, dres_dfree_site, dfree_site_conc, free_site_conc, rel_change;
+  double site_density = 0.0, damping_factor;
+  int r0 = cfg->srfcplxrxn_ptr[irxn], r1 = cfg->srfcplxrxn_ptr[irxn + 1];
+
+  for (i = 0; i < naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+  }
+  free_site_conc = fmax(*external_free_site_conc, 1.e-40);
+  for (i = 0; i < c->nsrfcplx; i++) srfcplx_conc[i] = 0.0;
+
+  switch (cfg->srfcplxrxn_surf_type[irxn]) {
+    case PFRX_MINERAL_SURFACE:
+      site_density = cfg->srfcplxrxn_site_density[irxn] * c->mnrl_volfrac[cfg->srfcplxrxn_to_surf[irxn]];
+      break;
+    case PFRX_ROCK_SURFACE:
+      site_density = cfg->srfcplxrxn_site_density[irxn] * c->soil_particle_density * (1.0 - c->porosity);
+      break;
+    default:
+      site_density = cfg->srfcplxrxn_site_density[irxn];
+  }
+
+  if (site_density < 1.e-40) {
+    *external_free_site_conc = 0.0;
+    if (srfcplx_out)
+      for (j = r0; j < r1; j++) srfcplx_out[cfg->srfcplxrxn_to_complex[j]] = 0.0;
+    return;
+  }
+
+  one_more = 0;
+  num_iterations = 0;
+  damping_factor = 1.0;
+  for (;;) {
+    num_iterations = num_iterations + 1;
+    total = free_site_conc;
+    ln_free_site = log(free_site_conc);
+    for (j = r0; j < r1; j++) {
+      icplx = cfg->srfcplxrxn_to_complex[j];
+      lnQK = -c->srfcplx_logK[icplx] * LOG_TO_LN;
+      if (cfg->srfcplx_h2ostoich[icplx] != 0.0) lnQK = lnQK + cfg->srfcplx_h2ostoich[icplx] * c->ln_act_h2o;
+      lnQK = lnQK + cfg->srfcplx_free_site_stoich[icplx] * ln_free_site;
+      for (i = cfg->srfcplx_ptr[icplx]; i < cfg->srfcplx_ptr[icplx + 1]; i++) {
+        icomp = cfg->srfcplx_specid[i];
+        lnQK = lnQK + cfg->srfcplx_stoich[i] * ln_act[icomp];
+      }
+      srfcplx_conc[icplx] = exp(lnQK);
+      total = total + cfg->srfcplx_free_site_stoich[icplx] * srfcplx_conc[icplx];
+    }
+    if (one_more) break;
+    if (cfg->srfcplxrxn_stoich_flag[irxn]) {
+      res = site_density - total;
+      dres_dfree_site = 1.0;
+      for (j = r0; j < r1; j++) {
+        icplx = cfg->srfcplxrxn_to_complex[j];
+        dres_dfree_site =
+            dres_dfree_site + cfg->srfcplx_free_site_stoich[icplx] * srfcplx_conc[icplx] / free_site_conc;
+      }
+      dfree_site_conc = res / dres_dfree_site;
+      if (num_iterations > 1000) damping_factor = 0.5;
+      free_site_conc = free_site_conc + damping_factor * dfree_site_conc;
+      rel_change = fabs(dfree_site_conc / free_site_conc);
+      if (rel_change < tol) one_more = 1;
+      if (num_iterations > 100000) { /* reference has no cap; avoid a hang */
+        c->option_ierror = 1;
+        one_more = 1;
+      }
+    } else {
+      total = total / free_site_conc;
+      free_site_conc = site_density / total;
+      one_more = 1;
+    }
+  }
+  *external_free_site_conc = free_site_conc;
+
+  for (i = 0; i < naq; i++) dSx_dmi[i] = 0.0;
+  tempreal = 0.0;
+  for (j = r0; j < r1; j++) {
+    icplx = cfg->srfcplxrxn_to_complex[j];
+    for (i = cfg->srfcplx_ptr[icplx]; i < cfg->srfcplx_ptr[icplx + 1]; i++) {
+      icomp = cfg->srfcplx_specid[i];
+      dSx_dmi[icomp] =
+          dSx_dmi[icomp] + cfg->srfcplx_stoich[i] * cfg->srfcplx_free_site_stoich[icplx] * srfcplx_conc[icplx];
+    }
+    tempreal = tempreal + cfg->srfcplx_free_site_stoich[icplx] * cfg->srfcplx_free_site_stoich[icplx] *
+                              srfcplx_conc[icplx];
+  }
+  tempreal = tempreal / free_site_conc;
+  tempreal = tempreal + 1.0;
+  for (i = 0; i < naq; i++) {
+    dSx_dmi[i] = -dSx_dmi[i] / tempreal;
+    dSx_dmi[i] = dSx_dmi[i] / c->pri_molal[i];
+  }
+  if (srfcplx_out)
+    for (i = 0; i < c->nsrfcplx; i++) srfcplx_out[i] = srfcplx_out[i] + srfcplx_conc[i];
+
+  for (k = r0; k < r1; k++) {
+    int p0, p1;
+    icplx = cfg->srfcplxrxn_to_complex[k];
+    p0 = cfg->srfcplx_ptr[icplx];
+    p1 = cfg->srfcplx_ptr[icplx + 1];
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->srfcplx_specid[i];
+      external_total_sorb[icomp] = external_total_sorb[icomp] + cfg->srfcplx_stoich[i] * srfcplx_conc[icplx];
+    }
+    nui_Si_over_Sx = cfg->srfcplx_free_site_stoich[icplx] * srfcplx_conc[icplx] / free_site_conc;
+    for (j = p0; j < p1; j++) {
+      jcomp = cfg->srfcplx_specid[j];
+      tempreal = cfg->srfcplx_stoich[j] * srfcplx_conc[icplx] / c->pri_molal[jcomp] + nui_Si_over_Sx * dSx_dmi[jcomp];
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->srfcplx_specid[i];
+        external_dtotal_sorb[icomp + jcomp * naq] =
+            external_dtotal_sorb[icomp + jcomp * naq] + cfg->srfcplx_stoich[i] * tempreal;
+      }
+    }
+  }
+}
+
+static int neqsorb(const pfrx_config *cfg) { return cfg->neqsrfcplxrxn; }
+
+/* reaction.F90:4783-4832 RTotalSorb (+RZeroSorb :4765); surface complexation
+ * branch reaction_surf_complex.F90:446-487 */
+static void r_total_sorb(cell_t *c, const pfrx_config *cfg) {
+  int i, ieq;
+  for (i = 0; i < c->naq; i++) c->total_sorb_eq[i] = 0.0;
+  for (i = 0; i < c->naq * c->naq; i++) c->dtotal_sorb_eq[i] = 0.0;
+  for (i = 0; i < c->nsrfcplx; i++) c->eqsrfcplx_conc[i] = 0.0;
+  for (ieq = 0; ieq < cfg->neqsrfcplxrxn; ieq++) {
+    int irxn = cfg->eqsrfcplxrxn_to_srfcplxrxn[ieq];
+    r_total_sorb_eq_surf_cplx1(c, cfg, irxn, &c->free_site[irxn], c->eqsrfcplx_conc, c->total_sorb_eq,
+                               c->dtotal_sorb_eq);
+  }
+}
+
+/* reaction.F90:4618-4661 RTotal == reaction.F90:5606 RTAuxVarCompute */
+static void rt_auxvar_compute(cell_t *c, const pfrx_config *cfg) {
+  int i;
+  for (i = 0; i < c->naq; i++) c->total[i] = 0.0;
+  if (c->naq > 0) r_total_aqueous(c, cfg);
+  if (neqsorb(cfg) > 0) r_total_sorb(c, cfg);
+}
+
+/* reaction.F90:5710-5771 RTAccumulation */
+static void rt_accumulation(const cell_t *c, const pfrx_config *cfg, double *Res) {
+  int i;
+  double psv_t;
+  for (i = 0; i < c->n; i++) Res[i] = 0.0;
+  if (c->sat < cfg->rt_min_saturation) return;
+  psv_t = c->porosity * c->sat * 1000.0 * c->volume;
+  for (i = 0; i < c->naq; i++) Res[i] = psv_t * c->total[i];
+  for (i = 0; i < c->nim; i++) Res[c->naq + i] = Res[c->naq + i] + c->immobile[i] * c->volume;
+}
+
+/* reaction.F90:5775-5848 RTAccumulationDerivative; J(i,j) at [i + j*n] */
+static void rt_accumulation_derivative(const cell_t *c, const pfrx_config *cfg, double tran_dt, double *J) {
+  int i, j, n = c->n, naq = c->naq;
+  double psvd_t;
+  for (i = 0; i < n * n; i++) J[i] = 0.0;
+  if (c->sat < cfg->rt_min_saturation) {
+    for (i = 0; i < n; i++) J[i + i * n] = 1.0;
+    return;
+  }
+  psvd_t = c->porosity * c->sat * 1000.0 * c->volume / tran_dt;
+  for (j = 0; j < naq; j++)
+    for (i = 0; i < naq; i++) J[i + j * n] = c->dtotal[i + j * naq] * psvd_t;
+  for (i = 0; i < c->nim; i++) J[(naq + i) + (naq + i) * n] = c->volume / tran_dt;
+}
+
+/* reaction.F90:5144-5172 / :5177-5207 */
+static void r_accumulation_sorb(const cell_t *c, double *Res) {
+  int i;
+  for (i = 0; i < c->naq; i++) Res[i] = Res[i] + c->total_sorb_eq[i] * c->volume;
+}
+static void r_accumulation_sorb_derivative(const cell_t *c, double tran_dt, double *J) {
+  int i, j, n = c->n, naq = c->naq;
+  double v_t = c->volume / tran_dt;
+  for (j = 0; j < naq; j++)
+    for (i = 0; i < naq; i++) J[i + j * n] = J[i + j * n] + c->dtotal_sorb_eq[i + j * naq] * v_t;
+}
+
+/* ------------------------------------------------------------------------ */
+/* reaction_mineral.F90:647-1078  RKineticMineral (non SOLID_SOLUTION build) */
+static void r_kinetic_mineral(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
+  int i, j, imnrl, icomp, jcomp, n = c->n, naq = c->naq;
+  int ipref, ipref_species;
+  double tempreal, affinity_factor, sign_, Im, Im_const, dIm_dQK;
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  double *ln_sec_act = NULL;
+  double QK, lnQK, dQK_dCj, dQK_dmj, den;
+  double ln_spec_act, spec_act_coef, ln_prefactor, ln_numerator, ln_denominator;
+  double prefactor[PFRX_MAX_PREFACTORS];
+  double ln_prefactor_spec[PFRX_MAX_PREFACTORS][PFRX_MAX_PREFACTOR_SPECIES];
+  double sum_prefactor_rate = 0.0, dIm_dsum_prefactor_rate, dIm_dspec;
+  double dprefactor_dprefactor_spec, dprefactor_spec_dspec;
+  double dprefactor_spec_dspec_numerator, dprefactor_spec_dspec_denominator;
+  double denominator, ln_gam_m_beta, arrhenius_factor;
+  const int MAXP = PFRX_MAX_PREFACTORS, MAXS = PFRX_MAX_PREFACTOR_SPECIES;
+
+  for (i = 0; i < naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+  }
+  if (c->ncplx > 0 && cfg->kinmnrl_num_prefactors) {
+    ln_sec_act = (double *)malloc(sizeof(double) * c->ncplx);
+    for (i = 0; i < c->ncplx; i++) ln_sec_act[i] = log(c->sec_molal[i]) + log(c->sec_act_coef[i]);
+  }
+  for (imnrl = 0; imnrl < c->nkin; imnrl++) c->mnrl_rate[imnrl] = 0.0;
+
+  for (imnrl = 0; imnrl < c->nkin; imnrl++) {
+    int p0 = cfg->kinmnrl_ptr[imnrl], p1 = cfg->kinmnrl_ptr[imnrl + 1];
+    int nprefactors = cfg->kinmnrl_num_prefactors ? cfg->kinmnrl_num_prefactors[imnrl] : 0;
+    lnQK = -c->kinmnrl_logK[imnrl] * LOG_TO_LN;
+    if (cfg->kinmnrl_h2ostoich[imnrl] != 0.0) lnQK = lnQK + cfg->kinmnrl_h2ostoich[imnrl] * c->ln_act_h2o;
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->kinmnrl_specid[i];
+      lnQK = lnQK + cfg->kinmnrl_stoich[i] * ln_act[icomp];
+    }
+    QK = exp(lnQK);
+
+    if (cfg->kinmnrl_Temkin_const) {
+      if (cfg->kinmnrl_min_scale_factor)
+        affinity_factor =
+            1.0 - pow(QK, 1.0 / (cfg->kinmnrl_min_scale_factor[imnrl] * cfg->kinmnrl_Temkin_const[imnrl]));
+      else
+        affinity_factor = 1.0 - pow(QK, 1.0 / cfg->kinmnrl_Temkin_const[imnrl]);
+    } else if (cfg->kinmnrl_min_scale_factor) {
+      affinity_factor = 1.0 - pow(QK, 1.0 / cfg->kinmnrl_min_scale_factor[imnrl]);
+    } else {
+      affinity_factor = 1.0 - QK;
+    }
+    sign_ = copysign(1.0, affinity_factor);
+
+    if (c->mnrl_volfrac[imnrl] > 0 || sign_ < 0.0) {
+      if (cfg->kinmnrl_irreversible[imnrl] == 1 && sign_ < 0.0) continue;
+      if (cfg->kinmnrl_affinity_threshold[imnrl] > 0.0) {
+        if (sign_ < 0.0 && QK < cfg->kinmnrl_affinity_threshold[imnrl]) continue;
+      }
+      if (cfg->kinmnrl_rate_limiter[imnrl] > 0.0) {
+        affinity_factor = affinity_factor / (1.0 + (1.0 - affinity_factor) / cfg->kinmnrl_rate_limiter[imnrl]);
+      }
+      if (nprefactors > 0) {
+        sum_prefactor_rate = 0.0;
+        memset(prefactor, 0, sizeof(prefactor));
+        memset(ln_prefactor_spec, 0, sizeof(ln_prefactor_spec));
+        for (ipref = 0; ipref < nprefactors; ipref++) {
+          int nps = cfg->kinmnrl_pref_nspec[imnrl * MAXP + ipref];
+          double eact = cfg->kinmnrl_pref_activation_energy[imnrl * MAXP + ipref];
+          ln_prefactor = 0.0;
+          for (ipref_species = 0; ipref_species < nps; ipref_species++) {
+            int q = (imnrl * MAXP + ipref) * MAXS + ipref_species;
+            icomp = cfg->kinmnrl_prefactor_id[q];
+            if (icomp >= 0)
+              ln_spec_act = ln_act[icomp];
+            else
+              ln_spec_act = ln_sec_act[-icomp - 1];
+            ln_numerator = cfg->kinmnrl_pref_alpha[q] * ln_spec_act;
+            ln_denominator =
+                log(1.0 + exp(log(cfg->kinmnrl_pref_atten_coef[q]) + cfg->kinmnrl_pref_beta[q] * ln_spec_act));
+            ln_prefactor = ln_prefactor + ln_numerator;
+            ln_prefactor = ln_prefactor - ln_denominator;
+            ln_prefactor_spec[ipref][ipref_species] = ln_numerator - ln_denominator;
+          }
+          prefactor[ipref] = exp(ln_prefactor);
+          arrhenius_factor = 1.0;
+          if (eact > 0.0)
+            arrhenius_factor = exp(eact / IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (c->temp + 273.15)));
+          sum_prefactor_rate =
+              sum_prefactor_rate + prefactor[ipref] * cfg->kinmnrl_pref_rate[imnrl * MAXP + ipref] * arrhenius_factor;
+        }
+      } else {
+        arrhenius_factor = 1.0;
+        if (cfg->kinmnrl_activation_energy[imnrl] > 0.0)
+          arrhenius_factor = exp(cfg->kinmnrl_activation_energy[imnrl] / IDEAL_GAS_CONSTANT *
+                                 (1.0 / (25.0 + 273.15) - 1.0 / (c->temp + 273.15)));
+        sum_prefactor_rate = cfg->kinmnrl_rate_constant[imnrl] * arrhenius_factor;
+      }
+      Im_const = -c->mnrl_area[imnrl];
+      if (cfg->kinmnrl_min_scale_factor) Im_const = Im_const / cfg->kinmnrl_min_scale_factor[imnrl];
+      if (cfg->kinmnrl_affinity_power)
+        Im = Im_const * sign_ * pow(fabs(affinity_factor), cfg->kinmnrl_affinity_power[imnrl]) * sum_prefactor_rate;
+      else
+        Im = Im_const * sign_ * fabs(affinity_factor) * sum_prefactor_rate;
+      c->mnrl_rate[imnrl] = Im;
+    } else {
+      continue;
+    }
+
+    Im_const = Im_const * c->volume;
+    Im = Im * c->volume;
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->kinmnrl_specid[i];
+      Res[icomp] = Res[icomp] + cfg->kinmnrl_stoich[i] * Im;
+    }
+    if (!compute_derivative) continue;
+
+    if (cfg->kinmnrl_affinity_power)
+      dIm_dQK = -Im * cfg->kinmnrl_affinity_power[imnrl] / fabs(affinity_factor);
+    else
+      dIm_dQK = -Im_const * sum_prefactor_rate;
+
+    if (cfg->kinmnrl_Temkin_const) {
+      if (cfg->kinmnrl_min_scale_factor)
+        dIm_dQK = dIm_dQK * (1.0 / (cfg->kinmnrl_min_scale_factor[imnrl] * cfg->kinmnrl_Temkin_const[imnrl])) / QK *
+                  (1.0 - affinity_factor);
+      else
+        dIm_dQK = dIm_dQK * (1.0 / cfg->kinmnrl_Temkin_const[imnrl]) / QK * (1.0 - affinity_factor);
+    } else if (cfg->kinmnrl_min_scale_factor) {
+      dIm_dQK = dIm_dQK * (1.0 / cfg->kinmnrl_min_scale_factor[imnrl]) / QK * (1.0 - affinity_factor);
+    }
+
+    if (cfg->kinmnrl_rate_limiter[imnrl] <= 0.0) {
+      for (j = p0; j < p1; j++) {
+        jcomp = cfg->kinmnrl_specid[j];
+        dQK_dCj = cfg->kinmnrl_stoich[j] * QK * exp(-ln_conc[jcomp]);
+        dQK_dmj = dQK_dCj * c->den_kg * 1.e-3;
+        for (i = p0; i < p1; i++) {
+          icomp = cfg->kinmnrl_specid[i];
+          Jac[icomp + jcomp * n] = Jac[icomp + jcomp * n] + cfg->kinmnrl_stoich[i] * dIm_dQK * dQK_dmj;
+        }
+      }
+    } else {
+      den = 1.0 + (1.0 - affinity_factor) / cfg->kinmnrl_rate_limiter[imnrl];
+      for (j = p0; j < p1; j++) {
+        jcomp = cfg->kinmnrl_specid[j];
+        dQK_dCj = cfg->kinmnrl_stoich[j] * QK * exp(-ln_conc[jcomp]);
+        dQK_dmj = dQK_dCj * c->den_kg * 1.e-3;
+        for (i = p0; i < p1; i++) {
+          icomp = cfg->kinmnrl_specid[i];
+          Jac[icomp + jcomp * n] =
+              Jac[icomp + jcomp * n] + cfg->kinmnrl_stoich[i] * dIm_dQK *
+                                           (1.0 + QK / cfg->kinmnrl_rate_limiter[imnrl] / den) * dQK_dmj / den;
+        }
+      }
+    }
+
+    if (nprefactors > 0) {
+      dIm_dsum_prefactor_rate = Im / sum_prefactor_rate;
+      for (ipref = 0; ipref < nprefactors; ipref++) {
+        int nps = cfg->kinmnrl_pref_nspec[imnrl * MAXP + ipref];
+        double eact = cfg->kinmnrl_pref_activation_energy[imnrl * MAXP + ipref];
+        arrhenius_factor = 1.0;
+        if (eact > 0.0)
+          arrhenius_factor = exp(eact / IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (c->temp + 273.15)));
+        ln_prefactor = log(prefactor[ipref]);
+        for (ipref_species = 0; ipref_species < nps; ipref_species++) {
+          int q = (imnrl * MAXP + ipref) * MAXS + ipref_species;
+          dprefactor_dprefactor_spec = exp(ln_prefactor - ln_prefactor_spec[ipref][ipref_species]);
+          icomp = cfg->kinmnrl_prefactor_id[q];
+          if (icomp >= 0) {
+            ln_spec_act = ln_act[icomp];
+            spec_act_coef = c->pri_act_coef[icomp];
+          } else {
+            ln_spec_act = ln_sec_act[-icomp - 1];
+            spec_act_coef = c->sec_act_coef[-icomp - 1];
+          }
+          dprefactor_spec_dspec_numerator =
+              cfg->kinmnrl_pref_alpha[q] * exp(ln_prefactor_spec[ipref][ipref_species] - ln_spec_act);
+          ln_gam_m_beta = cfg->kinmnrl_pref_beta[q] * ln_spec_act;
+          denominator = 1.0 + exp(log(cfg->kinmnrl_pref_atten_coef[q]) + ln_gam_m_beta);
+          dprefactor_spec_dspec_denominator = -1.0 * exp(ln_prefactor_spec[ipref][ipref_species]) / denominator *
+                                              cfg->kinmnrl_pref_atten_coef[q] * cfg->kinmnrl_pref_beta[q] *
+                                              exp(ln_gam_m_beta - ln_spec_act);
+          dprefactor_spec_dspec = dprefactor_spec_dspec_numerator + dprefactor_spec_dspec_denominator;
+          dprefactor_spec_dspec = dprefactor_spec_dspec * spec_act_coef;
+          dIm_dspec = dIm_dsum_prefactor_rate * dprefactor_dprefactor_spec * dprefactor_spec_dspec *
+                      cfg->kinmnrl_pref_rate[imnrl * MAXP + ipref] * arrhenius_factor;
+          if (icomp >= 0) {
+            for (i = p0; i < p1; i++) {
+              jcomp = cfg->kinmnrl_specid[i];
+              Jac[jcomp + icomp * n] = Jac[jcomp + icomp * n] + cfg->kinmnrl_stoich[i] * dIm_dspec;
+            }
+          } else {
+            /* secondary species: reference recomputes lnQK of the complex and
+             * (reaction_mineral.F90:1055) clobbers `ncomp`, so its i-loop runs
+             * over the COMPLEX's species, not the mineral's.  Restated as is. */
+            int icplx = -icomp - 1;
+            int q0 = cfg->eqcplx_ptr[icplx], q1 = cfg->eqcplx_ptr[icplx + 1];
+            int ii, jj;
+            lnQK = -c->eqcplx_logK[icplx] * LOG_TO_LN;
+            if (cfg->eqcplx_h2ostoich[icplx] != 0.0) lnQK = lnQK + cfg->eqcplx_h2ostoich[icplx] * c->ln_act_h2o;
+            for (ii = q0; ii < q1; ii++) lnQK = lnQK + cfg->eqcplx_stoich[ii] * ln_act[cfg->eqcplx_specid[ii]];
+            for (jj = q0; jj < q1; jj++) {
+              jcomp = cfg->eqcplx_specid[jj];
+              tempreal = cfg->eqcplx_stoich[jj] * exp(lnQK - ln_conc[jcomp]) / c->sec_act_coef[icplx];
+              for (ii = q0; ii < q1; ii++) {
+                int ic2 = cfg->eqcplx_specid[ii];
+                Jac[ic2 + jcomp * n] = Jac[ic2 + jcomp * n] + cfg->eqcplx_stoich[ii] * tempreal * dIm_dspec;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  free(ln_sec_act);
+}
+
+/* reaction_surf_complex.F90:552-637  RMultiRateSorption */
+static void r_multirate_sorption(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
+                                 int compute_derivative) {
+  int naq = c->naq, n = c->n, i, j, ikinmrrxn, irate;
+  double total_sorb_eq[PFRX_MAX_NCOMP * 4];
+  double *dtotal_sorb_eq = (double *)malloc(sizeof(double) * naq * naq);
+  for (ikinmrrxn = 0; ikinmrrxn < cfg->nkinmrsrfcplxrxn; ikinmrrxn++) {
+    int base = naq * (cfg->kinmr_rate_ptr[ikinmrrxn] + ikinmrrxn);
+    for (i = 0; i < naq; i++) c->kinmr_total_sorb[base + i] = 0.0;
+  }
+  for (ikinmrrxn = 0; ikinmrrxn < cfg->nkinmrsrfcplxrxn; ikinmrrxn++) {
+    int irxn = cfg->kinmrsrfcplxrxn_to_srfcplxrxn[ikinmrrxn];
+    int r0 = cfg->kinmr_rate_ptr[ikinmrrxn], r1 = cfg->kinmr_rate_ptr[ikinmrrxn + 1];
+    int base = naq * (r0 + ikinmrrxn);
+    for (i = 0; i < naq; i++) total_sorb_eq[i] = 0.0;
+    for (i = 0; i < naq * naq; i++) dtotal_sorb_eq[i] = 0.0;
+    r_total_sorb_eq_surf_cplx1(c, cfg, irxn, &c->free_site[irxn], NULL, total_sorb_eq, dtotal_sorb_eq);
+    for (irate = r0; irate < r1; irate++) {
+      double kdt = cfg->kinmr_rate[irate] * tran_dt;
+      double one_plus_kdt = 1.0 + kdt;
+      double k_over_one_plus_kdt = cfg->kinmr_rate[irate] / one_plus_kdt;
+      const double *S = c->kinmr_total_sorb + base + naq * (irate - r0 + 1);
+      for (i = 0; i < naq; i++)
+        Res[i] = Res[i] + c->volume * k_over_one_plus_kdt * (cfg->kinmr_frac[irate] * total_sorb_eq[i] - S[i]);
+      if (compute_derivative) {
+        for (j = 0; j < naq; j++)
+          for (i = 0; i < naq; i++)
+            Jac[i + j * n] =
+                Jac[i + j * n] + c->volume * k_over_one_plus_kdt * cfg->kinmr_frac[irate] * dtotal_sorb_eq[i + j * naq];
+      }
+    }
+    for (i = 0; i < naq; i++) c->kinmr_total_sorb[base + i] = total_sorb_eq[i];
+  }
+  free(dtotal_sorb_eq);
+}
+
+/* reaction_sandbox_clm_cn.F90:468-787  CLM_CN_React */
+static void clm_cn_react(cell_t *c, const pfrx_config *cfg, double *Residual, double *Jacobian,
+                         int compute_derivative) {
+  int n = c->n, off = c->naq;
+  int ipool_up, ipool_down, ispec_pool_down, ispecC_pool_up, ispecN_pool_up = -1;
+  int ires_pool_down = -1, ires_C, ires_N, iresC_pool_up, iresN_pool_up = -1, ispec_N, irxn;
+  double drate, scaled_rate_const, rate, F_t, F_theta, constant_inhibition, temp_K;
+  const double one_over_71_02 = 1.408054069e-2;
+  const double theta_min = 0.01;
+  const double one_over_log_theta_min = -2.17147241e-1;
+  double CN_ratio_up, CN_ratio_down, resp_frac, stoich_N, stoich_C;
+  double stoich_downstreamC_pool, stoich_upstreamC_pool, stoich_upstreamN_pool;
+  double N_inhibition, d_N_inhibition, drate_dN_inhibition = 0.0, temp_real;
+  int constant_CN_ratio_up, use_N_inhibition;
+#define JAC(i, j) Jacobian[(i) + (size_t)(j) * n]
+
+  temp_K = c->temp + 273.15;
+  if (temp_K > 227.15)
+    F_t = exp(308.56 * (one_over_71_02 - 1.0 / (temp_K - 227.13)));
+  else
+    return;
+  F_theta = log(theta_min / fmax(theta_min, c->sat)) * one_over_log_theta_min;
+  constant_inhibition = F_t * F_theta;
+
+  ires_C = off + cfg->clmcn_C_species_id;
+  ispec_N = cfg->clmcn_N_species_id;
+  ires_N = off + ispec_N;
+
+  for (irxn = 0; irxn < cfg->clmcn_nrxn; irxn++) {
+    scaled_rate_const = cfg->clmcn_rate_constant[irxn] * c->volume * constant_inhibition;
+    resp_frac = cfg->clmcn_respiration_fraction[irxn];
+    ipool_up = cfg->clmcn_upstream_pool_id[irxn];
+    constant_CN_ratio_up = (cfg->clmcn_pool_nspec[ipool_up] == 1);
+    if (!constant_CN_ratio_up) {
+      ispecC_pool_up = cfg->clmcn_pool_C_id[ipool_up];
+      ispecN_pool_up = cfg->clmcn_pool_N_id[ipool_up];
+      CN_ratio_up = c->immobile[ispecC_pool_up] / c->immobile[ispecN_pool_up];
+    } else {
+      ispecC_pool_up = cfg->clmcn_pool_C_id[ipool_up];
+      CN_ratio_up = cfg->clmcn_CN_ratio[ipool_up];
+    }
+    stoich_upstreamC_pool = 1.0;
+    stoich_upstreamN_pool = stoich_upstreamC_pool / CN_ratio_up;
+
+    ipool_down = cfg->clmcn_downstream_pool_id[irxn];
+    if (ipool_down >= 0) {
+      ispec_pool_down = cfg->clmcn_pool_C_id[ipool_down];
+      CN_ratio_down = cfg->clmcn_CN_ratio[ipool_down];
+      stoich_downstreamC_pool = (1.0 - resp_frac) * stoich_upstreamC_pool;
+    } else {
+      ispec_pool_down = -1;
+      stoich_downstreamC_pool = 0.0;
+      CN_ratio_down = 1.0;
+    }
+    stoich_C = resp_frac * stoich_upstreamC_pool;
+    stoich_N = stoich_upstreamN_pool - stoich_downstreamC_pool / CN_ratio_down;
+
+    if (cfg->clmcn_inhibition_constant[irxn] > 1.e-40 && stoich_N < 0.0) {
+      use_N_inhibition = 1;
+      temp_real = c->immobile[ispec_N] + cfg->clmcn_inhibition_constant[irxn];
+      N_inhibition = c->immobile[ispec_N] / temp_real;
+      d_N_inhibition = cfg->clmcn_inhibition_constant[irxn] / (temp_real * temp_real);
+    } else {
+      use_N_inhibition = 0;
+      N_inhibition = 1.0;
+      d_N_inhibition = 0.0;
+    }
+
+    rate = c->immobile[ispecC_pool_up] * scaled_rate_const * N_inhibition;
+
+    Residual[ires_C] = Residual[ires_C] - stoich_C * rate;
+    Residual[ires_N] = Residual[ires_N] - stoich_N * rate;
+    iresC_pool_up = off + ispecC_pool_up;
+    Residual[iresC_pool_up] = Residual[iresC_pool_up] - (-1.0) * stoich_upstreamC_pool * rate;
+    if (!constant_CN_ratio_up) {
+      iresN_pool_up = off + ispecN_pool_up;
+      Residual[iresN_pool_up] = Residual[iresN_pool_up] - (-1.0) * stoich_upstreamN_pool * rate;
+    }
+    if (ispec_pool_down >= 0) {
+      ires_pool_down = off + ispec_pool_down;
+      Residual[ires_pool_down] = Residual[ires_pool_down] - stoich_downstreamC_pool * rate;
+    }
+
+    if (compute_derivative) {
+      drate = scaled_rate_const * N_inhibition;
+      JAC(iresC_pool_up, iresC_pool_up) = JAC(iresC_pool_up, iresC_pool_up) - (-1.0) * stoich_upstreamC_pool * drate;
+      if (use_N_inhibition) {
+        drate_dN_inhibition = c->immobile[ispecC_pool_up] * scaled_rate_const * d_N_inhibition;
+        JAC(iresC_pool_up, ires_N) =
+            JAC(iresC_pool_up, ires_N) - (-1.0) * stoich_upstreamC_pool * drate_dN_inhibition;
+      }
+      if (ispec_pool_down >= 0) {
+        JAC(ires_pool_down, iresC_pool_up) = JAC(ires_pool_down, iresC_pool_up) - stoich_downstreamC_pool * drate;
+        if (use_N_inhibition)
+          JAC(ires_pool_down, ires_N) = JAC(ires_pool_down, ires_N) - stoich_downstreamC_pool * drate_dN_inhibition;
+      }
+      if (!constant_CN_ratio_up) {
+        JAC(iresN_pool_up, iresC_pool_up) =
+            JAC(iresN_pool_up, iresC_pool_up) - (-1.0) * stoich_upstreamN_pool * drate;
+        if (use_N_inhibition)
+          JAC(iresN_pool_up, ires_N) =
+              JAC(iresN_pool_up, ires_N) - (-1.0) * stoich_upstreamN_pool * drate_dN_inhibition;
+        JAC(iresN_pool_up, iresC_pool_up) =
+            JAC(iresN_pool_up, iresC_pool_up) - (-1.0) * (-1.0) * c->immobile[ispecN_pool_up] /
+                                                    c->immobile[ispecC_pool_up] * scaled_rate_const * N_inhibition;
+        JAC(iresN_pool_up, iresN_pool_up) =
+            JAC(iresN_pool_up, iresN_pool_up) - (-1.0) * scaled_rate_const * N_inhibition;
+        JAC(ires_N, iresC_pool_up) = JAC(ires_N, iresC_pool_up) - (-1.0) * c->immobile[ispecN_pool_up] /
+                                                                      c->immobile[ispecC_pool_up] *
+                                                                      scaled_rate_const * N_inhibition;
+        JAC(ires_N, iresN_pool_up) = JAC(ires_N, iresN_pool_up) - scaled_rate_const * N_inhibition;
+      }
+      JAC(ires_C, iresC_pool_up) = JAC(ires_C, iresC_pool_up) - stoich_C * drate;
+      JAC(ires_N, iresC_pool_up) = JAC(ires_N, iresC_pool_up) - stoich_N * drate;
+      if (use_N_inhibition) {
+        JAC(ires_C, ires_N) = JAC(ires_C, ires_N) - stoich_C * drate_dN_inhibition;
+        JAC(ires_N, ires_N) = JAC(ires_N, ires_N) - stoich_N * drate_dN_inhibition;
+      }
+    }
+  }
+#undef JAC
+}
+
+/* reaction.F90:4059-4130  RReaction (dispatch order preserved) */
+static void r_reaction(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac, int derivative) {
+  if (c->sat < cfg->rt_min_saturation) return;
+  if (c->nkin > 0) r_kinetic_mineral(c, cfg, Res, Jac, derivative);
+  if (cfg->nkinmrsrfcplxrxn > 0) r_multirate_sorption(c, cfg, tran_dt, Res, Jac, derivative);
+  if (cfg->clmcn_nrxn > 0) clm_cn_react(c, cfg, Res, Jac, derivative);
+}
+
+/* reaction.F90:5457-5516  RSolve -- WITH back-substitution */
+static int r_solve(double *Res, double *Jac, const double *conc, double *update, int ncomp, int use_log_formulation) {
+  int indices[PFRX_MAX_NCOMP * 4];
+  double rhs[PFRX_MAX_NCOMP * 4];
+  int icomp, j, ierror;
+  double norm;
+  for (icomp = 0; icomp < ncomp; icomp++) {
+    double m = 0.0;
+    for (j = 0; j < ncomp; j++) m = fmax(m, fabs(Jac[icomp + j * ncomp]));
+    norm = fmax(1.0, m);
+    norm = 1.0 / norm;
+    rhs[icomp] = Res[icomp] * norm;
+    for (j = 0; j < ncomp; j++) Jac[icomp + j * ncomp] = Jac[icomp + j * ncomp] * norm;
+  }
+  if (use_log_formulation) {
+    for (icomp = 0; icomp < ncomp; icomp++)
+      for (j = 0; j < ncomp; j++) Jac[j + icomp * ncomp] = Jac[j + icomp * ncomp] * conc[icomp];
+  }
+  ierror = lu_decomposition(Jac, ncomp, indices);
+  if (ierror != 0) return ierror;
+  if (g_ref_bug_compat) {
+    /* the fork returns here without touching `update` (reaction.F90:5501-5504);
+     * the golds show it reads as zeros */
+    for (icomp = 0; icomp < ncomp; icomp++) update[icomp] = 0.0;
+    return 0;
+  }
+  lu_back_substitution(Jac, ncomp, indices, rhs);
+  for (icomp = 0; icomp < ncomp; icomp++) update[icomp] = rhs[icomp];
+  return 0;
+}
+
+/* reaction.F90:3742-4055  RReact */
+static int r_react(cell_t *c, const pfrx_config *cfg, const double *guess, double tran_dt, int *num_iterations_out) {
+  int n = c->n, naq = c->naq, nim = c->nim, i, icomp;
+  double residual[PFRX_MAX_NCOMP * 4], fixed_accum[PFRX_MAX_NCOMP * 4];
+  double initial_total[PFRX_MAX_NCOMP * 4], prev_solution[PFRX_MAX_NCOMP * 4];
+  double latest_solution[PFRX_MAX_NCOMP * 4], update[PFRX_MAX_NCOMP * 4], conc[PFRX_MAX_NCOMP * 4];
+  double *J = (double *)malloc(sizeof(double) * n * n);
+  double maximum_relative_change, two_norm_r, two_norm_r0 = 0.0, rel_residual, ratio, min_ratio;
+  int num_iterations = 0, ierror = 0;
+
+  c->option_ierror = 0;
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(c, cfg);
+
+  rt_accumulation(c, cfg, fixed_accum);
+  if (neqsorb(cfg) > 0) r_accumulation_sorb(c, fixed_accum);
+
+  for (i = 0; i < naq; i++) initial_total[i] = c->total[i];
+  for (i = 0; i < nim; i++) initial_total[naq + i] = c->immobile[i];
+  for (i = 0; i < naq; i++) c->pri_molal[i] = guess[i];
+  for (i = 0; i < nim; i++) c->immobile[i] = guess[naq + i];
+
+  for (;;) {
+    num_iterations = num_iterations + 1;
+    if (cfg->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) r_activity_coefficients(c, cfg);
+    rt_auxvar_compute(c, cfg);
+
+    if (num_iterations > cfg->maximum_reaction_iterations) {
+      ierror = 1;
+      for (i = 0; i < naq; i++) c->total[i] = initial_total[i];
+      for (i = 0; i < nim; i++) c->immobile[i] = initial_total[naq + i];
+      goto done;
+    }
+
+    rt_accumulation(c, cfg, residual);
+    rt_accumulation_derivative(c, cfg, tran_dt, J);
+    if (neqsorb(cfg) > 0) {
+      r_accumulation_sorb(c, residual);
+      r_accumulation_sorb_derivative(c, tran_dt, J);
+    }
+    for (i = 0; i < n; i++) residual[i] = (residual[i] - fixed_accum[i]) / tran_dt;
+
+    r_reaction(c, cfg, tran_dt, residual, J, 1);
+
+    if (c->option_ierror != 0) {
+      ierror = c->option_ierror;
+      goto done;
+    }
+
+    two_norm_r = 0.0;
+    for (i = 0; i < n; i++) two_norm_r += residual[i] * residual[i];
+    two_norm_r = sqrt(two_norm_r);
+    if (num_iterations == 1) two_norm_r0 = two_norm_r;
+    rel_residual = two_norm_r / two_norm_r0;
+    {
+      double m = 0.0;
+      for (i = 0; i < n; i++) m = fmax(m, fabs(residual[i]));
+      /* maxval(abs(residual)) < tol; NaN-safe like the Fortran comparison */
+      if (m < cfg->max_residual_tolerance) break;
+    }
+    if (rel_residual < cfg->max_rel_residual_tolerance) break;
+
+    for (i = 0; i < naq; i++) conc[i] = c->pri_molal[i];
+    for (i = 0; i < nim; i++) conc[naq + i] = c->immobile[i];
+
+    if (r_solve(residual, J, conc, update, n, cfg->use_log_formulation) != 0) {
+      ierror = 1; /* solve_error branch, reaction.F90:3964-3967: no restore */
+      goto done;
+    }
+
+    for (i = 0; i < naq; i++) prev_solution[i] = c->pri_molal[i];
+    for (i = 0; i < nim; i++) prev_solution[naq + i] = c->immobile[i];
+
+    if (cfg->use_log_formulation) {
+      for (i = 0; i < n; i++) {
+        update[i] = copysign(1.0, update[i]) * fmin(fabs(update[i]), cfg->max_dlnC_rreact);
+        latest_solution[i] = prev_solution[i] * exp(-update[i]);
+      }
+    } else {
+      min_ratio = MAX_DOUBLE;
+      for (icomp = 0; icomp < n; icomp++) {
+        if (prev_solution[icomp] <= update[icomp]) {
+          ratio = fabs(prev_solution[icomp] / update[icomp]);
+          if (ratio < min_ratio) min_ratio = ratio;
+        }
+      }
+      if (min_ratio < 1.0)
+        for (i = 0; i < n; i++) update[i] = update[i] * min_ratio * 0.99;
+      for (i = 0; i < n; i++) latest_solution[i] = prev_solution[i] - update[i];
+    }
+
+    maximum_relative_change = 0.0;
+    {
+      /* maxval(abs((latest-prev)/prev)): gfortran's MAXVAL skips NaNs unless
+       * all are NaN; fmax reproduces that for the mixed case */
+      double m = -INFINITY;
+      int any = 0;
+      for (i = 0; i < n; i++) {
+        double v = fabs((latest_solution[i] - prev_solution[i]) / prev_solution[i]);
+        if (!isnan(v)) {
+          m = any ? fmax(m, v) : v;
+          any = 1;
+        }
+      }
+      maximum_relative_change = any ? m : NAN;
+    }
+    if (maximum_relative_change < cfg->max_relative_change_tolerance) break;
+
+    for (i = 0; i < naq; i++) c->pri_molal[i] = latest_solution[i];
+    for (i = 0; i < nim; i++) c->immobile[i] = latest_solution[naq + i];
+  }
+
+  /* one last update, reaction.F90:4052 */
+  rt_auxvar_compute(c, cfg);
+
+done:
+  free(J);
+  *num_iterations_out = num_iterations;
+  return ierror;
+}
+
+/* reaction_mineral.F90:1456-1525 MineralUpdateKineticState,
+ * reaction_surf_complex.F90:1107-1145 RSrfCplxMRUpdateKinState,
+ * reaction.F90:5935-5972 RUpdateKineticState */
+static int r_update_kinetic_state(cell_t *c, const pfrx_config *cfg, double tran_dt) {
+  int kinetic_state_updated = 0, imnrl, irxn, irate, i;
+  if (c->nkin > 0) {
+    double res[PFRX_MAX_NCOMP * 4];
+    double jac[1];
+    kinetic_state_updated = 1;
+    for (i = 0; i < c->n; i++) res[i] = 0.0;
+    r_kinetic_mineral(c, cfg, res, jac, 0);
+    for (imnrl = 0; imnrl < c->nkin; imnrl++) {
+      double delta_volfrac = c->mnrl_rate[imnrl] * cfg->kinmnrl_molar_vol[imnrl] * tran_dt;
+      c->mnrl_volfrac[imnrl] = c->mnrl_volfrac[imnrl] + delta_volfrac;
+      if (c->mnrl_volfrac[imnrl] < 0.0) c->mnrl_volfrac[imnrl] = 0.0;
+    }
+  }
+  for (irxn = 0; irxn < cfg->nkinmrsrfcplxrxn; irxn++) {
+    int r0 = cfg->kinmr_rate_ptr[irxn], r1 = cfg->kinmr_rate_ptr[irxn + 1];
+    int base = c->naq * (r0 + irxn);
+    kinetic_state_updated = 1;
+    for (irate = r0; irate < r1; irate++) {
+      double kdt = cfg->kinmr_rate[irate] * tran_dt;
+      double one_plus_kdt = 1.0 + kdt;
+      double *S = c->kinmr_total_sorb + base + c->naq * (irate - r0 + 1);
+      for (i = 0; i < c->naq; i++)
+        S[i] = (S[i] + kdt * cfg->kinmr_frac[irate] * c->kinmr_total_sorb[base + i]) / one_plus_kdt;
+    }
+  }
+  if (cfg->clmcn_nrxn > 0) kinetic_state_updated = 1; /* any sandbox => true, reaction.F90:5965 */
+  return kinetic_state_updated;
+}
+
+/* reaction.F90:3564-3738  RStep */
+static int r_step(cell_t *c, const pfrx_config *cfg, double *guess, double target_time, int *num_sub_steps_out,
+                  int *num_iterations_out, int *num_kinetic_state_updates_out, int *had_cut) {
+  int n = c->n, naq = c->naq, nim = c->nim, i;
+  int value_is_initially_small[PFRX_MAX_NCOMP * 4];
+  double initial_small_value[PFRX_MAX_NCOMP * 4];
+  int num_inner_iterations, num_constant_timesteps_after_cut = 0, num_cuts = 0;
+  int num_kinetic_state_updates = 0, num_sub_steps = 0, num_iterations = 0, ierror = 0;
+  double cumulative_time = 0.0, tran_dt = target_time;
+
+  *had_cut = 0;
+  if (!cfg->use_full_geochemistry) {
+    for (i = 0; i < naq; i++) c->pri_molal[i] = c->total[i] / c->den_kg * 1.e3;
+    *num_sub_steps_out = 0;
+    *num_iterations_out = 0;
+    *num_kinetic_state_updates_out = 0;
+    return 0;
+  }
+  for (i = 0; i < n; i++) value_is_initially_small[i] = 0;
+  for (i = 0; i < naq; i++) {
+    if (c->total[i] <= 1.e-40) {
+      value_is_initially_small[i] = 1;
+      initial_small_value[i] = c->total[i];
+      c->total[i] = 1.e-40;
+    }
+  }
+  for (i = 0; i < nim; i++) {
+    if (c->immobile[i] <= 1.e-40) {
+      value_is_initially_small[naq + i] = 1;
+      initial_small_value[naq + i] = c->immobile[i];
+      c->immobile[i] = 1.e-40;
+    }
+  }
+  if (cfg->use_total_as_guess)
+    for (i = 0; i < naq; i++) guess[i] = c->total[i]; /* guess(:) = total(:,1) */
+
+  for (;;) {
+    if (cumulative_time >= target_time) break;
+    ierror = r_react(c, cfg, guess, tran_dt, &num_inner_iterations);
+    num_iterations = num_iterations + num_inner_iterations;
+    if (ierror != 0) {
+      num_cuts = num_cuts + 1;
+      *had_cut = 1;
+      if (num_cuts > cfg->maximum_reaction_cuts) {
+        ierror = 1;
+        /* reference returns here WITHOUT restoring the small values */
+        *num_sub_steps_out = num_sub_steps;
+        *num_iterations_out = num_iterations;
+        *num_kinetic_state_updates_out = num_kinetic_state_updates;
+        return ierror;
+      }
+      tran_dt = 0.5 * tran_dt;
+      num_constant_timesteps_after_cut = 0;
+    } else {
+      int updated = r_update_kinetic_state(c, cfg, tran_dt);
+      cumulative_time = cumulative_time + tran_dt;
+      num_sub_steps = num_sub_steps + 1;
+      num_constant_timesteps_after_cut = num_constant_timesteps_after_cut + 1;
+      if (updated) num_kinetic_state_updates = num_kinetic_state_updates + 1;
+      for (i = 0; i < naq; i++) guess[i] = c->pri_molal[i];
+      for (i = 0; i < nim; i++) guess[naq + i] = c->immobile[i];
+      if (num_constant_timesteps_after_cut >= 4) {
+        num_cuts = num_cuts - 1;
+        tran_dt = fmin(2.0 * tran_dt, target_time - cumulative_time);
+      }
+    }
+  }
+  for (i = 0; i < naq; i++)
+    if (value_is_initially_small[i]) c->total[i] = initial_small_value[i];
+  for (i = 0; i < nim; i++)
+    if (value_is_initially_small[naq + i]) c->immobile[i] = initial_small_value[naq + i];
+
+  *num_sub_steps_out = num_sub_steps;
+  *num_iterations_out = num_iterations;
+  *num_kinetic_state_updates_out = num_kinetic_state_updates;
+  return ierror;
+}
+
+/* ------------------------------------------------------------------------ */
+/* The OS cell loop pmc_subsurface_osrt.F90:349-378 over a SoA shard.         */
+typedef struct {
+  const pfrx_config *cfg;
+  const pfrx_state *st;
+  int64_t c0, c1;
+  double tran_dt;
+  pfrx_step_result res;
+} job_t;
+
+static void *job_run(void *arg) {
+  job_t *jb = (job_t *)arg;
+  const pfrx_config *cfg = jb->cfg;
+  const pfrx_state *st = jb->st;
+  cell_t c;
+  double guess[PFRX_MAX_NCOMP * 4];
+  int64_t ic;
+  int i;
+  pfrx_step_result *r = &jb->res;
+  memset(r, 0, sizeof(*r));
+  r->first_failed_cell = -1;
+  cell_init(&c, cfg);
+  for (ic = jb->c0; ic < jb->c1; ic++) {
+    int nss = 0, nit = 0, nku = 0, had_cut = 0, ierr;
+    if (st->imat && st->imat[ic] <= 0) {
+      if (st->num_sub_steps) st->num_sub_steps[ic] = 0;
+      if (st->num_iterations) st->num_iterations[ic] = 0;
+      if (st->num_kinetic_state_updates) st->num_kinetic_state_updates[ic] = 0;
+      if (st->ierror) st->ierror[ic] = 0;
+      continue;
+    }
+    cell_gather(&c, cfg, st, ic);
+    /* guess has to be free ion concentration, :356-362 */
+    for (i = 0; i < c.naq; i++) guess[i] = c.pri_molal[i];
+    for (i = 0; i < c.nim; i++) guess[c.naq + i] = c.immobile[i];
+    ierr = r_step(&c, cfg, guess, jb->tran_dt, &nss, &nit, &nku, &had_cut);
+    cell_scatter(&c, st, ic);
+    if (st->num_sub_steps) st->num_sub_steps[ic] = nss;
+    if (st->num_iterations) st->num_iterations[ic] = nit;
+    if (st->num_kinetic_state_updates) st->num_kinetic_state_updates[ic] = nku;
+    if (st->ierror) st->ierror[ic] = ierr;
+    r->ncell_active++;
+    r->sum_newton_iterations += nit;
+    if (nit > r->max_newton_iterations) r->max_newton_iterations = nit;
+    if (nku > r->max_num_kinetic_state_updates) r->max_num_kinetic_state_updates = nku;
+    if (nss > r->max_sub_steps) r->max_sub_steps = nss;
+    if (ierr > r->rstep_error) r->rstep_error = ierr;
+    if (had_cut) r->num_cut_cells++;
+    if (ierr != 0 && r->first_failed_cell < 0) r->first_failed_cell = ic;
+  }
+  cell_free(&c);
+  return NULL;
+}
+
+static void merge_result(pfrx_step_result *a, const pfrx_step_result *b) {
+  a->ncell_active += b->ncell_active;
+  a->sum_newton_iterations += b->sum_newton_iterations;
+  if (b->max_newton_iterations > a->max_newton_iterations) a->max_newton_iterations = b->max_newton_iterations;
+  if (b->max_num_kinetic_state_updates > a->max_num_kinetic_state_updates)
+    a->max_num_kinetic_state_updates = b->max_num_kinetic_state_updates;
+  if (b->rstep_error > a->rstep_error) a->rstep_error = b->rstep_error;
+  if (b->max_sub_steps > a->max_sub_steps) a->max_sub_steps = b->max_sub_steps;
+  a->num_cut_cells += b->num_cut_cells;
+  if (b->first_failed_cell >= 0 && (a->first_failed_cell < 0 || b->first_failed_cell < a->first_failed_cell))
+    a->first_failed_cell = b->first_failed_cell;
+}
+
+/* All cells are processed (the reference stops its rank at the first failing
+ * cell, :370; first_failed_cell lets a caller reproduce that).  nthreads
+ * workers take static contiguous ranges, mimicking `mpirun -n P` ownership. */
+int pfrx_oracle_rstep(const pfrx_config *cfg, int64_t ncell, const pfrx_state *st, double tran_dt,
+                      pfrx_step_result *out, int nthreads) {
+  int t;
+  if (!cfg || !st || cfg->naqcomp + cfg->nimcomp > PFRX_MAX_NCOMP * 4) return PFRX_E_INVALID;
+  if (nthreads < 1) nthreads = 1;
+  if ((int64_t)nthreads > ncell) nthreads = ncell > 0 ? (int)ncell : 1;
+  job_t *jobs = (job_t *)calloc(nthreads, sizeof(job_t));
+  pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].cfg = cfg;
+    jobs[t].st = st;
+    jobs[t].tran_dt = tran_dt;
+    jobs[t].c0 = ncell * t / nthreads;
+    jobs[t].c1 = ncell * (t + 1) / nthreads;
+  }
+  if (nthreads == 1) {
+    job_run(&jobs[0]);
+  } else {
+    for (t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, job_run, &jobs[t]);
+    for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  }
+  memset(out, 0, sizeof(*out));
+  out->first_failed_cell = -1;
+  for (t = 0; t < nthreads; t++) merge_result(out, &jobs[t].res);
+  free(jobs);
+  free(th);
+  return PFRX_OK;
+}
+
+void pfrx_oracle_set_ref_bug_compat(int on) { g_ref_bug_compat = on; }
+
+/* ------------------------------------------------------------------------ */
+/* Single-cell entry points used by tests/ to replay the reference's GIRT     */
+/* batch golds and to check Jacobians.               */
+
+/* RActivityCoefficients on cell ic */
+int pfrx_oracle_activity(const pfrx_config *cfg, const pfrx_state *st, int64_t ic) {
+  cell_t c;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(&c, cfg);
+  r_activity_coefficients(&c, cfg);
+  cell_scatter(&c, st, ic);
+  int e = c.option_ierror;
+  cell_free(&c);
+  return e;
+}
+
+/* RTAuxVarCompute on cell ic (totals, sec_molal, sorbed totals) */
+int pfrx_oracle_auxvar_compute(const pfrx_config *cfg, const pfrx_state *st, int64_t ic) {
+  cell_t c;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(&c, cfg);
+  rt_auxvar_compute(&c, cfg);
+  cell_scatter(&c, st, ic);
+  cell_free(&c);
+  return 0;
+}
+
+/* GIRT single-cell residual and Jacobian (reactive_transport.F90:2398-2438,
+ * :2599-2642, :3088-3303):  Res = A(c)/dt + R(c)   (caller subtracts
+ * fixed_accum/dt), Jac = dA/dc/dt + dR/dc, column-major Jac[i + j*n].
+ * Also returns A(c) itself in accum[] when non-NULL.  State is updated the
+ * way RTAuxVarCompute does (total, sec_molal, sorbed, mnrl_rate). */
+int pfrx_oracle_girt_residual(const pfrx_config *cfg, const pfrx_state *st, int64_t ic, double tran_dt, double *Res,
+                              double *Jac, double *accum) {
+  cell_t c;
+  int n, i;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  n = c.n;
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(&c, cfg);
+  rt_auxvar_compute(&c, cfg);
+  rt_accumulation(&c, cfg, Res);
+  rt_accumulation_derivative(&c, cfg, tran_dt, Jac);
+  if (neqsorb(cfg) > 0) {
+    r_accumulation_sorb(&c, Res);
+    r_accumulation_sorb_derivative(&c, tran_dt, Jac);
+  }
+  if (accum)
+    for (i = 0; i < n; i++) accum[i] = Res[i];
+  for (i = 0; i < n; i++) Res[i] = Res[i] / tran_dt;
+  r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
+  cell_scatter(&c, st, ic);
+  int e = c.option_ierror;
+  cell_free(&c);
+  return e;
+}
+
+/* RUpdateKineticState on cell ic over tran_dt */
+int pfrx_oracle_update_kinetic_state(const pfrx_config *cfg, const pfrx_state *st, int64_t ic, double tran_dt) {
+  cell_t c;
+  int u;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(&c, cfg);
+  u = r_update_kinetic_state(&c, cfg, tran_dt);
+  cell_scatter(&c, st, ic);
+  cell_free(&c);
+  return u;
+}
+
+/* RSolve (row scaling, optional log scaling, LU, back-substitution) for KATs */
+int pfrx_oracle_rsolve(double *Res, double *Jac, const double *conc, double *update, int ncomp,
+                       int use_log_formulation) {
+  if (ncomp > PFRX_MAX_NCOMP * 4) return -1;
+  return r_solve(Res, Jac, conc, update, ncomp, use_log_formulation);
+}
+
+/* bare LU + back-substitution for KATs (utility.F90:597-735) */
+int pfrx_oracle_lu_solve(double *A, int N, double *B) {
+  int indx[PFRX_MAX_NCOMP * 4];
+  int e;
+  if (N > PFRX_MAX_NCOMP * 4) return -1;
+  e = lu_decomposition(A, N, indx);
+  if (e) return e;
+  lu_back_substitution(A, N, indx, B);
+  return 0;
+}

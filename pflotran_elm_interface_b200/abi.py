@@ -1,0 +1,445 @@
+"""ctypes mirror of ``include/pfrx.h`` and the flattening of a
+:class:`~.chem.ReactionNetwork` into ``pfrx_config``.
+
+The structures here are the C ABI itself (same field order as the header); the
+same definitions are used by the tests to drive the CPU oracle, which takes the
+identical structs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import chem as _chem
+
+PFRX_ABI_VERSION = 1
+PFRX_MAX_NCOMP = 32
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class PfrxConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("naqcomp", C.c_int32),
+        ("nimcomp", C.c_int32),
+        ("use_full_geochemistry", C.c_int32),
+        ("use_log_formulation", C.c_int32),
+        ("use_total_as_guess", C.c_int32),
+        ("use_isothermal", C.c_int32),
+        ("act_coef_update_frequency", C.c_int32),
+        ("act_coef_update_algorithm", C.c_int32),
+        ("use_activity_h2o", C.c_int32),
+        ("h2o_aq_id", C.c_int32),
+        ("maximum_reaction_iterations", C.c_int32),
+        ("maximum_reaction_cuts", C.c_int32),
+        ("max_dlnC_rreact", C.c_double),
+        ("max_relative_change_tolerance", C.c_double),
+        ("max_residual_tolerance", C.c_double),
+        ("max_rel_residual_tolerance", C.c_double),
+        ("rt_min_saturation", C.c_double),
+        ("debyeA", C.c_double),
+        ("debyeB", C.c_double),
+        ("debyeBdot", C.c_double),
+        ("primary_spec_Z", c_double_p),
+        ("primary_spec_a0", c_double_p),
+        ("neqcplx", C.c_int32),
+        ("eqcplx_ptr", c_int32_p),
+        ("eqcplx_specid", c_int32_p),
+        ("eqcplx_stoich", c_double_p),
+        ("eqcplx_h2ostoich", c_double_p),
+        ("eqcplx_logK", c_double_p),
+        ("eqcplx_logKcoef", c_double_p),
+        ("eqcplx_Z", c_double_p),
+        ("eqcplx_a0", c_double_p),
+        ("nkinmnrl", C.c_int32),
+        ("kinmnrl_ptr", c_int32_p),
+        ("kinmnrl_specid", c_int32_p),
+        ("kinmnrl_stoich", c_double_p),
+        ("kinmnrl_h2ostoich", c_double_p),
+        ("kinmnrl_logK", c_double_p),
+        ("kinmnrl_logKcoef", c_double_p),
+        ("kinmnrl_molar_vol", c_double_p),
+        ("kinmnrl_rate_constant", c_double_p),
+        ("kinmnrl_activation_energy", c_double_p),
+        ("kinmnrl_affinity_threshold", c_double_p),
+        ("kinmnrl_rate_limiter", c_double_p),
+        ("kinmnrl_irreversible", c_int32_p),
+        ("kinmnrl_Temkin_const", c_double_p),
+        ("kinmnrl_min_scale_factor", c_double_p),
+        ("kinmnrl_affinity_power", c_double_p),
+        ("kinmnrl_num_prefactors", c_int32_p),
+        ("kinmnrl_pref_nspec", c_int32_p),
+        ("kinmnrl_prefactor_id", c_int32_p),
+        ("kinmnrl_pref_alpha", c_double_p),
+        ("kinmnrl_pref_beta", c_double_p),
+        ("kinmnrl_pref_atten_coef", c_double_p),
+        ("kinmnrl_pref_rate", c_double_p),
+        ("kinmnrl_pref_activation_energy", c_double_p),
+        ("nsrfcplxrxn", C.c_int32),
+        ("nsrfcplx", C.c_int32),
+        ("srfcplxrxn_ptr", c_int32_p),
+        ("srfcplxrxn_to_complex", c_int32_p),
+        ("srfcplxrxn_surf_type", c_int32_p),
+        ("srfcplxrxn_to_surf", c_int32_p),
+        ("srfcplxrxn_site_density", c_double_p),
+        ("srfcplxrxn_stoich_flag", c_int32_p),
+        ("srfcplx_ptr", c_int32_p),
+        ("srfcplx_specid", c_int32_p),
+        ("srfcplx_stoich", c_double_p),
+        ("srfcplx_h2ostoich", c_double_p),
+        ("srfcplx_free_site_stoich", c_double_p),
+        ("srfcplx_logK", c_double_p),
+        ("srfcplx_logKcoef", c_double_p),
+        ("neqsrfcplxrxn", C.c_int32),
+        ("eqsrfcplxrxn_to_srfcplxrxn", c_int32_p),
+        ("nkinmrsrfcplxrxn", C.c_int32),
+        ("kinmrsrfcplxrxn_to_srfcplxrxn", c_int32_p),
+        ("kinmr_rate_ptr", c_int32_p),
+        ("kinmr_rate", c_double_p),
+        ("kinmr_frac", c_double_p),
+        ("clmcn_nrxn", C.c_int32),
+        ("clmcn_npool", C.c_int32),
+        ("clmcn_C_species_id", C.c_int32),
+        ("clmcn_N_species_id", C.c_int32),
+        ("clmcn_CN_ratio", c_double_p),
+        ("clmcn_pool_nspec", c_int32_p),
+        ("clmcn_pool_C_id", c_int32_p),
+        ("clmcn_pool_N_id", c_int32_p),
+        ("clmcn_upstream_pool_id", c_int32_p),
+        ("clmcn_downstream_pool_id", c_int32_p),
+        ("clmcn_rate_constant", c_double_p),
+        ("clmcn_respiration_fraction", c_double_p),
+        ("clmcn_inhibition_constant", c_double_p),
+    ]
+
+
+STATE_DOUBLE_FIELDS = [
+    "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
+    "mnrl_volfrac", "mnrl_area", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc",
+    "total_sorb_eq", "kinmr_total_sorb", "den_kg", "sat", "temp", "porosity", "volume",
+    "soil_particle_density",
+]
+STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
+# fields the step updates ("io" in pfrx.h) and per-cell results
+STATE_IO_FIELDS = [
+    "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
+    "mnrl_volfrac", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "total_sorb_eq",
+    "kinmr_total_sorb",
+]
+STATE_RESULT_FIELDS = ["num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
+
+
+class PfrxState(C.Structure):
+    _fields_ = (
+        [("ld", C.c_int64)]
+        + [(f, c_double_p) for f in STATE_DOUBLE_FIELDS]
+        + [(f, c_int32_p) for f in STATE_INT_FIELDS]
+    )
+
+
+class PfrxStepResult(C.Structure):
+    _fields_ = [
+        ("ncell_active", C.c_int64),
+        ("sum_newton_iterations", C.c_int64),
+        ("max_newton_iterations", C.c_int32),
+        ("max_num_kinetic_state_updates", C.c_int32),
+        ("rstep_error", C.c_int32),
+        ("max_sub_steps", C.c_int32),
+        ("num_cut_cells", C.c_int64),
+        ("first_failed_cell", C.c_int64),
+    ]
+
+    def as_dict(self) -> Dict[str, int]:
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None or a.size == 0:
+        return C.cast(None, c_double_p)
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a: Optional[np.ndarray]):
+    if a is None or a.size == 0:
+        return C.cast(None, c_int32_p)
+    return a.ctypes.data_as(c_int32_p)
+
+
+def _f64(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def _i32(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+
+
+class ReactionConfig:
+    """Owns the numpy tables and the ``pfrx_config`` that points into them."""
+
+    def __init__(self, net: _chem.ReactionNetwork):
+        self.net = net
+        self.arrays: Dict[str, np.ndarray] = {}
+        self.c = PfrxConfig()
+        self._build()
+
+    def _keep(self, name: str, arr: np.ndarray) -> np.ndarray:
+        self.arrays[name] = arr
+        return arr
+
+    def _build(self) -> None:
+        net, ch, c = self.net, self.net.chem, self.c
+        c.abi_version = PFRX_ABI_VERSION
+        c.naqcomp = net.naqcomp
+        c.nimcomp = net.nimcomp
+        c.use_full_geochemistry = 1
+        c.use_log_formulation = int(ch.use_log_formulation)
+        c.use_total_as_guess = int(ch.use_total_as_guess)
+        c.use_isothermal = int(net.use_isothermal)
+        c.act_coef_update_frequency = ch.act_coef_update_frequency
+        c.act_coef_update_algorithm = ch.act_coef_update_algorithm
+        c.use_activity_h2o = int(ch.use_activity_h2o)
+        c.h2o_aq_id = net.primary_names.index("H2O") if "H2O" in net.primary_names else -1
+        c.maximum_reaction_iterations = ch.maximum_reaction_iterations
+        c.maximum_reaction_cuts = ch.maximum_reaction_cuts
+        c.max_dlnC_rreact = ch.max_dlnC_rreact
+        c.max_relative_change_tolerance = ch.max_relative_change_tolerance
+        c.max_residual_tolerance = ch.max_residual_tolerance
+        c.max_rel_residual_tolerance = ch.max_rel_residual_tolerance
+        c.rt_min_saturation = 1.0e-40
+        c.debyeA, c.debyeB, c.debyeBdot = net.debyeA, net.debyeB, net.debyeBdot
+        c.primary_spec_Z = _dp(self._keep("primary_spec_Z", _f64(net.primary_Z)))
+        c.primary_spec_a0 = _dp(self._keep("primary_spec_a0", _f64(net.primary_a0)))
+
+        # secondary complexes
+        c.neqcplx = net.neqcplx
+        ptr, ids, st = net.csr(net.sec_rxn)
+        c.eqcplx_ptr = _ip(self._keep("eqcplx_ptr", ptr))
+        c.eqcplx_specid = _ip(self._keep("eqcplx_specid", ids))
+        c.eqcplx_stoich = _dp(self._keep("eqcplx_stoich", st))
+        c.eqcplx_h2ostoich = _dp(self._keep("eqcplx_h2ostoich", _f64([r.h2o_stoich for r in net.sec_rxn])))
+        c.eqcplx_logK = _dp(self._keep("eqcplx_logK", net.logKs(net.sec_rxn)))
+        if not net.use_isothermal and net.neqcplx:
+            c.eqcplx_logKcoef = _dp(self._keep("eqcplx_logKcoef", _f64(net.logK_coefs(net.sec_rxn))))
+        c.eqcplx_Z = _dp(self._keep("eqcplx_Z", _f64(net.eqcplx_Z)))
+        c.eqcplx_a0 = _dp(self._keep("eqcplx_a0", _f64(net.eqcplx_a0)))
+
+        # kinetic minerals
+        c.nkinmnrl = net.nkinmnrl
+        if net.nkinmnrl:
+            rx = [net.mnrl_rxn[n] for n in net.kinmnrl_names]
+            ptr, ids, st = net.csr(rx)
+            km = net.kinmnrl
+            c.kinmnrl_ptr = _ip(self._keep("kinmnrl_ptr", ptr))
+            c.kinmnrl_specid = _ip(self._keep("kinmnrl_specid", ids))
+            c.kinmnrl_stoich = _dp(self._keep("kinmnrl_stoich", st))
+            c.kinmnrl_h2ostoich = _dp(self._keep("kinmnrl_h2ostoich", _f64([r.h2o_stoich for r in rx])))
+            c.kinmnrl_logK = _dp(self._keep("kinmnrl_logK", net.logKs(rx)))
+            if not net.use_isothermal:
+                c.kinmnrl_logKcoef = _dp(self._keep("kinmnrl_logKcoef", _f64(net.logK_coefs(rx))))
+            c.kinmnrl_molar_vol = _dp(self._keep("kinmnrl_molar_vol",
+                                                  _f64([net.mnrl_molar_vol[n] for n in net.kinmnrl_names])))
+            c.kinmnrl_rate_constant = _dp(self._keep("kinmnrl_rate_constant", _f64([m.rate_constant for m in km])))
+            c.kinmnrl_activation_energy = _dp(self._keep("kinmnrl_activation_energy",
+                                                          _f64([m.activation_energy for m in km])))
+            c.kinmnrl_affinity_threshold = _dp(self._keep("kinmnrl_affinity_threshold",
+                                                           _f64([m.affinity_threshold for m in km])))
+            c.kinmnrl_rate_limiter = _dp(self._keep("kinmnrl_rate_limiter", _f64([m.rate_limiter for m in km])))
+            c.kinmnrl_irreversible = _ip(self._keep("kinmnrl_irreversible", _i32([m.irreversible for m in km])))
+            # optional arrays exist iff any mineral sets them
+            # (reaction_database.F90:2047-2092)
+            if any(m.temkin is not None for m in km):
+                c.kinmnrl_Temkin_const = _dp(self._keep(
+                    "kinmnrl_Temkin_const", _f64([1.0 if m.temkin is None else m.temkin for m in km])))
+            if any(m.min_scale_factor is not None for m in km):
+                c.kinmnrl_min_scale_factor = _dp(self._keep(
+                    "kinmnrl_min_scale_factor",
+                    _f64([1.0 if m.min_scale_factor is None else m.min_scale_factor for m in km])))
+            if any(m.affinity_power is not None for m in km):
+                c.kinmnrl_affinity_power = _dp(self._keep(
+                    "kinmnrl_affinity_power",
+                    _f64([1.0 if m.affinity_power is None else m.affinity_power for m in km])))
+            if any(m.prefactors for m in km):
+                MP, MS = _chem.MAX_PREFACTORS, _chem.MAX_PREFACTOR_SPECIES
+                n = net.nkinmnrl
+                npref = np.zeros(n, dtype=np.int32)
+                nspec = np.zeros(n * MP, dtype=np.int32)
+                pid = np.zeros(n * MP * MS, dtype=np.int32)
+                alpha = np.zeros(n * MP * MS)
+                beta = np.zeros(n * MP * MS)
+                atten = np.zeros(n * MP * MS)
+                prate = np.zeros(n * MP)
+                peact = np.zeros(n * MP)
+                for im, m in enumerate(km):
+                    npref[im] = len(m.prefactors)
+                    for ip, pf in enumerate(m.prefactors):
+                        nspec[im * MP + ip] = len(pf["species"])
+                        prate[im * MP + ip] = pf["rate"]
+                        peact[im * MP + ip] = pf["activation_energy"]
+                        for isp, sp in enumerate(pf["species"]):
+                            q = (im * MP + ip) * MS + isp
+                            if sp["name"] in net.primary_names:
+                                pid[q] = net.primary_names.index(sp["name"])
+                            else:
+                                pid[q] = -(net.secondary_names.index(sp["name"]) + 1)
+                            alpha[q], beta[q], atten[q] = sp["alpha"], sp["beta"], sp["atten"]
+                c.kinmnrl_num_prefactors = _ip(self._keep("kinmnrl_num_prefactors", npref))
+                c.kinmnrl_pref_nspec = _ip(self._keep("kinmnrl_pref_nspec", nspec))
+                c.kinmnrl_prefactor_id = _ip(self._keep("kinmnrl_prefactor_id", pid))
+                c.kinmnrl_pref_alpha = _dp(self._keep("kinmnrl_pref_alpha", alpha))
+                c.kinmnrl_pref_beta = _dp(self._keep("kinmnrl_pref_beta", beta))
+                c.kinmnrl_pref_atten_coef = _dp(self._keep("kinmnrl_pref_atten_coef", atten))
+                c.kinmnrl_pref_rate = _dp(self._keep("kinmnrl_pref_rate", prate))
+                c.kinmnrl_pref_activation_energy = _dp(self._keep("kinmnrl_pref_activation_energy", peact))
+
+        # surface complexation
+        nrxn = len(net.srfcplxrxn)
+        c.nsrfcplxrxn = nrxn
+        c.nsrfcplx = len(net.srfcplx_names)
+        if nrxn:
+            rptr = np.zeros(nrxn + 1, dtype=np.int32)
+            r2c: List[int] = []
+            for i, rx in enumerate(net.srfcplxrxn):
+                r2c += [net.srfcplx_names.index(n) for n in rx.complexes]
+                rptr[i + 1] = len(r2c)
+            c.srfcplxrxn_ptr = _ip(self._keep("srfcplxrxn_ptr", rptr))
+            c.srfcplxrxn_to_complex = _ip(self._keep("srfcplxrxn_to_complex", _i32(r2c)))
+            c.srfcplxrxn_surf_type = _ip(self._keep("srfcplxrxn_surf_type",
+                                                     _i32([r.surface_type for r in net.srfcplxrxn])))
+            to_surf = []
+            for r in net.srfcplxrxn:
+                if r.surface_type == _chem.MINERAL_SURFACE:
+                    # srfcplxrxn_to_surf indexes the kinetic-mineral list
+                    # (reaction_database.F90: mapping by kinmnrl_names)
+                    to_surf.append(net.kinmnrl_names.index(r.surface_name))
+                else:
+                    to_surf.append(-1)
+            c.srfcplxrxn_to_surf = _ip(self._keep("srfcplxrxn_to_surf", _i32(to_surf)))
+            c.srfcplxrxn_site_density = _dp(self._keep("srfcplxrxn_site_density",
+                                                        _f64([r.site_density for r in net.srfcplxrxn])))
+            flags = []
+            for r in net.srfcplxrxn:
+                fs = [net.srfcplx_free_site_stoich[net.srfcplx_names.index(n)] for n in r.complexes]
+                # reaction_database.F90: stoich_flag set when any free-site
+                # stoichiometry differs from 1
+                flags.append(int(any(abs(v - 1.0) > 1.0e-40 for v in fs)))
+            c.srfcplxrxn_stoich_flag = _ip(self._keep("srfcplxrxn_stoich_flag", _i32(flags)))
+            ptr, ids, st = net.csr(net.srfcplx_rxn)
+            c.srfcplx_ptr = _ip(self._keep("srfcplx_ptr", ptr))
+            c.srfcplx_specid = _ip(self._keep("srfcplx_specid", ids))
+            c.srfcplx_stoich = _dp(self._keep("srfcplx_stoich", st))
+            c.srfcplx_h2ostoich = _dp(self._keep("srfcplx_h2ostoich",
+                                                  _f64([r.h2o_stoich for r in net.srfcplx_rxn])))
+            c.srfcplx_free_site_stoich = _dp(self._keep("srfcplx_free_site_stoich",
+                                                         _f64(net.srfcplx_free_site_stoich)))
+            c.srfcplx_logK = _dp(self._keep("srfcplx_logK", net.logKs(net.srfcplx_rxn)))
+            if not net.use_isothermal:
+                c.srfcplx_logKcoef = _dp(self._keep("srfcplx_logKcoef", _f64(net.logK_coefs(net.srfcplx_rxn))))
+            c.neqsrfcplxrxn = len(net.eq_rxn_ids)
+            c.eqsrfcplxrxn_to_srfcplxrxn = _ip(self._keep("eqsrfcplxrxn_to_srfcplxrxn", _i32(net.eq_rxn_ids)))
+            c.nkinmrsrfcplxrxn = len(net.mr_rxn_ids)
+            if net.mr_rxn_ids:
+                c.kinmrsrfcplxrxn_to_srfcplxrxn = _ip(self._keep("kinmrsrfcplxrxn_to_srfcplxrxn",
+                                                                  _i32(net.mr_rxn_ids)))
+                mptr = np.zeros(len(net.mr_rxn_ids) + 1, dtype=np.int32)
+                rates: List[float] = []
+                fracs: List[float] = []
+                for k, i in enumerate(net.mr_rxn_ids):
+                    rates += net.srfcplxrxn[i].rates
+                    fracs += net.srfcplxrxn[i].site_fractions
+                    mptr[k + 1] = len(rates)
+                c.kinmr_rate_ptr = _ip(self._keep("kinmr_rate_ptr", mptr))
+                c.kinmr_rate = _dp(self._keep("kinmr_rate", _f64(rates)))
+                c.kinmr_frac = _dp(self._keep("kinmr_frac", _f64(fracs)))
+
+        # CLM-CN
+        cc = net.clmcn
+        if cc is not None:
+            c.clmcn_nrxn = cc["nrxn"]
+            c.clmcn_npool = cc["npool"]
+            c.clmcn_C_species_id = cc["C_id"]
+            c.clmcn_N_species_id = cc["N_id"]
+            c.clmcn_CN_ratio = _dp(self._keep("clmcn_CN_ratio", _f64(cc["CN_ratio"])))
+            c.clmcn_pool_nspec = _ip(self._keep("clmcn_pool_nspec", _i32(cc["pool_nspec"])))
+            c.clmcn_pool_C_id = _ip(self._keep("clmcn_pool_C_id", _i32(cc["pool_C_id"])))
+            c.clmcn_pool_N_id = _ip(self._keep("clmcn_pool_N_id", _i32(cc["pool_N_id"])))
+            c.clmcn_upstream_pool_id = _ip(self._keep("clmcn_upstream_pool_id", _i32(cc["up"])))
+            c.clmcn_downstream_pool_id = _ip(self._keep("clmcn_downstream_pool_id", _i32(cc["down"])))
+            c.clmcn_rate_constant = _dp(self._keep("clmcn_rate_constant", _f64(cc["rate_constant"])))
+            c.clmcn_respiration_fraction = _dp(self._keep("clmcn_respiration_fraction", _f64(cc["resp"])))
+            c.clmcn_inhibition_constant = _dp(self._keep("clmcn_inhibition_constant", _f64(cc["inhib"])))
+
+    # ------------------------------------------------------------------ #
+    @property
+    def ncomp(self) -> int:
+        return self.c.naqcomp + self.c.nimcomp
+
+    def field_rows(self) -> Dict[str, int]:
+        """number of components (rows) of every per-cell field"""
+        c = self.c
+        nmr = c.nkinmrsrfcplxrxn
+        mr_rows = 0
+        if nmr:
+            mr_rows = c.naqcomp * (int(self.arrays["kinmr_rate_ptr"][nmr]) + nmr)
+        return {
+            "total": c.naqcomp, "pri_molal": c.naqcomp, "immobile": c.nimcomp,
+            "pri_act_coef": c.naqcomp, "sec_act_coef": c.neqcplx, "sec_molal": c.neqcplx,
+            "ln_act_h2o": 1, "mnrl_volfrac": c.nkinmnrl, "mnrl_area": c.nkinmnrl, "mnrl_rate": c.nkinmnrl,
+            "srfcplxrxn_free_site_conc": c.nsrfcplxrxn, "eqsrfcplx_conc": c.nsrfcplx,
+            "total_sorb_eq": c.naqcomp if c.neqsrfcplxrxn > 0 else 0,
+            "kinmr_total_sorb": mr_rows,
+            "den_kg": 1, "sat": 1, "temp": 1, "porosity": 1, "volume": 1, "soil_particle_density": 1,
+            "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,
+        }
+
+
+class HostState:
+    """Cell-major SoA state in host (numpy) memory: ``field[k, cell]``."""
+
+    def __init__(self, cfg: ReactionConfig, ncell: int):
+        self.cfg = cfg
+        self.ncell = int(ncell)
+        self.a: Dict[str, np.ndarray] = {}
+        rows = cfg.field_rows()
+        for f in STATE_DOUBLE_FIELDS:
+            self.a[f] = np.zeros((rows[f], self.ncell), dtype=np.float64)
+        for f in STATE_INT_FIELDS:
+            self.a[f] = np.zeros((rows[f], self.ncell), dtype=np.int32)
+        # neutral defaults
+        self.a["pri_act_coef"][:] = 1.0
+        self.a["sec_act_coef"][:] = 1.0
+        self.a["den_kg"][:] = 1000.0
+        self.a["sat"][:] = 1.0
+        self.a["temp"][:] = 25.0
+        self.a["porosity"][:] = 0.25
+        self.a["volume"][:] = 1.0
+        self.a["soil_particle_density"][:] = 2650.0
+        self.a["imat"][:] = 1
+        self.a["srfcplxrxn_free_site_conc"][:] = 1.0e-9
+
+    def __getitem__(self, k: str) -> np.ndarray:
+        return self.a[k]
+
+    def copy(self) -> "HostState":
+        o = HostState.__new__(HostState)
+        o.cfg, o.ncell = self.cfg, self.ncell
+        o.a = {k: v.copy() for k, v in self.a.items()}
+        return o
+
+    def struct(self) -> PfrxState:
+        s = PfrxState()
+        s.ld = self.ncell
+        for f in STATE_DOUBLE_FIELDS:
+            setattr(s, f, _dp(self.a[f]))
+        for f in STATE_INT_FIELDS:
+            setattr(s, f, _ip(self.a[f]))
+        return s
+
+    def tile(self, reps: int) -> "HostState":
+        o = HostState.__new__(HostState)
+        o.cfg, o.ncell = self.cfg, self.ncell * reps
+        o.a = {k: np.ascontiguousarray(np.tile(v, (1, reps))) for k, v in self.a.items()}
+        return o

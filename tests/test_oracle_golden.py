@@ -1,0 +1,172 @@
+"""Pin the CPU oracle against the reference's own regression golds.
+
+Each case replays a single-cell GIRT batch deck of the reference
+(regression_tests/ascem/batch, regression_tests/ngee) with the oracle's
+residual/Jacobian functions and compares the end state with the committed
+``.regression.gold`` at the tolerance of the reference's own ``.cfg``
+(batch.cfg: 1e-12 absolute; ngee.cfg: 1e-10 relative on concentrations).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import girt
+import oracle_lib as orc
+from pflotran_elm_interface_b200 import abi, chem, constraint, eos
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _setup(deck, db, cons="initial"):
+    dk, net = chem.load_network(open(os.path.join(G, deck)).read(), open(os.path.join(G, db)).read())
+    assert dk.chemistry.unsupported == []
+    cfg = abi.ReactionConfig(net)
+    den = dk.reference_liquid_density or eos.water_density_ifc67(dk.reference_temperature)
+    por = dk.porosity[0]
+    sp = constraint.equilibrate_constraint(net, dk.constraints[cons], den_kg=den, porosity=por)
+    st = abi.HostState(cfg, 1)
+    constraint.fill_cells(st, sp)
+    st["den_kg"][:] = den
+    st["porosity"][:] = por
+    # CondControlAssignRTTranInitCond (condition_control.F90:1636-1650): cells
+    # start from the constraint's free-ion molalities with activity
+    # coefficients = 1, then RTotal, then two (act. coef., RTotal) sweeps
+    st["pri_act_coef"][:] = 1.0
+    st["sec_act_coef"][:] = 1.0
+    orc.auxvar_compute(cfg, st, 0)
+    if dk.chemistry.act_coef_update_frequency != chem.ACT_COEF_FREQUENCY_OFF:
+        for _ in range(2):
+            orc.activity(cfg, st, 0)
+            orc.auxvar_compute(cfg, st, 0)
+    return dk, net, cfg, st
+
+
+def _gold(name):
+    return girt.read_gold(os.path.join(G, name))
+
+
+def _val(gold, title):
+    return gold[title]["1"]
+
+
+def _check_abs(got, want, tol, what):
+    assert abs(got - want) <= tol, f"{what}: got {got!r} want {want!r} diff {abs(got - want):.3e} > {tol}"
+
+
+def _check_rel(got, want, tol, what):
+    assert abs(got - want) <= tol * abs(want), f"{what}: got {got!r} want {want!r} rel {abs(got - want) / abs(want):.3e}"
+
+
+def _pH(st, net=None):
+    i = net.primary_names.index("H+") if net is not None else 0
+    return -np.log10(st["pri_molal"][i, 0] * st["pri_act_coef"][i, 0])
+
+
+def test_density_ifc67():
+    # default water EOS at 25 C, 101325 Pa ~ 997.16 kg/m^3
+    assert abs(eos.water_density_ifc67() - 997.16) < 0.01
+
+
+@pytest.mark.parametrize("deck", ["calcite-kinetics", "calcite-kinetics-volume-fractions"])
+def test_calcite_kinetics_gold(deck):
+    dk, net, cfg, st = _setup(deck + ".in", "calcite.dat")
+    b = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold(deck + ".regression.gold")
+    sol = gold["SOLUTION: Transport"]
+    assert b.steps == int(sol["Time Steps"])
+    assert b.newton_its == int(sol["Newton Iterations"])
+    tol = 1.0e-12  # batch.cfg
+    _check_abs(_pH(st), _val(gold, "GENERIC: pH"), 1.0e-10, "pH")
+    for i, nm in enumerate(net.primary_names):
+        _check_abs(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), tol, f"Total {nm}")
+    _check_abs(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: Calcite VF"), tol, "Calcite VF")
+    _check_abs(st["mnrl_rate"][0, 0], _val(gold, "RATE: Calcite Rate"), tol, "Calcite rate")
+    # the stronger statement: all 14 printed digits of the gold
+    for i, nm in enumerate(net.primary_names):
+        _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm} (rel)")
+    _check_rel(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: Calcite VF"), 1.0e-12, "Calcite VF (rel)")
+    if deck == "calcite-kinetics":  # the other deck sits at equilibrium: rate = rounding noise of 1-QK
+        _check_rel(st["mnrl_rate"][0, 0], _val(gold, "RATE: Calcite Rate"), 1.0e-11, "Calcite rate (rel)")
+
+
+@pytest.mark.parametrize("deck,db", [
+    ("carbonate-unit-activity", "carbonate.dat"),
+    ("carbonate-debye-huckel-activity", "carbonate.dat"),
+    ("ca-carbonate-unit-activity", "ca-carbonate.dat"),
+    ("ca-carbonate-debye-huckel-activity", "ca-carbonate.dat"),
+])
+def test_speciation_gold(deck, db):
+    dk, net, cfg, st = _setup(deck + ".in", db)
+    b = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold(deck + ".regression.gold")
+    for title, sec in gold.items():
+        if title.startswith("CONCENTRATION: Total "):
+            nm = title[len("CONCENTRATION: Total "):]
+            i = net.primary_names.index(nm)
+            _check_abs(st["total"][i, 0], sec["1"], 1.0e-12, title)
+        elif title.startswith("CONCENTRATION: Free "):
+            nm = title[len("CONCENTRATION: Free "):]
+            i = net.primary_names.index(nm)
+            # "Free" is printed as molarity unless MOLAL is set
+            v = st["pri_molal"][i, 0] * st["den_kg"][0, 0] / 1000.0
+            _check_abs(v, sec["1"], 1.0e-12, title)
+        elif title == "GENERIC: pH":
+            _check_abs(_pH(st, net), sec["1"], 1.0e-12, "pH")
+        elif title.startswith("GENERIC: Gamma "):
+            nm = title[len("GENERIC: Gamma "):]
+            if nm in net.primary_names:
+                _check_abs(st["pri_act_coef"][net.primary_names.index(nm), 0], sec["1"], 1.0e-12, title)
+            else:
+                _check_abs(st["sec_act_coef"][net.secondary_names.index(nm), 0], sec["1"], 1.0e-12, title)
+    assert b.steps == int(gold["SOLUTION: Transport"]["Time Steps"])
+
+
+def test_clm_cn_gold():
+    """ngee/CLM-CN: CLM_CN_React over 400 d, 13 pools."""
+    dk, net, cfg, st = _setup("CLM-CN.in", "CLM-CN_database.dat")
+    b = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold("CLM-CN.regression.gold")
+    sol = gold["SOLUTION: Transport"]
+    assert b.steps == int(sol["Time Steps"])
+    # Newton-iteration totals in the gold are a sanity band, not an identity
+    assert abs(b.newton_its - int(sol["Newton Iterations"])) <= 10
+    for i, nm in enumerate(net.immobile_names):
+        want = _val(gold, f"CONCENTRATION: {nm}")
+        got = st["immobile"][i, 0]
+        if abs(want) < 1.0e-30:
+            # pools decayed to ~1e-38: far below any physical meaning
+            assert abs(got) < 1.0e-30
+        else:
+            _check_rel(got, want, 1.0e-10, nm)
+
+
+def test_surface_complexation_gold():
+    """ascem/batch/surface-complexation-1: equilibrium surface complexation with
+    three complexes on one site (RTotalSorbEqSurfCplx1)."""
+    dk, net, cfg, st = _setup("surface-complexation-1.in", "surface-complexation.dat")
+    b = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold("surface-complexation-1.regression.gold")
+    checked = 0
+    for title, sec in gold.items():
+        if title.startswith("CONCENTRATION: Total Sorbed "):
+            nm = title[len("CONCENTRATION: Total Sorbed "):]
+            i = net.primary_names.index(nm)
+            if sec["1"] == 0.0:
+                assert st["total_sorb_eq"][i, 0] == 0.0
+            else:
+                _check_rel(st["total_sorb_eq"][i, 0], sec["1"], 1.0e-12, title)
+            checked += 1
+        elif title == "CONCENTRATION: Free >FeOH_w":
+            _check_rel(st["srfcplxrxn_free_site_conc"][0, 0], sec["1"], 1.0e-12, title)
+            checked += 1
+        elif title.startswith("CONCENTRATION: >") and "Site Density" not in title:
+            nm = title[len("CONCENTRATION: "):]
+            _check_rel(st["eqsrfcplx_conc"][net.srfcplx_names.index(nm), 0], sec["1"], 1.0e-12, title)
+            checked += 1
+        elif title.startswith("CONCENTRATION: Total "):
+            nm = title[len("CONCENTRATION: Total "):]
+            i = net.primary_names.index(nm)
+            _check_abs(st["total"][i, 0], sec["1"], 1.0e-12, title)
+        elif title == "GENERIC: pH":
+            _check_abs(_pH(st, net), sec["1"], 1.0e-12, "pH")

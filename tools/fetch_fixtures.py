@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Copy the reference's OWN regression fixtures (decks, tiny .dat databases and
+.regression.gold files -- test data, not source) for the hot-path chemistry
+into tests/golden/, and write trimmed extracts of the big databases.
+
+Run in the build container (needs /root/reference); the GPU box only sees the
+committed copies.  Provenance of every file is recorded in
+tests/golden/PROVENANCE.txt.
+"""
+import os
+import shutil
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from pflotran_elm_interface_b200 import chem  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+
+COPY = [
+    # (reference path, local name)
+    ("regression_tests/ascem/batch/calcite-kinetics.in", None),
+    ("regression_tests/ascem/batch/calcite-kinetics.regression.gold", None),
+    ("regression_tests/ascem/batch/calcite-kinetics-volume-fractions.in", None),
+    ("regression_tests/ascem/batch/calcite-kinetics-volume-fractions.regression.gold", None),
+    ("regression_tests/ascem/batch/calcite.dat", None),
+    ("regression_tests/ascem/batch/carbonate-unit-activity.in", None),
+    ("regression_tests/ascem/batch/carbonate-unit-activity.regression.gold", None),
+    ("regression_tests/ascem/batch/carbonate-debye-huckel-activity.in", None),
+    ("regression_tests/ascem/batch/carbonate-debye-huckel-activity.regression.gold", None),
+    ("regression_tests/ascem/batch/carbonate.dat", None),
+    ("regression_tests/ascem/batch/ca-carbonate-unit-activity.in", None),
+    ("regression_tests/ascem/batch/ca-carbonate-unit-activity.regression.gold", None),
+    ("regression_tests/ascem/batch/ca-carbonate-debye-huckel-activity.in", None),
+    ("regression_tests/ascem/batch/ca-carbonate-debye-huckel-activity.regression.gold", None),
+    ("regression_tests/ascem/batch/ca-carbonate.dat", None),
+    ("regression_tests/ascem/batch/surface-complexation-1.in", None),
+    ("regression_tests/ascem/batch/surface-complexation-1.regression.gold", None),
+    ("regression_tests/ascem/batch/surface-complexation.dat", None),
+    ("regression_tests/ngee/CLM-CN.in", None),
+    ("regression_tests/ngee/CLM-CN.regression.gold", None),
+    ("regression_tests/ngee/CLM-CN_database.dat", None),
+    ("regression_tests/default/543/543_hanford_srfcplx_base.in", None),
+    ("regression_tests/default/543/543_hanford_srfcplx_base.regression.gold", None),
+    ("regression_tests/default/543/543_hanford_srfcplx_mr.in", None),
+    ("regression_tests/default/column/surface_complexation_mr_os.in", None),
+    ("regression_tests/default/column/tracer_os.in", None),
+    ("regression_tests/default/column/tracer_os.regression.gold", None),
+    ("regression_tests/default/column/tracer_os_no_geochem.regression.gold", None),
+    ("shortcourse/1D_Calcite/calcite_tran_only.in", None),
+]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    prov = []
+    for src, name in COPY:
+        p = os.path.join(REF, src)
+        if not os.path.exists(p):
+            print("missing", src)
+            continue
+        dst = os.path.join(OUT, name or os.path.basename(src))
+        shutil.copyfile(p, dst)
+        os.chmod(dst, 0o644)
+        prov.append(f"{os.path.basename(dst)} <- {src} (verbatim copy)")
+    # trimmed hanford.dat: only the species the Hanford decks and the C2/C5
+    # synthetic configurations name
+    with open(os.path.join(OUT, "543_hanford_srfcplx_base.in")) as f:
+        dk = chem.read_deck(f.read())
+    ch = dk.chemistry
+    names = (["H2O"] + ch.primary + ch.secondary + ch.gases + ch.minerals
+             + [c for r in ch.srfcplx_rxns for c in r.complexes]
+             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)"])
+    db = chem.Database.from_file(os.path.join(REF, "database/hanford.dat"))
+    with open(os.path.join(OUT, "hanford_subset.dat"), "w") as f:
+        f.write(db.subset_text(names))
+    prov.append("hanford_subset.dat <- database/hanford.dat (lines of the species named by "
+                "543_hanford_srfcplx_base.in, verbatim; made by tools/fetch_fixtures.py)")
+    with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
+        f.write("Reference fixtures (test data) copied from /root/reference by tools/fetch_fixtures.py\n")
+        f.write("\n".join(prov) + "\n")
+    print("\n".join(prov))
+
+
+if __name__ == "__main__":
+    main()
