@@ -239,6 +239,9 @@ typedef struct pfrx_handle pfrx_handle;
 /* library identification; safe to call without a GPU */
 int pfrx_abi_version(void);
 const char *pfrx_last_error(void);
+/* sizeof(pfrx_config | pfrx_state | pfrx_step_result) for which = 0 | 1 | 2:
+ * lets a foreign-language binding assert its struct layout */
+int64_t pfrx_sizeof(int which);
 
 /* Replaces nothing in the reference: flattening of reaction_rt_type is done by
  * the binding.  `device` is the CUDA ordinal this handle is tied to. */
@@ -281,6 +284,12 @@ int64_t pfrx_launch_count(pfrx_handle *h);
 /* bytes of state read+written per cell-solve by the bound configuration
  * (the algorithmic HBM traffic of SURVEY.md section 8(d))                    */
 int64_t pfrx_bytes_per_cell(pfrx_handle *h);
+
+/* kernel configuration chosen for this handle:
+ * info5 = {padded system size N, lanes per cell, threads per block,
+ *          resident blocks per SM, dynamic shared memory bytes per block}.
+ * PFRX_LANES / PFRX_THREADS in the environment override the defaults. */
+int pfrx_kernel_info(pfrx_handle *h, int *info5);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,731 @@
+// pfrx_api.cu -- C ABI of include/pfrx.h on top of the sm_100a kernels.
+// No torch, no CPU fallback: every compute entry point needs a CUDA device and
+// returns PFRX_E_CUDA otherwise.
+#include <dlfcn.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "pfrx_device.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define CUDA_OK(call)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) return set_err(PFRX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- NCCL through dlopen (works with the system or the torch-bundled copy) --
+typedef struct {
+  char internal[128];
+} NcclUid;
+typedef void *NcclComm;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(NcclUid *) = nullptr;
+  int (*CommInitRank)(NcclComm *, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return PFRX_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return set_err(PFRX_E_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+#define SYM(field, name)                                                      \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                 \
+  if (!g_nccl.field) return set_err(PFRX_E_NCCL, "NCCL symbol %s missing", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.lib = h;
+  return PFRX_OK;
+}
+
+// ---- handle -----------------------------------------------------------------
+struct pfrx_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  DevCfg cfg;
+  void *arena = nullptr;  // device copy of all tables
+  int n = 0, npad = 0, lanes = 1;
+  size_t smem_bytes = 0;
+  int threads = 128;
+  int blocks_per_sm = 1, sm_count = 1;
+  void (*kernel)(DevCfg, DevState, int64_t, double, DevSummary *) = nullptr;
+  // bound state
+  bool bound = false;
+  int64_t ncell = 0;
+  DevState st;
+  DevSummary *d_summ = nullptr;
+  DevSummary *h_summ = nullptr;  // pinned
+  bool pending = false;
+  int64_t launches = 0;
+  // row counts of every field, in pfrx_state order
+  std::vector<int> rows_d;  // 20 double fields
+  // owned device state for pfrx_rstep_host
+  void *own = nullptr;
+  int64_t own_ncell = 0;
+  DevState own_st;
+  // nccl
+  NcclComm comm = nullptr;
+  long long *d_red = nullptr;
+  long long *h_red = nullptr;
+  int nranks = 1;
+};
+
+// table arena builder
+struct Arena {
+  std::vector<unsigned char> bytes;
+  std::vector<std::pair<size_t, void **>> fix;  // (offset, address of device pointer field)
+  template <typename T>
+  void add(const T *src, size_t count, const T **field) {
+    if (!src || count == 0) {
+      *field = nullptr;
+      return;
+    }
+    size_t off = (bytes.size() + 15) & ~size_t(15);
+    bytes.resize(off + count * sizeof(T));
+    memcpy(bytes.data() + off, src, count * sizeof(T));
+    fix.push_back({off, (void **)field});
+  }
+};
+
+typedef void (*pfrx_kernel_fn)(DevCfg, DevState, int64_t, double, DevSummary *);
+// one getter per padded size N, defined in pfrx_kern.cu (see build.py)
+#define PFRX_DECL(N) extern "C" pfrx_kernel_fn pfrx_kernel_##N(int lanes);
+PFRX_DECL(3) PFRX_DECL(4) PFRX_DECL(8) PFRX_DECL(13) PFRX_DECL(15) PFRX_DECL(16) PFRX_DECL(32)
+struct KernelGetter {
+  int n;
+  pfrx_kernel_fn (*get)(int);
+};
+static const KernelGetter g_getters[] = {{3, pfrx_kernel_3},   {4, pfrx_kernel_4},   {8, pfrx_kernel_8},
+                                         {13, pfrx_kernel_13}, {15, pfrx_kernel_15}, {16, pfrx_kernel_16},
+                                         {32, pfrx_kernel_32}};
+
+static int default_lanes(int npad) {
+  if (npad <= 4) return 1;
+  if (npad <= 8) return 4;
+  if (npad <= 16) return 16;
+  return 32;
+}
+
+static int pick_kernel(pfrx_handle *h, int want_lanes) {
+  const KernelGetter *gt = nullptr;
+  for (const auto &k : g_getters)
+    if (k.n >= h->n && (!gt || k.n < gt->n)) gt = &k;
+  if (!gt) return set_err(PFRX_E_LIMIT, "ncomp exceeds PFRX_MAX_NCOMP%s", "");
+  int lanes = want_lanes > 0 ? want_lanes : default_lanes(gt->n);
+  pfrx_kernel_fn fn = gt->get(lanes);
+  if (!fn) {
+    // nearest instantiated lane count
+    const int cand[] = {1, 2, 4, 8, 16, 32};
+    int best = -1;
+    for (int c : cand)
+      if (gt->get(c) && (best < 0 || abs(c - lanes) < abs(best - lanes))) best = c;
+    if (best < 0) return set_err(PFRX_E_LIMIT, "no kernel variant for this size%s", "");
+    lanes = best;
+    fn = gt->get(lanes);
+  }
+  h->npad = gt->n;
+  h->lanes = lanes;
+  h->kernel = fn;
+  return PFRX_OK;
+}
+
+static int field_rows(const pfrx_config *c, int *rows /*20*/) {
+  int mr = 0;
+  if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
+  int r[20] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl, c->nkinmnrl,
+               c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, c->neqsrfcplxrxn > 0 ? c->naqcomp : 0, mr, 1, 1, 1, 1, 1, 1};
+  memcpy(rows, r, sizeof(r));
+  return 0;
+}
+
+extern "C" int pfrx_abi_version(void) { return PFRX_ABI_VERSION; }
+extern "C" const char *pfrx_last_error(void) { return g_err; }
+extern "C" int64_t pfrx_sizeof(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(pfrx_config);
+    case 1: return (int64_t)sizeof(pfrx_state);
+    case 2: return (int64_t)sizeof(pfrx_step_result);
+  }
+  return -1;
+}
+
+static int layout_and_launch_params(pfrx_handle *h) {
+  DevCfg &d = h->cfg;
+  const int N = h->npad;
+  int off = 0;
+  auto take = [&](int cnt) {
+    int o = off;
+    off += cnt;
+    return o;
+  };
+  d.off_c = take(N);
+  d.off_lnact = take(N);
+  d.off_invc = take(N);
+  d.off_x = take(2 * (N + 2));
+  d.off_xs = take(N);
+  d.off_sec = take(d.ncplx);
+  d.off_secg = take(d.ncplx);
+  d.js = N | 1;
+  d.off_J = take(N * d.js);
+  d.off_tmp = take(N + d.nsrfcplx + 1);
+  d.off_sc = take(d.nsrfcplx + 1);
+  d.ws_stride = off | 1;
+  int groups = h->threads / h->lanes;
+  h->smem_bytes = (size_t)groups * d.ws_stride * sizeof(double);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+    // shrink the block until the workspace fits
+    while (h->threads > 32 && h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+      h->threads /= 2;
+      groups = h->threads / h->lanes;
+      h->smem_bytes = (size_t)groups * d.ws_stride * sizeof(double);
+    }
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+      return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
+  }
+  CUDA_OK(cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->smem_bytes));
+  int nb = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)h->kernel, h->threads, h->smem_bytes));
+  if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+  h->blocks_per_sm = nb;
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) {
+  if (!c || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (c->abi_version != PFRX_ABI_VERSION) return set_err(PFRX_E_INVALID, "abi_version mismatch%s", "");
+  int n = c->naqcomp + c->nimcomp;
+  if (n < 1 || n > PFRX_MAX_NCOMP) return set_err(PFRX_E_LIMIT, "ncomp out of range%s", "");
+  if (c->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON &&
+      c->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER)
+    return set_err(PFRX_E_INVALID, "ACTIVITY_COEFFICIENTS NEWTON (iterated ionic strength) is not on the GPU path yet%s", "");
+  if (c->kinmnrl_num_prefactors) {
+    for (int m = 0; m < c->nkinmnrl; m++)
+      if (c->kinmnrl_num_prefactors[m] > 0)
+        return set_err(PFRX_E_INVALID, "mineral PREFACTOR kinetics are not on the GPU path yet%s", "");
+  }
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return set_err(PFRX_E_CUDA, "no such CUDA device%s", "");
+  CUDA_OK(cudaSetDevice(device));
+  pfrx_handle *h = new pfrx_handle();
+  h->device = device;
+  h->n = n;
+  DevCfg &d = h->cfg;
+  memset(&d, 0, sizeof(d));
+  d.naq = c->naqcomp;
+  d.nim = c->nimcomp;
+  d.n = n;
+  d.use_full_geochemistry = c->use_full_geochemistry;
+  d.use_log = c->use_log_formulation;
+  d.use_total_as_guess = c->use_total_as_guess;
+  d.use_isothermal = c->use_isothermal || !c->eqcplx_logKcoef;
+  if (!c->use_isothermal && c->neqcplx > 0 && !c->eqcplx_logKcoef) {
+    delete h;
+    return set_err(PFRX_E_INVALID, "anisothermal run needs eqcplx_logKcoef%s", "");
+  }
+  if (c->neqcplx == 0) d.use_isothermal = c->use_isothermal;
+  d.act_freq = c->act_coef_update_frequency;
+  d.act_alg = c->act_coef_update_algorithm;
+  d.use_act_h2o = c->use_activity_h2o;
+  d.h2o_aq_id = c->h2o_aq_id;
+  d.max_its = c->maximum_reaction_iterations;
+  d.max_cuts = c->maximum_reaction_cuts;
+  d.max_dlnC = c->max_dlnC_rreact;
+  d.tol_relchange = c->max_relative_change_tolerance;
+  d.tol_res = c->max_residual_tolerance;
+  d.tol_relres = c->max_rel_residual_tolerance;
+  d.min_sat = c->rt_min_saturation;
+  d.debyeA = c->debyeA;
+  d.debyeB = c->debyeB;
+  d.debyeBdot = c->debyeBdot;
+  d.ncplx = c->neqcplx;
+  d.nkin = c->nkinmnrl;
+  d.nsrfrxn = c->nsrfcplxrxn;
+  d.nsrfcplx = c->nsrfcplx;
+  d.neqsr = c->neqsrfcplxrxn;
+  d.nmr = c->nkinmrsrfcplxrxn;
+  d.cn_nrxn = c->clmcn_nrxn;
+  d.cn_C = c->clmcn_C_species_id;
+  d.cn_N = c->clmcn_N_species_id;
+
+  Arena A;
+  const int naq = c->naqcomp;
+  A.add(c->primary_spec_Z, naq, &d.pri_Z);
+  A.add(c->primary_spec_a0, naq, &d.pri_a0);
+  // species -> complexes (ascending complex id, the order RTotalAqueous adds)
+  std::vector<int> sp_ptr(naq + 1, 0), sp_cx;
+  std::vector<double> sp_st;
+  if (c->neqcplx > 0) {
+    int nnz = c->eqcplx_ptr[c->neqcplx];
+    A.add(c->eqcplx_ptr, c->neqcplx + 1, &d.cx_ptr);
+    A.add(c->eqcplx_specid, nnz, &d.cx_id);
+    A.add(c->eqcplx_stoich, nnz, &d.cx_st);
+    A.add(c->eqcplx_h2ostoich, c->neqcplx, &d.cx_h2o);
+    A.add(c->eqcplx_logK, c->neqcplx, &d.cx_logK);
+    A.add(c->eqcplx_logKcoef, c->eqcplx_logKcoef ? 5 * c->neqcplx : 0, &d.cx_logKcoef);
+    A.add(c->eqcplx_Z, c->neqcplx, &d.cx_Z);
+    A.add(c->eqcplx_a0, c->neqcplx, &d.cx_a0);
+    for (int i = 0; i < naq; i++) {
+      for (int k = 0; k < c->neqcplx; k++)
+        for (int p = c->eqcplx_ptr[k]; p < c->eqcplx_ptr[k + 1]; p++)
+          if (c->eqcplx_specid[p] == i) {
+            sp_cx.push_back(k);
+            sp_st.push_back(c->eqcplx_stoich[p]);
+          }
+      sp_ptr[i + 1] = (int)sp_cx.size();
+    }
+  }
+  A.add(sp_ptr.data(), sp_ptr.size(), &d.sp_ptr);
+  A.add(sp_cx.data(), sp_cx.size(), &d.sp_cx);
+  A.add(sp_st.data(), sp_st.size(), &d.sp_st);
+  if (c->nkinmnrl > 0) {
+    int nk = c->nkinmnrl, nnz = c->kinmnrl_ptr[nk];
+    A.add(c->kinmnrl_ptr, nk + 1, &d.mn_ptr);
+    A.add(c->kinmnrl_specid, nnz, &d.mn_id);
+    A.add(c->kinmnrl_stoich, nnz, &d.mn_st);
+    A.add(c->kinmnrl_h2ostoich, nk, &d.mn_h2o);
+    A.add(c->kinmnrl_logK, nk, &d.mn_logK);
+    A.add(c->kinmnrl_logKcoef, c->kinmnrl_logKcoef ? 5 * nk : 0, &d.mn_logKcoef);
+    A.add(c->kinmnrl_molar_vol, nk, &d.mn_vol);
+    A.add(c->kinmnrl_rate_constant, nk, &d.mn_rate);
+    A.add(c->kinmnrl_activation_energy, nk, &d.mn_eact);
+    A.add(c->kinmnrl_affinity_threshold, nk, &d.mn_thresh);
+    A.add(c->kinmnrl_rate_limiter, nk, &d.mn_limit);
+    A.add(c->kinmnrl_irreversible, nk, &d.mn_irrev);
+    A.add(c->kinmnrl_Temkin_const, c->kinmnrl_Temkin_const ? nk : 0, &d.mn_temkin);
+    A.add(c->kinmnrl_min_scale_factor, c->kinmnrl_min_scale_factor ? nk : 0, &d.mn_scale);
+    A.add(c->kinmnrl_affinity_power, c->kinmnrl_affinity_power ? nk : 0, &d.mn_power);
+  }
+  if (c->nsrfcplxrxn > 0) {
+    int nr = c->nsrfcplxrxn, ns = c->nsrfcplx;
+    A.add(c->srfcplxrxn_ptr, nr + 1, &d.sr_ptr);
+    A.add(c->srfcplxrxn_to_complex, c->srfcplxrxn_ptr[nr], &d.sr_cx);
+    A.add(c->srfcplxrxn_surf_type, nr, &d.sr_type);
+    A.add(c->srfcplxrxn_to_surf, nr, &d.sr_surf);
+    A.add(c->srfcplxrxn_stoich_flag, nr, &d.sr_flag);
+    A.add(c->srfcplxrxn_site_density, nr, &d.sr_dens);
+    A.add(c->srfcplx_ptr, ns + 1, &d.sc_ptr);
+    A.add(c->srfcplx_specid, c->srfcplx_ptr[ns], &d.sc_id);
+    A.add(c->srfcplx_stoich, c->srfcplx_ptr[ns], &d.sc_st);
+    A.add(c->srfcplx_h2ostoich, ns, &d.sc_h2o);
+    A.add(c->srfcplx_free_site_stoich, ns, &d.sc_fs);
+    A.add(c->srfcplx_logK, ns, &d.sc_logK);
+    A.add(c->srfcplx_logKcoef, c->srfcplx_logKcoef ? 5 * ns : 0, &d.sc_logKcoef);
+    A.add(c->eqsrfcplxrxn_to_srfcplxrxn, c->neqsrfcplxrxn, &d.eqsr);
+    if (c->nkinmrsrfcplxrxn > 0) {
+      int nm = c->nkinmrsrfcplxrxn;
+      A.add(c->kinmrsrfcplxrxn_to_srfcplxrxn, nm, &d.mr_rxn);
+      A.add(c->kinmr_rate_ptr, nm + 1, &d.mr_ptr);
+      A.add(c->kinmr_rate, c->kinmr_rate_ptr[nm], &d.mr_rate);
+      A.add(c->kinmr_frac, c->kinmr_rate_ptr[nm], &d.mr_frac);
+    }
+  }
+  if (c->clmcn_nrxn > 0) {
+    int nx = c->clmcn_nrxn, np = c->clmcn_npool;
+    A.add(c->clmcn_CN_ratio, np, &d.cn_CN);
+    A.add(c->clmcn_pool_nspec, np, &d.cn_nspec);
+    A.add(c->clmcn_pool_C_id, np, &d.cn_cid);
+    A.add(c->clmcn_pool_N_id, np, &d.cn_nid);
+    A.add(c->clmcn_upstream_pool_id, nx, &d.cn_up);
+    A.add(c->clmcn_downstream_pool_id, nx, &d.cn_down);
+    A.add(c->clmcn_rate_constant, nx, &d.cn_k);
+    A.add(c->clmcn_respiration_fraction, nx, &d.cn_resp);
+    A.add(c->clmcn_inhibition_constant, nx, &d.cn_inhib);
+  }
+  size_t asz = std::max<size_t>(A.bytes.size(), 16);
+  cudaError_t e = cudaMalloc(&h->arena, asz);
+  if (e != cudaSuccess) {
+    delete h;
+    return set_err(PFRX_E_CUDA, "cudaMalloc(tables): %s", cudaGetErrorString(e));
+  }
+  if (!A.bytes.empty()) cudaMemcpy(h->arena, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice);
+  for (auto &f : A.fix) *f.second = (unsigned char *)h->arena + f.first;
+
+  h->rows_d.resize(20);
+  field_rows(c, h->rows_d.data());
+
+  int want = 0;
+  if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
+  int rc = pick_kernel(h, want);
+  if (rc) {
+    cudaFree(h->arena);
+    delete h;
+    return rc;
+  }
+  if (const char *ev = getenv("PFRX_THREADS")) {
+    int t = atoi(ev);
+    if (t >= 32 && t <= 128 && (t % 32) == 0) h->threads = t;
+  }
+  rc = layout_and_launch_params(h);
+  if (rc) {
+    cudaFree(h->arena);
+    delete h;
+    return rc;
+  }
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  cudaMalloc(&h->d_summ, sizeof(DevSummary));
+  cudaMallocHost(&h->h_summ, sizeof(DevSummary));
+  *out = h;
+  return PFRX_OK;
+}
+
+extern "C" void pfrx_destroy(pfrx_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own) cudaFree(h->own);
+  if (h->arena) cudaFree(h->arena);
+  if (h->d_summ) cudaFree(h->d_summ);
+  if (h->h_summ) cudaFreeHost(h->h_summ);
+  if (h->d_red) cudaFree(h->d_red);
+  if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) {
+  const std::vector<int> &r = h->rows_d;
+  d->ld = s->ld;
+  d->total = s->total;
+  d->pri_molal = s->pri_molal;
+  d->immobile = s->immobile;
+  d->pri_act_coef = s->pri_act_coef;
+  d->sec_act_coef = s->sec_act_coef;
+  d->sec_molal = s->sec_molal;
+  d->ln_act_h2o = s->ln_act_h2o;
+  d->mnrl_volfrac = s->mnrl_volfrac;
+  d->mnrl_area = s->mnrl_area;
+  d->mnrl_rate = s->mnrl_rate;
+  d->free_site = s->srfcplxrxn_free_site_conc;
+  d->eqsrfcplx_conc = s->eqsrfcplx_conc;
+  d->total_sorb_eq = s->total_sorb_eq;
+  d->kinmr = s->kinmr_total_sorb;
+  d->den_kg = s->den_kg;
+  d->sat = s->sat;
+  d->temp = s->temp;
+  d->porosity = s->porosity;
+  d->volume = s->volume;
+  d->soil_particle_density = s->soil_particle_density;
+  d->imat = s->imat;
+  d->num_sub_steps = s->num_sub_steps;
+  d->num_iterations = s->num_iterations;
+  d->num_kinetic_state_updates = s->num_kinetic_state_updates;
+  d->ierror = s->ierror;
+  // required pointers
+  const void *req[] = {r[0] ? s->total : (void *)1,
+                       r[1] ? s->pri_molal : (void *)1,
+                       r[2] ? s->immobile : (void *)1,
+                       r[3] ? s->pri_act_coef : (void *)1,
+                       r[4] ? s->sec_act_coef : (void *)1,
+                       r[5] ? s->sec_molal : (void *)1,
+                       r[7] ? s->mnrl_volfrac : (void *)1,
+                       r[8] ? s->mnrl_area : (void *)1,
+                       r[9] ? s->mnrl_rate : (void *)1,
+                       r[10] ? s->srfcplxrxn_free_site_conc : (void *)1,
+                       r[12] ? s->total_sorb_eq : (void *)1,
+                       r[13] ? s->kinmr_total_sorb : (void *)1,
+                       s->den_kg,
+                       s->sat,
+                       s->temp,
+                       s->porosity,
+                       s->volume,
+                       s->num_sub_steps,
+                       s->num_iterations,
+                       s->num_kinetic_state_updates,
+                       s->ierror};
+  for (const void *p : req)
+    if (!p) return set_err(PFRX_E_INVALID, "a required pfrx_state pointer is NULL%s", "");
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_bind_state(pfrx_handle *h, int64_t ncell, const pfrx_state *dev) {
+  if (!h || !dev || ncell < 0 || dev->ld < ncell) return set_err(PFRX_E_INVALID, "bad bind_state arguments%s", "");
+  int rc = to_dev_state(h, dev, &h->st);
+  if (rc) return rc;
+  h->ncell = ncell;
+  h->bound = true;
+  return PFRX_OK;
+}
+
+static int launch(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
+  DevSummary z;
+  memset(&z, 0, sizeof(z));
+  z.first_failed = LLONG_MAX;
+  *h->h_summ = z;
+  CUDA_OK(cudaMemcpyAsync(h->d_summ, h->h_summ, sizeof(DevSummary), cudaMemcpyHostToDevice, s));
+  if (ncell > 0) {
+    int cpw = 32 / h->lanes;
+    int wpb = h->threads / 32;
+    int64_t need = (ncell + (int64_t)cpw * wpb - 1) / ((int64_t)cpw * wpb);
+    int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
+    int grid = (int)std::min<int64_t>(need, cap);
+    if (grid < 1) grid = 1;
+    h->kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, st, ncell, tran_dt, h->d_summ);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+  }
+  CUDA_OK(cudaMemcpyAsync(h->h_summ, h->d_summ, sizeof(DevSummary), cudaMemcpyDeviceToHost, s));
+  h->pending = true;
+  return PFRX_OK;
+}
+
+static void summary_out(const pfrx_handle *h, pfrx_step_result *out) {
+  const DevSummary &s = *h->h_summ;
+  out->ncell_active = (int64_t)s.ncell_active;
+  out->sum_newton_iterations = (int64_t)s.sum_its;
+  out->max_newton_iterations = s.max_its;
+  out->max_num_kinetic_state_updates = s.max_kin;
+  out->rstep_error = s.max_err;
+  out->max_sub_steps = s.max_sub;
+  out->num_cut_cells = (int64_t)s.num_cut_cells;
+  out->first_failed_cell = s.first_failed == LLONG_MAX ? -1 : s.first_failed;
+}
+
+extern "C" int pfrx_rstep_async(pfrx_handle *h, double tran_dt) {
+  if (!h) return set_err(PFRX_E_INVALID, "null handle%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  return launch(h, h->st, h->ncell, tran_dt, h->stream);
+}
+
+extern "C" int pfrx_rstep_finish(pfrx_handle *h, pfrx_step_result *out) {
+  if (!h || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->pending) return set_err(PFRX_E_INVALID, "no step in flight%s", "");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->pending = false;
+  summary_out(h, out);
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_rstep(pfrx_handle *h, double tran_dt, pfrx_step_result *out) {
+  int rc = pfrx_rstep_async(h, tran_dt);
+  if (rc) return rc;
+  return pfrx_rstep_finish(h, out);
+}
+
+// ---- host-resident state: H2D, kernel, D2H ------------------------------------
+static const int kNumD = 20;
+static size_t field_off(const int *rows, int64_t ld, int f) {
+  size_t o = 0;
+  for (int i = 0; i < f; i++) o += (size_t)rows[i] * ld;
+  return o;
+}
+
+extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *host, double tran_dt,
+                               pfrx_step_result *out) {
+  if (!h || !host || !out || ncell < 0 || host->ld < ncell) return set_err(PFRX_E_INVALID, "bad arguments%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int *rows = h->rows_d.data();
+  size_t ndbl = 0;
+  for (int i = 0; i < kNumD; i++) ndbl += (size_t)rows[i] * ncell;
+  size_t bytes = ndbl * sizeof(double) + (size_t)5 * ncell * sizeof(int);
+  if (h->own_ncell != ncell) {
+    if (h->own) CUDA_OK(cudaFree(h->own));
+    h->own = nullptr;
+    CUDA_OK(cudaMalloc(&h->own, std::max<size_t>(bytes, 16)));
+    h->own_ncell = ncell;
+    double *base = (double *)h->own;
+    double **dst[kNumD] = {&h->own_st.total,        &h->own_st.pri_molal,    &h->own_st.immobile,
+                           &h->own_st.pri_act_coef, &h->own_st.sec_act_coef, &h->own_st.sec_molal,
+                           &h->own_st.ln_act_h2o,   &h->own_st.mnrl_volfrac, &h->own_st.mnrl_area,
+                           &h->own_st.mnrl_rate,    &h->own_st.free_site,    &h->own_st.eqsrfcplx_conc,
+                           &h->own_st.total_sorb_eq, &h->own_st.kinmr,       (double **)&h->own_st.den_kg,
+                           (double **)&h->own_st.sat, (double **)&h->own_st.temp, (double **)&h->own_st.porosity,
+                           (double **)&h->own_st.volume, (double **)&h->own_st.soil_particle_density};
+    for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
+    int *ib = (int *)(base + ndbl);
+    h->own_st.imat = ib;
+    h->own_st.num_sub_steps = ib + ncell;
+    h->own_st.num_iterations = ib + 2 * ncell;
+    h->own_st.num_kinetic_state_updates = ib + 3 * ncell;
+    h->own_st.ierror = ib + 4 * ncell;
+    h->own_st.ld = ncell;
+  }
+  DevState d = h->own_st;
+  const double *src[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
+                              host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
+                              host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
+                              host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb, host->den_kg,
+                              host->sat,          host->temp,         host->porosity,  host->volume,
+                              host->soil_particle_density};
+  double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
+                         d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
+                         d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
+                         (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
+                         (double *)d.soil_particle_density};
+  cudaStream_t s = h->stream;
+  bool have_spd = host->soil_particle_density != nullptr;
+  if (!have_spd) d.soil_particle_density = nullptr;
+  bool have_lnw = host->ln_act_h2o != nullptr;
+  if (!have_lnw) d.ln_act_h2o = nullptr;
+  bool have_sc = host->eqsrfcplx_conc != nullptr;
+  if (!have_sc) d.eqsrfcplx_conc = nullptr;
+  for (int f = 0; f < kNumD; f++) {
+    if (!rows[f] || !src[f]) continue;
+    if (f == 11) continue;  // eqsrfcplx_conc is output only
+    if (host->ld == ncell) {
+      CUDA_OK(cudaMemcpyAsync(dptr[f], src[f], (size_t)rows[f] * ncell * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+      CUDA_OK(cudaMemcpy2DAsync(dptr[f], ncell * sizeof(double), src[f], host->ld * sizeof(double),
+                                ncell * sizeof(double), rows[f], cudaMemcpyHostToDevice, s));
+    }
+  }
+  if (host->imat) {
+    CUDA_OK(cudaMemcpyAsync((void *)d.imat, host->imat, ncell * sizeof(int), cudaMemcpyHostToDevice, s));
+  } else {
+    d.imat = nullptr;
+  }
+  DevState chk;
+  pfrx_state probe = *host;
+  int rc = to_dev_state(h, &probe, &chk);
+  if (rc) return rc;
+  rc = launch(h, d, ncell, tran_dt, s);
+  if (rc) return rc;
+  // D2H of every io field and the per-cell results
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13};
+  double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
+                         host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
+                         host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
+                         host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb, nullptr,
+                         nullptr,            nullptr,            nullptr,         nullptr,
+                         nullptr};
+  for (int f : io) {
+    if (!rows[f] || !hdst[f]) continue;
+    if (host->ld == ncell) {
+      CUDA_OK(cudaMemcpyAsync(hdst[f], dptr[f], (size_t)rows[f] * ncell * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      CUDA_OK(cudaMemcpy2DAsync(hdst[f], host->ld * sizeof(double), dptr[f], ncell * sizeof(double),
+                                ncell * sizeof(double), rows[f], cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(host->num_sub_steps, d.num_sub_steps, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host->num_iterations, d.num_iterations, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host->num_kinetic_state_updates, d.num_kinetic_state_updates, ncell * sizeof(int),
+                          cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host->ierror, d.ierror, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  h->pending = false;
+  summary_out(h, out);
+  return PFRX_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------
+extern "C" int pfrx_comm_unique_id(void *id128) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclUid id;
+  int e = g_nccl.GetUniqueId(&id);
+  if (e) return set_err(PFRX_E_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(e));
+  memcpy(id128, &id, sizeof(id));
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_comm_init(pfrx_handle *h, int nranks, int rank, const void *id128) {
+  if (!h || !id128) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  int rc = load_nccl();
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  NcclUid id;
+  memcpy(&id, id128, sizeof(id));
+  int e = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (e) return set_err(PFRX_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(e));
+  h->nranks = nranks;
+  CUDA_OK(cudaMalloc(&h->d_red, 8 * sizeof(long long)));
+  CUDA_OK(cudaMallocHost(&h->h_red, 8 * sizeof(long long)));
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_allreduce(pfrx_handle *h, pfrx_step_result *r) {
+  if (!h || !r) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->comm) return PFRX_OK;  // single rank: nothing to reduce
+  CUDA_OK(cudaSetDevice(h->device));
+  long long *b = h->h_red;
+  b[0] = r->ncell_active;
+  b[1] = r->sum_newton_iterations;
+  b[2] = r->num_cut_cells;
+  b[3] = 0;
+  b[4] = r->max_newton_iterations;
+  b[5] = r->max_num_kinetic_state_updates;
+  b[6] = r->rstep_error;
+  b[7] = r->max_sub_steps;
+  CUDA_OK(cudaMemcpyAsync(h->d_red, b, 8 * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  const int ncclInt64 = 4, ncclSum = 0, ncclMax = 2;
+  g_nccl.GroupStart();
+  int e1 = g_nccl.AllReduce(h->d_red, h->d_red, 4, ncclInt64, ncclSum, h->comm, h->stream);
+  int e2 = g_nccl.AllReduce(h->d_red + 4, h->d_red + 4, 4, ncclInt64, ncclMax, h->comm, h->stream);
+  int e3 = g_nccl.GroupEnd();
+  if (e1 || e2 || e3) return set_err(PFRX_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(e1 ? e1 : (e2 ? e2 : e3)));
+  CUDA_OK(cudaMemcpyAsync(b, h->d_red, 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  r->ncell_active = b[0];
+  r->sum_newton_iterations = b[1];
+  r->num_cut_cells = b[2];
+  r->max_newton_iterations = (int)b[4];
+  r->max_num_kinetic_state_updates = (int)b[5];
+  r->rstep_error = (int)b[6];
+  r->max_sub_steps = (int)b[7];
+  return PFRX_OK;
+}
+
+extern "C" void *pfrx_stream(pfrx_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int64_t pfrx_launch_count(pfrx_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
+  // every in/io field read once, every io field
+  // written once, four int32 results
+  if (!h) return 0;
+  const int *r = h->rows_d.data();
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13};
+  int64_t in = 0, outn = 0;
+  for (int f = 0; f < kNumD; f++)
+    if (f != 11) in += r[f];
+  for (int f : io) outn += r[f];
+  return 8 * (in + outn) + 16;
+}
+
+// kernel configuration report: N, lanes, threads, blocks/SM, smem bytes
+extern "C" int pfrx_kernel_info(pfrx_handle *h, int *info5) {
+  if (!h || !info5) return PFRX_E_INVALID;
+  info5[0] = h->npad;
+  info5[1] = h->lanes;
+  info5[2] = h->threads;
+  info5[3] = h->blocks_per_sm;
+  info5[4] = (int)h->smem_bytes;
+  return PFRX_OK;
+}

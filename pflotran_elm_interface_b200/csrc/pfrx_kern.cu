@@ -1,0 +1,26 @@
+// pfrx_kern.cu -- one translation unit per padded system size N.
+// Compiled as  nvcc -DPFRX_N=<N> -DPFRX_L0=<L> [-DPFRX_L1=<L> [-DPFRX_L2=<L>]]
+// by build.py; exports  pfrx_kernel_<N>(lanes)  to pfrx_api.cu.
+#include "pfrx_device.cuh"
+
+#ifndef PFRX_N
+#error "compile with -DPFRX_N=<N>"
+#endif
+
+#define PFRX_CAT2(a, b) a##b
+#define PFRX_CAT(a, b) PFRX_CAT2(a, b)
+
+typedef void (*pfrx_kernel_fn)(DevCfg, DevState, int64_t, double, DevSummary *);
+
+extern "C" pfrx_kernel_fn PFRX_CAT(pfrx_kernel_, PFRX_N)(int lanes) {
+#ifdef PFRX_L0
+  if (lanes == PFRX_L0) return pfrx_rstep_kernel<PFRX_N, PFRX_L0>;
+#endif
+#ifdef PFRX_L1
+  if (lanes == PFRX_L1) return pfrx_rstep_kernel<PFRX_N, PFRX_L1>;
+#endif
+#ifdef PFRX_L2
+  if (lanes == PFRX_L2) return pfrx_rstep_kernel<PFRX_N, PFRX_L2>;
+#endif
+  return nullptr;
+}

@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's operator-split reaction step on top of
+the C ABI (``include/pfrx.h`` -> ``libpfrx_b200.so``).
+
+``ChemistryStep.rstep`` is the cell loop of ``PMCSubsurfaceOSRTStepDT``
+(src/pflotran/pmc_subsurface_osrt.F90:346-383): every bound cell goes through
+``RStep`` (src/pflotran/reaction.F90:3564) over ``tran_dt``; the return value
+carries what the coupler accumulates after the loop (:364-388).  There is no
+CPU fallback: if the CUDA library is missing or no device is present the calls
+raise.
+
+PyTorch is used only for device memory, streams and ``torch.distributed``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import abi
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpfrx_b200.so")
+_lib = None
+
+
+class PfrxError(RuntimeError):
+    pass
+
+
+def lib():
+    """load libpfrx_b200.so (built in-tree by csrc/build.py); loud on failure"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise PfrxError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for the chemistry step)")
+    L = C.CDLL(_LIB_PATH)
+    cfgp, stp, resp = C.POINTER(abi.PfrxConfig), C.POINTER(abi.PfrxState), C.POINTER(abi.PfrxStepResult)
+    hp = C.c_void_p
+    L.pfrx_abi_version.restype = C.c_int
+    L.pfrx_last_error.restype = C.c_char_p
+    L.pfrx_sizeof.argtypes = [C.c_int]
+    L.pfrx_sizeof.restype = C.c_int64
+    L.pfrx_create.argtypes = [cfgp, C.c_int, C.POINTER(hp)]
+    L.pfrx_destroy.argtypes = [hp]
+    L.pfrx_destroy.restype = None
+    L.pfrx_bind_state.argtypes = [hp, C.c_int64, stp]
+    L.pfrx_rstep_async.argtypes = [hp, C.c_double]
+    L.pfrx_rstep_finish.argtypes = [hp, resp]
+    L.pfrx_rstep.argtypes = [hp, C.c_double, resp]
+    L.pfrx_rstep_host.argtypes = [hp, C.c_int64, stp, C.c_double, resp]
+    L.pfrx_comm_unique_id.argtypes = [C.c_void_p]
+    L.pfrx_comm_init.argtypes = [hp, C.c_int, C.c_int, C.c_void_p]
+    L.pfrx_allreduce.argtypes = [hp, resp]
+    L.pfrx_stream.argtypes = [hp]
+    L.pfrx_stream.restype = C.c_void_p
+    L.pfrx_launch_count.argtypes = [hp]
+    L.pfrx_launch_count.restype = C.c_int64
+    L.pfrx_bytes_per_cell.argtypes = [hp]
+    L.pfrx_bytes_per_cell.restype = C.c_int64
+    L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
+    if L.pfrx_abi_version() != abi.PFRX_ABI_VERSION:
+        raise PfrxError("libpfrx_b200.so ABI version mismatch")
+    if (L.pfrx_sizeof(0) != C.sizeof(abi.PfrxConfig) or L.pfrx_sizeof(1) != C.sizeof(abi.PfrxState)
+            or L.pfrx_sizeof(2) != C.sizeof(abi.PfrxStepResult)):
+        raise PfrxError("ctypes struct layout does not match include/pfrx.h")
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().pfrx_last_error().decode("utf-8", "replace")
+        raise PfrxError(f"{what} failed (code {rc}): {msg}")
+
+
+class DeviceState:
+    """Cell-major SoA state resident in HBM: one torch tensor ``[rows, ncell]``
+    per field of ``pfrx_state``."""
+
+    def __init__(self, cfg: abi.ReactionConfig, ncell: int, device):
+        import torch
+
+        self.cfg = cfg
+        self.ncell = int(ncell)
+        self.device = torch.device(device)
+        rows = cfg.field_rows()
+        self.t: Dict[str, "torch.Tensor"] = {}
+        for f in abi.STATE_DOUBLE_FIELDS:
+            self.t[f] = torch.zeros((rows[f], self.ncell), dtype=torch.float64, device=self.device)
+        for f in abi.STATE_INT_FIELDS:
+            self.t[f] = torch.zeros((rows[f], self.ncell), dtype=torch.int32, device=self.device)
+
+    @classmethod
+    def from_host(cls, host: abi.HostState, device) -> "DeviceState":
+        import torch
+
+        o = cls(host.cfg, host.ncell, device)
+        for k, v in host.a.items():
+            o.t[k].copy_(torch.from_numpy(v))
+        return o
+
+    def load(self, host: abi.HostState) -> None:
+        import torch
+
+        for k, v in host.a.items():
+            self.t[k].copy_(torch.from_numpy(v), non_blocking=True)
+
+    def to_host(self) -> abi.HostState:
+        h = abi.HostState(self.cfg, self.ncell)
+        for k in h.a:
+            h.a[k][...] = self.t[k].cpu().numpy()
+        return h
+
+    def struct(self) -> abi.PfrxState:
+        s = abi.PfrxState()
+        s.ld = self.ncell
+        for f in abi.STATE_DOUBLE_FIELDS:
+            t = self.t[f]
+            setattr(s, f, C.cast(t.data_ptr() if t.numel() else None, abi.c_double_p))
+        for f in abi.STATE_INT_FIELDS:
+            t = self.t[f]
+            setattr(s, f, C.cast(t.data_ptr() if t.numel() else None, abi.c_int32_p))
+        return s
+
+
+class PinnedHostState(abi.HostState):
+    """HostState whose arrays live in page-locked memory (what a coupler would
+    register once), so that the H2D/D2H legs of ``rstep_host`` are true DMA."""
+
+    def __init__(self, cfg: abi.ReactionConfig, ncell: int):
+        import torch
+
+        super().__init__(cfg, ncell)
+        self._pinned = {}
+        for k, v in list(self.a.items()):
+            t = torch.empty(v.shape, dtype=torch.float64 if v.dtype == np.float64 else torch.int32).pin_memory()
+            t.copy_(torch.from_numpy(v))
+            self._pinned[k] = t
+            self.a[k] = t.numpy()
+
+    def assign(self, host: abi.HostState) -> None:
+        for k, v in host.a.items():
+            self.a[k][...] = v
+
+
+class ChemistryStep:
+    """One reaction network on one GPU (``pfrx_handle``)."""
+
+    def __init__(self, cfg: abi.ReactionConfig, device: int = 0):
+        self.cfg = cfg
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self._state = None
+        _check(lib().pfrx_create(C.byref(cfg.c), self.device, C.byref(self._h)), "pfrx_create")
+
+    def close(self) -> None:
+        if self._h:
+            lib().pfrx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device-resident path ------------------------------------------------- #
+    def bind(self, state: DeviceState) -> None:
+        st = state.struct()
+        _check(lib().pfrx_bind_state(self._h, state.ncell, C.byref(st)), "pfrx_bind_state")
+        self._state = state  # keep tensors alive
+
+    def rstep_async(self, tran_dt: float) -> None:
+        _check(lib().pfrx_rstep_async(self._h, float(tran_dt)), "pfrx_rstep_async")
+
+    def rstep_finish(self) -> abi.PfrxStepResult:
+        res = abi.PfrxStepResult()
+        _check(lib().pfrx_rstep_finish(self._h, C.byref(res)), "pfrx_rstep_finish")
+        return res
+
+    def rstep(self, tran_dt: float) -> abi.PfrxStepResult:
+        res = abi.PfrxStepResult()
+        _check(lib().pfrx_rstep(self._h, float(tran_dt), C.byref(res)), "pfrx_rstep")
+        return res
+
+    # -- host-resident path (H2D + kernel + D2H inside the call) ---------------- #
+    def rstep_host(self, host: abi.HostState, tran_dt: float) -> abi.PfrxStepResult:
+        res = abi.PfrxStepResult()
+        st = host.struct()
+        _check(lib().pfrx_rstep_host(self._h, host.ncell, C.byref(st), float(tran_dt), C.byref(res)),
+               "pfrx_rstep_host")
+        return res
+
+    # -- multi-GPU --------------------------------------------------------------- #
+    def init_comm(self) -> None:
+        """one rank per GPU; the NCCL id travels through torch.distributed"""
+        import torch
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        buf = (C.c_ubyte * 128)()
+        if dist.get_rank() == 0:
+            _check(lib().pfrx_comm_unique_id(buf), "pfrx_comm_unique_id")
+        obj = [bytes(buf)]
+        dist.broadcast_object_list(obj, src=0)
+        ident = (C.c_ubyte * 128).from_buffer_copy(obj[0])
+        _check(lib().pfrx_comm_init(self._h, dist.get_world_size(), dist.get_rank(), ident), "pfrx_comm_init")
+
+    def allreduce(self, res: abi.PfrxStepResult) -> abi.PfrxStepResult:
+        _check(lib().pfrx_allreduce(self._h, C.byref(res)), "pfrx_allreduce")
+        return res
+
+    # -- introspection ------------------------------------------------------------ #
+    @property
+    def stream_ptr(self) -> int:
+        return int(lib().pfrx_stream(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().pfrx_launch_count(self._h))
+
+    @property
+    def bytes_per_cell(self) -> int:
+        return int(lib().pfrx_bytes_per_cell(self._h))
+
+    def kernel_info(self) -> Dict[str, int]:
+        a = (C.c_int * 5)()
+        _check(lib().pfrx_kernel_info(self._h, a), "pfrx_kernel_info")
+        return {"N": a[0], "lanes": a[1], "threads": a[2], "blocks_per_sm": a[3], "smem_bytes": a[4]}
+
+
+def shard_range(ncell: int, rank: int, world: int):
+    """contiguous ownership ranges, like PETSc DMDA local cells
+    (pmc_subsurface_osrt.F90:349-350)"""
+    lo = ncell * rank // world
+    hi = ncell * (rank + 1) // world
+    return lo, hi

@@ -1,0 +1,280 @@
+"""Synthetic per-cell states of the BASELINE.json configurations (SURVEY.md
+section 8(d)), seeded with ``numpy.random.default_rng(20261017)``.
+
+Every workload starts from waters speciated by
+:func:`~.constraint.equilibrate_constraint` (the constraints of the reference's
+own decks) and mixes them per cell the way a transport step would: totals mix
+linearly (transport is linear in totals), the free-ion guess is what the cell
+held before the step.  The decks/databases read here are the committed
+fixtures under ``tests/golden`` (verbatim reference test data) plus two small
+decks written for C2/C5 in the reference's input format.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import abi, chem, constraint, eos
+
+SEED = 20261017
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def _read(name: str) -> str:
+    with open(os.path.join(DATA, name)) as f:
+        return f.read()
+
+
+@dataclass
+class Workload:
+    name: str
+    cfg: abi.ReactionConfig
+    state: abi.HostState
+    tran_dt: float
+    net: chem.ReactionNetwork
+    note: str = ""
+
+
+# --------------------------------------------------------------------------- #
+C2_DECK = """
+# C2: 1D calcite column chemistry (H+/HCO3-/Ca++, 6 complexes, kinetic Calcite)
+CHEMISTRY
+  PRIMARY_SPECIES
+    H+
+    HCO3-
+    Ca++
+  /
+  SECONDARY_SPECIES
+    OH-
+    CO3--
+    CO2(aq)
+    CaOH+
+    CaHCO3+
+    CaCO3(aq)
+  /
+  MINERALS
+    Calcite
+  /
+  MINERAL_KINETICS
+    Calcite
+      RATE_CONSTANT 1.d-6 mol/m^2-sec
+    /
+  /
+  DATABASE ./calcite.dat
+  LOG_FORMULATION
+  ACTIVITY_COEFFICIENTS TIMESTEP
+END
+CONSTRAINT background
+  CONCENTRATIONS
+    H+     8.0     P
+    HCO3-  1.d-3   T
+    Ca++   5.d-4   M Calcite
+  /
+  MINERALS
+    Calcite 1.d-5 1.d0 m^2/m^3
+  /
+END
+CONSTRAINT inlet
+  CONCENTRATIONS
+    H+     5.0     P
+    HCO3-  1.d-3   T
+    Ca++   1.d-6   Z
+  /
+  MINERALS
+    Calcite 1.d-5 1.d0 m^2/m^3
+  /
+END
+"""
+
+
+def _mix_fill(state: abi.HostState, waters, weights: np.ndarray, rng, jitter: float = 0.01) -> None:
+    """cells = convex mixes of speciated waters.  weights [nwater, ncell]."""
+    a = state.a
+    ncell = state.ncell
+
+    def lin(field):
+        vals = [np.asarray(getattr(w, field), dtype=np.float64) for w in waters]
+        return sum(v[:, None] * weights[i][None, :] for i, v in enumerate(vals))
+
+    def geo(field):
+        vals = [np.log(np.maximum(np.asarray(getattr(w, field), dtype=np.float64), 1.0e-300)) for w in waters]
+        return np.exp(sum(v[:, None] * weights[i][None, :] for i, v in enumerate(vals)))
+
+    tot = lin("total")
+    if jitter > 0.0:
+        tot = tot * np.exp(jitter * rng.standard_normal(tot.shape))
+    a["total"][...] = tot
+    a["pri_molal"][...] = geo("pri_molal")
+    a["pri_act_coef"][...] = lin("pri_act_coef")
+    if a["sec_molal"].shape[0]:
+        a["sec_molal"][...] = geo("sec_molal")
+        a["sec_act_coef"][...] = lin("sec_act_coef")
+    assert ncell == tot.shape[1]
+
+
+def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED) -> Workload:
+    """C2: 10k-cell calcite column, post-transport totals on a logistic front."""
+    rng = np.random.default_rng(seed)
+    dk = chem.read_deck(C2_DECK)
+    net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("calcite.dat")))
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67()
+    bg = constraint.equilibrate_constraint(net, dk.constraints["background"], den_kg=den)
+    inl = constraint.equilibrate_constraint(net, dk.constraints["inlet"], den_kg=den)
+    st = abi.HostState(cfg, ncell)
+    x = (np.arange(ncell) + 0.5) / ncell
+    w = 1.0 / (1.0 + np.exp((x - 0.35) / 0.05))
+    _mix_fill(st, [bg, inl], np.stack([1.0 - w, w]), rng)
+    st["mnrl_volfrac"][...] = 1.0e-5
+    st["mnrl_area"][...] = 1.0
+    st["den_kg"][...] = den
+    st["porosity"][...] = 0.25
+    return Workload("c2_calcite_column", cfg, st, tran_dt, net,
+                    "H+/HCO3-/Ca++ + 6 complexes + kinetic Calcite, logistic inlet/background front")
+
+
+def calcite_batch() -> Workload:
+    """C1: the single cell of regression_tests/ascem/batch/calcite-kinetics."""
+    dk, net = chem.load_network(_read("calcite-kinetics.in"), _read("calcite.dat"))
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67()
+    sp = constraint.equilibrate_constraint(net, dk.constraints["initial"], den_kg=den, porosity=0.5)
+    st = abi.HostState(cfg, 1)
+    constraint.fill_cells(st, sp)
+    st["den_kg"][...] = den
+    st["porosity"][...] = 0.5
+    return Workload("c1_calcite_batch", cfg, st, 0.5, net, "ascem/batch/calcite-kinetics, one cell, dt = 0.5 s")
+
+
+# --------------------------------------------------------------------------- #
+def _hanford_network(variant: str = "base"):
+    deck = _read("543_hanford_srfcplx_base.in")
+    dk = chem.read_deck(deck)
+    ch = dk.chemistry
+    if variant == "mr":
+        # 50-rate multirate on rock density (543_hanford_srfcplx_mr.in /
+        # column/surface_complexation_mr_os.in)
+        dk_mr = chem.read_deck(_read("surface_complexation_mr_os.in"))
+        ch.srfcplx_rxns = dk_mr.chemistry.srfcplx_rxns
+    elif variant == "minerals":
+        # C5: Hanford basis, six kinetic minerals, no sorption
+        ch.srfcplx_rxns = []
+        rates = {"Calcite": 1.0e-8, "Metatorbernite": 2.0e-13, "Dolomite": 1.0e-9, "Gypsum": 1.0e-7,
+                 "Fluorite": 1.0e-9, "Schoepite": 1.0e-10}
+        ch.mineral_kinetics = [chem.MineralKinetics(n, rate_constant=r) for n, r in rates.items()]
+    net = chem.ReactionNetwork(ch, chem.Database(_read("hanford_subset.dat")))
+    return dk, net
+
+
+def hanford(ncell: int = 256 * 256 * 64, tran_dt: float = 3600.0, variant: str = "base",
+            seed: int = SEED) -> Workload:
+    """C3 (variant base|mr) and C5 (variant minerals): Hanford 15 primary / 88
+    secondary; cells are Dirichlet(1) mixes of the three deck waters."""
+    rng = np.random.default_rng(seed)
+    dk, net = _hanford_network(variant)
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67()
+    waters = []
+    for nm in ("groundwater", "U_source", "river_water"):
+        cons = dk.constraints[nm]
+        if variant == "minerals":
+            cons.minerals = {k: (0.05, 100.0) for k in net.kinmnrl_names}
+        waters.append(constraint.equilibrate_constraint(net, cons, den_kg=den, porosity=0.25,
+                                                        soil_particle_density=2500.0))
+    st = abi.HostState(cfg, ncell)
+    wts = rng.dirichlet(np.ones(3), size=ncell).T
+    _mix_fill(st, waters, wts, rng, jitter=0.0)
+    st["den_kg"][...] = den
+    st["porosity"][...] = rng.uniform(0.2, 0.3, ncell)
+    st["soil_particle_density"][...] = rng.choice([2000.0, 2500.0], ncell)
+    nk = net.nkinmnrl
+    if variant == "minerals":
+        st["mnrl_volfrac"][...] = rng.uniform(0.0, 0.1, (nk, ncell))
+        st["mnrl_area"][...] = 100.0
+    else:
+        st["mnrl_volfrac"][0, :] = rng.uniform(0.05, 0.15, ncell)          # Calcite
+        st["mnrl_volfrac"][1, :] = rng.choice([0.0, 1.0e-4], ncell)        # Metatorbernite
+        st["mnrl_area"][...] = 100.0                                       # 1 cm^2/cm^3
+    nr = len(net.srfcplxrxn)
+    if nr:
+        st["srfcplxrxn_free_site_conc"][...] = 1.0e-9
+        # sorbed state consistent with the mixed water: one RTotalSorb pass on
+        # the host would cost minutes at 4M cells; instead start the multirate
+        # sites from the mixed equilibrium sorbed totals of the three waters
+        if net.eq_rxn_ids:
+            vals = [w.total_sorb_eq for w in waters]
+            st["total_sorb_eq"][...] = sum(v[:, None] * wts[i][None, :] for i, v in enumerate(vals))
+        if net.mr_rxn_ids:
+            vals = [w.kinmr_total_sorb for w in waters]
+            st["kinmr_total_sorb"][...] = sum(v[:, None] * wts[i][None, :] for i, v in enumerate(vals))
+    name = {"base": "c3_hanford_srfcplx", "mr": "c3_hanford_multirate", "minerals": "c5_hanford_minerals"}[variant]
+    return Workload(name, cfg, st, tran_dt, net, f"Hanford 15/88, variant {variant}, Dirichlet mix of 3 deck waters")
+
+
+# --------------------------------------------------------------------------- #
+def clm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED) -> Workload:
+    """C4(a): regression_tests/ngee/CLM-CN network (1 aq + 12 immobile, 7 rxns)."""
+    rng = np.random.default_rng(seed)
+    dk, net = chem.load_network(_read("CLM-CN.in"), _read("CLM-CN_database.dat"))
+    cfg = abi.ReactionConfig(net)
+    sp = constraint.equilibrate_constraint(net, dk.constraints["initial"], den_kg=1000.0)
+    st = abi.HostState(cfg, ncell)
+    constraint.fill_cells(st, sp)
+    imm0 = sp.immobile
+    pools = imm0[:, None] * np.exp(rng.standard_normal((net.nimcomp, ncell)))
+    iN = net.immobile_names.index("N")
+    pools[iN, :] = 10.0 ** rng.uniform(-8.0, -4.0, ncell)
+    st["immobile"][...] = pools
+    st["temp"][...] = rng.uniform(-5.0, 30.0, ncell)
+    st["sat"][...] = rng.uniform(0.05, 1.0, ncell)
+    st["den_kg"][...] = 1000.0
+    st["porosity"][...] = 0.25
+    st["volume"][...] = 1.0
+    return Workload("c4_clm_cn", cfg, st, tran_dt, net, "ngee/CLM-CN 13-dof sandbox, lognormal pools")
+
+
+def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
+    table = {
+        "c1": (calcite_batch, {}),
+        "c2": (calcite_column, {}),
+        "c3": (hanford, {"variant": "base"}),
+        "c3mr": (hanford, {"variant": "mr"}),
+        "c4": (clm_cn, {}),
+        "c5": (hanford, {"variant": "minerals"}),
+    }
+    fn, kw = table[name]
+    kw = dict(kw)
+    if ncell is not None and name != "c1":
+        kw["ncell"] = ncell
+    if tran_dt is not None and name != "c1":
+        kw["tran_dt"] = tran_dt
+    return fn(**kw)
+
+
+# --------------------------------------------------------------------------- #
+def flops_per_iteration(net: chem.ReactionNetwork) -> float:
+    """Algorithmic flops of ONE Newton iteration, the closed form of SURVEY.md
+    section 8(d) (add/sub/mul/div/compare = 1, FMA = 2, exp/log/pow/sqrt = 20)."""
+    naq, n = net.naqcomp, net.ncomp
+    ncx = net.neqcplx
+    nnz = sum(len(r.ids) for r in net.sec_rxn)
+    nnz2 = sum(len(r.ids) ** 2 for r in net.sec_rxn)
+    f = 8.0 * nnz + 2.0 * nnz2 + 3.0 * ncx + 2.0 * naq * naq
+    f += 20.0 * (2.0 * naq + ncx + nnz)
+    if net.chem.act_coef_update_frequency == chem.ACT_COEF_FREQUENCY_NEWTON_ITER:
+        f += 9.0 * (naq + ncx) + 20.0 * (naq + ncx + 1)
+    f += (2.0 / 3.0) * n ** 3 + 5.0 * n * n
+    for nm in net.kinmnrl_names:
+        m = len(net.mnrl_rxn[nm].ids)
+        f += 60.0 + 20.0 * (m + 1)
+    for rx in net.srfcplxrxn:
+        f += 20.0 * (2 * len(rx.complexes) + 1) + 12.0 * len(rx.complexes) * 9
+        if rx.itype == "MULTIRATE_KINETIC":
+            f += 6.0 * len(rx.rates) * naq
+    if net.clmcn is not None:
+        f += 45.0 * net.clmcn["nrxn"] + 40.0
+    f += 10.0 * n + 20.0 * n
+    return f

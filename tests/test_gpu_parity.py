@@ -1,0 +1,196 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(libpfrx_b200.so), against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): <= 1e-10 relative on primary totals, free-ion
+concentrations, mineral rates / volume fractions, sorbed state and CN pools;
+identical Newton-iteration counts, sub-step counts and cut decisions.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from pflotran_elm_interface_b200 import abi, workloads as W
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1.0e-10
+
+
+def _gpu():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pflotran_elm_interface_b200 import rstep
+
+    rstep.lib()  # fail loudly if the extension is missing
+    return rstep
+
+
+def _compare(ref: abi.HostState, got: abi.HostState, what: str, rtol=RTOL, counts_exact=True):
+    for f in ("num_iterations", "num_sub_steps", "num_kinetic_state_updates", "ierror"):
+        a, b = ref.a[f], got.a[f]
+        bad = np.flatnonzero(a != b)
+        if counts_exact:
+            assert bad.size == 0, f"{what}: {f} differs in {bad.size}/{a.size} cells, first {bad[:5]}: {a.ravel()[bad[:5]]} vs {b.ravel()[bad[:5]]}"
+    ok = ref.a["ierror"][0] == 0
+    for f in abi.STATE_IO_FIELDS:
+        a, b = ref.a[f][:, ok], got.a[f][:, ok]
+        if a.size == 0:
+            continue
+        scale = np.maximum(np.abs(a), np.abs(b))
+        # entries below 1e-30 are the 1e-40 floors of RStep / exhausted pools
+        tiny = scale < 1.0e-30
+        err = np.where(tiny, 0.0, np.abs(a - b) / np.where(scale > 0, scale, 1.0))
+        if f == "mnrl_rate":
+            # rates near equilibrium are differences 1-QK of O(1) numbers:
+            # compare against the rate scale k*area instead
+            ref_scale = np.maximum(scale, 1.0e-12 * np.max(np.abs(a)) if a.size else 0.0)
+            err = np.abs(a - b) / np.where(ref_scale > 0, ref_scale, 1.0)
+        worst = float(err.max()) if err.size else 0.0
+        assert worst <= rtol, f"{what}: field {f} max rel err {worst:.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def _run_both(wl, host_path=False):
+    rstep = _gpu()
+    ref = wl.state.copy()
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    if host_path:
+        got = wl.state.copy()
+        res = step.rstep_host(got, wl.tran_dt)
+    else:
+        dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+        step.bind(dev)
+        res = step.rstep(wl.tran_dt)
+        got = dev.to_host()
+    info = step.kernel_info()
+    assert step.launch_count >= 1
+    step.close()
+    return ref, res_ref, got, res, info
+
+
+def _check_summary(res_ref, res):
+    a, b = res_ref.as_dict(), res.as_dict()
+    assert a == b, f"shard summary differs: oracle {a} gpu {b}"
+
+
+def test_c1_calcite_batch_cell():
+    wl = W.by_name("c1")
+    ref, rr, got, rg, info = _run_both(wl)
+    _compare(ref, got, "c1")
+    _check_summary(rr, rg)
+
+
+@pytest.mark.parametrize("dt", [3600.0, 86400.0, 0.25 * 365 * 86400.0])
+def test_c2_calcite_column(dt):
+    wl = W.by_name("c2", ncell=10000, tran_dt=dt)
+    ref, rr, got, rg, info = _run_both(wl)
+    assert info["lanes"] == 1  # thread-per-cell kernel
+    _compare(ref, got, f"c2 dt={dt}")
+    _check_summary(rr, rg)
+
+
+def test_c2_host_path_matches_device_path():
+    wl = W.by_name("c2", ncell=4097, tran_dt=3600.0)
+    ref, rr, got, rg, _ = _run_both(wl, host_path=True)
+    _compare(ref, got, "c2 host path")
+    _check_summary(rr, rg)
+
+
+@pytest.mark.parametrize("dt", [1800.0, 86400.0])
+def test_c4_clm_cn(dt):
+    wl = W.by_name("c4", ncell=20000, tran_dt=dt)
+    ref, rr, got, rg, info = _run_both(wl)
+    assert info["lanes"] > 1  # cooperative kernel
+    _compare(ref, got, f"c4 dt={dt}")
+    _check_summary(rr, rg)
+
+
+@pytest.mark.parametrize("variant,dt", [("c3", 3600.0), ("c3", 30 * 86400.0), ("c3mr", 3600.0), ("c5", 86400.0)])
+def test_hanford(variant, dt):
+    wl = W.by_name(variant, ncell=3000, tran_dt=dt)
+    ref, rr, got, rg, info = _run_both(wl)
+    _compare(ref, got, f"{variant} dt={dt}")
+    _check_summary(rr, rg)
+
+
+def test_lane_variants_agree(monkeypatch):
+    """the same cells through the thread-per-cell and the 4-lane kernels"""
+    wl = W.by_name("c2", ncell=2048, tran_dt=86400.0)
+    ref = wl.state.copy()
+    orc.rstep(wl.cfg, ref, wl.tran_dt, 2)
+    rstep = _gpu()
+    for lanes in ("1", "4"):
+        monkeypatch.setenv("PFRX_LANES", lanes)
+        step = rstep.ChemistryStep(wl.cfg, 0)
+        assert step.kernel_info()["lanes"] == int(lanes)
+        dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+        step.bind(dev)
+        step.rstep(wl.tran_dt)
+        _compare(ref, dev.to_host(), f"lanes={lanes}")
+        step.close()
+
+
+def test_inactive_and_dry_cells():
+    wl = W.by_name("c2", ncell=1000, tran_dt=3600.0)
+    wl.state["imat"][0, ::7] = 0          # inactive material: skipped
+    wl.state["sat"][0, 3::11] = 0.0       # dry: identity Jacobian, zero residual
+    ref, rr, got, rg, _ = _run_both(wl)
+    _compare(ref, got, "inactive/dry")
+    _check_summary(rr, rg)
+    assert rg.ncell_active == int((wl.state["imat"][0] > 0).sum())
+
+
+def test_empty_and_ragged_shards():
+    rstep = _gpu()
+    wl = W.by_name("c2", ncell=33, tran_dt=3600.0)   # not a multiple of the warp width
+    ref, rr, got, rg, _ = _run_both(wl)
+    _compare(ref, got, "ragged")
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    empty = abi.HostState(wl.cfg, 0)
+    res = step.rstep_host(empty, 3600.0)
+    assert res.ncell_active == 0 and res.rstep_error == 0 and res.first_failed_cell == -1
+    step.close()
+
+
+def test_failure_and_cut_decisions():
+    """a stiff step forces reaction-dt cuts; cut/failure flags must agree"""
+    wl = W.by_name("c2", ncell=2000, tran_dt=3600.0)
+    cfg = wl.cfg
+    cfg.c.maximum_reaction_iterations = 4   # most cells need more -> cuts
+    cfg.c.maximum_reaction_cuts = 3
+    ref, rr, got, rg, _ = _run_both(wl)
+    assert rr.num_cut_cells > 0
+    _compare(ref, got, "cuts")
+    _check_summary(rr, rg)
+
+
+def test_full_size_properties_c2():
+    """size-independent properties at a large size (no oracle): mass balance of
+    the calcite reaction, positivity, determinism"""
+    rstep = _gpu()
+    wl = W.by_name("c2", ncell=1 << 20, tran_dt=86400.0)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    outs = []
+    for _ in range(2):
+        dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+        step.bind(dev)
+        res = step.rstep(wl.tran_dt)
+        outs.append(dev.to_host())
+        assert res.rstep_error == 0 and res.ncell_active == wl.state.ncell
+    a, b = outs
+    for f in abi.STATE_IO_FIELDS:
+        assert np.array_equal(a.a[f], b.a[f]), f"{f} not deterministic"
+    # CaCO3 + H+ = Ca++ + HCO3-: d(total Ca) = d(total HCO3) = -d(total H+)
+    d = a["total"] - wl.state["total"]
+    scale = np.abs(wl.state["total"]).max()
+    assert np.abs(d[2] - d[1]).max() < 1e-9 * scale
+    assert np.abs(d[2] + d[0]).max() < 1e-9 * scale
+    # moles of calcite lost = moles of Ca gained (per m^3 bulk)
+    dvf = a["mnrl_volfrac"][0] - wl.state["mnrl_volfrac"][0]
+    mol = -dvf / 36.9340e-6
+    gained = d[2] * 1000.0 * wl.state["porosity"][0] * wl.state["sat"][0]
+    assert np.abs(mol - gained).max() < 1e-7 * np.abs(gained).max()
+    assert (a["pri_molal"] > 0).all()
+    step.close()
