@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- RStep cell-solves per second of the operator-split chemistry step.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+One "step" = one pass of the hot path (RStep over tran_dt) over one batch of
+synthetic post-transport cell states.  The default workload is C3 of
+BASELINE.json (Hanford U(VI), 256x256x64 = 4 194 304 cells, equilibrium surface
+complexation + 2 kinetic minerals): the largest single-GPU configuration.  The
+metric's C2 (10k-cell calcite column) cannot load a B200 (3 MB of state) and is
+a parity-test case; `--workload c2` benches it anyway.
+
+Multi-GPU: one rank per GPU (torchrun), cells sharded by contiguous ownership
+ranges with no data-path collective; the only communication is the NCCL
+allreduce of the step flags (pfrx_allreduce).  Scaling is WEAK: every rank
+steps a full-size shard.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DEFAULT_CELLS = {"c2": 10000, "c3": 256 * 256 * 64, "c3mr": 1 << 20, "c4": 2 * 1024 * 1024, "c5": 256 * 256 * 64}
+DEFAULT_DT = {"c2": 3600.0, "c3": 3600.0, "c3mr": 3600.0, "c4": 1800.0, "c5": 86400.0}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="c3", choices=sorted(DEFAULT_CELLS))
+    p.add_argument("--cells", type=int, default=None, help="cells per GPU")
+    p.add_argument("--dt", type=float, default=None)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(wl, seconds, threads):
+    """the oracle (a CPU port of the reference path: `kind` = port) on a bounded
+    sample of the same workload, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    from pflotran_elm_interface_b200 import abi
+
+    def sample(n):
+        st = abi.HostState(wl.cfg, n)
+        for k, v in wl.state.a.items():
+            st.a[k][...] = v[:, :n]
+        return st
+
+    probe_n = min(wl.state.ncell, 2048)
+    st = sample(probe_n)
+    t0 = time.perf_counter()
+    orc.rstep(wl.cfg, st, wl.tran_dt, threads)
+    rate = probe_n / max(time.perf_counter() - t0, 1e-6)
+    n = int(min(wl.state.ncell, max(probe_n, rate * seconds)))
+    st = sample(n)
+    t0 = time.perf_counter()
+    res = orc.rstep(wl.cfg, st, wl.tran_dt, threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "cell-solves/s", "cores": threads, "kind": "port",
+            "sample": f"first {n} cells of {wl.name} (same seeded states), {dt:.1f} s wall, "
+                      f"{res.sum_newton_iterations / max(1, res.ncell_active):.2f} Newton its/cell",
+            "per_core": n / dt / threads, "seconds": dt}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncell = a.cells or DEFAULT_CELLS[a.workload]
+    dt = a.dt or DEFAULT_DT[a.workload]
+    from pflotran_elm_interface_b200 import workloads
+
+    cfg_json = {"workload": a.workload, "cells_per_gpu": ncell, "tran_dt_s": dt,
+                "inputs": "larger than L2; state restored from a pristine HBM copy between steps",
+                "parallelism": f"cells sharded over {world} rank(s), no halo"}
+
+    # ------------------------------------------------------------------ CPU arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        wl = workloads.by_name(a.workload, ncell=min(ncell, 1 << 18), tran_dt=dt)
+        wl.name = workloads.by_name(a.workload, ncell=8, tran_dt=dt).name
+        per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r = cpu_baseline(wl, per_step, threads)
+            if i >= a.warmup:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        ms = 1000.0 * float(np.mean([r["seconds"] for r in vals]))
+        out = {"impl": "reference", "metric": "rstep_cell_solves_per_sec", "value": v, "unit": "cell-solves/s",
+               "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_json,
+               "cpu_baseline": {"value": v, "unit": "cell-solves/s", "cores": threads, "kind": "port",
+                                "sample": vals[-1]["sample"]},
+               "e2e": {"value": v, "unit": "cell-solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "note": "reference Fortran cannot be built in this image (no Fortran compiler/PETSc/MPI); this arm "
+                       "times the C oracle port of the same path with back-substitution enabled (SURVEY 0.2)"}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    from pflotran_elm_interface_b200 import abi, rstep
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    wl = workloads.by_name(a.workload, ncell=ncell, tran_dt=dt)
+    step = rstep.ChemistryStep(wl.cfg, local_rank)
+    step.init_comm()
+    info = step.kernel_info()
+    pristine = rstep.DeviceState.from_host(wl.state, dev)
+    work = rstep.DeviceState(wl.cfg, ncell, dev)
+    step.bind(work)
+    kstream = torch.cuda.ExternalStream(step.stream_ptr, device=dev)
+
+    def restore():
+        for k in work.t:
+            work.t[k].copy_(pristine.t[k])
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    res = None
+    for _ in range(a.warmup):
+        restore()
+        res = step.allreduce(step.rstep(dt))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = step.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kern_ms = []
+    wall0 = time.perf_counter()
+    for i in range(a.steps):
+        restore()
+        barrier()
+        ev[i][0].record(kstream)
+        step.rstep_async(dt)
+        ev[i][1].record(kstream)
+        res = step.rstep_finish()
+        res = step.allreduce(res)
+        kern_ms.append(ev[i][0].elapsed_time(ev[i][1]))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = step.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_local = float(np.sum(kern_ms)) * 1e-3
+    if world > 1:
+        t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t.item())
+    else:
+        t_max = t_local
+    total_cells = int(res.ncell_active) * a.steps
+    value = total_cells / t_max
+    ms_per_step = 1000.0 * t_max / a.steps
+
+    # ---- e2e through the C ABI with host buffers (H2D + kernel + D2H) ----------
+    e2e = None
+    if not a.no_e2e:
+        host = rstep.PinnedHostState(wl.cfg, ncell)
+        rows = wl.cfg.field_rows()
+        h2d = 8 * sum(rows[f] for f in abi.STATE_DOUBLE_FIELDS if f != "eqsrfcplx_conc") * ncell + 4 * ncell
+        d2h = 8 * sum(rows[f] for f in abi.STATE_IO_FIELDS) * ncell + 16 * ncell
+        ne = max(2, min(a.steps, 3))
+        host.assign(wl.state)
+        step.rstep_host(host, dt)  # warm-up (allocates the device mirror)
+        tt = []
+        for _ in range(ne):
+            host.assign(wl.state)
+            barrier()
+            t0 = time.perf_counter()
+            r2 = step.rstep_host(host, dt)
+            r2 = step.allreduce(r2)
+            torch.cuda.synchronize(dev)
+            tt.append(time.perf_counter() - t0)
+        te = float(np.mean(tt))
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        e2e = {"value": int(r2.ncell_active) / te, "unit": "cell-solves/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000.0 * te,
+               "api": "pfrx_rstep_host (C ABI, pinned host SoA buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel --------------------------------
+    hbm_gbs, which = peaks()
+    fp64_tf, mhz = rstep.fp64_peak_tflops(local_rank)
+    f_eval, f_solve = workloads.flops_model(wl.net)
+    cells_local = ncell
+    its_local = res.sum_newton_iterations / max(1, world)        # per rank (weak scaling: equal shards)
+    subs = cells_local                                          # >= one sub-step per cell
+    flops_launch = its_local * f_eval + max(0.0, its_local - subs) * f_solve
+    bytes_launch = step.bytes_per_cell * cells_local
+    t_launch = t_max / a.steps
+    ach_tf = flops_launch / t_launch / 1e12
+    ach_gbs = bytes_launch / t_launch / 1e9
+    frac_fp64 = ach_tf / fp64_tf if fp64_tf > 0 else None
+    frac_hbm = ach_gbs / hbm_gbs
+    if frac_fp64 is not None and frac_fp64 >= frac_hbm:
+        roof = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": frac_fp64,
+                "peak_source": "DFMA micro-benchmark in this run (pfrx_diag_fp64_peak)"}
+    else:
+        roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm,
+                "peak_source": f"MEASURED_PEAKS.json ({which})"}
+    roof.update({"traffic": None, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
+                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
+                 "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": step.bytes_per_cell,
+                 "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
+                 "kernel": f"pfrx_rstep_kernel<{info['N']},{info['lanes']}>", "kernel_ms": 1000.0 * t_launch,
+                 "fp64_peak_sm_mhz": mhz})
+
+    cpu = None
+    if not a.no_cpu:
+        cpu = cpu_baseline(wl, a.cpu_seconds, os.cpu_count() or 1)
+
+    out = {"metric": "rstep_cell_solves_per_sec", "value": value, "unit": "cell-solves/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": dict(cfg_json, name=wl.name, ncomp=wl.cfg.ncomp, neqcplx=int(wl.cfg.c.neqcplx),
+                          kernel=info, note=wl.note),
+           "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+           "result": res.as_dict(), "wall_s_timed_region": wall}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -291,6 +291,11 @@ int64_t pfrx_bytes_per_cell(pfrx_handle *h);
  * PFRX_LANES / PFRX_THREADS in the environment override the defaults. */
 int pfrx_kernel_info(pfrx_handle *h, int *info5);
 
+/* diagnostics: measured FP64 FMA peak of `device` in TFLOP/s (the FP64
+ * roofline denominator; MEASURED_PEAKS.json only carries HBM and bf16), and
+ * the SM clock it implies at 64 FMA/clk/SM. */
+int pfrx_diag_fp64_peak(int device, double *tflops, double *sm_mhz_est);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ OUT = os.path.join(HERE, "..", "libpfrx_b200.so")
 
 # padded size N -> lane counts instantiated (keep in sync with pfrx_api.cu)
 VARIANTS = {
-    3: [1],
+    3: [1, 4],
     4: [1, 4],
     8: [4],
     13: [8, 16],

@@ -551,6 +551,11 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                                pfrx_step_result *out) {
   if (!h || !host || !out || ncell < 0 || host->ld < ncell) return set_err(PFRX_E_INVALID, "bad arguments%s", "");
   CUDA_OK(cudaSetDevice(h->device));
+  if (ncell == 0) {  // empty shard: nothing to copy or launch
+    memset(out, 0, sizeof(*out));
+    out->first_failed_cell = -1;
+    return PFRX_OK;
+  }
   const int *rows = h->rows_d.data();
   size_t ndbl = 0;
   for (int i = 0; i < kNumD; i++) ndbl += (size_t)rows[i] * ncell;
@@ -727,5 +732,57 @@ extern "C" int pfrx_kernel_info(pfrx_handle *h, int *info5) {
   info5[2] = h->threads;
   info5[3] = h->blocks_per_sm;
   info5[4] = (int)h->smem_bytes;
+  return PFRX_OK;
+}
+
+// ---- diagnostics: FP64 FMA peak of the device (roofline denominator) -----------
+// 8 independent DFMA chains per thread, enough threads to fill every SM.
+__global__ void pfrx_dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+extern "C" int pfrx_diag_fp64_peak(int device, double *tflops, double *sm_mhz_est) {
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  double *d = nullptr;
+  CUDA_OK(cudaMalloc(&d, 8));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    pfrx_dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  if (sm_mhz_est) *sm_mhz_est = best * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
   return PFRX_OK;
 }

@@ -61,6 +61,7 @@ def lib():
     L.pfrx_bytes_per_cell.argtypes = [hp]
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
+    L.pfrx_diag_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if L.pfrx_abi_version() != abi.PFRX_ABI_VERSION:
         raise PfrxError("libpfrx_b200.so ABI version mismatch")
     if (L.pfrx_sizeof(0) != C.sizeof(abi.PfrxConfig) or L.pfrx_sizeof(1) != C.sizeof(abi.PfrxState)
@@ -231,6 +232,13 @@ class ChemistryStep:
         a = (C.c_int * 5)()
         _check(lib().pfrx_kernel_info(self._h, a), "pfrx_kernel_info")
         return {"N": a[0], "lanes": a[1], "threads": a[2], "blocks_per_sm": a[3], "smem_bytes": a[4]}
+
+
+def fp64_peak_tflops(device: int = 0):
+    """measured DFMA peak of the device (TFLOP/s) and the SM clock it implies"""
+    tf, mhz = C.c_double(), C.c_double()
+    _check(lib().pfrx_diag_fp64_peak(int(device), C.byref(tf), C.byref(mhz)), "pfrx_diag_fp64_peak")
+    return tf.value, mhz.value
 
 
 def shard_range(ncell: int, rank: int, world: int):

@@ -255,9 +255,12 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
 
 
 # --------------------------------------------------------------------------- #
-def flops_per_iteration(net: chem.ReactionNetwork) -> float:
-    """Algorithmic flops of ONE Newton iteration, the closed form of SURVEY.md
-    section 8(d) (add/sub/mul/div/compare = 1, FMA = 2, exp/log/pow/sqrt = 20)."""
+def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
+    """Algorithmic flops of one Newton iteration, split into
+    (residual/Jacobian evaluation, linear solve): the closed form of SURVEY.md
+    section 8(d) with add/sub/mul/div/compare = 1, FMA = 2 and
+    exp/log/pow/sqrt = 20.  A cell-substep that converges in k iterations
+    evaluates k times and solves k-1 times."""
     naq, n = net.naqcomp, net.ncomp
     ncx = net.neqcplx
     nnz = sum(len(r.ids) for r in net.sec_rxn)
@@ -266,7 +269,6 @@ def flops_per_iteration(net: chem.ReactionNetwork) -> float:
     f += 20.0 * (2.0 * naq + ncx + nnz)
     if net.chem.act_coef_update_frequency == chem.ACT_COEF_FREQUENCY_NEWTON_ITER:
         f += 9.0 * (naq + ncx) + 20.0 * (naq + ncx + 1)
-    f += (2.0 / 3.0) * n ** 3 + 5.0 * n * n
     for nm in net.kinmnrl_names:
         m = len(net.mnrl_rxn[nm].ids)
         f += 60.0 + 20.0 * (m + 1)
@@ -276,5 +278,6 @@ def flops_per_iteration(net: chem.ReactionNetwork) -> float:
             f += 6.0 * len(rx.rates) * naq
     if net.clmcn is not None:
         f += 45.0 * net.clmcn["nrxn"] + 40.0
-    f += 10.0 * n + 20.0 * n
-    return f
+    f += 10.0 * n
+    solve = (2.0 / 3.0) * n ** 3 + 5.0 * n * n + 20.0 * n
+    return f, solve
