@@ -193,11 +193,18 @@ static int layout_and_launch_params(pfrx_handle *h) {
   d.off_x = take(2 * (N + 2));
   d.off_xs = take(N);
   d.off_sec = take(d.ncplx);
-  d.off_secg = take(d.ncplx);
+  d.off_lng = take(d.ncplx);
   d.js = N | 1;
   d.off_J = take(N * d.js);
-  d.off_tmp = take(N + d.nsrfcplx + 1);
+  d.off_acc = take(d.nacc);
+  d.off_tmp = take(N + 2 * d.nsrfcplx + 2);
   d.off_sc = take(d.nsrfcplx + 1);
+  d.off_cls = take(d.ncls + 1);
+  d.off_mn = take(3 * d.nkin + 1);
+  d.off_fs = take(d.nsrfrxn + 1);
+  d.off_mr = take(2 * d.nmr * N + 1);
+  d.off_res = take(N);
+  d.off_ts = take(N);
   d.ws_stride = off | 1;
   int groups = h->threads / h->lanes;
   h->smem_bytes = (size_t)groups * d.ws_stride * sizeof(double);
@@ -281,13 +288,49 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.cn_C = c->clmcn_C_species_id;
   d.cn_N = c->clmcn_N_species_id;
 
+  // kernel variant first: the task partition depends on the lane count
+  {
+    int want = 0;
+    if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
+    int rc0 = pick_kernel(h, want);
+    if (rc0) {
+      delete h;
+      return rc0;
+    }
+  }
+  const int L = h->lanes;
   Arena A;
   const int naq = c->naqcomp;
-  A.add(c->primary_spec_Z, naq, &d.pri_Z);
-  A.add(c->primary_spec_a0, naq, &d.pri_a0);
-  // species -> complexes (ascending complex id, the order RTotalAqueous adds)
-  std::vector<int> sp_ptr(naq + 1, 0), sp_cx;
-  std::vector<double> sp_st;
+  // ---- activity classes: one Debye-Hueckel evaluation per distinct (Z, a0) ----
+  std::vector<double> pri_Z2(naq), cls_negz2, cls_a0, cx_Z2(std::max(c->neqcplx, 0));
+  std::vector<int> pri_cls(naq, -1), cx_cls(std::max(c->neqcplx, 0), -1);
+  auto class_of = [&](double z, double a0) {
+    if (!(fabs(z) > 1.e-10)) return -1;  // neutral: gamma = 1 (reaction.F90:4570)
+    for (size_t q = 0; q < cls_a0.size(); q++)
+      if (cls_negz2[q] == -z * z && cls_a0[q] == a0) return (int)q;
+    cls_negz2.push_back(-z * z);
+    cls_a0.push_back(a0);
+    return (int)cls_a0.size() - 1;
+  };
+  for (int i = 0; i < naq; i++) {
+    pri_Z2[i] = c->primary_spec_Z[i] * c->primary_spec_Z[i];
+    pri_cls[i] = class_of(c->primary_spec_Z[i], c->primary_spec_a0[i]);
+  }
+  for (int k = 0; k < c->neqcplx; k++) {
+    cx_Z2[k] = c->eqcplx_Z[k] * c->eqcplx_Z[k];
+    cx_cls[k] = class_of(c->eqcplx_Z[k], c->eqcplx_a0[k]);
+  }
+  d.ncls = (int)cls_a0.size();
+  A.add(pri_Z2.data(), pri_Z2.size(), &d.pri_Z2);
+  A.add(pri_cls.data(), pri_cls.size(), &d.pri_cls);
+  A.add(cls_negz2.data(), cls_negz2.size(), &d.cls_negz2);
+  A.add(cls_a0.data(), cls_a0.size(), &d.cls_a0);
+  // ---- balanced task lists: totals_i = sum_k nu_ki sec_k (slot i) and
+  //      S_ij = sum_k nu_ki nu_kj sec_k, i <= j (slot naq + tri(i,j)) --------------
+  std::vector<int> tk_k, sg_dst, sg_cnt, ln_task0(L + 1, 0), ln_seg0(L + 1, 0), fx_ptr(1, 0), fx_dst, fx_src;
+  std::vector<double> tk_w;
+  const int ntri = naq * (naq + 1) / 2;
+  int nacc = naq + ntri;
   if (c->neqcplx > 0) {
     int nnz = c->eqcplx_ptr[c->neqcplx];
     A.add(c->eqcplx_ptr, c->neqcplx + 1, &d.cx_ptr);
@@ -296,21 +339,77 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->eqcplx_h2ostoich, c->neqcplx, &d.cx_h2o);
     A.add(c->eqcplx_logK, c->neqcplx, &d.cx_logK);
     A.add(c->eqcplx_logKcoef, c->eqcplx_logKcoef ? 5 * c->neqcplx : 0, &d.cx_logKcoef);
-    A.add(c->eqcplx_Z, c->neqcplx, &d.cx_Z);
-    A.add(c->eqcplx_a0, c->neqcplx, &d.cx_a0);
-    for (int i = 0; i < naq; i++) {
-      for (int k = 0; k < c->neqcplx; k++)
-        for (int p = c->eqcplx_ptr[k]; p < c->eqcplx_ptr[k + 1]; p++)
-          if (c->eqcplx_specid[p] == i) {
-            sp_cx.push_back(k);
-            sp_st.push_back(c->eqcplx_stoich[p]);
-          }
-      sp_ptr[i + 1] = (int)sp_cx.size();
+    A.add(cx_Z2.data(), cx_Z2.size(), &d.cx_Z2);
+    A.add(cx_cls.data(), cx_cls.size(), &d.cx_cls);
+    struct Task {
+      int dst, k;
+      double w;
+    };
+    std::vector<Task> tasks;
+    auto tri = [&](int i, int j) { return naq + i * naq - (i * (i - 1)) / 2 + (j - i); };
+    for (int k = 0; k < c->neqcplx; k++) {
+      for (int p = c->eqcplx_ptr[k]; p < c->eqcplx_ptr[k + 1]; p++) {
+        int i = c->eqcplx_specid[p];
+        tasks.push_back({i, k, c->eqcplx_stoich[p]});
+        for (int p2 = c->eqcplx_ptr[k]; p2 < c->eqcplx_ptr[k + 1]; p2++) {
+          int j = c->eqcplx_specid[p2];
+          if (j >= i) tasks.push_back({tri(i, j), k, c->eqcplx_stoich[p] * c->eqcplx_stoich[p2]});
+        }
+      }
+    }
+    std::stable_sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.dst < b.dst; });
+    const int T = (int)tasks.size();
+    for (const auto &t : tasks) {
+      tk_k.push_back(t.k);
+      tk_w.push_back(t.w);
+    }
+    // cut into L contiguous ranges; an entry cut by a boundary is accumulated in
+    // partial slots and finished by a fix-up that adds them in range order
+    for (int l = 0; l < L; l++) {
+      int t0 = (int)((int64_t)T * l / L), t1 = (int)((int64_t)T * (l + 1) / L);
+      ln_task0[l] = t0;
+      ln_seg0[l] = (int)sg_dst.size();
+      int t = t0;
+      while (t < t1) {
+        int e = tasks[t].dst, u = t;
+        while (u < t1 && tasks[u].dst == e) u++;
+        bool starts = (t == 0) || tasks[t - 1].dst != e;
+        bool ends = (u == T) || tasks[u].dst != e;
+        sg_dst.push_back((starts && ends) ? e : -(e + 1));  // negative: partial of entry e
+        sg_cnt.push_back(u - t);
+        t = u;
+      }
+    }
+    ln_task0[L] = T;
+    ln_seg0[L] = (int)sg_dst.size();
+    // assign partial slots in segment order and build the fix-ups
+    std::vector<std::vector<int>> slots(naq + ntri);
+    for (size_t sgi = 0; sgi < sg_dst.size(); sgi++) {
+      if (sg_dst[sgi] < 0) {
+        int e = -sg_dst[sgi] - 1;
+        sg_dst[sgi] = nacc;
+        slots[e].push_back(nacc);
+        nacc++;
+      }
+    }
+    for (int e = 0; e < naq + ntri; e++) {
+      if (slots[e].empty()) continue;
+      fx_dst.push_back(e);
+      for (int sidx : slots[e]) fx_src.push_back(sidx);
+      fx_ptr.push_back((int)fx_src.size());
     }
   }
-  A.add(sp_ptr.data(), sp_ptr.size(), &d.sp_ptr);
-  A.add(sp_cx.data(), sp_cx.size(), &d.sp_cx);
-  A.add(sp_st.data(), sp_st.size(), &d.sp_st);
+  d.nacc = nacc;
+  d.nfix = (int)fx_dst.size();
+  A.add(tk_k.data(), tk_k.size(), &d.tk_k);
+  A.add(tk_w.data(), tk_w.size(), &d.tk_w);
+  A.add(ln_task0.data(), ln_task0.size(), &d.ln_task0);
+  A.add(ln_seg0.data(), ln_seg0.size(), &d.ln_seg0);
+  A.add(sg_dst.data(), sg_dst.size(), &d.sg_dst);
+  A.add(sg_cnt.data(), sg_cnt.size(), &d.sg_cnt);
+  A.add(fx_ptr.data(), fx_ptr.size(), &d.fx_ptr);
+  A.add(fx_dst.data(), fx_dst.size(), &d.fx_dst);
+  A.add(fx_src.data(), fx_src.size(), &d.fx_src);
   if (c->nkinmnrl > 0) {
     int nk = c->nkinmnrl, nnz = c->kinmnrl_ptr[nk];
     A.add(c->kinmnrl_ptr, nk + 1, &d.mn_ptr);
@@ -377,14 +476,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   h->rows_d.resize(20);
   field_rows(c, h->rows_d.data());
 
-  int want = 0;
-  if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
-  int rc = pick_kernel(h, want);
-  if (rc) {
-    cudaFree(h->arena);
-    delete h;
-    return rc;
-  }
+  int rc = 0;
   if (const char *ev = getenv("PFRX_THREADS")) {
     int t = atoi(ev);
     if (t >= 32 && t <= 128 && (t % 32) == 0) h->threads = t;

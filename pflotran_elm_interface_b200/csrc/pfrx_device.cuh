@@ -5,14 +5,27 @@
 //  * a GROUP of L lanes (L = 1,2,4,8,16,32; a power of two inside one warp)
 //    owns one cell at a time.  Row i of the Newton system belongs to lane
 //    i % L (R = ceil(N/L) rows per lane) and lives in REGISTERS with
-//    compile-time indices; everything a lane needs from its neighbours goes
-//    through a small per-group shared-memory workspace guarded by
-//    __syncwarp(group mask).  L = 1 is the thread-per-cell kernel.
-//  * LU is right-looking with implicit-scaled partial pivoting; the pivot
-//    row is published through shared memory, the argmax over the group is
-//    three REDUX (hi word, lo word, logical row) -- same pivot order and the
-//    same per-element operation order as the Crout loops of
-//    utility.F90:597-688, forward substitution fused into the elimination.
+//    compile-time indices; what a lane needs from its neighbours goes through
+//    a small per-group shared-memory workspace guarded by __syncwarp(group
+//    mask).  L = 1 is the thread-per-cell kernel.
+//  * the kernel is a persistent STATE MACHINE: every pass of one loop is one
+//    Newton iteration of whatever cell a group currently holds, so all groups
+//    of a warp execute the same instructions (no divergence between cells
+//    that need different iteration counts) and every routine exists exactly
+//    once in the instruction stream (the first version inlined RTotal /
+//    RKineticMineral several times, was 340 KB of SASS and fetch-bound).
+//  * totals and d(total)/d(free) are sparse weighted sums of the secondary
+//    molalities; the (entry, complex, weight) tasks are sorted by entry and
+//    cut into L equal contiguous ranges on the host, so the lanes are balanced
+//    even though H+ sits in 70 of the 88 Hanford complexes.  Entries cut by a
+//    range boundary are finished by a fixed-order fix-up (deterministic).
+//  * activity coefficients are evaluated once per (Z, a0) CLASS, and the
+//    secondary molality is exp(lnQK - ln gamma): one exp per complex.
+//  * LU is right-looking with implicit-scaled partial pivoting; the pivot row
+//    is published through shared memory, the argmax over the group is three
+//    REDUX (hi word, lo word, logical row) -- same pivot order and the same
+//    per-element operation order as the Crout loops of utility.F90:597-688,
+//    forward substitution fused into the elimination.
 //  * state is cell-major SoA in HBM, read once at cell entry and written once
 //    at exit; stoichiometry tables are read-only and L1/L2 resident.
 #pragma once
@@ -31,13 +44,26 @@ struct DevCfg {
   int max_its, max_cuts;
   double max_dlnC, tol_relchange, tol_res, tol_relres, min_sat;
   double debyeA, debyeB, debyeBdot;
-  const double *pri_Z, *pri_a0;
-  // complexes (CSR) + transposed lists (species -> complexes, CSC)
+  const double *pri_Z2;  // z_i^2 (ionic strength weights)
+  const int *pri_cls;    // activity class of a primary species, -1 = neutral
+  // complexes (CSR)
   int ncplx;
   const int *cx_ptr, *cx_id;
-  const double *cx_st, *cx_h2o, *cx_logK, *cx_logKcoef, *cx_Z, *cx_a0;
-  const int *sp_ptr, *sp_cx;  // species -> complex ids (ascending)
-  const double *sp_st;        // matching stoichiometry nu_ki
+  const double *cx_st, *cx_h2o, *cx_logK, *cx_logKcoef, *cx_Z2;
+  const int *cx_cls;
+  // activity classes
+  int ncls;
+  const double *cls_negz2, *cls_a0;
+  // balanced task lists for totals / dtotal (see header comment)
+  const int *tk_k;       // complex of task t
+  const double *tk_w;    // weight of task t
+  const int *ln_task0;   // [L+1] first task of lane l
+  const int *ln_seg0;    // [L+1] first segment of lane l
+  const int *sg_dst;     // accumulator slot of a segment
+  const int *sg_cnt;     // tasks in a segment
+  int nfix;
+  const int *fx_ptr, *fx_dst, *fx_src;
+  int nacc;              // accumulator slots: naq totals + naq(naq+1)/2 S + partials
   // kinetic minerals
   int nkin;
   const int *mn_ptr, *mn_id;
@@ -60,7 +86,8 @@ struct DevCfg {
   const double *cn_CN, *cn_k, *cn_resp, *cn_inhib;
   const int *cn_nspec, *cn_cid, *cn_nid, *cn_up, *cn_down;
   // workspace layout (doubles, per group)
-  int ws_stride, off_c, off_lnact, off_invc, off_x, off_xs, off_sec, off_secg, off_J, off_tmp, off_sc, js;
+  int ws_stride, off_c, off_lnact, off_invc, off_x, off_xs, off_sec, off_lng, off_J, off_acc, off_tmp, off_sc,
+      off_cls, off_mn, off_fs, off_mr, off_res, off_ts, js;
 };
 
 struct DevState {
@@ -72,7 +99,7 @@ struct DevState {
   int *num_sub_steps, *num_iterations, *num_kinetic_state_updates, *ierror;
 };
 
-// shard summary accumulated with atomics, one per block
+// shard summary accumulated with atomics, one set per warp
 struct DevSummary {
   unsigned long long ncell_active, sum_its, num_cut_cells;
   long long first_failed;
@@ -118,13 +145,14 @@ __device__ __forceinline__ double interp_logK(const double *c, double temp) {
   return c[0] * log(tk) + c[1] + c[2] * tk + c[3] / tk + c[4] / (tk * tk);
 }
 
-// per-cell scalars every lane of the group carries
-struct CellScalars {
-  double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
-};
+// pow() is ~250 instructions; only the Temkin / scale-factor / affinity-power
+// options of RKineticMineral use it, so keep one out-of-line copy.
+static __device__ __noinline__ double pfrx_pow(double x, double y) { return pow(x, y); }
+
+enum { MODE_LOAD = 0, MODE_ITER = 1, MODE_DONE = 2 };
 
 // ---------------------------------------------------------------------------
-// The kernel.  N = padded system size (>= ncomp), L = lanes per cell.
+// N = padded system size (>= ncomp), L = lanes per cell.
 template <int N, int L>
 struct CellSolver {
   static constexpr int R = (N + L - 1) / L;
@@ -132,191 +160,220 @@ struct CellSolver {
   const DevState &st;
   Grp<L> g;
   double *ws;
+  // ---- per-cell scalars (replicated on the lanes of the group) --------------
   int64_t cell;
-  CellScalars cs;
-  // per-row registers (row i = lane + r*L)
-  double cval[R];    // current iterate (pri_molal | immobile)
-  double guess[R];   // RStep guess
-  double totcur[R];  // rt_auxvar%total (aq rows) / rt_auxvar%immobile (imm rows)
-  double sorbcur[R]; // rt_auxvar%total_sorb_eq (aq rows)
-  double lngam[R];   // log(pri_act_coef) of aq rows
-  double gam[R];
-  double totnew[R];  // total(c) of the latest RTotal
-  double sorbnew[R];
+  double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
   bool dry;
+  // RStep (reaction.F90:3564) bookkeeping
+  double target, cumulative, dt;
+  int ncuts, nconst, nss, nit, nku, ierr;
+  bool had_cut, aborted;
+  // RReact (reaction.F90:3742) bookkeeping
+  int its;
+  double norm0;
+  // ---- per-row registers (row i = lane + r*L) --------------------------------
+  double cval[R];     // current iterate (pri_molal | immobile)
+  double guess[R];    // RStep guess
+  double totcur[R];   // rt_auxvar%total (aq rows) / rt_auxvar%immobile (imm rows)
+  double sorbcur[R];  // rt_auxvar%total_sorb_eq (aq rows)
+  double lngam[R];    // ln(pri_act_coef) of aq rows
+  double totnew[R];   // total(c) of the latest RTotal
+  double sorbnew[R];
+  double fixed[R], init_tot[R];
+  double small_val[R];
+  bool small[R];
 
   __device__ CellSolver(const DevCfg &c, const DevState &s, Grp<L> gg, double *w) : cfg(c), st(s), g(gg), ws(w) {}
 
   __device__ __forceinline__ int row(int r) const { return g.lane + r * L; }
   __device__ __forceinline__ double &W(int off, int i) { return ws[off + i]; }
   __device__ __forceinline__ double &Jm(int i, int j) { return ws[cfg.off_J + i * cfg.js + j]; }
+  __device__ __forceinline__ int symidx(int i, int j) const {
+    int a = min(i, j), b = max(i, j);
+    return cfg.naq + a * cfg.naq - (a * (a - 1)) / 2 + (b - a);
+  }
 
   // logK at the cell temperature (RUpdateTempDependentCoefs, reaction.F90:5976)
   __device__ __forceinline__ double cx_logK(int k) const {
-    return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, cs.temp);
+    return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, temp);
   }
   __device__ __forceinline__ double mn_logK(int m) const {
-    return (cfg.use_isothermal || !cfg.mn_logKcoef) ? cfg.mn_logK[m] : interp_logK(cfg.mn_logKcoef + 5 * m, cs.temp);
+    return (cfg.use_isothermal || !cfg.mn_logKcoef) ? cfg.mn_logK[m] : interp_logK(cfg.mn_logKcoef + 5 * m, temp);
   }
   __device__ __forceinline__ double sc_logK(int k) const {
-    return (cfg.use_isothermal || !cfg.sc_logKcoef) ? cfg.sc_logK[k] : interp_logK(cfg.sc_logKcoef + 5 * k, cs.temp);
+    return (cfg.use_isothermal || !cfg.sc_logKcoef) ? cfg.sc_logK[k] : interp_logK(cfg.sc_logKcoef + 5 * k, temp);
   }
 
   // ---- RActivityCoefficients, LAG branch (reaction.F90:4553-4612) ----------
-  // needs ws.c and ws.sec current; writes gam/lngam registers and ws.secg.
-  __device__ void activity() {
+  // one evaluation per (Z, a0) class; ws.c and ws.sec must be current.
+  __device__ __forceinline__ void activity() {
     const int naq = cfg.naq, ncx = cfg.ncplx;
-    double part = 0.0;
+    double part = 0.0, msum = 0.0;
+#pragma unroll 1
     for (int i = g.lane; i < naq; i += L) {
-      double z = cfg.pri_Z[i];
-      part += W(cfg.off_c, i) * z * z;
+      double c = W(cfg.off_c, i);
+      part += c * cfg.pri_Z2[i];
+      if (i != cfg.h2o_aq_id) msum += c;
     }
+#pragma unroll 1
     for (int k = g.lane; k < ncx; k += L) {
-      double z = cfg.cx_Z[k];
-      part += W(cfg.off_sec, k) * z * z;
+      double s = W(cfg.off_sec, k);
+      part += s * cfg.cx_Z2[k];
+      msum += s;
     }
     double I = 0.5 * g.sumd(part);
     double sq = sqrt(I);
-    double A = cfg.debyeA, B = cfg.debyeB, Bd = cfg.debyeBdot;
+#pragma unroll 1
+    for (int q = g.lane; q < cfg.ncls; q += L)
+      W(cfg.off_cls, q) = (cfg.cls_negz2[q] * sq * cfg.debyeA / (1.0 + cfg.cls_a0[q] * cfg.debyeB * sq) +
+                           cfg.debyeBdot * I) * PFRX_LOG_TO_LN;
+    if (cfg.use_act_h2o) {
+      double t = 1.0 - 0.017 * g.sumd(msum);
+      ln_act_h2o = t > 0.0 ? log(t) : 0.0;
+    }
+    g.sync();
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int i = row(r);
       if (i < naq) {
-        double z = cfg.pri_Z[i];
-        if (fabs(z) > 1.e-10) {
-          lngam[r] = (-z * z * sq * A / (1.0 + cfg.pri_a0[i] * B * sq) + Bd * I) * PFRX_LOG_TO_LN;
-          gam[r] = exp(lngam[r]);
-        } else {
-          lngam[r] = 0.0;
-          gam[r] = 1.0;
-        }
+        int q = cfg.pri_cls[i];
+        lngam[r] = q < 0 ? 0.0 : W(cfg.off_cls, q);
       }
     }
-    double sum_sec = 0.0;
+#pragma unroll 1
     for (int k = g.lane; k < ncx; k += L) {
-      double z = cfg.cx_Z[k];
-      double gk = 1.0;
-      if (fabs(z) > 1.e-10) gk = exp((-z * z * sq * A / (1.0 + cfg.cx_a0[k] * B * sq) + Bd * I) * PFRX_LOG_TO_LN);
-      W(cfg.off_secg, k) = gk;
-      sum_sec += W(cfg.off_sec, k);
+      int q = cfg.cx_cls[k];
+      W(cfg.off_lng, k) = q < 0 ? 0.0 : W(cfg.off_cls, q);
     }
-    if (cfg.use_act_h2o) {
-      double sp = 0.0;
-      for (int i = g.lane; i < naq; i += L)
-        if (i != cfg.h2o_aq_id) sp += W(cfg.off_c, i);
-      double t = 1.0 - 0.017 * (g.sumd(sp) + g.sumd(sum_sec));
-      cs.ln_act_h2o = t > 0.0 ? log(t) : 0.0;
-    }
-    g.sync();
   }
 
   // ---- RTotalSorbEqSurfCplx1 (reaction_surf_complex.F90:641-900) -----------
-  // Free-site solve is replicated on every lane (a handful of exps); each lane
-  // then adds the rows it owns.  tot_sorb[r] accumulates nu*S; when add_J the
-  // derivative rows are added into the shared Jacobian scaled by jscale.
-  __device__ void surf_cplx1(int irxn, double *tot_sorb, bool add_J, double jscale, bool store_conc) {
+  // tot_sorb[r] += nu*S on the rows this lane owns; the derivative rows go into
+  // the shared Jacobian scaled by jscale.  ws.fs[irxn] carries the free-site
+  // concentration of the cell (rt_auxvar%srfcplxrxn_free_site_conc).
+  __device__ __forceinline__ void surf_cplx1(int irxn, bool add_J, double jscale, bool store_conc) {
     const int naq = cfg.naq;
     const int r0 = cfg.sr_ptr[irxn], r1 = cfg.sr_ptr[irxn + 1];
-    double fs = fmax(st.free_site[irxn * st.ld + cell], 1.e-40);
+    double fs = fmax(W(cfg.off_fs, irxn), 1.e-40);
     double dens;
     int ty = cfg.sr_type[irxn];
     if (ty == PFRX_MINERAL_SURFACE)
       dens = cfg.sr_dens[irxn] * st.mnrl_volfrac[cfg.sr_surf[irxn] * st.ld + cell];
     else if (ty == PFRX_ROCK_SURFACE)
-      dens = cfg.sr_dens[irxn] * cs.spd * (1.0 - cs.por);
+      dens = cfg.sr_dens[irxn] * spd * (1.0 - por);
     else
       dens = cfg.sr_dens[irxn];
+    g.sync();
     if (dens < 1.e-40) {
-      g.sync();
       if (g.lane == 0) {
-        st.free_site[irxn * st.ld + cell] = 0.0;
+        W(cfg.off_fs, irxn) = 0.0;
         if (store_conc)
+#pragma unroll 1
           for (int q = r0; q < r1; q++) W(cfg.off_sc, cfg.sr_cx[q]) = 0.0;
       }
       g.sync();
       return;
     }
-    bool one_more = false;
-    int it = 0;
-    double damping = 1.0;
-    // per-complex concentrations live in ws.tmp[N + q - r0] (replicated value)
-    double *sconc = ws + cfg.off_tmp + N;
-    for (;;) {
-      it++;
-      double total = fs;
-      double lnfs = log(fs);
-      for (int q = r0; q < r1; q++) {
-        int k = cfg.sr_cx[q];
-        double lnQK = -sc_logK(k) * PFRX_LOG_TO_LN;
-        if (cfg.sc_h2o[k] != 0.0) lnQK += cfg.sc_h2o[k] * cs.ln_act_h2o;
-        lnQK += cfg.sc_fs[k] * lnfs;
-        for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++) lnQK += cfg.sc_st[p] * W(cfg.off_lnact, cfg.sc_id[p]);
-        double sck = exp(lnQK);
-        if (g.lane == 0) sconc[q - r0] = sck;
-        total += cfg.sc_fs[k] * sck;
+    // complex q of the reaction: ws.tmp[N+q] = lnQK without the free-site term
+    double *base = ws + cfg.off_tmp + N;
+#pragma unroll 1
+    for (int q = r0 + g.lane; q < r1; q += L) {
+      int k = cfg.sr_cx[q];
+      double lnQK = -sc_logK(k) * PFRX_LOG_TO_LN;
+      if (cfg.sc_h2o[k] != 0.0) lnQK += cfg.sc_h2o[k] * ln_act_h2o;
+#pragma unroll 1
+      for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++) lnQK += cfg.sc_st[p] * W(cfg.off_lnact, cfg.sc_id[p]);
+      base[q - r0] = lnQK;
+    }
+    g.sync();
+    double *sconc = base + (r1 - r0);
+    if (!cfg.sr_flag[irxn]) {
+      // every free-site stoichiometry is 1: S_q = exp(lnQK_q) * Sx and
+      // Sx = site density / (1 + sum_q exp(lnQK_q))   (closed form, :760-766)
+      double e = 0.0;
+#pragma unroll 1
+      for (int q = r0 + g.lane; q < r1; q += L) {
+        double v = exp(base[q - r0]);
+        sconc[q - r0] = v;
+        e += v;
       }
+      e = g.sumd(e);
+      fs = dens / (1.0 + e);
       g.sync();
-      if (one_more) break;
-      if (cfg.sr_flag[irxn]) {
-        double res = dens - total;
-        double d = 1.0;
+#pragma unroll 1
+      for (int q = r0 + g.lane; q < r1; q += L) sconc[q - r0] *= fs;
+      g.sync();
+    } else {
+      // general stoichiometry: Newton on the free-site concentration, replicated
+      bool one_more = false;
+      int it = 0;
+      double damping = 1.0;
+      for (;;) {
+        it++;
+        double total = fs, lnfs = log(fs);
+#pragma unroll 1
+        for (int q = r0; q < r1; q++) {
+          int k = cfg.sr_cx[q];
+          double sck = exp(base[q - r0] + cfg.sc_fs[k] * lnfs);
+          if (g.lane == 0) sconc[q - r0] = sck;
+          total += cfg.sc_fs[k] * sck;
+        }
+        g.sync();
+        if (one_more) break;
+        double res = dens - total, d = 1.0;
+#pragma unroll 1
         for (int q = r0; q < r1; q++) d += cfg.sc_fs[cfg.sr_cx[q]] * sconc[q - r0] / fs;
         double dfs = res / d;
         if (it > 1000) damping = 0.5;
         fs = fs + damping * dfs;
         if (fabs(dfs / fs) < 1.e-12 || it > 100000) one_more = true;
-      } else {
-        total = total / fs;
-        fs = dens / total;
-        one_more = true;
+        g.sync();
       }
-      g.sync();
     }
-    if (g.lane == 0) st.free_site[irxn * st.ld + cell] = fs;
+    if (g.lane == 0) W(cfg.off_fs, irxn) = fs;
     // dSx_dmi (eq. 2.3-46): the lane owning species j publishes entry j
     double denom = 0.0;
+#pragma unroll 1
     for (int q = r0; q < r1; q++) {
       int k = cfg.sr_cx[q];
       denom += cfg.sc_fs[k] * cfg.sc_fs[k] * sconc[q - r0];
     }
-    denom = denom / fs;
-    denom = denom + 1.0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      int i = row(r);
-      if (i < naq) {
-        double s = 0.0;
-        for (int q = r0; q < r1; q++) {
-          int k = cfg.sr_cx[q];
-          for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++)
-            if (cfg.sc_id[p] == i) s += cfg.sc_st[p] * cfg.sc_fs[k] * sconc[q - r0];
-        }
-        s = -s / denom;
-        W(cfg.off_tmp, i) = s / W(cfg.off_c, i);
+    denom = denom / fs + 1.0;
+#pragma unroll 1
+    for (int i = g.lane; i < naq; i += L) {
+      double s = 0.0;
+#pragma unroll 1
+      for (int q = r0; q < r1; q++) {
+        int k = cfg.sr_cx[q];
+#pragma unroll 1
+        for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++)
+          if (cfg.sc_id[p] == i) s += cfg.sc_st[p] * cfg.sc_fs[k] * sconc[q - r0];
       }
+      W(cfg.off_tmp, i) = (-s / denom) * W(cfg.off_invc, i);
     }
     g.sync();
     if (store_conc && g.lane == 0)
+#pragma unroll 1
       for (int q = r0; q < r1; q++) W(cfg.off_sc, cfg.sr_cx[q]) += sconc[q - r0];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      int i = row(r);
-      if (i < naq) {
-        for (int q = r0; q < r1; q++) {
-          int k = cfg.sr_cx[q];
-          double Sk = sconc[q - r0];
-          int p0 = cfg.sc_ptr[k], p1 = cfg.sc_ptr[k + 1];
-          for (int p = p0; p < p1; p++) {
-            if (cfg.sc_id[p] != i) continue;
-            double nui = cfg.sc_st[p];
-            tot_sorb[r] += nui * Sk;
-            if (add_J) {
-              double nuiSx = cfg.sc_fs[k] * Sk / fs;
-              for (int p2 = p0; p2 < p1; p2++) {
-                int j = cfg.sc_id[p2];
-                double t = cfg.sc_st[p2] * Sk / W(cfg.off_c, j) + nuiSx * W(cfg.off_tmp, j);
-                Jm(i, j) += jscale * (nui * t);
-              }
+#pragma unroll 1
+    for (int i = g.lane; i < naq; i += L) {
+#pragma unroll 1
+      for (int q = r0; q < r1; q++) {
+        int k = cfg.sr_cx[q];
+        double Sk = sconc[q - r0];
+        int p0 = cfg.sc_ptr[k], p1 = cfg.sc_ptr[k + 1];
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) {
+          if (cfg.sc_id[p] != i) continue;
+          double nui = cfg.sc_st[p];
+          W(cfg.off_ts, i) += nui * Sk;
+          if (add_J) {
+            double nuiSx = cfg.sc_fs[k] * Sk / fs;
+#pragma unroll 1
+            for (int p2 = p0; p2 < p1; p2++) {
+              int j = cfg.sc_id[p2];
+              double t = cfg.sc_st[p2] * Sk * W(cfg.off_invc, j) + nuiSx * W(cfg.off_tmp, j);
+              Jm(i, j) += jscale * (nui * t);
             }
           }
         }
@@ -325,103 +382,117 @@ struct CellSolver {
     g.sync();
   }
 
-  // ---- RTAuxVarCompute = RTotal (reaction.F90:4618-4759) --------------------
-  // Leaves: ws.lnact, ws.invc, ws.sec; totnew/sorbnew registers; when
-  // want_J the shared Jacobian holds d(accumulation)/dc / dt
-  // (RTAccumulationDerivative + RAccumulationSorbDerivative).
-  __device__ void auxvar_compute(bool want_J, double dt) {
+  // ---- RTAuxVarCompute = RTotal (reaction.F90:4618-4759) + accumulation -----
+  // Leaves ws.lnact/invc/sec, totnew/sorbnew, and the shared Jacobian
+  // d(accumulation)/dc/dt (RTAccumulationDerivative, reaction.F90:5775).
+  __device__ __forceinline__ void auxvar_compute() {
     const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int i = row(r);
       if (i < naq) {
-        double lnc = log(cval[r]);
-        W(cfg.off_lnact, i) = lnc + lngam[r];
+        W(cfg.off_lnact, i) = log(cval[r]) + lngam[r];
         W(cfg.off_invc, i) = 1.0 / cval[r];
       }
-      if (i < n) W(cfg.off_c, i) = cval[r];
     }
     g.sync();
-    // secondary species: lanes stride over complexes
+    // secondary species: lanes stride over complexes, one exp each
+#pragma unroll 1
     for (int k = g.lane; k < ncx; k += L) {
       double lnQK = -cx_logK(k) * PFRX_LOG_TO_LN;
       double h = cfg.cx_h2o[k];
-      if (h != 0.0) lnQK += h * cs.ln_act_h2o;
+      if (h != 0.0) lnQK += h * ln_act_h2o;
+#pragma unroll 1
       for (int p = cfg.cx_ptr[k]; p < cfg.cx_ptr[k + 1]; p++) lnQK += cfg.cx_st[p] * W(cfg.off_lnact, cfg.cx_id[p]);
-      W(cfg.off_sec, k) = exp(lnQK) / W(cfg.off_secg, k);
+      W(cfg.off_sec, k) = exp(lnQK - W(cfg.off_lng, k));
     }
-    if (want_J) {
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        int i = row(r);
-        if (i < n)
-          for (int j = 0; j < n; j++) Jm(i, j) = 0.0;
+    g.sync();
+    // balanced weighted sums of sec: totals and S_ij = sum_k nu_ki nu_kj sec_k
+    {
+      int t = cfg.ln_task0[g.lane];
+      const int s1 = cfg.ln_seg0[g.lane + 1];
+#pragma unroll 1
+      for (int s = cfg.ln_seg0[g.lane]; s < s1; s++) {
+        const int cnt = cfg.sg_cnt[s];
+        double acc = 0.0;
+#pragma unroll 1
+        for (int e = 0; e < cnt; e++, t++) acc += cfg.tk_w[t] * W(cfg.off_sec, cfg.tk_k[t]);
+        W(cfg.off_acc, cfg.sg_dst[s]) = acc;
       }
     }
     g.sync();
-    const double denL = cs.den_kg * 1.e-3;
-    const double psvd = cs.por * cs.sat * 1000.0 * cs.vol / dt;
+#pragma unroll 1
+    for (int f = g.lane; f < cfg.nfix; f += L) {
+      double acc = 0.0;
+#pragma unroll 1
+      for (int p = cfg.fx_ptr[f]; p < cfg.fx_ptr[f + 1]; p++) acc += W(cfg.off_acc, cfg.fx_src[p]);
+      W(cfg.off_acc, cfg.fx_dst[f]) = acc;
+    }
+    g.sync();
+    const double denL = den_kg * 1.e-3;
+    const double psvd = por * sat * 1000.0 * vol / dt;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int i = row(r);
       if (i < naq) {
-        double tot = cval[r];
-        for (int q = cfg.sp_ptr[i]; q < cfg.sp_ptr[i + 1]; q++) {
-          int k = cfg.sp_cx[q];
-          double nu_i = cfg.sp_st[q];
-          double sk = W(cfg.off_sec, k);
-          tot += nu_i * sk;
-          if (want_J && !dry) {
-            double t = nu_i * sk;
-            for (int p = cfg.cx_ptr[k]; p < cfg.cx_ptr[k + 1]; p++) Jm(i, cfg.cx_id[p]) += cfg.cx_st[p] * t;
+        totnew[r] = (cval[r] + W(cfg.off_acc, i)) * denL;
+        if (dry) {
+#pragma unroll 1
+          for (int j = 0; j < n; j++) Jm(i, j) = (i == j) ? 1.0 : 0.0;
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) {
+            double d = W(cfg.off_acc, symidx(i, j)) * W(cfg.off_invc, j) + (i == j ? 1.0 : 0.0);
+            Jm(i, j) = (d * denL) * psvd;
           }
-        }
-        totnew[r] = tot * denL;
-        if (want_J) {
-          if (dry) {
-            Jm(i, i) = 1.0;
-          } else {
-            for (int j = 0; j < naq; j++) {
-              double d = Jm(i, j) * W(cfg.off_invc, j) + (i == j ? 1.0 : 0.0);
-              Jm(i, j) = (d * denL) * psvd;
-            }
-          }
+#pragma unroll 1
+          for (int j = naq; j < n; j++) Jm(i, j) = 0.0;
         }
       } else if (i < n) {
         totnew[r] = cval[r];
-        if (want_J) Jm(i, i) = dry ? 1.0 : cs.vol / dt;
+#pragma unroll 1
+        for (int j = 0; j < n; j++) Jm(i, j) = 0.0;
+        Jm(i, i) = dry ? 1.0 : vol / dt;
       }
       sorbnew[r] = 0.0;
     }
     // equilibrium sorption (RTotalSorb, reaction.F90:4783)
     if (cfg.neqsr > 0) {
       if (g.lane == 0)
+#pragma unroll 1
         for (int k = 0; k < cfg.nsrfcplx; k++) W(cfg.off_sc, k) = 0.0;
-      g.sync();
-      for (int e = 0; e < cfg.neqsr; e++) surf_cplx1(cfg.eqsr[e], sorbnew, want_J, cs.vol / dt, true);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) W(cfg.off_ts, i) = 0.0;
+#pragma unroll 1
+      for (int e = 0; e < cfg.neqsr; e++) surf_cplx1(cfg.eqsr[e], true, vol / dt, true);
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (row(r) < naq) sorbnew[r] = W(cfg.off_ts, row(r));
     }
   }
 
   // ---- RKineticMineral (reaction_mineral.F90:647-1078), no prefactors ------
-  // Every lane evaluates the rate scalars; row owners add their entries.
-  // ws.lnact must be current.  rate_out (may be null) receives mnrl_rate.
-  __device__ void kinetic_mineral(double *res, bool derivative, bool store_rate) {
+  // lane m evaluates mineral m and publishes {rate, Im, dIm/dQK * extras, QK};
+  // row owners then add their residual / Jacobian entries.
+  __device__ __forceinline__ void kinetic_mineral(bool apply) {
     const int naq = cfg.naq;
-    for (int m = 0; m < cfg.nkin; m++) {
+#pragma unroll 1
+    for (int m = g.lane; m < cfg.nkin; m += L) {
       const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
-      double rate_vol = 0.0;  // mnrl_rate default
+      double rate_vol = 0.0, Im = 0.0, dfac = 0.0;
       double lnQK = -mn_logK(m) * PFRX_LOG_TO_LN;
-      if (cfg.mn_h2o[m] != 0.0) lnQK += cfg.mn_h2o[m] * cs.ln_act_h2o;
+      if (cfg.mn_h2o[m] != 0.0) lnQK += cfg.mn_h2o[m] * ln_act_h2o;
+#pragma unroll 1
       for (int p = p0; p < p1; p++) lnQK += cfg.mn_st[p] * W(cfg.off_lnact, cfg.mn_id[p]);
       double QK = exp(lnQK);
       double aff;
       if (cfg.mn_temkin) {
         if (cfg.mn_scale)
-          aff = 1.0 - pow(QK, 1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m]));
+          aff = 1.0 - pfrx_pow(QK, 1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m]));
         else
-          aff = 1.0 - pow(QK, 1.0 / cfg.mn_temkin[m]);
+          aff = 1.0 - pfrx_pow(QK, 1.0 / cfg.mn_temkin[m]);
       } else if (cfg.mn_scale) {
-        aff = 1.0 - pow(QK, 1.0 / cfg.mn_scale[m]);
+        aff = 1.0 - pfrx_pow(QK, 1.0 / cfg.mn_scale[m]);
       } else {
         aff = 1.0 - QK;
       }
@@ -435,118 +506,131 @@ struct CellSolver {
         if (lim > 0.0) aff = aff / (1.0 + (1.0 - aff) / lim);
         double arr = 1.0;
         if (cfg.mn_eact[m] > 0.0)
-          arr = exp(cfg.mn_eact[m] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (cs.temp + 273.15)));
+          arr = exp(cfg.mn_eact[m] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
         double spr = cfg.mn_rate[m] * arr;
         double Im_const = -st.mnrl_area[m * st.ld + cell];
         if (cfg.mn_scale) Im_const = Im_const / cfg.mn_scale[m];
-        double Im;
         if (cfg.mn_power)
-          Im = Im_const * sgn * pow(fabs(aff), cfg.mn_power[m]) * spr;
+          Im = Im_const * sgn * pfrx_pow(fabs(aff), cfg.mn_power[m]) * spr;
         else
           Im = Im_const * sgn * fabs(aff) * spr;
         rate_vol = Im;
-        Im_const = Im_const * cs.vol;
-        Im = Im * cs.vol;
-        double dIm_dQK = 0.0;
-        if (derivative) {
-          if (cfg.mn_power)
-            dIm_dQK = -Im * cfg.mn_power[m] / fabs(aff);
+        Im_const = Im_const * vol;
+        Im = Im * vol;
+        double dIm_dQK;
+        if (cfg.mn_power)
+          dIm_dQK = -Im * cfg.mn_power[m] / fabs(aff);
+        else
+          dIm_dQK = -Im_const * spr;
+        if (cfg.mn_temkin) {
+          if (cfg.mn_scale)
+            dIm_dQK = dIm_dQK * (1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m])) / QK * (1.0 - aff);
           else
-            dIm_dQK = -Im_const * spr;
-          if (cfg.mn_temkin) {
-            if (cfg.mn_scale)
-              dIm_dQK = dIm_dQK * (1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m])) / QK * (1.0 - aff);
-            else
-              dIm_dQK = dIm_dQK * (1.0 / cfg.mn_temkin[m]) / QK * (1.0 - aff);
-          } else if (cfg.mn_scale) {
-            dIm_dQK = dIm_dQK * (1.0 / cfg.mn_scale[m]) / QK * (1.0 - aff);
-          }
+            dIm_dQK = dIm_dQK * (1.0 / cfg.mn_temkin[m]) / QK * (1.0 - aff);
+        } else if (cfg.mn_scale) {
+          dIm_dQK = dIm_dQK * (1.0 / cfg.mn_scale[m]) / QK * (1.0 - aff);
         }
-        double den = 1.0, limfac = 1.0;
+        // Jac(i,j) += nu_i * dfac * nu_j / c_j   with everything else folded in
+        dfac = dIm_dQK * QK * (den_kg * 1.e-3);
         if (lim > 0.0) {
-          den = 1.0 + (1.0 - aff) / lim;
-          limfac = (1.0 + QK / lim / den);
+          double den = 1.0 + (1.0 - aff) / lim;
+          dfac = dIm_dQK * (1.0 + QK / lim / den) * QK * (den_kg * 1.e-3) / den;
         }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          int i = row(r);
-          if (i >= naq) continue;
-          for (int p = p0; p < p1; p++) {
-            if (cfg.mn_id[p] != i) continue;
-            double nui = cfg.mn_st[p];
-            if (res) res[r] += nui * Im;
-            if (derivative) {
-              for (int p2 = p0; p2 < p1; p2++) {
-                int j = cfg.mn_id[p2];
-                // exp(-ln c_j) = 1/c_j
-                double dQK_dmj = (cfg.mn_st[p2] * QK * W(cfg.off_invc, j)) * cs.den_kg * 1.e-3;
-                if (lim > 0.0)
-                  Jm(i, j) += nui * dIm_dQK * limfac * dQK_dmj / den;
-                else
-                  Jm(i, j) += nui * dIm_dQK * dQK_dmj;
-              }
-            }
+      }
+      W(cfg.off_mn, 3 * m + 0) = rate_vol;
+      W(cfg.off_mn, 3 * m + 1) = Im;
+      W(cfg.off_mn, 3 * m + 2) = dfac;
+    }
+    g.sync();
+    if (!apply) return;
+#pragma unroll 1
+    for (int i = g.lane; i < naq; i += L) {
+#pragma unroll 1
+      for (int m = 0; m < cfg.nkin; m++) {
+        double Im = W(cfg.off_mn, 3 * m + 1);
+        double df = W(cfg.off_mn, 3 * m + 2);
+        if (Im == 0.0 && df == 0.0) continue;
+        const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) {
+          if (cfg.mn_id[p] != i) continue;
+          double nui = cfg.mn_st[p];
+          W(cfg.off_res, i) += nui * Im;
+          double f = nui * df;
+#pragma unroll 1
+          for (int p2 = p0; p2 < p1; p2++) {
+            int j = cfg.mn_id[p2];
+            Jm(i, j) += f * (cfg.mn_st[p2] * W(cfg.off_invc, j));
           }
         }
       }
-      if (store_rate && g.lane == 0) st.mnrl_rate[m * st.ld + cell] = rate_vol;
     }
   }
 
   // ---- RMultiRateSorption (reaction_surf_complex.F90:552-637) --------------
-  __device__ void multirate(double *res, double dt) {
+  // Res_i += V * sum_k kk_k (f_k Seq_i - S_ki) = V * (A Seq_i - B_i) with
+  // A = sum_k kk_k f_k and B_i = sum_k kk_k S_ki (B is fixed within a sub-step).
+  __device__ __forceinline__ void multirate() {
     const int naq = cfg.naq;
+#pragma unroll 1
     for (int q = 0; q < cfg.nmr; q++) {
       int irxn = cfg.mr_rxn[q];
       int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
-      int64_t base = (int64_t)naq * (r0 + q);
-      double seq[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) seq[r] = 0.0;
-      // sum_k V k/(1+k dt) f : the Jacobian gets dtotal_sorb_eq times this
-      double jsum = 0.0;
-      for (int k = r0; k < r1; k++) {
-        double kk = cfg.mr_rate[k] / (1.0 + cfg.mr_rate[k] * dt);
-        jsum += cs.vol * kk * cfg.mr_frac[k];
+      double A = 0.0;
+#pragma unroll 1
+      for (int k = r0; k < r1; k++) A += cfg.mr_rate[k] / (1.0 + cfg.mr_rate[k] * dt) * cfg.mr_frac[k];
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) W(cfg.off_ts, i) = 0.0;
+      surf_cplx1(irxn, true, vol * A, false);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) {
+        double seq = W(cfg.off_ts, i);
+        W(cfg.off_res, i) += vol * (A * seq - W(cfg.off_mr, (2 * q + 1) * N + i));
+        W(cfg.off_mr, (2 * q) * N + i) = seq;  // kinmr_total_sorb(:,0,q): the equilibrium target
       }
-      surf_cplx1(irxn, seq, true, jsum, false);
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        int i = row(r);
-        if (i < naq) {
-          for (int k = r0; k < r1; k++) {
-            double kdt = cfg.mr_rate[k] * dt;
-            double kk = cfg.mr_rate[k] / (1.0 + kdt);
-            double S = st.kinmr[(base + (int64_t)naq * (k - r0 + 1) + i) * st.ld + cell];
-            res[r] += cs.vol * kk * (cfg.mr_frac[k] * seq[r] - S);
-          }
-          st.kinmr[(base + i) * st.ld + cell] = seq[r];
+    }
+  }
+
+  // B_i of every multirate reaction for the sub-step that starts now
+  __device__ __forceinline__ void multirate_begin() {
+    const int naq = cfg.naq;
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+      int64_t base = (int64_t)naq * (r0 + q);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) {
+        double B = 0.0;
+#pragma unroll 1
+        for (int k = r0; k < r1; k++) {
+          double kk = cfg.mr_rate[k] / (1.0 + cfg.mr_rate[k] * dt);
+          B += kk * st.kinmr[(base + (int64_t)naq * (k - r0 + 1) + i) * st.ld + cell];
         }
+        W(cfg.off_mr, (2 * q + 1) * N + i) = B;
       }
     }
   }
 
   // ---- CLM_CN_React (reaction_sandbox_clm_cn.F90:468-787) ------------------
-  __device__ void clm_cn(double *res, bool derivative) {
+  __device__ __forceinline__ void clm_cn() {
     const int off = cfg.naq;
-    double temp_K = cs.temp + 273.15;
+    double temp_K = temp + 273.15;
     if (!(temp_K > 227.15)) return;
     const double one_over_71_02 = 1.408054069e-2, theta_min = 0.01, one_over_log_theta_min = -2.17147241e-1;
     double F_t = exp(308.56 * (one_over_71_02 - 1.0 / (temp_K - 227.13)));
-    double F_theta = log(theta_min / fmax(theta_min, cs.sat)) * one_over_log_theta_min;
+    double F_theta = log(theta_min / fmax(theta_min, sat)) * one_over_log_theta_min;
     double cinh = F_t * F_theta;
     const int ires_C = off + cfg.cn_C, ispec_N = cfg.cn_N, ires_N = off + ispec_N;
     const double *imm = ws + cfg.off_c + off;  // immobile(:) of the current iterate
     auto addR = [&](int irow, double v) {
-#pragma unroll
-      for (int r = 0; r < R; r++)
-        if (row(r) == irow) res[r] += v;
+      if ((irow % L) == g.lane) W(cfg.off_res, irow) += v;
     };
     auto addJ = [&](int irow, int jcol, double v) {
       if ((irow % L) == g.lane) Jm(irow, jcol) += v;
     };
+#pragma unroll 1
     for (int x = 0; x < cfg.cn_nrxn; x++) {
-      double src = cfg.cn_k[x] * cs.vol * cinh;
+      double src = cfg.cn_k[x] * vol * cinh;
       double resp = cfg.cn_resp[x];
       int pu = cfg.cn_up[x];
       bool constCN = (cfg.cn_nspec[pu] == 1);
@@ -589,33 +673,31 @@ struct CellSolver {
       addR(rUC, -((-1.0) * sUC * rate));
       if (!constCN) addR(rUN, -((-1.0) * sUN * rate));
       if (id >= 0) addR(rD, -(sDC * rate));
-      if (derivative) {
-        double drate = src * Ninh;
-        double dInh = 0.0;
-        addJ(rUC, rUC, -((-1.0) * sUC * drate));
-        if (useInh) {
-          dInh = imm[iC] * src * dNinh;
-          addJ(rUC, ires_N, -((-1.0) * sUC * dInh));
-        }
-        if (id >= 0) {
-          addJ(rD, rUC, -(sDC * drate));
-          if (useInh) addJ(rD, ires_N, -(sDC * dInh));
-        }
-        if (!constCN) {
-          addJ(rUN, rUC, -((-1.0) * sUN * drate));
-          if (useInh) addJ(rUN, ires_N, -((-1.0) * sUN * dInh));
-          double nc = imm[iN] / imm[iC] * src * Ninh;
-          addJ(rUN, rUC, -((-1.0) * (-1.0) * nc));
-          addJ(rUN, rUN, -((-1.0) * src * Ninh));
-          addJ(ires_N, rUC, -((-1.0) * nc));
-          addJ(ires_N, rUN, -(src * Ninh));
-        }
-        addJ(ires_C, rUC, -(sC * drate));
-        addJ(ires_N, rUC, -(sN * drate));
-        if (useInh) {
-          addJ(ires_C, ires_N, -(sC * dInh));
-          addJ(ires_N, ires_N, -(sN * dInh));
-        }
+      double drate = src * Ninh;
+      double dInh = 0.0;
+      addJ(rUC, rUC, -((-1.0) * sUC * drate));
+      if (useInh) {
+        dInh = imm[iC] * src * dNinh;
+        addJ(rUC, ires_N, -((-1.0) * sUC * dInh));
+      }
+      if (id >= 0) {
+        addJ(rD, rUC, -(sDC * drate));
+        if (useInh) addJ(rD, ires_N, -(sDC * dInh));
+      }
+      if (!constCN) {
+        addJ(rUN, rUC, -((-1.0) * sUN * drate));
+        if (useInh) addJ(rUN, ires_N, -((-1.0) * sUN * dInh));
+        double nc = imm[iN] / imm[iC] * src * Ninh;
+        addJ(rUN, rUC, -((-1.0) * (-1.0) * nc));
+        addJ(rUN, rUN, -((-1.0) * src * Ninh));
+        addJ(ires_N, rUC, -((-1.0) * nc));
+        addJ(ires_N, rUN, -(src * Ninh));
+      }
+      addJ(ires_C, rUC, -(sC * drate));
+      addJ(ires_N, rUC, -(sN * drate));
+      if (useInh) {
+        addJ(ires_C, ires_N, -(sC * dInh));
+        addJ(ires_N, ires_N, -(sN * dInh));
       }
     }
   }
@@ -623,7 +705,7 @@ struct CellSolver {
   // ---- RSolve + LUDecomposition + LUBackSubstitution -----------------------
   // (reaction.F90:5457-5516, utility.F90:597-735).  a[][] rows in registers.
   // Returns false when a row is all zero (singular) -- the group agrees.
-  __device__ bool solve(double (&a)[R][N], double (&b)[R], double *xout /* ws, n entries */) {
+  __device__ __forceinline__ bool solve(double (&a)[R][N], double (&b)[R], double *xout /* ws, n entries */) {
     const int n = cfg.n;
     double vv[R];
     int pos[R], step[R];
@@ -733,93 +815,275 @@ struct CellSolver {
     return true;
   }
 
-  // ---- RReact (reaction.F90:3742-4055) -------------------------------------
-  // returns ierror; its = Newton iterations used
-  __device__ int react(double dt, int &its_out) {
+  // ---- start of RReact for a sub-step of length dt (reaction.F90:3826-3850) --
+  __device__ __forceinline__ void react_begin() {
     const int naq = cfg.naq, n = cfg.n;
-    double fixed[R], init_tot[R], res[R];
-    const double psv = cs.por * cs.sat * 1000.0 * cs.vol;
-    dry = cs.sat < cfg.min_sat;
+    const double psv = por * sat * 1000.0 * vol;
+    dry = sat < cfg.min_sat;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int i = row(r);
-      // RTAccumulation (+RAccumulationSorb) of total^*, immobile^k
       double f = 0.0;
       if (!dry) {
-        if (i < naq) {
+        if (i < naq)
           f = psv * totcur[r];
-        } else if (i < n) {
-          f = 0.0 + totcur[r] * cs.vol;
-        }
+        else if (i < n)
+          f = 0.0 + totcur[r] * vol;
       }
-      if (cfg.neqsr > 0 && i < naq) f = f + sorbcur[r] * cs.vol;
+      if (cfg.neqsr > 0 && i < naq) f = f + sorbcur[r] * vol;
       fixed[r] = f;
       init_tot[r] = totcur[r];
       cval[r] = guess[r];
     }
-    int its = 0;
-    double norm0 = 0.0;
-    int ierr = 0;
-    for (;;) {
-      its++;
-      if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) {
-        // needs ws.c of the current iterate
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (row(r) < n) W(cfg.off_c, row(r)) = cval[r];
-        g.sync();
-        activity();
-      }
-      auxvar_compute(true, dt);
-      if (its > cfg.max_its) {
-        ierr = 1;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          totcur[r] = init_tot[r];  // total and immobile restored (reaction.F90:3891-3894)
-          sorbcur[r] = sorbnew[r];  // total_sorb_eq is not
-        }
-        // immobile rows: rt_auxvar%immobile = initial_total -> cval mirrors it
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (row(r) >= naq) cval[r] = init_tot[r];
-        its_out = its;
-        return ierr;
-      }
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        int i = row(r);
-        double a = 0.0;
-        if (!dry) {
-          if (i < naq)
-            a = psv * totnew[r];
-          else if (i < n)
-            a = 0.0 + cval[r] * cs.vol;
-        }
-        if (cfg.neqsr > 0 && i < naq) a = a + sorbnew[r] * cs.vol;
-        res[r] = (a - fixed[r]) / dt;
-      }
-      // RReaction (reaction.F90:4059-4130), same order
-      if (!dry) {
-        if (cfg.nkin > 0) kinetic_mineral(res, true, true);
-        if (cfg.nmr > 0) multirate(res, dt);
-        if (cfg.cn_nrxn > 0) clm_cn(res, true);
-      }
-      g.sync();
-      double mabs = 0.0, ss = 0.0;
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (row(r) < n) {
-          mabs = fmax(mabs, fabs(res[r]));
-          ss += res[r] * res[r];
-        }
-      }
-      mabs = g.maxd(mabs);
-      double nrm = sqrt(g.sumd(ss));
-      if (its == 1) norm0 = nrm;
-      double rel = nrm / norm0;
-      if (mabs < cfg.tol_res) break;
-      if (rel < cfg.tol_relres) break;
+    its = 0;
+    norm0 = 0.0;
+    if (cfg.nmr > 0) multirate_begin();
+  }
 
+  // ---- load a cell and start RStep (reaction.F90:3564-3650) -----------------
+  __device__ __forceinline__ void load_cell(int64_t c) {
+    cell = c;
+    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
+    const int64_t ld = st.ld;
+    den_kg = st.den_kg[c];
+    sat = st.sat[c];
+    temp = st.temp[c];
+    por = st.porosity[c];
+    vol = st.volume[c];
+    spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
+    ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
+    nss = nit = nku = ierr = 0;
+    had_cut = aborted = false;
+    cumulative = 0.0;
+    dt = target;
+    ncuts = nconst = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      int i = row(r);
+      small[r] = false;
+      small_val[r] = 0.0;
+      lngam[r] = 0.0;
+      sorbcur[r] = 0.0;
+      totcur[r] = 0.0;
+      guess[r] = 1.0;
+      cval[r] = 1.0;
+            if (i < naq) {
+        totcur[r] = st.total[i * ld + c];
+        guess[r] = st.pri_molal[i * ld + c];
+        lngam[r] = log(st.pri_act_coef[i * ld + c]);
+        if (cfg.neqsr > 0) sorbcur[r] = st.total_sorb_eq[i * ld + c];
+      } else if (i < n) {
+        totcur[r] = st.immobile[(i - naq) * ld + c];
+        guess[r] = totcur[r];  // read before the 1e-40 clamp (pmc_subsurface_osrt.F90:356-362)
+      }
+    }
+    g.sync();  // previous cell's workspace readers are done
+#pragma unroll 1
+    for (int k = g.lane; k < ncx; k += L) {
+      W(cfg.off_sec, k) = st.sec_molal[k * ld + c];
+      W(cfg.off_lng, k) = log(st.sec_act_coef[k * ld + c]);
+    }
+#pragma unroll 1
+    for (int k = g.lane; k < cfg.nsrfrxn; k += L) W(cfg.off_fs, k) = st.free_site[k * ld + c];
+#pragma unroll 1
+    for (int k = g.lane; k < cfg.nsrfcplx; k += L) W(cfg.off_sc, k) = 0.0;
+#pragma unroll 1
+    for (int k = g.lane; k < cfg.nkin; k += L) W(cfg.off_mn, 3 * k) = st.mnrl_rate[k * ld + c];
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int64_t base = (int64_t)naq * (cfg.mr_ptr[q] + q);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) W(cfg.off_mr, (2 * q) * N + i) = st.kinmr[(base + i) * ld + c];
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      int i = row(r);
+      if (i < n && totcur[r] <= 1.e-40) {
+        small[r] = true;
+        small_val[r] = totcur[r];
+        totcur[r] = 1.e-40;
+      }
+      if (cfg.use_total_as_guess && i < naq) guess[r] = totcur[r];
+    }
+    g.sync();
+  }
+
+  // ---- write the cell back (rt_auxvar of the cell) ----------------------------
+  __device__ __forceinline__ void store_cell() {
+    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
+    const int64_t ld = st.ld, c = cell;
+    const bool act_upd = cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      int i = row(r);
+      if (i < naq) {
+        st.total[i * ld + c] = (small[r] && !aborted) ? small_val[r] : totcur[r];
+        st.pri_molal[i * ld + c] = cval[r];
+        if (act_upd) st.pri_act_coef[i * ld + c] = exp(lngam[r]);
+        if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = sorbcur[r];
+      } else if (i < n) {
+        st.immobile[(i - naq) * ld + c] = (small[r] && !aborted) ? small_val[r] : totcur[r];
+      }
+    }
+    g.sync();
+#pragma unroll 1
+    for (int k = g.lane; k < ncx; k += L) {
+      st.sec_molal[k * ld + c] = W(cfg.off_sec, k);
+      if (act_upd) st.sec_act_coef[k * ld + c] = exp(W(cfg.off_lng, k));
+    }
+#pragma unroll 1
+    for (int k = g.lane; k < cfg.nsrfrxn; k += L) st.free_site[k * ld + c] = W(cfg.off_fs, k);
+    if (cfg.neqsr > 0 && st.eqsrfcplx_conc)
+#pragma unroll 1
+      for (int k = g.lane; k < cfg.nsrfcplx; k += L) st.eqsrfcplx_conc[k * ld + c] = W(cfg.off_sc, k);
+#pragma unroll 1
+    for (int k = g.lane; k < cfg.nkin; k += L) st.mnrl_rate[k * ld + c] = W(cfg.off_mn, 3 * k);
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int64_t base = (int64_t)naq * (cfg.mr_ptr[q] + q);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) st.kinmr[(base + i) * ld + c] = W(cfg.off_mr, (2 * q) * N + i);
+    }
+    if (g.lane == 0) {
+      if (st.ln_act_h2o && cfg.use_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
+      st.num_sub_steps[c] = nss;
+      st.num_iterations[c] = nit;
+      st.num_kinetic_state_updates[c] = nku;
+      st.ierror[c] = ierr;
+    }
+  }
+
+  // ---- RReact failed (its > max or singular): RStep cuts dt (reaction.F90:3660) -
+  // returns true when the cell is finished (too many cuts)
+  __device__ __forceinline__ bool cut_or_abort() {
+    nit += its;
+    ncuts++;
+    had_cut = true;
+    if (ncuts > cfg.max_cuts) {
+      ierr = 1;
+      aborted = true;
+      return true;
+    }
+    dt = 0.5 * dt;
+    nconst = 0;
+    react_begin();
+    return false;
+  }
+
+  // ---- converged sub-step: RUpdateKineticState + RStep accounting ------------
+  // (reaction.F90:3681-3716, :5935-5972, reaction_mineral.F90:1456,
+  //  reaction_surf_complex.F90:1107).  Returns true when the cell is finished.
+  __device__ __forceinline__ bool finish_substep() {
+    const int naq = cfg.naq;
+    nit += its;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      totcur[r] = totnew[r];
+      sorbcur[r] = sorbnew[r];
+    }
+    bool upd = false;
+    if (cfg.nkin > 0) {
+      upd = true;
+      // the rates of the converged iterate are in ws.mn (same inputs as the
+      // RKineticMineral call MineralUpdateKineticState makes)
+#pragma unroll 1
+      for (int m = g.lane; m < cfg.nkin; m += L) {
+        double vf = st.mnrl_volfrac[m * st.ld + cell] + W(cfg.off_mn, 3 * m) * cfg.mn_vol[m] * dt;
+        if (vf < 0.0) vf = 0.0;
+        st.mnrl_volfrac[m * st.ld + cell] = vf;
+      }
+    }
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      upd = true;
+      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+      int64_t base = (int64_t)naq * (r0 + q);
+#pragma unroll 1
+      for (int i = g.lane; i < naq; i += L) {
+        double seq = W(cfg.off_mr, (2 * q) * N + i);
+#pragma unroll 1
+        for (int k = r0; k < r1; k++) {
+          double kdt = cfg.mr_rate[k] * dt;
+          int64_t ix = (base + (int64_t)naq * (k - r0 + 1) + i) * st.ld + cell;
+          st.kinmr[ix] = (st.kinmr[ix] + kdt * cfg.mr_frac[k] * seq) / (1.0 + kdt);
+        }
+      }
+    }
+    if (cfg.cn_nrxn > 0) upd = true;  // any sandbox => true (reaction.F90:5965)
+    cumulative += dt;
+    nss++;
+    nconst++;
+    if (upd) nku++;
+#pragma unroll
+    for (int r = 0; r < R; r++) guess[r] = cval[r];
+    if (nconst >= 4) {
+      ncuts--;
+      dt = fmin(2.0 * dt, target - cumulative);
+    }
+    if (cumulative >= target) return true;
+    g.sync();
+    react_begin();
+    return false;
+  }
+
+  // ---- one Newton iteration of RReact (reaction.F90:3853-4048) ---------------
+  // returns true when the cell is finished (stored by the caller)
+  __device__ __forceinline__ bool newton_pass() {
+    const int naq = cfg.naq, n = cfg.n;
+    its++;
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (row(r) < n) W(cfg.off_c, row(r)) = cval[r];
+    g.sync();
+    if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) activity();
+    auxvar_compute();
+    if (its > cfg.max_its) {
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        totcur[r] = init_tot[r];  // total and immobile restored (reaction.F90:3891-3894)
+        sorbcur[r] = sorbnew[r];  // total_sorb_eq is not
+        if (row(r) >= naq) cval[r] = init_tot[r];
+      }
+      return cut_or_abort();
+    }
+    const double psv = por * sat * 1000.0 * vol;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      int i = row(r);
+      double a = 0.0;
+      if (!dry) {
+        if (i < naq)
+          a = psv * totnew[r];
+        else if (i < n)
+          a = 0.0 + cval[r] * vol;
+      }
+      if (cfg.neqsr > 0 && i < naq) a = a + sorbnew[r] * vol;
+      if (i < n) W(cfg.off_res, i) = (a - fixed[r]) / dt;
+    }
+    // RReaction (reaction.F90:4059-4130), same order
+    if (cfg.nkin > 0) kinetic_mineral(!dry);
+    if (!dry) {
+      if (cfg.nmr > 0) multirate();
+      if (cfg.cn_nrxn > 0) clm_cn();
+    }
+    g.sync();
+    double res[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) res[r] = row(r) < n ? W(cfg.off_res, row(r)) : 0.0;
+    double mabs = 0.0, ss = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (row(r) < n) {
+        mabs = fmax(mabs, fabs(res[r]));
+        ss += res[r] * res[r];
+      }
+    }
+    mabs = g.maxd(mabs);
+    double nrm = sqrt(g.sumd(ss));
+    if (its == 1) norm0 = nrm;
+    double rel = nrm / norm0;
+    bool conv = (mabs < cfg.tol_res) || (rel < cfg.tol_relres);
+    if (!conv) {
       // RSolve: row scaling, optional d/dlnc scaling, LU, back-substitution
       double a[R][N], b[R];
 #pragma unroll
@@ -843,29 +1107,18 @@ struct CellSolver {
       }
       double *xs = ws + cfg.off_xs;
       if (!solve(a, b, xs)) {
-        ierr = 1;  // solve_error branch: no restore (reaction.F90:3964-3967)
+        // solve_error branch: no restore (reaction.F90:3964-3967)
 #pragma unroll
         for (int r = 0; r < R; r++) {
           totcur[r] = totnew[r];
           sorbcur[r] = sorbnew[r];
         }
-        its_out = its;
-        return ierr;
+        return cut_or_abort();
       }
       double cnew[R], maxrel = 0.0;
       bool anyv = false;
-      if (cfg.use_log) {
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          int i = row(r);
-          if (i < n) {
-            double u = xs[i];
-            u = copysign(1.0, u) * fmin(fabs(u), cfg.max_dlnC);
-            cnew[r] = cval[r] * exp(-u);
-          }
-        }
-      } else {
-        double minr = 1.e20;
+      double minr = 1.e20;
+      if (!cfg.use_log) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
           int i = row(r);
@@ -875,204 +1128,38 @@ struct CellSolver {
           }
         }
         minr = g.mind(minr);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          int i = row(r);
-          if (i < n) {
-            double u = xs[i];
-            if (minr < 1.0) u = u * minr * 0.99;
-            cnew[r] = cval[r] - u;
-          }
-        }
       }
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        if (row(r) < n) {
+        int i = row(r);
+        if (i < n) {
+          double u = xs[i];
+          if (cfg.use_log) {
+            u = copysign(1.0, u) * fmin(fabs(u), cfg.max_dlnC);
+            cnew[r] = cval[r] * exp(-u);
+          } else {
+            if (minr < 1.0) u = u * minr * 0.99;
+            cnew[r] = cval[r] - u;
+          }
           double v = fabs((cnew[r] - cval[r]) / cval[r]);
-          if (!isnan(v)) {
+          if (!isnan(v)) {  // NaN-skipping maxval, like gfortran's MAXVAL
             maxrel = anyv ? fmax(maxrel, v) : v;
             anyv = true;
           }
         }
       }
-      // NaN-skipping maxval, like gfortran's MAXVAL
       double mr = g.maxd(anyv ? maxrel : -1.0);
-      bool conv = (mr >= 0.0) && (mr < cfg.tol_relchange);
-      if (conv) break;
+      conv = (mr >= 0.0) && (mr < cfg.tol_relchange);
+      if (!conv) {
 #pragma unroll
-      for (int r = 0; r < R; r++)
-        if (row(r) < n) cval[r] = cnew[r];
-      g.sync();
-    }
-    // one last update (reaction.F90:4052)
-    auxvar_compute(false, dt);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      totcur[r] = totnew[r];
-      sorbcur[r] = sorbnew[r];
-    }
-    its_out = its;
-    return 0;
-  }
-
-  // ---- RUpdateKineticState (reaction.F90:5935-5972) ------------------------
-  __device__ bool update_kinetic_state(double dt) {
-    bool updated = false;
-    if (cfg.nkin > 0) {
-      updated = true;
-      // ws.lnact is that of the converged iterate (last auxvar_compute)
-      kinetic_mineral(nullptr, false, true);
-      g.sync();
-      if (g.lane == 0) {
-        for (int m = 0; m < cfg.nkin; m++) {
-          double rate = st.mnrl_rate[m * st.ld + cell];
-          double vf = st.mnrl_volfrac[m * st.ld + cell] + rate * cfg.mn_vol[m] * dt;
-          if (vf < 0.0) vf = 0.0;
-          st.mnrl_volfrac[m * st.ld + cell] = vf;
-        }
-      }
-      g.sync();
-    }
-    for (int q = 0; q < cfg.nmr; q++) {
-      updated = true;
-      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
-      int64_t base = (int64_t)cfg.naq * (r0 + q);
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        int i = row(r);
-        if (i < cfg.naq) {
-          double seq = st.kinmr[(base + i) * st.ld + cell];
-          for (int k = r0; k < r1; k++) {
-            double kdt = cfg.mr_rate[k] * dt;
-            int64_t ix = (base + (int64_t)cfg.naq * (k - r0 + 1) + i) * st.ld + cell;
-            st.kinmr[ix] = (st.kinmr[ix] + kdt * cfg.mr_frac[k] * seq) / (1.0 + kdt);
-          }
-        }
+        for (int r = 0; r < R; r++)
+          if (row(r) < n) cval[r] = cnew[r];
+        return false;
       }
     }
-    if (cfg.cn_nrxn > 0) updated = true;  // any sandbox => true
-    return updated;
-  }
-
-  // ---- RStep (reaction.F90:3564-3738) on cell `c` ---------------------------
-  __device__ void run(int64_t c, double target, int &nss, int &nit, int &nku, int &ierr, bool &had_cut) {
-    cell = c;
-    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
-    const int64_t ld = st.ld;
-    cs.den_kg = st.den_kg[c];
-    cs.sat = st.sat[c];
-    cs.temp = st.temp[c];
-    cs.por = st.porosity[c];
-    cs.vol = st.volume[c];
-    cs.spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
-    cs.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
-    nss = nit = nku = ierr = 0;
-    had_cut = false;
-    bool small[R];
-    double small_val[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      int i = row(r);
-      small[r] = false;
-      small_val[r] = 0.0;
-      gam[r] = 1.0;
-      lngam[r] = 0.0;
-      sorbcur[r] = 0.0;
-      totcur[r] = 0.0;
-      guess[r] = 1.0;
-      cval[r] = 1.0;
-      if (i < naq) {
-        totcur[r] = st.total[i * ld + c];
-        guess[r] = st.pri_molal[i * ld + c];
-        gam[r] = st.pri_act_coef[i * ld + c];
-        lngam[r] = log(gam[r]);
-        if (cfg.neqsr > 0) sorbcur[r] = st.total_sorb_eq[i * ld + c];
-      } else if (i < n) {
-        totcur[r] = st.immobile[(i - naq) * ld + c];
-        guess[r] = totcur[r];
-      }
-    }
-    if (!cfg.use_full_geochemistry) {
-#pragma unroll
-      for (int r = 0; r < R; r++)
-        if (row(r) < naq) st.pri_molal[row(r) * ld + c] = totcur[r] / cs.den_kg * 1.e3;
-      return;
-    }
-    for (int k = g.lane; k < ncx; k += L) {
-      W(cfg.off_sec, k) = st.sec_molal[k * ld + c];
-      W(cfg.off_secg, k) = st.sec_act_coef[k * ld + c];
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      int i = row(r);
-      if (i < n && totcur[r] <= 1.e-40) {
-        small[r] = true;
-        small_val[r] = totcur[r];
-        totcur[r] = 1.e-40;
-        if (i >= naq) guess[r] = guess[r];  // guess was read before the clamp (pmc_subsurface_osrt.F90:356-362)
-      }
-      if (cfg.use_total_as_guess && i < naq) guess[r] = totcur[r];
-    }
-    g.sync();
-    double cumulative = 0.0, dt = target;
-    int ncuts = 0, nconst = 0;
-    bool aborted = false;
-    for (;;) {
-      if (cumulative >= target) break;
-      int its = 0;
-      int e = react(dt, its);
-      nit += its;
-      if (e != 0) {
-        ncuts++;
-        had_cut = true;
-        if (ncuts > cfg.max_cuts) {
-          ierr = 1;
-          aborted = true;
-          break;
-        }
-        dt = 0.5 * dt;
-        nconst = 0;
-      } else {
-        bool upd = update_kinetic_state(dt);
-        cumulative += dt;
-        nss++;
-        nconst++;
-        if (upd) nku++;
-#pragma unroll
-        for (int r = 0; r < R; r++) guess[r] = cval[r];
-        if (nconst >= 4) {
-          ncuts--;
-          dt = fmin(2.0 * dt, target - cumulative);
-        }
-      }
-    }
-    if (!aborted) {
-#pragma unroll
-      for (int r = 0; r < R; r++)
-        if (small[r]) totcur[r] = small_val[r];
-    }
-    // write back (the rt_auxvar of the cell)
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      int i = row(r);
-      if (i < naq) {
-        st.total[i * ld + c] = totcur[r];
-        st.pri_molal[i * ld + c] = cval[r];
-        st.pri_act_coef[i * ld + c] = gam[r];
-        if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = sorbcur[r];
-      } else if (i < n) {
-        st.immobile[(i - naq) * ld + c] = small[r] && !aborted ? small_val[r] : (aborted ? totcur[r] : cval[r]);
-      }
-    }
-    g.sync();
-    for (int k = g.lane; k < ncx; k += L) {
-      st.sec_molal[k * ld + c] = W(cfg.off_sec, k);
-      st.sec_act_coef[k * ld + c] = W(cfg.off_secg, k);
-    }
-    if (cfg.neqsr > 0 && st.eqsrfcplx_conc)
-      for (int k = g.lane; k < cfg.nsrfcplx; k += L) st.eqsrfcplx_conc[k * ld + c] = W(cfg.off_sc, k);
-    if (g.lane == 0 && st.ln_act_h2o) st.ln_act_h2o[c] = cs.ln_act_h2o;
-    g.sync();
+    // converged: the reference's "one last update" (reaction.F90:4052) would
+    // recompute RTotal at the same c -- identical values, already in hand.
+    return finish_substep();
   }
 };
 
@@ -1089,7 +1176,11 @@ __global__ void __launch_bounds__(128) pfrx_rstep_kernel(DevCfg cfg, DevState st
   g.mask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (lane32 - g.lane));
   const int grp_in_block = threadIdx.x / L;
   double *ws = smem + (size_t)grp_in_block * cfg.ws_stride;
+#pragma unroll 1
+  for (int i = g.lane; i < cfg.ws_stride; i += L) ws[i] = 0.0;
+  g.sync();
   CellSolver<N, L> sol(cfg, st, g, ws);
+  sol.target = tran_dt;
 
   unsigned long long l_active = 0, l_its = 0, l_cut = 0;
   long long l_first = -1;
@@ -1097,34 +1188,62 @@ __global__ void __launch_bounds__(128) pfrx_rstep_kernel(DevCfg cfg, DevState st
 
   const int64_t gwarp = (int64_t)blockIdx.x * warps_per_block + warp_in_block;
   const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
-  for (int64_t base = gwarp * CPW; base < ncell; base += nwarps * CPW) {
-    int64_t c = base + lane32 / L;
-    if (c >= ncell) continue;
-    if (st.imat && st.imat[c] <= 0) {
-      if (g.lane == 0) {
-        st.num_sub_steps[c] = 0;
-        st.num_iterations[c] = 0;
-        st.num_kinetic_state_updates[c] = 0;
-        st.ierror[c] = 0;
+  int64_t next = gwarp * CPW + lane32 / L;  // this group's next cell
+  const int64_t stride = nwarps * CPW;
+  int mode = MODE_LOAD;
+
+  for (;;) {
+    if (!__any_sync(0xffffffffu, mode != MODE_DONE)) break;
+    if (mode == MODE_LOAD) {
+      // skip inactive cells (pmc_subsurface_osrt.F90:351)
+      while (next < ncell && st.imat && st.imat[next] <= 0) {
+        if (g.lane == 0) {
+          st.num_sub_steps[next] = 0;
+          st.num_iterations[next] = 0;
+          st.num_kinetic_state_updates[next] = 0;
+          st.ierror[next] = 0;
+        }
+        next += stride;
       }
-      continue;
+      if (next >= ncell) {
+        mode = MODE_DONE;
+      } else {
+        sol.load_cell(next);
+        next += stride;
+        if (!cfg.use_full_geochemistry) {
+          // RStep early-out (reaction.F90:3604-3608)
+#pragma unroll
+          for (int r = 0; r < sol.R; r++)
+            if (sol.row(r) < cfg.naq)
+              st.pri_molal[sol.row(r) * st.ld + sol.cell] = sol.totcur[r] / sol.den_kg * 1.e3;
+          if (g.lane == 0) {
+            st.num_sub_steps[sol.cell] = 0;
+            st.num_iterations[sol.cell] = 0;
+            st.num_kinetic_state_updates[sol.cell] = 0;
+            st.ierror[sol.cell] = 0;
+            l_active++;
+          }
+        } else {
+          sol.react_begin();
+          mode = MODE_ITER;
+        }
+      }
     }
-    int nss, nit, nku, ierr;
-    bool cut;
-    sol.run(c, tran_dt, nss, nit, nku, ierr, cut);
-    if (g.lane == 0) {
-      st.num_sub_steps[c] = nss;
-      st.num_iterations[c] = nit;
-      st.num_kinetic_state_updates[c] = nku;
-      st.ierror[c] = ierr;
-      l_active++;
-      l_its += (unsigned long long)nit;
-      if (cut) l_cut++;
-      if (ierr != 0 && (l_first < 0 || c < l_first)) l_first = c;
-      l_maxits = max(l_maxits, nit);
-      l_maxkin = max(l_maxkin, nku);
-      l_maxerr = max(l_maxerr, ierr);
-      l_maxsub = max(l_maxsub, nss);
+    if (mode == MODE_ITER) {
+      if (sol.newton_pass()) {
+        sol.store_cell();
+        if (g.lane == 0) {
+          l_active++;
+          l_its += (unsigned long long)sol.nit;
+          if (sol.had_cut) l_cut++;
+          if (sol.ierr != 0 && (l_first < 0 || sol.cell < l_first)) l_first = sol.cell;
+          l_maxits = max(l_maxits, sol.nit);
+          l_maxkin = max(l_maxkin, sol.nku);
+          l_maxerr = max(l_maxerr, sol.ierr);
+          l_maxsub = max(l_maxsub, sol.nss);
+        }
+        mode = MODE_LOAD;
+      }
     }
   }
   // shard summary: warp reduce, then one set of atomics per warp
