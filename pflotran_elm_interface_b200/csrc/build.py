@@ -19,8 +19,8 @@ VARIANTS = {
     3: [1, 4],
     4: [1, 4],
     8: [4],
-    13: [8, 16],
-    15: [8, 16],
+    13: [4, 8, 16],
+    15: [4, 8, 16],
     16: [16],
     32: [32],
 }

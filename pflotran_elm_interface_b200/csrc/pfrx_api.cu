@@ -196,7 +196,7 @@ static int layout_and_launch_params(pfrx_handle *h) {
   d.off_lng = take(d.ncplx);
   d.js = N | 1;
   d.off_J = take(N * d.js);
-  d.off_acc = take(d.nacc);
+  d.off_acc = take(d.nacc + 1);  // must follow ws.J: task destinations are offsets from ws.J
   d.off_tmp = take(N + 2 * d.nsrfcplx + 2);
   d.off_sc = take(d.nsrfcplx + 1);
   d.off_cls = take(d.ncls + 1);
@@ -235,6 +235,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->abi_version != PFRX_ABI_VERSION) return set_err(PFRX_E_INVALID, "abi_version mismatch%s", "");
   int n = c->naqcomp + c->nimcomp;
   if (n < 1 || n > PFRX_MAX_NCOMP) return set_err(PFRX_E_LIMIT, "ncomp out of range%s", "");
+  if (c->neqcplx > 4095) return set_err(PFRX_E_LIMIT, "more than 4095 secondary complexes%s", "");
   if (c->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON &&
       c->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER)
     return set_err(PFRX_E_INVALID, "ACTIVITY_COEFFICIENTS NEWTON (iterated ionic strength) is not on the GPU path yet%s", "");
@@ -325,12 +326,16 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   A.add(pri_cls.data(), pri_cls.size(), &d.pri_cls);
   A.add(cls_negz2.data(), cls_negz2.size(), &d.cls_negz2);
   A.add(cls_a0.data(), cls_a0.size(), &d.cls_a0);
-  // ---- balanced task lists: totals_i = sum_k nu_ki sec_k (slot i) and
-  //      S_ij = sum_k nu_ki nu_kj sec_k, i <= j (slot naq + tri(i,j)) --------------
-  std::vector<int> tk_k, sg_dst, sg_cnt, ln_task0(L + 1, 0), ln_seg0(L + 1, 0), fx_ptr(1, 0), fx_dst, fx_src;
+  // ---- balanced task lists: totals_i = sum_k nu_ki sec_k and
+  //      S_ij = sum_k nu_ki nu_kj sec_k (i <= j, stored to both triangles).
+  //      Destinations are offsets from ws.J: J(i,j) = i*js+j, totals = N*js+i,
+  //      partial sums of entries cut by a lane boundary = N*js+naq+p. ------------
+  const int Npad = h->npad, js = Npad | 1;
+  std::vector<int2> tk_kd;
+  std::vector<int> fx_ptr(1, 0), fx_dst, fx_dst2, fx_src;
   std::vector<double> tk_w;
-  const int ntri = naq * (naq + 1) / 2;
-  int nacc = naq + ntri;
+  std::vector<unsigned> row_mask(naq, 0u);
+  int npartial = 0;
   if (c->neqcplx > 0) {
     int nnz = c->eqcplx_ptr[c->neqcplx];
     A.add(c->eqcplx_ptr, c->neqcplx + 1, &d.cx_ptr);
@@ -342,73 +347,72 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(cx_Z2.data(), cx_Z2.size(), &d.cx_Z2);
     A.add(cx_cls.data(), cx_cls.size(), &d.cx_cls);
     struct Task {
-      int dst, k;
+      int key, d1, d2, k;  // key orders entries; d1/d2 destinations (d2 = -1: none)
       double w;
     };
     std::vector<Task> tasks;
-    auto tri = [&](int i, int j) { return naq + i * naq - (i * (i - 1)) / 2 + (j - i); };
     for (int k = 0; k < c->neqcplx; k++) {
       for (int p = c->eqcplx_ptr[k]; p < c->eqcplx_ptr[k + 1]; p++) {
         int i = c->eqcplx_specid[p];
-        tasks.push_back({i, k, c->eqcplx_stoich[p]});
+        tasks.push_back({i, Npad * js + i, -1, k, c->eqcplx_stoich[p]});
         for (int p2 = c->eqcplx_ptr[k]; p2 < c->eqcplx_ptr[k + 1]; p2++) {
           int j = c->eqcplx_specid[p2];
-          if (j >= i) tasks.push_back({tri(i, j), k, c->eqcplx_stoich[p] * c->eqcplx_stoich[p2]});
+          if (j < i) continue;
+          row_mask[i] |= 1u << j;
+          row_mask[j] |= 1u << i;
+          tasks.push_back({naq + i * naq + j, i * js + j, (i == j) ? -1 : j * js + i, k,
+                           c->eqcplx_stoich[p] * c->eqcplx_stoich[p2]});
         }
       }
     }
-    std::stable_sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.dst < b.dst; });
+    std::stable_sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.key < b.key; });
     const int T = (int)tasks.size();
-    for (const auto &t : tasks) {
-      tk_k.push_back(t.k);
-      tk_w.push_back(t.w);
-    }
-    // cut into L contiguous ranges; an entry cut by a boundary is accumulated in
-    // partial slots and finished by a fix-up that adds them in range order
+    const int tpl = (T + L - 1) / L;
+    d.tk_per_lane = tpl;
+    tk_kd.assign((size_t)tpl * L, make_int2(0, 0));
+    tk_w.assign((size_t)tpl * L, 0.0);
+    int last_key = -1;
     for (int l = 0; l < L; l++) {
-      int t0 = (int)((int64_t)T * l / L), t1 = (int)((int64_t)T * (l + 1) / L);
-      ln_task0[l] = t0;
-      ln_seg0[l] = (int)sg_dst.size();
-      int t = t0;
-      while (t < t1) {
-        int e = tasks[t].dst, u = t;
-        while (u < t1 && tasks[u].dst == e) u++;
-        bool starts = (t == 0) || tasks[t - 1].dst != e;
-        bool ends = (u == T) || tasks[u].dst != e;
-        sg_dst.push_back((starts && ends) ? e : -(e + 1));  // negative: partial of entry e
-        sg_cnt.push_back(u - t);
-        t = u;
+      int t0 = std::min(T, l * tpl), t1 = std::min(T, (l + 1) * tpl);
+      for (int t = t0; t < t1; t++) {
+        int e = tasks[t].key;
+        bool seg_end = (t + 1 == t1) || tasks[t + 1].key != e;
+        int d1 = -1, d2 = -1;
+        if (seg_end) {
+          int u = t;  // first task of this segment within the lane
+          while (u > t0 && tasks[u - 1].key == e) u--;
+          bool starts = (u == 0) || tasks[u - 1].key != e;
+          bool ends = (t + 1 == T) || tasks[t + 1].key != e;
+          if (starts && ends) {
+            d1 = tasks[t].d1;
+            d2 = tasks[t].d2;
+          } else {
+            d1 = Npad * js + naq + npartial;  // partial slot
+            if (e != last_key) {
+              fx_dst.push_back(tasks[t].d1);
+              fx_dst2.push_back(tasks[t].d2);
+              fx_ptr.push_back(fx_ptr.back());
+              last_key = e;
+            }
+            fx_src.push_back(d1);
+            fx_ptr.back() = (int)fx_src.size();
+            npartial++;
+          }
+        }
+        size_t ix = (size_t)(t - t0) * L + l;
+        tk_kd[ix] = make_int2(tasks[t].k | ((d1 + 1) << 16), d2 + 1);
+        tk_w[ix] = tasks[t].w;
       }
-    }
-    ln_task0[L] = T;
-    ln_seg0[L] = (int)sg_dst.size();
-    // assign partial slots in segment order and build the fix-ups
-    std::vector<std::vector<int>> slots(naq + ntri);
-    for (size_t sgi = 0; sgi < sg_dst.size(); sgi++) {
-      if (sg_dst[sgi] < 0) {
-        int e = -sg_dst[sgi] - 1;
-        sg_dst[sgi] = nacc;
-        slots[e].push_back(nacc);
-        nacc++;
-      }
-    }
-    for (int e = 0; e < naq + ntri; e++) {
-      if (slots[e].empty()) continue;
-      fx_dst.push_back(e);
-      for (int sidx : slots[e]) fx_src.push_back(sidx);
-      fx_ptr.push_back((int)fx_src.size());
     }
   }
-  d.nacc = nacc;
+  d.nacc = naq + npartial;
   d.nfix = (int)fx_dst.size();
-  A.add(tk_k.data(), tk_k.size(), &d.tk_k);
+  A.add(tk_kd.data(), tk_kd.size(), &d.tk_kd);
   A.add(tk_w.data(), tk_w.size(), &d.tk_w);
-  A.add(ln_task0.data(), ln_task0.size(), &d.ln_task0);
-  A.add(ln_seg0.data(), ln_seg0.size(), &d.ln_seg0);
-  A.add(sg_dst.data(), sg_dst.size(), &d.sg_dst);
-  A.add(sg_cnt.data(), sg_cnt.size(), &d.sg_cnt);
+  A.add(row_mask.data(), row_mask.size(), &d.row_mask);
   A.add(fx_ptr.data(), fx_ptr.size(), &d.fx_ptr);
   A.add(fx_dst.data(), fx_dst.size(), &d.fx_dst);
+  A.add(fx_dst2.data(), fx_dst2.size(), &d.fx_dst2);
   A.add(fx_src.data(), fx_src.size(), &d.fx_src);
   if (c->nkinmnrl > 0) {
     int nk = c->nkinmnrl, nnz = c->kinmnrl_ptr[nk];
@@ -427,6 +431,19 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->kinmnrl_Temkin_const, c->kinmnrl_Temkin_const ? nk : 0, &d.mn_temkin);
     A.add(c->kinmnrl_min_scale_factor, c->kinmnrl_min_scale_factor ? nk : 0, &d.mn_scale);
     A.add(c->kinmnrl_affinity_power, c->kinmnrl_affinity_power ? nk : 0, &d.mn_power);
+    std::vector<int> me_ptr(nk + 1, 0), me_ij;
+    std::vector<double> me_coef;
+    for (int m = 0; m < nk; m++) {
+      for (int p = c->kinmnrl_ptr[m]; p < c->kinmnrl_ptr[m + 1]; p++)
+        for (int p2 = c->kinmnrl_ptr[m]; p2 < c->kinmnrl_ptr[m + 1]; p2++) {
+          me_ij.push_back(c->kinmnrl_specid[p] | (c->kinmnrl_specid[p2] << 8));
+          me_coef.push_back(c->kinmnrl_stoich[p] * c->kinmnrl_stoich[p2]);
+        }
+      me_ptr[m + 1] = (int)me_ij.size();
+    }
+    A.add(me_ptr.data(), me_ptr.size(), &d.me_ptr);
+    A.add(me_ij.data(), me_ij.size(), &d.me_ij);
+    A.add(me_coef.data(), me_coef.size(), &d.me_coef);
   }
   if (c->nsrfcplxrxn > 0) {
     int nr = c->nsrfcplxrxn, ns = c->nsrfcplx;
@@ -444,6 +461,14 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->srfcplx_logK, ns, &d.sc_logK);
     A.add(c->srfcplx_logKcoef, c->srfcplx_logKcoef ? 5 * ns : 0, &d.sc_logKcoef);
     A.add(c->eqsrfcplxrxn_to_srfcplxrxn, c->neqsrfcplxrxn, &d.eqsr);
+    std::vector<int> se_ptr(ns + 1, 0), se_pp;
+    for (int k = 0; k < ns; k++) {
+      for (int p = c->srfcplx_ptr[k]; p < c->srfcplx_ptr[k + 1]; p++)
+        for (int p2 = c->srfcplx_ptr[k]; p2 < c->srfcplx_ptr[k + 1]; p2++) se_pp.push_back(p | (p2 << 16));
+      se_ptr[k + 1] = (int)se_pp.size();
+    }
+    A.add(se_ptr.data(), se_ptr.size(), &d.se_ptr);
+    A.add(se_pp.data(), se_pp.size(), &d.se_pp);
     if (c->nkinmrsrfcplxrxn > 0) {
       int nm = c->nkinmrsrfcplxrxn;
       A.add(c->kinmrsrfcplxrxn_to_srfcplxrxn, nm, &d.mr_rxn);

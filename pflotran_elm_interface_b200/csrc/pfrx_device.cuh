@@ -55,20 +55,20 @@ struct DevCfg {
   int ncls;
   const double *cls_negz2, *cls_a0;
   // balanced task lists for totals / dtotal (see header comment)
-  const int *tk_k;       // complex of task t
-  const double *tk_w;    // weight of task t
-  const int *ln_task0;   // [L+1] first task of lane l
-  const int *ln_seg0;    // [L+1] first segment of lane l
-  const int *sg_dst;     // accumulator slot of a segment
-  const int *sg_cnt;     // tasks in a segment
+  int tk_per_lane;       // tasks per lane (padded to the same count)
+  const int2 *tk_kd;     // [tk_per_lane*L] lane-interleaved: x = complex | (dst1+1)<<16, y = dst2+1
+  const double *tk_w;    // weight of the task
+  const unsigned *row_mask;  // [naq] bit j set when dtotal(i,j) has at least one task
   int nfix;
-  const int *fx_ptr, *fx_dst, *fx_src;
+  const int *fx_ptr, *fx_dst, *fx_dst2, *fx_src;
   int nacc;              // accumulator slots: naq totals + naq(naq+1)/2 S + partials
   // kinetic minerals
   int nkin;
   const int *mn_ptr, *mn_id;
   const double *mn_st, *mn_h2o, *mn_logK, *mn_logKcoef, *mn_vol, *mn_rate, *mn_eact, *mn_thresh, *mn_limit;
   const int *mn_irrev;
+  const int *me_ptr, *me_ij;   // per mineral: all (i,j) species pairs, i | j<<8
+  const double *me_coef;       // nu_i * nu_j
   const double *mn_temkin, *mn_scale, *mn_power;
   // surface complexation
   int nsrfrxn, nsrfcplx;
@@ -76,6 +76,7 @@ struct DevCfg {
   const double *sr_dens;
   const int *sc_ptr, *sc_id;
   const double *sc_st, *sc_h2o, *sc_fs, *sc_logK, *sc_logKcoef;
+  const int *se_ptr, *se_pp;   // per surface complex: all (p,p2) entry pairs, p | p2<<16
   int neqsr;
   const int *eqsr;
   int nmr;
@@ -145,9 +146,9 @@ __device__ __forceinline__ double interp_logK(const double *c, double temp) {
   return c[0] * log(tk) + c[1] + c[2] * tk + c[3] / tk + c[4] / (tk * tk);
 }
 
-// pow() is ~250 instructions; only the Temkin / scale-factor / affinity-power
-// options of RKineticMineral use it, so keep one out-of-line copy.
-static __device__ __noinline__ double pfrx_pow(double x, double y) { return pow(x, y); }
+// only the Temkin / scale-factor / affinity-power options of RKineticMineral
+// use pow(); the code is cold for every deck that leaves them out.
+static __device__ __forceinline__ double pfrx_pow(double x, double y) { return pow(x, y); }
 
 enum { MODE_LOAD = 0, MODE_ITER = 1, MODE_DONE = 2 };
 
@@ -188,11 +189,6 @@ struct CellSolver {
   __device__ __forceinline__ int row(int r) const { return g.lane + r * L; }
   __device__ __forceinline__ double &W(int off, int i) { return ws[off + i]; }
   __device__ __forceinline__ double &Jm(int i, int j) { return ws[cfg.off_J + i * cfg.js + j]; }
-  __device__ __forceinline__ int symidx(int i, int j) const {
-    int a = min(i, j), b = max(i, j);
-    return cfg.naq + a * cfg.naq - (a * (a - 1)) / 2 + (b - a);
-  }
-
   // logK at the cell temperature (RUpdateTempDependentCoefs, reaction.F90:5976)
   __device__ __forceinline__ double cx_logK(int k) const {
     return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, temp);
@@ -331,7 +327,9 @@ struct CellSolver {
       }
     }
     if (g.lane == 0) W(cfg.off_fs, irxn) = fs;
-    // dSx_dmi (eq. 2.3-46): the lane owning species j publishes entry j
+    // dSx_dmi (eq. 2.3-46) and the sorbed totals.  Within one complex every
+    // species appears once, so lanes stride over its species without conflicts;
+    // complexes are processed one after the other.
     double denom = 0.0;
 #pragma unroll 1
     for (int q = r0; q < r1; q++) {
@@ -340,46 +338,43 @@ struct CellSolver {
     }
     denom = denom / fs + 1.0;
 #pragma unroll 1
-    for (int i = g.lane; i < naq; i += L) {
-      double s = 0.0;
-#pragma unroll 1
-      for (int q = r0; q < r1; q++) {
-        int k = cfg.sr_cx[q];
-#pragma unroll 1
-        for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++)
-          if (cfg.sc_id[p] == i) s += cfg.sc_st[p] * cfg.sc_fs[k] * sconc[q - r0];
-      }
-      W(cfg.off_tmp, i) = (-s / denom) * W(cfg.off_invc, i);
-    }
+    for (int i = g.lane; i < naq; i += L) W(cfg.off_tmp, i) = 0.0;
     g.sync();
+#pragma unroll 1
+    for (int q = r0; q < r1; q++) {
+      int k = cfg.sr_cx[q];
+      double Sk = sconc[q - r0], fk = cfg.sc_fs[k];
+#pragma unroll 1
+      for (int p = cfg.sc_ptr[k] + g.lane; p < cfg.sc_ptr[k + 1]; p += L) {
+        int i = cfg.sc_id[p];
+        double nu = cfg.sc_st[p];
+        W(cfg.off_tmp, i) += nu * fk * Sk;
+        W(cfg.off_ts, i) += nu * Sk;
+      }
+      g.sync();
+    }
+#pragma unroll 1
+    for (int i = g.lane; i < naq; i += L) W(cfg.off_tmp, i) = (-W(cfg.off_tmp, i) / denom) * W(cfg.off_invc, i);
     if (store_conc && g.lane == 0)
-#pragma unroll 1
       for (int q = r0; q < r1; q++) W(cfg.off_sc, cfg.sr_cx[q]) += sconc[q - r0];
-#pragma unroll 1
-    for (int i = g.lane; i < naq; i += L) {
+    g.sync();
+    if (add_J) {
 #pragma unroll 1
       for (int q = r0; q < r1; q++) {
         int k = cfg.sr_cx[q];
         double Sk = sconc[q - r0];
-        int p0 = cfg.sc_ptr[k], p1 = cfg.sc_ptr[k + 1];
+        double nuiSx = cfg.sc_fs[k] * Sk / fs;
 #pragma unroll 1
-        for (int p = p0; p < p1; p++) {
-          if (cfg.sc_id[p] != i) continue;
-          double nui = cfg.sc_st[p];
-          W(cfg.off_ts, i) += nui * Sk;
-          if (add_J) {
-            double nuiSx = cfg.sc_fs[k] * Sk / fs;
-#pragma unroll 1
-            for (int p2 = p0; p2 < p1; p2++) {
-              int j = cfg.sc_id[p2];
-              double t = cfg.sc_st[p2] * Sk * W(cfg.off_invc, j) + nuiSx * W(cfg.off_tmp, j);
-              Jm(i, j) += jscale * (nui * t);
-            }
-          }
+        for (int e = cfg.se_ptr[k] + g.lane; e < cfg.se_ptr[k + 1]; e += L) {
+          int pp = cfg.se_pp[e];
+          int p = pp & 0xffff, p2 = pp >> 16;
+          int i = cfg.sc_id[p], j = cfg.sc_id[p2];
+          double t = cfg.sc_st[p2] * Sk * W(cfg.off_invc, j) + nuiSx * W(cfg.off_tmp, j);
+          Jm(i, j) += jscale * (cfg.sc_st[p] * t);
         }
+        g.sync();
       }
     }
-    g.sync();
   }
 
   // ---- RTAuxVarCompute = RTotal (reaction.F90:4618-4759) + accumulation -----
@@ -397,7 +392,7 @@ struct CellSolver {
     }
     g.sync();
     // secondary species: lanes stride over complexes, one exp each
-#pragma unroll 1
+#pragma unroll 2
     for (int k = g.lane; k < ncx; k += L) {
       double lnQK = -cx_logK(k) * PFRX_LOG_TO_LN;
       double h = cfg.cx_h2o[k];
@@ -407,17 +402,26 @@ struct CellSolver {
       W(cfg.off_sec, k) = exp(lnQK - W(cfg.off_lng, k));
     }
     g.sync();
-    // balanced weighted sums of sec: totals and S_ij = sum_k nu_ki nu_kj sec_k
+    // balanced weighted sums of sec: totals (-> ws.acc) and
+    // S_ij = sum_k nu_ki nu_kj sec_k (-> both triangles of the shared Jacobian).
+    // Every lane runs the same number of tasks (padded), tables are
+    // lane-interleaved, a task with dst1 >= 0 closes its segment.  Offsets are
+    // relative to ws.J; ws.acc follows it.
+    double *jb = ws + cfg.off_J;
     {
-      int t = cfg.ln_task0[g.lane];
-      const int s1 = cfg.ln_seg0[g.lane + 1];
-#pragma unroll 1
-      for (int s = cfg.ln_seg0[g.lane]; s < s1; s++) {
-        const int cnt = cfg.sg_cnt[s];
-        double acc = 0.0;
-#pragma unroll 1
-        for (int e = 0; e < cnt; e++, t++) acc += cfg.tk_w[t] * W(cfg.off_sec, cfg.tk_k[t]);
-        W(cfg.off_acc, cfg.sg_dst[s]) = acc;
+      double acc = 0.0;
+      const int tpl = cfg.tk_per_lane;
+#pragma unroll 4
+      for (int t = 0; t < tpl; t++) {
+        const int ix = t * L + g.lane;
+        const int2 kd = cfg.tk_kd[ix];
+        acc = fma(cfg.tk_w[ix], W(cfg.off_sec, kd.x & 0xffff), acc);
+        const int d1 = (kd.x >> 16) - 1;
+        if (d1 >= 0) {
+          jb[d1] = acc;
+          if (kd.y > 0) jb[kd.y - 1] = acc;
+          acc = 0.0;
+        }
       }
     }
     g.sync();
@@ -425,34 +429,40 @@ struct CellSolver {
     for (int f = g.lane; f < cfg.nfix; f += L) {
       double acc = 0.0;
 #pragma unroll 1
-      for (int p = cfg.fx_ptr[f]; p < cfg.fx_ptr[f + 1]; p++) acc += W(cfg.off_acc, cfg.fx_src[p]);
-      W(cfg.off_acc, cfg.fx_dst[f]) = acc;
+      for (int p = cfg.fx_ptr[f]; p < cfg.fx_ptr[f + 1]; p++) acc += jb[cfg.fx_src[p]];
+      jb[cfg.fx_dst[f]] = acc;
+      if (cfg.fx_dst2[f] >= 0) jb[cfg.fx_dst2[f]] = acc;
     }
     g.sync();
     const double denL = den_kg * 1.e-3;
     const double psvd = por * sat * 1000.0 * vol / dt;
+    const double *tot_acc = jb + N * cfg.js;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int i = row(r);
       if (i < naq) {
-        totnew[r] = (cval[r] + W(cfg.off_acc, i)) * denL;
+        totnew[r] = (cval[r] + tot_acc[i]) * denL;
+        double *jr = jb + i * cfg.js;
         if (dry) {
 #pragma unroll 1
-          for (int j = 0; j < n; j++) Jm(i, j) = (i == j) ? 1.0 : 0.0;
+          for (int j = 0; j < n; j++) jr[j] = (i == j) ? 1.0 : 0.0;
         } else {
+          const unsigned mask = cfg.row_mask[i];
+          const double f = denL * psvd;
 #pragma unroll 1
           for (int j = 0; j < naq; j++) {
-            double d = W(cfg.off_acc, symidx(i, j)) * W(cfg.off_invc, j) + (i == j ? 1.0 : 0.0);
-            Jm(i, j) = (d * denL) * psvd;
+            double sij = ((mask >> j) & 1u) ? jr[j] : 0.0;
+            jr[j] = fma(sij, W(cfg.off_invc, j), (i == j ? 1.0 : 0.0)) * f;
           }
 #pragma unroll 1
-          for (int j = naq; j < n; j++) Jm(i, j) = 0.0;
+          for (int j = naq; j < n; j++) jr[j] = 0.0;
         }
       } else if (i < n) {
         totnew[r] = cval[r];
+        double *jr = jb + i * cfg.js;
 #pragma unroll 1
-        for (int j = 0; j < n; j++) Jm(i, j) = 0.0;
-        Jm(i, i) = dry ? 1.0 : vol / dt;
+        for (int j = 0; j < n; j++) jr[j] = 0.0;
+        jr[i] = dry ? 1.0 : vol / dt;
       }
       sorbnew[r] = 0.0;
     }
@@ -475,7 +485,6 @@ struct CellSolver {
   // lane m evaluates mineral m and publishes {rate, Im, dIm/dQK * extras, QK};
   // row owners then add their residual / Jacobian entries.
   __device__ __forceinline__ void kinetic_mineral(bool apply) {
-    const int naq = cfg.naq;
 #pragma unroll 1
     for (int m = g.lane; m < cfg.nkin; m += L) {
       const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
@@ -543,27 +552,23 @@ struct CellSolver {
     }
     g.sync();
     if (!apply) return;
+    // within one mineral every (i,j) pair is distinct: lanes stride over the
+    // pairs; minerals are applied one after the other (reference order)
 #pragma unroll 1
-    for (int i = g.lane; i < naq; i += L) {
+    for (int m = 0; m < cfg.nkin; m++) {
+      const double Im = W(cfg.off_mn, 3 * m + 1);
+      const double df = W(cfg.off_mn, 3 * m + 2);
+      if (Im == 0.0 && df == 0.0) continue;
 #pragma unroll 1
-      for (int m = 0; m < cfg.nkin; m++) {
-        double Im = W(cfg.off_mn, 3 * m + 1);
-        double df = W(cfg.off_mn, 3 * m + 2);
-        if (Im == 0.0 && df == 0.0) continue;
-        const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
+      for (int p = cfg.mn_ptr[m] + g.lane; p < cfg.mn_ptr[m + 1]; p += L)
+        W(cfg.off_res, cfg.mn_id[p]) += cfg.mn_st[p] * Im;
 #pragma unroll 1
-        for (int p = p0; p < p1; p++) {
-          if (cfg.mn_id[p] != i) continue;
-          double nui = cfg.mn_st[p];
-          W(cfg.off_res, i) += nui * Im;
-          double f = nui * df;
-#pragma unroll 1
-          for (int p2 = p0; p2 < p1; p2++) {
-            int j = cfg.mn_id[p2];
-            Jm(i, j) += f * (cfg.mn_st[p2] * W(cfg.off_invc, j));
-          }
-        }
+      for (int e = cfg.me_ptr[m] + g.lane; e < cfg.me_ptr[m + 1]; e += L) {
+        int ij = cfg.me_ij[e];
+        int i = ij & 0xff, j = ij >> 8;
+        Jm(i, j) += (cfg.me_coef[e] * df) * W(cfg.off_invc, j);
       }
+      g.sync();
     }
   }
 
@@ -707,7 +712,7 @@ struct CellSolver {
   // Returns false when a row is all zero (singular) -- the group agrees.
   __device__ __forceinline__ bool solve(double (&a)[R][N], double (&b)[R], double *xout /* ws, n entries */) {
     const int n = cfg.n;
-    double vv[R];
+    double vv[R], dinv[R];
     int pos[R], step[R];
     bool done[R];
     bool bad = false;
@@ -716,6 +721,7 @@ struct CellSolver {
       int i = row(r);
       pos[r] = i;
       step[r] = -1;
+      dinv[r] = 0.0;
       done[r] = !(i < n);
       double m = 0.0;
 #pragma unroll
@@ -775,7 +781,8 @@ struct CellSolver {
             }
 #pragma unroll
             for (int j = k + 1; j < N; j++) buf[j] = a[r][j];
-            buf[k] = 1.0 / p;
+            dinv[r] = 1.0 / p;
+            buf[k] = dinv[r];
             buf[N] = b[r];
             done[r] = true;
             step[r] = k;
@@ -803,7 +810,7 @@ struct CellSolver {
       if (s < n) {
 #pragma unroll
         for (int r = 0; r < R; r++)
-          if (step[r] == s) xout[s] = b[r] / a[r][s];
+          if (step[r] == s) xout[s] = b[r] * dinv[r];  // B(i)=sum/A(i,i), reciprocal kept from the elimination
         g.sync();
         double xs = xout[s];
 #pragma unroll
@@ -881,7 +888,7 @@ struct CellSolver {
 #pragma unroll 1
     for (int k = g.lane; k < ncx; k += L) {
       W(cfg.off_sec, k) = st.sec_molal[k * ld + c];
-      W(cfg.off_lng, k) = log(st.sec_act_coef[k * ld + c]);
+      if (cfg.act_freq != PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) W(cfg.off_lng, k) = log(st.sec_act_coef[k * ld + c]);
     }
 #pragma unroll 1
     for (int k = g.lane; k < cfg.nsrfrxn; k += L) W(cfg.off_fs, k) = st.free_site[k * ld + c];
@@ -1164,7 +1171,7 @@ struct CellSolver {
 };
 
 template <int N, int L>
-__global__ void __launch_bounds__(128) pfrx_rstep_kernel(DevCfg cfg, DevState st, int64_t ncell, double tran_dt,
+__global__ void __launch_bounds__(128, (L >= 16 ? 4 : (L >= 8 ? 3 : 2))) pfrx_rstep_kernel(DevCfg cfg, DevState st, int64_t ncell, double tran_dt,
                                                           DevSummary *summ) {
   extern __shared__ double smem[];
   constexpr int CPW = 32 / L;  // cells per warp pass
