@@ -66,11 +66,16 @@ static int load_nccl() {
   return PFRX_OK;
 }
 
+#define PFRX_MAX_CHUNKS 32
+
 // ---- handle -----------------------------------------------------------------
 struct pfrx_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t ev_in[PFRX_MAX_CHUNKS], ev_k[PFRX_MAX_CHUNKS];
+  bool ev_ready = false;
   DevCfg cfg;
   void *arena = nullptr;  // device copy of all tables
   int n = 0, npad = 0, lanes = 1;
@@ -129,8 +134,11 @@ static const KernelGetter g_getters[] = {{3, pfrx_kernel_3},   {4, pfrx_kernel_4
                                          {32, pfrx_kernel_32}};
 
 static int default_lanes(int npad) {
+  // measured on B200 (profiles/): thread-per-cell up to 4 unknowns, 8 lanes for
+  // the 13-dof CLM-CN network, 16 lanes for the 15-dof Hanford network
   if (npad <= 4) return 1;
   if (npad <= 8) return 4;
+  if (npad <= 13) return 8;
   if (npad <= 16) return 16;
   return 32;
 }
@@ -533,6 +541,12 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->out_stream) cudaStreamDestroy(h->out_stream);
+  if (h->ev_ready)
+    for (int i = 0; i < PFRX_MAX_CHUNKS; i++) {
+      cudaEventDestroy(h->ev_in[i]);
+      cudaEventDestroy(h->ev_k[i]);
+    }
   delete h;
 }
 
@@ -600,23 +614,36 @@ extern "C" int pfrx_bind_state(pfrx_handle *h, int64_t ncell, const pfrx_state *
   return PFRX_OK;
 }
 
-static int launch(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
+static int summary_reset(pfrx_handle *h, cudaStream_t s) {
   DevSummary z;
   memset(&z, 0, sizeof(z));
   z.first_failed = LLONG_MAX;
   *h->h_summ = z;
   CUDA_OK(cudaMemcpyAsync(h->d_summ, h->h_summ, sizeof(DevSummary), cudaMemcpyHostToDevice, s));
-  if (ncell > 0) {
-    int cpw = 32 / h->lanes;
-    int wpb = h->threads / 32;
-    int64_t need = (ncell + (int64_t)cpw * wpb - 1) / ((int64_t)cpw * wpb);
-    int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
-    int grid = (int)std::min<int64_t>(need, cap);
-    if (grid < 1) grid = 1;
-    h->kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, st, ncell, tran_dt, h->d_summ);
-    CUDA_OK(cudaGetLastError());
-    h->launches++;
-  }
+  return PFRX_OK;
+}
+
+// one kernel launch over cells [0, ncell) of `st`; `cell0` is added to the
+// first-failed-cell index so that chunked launches report shard-local indices
+static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
+  if (ncell <= 0) return PFRX_OK;
+  int cpw = 32 / h->lanes;
+  int wpb = h->threads / 32;
+  int64_t need = (ncell + (int64_t)cpw * wpb - 1) / ((int64_t)cpw * wpb);
+  int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
+  int grid = (int)std::min<int64_t>(need, cap);
+  if (grid < 1) grid = 1;
+  h->kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, st, ncell, tran_dt, h->d_summ);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return PFRX_OK;
+}
+
+static int launch(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
+  int rc = summary_reset(h, s);
+  if (rc) return rc;
+  rc = launch_kernel(h, st, ncell, tran_dt, s);
+  if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(h->h_summ, h->d_summ, sizeof(DevSummary), cudaMemcpyDeviceToHost, s));
   h->pending = true;
   return PFRX_OK;
@@ -711,35 +738,39 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
                          (double *)d.soil_particle_density};
-  cudaStream_t s = h->stream;
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
   if (!have_lnw) d.ln_act_h2o = nullptr;
   bool have_sc = host->eqsrfcplx_conc != nullptr;
   if (!have_sc) d.eqsrfcplx_conc = nullptr;
-  for (int f = 0; f < kNumD; f++) {
-    if (!rows[f] || !src[f]) continue;
-    if (f == 11) continue;  // eqsrfcplx_conc is output only
-    if (host->ld == ncell) {
-      CUDA_OK(cudaMemcpyAsync(dptr[f], src[f], (size_t)rows[f] * ncell * sizeof(double), cudaMemcpyHostToDevice, s));
-    } else {
-      CUDA_OK(cudaMemcpy2DAsync(dptr[f], ncell * sizeof(double), src[f], host->ld * sizeof(double),
-                                ncell * sizeof(double), rows[f], cudaMemcpyHostToDevice, s));
+  if (!host->imat) d.imat = nullptr;
+  {
+    DevState chk;
+    pfrx_state probe = *host;
+    int rc0 = to_dev_state(h, &probe, &chk);
+    if (rc0) return rc0;
+  }
+  // Pipeline: the shard is cut into chunks; chunk i+1 uploads (copy-in stream)
+  // while chunk i computes (kernel stream) and chunk i-1 downloads (copy-out
+  // stream).  PCIe is full duplex, so the step costs about
+  // max(H2D, kernel, D2H) instead of their sum.
+  if (!h->ev_ready) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < PFRX_MAX_CHUNKS; i++) {
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
     }
+    h->ev_ready = true;
   }
-  if (host->imat) {
-    CUDA_OK(cudaMemcpyAsync((void *)d.imat, host->imat, ncell * sizeof(int), cudaMemcpyHostToDevice, s));
-  } else {
-    d.imat = nullptr;
-  }
-  DevState chk;
-  pfrx_state probe = *host;
-  int rc = to_dev_state(h, &probe, &chk);
+  int nchunk = 1;
+  if (const char *ev = getenv("PFRX_CHUNKS")) nchunk = atoi(ev);
+  else nchunk = (int)std::min<int64_t>(PFRX_MAX_CHUNKS, std::max<int64_t>(1, ncell / 131072));
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > PFRX_MAX_CHUNKS) nchunk = PFRX_MAX_CHUNKS;
+  cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
+  int rc = summary_reset(h, s_k);
   if (rc) return rc;
-  rc = launch(h, d, ncell, tran_dt, s);
-  if (rc) return rc;
-  // D2H of every io field and the per-cell results
   const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13};
   double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
                          host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
@@ -747,23 +778,77 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb, nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr};
-  for (int f : io) {
-    if (!rows[f] || !hdst[f]) continue;
-    if (host->ld == ncell) {
-      CUDA_OK(cudaMemcpyAsync(hdst[f], dptr[f], (size_t)rows[f] * ncell * sizeof(double), cudaMemcpyDeviceToHost, s));
-    } else {
-      CUDA_OK(cudaMemcpy2DAsync(hdst[f], host->ld * sizeof(double), dptr[f], ncell * sizeof(double),
-                                ncell * sizeof(double), rows[f], cudaMemcpyDeviceToHost, s));
+  const size_t w8 = sizeof(double);
+  for (int ch = 0; ch < nchunk; ch++) {
+    int64_t c0 = ncell * ch / nchunk, c1 = ncell * (ch + 1) / nchunk, nc = c1 - c0;
+    if (nc <= 0) continue;
+    for (int f = 0; f < kNumD; f++) {
+      if (!rows[f] || !src[f] || f == 11) continue;  // eqsrfcplx_conc is output only
+      CUDA_OK(cudaMemcpy2DAsync(dptr[f] + c0, ncell * w8, src[f] + c0, host->ld * w8, nc * w8, rows[f],
+                                cudaMemcpyHostToDevice, s_in));
     }
+    if (host->imat)
+      CUDA_OK(cudaMemcpyAsync((void *)(d.imat + c0), host->imat + c0, nc * sizeof(int), cudaMemcpyHostToDevice, s_in));
+    CUDA_OK(cudaEventRecord(h->ev_in[ch], s_in));
+    CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_in[ch], 0));
+    DevState dc = d;
+#define PFRX_OFF(field) \
+  if (dc.field) dc.field = dc.field + c0
+    PFRX_OFF(total);
+    PFRX_OFF(pri_molal);
+    PFRX_OFF(immobile);
+    PFRX_OFF(pri_act_coef);
+    PFRX_OFF(sec_act_coef);
+    PFRX_OFF(sec_molal);
+    PFRX_OFF(ln_act_h2o);
+    PFRX_OFF(mnrl_volfrac);
+    PFRX_OFF(mnrl_area);
+    PFRX_OFF(mnrl_rate);
+    PFRX_OFF(free_site);
+    PFRX_OFF(eqsrfcplx_conc);
+    PFRX_OFF(total_sorb_eq);
+    PFRX_OFF(kinmr);
+    PFRX_OFF(den_kg);
+    PFRX_OFF(sat);
+    PFRX_OFF(temp);
+    PFRX_OFF(porosity);
+    PFRX_OFF(volume);
+    PFRX_OFF(soil_particle_density);
+    PFRX_OFF(imat);
+    PFRX_OFF(num_sub_steps);
+    PFRX_OFF(num_iterations);
+    PFRX_OFF(num_kinetic_state_updates);
+    PFRX_OFF(ierror);
+#undef PFRX_OFF
+    rc = launch_kernel(h, dc, nc, tran_dt, s_k);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(h->ev_k[ch], s_k));
+    CUDA_OK(cudaStreamWaitEvent(s_out, h->ev_k[ch], 0));
+    for (int f : io) {
+      if (!rows[f] || !hdst[f]) continue;
+      CUDA_OK(cudaMemcpy2DAsync(hdst[f] + c0, host->ld * w8, dptr[f] + c0, ncell * w8, nc * w8, rows[f],
+                                cudaMemcpyDeviceToHost, s_out));
+    }
+    CUDA_OK(cudaMemcpyAsync(host->num_sub_steps + c0, d.num_sub_steps + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    CUDA_OK(cudaMemcpyAsync(host->num_iterations + c0, d.num_iterations + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    CUDA_OK(cudaMemcpyAsync(host->num_kinetic_state_updates + c0, d.num_kinetic_state_updates + c0, nc * sizeof(int),
+                            cudaMemcpyDeviceToHost, s_out));
+    CUDA_OK(cudaMemcpyAsync(host->ierror + c0, d.ierror + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, s_out));
   }
-  CUDA_OK(cudaMemcpyAsync(host->num_sub_steps, d.num_sub_steps, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host->num_iterations, d.num_iterations, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host->num_kinetic_state_updates, d.num_kinetic_state_updates, ncell * sizeof(int),
-                          cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host->ierror, d.ierror, ncell * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  CUDA_OK(cudaMemcpyAsync(h->h_summ, h->d_summ, sizeof(DevSummary), cudaMemcpyDeviceToHost, s_k));
+  CUDA_OK(cudaStreamSynchronize(s_k));
+  CUDA_OK(cudaStreamSynchronize(s_out));
   h->pending = false;
   summary_out(h, out);
+  // first_failed_cell of chunked launches is chunk-local; recover the shard index
+  if (out->first_failed_cell >= 0 && nchunk > 1) {
+    out->first_failed_cell = -1;
+    for (int64_t c = 0; c < ncell; c++)
+      if (host->ierror[c] != 0) {
+        out->first_failed_cell = c;
+        break;
+      }
+  }
   return PFRX_OK;
 }
 

@@ -241,6 +241,31 @@ def fp64_peak_tflops(device: int = 0):
     return tf.value, mhz.value
 
 
+def reduce_results(res: abi.PfrxStepResult, group=None) -> abi.PfrxStepResult:
+    """The collective that replaces MPI_Allreduce(rstep_error, MAX) + MPI_Barrier
+    (pmc_subsurface_osrt.F90:381-383), through torch.distributed: SUM of the
+    cell / iteration / cut-cell counts, MAX of the error flag and of the per-cell
+    maxima.  Works on any backend (gloo on CPU hosts, nccl on GPUs); the C-ABI
+    twin is pfrx_allreduce()."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return res
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    s = torch.tensor([res.ncell_active, res.sum_newton_iterations, res.num_cut_cells], dtype=torch.int64, device=dev)
+    m = torch.tensor([res.max_newton_iterations, res.max_num_kinetic_state_updates, res.rstep_error,
+                      res.max_sub_steps], dtype=torch.int64, device=dev)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    out = abi.PfrxStepResult()
+    out.ncell_active, out.sum_newton_iterations, out.num_cut_cells = (int(v) for v in s.tolist())
+    (out.max_newton_iterations, out.max_num_kinetic_state_updates, out.rstep_error,
+     out.max_sub_steps) = (int(v) for v in m.tolist())
+    out.first_failed_cell = res.first_failed_cell  # shard-local by definition
+    return out
+
+
 def shard_range(ncell: int, rank: int, world: int):
     """contiguous ownership ranges, like PETSc DMDA local cells
     (pmc_subsurface_osrt.F90:349-350)"""
