@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, f"kern_{n}.o")
         objs.append(o)
         src = os.path.join(HERE, "pfrx_kern.cu")
-        if force or _newer(hdrs + [src], o):
+        if force or _newer(hdrs + [src, os.path.join(HERE, "pfrx_tpc.cuh")], o):
             defs = [f"-DPFRX_N={n}"] + [f"-DPFRX_L{i}={l}" for i, l in enumerate(lanes)]
             jobs.append((FLAGS_CMD(defs, src, o), os.path.join(OBJ, f"kern_{n}.log")))
     o = os.path.join(OBJ, "api.o")

@@ -79,6 +79,7 @@ struct pfrx_handle {
   DevCfg cfg;
   void *arena = nullptr;  // device copy of all tables
   int n = 0, npad = 0, lanes = 1;
+  bool tpc = false;  // thread-per-cell kernel (pfrx_tpc.cuh)
   size_t smem_bytes = 0;
   int threads = 128;
   int blocks_per_sm = 1, sm_count = 1;
@@ -133,6 +134,12 @@ static const KernelGetter g_getters[] = {{3, pfrx_kernel_3},   {4, pfrx_kernel_4
                                          {13, pfrx_kernel_13}, {15, pfrx_kernel_15}, {16, pfrx_kernel_16},
                                          {32, pfrx_kernel_32}};
 
+static bool default_tpc(int npad) {
+  // measured on B200: the thread-per-cell kernel wins for small networks (C2: 2.6x);
+  // at 13-15 unknowns its Jacobians leave room for only two warps per SM
+  return npad <= 4;
+}
+
 static int default_lanes(int npad) {
   // measured on B200 (profiles/): thread-per-cell up to 4 unknowns, 8 lanes for
   // the 13-dof CLM-CN network, 16 lanes for the 15-dof Hanford network
@@ -149,6 +156,20 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
     if (k.n >= h->n && (!gt || k.n < gt->n)) gt = &k;
   if (!gt) return set_err(PFRX_E_LIMIT, "ncomp exceeds PFRX_MAX_NCOMP%s", "");
   int lanes = want_lanes > 0 ? want_lanes : default_lanes(gt->n);
+  if (want_lanes == 0) {
+    if (const char *ev = getenv("PFRX_TPC")) {
+      if (atoi(ev) != 0) lanes = 0;
+    } else if (default_tpc(gt->n)) {
+      lanes = 0;
+    }
+  }
+  if (lanes == 0) {
+    h->npad = gt->n;
+    h->lanes = 1;
+    h->tpc = true;
+    h->kernel = gt->get(0);
+    return PFRX_OK;
+  }
   pfrx_kernel_fn fn = gt->get(lanes);
   if (!fn) {
     // nearest instantiated lane count
@@ -195,6 +216,48 @@ static int layout_and_launch_params(pfrx_handle *h) {
     off += cnt;
     return o;
   };
+  if (h->tpc) {
+    // thread-per-cell: one workspace per THREAD, exact-size Jacobian
+    const bool act_upd = d.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+    d.off_c = take(N);
+    d.off_lnact = take(N);
+    d.off_invc = take(N);
+    d.off_res = take(N);
+    d.off_acc = take(N);
+    d.off_tmp = take(N + 2 * d.nsrfcplx + 2);
+    d.off_ts = take(N);
+    d.js = d.n;
+    d.off_J = take(d.n * d.n);
+    d.off_cls = take(d.ncls + 1);
+    d.off_x = take((N + 1) / 2 + 1);
+    d.off_xs = take(N);
+    d.off_sc = take(d.nsrfcplx + 1);
+    d.off_mn = take(d.nkin + 1);
+    d.off_fs = take(d.nsrfrxn + 1);
+    d.off_mr = take(2 * d.nmr * N + 1);
+    d.off_lng = act_upd ? 0 : take(d.ncplx);
+    d.off_sec = 0;
+    d.ws_stride = off | 1;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    size_t per_thread = (size_t)d.ws_stride * sizeof(double);
+    // the largest block (<= 128 threads) whose workspaces fit, preferring a
+    // size that lets several blocks share an SM
+    int t = h->threads;
+    while (t > 32 && per_thread * t > (size_t)prop.sharedMemPerBlockOptin) t /= 2;
+    if (per_thread * t > (size_t)prop.sharedMemPerBlockOptin)
+      return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
+    h->threads = t;
+    h->smem_bytes = per_thread * t;
+    CUDA_OK(cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_bytes));
+    int nb = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)h->kernel, h->threads, h->smem_bytes));
+    if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+    h->blocks_per_sm = nb;
+    return PFRX_OK;
+  }
   d.off_c = take(N);
   d.off_lnact = take(N);
   d.off_invc = take(N);
@@ -301,7 +364,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   {
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
-    int rc0 = pick_kernel(h, want);
+    int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
     if (rc0) {
       delete h;
       return rc0;
@@ -630,6 +693,7 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
   int cpw = 32 / h->lanes;
   int wpb = h->threads / 32;
   int64_t need = (ncell + (int64_t)cpw * wpb - 1) / ((int64_t)cpw * wpb);
+  if (h->tpc) need = (ncell + h->threads - 1) / h->threads;
   int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
   int grid = (int)std::min<int64_t>(need, cap);
   if (grid < 1) grid = 1;
@@ -930,7 +994,7 @@ extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
 extern "C" int pfrx_kernel_info(pfrx_handle *h, int *info5) {
   if (!h || !info5) return PFRX_E_INVALID;
   info5[0] = h->npad;
-  info5[1] = h->lanes;
+  info5[1] = h->tpc ? 0 : h->lanes;
   info5[2] = h->threads;
   info5[3] = h->blocks_per_sm;
   info5[4] = (int)h->smem_bytes;

@@ -1,7 +1,7 @@
 // pfrx_kern.cu -- one translation unit per padded system size N.
 // Compiled as  nvcc -DPFRX_N=<N> -DPFRX_L0=<L> [-DPFRX_L1=<L> [-DPFRX_L2=<L>]]
 // by build.py; exports  pfrx_kernel_<N>(lanes)  to pfrx_api.cu.
-#include "pfrx_device.cuh"
+#include "pfrx_tpc.cuh"
 
 #ifndef PFRX_N
 #error "compile with -DPFRX_N=<N>"
@@ -13,6 +13,7 @@
 typedef void (*pfrx_kernel_fn)(DevCfg, DevState, int64_t, double, DevSummary *);
 
 extern "C" pfrx_kernel_fn PFRX_CAT(pfrx_kernel_, PFRX_N)(int lanes) {
+  if (lanes == 0) return pfrx_rstep_tpc_kernel<PFRX_N>;  // thread-per-cell variant
 #ifdef PFRX_L0
   if (lanes == PFRX_L0) return pfrx_rstep_kernel<PFRX_N, PFRX_L0>;
 #endif

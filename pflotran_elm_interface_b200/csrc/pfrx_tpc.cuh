@@ -1,0 +1,940 @@
+// pfrx_tpc.cuh -- THREAD-PER-CELL kernel of the operator-split chemistry step.
+//
+// The cell-group kernel (pfrx_device.cuh) spends ~4 300 warp-instructions per
+// cell-iteration on the 15/88 Hanford network: every table-driven FMA drags
+// ~10 integer/address/sync instructions along and a warp serves only two
+// cells.  Here one THREAD owns one cell, a warp serves 32 cells per
+// instruction, and nothing has to be communicated between lanes:
+//  * all per-cell arrays whose index comes from a stoichiometry table (c,
+//    ln a, 1/c, totals, residual, the n x n Jacobian) live in a per-thread
+//    slice of shared memory (odd stride => conflict free); arrays that are only
+//    walked with compile-time indices (fixed accumulation, ln gamma, the
+//    small-value bookkeeping of RStep) stay in registers;
+//  * the Jacobian is assembled the way RTotalAqueous does it -- complex by
+//    complex, nu_i * (nu_j m_k / c_j) scattered into d(total)/d(free) -- so the
+//    operation order is the reference's; secondary molalities are not kept
+//    on chip: they stream to HBM as they are computed and only their ionic
+//    strength / molality sums are carried to the next activity update;
+//  * LU (Crout order, implicit-scaled partial pivoting, utility.F90:597-735)
+//    runs in shared memory on logical row offsets (no physical row swaps);
+//  * a warp loads 32 consecutive cells (coalesced SoA), every lane runs RStep on
+//    its own cell -- SIMT keeps lanes that need more Newton iterations or
+//    sub-steps in the same loop -- and the warp stores and moves on.
+// Occupancy is deliberately low (the Jacobians of 64-96 cells fill the shared
+// memory of an SM); throughput comes from instruction efficiency and ILP.
+#pragma once
+#include "pfrx_device.cuh"
+
+template <int N>
+struct CellT {
+  const DevCfg &cfg;
+  const DevState &st;
+  double *ws;
+  int64_t cell;
+  // per-cell scalars
+  double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
+  double Isum, msum;  // sum z^2 m and sum m over the secondary species of the latest RTotal
+  bool dry;
+  // register-resident per-component arrays (compile-time indices only)
+  double fixed[N], lngam[N], small_val[N], guess[N];
+  unsigned small_mask;
+
+  __device__ CellT(const DevCfg &c, const DevState &s, double *w) : cfg(c), st(s), ws(w) {}
+
+  __device__ __forceinline__ double &C(int i) { return ws[cfg.off_c + i]; }
+  __device__ __forceinline__ double &LNA(int i) { return ws[cfg.off_lnact + i]; }
+  __device__ __forceinline__ double &INVC(int i) { return ws[cfg.off_invc + i]; }
+  __device__ __forceinline__ double &RES(int i) { return ws[cfg.off_res + i]; }
+  __device__ __forceinline__ double &TOT(int i) { return ws[cfg.off_acc + i]; }
+  __device__ __forceinline__ double &TMP(int i) { return ws[cfg.off_tmp + i]; }
+  __device__ __forceinline__ double &TS(int i) { return ws[cfg.off_ts + i]; }
+  __device__ __forceinline__ double &J(int i, int j) { return ws[cfg.off_J + i * cfg.js + j]; }
+
+  __device__ __forceinline__ double cx_logK(int k) const {
+    return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, temp);
+  }
+  __device__ __forceinline__ double mn_logK(int m) const {
+    return (cfg.use_isothermal || !cfg.mn_logKcoef) ? cfg.mn_logK[m] : interp_logK(cfg.mn_logKcoef + 5 * m, temp);
+  }
+  __device__ __forceinline__ double sc_logK(int k) const {
+    return (cfg.use_isothermal || !cfg.sc_logKcoef) ? cfg.sc_logK[k] : interp_logK(cfg.sc_logKcoef + 5 * k, temp);
+  }
+
+  // ---- RActivityCoefficients, LAG branch (reaction.F90:4553-4612) -----------
+  // ionic strength from the current c and the secondary sums of the last RTotal
+  __device__ __forceinline__ void activity() {
+    const int naq = cfg.naq;
+    double part = 0.0, mp = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) {
+      double c = C(i);
+      part += c * cfg.pri_Z2[i];
+      if (i != cfg.h2o_aq_id) mp += c;
+    }
+    double I = 0.5 * (part + Isum);
+    double sq = sqrt(I);
+#pragma unroll 1
+    for (int q = 0; q < cfg.ncls; q++)
+      ws[cfg.off_cls + q] = (cfg.cls_negz2[q] * sq * cfg.debyeA / (1.0 + cfg.cls_a0[q] * cfg.debyeB * sq) +
+                             cfg.debyeBdot * I) * PFRX_LOG_TO_LN;
+    if (cfg.use_act_h2o) {
+      double t = 1.0 - 0.017 * (mp + msum);
+      ln_act_h2o = t > 0.0 ? log(t) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) {
+        int q = cfg.pri_cls[i];
+        lngam[i] = q < 0 ? 0.0 : ws[cfg.off_cls + q];
+      }
+  }
+
+  // ---- RTotalSorbEqSurfCplx1 (reaction_surf_complex.F90:641-900) -------------
+  // adds nu*S to ws.ts and (add_J) jscale * dtotal_sorb to the Jacobian
+  __device__ __forceinline__ void surf_cplx1(int irxn, double *tsacc, bool add_J, double jscale, bool store_conc) {
+    const int naq = cfg.naq;
+    const int r0 = cfg.sr_ptr[irxn], r1 = cfg.sr_ptr[irxn + 1];
+    double fs = fmax(ws[cfg.off_fs + irxn], 1.e-40);
+    double dens;
+    int ty = cfg.sr_type[irxn];
+    if (ty == PFRX_MINERAL_SURFACE)
+      dens = cfg.sr_dens[irxn] * st.mnrl_volfrac[cfg.sr_surf[irxn] * st.ld + cell];
+    else if (ty == PFRX_ROCK_SURFACE)
+      dens = cfg.sr_dens[irxn] * spd * (1.0 - por);
+    else
+      dens = cfg.sr_dens[irxn];
+    if (dens < 1.e-40) {
+      ws[cfg.off_fs + irxn] = 0.0;
+      if (store_conc)
+        for (int q = r0; q < r1; q++) ws[cfg.off_sc + cfg.sr_cx[q]] = 0.0;
+      return;
+    }
+    double *base = ws + cfg.off_tmp + N;  // lnQK without the free-site term, then S_q
+#pragma unroll 1
+    for (int q = r0; q < r1; q++) {
+      int k = cfg.sr_cx[q];
+      double lnQK = -sc_logK(k) * PFRX_LOG_TO_LN;
+      if (cfg.sc_h2o[k] != 0.0) lnQK += cfg.sc_h2o[k] * ln_act_h2o;
+#pragma unroll 1
+      for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++) lnQK += cfg.sc_st[p] * LNA(cfg.sc_id[p]);
+      base[q - r0] = lnQK;
+    }
+    if (!cfg.sr_flag[irxn]) {
+      // unit free-site stoichiometry: Sx = rho / (1 + sum_q exp(lnQK_q)), S_q = exp(lnQK_q) Sx
+      double e = 0.0;
+#pragma unroll 1
+      for (int q = r0; q < r1; q++) {
+        double v = exp(base[q - r0]);
+        base[q - r0] = v;
+        e += v;
+      }
+      fs = dens / (1.0 + e);
+#pragma unroll 1
+      for (int q = r0; q < r1; q++) base[q - r0] *= fs;
+    } else {
+      double *sconc = base + (r1 - r0);
+      bool one_more = false;
+      int it = 0;
+      double damping = 1.0;
+      for (;;) {
+        it++;
+        double total = fs, lnfs = log(fs);
+#pragma unroll 1
+        for (int q = r0; q < r1; q++) {
+          int k = cfg.sr_cx[q];
+          double sck = exp(base[q - r0] + cfg.sc_fs[k] * lnfs);
+          sconc[q - r0] = sck;
+          total += cfg.sc_fs[k] * sck;
+        }
+        if (one_more) break;
+        double res = dens - total, d = 1.0;
+#pragma unroll 1
+        for (int q = r0; q < r1; q++) d += cfg.sc_fs[cfg.sr_cx[q]] * sconc[q - r0] / fs;
+        double dfs = res / d;
+        if (it > 1000) damping = 0.5;
+        fs = fs + damping * dfs;
+        if (fabs(dfs / fs) < 1.e-12 || it > 100000) one_more = true;
+      }
+#pragma unroll 1
+      for (int q = r0; q < r1; q++) base[q - r0] = sconc[q - r0];
+    }
+    ws[cfg.off_fs + irxn] = fs;
+    double denom = 0.0;
+#pragma unroll 1
+    for (int q = r0; q < r1; q++) {
+      int k = cfg.sr_cx[q];
+      denom += cfg.sc_fs[k] * cfg.sc_fs[k] * base[q - r0];
+    }
+    denom = denom / fs + 1.0;
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) TMP(i) = 0.0;
+#pragma unroll 1
+    for (int q = r0; q < r1; q++) {
+      int k = cfg.sr_cx[q];
+      double Sk = base[q - r0], fk = cfg.sc_fs[k];
+      if (store_conc) ws[cfg.off_sc + k] += Sk;
+#pragma unroll 1
+      for (int p = cfg.sc_ptr[k]; p < cfg.sc_ptr[k + 1]; p++) {
+        int i = cfg.sc_id[p];
+        double nu = cfg.sc_st[p];
+        TMP(i) += nu * fk * Sk;
+        tsacc[i] += nu * Sk;
+      }
+    }
+    if (!add_J) return;
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) TMP(i) = (-TMP(i) / denom) * INVC(i);
+#pragma unroll 1
+    for (int q = r0; q < r1; q++) {
+      int k = cfg.sr_cx[q];
+      double Sk = base[q - r0];
+      double nuiSx = cfg.sc_fs[k] * Sk / fs;
+      const int p0 = cfg.sc_ptr[k], p1 = cfg.sc_ptr[k + 1];
+#pragma unroll 1
+      for (int p2 = p0; p2 < p1; p2++) {
+        int j = cfg.sc_id[p2];
+        double t = jscale * (cfg.sc_st[p2] * Sk * INVC(j) + nuiSx * TMP(j));
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) J(cfg.sc_id[p], j) += cfg.sc_st[p] * t;
+      }
+    }
+  }
+
+  // ---- RTAuxVarCompute = RTotal (reaction.F90:4618-4759) + accumulation terms --
+  // want_J: also d(accumulation)/dc/dt into the Jacobian (reaction.F90:5775-5848)
+  __device__ __forceinline__ void auxvar_compute(bool want_J, double dt) {
+    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
+    const double denL = den_kg * 1.e-3;
+    const double f = denL * (por * sat * 1000.0 * vol / dt);  // dtotal -> Jacobian
+    const bool act_upd = cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) {
+        double c = C(i);
+        LNA(i) = log(c) + lngam[i];
+        INVC(i) = 1.0 / c;
+        TOT(i) = c;
+      }
+    if (want_J) {
+#pragma unroll 1
+      for (int e = 0; e < n * cfg.js; e++) ws[cfg.off_J + e] = 0.0;
+    }
+    double Is = 0.0, ms = 0.0;
+    const int64_t ld = st.ld;
+#pragma unroll 2
+    for (int k = 0; k < ncx; k++) {
+      const int p0 = cfg.cx_ptr[k], p1 = cfg.cx_ptr[k + 1];
+      double lnQK = -cx_logK(k) * PFRX_LOG_TO_LN;
+      double h = cfg.cx_h2o[k];
+      if (h != 0.0) lnQK += h * ln_act_h2o;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) lnQK += cfg.cx_st[p] * LNA(cfg.cx_id[p]);
+      double lg;
+      if (act_upd) {
+        int q = cfg.cx_cls[k];
+        lg = q < 0 ? 0.0 : ws[cfg.off_cls + q];
+      } else {
+        lg = ws[cfg.off_lng + k];
+      }
+      double sk = exp(lnQK - lg);
+      st.sec_molal[k * ld + cell] = sk;  // streams to HBM; never re-read in this step
+      Is += sk * cfg.cx_Z2[k];
+      ms += sk;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) {
+        int i = cfg.cx_id[p];
+        double nu_i = cfg.cx_st[p];
+        TOT(i) += nu_i * sk;
+      }
+      if (want_J && !dry) {
+#pragma unroll 1
+        for (int p2 = p0; p2 < p1; p2++) {
+          int j = cfg.cx_id[p2];
+          double t = (cfg.cx_st[p2] * sk) * INVC(j);  // nu_j exp(lnQK - ln c_j)/gamma
+#pragma unroll 1
+          for (int p = p0; p < p1; p++) J(cfg.cx_id[p], j) += cfg.cx_st[p] * t;
+        }
+      }
+    }
+    Isum = Is;
+    msum = ms;
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) TOT(i) *= denL;
+    if (want_J) {
+      if (dry) {
+#pragma unroll 1
+        for (int i = 0; i < n; i++) J(i, i) = 1.0;
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) {
+          J(i, i) += 1.0;
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) J(i, j) *= f;
+        }
+#pragma unroll 1
+        for (int i = naq; i < n; i++) J(i, i) = vol / dt;
+      }
+    }
+#pragma unroll 1
+    for (int i = naq; i < n; i++) TOT(i) = C(i);
+    if (cfg.neqsr > 0) {
+#pragma unroll 1
+      for (int k = 0; k < cfg.nsrfcplx; k++) ws[cfg.off_sc + k] = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) TS(i) = 0.0;
+#pragma unroll 1
+      for (int e = 0; e < cfg.neqsr; e++) surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, vol / dt, true);
+    }
+  }
+
+  // ---- RKineticMineral (reaction_mineral.F90:647-1078), no prefactors ---------
+  __device__ __forceinline__ void kinetic_mineral(bool apply) {
+#pragma unroll 1
+    for (int m = 0; m < cfg.nkin; m++) {
+      const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
+      double rate_vol = 0.0, Im = 0.0, dfac = 0.0;
+      double lnQK = -mn_logK(m) * PFRX_LOG_TO_LN;
+      if (cfg.mn_h2o[m] != 0.0) lnQK += cfg.mn_h2o[m] * ln_act_h2o;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) lnQK += cfg.mn_st[p] * LNA(cfg.mn_id[p]);
+      double QK = exp(lnQK);
+      double aff;
+      if (cfg.mn_temkin) {
+        if (cfg.mn_scale)
+          aff = 1.0 - pfrx_pow(QK, 1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m]));
+        else
+          aff = 1.0 - pfrx_pow(QK, 1.0 / cfg.mn_temkin[m]);
+      } else if (cfg.mn_scale) {
+        aff = 1.0 - pfrx_pow(QK, 1.0 / cfg.mn_scale[m]);
+      } else {
+        aff = 1.0 - QK;
+      }
+      double sgn = copysign(1.0, aff);
+      double volfrac = st.mnrl_volfrac[m * st.ld + cell];
+      bool active = (volfrac > 0.0 || sgn < 0.0);
+      if (active && cfg.mn_irrev[m] == 1 && sgn < 0.0) active = false;
+      if (active && cfg.mn_thresh[m] > 0.0 && sgn < 0.0 && QK < cfg.mn_thresh[m]) active = false;
+      if (active) {
+        double lim = cfg.mn_limit[m];
+        if (lim > 0.0) aff = aff / (1.0 + (1.0 - aff) / lim);
+        double arr = 1.0;
+        if (cfg.mn_eact[m] > 0.0)
+          arr = exp(cfg.mn_eact[m] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
+        double spr = cfg.mn_rate[m] * arr;
+        double Im_const = -st.mnrl_area[m * st.ld + cell];
+        if (cfg.mn_scale) Im_const = Im_const / cfg.mn_scale[m];
+        if (cfg.mn_power)
+          Im = Im_const * sgn * pfrx_pow(fabs(aff), cfg.mn_power[m]) * spr;
+        else
+          Im = Im_const * sgn * fabs(aff) * spr;
+        rate_vol = Im;
+        Im_const = Im_const * vol;
+        Im = Im * vol;
+        double dIm_dQK;
+        if (cfg.mn_power)
+          dIm_dQK = -Im * cfg.mn_power[m] / fabs(aff);
+        else
+          dIm_dQK = -Im_const * spr;
+        if (cfg.mn_temkin) {
+          if (cfg.mn_scale)
+            dIm_dQK = dIm_dQK * (1.0 / (cfg.mn_scale[m] * cfg.mn_temkin[m])) / QK * (1.0 - aff);
+          else
+            dIm_dQK = dIm_dQK * (1.0 / cfg.mn_temkin[m]) / QK * (1.0 - aff);
+        } else if (cfg.mn_scale) {
+          dIm_dQK = dIm_dQK * (1.0 / cfg.mn_scale[m]) / QK * (1.0 - aff);
+        }
+        dfac = dIm_dQK * QK * (den_kg * 1.e-3);
+        if (lim > 0.0) {
+          double den = 1.0 + (1.0 - aff) / lim;
+          dfac = dIm_dQK * (1.0 + QK / lim / den) * QK * (den_kg * 1.e-3) / den;
+        }
+      }
+      ws[cfg.off_mn + m] = rate_vol;
+      if (!apply || (Im == 0.0 && dfac == 0.0)) continue;
+#pragma unroll 1
+      for (int p2 = p0; p2 < p1; p2++) {
+        int j = cfg.mn_id[p2];
+        double t = dfac * (cfg.mn_st[p2] * INVC(j));
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) J(cfg.mn_id[p], j) += cfg.mn_st[p] * t;
+      }
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) RES(cfg.mn_id[p]) += cfg.mn_st[p] * Im;
+    }
+  }
+
+  // ---- RMultiRateSorption (reaction_surf_complex.F90:552-637) -----------------
+  __device__ __forceinline__ void multirate(double dt) {
+    const int naq = cfg.naq;
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int irxn = cfg.mr_rxn[q];
+      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+      double A = 0.0;
+#pragma unroll 1
+      for (int k = r0; k < r1; k++) A += cfg.mr_rate[k] / (1.0 + cfg.mr_rate[k] * dt) * cfg.mr_frac[k];
+      double *seq = ws + cfg.off_mr + (2 * q) * N;  // kinmr_total_sorb(:,0,q): the equilibrium target
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) seq[i] = 0.0;
+      surf_cplx1(irxn, seq, true, vol * A, false);
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) RES(i) += vol * (A * seq[i] - ws[cfg.off_mr + (2 * q + 1) * N + i]);
+    }
+  }
+
+  __device__ __forceinline__ void multirate_begin(double dt) {
+    const int naq = cfg.naq;
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+      int64_t base = (int64_t)naq * (r0 + q);
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) {
+        double B = 0.0;
+#pragma unroll 1
+        for (int k = r0; k < r1; k++) {
+          double kk = cfg.mr_rate[k] / (1.0 + cfg.mr_rate[k] * dt);
+          B += kk * st.kinmr[(base + (int64_t)naq * (k - r0 + 1) + i) * st.ld + cell];
+        }
+        ws[cfg.off_mr + (2 * q + 1) * N + i] = B;
+      }
+    }
+  }
+
+  // ---- CLM_CN_React (reaction_sandbox_clm_cn.F90:468-787) ----------------------
+  __device__ __forceinline__ void clm_cn() {
+    const int off = cfg.naq;
+    double temp_K = temp + 273.15;
+    if (!(temp_K > 227.15)) return;
+    const double one_over_71_02 = 1.408054069e-2, theta_min = 0.01, one_over_log_theta_min = -2.17147241e-1;
+    double F_t = exp(308.56 * (one_over_71_02 - 1.0 / (temp_K - 227.13)));
+    double F_theta = log(theta_min / fmax(theta_min, sat)) * one_over_log_theta_min;
+    double cinh = F_t * F_theta;
+    const int ires_C = off + cfg.cn_C, ispec_N = cfg.cn_N, ires_N = off + ispec_N;
+    const double *imm = ws + cfg.off_c + off;
+#pragma unroll 1
+    for (int x = 0; x < cfg.cn_nrxn; x++) {
+      double src = cfg.cn_k[x] * vol * cinh;
+      double resp = cfg.cn_resp[x];
+      int pu = cfg.cn_up[x];
+      bool constCN = (cfg.cn_nspec[pu] == 1);
+      int iC = cfg.cn_cid[pu], iN = -1;
+      double CNu;
+      if (!constCN) {
+        iN = cfg.cn_nid[pu];
+        CNu = imm[iC] / imm[iN];
+      } else {
+        CNu = cfg.cn_CN[pu];
+      }
+      double sUC = 1.0;
+      double sUN = sUC / CNu;
+      int pd = cfg.cn_down[x];
+      int id = -1;
+      double sDC = 0.0, CNd = 1.0;
+      if (pd >= 0) {
+        id = cfg.cn_cid[pd];
+        CNd = cfg.cn_CN[pd];
+        sDC = (1.0 - resp) * sUC;
+      }
+      double sC = resp * sUC;
+      double sN = sUN - sDC / CNd;
+      bool useInh;
+      double Ninh, dNinh;
+      if (cfg.cn_inhib[x] > 1.e-40 && sN < 0.0) {
+        useInh = true;
+        double t = imm[ispec_N] + cfg.cn_inhib[x];
+        Ninh = imm[ispec_N] / t;
+        dNinh = cfg.cn_inhib[x] / (t * t);
+      } else {
+        useInh = false;
+        Ninh = 1.0;
+        dNinh = 0.0;
+      }
+      double rate = imm[iC] * src * Ninh;
+      int rUC = off + iC, rUN = off + iN, rD = off + id;
+      RES(ires_C) -= sC * rate;
+      RES(ires_N) -= sN * rate;
+      RES(rUC) -= (-1.0) * sUC * rate;
+      if (!constCN) RES(rUN) -= (-1.0) * sUN * rate;
+      if (id >= 0) RES(rD) -= sDC * rate;
+      double drate = src * Ninh;
+      double dInh = 0.0;
+      J(rUC, rUC) -= (-1.0) * sUC * drate;
+      if (useInh) {
+        dInh = imm[iC] * src * dNinh;
+        J(rUC, ires_N) -= (-1.0) * sUC * dInh;
+      }
+      if (id >= 0) {
+        J(rD, rUC) -= sDC * drate;
+        if (useInh) J(rD, ires_N) -= sDC * dInh;
+      }
+      if (!constCN) {
+        J(rUN, rUC) -= (-1.0) * sUN * drate;
+        if (useInh) J(rUN, ires_N) -= (-1.0) * sUN * dInh;
+        double nc = imm[iN] / imm[iC] * src * Ninh;
+        J(rUN, rUC) -= (-1.0) * (-1.0) * nc;
+        J(rUN, rUN) -= (-1.0) * src * Ninh;
+        J(ires_N, rUC) -= (-1.0) * nc;
+        J(ires_N, rUN) -= src * Ninh;
+      }
+      J(ires_C, rUC) -= sC * drate;
+      J(ires_N, rUC) -= sN * drate;
+      if (useInh) {
+        J(ires_C, ires_N) -= sC * dInh;
+        J(ires_N, ires_N) -= sN * dInh;
+      }
+    }
+  }
+
+  // ---- RSolve (reaction.F90:5457-5516) + LU (utility.F90:597-735) in shared ---
+  // Jacobian rows are addressed through logical row offsets ro[] (ints kept in
+  // ws.x), so a row interchange swaps two offsets.  The update lands in RES.
+  __device__ __forceinline__ bool solve() {
+    const int n = cfg.n, js = cfg.js;
+    double *A = ws + cfg.off_J;
+    int *ro = reinterpret_cast<int *>(ws + cfg.off_x);  // n row offsets
+    double *vv = ws + cfg.off_xs;                        // implicit scaling
+    // row scaling, optional d/dlnc scaling, vv (reaction.F90:5485-5498, utility.F90:620-640)
+    bool bad = false;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      double *row = A + i * js;
+      double m = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < n; j++) m = fmax(m, fabs(row[j]));
+      double nm = 1.0 / fmax(1.0, m);
+      RES(i) *= nm;
+      double m2 = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < n; j++) {
+        double v = row[j] * nm;
+        if (cfg.use_log) v *= C(j);
+        row[j] = v;
+        m2 = fmax(m2, fabs(v));
+      }
+      if (!(m2 > 0.0)) bad = true;
+      vv[i] = 1. / m2;
+      ro[i] = i * js;
+    }
+    if (bad) return false;
+    // Crout's method in the reference's loop order (column by column)
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+#pragma unroll 1
+      for (int i = 0; i < j; i++) {
+        const double *ri = A + ro[i];
+        double sum = ri[j];
+#pragma unroll 1
+        for (int k = 0; k < i; k++) sum -= ri[k] * A[ro[k] + j];
+        A[ro[i] + j] = sum;
+      }
+      double aamax = 0.0;
+      int imax = j;
+#pragma unroll 1
+      for (int i = j; i < n; i++) {
+        const double *ri = A + ro[i];
+        double sum = ri[j];
+#pragma unroll 1
+        for (int k = 0; k < j; k++) sum -= ri[k] * A[ro[k] + j];
+        A[ro[i] + j] = sum;
+        double dum = vv[i] * fabs(sum);
+        if (dum >= aamax) {
+          imax = i;
+          aamax = dum;
+        }
+      }
+      if (j != imax) {
+        int t = ro[imax];
+        ro[imax] = ro[j];
+        ro[j] = t;
+        double b = RES(imax);  // the permutation is applied to the rhs right away
+        RES(imax) = RES(j);
+        RES(j) = b;
+        vv[imax] = vv[j];
+      }
+      double *rj = A + ro[j];
+      if (rj[j] == 0.0) rj[j] = 1.0e-20;
+      if (j != n - 1) {
+        double dum = 1.0 / rj[j];
+#pragma unroll 1
+        for (int i = j + 1; i < n; i++) A[ro[i] + j] *= dum;
+      }
+    }
+    // forward and back substitution (rhs already permuted)
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      const double *ri = A + ro[i];
+      double sum = RES(i);
+#pragma unroll 1
+      for (int k = 0; k < i; k++) sum -= ri[k] * RES(k);
+      RES(i) = sum;
+    }
+#pragma unroll 1
+    for (int i = n - 1; i >= 0; i--) {
+      const double *ri = A + ro[i];
+      double sum = RES(i);
+#pragma unroll 1
+      for (int k = i + 1; k < n; k++) sum -= ri[k] * RES(k);
+      RES(i) = sum / ri[i];
+    }
+    return true;
+  }
+
+  // ---- RReact (reaction.F90:3742-4055) -------------------------------------------
+  // state in: st.total / st.immobile / st.total_sorb_eq hold total*, the guess is
+  // in st.pri_molal / st.immobile.  Returns ierror; on success the converged state
+  // has been written back (total, pri_molal, immobile, total_sorb_eq).
+  __device__ __forceinline__ int react(double dt, int &its_out) {
+    const int naq = cfg.naq, n = cfg.n;
+    const int64_t ld = st.ld, c = cell;
+    const double psv = por * sat * 1000.0 * vol;
+    dry = sat < cfg.min_sat;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double f = 0.0;
+      if (i < naq) {
+        if (!dry) f = psv * st.total[i * ld + c];
+        if (cfg.neqsr > 0) f = f + st.total_sorb_eq[i * ld + c] * vol;
+        C(i) = guess[i];
+      } else if (i < n) {
+        if (!dry) f = 0.0 + st.immobile[(i - naq) * ld + c] * vol;
+        C(i) = guess[i];
+      }
+      fixed[i] = f;
+    }
+    if (cfg.nmr > 0) multirate_begin(dt);
+    int its = 0;
+    double norm0 = 0.0;
+    for (;;) {
+      its++;
+      if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) activity();
+      auxvar_compute(true, dt);
+      if (its > cfg.max_its) {
+        // total and immobile keep their initial values (never overwritten in
+        // HBM); total_sorb_eq is not restored (reaction.F90:3891-3894)
+        if (cfg.neqsr > 0)
+          for (int i = 0; i < naq; i++) st.total_sorb_eq[i * ld + c] = TS(i);
+        its_out = its;
+        return 1;
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i < n) {
+          double a = 0.0;
+          if (!dry) a = (i < naq) ? psv * TOT(i) : 0.0 + C(i) * vol;
+          if (cfg.neqsr > 0 && i < naq) a = a + TS(i) * vol;
+          RES(i) = (a - fixed[i]) / dt;
+        }
+      }
+      if (cfg.nkin > 0) kinetic_mineral(!dry);
+      if (!dry) {
+        if (cfg.nmr > 0) multirate(dt);
+        if (cfg.cn_nrxn > 0) clm_cn();
+      }
+      double mabs = 0.0, ss = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        double r = RES(i);
+        mabs = fmax(mabs, fabs(r));
+        ss += r * r;
+      }
+      double nrm = sqrt(ss);
+      if (its == 1) norm0 = nrm;
+      double rel = nrm / norm0;
+      if (mabs < cfg.tol_res) break;
+      if (rel < cfg.tol_relres) break;
+      if (!solve()) {
+        // solve_error branch: no restore (reaction.F90:3964-3967)
+        for (int i = 0; i < naq; i++) {
+          st.total[i * ld + c] = TOT(i);
+          if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = TS(i);
+        }
+        for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
+        its_out = its;
+        return 1;
+      }
+      // update (reaction.F90:3993-4041); the candidate goes to TMP
+      double maxrel = -1.0;
+      if (cfg.use_log) {
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+          double u = RES(i);
+          u = copysign(1.0, u) * fmin(fabs(u), cfg.max_dlnC);
+          double cc = C(i), cn = cc * exp(-u);
+          TMP(i) = cn;
+          double v = fabs((cn - cc) / cc);
+          if (!isnan(v)) maxrel = fmax(maxrel, v);
+        }
+      } else {
+        double minr = 1.e20;
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+          double u = RES(i), cc = C(i);
+          if (cc <= u) minr = fmin(minr, fabs(cc / u));
+        }
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+          double u = RES(i), cc = C(i);
+          if (minr < 1.0) u = u * minr * 0.99;
+          double cn = cc - u;
+          TMP(i) = cn;
+          double v = fabs((cn - cc) / cc);
+          if (!isnan(v)) maxrel = fmax(maxrel, v);
+        }
+      }
+      if (maxrel >= 0.0 && maxrel < cfg.tol_relchange) break;
+#pragma unroll 1
+      for (int i = 0; i < n; i++) C(i) = TMP(i);
+    }
+    // converged; the reference's "one last update" (reaction.F90:4052) recomputes
+    // RTotal at the same c: TOT / TS / sec_molal already hold those values
+    for (int i = 0; i < naq; i++) {
+      st.total[i * ld + c] = TOT(i);
+      if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = TS(i);
+    }
+    for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < n) guess[i] = C(i);
+    its_out = its;
+    return 0;
+  }
+
+  // ---- RUpdateKineticState (reaction.F90:5935-5972) ------------------------------
+  __device__ __forceinline__ bool update_kinetic_state(double dt) {
+    const int naq = cfg.naq;
+    bool upd = false;
+    if (cfg.nkin > 0) {
+      upd = true;
+      // rates of the converged iterate are in ws.mn (same inputs as the
+      // RKineticMineral call of MineralUpdateKineticState)
+#pragma unroll 1
+      for (int m = 0; m < cfg.nkin; m++) {
+        double vf = st.mnrl_volfrac[m * st.ld + cell] + ws[cfg.off_mn + m] * cfg.mn_vol[m] * dt;
+        if (vf < 0.0) vf = 0.0;
+        st.mnrl_volfrac[m * st.ld + cell] = vf;
+      }
+    }
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      upd = true;
+      int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+      int64_t base = (int64_t)naq * (r0 + q);
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) {
+        double seq = ws[cfg.off_mr + (2 * q) * N + i];
+#pragma unroll 1
+        for (int k = r0; k < r1; k++) {
+          double kdt = cfg.mr_rate[k] * dt;
+          int64_t ix = (base + (int64_t)naq * (k - r0 + 1) + i) * st.ld + cell;
+          st.kinmr[ix] = (st.kinmr[ix] + kdt * cfg.mr_frac[k] * seq) / (1.0 + kdt);
+        }
+      }
+    }
+    if (cfg.cn_nrxn > 0) upd = true;
+    return upd;
+  }
+
+  // ---- RStep (reaction.F90:3564-3738) ----------------------------------------------
+  __device__ __forceinline__ void run(int64_t c, double target, int &nss, int &nit, int &nku, int &ierr, bool &had_cut) {
+    cell = c;
+    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
+    const int64_t ld = st.ld;
+    den_kg = st.den_kg[c];
+    sat = st.sat[c];
+    temp = st.temp[c];
+    por = st.porosity[c];
+    vol = st.volume[c];
+    spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
+    ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
+    nss = nit = nku = ierr = 0;
+    had_cut = false;
+    if (!cfg.use_full_geochemistry) {
+      for (int i = 0; i < naq; i++) st.pri_molal[i * ld + c] = st.total[i * ld + c] / den_kg * 1.e3;
+      return;
+    }
+    const bool act_upd = cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+    // secondary sums of the incoming state (ionic strength of the first update)
+    double Is = 0.0, ms = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < ncx; k++) {
+      double s = st.sec_molal[k * ld + c];
+      Is += s * cfg.cx_Z2[k];
+      ms += s;
+      if (!act_upd) ws[cfg.off_lng + k] = log(st.sec_act_coef[k * ld + c]);
+    }
+    Isum = Is;
+    msum = ms;
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsrfrxn; k++) ws[cfg.off_fs + k] = st.free_site[k * ld + c];
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsrfcplx; k++) ws[cfg.off_sc + k] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < cfg.nkin; k++) ws[cfg.off_mn + k] = st.mnrl_rate[k * ld + c];
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int64_t base = (int64_t)naq * (cfg.mr_ptr[q] + q);
+      for (int i = 0; i < naq; i++) ws[cfg.off_mr + (2 * q) * N + i] = st.kinmr[(base + i) * ld + c];
+    }
+    small_mask = 0u;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      small_val[i] = 0.0;
+      lngam[i] = 0.0;
+      guess[i] = 1.0;
+      if (i < naq) {
+        lngam[i] = log(st.pri_act_coef[i * ld + c]);
+        guess[i] = st.pri_molal[i * ld + c];
+        double t = st.total[i * ld + c];
+        if (t <= 1.e-40) {
+          small_mask |= 1u << i;
+          small_val[i] = t;
+          t = 1.e-40;
+          st.total[i * ld + c] = t;
+        }
+        if (cfg.use_total_as_guess) guess[i] = t;
+      } else if (i < n) {
+        double t = st.immobile[(i - naq) * ld + c];
+        guess[i] = t;  // the guess keeps the unclamped value (pmc_subsurface_osrt.F90:356-362)
+        if (t <= 1.e-40) {
+          small_mask |= 1u << i;
+          small_val[i] = t;
+          st.immobile[(i - naq) * ld + c] = 1.e-40;
+        }
+      }
+    }
+    double cumulative = 0.0, dt = target;
+    int ncuts = 0, nconst = 0;
+    bool aborted = false;
+    for (;;) {
+      if (cumulative >= target) break;
+      int its = 0;
+      int e = react(dt, its);
+      nit += its;
+      if (!step_bookkeeping(e, dt, cumulative, target, ncuts, nconst, nss, nku, had_cut, aborted)) break;
+    }
+    if (aborted) ierr = 1;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) st.pri_molal[i * ld + c] = aborted ? C(i) : guess[i];
+    if (!aborted) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if ((small_mask >> i) & 1u) {
+          if (i < naq)
+            st.total[i * ld + c] = small_val[i];
+          else if (i < n)
+            st.immobile[(i - naq) * ld + c] = small_val[i];
+        }
+      }
+    }
+    if (act_upd) {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (i < naq) st.pri_act_coef[i * ld + c] = exp(lngam[i]);
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++) {
+        int q = cfg.cx_cls[k];
+        st.sec_act_coef[k * ld + c] = q < 0 ? 1.0 : exp(ws[cfg.off_cls + q]);
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsrfrxn; k++) st.free_site[k * ld + c] = ws[cfg.off_fs + k];
+    if (cfg.neqsr > 0 && st.eqsrfcplx_conc)
+      for (int k = 0; k < cfg.nsrfcplx; k++) st.eqsrfcplx_conc[k * ld + c] = ws[cfg.off_sc + k];
+#pragma unroll 1
+    for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
+#pragma unroll 1
+    for (int q = 0; q < cfg.nmr; q++) {
+      int64_t base = (int64_t)naq * (cfg.mr_ptr[q] + q);
+      for (int i = 0; i < naq; i++) st.kinmr[(base + i) * ld + c] = ws[cfg.off_mr + (2 * q) * N + i];
+    }
+    if (st.ln_act_h2o && cfg.use_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
+  }
+
+  // RStep's reaction to the outcome of one RReact (reaction.F90:3660-3716);
+  // returns false when the cell is finished
+  __device__ __forceinline__ bool step_bookkeeping(int e, double &dt, double &cumulative, double target, int &ncuts,
+                                                   int &nconst, int &nss, int &nku, bool &had_cut, bool &aborted) {
+    if (e != 0) {
+      ncuts++;
+      had_cut = true;
+      if (ncuts > cfg.max_cuts) {
+        aborted = true;
+        return false;
+      }
+      dt = 0.5 * dt;
+      nconst = 0;
+    } else {
+      bool upd = update_kinetic_state(dt);
+      cumulative += dt;
+      nss++;
+      nconst++;
+      if (upd) nku++;
+      if (nconst >= 4) {
+        ncuts--;
+        dt = fmin(2.0 * dt, target - cumulative);
+      }
+    }
+    return true;
+  }
+};
+
+template <int N>
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1))) pfrx_rstep_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, double tran_dt,
+                                                                 DevSummary *summ) {
+  extern __shared__ double smem[];
+  const int lane32 = threadIdx.x & 31;
+  double *ws = smem + (size_t)threadIdx.x * cfg.ws_stride;
+  CellT<N> sol(cfg, st, ws);
+
+  unsigned long long l_active = 0, l_its = 0, l_cut = 0;
+  long long l_first = -1;
+  int l_maxits = 0, l_maxkin = 0, l_maxerr = 0, l_maxsub = 0;
+
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = gthread; c < ncell; c += nthreads) {
+    int nss = 0, nit = 0, nku = 0, ierr = 0;
+    bool cut = false;
+    bool active = !(st.imat && st.imat[c] <= 0);
+    if (active) sol.run(c, tran_dt, nss, nit, nku, ierr, cut);
+    st.num_sub_steps[c] = nss;
+    st.num_iterations[c] = nit;
+    st.num_kinetic_state_updates[c] = nku;
+    st.ierror[c] = ierr;
+    if (active) {
+      l_active++;
+      l_its += (unsigned long long)nit;
+      if (cut) l_cut++;
+      if (ierr != 0 && (l_first < 0 || c < l_first)) l_first = c;
+      l_maxits = max(l_maxits, nit);
+      l_maxkin = max(l_maxkin, nku);
+      l_maxerr = max(l_maxerr, ierr);
+      l_maxsub = max(l_maxsub, nss);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l_active += __shfl_xor_sync(0xffffffffu, l_active, o);
+    l_its += __shfl_xor_sync(0xffffffffu, l_its, o);
+    l_cut += __shfl_xor_sync(0xffffffffu, l_cut, o);
+    long long f = __shfl_xor_sync(0xffffffffu, l_first, o);
+    if (f >= 0 && (l_first < 0 || f < l_first)) l_first = f;
+    l_maxits = max(l_maxits, __shfl_xor_sync(0xffffffffu, l_maxits, o));
+    l_maxkin = max(l_maxkin, __shfl_xor_sync(0xffffffffu, l_maxkin, o));
+    l_maxerr = max(l_maxerr, __shfl_xor_sync(0xffffffffu, l_maxerr, o));
+    l_maxsub = max(l_maxsub, __shfl_xor_sync(0xffffffffu, l_maxsub, o));
+  }
+  if (lane32 == 0) {
+    atomicAdd(&summ->ncell_active, l_active);
+    atomicAdd(&summ->sum_its, l_its);
+    atomicAdd(&summ->num_cut_cells, l_cut);
+    if (l_first >= 0) atomicMin(&summ->first_failed, l_first);
+    atomicMax(&summ->max_its, l_maxits);
+    atomicMax(&summ->max_kin, l_maxkin);
+    atomicMax(&summ->max_err, l_maxerr);
+    atomicMax(&summ->max_sub, l_maxsub);
+  }
+}

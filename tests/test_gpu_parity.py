@@ -88,7 +88,7 @@ def test_c1_calcite_batch_cell():
 def test_c2_calcite_column(dt):
     wl = W.by_name("c2", ncell=10000, tran_dt=dt)
     ref, rr, got, rg, info = _run_both(wl)
-    assert info["lanes"] == 1  # thread-per-cell kernel
+    assert info["lanes"] in (0, 1)  # thread-per-cell kernel
     _compare(ref, got, f"c2 dt={dt}")
     _check_summary(rr, rg)
 
@@ -117,14 +117,31 @@ def test_hanford(variant, dt):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("variant", ["c3", "c3mr", "c4", "c5"])
+def test_thread_per_cell_kernel_on_large_networks(variant, monkeypatch):
+    """the thread-per-cell kernel is not the default above 4 unknowns but must
+    agree with the oracle there too"""
+    monkeypatch.setenv("PFRX_TPC", "1")
+    wl = W.by_name(variant, ncell=2000)
+    ref, rr, got, rg, info = _run_both(wl)
+    assert info["lanes"] == 0
+    _compare(ref, got, f"{variant} tpc")
+    _check_summary(rr, rg)
+
+
 def test_lane_variants_agree(monkeypatch):
     """the same cells through the thread-per-cell and the 4-lane kernels"""
     wl = W.by_name("c2", ncell=2048, tran_dt=86400.0)
     ref = wl.state.copy()
     orc.rstep(wl.cfg, ref, wl.tran_dt, 2)
     rstep = _gpu()
-    for lanes in ("1", "4"):
-        monkeypatch.setenv("PFRX_LANES", lanes)
+    for lanes in ("0", "1", "4"):   # 0 = thread-per-cell kernel (pfrx_tpc.cuh)
+        if lanes == "0":
+            monkeypatch.delenv("PFRX_LANES", raising=False)
+            monkeypatch.setenv("PFRX_TPC", "1")
+        else:
+            monkeypatch.setenv("PFRX_TPC", "0")
+            monkeypatch.setenv("PFRX_LANES", lanes)
         step = rstep.ChemistryStep(wl.cfg, 0)
         assert step.kernel_info()["lanes"] == int(lanes)
         dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
