@@ -33,6 +33,14 @@ DEFAULT_CELLS = {"c2": 10000, "c3": 256 * 256 * 64, "c3mr": 1 << 20, "c4": 2 * 1
 DEFAULT_DT = {"c2": 3600.0, "c3": 3600.0, "c3mr": 3600.0, "c4": 1800.0, "c5": 86400.0}
 
 
+def _kernel_name(info) -> str:
+    if info["lanes"] < 0:
+        return f"pfrx_spec_kernel[N={info['N']}]"
+    if info["lanes"] == 0:
+        return f"pfrx_rstep_tpc_kernel<{info['N']}>"
+    return f"pfrx_rstep_kernel<{info['N']},{info['lanes']}>"
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -42,6 +50,8 @@ def parse():
     p.add_argument("--workload", default="c3", choices=sorted(DEFAULT_CELLS))
     p.add_argument("--cells", type=int, default=None, help="cells per GPU")
     p.add_argument("--dt", type=float, default=None)
+    p.add_argument("--kernel", default="auto", choices=["auto", "generic", "spec"],
+                   help="auto: the network-specialised kernel when its cubin was built, else the generic one")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -191,6 +201,8 @@ def main():
     wl = workloads.by_name(a.workload, ncell=ncell, tran_dt=dt)
     step = rstep.ChemistryStep(wl.cfg, local_rank)
     step.init_comm()
+    if a.kernel != "generic":
+        step.specialize(required=(a.kernel == "spec"))
     info = step.kernel_info()
     pristine = rstep.DeviceState.from_host(wl.state, dev)
     work = rstep.DeviceState(wl.cfg, ncell, dev)
@@ -300,7 +312,7 @@ def main():
                  "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
                  "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": step.bytes_per_cell,
                  "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
-                 "kernel": f"pfrx_rstep_kernel<{info['N']},{info['lanes']}>", "kernel_ms": 1000.0 * t_launch,
+                 "kernel": _kernel_name(info), "kernel_ms": 1000.0 * t_launch,
                  "fp64_peak_sm_mhz": mhz})
 
     cpu = None

@@ -291,6 +291,20 @@ int64_t pfrx_bytes_per_cell(pfrx_handle *h);
  * PFRX_LANES / PFRX_THREADS in the environment override the defaults. */
 int pfrx_kernel_info(pfrx_handle *h, int *info5);
 
+/* ---- network-specialised kernels -------------------------------------------
+ * The generic kernels read the reaction network from tables, the way the
+ * reference's RTotalAqueous / RKineticMineral loops read reaction%eqcplxspecid
+ * etc. (reaction.F90:4708-4757).  For a fixed network
+ * pflotran_elm_interface_b200/specialize.py writes the same arithmetic with
+ * every stoichiometric coefficient, logK and index as an immediate and nvcc
+ * turns it into a cubin; pfrx_load_specialized attaches that cubin to a handle
+ * and all later pfrx_rstep* calls launch it.  The cubin embeds
+ * pfrx_config_signature() of the configuration it was generated from; a cubin
+ * whose signature differs from the handle's is refused with PFRX_E_INVALID.
+ * cubin_path == NULL detaches (back to the generic kernel).                  */
+int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path);
+uint64_t pfrx_config_signature(pfrx_handle *h);
+
 /* diagnostics: measured FP64 FMA peak of `device` in TFLOP/s (the FP64
  * roofline denominator; MEASURED_PEAKS.json only carries HBM and bf16), and
  * the SM clock it implies at 64 FMA/clk/SM. */

@@ -66,6 +66,123 @@ static int load_nccl() {
   return PFRX_OK;
 }
 
+
+// ---- CUDA driver API through dlopen (cubin loader for specialised kernels) ------
+struct DrvApi {
+  void *lib = nullptr;
+  int (*ModuleLoad)(void **, const char *) = nullptr;
+  int (*ModuleUnload)(void *) = nullptr;
+  int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+  int (*ModuleGetGlobal)(unsigned long long *, size_t *, void *, const char *) = nullptr;
+  int (*MemcpyDtoH)(void *, unsigned long long, size_t) = nullptr;
+  int (*FuncSetAttribute)(void *, int, int) = nullptr;
+  int (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, void *, int, size_t) = nullptr;
+  int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, cudaStream_t,
+                      void **, void **) = nullptr;
+  int (*GetErrorString)(int, const char **) = nullptr;
+};
+static DrvApi g_drv;
+
+static int load_driver() {
+  if (g_drv.lib) return PFRX_OK;
+  void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return set_err(PFRX_E_CUDA, "dlopen(libcuda.so.1) failed: %s", dlerror());
+#define SYM(field, name)                                                     \
+  *(void **)(&g_drv.field) = dlsym(h, name);                                 \
+  if (!g_drv.field) return set_err(PFRX_E_CUDA, "driver symbol %s missing", name);
+  SYM(ModuleLoad, "cuModuleLoad")
+  SYM(ModuleUnload, "cuModuleUnload")
+  SYM(ModuleGetFunction, "cuModuleGetFunction")
+  SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2")
+  SYM(MemcpyDtoH, "cuMemcpyDtoH_v2")
+  SYM(FuncSetAttribute, "cuFuncSetAttribute")
+  SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+  SYM(LaunchKernel, "cuLaunchKernel")
+  SYM(GetErrorString, "cuGetErrorString")
+#undef SYM
+  g_drv.lib = h;
+  return PFRX_OK;
+}
+static const char *drv_err(int rc) {
+  const char *m = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(rc, &m);
+  return m ? m : "unknown driver error";
+}
+#define DRV_OK(call)                                                                  \
+  do {                                                                                \
+    int rc_ = (call);                                                                 \
+    if (rc_ != 0) return set_err(PFRX_E_CUDA, "%s: %s", #call, drv_err(rc_));        \
+  } while (0)
+
+// ---- signature of the tables a specialised kernel bakes in ------------------------
+// FNV-1a over the same byte sequence as specialize.py:signature()
+static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; i++) {
+    h ^= b[i];
+    h *= 0x100000001B3ull;
+  }
+  return h;
+}
+static uint64_t config_signature(const pfrx_config *c) {
+  uint64_t h = 0xCBF29CE484222325ull;
+  int32_t head[12] = {c->naqcomp,          c->nimcomp,
+                      c->neqcplx,          c->nkinmnrl,
+                      c->nsrfcplxrxn,      c->nsrfcplx,
+                      c->neqsrfcplxrxn,    c->nkinmrsrfcplxrxn,
+                      c->clmcn_nrxn,       c->use_log_formulation,
+                      c->act_coef_update_frequency, c->use_activity_h2o};
+  double dh[3] = {c->debyeA, c->debyeB, c->debyeBdot};
+  h = fnv1a(h, head, sizeof(head));
+  h = fnv1a(h, dh, sizeof(dh));
+#define ADD(ptr, count)                                                  \
+  if ((ptr) && (count) > 0) h = fnv1a(h, (ptr), sizeof(*(ptr)) * (size_t)(count));
+  ADD(c->primary_spec_Z, c->naqcomp)
+  ADD(c->primary_spec_a0, c->naqcomp)
+  if (c->neqcplx > 0 && c->eqcplx_ptr) {
+    int nnz = c->eqcplx_ptr[c->neqcplx];
+    ADD(c->eqcplx_ptr, c->neqcplx + 1)
+    ADD(c->eqcplx_specid, nnz)
+    ADD(c->eqcplx_stoich, nnz)
+    ADD(c->eqcplx_h2ostoich, c->neqcplx)
+    ADD(c->eqcplx_logK, c->neqcplx)
+    ADD(c->eqcplx_Z, c->neqcplx)
+    ADD(c->eqcplx_a0, c->neqcplx)
+  }
+  if (c->nkinmnrl > 0 && c->kinmnrl_ptr) {
+    int nnz = c->kinmnrl_ptr[c->nkinmnrl];
+    ADD(c->kinmnrl_ptr, c->nkinmnrl + 1)
+    ADD(c->kinmnrl_specid, nnz)
+    ADD(c->kinmnrl_stoich, nnz)
+    ADD(c->kinmnrl_h2ostoich, c->nkinmnrl)
+    ADD(c->kinmnrl_logK, c->nkinmnrl)
+    ADD(c->kinmnrl_molar_vol, c->nkinmnrl)
+    ADD(c->kinmnrl_rate_constant, c->nkinmnrl)
+    ADD(c->kinmnrl_activation_energy, c->nkinmnrl)
+    ADD(c->kinmnrl_affinity_threshold, c->nkinmnrl)
+    ADD(c->kinmnrl_rate_limiter, c->nkinmnrl)
+    ADD(c->kinmnrl_irreversible, c->nkinmnrl)
+  }
+  if (c->nsrfcplxrxn > 0 && c->srfcplxrxn_ptr && c->srfcplx_ptr) {
+    int nnz = c->srfcplx_ptr[c->nsrfcplx];
+    ADD(c->srfcplxrxn_ptr, c->nsrfcplxrxn + 1)
+    ADD(c->srfcplxrxn_to_complex, c->srfcplxrxn_ptr[c->nsrfcplxrxn])
+    ADD(c->srfcplxrxn_surf_type, c->nsrfcplxrxn)
+    ADD(c->srfcplxrxn_to_surf, c->nsrfcplxrxn)
+    ADD(c->srfcplxrxn_site_density, c->nsrfcplxrxn)
+    ADD(c->srfcplx_ptr, c->nsrfcplx + 1)
+    ADD(c->srfcplx_specid, nnz)
+    ADD(c->srfcplx_stoich, nnz)
+    ADD(c->srfcplx_h2ostoich, c->nsrfcplx)
+    ADD(c->srfcplx_free_site_stoich, c->nsrfcplx)
+    ADD(c->srfcplx_logK, c->nsrfcplx)
+    ADD(c->eqsrfcplxrxn_to_srfcplxrxn, c->neqsrfcplxrxn)
+  }
+#undef ADD
+  return h;
+}
+
 #define PFRX_MAX_CHUNKS 32
 
 // ---- handle -----------------------------------------------------------------
@@ -98,6 +215,12 @@ struct pfrx_handle {
   void *own = nullptr;
   int64_t own_ncell = 0;
   DevState own_st;
+  // network-specialised kernel (pfrx_load_specialized)
+  uint64_t sig = 0;
+  SpecParams spec_prm;
+  void *spec_module = nullptr, *spec_func = nullptr;
+  int spec_threads = 0, spec_blocks_per_sm = 0, spec_stride = 0;
+  size_t spec_smem = 0;
   // nccl
   NcclComm comm = nullptr;
   long long *d_red = nullptr;
@@ -347,6 +470,14 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.tol_res = c->max_residual_tolerance;
   d.tol_relres = c->max_rel_residual_tolerance;
   d.min_sat = c->rt_min_saturation;
+  h->sig = config_signature(c);
+  h->spec_prm.max_its = d.max_its;
+  h->spec_prm.max_cuts = d.max_cuts;
+  h->spec_prm.max_dlnC = d.max_dlnC;
+  h->spec_prm.tol_relchange = d.tol_relchange;
+  h->spec_prm.tol_res = d.tol_res;
+  h->spec_prm.tol_relres = d.tol_relres;
+  h->spec_prm.min_sat = d.min_sat;
   d.debyeA = c->debyeA;
   d.debyeB = c->debyeB;
   d.debyeBdot = c->debyeBdot;
@@ -596,6 +727,7 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->spec_module && g_drv.ModuleUnload) g_drv.ModuleUnload(h->spec_module);
   if (h->own) cudaFree(h->own);
   if (h->arena) cudaFree(h->arena);
   if (h->d_summ) cudaFree(h->d_summ);
@@ -695,6 +827,21 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
   int64_t need = (ncell + (int64_t)cpw * wpb - 1) / ((int64_t)cpw * wpb);
   if (h->tpc) need = (ncell + h->threads - 1) / h->threads;
   int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
+  if (h->spec_func) {
+    need = (ncell + h->spec_threads - 1) / h->spec_threads;
+    cap = (int64_t)h->sm_count * h->spec_blocks_per_sm;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, cap));
+    DevState st_arg = st;
+    long long n_arg = ncell;
+    double dt_arg = tran_dt;
+    SpecParams prm = h->spec_prm;
+    DevSummary *summ = h->d_summ;
+    void *args[] = {&st_arg, &n_arg, &dt_arg, &prm, &summ};
+    DRV_OK(g_drv.LaunchKernel(h->spec_func, (unsigned)grid, 1, 1, (unsigned)h->spec_threads, 1, 1,
+                              (unsigned)h->spec_smem, s, args, nullptr));
+    h->launches++;
+    return PFRX_OK;
+  }
   int grid = (int)std::min<int64_t>(need, cap);
   if (grid < 1) grid = 1;
   h->kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, st, ncell, tran_dt, h->d_summ);
@@ -998,6 +1145,75 @@ extern "C" int pfrx_kernel_info(pfrx_handle *h, int *info5) {
   info5[2] = h->threads;
   info5[3] = h->blocks_per_sm;
   info5[4] = (int)h->smem_bytes;
+  if (h->spec_func) {  // specialised kernel: lanes reported as -1
+    info5[0] = h->n;
+    info5[1] = -1;
+    info5[2] = h->spec_threads;
+    info5[3] = h->spec_blocks_per_sm;
+    info5[4] = (int)h->spec_smem;
+  }
+  return PFRX_OK;
+}
+
+extern "C" uint64_t pfrx_config_signature(pfrx_handle *h) { return h ? h->sig : 0; }
+
+// Attach a network-specialised kernel (cubin written by specialize.py / nvcc).
+// The cubin carries the signature of the tables it was generated from; a cubin
+// for another network is refused.  path == NULL detaches.
+extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
+  if (!h) return set_err(PFRX_E_INVALID, "null handle%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->pending) CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->spec_module) {
+    g_drv.ModuleUnload(h->spec_module);
+    h->spec_module = h->spec_func = nullptr;
+  }
+  if (!cubin_path) return PFRX_OK;
+  // features outside what specialize.py generates (its supported() is the twin of this test)
+  const DevCfg &d = h->cfg;
+  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess || d.nmr > 0 || d.cn_nrxn > 0 ||
+      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG)
+    return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
+  int rc = load_driver();
+  if (rc) return rc;
+  CUDA_OK(cudaFree(0));  // make the primary context current for the driver API
+  void *mod = nullptr, *fn = nullptr;
+  DRV_OK(g_drv.ModuleLoad(&mod, cubin_path));
+  unsigned long long dptr = 0;
+  size_t bytes = 0;
+  unsigned long long sig = 0;
+  int info[4] = {0, 0, 0, 0};
+  int e = g_drv.ModuleGetGlobal(&dptr, &bytes, mod, "pfrx_spec_sig");
+  if (!e && bytes == sizeof(sig)) e = g_drv.MemcpyDtoH(&sig, dptr, sizeof(sig));
+  if (!e) e = g_drv.ModuleGetGlobal(&dptr, &bytes, mod, "pfrx_spec_info");
+  if (!e && bytes == sizeof(info)) e = g_drv.MemcpyDtoH(info, dptr, sizeof(info));
+  if (!e) e = g_drv.ModuleGetFunction(&fn, mod, "pfrx_spec_kernel");
+  if (e) {
+    g_drv.ModuleUnload(mod);
+    return set_err(PFRX_E_CUDA, "not a pfrx specialised cubin (%s): %s", cubin_path, drv_err(e));
+  }
+  if (sig != h->sig || info[0] != h->n) {
+    g_drv.ModuleUnload(mod);
+    char a[24], b[24];
+    snprintf(a, sizeof(a), "%016llx", sig);
+    snprintf(b, sizeof(b), "%016llx", (unsigned long long)h->sig);
+    return set_err(PFRX_E_INVALID, "specialised kernel was generated for another network (signature %s, need %s)", a, b);
+  }
+  int threads = info[2];
+  size_t smem = (size_t)info[1] * sizeof(double) * threads;
+  int nb = 0;
+  e = g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
+  if (!e) e = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem);
+  if (e || nb < 1) {
+    g_drv.ModuleUnload(mod);
+    return set_err(PFRX_E_LIMIT, "specialised kernel does not fit on an SM: %s", e ? drv_err(e) : "0 blocks");
+  }
+  h->spec_module = mod;
+  h->spec_func = fn;
+  h->spec_threads = threads;
+  h->spec_stride = info[1];
+  h->spec_smem = smem;
+  h->spec_blocks_per_sm = nb;
   return PFRX_OK;
 }
 

@@ -1,0 +1,519 @@
+// pfrx_spec.cuh -- network-SPECIALISED thread-per-cell kernel (template part).
+//
+// specialize.py generates, for one reaction network, a .cu file that defines
+//   SPEC_N, SPEC_NAQ, SPEC_NC, SPEC_NCX, SPEC_NCLS, SPEC_NKIN, SPEC_NSRFRXN,
+//   SPEC_NSRFCPLX, SPEC_NEQSR, SPEC_USE_LOG, SPEC_ACT_UPD, SPEC_USE_ACT_H2O, SPEC_SIG,
+//   SPEC_THREADS, SPEC_MINBLOCKS, the index maps spec_cmap() / spec_sp_of() and the
+//   straight-line device functions
+//   spec_activity(), spec_rtotal(), spec_minerals(), spec_sorption()
+// with every stoichiometric coefficient, logK, charge and index as an immediate,
+// and includes this file, which holds what does not depend on the network:
+// RStep / RReact control flow (reaction.F90:3564-4055), the unrolled LU
+// (utility.F90:597-735) and the launch skeleton.
+//
+// One thread owns one cell.  c, ln a, 1/c, totals, residual, ln gamma are
+// register arrays (all indices are literals after unrolling).  Shared memory
+// holds, per thread, the Jacobian of the COUPLED species (those that occur in
+// some reaction; NC of them) as NC rows of NC+1 doubles -- the extra column is
+// the row's implicit-scaling factor during the decomposition and the right-hand
+// side afterwards -- and the fixed accumulation / guess vectors (+ ln gamma of
+// the complexes when activity coefficients are frozen).  Species that occur in
+// no reaction (tracers, immobile species without a sandbox) have a diagonal
+// Jacobian row and column: their update is res/J, bit-identical to what the
+// reference's full LU returns for them, and they stay out of the matrix.
+//
+// Element e of a thread's slice is at slice[e * 32 + lane]: any per-lane row
+// permutation of the LU stays bank-conflict free.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pfrx_types.cuh"
+
+#define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
+
+// shared-memory slots of a thread (doubles)
+#define SPEC_JS (SPEC_NC + 1)
+#define SPEC_OFF_FIXED (SPEC_NC * SPEC_JS)
+#define SPEC_OFF_GUESS (SPEC_OFF_FIXED + SPEC_N)
+#define SPEC_OFF_LNGSEC (SPEC_OFF_GUESS + SPEC_N)
+#define SPEC_SLOTS (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
+// slot -> index relative to the thread's base pointer
+#define SW(e) W[(e) * 32]
+#define JX(ci, cj) (((ci) * SPEC_JS + (cj)) * 32)
+
+extern "C" {
+__device__ const unsigned long long pfrx_spec_sig = SPEC_SIG;
+__device__ const int pfrx_spec_info[4] = {SPEC_N, SPEC_SLOTS, SPEC_THREADS, SPEC_MINBLOCKS};
+}
+
+struct SpecCell {
+  // per-cell scalars
+  double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
+  double Isec, msec;  // sum z^2 m, sum m over secondary species of the latest RTotal
+  double lgcls[SPEC_NCLS > 0 ? SPEC_NCLS : 1];
+  double lngam[SPEC_N];
+  double fsite[SPEC_NSRFRXN > 0 ? SPEC_NSRFRXN : 1];
+  double scconc[SPEC_NSRFCPLX > 0 ? SPEC_NSRFCPLX : 1];
+  double mrate[SPEC_NKIN > 0 ? SPEC_NKIN : 1];
+  bool dry;
+};
+
+// ---- generated for the network (declared here, defined by the generator) ------
+__device__ __forceinline__ void spec_activity(const double (&c)[SPEC_N], SpecCell &s);
+__device__ __forceinline__ void spec_rtotal(const double (&c)[SPEC_N], double (&lna)[SPEC_N], double (&ic)[SPEC_N],
+                                            double (&tot)[SPEC_N], SpecCell &s, double *W, double *sec_out, long long ld,
+                                            double dt);
+__device__ __forceinline__ void spec_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],
+                                              double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st,
+                                              long long cell, double jscale);
+__device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],
+                                              double (&res)[SPEC_N], SpecCell &s, double *W, const DevState &st,
+                                              long long cell, bool apply);
+
+// ---- RSolve + LU (reaction.F90:5457-5516, utility.F90:597-735) -------------------
+// W = thread's slice (Jacobian of the coupled species), res = residual in
+// registers (overwritten by the update).  Crout's method in the reference's
+// column order with implicit-scaled partial pivoting.  Rows are never moved:
+// ro[i] is the slice offset of the row at logical position i, an interchange
+// swaps two offsets, and the scaling factor / right-hand side travel with the
+// row in its extra column.  Every register array is indexed by literals.
+__device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
+                                           const SpecCell &s, double dt) {
+  constexpr int N = SPEC_N, NC = SPEC_NC, NCA = NC > 0 ? NC : 1;
+  bool bad = false;
+  // species outside the matrix: J is diagonal (RTAccumulationDerivative only)
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (spec_cmap(i) < 0) {
+      double Jd = (i < SPEC_NAQ) ? (1.0 * (s.den_kg * 1.e-3)) * (s.por * s.sat * 1000.0 * s.vol / dt) : s.vol / dt;
+      if (s.dry) Jd = 1.0;
+      double nm = 1.0 / fmax(1.0, fabs(Jd));
+      double a = Jd * nm;
+      if (SPEC_USE_LOG) a *= c[i];
+      if (!(fabs(a) > 0.0)) bad = true;
+      res[i] = (res[i] * nm) / a;
+    }
+  }
+  if (NC == 0) return !bad;
+  double b[NCA];
+#pragma unroll
+  for (int i = 0; i < NC; i++) {
+    double row[NCA];
+    double m = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      row[j] = W[JX(i, j)];
+      m = fmax(m, fabs(row[j]));
+    }
+    double nm = 1.0 / fmax(1.0, m);
+    b[i] = res[spec_sp_of(i)] * nm;
+    double m2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      double v = row[j] * nm;
+      if (SPEC_USE_LOG) v *= c[spec_sp_of(j)];
+      W[JX(i, j)] = v;
+      m2 = fmax(m2, fabs(v));
+    }
+    if (!(m2 > 0.0)) bad = true;
+    W[JX(i, NC)] = 1. / m2;
+  }
+  if (bad) return false;
+  int ro[NCA];
+#pragma unroll
+  for (int i = 0; i < NC; i++) ro[i] = JX(i, 0);
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    double u[NCA], sv[NCA];
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      if (k < j) {
+        const double *r = W + ro[k];
+        double sum = r[j * 32];
+#pragma unroll
+        for (int m = 0; m < NC; m++)
+          if (m < k) sum -= r[m * 32] * u[m];
+        u[k] = sum;
+        if (k > 0) W[ro[k] + j * 32] = sum;
+      }
+    }
+    double aamax = 0.0;
+    int imax = j;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+      if (i >= j) {
+        const double *r = W + ro[i];
+        double sum = r[j * 32];
+#pragma unroll
+        for (int m = 0; m < NC; m++)
+          if (m < j) sum -= r[m * 32] * u[m];
+        sv[i] = sum;
+        double dum = r[NC * 32] * fabs(sum);
+        bool ge = dum >= aamax;
+        imax = ge ? i : imax;
+        aamax = ge ? dum : aamax;
+      }
+    }
+    const int rj = ro[j];
+    int rmax = rj;
+    double pv = sv[j];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+      if (i > j) {
+        bool p = (i == imax);
+        rmax = p ? ro[i] : rmax;
+        pv = p ? sv[i] : pv;
+        ro[i] = p ? rj : ro[i];
+      }
+    }
+    ro[j] = rmax;
+    if (pv == 0.0) pv = 1.0e-20;
+    if (j != NC - 1) {
+      double dum = 1.0 / pv;
+      // the logical order has changed already: position imax holds old row j
+#pragma unroll
+      for (int i = 0; i < NC; i++) {
+        if (i > j) {
+          bool p = (i == imax);
+          double v = p ? sv[j] : sv[i];
+          W[ro[i] + j * 32] = v * dum;
+        }
+      }
+    }
+    W[rmax + j * 32] = pv;
+  }
+  // right-hand side into the rows' extra column, then forward / back substitution
+#pragma unroll
+  for (int i = 0; i < NC; i++) W[JX(i, NC)] = b[i];
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+    const double *r = W + ro[k];
+    double sum = r[NC * 32];
+#pragma unroll
+    for (int m = 0; m < NC; m++)
+      if (m < k) sum -= r[m * 32] * b[m];
+    b[k] = sum;
+  }
+#pragma unroll
+  for (int k = NC - 1; k >= 0; k--) {
+    const double *r = W + ro[k];
+    double sum = b[k];
+#pragma unroll
+    for (int m = 0; m < NC; m++)
+      if (m > k) sum -= r[m * 32] * b[m];
+    b[k] = sum / r[k * 32];
+  }
+#pragma unroll
+  for (int k = 0; k < NC; k++) res[spec_sp_of(k)] = b[k];
+  return true;
+}
+
+// ---- RReact (reaction.F90:3742-4055) ------------------------------------------------
+// rt_auxvar%total / %immobile / %total_sorb_eq stay in HBM (st.*), the guess is in
+// the thread's shared slice.  Returns ierror; the last iterate is left in c.
+__device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &prm, SpecCell &s, double *W,
+                                          long long cell, double dt, double (&c)[SPEC_N], int &its_out) {
+  constexpr int N = SPEC_N, NAQ = SPEC_NAQ;
+  const long long ld = st.ld;
+  const double psv = s.por * s.sat * 1000.0 * s.vol;
+  s.dry = s.sat < prm.min_sat;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    double f = 0.0;
+    if (i < NAQ) {
+      if (!s.dry) f = psv * st.total[i * ld + cell];
+      if (SPEC_NEQSR > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
+    } else {
+      if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
+    }
+    SW(SPEC_OFF_FIXED + i) = f;
+    c[i] = SW(SPEC_OFF_GUESS + i);
+  }
+  int its = 0;
+  double norm0 = 0.0;
+  double lna[N], ic[N], tot[N], res[N], ts[N];
+  for (;;) {
+    its++;
+    if (SPEC_ACT_UPD) spec_activity(c, s);
+    spec_rtotal(c, lna, ic, tot, s, W, st.sec_molal + cell, ld, dt);
+#pragma unroll
+    for (int i = 0; i < N; i++) ts[i] = 0.0;
+    if (SPEC_NEQSR > 0) spec_sorption(lna, ic, ts, s, W, st, cell, s.vol / dt);
+    if (its > prm.max_its) {
+      // total / immobile keep their initial values in HBM; total_sorb_eq does not
+      if (SPEC_NEQSR > 0) {
+#pragma unroll
+        for (int i = 0; i < NAQ; i++) st.total_sorb_eq[i * ld + cell] = ts[i];
+      }
+      its_out = its;
+      return 1;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double a = 0.0;
+      if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
+      if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
+      res[i] = (a - SW(SPEC_OFF_FIXED + i)) / dt;
+    }
+    if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
+    double mabs = 0.0, ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      mabs = fmax(mabs, fabs(res[i]));
+      ss += res[i] * res[i];
+    }
+    double nrm = sqrt(ss);
+    if (its == 1) norm0 = nrm;
+    double rel = nrm / norm0;
+    bool conv = (mabs < prm.tol_res) || (rel < prm.tol_relres);
+    if (!conv) {
+      if (!spec_solve(W, res, c, s, dt)) {
+        // solve_error branch: no restore (reaction.F90:3964-3967)
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          if (i < NAQ) {
+            st.total[i * ld + cell] = tot[i];
+            if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+          } else {
+            st.immobile[(i - NAQ) * ld + cell] = c[i];
+          }
+        }
+        its_out = its;
+        return 1;
+      }
+      double cn[N], maxrel = -1.0;
+      double minr = 1.e20;
+      if (!SPEC_USE_LOG) {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+          if (c[i] <= res[i]) minr = fmin(minr, fabs(c[i] / res[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double u = res[i];
+        if (SPEC_USE_LOG) {
+          u = copysign(1.0, u) * fmin(fabs(u), prm.max_dlnC);
+          cn[i] = c[i] * exp(-u);
+        } else {
+          if (minr < 1.0) u = u * minr * 0.99;
+          cn[i] = c[i] - u;
+        }
+        double v = fabs((cn[i] - c[i]) / c[i]);
+        if (!isnan(v)) maxrel = fmax(maxrel, v);
+      }
+      conv = (maxrel >= 0.0) && (maxrel < prm.tol_relchange);
+      if (!conv) {
+#pragma unroll
+        for (int i = 0; i < N; i++) c[i] = cn[i];
+        continue;
+      }
+    }
+    break;
+  }
+  // converged: the reference's last RTAuxVarCompute (reaction.F90:4052) recomputes
+  // RTotal at the same c -- the values are in tot / ts / st.sec_molal already
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (i < NAQ) {
+      st.total[i * ld + cell] = tot[i];
+      if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+    } else {
+      st.immobile[(i - NAQ) * ld + cell] = c[i];
+    }
+    SW(SPEC_OFF_GUESS + i) = c[i];
+  }
+  its_out = its;
+  return 0;
+}
+
+// ---- RStep (reaction.F90:3564-3738) for one cell ---------------------------------------
+__device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &prm, double *W, long long cell,
+                                         double target, int &nss, int &nit, int &nku, int &ierr, bool &had_cut) {
+  constexpr int N = SPEC_N, NAQ = SPEC_NAQ;
+  const long long ld = st.ld;
+  SpecCell s;
+  s.den_kg = st.den_kg[cell];
+  s.sat = st.sat[cell];
+  s.temp = st.temp[cell];
+  s.por = st.porosity[cell];
+  s.vol = st.volume[cell];
+  s.spd = st.soil_particle_density ? st.soil_particle_density[cell] : 0.0;
+  s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
+  nss = nit = nku = ierr = 0;
+  had_cut = false;
+  double Is = 0.0, ms = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < SPEC_NCX; k++) {
+    double m = st.sec_molal[k * ld + cell];
+    Is += m * spec_cx_z2(k);
+    ms += m;
+    if (!SPEC_ACT_UPD) SW(SPEC_OFF_LNGSEC + k) = log(st.sec_act_coef[k * ld + cell]);
+  }
+  s.Isec = Is;
+  s.msec = ms;
+#pragma unroll
+  for (int k = 0; k < (SPEC_NCLS > 0 ? SPEC_NCLS : 1); k++) s.lgcls[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < SPEC_NSRFRXN; k++) s.fsite[k] = st.free_site[k * ld + cell];
+#pragma unroll
+  for (int k = 0; k < SPEC_NSRFCPLX; k++) s.scconc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < SPEC_NKIN; k++) s.mrate[k] = st.mnrl_rate[k * ld + cell];
+  unsigned small_mask = 0u;
+  double small_val[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    small_val[i] = 0.0;
+    s.lngam[i] = 0.0;
+    if (i < NAQ) {
+      s.lngam[i] = log(st.pri_act_coef[i * ld + cell]);
+      double g = st.pri_molal[i * ld + cell];
+      double t = st.total[i * ld + cell];
+      if (t <= 1.e-40) {
+        small_mask |= 1u << i;
+        small_val[i] = t;
+        t = 1.e-40;
+        st.total[i * ld + cell] = t;
+      }
+      SW(SPEC_OFF_GUESS + i) = g;
+    } else {
+      double t = st.immobile[(i - NAQ) * ld + cell];
+      SW(SPEC_OFF_GUESS + i) = t;  // the guess keeps the unclamped value
+      if (t <= 1.e-40) {
+        small_mask |= 1u << i;
+        small_val[i] = t;
+        st.immobile[(i - NAQ) * ld + cell] = 1.e-40;
+      }
+    }
+  }
+  double cumulative = 0.0, dt = target;
+  int ncuts = 0, nconst = 0;
+  bool aborted = false;
+  double c[N];
+  for (;;) {
+    if (cumulative >= target) break;
+    int its = 0;
+    int e = spec_react(st, prm, s, W, cell, dt, c, its);
+    nit += its;
+    if (e != 0) {
+      ncuts++;
+      had_cut = true;
+      if (ncuts > prm.max_cuts) {
+        aborted = true;
+        break;
+      }
+      dt = 0.5 * dt;
+      nconst = 0;
+    } else {
+      // RUpdateKineticState: the rates of the converged iterate are in s.mrate
+      bool upd = false;
+      if (SPEC_NKIN > 0) {
+        upd = true;
+#pragma unroll
+        for (int m = 0; m < SPEC_NKIN; m++) {
+          double vf = st.mnrl_volfrac[m * ld + cell] + s.mrate[m] * spec_mn_vol(m) * dt;
+          if (vf < 0.0) vf = 0.0;
+          st.mnrl_volfrac[m * ld + cell] = vf;
+        }
+      }
+      cumulative += dt;
+      nss++;
+      nconst++;
+      if (upd) nku++;
+      if (nconst >= 4) {
+        ncuts--;
+        dt = fmin(2.0 * dt, target - cumulative);
+      }
+    }
+  }
+  if (aborted) ierr = 1;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (i < NAQ) st.pri_molal[i * ld + cell] = aborted ? c[i] : SW(SPEC_OFF_GUESS + i);
+    if (!aborted && ((small_mask >> i) & 1u)) {
+      if (i < NAQ)
+        st.total[i * ld + cell] = small_val[i];
+      else
+        st.immobile[(i - NAQ) * ld + cell] = small_val[i];
+    }
+  }
+  if (SPEC_ACT_UPD) {
+#pragma unroll
+    for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = exp(s.lngam[i]);
+#pragma unroll 4
+    for (int k = 0; k < SPEC_NCX; k++) {
+      int q = spec_cx_cls(k);
+      double lg = 0.0;
+#pragma unroll
+      for (int z = 0; z < SPEC_NCLS; z++)
+        if (z == q) lg = s.lgcls[z];
+      st.sec_act_coef[k * ld + cell] = q < 0 ? 1.0 : exp(lg);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < SPEC_NSRFRXN; k++) st.free_site[k * ld + cell] = s.fsite[k];
+  if (SPEC_NEQSR > 0 && st.eqsrfcplx_conc) {
+#pragma unroll
+    for (int k = 0; k < SPEC_NSRFCPLX; k++) st.eqsrfcplx_conc[k * ld + cell] = s.scconc[k];
+  }
+#pragma unroll
+  for (int k = 0; k < SPEC_NKIN; k++) st.mnrl_rate[k * ld + cell] = s.mrate[k];
+  if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = s.ln_act_h2o;
+}
+
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
+    pfrx_spec_kernel(DevState st, long long ncell, double tran_dt, SpecParams prm, DevSummary *summ) {
+  extern __shared__ double smem[];
+  const int lane32 = threadIdx.x & 31;
+  double *W = smem + (size_t)(threadIdx.x >> 5) * (SPEC_SLOTS * 32) + lane32;
+
+  unsigned long long l_active = 0, l_its = 0, l_cut = 0;
+  long long l_first = -1;
+  int l_maxits = 0, l_maxkin = 0, l_maxerr = 0, l_maxsub = 0;
+
+  const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long cell = gthread; cell < ncell; cell += nthreads) {
+    int nss = 0, nit = 0, nku = 0, ierr = 0;
+    bool cut = false;
+    bool active = !(st.imat && st.imat[cell] <= 0);
+    if (active) spec_run(st, prm, W, cell, tran_dt, nss, nit, nku, ierr, cut);
+    st.num_sub_steps[cell] = nss;
+    st.num_iterations[cell] = nit;
+    st.num_kinetic_state_updates[cell] = nku;
+    st.ierror[cell] = ierr;
+    if (active) {
+      l_active++;
+      l_its += (unsigned long long)nit;
+      if (cut) l_cut++;
+      if (ierr != 0 && (l_first < 0 || cell < l_first)) l_first = cell;
+      l_maxits = max(l_maxits, nit);
+      l_maxkin = max(l_maxkin, nku);
+      l_maxerr = max(l_maxerr, ierr);
+      l_maxsub = max(l_maxsub, nss);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l_active += __shfl_xor_sync(0xffffffffu, l_active, o);
+    l_its += __shfl_xor_sync(0xffffffffu, l_its, o);
+    l_cut += __shfl_xor_sync(0xffffffffu, l_cut, o);
+    long long f = __shfl_xor_sync(0xffffffffu, l_first, o);
+    if (f >= 0 && (l_first < 0 || f < l_first)) l_first = f;
+    l_maxits = max(l_maxits, __shfl_xor_sync(0xffffffffu, l_maxits, o));
+    l_maxkin = max(l_maxkin, __shfl_xor_sync(0xffffffffu, l_maxkin, o));
+    l_maxerr = max(l_maxerr, __shfl_xor_sync(0xffffffffu, l_maxerr, o));
+    l_maxsub = max(l_maxsub, __shfl_xor_sync(0xffffffffu, l_maxsub, o));
+  }
+  if (lane32 == 0) {
+    atomicAdd(&summ->ncell_active, l_active);
+    atomicAdd(&summ->sum_its, l_its);
+    atomicAdd(&summ->num_cut_cells, l_cut);
+    if (l_first >= 0) atomicMin(&summ->first_failed, l_first);
+    atomicMax(&summ->max_its, l_maxits);
+    atomicMax(&summ->max_kin, l_maxkin);
+    atomicMax(&summ->max_err, l_maxerr);
+    atomicMax(&summ->max_sub, l_maxsub);
+  }
+}

@@ -1,0 +1,27 @@
+// pfrx_types.cuh -- kernel argument structs shared by the generic kernels
+// (pfrx_device.cuh, pfrx_tpc.cuh) and the network-specialised ones (pfrx_spec.cuh).
+#pragma once
+#include <stdint.h>
+
+struct DevState {
+  int64_t ld;
+  double *total, *pri_molal, *immobile, *pri_act_coef, *sec_act_coef, *sec_molal, *ln_act_h2o;
+  double *mnrl_volfrac, *mnrl_area, *mnrl_rate, *free_site, *eqsrfcplx_conc, *total_sorb_eq, *kinmr;
+  const double *den_kg, *sat, *temp, *porosity, *volume, *soil_particle_density;
+  const int *imat;
+  int *num_sub_steps, *num_iterations, *num_kinetic_state_updates, *ierror;
+};
+
+// shard summary accumulated with atomics, one set per warp
+struct DevSummary {
+  unsigned long long ncell_active, sum_its, num_cut_cells;
+  long long first_failed;
+  int max_its, max_kin, max_err, max_sub;
+};
+
+
+// launch parameters of a network-specialised kernel (pfrx_spec.cuh)
+struct SpecParams {
+  int max_its, max_cuts;
+  double max_dlnC, tol_relchange, tol_res, tol_relres, min_sat;
+};

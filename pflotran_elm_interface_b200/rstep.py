@@ -61,6 +61,9 @@ def lib():
     L.pfrx_bytes_per_cell.argtypes = [hp]
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
+    L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
+    L.pfrx_config_signature.argtypes = [hp]
+    L.pfrx_config_signature.restype = C.c_uint64
     L.pfrx_diag_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if L.pfrx_abi_version() != abi.PFRX_ABI_VERSION:
         raise PfrxError("libpfrx_b200.so ABI version mismatch")
@@ -227,6 +230,35 @@ class ChemistryStep:
     @property
     def bytes_per_cell(self) -> int:
         return int(lib().pfrx_bytes_per_cell(self._h))
+
+    @property
+    def signature(self) -> int:
+        return int(lib().pfrx_config_signature(self._h))
+
+    def load_specialized(self, cubin_path: Optional[str]) -> None:
+        """attach a cubin written by :mod:`.specialize` (None detaches)"""
+        arg = None if cubin_path is None else os.fsencode(cubin_path)
+        _check(lib().pfrx_load_specialized(self._h, arg), "pfrx_load_specialized")
+
+    def specialize(self, required: bool = False) -> bool:
+        """Attach the network-specialised kernel for this configuration.
+
+        The cubin must have been built beforehand (``specialize.build`` -- done by
+        ``__graft_entry__.build()`` for the stock workloads; nvcc is not needed at
+        run time).  Returns False when the network uses features the generator
+        does not cover or no cubin exists, unless ``required``."""
+        from . import specialize as _sp
+
+        ok, why = _sp.supported(self.cfg)
+        path = _sp.cubin_path(self.cfg) if ok else None
+        if ok and not os.path.exists(path):
+            ok, why = False, "no cubin at " + path
+        if not ok:
+            if required:
+                raise PfrxError("specialised kernel unavailable: " + why)
+            return False
+        self.load_specialized(path)
+        return True
 
     def kernel_info(self) -> Dict[str, int]:
         a = (C.c_int * 5)()

@@ -1,0 +1,553 @@
+"""Code generator for network-specialised kernels.
+
+For one reaction network (:class:`~.abi.ReactionConfig`) this module writes a
+CUDA translation unit in which every stoichiometric coefficient, logK, charge
+and species index of the reference's per-cell routines is an immediate:
+
+* ``spec_activity``  -- RActivityCoefficients, LAG branch   (reaction.F90:4553-4612)
+* ``spec_rtotal``    -- RTotalAqueous + RTAccumulationDerivative (reaction.F90:4665-4759, 5775)
+* ``spec_sorption``  -- RTotalSorbEqSurfCplx1, unit free-site stoichiometry (reaction_surf_complex.F90:641-900)
+* ``spec_minerals``  -- RKineticMineral, TST without prefactors (reaction_mineral.F90:647-1078)
+
+and includes ``csrc/pfrx_spec.cuh`` (RStep/RReact control flow, unrolled LU,
+launch skeleton).  The result is compiled with nvcc for sm_100a into a cubin
+that ``pfrx_load_specialized`` attaches to a handle; the cubin carries a
+signature of the tables it was generated from and the library refuses a cubin
+whose signature differs from the handle's configuration.
+
+Networks the generator does not cover (multirate sorption, sandboxes, general
+free-site stoichiometry, Temkin/affinity-power minerals, anisothermal logK) keep
+running on the generic kernels.
+"""
+from __future__ import annotations
+
+import os
+import struct
+import subprocess
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import abi, chem
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(CSRC, "_spec")
+
+LOG_TO_LN = chem.LOG_TO_LN
+
+def _fnv1a(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in data:
+        h ^= b
+        h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def signature(cfg: abi.ReactionConfig) -> int:
+    """FNV-1a over the tables the generated code bakes in; the byte sequence is
+    the one config_signature() in csrc/pfrx_api.cu hashes"""
+    c, a = cfg.c, cfg.arrays
+    parts = [struct.pack("<12i3d", c.naqcomp, c.nimcomp, c.neqcplx, c.nkinmnrl, c.nsrfcplxrxn, c.nsrfcplx,
+                         c.neqsrfcplxrxn, c.nkinmrsrfcplxrxn, c.clmcn_nrxn, c.use_log_formulation,
+                         c.act_coef_update_frequency, c.use_activity_h2o, c.debyeA, c.debyeB, c.debyeBdot)]
+
+    def add(name: str, count: int, dtype) -> None:
+        if count > 0:
+            arr = np.ascontiguousarray(a[name], dtype=dtype)
+            assert arr.size == count, (name, arr.size, count)
+            parts.append(arr.tobytes())
+
+    f8, i4 = np.float64, np.int32
+    add("primary_spec_Z", c.naqcomp, f8)
+    add("primary_spec_a0", c.naqcomp, f8)
+    if c.neqcplx > 0:
+        n, nnz = c.neqcplx, int(a["eqcplx_ptr"][c.neqcplx])
+        add("eqcplx_ptr", n + 1, i4)
+        add("eqcplx_specid", nnz, i4)
+        add("eqcplx_stoich", nnz, f8)
+        for k in ("eqcplx_h2ostoich", "eqcplx_logK", "eqcplx_Z", "eqcplx_a0"):
+            add(k, n, f8)
+    if c.nkinmnrl > 0:
+        n, nnz = c.nkinmnrl, int(a["kinmnrl_ptr"][c.nkinmnrl])
+        add("kinmnrl_ptr", n + 1, i4)
+        add("kinmnrl_specid", nnz, i4)
+        add("kinmnrl_stoich", nnz, f8)
+        for k in ("kinmnrl_h2ostoich", "kinmnrl_logK", "kinmnrl_molar_vol", "kinmnrl_rate_constant",
+                  "kinmnrl_activation_energy", "kinmnrl_affinity_threshold", "kinmnrl_rate_limiter"):
+            add(k, n, f8)
+        add("kinmnrl_irreversible", n, i4)
+    if c.nsrfcplxrxn > 0:
+        nr, ns = c.nsrfcplxrxn, c.nsrfcplx
+        nnz = int(a["srfcplx_ptr"][ns])
+        add("srfcplxrxn_ptr", nr + 1, i4)
+        add("srfcplxrxn_to_complex", int(a["srfcplxrxn_ptr"][nr]), i4)
+        add("srfcplxrxn_surf_type", nr, i4)
+        add("srfcplxrxn_to_surf", nr, i4)
+        add("srfcplxrxn_site_density", nr, f8)
+        add("srfcplx_ptr", ns + 1, i4)
+        add("srfcplx_specid", nnz, i4)
+        add("srfcplx_stoich", nnz, f8)
+        for k in ("srfcplx_h2ostoich", "srfcplx_free_site_stoich", "srfcplx_logK"):
+            add(k, ns, f8)
+        add("eqsrfcplxrxn_to_srfcplxrxn", c.neqsrfcplxrxn, i4)
+    return _fnv1a(b"".join(parts))
+
+
+def cubin_path(cfg: abi.ReactionConfig) -> str:
+    return os.path.join(OUT, f"spec_{signature(cfg):016x}.cubin")
+
+
+def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
+    c, a = cfg.c, cfg.arrays
+    n = c.naqcomp + c.nimcomp
+    if n > 20:
+        return False, "more than 20 unknowns"
+    if not c.use_isothermal:
+        return False, "anisothermal logK"
+    if c.act_coef_update_algorithm != abi._chem.ACT_COEF_ALGORITHM_LAG:
+        return False, "activity algorithm NEWTON"
+    if c.nkinmrsrfcplxrxn > 0:
+        return False, "multirate sorption"
+    if c.clmcn_nrxn > 0:
+        return False, "reaction sandbox"
+    if c.nsrfcplxrxn != c.neqsrfcplxrxn:
+        return False, "non-equilibrium surface complexation"
+    if c.nsrfcplxrxn and np.any(a["srfcplxrxn_stoich_flag"] != 0):
+        return False, "free-site stoichiometry other than 1"
+    for k in ("kinmnrl_Temkin_const", "kinmnrl_min_scale_factor", "kinmnrl_affinity_power",
+              "kinmnrl_num_prefactors"):
+        if k in a:
+            return False, k
+    if c.use_total_as_guess:
+        return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
+    return True, ""
+
+
+def _lit(x: float) -> str:
+    """exact C++17 hexadecimal floating literal"""
+    x = float(x)
+    if x == 0.0:
+        return "0.0"
+    if x == int(x) and abs(x) < 1e6:
+        return f"{x:.1f}"
+    return float.hex(x)
+
+
+def _term(st: float, expr: str) -> str:
+    """' + st*expr' with exact simplifications for +-1"""
+    if st == 1.0:
+        return f" + {expr}"
+    if st == -1.0:
+        return f" - {expr}"
+    return f" + {_lit(st)} * {expr}"
+
+
+class _Gen:
+    def __init__(self, cfg: abi.ReactionConfig):
+        ok, why = supported(cfg)
+        if not ok:
+            raise ValueError("network not supported by the specialiser: " + why)
+        self.cfg = cfg
+        self.c = cfg.c
+        self.a = cfg.arrays
+        self.naq = cfg.c.naqcomp
+        self.n = cfg.c.naqcomp + cfg.c.nimcomp
+        self.ncx = cfg.c.neqcplx
+        self.act_upd = cfg.c.act_coef_update_frequency == chem.ACT_COEF_FREQUENCY_NEWTON_ITER
+        # activity classes (one Debye-Hueckel evaluation per distinct (Z, a0))
+        self.cls: List[Tuple[float, float]] = []
+        self.pri_cls = [self._class_of(z, a0) for z, a0 in zip(self.a["primary_spec_Z"], self.a["primary_spec_a0"])]
+        self.cx_cls = ([self._class_of(z, a0) for z, a0 in zip(self.a["eqcplx_Z"], self.a["eqcplx_a0"])]
+                       if self.ncx else [])
+        self.out: List[str] = []
+        # species that occur in some reaction form the matrix; the others are
+        # diagonal rows/columns handled as scalars by pfrx_spec.cuh
+        used = set()
+        for ids in ("eqcplx_specid", "kinmnrl_specid", "srfcplx_specid"):
+            if ids in self.a:
+                used.update(int(v) for v in self.a[ids])
+        self.coupled = sorted(used)
+        self.cpos = {sp: ci for ci, sp in enumerate(self.coupled)}
+        self.nc = len(self.coupled)
+
+    def J(self, i: int, j: int) -> str:
+        return f"W[JX({self.cpos[i]}, {self.cpos[j]})]"
+
+    def _class_of(self, z: float, a0: float) -> int:
+        if not abs(z) > 1.0e-10:
+            return -1
+        key = (-z * z, float(a0))
+        if key not in self.cls:
+            self.cls.append(key)
+        return self.cls.index(key)
+
+    def w(self, s: str = "") -> None:
+        self.out.append(s)
+
+    # ------------------------------------------------------------------ pieces
+    def gen_tables(self) -> None:
+        z2 = [float(z) * float(z) for z in self.a["eqcplx_Z"]] if self.ncx else [0.0]
+        cls = self.cx_cls if self.ncx else [-1]
+        vol = [float(v) for v in self.a["kinmnrl_molar_vol"]] if self.c.nkinmnrl else [0.0]
+        self.w("static __device__ const double spec_cx_z2_tab[] = {" + ", ".join(_lit(v) for v in z2) + "};")
+        self.w("static __device__ const int spec_cx_cls_tab[] = {" + ", ".join(str(v) for v in cls) + "};")
+        self.w("static __device__ const double spec_mn_vol_tab[] = {" + ", ".join(_lit(v) for v in vol) + "};")
+        self.w("__device__ __forceinline__ double spec_cx_z2(int k) { return spec_cx_z2_tab[k]; }")
+        self.w("__device__ __forceinline__ int spec_cx_cls(int k) { return spec_cx_cls_tab[k]; }")
+        self.w("__device__ __forceinline__ double spec_mn_vol(int m) { return spec_mn_vol_tab[m]; }")
+        self.w()
+
+    def gen_activity(self) -> None:
+        c, a = self.c, self.a
+        self.w("__device__ __forceinline__ void spec_activity(const double (&c)[SPEC_N], SpecCell &s) {")
+        terms = []
+        for i in range(self.naq):
+            z2 = float(a["primary_spec_Z"][i]) ** 2
+            if z2 != 0.0:
+                terms.append(f"c[{i}] * {_lit(z2)}")
+        self.w("  double Ip = 0.0;")
+        for t in terms:
+            self.w(f"  Ip += {t};")
+        self.w("  const double I = 0.5 * (Ip + s.Isec);")
+        self.w("  const double sq = sqrt(I);")
+        A, B, Bd = _lit(c.debyeA), _lit(c.debyeB), _lit(c.debyeBdot)
+        for q, (negz2, a0) in enumerate(self.cls):
+            self.w(f"  s.lgcls[{q}] = ({_lit(negz2)} * sq * {A} / (1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
+        for i in range(self.naq):
+            q = self.pri_cls[i]
+            self.w(f"  s.lngam[{i}] = {'0.0' if q < 0 else f's.lgcls[{q}]'};")
+        if c.use_activity_h2o:
+            mp = " + ".join(f"c[{i}]" for i in range(self.naq) if i != c.h2o_aq_id) or "0.0"
+            self.w(f"  {{ double t = 1.0 - 0.017 * (({mp}) + s.msec); s.ln_act_h2o = t > 0.0 ? log(t) : 0.0; }}")
+        self.w("}")
+        self.w()
+
+    def gen_rtotal(self) -> None:
+        a, n, naq = self.a, self.n, self.naq
+        self.w("__device__ __forceinline__ void spec_rtotal(const double (&c)[SPEC_N], double (&lna)[SPEC_N],")
+        self.w("    double (&ic)[SPEC_N], double (&tot)[SPEC_N], SpecCell &s, double *W, double *sec_out,")
+        self.w("    long long ld, double dt) {")
+        self.w("  const double denL = s.den_kg * 1.e-3;")
+        self.w("  const double psvd = s.por * s.sat * 1000.0 * s.vol / dt;")
+        for i in range(n):
+            if i < naq:
+                self.w(f"  lna[{i}] = log(c[{i}]) + s.lngam[{i}]; ic[{i}] = 1.0 / c[{i}]; tot[{i}] = c[{i}];")
+            else:
+                self.w(f"  lna[{i}] = 0.0; ic[{i}] = 0.0; tot[{i}] = c[{i}];")
+        self.w("  double Is = 0.0, ms = 0.0;")
+        # how often each Jacobian entry is hit -> hot entries accumulate in registers
+        hits = {}
+        if self.ncx:
+            ptr, ids, st = a["eqcplx_ptr"], a["eqcplx_specid"], a["eqcplx_stoich"]
+            for k in range(self.ncx):
+                sp = range(ptr[k], ptr[k + 1])
+                for p2 in sp:
+                    for p in sp:
+                        e = (int(ids[p]), int(ids[p2]))
+                        hits[e] = hits.get(e, 0) + 1
+        budget = 20 if n > 8 else 9
+        hot = sorted(hits, key=lambda e: -hits[e])[:budget]
+        hot = [e for e in hot if hits[e] >= 4]
+        for (i, j) in hot:
+            self.w(f"  double jh_{i}_{j} = {'1.0' if i == j else '0.0'};")
+        written = set()
+        if self.ncx:
+            for k in range(self.ncx):
+                sp = list(range(ptr[k], ptr[k + 1]))
+                self.w("  {")
+                lq = _lit(-float(a["eqcplx_logK"][k]) * LOG_TO_LN)
+                expr = lq
+                h2o = float(a["eqcplx_h2ostoich"][k])
+                if h2o != 0.0:
+                    expr += _term(h2o, "s.ln_act_h2o")
+                for p in sp:
+                    expr += _term(float(st[p]), f"lna[{int(ids[p])}]")
+                if self.act_upd:
+                    q = self.cx_cls[k]
+                    arg = f"({expr})" if q < 0 else f"({expr}) - s.lgcls[{q}]"
+                else:
+                    arg = f"({expr}) - SW(SPEC_OFF_LNGSEC + {k})"
+                self.w(f"    const double sk = exp({arg});")
+                self.w(f"    sec_out[{k} * ld] = sk;")
+                z2 = float(a["eqcplx_Z"][k]) ** 2
+                if z2 != 0.0:
+                    self.w(f"    Is += sk * {_lit(z2)};")
+                self.w("    ms += sk;")
+                for p in sp:
+                    i, s_i = int(ids[p]), float(st[p])
+                    self.w(f"    tot[{i}] +={_term(s_i, 'sk')[2:]};" if s_i in (1.0,) else
+                           (f"    tot[{i}] -= sk;" if s_i == -1.0 else f"    tot[{i}] += {_lit(s_i)} * sk;"))
+                for p2 in sp:
+                    j, s_j = int(ids[p2]), float(st[p2])
+                    tj = f"(sk * ic[{j}])" if s_j == 1.0 else f"(({_lit(s_j)} * sk) * ic[{j}])"
+                    self.w(f"    {{ const double t = {tj};")
+                    for p in sp:
+                        i, s_i = int(ids[p]), float(st[p])
+                        val = "t" if s_i == 1.0 else f"{_lit(s_i)} * t"
+                        if (i, j) in hot:
+                            self.w(f"      jh_{i}_{j} += {val};")
+                        else:
+                            e = self.J(i, j)
+                            if (i, j) in written:
+                                self.w(f"      {e} += {val};")
+                            else:
+                                init = "1.0 + " if i == j else ""
+                                self.w(f"      {e} = {init}{val};")
+                                written.add((i, j))
+                    self.w("    }")
+                self.w("  }")
+        self.w("  s.Isec = Is; s.msec = ms;")
+        for i in range(naq):
+            self.w(f"  tot[{i}] *= denL;")
+        # finalise d(total)/d(free) * denL * psvd (RTAccumulationDerivative); only
+        # aqueous species can be coupled (immobile ones need a sandbox)
+        for i in self.coupled:
+            for j in self.coupled:
+                e = self.J(i, j)
+                if (i, j) in hot:
+                    self.w(f"  {e} = (jh_{i}_{j} * denL) * psvd;")
+                elif (i, j) in written:
+                    self.w(f"  {e} = ({e} * denL) * psvd;")
+                elif i == j:
+                    self.w(f"  {e} = (1.0 * denL) * psvd;")
+                else:
+                    self.w(f"  {e} = 0.0;")
+        if self.nc:
+            self.w("  if (s.dry) {")
+            self.w("#pragma unroll 1")
+            self.w("    for (int e = 0; e < SPEC_NC * SPEC_JS; e++) SW(e) = 0.0;")
+            self.w("#pragma unroll 1")
+            self.w("    for (int i = 0; i < SPEC_NC; i++) SW(i * (SPEC_JS + 1)) = 1.0;")
+            self.w("  }")
+        self.w("}")
+        self.w()
+
+    def gen_sorption(self) -> None:
+        c, a, n = self.c, self.a, self.n
+        self.w("__device__ __forceinline__ void spec_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],")
+        self.w("    double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st, long long cell, double jscale) {")
+        for k in range(c.nsrfcplx):
+            self.w(f"  s.scconc[{k}] = 0.0;")
+        for e in range(c.neqsrfcplxrxn):
+            r = int(a["eqsrfcplxrxn_to_srfcplxrxn"][e])
+            cx = [int(v) for v in a["srfcplxrxn_to_complex"][a["srfcplxrxn_ptr"][r]:a["srfcplxrxn_ptr"][r + 1]]]
+            ty = int(a["srfcplxrxn_surf_type"][r])
+            dens = _lit(float(a["srfcplxrxn_site_density"][r]))
+            self.w("  {")
+            if ty == chem.MINERAL_SURFACE:
+                self.w(f"    const double dens = {dens} * st.mnrl_volfrac[{int(a['srfcplxrxn_to_surf'][r])} * st.ld + cell];")
+            elif ty == chem.ROCK_SURFACE:
+                self.w(f"    const double dens = {dens} * s.spd * (1.0 - s.por);")
+            else:
+                self.w(f"    const double dens = {dens};")
+            self.w("    if (dens < 1.e-40) {")
+            self.w(f"      s.fsite[{r}] = 0.0;")
+            self.w("    } else {")
+            ptr, ids, st_ = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
+            for q, k in enumerate(cx):
+                expr = _lit(-float(a["srfcplx_logK"][k]) * LOG_TO_LN)
+                h2o = float(a["srfcplx_h2ostoich"][k])
+                if h2o != 0.0:
+                    expr += _term(h2o, "s.ln_act_h2o")
+                for p in range(ptr[k], ptr[k + 1]):
+                    expr += _term(float(st_[p]), f"lna[{int(ids[p])}]")
+                self.w(f"      const double e{q} = exp({expr});")
+            self.w("      double esum = 0.0;")
+            for q in range(len(cx)):
+                self.w(f"      esum += e{q};")
+            self.w("      const double fs = dens / (1.0 + esum);")
+            self.w(f"      s.fsite[{r}] = fs;")
+            for q, k in enumerate(cx):
+                self.w(f"      const double S{q} = e{q} * fs;")
+                self.w(f"      s.scconc[{k}] += S{q};")
+            self.w("      double den = 0.0;")
+            for q in range(len(cx)):
+                self.w(f"      den += S{q};")
+            self.w("      den = den / fs + 1.0;")
+            species = sorted({int(ids[p]) for k in cx for p in range(ptr[k], ptr[k + 1])})
+            for i in species:
+                self.w(f"      double tmp{i} = 0.0;")
+            for q, k in enumerate(cx):
+                for p in range(ptr[k], ptr[k + 1]):
+                    i, nu = int(ids[p]), float(st_[p])
+                    v = f"S{q}" if nu == 1.0 else f"{_lit(nu)} * S{q}"
+                    self.w(f"      tmp{i} += {v}; ts[{i}] += {v};")
+            for i in species:
+                self.w(f"      const double dsx{i} = (-tmp{i} / den) * ic[{i}];")
+            for q, k in enumerate(cx):
+                sp = list(range(ptr[k], ptr[k + 1]))
+                self.w(f"      {{ const double nuiSx = S{q} / fs;")
+                for p2 in sp:
+                    j, nu_j = int(ids[p2]), float(st_[p2])
+                    a1 = f"S{q} * ic[{j}]" if nu_j == 1.0 else f"{_lit(nu_j)} * S{q} * ic[{j}]"
+                    self.w(f"        {{ const double t = {a1} + nuiSx * dsx{j};")
+                    for p in sp:
+                        i, nu_i = int(ids[p]), float(st_[p])
+                        v = "t" if nu_i == 1.0 else f"({_lit(nu_i)} * t)"
+                        self.w(f"          {self.J(i, j)} += jscale * {v};")
+                    self.w("        }")
+                self.w("      }")
+            self.w("    }")
+            self.w("  }")
+        self.w("}")
+        self.w()
+
+    def gen_minerals(self) -> None:
+        c, a, n = self.c, self.a, self.n
+        self.w("__device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],")
+        self.w("    double (&res)[SPEC_N], SpecCell &s, double *W, const DevState &st, long long cell, bool apply) {")
+        for m in range(c.nkinmnrl):
+            ptr, ids, st_ = a["kinmnrl_ptr"], a["kinmnrl_specid"], a["kinmnrl_stoich"]
+            sp = list(range(ptr[m], ptr[m + 1]))
+            expr = _lit(-float(a["kinmnrl_logK"][m]) * LOG_TO_LN)
+            h2o = float(a["kinmnrl_h2ostoich"][m])
+            if h2o != 0.0:
+                expr += _term(h2o, "s.ln_act_h2o")
+            for p in sp:
+                expr += _term(float(st_[p]), f"lna[{int(ids[p])}]")
+            thr = float(a["kinmnrl_affinity_threshold"][m])
+            lim = float(a["kinmnrl_rate_limiter"][m])
+            eact = float(a["kinmnrl_activation_energy"][m])
+            irr = int(a["kinmnrl_irreversible"][m])
+            rate = _lit(float(a["kinmnrl_rate_constant"][m]))
+            self.w("  {")
+            self.w(f"    const double QK = exp({expr});")
+            self.w("    double aff = 1.0 - QK;")
+            self.w("    const double sgn = copysign(1.0, aff);")
+            self.w(f"    bool active = (st.mnrl_volfrac[{m} * st.ld + cell] > 0.0 || sgn < 0.0);")
+            if irr == 1:
+                self.w("    if (sgn < 0.0) active = false;")
+            if thr > 0.0:
+                self.w(f"    if (sgn < 0.0 && QK < {_lit(thr)}) active = false;")
+            self.w("    double rate_vol = 0.0;")
+            self.w("    if (active) {")
+            if lim > 0.0:
+                self.w(f"      aff = aff / (1.0 + (1.0 - aff) / {_lit(lim)});")
+            if eact > 0.0:
+                self.w(f"      const double spr = {rate} * exp({_lit(eact)} / 8.31446 * "
+                       "(1.0 / (25.0 + 273.15) - 1.0 / (s.temp + 273.15)));")
+            else:
+                self.w(f"      const double spr = {rate} * 1.0;")
+            self.w(f"      double Im_const = -st.mnrl_area[{m} * st.ld + cell];")
+            self.w("      double Im = Im_const * sgn * fabs(aff) * spr;")
+            self.w("      rate_vol = Im;")
+            self.w("      if (apply) {")
+            self.w("        Im_const = Im_const * s.vol;")
+            self.w("        Im = Im * s.vol;")
+            self.w("        const double dIm_dQK = -Im_const * spr;")
+            if lim > 0.0:
+                self.w(f"        const double den = 1.0 + (1.0 - aff) / {_lit(lim)};")
+                self.w(f"        const double dfac = dIm_dQK * (1.0 + QK / {_lit(lim)} / den) * QK * (s.den_kg * 1.e-3) / den;")
+            else:
+                self.w("        const double dfac = dIm_dQK * QK * (s.den_kg * 1.e-3);")
+            for p in sp:
+                i, nu = int(ids[p]), float(st_[p])
+                self.w(f"        res[{i}] +={' ' if nu == 1.0 else f' {_lit(nu)} *'} Im;")
+            for p2 in sp:
+                j, nu_j = int(ids[p2]), float(st_[p2])
+                self.w(f"        {{ const double t = dfac * ({_lit(nu_j)} * ic[{j}]);")
+                for p in sp:
+                    i, nu_i = int(ids[p]), float(st_[p])
+                    v = "t" if nu_i == 1.0 else f"{_lit(nu_i)} * t"
+                    self.w(f"          {self.J(i, j)} += {v};")
+                self.w("        }")
+            self.w("      }")
+            self.w("    }")
+            self.w(f"    s.mrate[{m}] = rate_vol;")
+            self.w("  }")
+        self.w("}")
+        self.w()
+
+    # ------------------------------------------------------------------ whole file
+    def source(self) -> str:
+        c = self.c
+        n = self.n
+        slots = self.nc * (self.nc + 1) + 2 * n + (0 if self.act_upd else self.ncx)
+        per_warp = slots * 32 * 8 + 1024  # + the per-block reservation when a block is one warp
+        if slots * 32 * 8 > 160 * 1024:
+            threads = 32
+            minblocks = 1
+        elif n > 8:
+            threads = 32
+            minblocks = max(1, min(8, (228 * 1024) // per_warp))
+        else:
+            threads = 128
+            minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
+        self.threads, self.minblocks, self.slots = threads, minblocks, slots
+        o = self.out
+        o.clear()
+        self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
+        self.w(f"#define SPEC_N {n}")
+        self.w(f"#define SPEC_NAQ {self.naq}")
+        self.w(f"#define SPEC_NC {self.nc}")
+        self.w(f"#define SPEC_NCX {self.ncx}")
+        self.w(f"#define SPEC_NCLS {len(self.cls)}")
+        self.w(f"#define SPEC_NKIN {c.nkinmnrl}")
+        self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
+        self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
+        self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
+        self.w(f"#define SPEC_USE_LOG {int(c.use_log_formulation)}")
+        self.w(f"#define SPEC_ACT_UPD {int(self.act_upd)}")
+        self.w(f"#define SPEC_USE_ACT_H2O {int(c.use_activity_h2o)}")
+        self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
+        self.w(f"#define SPEC_THREADS {threads}")
+        self.w(f"#define SPEC_MINBLOCKS {minblocks}")
+        cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
+        so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
+        self.w("__host__ __device__ constexpr int spec_cmap(int i) { return " + (cm + " : -1" if cm else "-1") + "; }")
+        self.w("__host__ __device__ constexpr int spec_sp_of(int ci) { return " + (so + " : 0" if so else "0") + "; }")
+        self.w("__device__ __forceinline__ double spec_cx_z2(int k);")
+        self.w("__device__ __forceinline__ int spec_cx_cls(int k);")
+        self.w("__device__ __forceinline__ double spec_mn_vol(int m);")
+        self.w('#include "pfrx_spec.cuh"')
+        self.w()
+        self.gen_tables()
+        self.gen_activity()
+        self.gen_rtotal()
+        self.gen_sorption()
+        self.gen_minerals()
+        return "\n".join(o) + "\n"
+
+
+def generate_source(cfg: abi.ReactionConfig) -> str:
+    return _Gen(cfg).source()
+
+
+def _stamp(src: str) -> str:
+    import hashlib
+
+    h = hashlib.sha1(src.encode())
+    for d in ("pfrx_spec.cuh", "pfrx_types.cuh"):
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build(cfg: abi.ReactionConfig, force: bool = False, verbose: bool = False) -> str:
+    """generate + ``nvcc -cubin``; returns the cubin path.  The cubin is cached
+    under csrc/_spec/ by configuration signature, with a stamp of the generated
+    source and the headers it includes."""
+    os.makedirs(OUT, exist_ok=True)
+    cubin = cubin_path(cfg)
+    base = cubin[:-len(".cubin")]
+    cu, stamp_file = base + ".cu", base + ".stamp"
+    src = generate_source(cfg)
+    stamp = _stamp(src)
+    if (not force and os.path.exists(cubin) and os.path.exists(stamp_file)
+            and open(stamp_file).read().strip() == stamp):
+        return cubin
+    with open(cu, "w") as f:
+        f.write(src)
+    cmd = [os.environ.get("NVCC", "nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+           "-std=c++17", "-cubin", "-I", CSRC, "-Xptxas", "-v", "-o", cubin, cu]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(base + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + p.stdout)
+    if p.returncode != 0:
+        raise RuntimeError("nvcc failed for the specialised kernel:\n" + p.stdout[-4000:])
+    with open(stamp_file, "w") as f:
+        f.write(stamp + "\n")
+    if verbose:
+        print(p.stdout)
+    return cubin

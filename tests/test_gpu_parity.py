@@ -53,11 +53,16 @@ def _compare(ref: abi.HostState, got: abi.HostState, what: str, rtol=RTOL, count
         assert worst <= rtol, f"{what}: field {f} max rel err {worst:.3e} at {np.unravel_index(err.argmax(), err.shape)}"
 
 
-def _run_both(wl, host_path=False):
+def _run_both(wl, host_path=False, spec=False):
     rstep = _gpu()
     ref = wl.state.copy()
     res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
     step = rstep.ChemistryStep(wl.cfg, 0)
+    if spec:
+        from pflotran_elm_interface_b200 import specialize
+
+        specialize.build(wl.cfg)  # cached by __graft_entry__.build()
+        assert step.specialize(required=True)
     if host_path:
         got = wl.state.copy()
         res = step.rstep_host(got, wl.tran_dt)
@@ -115,6 +120,35 @@ def test_hanford(variant, dt):
     ref, rr, got, rg, info = _run_both(wl)
     _compare(ref, got, f"{variant} dt={dt}")
     _check_summary(rr, rg)
+
+
+@pytest.mark.parametrize("variant,dt,host", [("c1", 3600.0, False), ("c2", 3600.0, False), ("c2", 86400.0 * 91, True),
+                                             ("c3", 3600.0, False), ("c3", 30 * 86400.0, True),
+                                             ("c5", 86400.0, False)])
+def test_specialized_kernel(variant, dt, host):
+    """the code-generated kernel (specialize.py + pfrx_spec.cuh) against the oracle"""
+    wl = W.by_name(variant, ncell=1 if variant == "c1" else 1500, tran_dt=dt)
+    ref, res_ref, got, res, info = _run_both(wl, host_path=host, spec=True)
+    assert info["lanes"] == -1, info
+    _compare(ref, got, f"specialised {variant} dt={dt}")
+    _check_summary(res_ref, res)
+
+
+def test_specialized_kernel_refuses_other_network():
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    c2, c3 = W.by_name("c2", ncell=4), W.by_name("c3", ncell=4)
+    step = rstep.ChemistryStep(c2.cfg, 0)
+    assert step.signature == specialize.signature(c2.cfg)
+    with pytest.raises(rstep.PfrxError, match="another network"):
+        step.load_specialized(specialize.build(c3.cfg))
+    unsupported = W.by_name("c4", ncell=4)
+    assert not specialize.supported(unsupported.cfg)[0]
+    step4 = rstep.ChemistryStep(unsupported.cfg, 0)
+    assert step4.specialize() is False
+    with pytest.raises(rstep.PfrxError):
+        step4.specialize(required=True)
 
 
 @pytest.mark.parametrize("variant", ["c3", "c3mr", "c4", "c5"])
