@@ -219,7 +219,7 @@ struct pfrx_handle {
   uint64_t sig = 0;
   SpecParams spec_prm;
   void *spec_module = nullptr, *spec_func = nullptr;
-  int spec_threads = 0, spec_blocks_per_sm = 0, spec_stride = 0;
+  int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
   size_t spec_smem = 0;
   // nccl
   NcclComm comm = nullptr;
@@ -828,7 +828,7 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
   if (h->tpc) need = (ncell + h->threads - 1) / h->threads;
   int64_t cap = (int64_t)h->sm_count * h->blocks_per_sm;
   if (h->spec_func) {
-    need = (ncell + h->spec_threads - 1) / h->spec_threads;
+    need = (ncell + h->spec_cells - 1) / h->spec_cells;
     cap = (int64_t)h->sm_count * h->spec_blocks_per_sm;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, cap));
     DevState st_arg = st;
@@ -1182,7 +1182,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   unsigned long long dptr = 0;
   size_t bytes = 0;
   unsigned long long sig = 0;
-  int info[4] = {0, 0, 0, 0};
+  int info[5] = {0, 0, 0, 0, 0};
   int e = g_drv.ModuleGetGlobal(&dptr, &bytes, mod, "pfrx_spec_sig");
   if (!e && bytes == sizeof(sig)) e = g_drv.MemcpyDtoH(&sig, dptr, sizeof(sig));
   if (!e) e = g_drv.ModuleGetGlobal(&dptr, &bytes, mod, "pfrx_spec_info");
@@ -1200,8 +1200,13 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
     return set_err(PFRX_E_INVALID, "specialised kernel was generated for another network (signature %s, need %s)", a, b);
   }
   int threads = info[2];
-  size_t smem = (size_t)info[1] * sizeof(double) * threads;
+  size_t smem = (size_t)info[1] * sizeof(double);
   int nb = 0;
+  if (const char *ev = getenv("PFRX_SPEC_MAXBLOCKS")) {
+    // diagnostics: limit residency by asking for more shared memory than needed
+    int mb = atoi(ev);
+    if (mb >= 1) smem = std::max(smem, (size_t)(232448 / mb - 1024) & ~(size_t)1023);
+  }
   e = g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
   if (!e) e = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem);
   if (e || nb < 1) {
@@ -1211,7 +1216,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   h->spec_module = mod;
   h->spec_func = fn;
   h->spec_threads = threads;
-  h->spec_stride = info[1];
+  h->spec_cells = info[4];
   h->spec_smem = smem;
   h->spec_blocks_per_sm = nb;
   return PFRX_OK;

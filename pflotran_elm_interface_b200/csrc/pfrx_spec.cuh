@@ -43,7 +43,8 @@
 
 extern "C" {
 __device__ const unsigned long long pfrx_spec_sig = SPEC_SIG;
-__device__ const int pfrx_spec_info[4] = {SPEC_N, SPEC_SLOTS, SPEC_THREADS, SPEC_MINBLOCKS};
+// {N, shared doubles per block, threads per block, min blocks per SM, cells per block}
+__device__ const int pfrx_spec_info[5] = {SPEC_N, SPEC_SLOTS * SPEC_THREADS, SPEC_THREADS, SPEC_MINBLOCKS, SPEC_THREADS};
 }
 
 struct SpecCell {
