@@ -94,9 +94,15 @@ def signature(cfg: abi.ReactionConfig) -> int:
     return _fnv1a(b"".join(parts))
 
 
-def cubin_path(cfg: abi.ReactionConfig, warps: Optional[int] = None) -> str:
-    warps = default_warps(cfg) if warps is None else warps
-    return os.path.join(OUT, f"spec_{signature(cfg):016x}_w{warps}.cubin")
+def _variant(cfg: abi.ReactionConfig, warps: Optional[int], style: Optional[str]) -> Tuple[int, str]:
+    """(warps per 32 cells, code style) -- defaults from default_variant()"""
+    dw, ds = default_variant(cfg)
+    return (dw if warps is None else warps), (ds if style is None else style)
+
+
+def cubin_path(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
+    warps, style = _variant(cfg, warps, style)
+    return os.path.join(OUT, f"spec_{signature(cfg):016x}_{style[0]}{warps}.cubin")
 
 
 def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
@@ -247,7 +253,7 @@ class _Gen:
                     for p in sp:
                         e = (int(ids[p]), int(ids[p2]))
                         hits[e] = hits.get(e, 0) + 1
-        budget = 20 if n > 8 else 9
+        budget = int(os.environ.get("PFRX_SPEC_HOT", 20 if n > 8 else 9))
         hot = sorted(hits, key=lambda e: -hits[e])[:budget]
         hot = [e for e in hot if hits[e] >= 4]
         for (i, j) in hot:
@@ -867,6 +873,119 @@ class _GenW(_Gen):
         return "\n".join(self.out) + "\n"
 
 
+class _GenR(_GenW):
+    """rolled variant (csrc/pfrx_specr.cuh): the network as __constant__ tables, sizes
+    as macros, one instruction stream for the SPEC_W warps of a group"""
+
+    def table(self, ctype: str, name: str, vals, fmt) -> None:
+        vals = list(vals)
+        body = ", ".join(fmt(v) for v in vals) if vals else ("0" if ctype == "int" else "0.0")
+        self.w(f"__constant__ {ctype} {name}[{max(1, len(vals))}] = {{{body}}};")
+
+    def source(self) -> str:
+        c, a, n, W = self.c, self.a, self.n, self.W
+        I = lambda v: str(int(v))
+        D = lambda v: _lit(float(v))
+        slots = self.nc * (self.nc + 1) + 2 * self.nc + 3 * W
+        per_block = slots * 32 * 8 + 1024
+        groups = max(1, min(16 // W, (227 * 1024) // per_block))
+        self.threads, self.minblocks, self.slots = 32 * W, groups, slots
+        nr = c.nsrfcplxrxn
+        maxq = 1
+        if nr:
+            rp = a["srfcplxrxn_ptr"]
+            maxq = max(int(rp[r + 1] - rp[r]) for r in range(nr))
+            cxs = [int(v) for v in a["srfcplxrxn_to_complex"]]
+            if len(set(cxs)) != len(cxs):
+                raise ValueError("a surface complex that belongs to two reactions")
+        self.out.clear()
+        self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
+        for k, v in (("SPEC_N", n), ("SPEC_NAQ", self.naq), ("SPEC_NC", self.nc), ("SPEC_NCX", self.ncx),
+                     ("SPEC_NCLS", len(self.cls)), ("SPEC_NKIN", c.nkinmnrl), ("SPEC_NSRFRXN", nr),
+                     ("SPEC_NSRFCPLX", c.nsrfcplx), ("SPEC_NEQSR", c.neqsrfcplxrxn), ("SPEC_MAXQ", maxq),
+                     ("SPEC_USE_LOG", int(c.use_log_formulation)), ("SPEC_ACT_UPD", int(self.act_upd)),
+                     ("SPEC_W", W), ("SPEC_MINBLOCKS", groups), ("SPEC_DEBYE_A", _lit(c.debyeA)),
+                     ("SPEC_DEBYE_B", _lit(c.debyeB)), ("SPEC_DEBYE_BDOT", _lit(c.debyeBdot))):
+            self.w(f"#define {k} {v}")
+        self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
+        self.w("#include <cuda_runtime.h>")
+        cp = self.cpos
+        self.table("int", "T_cmap", [cp.get(i, -1) for i in range(n)], I)
+        self.table("double", "T_z2", [float(a["primary_spec_Z"][i]) ** 2 if i < self.naq else 0.0 for i in range(n)], D)
+        self.table("int", "T_pcls", [self.pri_cls[i] if i < self.naq else -1 for i in range(n)], I)
+        self.table("double", "T_cls_negz2", [q[0] for q in self.cls], D)
+        self.table("double", "T_cls_a0", [q[1] for q in self.cls], D)
+        # secondary complexes and their transpose (species -> complexes, ascending k)
+        if self.ncx:
+            ptr, ids, st = a["eqcplx_ptr"], a["eqcplx_specid"], a["eqcplx_stoich"]
+        else:
+            ptr, ids, st = [0], [], []
+        self.table("int", "T_cx_ptr", ptr, I)
+        self.table("int", "T_cx_id", [cp[int(v)] for v in ids], I)
+        self.table("double", "T_cx_nu", st, D)
+        self.table("double", "T_cx_lnk", [-float(v) * LOG_TO_LN for v in (a["eqcplx_logK"] if self.ncx else [])], D)
+        self.table("double", "T_cx_h2o", a["eqcplx_h2ostoich"] if self.ncx else [], D)
+        self.table("double", "T_cx_z2", [float(v) ** 2 for v in (a["eqcplx_Z"] if self.ncx else [])], D)
+        self.table("int", "T_cx_cls", self.cx_cls, I)
+        sp_ptr, sp_cx, sp_nu = [0], [], []
+        for ci, sp in enumerate(self.coupled):
+            for k in range(self.ncx):
+                for p in range(ptr[k], ptr[k + 1]):
+                    if int(ids[p]) == sp:
+                        sp_cx.append(k)
+                        sp_nu.append(float(st[p]))
+            sp_ptr.append(len(sp_cx))
+        self.table("int", "T_sp_ptr", sp_ptr, I)
+        self.table("int", "T_sp_cx", sp_cx, I)
+        self.table("double", "T_sp_nu", sp_nu, D)
+        # kinetic minerals
+        nk = c.nkinmnrl
+        if nk:
+            mptr, mids, mst = a["kinmnrl_ptr"], a["kinmnrl_specid"], a["kinmnrl_stoich"]
+        else:
+            mptr, mids, mst = [0], [], []
+        self.table("int", "T_mn_ptr", mptr, I)
+        self.table("int", "T_mn_id", [cp[int(v)] for v in mids], I)
+        self.table("int", "T_mn_sp", mids, I)
+        self.table("double", "T_mn_nu", mst, D)
+        self.table("double", "T_mn_lnk", [-float(v) * LOG_TO_LN for v in (a["kinmnrl_logK"] if nk else [])], D)
+        for nm, key in (("T_mn_h2o", "kinmnrl_h2ostoich"), ("T_mn_vol", "kinmnrl_molar_vol"),
+                        ("T_mn_rate", "kinmnrl_rate_constant"), ("T_mn_eact", "kinmnrl_activation_energy"),
+                        ("T_mn_thr", "kinmnrl_affinity_threshold"), ("T_mn_lim", "kinmnrl_rate_limiter")):
+            self.table("double", nm, a[key] if nk else [], D)
+        self.table("int", "T_mn_irr", a["kinmnrl_irreversible"] if nk else [], I)
+        # equilibrium surface complexation
+        if nr:
+            kinds = {chem.MINERAL_SURFACE: 1, chem.ROCK_SURFACE: 2}
+            self.table("int", "T_sr_ptr", a["srfcplxrxn_ptr"], I)
+            self.table("int", "T_sr_cx", a["srfcplxrxn_to_complex"], I)
+            self.table("int", "T_sr_type", [kinds.get(int(v), 0) for v in a["srfcplxrxn_surf_type"]], I)
+            self.table("int", "T_sr_surf", [max(0, int(v)) for v in a["srfcplxrxn_to_surf"]], I)
+            self.table("double", "T_sr_dens", a["srfcplxrxn_site_density"], D)
+            sptr, sids, sst = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
+            self.table("int", "T_sc_ptr", sptr, I)
+            self.table("int", "T_sc_id", [cp[int(v)] for v in sids], I)
+            self.table("int", "T_sc_sp", sids, I)
+            self.table("double", "T_sc_nu", sst, D)
+            self.table("double", "T_sc_lnk", [-float(v) * LOG_TO_LN for v in a["srfcplx_logK"]], D)
+            self.table("double", "T_sc_h2o", a["srfcplx_h2ostoich"], D)
+            self.table("int", "T_eq", a["eqsrfcplxrxn_to_srfcplxrxn"], I)
+            dnu = [0.0] * (nr * maxq * self.nc)
+            rp = a["srfcplxrxn_ptr"]
+            for r in range(nr):
+                for qq, k in enumerate(a["srfcplxrxn_to_complex"][rp[r]:rp[r + 1]]):
+                    for p in range(sptr[k], sptr[k + 1]):
+                        dnu[(r * maxq + qq) * self.nc + cp[int(sids[p])]] = float(sst[p])
+            self.table("double", "T_sr_dnu", dnu, D)
+        else:
+            for nm in ("T_sr_ptr", "T_sr_cx", "T_sr_type", "T_sr_surf", "T_sc_ptr", "T_sc_id", "T_sc_sp", "T_eq"):
+                self.table("int", nm, [0, 0] if nm.endswith("ptr") else [], I)
+            for nm in ("T_sr_dens", "T_sc_nu", "T_sc_lnk", "T_sc_h2o", "T_sr_dnu"):
+                self.table("double", nm, [], D)
+        self.w('#include "pfrx_specr.cuh"')
+        return "\n".join(self.out) + "\n"
+
+
 def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]:
     ok, why = supported(cfg)
     if not ok:
@@ -889,20 +1008,23 @@ def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]
     return True, ""
 
 
-def default_warps(cfg: abi.ReactionConfig) -> int:
-    """warps per 32 cells: one while a thread's Jacobian is small enough for many
-    resident warps, four when shared memory would hold only a handful"""
-    env = os.environ.get("PFRX_SPEC_WARPS")
+def default_variant(cfg: abi.ReactionConfig) -> Tuple[int, str]:
+    """(warps per 32 cells, style).  Measured on B200 with the Hanford 15/88 network
+    (profiles/r01_spec_variants.md): straight-line code with one warp per 32 cells
+    135 ms, rolled tables with four warps 396 ms, straight-line with four warps
+    635 ms per 4.19 M cells -- so the first is the default for every network; the
+    other two stay selectable for experiments:
+    PFRX_SPEC_VARIANT=<style><warps> with style s (straight) or r (rolled)."""
+    env = os.environ.get("PFRX_SPEC_VARIANT")
     if env:
-        return int(env)
-    n = cfg.c.naqcomp + cfg.c.nimcomp
-    if n > 8 and supported_multiwarp(cfg, 4)[0]:
-        return 4
-    return 1
+        return int(env[1:]), {"s": "straight", "r": "rolled"}[env[0]]
+    return 1, "straight"
 
 
-def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None) -> str:
-    warps = default_warps(cfg) if warps is None else warps
+def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
+    warps, style = _variant(cfg, warps, style)
+    if style == "rolled":
+        return _GenR(cfg, warps).source()
     return _GenW(cfg, warps).source() if warps > 1 else _Gen(cfg).source()
 
 
@@ -910,21 +1032,22 @@ def _stamp(src: str) -> str:
     import hashlib
 
     h = hashlib.sha1(src.encode())
-    for d in ("pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_types.cuh"):
+    for d in ("pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh"):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(f.read())
     return h.hexdigest()
 
 
-def build(cfg: abi.ReactionConfig, force: bool = False, verbose: bool = False, warps: Optional[int] = None) -> str:
+def build(cfg: abi.ReactionConfig, force: bool = False, verbose: bool = False, warps: Optional[int] = None,
+          style: Optional[str] = None) -> str:
     """generate + ``nvcc -cubin``; returns the cubin path.  The cubin is cached
     under csrc/_spec/ by configuration signature, with a stamp of the generated
     source and the headers it includes."""
     os.makedirs(OUT, exist_ok=True)
-    cubin = cubin_path(cfg, warps)
+    cubin = cubin_path(cfg, warps, style)
     base = cubin[:-len(".cubin")]
     cu, stamp_file = base + ".cu", base + ".stamp"
-    src = generate_source(cfg, warps)
+    src = generate_source(cfg, warps, style)
     stamp = _stamp(src)
     if (not force and os.path.exists(cubin) and os.path.exists(stamp_file)
             and open(stamp_file).read().strip() == stamp):
