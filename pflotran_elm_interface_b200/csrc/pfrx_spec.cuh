@@ -104,7 +104,8 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
 #pragma unroll
     for (int j = 0; j < NC; j++) {
       row[j] = W[JX(i, j)];
-      m = fmax(m, fabs(row[j]));
+      const double av = fabs(row[j]);
+      m = av > m ? av : m;  // maxval(abs()) without fmax's NaN plumbing
     }
     double nm = 1.0 / fmax(1.0, m);
     b[i] = res[spec_sp_of(i)] * nm;
@@ -114,7 +115,8 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
       double v = row[j] * nm;
       if (SPEC_USE_LOG) v *= c[spec_sp_of(j)];
       W[JX(i, j)] = v;
-      m2 = fmax(m2, fabs(v));
+      const double av = fabs(v);
+      m2 = av > m2 ? av : m2;
     }
     if (!(m2 > 0.0)) bad = true;
     W[JX(i, NC)] = 1. / m2;
@@ -343,7 +345,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   nss = nit = nku = ierr = 0;
   had_cut = false;
   double Is = 0.0, ms = 0.0;
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < SPEC_NCX; k++) {
     double m = st.sec_molal[k * ld + cell];
     Is += m * spec_cx_z2(k);
@@ -362,14 +364,22 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   for (int k = 0; k < SPEC_NKIN; k++) s.mrate[k] = st.mnrl_rate[k * ld + cell];
   unsigned small_mask = 0u;
   double small_val[N];
+  // all loads first: the clamping stores below would otherwise order them
+  double in_t[N], in_g[N], in_a[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    in_a[i] = (i < NAQ) ? st.pri_act_coef[i * ld + cell] : 1.0;
+    in_g[i] = (i < NAQ) ? st.pri_molal[i * ld + cell] : 0.0;
+    in_t[i] = (i < NAQ) ? st.total[i * ld + cell] : st.immobile[(i - NAQ) * ld + cell];
+  }
 #pragma unroll
   for (int i = 0; i < N; i++) {
     small_val[i] = 0.0;
     s.lngam[i] = 0.0;
     if (i < NAQ) {
-      s.lngam[i] = log(st.pri_act_coef[i * ld + cell]);
-      double g = st.pri_molal[i * ld + cell];
-      double t = st.total[i * ld + cell];
+      s.lngam[i] = log(in_a[i]);
+      double g = in_g[i];
+      double t = in_t[i];
       if (t <= 1.e-40) {
         small_mask |= 1u << i;
         small_val[i] = t;
@@ -378,7 +388,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
       }
       SW(SPEC_OFF_GUESS + i) = g;
     } else {
-      double t = st.immobile[(i - NAQ) * ld + cell];
+      double t = in_t[i];
       SW(SPEC_OFF_GUESS + i) = t;  // the guess keeps the unclamped value
       if (t <= 1.e-40) {
         small_mask |= 1u << i;
