@@ -1209,6 +1209,23 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   }
   e = g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
   if (!e) e = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem);
+  if (!e && info[3] >= 1 && nb > info[3]) {
+    // the kernel asks for at most info[3] resident blocks per SM: ask for just enough
+    // shared memory that one more does not fit (the rest stays L1 for its spills)
+    size_t pad = ((size_t)232448 / (info[3] + 1) - 1024 + 1024) & ~(size_t)255;
+    while (pad > smem) {
+      int nb2 = 0;
+      if (g_drv.FuncSetAttribute(fn, 8, (int)pad)) break;
+      if (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb2, fn, threads, pad)) break;
+      if (nb2 <= info[3] && nb2 >= 1) {
+        smem = pad;
+        nb = nb2;
+        break;
+      }
+      pad += 1024;
+      if (pad > 200 * 1024) break;
+    }
+  }
   if (e || nb < 1) {
     g_drv.ModuleUnload(mod);
     return set_err(PFRX_E_LIMIT, "specialised kernel does not fit on an SM: %s", e ? drv_err(e) : "0 blocks");

@@ -477,7 +477,9 @@ class _Gen:
             minblocks = 1
         elif n > 8:
             threads = 32
-            minblocks = max(1, min(8, (228 * 1024) // per_warp))
+            # measured (profiles/r01_occupancy_sweep_spec.txt): one warp per scheduler is the
+            # optimum for these 255-register kernels; a fifth warp per SM costs 12 %
+            minblocks = max(1, min(4, (228 * 1024) // per_warp))
         else:
             threads = 128
             minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
