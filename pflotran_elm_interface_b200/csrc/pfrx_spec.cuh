@@ -27,7 +27,18 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pfrx_fastmath.cuh"
 #include "pfrx_types.cuh"
+
+// SPEC_FASTMATH 1: branch-free exp / log / division (pfrx_fastmath.cuh) in the hot
+// places whose arguments are known to be normal numbers; 0: CUDA's own everywhere
+#ifndef SPEC_FASTMATH
+#define SPEC_FASTMATH 1
+#endif
+__device__ __forceinline__ double sx_exp(double x) { return SPEC_FASTMATH ? pfrx_exp(x) : exp(x); }
+__device__ __forceinline__ double sx_log(double x) { return SPEC_FASTMATH ? pfrx_log(x) : log(x); }
+__device__ __forceinline__ double sx_rcp(double x) { return SPEC_FASTMATH ? pfrx_rcp(x) : 1.0 / x; }
+__device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTMATH ? pfrx_div(a, b) : a / b; }
 
 #define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 
@@ -88,11 +99,11 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
     if (spec_cmap(i) < 0) {
       double Jd = (i < SPEC_NAQ) ? (1.0 * (s.den_kg * 1.e-3)) * (s.por * s.sat * 1000.0 * s.vol / dt) : s.vol / dt;
       if (s.dry) Jd = 1.0;
-      double nm = 1.0 / fmax(1.0, fabs(Jd));
+      double nm = sx_rcp(fmax(1.0, fabs(Jd)));
       double a = Jd * nm;
       if (SPEC_USE_LOG) a *= c[i];
       if (!(fabs(a) > 0.0)) bad = true;
-      res[i] = (res[i] * nm) / a;
+      res[i] = sx_div(res[i] * nm, a);
     }
   }
   if (NC == 0) return !bad;
@@ -107,7 +118,7 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
       const double av = fabs(row[j]);
       m = av > m ? av : m;  // maxval(abs()) without fmax's NaN plumbing
     }
-    double nm = 1.0 / fmax(1.0, m);
+    double nm = sx_rcp(fmax(1.0, m));
     b[i] = res[spec_sp_of(i)] * nm;
     double m2 = 0.0;
 #pragma unroll
@@ -119,7 +130,7 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
       m2 = av > m2 ? av : m2;
     }
     if (!(m2 > 0.0)) bad = true;
-    W[JX(i, NC)] = 1. / m2;
+    W[JX(i, NC)] = sx_rcp(m2);
   }
   if (bad) return false;
   int ro[NCA];
@@ -172,7 +183,7 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
     ro[j] = rmax;
     if (pv == 0.0) pv = 1.0e-20;
     if (j != NC - 1) {
-      double dum = 1.0 / pv;
+      double dum = sx_rcp(pv);
       // the logical order has changed already: position imax holds old row j
 #pragma unroll
       for (int i = 0; i < NC; i++) {
@@ -204,7 +215,7 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
 #pragma unroll
     for (int m = 0; m < NC; m++)
       if (m > k) sum -= r[m * 32] * b[m];
-    b[k] = sum / r[k * 32];
+    b[k] = sx_div(sum, r[k * 32]);
   }
 #pragma unroll
   for (int k = 0; k < NC; k++) res[spec_sp_of(k)] = b[k];
@@ -256,7 +267,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       double a = 0.0;
       if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
       if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
-      res[i] = (a - SW(SPEC_OFF_FIXED + i)) / dt;
+      res[i] = sx_div(a - SW(SPEC_OFF_FIXED + i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
     double mabs = 0.0, ss = 0.0;
@@ -296,12 +307,12 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
         double u = res[i];
         if (SPEC_USE_LOG) {
           u = copysign(1.0, u) * fmin(fabs(u), prm.max_dlnC);
-          cn[i] = c[i] * exp(-u);
+          cn[i] = c[i] * sx_exp(-u);
         } else {
           if (minr < 1.0) u = u * minr * 0.99;
           cn[i] = c[i] - u;
         }
-        double v = fabs((cn[i] - c[i]) / c[i]);
+        double v = fabs(sx_div(cn[i] - c[i], c[i]));
         if (!isnan(v)) maxrel = fmax(maxrel, v);
       }
       conv = (maxrel >= 0.0) && (maxrel < prm.tol_relchange);
@@ -450,7 +461,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   }
   if (SPEC_ACT_UPD) {
 #pragma unroll
-    for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = exp(s.lngam[i]);
+    for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = sx_exp(s.lngam[i]);
 #pragma unroll 4
     for (int k = 0; k < SPEC_NCX; k++) {
       int q = spec_cx_cls(k);
@@ -458,7 +469,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
 #pragma unroll
       for (int z = 0; z < SPEC_NCLS; z++)
         if (z == q) lg = s.lgcls[z];
-      st.sec_act_coef[k * ld + cell] = q < 0 ? 1.0 : exp(lg);
+      st.sec_act_coef[k * ld + cell] = q < 0 ? 1.0 : sx_exp(lg);
     }
   }
 #pragma unroll

@@ -220,7 +220,7 @@ class _Gen:
         self.w("  const double sq = sqrt(I);")
         A, B, Bd = _lit(c.debyeA), _lit(c.debyeB), _lit(c.debyeBdot)
         for q, (negz2, a0) in enumerate(self.cls):
-            self.w(f"  s.lgcls[{q}] = ({_lit(negz2)} * sq * {A} / (1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
+            self.w(f"  s.lgcls[{q}] = (sx_div({_lit(negz2)} * sq * {A}, 1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
         for i in range(self.naq):
             q = self.pri_cls[i]
             self.w(f"  s.lngam[{i}] = {'0.0' if q < 0 else f's.lgcls[{q}]'};")
@@ -239,7 +239,7 @@ class _Gen:
         self.w("  const double psvd = s.por * s.sat * 1000.0 * s.vol / dt;")
         for i in range(n):
             if i < naq:
-                self.w(f"  lna[{i}] = log(c[{i}]) + s.lngam[{i}]; ic[{i}] = 1.0 / c[{i}]; tot[{i}] = c[{i}];")
+                self.w(f"  lna[{i}] = sx_log(c[{i}]) + s.lngam[{i}]; ic[{i}] = sx_rcp(c[{i}]); tot[{i}] = c[{i}];")
             else:
                 self.w(f"  lna[{i}] = 0.0; ic[{i}] = 0.0; tot[{i}] = c[{i}];")
         self.w("  double Is = 0.0, ms = 0.0;")
@@ -275,7 +275,7 @@ class _Gen:
                     arg = f"({expr})" if q < 0 else f"({expr}) - s.lgcls[{q}]"
                 else:
                     arg = f"({expr}) - SW(SPEC_OFF_LNGSEC + {k})"
-                self.w(f"    const double sk = exp({arg});")
+                self.w(f"    const double sk = sx_exp({arg});")
                 self.w(f"    sec_out[{k} * ld] = sk;")
                 z2 = float(a["eqcplx_Z"][k]) ** 2
                 if z2 != 0.0:
@@ -359,7 +359,7 @@ class _Gen:
                     expr += _term(h2o, "s.ln_act_h2o")
                 for p in range(ptr[k], ptr[k + 1]):
                     expr += _term(float(st_[p]), f"lna[{int(ids[p])}]")
-                self.w(f"      const double e{q} = exp({expr});")
+                self.w(f"      const double e{q} = sx_exp({expr});")
             self.w("      double esum = 0.0;")
             for q in range(len(cx)):
                 self.w(f"      esum += e{q};")
@@ -419,7 +419,7 @@ class _Gen:
             irr = int(a["kinmnrl_irreversible"][m])
             rate = _lit(float(a["kinmnrl_rate_constant"][m]))
             self.w("  {")
-            self.w(f"    const double QK = exp({expr});")
+            self.w(f"    const double QK = sx_exp({expr});")
             self.w("    double aff = 1.0 - QK;")
             self.w("    const double sgn = copysign(1.0, aff);")
             self.w(f"    bool active = (st.mnrl_volfrac[{m} * st.ld + cell] > 0.0 || sgn < 0.0);")
@@ -501,6 +501,7 @@ class _Gen:
         self.w(f"#define SPEC_USE_ACT_H2O {int(c.use_activity_h2o)}")
         self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
         self.w(f"#define SPEC_THREADS {threads}")
+        self.w(f"#define SPEC_FASTMATH {int(os.environ.get('PFRX_SPEC_FASTMATH', '1'))}")
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")
         cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
         so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
@@ -1034,7 +1035,7 @@ def _stamp(src: str) -> str:
     import hashlib
 
     h = hashlib.sha1(src.encode())
-    for d in ("pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh"):
+    for d in ("pfrx_fastmath.cuh", "pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh"):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(f.read())
     return h.hexdigest()
