@@ -275,6 +275,7 @@ def main():
             torch.cuda.synchronize(dev)
             tt.append(time.perf_counter() - t0)
         te = float(np.mean(tt))
+        h2d, d2h = step.last_transfer_bytes()  # counted by the library from the copies it issued
         if world > 1:
             t = torch.tensor([te], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -285,6 +285,12 @@ int64_t pfrx_launch_count(pfrx_handle *h);
  * (the algorithmic HBM traffic of SURVEY.md section 8(d))                    */
 int64_t pfrx_bytes_per_cell(pfrx_handle *h);
 
+/* bytes the latest pfrx_rstep_host moved over the host link in each direction.
+ * Fields that every active cell overwrites before reading (activity
+ * coefficients when they are updated per Newton iteration, mineral rates) are
+ * not uploaded when the shard has no inactive cells (imat NULL or all > 0).   */
+int pfrx_last_transfer_bytes(pfrx_handle *h, int64_t *h2d, int64_t *d2h);
+
 /* kernel configuration chosen for this handle:
  * info5 = {padded system size N, lanes per cell, threads per block,
  *          resident blocks per SM, dynamic shared memory bytes per block}.

@@ -221,6 +221,7 @@ struct pfrx_handle {
   void *spec_module = nullptr, *spec_func = nullptr;
   int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
   size_t spec_smem = 0;
+  int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host
   // nccl
   NcclComm comm = nullptr;
   long long *d_red = nullptr;
@@ -915,7 +916,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   size_t ndbl = 0;
   for (int i = 0; i < kNumD; i++) ndbl += (size_t)rows[i] * ncell;
   size_t bytes = ndbl * sizeof(double) + (size_t)5 * ncell * sizeof(int);
+  bool fresh_alloc = false;
   if (h->own_ncell != ncell) {
+    fresh_alloc = true;
     if (h->own) CUDA_OK(cudaFree(h->own));
     h->own = nullptr;
     CUDA_OK(cudaMalloc(&h->own, std::max<size_t>(bytes, 16)));
@@ -990,16 +993,42 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr};
   const size_t w8 = sizeof(double);
+  // Fields every active cell overwrites before it reads them need no upload -- as
+  // long as every cell is active (imat absent or all positive), otherwise the download would hand the
+  // inactive cells garbage.  With activity coefficients updated in every Newton
+  // iteration (reaction.F90:3868) both coefficient arrays are outputs only; with
+  // frozen coefficients the complex concentrations are (RTotal rewrites them before
+  // anything reads them); mineral rates always are.
+  bool skip_in[kNumD] = {false};
+  bool all_active = true;
+  if (host->imat)
+    for (int64_t c = 0; c < ncell && all_active; c++) all_active = host->imat[c] > 0;
+  if (all_active && h->cfg.use_full_geochemistry && !getenv("PFRX_UPLOAD_ALL")) {
+    const bool act_upd = h->cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+    if (act_upd) skip_in[3] = skip_in[4] = true;
+    if (!act_upd && !h->cfg.use_act_h2o) skip_in[5] = true;
+    if (h->cfg.nkin > 0) skip_in[9] = true;
+  }
+  if (fresh_alloc) {
+    // poison what is never uploaded: a kernel that reads it anyway shows up as NaN
+    for (int f = 0; f < kNumD; f++)
+      if (skip_in[f] && rows[f]) CUDA_OK(cudaMemsetAsync(dptr[f], 0xff, (size_t)rows[f] * ncell * w8, s_in));
+  }
+  h->last_h2d = h->last_d2h = 0;
   for (int ch = 0; ch < nchunk; ch++) {
     int64_t c0 = ncell * ch / nchunk, c1 = ncell * (ch + 1) / nchunk, nc = c1 - c0;
     if (nc <= 0) continue;
     for (int f = 0; f < kNumD; f++) {
       if (!rows[f] || !src[f] || f == 11) continue;  // eqsrfcplx_conc is output only
+      if (skip_in[f]) continue;
       CUDA_OK(cudaMemcpy2DAsync(dptr[f] + c0, ncell * w8, src[f] + c0, host->ld * w8, nc * w8, rows[f],
                                 cudaMemcpyHostToDevice, s_in));
+      h->last_h2d += (int64_t)(nc * w8) * rows[f];
     }
-    if (host->imat)
+    if (host->imat) {
       CUDA_OK(cudaMemcpyAsync((void *)(d.imat + c0), host->imat + c0, nc * sizeof(int), cudaMemcpyHostToDevice, s_in));
+      h->last_h2d += nc * (int64_t)sizeof(int);
+    }
     CUDA_OK(cudaEventRecord(h->ev_in[ch], s_in));
     CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_in[ch], 0));
     DevState dc = d;
@@ -1039,7 +1068,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
       if (!rows[f] || !hdst[f]) continue;
       CUDA_OK(cudaMemcpy2DAsync(hdst[f] + c0, host->ld * w8, dptr[f] + c0, ncell * w8, nc * w8, rows[f],
                                 cudaMemcpyDeviceToHost, s_out));
+      h->last_d2h += (int64_t)(nc * w8) * rows[f];
     }
+    h->last_d2h += 4 * nc * (int64_t)sizeof(int);
     CUDA_OK(cudaMemcpyAsync(host->num_sub_steps + c0, d.num_sub_steps + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, s_out));
     CUDA_OK(cudaMemcpyAsync(host->num_iterations + c0, d.num_iterations + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, s_out));
     CUDA_OK(cudaMemcpyAsync(host->num_kinetic_state_updates + c0, d.num_kinetic_state_updates + c0, nc * sizeof(int),
@@ -1118,6 +1149,13 @@ extern "C" int pfrx_allreduce(pfrx_handle *h, pfrx_step_result *r) {
   r->max_num_kinetic_state_updates = (int)b[5];
   r->rstep_error = (int)b[6];
   r->max_sub_steps = (int)b[7];
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_last_transfer_bytes(pfrx_handle *h, int64_t *h2d, int64_t *d2h) {
+  if (!h || !h2d || !d2h) return PFRX_E_INVALID;
+  *h2d = h->last_h2d;
+  *d2h = h->last_d2h;
   return PFRX_OK;
 }
 

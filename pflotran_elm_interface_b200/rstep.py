@@ -61,6 +61,7 @@ def lib():
     L.pfrx_bytes_per_cell.argtypes = [hp]
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
+    L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
     L.pfrx_config_signature.restype = C.c_uint64
@@ -259,6 +260,12 @@ class ChemistryStep:
             return False
         self.load_specialized(path)
         return True
+
+    def last_transfer_bytes(self):
+        """(H2D, D2H) bytes of the latest rstep_host"""
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().pfrx_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "pfrx_last_transfer_bytes")
+        return a.value, b.value
 
     def kernel_info(self) -> Dict[str, int]:
         a = (C.c_int * 5)()
