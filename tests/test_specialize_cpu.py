@@ -1,0 +1,74 @@
+"""The code generator for network-specialised kernels (no GPU needed): what it
+accepts, that its output is deterministic and complete, and that the signature
+tracks the tables the generated code bakes in."""
+import copy
+import re
+import shutil
+
+import numpy as np
+import pytest
+
+from pflotran_elm_interface_b200 import specialize, workloads as W
+
+
+def test_supported_networks():
+    for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", False), ("c4", False)):
+        wl = W.by_name(name, ncell=2)
+        got, why = specialize.supported(wl.cfg)
+        assert got is ok, (name, why)
+        if not ok:
+            assert why
+            with pytest.raises(ValueError):
+                specialize.generate_source(wl.cfg)
+
+
+def test_source_is_deterministic_and_covers_the_network():
+    wl = W.by_name("c3", ncell=2)
+    a = specialize.generate_source(wl.cfg)
+    b = specialize.generate_source(W.by_name("c3", ncell=2).cfg)
+    assert a == b
+    c = wl.cfg.c
+    # one exp per secondary complex, streamed to rt_auxvar%sec_molal
+    assert len(re.findall(r"sec_out\[\d+ \* ld\] = sk;", a)) == c.neqcplx
+    # tracers stay out of the matrix (two of the 15 Hanford primaries occur in no reaction)
+    assert f"#define SPEC_N {c.naqcomp + c.nimcomp}" in a
+    assert "#define SPEC_NC 13" in a
+    assert f"#define SPEC_SIG {specialize.signature(wl.cfg)}ull" in a
+    # every literal is an exact hexadecimal float or a small integer constant
+    assert "0x1." in a and "nan" not in a.lower().replace("isnan", "")
+    for routine in ("spec_activity", "spec_rtotal", "spec_sorption", "spec_minerals"):
+        assert f"void {routine}(" in a
+
+
+def test_signature_tracks_tables():
+    wl = W.by_name("c2", ncell=2)
+    s0 = specialize.signature(wl.cfg)
+    assert s0 == specialize.signature(W.by_name("c2", ncell=7).cfg)  # cells do not matter
+    assert s0 != specialize.signature(W.by_name("c3", ncell=2).cfg)
+    cfg = W.by_name("c2", ncell=2).cfg
+    cfg.arrays["eqcplx_logK"][0] += 1.0e-12  # in place: the ctypes struct points at this buffer
+    assert specialize.signature(cfg) != s0
+
+
+def test_variants_generate():
+    wl = W.by_name("c3", ncell=2)
+    straight4 = specialize.generate_source(wl.cfg, warps=4, style="straight")
+    rolled4 = specialize.generate_source(wl.cfg, warps=4, style="rolled")
+    assert '#include "pfrx_specw.cuh"' in straight4 and "specw_rows<3>" in straight4
+    assert '#include "pfrx_specr.cuh"' in rolled4 and "__constant__ double T_cx_lnk" in rolled4
+    ok, why = specialize.supported_multiwarp(W.by_name("c2", ncell=2).cfg, 4)
+    assert not ok and "coupled" in why
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc")
+def test_build_is_cached(tmp_path, monkeypatch):
+    monkeypatch.setattr(specialize, "OUT", str(tmp_path))
+    wl = W.by_name("c2", ncell=2)
+    p = specialize.build(wl.cfg)
+    assert p.endswith("_s1.cubin")
+    import os
+
+    t0 = os.path.getmtime(p)
+    assert specialize.build(wl.cfg) == p and os.path.getmtime(p) == t0  # stamp hit, no recompile
+    log = open(p[:-6] + ".log").read()
+    assert "sm_100a" in log and re.search(r"Used \d+ registers", log)
