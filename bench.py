@@ -309,7 +309,17 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm,
                 "peak_source": f"MEASURED_PEAKS.json ({which})"}
-    roof.update({"traffic": None, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
+    # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            tr = json.load(f).get(a.workload)
+        if tr and tr["kernel"] == _kernel_name(info):
+            traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / tr["cells"] * cells_local
+            traffic_src = tr["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roof.update({"traffic": traffic, "traffic_source": traffic_src, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
                  "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
                  "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": step.bytes_per_cell,
                  "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
