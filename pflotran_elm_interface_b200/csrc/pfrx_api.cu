@@ -179,6 +179,19 @@ static uint64_t config_signature(const pfrx_config *c) {
     ADD(c->srfcplx_logK, c->nsrfcplx)
     ADD(c->eqsrfcplxrxn_to_srfcplxrxn, c->neqsrfcplxrxn)
   }
+  if (c->clmcn_nrxn > 0) {
+    int32_t ch[3] = {c->clmcn_npool, c->clmcn_C_species_id, c->clmcn_N_species_id};
+    h = fnv1a(h, ch, sizeof(ch));
+    ADD(c->clmcn_CN_ratio, c->clmcn_npool)
+    ADD(c->clmcn_pool_nspec, c->clmcn_npool)
+    ADD(c->clmcn_pool_C_id, c->clmcn_npool)
+    ADD(c->clmcn_pool_N_id, c->clmcn_npool)
+    ADD(c->clmcn_upstream_pool_id, c->clmcn_nrxn)
+    ADD(c->clmcn_downstream_pool_id, c->clmcn_nrxn)
+    ADD(c->clmcn_rate_constant, c->clmcn_nrxn)
+    ADD(c->clmcn_respiration_fraction, c->clmcn_nrxn)
+    ADD(c->clmcn_inhibition_constant, c->clmcn_nrxn)
+  }
 #undef ADD
   return h;
 }
@@ -1209,7 +1222,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   if (!cubin_path) return PFRX_OK;
   // features outside what specialize.py generates (its supported() is the twin of this test)
   const DevCfg &d = h->cfg;
-  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess || d.nmr > 0 || d.cn_nrxn > 0 ||
+  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess || d.nmr > 0 ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();

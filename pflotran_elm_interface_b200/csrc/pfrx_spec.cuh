@@ -82,6 +82,12 @@ __device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const
                                               double (&res)[SPEC_N], SpecCell &s, double *W, const DevState &st,
                                               long long cell, bool apply);
 
+#ifndef SPEC_NCLM
+#define SPEC_NCLM 0
+#endif
+__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], double (&res)[SPEC_N], const SpecCell &s,
+                                             double *W);
+
 // ---- RSolve + LU (reaction.F90:5457-5516, utility.F90:597-735) -------------------
 // W = thread's slice (Jacobian of the coupled species), res = residual in
 // registers (overwritten by the update).  Crout's method in the reference's
@@ -270,6 +276,9 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       res[i] = sx_div(a - SW(SPEC_OFF_FIXED + i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
+#if SPEC_NCLM > 0
+    if (!s.dry) spec_sandbox(c, res, s, W);  // RReaction returns before the sandboxes in a dry cell
+#endif
     double mabs = 0.0, ss = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -428,7 +437,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
       nconst = 0;
     } else {
       // RUpdateKineticState: the rates of the converged iterate are in s.mrate
-      bool upd = false;
+      bool upd = SPEC_NCLM > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
       if (SPEC_NKIN > 0) {
         upd = true;
 #pragma unroll

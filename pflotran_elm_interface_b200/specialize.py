@@ -91,6 +91,15 @@ def signature(cfg: abi.ReactionConfig) -> int:
         for k in ("srfcplx_h2ostoich", "srfcplx_free_site_stoich", "srfcplx_logK"):
             add(k, ns, f8)
         add("eqsrfcplxrxn_to_srfcplxrxn", c.neqsrfcplxrxn, i4)
+    if c.clmcn_nrxn > 0:
+        parts.append(struct.pack("<3i", c.clmcn_npool, c.clmcn_C_species_id, c.clmcn_N_species_id))
+        add("clmcn_CN_ratio", c.clmcn_npool, f8)
+        for k in ("clmcn_pool_nspec", "clmcn_pool_C_id", "clmcn_pool_N_id"):
+            add(k, c.clmcn_npool, i4)
+        for k in ("clmcn_upstream_pool_id", "clmcn_downstream_pool_id"):
+            add(k, c.clmcn_nrxn, i4)
+        for k in ("clmcn_rate_constant", "clmcn_respiration_fraction", "clmcn_inhibition_constant"):
+            add(k, c.clmcn_nrxn, f8)
     return _fnv1a(b"".join(parts))
 
 
@@ -116,8 +125,6 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "activity algorithm NEWTON"
     if c.nkinmrsrfcplxrxn > 0:
         return False, "multirate sorption"
-    if c.clmcn_nrxn > 0:
-        return False, "reaction sandbox"
     if c.nsrfcplxrxn != c.neqsrfcplxrxn:
         return False, "non-equilibrium surface complexation"
     if c.nsrfcplxrxn and np.any(a["srfcplxrxn_stoich_flag"] != 0):
@@ -174,6 +181,14 @@ class _Gen:
         for ids in ("eqcplx_specid", "kinmnrl_specid", "srfcplx_specid"):
             if ids in self.a:
                 used.update(int(v) for v in self.a[ids])
+        if self.c.clmcn_nrxn > 0:
+            naq = self.c.naqcomp
+            used.add(naq + int(self.c.clmcn_C_species_id))
+            used.add(naq + int(self.c.clmcn_N_species_id))
+            for k in range(self.c.clmcn_npool):
+                used.add(naq + int(self.a["clmcn_pool_C_id"][k]))
+                if int(self.a["clmcn_pool_nspec"][k]) == 2:
+                    used.add(naq + int(self.a["clmcn_pool_N_id"][k]))
         self.coupled = sorted(used)
         self.cpos = {sp: ci for ci, sp in enumerate(self.coupled)}
         self.nc = len(self.coupled)
@@ -312,7 +327,10 @@ class _Gen:
         for i in self.coupled:
             for j in self.coupled:
                 e = self.J(i, j)
-                if (i, j) in hot:
+                if i >= naq or j >= naq:
+                    # immobile species: accumulation V/dt on the diagonal (reaction.F90:5775-5848)
+                    self.w(f"  {e} = {'s.vol / dt' if i == j else '0.0'};")
+                elif (i, j) in hot:
                     self.w(f"  {e} = (jh_{i}_{j} * denL) * psvd;")
                 elif (i, j) in written:
                     self.w(f"  {e} = ({e} * denL) * psvd;")
@@ -466,6 +484,84 @@ class _Gen:
         self.w("}")
         self.w()
 
+    def gen_sandbox(self) -> None:
+        """CLM_CN_React (reaction_sandbox_clm_cn.F90:468-787), one straight-line block per reaction"""
+        c, a, naq = self.c, self.a, self.naq
+        self.w("__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], double (&res)[SPEC_N],")
+        self.w("    const SpecCell &s, double *W) {")
+        self.w("  const double temp_K = s.temp + 273.15;")
+        self.w("  if (!(temp_K > 227.15)) return;")
+        self.w("  const double F_t = exp(308.56 * (1.408054069e-2 - 1.0 / (temp_K - 227.13)));")
+        self.w("  const double F_theta = log(0.01 / fmax(0.01, s.sat)) * -2.17147241e-1;")
+        self.w("  const double cinh = F_t * F_theta;")
+        iC = naq + int(c.clmcn_C_species_id)
+        iN = naq + int(c.clmcn_N_species_id)
+        J = self.J
+        for r in range(c.clmcn_nrxn):
+            up = int(a["clmcn_upstream_pool_id"][r])
+            down = int(a["clmcn_downstream_pool_id"][r])
+            resp = float(a["clmcn_respiration_fraction"][r])
+            inhib = float(a["clmcn_inhibition_constant"][r])
+            litter = int(a["clmcn_pool_nspec"][up]) != 1
+            iCu = naq + int(a["clmcn_pool_C_id"][up])
+            iNu = naq + int(a["clmcn_pool_N_id"][up]) if litter else -1
+            self.w("  {")
+            self.w(f"    const double k = {_lit(float(a['clmcn_rate_constant'][r]))} * s.vol * cinh;")
+            if litter:
+                self.w(f"    const double cn_up = c[{iCu}] / c[{iNu}];")
+            else:
+                self.w(f"    const double cn_up = {_lit(float(a['clmcn_CN_ratio'][up]))};")
+            self.w("    const double st_upN = 1.0 / cn_up;")
+            if down >= 0:
+                iD = naq + int(a["clmcn_pool_C_id"][down])
+                self.w(f"    const double st_dn = {_lit((1.0 - resp) * 1.0)};")
+                self.w(f"    const double cn_dn = {_lit(float(a['clmcn_CN_ratio'][down]))};")
+            else:
+                iD = -1
+                self.w("    const double st_dn = 0.0;")
+                self.w("    const double cn_dn = 1.0;")
+            self.w(f"    const double st_C = {_lit(resp * 1.0)};")
+            self.w("    const double st_N = st_upN - st_dn / cn_dn;")
+            if inhib > 1.0e-40:
+                self.w("    const bool inh = st_N < 0.0;")
+                self.w(f"    const double tr = c[{iN}] + {_lit(inhib)};")
+                self.w(f"    const double Ninh = inh ? c[{iN}] / tr : 1.0;")
+                self.w(f"    const double dNinh = inh ? {_lit(inhib)} / (tr * tr) : 0.0;")
+            else:
+                self.w("    const bool inh = false;")
+                self.w("    const double Ninh = 1.0, dNinh = 0.0;")
+            self.w(f"    const double rate = c[{iCu}] * k * Ninh;")
+            self.w(f"    res[{iC}] = res[{iC}] - st_C * rate;")
+            self.w(f"    res[{iN}] = res[{iN}] - st_N * rate;")
+            self.w(f"    res[{iCu}] = res[{iCu}] - (-1.0) * 1.0 * rate;")
+            if litter:
+                self.w(f"    res[{iNu}] = res[{iNu}] - (-1.0) * st_upN * rate;")
+            if iD >= 0:
+                self.w(f"    res[{iD}] = res[{iD}] - st_dn * rate;")
+            self.w("    const double drate = k * Ninh;")
+            self.w(f"    const double dinh = c[{iCu}] * k * dNinh;")
+            self.w(f"    {J(iCu, iCu)} = {J(iCu, iCu)} - (-1.0) * 1.0 * drate;")
+            self.w(f"    if (inh) {J(iCu, iN)} = {J(iCu, iN)} - (-1.0) * 1.0 * dinh;")
+            if iD >= 0:
+                self.w(f"    {J(iD, iCu)} = {J(iD, iCu)} - st_dn * drate;")
+                self.w(f"    if (inh) {J(iD, iN)} = {J(iD, iN)} - st_dn * dinh;")
+            if litter:
+                self.w(f"    {J(iNu, iCu)} = {J(iNu, iCu)} - (-1.0) * st_upN * drate;")
+                self.w(f"    if (inh) {J(iNu, iN)} = {J(iNu, iN)} - (-1.0) * st_upN * dinh;")
+                self.w(f"    {J(iNu, iCu)} = {J(iNu, iCu)} - (-1.0) * (-1.0) * c[{iNu}] / c[{iCu}] * k * Ninh;")
+                self.w(f"    {J(iNu, iNu)} = {J(iNu, iNu)} - (-1.0) * k * Ninh;")
+                self.w(f"    {J(iN, iCu)} = {J(iN, iCu)} - (-1.0) * c[{iNu}] / c[{iCu}] * k * Ninh;")
+                self.w(f"    {J(iN, iNu)} = {J(iN, iNu)} - k * Ninh;")
+            self.w(f"    {J(iC, iCu)} = {J(iC, iCu)} - st_C * drate;")
+            self.w(f"    {J(iN, iCu)} = {J(iN, iCu)} - st_N * drate;")
+            self.w("    if (inh) {")
+            self.w(f"      {J(iC, iN)} = {J(iC, iN)} - st_C * dinh;")
+            self.w(f"      {J(iN, iN)} = {J(iN, iN)} - st_N * dinh;")
+            self.w("    }")
+            self.w("  }")
+        self.w("}")
+        self.w()
+
     # ------------------------------------------------------------------ whole file
     def source(self) -> str:
         c = self.c
@@ -496,6 +592,7 @@ class _Gen:
         self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
         self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
         self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
+        self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
         self.w(f"#define SPEC_USE_LOG {int(c.use_log_formulation)}")
         self.w(f"#define SPEC_ACT_UPD {int(self.act_upd)}")
         self.w(f"#define SPEC_USE_ACT_H2O {int(c.use_activity_h2o)}")
@@ -517,6 +614,8 @@ class _Gen:
         self.gen_rtotal()
         self.gen_sorption()
         self.gen_minerals()
+        if c.clmcn_nrxn > 0:
+            self.gen_sandbox()
         return "\n".join(o) + "\n"
 
 
@@ -1000,6 +1099,8 @@ def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]
             used.update(int(v) for v in cfg.arrays[ids])
     if warps not in (2, 4, 8):
         return False, "2, 4 or 8 warps"
+    if c.clmcn_nrxn > 0:
+        return False, "reaction sandbox"
     if len(used) < 2 * warps:
         return False, "too few coupled species for that many warps"
     if not c.use_log_formulation:

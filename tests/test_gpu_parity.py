@@ -124,7 +124,7 @@ def test_hanford(variant, dt):
 
 @pytest.mark.parametrize("variant,dt,host", [("c1", 3600.0, False), ("c2", 3600.0, False), ("c2", 86400.0 * 91, True),
                                              ("c3", 3600.0, False), ("c3", 30 * 86400.0, True),
-                                             ("c5", 86400.0, False)])
+                                             ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True)])
 def test_specialized_kernel(variant, dt, host):
     """the code-generated kernel (specialize.py + pfrx_spec.cuh) against the oracle"""
     wl = W.by_name(variant, ncell=1 if variant == "c1" else 1500, tran_dt=dt)
@@ -143,7 +143,7 @@ def test_specialized_kernel_refuses_other_network():
     assert step.signature == specialize.signature(c2.cfg)
     with pytest.raises(rstep.PfrxError, match="another network"):
         step.load_specialized(specialize.build(c3.cfg))
-    unsupported = W.by_name("c4", ncell=4)
+    unsupported = W.by_name("c3mr", ncell=4)
     assert not specialize.supported(unsupported.cfg)[0]
     step4 = rstep.ChemistryStep(unsupported.cfg, 0)
     assert step4.specialize() is False

@@ -12,7 +12,7 @@ from pflotran_elm_interface_b200 import specialize, workloads as W
 
 
 def test_supported_networks():
-    for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", False), ("c4", False)):
+    for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", False), ("c4", True)):
         wl = W.by_name(name, ncell=2)
         got, why = specialize.supported(wl.cfg)
         assert got is ok, (name, why)
@@ -48,6 +48,14 @@ def test_signature_tracks_tables():
     cfg = W.by_name("c2", ncell=2).cfg
     cfg.arrays["eqcplx_logK"][0] += 1.0e-12  # in place: the ctypes struct points at this buffer
     assert specialize.signature(cfg) != s0
+
+
+def test_sandbox_network():
+    wl = W.by_name("c4", ncell=2)
+    src = specialize.generate_source(wl.cfg)
+    assert "#define SPEC_NCLM 7" in src and "void spec_sandbox(" in src
+    assert "#define SPEC_NC 12" in src  # the aqueous tracer of the CLM-CN deck stays out of the matrix
+    assert not specialize.supported_multiwarp(wl.cfg, 4)[0]
 
 
 def test_variants_generate():
