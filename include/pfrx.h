@@ -297,6 +297,20 @@ int pfrx_last_transfer_bytes(pfrx_handle *h, int64_t *h2d, int64_t *d2h);
  * PFRX_LANES / PFRX_THREADS in the environment override the defaults. */
 int pfrx_kernel_info(pfrx_handle *h, int *info5);
 
+/* ---- batched RReaction / RReactionDerivative --------------------------------
+ * What the fully implicit (GIRT) and ELM callers take from the chemistry
+ * module (reactive_transport.F90:2627 RReaction, :3288 RReactionDerivative;
+ * reaction.F90:4059-4208): the kinetic terms -- mineral precipitation /
+ * dissolution and the reaction sandboxes -- of every active cell of the bound
+ * state, evaluated from rt_auxvar as it stands (pri_molal, pri_act_coef,
+ * immobile, mnrl_volfrac/area; no RTAuxVarCompute).  Device pointers, ld of the
+ * bound state:  res[i*ld + cell]  (mol/s, the sign convention of Residual),
+ * jac[(i*ncomp + j)*ld + cell] = d res_i / d c_j  (written when want_jacobian).
+ * Side effect as in the reference: mnrl_rate of the bound state is updated.
+ * Inactive cells (imat <= 0) get zeros; dry cells get zeros (reaction.F90:4085).
+ * Multirate sorption is not covered yet (PFRX_E_INVALID).                     */
+int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, double *jac);
+
 /* ---- network-specialised kernels -------------------------------------------
  * The generic kernels read the reaction network from tables, the way the
  * reference's RTotalAqueous / RKineticMineral loops read reaction%eqcplxspecid

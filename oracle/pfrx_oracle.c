@@ -1465,6 +1465,24 @@ int pfrx_oracle_girt_residual(const pfrx_config *cfg, const pfrx_state *st, int6
   return e;
 }
 
+/* RReaction + RReactionDerivative alone (reaction.F90:4059-4208) on cell ic, the way the
+ * GIRT / ELM caller uses them (reactive_transport.F90:2627, 3288): rt_auxvar as it stands,
+ * Res / Jac start from zero, Jac column-major Jac[i + j*n]; mnrl_rate is written back. */
+int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t ic, double tran_dt, double *Res,
+                         double *Jac) {
+  cell_t c;
+  int n, i;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  n = c.n;
+  for (i = 0; i < n; i++) Res[i] = 0.0;
+  for (i = 0; i < n * n; i++) Jac[i] = 0.0;
+  r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
+  for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];
+  cell_free(&c);
+  return 0;
+}
+
 /* RUpdateKineticState on cell ic over tran_dt */
 int pfrx_oracle_update_kinetic_state(const pfrx_config *cfg, const pfrx_state *st, int64_t ic, double tran_dt) {
   cell_t c;

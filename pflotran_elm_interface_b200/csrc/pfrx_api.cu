@@ -235,6 +235,11 @@ struct pfrx_handle {
   int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
   size_t spec_smem = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host
+  // batched RReaction (pfrx_reaction): always the thread-per-cell layout
+  DevCfg rx_cfg;
+  void (*rx_kernel)(DevCfg, DevState, int64_t, int, double *, double *) = nullptr;
+  int rx_threads = 0, rx_blocks_per_sm = 0;
+  size_t rx_smem = 0;
   // nccl
   NcclComm comm = nullptr;
   long long *d_red = nullptr;
@@ -263,13 +268,19 @@ typedef void (*pfrx_kernel_fn)(DevCfg, DevState, int64_t, double, DevSummary *);
 // one getter per padded size N, defined in pfrx_kern.cu (see build.py)
 #define PFRX_DECL(N) extern "C" pfrx_kernel_fn pfrx_kernel_##N(int lanes);
 PFRX_DECL(3) PFRX_DECL(4) PFRX_DECL(8) PFRX_DECL(13) PFRX_DECL(15) PFRX_DECL(16) PFRX_DECL(32)
+typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *);
+#define PFRX_DECLR(N) extern "C" pfrx_reaction_fn pfrx_reaction_kernel_##N(void);
+PFRX_DECLR(3) PFRX_DECLR(4) PFRX_DECLR(8) PFRX_DECLR(13) PFRX_DECLR(15) PFRX_DECLR(16) PFRX_DECLR(32)
 struct KernelGetter {
   int n;
   pfrx_kernel_fn (*get)(int);
+  pfrx_reaction_fn (*get_rx)(void);
 };
-static const KernelGetter g_getters[] = {{3, pfrx_kernel_3},   {4, pfrx_kernel_4},   {8, pfrx_kernel_8},
-                                         {13, pfrx_kernel_13}, {15, pfrx_kernel_15}, {16, pfrx_kernel_16},
-                                         {32, pfrx_kernel_32}};
+static const KernelGetter g_getters[] = {
+    {3, pfrx_kernel_3, pfrx_reaction_kernel_3},    {4, pfrx_kernel_4, pfrx_reaction_kernel_4},
+    {8, pfrx_kernel_8, pfrx_reaction_kernel_8},    {13, pfrx_kernel_13, pfrx_reaction_kernel_13},
+    {15, pfrx_kernel_15, pfrx_reaction_kernel_15}, {16, pfrx_kernel_16, pfrx_reaction_kernel_16},
+    {32, pfrx_kernel_32, pfrx_reaction_kernel_32}};
 
 static bool default_tpc(int npad) {
   // measured on B200: the thread-per-cell kernel wins for small networks (C2: 2.6x);
@@ -344,6 +355,36 @@ extern "C" int64_t pfrx_sizeof(int which) {
   return -1;
 }
 
+// thread-per-cell workspace: one slice per THREAD, exact-size Jacobian
+static void tpc_layout(DevCfg &d, int N) {
+  int off = 0;
+  auto take = [&](int cnt) {
+    int o = off;
+    off += cnt;
+    return o;
+  };
+  const bool act_upd = d.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+  d.off_c = take(N);
+  d.off_lnact = take(N);
+  d.off_invc = take(N);
+  d.off_res = take(N);
+  d.off_acc = take(N);
+  d.off_tmp = take(N + 2 * d.nsrfcplx + 2);
+  d.off_ts = take(N);
+  d.js = d.n;
+  d.off_J = take(d.n * d.n);
+  d.off_cls = take(d.ncls + 1);
+  d.off_x = take((N + 1) / 2 + 1);
+  d.off_xs = take(N);
+  d.off_sc = take(d.nsrfcplx + 1);
+  d.off_mn = take(d.nkin + 1);
+  d.off_fs = take(d.nsrfrxn + 1);
+  d.off_mr = take(2 * d.nmr * N + 1);
+  d.off_lng = act_upd ? 0 : take(d.ncplx);
+  d.off_sec = 0;
+  d.ws_stride = off | 1;
+}
+
 static int layout_and_launch_params(pfrx_handle *h) {
   DevCfg &d = h->cfg;
   const int N = h->npad;
@@ -354,27 +395,7 @@ static int layout_and_launch_params(pfrx_handle *h) {
     return o;
   };
   if (h->tpc) {
-    // thread-per-cell: one workspace per THREAD, exact-size Jacobian
-    const bool act_upd = d.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
-    d.off_c = take(N);
-    d.off_lnact = take(N);
-    d.off_invc = take(N);
-    d.off_res = take(N);
-    d.off_acc = take(N);
-    d.off_tmp = take(N + 2 * d.nsrfcplx + 2);
-    d.off_ts = take(N);
-    d.js = d.n;
-    d.off_J = take(d.n * d.n);
-    d.off_cls = take(d.ncls + 1);
-    d.off_x = take((N + 1) / 2 + 1);
-    d.off_xs = take(N);
-    d.off_sc = take(d.nsrfcplx + 1);
-    d.off_mn = take(d.nkin + 1);
-    d.off_fs = take(d.nsrfrxn + 1);
-    d.off_mr = take(2 * d.nmr * N + 1);
-    d.off_lng = act_upd ? 0 : take(d.ncplx);
-    d.off_sec = 0;
-    d.ws_stride = off | 1;
+    tpc_layout(d, N);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
@@ -906,6 +927,47 @@ extern "C" int pfrx_rstep(pfrx_handle *h, double tran_dt, pfrx_step_result *out)
   int rc = pfrx_rstep_async(h, tran_dt);
   if (rc) return rc;
   return pfrx_rstep_finish(h, out);
+}
+
+// ---- batched RReaction / RReactionDerivative for the GIRT / ELM caller ----------
+extern "C" int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, double *jac) {
+  if (!h || !res || (want_jacobian && !jac)) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  if (h->cfg.nmr > 0)
+    return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover multirate sorption yet%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!h->rx_kernel) {
+    const KernelGetter *gt = nullptr;
+    for (const auto &k : g_getters)
+      if (k.n == h->npad) gt = &k;
+    if (!gt) return set_err(PFRX_E_LIMIT, "no kernel variant for this size%s", "");
+    h->rx_cfg = h->cfg;
+    tpc_layout(h->rx_cfg, h->npad);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+    size_t per_thread = (size_t)h->rx_cfg.ws_stride * sizeof(double);
+    int t = 128;
+    while (t > 32 && per_thread * t > (size_t)prop.sharedMemPerBlockOptin) t /= 2;
+    if (per_thread * t > (size_t)prop.sharedMemPerBlockOptin)
+      return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
+    pfrx_reaction_fn fn = gt->get_rx();
+    CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_thread * t)));
+    int nb = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, t, per_thread * t));
+    if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+    h->rx_threads = t;
+    h->rx_smem = per_thread * t;
+    h->rx_blocks_per_sm = nb;
+    h->rx_kernel = fn;
+  }
+  if (h->ncell <= 0) return PFRX_OK;
+  int64_t need = (h->ncell + h->rx_threads - 1) / h->rx_threads;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * h->rx_blocks_per_sm));
+  h->rx_kernel<<<grid, h->rx_threads, h->rx_smem, h->stream>>>(h->rx_cfg, h->st, h->ncell, want_jacobian, res, jac);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PFRX_OK;
 }
 
 // ---- host-resident state: H2D, kernel, D2H ------------------------------------

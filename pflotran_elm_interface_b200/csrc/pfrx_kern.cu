@@ -25,3 +25,6 @@ extern "C" pfrx_kernel_fn PFRX_CAT(pfrx_kernel_, PFRX_N)(int lanes) {
 #endif
   return nullptr;
 }
+
+typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *);
+extern "C" pfrx_reaction_fn PFRX_CAT(pfrx_reaction_kernel_, PFRX_N)(void) { return pfrx_reaction_tpc_kernel<PFRX_N>; }

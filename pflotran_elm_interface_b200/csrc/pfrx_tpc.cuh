@@ -735,6 +735,54 @@ struct CellT {
     return upd;
   }
 
+  // ---- RReaction + RReactionDerivative (reaction.F90:4059-4130, 4134-4208) for one cell ----
+  // The GIRT / ELM caller (reactive_transport.F90:2627, 3288) adds these kinetic terms to
+  // its own residual and Jacobian; rt_auxvar is taken as it stands (no RTAuxVarCompute).
+  // res[i*ld + c] (mol/s), jac[(i*n + j)*ld + c] = d res_i / d c_j.
+  __device__ __forceinline__ void reaction(int64_t c, bool want_jac, double *res, double *jac) {
+    cell = c;
+    const int naq = cfg.naq, n = cfg.n;
+    const int64_t ld = st.ld;
+    den_kg = st.den_kg[c];
+    sat = st.sat[c];
+    temp = st.temp[c];
+    por = st.porosity[c];
+    vol = st.volume[c];
+    spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
+    ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
+    dry = sat < cfg.min_sat;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (i < naq) {
+        double cc = st.pri_molal[i * ld + c];
+        C(i) = cc;
+        LNA(i) = log(cc) + log(st.pri_act_coef[i * ld + c]);
+        INVC(i) = 1.0 / cc;
+      } else if (i < n) {
+        C(i) = st.immobile[(i - naq) * ld + c];
+      }
+      if (i < n) RES(i) = 0.0;
+    }
+#pragma unroll 1
+    for (int e = 0; e < n * cfg.js; e++) ws[cfg.off_J + e] = 0.0;
+    if (!dry) {  // RReaction returns at once in a dry cell (reaction.F90:4085)
+      if (cfg.nkin > 0) {
+        kinetic_mineral(true);
+#pragma unroll 1
+        for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
+      }
+      if (cfg.cn_nrxn > 0) clm_cn();
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      res[i * ld + c] = RES(i);
+      if (want_jac) {
+#pragma unroll 1
+        for (int j = 0; j < n; j++) jac[((int64_t)i * n + j) * ld + c] = J(i, j);
+      }
+    }
+  }
+
   // ---- RStep (reaction.F90:3564-3738) ----------------------------------------------
   __device__ __forceinline__ void run(int64_t c, double target, int &nss, int &nit, int &nku, int &ierr, bool &had_cut) {
     cell = c;
@@ -936,5 +984,27 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1))) pfrx_rst
     atomicMax(&summ->max_kin, l_maxkin);
     atomicMax(&summ->max_err, l_maxerr);
     atomicMax(&summ->max_sub, l_maxsub);
+  }
+}
+
+// batched RReaction(+Derivative): one thread per cell, inactive cells get zeros
+template <int N>
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1)))
+    pfrx_reaction_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, int want_jac, double *res, double *jac) {
+  extern __shared__ double smem[];
+  double *ws = smem + (size_t)threadIdx.x * cfg.ws_stride;
+  CellT<N> sol(cfg, st, ws);
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = gthread; c < ncell; c += nthreads) {
+    if (st.imat && st.imat[c] <= 0) {
+      for (int i = 0; i < cfg.n; i++) {
+        res[i * st.ld + c] = 0.0;
+        if (want_jac)
+          for (int j = 0; j < cfg.n; j++) jac[((int64_t)i * cfg.n + j) * st.ld + c] = 0.0;
+      }
+      continue;
+    }
+    sol.reaction(c, want_jac != 0, res, jac);
   }
 }

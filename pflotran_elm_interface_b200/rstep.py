@@ -61,6 +61,7 @@ def lib():
     L.pfrx_bytes_per_cell.argtypes = [hp]
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
+    L.pfrx_reaction.argtypes = [hp, C.c_int, C.c_void_p, C.c_void_p]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
@@ -190,6 +191,21 @@ class ChemistryStep:
         res = abi.PfrxStepResult()
         _check(lib().pfrx_rstep(self._h, float(tran_dt), C.byref(res)), "pfrx_rstep")
         return res
+
+    def reaction(self, want_jacobian: bool = True):
+        """batched RReaction (+ RReactionDerivative) on the bound state: returns
+        ``res[ncomp, ncell]`` and ``jac[ncomp, ncomp, ncell]`` (or None) as torch tensors"""
+        import torch
+
+        st = self._state
+        if st is None:
+            raise PfrxError("bind() a DeviceState first")
+        n = self.cfg.c.naqcomp + self.cfg.c.nimcomp
+        res = torch.empty((n, st.ncell), dtype=torch.float64, device=st.device)
+        jac = torch.empty((n, n, st.ncell), dtype=torch.float64, device=st.device) if want_jacobian else None
+        _check(lib().pfrx_reaction(self._h, int(bool(want_jacobian)), res.data_ptr(),
+                                   jac.data_ptr() if jac is not None else None), "pfrx_reaction")
+        return res, jac
 
     # -- host-resident path (H2D + kernel + D2H inside the call) ---------------- #
     def rstep_host(self, host: abi.HostState, tran_dt: float) -> abi.PfrxStepResult:

@@ -33,6 +33,7 @@ def lib():
     L.pfrx_oracle_activity.argtypes = [cfgp, stp, C.c_int64]
     L.pfrx_oracle_auxvar_compute.argtypes = [cfgp, stp, C.c_int64]
     L.pfrx_oracle_girt_residual.argtypes = [cfgp, stp, C.c_int64, C.c_double, dp, dp, dp]
+    L.pfrx_oracle_reaction.argtypes = [cfgp, stp, C.c_int64, C.c_double, dp, dp]
     L.pfrx_oracle_update_kinetic_state.argtypes = [cfgp, stp, C.c_int64, C.c_double]
     L.pfrx_oracle_rsolve.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int]
     L.pfrx_oracle_lu_solve.argtypes = [dp, C.c_int, dp]
@@ -62,6 +63,17 @@ def girt_residual(cfg, state, ic, dt):
     st = state.struct()
     e = lib().pfrx_oracle_girt_residual(C.byref(cfg.c), C.byref(st), ic, float(dt), _dp(Res), _dp(Jac), _dp(acc))
     return e, Res, Jac, acc
+
+
+def reaction(cfg, state, ic, dt):
+    """RReaction + RReactionDerivative alone on one cell: Res[n], Jac[n, n] (Jac[i, j] = dRes_i/dc_j)"""
+    n = cfg.ncomp
+    Res = np.zeros(n)
+    Jac = np.zeros((n, n), order="F")
+    st = state.struct()
+    e = lib().pfrx_oracle_reaction(C.byref(cfg.c), C.byref(st), ic, float(dt), _dp(Res), _dp(Jac))
+    assert e == 0
+    return Res, Jac
 
 
 def activity(cfg, state, ic=0):

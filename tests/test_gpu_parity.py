@@ -134,6 +134,46 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
+@pytest.mark.parametrize("variant", ["c2", "c5", "c4"])
+def test_batched_reaction_matches_oracle(variant):
+    """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
+    import torch
+
+    rstep = _gpu()
+    wl = W.by_name(variant, ncell=300)
+    if variant == "c4":
+        wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
+        wl.state.a["sat"][0, 9] = 1.0e-50
+    ref = wl.state.copy()
+    n = wl.cfg.ncomp
+    R0 = np.zeros((n, 300))
+    J0 = np.zeros((n, n, 300))
+    for c in range(300):
+        if ref.a["imat"][0, c] <= 0:
+            continue
+        r, j = orc.reaction(wl.cfg, ref, c, wl.tran_dt)
+        R0[:, c], J0[:, :, c] = r, j
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    res, jac = step.reaction(True)
+    torch.cuda.synchronize()
+    R1, J1 = res.cpu().numpy(), jac.cpu().numpy()
+    scale = np.abs(R0).max(axis=0, keepdims=True) + 1e-300  # per cell
+    assert (np.abs(R1 - R0) / scale).max() <= 1e-10, (np.abs(R1 - R0) / scale).max()
+    jscale = np.abs(J0).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(J1 - J0) / jscale).max() <= 1e-10
+    assert np.abs(R0).max() > 0 and np.abs(J0).max() > 0
+    if wl.cfg.c.nkinmnrl:
+        got = dev.to_host()
+        a, b = ref.a["mnrl_rate"], got.a["mnrl_rate"]
+        kA = wl.cfg.arrays["kinmnrl_rate_constant"][:, None] * ref.a["mnrl_area"]
+        assert (np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), kA)).max() <= 1e-10
+    r_only, none = step.reaction(False)
+    assert none is None and torch.equal(r_only, res)
+    step.close()
+
+
 def test_specialized_kernel_refuses_other_network():
     rstep = _gpu()
     from pflotran_elm_interface_b200 import specialize
