@@ -32,6 +32,13 @@
 
 // SPEC_FASTMATH 1: branch-free exp / log / division (pfrx_fastmath.cuh) in the hot
 // places whose arguments are known to be normal numbers; 0: CUDA's own everywhere
+// SPEC_LOOP_LU 1: the dense solve as rolled loops over shared memory (~400 instructions
+// that stay in the instruction cache); 0: fully unrolled Crout with the current column in
+// registers (~5 500 straight-line instructions).  Measured: unrolled wins for C3 / C4 / C2,
+// rolled wins for C5 (profiles/r01_spec_variants.md).
+#ifndef SPEC_LOOP_LU
+#define SPEC_LOOP_LU 0
+#endif
 #ifndef SPEC_FASTMATH
 #define SPEC_FASTMATH 1
 #endif
@@ -43,10 +50,9 @@ __device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTM
 #define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 
 // shared-memory slots of a thread (doubles)
-#define SPEC_JS (SPEC_NC + 1)
-#define SPEC_OFF_FIXED (SPEC_NC * SPEC_JS)
-#define SPEC_OFF_GUESS (SPEC_OFF_FIXED + SPEC_N)
-#define SPEC_OFF_LNGSEC (SPEC_OFF_GUESS + SPEC_N)
+#define SPEC_JS (SPEC_NC + 2)  // + right-hand side column + scaling-factor / solution column
+#define SPEC_OFF_C (SPEC_NC * SPEC_JS)
+#define SPEC_OFF_LNGSEC (SPEC_OFF_C + SPEC_NC)
 #define SPEC_SLOTS (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
 // slot -> index relative to the thread's base pointer
 #define SW(e) W[(e) * 32]
@@ -112,6 +118,103 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
       res[i] = sx_div(res[i] * nm, a);
     }
   }
+#if SPEC_LOOP_LU
+  if (NC == 0) return !bad;
+  // The dense part runs as ROLLED loops over the thread's shared-memory slice: the
+  // straight-line kernels are bound by instruction fetch (every 128-byte line comes
+  // from L2 once per Newton iteration), and an unrolled 13 x 13 LU is 5 500 of those
+  // instructions; as loops it is ~300 that stay in the instruction cache.
+  constexpr int JS = SPEC_JS, RB = NC, RV = NC + 1;  // columns: right-hand side, scaling factor / solution
+  // stage the right-hand side and the iterate (column scaling) -- literal indices
+#pragma unroll
+  for (int i = 0; i < NC; i++) {
+    W[JX(i, RB)] = res[spec_sp_of(i)];
+    SW(SPEC_OFF_C + i) = c[spec_sp_of(i)];
+  }
+  // RSolve: row scaling 1/max(1, max|J_ij|), log formulation column scaling by c_j; the
+  // implicit scaling factor of the decomposition in the same pass (utility.F90:611-622)
+#pragma unroll 1
+  for (int i = 0; i < NC; i++) {
+    double *r = W + i * (JS * 32);
+    double m = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      const double av = fabs(r[j * 32]);
+      m = av > m ? av : m;
+    }
+    const double nm = sx_rcp(fmax(1.0, m));
+    r[RB * 32] = r[RB * 32] * nm;
+    double m2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      double v = r[j * 32] * nm;
+      if (SPEC_USE_LOG) v *= SW(SPEC_OFF_C + j);
+      r[j * 32] = v;
+      const double av = fabs(v);
+      m2 = av > m2 ? av : m2;
+    }
+    if (!(m2 > 0.0)) bad = true;
+    r[RV * 32] = sx_rcp(m2);
+  }
+  if (bad) return false;
+  // LU with implicit-scaled partial pivoting in right-looking order (same operation
+  // sequence per element as the reference's Crout loops), forward substitution fused
+  // (the right-hand side is column NC of the augmented rows).  Rows never move:
+  // nibble i of perm is the row at logical position i.
+  unsigned long long perm = 0xFEDCBA9876543210ull;
+#pragma unroll 1
+  for (int k = 0; k < NC; k++) {
+    double aamax = 0.0;
+    int imax = k;
+#pragma unroll 1
+    for (int i = k; i < NC; i++) {
+      const double *r = W + (int)((perm >> (4 * i)) & 15ull) * (JS * 32);
+      const double dum = r[RV * 32] * fabs(r[k * 32]);
+      if (dum >= aamax) {  // the last maximum wins, like dum.ge.aamax
+        imax = i;
+        aamax = dum;
+      }
+    }
+    {
+      const unsigned long long x = ((perm >> (4 * k)) ^ (perm >> (4 * imax))) & 15ull;
+      perm ^= (x << (4 * k)) | (x << (4 * imax));
+    }
+    double *pr = W + (int)((perm >> (4 * k)) & 15ull) * (JS * 32);
+    double pv = pr[k * 32];
+    if (pv == 0.0) {
+      pv = 1.0e-20;
+      pr[k * 32] = pv;
+    }
+    if (k == NC - 1) break;
+    const double rpv = sx_rcp(pv);
+    const double *pk = pr + (k + 1) * 32;
+    const int cnt = NC - k;  // columns k+1 .. NC-1 and the right-hand side
+    // (a version with the pivot row in registers and the tail of a literal-range loop
+    // predicated off was measured 60 % slower: 194 vs 122 ms on C3)
+#pragma unroll 1
+    for (int i = k + 1; i < NC; i++) {
+      double *r = W + (int)((perm >> (4 * i)) & 15ull) * (JS * 32) + k * 32;
+      const double l = r[0] * rpv;
+      r[0] = l;
+      r += 32;
+#pragma unroll 4
+      for (int t = 0; t < cnt; t++) r[t * 32] -= l * pk[t * 32];
+    }
+  }
+  // back substitution (utility.F90:716-735); the solution goes to column RV by logical index
+#pragma unroll 1
+  for (int i = NC - 1; i >= 0; i--) {
+    const double *r = W + (int)((perm >> (4 * i)) & 15ull) * (JS * 32);
+    double sum = r[RB * 32];
+#pragma unroll 1
+    for (int j = i + 1; j < NC; j++) sum -= r[j * 32] * W[JX(j, RV)];
+    W[JX(i, RV)] = sx_div(sum, r[i * 32]);
+  }
+#pragma unroll
+  for (int k = 0; k < NC; k++) res[spec_sp_of(k)] = W[JX(k, RV)];
+  return true;
+}
+#else
   if (NC == 0) return !bad;
   double b[NCA];
 #pragma unroll
@@ -227,16 +330,19 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
   for (int k = 0; k < NC; k++) res[spec_sp_of(k)] = b[k];
   return true;
 }
+#endif
 
 // ---- RReact (reaction.F90:3742-4055) ------------------------------------------------
 // rt_auxvar%total / %immobile / %total_sorb_eq stay in HBM (st.*), the guess is in
 // the thread's shared slice.  Returns ierror; the last iterate is left in c.
 __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &prm, SpecCell &s, double *W,
-                                          long long cell, double dt, double (&c)[SPEC_N], int &its_out) {
+                                          long long cell, double dt, double (&c)[SPEC_N], double (&guess)[SPEC_N],
+                                          int &its_out) {
   constexpr int N = SPEC_N, NAQ = SPEC_NAQ;
   const long long ld = st.ld;
   const double psv = s.por * s.sat * 1000.0 * s.vol;
   s.dry = s.sat < prm.min_sat;
+  double fixed[N];  // read once per iteration: registers or local memory, ptxas decides
 #pragma unroll
   for (int i = 0; i < N; i++) {
     double f = 0.0;
@@ -246,8 +352,8 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     } else {
       if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
     }
-    SW(SPEC_OFF_FIXED + i) = f;
-    c[i] = SW(SPEC_OFF_GUESS + i);
+    fixed[i] = f;
+    c[i] = guess[i];
   }
   int its = 0;
   double norm0 = 0.0;
@@ -273,7 +379,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       double a = 0.0;
       if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
       if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
-      res[i] = sx_div(a - SW(SPEC_OFF_FIXED + i), dt);
+      res[i] = sx_div(a - fixed[i], dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
 #if SPEC_NCLM > 0
@@ -343,7 +449,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     } else {
       st.immobile[(i - NAQ) * ld + cell] = c[i];
     }
-    SW(SPEC_OFF_GUESS + i) = c[i];
+    guess[i] = c[i];
   }
   its_out = its;
   return 0;
@@ -383,7 +489,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
 #pragma unroll
   for (int k = 0; k < SPEC_NKIN; k++) s.mrate[k] = st.mnrl_rate[k * ld + cell];
   unsigned small_mask = 0u;
-  double small_val[N];
+  double small_val[N], guess[N];
   // all loads first: the clamping stores below would otherwise order them
   double in_t[N], in_g[N], in_a[N];
 #pragma unroll
@@ -406,10 +512,10 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
         t = 1.e-40;
         st.total[i * ld + cell] = t;
       }
-      SW(SPEC_OFF_GUESS + i) = g;
+      guess[i] = g;
     } else {
       double t = in_t[i];
-      SW(SPEC_OFF_GUESS + i) = t;  // the guess keeps the unclamped value
+      guess[i] = t;  // the guess keeps the unclamped value
       if (t <= 1.e-40) {
         small_mask |= 1u << i;
         small_val[i] = t;
@@ -424,7 +530,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   for (;;) {
     if (cumulative >= target) break;
     int its = 0;
-    int e = spec_react(st, prm, s, W, cell, dt, c, its);
+    int e = spec_react(st, prm, s, W, cell, dt, c, guess, its);
     nit += its;
     if (e != 0) {
       ncuts++;
@@ -460,7 +566,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   if (aborted) ierr = 1;
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    if (i < NAQ) st.pri_molal[i * ld + cell] = aborted ? c[i] : SW(SPEC_OFF_GUESS + i);
+    if (i < NAQ) st.pri_molal[i * ld + cell] = aborted ? c[i] : guess[i];
     if (!aborted && ((small_mask >> i) & 1u)) {
       if (i < NAQ)
         st.total[i * ld + cell] = small_val[i];

@@ -158,6 +158,8 @@ def _term(st: float, expr: str) -> str:
 
 
 class _Gen:
+    loop_lu = False  # dense solve as rolled loops (style "looplu")
+
     def __init__(self, cfg: abi.ReactionConfig):
         ok, why = supported(cfg)
         if not ok:
@@ -566,7 +568,7 @@ class _Gen:
     def source(self) -> str:
         c = self.c
         n = self.n
-        slots = self.nc * (self.nc + 1) + 2 * n + (0 if self.act_upd else self.ncx)
+        slots = max(1, self.nc * (self.nc + 2) + self.nc + (0 if self.act_upd else self.ncx))
         per_warp = slots * 32 * 8 + 1024  # + the per-block reservation when a block is one warp
         if slots * 32 * 8 > 160 * 1024:
             threads = 32
@@ -599,6 +601,7 @@ class _Gen:
         self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
         self.w(f"#define SPEC_THREADS {threads}")
         self.w(f"#define SPEC_FASTMATH {int(os.environ.get('PFRX_SPEC_FASTMATH', '1'))}")
+        self.w(f"#define SPEC_LOOP_LU {int(self.loop_lu)}")
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")
         cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
         so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
@@ -1118,10 +1121,11 @@ def default_variant(cfg: abi.ReactionConfig) -> Tuple[int, str]:
     135 ms, rolled tables with four warps 396 ms, straight-line with four warps
     635 ms per 4.19 M cells -- so the first is the default for every network; the
     other two stay selectable for experiments:
-    PFRX_SPEC_VARIANT=<style><warps> with style s (straight) or r (rolled)."""
+    PFRX_SPEC_VARIANT=<style><warps> with style s (straight), r (rolled) or l (straight-line
+    assembly, dense solve as rolled loops; one warp only)."""
     env = os.environ.get("PFRX_SPEC_VARIANT")
     if env:
-        return int(env[1:]), {"s": "straight", "r": "rolled"}[env[0]]
+        return int(env[1:]), {"s": "straight", "r": "rolled", "l": "looplu"}[env[0]]
     return 1, "straight"
 
 
@@ -1129,7 +1133,11 @@ def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style:
     warps, style = _variant(cfg, warps, style)
     if style == "rolled":
         return _GenR(cfg, warps).source()
-    return _GenW(cfg, warps).source() if warps > 1 else _Gen(cfg).source()
+    if warps > 1:
+        return _GenW(cfg, warps).source()
+    g = _Gen(cfg)
+    g.loop_lu = style == "looplu"
+    return g.source()
 
 
 def _stamp(src: str) -> str:
