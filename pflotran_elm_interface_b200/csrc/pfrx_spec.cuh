@@ -50,9 +50,23 @@ __device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTM
 #define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 
 // shared-memory slots of a thread (doubles)
+#ifndef SPEC_LOOP_LU
+#define SPEC_LOOP_LU 0
+#endif
+#if SPEC_LOOP_LU
 #define SPEC_JS (SPEC_NC + 2)  // + right-hand side column + scaling-factor / solution column
+#else
+#define SPEC_JS (SPEC_NC + 1)  // + one column: scaling factor, then right-hand side
+#endif
+#if SPEC_LOOP_LU
 #define SPEC_OFF_C (SPEC_NC * SPEC_JS)
 #define SPEC_OFF_LNGSEC (SPEC_OFF_C + SPEC_NC)
+#define SPEC_FIXED(i) fixed[i]  // no slots left: registers / local memory
+#else
+#define SPEC_OFF_FIXED (SPEC_NC * SPEC_JS)
+#define SPEC_OFF_LNGSEC (SPEC_OFF_FIXED + SPEC_N)
+#define SPEC_FIXED(i) SW(SPEC_OFF_FIXED + (i))  // read once per iteration, constant over a sub-step
+#endif
 #define SPEC_SLOTS (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
 // slot -> index relative to the thread's base pointer
 #define SW(e) W[(e) * 32]
@@ -69,12 +83,17 @@ struct SpecCell {
   double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
   double Isec, msec;  // sum z^2 m, sum m over secondary species of the latest RTotal
   double lgcls[SPEC_NCLS > 0 ? SPEC_NCLS : 1];
-  double lngam[SPEC_N];
+  double lngam[SPEC_ACT_UPD ? 1 : SPEC_N];  // frozen coefficients only; otherwise ln gamma_i is lgcls[class of i]
   double fsite[SPEC_NSRFRXN > 0 ? SPEC_NSRFRXN : 1];
   double scconc[SPEC_NSRFCPLX > 0 ? SPEC_NSRFCPLX : 1];
   double mrate[SPEC_NKIN > 0 ? SPEC_NKIN : 1];
   bool dry;
+  bool store;  // false: the lane has finished its cell, rt_auxvar%sec_molal must not be touched
 };
+
+// ln gamma of primary species i (literal i)
+#define SPEC_LNGAM(s, i) \
+  (SPEC_ACT_UPD ? (spec_pri_cls(i) < 0 ? 0.0 : (s).lgcls[spec_pri_cls(i) < 0 ? 0 : spec_pri_cls(i)]) : (s).lngam[SPEC_ACT_UPD ? 0 : (i)])
 
 // ---- generated for the network (declared here, defined by the generator) ------
 __device__ __forceinline__ void spec_activity(const double (&c)[SPEC_N], SpecCell &s);
@@ -332,6 +351,10 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
 }
 #endif
 
+#ifndef SPEC_LOCKSTEP
+#define SPEC_LOCKSTEP 0
+#endif
+#if !SPEC_LOCKSTEP
 // ---- RReact (reaction.F90:3742-4055) ------------------------------------------------
 // rt_auxvar%total / %immobile / %total_sorb_eq stay in HBM (st.*), the guess is in
 // the thread's shared slice.  Returns ierror; the last iterate is left in c.
@@ -352,7 +375,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     } else {
       if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
     }
-    fixed[i] = f;
+    SPEC_FIXED(i) = f;
     c[i] = guess[i];
   }
   int its = 0;
@@ -379,7 +402,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       double a = 0.0;
       if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
       if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
-      res[i] = sx_div(a - fixed[i], dt);
+      res[i] = sx_div(a - SPEC_FIXED(i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
 #if SPEC_NCLM > 0
@@ -461,6 +484,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   constexpr int N = SPEC_N, NAQ = SPEC_NAQ;
   const long long ld = st.ld;
   SpecCell s;
+  s.store = true;
   s.den_kg = st.den_kg[cell];
   s.sat = st.sat[cell];
   s.temp = st.temp[cell];
@@ -501,9 +525,9 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
 #pragma unroll
   for (int i = 0; i < N; i++) {
     small_val[i] = 0.0;
-    s.lngam[i] = 0.0;
+    if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = 0.0;
     if (i < NAQ) {
-      s.lngam[i] = log(in_a[i]);
+      if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = log(in_a[i]);
       double g = in_g[i];
       double t = in_t[i];
       if (t <= 1.e-40) {
@@ -576,7 +600,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   }
   if (SPEC_ACT_UPD) {
 #pragma unroll
-    for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = sx_exp(s.lngam[i]);
+    for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = sx_exp(SPEC_LNGAM(s, i));
 #pragma unroll 4
     for (int k = 0; k < SPEC_NCX; k++) {
       int q = spec_cx_cls(k);
@@ -654,3 +678,342 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
     atomicMax(&summ->max_sub, l_maxsub);
   }
 }
+#else
+
+// ======================================================================================
+// Lock-step skeleton (SPEC_LOCKSTEP 1): the four warps of a 128-thread block execute the
+// SAME Newton iteration at the same time.
+//
+// Why (profiles/r01_ncu_c5_spec_s1.txt vs r01_ncu_c3_spec_s1f.txt): the generated code is
+// 280 KB per Newton iteration and an SM can pull only ~6 B/clk of DISTINCT instruction
+// bytes out of L2.  Four warps that drift apart are four streams (C5: iteration counts
+// differ from cell to cell, 6.7 fetch-stall cycles per instruction); four warps at the
+// same place are one stream delivered four times.  So RStep / RReact are restated as a
+// state machine per lane: one pass of the block loop = one Newton iteration of every
+// unfinished cell; a finished lane keeps executing with its stores disabled; the two
+// block votes per pass are the barriers that keep the warps together.
+// ======================================================================================
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
+    pfrx_spec_kernel(DevState st, long long ncell, double tran_dt, SpecParams prm, DevSummary *summ) {
+  constexpr int N = SPEC_N, NAQ = SPEC_NAQ;
+  extern __shared__ double smem[];
+  const int lane32 = threadIdx.x & 31;
+  double *W = smem + (size_t)(threadIdx.x >> 5) * (SPEC_SLOTS * 32) + lane32;
+  const long long ld = st.ld;
+  const double target = tran_dt;
+
+  unsigned long long l_active = 0, l_its = 0, l_cut = 0;
+  long long l_first = -1;
+  int l_maxits = 0, l_maxkin = 0, l_maxerr = 0, l_maxsub = 0;
+
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < ncell; base += (long long)gridDim.x * blockDim.x) {
+    const bool inrange = base + threadIdx.x < ncell;
+    const long long cell = inrange ? base + threadIdx.x : ncell - 1;
+    const bool live = inrange && !(st.imat && st.imat[cell] <= 0);
+
+    // ---- RStep entry (reaction.F90:3600-3650)
+    SpecCell s;
+    s.den_kg = st.den_kg[cell];
+    s.sat = st.sat[cell];
+    s.temp = st.temp[cell];
+    s.por = st.porosity[cell];
+    s.vol = st.volume[cell];
+    s.spd = st.soil_particle_density ? st.soil_particle_density[cell] : 0.0;
+    s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
+    s.dry = s.sat < prm.min_sat;
+    const double psv = s.por * s.sat * 1000.0 * s.vol;
+    {
+      double Is = 0.0, ms = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < SPEC_NCX; k++) {
+        double m = st.sec_molal[k * ld + cell];
+        Is += m * spec_cx_z2(k);
+        ms += m;
+        if (!SPEC_ACT_UPD) SW(SPEC_OFF_LNGSEC + k) = log(st.sec_act_coef[k * ld + cell]);
+      }
+      s.Isec = Is;
+      s.msec = ms;
+    }
+#pragma unroll
+    for (int k = 0; k < (SPEC_NCLS > 0 ? SPEC_NCLS : 1); k++) s.lgcls[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SPEC_NSRFRXN; k++) s.fsite[k] = st.free_site[k * ld + cell];
+#pragma unroll
+    for (int k = 0; k < SPEC_NSRFCPLX; k++) s.scconc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SPEC_NKIN; k++) s.mrate[k] = st.mnrl_rate[k * ld + cell];
+    unsigned small_mask = 0u;
+    // the guess of the next sub-step is kept where it ends up anyway: rt_auxvar%pri_molal
+    // (aqueous species); immobile species keep theirs in registers
+    double small_val[N], gimm[N > NAQ ? N - NAQ : 1], fixed[N], c[N];
+    {
+      double in_t[N], in_g[N], in_a[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        in_a[i] = (i < NAQ) ? st.pri_act_coef[i * ld + cell] : 1.0;
+        in_g[i] = (i < NAQ) ? st.pri_molal[i * ld + cell] : 0.0;
+        in_t[i] = (i < NAQ) ? st.total[i * ld + cell] : st.immobile[(i - NAQ) * ld + cell];
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        small_val[i] = 0.0;
+        SPEC_FIXED(i) = 0.0;
+        if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = 0.0;
+        if (i < NAQ) {
+          if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = log(in_a[i]);
+          c[i] = in_g[i];
+          if (in_t[i] <= 1.e-40) {
+            small_mask |= 1u << i;
+            small_val[i] = in_t[i];
+            if (live) st.total[i * ld + cell] = 1.e-40;
+          }
+        } else {
+          gimm[i - NAQ] = in_t[i];  // the guess keeps the unclamped value
+          c[i] = in_t[i];
+          if (in_t[i] <= 1.e-40) {
+            small_mask |= 1u << i;
+            small_val[i] = in_t[i];
+            if (live) st.immobile[(i - NAQ) * ld + cell] = 1.e-40;
+          }
+        }
+      }
+    }
+    double cumulative = 0.0, dt = target, norm0 = 0.0;
+    int ncuts = 0, nconst = 0, nss = 0, nit = 0, nku = 0, its = 0;
+    bool done = !live, aborted = false, had_cut = false, need_begin = true;
+
+    for (;;) {
+      // ---- RReact entry (reaction.F90:3829-3850) for lanes that start a sub-step
+      if (!done && need_begin) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          double f = 0.0;
+          if (i < NAQ) {
+            if (!s.dry) f = psv * st.total[i * ld + cell];
+            if (SPEC_NEQSR > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
+          } else {
+            if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
+          }
+          SPEC_FIXED(i) = f;
+          c[i] = (i < NAQ) ? st.pri_molal[i * ld + cell] : gimm[i - NAQ];
+        }
+        its = 0;
+        need_begin = false;
+      }
+      if (!done) its++;
+      s.store = !done;
+
+      // ---- one Newton iteration (reaction.F90:3860-4041), every lane of the block
+      double lna[N], ic[N], tot[N], res[N], ts[N];
+      if (SPEC_ACT_UPD) spec_activity(c, s);
+      spec_rtotal(c, lna, ic, tot, s, W, st.sec_molal + cell, ld, dt);
+#pragma unroll
+      for (int i = 0; i < N; i++) ts[i] = 0.0;
+      if (SPEC_NEQSR > 0) spec_sorption(lna, ic, ts, s, W, st, cell, s.vol / dt);
+      const bool over = its > prm.max_its;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double a = 0.0;
+        if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
+        if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
+        res[i] = sx_div(a - SPEC_FIXED(i), dt);
+      }
+      if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
+#if SPEC_NCLM > 0
+      if (!s.dry) spec_sandbox(c, res, s, W);
+#endif
+      double mabs = 0.0, ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        mabs = fmax(mabs, fabs(res[i]));
+        ss += res[i] * res[i];
+      }
+      const double nrm = sqrt(ss);
+      if (its == 1) norm0 = nrm;
+      const double rel = nrm / norm0;
+      bool conv = (mabs < prm.tol_res) || (rel < prm.tol_relres);
+      const bool need_solve = !done && !over && !conv;
+      bool fail = !done && over;
+      bool solve_error = false;
+
+      if (__syncthreads_or(need_solve ? 1 : 0)) {
+        const bool ok = spec_solve(W, res, c, s, dt);
+        if (need_solve) {
+          if (!ok) {
+            fail = true;
+            solve_error = true;
+          } else {
+            double cn[N], maxrel = -1.0, minr = 1.e20;
+            if (!SPEC_USE_LOG) {
+#pragma unroll
+              for (int i = 0; i < N; i++)
+                if (c[i] <= res[i]) minr = fmin(minr, fabs(c[i] / res[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+              double u = res[i];
+              if (SPEC_USE_LOG) {
+                u = copysign(1.0, u) * fmin(fabs(u), prm.max_dlnC);
+                cn[i] = c[i] * sx_exp(-u);
+              } else {
+                if (minr < 1.0) u = u * minr * 0.99;
+                cn[i] = c[i] - u;
+              }
+              double v = fabs(sx_div(cn[i] - c[i], c[i]));
+              if (!isnan(v)) maxrel = fmax(maxrel, v);
+            }
+            if ((maxrel >= 0.0) && (maxrel < prm.tol_relchange)) {
+              conv = true;
+            } else {
+#pragma unroll
+              for (int i = 0; i < N; i++) c[i] = cn[i];
+            }
+          }
+        }
+      }
+
+      // ---- what this pass decided for the lane (RReact exit + RStep, reaction.F90:3655-3738)
+      if (!done) {
+        if (fail) {
+          nit += its;
+          // its > max: total / immobile keep their values in HBM, total_sorb_eq does not;
+          // solve error: no restore (reaction.F90:3964-3967)
+#pragma unroll
+          for (int i = 0; i < N; i++) {
+            if (i < NAQ) {
+              if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+              if (solve_error) st.total[i * ld + cell] = tot[i];
+            } else if (solve_error) {
+              st.immobile[(i - NAQ) * ld + cell] = c[i];
+            }
+          }
+          ncuts++;
+          had_cut = true;
+          if (ncuts > prm.max_cuts) {
+            aborted = true;
+            done = true;
+          } else {
+            dt = 0.5 * dt;
+            nconst = 0;
+            need_begin = true;
+          }
+        } else if (conv) {
+          nit += its;
+#pragma unroll
+          for (int i = 0; i < N; i++) {
+            if (i < NAQ) {
+              st.total[i * ld + cell] = tot[i];
+              if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+              st.pri_molal[i * ld + cell] = c[i];
+            } else {
+              st.immobile[(i - NAQ) * ld + cell] = c[i];
+              gimm[i - NAQ] = c[i];
+            }
+          }
+          bool upd = SPEC_NCLM > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
+          if (SPEC_NKIN > 0) {
+            upd = true;
+#pragma unroll
+            for (int m = 0; m < SPEC_NKIN; m++) {
+              double vf = st.mnrl_volfrac[m * ld + cell] + s.mrate[m] * spec_mn_vol(m) * dt;
+              if (vf < 0.0) vf = 0.0;
+              st.mnrl_volfrac[m * ld + cell] = vf;
+            }
+          }
+          cumulative += dt;
+          nss++;
+          nconst++;
+          if (upd) nku++;
+          if (nconst >= 4) {
+            ncuts--;
+            dt = fmin(2.0 * dt, target - cumulative);
+          }
+          if (cumulative >= target)
+            done = true;
+          else
+            need_begin = true;
+        }
+      }
+      if (__syncthreads_and(done ? 1 : 0)) break;
+    }
+
+    // ---- publish the cell (reaction.F90:3700-3738); the generated routines stop updating a
+    // lane's activity / sorption / rate state once s.store is false, so this is the state of
+    // the lane's last own pass
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i < NAQ && aborted) st.pri_molal[i * ld + cell] = c[i];
+        if (!aborted && ((small_mask >> i) & 1u)) {
+          if (i < NAQ)
+            st.total[i * ld + cell] = small_val[i];
+          else
+            st.immobile[(i - NAQ) * ld + cell] = small_val[i];
+        }
+      }
+      if (SPEC_ACT_UPD) {
+#pragma unroll
+        for (int i = 0; i < NAQ; i++) st.pri_act_coef[i * ld + cell] = sx_exp(SPEC_LNGAM(s, i));
+#pragma unroll 4
+        for (int k = 0; k < SPEC_NCX; k++) {
+          int q = spec_cx_cls(k);
+          double lg = 0.0;
+#pragma unroll
+          for (int z = 0; z < SPEC_NCLS; z++)
+            if (z == q) lg = s.lgcls[z];
+          st.sec_act_coef[k * ld + cell] = q < 0 ? 1.0 : sx_exp(lg);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SPEC_NSRFRXN; k++) st.free_site[k * ld + cell] = s.fsite[k];
+      if (SPEC_NEQSR > 0 && st.eqsrfcplx_conc) {
+#pragma unroll
+        for (int k = 0; k < SPEC_NSRFCPLX; k++) st.eqsrfcplx_conc[k * ld + cell] = s.scconc[k];
+      }
+#pragma unroll
+      for (int k = 0; k < SPEC_NKIN; k++) st.mnrl_rate[k * ld + cell] = s.mrate[k];
+      if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = s.ln_act_h2o;
+    }
+
+    if (inrange) {
+      st.num_sub_steps[cell] = nss;
+      st.num_iterations[cell] = nit;
+      st.num_kinetic_state_updates[cell] = nku;
+      st.ierror[cell] = aborted ? 1 : 0;
+      if (live) {
+        l_active++;
+        l_its += (unsigned long long)nit;
+        if (had_cut) l_cut++;
+        if (aborted && (l_first < 0 || cell < l_first)) l_first = cell;
+        l_maxits = max(l_maxits, nit);
+        l_maxkin = max(l_maxkin, nku);
+        l_maxerr = max(l_maxerr, aborted ? 1 : 0);
+        l_maxsub = max(l_maxsub, nss);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l_active += __shfl_xor_sync(0xffffffffu, l_active, o);
+    l_its += __shfl_xor_sync(0xffffffffu, l_its, o);
+    l_cut += __shfl_xor_sync(0xffffffffu, l_cut, o);
+    long long f = __shfl_xor_sync(0xffffffffu, l_first, o);
+    if (f >= 0 && (l_first < 0 || f < l_first)) l_first = f;
+    l_maxits = max(l_maxits, __shfl_xor_sync(0xffffffffu, l_maxits, o));
+    l_maxkin = max(l_maxkin, __shfl_xor_sync(0xffffffffu, l_maxkin, o));
+    l_maxerr = max(l_maxerr, __shfl_xor_sync(0xffffffffu, l_maxerr, o));
+    l_maxsub = max(l_maxsub, __shfl_xor_sync(0xffffffffu, l_maxsub, o));
+  }
+  if (lane32 == 0) {
+    atomicAdd(&summ->ncell_active, l_active);
+    atomicAdd(&summ->sum_its, l_its);
+    atomicAdd(&summ->num_cut_cells, l_cut);
+    if (l_first >= 0) atomicMin(&summ->first_failed, l_first);
+    atomicMax(&summ->max_its, l_maxits);
+    atomicMax(&summ->max_kin, l_maxkin);
+    atomicMax(&summ->max_err, l_maxerr);
+    atomicMax(&summ->max_sub, l_maxsub);
+  }
+}
+#endif

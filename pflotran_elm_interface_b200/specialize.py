@@ -111,7 +111,8 @@ def _variant(cfg: abi.ReactionConfig, warps: Optional[int], style: Optional[str]
 
 def cubin_path(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
     warps, style = _variant(cfg, warps, style)
-    return os.path.join(OUT, f"spec_{signature(cfg):016x}_{style[0]}{warps}.cubin")
+    tag = {"straight": "s", "rolled": "r", "looplu": "l", "lockstep": "k", "klooplu": "m"}[style]
+    return os.path.join(OUT, f"spec_{signature(cfg):016x}_{tag}{warps}.cubin")
 
 
 def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
@@ -159,6 +160,7 @@ def _term(st: float, expr: str) -> str:
 
 class _Gen:
     loop_lu = False  # dense solve as rolled loops (style "looplu")
+    lockstep = False  # 128-thread blocks whose warps execute the same Newton iteration (style "lockstep")
 
     def __init__(self, cfg: abi.ReactionConfig):
         ok, why = supported(cfg)
@@ -237,13 +239,10 @@ class _Gen:
         self.w("  const double sq = sqrt(I);")
         A, B, Bd = _lit(c.debyeA), _lit(c.debyeB), _lit(c.debyeBdot)
         for q, (negz2, a0) in enumerate(self.cls):
-            self.w(f"  s.lgcls[{q}] = (sx_div({_lit(negz2)} * sq * {A}, 1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
-        for i in range(self.naq):
-            q = self.pri_cls[i]
-            self.w(f"  s.lngam[{i}] = {'0.0' if q < 0 else f's.lgcls[{q}]'};")
+            self.w(f"  if (s.store) s.lgcls[{q}] = (sx_div({_lit(negz2)} * sq * {A}, 1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
         if c.use_activity_h2o:
             mp = " + ".join(f"c[{i}]" for i in range(self.naq) if i != c.h2o_aq_id) or "0.0"
-            self.w(f"  {{ double t = 1.0 - 0.017 * (({mp}) + s.msec); s.ln_act_h2o = t > 0.0 ? log(t) : 0.0; }}")
+            self.w(f"  if (s.store) {{ double t = 1.0 - 0.017 * (({mp}) + s.msec); s.ln_act_h2o = t > 0.0 ? log(t) : 0.0; }}")
         self.w("}")
         self.w()
 
@@ -256,7 +255,11 @@ class _Gen:
         self.w("  const double psvd = s.por * s.sat * 1000.0 * s.vol / dt;")
         for i in range(n):
             if i < naq:
-                self.w(f"  lna[{i}] = sx_log(c[{i}]) + s.lngam[{i}]; ic[{i}] = sx_rcp(c[{i}]); tot[{i}] = c[{i}];")
+                if self.act_upd:
+                    lg = "" if self.pri_cls[i] < 0 else f" + s.lgcls[{self.pri_cls[i]}]"
+                else:
+                    lg = f" + s.lngam[{i}]"
+                self.w(f"  lna[{i}] = sx_log(c[{i}]){lg}; ic[{i}] = sx_rcp(c[{i}]); tot[{i}] = c[{i}];")
             else:
                 self.w(f"  lna[{i}] = 0.0; ic[{i}] = 0.0; tot[{i}] = c[{i}];")
         self.w("  double Is = 0.0, ms = 0.0;")
@@ -293,7 +296,7 @@ class _Gen:
                 else:
                     arg = f"({expr}) - SW(SPEC_OFF_LNGSEC + {k})"
                 self.w(f"    const double sk = sx_exp({arg});")
-                self.w(f"    sec_out[{k} * ld] = sk;")
+                self.w(f"    if (s.store) sec_out[{k} * ld] = sk;")
                 z2 = float(a["eqcplx_Z"][k]) ** 2
                 if z2 != 0.0:
                     self.w(f"    Is += sk * {_lit(z2)};")
@@ -355,7 +358,7 @@ class _Gen:
         self.w("__device__ __forceinline__ void spec_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],")
         self.w("    double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st, long long cell, double jscale) {")
         for k in range(c.nsrfcplx):
-            self.w(f"  s.scconc[{k}] = 0.0;")
+            self.w(f"  if (s.store) s.scconc[{k}] = 0.0;")
         for e in range(c.neqsrfcplxrxn):
             r = int(a["eqsrfcplxrxn_to_srfcplxrxn"][e])
             cx = [int(v) for v in a["srfcplxrxn_to_complex"][a["srfcplxrxn_ptr"][r]:a["srfcplxrxn_ptr"][r + 1]]]
@@ -369,7 +372,7 @@ class _Gen:
             else:
                 self.w(f"    const double dens = {dens};")
             self.w("    if (dens < 1.e-40) {")
-            self.w(f"      s.fsite[{r}] = 0.0;")
+            self.w(f"      if (s.store) s.fsite[{r}] = 0.0;")
             self.w("    } else {")
             ptr, ids, st_ = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
             for q, k in enumerate(cx):
@@ -384,10 +387,10 @@ class _Gen:
             for q in range(len(cx)):
                 self.w(f"      esum += e{q};")
             self.w("      const double fs = dens / (1.0 + esum);")
-            self.w(f"      s.fsite[{r}] = fs;")
+            self.w(f"      if (s.store) s.fsite[{r}] = fs;")
             for q, k in enumerate(cx):
                 self.w(f"      const double S{q} = e{q} * fs;")
-                self.w(f"      s.scconc[{k}] += S{q};")
+                self.w(f"      if (s.store) s.scconc[{k}] += S{q};")
             self.w("      double den = 0.0;")
             for q in range(len(cx)):
                 self.w(f"      den += S{q};")
@@ -481,7 +484,7 @@ class _Gen:
                 self.w("        }")
             self.w("      }")
             self.w("    }")
-            self.w(f"    s.mrate[{m}] = rate_vol;")
+            self.w(f"    if (s.store) s.mrate[{m}] = rate_vol;")
             self.w("  }")
         self.w("}")
         self.w()
@@ -568,7 +571,11 @@ class _Gen:
     def source(self) -> str:
         c = self.c
         n = self.n
-        slots = max(1, self.nc * (self.nc + 2) + self.nc + (0 if self.act_upd else self.ncx))
+        if self.loop_lu:
+            slots = self.nc * (self.nc + 2) + self.nc
+        else:
+            slots = self.nc * (self.nc + 1) + n
+        slots = max(1, slots + (0 if self.act_upd else self.ncx))
         per_warp = slots * 32 * 8 + 1024  # + the per-block reservation when a block is one warp
         if slots * 32 * 8 > 160 * 1024:
             threads = 32
@@ -581,6 +588,10 @@ class _Gen:
         else:
             threads = 128
             minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
+        if self.lockstep and threads == 32:
+            # the warps that shared an SM as separate blocks become one block that votes
+            threads = 32 * minblocks
+            minblocks = 1
         self.threads, self.minblocks, self.slots = threads, minblocks, slots
         o = self.out
         o.clear()
@@ -602,11 +613,14 @@ class _Gen:
         self.w(f"#define SPEC_THREADS {threads}")
         self.w(f"#define SPEC_FASTMATH {int(os.environ.get('PFRX_SPEC_FASTMATH', '1'))}")
         self.w(f"#define SPEC_LOOP_LU {int(self.loop_lu)}")
+        self.w(f"#define SPEC_LOCKSTEP {int(self.lockstep)}")
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")
         cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
         so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
         self.w("__host__ __device__ constexpr int spec_cmap(int i) { return " + (cm + " : -1" if cm else "-1") + "; }")
         self.w("__host__ __device__ constexpr int spec_sp_of(int ci) { return " + (so + " : 0" if so else "0") + "; }")
+        pc = " : ".join(f"i == {i} ? {q}" for i, q in enumerate(self.pri_cls) if q >= 0)
+        self.w("__host__ __device__ constexpr int spec_pri_cls(int i) { return " + (pc + " : -1" if pc else "-1") + "; }")
         self.w("__device__ __forceinline__ double spec_cx_z2(int k);")
         self.w("__device__ __forceinline__ int spec_cx_cls(int k);")
         self.w("__device__ __forceinline__ double spec_mn_vol(int m);")
@@ -1125,7 +1139,7 @@ def default_variant(cfg: abi.ReactionConfig) -> Tuple[int, str]:
     assembly, dense solve as rolled loops; one warp only)."""
     env = os.environ.get("PFRX_SPEC_VARIANT")
     if env:
-        return int(env[1:]), {"s": "straight", "r": "rolled", "l": "looplu"}[env[0]]
+        return int(env[1:]), {"s": "straight", "r": "rolled", "l": "looplu", "k": "lockstep", "m": "klooplu"}[env[0]]
     return 1, "straight"
 
 
@@ -1136,7 +1150,8 @@ def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style:
     if warps > 1:
         return _GenW(cfg, warps).source()
     g = _Gen(cfg)
-    g.loop_lu = style == "looplu"
+    g.loop_lu = style in ("looplu", "klooplu")
+    g.lockstep = style in ("lockstep", "klooplu")
     return g.source()
 
 
