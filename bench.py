@@ -207,6 +207,13 @@ def main():
     pristine = rstep.DeviceState.from_host(wl.state, dev)
     work = rstep.DeviceState(wl.cfg, ncell, dev)
     step.bind(work)
+    tuned = None
+    if a.kernel == "auto" and info["lanes"] < 0 and not os.environ.get("PFRX_SPEC_VARIANT"):
+        # untimed set-up: time both skeletons of the specialised kernel on a copy of the
+        # first cells of this shard and keep the faster one (rstep.ChemistryStep.autotune)
+        tuned = step.autotune(pristine, dt)
+        step.bind(work)
+        info = step.kernel_info()
     kstream = torch.cuda.ExternalStream(step.stream_ptr, device=dev)
 
     def restore():
@@ -345,7 +352,7 @@ def main():
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": dict(cfg_json, name=wl.name, ncomp=wl.cfg.ncomp, neqcplx=int(wl.cfg.c.neqcplx),
-                          kernel=info, note=wl.note),
+                          kernel=info, kernel_variant=step.variant, autotune_s=tuned, note=wl.note),
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
            "result": res.as_dict(), "wall_s_timed_region": wall}
     print(json.dumps(out))

@@ -114,6 +114,13 @@ class DeviceState:
         for k, v in host.a.items():
             self.t[k].copy_(torch.from_numpy(v), non_blocking=True)
 
+    def prefix(self, ncell: int) -> "DeviceState":
+        """an independent copy of the first ``ncell`` cells"""
+        o = DeviceState(self.cfg, min(int(ncell), self.ncell), self.device)
+        for k, v in self.t.items():
+            o.t[k].copy_(v[:, : o.ncell])
+        return o
+
     def to_host(self) -> abi.HostState:
         h = abi.HostState(self.cfg, self.ncell)
         for k in h.a:
@@ -160,6 +167,7 @@ class ChemistryStep:
         self.device = int(device)
         self._h = C.c_void_p()
         self._state = None
+        self.variant = "generic"
         _check(lib().pfrx_create(C.byref(cfg.c), self.device, C.byref(self._h)), "pfrx_create")
 
     def close(self) -> None:
@@ -275,6 +283,8 @@ class ChemistryStep:
                 raise PfrxError("specialised kernel unavailable: " + why)
             return False
         self.load_specialized(path)
+        self.variant = "".join(k for k, v in _sp.VARIANT_STYLES.items() if v == _sp.default_variant(self.cfg)[1]) + \
+            str(_sp.default_variant(self.cfg)[0])
         return True
 
     def last_transfer_bytes(self):
@@ -282,6 +292,56 @@ class ChemistryStep:
         a, b = C.c_int64(), C.c_int64()
         _check(lib().pfrx_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "pfrx_last_transfer_bytes")
         return a.value, b.value
+
+    def autotune(self, state: DeviceState, tran_dt: float, variants=("s1", "k1"), sample: int = 303104,
+                 repeats: int = 2) -> Dict[str, float]:
+        """Pick the specialised-kernel variant that is fastest on THIS state.
+
+        Which skeleton wins depends on the data, not only on the network: when
+        the cells of a block need different numbers of Newton iterations the
+        one-warp-per-block kernel's warps drift apart in its 280 KB instruction
+        stream and stall on instruction fetch (C5: 2.4x slower than lock-step),
+        when they need the same number the lock-step kernel only adds votes and
+        register pressure (C3: 12 % slower).  So both are timed on a private copy
+        of the first ``sample`` cells (a few milliseconds each) and the winner is
+        attached.  ``state`` itself is not modified; it is bound on return.
+        Returns {variant: seconds}; variants without a cubin are skipped."""
+        import torch
+
+        from . import specialize as _sp
+
+        ok, why = _sp.supported(self.cfg)
+        times: Dict[str, float] = {}
+        if not ok:
+            self.bind(state)
+            return times
+        stream = torch.cuda.ExternalStream(self.stream_ptr, device=state.device)
+        for v in variants:
+            warps, style = int(v[1:]), _sp.VARIANT_STYLES[v[0]]
+            path = _sp.cubin_path(self.cfg, warps, style)
+            if not os.path.exists(path):
+                continue
+            self.load_specialized(path)
+            best = None
+            for r in range(repeats + 1):
+                trial = state.prefix(sample)
+                self.bind(trial)
+                torch.cuda.synchronize(state.device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                self.rstep_async(tran_dt)
+                e1.record(stream)
+                self.rstep_finish()
+                t = e0.elapsed_time(e1) * 1e-3
+                if r > 0:  # the first run pays module load and first touch
+                    best = t if best is None else min(best, t)
+            times[v] = best
+        if times:
+            win = min(times, key=times.get)
+            self.load_specialized(_sp.cubin_path(self.cfg, int(win[1:]), _sp.VARIANT_STYLES[win[0]]))
+            self.variant = win
+        self.bind(state)
+        return times
 
     def kernel_info(self) -> Dict[str, int]:
         a = (C.c_int * 5)()

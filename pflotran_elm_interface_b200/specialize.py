@@ -36,6 +36,10 @@ OUT = os.path.join(CSRC, "_spec")
 
 LOG_TO_LN = chem.LOG_TO_LN
 
+# variant letter -> code style (PFRX_SPEC_VARIANT=<letter><warps per 32 cells>)
+VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled"}
+
+
 def _fnv1a(data: bytes) -> int:
     h = 0xCBF29CE484222325
     for b in data:
@@ -111,7 +115,7 @@ def _variant(cfg: abi.ReactionConfig, warps: Optional[int], style: Optional[str]
 
 def cubin_path(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
     warps, style = _variant(cfg, warps, style)
-    tag = {"straight": "s", "rolled": "r", "looplu": "l", "lockstep": "k", "klooplu": "m"}[style]
+    tag = {v: k for k, v in VARIANT_STYLES.items()}[style]
     return os.path.join(OUT, f"spec_{signature(cfg):016x}_{tag}{warps}.cubin")
 
 
@@ -1139,7 +1143,7 @@ def default_variant(cfg: abi.ReactionConfig) -> Tuple[int, str]:
     assembly, dense solve as rolled loops; one warp only)."""
     env = os.environ.get("PFRX_SPEC_VARIANT")
     if env:
-        return int(env[1:]), {"s": "straight", "r": "rolled", "l": "looplu", "k": "lockstep", "m": "klooplu"}[env[0]]
+        return int(env[1:]), VARIANT_STYLES[env[0]]
     return 1, "straight"
 
 

@@ -174,6 +174,49 @@ def test_batched_reaction_matches_oracle(variant):
     step.close()
 
 
+@pytest.mark.parametrize("variant", ["s1", "k1", "l1"])
+def test_specialized_skeletons_agree_with_oracle(variant):
+    """one-warp blocks, lock-step blocks and the rolled dense solve are the same arithmetic"""
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    wl = W.by_name("c5", ncell=700, tran_dt=86400.0)  # ragged: 700 is not a multiple of 128
+    wl.state.a["imat"][0, 13] = 0
+    ref = wl.state.copy()
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    step.load_specialized(specialize.build(wl.cfg, warps=int(variant[1:]), style=specialize.VARIANT_STYLES[variant[0]]))
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    res = step.rstep(wl.tran_dt)
+    _compare(ref, dev.to_host(), f"specialised c5 {variant}")
+    _check_summary(res_ref, res)
+    step.close()
+
+
+def test_autotune_picks_a_variant_and_leaves_state_alone():
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    wl = W.by_name("c2", ncell=5000)
+    for v in ("s1", "k1"):
+        specialize.build(wl.cfg, warps=1, style=specialize.VARIANT_STYLES[v])
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    before = dev.to_host()
+    times = step.autotune(dev, wl.tran_dt, sample=2048)
+    assert set(times) == {"s1", "k1"} and step.variant in times and all(t > 0 for t in times.values())
+    after = dev.to_host()
+    for f in abi.STATE_IO_FIELDS:
+        assert np.array_equal(before.a[f], after.a[f]), f
+    ref = wl.state.copy()
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 2)
+    res = step.rstep(wl.tran_dt)  # bound to `dev` again
+    _compare(ref, dev.to_host(), "after autotune")
+    _check_summary(res_ref, res)
+    step.close()
+
+
 def test_specialized_kernel_refuses_other_network():
     rstep = _gpu()
     from pflotran_elm_interface_b200 import specialize
