@@ -62,10 +62,13 @@ __device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTM
 #define SPEC_OFF_C (SPEC_NC * SPEC_JS)
 #define SPEC_OFF_LNGSEC (SPEC_OFF_C + SPEC_NC)
 #define SPEC_FIXED(i) fixed[i]  // no slots left: registers / local memory
+#define SPEC_SMALL(i) small_val[i]
 #else
 #define SPEC_OFF_FIXED (SPEC_NC * SPEC_JS)
-#define SPEC_OFF_LNGSEC (SPEC_OFF_FIXED + SPEC_N)
+#define SPEC_OFF_SMALL (SPEC_OFF_FIXED + SPEC_N)
+#define SPEC_OFF_LNGSEC (SPEC_OFF_SMALL + SPEC_N)
 #define SPEC_FIXED(i) SW(SPEC_OFF_FIXED + (i))  // read once per iteration, constant over a sub-step
+#define SPEC_SMALL(i) SW(SPEC_OFF_SMALL + (i))  // totals <= 1e-40 to put back at the end (rare)
 #endif
 #define SPEC_SLOTS (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
 // slot -> index relative to the thread's base pointer
@@ -524,7 +527,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   }
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    small_val[i] = 0.0;
+    SPEC_SMALL(i) = 0.0;
     if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = 0.0;
     if (i < NAQ) {
       if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = log(in_a[i]);
@@ -532,7 +535,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
       double t = in_t[i];
       if (t <= 1.e-40) {
         small_mask |= 1u << i;
-        small_val[i] = t;
+        SPEC_SMALL(i) = t;
         t = 1.e-40;
         st.total[i * ld + cell] = t;
       }
@@ -542,7 +545,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
       guess[i] = t;  // the guess keeps the unclamped value
       if (t <= 1.e-40) {
         small_mask |= 1u << i;
-        small_val[i] = t;
+        SPEC_SMALL(i) = t;
         st.immobile[(i - NAQ) * ld + cell] = 1.e-40;
       }
     }
@@ -593,9 +596,9 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
     if (i < NAQ) st.pri_molal[i * ld + cell] = aborted ? c[i] : guess[i];
     if (!aborted && ((small_mask >> i) & 1u)) {
       if (i < NAQ)
-        st.total[i * ld + cell] = small_val[i];
+        st.total[i * ld + cell] = SPEC_SMALL(i);
       else
-        st.immobile[(i - NAQ) * ld + cell] = small_val[i];
+        st.immobile[(i - NAQ) * ld + cell] = SPEC_SMALL(i);
     }
   }
   if (SPEC_ACT_UPD) {
@@ -756,7 +759,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
-        small_val[i] = 0.0;
+        SPEC_SMALL(i) = 0.0;
         SPEC_FIXED(i) = 0.0;
         if (!SPEC_ACT_UPD) s.lngam[SPEC_ACT_UPD ? 0 : i] = 0.0;
         if (i < NAQ) {
@@ -764,7 +767,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
           c[i] = in_g[i];
           if (in_t[i] <= 1.e-40) {
             small_mask |= 1u << i;
-            small_val[i] = in_t[i];
+            SPEC_SMALL(i) = in_t[i];
             if (live) st.total[i * ld + cell] = 1.e-40;
           }
         } else {
@@ -772,7 +775,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
           c[i] = in_t[i];
           if (in_t[i] <= 1.e-40) {
             small_mask |= 1u << i;
-            small_val[i] = in_t[i];
+            SPEC_SMALL(i) = in_t[i];
             if (live) st.immobile[(i - NAQ) * ld + cell] = 1.e-40;
           }
         }
@@ -946,9 +949,9 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
         if (i < NAQ && aborted) st.pri_molal[i * ld + cell] = c[i];
         if (!aborted && ((small_mask >> i) & 1u)) {
           if (i < NAQ)
-            st.total[i * ld + cell] = small_val[i];
+            st.total[i * ld + cell] = SPEC_SMALL(i);
           else
-            st.immobile[(i - NAQ) * ld + cell] = small_val[i];
+            st.immobile[(i - NAQ) * ld + cell] = SPEC_SMALL(i);
         }
       }
       if (SPEC_ACT_UPD) {

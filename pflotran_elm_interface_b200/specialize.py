@@ -578,7 +578,7 @@ class _Gen:
         if self.loop_lu:
             slots = self.nc * (self.nc + 2) + self.nc
         else:
-            slots = self.nc * (self.nc + 1) + n
+            slots = self.nc * (self.nc + 1) + 2 * n
         slots = max(1, slots + (0 if self.act_upd else self.ncx))
         per_warp = slots * 32 * 8 + 1024  # + the per-block reservation when a block is one warp
         if slots * 32 * 8 > 160 * 1024:
