@@ -468,10 +468,17 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON &&
       c->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER)
     return set_err(PFRX_E_INVALID, "ACTIVITY_COEFFICIENTS NEWTON (iterated ionic strength) is not on the GPU path yet%s", "");
+  bool has_pref = false;
   if (c->kinmnrl_num_prefactors) {
-    for (int m = 0; m < c->nkinmnrl; m++)
-      if (c->kinmnrl_num_prefactors[m] > 0)
-        return set_err(PFRX_E_INVALID, "mineral PREFACTOR kinetics are not on the GPU path yet%s", "");
+    for (int m = 0; m < c->nkinmnrl; m++) {
+      const int np = c->kinmnrl_num_prefactors[m];
+      if (np < 0 || np > PFRX_MAX_PREFACTORS) return set_err(PFRX_E_LIMIT, "more than 10 prefactors%s", "");
+      has_pref = has_pref || np > 0;
+    }
+    if (has_pref && (!c->kinmnrl_pref_nspec || !c->kinmnrl_prefactor_id || !c->kinmnrl_pref_alpha ||
+                     !c->kinmnrl_pref_beta || !c->kinmnrl_pref_atten_coef || !c->kinmnrl_pref_rate ||
+                     !c->kinmnrl_pref_activation_energy))
+      return set_err(PFRX_E_INVALID, "prefactor arrays missing%s", "");
   }
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -531,6 +538,15 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
+    if (!rc0 && has_pref && !h->tpc) {
+      // mineral prefactors live in the thread-per-cell kernel only
+      const KernelGetter *gt = nullptr;
+      for (const auto &k : g_getters)
+        if (k.n == h->npad) gt = &k;
+      h->lanes = 1;
+      h->tpc = true;
+      h->kernel = gt->get(0);
+    }
     if (rc0) {
       delete h;
       return rc0;
@@ -668,6 +684,17 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->kinmnrl_Temkin_const, c->kinmnrl_Temkin_const ? nk : 0, &d.mn_temkin);
     A.add(c->kinmnrl_min_scale_factor, c->kinmnrl_min_scale_factor ? nk : 0, &d.mn_scale);
     A.add(c->kinmnrl_affinity_power, c->kinmnrl_affinity_power ? nk : 0, &d.mn_power);
+    {
+      const int np = has_pref ? nk * PFRX_MAX_PREFACTORS : 0, ns = np * PFRX_MAX_PREFACTOR_SPECIES;
+      A.add(c->kinmnrl_num_prefactors, has_pref ? nk : 0, &d.mn_npref);
+      A.add(c->kinmnrl_pref_nspec, np, &d.mn_pref_nspec);
+      A.add(c->kinmnrl_prefactor_id, ns, &d.mn_pref_id);
+      A.add(c->kinmnrl_pref_alpha, ns, &d.mn_pref_alpha);
+      A.add(c->kinmnrl_pref_beta, ns, &d.mn_pref_beta);
+      A.add(c->kinmnrl_pref_atten_coef, ns, &d.mn_pref_atten);
+      A.add(c->kinmnrl_pref_rate, np, &d.mn_pref_rate);
+      A.add(c->kinmnrl_pref_activation_energy, np, &d.mn_pref_eact);
+    }
     std::vector<int> me_ptr(nk + 1, 0), me_ij;
     std::vector<double> me_coef;
     for (int m = 0; m < nk; m++) {
@@ -935,6 +962,8 @@ extern "C" int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, dou
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   if (h->cfg.nmr > 0)
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover multirate sorption yet%s", "");
+  if (h->cfg.mn_npref)
+    return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover mineral prefactors yet%s", "");
   CUDA_OK(cudaSetDevice(h->device));
   if (!h->rx_kernel) {
     const KernelGetter *gt = nullptr;

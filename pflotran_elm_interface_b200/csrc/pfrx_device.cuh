@@ -70,6 +70,9 @@ struct DevCfg {
   const int *me_ptr, *me_ij;   // per mineral: all (i,j) species pairs, i | j<<8
   const double *me_coef;       // nu_i * nu_j
   const double *mn_temkin, *mn_scale, *mn_power;
+  // prefactors (reaction_mineral.F90:838-890), dense [(m*MAXP + p)*MAXS + s]; thread-per-cell kernel only
+  const int *mn_npref, *mn_pref_nspec, *mn_pref_id;
+  const double *mn_pref_alpha, *mn_pref_beta, *mn_pref_atten, *mn_pref_rate, *mn_pref_eact;
   // surface complexation
   int nsrfrxn, nsrfcplx;
   const int *sr_ptr, *sr_cx, *sr_type, *sr_surf, *sr_flag;

@@ -292,7 +292,9 @@ struct CellT {
 #pragma unroll 1
     for (int m = 0; m < cfg.nkin; m++) {
       const int p0 = cfg.mn_ptr[m], p1 = cfg.mn_ptr[m + 1];
-      double rate_vol = 0.0, Im = 0.0, dfac = 0.0;
+      double rate_vol = 0.0, Im = 0.0, dfac = 0.0, sprm = 0.0;
+      const int npf = cfg.mn_npref ? cfg.mn_npref[m] : 0;
+      double pref[PFRX_MAX_PREFACTORS], lnps[PFRX_MAX_PREFACTORS * PFRX_MAX_PREFACTOR_SPECIES];
       double lnQK = -mn_logK(m) * PFRX_LOG_TO_LN;
       if (cfg.mn_h2o[m] != 0.0) lnQK += cfg.mn_h2o[m] * ln_act_h2o;
 #pragma unroll 1
@@ -317,10 +319,38 @@ struct CellT {
       if (active) {
         double lim = cfg.mn_limit[m];
         if (lim > 0.0) aff = aff / (1.0 + (1.0 - aff) / lim);
-        double arr = 1.0;
-        if (cfg.mn_eact[m] > 0.0)
-          arr = exp(cfg.mn_eact[m] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
-        double spr = cfg.mn_rate[m] * arr;
+        double spr;  // sum_prefactor_rate
+        if (npf > 0) {
+          // rate = sum over parallel mechanisms of k_p * prod_s a^alpha / (1 + K a^beta) * Arrhenius
+          // (reaction_mineral.F90:838-890)
+          spr = 0.0;
+#pragma unroll 1
+          for (int ip = 0; ip < npf; ip++) {
+            const int pp = m * PFRX_MAX_PREFACTORS + ip;
+            double lnp = 0.0;
+#pragma unroll 1
+            for (int is = 0; is < cfg.mn_pref_nspec[pp]; is++) {
+              const int q = pp * PFRX_MAX_PREFACTOR_SPECIES + is;
+              const double lsa = pref_ln_act(cfg.mn_pref_id[q]);
+              const double lnum = cfg.mn_pref_alpha[q] * lsa;
+              const double lden = log(1.0 + exp(log(cfg.mn_pref_atten[q]) + cfg.mn_pref_beta[q] * lsa));
+              lnp = lnp + lnum;
+              lnp = lnp - lden;
+              lnps[ip * PFRX_MAX_PREFACTOR_SPECIES + is] = lnum - lden;
+            }
+            pref[ip] = exp(lnp);
+            double arr = 1.0;
+            if (cfg.mn_pref_eact[pp] > 0.0)
+              arr = exp(cfg.mn_pref_eact[pp] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
+            spr = spr + pref[ip] * cfg.mn_pref_rate[pp] * arr;
+          }
+        } else {
+          double arr = 1.0;
+          if (cfg.mn_eact[m] > 0.0)
+            arr = exp(cfg.mn_eact[m] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
+          spr = cfg.mn_rate[m] * arr;
+        }
+        sprm = spr;
         double Im_const = -st.mnrl_area[m * st.ld + cell];
         if (cfg.mn_scale) Im_const = Im_const / cfg.mn_scale[m];
         if (cfg.mn_power)
@@ -360,7 +390,81 @@ struct CellT {
       }
 #pragma unroll 1
       for (int p = p0; p < p1; p++) RES(cfg.mn_id[p]) += cfg.mn_st[p] * Im;
+      if (npf > 0 && Im != 0.0) {
+        // d Im / d (prefactor species) (reaction_mineral.F90:985-1075)
+        const double dIm_dspr = Im / sprm;
+#pragma unroll 1
+        for (int ip = 0; ip < npf; ip++) {
+          const int pp = m * PFRX_MAX_PREFACTORS + ip;
+          double arr = 1.0;
+          if (cfg.mn_pref_eact[pp] > 0.0)
+            arr = exp(cfg.mn_pref_eact[pp] / PFRX_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));
+          const double lnp = log(pref[ip]);
+#pragma unroll 1
+          for (int is = 0; is < cfg.mn_pref_nspec[pp]; is++) {
+            const int q = pp * PFRX_MAX_PREFACTOR_SPECIES + is;
+            const double lps = lnps[ip * PFRX_MAX_PREFACTOR_SPECIES + is];
+            const double dp_dps = exp(lnp - lps);
+            const int id = cfg.mn_pref_id[q];
+            const double lsa = pref_ln_act(id);
+            const double gam = pref_act_coef(id);
+            const double dnum = cfg.mn_pref_alpha[q] * exp(lps - lsa);
+            const double lgb = cfg.mn_pref_beta[q] * lsa;
+            const double den = 1.0 + exp(log(cfg.mn_pref_atten[q]) + lgb);
+            const double dden = -1.0 * exp(lps) / den * cfg.mn_pref_atten[q] * cfg.mn_pref_beta[q] * exp(lgb - lsa);
+            double dps = dnum + dden;
+            dps = dps * gam;
+            const double dIm_dspec = dIm_dspr * dp_dps * dps * cfg.mn_pref_rate[pp] * arr;
+            if (id >= 0) {
+#pragma unroll 1
+              for (int p = p0; p < p1; p++) J(cfg.mn_id[p], id) += cfg.mn_st[p] * dIm_dspec;
+            } else {
+              // a secondary species: the reference's loop runs over the COMPLEX's species here
+              // (reaction_mineral.F90:1055 overwrites ncomp); restated as it executes
+              const int k = -id - 1;
+              const int q0 = cfg.cx_ptr[k], q1 = cfg.cx_ptr[k + 1];
+              const double lq = cx_lnQK(k);
+              const double gs = pref_act_coef(id);
+#pragma unroll 1
+              for (int jj = q0; jj < q1; jj++) {
+                const int jc = cfg.cx_id[jj];
+                const double tr = cfg.cx_st[jj] * exp(lq - log(C(jc))) / gs;
+#pragma unroll 1
+                for (int ii = q0; ii < q1; ii++) J(cfg.cx_id[ii], jc) += cfg.cx_st[ii] * tr * dIm_dspec;
+              }
+            }
+          }
+        }
+      }
     }
+  }
+
+  // ln activity / activity coefficient of a prefactor species: id >= 0 primary, else complex -(id+1)
+  __device__ __forceinline__ double cx_lnQK(int k) const {
+    double lq = -cx_logK(k) * PFRX_LOG_TO_LN;
+    if (cfg.cx_h2o[k] != 0.0) lq = lq + cfg.cx_h2o[k] * ln_act_h2o;
+#pragma unroll 1
+    for (int p = cfg.cx_ptr[k]; p < cfg.cx_ptr[k + 1]; p++) lq = lq + cfg.cx_st[p] * ws[cfg.off_lnact + cfg.cx_id[p]];
+    return lq;
+  }
+  __device__ __forceinline__ double sec_ln_gamma(int k) const {
+    if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) {
+      const int q = cfg.cx_cls[k];
+      return q < 0 ? 0.0 : ws[cfg.off_cls + q];
+    }
+    return ws[cfg.off_lng + k];
+  }
+  __device__ __forceinline__ double pref_ln_act(int id) const {
+    // ln(m_k gamma_k) of a complex is its lnQK (m_k = exp(lnQK) / gamma_k)
+    return id >= 0 ? ws[cfg.off_lnact + id] : cx_lnQK(-id - 1);
+  }
+  __device__ __forceinline__ double pref_act_coef(int id) const {
+    if (id < 0) return exp(sec_ln_gamma(-id - 1));
+    double lg = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i == id) lg = lngam[i];
+    return exp(lg);
   }
 
   // ---- RMultiRateSorption (reaction_surf_complex.F90:552-637) -----------------

@@ -115,10 +115,28 @@ def _mix_fill(state: abi.HostState, waters, weights: np.ndarray, rng, jitter: fl
     assert ncell == tot.shape[1]
 
 
-def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED) -> Workload:
-    """C2: 10k-cell calcite column, post-transport totals on a logistic front."""
+def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED, prefactors: bool = False) -> Workload:
+    """C2: 10k-cell calcite column, post-transport totals on a logistic front.
+
+    ``prefactors``: the calcite rate as the sum of three parallel mechanisms in the
+    PREFACTOR form of reaction_mineral.F90:838-890 (acid, carbonic-acid and neutral, the
+    shape of the Plummer/Chou rate laws): an H+ term, a term in the SECONDARY species
+    CO2(aq) with an attenuation denominator, and a species-free term with an activation
+    energy."""
     rng = np.random.default_rng(seed)
     dk = chem.read_deck(C2_DECK)
+    if prefactors:
+        # prefactors == "primary": the second mechanism in primary species only (its analytic
+        # Jacobian is then a true derivative and can be checked by finite differences)
+        second = "HCO3-" if prefactors == "primary" else "CO2(aq)"
+        dk.chemistry.mineral_kinetics[0].prefactors = [
+            {"rate": 8.9e-1 * 1.0e-4, "activation_energy": 0.0,
+             "species": [{"name": "H+", "alpha": 1.0, "beta": 0.0, "atten": 0.0}]},
+            {"rate": 5.0e-4 * 1.0e-4, "activation_energy": 0.0,
+             "species": [{"name": second, "alpha": 1.0, "beta": 0.5, "atten": 40.0},
+                         {"name": "Ca++", "alpha": 0.25, "beta": 1.0, "atten": 3.0}]},
+            {"rate": 6.5e-7 * 1.0e-4, "activation_energy": 23500.0, "species": []},
+        ]
     net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("calcite.dat")))
     cfg = abi.ReactionConfig(net)
     den = eos.water_density_ifc67()
@@ -132,6 +150,10 @@ def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED
     st["mnrl_area"][...] = 1.0
     st["den_kg"][...] = den
     st["porosity"][...] = 0.25
+    if prefactors:
+        st["temp"][...] = rng.uniform(10.0, 40.0, ncell)
+        return Workload("c2_calcite_prefactors", cfg, st, tran_dt, net,
+                        "C2 with a three-mechanism PREFACTOR rate law for Calcite")
     return Workload("c2_calcite_column", cfg, st, tran_dt, net,
                     "H+/HCO3-/Ca++ + 6 complexes + kinetic Calcite, logistic inlet/background front")
 
@@ -240,6 +262,8 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
     table = {
         "c1": (calcite_batch, {}),
         "c2": (calcite_column, {}),
+        "c2pf": (calcite_column, {"prefactors": "full"}),
+        "c2pfp": (calcite_column, {"prefactors": "primary"}),
         "c3": (hanford, {"variant": "base"}),
         "c3mr": (hanford, {"variant": "mr"}),
         "c4": (clm_cn, {}),

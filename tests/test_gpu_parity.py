@@ -234,6 +234,18 @@ def test_specialized_kernel_refuses_other_network():
         step4.specialize(required=True)
 
 
+@pytest.mark.parametrize("variant,dt", [("c2pf", 3600.0), ("c2pf", 86400.0 * 30), ("c2pfp", 3600.0)])
+def test_mineral_prefactors(variant, dt):
+    """PREFACTOR rate laws (reaction_mineral.F90:838-890, 985-1075) incl. a secondary prefactor
+    species with the reference's complex-species Jacobian loop; thread-per-cell kernel"""
+    wl = W.by_name(variant, ncell=2000, tran_dt=dt)
+    ref, res_ref, got, res, info = _run_both(wl)
+    assert info["lanes"] == 0, info  # routed to the thread-per-cell kernel
+    _compare(ref, got, f"{variant} dt={dt}")
+    _check_summary(res_ref, res)
+    assert np.abs(ref.a["mnrl_rate"]).max() > 0
+
+
 @pytest.mark.parametrize("variant", ["c3", "c3mr", "c4", "c5"])
 def test_thread_per_cell_kernel_on_large_networks(variant, monkeypatch):
     """the thread-per-cell kernel is not the default above 4 unknowns but must

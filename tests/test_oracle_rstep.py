@@ -53,7 +53,7 @@ def test_rsolve_scaling_and_log_formulation():
 
 
 # ---- analytic Jacobian vs finite differences (perturbation 1e-5..1e-7) -------------
-@pytest.mark.parametrize("name,n", [("c2", 16), ("c4", 16), ("c3", 6), ("c3mr", 4), ("c5", 4)])
+@pytest.mark.parametrize("name,n", [("c2", 16), ("c2pfp", 16), ("c4", 16), ("c3", 6), ("c3mr", 4), ("c5", 4)])
 def test_jacobian_matches_finite_differences(name, n):
     wl = W.by_name(name, ncell=n)
     cfg, dt = wl.cfg, wl.tran_dt
