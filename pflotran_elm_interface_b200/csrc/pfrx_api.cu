@@ -465,9 +465,8 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   int n = c->naqcomp + c->nimcomp;
   if (n < 1 || n > PFRX_MAX_NCOMP) return set_err(PFRX_E_LIMIT, "ncomp out of range%s", "");
   if (c->neqcplx > 4095) return set_err(PFRX_E_LIMIT, "more than 4095 secondary complexes%s", "");
-  if (c->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON &&
-      c->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER)
-    return set_err(PFRX_E_INVALID, "ACTIVITY_COEFFICIENTS NEWTON (iterated ionic strength) is not on the GPU path yet%s", "");
+  const bool act_newton = c->act_coef_update_algorithm == PFRX_ACT_COEF_ALGORITHM_NEWTON &&
+                          c->act_coef_update_frequency == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
   bool has_pref = false;
   if (c->kinmnrl_num_prefactors) {
     for (int m = 0; m < c->nkinmnrl; m++) {
@@ -538,8 +537,8 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
-    if (!rc0 && has_pref && !h->tpc) {
-      // mineral prefactors live in the thread-per-cell kernel only
+    if (!rc0 && (has_pref || act_newton) && !h->tpc) {
+      // mineral prefactors and the iterated ionic strength live in the thread-per-cell kernel only
       const KernelGetter *gt = nullptr;
       for (const auto &k : g_getters)
         if (k.n == h->npad) gt = &k;
@@ -1109,7 +1108,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     for (int64_t c = 0; c < ncell && all_active; c++) all_active = host->imat[c] > 0;
   if (all_active && h->cfg.use_full_geochemistry && !getenv("PFRX_UPLOAD_ALL")) {
     const bool act_upd = h->cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
-    if (act_upd) skip_in[3] = skip_in[4] = true;
+    if (act_upd && h->cfg.act_alg != PFRX_ACT_COEF_ALGORITHM_NEWTON) skip_in[3] = skip_in[4] = true;
     if (!act_upd && !h->cfg.use_act_h2o) skip_in[5] = true;
     if (h->cfg.nkin > 0) skip_in[9] = true;
   }

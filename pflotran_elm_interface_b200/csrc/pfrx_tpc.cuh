@@ -89,6 +89,93 @@ struct CellT {
       }
   }
 
+  // ---- RActivityCoefficients, NEWTON branch (reaction.F90:4403-4551): the ionic strength is
+  // iterated (<= 50 times) together with the complex concentrations it depends on.  As in
+  // the reference, ln a_j of the primary species keeps the coefficients the routine was
+  // entered with.  Complex concentrations live in rt_auxvar%sec_molal (HBM / L2).
+  // Returns false where the reference poisons the state with NaN (no convergence, I < 0).
+  __device__ __forceinline__ bool activity_newton() {
+    const int naq = cfg.naq, ncx = cfg.ncplx;
+    const int64_t ld = st.ld;
+    double fpri = 0.0, mp = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) {
+        const double c = C(i);
+        LNA(i) = log(c) + lngam[i];
+        fpri = fpri + c * cfg.pri_Z2[i];
+        if (i != cfg.h2o_aq_id) mp += c;
+      }
+    int it = 0;
+    double II = 0.0;
+    for (;;) {
+      it++;
+      if (it > 50) return false;
+      double I = fpri;
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++) I = I + st.sec_molal[k * ld + cell] * cfg.cx_Z2[k];
+      I = 0.5 * I;
+      const double f = I;
+      if (fabs(I - II) < 1.e-6 * I) break;
+      if (ncx > 0) {
+        double didi = 0.0;
+        const double sq = sqrt(I);
+#pragma unroll 1
+        for (int k = 0; k < ncx; k++) {
+          const int qk = cfg.cx_cls[k];
+          if (qk < 0) continue;
+          const double t = 1.0 + cfg.debyeB * cfg.cls_a0[qk] * sq;
+          double sum = 0.5 * cfg.debyeA * cfg.cx_Z2[k] / (sq * (t * t)) - cfg.debyeBdot;
+#pragma unroll 1
+          for (int p = cfg.cx_ptr[k]; p < cfg.cx_ptr[k + 1]; p++) {
+            const int qj = cfg.pri_cls[cfg.cx_id[p]];
+            if (qj >= 0) {
+              const double tj = 1.0 + cfg.debyeB * cfg.cls_a0[qj] * sq;
+              const double dgamdi = -0.5 * cfg.debyeA * (-cfg.cls_negz2[qj]) / (sq * (tj * tj)) + cfg.debyeBdot;
+              sum = sum + cfg.cx_st[p] * dgamdi;
+            }
+          }
+          const double dcdi = st.sec_molal[k * ld + cell] * PFRX_LOG_TO_LN * sum;
+          didi = didi + 0.5 * cfg.cx_Z2[k] * dcdi;
+        }
+        const double den = 1.0 - didi;
+        II = fabs(den) > 0.0 ? (f - I * didi) / den : f;
+      } else {
+        II = f;
+      }
+      if (II < 0.0) return false;
+      I = II;
+      const double sq = sqrt(I);
+#pragma unroll 1
+      for (int q = 0; q < cfg.ncls; q++)
+        ws[cfg.off_cls + q] = (cfg.cls_negz2[q] * sq * cfg.debyeA / (1.0 + cfg.cls_a0[q] * cfg.debyeB * sq) +
+                               cfg.debyeBdot * I) * PFRX_LOG_TO_LN;
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (i < naq) {
+          const int q = cfg.pri_cls[i];
+          lngam[i] = q < 0 ? 0.0 : ws[cfg.off_cls + q];
+        }
+      double ms = 0.0, Is = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++) {
+        const int q = cfg.cx_cls[k];
+        const double g = q < 0 ? 1.0 : exp(ws[cfg.off_cls + q]);
+        const double sk = exp(cx_lnQK(k)) / g;
+        st.sec_molal[k * ld + cell] = sk;
+        ms += sk;
+        Is += sk * cfg.cx_Z2[k];
+      }
+      Isum = Is;
+      msum = ms;
+      if (cfg.use_act_h2o) {
+        const double t = 1.0 - 0.017 * (mp + ms);
+        ln_act_h2o = t > 0.0 ? log(t) : 0.0;
+      }
+    }
+    return true;
+  }
+
   // ---- RTotalSorbEqSurfCplx1 (reaction_surf_complex.F90:641-900) -------------
   // adds nu*S to ws.ts and (add_J) jscale * dtotal_sorb to the Jacobian
   __device__ __forceinline__ void surf_cplx1(int irxn, double *tsacc, bool add_J, double jscale, bool store_conc) {
@@ -711,7 +798,13 @@ struct CellT {
     double norm0 = 0.0;
     for (;;) {
       its++;
-      if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) activity();
+      bool act_ok = true;
+      if (cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) {
+        if (cfg.act_alg == PFRX_ACT_COEF_ALGORITHM_NEWTON)
+          act_ok = activity_newton();
+        else
+          activity();
+      }
       auxvar_compute(true, dt);
       if (its > cfg.max_its) {
         // total and immobile keep their initial values (never overwritten in
@@ -734,6 +827,12 @@ struct CellT {
       if (!dry) {
         if (cfg.nmr > 0) multirate(dt);
         if (cfg.cn_nrxn > 0) clm_cn();
+      }
+      if (!act_ok) {
+        // the reference has filled the state with NaN by now and leaves RReact with
+        // option%ierror set after RReaction (reaction.F90:3921); no restore
+        its_out = its;
+        return 1;
       }
       double mabs = 0.0, ss = 0.0;
 #pragma unroll 1
@@ -917,6 +1016,15 @@ struct CellT {
     }
     Isum = Is;
     msum = ms;
+    if (act_upd && cfg.act_alg == PFRX_ACT_COEF_ALGORITHM_NEWTON) {
+      // this branch may leave the coefficients it was entered with (|dI| < 1e-6 I at once)
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++)
+        if (cfg.cx_cls[k] >= 0) ws[cfg.off_cls + cfg.cx_cls[k]] = log(st.sec_act_coef[k * ld + c]);
+#pragma unroll 1
+      for (int i = 0; i < naq; i++)
+        if (cfg.pri_cls[i] >= 0) ws[cfg.off_cls + cfg.pri_cls[i]] = log(st.pri_act_coef[i * ld + c]);
+    }
 #pragma unroll 1
     for (int k = 0; k < cfg.nsrfrxn; k++) ws[cfg.off_fs + k] = st.free_site[k * ld + c];
 #pragma unroll 1

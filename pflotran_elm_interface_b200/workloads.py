@@ -172,10 +172,13 @@ def calcite_batch() -> Workload:
 
 
 # --------------------------------------------------------------------------- #
-def _hanford_network(variant: str = "base"):
+def _hanford_network(variant: str = "base", activity_newton: bool = False):
     deck = _read("543_hanford_srfcplx_base.in")
     dk = chem.read_deck(deck)
     ch = dk.chemistry
+    if activity_newton:
+        # ACTIVITY_COEFFICIENTS NEWTON NEWTON_ITERATION: ionic strength iterated to 1e-6
+        ch.act_coef_update_algorithm = chem.ACT_COEF_ALGORITHM_NEWTON
     if variant == "mr":
         # 50-rate multirate on rock density (543_hanford_srfcplx_mr.in /
         # column/surface_complexation_mr_os.in)
@@ -192,11 +195,11 @@ def _hanford_network(variant: str = "base"):
 
 
 def hanford(ncell: int = 256 * 256 * 64, tran_dt: float = 3600.0, variant: str = "base",
-            seed: int = SEED) -> Workload:
+            seed: int = SEED, activity_newton: bool = False) -> Workload:
     """C3 (variant base|mr) and C5 (variant minerals): Hanford 15 primary / 88
     secondary; cells are Dirichlet(1) mixes of the three deck waters."""
     rng = np.random.default_rng(seed)
-    dk, net = _hanford_network(variant)
+    dk, net = _hanford_network(variant, activity_newton)
     cfg = abi.ReactionConfig(net)
     den = eos.water_density_ifc67()
     waters = []
@@ -266,6 +269,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c2pfp": (calcite_column, {"prefactors": "primary"}),
         "c3": (hanford, {"variant": "base"}),
         "c3mr": (hanford, {"variant": "mr"}),
+        "c3an": (hanford, {"variant": "base", "activity_newton": True}),
         "c4": (clm_cn, {}),
         "c5": (hanford, {"variant": "minerals"}),
     }

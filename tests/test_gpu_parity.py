@@ -246,6 +246,17 @@ def test_mineral_prefactors(variant, dt):
     assert np.abs(ref.a["mnrl_rate"]).max() > 0
 
 
+@pytest.mark.parametrize("dt", [3600.0, 30 * 86400.0])
+def test_activity_newton_algorithm(dt):
+    """ACTIVITY_COEFFICIENTS NEWTON NEWTON_ITERATION: the ionic strength iterated together with the
+    complexes (reaction.F90:4403-4551); LAG and NEWTON differ by ~6e-10 on this state, the bar is 1e-10"""
+    wl = W.by_name("c3an", ncell=1200, tran_dt=dt)
+    ref, res_ref, got, res, info = _run_both(wl)
+    assert info["lanes"] == 0, info
+    _compare(ref, got, f"c3an dt={dt}")
+    _check_summary(res_ref, res)
+
+
 @pytest.mark.parametrize("variant", ["c3", "c3mr", "c4", "c5"])
 def test_thread_per_cell_kernel_on_large_networks(variant, monkeypatch):
     """the thread-per-cell kernel is not the default above 4 unknowns but must
