@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 1
+#define PFRX_ABI_VERSION 2
 
 /* error classes */
 #define PFRX_OK 0
@@ -59,12 +59,109 @@ extern "C" {
 #define PFRX_MAX_PREFACTORS 10      /* reaction_mineral.F90:688 */
 #define PFRX_MAX_PREFACTOR_SPECIES 5
 
+/* species kinds used by the ELM-CN sandboxes (reaction_sandbox_somdec.F90:160-162;
+ * ITYPE_GAS is not supported by the CUDA path) */
+#define PFRX_SPEC_AQUEOUS 0
+#define PFRX_SPEC_IMMOBILE 2
+
+/* elm_rspfuncs.F90:17-47 */
+#define PFRX_TEMPERATURE_RESPONSE_OFF 0
+#define PFRX_TEMPERATURE_RESPONSE_CLMCN 1
+#define PFRX_TEMPERATURE_RESPONSE_Q10 2
+#define PFRX_TEMPERATURE_RESPONSE_DLEM 3
+#define PFRX_TEMPERATURE_RESPONSE_ARRHENIUS 4
+#define PFRX_MOISTURE_RESPONSE_OFF 0
+#define PFRX_MOISTURE_RESPONSE_CLMCN 1
+#define PFRX_MOISTURE_RESPONSE_DLEM 2
+#define PFRX_MOISTURE_RESPONSE_LOGTHETA 3
+#define PFRX_OX_RESPONSE_OFF 0
+#define PFRX_OX_RESPONSE_MONOD 1
+#define PFRX_OX_RESPONSE_WFPS 2
+#define PFRX_INHIBITION_THRESHOLD 1
+#define PFRX_INHIBITION_MONOD 3
+#define PFRX_INHIBITION_INVERSE_MONOD 4
+
+/* reaction sandboxes in the order of the deck's REACTION_SANDBOX block
+ * (RSandboxEvaluate walks the list, reaction_sandbox.F90:294-330) */
+#define PFRX_SANDBOX_CLM_CN 1
+#define PFRX_SANDBOX_SOMDEC 2
+#define PFRX_SANDBOX_NITRIF 3
+#define PFRX_SANDBOX_DENITR 4
+
+/*
+ * SOMDECOMP sandbox: reaction_sandbox_somdec_type after SomDecSetup
+ * (reaction_sandbox_somdec.F90:21-113, 987-1501), flattened.  Species ids are
+ * 0-based, -1 = absent (the reference tests `> 0` on 1-based ids).  The
+ * reference keeps per-reaction scratch (upstream_nc, downstream_nc,
+ * mineral_c/n_stoich of variable-C:N pools) in the shared object; here the
+ * N:C ratios that survive between evaluations are per-cell state
+ * (pfrx_state.somdec_nc) initialised from the set-up values below.
+ */
+typedef struct pfrx_somdec {
+  int32_t nrxn;
+  int32_t co2_id, co2_itype;      /* species_id_co2 / species_itype_co2 */
+  int32_t o2_id, o2_itype;        /* -1: no O2 species named */
+  int32_t nh4_id, no3_id, n2o_id, proton_id;            /* primary ids */
+  int32_t hr_id, nmin_id, nimm_id, nimp_id, ngasmin_id; /* immobile ids */
+  double x0eps;                   /* 1e-20 */
+  double n2o_frac_mineralization; /* 0.02 */
+  double inhibition_nh4_no3;      /* 1.0 */
+  /* per reaction [nrxn] */
+  const double *rate_constant;      /* 1/s, <0 => use rate_decomposition */
+  const double *rate_decomposition; /* 1/s */
+  const double *rate_ad_factor;
+  const int32_t *upstream_c_id;
+  const int32_t *upstream_n_id;     /* >=0 => variable C:N upstream pool */
+  const int32_t *upstream_is_aqueous;
+  const int32_t *upstream_hr_id, *upstream_nmin_id, *upstream_nimp_id, *upstream_nimm_id;
+  const double *upstream_nc;        /* mol N / mol C; -999 for variable pools */
+  const double *mineral_c_stoich;   /* SomDecSetup values (fixed C:N)       */
+  const double *mineral_n_stoich;
+  /* downstream pools, CSR over reactions */
+  const int32_t *downstream_ptr;    /* [nrxn+1] */
+  const int32_t *downstream_c_id, *downstream_n_id, *downstream_is_aqueous;
+  const double *downstream_stoich, *downstream_nc;
+  /* abiotic factors of each reaction (abiotic_factors_type) */
+  const int32_t *temperature_response_function;
+  const int32_t *moisture_response_function;
+  const int32_t *ox_response_function;
+  const double *q10, *ea, *ox_half_saturation, *decomp_depth_efolding;
+  const int32_t *ox_specid, *ox_specitype;   /* rxn%Ox_specid, -1 none */
+  /* MONOD terms, CSR over reactions (monod2_type) */
+  const int32_t *monod_ptr;         /* [nrxn+1] */
+  const int32_t *monod_specid, *monod_specitype, *monod_pool_normalized;
+  const double *monod_half_saturation, *monod_threshold;
+  /* INHIBITION terms, CSR over reactions (inhibition2_type) */
+  const int32_t *inhib_ptr;         /* [nrxn+1] */
+  const int32_t *inhib_itype, *inhib_specid, *inhib_specitype;
+  const double *inhib_constant, *inhib_constant2;
+} pfrx_somdec;
+
+/* NITRIFICATION sandbox (reaction_sandbox_nitrif.F90:20-36, 234-502) */
+typedef struct pfrx_nitrif {
+  int32_t proton_id, nh4_id, no3_id, n2o_id; /* primary ids, -1 absent */
+  int32_t ngasnit_id;                        /* immobile id, -1 absent */
+  double k_nitr_max;                         /* 1e-6 1/s  */
+  double k_nitr_n2o;                         /* 3.5e-8 1/s */
+  double x0eps;                              /* 1e-20 */
+} pfrx_nitrif;
+
+/* DENITRIFICATION sandbox (reaction_sandbox_denitr.F90:18-33, 212-404) */
+typedef struct pfrx_denitr {
+  int32_t no3_id, n2_id, n2o_id;  /* primary ids, -1 absent */
+  int32_t ngasdeni_id;            /* immobile id, -1 absent */
+  double half_saturation;         /* 1e-15 */
+  double k_deni_max;              /* 2.5e-6 1/s */
+  double x0eps;                   /* 1e-20 */
+} pfrx_denitr;
+
 /*
  * Flattened, read-only reaction description: the subset of
  *   reaction_rt_type            reaction_aux.F90:123-311
  *   mineral_type                reaction_mineral_aux.F90:82-138
  *   surface_complexation_type   reaction_surf_complex_aux.F90:68-128
  *   reaction_sandbox_clm_cn_type reaction_sandbox_clm_cn.F90:22-42
+ *   reaction_sandbox_somdec / nitrif / denitr types (pfrx_somdec etc. above)
  * that RStep and its callees read.  pfrx_create() copies everything; the
  * caller keeps ownership of the arrays.
  */
@@ -176,6 +273,21 @@ typedef struct pfrx_config {
   const double *clmcn_rate_constant;     /* [nrxn] 1/s */
   const double *clmcn_respiration_fraction; /* [nrxn] */
   const double *clmcn_inhibition_constant;  /* [nrxn] */
+
+  /* ---- ELM-CN sandboxes (NULL => absent) ---------------------------------- */
+  const pfrx_somdec *somdec;     /* reaction_sandbox_somdec.F90:1504-3640 */
+  const pfrx_nitrif *nitrif;     /* reaction_sandbox_nitrif.F90:234-502   */
+  const pfrx_denitr *denitr;     /* reaction_sandbox_denitr.F90:212-404   */
+  /* evaluation order of the sandboxes (PFRX_SANDBOX_*); NULL => the order
+   * CLM-CN, SOMDEC, NITRIF, DENITR */
+  int32_t nsandbox;
+  const int32_t *sandbox_list;
+  /* 1 => the behaviour of a reference built with -DELM_PFLOTRAN in BGC-only
+   * coupling (option%nflowspec == 0): moisture / oxygen / temperature scalars,
+   * soil depth, decomposition scalar, dry bulk density and Clapp-Hornberger b
+   * come per cell from ELM (pfrx_state.elm_*) instead of the response
+   * functions / constants of the stand-alone build */
+  int32_t elm_pflotran;
 } pfrx_config;
 
 /*
@@ -214,6 +326,27 @@ typedef struct pfrx_state {
   const double *soil_particle_density; /* in [1] or NULL */
   const int32_t *imat;         /* in [1] or NULL; <=0 => inactive, skipped
                                   (pmc_subsurface_osrt.F90:351)               */
+  /* ELM per-cell scalars (elm_pflotran_interface_data: w_scalar_pfs,
+   * o_scalar_pfs, t_scalar_pfs, zsoil_pfs, kscalar_decomp_c_pfs,
+   * bulkdensity_dry_pfs, bsw_pfs), read through option%iflag in the reference
+   * (reaction_sandbox_somdec.F90:1593,1647-1735).  in [1] each; needed only
+   * when pfrx_config.elm_pflotran != 0, else NULL */
+  const double *elm_w_scalar;
+  const double *elm_o_scalar;
+  const double *elm_t_scalar;
+  const double *elm_zsoil;
+  const double *elm_kscalar_decomp_c;
+  const double *elm_bulkdensity_dry;
+  const double *elm_bsw;
+  /* SOMDECOMP: last N:C ratios of the variable-C:N pools, io
+   * [somdec.nrxn + somdec.downstream_ptr[nrxn]]: upstream_nc(irxn) then
+   * downstream_nc(j).  The reference keeps them in the sandbox object and only
+   * refreshes a ratio while both pool concentrations are >= x0eps
+   * (reaction_sandbox_somdec.F90:1795-1822), so a pool that has decayed below
+   * x0eps goes on with its last ratio; here that memory is per cell.  Initial
+   * value: pfrx_somdec.upstream_nc / downstream_nc.  NULL => every evaluation
+   * starts from those set-up values. */
+  double *somdec_nc;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

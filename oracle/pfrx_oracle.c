@@ -50,6 +50,10 @@ typedef struct {
   double *dtotal;      /* dtotal(i,j) at [i + j*naq] */
   double ln_act_h2o;
   double den_kg, sat, temp, porosity, volume, soil_particle_density;
+  /* ELM per-cell scalars (elm_pflotran builds) */
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;
+  double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
+  int nsomdec_nc;
   /* per-cell copies of the temperature dependent tables
    * (the reference overwrites the shared ones, reaction.F90:6003-6031) */
   double *eqcplx_logK, *kinmnrl_logK, *srfcplx_logK;
@@ -67,8 +71,9 @@ static int mr_rows(const pfrx_config *cfg) {
 static size_t cell_doubles(const pfrx_config *cfg) {
   size_t naq = cfg->naqcomp, nim = cfg->nimcomp, nc = cfg->neqcplx;
   size_t nk = cfg->nkinmnrl, nr = cfg->nsrfcplxrxn, ns = cfg->nsrfcplx;
+  size_t nsd = cfg->somdec ? (size_t)(cfg->somdec->nrxn + cfg->somdec->downstream_ptr[cfg->somdec->nrxn]) : 0;
   return 4 * naq + nim + 3 * nc + 4 * nk + nr + 2 * ns + naq + 2 * naq * naq +
-         mr_rows(cfg) + 64;
+         mr_rows(cfg) + nsd + 64;
 }
 
 static void cell_init(cell_t *c, const pfrx_config *cfg) {
@@ -104,6 +109,8 @@ static void cell_init(cell_t *c, const pfrx_config *cfg) {
   TAKE(eqcplx_logK, c->ncplx);
   TAKE(kinmnrl_logK, c->nkin);
   TAKE(srfcplx_logK, c->nsrfcplx);
+  c->nsomdec_nc = cfg->somdec ? cfg->somdec->nrxn + cfg->somdec->downstream_ptr[cfg->somdec->nrxn] : 0;
+  TAKE(somdec_nc, c->nsomdec_nc);
 #undef TAKE
   if (c->ncplx) memcpy(c->eqcplx_logK, cfg->eqcplx_logK, sizeof(double) * c->ncplx);
   if (c->nkin) memcpy(c->kinmnrl_logK, cfg->kinmnrl_logK, sizeof(double) * c->nkin);
@@ -117,7 +124,13 @@ static void cell_free(cell_t *c) { free(c->buf); }
 static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
                         int64_t ic) {
   int k;
-  (void)cfg;
+  for (k = 0; k < c->nsomdec_nc; k++) {
+    const pfrx_somdec *sd = cfg->somdec;
+    if (st->somdec_nc)
+      c->somdec_nc[k] = LD(st->somdec_nc, k);
+    else
+      c->somdec_nc[k] = k < sd->nrxn ? sd->upstream_nc[k] : sd->downstream_nc[k - sd->nrxn];
+  }
   for (k = 0; k < c->naq; k++) {
     c->total[k] = LD(st->total, k);
     c->pri_molal[k] = LD(st->pri_molal, k);
@@ -145,6 +158,13 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->porosity = LD(st->porosity, 0);
   c->volume = LD(st->volume, 0);
   c->soil_particle_density = st->soil_particle_density ? LD(st->soil_particle_density, 0) : 0.0;
+  c->elm_w = st->elm_w_scalar ? LD(st->elm_w_scalar, 0) : 1.0;
+  c->elm_o = st->elm_o_scalar ? LD(st->elm_o_scalar, 0) : 1.0;
+  c->elm_t = st->elm_t_scalar ? LD(st->elm_t_scalar, 0) : 1.0;
+  c->elm_zsoil = st->elm_zsoil ? LD(st->elm_zsoil, 0) : 0.0;
+  c->elm_kscalar = st->elm_kscalar_decomp_c ? LD(st->elm_kscalar_decomp_c, 0) : 1.0;
+  c->elm_bd_dry = st->elm_bulkdensity_dry ? LD(st->elm_bulkdensity_dry, 0) : 1.25e3;
+  c->elm_bsw = st->elm_bsw ? LD(st->elm_bsw, 0) : 1.0;
   c->option_ierror = 0;
 }
 
@@ -170,6 +190,8 @@ static void cell_scatter(const cell_t *c, const pfrx_state *st, int64_t ic) {
   if (st->eqsrfcplx_conc)
     for (k = 0; k < c->nsrfcplx; k++) LD(st->eqsrfcplx_conc, k) = c->eqsrfcplx_conc[k];
   for (k = 0; k < c->nmrrows; k++) LD(st->kinmr_total_sorb, k) = c->kinmr_total_sorb[k];
+  if (st->somdec_nc)
+    for (k = 0; k < c->nsomdec_nc; k++) LD(st->somdec_nc, k) = c->somdec_nc[k];
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1035,12 +1057,917 @@ static void clm_cn_react(cell_t *c, const pfrx_config *cfg, double *Residual, do
 #undef JAC
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* ELM-CN sandboxes                                                           */
+
+/* utility.F90:2542-2597  HfunctionSmooth */
+static void hfunction_smooth(double x, double x_1, double x_0, double *H, double *dH) {
+  if (fabs(x_1 - x_0) < 1.e-50) {
+    *H = copysign(0.5, (x - x_1)) + 0.5;
+    *dH = 0.0;
+    return;
+  }
+  if (((x - x_0) / (x_1 - x_0)) < 0.0) {
+    *H = 0.0;
+    *dH = 0.0;
+  } else if (((x - x_0) / (x_1 - x_0)) > 1.0) {
+    *H = 1.0;
+    *dH = 0.0;
+  } else {
+    double x_star = 1.0 - (x - x_0) * (x - x_0) / (x_1 - x_0) / (x_1 - x_0);
+    *H = 1.0 - x_star * x_star;
+    *dH = 4.0 * x_star * (x - x_0) / (x_1 - x_0) / (x_1 - x_0);
+  }
+}
+
+/* elm_rspfuncs.F90:321-338  FuncMonod */
+static double func_monod(double conc, double monod_k, int compute_derivative) {
+  if (!compute_derivative) return conc / (conc + monod_k);
+  return monod_k / (conc + monod_k) / (conc + monod_k);
+}
+
+/* elm_rspfuncs.F90:342-375  FuncInhibition (PI = 3.14159265358979323846, pflotran_constants.F90) */
+static double func_inhibition(int compute_derivative, double conc, double inhibition_C, int has_C2,
+                              double inhibition_C2) {
+  const double PI = 3.14159265358979323846;
+  if (!has_C2) {
+    if (compute_derivative) return -inhibition_C / (conc + inhibition_C) / (conc + inhibition_C);
+    return inhibition_C / (conc + inhibition_C);
+  }
+  if (compute_derivative) {
+    double tempreal = (conc - inhibition_C) * inhibition_C2;
+    return (inhibition_C2 / (1.0 + tempreal * tempreal)) / PI;
+  }
+  return 0.5 + atan((conc - inhibition_C) * inhibition_C2) / PI;
+}
+
+/* elm_rspfuncs.F90:61-123  GetTemperatureResponse */
+static double get_temperature_response(double tc, int itype, double Q10orEA) {
+  const double one_over_71_02 = 1.408054069e-2;
+  const double Frz_Q10 = 2.0;
+  double Ft, tk;
+  switch (itype) {
+    case PFRX_TEMPERATURE_RESPONSE_Q10:
+      if (tc > 0.0)
+        Ft = pow(Q10orEA, (tc - 25.0) / 10.0);
+      else
+        Ft = pow(Q10orEA, -25.0 / 10.0) * pow(Frz_Q10, tc / 10.0);
+      break;
+    case PFRX_TEMPERATURE_RESPONSE_CLMCN:
+      tk = tc + 273.15;
+      if (tk > 227.15)
+        Ft = exp(308.56 * (one_over_71_02 - 1.0 / (tk - 227.13)));
+      else
+        Ft = 0.0;
+      break;
+    case PFRX_TEMPERATURE_RESPONSE_DLEM:
+      if (tc < -5.0)
+        Ft = 0.0;
+      else if (tc >= 30.0)
+        Ft = 1.0;
+      else
+        Ft = pow(Q10orEA, (tc - 30.0) / 10.0);
+      break;
+    case PFRX_TEMPERATURE_RESPONSE_ARRHENIUS:
+      Ft = exp(Q10orEA / IDEAL_GAS_CONSTANT * (1.0 / 298.15 - 1.0 / (tc + 273.15)));
+      break;
+    default:
+      Ft = 1.0;
+  }
+  return Ft;
+}
+
+/* elm_rspfuncs.F90:287-317  GetAerobicCondition */
+static double get_aerobic_condition(double OXorWFPS, double K_Ox, int itype, int compute_derivative) {
+  double F_Ox;
+  switch (itype) {
+    case PFRX_OX_RESPONSE_MONOD:
+      F_Ox = func_monod(OXorWFPS, K_Ox, compute_derivative);
+      break;
+    case PFRX_OX_RESPONSE_WFPS:
+      F_Ox = pow((1.27 - OXorWFPS) / 0.67, 3.1777) * pow((OXorWFPS - 0.0012) / 0.5988, 2.84);
+      if (compute_derivative) F_Ox = 0.0;
+      break;
+    default:
+      F_Ox = 1.0;
+      if (compute_derivative) F_Ox = 0.0;
+  }
+  return F_Ox;
+}
+
+/* reaction_sandbox_somdec.F90:3809-3870  SomDec_SpeciesConc (total / immobile) */
+static double somdec_species_conc(const cell_t *c, int id, int itype) {
+  if (itype == PFRX_SPEC_AQUEOUS) return c->total[id];
+  return c->immobile[id];
+}
+
+/* per-evaluation copy of the reference's `this%` scratch (see pfrx_somdec) */
+typedef struct {
+  double upstream_nc, mineral_c_stoich, mineral_n_stoich;
+  double downstream_nc[16];
+} somdec_scratch_t;
+
+#define SD_RES(itype, id) ((itype) == PFRX_SPEC_AQUEOUS ? (id) : off + (id))
+#define JAC(i, j) Jacobian[(i) + (size_t)(j) * n]
+#define DTOT(i, j) c->dtotal[(i) + (size_t)(j) * c->naq]
+
+/* the factors shared by SomDecReact1/2: MONOD list (other than the NH4/NO3
+ * ones when `react2`), INHIBITION list, Ox Monod term.
+ * reaction_sandbox_somdec.F90:2062-2150 and :2700-2800 */
+static void somdec_rate_modifiers(const cell_t *c, const pfrx_somdec *sd, int rxn, int ispec_uc, int react2,
+                                  double theta, double c_nh4, double c_no3, double *crate_uc,
+                                  double *dcrate_uc_duc, double *fnh4, double *dfnh4_dnh4, double *fno3,
+                                  double *dfno3_dno3) {
+  double fmb = 1.0, dfmb = 0.0, fx, dfx, tempreal, f_ox, df_ox;
+  int k;
+  for (k = sd->monod_ptr[rxn]; k < sd->monod_ptr[rxn + 1]; k++) {
+    double monod_k = sd->monod_half_saturation[k];
+    double monod_threshold = sd->monod_threshold[k];
+    if (react2 && sd->nh4_id >= 0 && sd->nh4_id == sd->monod_specid[k]) {
+      tempreal = fmax(0.0, c_nh4 - monod_threshold);
+      if (sd->monod_pool_normalized[k]) tempreal = tempreal / c->immobile[ispec_uc];
+      *fnh4 = func_monod(tempreal, monod_k, 0);
+      *dfnh4_dnh4 = func_monod(tempreal, monod_k, 1);
+    } else if (react2 && sd->no3_id >= 0 && sd->no3_id == sd->monod_specid[k]) {
+      tempreal = fmax(0.0, c_no3 - monod_threshold);
+      if (sd->monod_pool_normalized[k]) tempreal = tempreal / c->immobile[ispec_uc];
+      *fno3 = func_monod(tempreal, monod_k, 0);
+      *dfno3_dno3 = func_monod(tempreal, monod_k, 1);
+    } else {
+      tempreal = somdec_species_conc(c, sd->monod_specid[k], sd->monod_specitype[k]);
+      tempreal = fmax(0.0, tempreal - monod_threshold);
+      if (sd->monod_pool_normalized[k]) {
+        tempreal = tempreal / c->immobile[ispec_uc];
+        if (sd->monod_specitype[k] == PFRX_SPEC_AQUEOUS) {
+          if (react2)
+            tempreal = tempreal * theta * 1000.0;
+          else
+            tempreal = tempreal * c->porosity * c->sat * 1000.0;
+        }
+      }
+      fx = func_monod(tempreal, monod_k, 0);
+      dfx = func_monod(tempreal, monod_k, 1);
+      if (ispec_uc != sd->monod_specid[k]) dfx = 0.0;
+      dfmb = dfmb * fx + fmb * dfx;
+      fmb = fmb * fx;
+    }
+  }
+  for (k = sd->inhib_ptr[rxn]; k < sd->inhib_ptr[rxn + 1]; k++) {
+    double inhibition_k = sd->inhib_constant[k], inhibition_k2 = sd->inhib_constant2[k];
+    tempreal = somdec_species_conc(c, sd->inhib_specid[k], sd->inhib_specitype[k]);
+    fx = 1.0;
+    dfx = 0.0;
+    if (inhibition_k2 == -999.0 || sd->inhib_itype[k] != PFRX_INHIBITION_THRESHOLD) {
+      if (sd->inhib_itype[k] == PFRX_INHIBITION_MONOD) {
+        fx = func_inhibition(0, tempreal, inhibition_k, 0, 0.0);
+        dfx = func_inhibition(1, tempreal, inhibition_k, 0, 0.0);
+      } else if (sd->inhib_itype[k] == PFRX_INHIBITION_INVERSE_MONOD) {
+        fx = func_monod(tempreal, inhibition_k, 0);
+        dfx = func_monod(tempreal, inhibition_k, 1);
+      }
+    } else {
+      fx = func_inhibition(0, tempreal, inhibition_k, 1, inhibition_k2);
+      dfx = func_inhibition(1, tempreal, inhibition_k, 1, inhibition_k2);
+    }
+    if (ispec_uc != sd->inhib_specid[k]) dfx = 0.0;
+    dfmb = dfmb * fx + fmb * dfx;
+    fmb = fmb * fx;
+  }
+  *dcrate_uc_duc = *dcrate_uc_duc * fmb + *crate_uc * dfmb;
+  *crate_uc = *crate_uc * fmb;
+
+  if (sd->ox_response_function[rxn] == PFRX_OX_RESPONSE_MONOD && sd->ox_specid[rxn] >= 0) {
+    double Ox = somdec_species_conc(c, sd->ox_specid[rxn], sd->ox_specitype[rxn]);
+    f_ox = get_aerobic_condition(Ox, sd->ox_half_saturation[rxn], sd->ox_response_function[rxn], 0);
+    df_ox = get_aerobic_condition(Ox, sd->ox_half_saturation[rxn], sd->ox_response_function[rxn], 1);
+  } else {
+    f_ox = 1.0;
+    df_ox = 0.0;
+  }
+  *dcrate_uc_duc = *dcrate_uc_duc * f_ox + *crate_uc * df_ox;
+  *crate_uc = *crate_uc * f_ox;
+}
+
+/* residual entries common to SomDecReact1/2: upstream C, CO2 (+ trackers), O2,
+ * downstream C, upstream N.  reaction_sandbox_somdec.F90:2160-2215, :2880-2935 */
+static void somdec_common_residual(const cell_t *c, const pfrx_somdec *sd, int irxn, const somdec_scratch_t *w,
+                                   double crate, double *Residual, int *ires_ox_out) {
+  int off = c->naq, j;
+  int ires_uc = SD_RES(sd->upstream_is_aqueous[irxn] ? PFRX_SPEC_AQUEOUS : PFRX_SPEC_IMMOBILE, sd->upstream_c_id[irxn]);
+  int ires_co2 = SD_RES(sd->co2_itype, sd->co2_id);
+  Residual[ires_uc] = Residual[ires_uc] + crate;
+  Residual[ires_co2] = Residual[ires_co2] - w->mineral_c_stoich * crate;
+  if (sd->upstream_hr_id[irxn] >= 0)
+    Residual[off + sd->upstream_hr_id[irxn]] = Residual[off + sd->upstream_hr_id[irxn]] - w->mineral_c_stoich * crate;
+  if (sd->hr_id >= 0) Residual[off + sd->hr_id] = Residual[off + sd->hr_id] - w->mineral_c_stoich * crate;
+  *ires_ox_out = -1;
+  if (sd->o2_id >= 0) {
+    int ires_ox = SD_RES(sd->o2_itype, sd->o2_id);
+    Residual[ires_ox] = Residual[ires_ox] + w->mineral_c_stoich * crate;
+    *ires_ox_out = ires_ox;
+  }
+  for (j = sd->downstream_ptr[irxn]; j < sd->downstream_ptr[irxn + 1]; j++) {
+    int ispec_dc = sd->downstream_c_id[j];
+    int ires_dc = sd->downstream_is_aqueous[j] ? ispec_dc : off + ispec_dc;
+    if (ispec_dc >= 0) Residual[ires_dc] = Residual[ires_dc] - sd->downstream_stoich[j] * crate;
+  }
+  if (sd->upstream_n_id[irxn] >= 0) {
+    int ires_un = sd->upstream_is_aqueous[irxn] ? sd->upstream_n_id[irxn] : off + sd->upstream_n_id[irxn];
+    Residual[ires_un] = Residual[ires_un] + w->upstream_nc * crate;
+  }
+}
+
+/* residual of variable-C:N downstream N.  :2238-2252, :2975-2990 */
+static void somdec_downstream_n_residual(const cell_t *c, const pfrx_somdec *sd, int irxn, const somdec_scratch_t *w,
+                                         double crate, double *Residual) {
+  int off = c->naq, j;
+  for (j = sd->downstream_ptr[irxn]; j < sd->downstream_ptr[irxn + 1]; j++) {
+    int ispec_dn = sd->downstream_n_id[j];
+    if (ispec_dn >= 0) {
+      int ires_dn = sd->downstream_is_aqueous[j] ? ispec_dn : off + ispec_dn;
+      Residual[ires_dn] =
+          Residual[ires_dn] - sd->downstream_stoich[j] * crate * w->downstream_nc[j - sd->downstream_ptr[irxn]];
+    }
+  }
+}
+
+/* Jacobian column `jcol` (derivative w.r.t. species of primary id jaq, or an
+ * immobile upstream pool when jaq < 0) of the entries every branch shares:
+ * CO2 (+O2, trackers), upstream C, downstream C, upstream N, downstream N.
+ * d*_dx follow the reference's names with x = uc / nh4 / no3. */
+static void somdec_common_jacobian(const cell_t *c, const pfrx_somdec *sd, int irxn, const somdec_scratch_t *w,
+                                   int jcol, int jaq, int ires_ox, double dco2_dx, double duc_dx, double dun_dx,
+                                   int wrt_uc, double *Jacobian) {
+  int off = c->naq, n = c->n, j;
+  int up_aq = sd->upstream_is_aqueous[irxn];
+  int ispec_uc = sd->upstream_c_id[irxn];
+  int ires_uc = up_aq ? ispec_uc : off + ispec_uc;
+  int ires_co2 = SD_RES(sd->co2_itype, sd->co2_id);
+  /* the reference multiplies by dtotal when the column species is aqueous:
+   * for x = uc only when the upstream pool is aqueous; for x = nh4/no3 on the
+   * CO2 row always, on pool rows when the pool is aqueous */
+  if (wrt_uc) {
+    if (up_aq)
+      JAC(ires_co2, jcol) = JAC(ires_co2, jcol) - dco2_dx * DTOT(sd->co2_id, ispec_uc);
+    else
+      JAC(ires_co2, jcol) = JAC(ires_co2, jcol) - dco2_dx;
+    if (sd->o2_id >= 0) {
+      if (up_aq)
+        JAC(ires_ox, jcol) = JAC(ires_ox, jcol) + dco2_dx * DTOT(sd->co2_id, ispec_uc);
+      else
+        JAC(ires_ox, jcol) = JAC(ires_ox, jcol) + dco2_dx;
+    }
+  } else {
+    JAC(ires_co2, jcol) = JAC(ires_co2, jcol) - dco2_dx * DTOT(sd->co2_id, jaq);
+  }
+  if (sd->upstream_hr_id[irxn] >= 0)
+    JAC(off + sd->upstream_hr_id[irxn], jcol) = JAC(off + sd->upstream_hr_id[irxn], jcol) - dco2_dx;
+  if (sd->hr_id >= 0) JAC(off + sd->hr_id, jcol) = JAC(off + sd->hr_id, jcol) - dco2_dx;
+
+  if (up_aq)
+    JAC(ires_uc, jcol) = JAC(ires_uc, jcol) - duc_dx * DTOT(ispec_uc, wrt_uc ? ispec_uc : jaq);
+  else
+    JAC(ires_uc, jcol) = JAC(ires_uc, jcol) - duc_dx;
+
+  for (j = sd->downstream_ptr[irxn]; j < sd->downstream_ptr[irxn + 1]; j++) {
+    int ispec_dc = sd->downstream_c_id[j];
+    double ddc_dx = sd->downstream_stoich[j] * (-1.0 * duc_dx);
+    if (wrt_uc) {
+      int ires_dc = sd->downstream_is_aqueous[j] ? ispec_dc : off + ispec_dc;
+      if (up_aq && sd->downstream_is_aqueous[j])
+        JAC(ires_dc, jcol) = JAC(ires_dc, jcol) - ddc_dx * DTOT(ispec_dc, ispec_uc);
+      else
+        JAC(ires_dc, jcol) = JAC(ires_dc, jcol) - ddc_dx;
+    } else {
+      if (sd->downstream_is_aqueous[j])
+        JAC(ispec_dc, jcol) = JAC(ispec_dc, jcol) - ddc_dx * DTOT(ispec_dc, jaq);
+      else
+        JAC(off + ispec_dc, jcol) = JAC(off + ispec_dc, jcol) - ddc_dx;
+    }
+  }
+  (void)dun_dx;
+}
+
+/* upstream-N and downstream-N rows of column jcol (written after the NH4/NO3
+ * rows in the reference, so kept separate to preserve the order of updates) */
+static void somdec_n_rows_jacobian(const cell_t *c, const pfrx_somdec *sd, int irxn, const somdec_scratch_t *w,
+                                   int jcol, int jaq, double duc_dx, double dun_dx, int wrt_uc, double *Jacobian) {
+  int off = c->naq, n = c->n, j;
+  int up_aq = sd->upstream_is_aqueous[irxn];
+  int ispec_uc = sd->upstream_c_id[irxn];
+  if (sd->upstream_n_id[irxn] >= 0) {
+    int ispec_un = sd->upstream_n_id[irxn];
+    int ires_un = up_aq ? ispec_un : off + ispec_un;
+    if (up_aq)
+      JAC(ires_un, jcol) = JAC(ires_un, jcol) - dun_dx * DTOT(ispec_un, wrt_uc ? ispec_uc : jaq);
+    else
+      JAC(ires_un, jcol) = JAC(ires_un, jcol) - dun_dx;
+  }
+  for (j = sd->downstream_ptr[irxn]; j < sd->downstream_ptr[irxn + 1]; j++) {
+    int ispec_dn = sd->downstream_n_id[j];
+    if (ispec_dn >= 0) {
+      int ires_dn = sd->downstream_is_aqueous[j] ? ispec_dn : off + ispec_dn;
+      double ddn_dx = sd->downstream_stoich[j] * (-1.0 * duc_dx) * w->downstream_nc[j - sd->downstream_ptr[irxn]];
+      if (up_aq && sd->downstream_is_aqueous[j])
+        JAC(ires_dn, jcol) = JAC(ires_dn, jcol) - ddn_dx * DTOT(ispec_dn, wrt_uc ? ispec_uc : jaq);
+      else
+        JAC(ires_dn, jcol) = JAC(ires_dn, jcol) - ddn_dx;
+    }
+  }
+}
+
+/* reaction_sandbox_somdec.F90:1914-2418  SomDecReact1 (N mineralisation type) */
+static void somdec_react1(const cell_t *c, const pfrx_somdec *sd, int irxn, int rxn, const somdec_scratch_t *w,
+                          double crate_uc, double dcrate_uc_duc, double *nmin, double *Residual, double *Jacobian,
+                          int compute_derivative) {
+  int off = c->naq, n = c->n;
+  int ispec_uc = sd->upstream_c_id[irxn];
+  int up_aq = sd->upstream_is_aqueous[irxn];
+  int ires_uc = up_aq ? ispec_uc : off + ispec_uc;
+  int ires_nh4 = sd->nh4_id, ires_ox;
+  double crate, dummy1 = 1.0, dummy2 = 0.0, dummy3 = 1.0, dummy4 = 0.0;
+  *nmin = 0.0;
+  if (w->mineral_n_stoich < 0.0) return;
+  somdec_rate_modifiers(c, sd, rxn, ispec_uc, 0, 0.0, 0.0, 0.0, &crate_uc, &dcrate_uc_duc, &dummy1, &dummy2, &dummy3,
+                        &dummy4);
+  crate = crate_uc;
+  somdec_common_residual(c, sd, irxn, w, crate, Residual, &ires_ox);
+  if (w->mineral_n_stoich >= 0.0) {
+    Residual[ires_nh4] = Residual[ires_nh4] - w->mineral_n_stoich * crate;
+    *nmin = w->mineral_n_stoich * crate;
+    if (sd->upstream_nmin_id[irxn] >= 0)
+      Residual[off + sd->upstream_nmin_id[irxn]] =
+          Residual[off + sd->upstream_nmin_id[irxn]] - w->mineral_n_stoich * crate;
+    if (sd->nmin_id >= 0) Residual[off + sd->nmin_id] = Residual[off + sd->nmin_id] - w->mineral_n_stoich * crate;
+  }
+  somdec_downstream_n_residual(c, sd, irxn, w, crate, Residual);
+
+  if (compute_derivative) {
+    double dcrate_dx = dcrate_uc_duc;
+    double dco2_duc = dcrate_dx * w->mineral_c_stoich;
+    double duc_duc = -1.0 * dcrate_dx;
+    double dnh4_duc = dco2_duc * w->mineral_n_stoich; /* sic: reaction_sandbox_somdec.F90:2283 */
+    double dun_duc = w->upstream_nc * duc_duc;
+    somdec_common_jacobian(c, sd, irxn, w, ires_uc, -1, ires_ox, dco2_duc, duc_duc, dun_duc, 1, Jacobian);
+    if (up_aq)
+      JAC(ires_nh4, ires_uc) = JAC(ires_nh4, ires_uc) - dnh4_duc * DTOT(sd->nh4_id, ispec_uc);
+    else
+      JAC(ires_nh4, ires_uc) = JAC(ires_nh4, ires_uc) - dnh4_duc;
+    if (w->mineral_n_stoich >= 0.0) {
+      if (sd->upstream_nmin_id[irxn] >= 0)
+        JAC(off + sd->upstream_nmin_id[irxn], ires_uc) = JAC(off + sd->upstream_nmin_id[irxn], ires_uc) - dnh4_duc;
+      if (sd->nmin_id >= 0) JAC(off + sd->nmin_id, ires_uc) = JAC(off + sd->nmin_id, ires_uc) - dnh4_duc;
+    }
+    somdec_n_rows_jacobian(c, sd, irxn, w, ires_uc, -1, duc_duc, dun_duc, 1, Jacobian);
+  }
+}
+
+/* reaction_sandbox_somdec.F90:2423-3472  SomDecReact2 (N immobilisation type) */
+static void somdec_react2(const cell_t *c, const pfrx_somdec *sd, int irxn, int rxn, const somdec_scratch_t *w,
+                          double tran_dt, double crate_uc, double dcrate_uc_duc, double *nimm, double *Residual,
+                          double *Jacobian, int compute_derivative) {
+  int off = c->naq, n = c->n;
+  int ispec_uc = sd->upstream_c_id[irxn];
+  int up_aq = sd->upstream_is_aqueous[irxn];
+  int ires_uc = up_aq ? ispec_uc : off + ispec_uc;
+  int ires_nh4 = sd->nh4_id, ires_no3 = sd->no3_id, ires_ox;
+  double theta, volume, c_nh4 = 0.0, c_no3 = 0.0;
+  double fnh4_inhibit_no3 = 1.0, dfnh4_inhibit_no3_dnh4 = 0.0, dfnh4_inhibit_no3_dno3 = 0.0;
+  double fnh4 = 1.0, dfnh4_dnh4 = 0.0, fno3 = 1.0, dfno3_dno3 = 0.0;
+  double feps0, dfeps0_dx, dtmin, nratecap, fnratecap, dfnratecap_dnh4, dfnratecap_dno3;
+  double crate_nh4, crate_no3, crate, temp_real;
+  double ns = w->mineral_n_stoich;
+  *nimm = 0.0;
+  if (w->mineral_n_stoich >= 0.0) return;
+  theta = c->sat * c->porosity;
+  volume = c->volume;
+  if (sd->nh4_id >= 0) c_nh4 = c->total[sd->nh4_id] * theta * 1000.0;
+  if (sd->no3_id >= 0) c_no3 = c->total[sd->no3_id] * theta * 1000.0;
+
+  if (sd->inhibition_nh4_no3 > 0.0) {
+    if (c_nh4 > sd->x0eps && c_no3 > sd->x0eps) {
+      temp_real = c_nh4 / c_no3;
+      fnh4_inhibit_no3 = func_monod(temp_real, 1.0 / sd->inhibition_nh4_no3, 0);
+    } else {
+      if (c_nh4 > sd->x0eps && c_no3 <= sd->x0eps)
+        fnh4_inhibit_no3 = 1.0;
+      else if (c_nh4 <= sd->x0eps && c_no3 > sd->x0eps)
+        fnh4_inhibit_no3 = 0.0;
+      else
+        return;
+    }
+  }
+
+  somdec_rate_modifiers(c, sd, rxn, ispec_uc, 1, theta, c_nh4, c_no3, &crate_uc, &dcrate_uc_duc, &fnh4, &dfnh4_dnh4,
+                        &fno3, &dfno3_dno3);
+
+  if (sd->nh4_id >= 0) {
+    if (sd->x0eps > 0.0) {
+      hfunction_smooth(c_nh4, sd->x0eps * 10.0, sd->x0eps, &feps0, &dfeps0_dx);
+    } else {
+      feps0 = 1.0;
+      dfeps0_dx = 0.0;
+    }
+    dfnh4_dnh4 = dfnh4_dnh4 * feps0 + fnh4 * dfeps0_dx;
+    fnh4 = fnh4 * feps0;
+  }
+  if (sd->no3_id >= 0) {
+    if (sd->x0eps > 0.0) {
+      hfunction_smooth(c_no3, sd->x0eps * 10.0, sd->x0eps, &feps0, &dfeps0_dx);
+    } else {
+      feps0 = 1.0;
+      dfeps0_dx = 0.0;
+    }
+    dfno3_dno3 = dfno3_dno3 * feps0 + fno3 * dfeps0_dx;
+    fno3 = fno3 * feps0;
+  }
+
+  dtmin = tran_dt;
+  nratecap = -crate_uc * ns * dtmin / 0.45;
+  if (sd->nh4_id >= 0) {
+    if (nratecap * fnh4_inhibit_no3 > c_nh4 * volume) {
+      fnratecap = func_monod(c_nh4 * volume, nratecap * fnh4_inhibit_no3 - c_nh4 * volume, 0);
+      dfnratecap_dnh4 = func_monod(c_nh4 * volume, nratecap * fnh4_inhibit_no3 - c_nh4 * volume, 1);
+    } else {
+      fnratecap = 1.0;
+      dfnratecap_dnh4 = 0.0;
+    }
+    dfnh4_dnh4 = dfnh4_dnh4 * fnratecap + fnh4 * dfnratecap_dnh4;
+    fnh4 = fnh4 * fnratecap;
+  }
+  if (sd->no3_id >= 0) {
+    if (nratecap * (1.0 - fnh4_inhibit_no3) > c_no3 * volume) {
+      fnratecap = func_monod(c_no3 * volume, nratecap * (1.0 - fnh4_inhibit_no3) - c_no3 * volume, 0);
+      dfnratecap_dno3 = func_monod(c_no3 * volume, nratecap * (1.0 - fnh4_inhibit_no3) - c_no3 * volume, 1);
+    } else {
+      fnratecap = 1.0;
+      dfnratecap_dno3 = 0.0;
+    }
+    dfno3_dno3 = dfno3_dno3 * fnratecap + fno3 * dfnratecap_dno3;
+    fno3 = fno3 * fnratecap;
+  }
+
+  crate_nh4 = crate_uc * fnh4 * fnh4_inhibit_no3;
+  crate_no3 = crate_uc * fno3 * (1.0 - fnh4_inhibit_no3);
+  crate = crate_nh4 + crate_no3;
+
+  somdec_common_residual(c, sd, irxn, w, crate, Residual, &ires_ox);
+  *nimm = 0.0;
+  if (sd->nh4_id >= 0) {
+    Residual[ires_nh4] = Residual[ires_nh4] - ns * crate_nh4;
+    *nimm = *nimm + ns * crate_nh4;
+  }
+  if (sd->no3_id >= 0) {
+    Residual[ires_no3] = Residual[ires_no3] - ns * crate_no3;
+    *nimm = *nimm + ns * crate_no3;
+  }
+  if (sd->upstream_nimm_id[irxn] >= 0)
+    Residual[off + sd->upstream_nimm_id[irxn]] = Residual[off + sd->upstream_nimm_id[irxn]] + ns * crate;
+  if (sd->upstream_nimp_id[irxn] >= 0)
+    Residual[off + sd->upstream_nimp_id[irxn]] = Residual[off + sd->upstream_nimp_id[irxn]] + ns * crate_uc;
+  if (sd->nimm_id >= 0) Residual[off + sd->nimm_id] = Residual[off + sd->nimm_id] + ns * crate;
+  if (sd->nimp_id >= 0) Residual[off + sd->nimp_id] = Residual[off + sd->nimp_id] + ns * crate_uc;
+  somdec_downstream_n_residual(c, sd, irxn, w, crate, Residual);
+
+  if (compute_derivative) {
+    double dcrate_dx, dco2_duc, duc_duc, dnh4_duc, dno3_duc, dun_duc;
+    double dco2_dnh4, duc_dnh4, dnh4_dnh4, dno3_dnh4, dun_dnh4;
+    double dco2_dno3, duc_dno3, dnh4_dno3, dno3_dno3, dun_dno3;
+    int unimm = sd->upstream_nimm_id[irxn];
+    /* -- d/d(uc) :3000-3010 */
+    dcrate_dx = dcrate_uc_duc * (fnh4 * fnh4_inhibit_no3 + fno3 - fno3 * fnh4_inhibit_no3);
+    dco2_duc = dcrate_dx * w->mineral_c_stoich;
+    duc_duc = -1.0 * dcrate_dx;
+    dnh4_duc = dcrate_uc_duc * ns * fnh4 * fnh4_inhibit_no3;
+    dno3_duc = dcrate_uc_duc * ns * fno3 * (1.0 - fnh4_inhibit_no3);
+    dun_duc = w->upstream_nc * duc_duc;
+    /* -- d/d(nh4) */
+    dcrate_dx = (dfnh4_dnh4 * fnh4_inhibit_no3 + (fnh4 - fno3) * dfnh4_inhibit_no3_dnh4);
+    dcrate_dx = dcrate_dx * crate_uc;
+    dco2_dnh4 = dcrate_dx * w->mineral_c_stoich;
+    duc_dnh4 = -1.0 * dcrate_dx;
+    dnh4_dnh4 = fnh4 * dfnh4_inhibit_no3_dnh4 + dfnh4_dnh4 * fnh4_inhibit_no3;
+    dnh4_dnh4 = dnh4_dnh4 * crate_uc * ns;
+    dno3_dnh4 = -1.0 * fno3 * dfnh4_inhibit_no3_dnh4;
+    dno3_dnh4 = dno3_dnh4 * crate_uc * ns;
+    dun_dnh4 = w->upstream_nc * duc_dnh4;
+    /* -- d/d(no3) */
+    dcrate_dx = (fnh4 - fno3) * dfnh4_inhibit_no3_dno3 + dfno3_dno3 * (1.0 - fnh4 * fnh4_inhibit_no3);
+    dcrate_dx = dcrate_dx * crate_uc;
+    dco2_dno3 = dcrate_dx * w->mineral_c_stoich;
+    duc_dno3 = -1.0 * dcrate_dx;
+    dnh4_dno3 = fnh4 * dfnh4_inhibit_no3_dno3 * crate_uc * ns;
+    dno3_dno3 = -1.0 * fno3 * dfnh4_inhibit_no3_dno3 + dfno3_dno3 * (1.0 - fnh4_inhibit_no3);
+    dno3_dno3 = dno3_dno3 * crate_uc * ns;
+    dun_dno3 = w->upstream_nc * duc_dno3;
+
+    /* column uc */
+    somdec_common_jacobian(c, sd, irxn, w, ires_uc, -1, ires_ox, dco2_duc, duc_duc, dun_duc, 1, Jacobian);
+    if (sd->nh4_id >= 0) {
+      if (up_aq)
+        JAC(ires_nh4, ires_uc) = JAC(ires_nh4, ires_uc) - dnh4_duc * DTOT(sd->nh4_id, ispec_uc);
+      else
+        JAC(ires_nh4, ires_uc) = JAC(ires_nh4, ires_uc) - dnh4_duc;
+      if (unimm >= 0) JAC(off + unimm, ires_uc) = JAC(off + unimm, ires_uc) + dnh4_duc;
+      if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_uc) = JAC(off + sd->nimm_id, ires_uc) + dnh4_duc;
+    }
+    if (sd->no3_id >= 0) {
+      if (up_aq)
+        JAC(ires_no3, ires_uc) = JAC(ires_no3, ires_uc) - dno3_duc * DTOT(sd->no3_id, ispec_uc);
+      else
+        JAC(ires_no3, ires_uc) = JAC(ires_no3, ires_uc) - dno3_duc;
+      if (unimm >= 0) JAC(off + unimm, ires_uc) = JAC(off + unimm, ires_uc) + dno3_duc;
+      if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_uc) = JAC(off + sd->nimm_id, ires_uc) + dno3_duc;
+    }
+    somdec_n_rows_jacobian(c, sd, irxn, w, ires_uc, -1, duc_duc, dun_duc, 1, Jacobian);
+
+    /* column nh4 */
+    if (sd->nh4_id >= 0) {
+      somdec_common_jacobian(c, sd, irxn, w, ires_nh4, sd->nh4_id, ires_ox, dco2_dnh4, duc_dnh4, dun_dnh4, 0,
+                             Jacobian);
+      JAC(ires_nh4, ires_nh4) = JAC(ires_nh4, ires_nh4) - dnh4_dnh4 * DTOT(sd->nh4_id, sd->nh4_id);
+      if (unimm >= 0) JAC(off + unimm, ires_nh4) = JAC(off + unimm, ires_nh4) + dnh4_dnh4;
+      if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_nh4) = JAC(off + sd->nimm_id, ires_nh4) + dnh4_dnh4;
+      if (sd->no3_id >= 0) {
+        JAC(ires_no3, ires_nh4) = JAC(ires_no3, ires_nh4) - dno3_dnh4 * DTOT(sd->no3_id, sd->nh4_id);
+        if (unimm >= 0) JAC(off + unimm, ires_nh4) = JAC(off + unimm, ires_nh4) + dno3_dnh4;
+        if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_nh4) = JAC(off + sd->nimm_id, ires_nh4) + dno3_dnh4;
+      }
+      somdec_n_rows_jacobian(c, sd, irxn, w, ires_nh4, sd->nh4_id, duc_dnh4, dun_dnh4, 0, Jacobian);
+    }
+    /* column no3 */
+    if (sd->no3_id >= 0) {
+      somdec_common_jacobian(c, sd, irxn, w, ires_no3, sd->no3_id, ires_ox, dco2_dno3, duc_dno3, dun_dno3, 0,
+                             Jacobian);
+      if (sd->nh4_id >= 0) {
+        JAC(ires_nh4, ires_no3) = JAC(ires_nh4, ires_no3) - dnh4_dno3 * DTOT(sd->nh4_id, sd->no3_id);
+        if (unimm >= 0) JAC(off + unimm, ires_no3) = JAC(off + unimm, ires_no3) + dnh4_dno3;
+        if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_no3) = JAC(off + sd->nimm_id, ires_no3) + dnh4_dno3;
+      }
+      JAC(ires_no3, ires_no3) = JAC(ires_no3, ires_no3) - dno3_dno3 * DTOT(sd->no3_id, sd->no3_id);
+      if (unimm >= 0) JAC(off + unimm, ires_no3) = JAC(off + unimm, ires_no3) + dno3_dno3;
+      if (sd->nimm_id >= 0) JAC(off + sd->nimm_id, ires_no3) = JAC(off + sd->nimm_id, ires_no3) + dno3_dno3;
+      somdec_n_rows_jacobian(c, sd, irxn, w, ires_no3, sd->no3_id, duc_dno3, dun_dno3, 0, Jacobian);
+    }
+  }
+}
+
+/* reaction_sandbox_somdec.F90:3477-3640  SomDecNemission */
+static void somdec_nemission(const cell_t *c, const pfrx_somdec *sd, double tran_dt, double net_nmin_rate,
+                             double *Residual, double *Jacobian, int compute_derivative) {
+  const double rpi = 3.14159265358979323846;
+  int off = c->naq, n = c->n;
+  double porosity = c->porosity, volume = c->volume, saturation = c->sat;
+  double theta = saturation * porosity, tc = c->temp;
+  int ires_nh4 = sd->nh4_id, ires_n2o = sd->n2o_id;
+  double c_nh4 = c->total[ires_nh4] * theta * 1000.0;
+  double f_t, f_w, ph, f_ph, temp_real, feps0, dfeps0_dx, dtmin, nratecap, fnratecap, dfnratecap_dnh4, rate_n2o;
+  if (sd->n2o_id >= 0 && net_nmin_rate > sd->x0eps) {
+    f_t = -0.06 + 0.13 * exp(0.07 * tc);
+    f_w = pow((1.27 - saturation) / 0.67, 3.1777) * pow((saturation - 0.0012) / 0.5988, 2.84);
+    ph = 6.5;
+    if (sd->proton_id >= 0) ph = -log10(c->pri_molal[sd->proton_id] * c->pri_act_coef[sd->proton_id]);
+    f_ph = 0.56 + atan(rpi * 0.45 * (-5.0 + ph)) / rpi;
+    if (f_t > sd->x0eps && f_w > sd->x0eps && f_ph > sd->x0eps) {
+      f_t = fmin(f_t, 1.0);
+      f_w = fmin(f_w, 1.0);
+      f_ph = fmin(f_ph, 1.0);
+      temp_real = f_t * f_w * f_ph;
+      if (sd->x0eps > 0.0) {
+        hfunction_smooth(c_nh4, sd->x0eps * 10.0, sd->x0eps, &feps0, &dfeps0_dx);
+      } else {
+        feps0 = 1.0;
+        dfeps0_dx = 0.0;
+      }
+      dtmin = tran_dt;
+      nratecap = temp_real * sd->n2o_frac_mineralization * net_nmin_rate * dtmin;
+      if (nratecap > c_nh4 * volume) {
+        fnratecap = func_monod(c_nh4 * volume, nratecap - c_nh4 * volume, 0);
+        dfnratecap_dnh4 = func_monod(c_nh4 * volume, nratecap - c_nh4 * volume, 1);
+      } else {
+        fnratecap = 1.0;
+        dfnratecap_dnh4 = 0.0;
+      }
+      dfeps0_dx = dfeps0_dx * fnratecap + feps0 * dfnratecap_dnh4;
+      feps0 = feps0 * fnratecap;
+      rate_n2o = temp_real * sd->n2o_frac_mineralization * net_nmin_rate * feps0;
+      Residual[ires_nh4] = Residual[ires_nh4] + rate_n2o;
+      Residual[ires_n2o] = Residual[ires_n2o] - 0.5 * rate_n2o;
+      if (sd->ngasmin_id >= 0) Residual[off + sd->ngasmin_id] = Residual[off + sd->ngasmin_id] - rate_n2o;
+      if (compute_derivative) {
+        double drate_n2o_dx = temp_real * sd->n2o_frac_mineralization * net_nmin_rate * dfeps0_dx;
+        JAC(ires_nh4, ires_nh4) = JAC(ires_nh4, ires_nh4) + drate_n2o_dx * DTOT(sd->nh4_id, sd->nh4_id);
+        JAC(ires_n2o, ires_nh4) = JAC(ires_n2o, ires_nh4) - 0.5 * drate_n2o_dx * DTOT(sd->n2o_id, sd->nh4_id);
+        if (sd->ngasmin_id >= 0) JAC(off + sd->ngasmin_id, ires_nh4) = JAC(off + sd->ngasmin_id, ires_nh4) - drate_n2o_dx;
+      }
+    }
+  }
+}
+
+/* reaction_sandbox_somdec.F90:1504-1910  SomDecReact */
+static void somdec_react(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Residual, double *Jacobian,
+                         int compute_derivative) {
+  const pfrx_somdec *sd = cfg->somdec;
+  double porosity = c->porosity, volume = c->volume, saturation = c->sat;
+  double theta = saturation * porosity, tc = c->temp;
+  double net_nmin_rate = 0.0, nmin = 0.0, nimm = 0.0;
+  int irxn, cur = 0, j;
+  for (irxn = 0; irxn < sd->nrxn; irxn++) {
+    /* `cur` is the reference's cur_rxn, which is NOT advanced by the `cycle`
+     * statements below (reaction_sandbox_somdec.F90:1744,1783 vs :1869) */
+    double f_w, f_t, f_depth, kd_scalar, k_decomp = 0.0, scaled_crate_const, c_uc, feps0, dfeps0_dx;
+    double crate_uc, dcrate_uc_duc;
+    int ispec_uc, nd = sd->downstream_ptr[irxn + 1] - sd->downstream_ptr[irxn];
+    somdec_scratch_t w;
+    if (cfg->elm_pflotran) {
+      /* BGC-only coupling (option%nflowspec == 0): factors from ELM, :1634-1641 */
+      f_w = c->elm_w;
+    } else {
+      if (sd->moisture_response_function[cur] == PFRX_MOISTURE_RESPONSE_LOGTHETA) {
+        /* the reference writes these literals without a kind suffix, so they
+         * are single precision (reaction_sandbox_somdec.F90:1645-1649) */
+        if (theta <= (double)0.08f)
+          f_w = (double)0.01f;
+        else
+          f_w = log(theta / (double)0.08f) / (double)logf(1.0f / 0.08f);
+      } else {
+        f_w = 1.0;
+      }
+    }
+    if (sd->ox_response_function[cur] == PFRX_OX_RESPONSE_WFPS) {
+      f_w = f_w * get_aerobic_condition(saturation, sd->ox_half_saturation[cur], sd->ox_response_function[cur], 0);
+    } else {
+      if (cfg->elm_pflotran) f_w = f_w * c->elm_o;
+    }
+    switch (sd->temperature_response_function[cur]) {
+      case PFRX_TEMPERATURE_RESPONSE_ARRHENIUS:
+        f_t = get_temperature_response(tc, sd->temperature_response_function[cur], sd->ea[cur]);
+        break;
+      case PFRX_TEMPERATURE_RESPONSE_CLMCN:
+        f_t = get_temperature_response(tc, sd->temperature_response_function[cur], 0.0);
+        break;
+      case PFRX_TEMPERATURE_RESPONSE_Q10:
+      case PFRX_TEMPERATURE_RESPONSE_DLEM:
+        f_t = get_temperature_response(tc, sd->temperature_response_function[cur], sd->q10[cur]);
+        break;
+      default:
+        f_t = cfg->elm_pflotran ? c->elm_t : 1.0;
+    }
+    if (cfg->elm_pflotran) {
+      if (sd->decomp_depth_efolding[cur] > 0.0) {
+        f_depth = exp(-c->elm_zsoil / sd->decomp_depth_efolding[cur]);
+        f_depth = fmin(1.0, fmax(1.e-20, f_depth));
+      } else {
+        f_depth = 1.0;
+      }
+      kd_scalar = c->elm_kscalar;
+    } else {
+      f_depth = 1.0;
+      kd_scalar = 1.0;
+    }
+    if (f_t < 1.0e-20 || f_w < 1.0e-20 || f_depth < 1.0e-20) continue;
+
+    if (sd->rate_constant[irxn] >= 0.0) {
+      k_decomp = sd->rate_constant[irxn];
+    } else if (sd->rate_decomposition[irxn] >= 0.0) {
+      k_decomp = 1.0 - exp(-sd->rate_decomposition[irxn] * tran_dt);
+      k_decomp = k_decomp / tran_dt;
+    }
+    k_decomp = sd->rate_ad_factor[irxn] * k_decomp;
+    if (kd_scalar > 0.0 && sd->rate_ad_factor[irxn] > 1.0) k_decomp = k_decomp / kd_scalar;
+    k_decomp = fmin(k_decomp, 1.0 / tran_dt);
+    scaled_crate_const = k_decomp * volume * f_t * f_w * f_depth;
+
+    ispec_uc = sd->upstream_c_id[irxn];
+    if (sd->upstream_is_aqueous[irxn]) {
+      c_uc = c->total[ispec_uc];
+      c_uc = theta * 1000.0 * c_uc;
+    } else {
+      c_uc = c->immobile[ispec_uc];
+    }
+    if (sd->x0eps > 0.0) {
+      hfunction_smooth(c_uc, sd->x0eps * 10.0, sd->x0eps, &feps0, &dfeps0_dx);
+    } else {
+      feps0 = 1.0;
+      dfeps0_dx = 0.0;
+      if (c_uc <= sd->x0eps) continue;
+    }
+    crate_uc = scaled_crate_const * c_uc * feps0;
+    dcrate_uc_duc = scaled_crate_const * (feps0 + c_uc * dfeps0_dx);
+
+    /* scratch: the persisted ratios, then the on-the-fly N:C ratios */
+    w.upstream_nc = c->somdec_nc[irxn];
+    w.mineral_c_stoich = sd->mineral_c_stoich[irxn];
+    w.mineral_n_stoich = sd->mineral_n_stoich[irxn];
+    for (j = 0; j < nd; j++) {
+      int jj = sd->downstream_ptr[irxn] + j;
+      w.downstream_nc[j] = c->somdec_nc[sd->nrxn + jj];
+      if (sd->downstream_n_id[jj] >= 0 && sd->downstream_c_id[jj] >= 0) {
+        double c_dc, c_dn;
+        if (sd->downstream_is_aqueous[jj]) {
+          c_dc = c->total[sd->downstream_c_id[jj]];
+          c_dc = theta * 1000.0 * c_dc;
+          c_dn = c->total[sd->downstream_n_id[jj]];
+          c_dn = theta * 1000.0 * c_dn;
+        } else {
+          c_dc = c->immobile[sd->downstream_c_id[jj]];
+          c_dn = c->immobile[sd->downstream_n_id[jj]];
+        }
+        if (c_dn >= sd->x0eps && c_dc >= sd->x0eps) w.downstream_nc[j] = c_dn / c_dc;
+        c->somdec_nc[sd->nrxn + jj] = w.downstream_nc[j];
+      }
+    }
+    if (sd->upstream_n_id[irxn] >= 0) {
+      double c_un, stoich_c, stoich_n;
+      if (sd->upstream_is_aqueous[irxn]) {
+        c_un = c->total[sd->upstream_n_id[irxn]];
+        c_un = theta * 1000.0 * c_un;
+      } else {
+        c_un = c->immobile[sd->upstream_n_id[irxn]];
+      }
+      if (c_un >= sd->x0eps && c_uc >= sd->x0eps) w.upstream_nc = c_un / c_uc;
+      c->somdec_nc[irxn] = w.upstream_nc;
+      stoich_c = 1.0;
+      for (j = 0; j < nd; j++) stoich_c = stoich_c - sd->downstream_stoich[sd->downstream_ptr[irxn] + j];
+      w.mineral_c_stoich = stoich_c;
+      stoich_n = w.upstream_nc;
+      for (j = 0; j < nd; j++)
+        stoich_n = stoich_n - sd->downstream_stoich[sd->downstream_ptr[irxn] + j] * w.downstream_nc[j];
+      w.mineral_n_stoich = stoich_n;
+    }
+
+    if (w.mineral_n_stoich >= 0.0) {
+      somdec_react1(c, sd, irxn, cur, &w, crate_uc, dcrate_uc_duc, &nmin, Residual, Jacobian, compute_derivative);
+      net_nmin_rate = net_nmin_rate + nmin;
+    } else {
+      somdec_react2(c, sd, irxn, cur, &w, tran_dt, crate_uc, dcrate_uc_duc, &nimm, Residual, Jacobian,
+                    compute_derivative);
+      net_nmin_rate = net_nmin_rate + nimm;
+    }
+    cur++;
+  }
+  if (net_nmin_rate > sd->x0eps)
+    somdec_nemission(c, sd, tran_dt, net_nmin_rate, Residual, Jacobian, compute_derivative);
+}
+
+/* reaction_sandbox_nitrif.F90:234-502  NitrifReact */
+static void nitrif_react(cell_t *c, const pfrx_config *cfg, double *Residual, double *Jacobian,
+                         int compute_derivative) {
+  const pfrx_nitrif *nt = cfg->nitrif;
+  const double rpi = 3.14159265358979323846;
+  const double N_molecular_weight = 14.0067;
+  int off = c->naq, n = c->n;
+  double porosity = c->porosity, volume = c->volume, saturation = c->sat;
+  double theta = saturation * porosity, L_water = theta * 1.0e3, tc = c->temp;
+  int ires_nh4 = nt->nh4_id, ires_no3 = nt->no3_id, ires_n2o = nt->n2o_id;
+  double c_nh4, feps0, dfeps0_dx, rate_nitri, drate_nitri_dnh4, f_t, f_w, f_ph, temp_real, rho_b, M_2_ug_per_g;
+  double c_nh4_ugg, rate_n2o, drate_n2o_dnh4, ph;
+  c_nh4 = c->total[nt->nh4_id] * L_water;
+  if (nt->x0eps > 0.0) {
+    hfunction_smooth(c_nh4, nt->x0eps * 10.0, nt->x0eps, &feps0, &dfeps0_dx);
+  } else {
+    feps0 = 1.0;
+    dfeps0_dx = 0.0;
+    if (c_nh4 < nt->x0eps) return;
+  }
+  if (nt->nh4_id >= 0 && nt->no3_id >= 0) {
+    f_t = exp(0.08 * (tc - 25.0));
+    saturation = fmax(0.0, fmin(saturation, 1.0));
+    f_w = saturation * (1.0 - saturation) / 0.25;
+    temp_real = fmin(nt->k_nitr_max * f_t * f_w * volume, 1.0);
+    rate_nitri = temp_real * (c_nh4 * feps0) * (c_nh4 / (c_nh4 + 4.0));
+    Residual[ires_nh4] = Residual[ires_nh4] + rate_nitri;
+    Residual[ires_no3] = Residual[ires_no3] - rate_nitri;
+    if (compute_derivative) {
+      temp_real = c_nh4 * c_nh4 / (c_nh4 + 4.0) * dfeps0_dx +
+                  c_nh4 * (c_nh4 + 8.0) / (c_nh4 + 4.0) / (c_nh4 + 4.0) * feps0;
+      drate_nitri_dnh4 = nt->k_nitr_max * f_t * f_w * volume * temp_real;
+      JAC(ires_nh4, ires_nh4) = JAC(ires_nh4, ires_nh4) + drate_nitri_dnh4 * DTOT(nt->nh4_id, nt->nh4_id);
+      JAC(ires_no3, ires_nh4) = JAC(ires_no3, ires_nh4) - drate_nitri_dnh4 * DTOT(nt->no3_id, nt->nh4_id);
+    }
+  }
+  rho_b = cfg->elm_pflotran ? c->elm_bd_dry : 1.25e3;
+  temp_real = N_molecular_weight * 1.0e6;
+  M_2_ug_per_g = temp_real / (volume * rho_b * 1.e3);
+  c_nh4_ugg = c_nh4 * volume * M_2_ug_per_g;
+  if (nt->n2o_id >= 0 && c_nh4_ugg > 3.0) {
+    f_t = -0.06 + 0.13 * exp(0.07 * tc);
+    f_w = pow((1.27 - saturation) / 0.67, 3.1777) * pow((saturation - 0.0012) / 0.5988, 2.84);
+    ph = 6.5;
+    if (nt->proton_id >= 0) ph = -log10(c->pri_molal[nt->proton_id] * c->pri_act_coef[nt->proton_id]);
+    f_ph = 0.56 + atan(rpi * 0.45 * (-5.0 + ph)) / rpi;
+    if (f_t > 0.0 && f_w > 0.0 && f_ph > 0.0) {
+      f_t = fmin(f_t, 1.0);
+      f_w = fmin(f_w, 1.0);
+      f_ph = fmin(f_ph, 1.0);
+      temp_real = (1.0 - exp(-0.0105 * c_nh4_ugg)) * f_t * f_w * f_ph * nt->k_nitr_n2o;
+      rate_n2o = temp_real * (c_nh4 * feps0) * volume;
+      Residual[ires_nh4] = Residual[ires_nh4] + rate_n2o;
+      Residual[ires_n2o] = Residual[ires_n2o] - 0.5 * rate_n2o;
+      if (nt->ngasnit_id >= 0) Residual[off + nt->ngasnit_id] = Residual[off + nt->ngasnit_id] - rate_n2o;
+      if (compute_derivative) {
+        temp_real = (c_nh4 * dfeps0_dx + feps0) * (1.0 - exp(-0.0105 * c_nh4_ugg));
+        temp_real = temp_real + (c_nh4 * feps0) * 0.0105 * M_2_ug_per_g * exp(-0.0105 * c_nh4_ugg);
+        drate_n2o_dnh4 = temp_real * nt->k_nitr_n2o * f_t * f_w * f_ph * volume;
+        JAC(ires_nh4, ires_nh4) = JAC(ires_nh4, ires_nh4) + drate_n2o_dnh4 * DTOT(nt->nh4_id, nt->nh4_id);
+        JAC(ires_n2o, ires_nh4) = JAC(ires_n2o, ires_nh4) - 0.5 * drate_n2o_dnh4 * DTOT(nt->n2o_id, nt->nh4_id);
+        if (nt->ngasnit_id >= 0)
+          JAC(off + nt->ngasnit_id, ires_nh4) = JAC(off + nt->ngasnit_id, ires_nh4) - drate_n2o_dnh4;
+      }
+    }
+  }
+}
+
+/* reaction_sandbox_denitr.F90:212-404  DenitrReact */
+static void denitr_react(cell_t *c, const pfrx_config *cfg, double *Residual, double *Jacobian,
+                         int compute_derivative) {
+  const pfrx_denitr *dn = cfg->denitr;
+  int off = c->naq, n = c->n;
+  double porosity = c->porosity, volume = c->volume, saturation = c->sat, tc = c->temp;
+  double L_water = porosity * saturation * 1.e3;
+  int ires_no3 = dn->no3_id, ires_n2 = dn->n2_id;
+  double temp_real, f_t, s_min, f_w, c_no3, feps0, dfeps0_dx, fno3, dfno3_dno3, rate_deni, drate_deni_dno3;
+  if (dn->n2_id < 0) return;
+  temp_real = cfg->elm_pflotran ? c->elm_bsw : 1.0;
+  f_t = exp(0.08 * (tc - 25.0));
+  s_min = 0.6;
+  f_w = 0.0;
+  if (saturation > s_min) {
+    f_w = (saturation - s_min) / (1.0 - s_min);
+    f_w = pow(f_w, temp_real);
+  }
+  c_no3 = c->total[ires_no3] * L_water;
+  if (dn->x0eps > 0.0) {
+    hfunction_smooth(c_no3, dn->x0eps * 10.0, dn->x0eps, &feps0, &dfeps0_dx);
+  } else {
+    feps0 = 1.0;
+    dfeps0_dx = 0.0;
+    if (c_no3 <= dn->x0eps) return;
+  }
+  if (dn->half_saturation > 0.0) {
+    fno3 = func_monod(c_no3, dn->half_saturation, 0);
+    dfno3_dno3 = func_monod(c_no3, dn->half_saturation, 1);
+  } else {
+    fno3 = 1.0;
+    dfno3_dno3 = 0.0;
+  }
+  if (f_t > 0.0 && f_w > 0.0) {
+    rate_deni = dn->k_deni_max * f_t * f_w * fno3 * (c_no3 * volume * feps0);
+    Residual[ires_no3] = Residual[ires_no3] + rate_deni;
+    Residual[ires_n2] = Residual[ires_n2] - 0.5 * rate_deni;
+    if (dn->ngasdeni_id >= 0) Residual[off + dn->ngasdeni_id] = Residual[off + dn->ngasdeni_id] - rate_deni;
+    if (compute_derivative) {
+      temp_real = dfno3_dno3 * (c_no3 * volume * feps0) + fno3 * (c_no3 * volume * dfeps0_dx + feps0);
+      drate_deni_dno3 = dn->k_deni_max * f_t * f_w * temp_real;
+      JAC(ires_no3, ires_no3) = JAC(ires_no3, ires_no3) + drate_deni_dno3 * DTOT(dn->no3_id, dn->no3_id);
+      JAC(ires_n2, ires_no3) = JAC(ires_n2, ires_no3) - 0.5 * drate_deni_dno3 * DTOT(dn->n2_id, dn->no3_id);
+      if (dn->ngasdeni_id >= 0)
+        JAC(off + dn->ngasdeni_id, ires_no3) = JAC(off + dn->ngasdeni_id, ires_no3) - drate_deni_dno3;
+    }
+  }
+}
+#undef SD_RES
+#undef JAC
+#undef DTOT
+
+static int n_sandboxes(const pfrx_config *cfg) {
+  return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL);
+}
+
+/* reaction_sandbox.F90:294-330  RSandboxEvaluate: walk the list in deck order */
+static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
+                               int derivative) {
+  static const int32_t default_order[4] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
+                                           PFRX_SANDBOX_DENITR};
+  const int32_t *order = cfg->sandbox_list ? cfg->sandbox_list : default_order;
+  int ns = cfg->sandbox_list ? cfg->nsandbox : 4, k;
+  for (k = 0; k < ns; k++) {
+    switch (order[k]) {
+      case PFRX_SANDBOX_CLM_CN:
+        if (cfg->clmcn_nrxn > 0) clm_cn_react(c, cfg, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_SOMDEC:
+        if (cfg->somdec) somdec_react(c, cfg, tran_dt, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_NITRIF:
+        if (cfg->nitrif) nitrif_react(c, cfg, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_DENITR:
+        if (cfg->denitr) denitr_react(c, cfg, Res, Jac, derivative);
+        break;
+      default:
+        break;
+    }
+  }
+}
+
 /* reaction.F90:4059-4130  RReaction (dispatch order preserved) */
 static void r_reaction(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac, int derivative) {
   if (c->sat < cfg->rt_min_saturation) return;
   if (c->nkin > 0) r_kinetic_mineral(c, cfg, Res, Jac, derivative);
   if (cfg->nkinmrsrfcplxrxn > 0) r_multirate_sorption(c, cfg, tran_dt, Res, Jac, derivative);
-  if (cfg->clmcn_nrxn > 0) clm_cn_react(c, cfg, Res, Jac, derivative);
+  if (n_sandboxes(cfg) > 0) r_sandbox_evaluate(c, cfg, tran_dt, Res, Jac, derivative);
 }
 
 /* reaction.F90:5457-5516  RSolve -- WITH back-substitution */
@@ -1223,7 +2150,7 @@ static int r_update_kinetic_state(cell_t *c, const pfrx_config *cfg, double tran
         S[i] = (S[i] + kdt * cfg->kinmr_frac[irate] * c->kinmr_total_sorb[base + i]) / one_plus_kdt;
     }
   }
-  if (cfg->clmcn_nrxn > 0) kinetic_state_updated = 1; /* any sandbox => true, reaction.F90:5965 */
+  if (n_sandboxes(cfg) > 0) kinetic_state_updated = 1; /* any sandbox => true, reaction.F90:5965 */
   return kinetic_state_updated;
 }
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 1
+PFRX_ABI_VERSION = 2
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -114,7 +114,51 @@ class PfrxConfig(C.Structure):
         ("clmcn_rate_constant", c_double_p),
         ("clmcn_respiration_fraction", c_double_p),
         ("clmcn_inhibition_constant", c_double_p),
+        ("somdec", C.c_void_p),
+        ("nitrif", C.c_void_p),
+        ("denitr", C.c_void_p),
+        ("nsandbox", C.c_int32),
+        ("sandbox_list", c_int32_p),
+        ("elm_pflotran", C.c_int32),
     ]
+
+
+SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR = 1, 2, 3, 4
+SPEC_AQUEOUS, SPEC_IMMOBILE = 0, 2
+
+
+class PfrxSomdec(C.Structure):
+    _fields_ = (
+        [(f, C.c_int32) for f in (
+            "nrxn", "co2_id", "co2_itype", "o2_id", "o2_itype", "nh4_id", "no3_id", "n2o_id", "proton_id",
+            "hr_id", "nmin_id", "nimm_id", "nimp_id", "ngasmin_id")]
+        + [(f, C.c_double) for f in ("x0eps", "n2o_frac_mineralization", "inhibition_nh4_no3")]
+        + [(f, c_double_p) for f in ("rate_constant", "rate_decomposition", "rate_ad_factor")]
+        + [(f, c_int32_p) for f in ("upstream_c_id", "upstream_n_id", "upstream_is_aqueous", "upstream_hr_id",
+                                    "upstream_nmin_id", "upstream_nimp_id", "upstream_nimm_id")]
+        + [(f, c_double_p) for f in ("upstream_nc", "mineral_c_stoich", "mineral_n_stoich")]
+        + [(f, c_int32_p) for f in ("downstream_ptr", "downstream_c_id", "downstream_n_id",
+                                    "downstream_is_aqueous")]
+        + [(f, c_double_p) for f in ("downstream_stoich", "downstream_nc")]
+        + [(f, c_int32_p) for f in ("temperature_response_function", "moisture_response_function",
+                                    "ox_response_function")]
+        + [(f, c_double_p) for f in ("q10", "ea", "ox_half_saturation", "decomp_depth_efolding")]
+        + [(f, c_int32_p) for f in ("ox_specid", "ox_specitype")]
+        + [(f, c_int32_p) for f in ("monod_ptr", "monod_specid", "monod_specitype", "monod_pool_normalized")]
+        + [(f, c_double_p) for f in ("monod_half_saturation", "monod_threshold")]
+        + [(f, c_int32_p) for f in ("inhib_ptr", "inhib_itype", "inhib_specid", "inhib_specitype")]
+        + [(f, c_double_p) for f in ("inhib_constant", "inhib_constant2")]
+    )
+
+
+class PfrxNitrif(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("proton_id", "nh4_id", "no3_id", "n2o_id", "ngasnit_id")]
+                + [(f, C.c_double) for f in ("k_nitr_max", "k_nitr_n2o", "x0eps")])
+
+
+class PfrxDenitr(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
+                + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])
 
 
 STATE_DOUBLE_FIELDS = [
@@ -123,12 +167,16 @@ STATE_DOUBLE_FIELDS = [
     "total_sorb_eq", "kinmr_total_sorb", "den_kg", "sat", "temp", "porosity", "volume",
     "soil_particle_density",
 ]
+# ELM per-cell scalars (pfrx_state.elm_*): present when the configuration sets
+# elm_pflotran, NULL otherwise
+STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
+                    "elm_bulkdensity_dry", "elm_bsw", "somdec_nc"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
     "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
     "mnrl_volfrac", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "total_sorb_eq",
-    "kinmr_total_sorb",
+    "kinmr_total_sorb", "somdec_nc",
 ]
 STATE_RESULT_FIELDS = ["num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 
@@ -137,7 +185,9 @@ class PfrxState(C.Structure):
     _fields_ = (
         [("ld", C.c_int64)]
         + [(f, c_double_p) for f in STATE_DOUBLE_FIELDS]
-        + [(f, c_int32_p) for f in STATE_INT_FIELDS]
+        + [("imat", c_int32_p)]
+        + [(f, c_double_p) for f in STATE_ELM_FIELDS]
+        + [(f, c_int32_p) for f in STATE_INT_FIELDS if f != "imat"]
     )
 
 
@@ -372,6 +422,45 @@ class ReactionConfig:
             c.clmcn_respiration_fraction = _dp(self._keep("clmcn_respiration_fraction", _f64(cc["resp"])))
             c.clmcn_inhibition_constant = _dp(self._keep("clmcn_inhibition_constant", _f64(cc["inhib"])))
 
+        self._sandboxes()
+
+    def _sandboxes(self) -> None:
+        """SOMDECOMP / NITRIFICATION / DENITRIFICATION tables (pfrx_somdec etc.)"""
+        net, c = self.net, self.c
+        order: List[int] = []
+        for kind in getattr(net, "sandbox_order", []):
+            order.append({"CLM-CN": SANDBOX_CLM_CN, "SOMDECOMP": SANDBOX_SOMDEC, "NITRIFICATION": SANDBOX_NITRIF,
+                          "DENITRIFICATION": SANDBOX_DENITR}[kind])
+        if order:
+            c.nsandbox = len(order)
+            c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
+        c.elm_pflotran = int(getattr(net, "elm_pflotran", False))
+        sd = getattr(net, "somdec", None)
+        if sd is not None:
+            o = PfrxSomdec()
+            for k, v in sd["scalars"].items():
+                setattr(o, k, v)
+            for k, v in sd["int_arrays"].items():
+                setattr(o, k, _ip(self._keep("somdec_" + k, _i32(v))))
+            for k, v in sd["real_arrays"].items():
+                setattr(o, k, _dp(self._keep("somdec_" + k, _f64(v))))
+            self.somdec = o
+            c.somdec = C.cast(C.pointer(o), C.c_void_p)
+        nt = getattr(net, "nitrif", None)
+        if nt is not None:
+            o = PfrxNitrif()
+            for k, v in nt.items():
+                setattr(o, k, v)
+            self.nitrif = o
+            c.nitrif = C.cast(C.pointer(o), C.c_void_p)
+        dn = getattr(net, "denitr", None)
+        if dn is not None:
+            o = PfrxDenitr()
+            for k, v in dn.items():
+                setattr(o, k, v)
+            self.denitr = o
+            c.denitr = C.cast(C.pointer(o), C.c_void_p)
+
     # ------------------------------------------------------------------ #
     @property
     def ncomp(self) -> int:
@@ -392,6 +481,9 @@ class ReactionConfig:
             "total_sorb_eq": c.naqcomp if c.neqsrfcplxrxn > 0 else 0,
             "kinmr_total_sorb": mr_rows,
             "den_kg": 1, "sat": 1, "temp": 1, "porosity": 1, "volume": 1, "soil_particle_density": 1,
+            **{f: (1 if c.elm_pflotran else 0) for f in STATE_ELM_FIELDS},
+            "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
+                          if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,
         }
 
@@ -404,7 +496,7 @@ class HostState:
         self.ncell = int(ncell)
         self.a: Dict[str, np.ndarray] = {}
         rows = cfg.field_rows()
-        for f in STATE_DOUBLE_FIELDS:
+        for f in STATE_DOUBLE_FIELDS + STATE_ELM_FIELDS:
             self.a[f] = np.zeros((rows[f], self.ncell), dtype=np.float64)
         for f in STATE_INT_FIELDS:
             self.a[f] = np.zeros((rows[f], self.ncell), dtype=np.int32)
@@ -419,6 +511,13 @@ class HostState:
         self.a["soil_particle_density"][:] = 2650.0
         self.a["imat"][:] = 1
         self.a["srfcplxrxn_free_site_conc"][:] = 1.0e-9
+        for f in ("elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_kscalar_decomp_c", "elm_bsw"):
+            self.a[f][:] = 1.0
+        self.a["elm_bulkdensity_dry"][:] = 1.25e3
+        if rows["somdec_nc"]:
+            nc0 = np.concatenate([cfg.arrays["somdec_upstream_nc"],
+                                  cfg.arrays.get("somdec_downstream_nc", np.zeros(0))])
+            self.a["somdec_nc"][:] = nc0[:, None]
 
     def __getitem__(self, k: str) -> np.ndarray:
         return self.a[k]
@@ -432,7 +531,7 @@ class HostState:
     def struct(self) -> PfrxState:
         s = PfrxState()
         s.ld = self.ncell
-        for f in STATE_DOUBLE_FIELDS:
+        for f in STATE_DOUBLE_FIELDS + STATE_ELM_FIELDS:
             setattr(s, f, _dp(self.a[f]))
         for f in STATE_INT_FIELDS:
             setattr(s, f, _ip(self.a[f]))

@@ -325,6 +325,19 @@ class ClmCnSandbox:
 
 
 @dataclass
+class SomDecSandbox:
+    """SOMDECOMP block as read (SomDecRead, reaction_sandbox_somdec.F90:350-830)"""
+    pools: List[Tuple[str, Optional[float]]] = field(default_factory=list)   # (name, N:C mol or None)
+    reactions: List[dict] = field(default_factory=list)
+    abiotic: dict = field(default_factory=dict)
+    o2_species: str = ""
+    co2_species: str = ""
+    x0eps: float = 1.0e-20
+    inhibition_nh4_no3: float = 1.0
+    n2o_frac_mineralization: float = 0.02
+
+
+@dataclass
 class Chemistry:
     primary: List[str] = field(default_factory=list)
     secondary: List[str] = field(default_factory=list)
@@ -335,6 +348,10 @@ class Chemistry:
     mineral_kinetics: List[MineralKinetics] = field(default_factory=list)
     srfcplx_rxns: List[SrfCplxRxn] = field(default_factory=list)
     clm_cn: Optional[ClmCnSandbox] = None
+    somdec: Optional[SomDecSandbox] = None
+    nitrif: Optional[dict] = None
+    denitr: Optional[dict] = None
+    sandbox_order: List[str] = field(default_factory=list)
     database: str = ""
     use_log_formulation: bool = False
     act_coef_update_frequency: int = ACT_COEF_FREQUENCY_OFF
@@ -504,6 +521,189 @@ def _read_clm_cn(cur: _Cursor) -> ClmCnSandbox:
     return sb
 
 
+# elm_rspfuncs.F90:17-47
+TEMPERATURE_RESPONSE = {"OFF": 0, "CLMCN": 1, "Q10": 2, "DLEM": 3, "ARRHENIUS": 4}
+MOISTURE_RESPONSE = {"OFF": 0, "CLMCN": 1, "DLEM": 2, "LOGTHETA": 3}
+OX_RESPONSE = {"OFF": 0, "MONOD": 1, "WFPS": 2}
+INHIBITION_TYPE = {"THRESHOLD": 1, "MONOD": 3, "INVERSE_MONOD": 4}
+CN_RATIO_MASS_TO_MOL = 1.166156023644992  # elm_rspfuncs.F90:36
+
+
+def _default_abiotic() -> dict:
+    # AbioticFactorsCreate, reaction_sandbox_somdec.F90:239-262
+    return {"temperature": 0, "moisture": 0, "q10": 1.5, "ea": 51.7, "ox": 0, "ox_half_saturation": 1.0e-15,
+            "depth_efolding": 0.0}
+
+
+def _read_abiotic_factors(cur: _Cursor, ab: dict) -> None:
+    # SomDecRead_AbioticFactors, reaction_sandbox_somdec.F90:834-983
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "TEMPERATURE_RESPONSE_FUNCTION":
+            for u in cur.block():
+                k2 = u[0].upper()
+                ab["temperature"] = TEMPERATURE_RESPONSE.get(k2, 0)
+                if k2 in ("DLEM", "Q10"):
+                    ab["q10"] = _fnum(u[1])
+                elif k2 == "ARRHENIUS":
+                    ab["ea"] = _fnum(u[1])
+        elif key == "MOISTURE_RESPONSE_FUNCTION":
+            for u in cur.block():
+                ab["moisture"] = MOISTURE_RESPONSE.get(u[0].upper(), 0)
+        elif key == "OX_RESPONSE_FUNCTION":
+            for u in cur.block():
+                k2 = u[0].upper()
+                ab["ox"] = OX_RESPONSE.get(k2, 0)
+                if k2 == "MONOD":
+                    ab["ox_half_saturation"] = _fnum(u[1])
+        elif key == "DECOMP_DEPTH_EFOLDING":
+            ab["depth_efolding"] = _fnum(t[1])
+        else:
+            raise ValueError(f"SOMDECOMP ABIOTIC_FACTORS keyword {key}")
+
+
+def _rate_per_sec(value: float, unit: Optional[str]) -> float:
+    """'x unitless/d', '1/s' ... -> 1/s (UnitsConvertToInternal on the time part)"""
+    if not unit:
+        return value
+    return value / time_to_sec(1.0, unit.split("/")[-1])
+
+
+def _read_somdec(cur: _Cursor) -> SomDecSandbox:
+    sb = SomDecSandbox()
+    sb.abiotic = _default_abiotic()
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "O2_SPECIES_NAME":
+            sb.o2_species = t[1]
+        elif key == "CO2_SPECIES_NAME":
+            sb.co2_species = t[1]
+        elif key == "ABIOTIC_FACTORS":
+            _read_abiotic_factors(cur, sb.abiotic)
+        elif key == "X0EPS":
+            sb.x0eps = _fnum(t[1])
+        elif key == "AMMONIUM_INHIBITION_NITRATE":
+            sb.inhibition_nh4_no3 = _fnum(t[1])
+        elif key == "N2O_FRAC_MINERALIZATION":
+            sb.n2o_frac_mineralization = _fnum(t[1])
+        elif key == "POOLS":
+            for u in cur.block():
+                if len(u) > 1 and _is_num(u[1]) and _fnum(u[1]) > 0.0:
+                    sb.pools.append((u[0], 1.0 / _fnum(u[1]) / CN_RATIO_MASS_TO_MOL))
+                else:
+                    sb.pools.append((u[0], None))
+        elif key == "REACTION":
+            rx = {"up": "", "down": [], "rate_constant": -1.0, "turnover": -1.0, "rate_decomposition": -1.0,
+                  "rate_ad_factor": 1.0, "monod": [], "inhibition": [], "abiotic": None, "ox_species": "",
+                  "cox_species": ""}
+            for u in cur.block():
+                k2 = u[0].upper()
+                if k2 == "UPSTREAM_POOL":
+                    rx["up"] = u[1]
+                elif k2 == "DOWNSTREAM_POOL":
+                    rx["down"].append((u[1], _fnum(u[2])))
+                elif k2 == "RATE_CONSTANT":
+                    rx["rate_constant"] = _rate_per_sec(_fnum(u[1]), u[2] if len(u) > 2 else None)
+                elif k2 == "TURNOVER_TIME":
+                    rx["turnover"] = time_to_sec(_fnum(u[1]), u[2]) if len(u) > 2 else _fnum(u[1])
+                elif k2 == "RATE_DECOMPOSITION":
+                    rx["rate_decomposition"] = _rate_per_sec(_fnum(u[1]), u[2] if len(u) > 2 else None)
+                elif k2 == "RATE_AD_FACTOR":
+                    rx["rate_ad_factor"] = _fnum(u[1])
+                elif k2 == "MONOD":
+                    m = {"species": "", "half_saturation": 1.0e-15, "threshold": 0.0, "pool_normalized": 0}
+                    for v in cur.block():
+                        k3 = v[0].upper()
+                        if k3 == "SPECIES_NAME":
+                            m["species"] = v[1]
+                        elif k3 == "HALF_SATURATION_CONSTANT":
+                            m["half_saturation"] = _fnum(v[1])
+                        elif k3 == "THRESHOLD_CONCENTRATION":
+                            m["threshold"] = _fnum(v[1])
+                        elif k3 == "POOL_NORMALIZED":
+                            m["pool_normalized"] = 1
+                        else:
+                            raise ValueError(f"SOMDECOMP MONOD keyword {k3}")
+                    rx["monod"].append(m)
+                elif k2 == "INHIBITION":
+                    ih = {"species": "", "itype": -999, "constant": 1.0e-15, "constant2": 0.0}
+                    for v in cur.block():
+                        k3 = v[0].upper()
+                        if k3 == "SPECIES_NAME":
+                            ih["species"] = v[1]
+                        elif k3 == "TYPE":
+                            ih["itype"] = INHIBITION_TYPE[v[1].upper()]
+                            if v[1].upper() == "THRESHOLD":
+                                ih["constant2"] = _fnum(v[2])
+                        elif k3 == "INHIBITION_CONSTANT":
+                            ih["constant"] = _fnum(v[1])
+                        else:
+                            raise ValueError(f"SOMDECOMP INHIBITION keyword {k3}")
+                    rx["inhibition"].append(ih)
+                elif k2 == "ABIOTIC_FACTORS":
+                    rx["abiotic"] = _default_abiotic()
+                    _read_abiotic_factors(cur, rx["abiotic"])
+                elif k2 == "OX_SPECIES_NAME":
+                    rx["ox_species"] = u[1]
+                elif k2 == "COX_SPECIES_NAME":
+                    rx["cox_species"] = u[1]
+                else:
+                    raise ValueError(f"SOMDECOMP REACTION keyword {k2}")
+            nset = sum(1 for k in ("turnover", "rate_constant", "rate_decomposition") if rx[k] > 0.0)
+            if nset != 1:
+                raise ValueError("exactly one of TURNOVER_TIME / RATE_CONSTANT / RATE_DECOMPOSITION per SOMDECOMP reaction")
+            if rx["turnover"] > 0.0:
+                rx["rate_constant"] = 1.0 / rx["turnover"]
+            sb.reactions.append(rx)
+        else:
+            raise ValueError(f"SOMDECOMP keyword {key}")
+    # reactions without their own block copy the sandbox-wide factors as they
+    # stand when the reaction is read (reaction_sandbox_somdec.F90:783-788);
+    # decks put ABIOTIC_FACTORS first, so the final values are the same
+    for rx in sb.reactions:
+        if rx["abiotic"] is None:
+            rx["abiotic"] = dict(sb.abiotic)
+    return sb
+
+
+def _read_nitrif(cur: _Cursor) -> dict:
+    # NitrifCreate/NitrifRead, reaction_sandbox_nitrif.F90:58-150
+    d = {"k_nitr_max": 1.0e-6, "k_nitr_n2o": 3.5e-8, "x0eps": 1.0e-20}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "TEMPERATURE_RESPONSE_FUNCTION":
+            cur.skip_block()   # read by the reference but not used by NitrifReact
+        elif key == "X0EPS":
+            d["x0eps"] = _fnum(t[1])
+        elif key == "NITRIFICATION_RATE_COEF":
+            d["k_nitr_max"] = _fnum(t[1])
+        elif key == "N2O_RATE_COEF_NITRIFICATION":
+            d["k_nitr_n2o"] = _fnum(t[1])
+        elif key == "AMMONIUM_HALF_SATURATION":
+            pass               # stored, never used (reaction_sandbox_nitrif.F90:234-502)
+        else:
+            raise ValueError(f"NITRIFICATION keyword {key}")
+    return d
+
+
+def _read_denitr(cur: _Cursor) -> dict:
+    # DenitrCreate/DenitrRead, reaction_sandbox_denitr.F90:38-150
+    d = {"half_saturation": 1.0e-15, "k_deni_max": 2.5e-6, "x0eps": 1.0e-20}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "TEMPERATURE_RESPONSE_FUNCTION":
+            cur.skip_block()   # not used by DenitrReact
+        elif key == "DENITRIFICATION_RATE_COEF":
+            d["k_deni_max"] = _fnum(t[1])
+        elif key == "NITRATE_HALF_SATURATION":
+            d["half_saturation"] = _fnum(t[1])
+        elif key == "X0EPS":
+            d["x0eps"] = _fnum(t[1])
+        else:
+            raise ValueError(f"DENITRIFICATION keyword {key}")
+    return d
+
+
 def read_chemistry(cur: _Cursor) -> Chemistry:
     """CHEMISTRY block (ReactionReadPass1, reaction.F90:121-936)."""
     ch = Chemistry()
@@ -538,6 +738,16 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                 k2 = u[0].upper()
                 if k2 == "CLM-CN":
                     ch.clm_cn = _read_clm_cn(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "SOMDECOMP" and ch.somdec is None:
+                    ch.somdec = _read_somdec(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "NITRIFICATION" and ch.nitrif is None:
+                    ch.nitrif = _read_nitrif(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "DENITRIFICATION" and ch.denitr is None:
+                    ch.denitr = _read_denitr(cur)
+                    ch.sandbox_order.append(k2)
                 else:
                     ch.unsupported.append("REACTION_SANDBOX," + k2)
                     _skip_nested(cur)
@@ -654,6 +864,7 @@ class Deck:
     final_time: float = 0.0
     initial_dt: float = 1.0
     maximum_dt: float = 1.0e20
+    minimum_dt: float = 1.0e-20      # timestepper_base.F90:23 default_dt_min
     ts_acceleration: int = 5
     newton: Dict[str, float] = field(default_factory=dict)
     osrt: bool = False
@@ -690,6 +901,8 @@ def read_deck(text: str) -> Deck:
             dk.initial_dt = time_to_sec(_fnum(t[1]), t[2])
         elif key == "MAXIMUM_TIMESTEP_SIZE" and len(t) == 3:
             dk.maximum_dt = time_to_sec(_fnum(t[1]), t[2])
+        elif key == "MINIMUM_TIMESTEP_SIZE" and len(t) == 3:
+            dk.minimum_dt = time_to_sec(_fnum(t[1]), t[2])
         elif key == "NUMERICAL_METHODS":
             in_transport_nm = len(t) > 1 and t[1].upper() == "TRANSPORT"
         elif key == "MAX_STEPS" and in_transport_nm:
@@ -775,6 +988,10 @@ class ReactionNetwork:
         self._minerals()
         self._surface_complexation()
         self._clm_cn()
+        self.sandbox_order = list(chem.sandbox_order)
+        self.elm_pflotran = False
+        self._somdec()
+        self._nitrif_denitr()
 
     # -- temperature handling (reaction_database.F90:1025-1050) ------------- #
     def _itemp(self):
@@ -981,6 +1198,173 @@ class ReactionNetwork:
             resp=np.array([r["resp"] for r in sb.reactions], dtype=np.float64),
             inhib=np.array([r["inhib"] for r in sb.reactions], dtype=np.float64),
         )
+
+    # -- SOMDECOMP (SomDecSetup, reaction_sandbox_somdec.F90:987-1501) -------- #
+    def _species(self, name: str) -> Tuple[int, int]:
+        """SomDec_SpeciesID (:3744-3806): primary first, then immobile; gases are
+        not supported on this path"""
+        if name in self.primary_names:
+            return self.primary_names.index(name), 0
+        if name in self.immobile_names:
+            return self.immobile_names.index(name), 2
+        raise KeyError(f"species {name} is neither a primary nor an immobile species")
+
+    def _somdec(self):
+        sb = self.chem.somdec
+        self.somdec = None
+        if sb is None:
+            return
+        pri = {n: i for i, n in enumerate(self.primary_names)}
+        imm = {n: i for i, n in enumerate(self.immobile_names)}
+        pool = {}
+        for nm, nc in sb.pools:
+            d = {"nc": -999.0 if nc is None else nc, "aq": 0, "c": -1, "n": -1}
+            if nc is None:
+                if nm + "C" in imm:
+                    d["c"], d["n"] = imm[nm + "C"], imm.get(nm + "N", -1)
+                elif nm + "C" in pri:
+                    d["c"], d["n"], d["aq"] = pri[nm + "C"], pri.get(nm + "N", -1), 1
+                if d["c"] < 0 or d["n"] < 0:
+                    raise KeyError(f"SOMDECOMP pool {nm}: species {nm}C / {nm}N not found")
+            else:
+                if nm in imm:
+                    d["c"] = imm[nm]
+                elif nm in pri:
+                    d["c"], d["aq"] = pri[nm], 1
+                else:
+                    raise KeyError(f"SOMDECOMP pool {nm} not found")
+            for tag, key in (("CHR", "hr"), ("NMIN", "nmin"), ("NIMP", "nimp"), ("NIMM", "nimm")):
+                d[key] = imm.get(nm + tag, -1)
+            pool[nm] = d
+        nrxn = len(sb.reactions)
+        I = {k: [] for k in ("upstream_c_id", "upstream_n_id", "upstream_is_aqueous", "upstream_hr_id",
+                             "upstream_nmin_id", "upstream_nimp_id", "upstream_nimm_id", "downstream_ptr",
+                             "downstream_c_id", "downstream_n_id", "downstream_is_aqueous",
+                             "temperature_response_function", "moisture_response_function",
+                             "ox_response_function", "ox_specid", "ox_specitype", "monod_ptr", "monod_specid",
+                             "monod_specitype", "monod_pool_normalized", "inhib_ptr", "inhib_itype",
+                             "inhib_specid", "inhib_specitype")}
+        R = {k: [] for k in ("rate_constant", "rate_decomposition", "rate_ad_factor", "upstream_nc",
+                             "mineral_c_stoich", "mineral_n_stoich", "downstream_stoich", "downstream_nc", "q10",
+                             "ea", "ox_half_saturation", "decomp_depth_efolding", "monod_half_saturation",
+                             "monod_threshold", "inhib_constant", "inhib_constant2")}
+        I["downstream_ptr"].append(0)
+        I["monod_ptr"].append(0)
+        I["inhib_ptr"].append(0)
+        for rx in sb.reactions:
+            up = pool[rx["up"]]
+            I["upstream_c_id"].append(up["c"])
+            I["upstream_n_id"].append(up["n"])
+            I["upstream_is_aqueous"].append(up["aq"])
+            for key in ("hr", "nmin", "nimp", "nimm"):
+                I[f"upstream_{key}_id"].append(up[key])
+            R["upstream_nc"].append(up["nc"])
+            if up["n"] < 0 and up["nc"] < 0.0:
+                raise ValueError("SOMDECOMP upstream pool has a negative C:N ratio")
+            for nm, st in rx["down"]:
+                dn = pool[nm]
+                I["downstream_c_id"].append(dn["c"])
+                I["downstream_n_id"].append(dn["n"])
+                I["downstream_is_aqueous"].append(dn["aq"])
+                R["downstream_stoich"].append(st)
+                R["downstream_nc"].append(dn["nc"])
+            I["downstream_ptr"].append(len(I["downstream_c_id"]))
+            if rx["rate_constant"] > 0.0:
+                R["rate_constant"].append(rx["rate_constant"])
+                R["rate_decomposition"].append(-1.0)
+            else:
+                R["rate_constant"].append(-1.0)
+                R["rate_decomposition"].append(rx["rate_decomposition"])
+            R["rate_ad_factor"].append(rx["rate_ad_factor"])
+            # fixed C:N reactions: stoichiometry at set-up (:1395-1425)
+            if up["n"] >= 0:
+                R["mineral_c_stoich"].append(0.0)
+                R["mineral_n_stoich"].append(0.0)
+            else:
+                sc, sn = 1.0, up["nc"]
+                for nm, st in rx["down"]:
+                    sc = sc - st
+                    sn = sn - st * pool[nm]["nc"]
+                if abs(sc) < 1.0e-15:
+                    sc = 0.0
+                if abs(sn) < 1.0e-15:
+                    sn = 0.0
+                if sc < 0.0 or sn < 0.0:
+                    raise ValueError("SOMDECOMP fixed-C:N reaction with negative respiration or N mineralisation")
+                R["mineral_c_stoich"].append(sc)
+                R["mineral_n_stoich"].append(sn)
+            ab = rx["abiotic"]
+            I["temperature_response_function"].append(ab["temperature"])
+            I["moisture_response_function"].append(ab["moisture"])
+            I["ox_response_function"].append(ab["ox"])
+            R["q10"].append(ab["q10"])
+            R["ea"].append(ab["ea"])
+            R["ox_half_saturation"].append(ab["ox_half_saturation"])
+            R["decomp_depth_efolding"].append(ab["depth_efolding"])
+            if rx["ox_species"]:
+                sid, st = self._species(rx["ox_species"])
+            else:
+                sid, st = -1, -1
+            I["ox_specid"].append(sid)
+            I["ox_specitype"].append(st)
+            for m in rx["monod"]:
+                sid, st = self._species(m["species"])
+                I["monod_specid"].append(sid)
+                I["monod_specitype"].append(st)
+                I["monod_pool_normalized"].append(m["pool_normalized"])
+                R["monod_half_saturation"].append(m["half_saturation"])
+                R["monod_threshold"].append(m["threshold"])
+            I["monod_ptr"].append(len(I["monod_specid"]))
+            for ih in rx["inhibition"]:
+                sid, st = self._species(ih["species"])
+                I["inhib_itype"].append(ih["itype"])
+                I["inhib_specid"].append(sid)
+                I["inhib_specitype"].append(st)
+                R["inhib_constant"].append(ih["constant"])
+                R["inhib_constant2"].append(ih["constant2"])
+            I["inhib_ptr"].append(len(I["inhib_specid"]))
+        # CO2 species (:1437-1472)
+        if sb.co2_species:
+            co2_id, co2_itype = self._species(sb.co2_species)
+        else:
+            co2_itype = 0
+            for nm in ("CO2(g)*", "CO2(aq)", "HCO3-"):
+                if nm in pri:
+                    co2_id = pri[nm]
+                    break
+            else:
+                raise KeyError("SOMDECOMP: none of CO2(g)*, CO2(aq), HCO3- is a primary species")
+        o2_id, o2_itype = self._species(sb.o2_species) if sb.o2_species else (-1, -1)
+        scal = dict(nrxn=nrxn, co2_id=co2_id, co2_itype=co2_itype, o2_id=o2_id, o2_itype=o2_itype,
+                    nh4_id=pri.get("NH4+", -1), no3_id=pri.get("NO3-", -1), n2o_id=pri.get("N2O(aq)", -1),
+                    proton_id=pri.get("H+", -1), hr_id=imm.get("HRimm", -1), nmin_id=imm.get("Nmin", -1),
+                    nimm_id=imm.get("Nimm", -1), nimp_id=imm.get("Nimp", -1), ngasmin_id=imm.get("NGASmin", -1),
+                    x0eps=sb.x0eps, n2o_frac_mineralization=sb.n2o_frac_mineralization,
+                    inhibition_nh4_no3=sb.inhibition_nh4_no3)
+        self.somdec = {"scalars": scal, "int_arrays": I, "real_arrays": R}
+
+    def _nitrif_denitr(self):
+        pri = {n: i for i, n in enumerate(self.primary_names)}
+        imm = {n: i for i, n in enumerate(self.immobile_names)}
+        self.nitrif = self.denitr = None
+        if self.chem.nitrif is not None:
+            # NitrifSetup, reaction_sandbox_nitrif.F90:160-232
+            d = dict(self.chem.nitrif)
+            for nm, key in (("H+", "proton_id"), ("NH4+", "nh4_id"), ("NO3-", "no3_id"), ("N2O(aq)", "n2o_id")):
+                d[key] = pri.get(nm, -1)
+            if d["nh4_id"] < 0:
+                raise KeyError("NITRIFICATION needs NH4+ as a primary species")
+            d["ngasnit_id"] = imm.get("NGASnitr", -1)
+            self.nitrif = d
+        if self.chem.denitr is not None:
+            # DenitrSetup, reaction_sandbox_denitr.F90:152-210
+            d = dict(self.chem.denitr)
+            for nm, key in (("NO3-", "no3_id"), ("N2(aq)", "n2_id"), ("N2O(aq)", "n2o_id")):
+                d[key] = pri.get(nm, -1)
+            if d["no3_id"] < 0:
+                raise KeyError("DENITRIFICATION needs NO3- as a primary species")
+            d["ngasdeni_id"] = imm.get("NGASdeni", -1)
+            self.denitr = d
 
     # -- helpers -------------------------------------------------------------- #
     def csr(self, rxns: Sequence[Rxn]):

@@ -94,7 +94,7 @@ class DeviceState:
         self.device = torch.device(device)
         rows = cfg.field_rows()
         self.t: Dict[str, "torch.Tensor"] = {}
-        for f in abi.STATE_DOUBLE_FIELDS:
+        for f in abi.STATE_DOUBLE_FIELDS + abi.STATE_ELM_FIELDS:
             self.t[f] = torch.zeros((rows[f], self.ncell), dtype=torch.float64, device=self.device)
         for f in abi.STATE_INT_FIELDS:
             self.t[f] = torch.zeros((rows[f], self.ncell), dtype=torch.int32, device=self.device)
@@ -130,7 +130,7 @@ class DeviceState:
     def struct(self) -> abi.PfrxState:
         s = abi.PfrxState()
         s.ld = self.ncell
-        for f in abi.STATE_DOUBLE_FIELDS:
+        for f in abi.STATE_DOUBLE_FIELDS + abi.STATE_ELM_FIELDS:
             t = self.t[f]
             setattr(s, f, C.cast(t.data_ptr() if t.numel() else None, abi.c_double_p))
         for f in abi.STATE_INT_FIELDS:

@@ -116,6 +116,7 @@ class GirtBatch:
             else:
                 fac = 0.5
             dt = min(min(2.0 * dt_step, fac * dt_step), dk.maximum_dt)
+            dt = max(dt, dk.minimum_dt)   # pm_rt.F90:780
         return self
 
 

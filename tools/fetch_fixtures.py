@@ -48,6 +48,40 @@ COPY = [
     ("regression_tests/default/column/tracer_os.regression.gold", None),
     ("regression_tests/default/column/tracer_os_no_geochem.regression.gold", None),
     ("shortcourse/1D_Calcite/calcite_tran_only.in", None),
+    # SOMDECOMP sandbox golds (ngee/CLMCNplus, the decks that use SOMDECOMP only)
+    ("regression_tests/ngee/CLMCNplus/clm_lit1.in", "clmcnplus_clm_lit1.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_lit1.regression.gold", "clmcnplus_clm_lit1.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_lit2.in", "clmcnplus_clm_lit2.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_lit2.regression.gold", "clmcnplus_clm_lit2.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_lit3.in", "clmcnplus_clm_lit3.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_lit3.regression.gold", "clmcnplus_clm_lit3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_som1.in", "clmcnplus_clm_som1.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_som1.regression.gold", "clmcnplus_clm_som1.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_som2.in", "clmcnplus_clm_som2.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_som2.regression.gold", "clmcnplus_clm_som2.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_som3.in", "clmcnplus_clm_som3.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_som3.regression.gold", "clmcnplus_clm_som3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_som4.in", "clmcnplus_clm_som4.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_som4.regression.gold", "clmcnplus_clm_som4.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nmin.in", "clmcnplus_clm_nmin.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nmin.regression.gold", "clmcnplus_clm_nmin.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm1.in", "clmcnplus_clm_nimm1.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm1.regression.gold", "clmcnplus_clm_nimm1.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm2.in", "clmcnplus_clm_nimm2.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm2.regression.gold", "clmcnplus_clm_nimm2.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm3.in", "clmcnplus_clm_nimm3.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm3.regression.gold", "clmcnplus_clm_nimm3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm4.in", "clmcnplus_clm_nimm4.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nimm4.regression.gold", "clmcnplus_clm_nimm4.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nmit.in", "clmcnplus_clm_nmit.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nmit.regression.gold", "clmcnplus_clm_nmit.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn1.in", "clmcnplus_clm_cn1.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn1.regression.gold", "clmcnplus_clm_cn1.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn2.in", "clmcnplus_clm_cn2.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn2.regression.gold", "clmcnplus_clm_cn2.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn3.in", "clmcnplus_clm_cn3.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_cn3.regression.gold", "clmcnplus_clm_cn3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/CLM-CN_database.dat", "clmcnplus_CLM-CN_database.dat"),
 ]
 
 
