@@ -441,8 +441,11 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * jac[(i*ncomp + j)*ld + cell] = d res_i / d c_j  (written when want_jacobian).
  * Side effect as in the reference: mnrl_rate of the bound state is updated.
  * Inactive cells (imat <= 0) get zeros; dry cells get zeros (reaction.F90:4085).
+ * tran_dt is option%tran_dt, which the SOMDECOMP sandbox reads (rate caps,
+ * reaction_sandbox_somdec.F90:1762,2853); the aqueous totals the sandboxes
+ * read are pfrx_state.total, d(total)/d(free) is recomputed from the state.
  * Multirate sorption is not covered yet (PFRX_E_INVALID).                     */
-int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, double *jac);
+int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
 /* ---- network-specialised kernels -------------------------------------------
  * The generic kernels read the reaction network from tables, the way the

@@ -49,7 +49,8 @@ def _run(cmd, log):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = [os.path.join(HERE, "pfrx_device.cuh"), os.path.join(HERE, "..", "..", "include", "pfrx.h"),
+    hdrs = [os.path.join(HERE, "pfrx_device.cuh"), os.path.join(HERE, "pfrx_types.cuh"),
+            os.path.join(HERE, "pfrx_sandbox.cuh"), os.path.join(HERE, "..", "..", "include", "pfrx.h"),
             os.path.abspath(__file__)]
     jobs = []
     objs = []

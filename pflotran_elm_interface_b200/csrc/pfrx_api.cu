@@ -127,6 +127,11 @@ static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
 }
 static uint64_t config_signature(const pfrx_config *c) {
   uint64_t h = 0xCBF29CE484222325ull;
+  {
+    // sandboxes the generator does not cover change the signature outright
+    int32_t sb[4] = {c->somdec ? c->somdec->nrxn : 0, c->nitrif ? 1 : 0, c->denitr ? 1 : 0, c->elm_pflotran};
+    if (sb[0] || sb[1] || sb[2]) h = fnv1a(h, sb, sizeof(sb));
+  }
   int32_t head[12] = {c->naqcomp,          c->nimcomp,
                       c->neqcplx,          c->nkinmnrl,
                       c->nsrfcplxrxn,      c->nsrfcplx,
@@ -237,7 +242,7 @@ struct pfrx_handle {
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host
   // batched RReaction (pfrx_reaction): always the thread-per-cell layout
   DevCfg rx_cfg;
-  void (*rx_kernel)(DevCfg, DevState, int64_t, int, double *, double *) = nullptr;
+  void (*rx_kernel)(DevCfg, DevState, int64_t, int, double *, double *, double) = nullptr;
   int rx_threads = 0, rx_blocks_per_sm = 0;
   size_t rx_smem = 0;
   // nccl
@@ -268,7 +273,7 @@ typedef void (*pfrx_kernel_fn)(DevCfg, DevState, int64_t, double, DevSummary *);
 // one getter per padded size N, defined in pfrx_kern.cu (see build.py)
 #define PFRX_DECL(N) extern "C" pfrx_kernel_fn pfrx_kernel_##N(int lanes);
 PFRX_DECL(3) PFRX_DECL(4) PFRX_DECL(8) PFRX_DECL(13) PFRX_DECL(15) PFRX_DECL(16) PFRX_DECL(32)
-typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *);
+typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *, double);
 #define PFRX_DECLR(N) extern "C" pfrx_reaction_fn pfrx_reaction_kernel_##N(void);
 PFRX_DECLR(3) PFRX_DECLR(4) PFRX_DECLR(8) PFRX_DECLR(13) PFRX_DECLR(15) PFRX_DECLR(16) PFRX_DECLR(32)
 struct KernelGetter {
@@ -335,11 +340,17 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
   return PFRX_OK;
 }
 
-static int field_rows(const pfrx_config *c, int *rows /*20*/) {
+// double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
+// scalars and the SOMDECOMP N:C memory
+#define PFRX_NUM_D 28
+static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
-  int r[20] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl, c->nkinmnrl,
-               c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, c->neqsrfcplxrxn > 0 ? c->naqcomp : 0, mr, 1, 1, 1, 1, 1, 1};
+  const int e = c->elm_pflotran ? 1 : 0;
+  const int nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
+  int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
+                       c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, c->neqsrfcplxrxn > 0 ? c->naqcomp : 0,
+                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -382,6 +393,8 @@ static void tpc_layout(DevCfg &d, int N) {
   d.off_mr = take(2 * d.nmr * N + 1);
   d.off_lng = act_upd ? 0 : take(d.ncplx);
   d.off_sec = 0;
+  d.off_dt = d.need_dt ? take(d.naq * d.naq) : 0;
+  d.off_nc = d.n_nc > 0 ? take(d.n_nc) : 0;
   d.ws_stride = off | 1;
 }
 
@@ -479,6 +492,35 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
                      !c->kinmnrl_pref_activation_energy))
       return set_err(PFRX_E_INVALID, "prefactor arrays missing%s", "");
   }
+  // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
+  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr;
+  if (c->somdec) {
+    const pfrx_somdec *sd = c->somdec;
+    if (sd->nrxn < 1 || !sd->downstream_ptr || !sd->monod_ptr || !sd->inhib_ptr || !sd->upstream_c_id)
+      return set_err(PFRX_E_INVALID, "pfrx_somdec tables missing%s", "");
+    auto kind_ok = [](int t) { return t == PFRX_SPEC_AQUEOUS || t == PFRX_SPEC_IMMOBILE; };
+    if (sd->co2_id < 0 || !kind_ok(sd->co2_itype) || (sd->o2_id >= 0 && !kind_ok(sd->o2_itype)))
+      return set_err(PFRX_E_INVALID, "SOMDECOMP: CO2 / O2 must be primary or immobile species (gas not supported)%s", "");
+    if (sd->nh4_id < 0) return set_err(PFRX_E_INVALID, "SOMDECOMP needs NH4+ as a primary species%s", "");
+    for (int k = 0; k < sd->monod_ptr[sd->nrxn]; k++)
+      if (!kind_ok(sd->monod_specitype[k])) return set_err(PFRX_E_INVALID, "SOMDECOMP MONOD on a gas species%s", "");
+    for (int k = 0; k < sd->inhib_ptr[sd->nrxn]; k++)
+      if (!kind_ok(sd->inhib_specitype[k])) return set_err(PFRX_E_INVALID, "SOMDECOMP INHIBITION on a gas species%s", "");
+    for (int r = 0; r < sd->nrxn; r++)
+      if (sd->ox_specid[r] >= 0 && !kind_ok(sd->ox_specitype[r]))
+        return set_err(PFRX_E_INVALID, "SOMDECOMP Ox species must be primary or immobile%s", "");
+    if (c->elm_pflotran)
+      for (int r = 0; r < sd->nrxn; r++)
+        if (sd->moisture_response_function[r] != PFRX_MOISTURE_RESPONSE_OFF)
+          return set_err(PFRX_E_INVALID,
+                         "ELM build with a MOISTURE_RESPONSE_FUNCTION (flow-coupled mode) is not covered%s", "");
+  }
+  if (c->nitrif && c->nitrif->nh4_id < 0) return set_err(PFRX_E_INVALID, "NITRIFICATION needs NH4+%s", "");
+  if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
+  if (c->sandbox_list)
+    for (int k = 0; k < c->nsandbox; k++)
+      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_DENITR || c->nsandbox > 4)
+        return set_err(PFRX_E_INVALID, "bad sandbox_list%s", "");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return set_err(PFRX_E_CUDA, "no such CUDA device%s", "");
@@ -531,14 +573,36 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.cn_nrxn = c->clmcn_nrxn;
   d.cn_C = c->clmcn_C_species_id;
   d.cn_N = c->clmcn_N_species_id;
+  d.has_sd = c->somdec ? 1 : 0;
+  d.has_nt = c->nitrif ? 1 : 0;
+  d.has_dn = c->denitr ? 1 : 0;
+  d.elm = c->elm_pflotran ? 1 : 0;
+  d.need_dt = has_sbx3 ? 1 : 0;
+  d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
+  {
+    static const int def_order[4] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF, PFRX_SANDBOX_DENITR};
+    const int32_t *ord = c->sandbox_list ? c->sandbox_list : def_order;
+    const int no = c->sandbox_list ? c->nsandbox : 4;
+    d.nsbx = 0;
+    for (int k = 0; k < no; k++) {
+      const int kind = ord[k];
+      const bool present = (kind == PFRX_SANDBOX_CLM_CN && c->clmcn_nrxn > 0) ||
+                           (kind == PFRX_SANDBOX_SOMDEC && c->somdec) || (kind == PFRX_SANDBOX_NITRIF && c->nitrif) ||
+                           (kind == PFRX_SANDBOX_DENITR && c->denitr);
+      if (present) d.sbx[d.nsbx++] = kind;
+    }
+  }
+  if (c->nitrif) d.nt = *c->nitrif;
+  if (c->denitr) d.dn = *c->denitr;
 
   // kernel variant first: the task partition depends on the lane count
   {
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
-    if (!rc0 && (has_pref || act_newton) && !h->tpc) {
-      // mineral prefactors and the iterated ionic strength live in the thread-per-cell kernel only
+    if (!rc0 && (has_pref || act_newton || has_sbx3) && !h->tpc) {
+      // mineral prefactors, the iterated ionic strength and the SOMDECOMP / NITRIFICATION /
+      // DENITRIFICATION sandboxes live in the thread-per-cell kernel only
       const KernelGetter *gt = nullptr;
       for (const auto &k : g_getters)
         if (k.n == h->npad) gt = &k;
@@ -752,6 +816,53 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->clmcn_respiration_fraction, nx, &d.cn_resp);
     A.add(c->clmcn_inhibition_constant, nx, &d.cn_inhib);
   }
+  if (c->somdec) {
+    const pfrx_somdec *sd = c->somdec;
+    d.sd = *sd;  // scalars; every pointer below is re-homed into the arena
+    const int nx = sd->nrxn, nd = sd->downstream_ptr[nx], nm = sd->monod_ptr[nx], ni = sd->inhib_ptr[nx];
+#define SD_ADD(field, count) A.add(sd->field, (size_t)(count), &d.sd.field)
+    SD_ADD(rate_constant, nx);
+    SD_ADD(rate_decomposition, nx);
+    SD_ADD(rate_ad_factor, nx);
+    SD_ADD(upstream_c_id, nx);
+    SD_ADD(upstream_n_id, nx);
+    SD_ADD(upstream_is_aqueous, nx);
+    SD_ADD(upstream_hr_id, nx);
+    SD_ADD(upstream_nmin_id, nx);
+    SD_ADD(upstream_nimp_id, nx);
+    SD_ADD(upstream_nimm_id, nx);
+    SD_ADD(upstream_nc, nx);
+    SD_ADD(mineral_c_stoich, nx);
+    SD_ADD(mineral_n_stoich, nx);
+    SD_ADD(downstream_ptr, nx + 1);
+    SD_ADD(downstream_c_id, nd);
+    SD_ADD(downstream_n_id, nd);
+    SD_ADD(downstream_is_aqueous, nd);
+    SD_ADD(downstream_stoich, nd);
+    SD_ADD(downstream_nc, nd);
+    SD_ADD(temperature_response_function, nx);
+    SD_ADD(moisture_response_function, nx);
+    SD_ADD(ox_response_function, nx);
+    SD_ADD(q10, nx);
+    SD_ADD(ea, nx);
+    SD_ADD(ox_half_saturation, nx);
+    SD_ADD(decomp_depth_efolding, nx);
+    SD_ADD(ox_specid, nx);
+    SD_ADD(ox_specitype, nx);
+    SD_ADD(monod_ptr, nx + 1);
+    SD_ADD(monod_specid, nm);
+    SD_ADD(monod_specitype, nm);
+    SD_ADD(monod_pool_normalized, nm);
+    SD_ADD(monod_half_saturation, nm);
+    SD_ADD(monod_threshold, nm);
+    SD_ADD(inhib_ptr, nx + 1);
+    SD_ADD(inhib_itype, ni);
+    SD_ADD(inhib_specid, ni);
+    SD_ADD(inhib_specitype, ni);
+    SD_ADD(inhib_constant, ni);
+    SD_ADD(inhib_constant2, ni);
+#undef SD_ADD
+  }
   size_t asz = std::max<size_t>(A.bytes.size(), 16);
   cudaError_t e = cudaMalloc(&h->arena, asz);
   if (e != cudaSuccess) {
@@ -761,7 +872,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (!A.bytes.empty()) cudaMemcpy(h->arena, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice);
   for (auto &f : A.fix) *f.second = (unsigned char *)h->arena + f.first;
 
-  h->rows_d.resize(20);
+  h->rows_d.resize(PFRX_NUM_D);
   field_rows(c, h->rows_d.data());
 
   int rc = 0;
@@ -834,6 +945,14 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->num_iterations = s->num_iterations;
   d->num_kinetic_state_updates = s->num_kinetic_state_updates;
   d->ierror = s->ierror;
+  d->elm_w = s->elm_w_scalar;
+  d->elm_o = s->elm_o_scalar;
+  d->elm_t = s->elm_t_scalar;
+  d->elm_zsoil = s->elm_zsoil;
+  d->elm_kscalar = s->elm_kscalar_decomp_c;
+  d->elm_bd_dry = s->elm_bulkdensity_dry;
+  d->elm_bsw = s->elm_bsw;
+  d->somdec_nc = s->somdec_nc;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -956,8 +1075,9 @@ extern "C" int pfrx_rstep(pfrx_handle *h, double tran_dt, pfrx_step_result *out)
 }
 
 // ---- batched RReaction / RReactionDerivative for the GIRT / ELM caller ----------
-extern "C" int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, double *jac) {
+extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac) {
   if (!h || !res || (want_jacobian && !jac)) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!(tran_dt > 0.0)) return set_err(PFRX_E_INVALID, "tran_dt must be positive%s", "");
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   if (h->cfg.nmr > 0)
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover multirate sorption yet%s", "");
@@ -991,7 +1111,8 @@ extern "C" int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, dou
   if (h->ncell <= 0) return PFRX_OK;
   int64_t need = (h->ncell + h->rx_threads - 1) / h->rx_threads;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * h->rx_blocks_per_sm));
-  h->rx_kernel<<<grid, h->rx_threads, h->rx_smem, h->stream>>>(h->rx_cfg, h->st, h->ncell, want_jacobian, res, jac);
+  h->rx_kernel<<<grid, h->rx_threads, h->rx_smem, h->stream>>>(h->rx_cfg, h->st, h->ncell, want_jacobian, res, jac,
+                                                               tran_dt);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -999,7 +1120,7 @@ extern "C" int pfrx_reaction(pfrx_handle *h, int want_jacobian, double *res, dou
 }
 
 // ---- host-resident state: H2D, kernel, D2H ------------------------------------
-static const int kNumD = 20;
+static const int kNumD = PFRX_NUM_D;
 static size_t field_off(const int *rows, int64_t ld, int f) {
   size_t o = 0;
   for (int i = 0; i < f; i++) o += (size_t)rows[i] * ld;
@@ -1033,7 +1154,10 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            &h->own_st.mnrl_rate,    &h->own_st.free_site,    &h->own_st.eqsrfcplx_conc,
                            &h->own_st.total_sorb_eq, &h->own_st.kinmr,       (double **)&h->own_st.den_kg,
                            (double **)&h->own_st.sat, (double **)&h->own_st.temp, (double **)&h->own_st.porosity,
-                           (double **)&h->own_st.volume, (double **)&h->own_st.soil_particle_density};
+                           (double **)&h->own_st.volume, (double **)&h->own_st.soil_particle_density,
+                           (double **)&h->own_st.elm_w, (double **)&h->own_st.elm_o, (double **)&h->own_st.elm_t,
+                           (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
+                           (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -1049,12 +1173,16 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
                               host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb, host->den_kg,
                               host->sat,          host->temp,         host->porosity,  host->volume,
-                              host->soil_particle_density};
+                              host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
+                              host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
+                              host->somdec_nc};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
-                         (double *)d.soil_particle_density};
+                         (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
+                         (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
+                         d.somdec_nc};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -1062,6 +1190,14 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   bool have_sc = host->eqsrfcplx_conc != nullptr;
   if (!have_sc) d.eqsrfcplx_conc = nullptr;
   if (!host->imat) d.imat = nullptr;
+  if (!host->elm_w_scalar) d.elm_w = nullptr;
+  if (!host->elm_o_scalar) d.elm_o = nullptr;
+  if (!host->elm_t_scalar) d.elm_t = nullptr;
+  if (!host->elm_zsoil) d.elm_zsoil = nullptr;
+  if (!host->elm_kscalar_decomp_c) d.elm_kscalar = nullptr;
+  if (!host->elm_bulkdensity_dry) d.elm_bd_dry = nullptr;
+  if (!host->elm_bsw) d.elm_bsw = nullptr;
+  if (!host->somdec_nc) d.somdec_nc = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -1088,13 +1224,15 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   int rc = summary_reset(h, s_k);
   if (rc) return rc;
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27};
   double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
                          host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
                          host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
                          host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb, nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
-                         nullptr};
+                         nullptr,            nullptr,            nullptr,         nullptr,
+                         nullptr,            nullptr,            nullptr,         nullptr,
+                         host->somdec_nc};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the
@@ -1157,6 +1295,14 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     PFRX_OFF(porosity);
     PFRX_OFF(volume);
     PFRX_OFF(soil_particle_density);
+    PFRX_OFF(elm_w);
+    PFRX_OFF(elm_o);
+    PFRX_OFF(elm_t);
+    PFRX_OFF(elm_zsoil);
+    PFRX_OFF(elm_kscalar);
+    PFRX_OFF(elm_bd_dry);
+    PFRX_OFF(elm_bsw);
+    PFRX_OFF(somdec_nc);
     PFRX_OFF(imat);
     PFRX_OFF(num_sub_steps);
     PFRX_OFF(num_iterations);
@@ -1270,7 +1416,7 @@ extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
   // written once, four int32 results
   if (!h) return 0;
   const int *r = h->rows_d.data();
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27};
   int64_t in = 0, outn = 0;
   for (int f = 0; f < kNumD; f++)
     if (f != 11) in += r[f];

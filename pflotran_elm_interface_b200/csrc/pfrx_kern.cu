@@ -26,5 +26,5 @@ extern "C" pfrx_kernel_fn PFRX_CAT(pfrx_kernel_, PFRX_N)(int lanes) {
   return nullptr;
 }
 
-typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *);
+typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *, double);
 extern "C" pfrx_reaction_fn PFRX_CAT(pfrx_reaction_kernel_, PFRX_N)(void) { return pfrx_reaction_tpc_kernel<PFRX_N>; }

@@ -24,6 +24,7 @@
 // memory of an SM); throughput comes from instruction efficiency and ILP.
 #pragma once
 #include "pfrx_device.cuh"
+#include "pfrx_sandbox.cuh"
 
 template <int N>
 struct CellT {
@@ -33,6 +34,7 @@ struct CellT {
   int64_t cell;
   // per-cell scalars
   double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;  // ELM scalars (sandboxes)
   double Isum, msum;  // sum z^2 m and sum m over the secondary species of the latest RTotal
   bool dry;
   // register-resident per-component arrays (compile-time indices only)
@@ -49,6 +51,12 @@ struct CellT {
   __device__ __forceinline__ double &TMP(int i) { return ws[cfg.off_tmp + i]; }
   __device__ __forceinline__ double &TS(int i) { return ws[cfg.off_ts + i]; }
   __device__ __forceinline__ double &J(int i, int j) { return ws[cfg.off_J + i * cfg.js + j]; }
+  // views used by the ELM-CN sandboxes (pfrx_sandbox.cuh)
+  __device__ __forceinline__ double Cc(int i) const { return ws[cfg.off_c + i]; }
+  __device__ __forceinline__ double TOTc(int i) const { return ws[cfg.off_acc + i]; }
+  __device__ __forceinline__ double LNAc(int i) const { return ws[cfg.off_lnact + i]; }
+  __device__ __forceinline__ double &DT(int i, int j) { return ws[cfg.off_dt + i * cfg.naq + j]; }
+  __device__ __forceinline__ double &NC(int k) { return ws[cfg.off_nc + k]; }
 
   __device__ __forceinline__ double cx_logK(int k) const {
     return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, temp);
@@ -355,6 +363,10 @@ struct CellT {
 #pragma unroll 1
         for (int i = 0; i < naq; i++) {
           J(i, i) += 1.0;
+          if (cfg.need_dt) {  // rt_auxvar%aqueous%dtotal for the sandboxes (reaction.F90:4757)
+#pragma unroll 1
+            for (int j = 0; j < naq; j++) DT(i, j) = J(i, j) * denL;
+          }
 #pragma unroll 1
           for (int j = 0; j < naq; j++) J(i, j) *= f;
         }
@@ -677,6 +689,86 @@ struct CellT {
     }
   }
 
+  // ---- RSandboxEvaluate (reaction_sandbox.F90:294-330): the deck's order ----------
+  __device__ __forceinline__ void sandboxes(double dt) {
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsbx; k++) {
+      const int kind = cfg.sbx[k];
+      if (kind == PFRX_SANDBOX_CLM_CN) {
+        if (cfg.cn_nrxn > 0) clm_cn();
+      } else if (kind == PFRX_SANDBOX_SOMDEC) {
+        if (cfg.has_sd) {
+          pfrx_sbx::SomDec<CellT<N>> sdx(*this, dt);
+          sdx.react();
+        }
+      } else if (kind == PFRX_SANDBOX_NITRIF) {
+        if (cfg.has_nt) pfrx_sbx::nitrif_react(*this);
+      } else if (kind == PFRX_SANDBOX_DENITR) {
+        if (cfg.has_dn) pfrx_sbx::denitr_react(*this);
+      }
+    }
+  }
+
+  // per-cell inputs of the sandboxes; NC() <- persisted ratios or the set-up values
+  __device__ __forceinline__ void sandbox_load(int64_t c) {
+    if (cfg.elm) {
+      elm_w = st.elm_w ? st.elm_w[c] : 1.0;
+      elm_o = st.elm_o ? st.elm_o[c] : 1.0;
+      elm_t = st.elm_t ? st.elm_t[c] : 1.0;
+      elm_zsoil = st.elm_zsoil ? st.elm_zsoil[c] : 0.0;
+      elm_kscalar = st.elm_kscalar ? st.elm_kscalar[c] : 1.0;
+      elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[c] : 1.25e3;
+      elm_bsw = st.elm_bsw ? st.elm_bsw[c] : 1.0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < cfg.n_nc; k++) {
+      double v;
+      if (st.somdec_nc)
+        v = st.somdec_nc[k * st.ld + c];
+      else
+        v = k < cfg.sd.nrxn ? cfg.sd.upstream_nc[k] : cfg.sd.downstream_nc[k - cfg.sd.nrxn];
+      NC(k) = v;
+    }
+  }
+  __device__ __forceinline__ void sandbox_store(int64_t c) {
+    if (st.somdec_nc) {
+#pragma unroll 1
+      for (int k = 0; k < cfg.n_nc; k++) st.somdec_nc[k * st.ld + c] = NC(k);
+    }
+  }
+
+  // rt_auxvar%aqueous%dtotal from the state as it stands, for pfrx_reaction (the
+  // GIRT caller has it from its own RTAuxVarCompute, reaction.F90:4665-4759)
+  __device__ __forceinline__ void dtotal_from_state() {
+    const int naq = cfg.naq, ncx = cfg.ncplx;
+    const double denL = den_kg * 1.e-3;
+#pragma unroll 1
+    for (int e = 0; e < naq * naq; e++) ws[cfg.off_dt + e] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < ncx; k++) {
+      const int p0 = cfg.cx_ptr[k], p1 = cfg.cx_ptr[k + 1];
+      double lnQK = -cx_logK(k) * PFRX_LOG_TO_LN;
+      double h = cfg.cx_h2o[k];
+      if (h != 0.0) lnQK += h * ln_act_h2o;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) lnQK += cfg.cx_st[p] * LNA(cfg.cx_id[p]);
+      const double sk = exp(lnQK) / st.sec_act_coef[k * st.ld + cell];
+#pragma unroll 1
+      for (int p2 = p0; p2 < p1; p2++) {
+        const int j = cfg.cx_id[p2];
+        const double t = (cfg.cx_st[p2] * sk) * INVC(j);
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) DT(cfg.cx_id[p], j) += cfg.cx_st[p] * t;
+      }
+    }
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) {
+      DT(i, i) += 1.0;
+#pragma unroll 1
+      for (int j = 0; j < naq; j++) DT(i, j) *= denL;
+    }
+  }
+
   // ---- RSolve (reaction.F90:5457-5516) + LU (utility.F90:597-735) in shared ---
   // Jacobian rows are addressed through logical row offsets ro[] (ints kept in
   // ws.x), so a row interchange swaps two offsets.  The update lands in RES.
@@ -826,7 +918,7 @@ struct CellT {
       if (cfg.nkin > 0) kinetic_mineral(!dry);
       if (!dry) {
         if (cfg.nmr > 0) multirate(dt);
-        if (cfg.cn_nrxn > 0) clm_cn();
+        if (cfg.nsbx > 0) sandboxes(dt);
       }
       if (!act_ok) {
         // the reference has filled the state with NaN by now and leaves RReact with
@@ -934,7 +1026,7 @@ struct CellT {
         }
       }
     }
-    if (cfg.cn_nrxn > 0) upd = true;
+    if (cfg.nsbx > 0) upd = true;  // any sandbox => true (reaction.F90:5965)
     return upd;
   }
 
@@ -942,7 +1034,7 @@ struct CellT {
   // The GIRT / ELM caller (reactive_transport.F90:2627, 3288) adds these kinetic terms to
   // its own residual and Jacobian; rt_auxvar is taken as it stands (no RTAuxVarCompute).
   // res[i*ld + c] (mol/s), jac[(i*n + j)*ld + c] = d res_i / d c_j.
-  __device__ __forceinline__ void reaction(int64_t c, bool want_jac, double *res, double *jac) {
+  __device__ __forceinline__ void reaction(int64_t c, bool want_jac, double *res, double *jac, double tran_dt) {
     cell = c;
     const int naq = cfg.naq, n = cfg.n;
     const int64_t ld = st.ld;
@@ -974,7 +1066,16 @@ struct CellT {
 #pragma unroll 1
         for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
       }
-      if (cfg.cn_nrxn > 0) clm_cn();
+      if (cfg.nsbx > 0) {
+        if (cfg.need_dt) {
+#pragma unroll 1
+          for (int i = 0; i < naq; i++) TOT(i) = st.total[i * ld + c];
+          dtotal_from_state();
+        }
+        sandbox_load(c);
+        sandboxes(tran_dt);
+        sandbox_store(c);
+      }
     }
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
@@ -1036,6 +1137,7 @@ struct CellT {
       int64_t base = (int64_t)naq * (cfg.mr_ptr[q] + q);
       for (int i = 0; i < naq; i++) ws[cfg.off_mr + (2 * q) * N + i] = st.kinmr[(base + i) * ld + c];
     }
+    if (cfg.nsbx > 0) sandbox_load(c);
     small_mask = 0u;
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -1110,6 +1212,7 @@ struct CellT {
       for (int i = 0; i < naq; i++) st.kinmr[(base + i) * ld + c] = ws[cfg.off_mr + (2 * q) * N + i];
     }
     if (st.ln_act_h2o && cfg.use_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
+    if (cfg.n_nc > 0) sandbox_store(c);
   }
 
   // RStep's reaction to the outcome of one RReact (reaction.F90:3660-3716);
@@ -1202,7 +1305,8 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1))) pfrx_rst
 // batched RReaction(+Derivative): one thread per cell, inactive cells get zeros
 template <int N>
 __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1)))
-    pfrx_reaction_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, int want_jac, double *res, double *jac) {
+    pfrx_reaction_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, int want_jac, double *res, double *jac,
+                             double tran_dt) {
   extern __shared__ double smem[];
   double *ws = smem + (size_t)threadIdx.x * cfg.ws_stride;
   CellT<N> sol(cfg, st, ws);
@@ -1217,6 +1321,6 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1)))
       }
       continue;
     }
-    sol.reaction(c, want_jac != 0, res, jac);
+    sol.reaction(c, want_jac != 0, res, jac, tran_dt);
   }
 }

@@ -10,6 +10,10 @@ struct DevState {
   const double *den_kg, *sat, *temp, *porosity, *volume, *soil_particle_density;
   const int *imat;
   int *num_sub_steps, *num_iterations, *num_kinetic_state_updates, *ierror;
+  // appended (ABI v2) so that the leading layout the specialised cubins read is unchanged:
+  // ELM per-cell scalars and the persisted N:C ratios of the SOMDECOMP sandbox
+  const double *elm_w, *elm_o, *elm_t, *elm_zsoil, *elm_kscalar, *elm_bd_dry, *elm_bsw;
+  double *somdec_nc;
 };
 
 // shard summary accumulated with atomics, one set per warp

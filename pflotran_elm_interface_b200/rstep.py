@@ -61,7 +61,7 @@ def lib():
     L.pfrx_bytes_per_cell.argtypes = [hp]
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
-    L.pfrx_reaction.argtypes = [hp, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfrx_reaction.argtypes = [hp, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
@@ -200,9 +200,10 @@ class ChemistryStep:
         _check(lib().pfrx_rstep(self._h, float(tran_dt), C.byref(res)), "pfrx_rstep")
         return res
 
-    def reaction(self, want_jacobian: bool = True):
+    def reaction(self, want_jacobian: bool = True, tran_dt: float = 1.0):
         """batched RReaction (+ RReactionDerivative) on the bound state: returns
-        ``res[ncomp, ncell]`` and ``jac[ncomp, ncomp, ncell]`` (or None) as torch tensors"""
+        ``res[ncomp, ncell]`` and ``jac[ncomp, ncomp, ncell]`` (or None) as torch tensors;
+        ``tran_dt`` is option%tran_dt as the SOMDECOMP sandbox reads it"""
         import torch
 
         st = self._state
@@ -211,7 +212,7 @@ class ChemistryStep:
         n = self.cfg.c.naqcomp + self.cfg.c.nimcomp
         res = torch.empty((n, st.ncell), dtype=torch.float64, device=st.device)
         jac = torch.empty((n, n, st.ncell), dtype=torch.float64, device=st.device) if want_jacobian else None
-        _check(lib().pfrx_reaction(self._h, int(bool(want_jacobian)), res.data_ptr(),
+        _check(lib().pfrx_reaction(self._h, float(tran_dt), int(bool(want_jacobian)), res.data_ptr(),
                                    jac.data_ptr() if jac is not None else None), "pfrx_reaction")
         return res, jac
 

@@ -140,6 +140,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
             return False, k
     if c.use_total_as_guess:
         return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
+    if c.somdec or c.nitrif or c.denitr:
+        return False, "SOMDECOMP / NITRIFICATION / DENITRIFICATION sandbox"
     return True, ""
 
 

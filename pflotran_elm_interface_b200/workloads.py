@@ -261,6 +261,189 @@ def clm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
     return Workload("c4_clm_cn", cfg, st, tran_dt, net, "ngee/CLM-CN 13-dof sandbox, lognormal pools")
 
 
+# --------------------------------------------------------------------------- #
+C4S_DECK = """
+# C4(b): ngee-style ELM-CN network -- SOM decomposition (the CLM-CN cascade of
+# ngee/CLMCNplus/clm_cn1.in with N immobilisation from NH4+/NO3- as in clm_nimm4.in
+# and the N tracking species of clm_nmit.in), nitrification and denitrification
+CHEMISTRY
+  PRIMARY_SPECIES
+    CO2(aq)
+    N2O(aq)
+    NH4+
+    NO3-
+    N2(aq)
+    H+
+  /
+  IMMOBILE_SPECIES
+    SOM1
+    SOM2
+    SOM3
+    SOM4
+    Lit1C
+    Lit2C
+    Lit3C
+    Lit1N
+    Lit2N
+    Lit3N
+  /
+  REACTION_SANDBOX
+    SOMDECOMP
+      __ABIOTIC__
+      POOLS
+        SOM1 12.d0
+        SOM2 12.d0
+        SOM3 10.d0
+        SOM4 10.d0
+        Lit1
+        Lit2
+        Lit3
+      /
+      REACTION
+        UPSTREAM_POOL Lit1
+        DOWNSTREAM_POOL SOM1 0.61d0
+        TURNOVER_TIME 20. h
+        MONOD
+          SPECIES_NAME NH4+
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+        MONOD
+          SPECIES_NAME NO3-
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+      /
+      REACTION
+        UPSTREAM_POOL Lit2
+        DOWNSTREAM_POOL SOM2 0.45
+        TURNOVER_TIME 14. d
+        MONOD
+          SPECIES_NAME NH4+
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+        MONOD
+          SPECIES_NAME NO3-
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+      /
+      REACTION
+        UPSTREAM_POOL Lit3
+        DOWNSTREAM_POOL SOM3 0.71d0
+        TURNOVER_TIME 71. d
+        MONOD
+          SPECIES_NAME NH4+
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+        MONOD
+          SPECIES_NAME NO3-
+          HALF_SATURATION_CONSTANT 1.d-5
+        /
+      /
+      REACTION
+        UPSTREAM_POOL SOM1
+        DOWNSTREAM_POOL SOM2 0.72d0
+        TURNOVER_TIME 14. d
+      /
+      REACTION
+        UPSTREAM_POOL SOM2
+        DOWNSTREAM_POOL SOM3 0.54d0
+        TURNOVER_TIME 71. d
+      /
+      REACTION
+        UPSTREAM_POOL SOM3
+        DOWNSTREAM_POOL SOM4 0.45d0
+        TURNOVER_TIME 2. y
+      /
+      REACTION
+        UPSTREAM_POOL SOM4
+        TURNOVER_TIME 27.4 y
+      /
+    /
+    NITRIFICATION
+      NITRIFICATION_RATE_COEF 1.d-6
+      N2O_RATE_COEF_NITRIFICATION 3.5d-8
+    /
+    DENITRIFICATION
+      DENITRIFICATION_RATE_COEF 2.5d-6
+      NITRATE_HALF_SATURATION 1.d-9
+    /
+  /
+  DATABASE ./CLM-CN_database.dat
+END
+CONSTRAINT initial
+  CONCENTRATIONS
+    NH4+    4.d-5      T
+    NO3-    2.d-5      T
+    CO2(aq) 1.d-10     T
+    N2O(aq) 1.d-12     T
+    N2(aq)  1.d-10     T
+    H+      6.0d0      pH
+  /
+  IMMOBILE
+    SOM1  1.d-2
+    SOM2  1.d-2
+    SOM3  1.d-1
+    SOM4  1.d-1
+    Lit1C 0.1852d-0
+    Lit2C 0.4578d-0
+    Lit3C 0.2662d-0
+    Lit1N 0.00508954d-0
+    Lit2N 0.01258096d-0
+    Lit3N 0.00731553d-0
+  /
+END
+"""
+
+
+def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False) -> Workload:
+    """C4(b): SOMDECOMP + NITRIFICATION + DENITRIFICATION on 6 aqueous + 10
+    immobile species.  ``elm=True`` is the ELM_PFLOTRAN build in BGC-only
+    coupling: the moisture / oxygen / temperature scalars, soil depth,
+    decomposition scalar, dry bulk density and Clapp-Hornberger b are per-cell
+    ELM inputs; otherwise the CLM-CN temperature response and the log-theta
+    moisture response of the stand-alone build are evaluated from T and theta."""
+    rng = np.random.default_rng(seed)
+    abiotic = "" if elm else """ABIOTIC_FACTORS
+        TEMPERATURE_RESPONSE_FUNCTION
+          CLMCN
+        /
+        MOISTURE_RESPONSE_FUNCTION
+          LOGTHETA
+        /
+      /"""
+    dk, net = chem.load_network(C4S_DECK.replace("__ABIOTIC__", abiotic), _read("clmcnplus_CLM-CN_database.dat"))
+    assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
+    net.elm_pflotran = bool(elm)
+    cfg = abi.ReactionConfig(net)
+    sp = constraint.equilibrate_constraint(net, dk.constraints["initial"], den_kg=1000.0)
+    st = abi.HostState(cfg, ncell)
+    constraint.fill_cells(st, sp)
+    st["immobile"][...] = sp.immobile[:, None] * np.exp(rng.standard_normal((net.nimcomp, ncell)))
+    # mineral N from depleted to fertilised, independent of the pH
+    scale = np.ones((net.naqcomp, ncell))
+    for nm, lo, hi in (("NH4+", -7.0, -2.3), ("NO3-", -8.0, -3.5), ("CO2(aq)", -10.0, -4.0)):
+        i = net.primary_names.index(nm)
+        v = 10.0 ** rng.uniform(lo, hi, ncell)
+        scale[i] = v / st["total"][i]
+    st["total"][...] *= scale
+    st["pri_molal"][...] *= scale
+    st["temp"][...] = rng.uniform(-5.0, 30.0, ncell)
+    st["sat"][...] = rng.uniform(0.3, 1.0, ncell)
+    st["den_kg"][...] = 1000.0
+    st["porosity"][...] = rng.uniform(0.25, 0.5, ncell)
+    st["volume"][...] = 1.0
+    if elm:
+        st["elm_w_scalar"][...] = rng.uniform(0.05, 1.0, ncell)
+        st["elm_o_scalar"][...] = rng.uniform(0.2, 1.0, ncell)
+        st["elm_t_scalar"][...] = rng.uniform(0.05, 1.5, ncell)
+        st["elm_zsoil"][...] = rng.uniform(0.01, 3.0, ncell)
+        st["elm_kscalar_decomp_c"][...] = 1.0
+        st["elm_bulkdensity_dry"][...] = rng.uniform(900.0, 1600.0, ncell)
+        st["elm_bsw"][...] = rng.uniform(2.0, 10.0, ncell)
+    name = "c4s_elm_cn_elmscalars" if elm else "c4s_elm_cn"
+    return Workload(name, cfg, st, tran_dt, net,
+                    "SOMDECOMP (7 rxns, N immobilisation from NH4+/NO3-) + NITRIFICATION + DENITRIFICATION, 16 dof")
+
+
 def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
     table = {
         "c1": (calcite_batch, {}),
@@ -271,6 +454,8 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c3mr": (hanford, {"variant": "mr"}),
         "c3an": (hanford, {"variant": "base", "activity_newton": True}),
         "c4": (clm_cn, {}),
+        "c4s": (elm_cn, {}),
+        "c4se": (elm_cn, {"elm": True}),
         "c5": (hanford, {"variant": "minerals"}),
     }
     fn, kw = table[name]
@@ -306,6 +491,14 @@ def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
             f += 6.0 * len(rx.rates) * naq
     if net.clmcn is not None:
         f += 45.0 * net.clmcn["nrxn"] + 40.0
+    if getattr(net, "somdec", None) is not None:
+        # per reaction: abiotic factors, smoothing, Monod terms, rate caps, ~25 residual /
+        # Jacobian updates per column (3 columns in the immobilisation branch)
+        f += 150.0 * net.somdec["scalars"]["nrxn"] + 20.0 * 6
+    if getattr(net, "nitrif", None) is not None:
+        f += 60.0 + 20.0 * 7
+    if getattr(net, "denitr", None) is not None:
+        f += 40.0 + 20.0 * 2
     f += 10.0 * n
     solve = (2.0 / 3.0) * n ** 3 + 5.0 * n * n + 20.0 * n
     return f, solve

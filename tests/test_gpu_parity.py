@@ -114,6 +114,23 @@ def test_c4_clm_cn(dt):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("variant,dt,host", [("c4s", 1800.0, False), ("c4s", 86400.0, False), ("c4s", 1800.0, True),
+                                             ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True)])
+def test_c4s_elm_cn_sandboxes(variant, dt, host):
+    """SOMDECOMP + NITRIFICATION + DENITRIFICATION (SomDecReact/React1/React2/Nemission,
+    NitrifReact, DenitrReact) in the thread-per-cell kernel, stand-alone and ELM builds;
+    the persisted N:C ratios (pfrx_state.somdec_nc) are part of the compared state"""
+    wl = W.by_name(variant, ncell=6000, tran_dt=dt)
+    wl.state.a["imat"][0, 11] = 0
+    wl.state.a["sat"][0, 17] = 1.0e-50   # dry cell: RReaction skipped
+    wl.state.a["temp"][0, 19] = -60.0    # below the CLM-CN temperature cut-off
+    ref, rr, got, rg, info = _run_both(wl, host_path=host)
+    assert info["lanes"] in (0, 1)
+    _compare(ref, got, f"{variant} dt={dt}")
+    _check_summary(rr, rg)
+    assert rr.num_cut_cells > 0  # the workload exercises the sub-step logic
+
+
 @pytest.mark.parametrize("variant,dt", [("c3", 3600.0), ("c3", 30 * 86400.0), ("c3mr", 3600.0), ("c5", 86400.0)])
 def test_hanford(variant, dt):
     wl = W.by_name(variant, ncell=3000, tran_dt=dt)
@@ -134,14 +151,14 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c5", "c4"])
+@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
 
     rstep = _gpu()
     wl = W.by_name(variant, ncell=300)
-    if variant == "c4":
+    if variant.startswith("c4"):
         wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
         wl.state.a["sat"][0, 9] = 1.0e-50
     ref = wl.state.copy()
@@ -156,7 +173,7 @@ def test_batched_reaction_matches_oracle(variant):
     step = rstep.ChemistryStep(wl.cfg, 0)
     dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
     step.bind(dev)
-    res, jac = step.reaction(True)
+    res, jac = step.reaction(True, wl.tran_dt)
     torch.cuda.synchronize()
     R1, J1 = res.cpu().numpy(), jac.cpu().numpy()
     scale = np.abs(R0).max(axis=0, keepdims=True) + 1e-300  # per cell
@@ -169,7 +186,7 @@ def test_batched_reaction_matches_oracle(variant):
         a, b = ref.a["mnrl_rate"], got.a["mnrl_rate"]
         kA = wl.cfg.arrays["kinmnrl_rate_constant"][:, None] * ref.a["mnrl_area"]
         assert (np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), kA)).max() <= 1e-10
-    r_only, none = step.reaction(False)
+    r_only, none = step.reaction(False, wl.tran_dt)
     assert none is None and torch.equal(r_only, res)
     step.close()
 
