@@ -126,4 +126,4 @@ def test_rstep_on_elm_cn_workload(name, dt):
         return t
 
     n0, n1 = total_n(before), total_n(st)
-    assert np.all(np.abs(n1 - n0) <= 1e-6 * np.abs(n0))  # Newton tolerance (1e-8 relative residual)
+    assert np.all(np.abs(n1 - n0) <= 1e-5 * np.abs(n0))  # Newton stops at 1e-6 relative change
