@@ -127,11 +127,7 @@ static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
 }
 static uint64_t config_signature(const pfrx_config *c) {
   uint64_t h = 0xCBF29CE484222325ull;
-  {
-    // sandboxes the generator does not cover change the signature outright
-    int32_t sb[4] = {c->somdec ? c->somdec->nrxn : 0, c->nitrif ? 1 : 0, c->denitr ? 1 : 0, c->elm_pflotran};
-    if (sb[0] || sb[1] || sb[2]) h = fnv1a(h, sb, sizeof(sb));
-  }
+
   int32_t head[12] = {c->naqcomp,          c->nimcomp,
                       c->neqcplx,          c->nkinmnrl,
                       c->nsrfcplxrxn,      c->nsrfcplx,
@@ -196,6 +192,75 @@ static uint64_t config_signature(const pfrx_config *c) {
     ADD(c->clmcn_rate_constant, c->clmcn_nrxn)
     ADD(c->clmcn_respiration_fraction, c->clmcn_nrxn)
     ADD(c->clmcn_inhibition_constant, c->clmcn_nrxn)
+  }
+  // ELM-CN sandboxes: every parameter the generated code bakes in
+  if (c->somdec) {
+    const pfrx_somdec *sd = c->somdec;
+    int32_t hi[14] = {sd->nrxn,   sd->co2_id,  sd->co2_itype, sd->o2_id,   sd->o2_itype, sd->nh4_id,  sd->no3_id,
+                      sd->n2o_id, sd->proton_id, sd->hr_id,   sd->nmin_id, sd->nimm_id,  sd->nimp_id, sd->ngasmin_id};
+    double hd[3] = {sd->x0eps, sd->n2o_frac_mineralization, sd->inhibition_nh4_no3};
+    h = fnv1a(h, hi, sizeof(hi));
+    h = fnv1a(h, hd, sizeof(hd));
+    const int nx = sd->nrxn, nd = sd->downstream_ptr[nx], nm = sd->monod_ptr[nx], ni = sd->inhib_ptr[nx];
+    ADD(sd->rate_constant, nx)
+    ADD(sd->rate_decomposition, nx)
+    ADD(sd->rate_ad_factor, nx)
+    ADD(sd->upstream_c_id, nx)
+    ADD(sd->upstream_n_id, nx)
+    ADD(sd->upstream_is_aqueous, nx)
+    ADD(sd->upstream_hr_id, nx)
+    ADD(sd->upstream_nmin_id, nx)
+    ADD(sd->upstream_nimp_id, nx)
+    ADD(sd->upstream_nimm_id, nx)
+    ADD(sd->upstream_nc, nx)
+    ADD(sd->mineral_c_stoich, nx)
+    ADD(sd->mineral_n_stoich, nx)
+    ADD(sd->downstream_ptr, nx + 1)
+    ADD(sd->downstream_c_id, nd)
+    ADD(sd->downstream_n_id, nd)
+    ADD(sd->downstream_is_aqueous, nd)
+    ADD(sd->downstream_stoich, nd)
+    ADD(sd->downstream_nc, nd)
+    ADD(sd->temperature_response_function, nx)
+    ADD(sd->moisture_response_function, nx)
+    ADD(sd->ox_response_function, nx)
+    ADD(sd->q10, nx)
+    ADD(sd->ea, nx)
+    ADD(sd->ox_half_saturation, nx)
+    ADD(sd->decomp_depth_efolding, nx)
+    ADD(sd->ox_specid, nx)
+    ADD(sd->ox_specitype, nx)
+    ADD(sd->monod_ptr, nx + 1)
+    ADD(sd->monod_specid, nm)
+    ADD(sd->monod_specitype, nm)
+    ADD(sd->monod_pool_normalized, nm)
+    ADD(sd->monod_half_saturation, nm)
+    ADD(sd->monod_threshold, nm)
+    ADD(sd->inhib_ptr, nx + 1)
+    ADD(sd->inhib_itype, ni)
+    ADD(sd->inhib_specid, ni)
+    ADD(sd->inhib_specitype, ni)
+    ADD(sd->inhib_constant, ni)
+    ADD(sd->inhib_constant2, ni)
+  }
+  if (c->nitrif) {
+    const pfrx_nitrif *nt = c->nitrif;
+    int32_t hi[5] = {nt->proton_id, nt->nh4_id, nt->no3_id, nt->n2o_id, nt->ngasnit_id};
+    double hd[3] = {nt->k_nitr_max, nt->k_nitr_n2o, nt->x0eps};
+    h = fnv1a(h, hi, sizeof(hi));
+    h = fnv1a(h, hd, sizeof(hd));
+  }
+  if (c->denitr) {
+    const pfrx_denitr *dn = c->denitr;
+    int32_t hi[4] = {dn->no3_id, dn->n2_id, dn->n2o_id, dn->ngasdeni_id};
+    double hd[3] = {dn->half_saturation, dn->k_deni_max, dn->x0eps};
+    h = fnv1a(h, hi, sizeof(hi));
+    h = fnv1a(h, hd, sizeof(hd));
+  }
+  if (c->somdec || c->nitrif || c->denitr) {
+    int32_t e = c->elm_pflotran ? 1 : 0;
+    h = fnv1a(h, &e, sizeof(e));
+    if (c->sandbox_list) ADD(c->sandbox_list, c->nsandbox)
   }
 #undef ADD
   return h;

@@ -27,8 +27,23 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../../include/pfrx.h"
 #include "pfrx_fastmath.cuh"
 #include "pfrx_types.cuh"
+#ifndef PFRX_IDEAL_GAS_CONSTANT
+#define PFRX_IDEAL_GAS_CONSTANT 8.31446
+#endif
+#include "pfrx_sandbox.cuh"  // response functions shared with the generic kernels
+
+#ifndef SPEC_NSBX
+#define SPEC_NSBX 0  // reaction sandboxes of any kind
+#endif
+#ifndef SPEC_NNC
+#define SPEC_NNC 0   // persisted N:C ratios of the SOMDECOMP sandbox (pfrx_state.somdec_nc)
+#endif
+#ifndef SPEC_ELM
+#define SPEC_ELM 0   // ELM_PFLOTRAN build: per-cell ELM scalars
+#endif
 
 // SPEC_FASTMATH 1: branch-free exp / log / division (pfrx_fastmath.cuh) in the hot
 // places whose arguments are known to be normal numbers; 0: CUDA's own everywhere
@@ -90,6 +105,8 @@ struct SpecCell {
   double fsite[SPEC_NSRFRXN > 0 ? SPEC_NSRFRXN : 1];
   double scconc[SPEC_NSRFCPLX > 0 ? SPEC_NSRFCPLX : 1];
   double mrate[SPEC_NKIN > 0 ? SPEC_NKIN : 1];
+  double nc[SPEC_NNC > 0 ? SPEC_NNC : 1];  // N:C ratios that persist between evaluations
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;
   bool dry;
   bool store;  // false: the lane has finished its cell, rt_auxvar%sec_molal must not be touched
 };
@@ -113,8 +130,34 @@ __device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const
 #ifndef SPEC_NCLM
 #define SPEC_NCLM 0
 #endif
-__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], double (&res)[SPEC_N], const SpecCell &s,
-                                             double *W);
+__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],
+                                             const double (&tot)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W,
+                                             double dt);
+
+// per-cell inputs of the ELM-CN sandboxes
+__device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &st, long long cell) {
+#if SPEC_ELM
+  s.elm_w = st.elm_w ? st.elm_w[cell] : 1.0;
+  s.elm_o = st.elm_o ? st.elm_o[cell] : 1.0;
+  s.elm_t = st.elm_t ? st.elm_t[cell] : 1.0;
+  s.elm_zsoil = st.elm_zsoil ? st.elm_zsoil[cell] : 0.0;
+  s.elm_kscalar = st.elm_kscalar ? st.elm_kscalar[cell] : 1.0;
+  s.elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[cell] : 1.25e3;
+  s.elm_bsw = st.elm_bsw ? st.elm_bsw[cell] : 1.0;
+#endif
+#if SPEC_NNC > 0
+#pragma unroll
+  for (int k = 0; k < SPEC_NNC; k++) s.nc[k] = st.somdec_nc ? st.somdec_nc[k * st.ld + cell] : spec_nc0_tab[k];
+#endif
+}
+__device__ __forceinline__ void spec_sandbox_store(const SpecCell &s, const DevState &st, long long cell) {
+#if SPEC_NNC > 0
+  if (st.somdec_nc) {
+#pragma unroll
+    for (int k = 0; k < SPEC_NNC; k++) st.somdec_nc[k * st.ld + cell] = s.nc[k];
+  }
+#endif
+}
 
 // ---- RSolve + LU (reaction.F90:5457-5516, utility.F90:597-735) -------------------
 // W = thread's slice (Jacobian of the coupled species), res = residual in
@@ -408,8 +451,8 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       res[i] = sx_div(a - SPEC_FIXED(i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
-#if SPEC_NCLM > 0
-    if (!s.dry) spec_sandbox(c, res, s, W);  // RReaction returns before the sandboxes in a dry cell
+#if SPEC_NSBX > 0
+    if (!s.dry) spec_sandbox(c, lna, tot, res, s, W, dt);  // RReaction returns before the sandboxes in a dry cell
 #endif
     double mabs = 0.0, ss = 0.0;
 #pragma unroll
@@ -495,6 +538,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   s.vol = st.volume[cell];
   s.spd = st.soil_particle_density ? st.soil_particle_density[cell] : 0.0;
   s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
+  spec_sandbox_load(s, st, cell);
   nss = nit = nku = ierr = 0;
   had_cut = false;
   double Is = 0.0, ms = 0.0;
@@ -570,7 +614,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
       nconst = 0;
     } else {
       // RUpdateKineticState: the rates of the converged iterate are in s.mrate
-      bool upd = SPEC_NCLM > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
+      bool upd = SPEC_NSBX > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
       if (SPEC_NKIN > 0) {
         upd = true;
 #pragma unroll
@@ -623,6 +667,7 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
 #pragma unroll
   for (int k = 0; k < SPEC_NKIN; k++) st.mnrl_rate[k * ld + cell] = s.mrate[k];
   if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = s.ln_act_h2o;
+  spec_sandbox_store(s, st, cell);
 }
 
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
@@ -723,6 +768,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
     s.vol = st.volume[cell];
     s.spd = st.soil_particle_density ? st.soil_particle_density[cell] : 0.0;
     s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
+    spec_sandbox_load(s, st, cell);
     s.dry = s.sat < prm.min_sat;
     const double psv = s.por * s.sat * 1000.0 * s.vol;
     {
@@ -822,8 +868,8 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
         res[i] = sx_div(a - SPEC_FIXED(i), dt);
       }
       if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
-#if SPEC_NCLM > 0
-      if (!s.dry) spec_sandbox(c, res, s, W);
+#if SPEC_NSBX > 0
+      if (!s.dry) spec_sandbox(c, lna, tot, res, s, W, dt);
 #endif
       double mabs = 0.0, ss = 0.0;
 #pragma unroll
@@ -913,7 +959,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
               gimm[i - NAQ] = c[i];
             }
           }
-          bool upd = SPEC_NCLM > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
+          bool upd = SPEC_NSBX > 0;  // a sandbox forces the kinetic-state update (reaction.F90:5935-5972)
           if (SPEC_NKIN > 0) {
             upd = true;
 #pragma unroll
@@ -976,6 +1022,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
 #pragma unroll
       for (int k = 0; k < SPEC_NKIN; k++) st.mnrl_rate[k * ld + cell] = s.mrate[k];
       if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = s.ln_act_h2o;
+      spec_sandbox_store(s, st, cell);
     }
 
     if (inrange) {

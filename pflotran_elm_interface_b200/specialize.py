@@ -104,6 +104,27 @@ def signature(cfg: abi.ReactionConfig) -> int:
             add(k, c.clmcn_nrxn, i4)
         for k in ("clmcn_rate_constant", "clmcn_respiration_fraction", "clmcn_inhibition_constant"):
             add(k, c.clmcn_nrxn, f8)
+    if c.somdec:
+        sd = cfg.somdec
+        parts.append(struct.pack("<14i3d", *[getattr(sd, k) for k in (
+            "nrxn", "co2_id", "co2_itype", "o2_id", "o2_itype", "nh4_id", "no3_id", "n2o_id", "proton_id", "hr_id",
+            "nmin_id", "nimm_id", "nimp_id", "ngasmin_id", "x0eps", "n2o_frac_mineralization",
+            "inhibition_nh4_no3")]))
+        for name, ctype in abi.PfrxSomdec._fields_[17:]:
+            arr = a["somdec_" + name]
+            parts.append(np.ascontiguousarray(arr, dtype=(f8 if ctype is abi.c_double_p else i4)).tobytes())
+    if c.nitrif:
+        nt = cfg.nitrif
+        parts.append(struct.pack("<5i3d", nt.proton_id, nt.nh4_id, nt.no3_id, nt.n2o_id, nt.ngasnit_id,
+                                 nt.k_nitr_max, nt.k_nitr_n2o, nt.x0eps))
+    if c.denitr:
+        dn = cfg.denitr
+        parts.append(struct.pack("<4i3d", dn.no3_id, dn.n2_id, dn.n2o_id, dn.ngasdeni_id, dn.half_saturation,
+                                 dn.k_deni_max, dn.x0eps))
+    if c.somdec or c.nitrif or c.denitr:
+        parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
+        if c.nsandbox:
+            parts.append(np.ascontiguousarray(a["sandbox_list"], dtype=i4).tobytes())
     return _fnv1a(b"".join(parts))
 
 
@@ -141,7 +162,27 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
     if c.use_total_as_guess:
         return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
     if c.somdec or c.nitrif or c.denitr:
-        return False, "SOMDECOMP / NITRIFICATION / DENITRIFICATION sandbox"
+        if os.environ.get("PFRX_SPEC_NO_ELMCN"):
+            return False, "ELM-CN sandboxes disabled by PFRX_SPEC_NO_ELMCN"
+        # the generated code uses dtotal = delta_ij * den/1000
+        if c.neqcplx > 0:
+            return False, "ELM-CN sandboxes together with secondary complexes"
+    if c.somdec:
+        sd, sa = cfg.somdec, {k[7:]: v for k, v in a.items() if k.startswith("somdec_")}
+        if sd.x0eps <= 0.0:
+            return False, "SOMDECOMP X0EPS <= 0"
+        if sd.co2_itype != abi.SPEC_AQUEOUS or sd.o2_id >= 0 or sd.nh4_id < 0:
+            return False, "SOMDECOMP CO2 must be aqueous, no O2 species, NH4+ present"
+        if np.any(sa["upstream_is_aqueous"] != 0) or np.any(sa["downstream_is_aqueous"] != 0):
+            return False, "SOMDECOMP aqueous pools"
+        for k in ("temperature_response_function", "moisture_response_function", "ox_response_function", "q10", "ea",
+                  "ox_half_saturation", "decomp_depth_efolding"):
+            if np.any(sa[k] != sa[k][0]):
+                return False, "SOMDECOMP reactions with different ABIOTIC_FACTORS"
+        if np.any(sa["ox_specid"] >= 0):
+            return False, "SOMDECOMP Ox species"
+        if c.elm_pflotran and int(sa["moisture_response_function"][0]) != 0:
+            return False, "ELM build with a moisture response function"
     return True, ""
 
 
@@ -199,6 +240,31 @@ class _Gen:
                 used.add(naq + int(self.a["clmcn_pool_C_id"][k]))
                 if int(self.a["clmcn_pool_nspec"][k]) == 2:
                     used.add(naq + int(self.a["clmcn_pool_N_id"][k]))
+        naq = self.c.naqcomp
+        if self.c.somdec:
+            sd = cfg.somdec
+            sa = {k[7:]: v for k, v in self.a.items() if k.startswith("somdec_")}
+            used.update(int(v) for v in (sd.co2_id, sd.nh4_id) if v >= 0)
+            if sd.no3_id >= 0:
+                used.add(int(sd.no3_id))
+            if sd.n2o_id >= 0:
+                used.add(int(sd.n2o_id))
+            for v in (sd.hr_id, sd.nmin_id, sd.nimm_id, sd.nimp_id, sd.ngasmin_id):
+                if v >= 0:
+                    used.add(naq + int(v))
+            for k in ("upstream_c_id", "upstream_n_id", "upstream_hr_id", "upstream_nmin_id", "upstream_nimp_id",
+                      "upstream_nimm_id", "downstream_c_id", "downstream_n_id"):
+                used.update(naq + int(v) for v in sa[k] if v >= 0)
+        if self.c.nitrif:
+            nt = cfg.nitrif
+            used.update(int(v) for v in (nt.nh4_id, nt.no3_id, nt.n2o_id) if v >= 0)
+            if nt.ngasnit_id >= 0:
+                used.add(naq + int(nt.ngasnit_id))
+        if self.c.denitr:
+            dn = cfg.denitr
+            used.update(int(v) for v in (dn.no3_id, dn.n2_id) if v >= 0)
+            if dn.ngasdeni_id >= 0:
+                used.add(naq + int(dn.ngasdeni_id))
         self.coupled = sorted(used)
         self.cpos = {sp: ci for ci, sp in enumerate(self.coupled)}
         self.nc = len(self.coupled)
@@ -496,12 +562,517 @@ class _Gen:
         self.w()
 
     def gen_sandbox(self) -> None:
+        """RSandboxEvaluate (reaction_sandbox.F90:294-330): the sandboxes in the deck's order, each as
+        straight-line code with the network's ids and constants as literals"""
+        c = self.c
+        order = [int(v) for v in self.a["sandbox_list"]] if c.nsandbox else [1, 2, 3, 4]
+        self.w("__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],")
+        self.w("    const double (&tot)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W, double dt) {")
+        self.w("  const double denL = s.den_kg * 1.e-3;  // dtotal(i,i) of a network without complexes")
+        self.w("  (void)denL; (void)lna; (void)tot; (void)dt;")
+        for kind in order:
+            if kind == abi.SANDBOX_CLM_CN and c.clmcn_nrxn > 0:
+                self.w("  do {  // CLM-CN")
+                self._emit_clm_cn()
+                self.w("  } while (0);")
+            elif kind == abi.SANDBOX_SOMDEC and c.somdec:
+                self.w("  do {  // SOMDECOMP")
+                self._emit_somdec()
+                self.w("  } while (0);")
+            elif kind == abi.SANDBOX_NITRIF and c.nitrif:
+                self.w("  do {  // NITRIFICATION")
+                self._emit_nitrif()
+                self.w("  } while (0);")
+            elif kind == abi.SANDBOX_DENITR and c.denitr:
+                self.w("  do {  // DENITRIFICATION")
+                self._emit_denitr()
+                self.w("  } while (0);")
+        self.w("}")
+        self.w()
+
+    # -- helpers of the ELM-CN emitters: dtotal = delta_ij * denL (no complexes) ------------
+    def _Jsub(self, i: int, j: int, expr: str) -> None:
+        self.w(f"    {self.J(i, j)} = {self.J(i, j)} - {expr};")
+
+    def _Jadd(self, i: int, j: int, expr: str) -> None:
+        self.w(f"    {self.J(i, j)} = {self.J(i, j)} + {expr};")
+
+    def _conc(self, sid: int, itype: int) -> str:
+        return f"tot[{sid}]" if itype == abi.SPEC_AQUEOUS else f"c[{self.naq + sid}]"
+
+    def _emit_ph(self, proton_id: int) -> None:
+        if proton_id >= 0:
+            self.w(f"    const double ph = -lna[{proton_id}] * 0.43429448190325182765;")
+        else:
+            self.w("    const double ph = 6.5;")
+        self.w("    double f_ph = 0.56 + atan(3.14159265358979323846 * 0.45 * (-5.0 + ph)) / 3.14159265358979323846;")
+
+    def _emit_somdec(self) -> None:
+        """SomDecReact / React1 / React2 / Nemission (reaction_sandbox_somdec.F90:1504-3640); the
+        operation order of pfrx_sandbox.cuh, which is the reference's"""
+        c, naq = self.c, self.naq
+        sd = self.cfg.somdec
+        sa = {k[7:]: v for k, v in self.a.items() if k.startswith("somdec_")}
+        nrxn = int(sd.nrxn)
+        x0 = _lit(sd.x0eps)
+        x1 = _lit(sd.x0eps * 10.0)
+        elm = bool(c.elm_pflotran)
+        w = self.w
+        w("    const double theta = s.sat * s.por;")
+        # abiotic factors: identical for every reaction (supported())
+        mf, of, tf = (int(sa[k][0]) for k in ("moisture_response_function", "ox_response_function",
+                                              "temperature_response_function"))
+        if elm:
+            w("    double f_w = s.elm_w;")
+        elif mf == 3:
+            w("    double f_w;")
+            w("    if (theta <= (double)0.08f) f_w = (double)0.01f;")
+            w("    else f_w = log(theta / (double)0.08f) / 2.525728702545166015625;")
+        else:
+            w("    double f_w = 1.0;")
+        if of == 2:
+            w("    f_w = f_w * pfrx_sbx::wfps(s.sat);")
+        elif elm:
+            w("    f_w = f_w * s.elm_o;")
+        if tf == 4:
+            w(f"    const double f_t = pfrx_sbx::temperature_response(s.temp, 4, {_lit(float(sa['ea'][0]))});")
+        elif tf == 1:
+            w("    const double f_t = pfrx_sbx::temperature_response(s.temp, 1, 0.0);")
+        elif tf in (2, 3):
+            w(f"    const double f_t = pfrx_sbx::temperature_response(s.temp, {tf}, {_lit(float(sa['q10'][0]))});")
+        else:
+            w("    const double f_t = " + ("s.elm_t;" if elm else "1.0;"))
+        ef = float(sa["decomp_depth_efolding"][0])
+        if elm and ef > 0.0:
+            w(f"    const double f_depth = fmin(1.0, fmax(1.e-20, exp(-s.elm_zsoil / {_lit(ef)})));")
+        else:
+            w("    const double f_depth = 1.0;")
+        w("    if (f_t < 1.0e-20 || f_w < 1.0e-20 || f_depth < 1.0e-20) break;")
+        w("    double net_nmin_rate = 0.0;")
+        nh4, no3 = int(sd.nh4_id), int(sd.no3_id)
+        co2 = int(sd.co2_id)
+        dptr = sa["downstream_ptr"]
+        for r in range(nrxn):
+            uc = naq + int(sa["upstream_c_id"][r])
+            ucid = int(sa["upstream_c_id"][r])
+            un = naq + int(sa["upstream_n_id"][r]) if sa["upstream_n_id"][r] >= 0 else -1
+            down = list(range(int(dptr[r]), int(dptr[r + 1])))
+            w(f"    {{  // reaction {r}")
+            rc, rd, ad = float(sa["rate_constant"][r]), float(sa["rate_decomposition"][r]), float(sa["rate_ad_factor"][r])
+            if rc >= 0.0:
+                w(f"    double k_decomp = {_lit(rc)};")
+            elif rd >= 0.0:
+                w(f"    double k_decomp = 1.0 - exp(-{_lit(rd)} * dt);")
+                w("    k_decomp = k_decomp / dt;")
+            else:
+                w("    double k_decomp = 0.0;")
+            w(f"    k_decomp = {_lit(ad)} * k_decomp;")
+            if elm and ad > 1.0:
+                w("    if (s.elm_kscalar > 0.0) k_decomp = k_decomp / s.elm_kscalar;")
+            w("    k_decomp = fmin(k_decomp, 1.0 / dt);")
+            w("    const double scaled = k_decomp * s.vol * f_t * f_w * f_depth;")
+            w(f"    const double c_uc = c[{uc}];")
+            w("    double feps0, dfeps0;")
+            w(f"    pfrx_sbx::hsmooth(c_uc, {x1}, {x0}, feps0, dfeps0);")
+            w("    double crate_uc = scaled * c_uc * feps0;")
+            w("    double dcrate_uc_duc = scaled * (feps0 + c_uc * dfeps0);")
+            # downstream N:C ratios
+            ncd = {}
+            for j in down:
+                dn = int(sa["downstream_n_id"][j])
+                dc = int(sa["downstream_c_id"][j])
+                if dn >= 0 and dc >= 0:
+                    w(f"    double ncd{j} = s.nc[{nrxn + j}];")
+                    w(f"    if (c[{naq + dn}] >= {x0} && c[{naq + dc}] >= {x0}) {{ ncd{j} = c[{naq + dn}] / c[{naq + dc}]; "
+                      f"if (s.store) s.nc[{nrxn + j}] = ncd{j}; }}")
+                    ncd[j] = f"ncd{j}"
+                else:
+                    ncd[j] = _lit(float(sa["downstream_nc"][j]))
+            if un >= 0:
+                w(f"    double unc = s.nc[{r}];")
+                w(f"    if (c[{un}] >= {x0} && c_uc >= {x0}) {{ unc = c[{un}] / c_uc; if (s.store) s.nc[{r}] = unc; }}")
+                cst = 1.0
+                for j in down:
+                    cst = cst - float(sa["downstream_stoich"][j])
+                w(f"    const double cst = {_lit(cst)};")
+                w("    double nst = unc;")
+                for j in down:
+                    w(f"    nst = nst - {_lit(float(sa['downstream_stoich'][j]))} * {ncd[j]};")
+                branches = ("both",)
+            else:
+                w(f"    const double unc = {_lit(float(sa['upstream_nc'][r]))};")
+                w(f"    const double cst = {_lit(float(sa['mineral_c_stoich'][r]))};")
+                w(f"    const double nst = {_lit(float(sa['mineral_n_stoich'][r]))};")
+                branches = ("r1",) if float(sa["mineral_n_stoich"][r]) >= 0.0 else ("r2",)
+            if branches == ("both",):
+                w("    if (nst >= 0.0) {")
+                self._emit_somdec_react(r, 1, sa, sd, uc, ucid, un, down, ncd)
+                w("    } else {")
+                self._emit_somdec_react(r, 2, sa, sd, uc, ucid, un, down, ncd)
+                w("    }")
+            else:
+                w("    {")
+                self._emit_somdec_react(r, 1 if branches == ("r1",) else 2, sa, sd, uc, ucid, un, down, ncd)
+                w("    }")
+            w("    }")
+        # SomDecNemission (:3477-3640)
+        if sd.n2o_id >= 0:
+            n2o = int(sd.n2o_id)
+            w(f"    if (net_nmin_rate > {x0}) {{")
+            w(f"    const double c_nh4 = tot[{nh4}] * theta * 1000.0;")
+            w("    double f_t2 = -0.06 + 0.13 * exp(0.07 * s.temp);")
+            w("    double f_w2 = pfrx_sbx::wfps(s.sat);")
+            self._emit_ph(int(sd.proton_id))
+            w(f"    if (f_t2 > {x0} && f_w2 > {x0} && f_ph > {x0}) {{")
+            w("    f_t2 = fmin(f_t2, 1.0); f_w2 = fmin(f_w2, 1.0); f_ph = fmin(f_ph, 1.0);")
+            w("    const double temp_real = f_t2 * f_w2 * f_ph;")
+            w("    double feps0, dfeps0;")
+            w(f"    pfrx_sbx::hsmooth(c_nh4, {x1}, {x0}, feps0, dfeps0);")
+            fr = _lit(sd.n2o_frac_mineralization)
+            w(f"    const double nratecap = temp_real * {fr} * net_nmin_rate * dt;")
+            w("    double fcap = 1.0, dfcap = 0.0;")
+            w("    if (nratecap > c_nh4 * s.vol) {")
+            w("      fcap = pfrx_sbx::monod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
+            w("      dfcap = pfrx_sbx::dmonod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
+            w("    }")
+            w("    dfeps0 = dfeps0 * fcap + feps0 * dfcap;")
+            w("    feps0 = feps0 * fcap;")
+            w(f"    const double rate_n2o = temp_real * {fr} * net_nmin_rate * feps0;")
+            w(f"    res[{nh4}] = res[{nh4}] + rate_n2o;")
+            w(f"    res[{n2o}] = res[{n2o}] - 0.5 * rate_n2o;")
+            if sd.ngasmin_id >= 0:
+                w(f"    res[{naq + int(sd.ngasmin_id)}] -= rate_n2o;")
+            w(f"    const double drate = temp_real * {fr} * net_nmin_rate * dfeps0;")
+            self._Jadd(nh4, nh4, "drate * denL")
+            if sd.ngasmin_id >= 0:
+                self._Jsub(naq + int(sd.ngasmin_id), nh4, "drate")
+            w("    }")
+            w("    }")
+
+    def _emit_somdec_react(self, r, which, sa, sd, uc, ucid, un, down, ncd) -> None:
+        """SomDecReact1 (which == 1) or SomDecReact2 (which == 2) of reaction r; crate_uc, dcrate_uc_duc,
+        cst, nst, unc are in scope"""
+        naq, w = self.naq, self.w
+        nh4, no3, co2 = int(sd.nh4_id), int(sd.no3_id), int(sd.co2_id)
+        x0 = _lit(sd.x0eps)
+        x1 = _lit(sd.x0eps * 10.0)
+        react2 = which == 2
+        if react2:
+            w(f"    const double c_nh4 = tot[{nh4}] * theta * 1000.0;")
+            w(f"    const double c_no3 = {('tot[%d] * theta * 1000.0' % no3) if no3 >= 0 else '0.0'};")
+            w("    double finh = 1.0; bool skip = false;")
+            if sd.inhibition_nh4_no3 > 0.0:
+                w(f"    if (c_nh4 > {x0} && c_no3 > {x0}) finh = pfrx_sbx::monod(c_nh4 / c_no3, {_lit(1.0 / sd.inhibition_nh4_no3)});")
+                w(f"    else if (c_nh4 > {x0} && c_no3 <= {x0}) finh = 1.0;")
+                w(f"    else if (c_nh4 <= {x0} && c_no3 > {x0}) finh = 0.0;")
+                w("    else skip = true;")
+            w("    if (!skip) {")
+            w("    double fnh4 = 1.0, dfnh4 = 0.0, fno3 = 1.0, dfno3 = 0.0;")
+        # MONOD / INHIBITION lists
+        w("    double fmb = 1.0, dfmb = 0.0;")
+        for k in range(int(sa["monod_ptr"][r]), int(sa["monod_ptr"][r + 1])):
+            sid, sty = int(sa["monod_specid"][k]), int(sa["monod_specitype"][k])
+            mk, thr = _lit(float(sa["monod_half_saturation"][k])), _lit(float(sa["monod_threshold"][k]))
+            pn = bool(sa["monod_pool_normalized"][k])
+            w("    {")
+            if react2 and sid == nh4:
+                w(f"      double t = fmax(0.0, c_nh4 - {thr});")
+                if pn:
+                    w(f"      t = t / c[{uc}];")
+                w(f"      fnh4 = pfrx_sbx::monod(t, {mk}); dfnh4 = pfrx_sbx::dmonod(t, {mk});")
+            elif react2 and no3 >= 0 and sid == no3:
+                w(f"      double t = fmax(0.0, c_no3 - {thr});")
+                if pn:
+                    w(f"      t = t / c[{uc}];")
+                w(f"      fno3 = pfrx_sbx::monod(t, {mk}); dfno3 = pfrx_sbx::dmonod(t, {mk});")
+            else:
+                w(f"      double t = fmax(0.0, {self._conc(sid, sty)} - {thr});")
+                if pn:
+                    w(f"      t = t / c[{uc}];")
+                    if sty == abi.SPEC_AQUEOUS:
+                        w("      t = t * theta * 1000.0;" if react2 else "      t = t * s.por * s.sat * 1000.0;")
+                w(f"      const double fx = pfrx_sbx::monod(t, {mk});")
+                w(f"      const double dfx = {'pfrx_sbx::dmonod(t, ' + mk + ')' if ucid == sid else '0.0'};")
+                w("      dfmb = dfmb * fx + fmb * dfx; fmb = fmb * fx;")
+            w("    }")
+        for k in range(int(sa["inhib_ptr"][r]), int(sa["inhib_ptr"][r + 1])):
+            sid, sty, ity = int(sa["inhib_specid"][k]), int(sa["inhib_specitype"][k]), int(sa["inhib_itype"][k])
+            ik, ik2 = float(sa["inhib_constant"][k]), float(sa["inhib_constant2"][k])
+            w("    {")
+            w(f"      const double t = {self._conc(sid, sty)};")
+            if ik2 == -999.0 or ity != 1:
+                if ity == 3:
+                    w(f"      const double fx = {_lit(ik)} / (t + {_lit(ik)});")
+                    w(f"      double dfx = -{_lit(ik)} / (t + {_lit(ik)}) / (t + {_lit(ik)});")
+                elif ity == 4:
+                    w(f"      const double fx = pfrx_sbx::monod(t, {_lit(ik)});")
+                    w(f"      double dfx = pfrx_sbx::dmonod(t, {_lit(ik)});")
+                else:
+                    w("      const double fx = 1.0; double dfx = 0.0;")
+            else:
+                w(f"      const double fx = 0.5 + atan((t - {_lit(ik)}) * {_lit(ik2)}) / 3.14159265358979323846;")
+                w(f"      const double u = (t - {_lit(ik)}) * {_lit(ik2)};")
+                w(f"      double dfx = ({_lit(ik2)} / (1.0 + u * u)) / 3.14159265358979323846;")
+            if ucid != sid:
+                w("      dfx = 0.0;")
+            w("      dfmb = dfmb * fx + fmb * dfx; fmb = fmb * fx;")
+            w("    }")
+        w("    dcrate_uc_duc = dcrate_uc_duc * fmb + crate_uc * dfmb;")
+        w("    crate_uc = crate_uc * fmb;")
+        # Ox Monod term: no Ox species (supported()) => f_ox = 1, df_ox = 0
+        w("    dcrate_uc_duc = dcrate_uc_duc * 1.0 + crate_uc * 0.0;")
+        w("    crate_uc = crate_uc * 1.0;")
+        if react2:
+            w("    { double feps0, dfeps0;")
+            w(f"      pfrx_sbx::hsmooth(c_nh4, {x1}, {x0}, feps0, dfeps0);")
+            w("      dfnh4 = dfnh4 * feps0 + fnh4 * dfeps0; fnh4 = fnh4 * feps0;")
+            if no3 >= 0:
+                w(f"      pfrx_sbx::hsmooth(c_no3, {x1}, {x0}, feps0, dfeps0);")
+                w("      dfno3 = dfno3 * feps0 + fno3 * dfeps0; fno3 = fno3 * feps0;")
+            w("    }")
+            w("    const double nratecap = -crate_uc * nst * dt / 0.45;")
+            w("    { double fcap = 1.0, dfcap = 0.0;")
+            w("      if (nratecap * finh > c_nh4 * s.vol) {")
+            w("        fcap = pfrx_sbx::monod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
+            w("        dfcap = pfrx_sbx::dmonod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
+            w("      }")
+            w("      dfnh4 = dfnh4 * fcap + fnh4 * dfcap; fnh4 = fnh4 * fcap; }")
+            if no3 >= 0:
+                w("    { double fcap = 1.0, dfcap = 0.0;")
+                w("      if (nratecap * (1.0 - finh) > c_no3 * s.vol) {")
+                w("        fcap = pfrx_sbx::monod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
+                w("        dfcap = pfrx_sbx::dmonod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
+                w("      }")
+                w("      dfno3 = dfno3 * fcap + fno3 * dfcap; fno3 = fno3 * fcap; }")
+            w("    const double crate_nh4 = crate_uc * fnh4 * finh;")
+            w("    const double crate_no3 = crate_uc * fno3 * (1.0 - finh);")
+            w("    const double crate = crate_nh4 + crate_no3;")
+        else:
+            w("    const double crate = crate_uc;")
+        # residual, common part
+        uhr = int(sa["upstream_hr_id"][r])
+        w(f"    res[{uc}] = res[{uc}] + crate;")
+        w(f"    res[{co2}] = res[{co2}] - cst * crate;")
+        if uhr >= 0:
+            w(f"    res[{naq + uhr}] -= cst * crate;")
+        if sd.hr_id >= 0:
+            w(f"    res[{naq + int(sd.hr_id)}] -= cst * crate;")
+        for j in down:
+            dc = int(sa["downstream_c_id"][j])
+            if dc >= 0:
+                w(f"    res[{naq + dc}] = res[{naq + dc}] - {_lit(float(sa['downstream_stoich'][j]))} * crate;")
+        if un >= 0:
+            w(f"    res[{un}] = res[{un}] + unc * crate;")
+        unmin, unimm, unimp = (int(sa[k][r]) for k in ("upstream_nmin_id", "upstream_nimm_id", "upstream_nimp_id"))
+        if not react2:
+            w(f"    res[{nh4}] = res[{nh4}] - nst * crate;")
+            w("    net_nmin_rate = net_nmin_rate + nst * crate;")
+            if unmin >= 0:
+                w(f"    res[{naq + unmin}] -= nst * crate;")
+            if sd.nmin_id >= 0:
+                w(f"    res[{naq + int(sd.nmin_id)}] -= nst * crate;")
+        else:
+            w("    double nimm = 0.0;")
+            w(f"    res[{nh4}] = res[{nh4}] - nst * crate_nh4; nimm = nimm + nst * crate_nh4;")
+            if no3 >= 0:
+                w(f"    res[{no3}] = res[{no3}] - nst * crate_no3; nimm = nimm + nst * crate_no3;")
+            w("    net_nmin_rate = net_nmin_rate + nimm;")
+            if unimm >= 0:
+                w(f"    res[{naq + unimm}] += nst * crate;")
+            if unimp >= 0:
+                w(f"    res[{naq + unimp}] += nst * crate_uc;")
+            if sd.nimm_id >= 0:
+                w(f"    res[{naq + int(sd.nimm_id)}] += nst * crate;")
+            if sd.nimp_id >= 0:
+                w(f"    res[{naq + int(sd.nimp_id)}] += nst * crate_uc;")
+        for j in down:
+            dn = int(sa["downstream_n_id"][j])
+            if dn >= 0:
+                w(f"    res[{naq + dn}] = res[{naq + dn}] - {_lit(float(sa['downstream_stoich'][j]))} * crate * {ncd[j]};")
+
+        # Jacobian columns; all pools immobile, CO2 aqueous, dtotal = delta * denL
+        def column(jcol, dco2, duc, dun, wrt_uc):
+            if wrt_uc:
+                self._Jsub(co2, jcol, dco2)
+            # else: CO2 row gets dco2 * dtotal(co2, nh4|no3) = 0
+            if uhr >= 0:
+                self._Jsub(naq + uhr, jcol, dco2)
+            if sd.hr_id >= 0:
+                self._Jsub(naq + int(sd.hr_id), jcol, dco2)
+            self._Jsub(uc, jcol, duc)
+            for j in down:
+                dc = int(sa["downstream_c_id"][j])
+                self._Jsub(naq + dc, jcol, f"{_lit(float(sa['downstream_stoich'][j]))} * (-1.0 * {duc})")
+
+        def nrows(jcol, duc, dun):
+            if un >= 0:
+                self._Jsub(un, jcol, dun)
+            for j in down:
+                dn = int(sa["downstream_n_id"][j])
+                if dn >= 0:
+                    self._Jsub(naq + dn, jcol, f"{_lit(float(sa['downstream_stoich'][j]))} * (-1.0 * {duc}) * {ncd[j]}")
+
+        if not react2:
+            w("    const double dco2_duc = dcrate_uc_duc * cst;")
+            w("    const double duc_duc = -1.0 * dcrate_uc_duc;")
+            w("    const double dnh4_duc = dco2_duc * nst;")
+            w("    const double dun_duc = unc * duc_duc;")
+            column(uc, "dco2_duc", "duc_duc", "dun_duc", True)
+            self._Jsub(nh4, uc, "dnh4_duc")
+            if unmin >= 0:
+                self._Jsub(naq + unmin, uc, "dnh4_duc")
+            if sd.nmin_id >= 0:
+                self._Jsub(naq + int(sd.nmin_id), uc, "dnh4_duc")
+            nrows(uc, "duc_duc", "dun_duc")
+        else:
+            w("    double dcrate_dx = dcrate_uc_duc * (fnh4 * finh + fno3 - fno3 * finh);")
+            w("    const double dco2_duc = dcrate_dx * cst;")
+            w("    const double duc_duc = -1.0 * dcrate_dx;")
+            w("    const double dnh4_duc = dcrate_uc_duc * nst * fnh4 * finh;")
+            w("    const double dno3_duc = dcrate_uc_duc * nst * fno3 * (1.0 - finh);")
+            w("    const double dun_duc = unc * duc_duc;")
+            w("    dcrate_dx = (dfnh4 * finh + (fnh4 - fno3) * 0.0);")
+            w("    dcrate_dx = dcrate_dx * crate_uc;")
+            w("    const double duc_dnh4 = -1.0 * dcrate_dx;")
+            w("    const double dco2_dnh4 = dcrate_dx * cst;")
+            w("    double dnh4_dnh4 = fnh4 * 0.0 + dfnh4 * finh;")
+            w("    dnh4_dnh4 = dnh4_dnh4 * crate_uc * nst;")
+            w("    const double dun_dnh4 = unc * duc_dnh4;")
+            w("    dcrate_dx = (fnh4 - fno3) * 0.0 + dfno3 * (1.0 - fnh4 * finh);")
+            w("    dcrate_dx = dcrate_dx * crate_uc;")
+            w("    const double duc_dno3 = -1.0 * dcrate_dx;")
+            w("    const double dco2_dno3 = dcrate_dx * cst;")
+            w("    double dno3_dno3 = -1.0 * fno3 * 0.0 + dfno3 * (1.0 - finh);")
+            w("    dno3_dno3 = dno3_dno3 * crate_uc * nst;")
+            w("    const double dun_dno3 = unc * duc_dno3;")
+            # column uc
+            column(uc, "dco2_duc", "duc_duc", "dun_duc", True)
+            self._Jsub(nh4, uc, "dnh4_duc")
+            if unimm >= 0:
+                self._Jadd(naq + unimm, uc, "dnh4_duc")
+            if sd.nimm_id >= 0:
+                self._Jadd(naq + int(sd.nimm_id), uc, "dnh4_duc")
+            if no3 >= 0:
+                self._Jsub(no3, uc, "dno3_duc")
+                if unimm >= 0:
+                    self._Jadd(naq + unimm, uc, "dno3_duc")
+                if sd.nimm_id >= 0:
+                    self._Jadd(naq + int(sd.nimm_id), uc, "dno3_duc")
+            nrows(uc, "duc_duc", "dun_duc")
+            # column nh4
+            column(nh4, "dco2_dnh4", "duc_dnh4", "dun_dnh4", False)
+            self._Jsub(nh4, nh4, "dnh4_dnh4 * denL")
+            if unimm >= 0:
+                self._Jadd(naq + unimm, nh4, "dnh4_dnh4")
+            if sd.nimm_id >= 0:
+                self._Jadd(naq + int(sd.nimm_id), nh4, "dnh4_dnh4")
+            nrows(nh4, "duc_dnh4", "dun_dnh4")
+            # column no3
+            if no3 >= 0:
+                column(no3, "dco2_dno3", "duc_dno3", "dun_dno3", False)
+                self._Jsub(no3, no3, "dno3_dno3 * denL")
+                if unimm >= 0:
+                    self._Jadd(naq + unimm, no3, "dno3_dno3")
+                if sd.nimm_id >= 0:
+                    self._Jadd(naq + int(sd.nimm_id), no3, "dno3_dno3")
+                nrows(no3, "duc_dno3", "dun_dno3")
+            w("    }")  # if (!skip)
+
+    def _emit_nitrif(self) -> None:
+        """NitrifReact (reaction_sandbox_nitrif.F90:234-502)"""
+        naq, w = self.naq, self.w
+        nt = self.cfg.nitrif
+        nh4, no3, n2o = int(nt.nh4_id), int(nt.no3_id), int(nt.n2o_id)
+        w("    double saturation = s.sat;")
+        w("    const double L_water = saturation * s.por * 1.0e3;")
+        w(f"    const double c_nh4 = tot[{nh4}] * L_water;")
+        w("    double feps0, dfeps0;")
+        if nt.x0eps > 0.0:
+            w(f"    pfrx_sbx::hsmooth(c_nh4, {_lit(nt.x0eps * 10.0)}, {_lit(nt.x0eps)}, feps0, dfeps0);")
+        else:
+            w("    feps0 = 1.0; dfeps0 = 0.0;")
+            w(f"    if (c_nh4 < {_lit(nt.x0eps)}) break;")
+        if nh4 >= 0 and no3 >= 0:
+            w("    {")
+            w("    const double f_t = exp(0.08 * (s.temp - 25.0));")
+            w("    saturation = fmax(0.0, fmin(saturation, 1.0));")
+            w("    const double f_w = saturation * (1.0 - saturation) / 0.25;")
+            w(f"    double t = fmin({_lit(nt.k_nitr_max)} * f_t * f_w * s.vol, 1.0);")
+            w("    const double rate = t * (c_nh4 * feps0) * (c_nh4 / (c_nh4 + 4.0));")
+            w(f"    res[{nh4}] = res[{nh4}] + rate;")
+            w(f"    res[{no3}] = res[{no3}] - rate;")
+            w("    t = c_nh4 * c_nh4 / (c_nh4 + 4.0) * dfeps0 + c_nh4 * (c_nh4 + 8.0) / (c_nh4 + 4.0) / (c_nh4 + 4.0) * feps0;")
+            w(f"    const double drate = {_lit(nt.k_nitr_max)} * f_t * f_w * s.vol * t;")
+            self._Jadd(nh4, nh4, "drate * denL")
+            w("    }")
+        w("    const double rho_b = " + ("s.elm_bd_dry;" if self.c.elm_pflotran else "1.25e3;"))
+        w("    const double M_2_ug_per_g = (14.0067 * 1.0e6) / (s.vol * rho_b * 1.e3);")
+        w("    const double c_nh4_ugg = c_nh4 * s.vol * M_2_ug_per_g;")
+        if n2o >= 0:
+            w("    if (c_nh4_ugg > 3.0) {")
+            w("    double f_t = -0.06 + 0.13 * exp(0.07 * s.temp);")
+            w("    double f_w = pfrx_sbx::wfps(saturation);")
+            self._emit_ph(int(nt.proton_id))
+            w("    if (f_t > 0.0 && f_w > 0.0 && f_ph > 0.0) {")
+            w("    f_t = fmin(f_t, 1.0); f_w = fmin(f_w, 1.0); f_ph = fmin(f_ph, 1.0);")
+            w("    const double ex = exp(-0.0105 * c_nh4_ugg);")
+            w(f"    double t = (1.0 - ex) * f_t * f_w * f_ph * {_lit(nt.k_nitr_n2o)};")
+            w("    const double rate_n2o = t * (c_nh4 * feps0) * s.vol;")
+            w(f"    res[{nh4}] = res[{nh4}] + rate_n2o;")
+            w(f"    res[{n2o}] = res[{n2o}] - 0.5 * rate_n2o;")
+            if nt.ngasnit_id >= 0:
+                w(f"    res[{naq + int(nt.ngasnit_id)}] -= rate_n2o;")
+            w("    t = (c_nh4 * dfeps0 + feps0) * (1.0 - ex);")
+            w("    t = t + (c_nh4 * feps0) * 0.0105 * M_2_ug_per_g * ex;")
+            w(f"    const double drate = t * {_lit(nt.k_nitr_n2o)} * f_t * f_w * f_ph * s.vol;")
+            self._Jadd(nh4, nh4, "drate * denL")
+            if nt.ngasnit_id >= 0:
+                self._Jsub(naq + int(nt.ngasnit_id), nh4, "drate")
+            w("    }")
+            w("    }")
+
+    def _emit_denitr(self) -> None:
+        """DenitrReact (reaction_sandbox_denitr.F90:212-404)"""
+        naq, w = self.naq, self.w
+        dn = self.cfg.denitr
+        no3, n2 = int(dn.no3_id), int(dn.n2_id)
+        if n2 < 0:
+            return
+        w("    const double L_water = s.por * s.sat * 1.e3;")
+        w("    const double bsw = " + ("s.elm_bsw;" if self.c.elm_pflotran else "1.0;"))
+        w("    const double f_t = exp(0.08 * (s.temp - 25.0));")
+        w("    double f_w = 0.0;")
+        w("    if (s.sat > 0.6) { f_w = (s.sat - 0.6) / (1.0 - 0.6); f_w = pow(f_w, bsw); }")
+        w(f"    const double c_no3 = tot[{no3}] * L_water;")
+        w("    double feps0, dfeps0;")
+        if dn.x0eps > 0.0:
+            w(f"    pfrx_sbx::hsmooth(c_no3, {_lit(dn.x0eps * 10.0)}, {_lit(dn.x0eps)}, feps0, dfeps0);")
+        else:
+            w("    feps0 = 1.0; dfeps0 = 0.0;")
+            w(f"    if (c_no3 <= {_lit(dn.x0eps)}) break;")
+        if dn.half_saturation > 0.0:
+            w(f"    const double fno3 = pfrx_sbx::monod(c_no3, {_lit(dn.half_saturation)});")
+            w(f"    const double dfno3 = pfrx_sbx::dmonod(c_no3, {_lit(dn.half_saturation)});")
+        else:
+            w("    const double fno3 = 1.0, dfno3 = 0.0;")
+        w("    if (f_t > 0.0 && f_w > 0.0) {")
+        w(f"    const double rate = {_lit(dn.k_deni_max)} * f_t * f_w * fno3 * (c_no3 * s.vol * feps0);")
+        w(f"    res[{no3}] = res[{no3}] + rate;")
+        w(f"    res[{n2}] = res[{n2}] - 0.5 * rate;")
+        if dn.ngasdeni_id >= 0:
+            w(f"    res[{naq + int(dn.ngasdeni_id)}] -= rate;")
+        w("    const double t = dfno3 * (c_no3 * s.vol * feps0) + fno3 * (c_no3 * s.vol * dfeps0 + feps0);")
+        w(f"    const double drate = {_lit(dn.k_deni_max)} * f_t * f_w * t;")
+        self._Jadd(no3, no3, "drate * denL")
+        if dn.ngasdeni_id >= 0:
+            self._Jsub(naq + int(dn.ngasdeni_id), no3, "drate")
+        w("    }")
+
+    def _emit_clm_cn(self) -> None:
         """CLM_CN_React (reaction_sandbox_clm_cn.F90:468-787), one straight-line block per reaction"""
         c, a, naq = self.c, self.a, self.naq
-        self.w("__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], double (&res)[SPEC_N],")
-        self.w("    const SpecCell &s, double *W) {")
         self.w("  const double temp_K = s.temp + 273.15;")
-        self.w("  if (!(temp_K > 227.15)) return;")
+        self.w("  if (!(temp_K > 227.15)) break;")
         self.w("  const double F_t = exp(308.56 * (1.408054069e-2 - 1.0 / (temp_K - 227.13)));")
         self.w("  const double F_theta = log(0.01 / fmax(0.01, s.sat)) * -2.17147241e-1;")
         self.w("  const double cinh = F_t * F_theta;")
@@ -570,8 +1141,6 @@ class _Gen:
             self.w(f"      {J(iN, iN)} = {J(iN, iN)} - st_N * dinh;")
             self.w("    }")
             self.w("  }")
-        self.w("}")
-        self.w()
 
     # ------------------------------------------------------------------ whole file
     def source(self) -> str:
@@ -611,7 +1180,15 @@ class _Gen:
         self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
         self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
         self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
+        nsbx = int(c.clmcn_nrxn > 0) + int(bool(c.somdec)) + int(bool(c.nitrif)) + int(bool(c.denitr))
+        nnc = (len(self.a["somdec_upstream_nc"]) + len(self.a["somdec_downstream_nc"])) if c.somdec else 0
         self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
+        self.w(f"#define SPEC_NSBX {nsbx}")
+        self.w(f"#define SPEC_NNC {nnc}")
+        self.w(f"#define SPEC_ELM {int(bool(c.elm_pflotran))}")
+        if nnc:
+            nc0 = list(self.a["somdec_upstream_nc"]) + list(self.a["somdec_downstream_nc"])
+            self.w("static __device__ const double spec_nc0_tab[] = {" + ", ".join(_lit(float(v)) for v in nc0) + "};")
         self.w(f"#define SPEC_USE_LOG {int(c.use_log_formulation)}")
         self.w(f"#define SPEC_ACT_UPD {int(self.act_upd)}")
         self.w(f"#define SPEC_USE_ACT_H2O {int(c.use_activity_h2o)}")
@@ -637,7 +1214,7 @@ class _Gen:
         self.gen_rtotal()
         self.gen_sorption()
         self.gen_minerals()
-        if c.clmcn_nrxn > 0:
+        if nsbx > 0:
             self.gen_sandbox()
         return "\n".join(o) + "\n"
 
@@ -1122,7 +1699,7 @@ def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]
             used.update(int(v) for v in cfg.arrays[ids])
     if warps not in (2, 4, 8):
         return False, "2, 4 or 8 warps"
-    if c.clmcn_nrxn > 0:
+    if c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr:
         return False, "reaction sandbox"
     if len(used) < 2 * warps:
         return False, "too few coupled species for that many warps"

@@ -141,10 +141,16 @@ def test_hanford(variant, dt):
 
 @pytest.mark.parametrize("variant,dt,host", [("c1", 3600.0, False), ("c2", 3600.0, False), ("c2", 86400.0 * 91, True),
                                              ("c3", 3600.0, False), ("c3", 30 * 86400.0, True),
-                                             ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True)])
+                                             ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True),
+                                             ("c4s", 1800.0, False), ("c4s", 86400.0, True), ("c4se", 1800.0, False),
+                                             ("c4se", 6 * 3600.0, True)])
 def test_specialized_kernel(variant, dt, host):
     """the code-generated kernel (specialize.py + pfrx_spec.cuh) against the oracle"""
-    wl = W.by_name(variant, ncell=1 if variant == "c1" else 1500, tran_dt=dt)
+    wl = W.by_name(variant, ncell=1 if variant == "c1" else (6000 if variant.startswith("c4s") else 1500), tran_dt=dt)
+    if variant.startswith("c4s"):
+        wl.state.a["imat"][0, 11] = 0
+        wl.state.a["sat"][0, 17] = 1.0e-50   # dry cell
+        wl.state.a["temp"][0, 19] = -60.0    # below the CLM-CN temperature cut-off
     ref, res_ref, got, res, info = _run_both(wl, host_path=host, spec=True)
     assert info["lanes"] == -1, info
     _compare(ref, got, f"specialised {variant} dt={dt}")
