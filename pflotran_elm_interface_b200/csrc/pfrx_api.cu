@@ -1082,6 +1082,8 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
     SpecParams prm = h->spec_prm;
     DevSummary *summ = h->d_summ;
     void *args[] = {&st_arg, &n_arg, &dt_arg, &prm, &summ};
+    // work counter of the refill skeleton (pfrx_spec.cuh, SPEC_REFILL): per launch, not per step
+    CUDA_OK(cudaMemsetAsync(&h->d_summ->next_cell, 0, sizeof(unsigned long long), s));
     DRV_OK(g_drv.LaunchKernel(h->spec_func, (unsigned)grid, 1, 1, (unsigned)h->spec_threads, 1, 1,
                               (unsigned)h->spec_smem, s, args, nullptr));
     h->launches++;

@@ -38,6 +38,9 @@
 #ifndef SPEC_NSBX
 #define SPEC_NSBX 0  // reaction sandboxes of any kind
 #endif
+#ifndef SPEC_REFILL
+#define SPEC_REFILL 0  // lock-step skeleton: finished lanes fetch the next cell (variant "q")
+#endif
 #ifndef SPEC_NNC
 #define SPEC_NNC 0   // persisted N:C ratios of the SOMDECOMP sandbox (pfrx_state.somdec_nc)
 #endif
@@ -754,13 +757,69 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
   long long l_first = -1;
   int l_maxits = 0, l_maxkin = 0, l_maxerr = 0, l_maxsub = 0;
 
-  for (long long base = (long long)blockIdx.x * blockDim.x; base < ncell; base += (long long)gridDim.x * blockDim.x) {
-    const bool inrange = base + threadIdx.x < ncell;
-    const long long cell = inrange ? base + threadIdx.x : ncell - 1;
-    const bool live = inrange && !(st.imat && st.imat[cell] <= 0);
+  // per-lane state of the cell a lane holds (declared here: it survives passes of the loop)
+  SpecCell s;
+  s.store = false;
+  s.dry = false;
+  unsigned small_mask = 0u;
+  // the guess of the next sub-step is kept where it ends up anyway: rt_auxvar%pri_molal
+  // (aqueous species); immobile species keep theirs in registers
+  double small_val[N], gimm[N > NAQ ? N - NAQ : 1], fixed[N], c[N];
+  double cumulative = 0.0, dt = target, norm0 = 0.0, psv = 0.0;
+  int ncuts = 0, nconst = 0, nss = 0, nit = 0, nku = 0, its = 0;
+  bool done = true, aborted = false, had_cut = false, need_begin = false;
+  long long cell = ncell - 1;
+  bool inrange = false, live = false;
+#if SPEC_REFILL
+  // Refill (variant "q"): a lane whose cell is finished takes the next unprocessed cell
+  // instead of riding along until the slowest cell of its block is done.  Cells are handed
+  // out by a warp-aggregated atomic counter; which lane gets which cell does not matter,
+  // every cell is computed from its own state only.
+  bool have = false, loaded_once = false;
+#else
+  long long base = (long long)blockIdx.x * blockDim.x;
+  bool need_new = true;
+#endif
 
+  for (;;) {
+    bool fresh = false;
+#if SPEC_REFILL
+    {
+      const unsigned want = __ballot_sync(0xffffffffu, !have);
+      if (!have) {
+        const int leader = __ffs(want) - 1;
+        unsigned long long first = 0;
+        if (lane32 == leader) first = atomicAdd(&summ->next_cell, (unsigned long long)__popc(want));
+        first = __shfl_sync(want, first, leader);
+        const long long mine = (long long)first + __popc(want & ((1u << lane32) - 1u));
+        if (mine < ncell) {
+          cell = mine;
+          inrange = true;
+          live = !(st.imat && st.imat[cell] <= 0);
+          fresh = true;
+          have = true;
+        } else if (!loaded_once) {
+          cell = ncell - 1;  // never got a cell: hold a valid state to ride along with
+          inrange = false;
+          live = false;
+          fresh = true;
+        }
+      }
+      loaded_once = true;
+    }
+#else
+    if (need_new) {
+      if (base >= ncell) break;
+      inrange = base + threadIdx.x < ncell;
+      cell = inrange ? base + threadIdx.x : ncell - 1;
+      live = inrange && !(st.imat && st.imat[cell] <= 0);
+      base += (long long)gridDim.x * blockDim.x;
+      need_new = false;
+      fresh = true;
+    }
+#endif
+    if (fresh) {
     // ---- RStep entry (reaction.F90:3600-3650)
-    SpecCell s;
     s.den_kg = st.den_kg[cell];
     s.sat = st.sat[cell];
     s.temp = st.temp[cell];
@@ -770,7 +829,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
     s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
     spec_sandbox_load(s, st, cell);
     s.dry = s.sat < prm.min_sat;
-    const double psv = s.por * s.sat * 1000.0 * s.vol;
+    psv = s.por * s.sat * 1000.0 * s.vol;
     {
       double Is = 0.0, ms = 0.0;
 #pragma unroll 8
@@ -791,10 +850,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
     for (int k = 0; k < SPEC_NSRFCPLX; k++) s.scconc[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < SPEC_NKIN; k++) s.mrate[k] = st.mnrl_rate[k * ld + cell];
-    unsigned small_mask = 0u;
-    // the guess of the next sub-step is kept where it ends up anyway: rt_auxvar%pri_molal
-    // (aqueous species); immobile species keep theirs in registers
-    double small_val[N], gimm[N > NAQ ? N - NAQ : 1], fixed[N], c[N];
+    small_mask = 0u;
     {
       double in_t[N], in_g[N], in_a[N];
 #pragma unroll
@@ -827,11 +883,20 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
         }
       }
     }
-    double cumulative = 0.0, dt = target, norm0 = 0.0;
-    int ncuts = 0, nconst = 0, nss = 0, nit = 0, nku = 0, its = 0;
-    bool done = !live, aborted = false, had_cut = false, need_begin = true;
+    cumulative = 0.0;
+    dt = target;
+    norm0 = 0.0;
+    ncuts = nconst = nss = nit = nku = its = 0;
+    done = !live;
+    aborted = false;
+    had_cut = false;
+    need_begin = true;
+    }  // fresh
+#if SPEC_REFILL
+    if (__syncthreads_and(have ? 0 : 1)) break;  // every cell has been handed out and finished
+#endif
 
-    for (;;) {
+    {
       // ---- RReact entry (reaction.F90:3829-3850) for lanes that start a sub-step
       if (!done && need_begin) {
 #pragma unroll
@@ -983,9 +1048,14 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
             need_begin = true;
         }
       }
-      if (__syncthreads_and(done ? 1 : 0)) break;
     }
-
+#if SPEC_REFILL
+    const bool publish = have && done;
+#else
+    const bool publish = __syncthreads_and(done ? 1 : 0) != 0;
+    if (publish) need_new = true;
+#endif
+    if (publish) {
     // ---- publish the cell (reaction.F90:3700-3738); the generated routines stop updating a
     // lane's activity / sorption / rate state once s.store is false, so this is the state of
     // the lane's last own pass
@@ -1041,6 +1111,10 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
         l_maxsub = max(l_maxsub, nss);
       }
     }
+#if SPEC_REFILL
+    have = false;
+#endif
+    }  // publish
   }
   __syncwarp();
 #pragma unroll

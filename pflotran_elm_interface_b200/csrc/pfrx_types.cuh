@@ -21,6 +21,7 @@ struct DevSummary {
   unsigned long long ncell_active, sum_its, num_cut_cells;
   long long first_failed;
   int max_its, max_kin, max_err, max_sub;
+  unsigned long long next_cell;  // work counter of the refill skeleton, zeroed before every launch
 };
 
 

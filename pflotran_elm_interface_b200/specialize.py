@@ -37,7 +37,7 @@ OUT = os.path.join(CSRC, "_spec")
 LOG_TO_LN = chem.LOG_TO_LN
 
 # variant letter -> code style (PFRX_SPEC_VARIANT=<letter><warps per 32 cells>)
-VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled"}
+VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled", "q": "refill"}
 
 
 def _fnv1a(data: bytes) -> int:
@@ -208,6 +208,7 @@ def _term(st: float, expr: str) -> str:
 class _Gen:
     loop_lu = False  # dense solve as rolled loops (style "looplu")
     lockstep = False  # 128-thread blocks whose warps execute the same Newton iteration (style "lockstep")
+    refill = False  # lock-step blocks whose finished lanes fetch the next cell (style "refill")
 
     def __init__(self, cfg: abi.ReactionConfig):
         ok, why = supported(cfg)
@@ -1197,6 +1198,7 @@ class _Gen:
         self.w(f"#define SPEC_FASTMATH {int(os.environ.get('PFRX_SPEC_FASTMATH', '1'))}")
         self.w(f"#define SPEC_LOOP_LU {int(self.loop_lu)}")
         self.w(f"#define SPEC_LOCKSTEP {int(self.lockstep)}")
+        self.w(f"#define SPEC_REFILL {int(self.refill)}")
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")
         cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
         so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
@@ -1734,7 +1736,8 @@ def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style:
         return _GenW(cfg, warps).source()
     g = _Gen(cfg)
     g.loop_lu = style in ("looplu", "klooplu")
-    g.lockstep = style in ("lockstep", "klooplu")
+    g.lockstep = style in ("lockstep", "klooplu", "refill")
+    g.refill = style == "refill"
     return g.source()
 
 
@@ -1742,7 +1745,8 @@ def _stamp(src: str) -> str:
     import hashlib
 
     h = hashlib.sha1(src.encode())
-    for d in ("pfrx_fastmath.cuh", "pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh"):
+    for d in ("pfrx_fastmath.cuh", "pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh",
+              "pfrx_sandbox.cuh"):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(f.read())
     return h.hexdigest()

@@ -197,7 +197,7 @@ def test_batched_reaction_matches_oracle(variant):
     step.close()
 
 
-@pytest.mark.parametrize("variant", ["s1", "k1", "l1"])
+@pytest.mark.parametrize("variant", ["s1", "k1", "l1", "q1"])
 def test_specialized_skeletons_agree_with_oracle(variant):
     """one-warp blocks, lock-step blocks and the rolled dense solve are the same arithmetic"""
     rstep = _gpu()
@@ -213,6 +213,36 @@ def test_specialized_skeletons_agree_with_oracle(variant):
     step.bind(dev)
     res = step.rstep(wl.tran_dt)
     _compare(ref, dev.to_host(), f"specialised c5 {variant}")
+    _check_summary(res_ref, res)
+    step.close()
+
+
+@pytest.mark.parametrize("name,n,dt,host", [("c4s", 20000, 1800.0, False), ("c4s", 300000, 1800.0, True),
+                                            ("c3", 5000, 3600.0, False), ("c2", 50, 3600.0, False)])
+def test_refill_skeleton(name, n, dt, host):
+    """variant q1: finished lanes fetch the next cell from an atomic counter.  Which lane
+    computes which cell must not matter: results equal the oracle's cell by cell, on the
+    device path and on the chunked host path (one counter reset per launch), for shards
+    smaller than one block and with inactive cells"""
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    wl = W.by_name(name, ncell=n, tran_dt=dt)
+    wl.state.a["imat"][0, 3] = 0
+    ref = wl.state.copy()
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 8)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    step.load_specialized(specialize.build(wl.cfg, warps=1, style="refill"))
+    if host:
+        got = wl.state.copy()
+        res = step.rstep_host(got, wl.tran_dt)
+    else:
+        dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+        step.bind(dev)
+        res = step.rstep(wl.tran_dt)
+        res2 = None
+        got = dev.to_host()
+    _compare(ref, got, f"refill {name}")
     _check_summary(res_ref, res)
     step.close()
 
