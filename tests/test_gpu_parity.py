@@ -258,7 +258,7 @@ def test_autotune_picks_a_variant_and_leaves_state_alone():
     dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
     before = dev.to_host()
     times = step.autotune(dev, wl.tran_dt, sample=2048)
-    assert set(times) == {"s1", "k1"} and step.variant in times and all(t > 0 for t in times.values())
+    assert {"s1", "k1"} <= set(times) and step.variant in times and all(t > 0 for t in times.values())
     after = dev.to_host()
     for f in before.a:
         assert np.array_equal(before.a[f], after.a[f]), f
