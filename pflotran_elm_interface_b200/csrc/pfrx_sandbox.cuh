@@ -28,6 +28,25 @@ __device__ __forceinline__ void hsmooth(double x, double x_1, double x_0, double
     dH = 0.0;
     return;
   }
+  {
+    // Far from the transition the quotient below is decided by comparisons: beyond one
+    // transition width on either side it is certainly > 1 or < 0.  Same results, and the
+    // five divisions are skipped for every concentration that is not within a decade of
+    // the cut-off (all but exhausted pools).
+    const double d = x_1 - x_0;
+    if (d > 0.0) {
+      if (x > x_1 + d) {
+        H = 1.0;
+        dH = 0.0;
+        return;
+      }
+      if (x < x_0 - d) {
+        H = 0.0;
+        dH = 0.0;
+        return;
+      }
+    }
+  }
   const double r = (x - x_0) / (x_1 - x_0);
   if (r < 0.0) {
     H = 0.0;

@@ -64,6 +64,9 @@ __device__ __forceinline__ double sx_exp(double x) { return SPEC_FASTMATH ? pfrx
 __device__ __forceinline__ double sx_log(double x) { return SPEC_FASTMATH ? pfrx_log(x) : log(x); }
 __device__ __forceinline__ double sx_rcp(double x) { return SPEC_FASTMATH ? pfrx_rcp(x) : 1.0 / x; }
 __device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTMATH ? pfrx_div(a, b) : a / b; }
+// FuncMonod and its derivative (elm_rspfuncs.F90:321-338) for the generated sandbox code
+__device__ __forceinline__ double sx_monod(double c, double k) { return sx_div(c, c + k); }
+__device__ __forceinline__ double sx_dmonod(double c, double k) { return sx_div(sx_div(k, c + k), c + k); }
 
 #define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 

@@ -37,7 +37,8 @@ OUT = os.path.join(CSRC, "_spec")
 LOG_TO_LN = chem.LOG_TO_LN
 
 # variant letter -> code style (PFRX_SPEC_VARIANT=<letter><warps per 32 cells>)
-VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled", "q": "refill"}
+VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled", "q": "refill",
+                  "p": "refill_looplu"}
 
 
 def _fnv1a(data: bytes) -> int:
@@ -733,8 +734,8 @@ class _Gen:
             w(f"    const double nratecap = temp_real * {fr} * net_nmin_rate * dt;")
             w("    double fcap = 1.0, dfcap = 0.0;")
             w("    if (nratecap > c_nh4 * s.vol) {")
-            w("      fcap = pfrx_sbx::monod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
-            w("      dfcap = pfrx_sbx::dmonod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
+            w("      fcap = sx_monod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
+            w("      dfcap = sx_dmonod(c_nh4 * s.vol, nratecap - c_nh4 * s.vol);")
             w("    }")
             w("    dfeps0 = dfeps0 * fcap + feps0 * dfcap;")
             w("    feps0 = feps0 * fcap;")
@@ -763,7 +764,7 @@ class _Gen:
             w(f"    const double c_no3 = {('tot[%d] * theta * 1000.0' % no3) if no3 >= 0 else '0.0'};")
             w("    double finh = 1.0; bool skip = false;")
             if sd.inhibition_nh4_no3 > 0.0:
-                w(f"    if (c_nh4 > {x0} && c_no3 > {x0}) finh = pfrx_sbx::monod(c_nh4 / c_no3, {_lit(1.0 / sd.inhibition_nh4_no3)});")
+                w(f"    if (c_nh4 > {x0} && c_no3 > {x0}) finh = sx_monod(c_nh4 / c_no3, {_lit(1.0 / sd.inhibition_nh4_no3)});")
                 w(f"    else if (c_nh4 > {x0} && c_no3 <= {x0}) finh = 1.0;")
                 w(f"    else if (c_nh4 <= {x0} && c_no3 > {x0}) finh = 0.0;")
                 w("    else skip = true;")
@@ -780,20 +781,20 @@ class _Gen:
                 w(f"      double t = fmax(0.0, c_nh4 - {thr});")
                 if pn:
                     w(f"      t = t / c[{uc}];")
-                w(f"      fnh4 = pfrx_sbx::monod(t, {mk}); dfnh4 = pfrx_sbx::dmonod(t, {mk});")
+                w(f"      fnh4 = sx_monod(t, {mk}); dfnh4 = sx_dmonod(t, {mk});")
             elif react2 and no3 >= 0 and sid == no3:
                 w(f"      double t = fmax(0.0, c_no3 - {thr});")
                 if pn:
                     w(f"      t = t / c[{uc}];")
-                w(f"      fno3 = pfrx_sbx::monod(t, {mk}); dfno3 = pfrx_sbx::dmonod(t, {mk});")
+                w(f"      fno3 = sx_monod(t, {mk}); dfno3 = sx_dmonod(t, {mk});")
             else:
                 w(f"      double t = fmax(0.0, {self._conc(sid, sty)} - {thr});")
                 if pn:
                     w(f"      t = t / c[{uc}];")
                     if sty == abi.SPEC_AQUEOUS:
                         w("      t = t * theta * 1000.0;" if react2 else "      t = t * s.por * s.sat * 1000.0;")
-                w(f"      const double fx = pfrx_sbx::monod(t, {mk});")
-                w(f"      const double dfx = {'pfrx_sbx::dmonod(t, ' + mk + ')' if ucid == sid else '0.0'};")
+                w(f"      const double fx = sx_monod(t, {mk});")
+                w(f"      const double dfx = {'sx_dmonod(t, ' + mk + ')' if ucid == sid else '0.0'};")
                 w("      dfmb = dfmb * fx + fmb * dfx; fmb = fmb * fx;")
             w("    }")
         for k in range(int(sa["inhib_ptr"][r]), int(sa["inhib_ptr"][r + 1])):
@@ -806,8 +807,8 @@ class _Gen:
                     w(f"      const double fx = {_lit(ik)} / (t + {_lit(ik)});")
                     w(f"      double dfx = -{_lit(ik)} / (t + {_lit(ik)}) / (t + {_lit(ik)});")
                 elif ity == 4:
-                    w(f"      const double fx = pfrx_sbx::monod(t, {_lit(ik)});")
-                    w(f"      double dfx = pfrx_sbx::dmonod(t, {_lit(ik)});")
+                    w(f"      const double fx = sx_monod(t, {_lit(ik)});")
+                    w(f"      double dfx = sx_dmonod(t, {_lit(ik)});")
                 else:
                     w("      const double fx = 1.0; double dfx = 0.0;")
             else:
@@ -834,15 +835,15 @@ class _Gen:
             w("    const double nratecap = -crate_uc * nst * dt / 0.45;")
             w("    { double fcap = 1.0, dfcap = 0.0;")
             w("      if (nratecap * finh > c_nh4 * s.vol) {")
-            w("        fcap = pfrx_sbx::monod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
-            w("        dfcap = pfrx_sbx::dmonod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
+            w("        fcap = sx_monod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
+            w("        dfcap = sx_dmonod(c_nh4 * s.vol, nratecap * finh - c_nh4 * s.vol);")
             w("      }")
             w("      dfnh4 = dfnh4 * fcap + fnh4 * dfcap; fnh4 = fnh4 * fcap; }")
             if no3 >= 0:
                 w("    { double fcap = 1.0, dfcap = 0.0;")
                 w("      if (nratecap * (1.0 - finh) > c_no3 * s.vol) {")
-                w("        fcap = pfrx_sbx::monod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
-                w("        dfcap = pfrx_sbx::dmonod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
+                w("        fcap = sx_monod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
+                w("        dfcap = sx_dmonod(c_no3 * s.vol, nratecap * (1.0 - finh) - c_no3 * s.vol);")
                 w("      }")
                 w("      dfno3 = dfno3 * fcap + fno3 * dfcap; fno3 = fno3 * fcap; }")
             w("    const double crate_nh4 = crate_uc * fnh4 * finh;")
@@ -1052,8 +1053,8 @@ class _Gen:
             w("    feps0 = 1.0; dfeps0 = 0.0;")
             w(f"    if (c_no3 <= {_lit(dn.x0eps)}) break;")
         if dn.half_saturation > 0.0:
-            w(f"    const double fno3 = pfrx_sbx::monod(c_no3, {_lit(dn.half_saturation)});")
-            w(f"    const double dfno3 = pfrx_sbx::dmonod(c_no3, {_lit(dn.half_saturation)});")
+            w(f"    const double fno3 = sx_monod(c_no3, {_lit(dn.half_saturation)});")
+            w(f"    const double dfno3 = sx_dmonod(c_no3, {_lit(dn.half_saturation)});")
         else:
             w("    const double fno3 = 1.0, dfno3 = 0.0;")
         w("    if (f_t > 0.0 && f_w > 0.0) {")
@@ -1735,9 +1736,9 @@ def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style:
     if warps > 1:
         return _GenW(cfg, warps).source()
     g = _Gen(cfg)
-    g.loop_lu = style in ("looplu", "klooplu")
-    g.lockstep = style in ("lockstep", "klooplu", "refill")
-    g.refill = style == "refill"
+    g.loop_lu = style in ("looplu", "klooplu", "refill_looplu")
+    g.lockstep = style in ("lockstep", "klooplu", "refill", "refill_looplu")
+    g.refill = style in ("refill", "refill_looplu")
     return g.source()
 
 

@@ -197,7 +197,7 @@ def test_batched_reaction_matches_oracle(variant):
     step.close()
 
 
-@pytest.mark.parametrize("variant", ["s1", "k1", "l1", "q1"])
+@pytest.mark.parametrize("variant", ["s1", "k1", "l1", "q1", "p1"])
 def test_specialized_skeletons_agree_with_oracle(variant):
     """one-warp blocks, lock-step blocks and the rolled dense solve are the same arithmetic"""
     rstep = _gpu()
@@ -217,9 +217,10 @@ def test_specialized_skeletons_agree_with_oracle(variant):
     step.close()
 
 
+@pytest.mark.parametrize("style", ["refill", "refill_looplu"])
 @pytest.mark.parametrize("name,n,dt,host", [("c4s", 20000, 1800.0, False), ("c4s", 300000, 1800.0, True),
                                             ("c3", 5000, 3600.0, False), ("c2", 50, 3600.0, False)])
-def test_refill_skeleton(name, n, dt, host):
+def test_refill_skeleton(name, n, dt, host, style):
     """variant q1: finished lanes fetch the next cell from an atomic counter.  Which lane
     computes which cell must not matter: results equal the oracle's cell by cell, on the
     device path and on the chunked host path (one counter reset per launch), for shards
@@ -232,7 +233,7 @@ def test_refill_skeleton(name, n, dt, host):
     ref = wl.state.copy()
     res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 8)
     step = rstep.ChemistryStep(wl.cfg, 0)
-    step.load_specialized(specialize.build(wl.cfg, warps=1, style="refill"))
+    step.load_specialized(specialize.build(wl.cfg, warps=1, style=style))
     if host:
         got = wl.state.copy()
         res = step.rstep_host(got, wl.tran_dt)
