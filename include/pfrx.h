@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 2
+#define PFRX_ABI_VERSION 3
 
 /* error classes */
 #define PFRX_OK 0
@@ -87,6 +87,9 @@ extern "C" {
 #define PFRX_SANDBOX_SOMDEC 2
 #define PFRX_SANDBOX_NITRIF 3
 #define PFRX_SANDBOX_DENITR 4
+#define PFRX_SANDBOX_PLANTN 5
+#define PFRX_SANDBOX_LANGMUIR 6
+#define PFRX_MAX_SANDBOXES 8
 
 /*
  * SOMDECOMP sandbox: reaction_sandbox_somdec_type after SomDecSetup
@@ -154,6 +157,29 @@ typedef struct pfrx_denitr {
   double k_deni_max;              /* 2.5e-6 1/s */
   double x0eps;                   /* 1e-20 */
 } pfrx_denitr;
+
+/* PLANTN sandbox: plant N uptake from NH4+ / NO3- (reaction_sandbox_plantn.F90:18-56, 222-640).
+ * In the ELM build the demand comes per cell from ELM (pfrx_state.elm_rate_plantndemand,
+ * mol/m^3/s), otherwise it is 1e-2 * volume as in the reference's stand-alone build. */
+typedef struct pfrx_plantn {
+  int32_t nh4_id, no3_id;                 /* primary ids, -1 absent */
+  int32_t plantn_id;                      /* immobile id of PlantN (required) */
+  int32_t plantndemand_id, plantnh4uptake_id, plantno3uptake_id; /* immobile trackers, -1 absent */
+  double half_saturation_nh4;             /* 1e-15 */
+  double half_saturation_no3;             /* 1e-15 */
+  double inhibition_nh4_no3;              /* 1.0 */
+  double x0eps_nh4, x0eps_no3;            /* 1e-20 */
+} pfrx_plantn;
+
+/* LANGMUIR sandbox: kinetic Langmuir sorption of one aqueous species onto one immobile
+ * species (reaction_sandbox_langmu.F90:20-58, 183-330) */
+typedef struct pfrx_langmuir {
+  int32_t aq_id;                          /* primary id */
+  int32_t sorb_id;                        /* immobile id */
+  double k_kinetic;                       /* 1e-5 1/s */
+  double k_equilibrium;                   /* 2.5e3 */
+  double s_max;                           /* 1e-3 mol/m^3 */
+} pfrx_langmuir;
 
 /*
  * Flattened, read-only reaction description: the subset of
@@ -278,8 +304,10 @@ typedef struct pfrx_config {
   const pfrx_somdec *somdec;     /* reaction_sandbox_somdec.F90:1504-3640 */
   const pfrx_nitrif *nitrif;     /* reaction_sandbox_nitrif.F90:234-502   */
   const pfrx_denitr *denitr;     /* reaction_sandbox_denitr.F90:212-404   */
+  const pfrx_plantn *plantn;     /* reaction_sandbox_plantn.F90:222-640   */
+  const pfrx_langmuir *langmuir; /* reaction_sandbox_langmu.F90:183-330   */
   /* evaluation order of the sandboxes (PFRX_SANDBOX_*); NULL => the order
-   * CLM-CN, SOMDEC, NITRIF, DENITR */
+   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR */
   int32_t nsandbox;
   const int32_t *sandbox_list;
   /* 1 => the behaviour of a reference built with -DELM_PFLOTRAN in BGC-only
@@ -338,6 +366,7 @@ typedef struct pfrx_state {
   const double *elm_kscalar_decomp_c;
   const double *elm_bulkdensity_dry;
   const double *elm_bsw;
+  const double *elm_rate_plantndemand;   /* rate_plantndemand_pfs, mol/m^3/s (PLANTN) */
   /* SOMDECOMP: last N:C ratios of the variable-C:N pools, io
    * [somdec.nrxn + somdec.downstream_ptr[nrxn]]: upstream_nc(irxn) then
    * downstream_nc(j).  The reference keeps them in the sandbox object and only

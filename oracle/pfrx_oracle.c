@@ -51,7 +51,7 @@ typedef struct {
   double ln_act_h2o;
   double den_kg, sat, temp, porosity, volume, soil_particle_density;
   /* ELM per-cell scalars (elm_pflotran builds) */
-  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
   int nsomdec_nc;
   /* per-cell copies of the temperature dependent tables
@@ -165,6 +165,7 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->elm_kscalar = st->elm_kscalar_decomp_c ? LD(st->elm_kscalar_decomp_c, 0) : 1.0;
   c->elm_bd_dry = st->elm_bulkdensity_dry ? LD(st->elm_bulkdensity_dry, 0) : 1.25e3;
   c->elm_bsw = st->elm_bsw ? LD(st->elm_bsw, 0) : 1.0;
+  c->elm_plantndemand = st->elm_rate_plantndemand ? LD(st->elm_rate_plantndemand, 0) : 0.0;
   c->option_ierror = 0;
 }
 
@@ -1931,17 +1932,217 @@ static void denitr_react(cell_t *c, const pfrx_config *cfg, double *Residual, do
 #undef JAC
 #undef DTOT
 
+/* reaction_sandbox_plantn.F90:222-640  PlantNReact */
+static void plantn_react(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Residual, double *Jacobian,
+                         int compute_derivative) {
+  const pfrx_plantn *pn = cfg->plantn;
+  int off = c->naq, n = c->n;
+  double volume = c->volume, porosity = c->porosity, saturation = c->sat, tc = c->temp;
+  double theta, L_water, c_nh4 = 0.0, c_no3 = 0.0;
+  double fnh4 = 1.0, dfnh4_dnh4 = 0.0, fno3 = 1.0, dfno3_dno3 = 0.0;
+  double fnh4_inhibit_no3 = 1.0, dfnh4_inhibit_no3_dnh4 = 0.0, dfnh4_inhibit_no3_dno3 = 0.0;
+  double temp_real, feps0, dfeps0_dx, rate_plantndemand, dtmin, nratecap, fnratecap, dfnratecap_dnh4,
+      dfnratecap_dno3;
+  int ires_plantn = off + pn->plantn_id, ires_nh4 = pn->nh4_id, ires_no3 = pn->no3_id;
+  if (saturation < 0.01) return;
+  theta = saturation * porosity;
+  L_water = theta * 1.0e3;
+  if (tc < -0.1) return;
+  if (pn->nh4_id >= 0 && pn->no3_id >= 0) {
+    c_nh4 = c->total[pn->nh4_id] * L_water;
+    c_no3 = c->total[pn->no3_id] * L_water;
+    if ((c_nh4 > pn->x0eps_nh4 && c_no3 > pn->x0eps_no3) && pn->inhibition_nh4_no3 > 0.0) {
+      temp_real = c_nh4 / c_no3;
+      fnh4_inhibit_no3 = func_monod(temp_real, 1.0 / pn->inhibition_nh4_no3, 0);
+    } else {
+      if (c_nh4 > pn->x0eps_nh4 && c_no3 <= pn->x0eps_no3)
+        fnh4_inhibit_no3 = 1.0;
+      else if (c_nh4 <= pn->x0eps_nh4 && c_no3 > pn->x0eps_no3)
+        fnh4_inhibit_no3 = 0.0;
+      else
+        return;
+    }
+  }
+  if (pn->nh4_id >= 0) {
+    c_nh4 = c->total[pn->nh4_id] * L_water;
+    fnh4 = func_monod(c_nh4, pn->half_saturation_nh4, 0);
+    dfnh4_dnh4 = func_monod(c_nh4, pn->half_saturation_nh4, 1);
+    if (pn->x0eps_nh4 > 0.0) {
+      hfunction_smooth(c_nh4, pn->x0eps_nh4 * 10.0, pn->x0eps_nh4, &feps0, &dfeps0_dx);
+    } else {
+      feps0 = 1.0;
+      dfeps0_dx = 0.0;
+    }
+    dfnh4_dnh4 = dfnh4_dnh4 * feps0 + fnh4 * dfeps0_dx;
+    fnh4 = fnh4 * feps0;
+  }
+  if (pn->no3_id >= 0) {
+    c_no3 = c->total[pn->no3_id] * L_water;
+    fno3 = func_monod(c_no3, pn->half_saturation_no3, 0);
+    dfno3_dno3 = func_monod(c_no3, pn->half_saturation_no3, 1);
+    if (pn->x0eps_no3 > 0.0) {
+      hfunction_smooth(c_no3, pn->x0eps_no3 * 10.0, pn->x0eps_no3, &feps0, &dfeps0_dx);
+    } else {
+      feps0 = 1.0;
+      dfeps0_dx = 0.0;
+    }
+    dfno3_dno3 = dfno3_dno3 * feps0 + fno3 * dfeps0_dx;
+    fno3 = fno3 * feps0;
+  }
+  if (cfg->elm_pflotran) {
+    rate_plantndemand = fmax(0.0, c->elm_plantndemand * volume);
+    if (rate_plantndemand <= 0.0) return;
+  } else {
+    rate_plantndemand = 1.e-2 * volume;
+  }
+  if (pn->plantndemand_id >= 0)
+    Residual[off + pn->plantndemand_id] = Residual[off + pn->plantndemand_id] - rate_plantndemand;
+  if (rate_plantndemand > 0.0) {
+    dtmin = tran_dt;
+    if (pn->nh4_id >= 0) {
+      nratecap = rate_plantndemand * dtmin;
+      if (pn->no3_id >= 0) nratecap = rate_plantndemand * fnh4_inhibit_no3 * dtmin;
+      if (nratecap > c_nh4 * volume) {
+        fnratecap = func_monod(c_nh4 * volume, nratecap - c_nh4 * volume, 0);
+        dfnratecap_dnh4 = func_monod(c_nh4 * volume, nratecap - c_nh4 * volume, 1);
+      } else {
+        fnratecap = 1.0;
+        dfnratecap_dnh4 = 0.0;
+      }
+      dfnh4_dnh4 = dfnh4_dnh4 * fnratecap + fnh4 * dfnratecap_dnh4;
+      fnh4 = fnh4 * fnratecap;
+    }
+    if (pn->no3_id >= 0) {
+      nratecap = rate_plantndemand * dtmin;
+      if (pn->nh4_id >= 0) nratecap = rate_plantndemand * (1.0 - fnh4_inhibit_no3) * dtmin;
+      if (nratecap > c_no3 * volume) {
+        fnratecap = func_monod(c_no3 * volume, nratecap - c_no3 * volume, 0);
+        dfnratecap_dno3 = func_monod(c_no3 * volume, nratecap - c_no3 * volume, 1);
+      } else {
+        fnratecap = 1.0;
+        dfnratecap_dno3 = 0.0;
+      }
+      dfno3_dno3 = dfno3_dno3 * fnratecap + fno3 * dfnratecap_dno3;
+      fno3 = fno3 * fnratecap;
+    }
+  }
+#define JAC(i, j) Jacobian[(i) + (size_t)(j) * n]
+#define DTOT(i, j) c->dtotal[(i) + (size_t)(j) * c->naq]
+  if (pn->nh4_id >= 0) {
+    double nrate_nh4 = rate_plantndemand * fnh4;
+    if (pn->no3_id >= 0) nrate_nh4 = rate_plantndemand * fnh4 * fnh4_inhibit_no3;
+    Residual[ires_nh4] = Residual[ires_nh4] + nrate_nh4;
+    Residual[ires_plantn] = Residual[ires_plantn] - nrate_nh4;
+    if (pn->plantnh4uptake_id >= 0)
+      Residual[off + pn->plantnh4uptake_id] = Residual[off + pn->plantnh4uptake_id] - nrate_nh4;
+    if (compute_derivative) {
+      double dnrate_nh4_dnh4 = rate_plantndemand * dfnh4_dnh4;
+      if (pn->no3_id >= 0) {
+        temp_real = fnh4 * dfnh4_inhibit_no3_dnh4 + fnh4_inhibit_no3 * dfnh4_dnh4;
+        dnrate_nh4_dnh4 = rate_plantndemand * temp_real;
+      }
+      JAC(ires_nh4, ires_nh4) = JAC(ires_nh4, ires_nh4) + dnrate_nh4_dnh4 * DTOT(pn->nh4_id, pn->nh4_id);
+      JAC(ires_plantn, ires_nh4) = JAC(ires_plantn, ires_nh4) - dnrate_nh4_dnh4;
+      if (pn->plantnh4uptake_id >= 0)
+        JAC(off + pn->plantnh4uptake_id, ires_nh4) = JAC(off + pn->plantnh4uptake_id, ires_nh4) - dnrate_nh4_dnh4;
+    }
+  }
+  if (pn->no3_id >= 0) {
+    double nrate_no3 = rate_plantndemand * fno3;
+    if (pn->nh4_id >= 0) nrate_no3 = rate_plantndemand * fno3 * (1.0 - fnh4_inhibit_no3);
+    Residual[ires_no3] = Residual[ires_no3] + nrate_no3;
+    Residual[ires_plantn] = Residual[ires_plantn] - nrate_no3;
+    if (pn->plantno3uptake_id >= 0)
+      Residual[off + pn->plantno3uptake_id] = Residual[off + pn->plantno3uptake_id] - nrate_no3;
+    if (compute_derivative) {
+      double dnrate_no3_dno3 = rate_plantndemand * dfno3_dno3;
+      if (pn->nh4_id >= 0) {
+        temp_real = dfno3_dno3 * (1.0 - fnh4_inhibit_no3) + fno3 * (-1.0 * dfnh4_inhibit_no3_dno3);
+        dnrate_no3_dno3 = rate_plantndemand * temp_real;
+      }
+      JAC(ires_no3, ires_no3) = JAC(ires_no3, ires_no3) + dnrate_no3_dno3 * DTOT(pn->no3_id, pn->no3_id);
+      JAC(ires_plantn, ires_no3) = JAC(ires_plantn, ires_no3) - dnrate_no3_dno3;
+      if (pn->plantno3uptake_id >= 0)
+        JAC(off + pn->plantno3uptake_id, ires_no3) = JAC(off + pn->plantno3uptake_id, ires_no3) - dnrate_no3_dno3;
+    }
+  }
+}
+
+/* reaction_sandbox_langmu.F90:183-330  LangmuirReact */
+static void langmuir_react(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Residual, double *Jacobian,
+                           int compute_derivative) {
+  const pfrx_langmuir *lg = cfg->langmuir;
+  int off = c->naq, n = c->n;
+  double porosity = c->porosity, volume = c->volume;
+  double Lwater = volume * 1000.0 * porosity * c->sat;
+  int ires_aq = lg->aq_id, ires_sorb = off + lg->sorb_id;
+  double c_aq = c->total[lg->aq_id], c_sorb = c->immobile[lg->sorb_id];
+  double rate, drate_daq, drate_dsorb, dtmin, c_aq_eq, temp_real, ratecap, fratecap, dfratecap_dx;
+  if (lg->s_max < c_sorb) {
+    dtmin = tran_dt;
+    rate = (lg->s_max - c_sorb) * volume / dtmin;
+    drate_dsorb = -1.0 / dtmin;
+    drate_daq = 0.0;
+  } else {
+    c_aq_eq = 0.999 * c_sorb / (lg->s_max - 0.999 * c_sorb) / lg->k_equilibrium;
+    rate = lg->k_kinetic * (c_aq - c_aq_eq) * Lwater;
+    temp_real = -lg->k_kinetic / lg->k_equilibrium * Lwater / volume;
+    drate_dsorb = temp_real * lg->s_max / (lg->s_max - 0.999 * c_sorb) / (lg->s_max - 0.999 * c_sorb);
+    drate_daq = lg->k_kinetic;
+    fratecap = 1.0;
+    dfratecap_dx = 0.0;
+    if (rate > 0.0) {
+      dtmin = tran_dt;
+      ratecap = 0.999 * (lg->s_max - c_sorb) * volume / dtmin;
+      if (ratecap < rate) {
+        fratecap = ratecap / rate;
+        if (compute_derivative) {
+          temp_real = -0.999 / dtmin;
+          dfratecap_dx = (ratecap * drate_dsorb - rate * temp_real) / rate / rate;
+          drate_dsorb = fratecap * drate_dsorb + rate * dfratecap_dx;
+        }
+        rate = rate * fratecap;
+      }
+      ratecap = 0.999 * (c_aq - c_aq_eq) * Lwater / dtmin;
+      if (ratecap < rate) {
+        fratecap = ratecap / rate;
+        if (compute_derivative) {
+          temp_real = -0.999 / lg->k_equilibrium * Lwater / volume / dtmin;
+          temp_real = temp_real * lg->s_max / (lg->s_max - 0.999 * c_sorb) / (lg->s_max - 0.999 * c_sorb);
+          dfratecap_dx = (ratecap * drate_dsorb - rate * temp_real) / rate / rate;
+          drate_dsorb = fratecap * drate_dsorb + rate * dfratecap_dx;
+          temp_real = 0.999 / dtmin;
+          dfratecap_dx = (ratecap * drate_daq - rate * temp_real) / rate / rate;
+          drate_daq = fratecap * drate_daq + rate * dfratecap_dx;
+        }
+        rate = rate * fratecap;
+      }
+    }
+  }
+  Residual[ires_aq] = Residual[ires_aq] + rate;
+  Residual[ires_sorb] = Residual[ires_sorb] - rate;
+  if (compute_derivative) {
+    JAC(ires_aq, ires_aq) = JAC(ires_aq, ires_aq) + drate_daq * DTOT(lg->aq_id, lg->aq_id);
+    JAC(ires_sorb, ires_aq) = JAC(ires_sorb, ires_aq) - drate_daq;
+    JAC(ires_aq, ires_sorb) = JAC(ires_aq, ires_sorb) + drate_dsorb;
+    JAC(ires_sorb, ires_sorb) = JAC(ires_sorb, ires_sorb) - drate_dsorb;
+  }
+#undef JAC
+#undef DTOT
+}
+
 static int n_sandboxes(const pfrx_config *cfg) {
-  return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL);
+  return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL) +
+         (cfg->plantn != NULL) + (cfg->langmuir != NULL);
 }
 
 /* reaction_sandbox.F90:294-330  RSandboxEvaluate: walk the list in deck order */
 static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
                                int derivative) {
-  static const int32_t default_order[4] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
-                                           PFRX_SANDBOX_DENITR};
+  static const int32_t default_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
+                                           PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR};
   const int32_t *order = cfg->sandbox_list ? cfg->sandbox_list : default_order;
-  int ns = cfg->sandbox_list ? cfg->nsandbox : 4, k;
+  int ns = cfg->sandbox_list ? cfg->nsandbox : 6, k;
   for (k = 0; k < ns; k++) {
     switch (order[k]) {
       case PFRX_SANDBOX_CLM_CN:
@@ -1955,6 +2156,12 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
         break;
       case PFRX_SANDBOX_DENITR:
         if (cfg->denitr) denitr_react(c, cfg, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_PLANTN:
+        if (cfg->plantn) plantn_react(c, cfg, tran_dt, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_LANGMUIR:
+        if (cfg->langmuir) langmuir_react(c, cfg, tran_dt, Res, Jac, derivative);
         break;
       default:
         break;
@@ -2406,7 +2613,7 @@ int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   for (i = 0; i < n * n; i++) Jac[i] = 0.0;
   /* the GIRT caller has just run RTAuxVarCompute (reactive_transport.F90:2599-2642):
    * the sandboxes that read rt_auxvar%aqueous%dtotal need it here too */
-  if (cfg->somdec || cfg->nitrif || cfg->denitr) rt_auxvar_compute(&c, cfg);
+  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir) rt_auxvar_compute(&c, cfg);
   r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
   for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];
   if (st->somdec_nc)

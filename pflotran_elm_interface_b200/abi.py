@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 2
+PFRX_ABI_VERSION = 3
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -117,13 +117,15 @@ class PfrxConfig(C.Structure):
         ("somdec", C.c_void_p),
         ("nitrif", C.c_void_p),
         ("denitr", C.c_void_p),
+        ("plantn", C.c_void_p),
+        ("langmuir", C.c_void_p),
         ("nsandbox", C.c_int32),
         ("sandbox_list", c_int32_p),
         ("elm_pflotran", C.c_int32),
     ]
 
 
-SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR = 1, 2, 3, 4
+SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR, SANDBOX_PLANTN, SANDBOX_LANGMUIR = 1, 2, 3, 4, 5, 6
 SPEC_AQUEOUS, SPEC_IMMOBILE = 0, 2
 
 
@@ -156,6 +158,18 @@ class PfrxNitrif(C.Structure):
                 + [(f, C.c_double) for f in ("k_nitr_max", "k_nitr_n2o", "x0eps")])
 
 
+class PfrxPlantn(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("nh4_id", "no3_id", "plantn_id", "plantndemand_id", "plantnh4uptake_id",
+                                          "plantno3uptake_id")]
+                + [(f, C.c_double) for f in ("half_saturation_nh4", "half_saturation_no3", "inhibition_nh4_no3",
+                                             "x0eps_nh4", "x0eps_no3")])
+
+
+class PfrxLangmuir(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("aq_id", "sorb_id")]
+                + [(f, C.c_double) for f in ("k_kinetic", "k_equilibrium", "s_max")])
+
+
 class PfrxDenitr(C.Structure):
     _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
                 + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])
@@ -170,7 +184,7 @@ STATE_DOUBLE_FIELDS = [
 # ELM per-cell scalars (pfrx_state.elm_*): present when the configuration sets
 # elm_pflotran, NULL otherwise
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
-                    "elm_bulkdensity_dry", "elm_bsw", "somdec_nc"]
+                    "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
@@ -430,7 +444,8 @@ class ReactionConfig:
         order: List[int] = []
         for kind in getattr(net, "sandbox_order", []):
             order.append({"CLM-CN": SANDBOX_CLM_CN, "SOMDECOMP": SANDBOX_SOMDEC, "NITRIFICATION": SANDBOX_NITRIF,
-                          "DENITRIFICATION": SANDBOX_DENITR}[kind])
+                          "DENITRIFICATION": SANDBOX_DENITR, "PLANTN": SANDBOX_PLANTN,
+                          "LANGMUIR": SANDBOX_LANGMUIR}[kind])
         if order:
             c.nsandbox = len(order)
             c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
@@ -460,6 +475,20 @@ class ReactionConfig:
                 setattr(o, k, v)
             self.denitr = o
             c.denitr = C.cast(C.pointer(o), C.c_void_p)
+        pn = getattr(net, "plantn", None)
+        if pn is not None:
+            o = PfrxPlantn()
+            for k, v in pn.items():
+                setattr(o, k, v)
+            self.plantn = o
+            c.plantn = C.cast(C.pointer(o), C.c_void_p)
+        lg = getattr(net, "langmuir", None)
+        if lg is not None:
+            o = PfrxLangmuir()
+            for k, v in lg.items():
+                setattr(o, k, v)
+            self.langmuir = o
+            c.langmuir = C.cast(C.pointer(o), C.c_void_p)
 
     # ------------------------------------------------------------------ #
     @property
@@ -511,6 +540,7 @@ class HostState:
         self.a["soil_particle_density"][:] = 2650.0
         self.a["imat"][:] = 1
         self.a["srfcplxrxn_free_site_conc"][:] = 1.0e-9
+        self.a["elm_rate_plantndemand"][:] = 1.0e-2
         for f in ("elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_kscalar_decomp_c", "elm_bsw"):
             self.a[f][:] = 1.0
         self.a["elm_bulkdensity_dry"][:] = 1.25e3

@@ -351,6 +351,8 @@ class Chemistry:
     somdec: Optional[SomDecSandbox] = None
     nitrif: Optional[dict] = None
     denitr: Optional[dict] = None
+    plantn: Optional[dict] = None
+    langmuir: Optional[dict] = None
     sandbox_order: List[str] = field(default_factory=list)
     database: str = ""
     use_log_formulation: bool = False
@@ -704,6 +706,43 @@ def _read_denitr(cur: _Cursor) -> dict:
     return d
 
 
+def _read_plantn(cur: _Cursor) -> dict:
+    # PlantNCreate/PlantNRead, reaction_sandbox_plantn.F90:40-150
+    d = {"half_saturation_nh4": 1.0e-15, "half_saturation_no3": 1.0e-15, "inhibition_nh4_no3": 1.0,
+         "x0eps_nh4": 1.0e-20, "x0eps_no3": 1.0e-20}
+    keys = {"AMMONIUM_HALF_SATURATION": "half_saturation_nh4", "NITRATE_HALF_SATURATION": "half_saturation_no3",
+            "AMMONIUM_INHIBITION_NITRATE": "inhibition_nh4_no3", "X0EPS_NH4": "x0eps_nh4", "X0EPS_NO3": "x0eps_no3"}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "RATE_PLANTNDEMAND":
+            pass      # read, then overwritten by PlantNReact (reaction_sandbox_plantn.F90:399-409)
+        elif key in keys:
+            d[keys[key]] = _fnum(t[1])
+        else:
+            raise ValueError(f"PLANTN keyword {key}")
+    return d
+
+
+def _read_langmuir(cur: _Cursor) -> dict:
+    # LangmuirCreate/LangmuirRead, reaction_sandbox_langmu.F90:44-140
+    d = {"name_aq": "", "name_sorb": "", "k_kinetic": 1.0e-5, "k_equilibrium": 2.5e3, "s_max": 1.0e-3}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "NAME_AQ":
+            d["name_aq"] = t[1]
+        elif key == "NAME_SORB":
+            d["name_sorb"] = t[1]
+        elif key == "EQUILIBRIUM_CONSTANT":
+            d["k_equilibrium"] = _fnum(t[1])
+        elif key == "KINETIC_CONSTANT":
+            d["k_kinetic"] = _fnum(t[1])
+        elif key == "S_MAX":
+            d["s_max"] = _fnum(t[1])
+        else:
+            raise ValueError(f"LANGMUIR keyword {key}")
+    return d
+
+
 def read_chemistry(cur: _Cursor) -> Chemistry:
     """CHEMISTRY block (ReactionReadPass1, reaction.F90:121-936)."""
     ch = Chemistry()
@@ -747,6 +786,12 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                     ch.sandbox_order.append(k2)
                 elif k2 == "DENITRIFICATION" and ch.denitr is None:
                     ch.denitr = _read_denitr(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "PLANTN" and ch.plantn is None:
+                    ch.plantn = _read_plantn(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "LANGMUIR" and ch.langmuir is None:
+                    ch.langmuir = _read_langmuir(cur)
                     ch.sandbox_order.append(k2)
                 else:
                     ch.unsupported.append("REACTION_SANDBOX," + k2)
@@ -869,6 +914,7 @@ class Deck:
     newton: Dict[str, float] = field(default_factory=dict)
     osrt: bool = False
     max_steps: Optional[int] = None
+    numerical_jacobian: bool = False
 
 
 def read_deck(text: str) -> Deck:
@@ -907,6 +953,8 @@ def read_deck(text: str) -> Deck:
             in_transport_nm = len(t) > 1 and t[1].upper() == "TRANSPORT"
         elif key == "MAX_STEPS" and in_transport_nm:
             dk.max_steps = int(t[1])
+        elif key == "NUMERICAL_JACOBIAN" and in_transport_nm:
+            dk.numerical_jacobian = True
         elif key == "TS_ACCELERATION" and in_transport_nm:
             dk.ts_acceleration = int(t[1])
         elif key in ("ATOL", "RTOL", "STOL", "MAXIMUM_NUMBER_OF_ITERATIONS", "MAXIT") and in_transport_nm:
@@ -1365,6 +1413,25 @@ class ReactionNetwork:
                 raise KeyError("DENITRIFICATION needs NO3- as a primary species")
             d["ngasdeni_id"] = imm.get("NGASdeni", -1)
             self.denitr = d
+        self.plantn = self.langmuir = None
+        if self.chem.plantn is not None:
+            # PlantNSetup, reaction_sandbox_plantn.F90:152-220
+            d = dict(self.chem.plantn)
+            d["nh4_id"], d["no3_id"] = pri.get("NH4+", -1), pri.get("NO3-", -1)
+            if d["nh4_id"] < 0 and d["no3_id"] < 0:
+                raise KeyError("PLANTN needs NH4+ or NO3- as a primary species")
+            if "PlantN" not in imm:
+                raise KeyError("PLANTN needs the immobile species PlantN")
+            d["plantn_id"] = imm["PlantN"]
+            d["plantndemand_id"] = imm.get("Plantndemand", -1)
+            d["plantnh4uptake_id"] = imm.get("Plantnh4uptake", -1)
+            d["plantno3uptake_id"] = imm.get("Plantno3uptake", -1)
+            self.plantn = d
+        if self.chem.langmuir is not None:
+            # LangmuirSetup, reaction_sandbox_langmu.F90:142-181
+            g = self.chem.langmuir
+            self.langmuir = {"aq_id": pri[g["name_aq"]], "sorb_id": imm[g["name_sorb"]],
+                             "k_kinetic": g["k_kinetic"], "k_equilibrium": g["k_equilibrium"], "s_max": g["s_max"]}
 
     # -- helpers -------------------------------------------------------------- #
     def csr(self, rxns: Sequence[Rxn]):

@@ -81,6 +81,16 @@ COPY = [
     ("regression_tests/ngee/CLMCNplus/clm_cn2.regression.gold", "clmcnplus_clm_cn2.regression.gold"),
     ("regression_tests/ngee/CLMCNplus/clm_cn3.in", "clmcnplus_clm_cn3.in"),
     ("regression_tests/ngee/CLMCNplus/clm_cn3.regression.gold", "clmcnplus_clm_cn3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake1.in", "clmcnplus_clm_nuptake1.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake1.regression.gold", "clmcnplus_clm_nuptake1.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake2.in", "clmcnplus_clm_nuptake2.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake2.regression.gold", "clmcnplus_clm_nuptake2.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake3.in", "clmcnplus_clm_nuptake3.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nuptake3.regression.gold", "clmcnplus_clm_nuptake3.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nh4absorption.in", "clmcnplus_clm_nh4absorption.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nh4absorption.regression.gold", "clmcnplus_clm_nh4absorption.regression.gold"),
+    ("regression_tests/ngee/CLMCNplus/clm_nh4desorption.in", "clmcnplus_clm_nh4desorption.in"),
+    ("regression_tests/ngee/CLMCNplus/clm_nh4desorption.regression.gold", "clmcnplus_clm_nh4desorption.regression.gold"),
     ("regression_tests/ngee/CLMCNplus/CLM-CN_database.dat", "clmcnplus_CLM-CN_database.dat"),
 ]
 
