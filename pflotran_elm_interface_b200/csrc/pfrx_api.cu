@@ -257,7 +257,23 @@ static uint64_t config_signature(const pfrx_config *c) {
     h = fnv1a(h, hi, sizeof(hi));
     h = fnv1a(h, hd, sizeof(hd));
   }
-  if (c->somdec || c->nitrif || c->denitr) {
+  if (c->plantn) {
+    const pfrx_plantn *pn = c->plantn;
+    int32_t hi[6] = {pn->nh4_id, pn->no3_id, pn->plantn_id, pn->plantndemand_id, pn->plantnh4uptake_id,
+                     pn->plantno3uptake_id};
+    double hd[5] = {pn->half_saturation_nh4, pn->half_saturation_no3, pn->inhibition_nh4_no3, pn->x0eps_nh4,
+                    pn->x0eps_no3};
+    h = fnv1a(h, hi, sizeof(hi));
+    h = fnv1a(h, hd, sizeof(hd));
+  }
+  if (c->langmuir) {
+    const pfrx_langmuir *lg = c->langmuir;
+    int32_t hi[2] = {lg->aq_id, lg->sorb_id};
+    double hd[3] = {lg->k_kinetic, lg->k_equilibrium, lg->s_max};
+    h = fnv1a(h, hi, sizeof(hi));
+    h = fnv1a(h, hd, sizeof(hd));
+  }
+  if (c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir) {
     int32_t e = c->elm_pflotran ? 1 : 0;
     h = fnv1a(h, &e, sizeof(e));
     if (c->sandbox_list) ADD(c->sandbox_list, c->nsandbox)
@@ -407,7 +423,7 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 28
+#define PFRX_NUM_D 29
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
@@ -415,7 +431,7 @@ static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   const int nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
                        c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, c->neqsrfcplxrxn > 0 ? c->naqcomp : 0,
-                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc};
+                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -558,7 +574,11 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
       return set_err(PFRX_E_INVALID, "prefactor arrays missing%s", "");
   }
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
-  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr;
+  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir;
+  if (c->plantn && (c->plantn->plantn_id < 0 || (c->plantn->nh4_id < 0 && c->plantn->no3_id < 0)))
+    return set_err(PFRX_E_INVALID, "PLANTN needs PlantN and NH4+ or NO3-%s", "");
+  if (c->langmuir && (c->langmuir->aq_id < 0 || c->langmuir->sorb_id < 0))
+    return set_err(PFRX_E_INVALID, "LANGMUIR needs its aqueous and sorbed species%s", "");
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
     if (sd->nrxn < 1 || !sd->downstream_ptr || !sd->monod_ptr || !sd->inhib_ptr || !sd->upstream_c_id)
@@ -584,7 +604,8 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
   if (c->sandbox_list)
     for (int k = 0; k < c->nsandbox; k++)
-      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_DENITR || c->nsandbox > 4)
+      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_LANGMUIR ||
+          c->nsandbox > PFRX_MAX_SANDBOXES)
         return set_err(PFRX_E_INVALID, "bad sandbox_list%s", "");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -641,24 +662,30 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_sd = c->somdec ? 1 : 0;
   d.has_nt = c->nitrif ? 1 : 0;
   d.has_dn = c->denitr ? 1 : 0;
+  d.has_pn = c->plantn ? 1 : 0;
+  d.has_lg = c->langmuir ? 1 : 0;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = has_sbx3 ? 1 : 0;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
-    static const int def_order[4] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF, PFRX_SANDBOX_DENITR};
+    static const int def_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
+                                     PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR};
     const int32_t *ord = c->sandbox_list ? c->sandbox_list : def_order;
-    const int no = c->sandbox_list ? c->nsandbox : 4;
+    const int no = c->sandbox_list ? c->nsandbox : 6;
     d.nsbx = 0;
     for (int k = 0; k < no; k++) {
       const int kind = ord[k];
       const bool present = (kind == PFRX_SANDBOX_CLM_CN && c->clmcn_nrxn > 0) ||
                            (kind == PFRX_SANDBOX_SOMDEC && c->somdec) || (kind == PFRX_SANDBOX_NITRIF && c->nitrif) ||
-                           (kind == PFRX_SANDBOX_DENITR && c->denitr);
+                           (kind == PFRX_SANDBOX_DENITR && c->denitr) || (kind == PFRX_SANDBOX_PLANTN && c->plantn) ||
+                           (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir);
       if (present) d.sbx[d.nsbx++] = kind;
     }
   }
   if (c->nitrif) d.nt = *c->nitrif;
   if (c->denitr) d.dn = *c->denitr;
+  if (c->plantn) d.pn = *c->plantn;
+  if (c->langmuir) d.lg = *c->langmuir;
 
   // kernel variant first: the task partition depends on the lane count
   {
@@ -1018,6 +1045,7 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->elm_bd_dry = s->elm_bulkdensity_dry;
   d->elm_bsw = s->elm_bsw;
   d->somdec_nc = s->somdec_nc;
+  d->elm_plantndemand = s->elm_rate_plantndemand;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -1224,7 +1252,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.volume, (double **)&h->own_st.soil_particle_density,
                            (double **)&h->own_st.elm_w, (double **)&h->own_st.elm_o, (double **)&h->own_st.elm_t,
                            (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
-                           (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc};
+                           (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
+                           (double **)&h->own_st.elm_plantndemand};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -1242,14 +1271,14 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->sat,          host->temp,         host->porosity,  host->volume,
                               host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
-                              host->somdec_nc};
+                              host->somdec_nc,    host->elm_rate_plantndemand};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
-                         d.somdec_nc};
+                         d.somdec_nc,    (double *)d.elm_plantndemand};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -1265,6 +1294,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (!host->elm_bulkdensity_dry) d.elm_bd_dry = nullptr;
   if (!host->elm_bsw) d.elm_bsw = nullptr;
   if (!host->somdec_nc) d.somdec_nc = nullptr;
+  if (!host->elm_rate_plantndemand) d.elm_plantndemand = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -1299,7 +1329,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
-                         host->somdec_nc};
+                         host->somdec_nc,    nullptr};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the
@@ -1370,6 +1400,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     PFRX_OFF(elm_bd_dry);
     PFRX_OFF(elm_bsw);
     PFRX_OFF(somdec_nc);
+    PFRX_OFF(elm_plantndemand);
     PFRX_OFF(imat);
     PFRX_OFF(num_sub_steps);
     PFRX_OFF(num_iterations);

@@ -87,13 +87,15 @@ struct DevCfg {
   const double *mr_rate, *mr_frac;
   // CLM-CN
   // ELM-CN sandboxes (pfrx_sandbox.cuh): tables as in include/pfrx.h with device pointers
-  int nsbx, sbx[4];      // evaluation order, PFRX_SANDBOX_*
-  int has_sd, has_nt, has_dn, elm;
+  int nsbx, sbx[PFRX_MAX_SANDBOXES];  // evaluation order, PFRX_SANDBOX_*
+  int has_sd, has_nt, has_dn, has_pn, has_lg, elm;
   int need_dt;           // a sandbox reads d(total)/d(free): keep a copy next to the Jacobian
   int off_dt, off_nc, n_nc;
   pfrx_somdec sd;
   pfrx_nitrif nt;
   pfrx_denitr dn;
+  pfrx_plantn pn;
+  pfrx_langmuir lg;
   int cn_nrxn, cn_C, cn_N;
   const double *cn_CN, *cn_k, *cn_resp, *cn_inhib;
   const int *cn_nspec, *cn_cid, *cn_nid, *cn_up, *cn_down;

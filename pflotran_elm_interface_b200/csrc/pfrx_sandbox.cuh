@@ -752,4 +752,165 @@ __device__ __forceinline__ void denitr_react(Cell &s) {
   }
 }
 
+// ---- PLANTN (reaction_sandbox_plantn.F90:222-640) -------------------------------------
+template <class Cell>
+__device__ __forceinline__ void plantn_react(Cell &s, double tran_dt) {
+  const pfrx_plantn &pn = s.cfg.pn;
+  const int off = s.cfg.naq;
+  const double volume = s.vol, saturation = s.sat, tc = s.temp;
+  if (saturation < 0.01) return;
+  const double L_water = saturation * s.por * 1.0e3;
+  if (tc < -0.1) return;
+  const int ires_plantn = off + pn.plantn_id, ires_nh4 = pn.nh4_id, ires_no3 = pn.no3_id;
+  double c_nh4 = 0.0, c_no3 = 0.0, fnh4 = 1.0, dfnh4 = 0.0, fno3 = 1.0, dfno3 = 0.0, finh = 1.0;
+  if (pn.nh4_id >= 0 && pn.no3_id >= 0) {
+    c_nh4 = s.TOTc(pn.nh4_id) * L_water;
+    c_no3 = s.TOTc(pn.no3_id) * L_water;
+    if ((c_nh4 > pn.x0eps_nh4 && c_no3 > pn.x0eps_no3) && pn.inhibition_nh4_no3 > 0.0) {
+      finh = monod(c_nh4 / c_no3, 1.0 / pn.inhibition_nh4_no3);
+    } else {
+      if (c_nh4 > pn.x0eps_nh4 && c_no3 <= pn.x0eps_no3)
+        finh = 1.0;
+      else if (c_nh4 <= pn.x0eps_nh4 && c_no3 > pn.x0eps_no3)
+        finh = 0.0;
+      else
+        return;
+    }
+  }
+  double feps0, dfeps0;
+  if (pn.nh4_id >= 0) {
+    c_nh4 = s.TOTc(pn.nh4_id) * L_water;
+    fnh4 = monod(c_nh4, pn.half_saturation_nh4);
+    dfnh4 = dmonod(c_nh4, pn.half_saturation_nh4);
+    if (pn.x0eps_nh4 > 0.0) {
+      hsmooth(c_nh4, pn.x0eps_nh4 * 10.0, pn.x0eps_nh4, feps0, dfeps0);
+    } else {
+      feps0 = 1.0;
+      dfeps0 = 0.0;
+    }
+    dfnh4 = dfnh4 * feps0 + fnh4 * dfeps0;
+    fnh4 = fnh4 * feps0;
+  }
+  if (pn.no3_id >= 0) {
+    c_no3 = s.TOTc(pn.no3_id) * L_water;
+    fno3 = monod(c_no3, pn.half_saturation_no3);
+    dfno3 = dmonod(c_no3, pn.half_saturation_no3);
+    if (pn.x0eps_no3 > 0.0) {
+      hsmooth(c_no3, pn.x0eps_no3 * 10.0, pn.x0eps_no3, feps0, dfeps0);
+    } else {
+      feps0 = 1.0;
+      dfeps0 = 0.0;
+    }
+    dfno3 = dfno3 * feps0 + fno3 * dfeps0;
+    fno3 = fno3 * feps0;
+  }
+  double demand;
+  if (s.cfg.elm) {
+    demand = fmax(0.0, s.elm_plantndemand * volume);
+    if (demand <= 0.0) return;
+  } else {
+    demand = 1.e-2 * volume;
+  }
+  if (pn.plantndemand_id >= 0) s.RES(off + pn.plantndemand_id) -= demand;
+  if (demand > 0.0) {
+    if (pn.nh4_id >= 0) {
+      double cap = demand * tran_dt;
+      if (pn.no3_id >= 0) cap = demand * finh * tran_dt;
+      double fcap = 1.0, dfcap = 0.0;
+      if (cap > c_nh4 * volume) {
+        fcap = monod(c_nh4 * volume, cap - c_nh4 * volume);
+        dfcap = dmonod(c_nh4 * volume, cap - c_nh4 * volume);
+      }
+      dfnh4 = dfnh4 * fcap + fnh4 * dfcap;
+      fnh4 = fnh4 * fcap;
+    }
+    if (pn.no3_id >= 0) {
+      double cap = demand * tran_dt;
+      if (pn.nh4_id >= 0) cap = demand * (1.0 - finh) * tran_dt;
+      double fcap = 1.0, dfcap = 0.0;
+      if (cap > c_no3 * volume) {
+        fcap = monod(c_no3 * volume, cap - c_no3 * volume);
+        dfcap = dmonod(c_no3 * volume, cap - c_no3 * volume);
+      }
+      dfno3 = dfno3 * fcap + fno3 * dfcap;
+      fno3 = fno3 * fcap;
+    }
+  }
+  if (pn.nh4_id >= 0) {
+    double nrate = demand * fnh4;
+    if (pn.no3_id >= 0) nrate = demand * fnh4 * finh;
+    s.RES(ires_nh4) = s.RES(ires_nh4) + nrate;
+    s.RES(ires_plantn) = s.RES(ires_plantn) - nrate;
+    if (pn.plantnh4uptake_id >= 0) s.RES(off + pn.plantnh4uptake_id) -= nrate;
+    double dn = demand * dfnh4;
+    if (pn.no3_id >= 0) dn = demand * (fnh4 * 0.0 + finh * dfnh4);
+    s.J(ires_nh4, ires_nh4) = s.J(ires_nh4, ires_nh4) + dn * s.DT(pn.nh4_id, pn.nh4_id);
+    s.J(ires_plantn, ires_nh4) = s.J(ires_plantn, ires_nh4) - dn;
+    if (pn.plantnh4uptake_id >= 0) s.J(off + pn.plantnh4uptake_id, ires_nh4) -= dn;
+  }
+  if (pn.no3_id >= 0) {
+    double nrate = demand * fno3;
+    if (pn.nh4_id >= 0) nrate = demand * fno3 * (1.0 - finh);
+    s.RES(ires_no3) = s.RES(ires_no3) + nrate;
+    s.RES(ires_plantn) = s.RES(ires_plantn) - nrate;
+    if (pn.plantno3uptake_id >= 0) s.RES(off + pn.plantno3uptake_id) -= nrate;
+    double dn = demand * dfno3;
+    if (pn.nh4_id >= 0) dn = demand * (dfno3 * (1.0 - finh) + fno3 * (-1.0 * 0.0));
+    s.J(ires_no3, ires_no3) = s.J(ires_no3, ires_no3) + dn * s.DT(pn.no3_id, pn.no3_id);
+    s.J(ires_plantn, ires_no3) = s.J(ires_plantn, ires_no3) - dn;
+    if (pn.plantno3uptake_id >= 0) s.J(off + pn.plantno3uptake_id, ires_no3) -= dn;
+  }
+}
+
+// ---- LANGMUIR (reaction_sandbox_langmu.F90:183-330) ------------------------------------
+template <class Cell>
+__device__ __forceinline__ void langmuir_react(Cell &s, double tran_dt) {
+  const pfrx_langmuir &lg = s.cfg.lg;
+  const int off = s.cfg.naq;
+  const double volume = s.vol;
+  const double Lwater = volume * 1000.0 * s.por * s.sat;
+  const int ires_aq = lg.aq_id, ires_sorb = off + lg.sorb_id;
+  const double c_aq = s.TOTc(lg.aq_id), c_sorb = s.Cc(off + lg.sorb_id);
+  double rate, drate_daq, drate_dsorb;
+  if (lg.s_max < c_sorb) {
+    rate = (lg.s_max - c_sorb) * volume / tran_dt;
+    drate_dsorb = -1.0 / tran_dt;
+    drate_daq = 0.0;
+  } else {
+    const double c_aq_eq = 0.999 * c_sorb / (lg.s_max - 0.999 * c_sorb) / lg.k_equilibrium;
+    rate = lg.k_kinetic * (c_aq - c_aq_eq) * Lwater;
+    double t = -lg.k_kinetic / lg.k_equilibrium * Lwater / volume;
+    drate_dsorb = t * lg.s_max / (lg.s_max - 0.999 * c_sorb) / (lg.s_max - 0.999 * c_sorb);
+    drate_daq = lg.k_kinetic;
+    if (rate > 0.0) {
+      double ratecap = 0.999 * (lg.s_max - c_sorb) * volume / tran_dt;
+      if (ratecap < rate) {
+        const double fcap = ratecap / rate;
+        t = -0.999 / tran_dt;
+        const double dfcap = (ratecap * drate_dsorb - rate * t) / rate / rate;
+        drate_dsorb = fcap * drate_dsorb + rate * dfcap;
+        rate = rate * fcap;
+      }
+      ratecap = 0.999 * (c_aq - c_aq_eq) * Lwater / tran_dt;
+      if (ratecap < rate) {
+        const double fcap = ratecap / rate;
+        t = -0.999 / lg.k_equilibrium * Lwater / volume / tran_dt;
+        t = t * lg.s_max / (lg.s_max - 0.999 * c_sorb) / (lg.s_max - 0.999 * c_sorb);
+        double dfcap = (ratecap * drate_dsorb - rate * t) / rate / rate;
+        drate_dsorb = fcap * drate_dsorb + rate * dfcap;
+        t = 0.999 / tran_dt;
+        dfcap = (ratecap * drate_daq - rate * t) / rate / rate;
+        drate_daq = fcap * drate_daq + rate * dfcap;
+        rate = rate * fcap;
+      }
+    }
+  }
+  s.RES(ires_aq) = s.RES(ires_aq) + rate;
+  s.RES(ires_sorb) = s.RES(ires_sorb) - rate;
+  s.J(ires_aq, ires_aq) = s.J(ires_aq, ires_aq) + drate_daq * s.DT(lg.aq_id, lg.aq_id);
+  s.J(ires_sorb, ires_aq) = s.J(ires_sorb, ires_aq) - drate_daq;
+  s.J(ires_aq, ires_sorb) = s.J(ires_aq, ires_sorb) + drate_dsorb;
+  s.J(ires_sorb, ires_sorb) = s.J(ires_sorb, ires_sorb) - drate_dsorb;
+}
+
 }  // namespace pfrx_sbx

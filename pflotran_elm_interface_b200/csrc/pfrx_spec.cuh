@@ -112,7 +112,7 @@ struct SpecCell {
   double scconc[SPEC_NSRFCPLX > 0 ? SPEC_NSRFCPLX : 1];
   double mrate[SPEC_NKIN > 0 ? SPEC_NKIN : 1];
   double nc[SPEC_NNC > 0 ? SPEC_NNC : 1];  // N:C ratios that persist between evaluations
-  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   bool dry;
   bool store;  // false: the lane has finished its cell, rt_auxvar%sec_molal must not be touched
 };
@@ -150,6 +150,7 @@ __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &s
   s.elm_kscalar = st.elm_kscalar ? st.elm_kscalar[cell] : 1.0;
   s.elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[cell] : 1.25e3;
   s.elm_bsw = st.elm_bsw ? st.elm_bsw[cell] : 1.0;
+  s.elm_plantndemand = st.elm_plantndemand ? st.elm_plantndemand[cell] : 0.0;
 #endif
 #if SPEC_NNC > 0
 #pragma unroll

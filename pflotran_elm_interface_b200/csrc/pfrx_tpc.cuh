@@ -34,7 +34,7 @@ struct CellT {
   int64_t cell;
   // per-cell scalars
   double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
-  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw;  // ELM scalars (sandboxes)
+  double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;  // ELM scalars
   double Isum, msum;  // sum z^2 m and sum m over the secondary species of the latest RTotal
   bool dry;
   // register-resident per-component arrays (compile-time indices only)
@@ -705,6 +705,10 @@ struct CellT {
         if (cfg.has_nt) pfrx_sbx::nitrif_react(*this);
       } else if (kind == PFRX_SANDBOX_DENITR) {
         if (cfg.has_dn) pfrx_sbx::denitr_react(*this);
+      } else if (kind == PFRX_SANDBOX_PLANTN) {
+        if (cfg.has_pn) pfrx_sbx::plantn_react(*this, dt);
+      } else if (kind == PFRX_SANDBOX_LANGMUIR) {
+        if (cfg.has_lg) pfrx_sbx::langmuir_react(*this, dt);
       }
     }
   }
@@ -719,6 +723,7 @@ struct CellT {
       elm_kscalar = st.elm_kscalar ? st.elm_kscalar[c] : 1.0;
       elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[c] : 1.25e3;
       elm_bsw = st.elm_bsw ? st.elm_bsw[c] : 1.0;
+      elm_plantndemand = st.elm_plantndemand ? st.elm_plantndemand[c] : 0.0;
     }
 #pragma unroll 1
     for (int k = 0; k < cfg.n_nc; k++) {

@@ -14,6 +14,7 @@ struct DevState {
   // ELM per-cell scalars and the persisted N:C ratios of the SOMDECOMP sandbox
   const double *elm_w, *elm_o, *elm_t, *elm_zsoil, *elm_kscalar, *elm_bd_dry, *elm_bsw;
   double *somdec_nc;
+  const double *elm_plantndemand;
 };
 
 // shard summary accumulated with atomics, one set per warp

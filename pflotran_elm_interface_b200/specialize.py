@@ -122,7 +122,15 @@ def signature(cfg: abi.ReactionConfig) -> int:
         dn = cfg.denitr
         parts.append(struct.pack("<4i3d", dn.no3_id, dn.n2_id, dn.n2o_id, dn.ngasdeni_id, dn.half_saturation,
                                  dn.k_deni_max, dn.x0eps))
-    if c.somdec or c.nitrif or c.denitr:
+    if c.plantn:
+        pn = cfg.plantn
+        parts.append(struct.pack("<6i5d", pn.nh4_id, pn.no3_id, pn.plantn_id, pn.plantndemand_id,
+                                 pn.plantnh4uptake_id, pn.plantno3uptake_id, pn.half_saturation_nh4,
+                                 pn.half_saturation_no3, pn.inhibition_nh4_no3, pn.x0eps_nh4, pn.x0eps_no3))
+    if c.langmuir:
+        lg = cfg.langmuir
+        parts.append(struct.pack("<2i3d", lg.aq_id, lg.sorb_id, lg.k_kinetic, lg.k_equilibrium, lg.s_max))
+    if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
         if c.nsandbox:
             parts.append(np.ascontiguousarray(a["sandbox_list"], dtype=i4).tobytes())
@@ -162,7 +170,7 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
             return False, k
     if c.use_total_as_guess:
         return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
-    if c.somdec or c.nitrif or c.denitr:
+    if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         if os.environ.get("PFRX_SPEC_NO_ELMCN"):
             return False, "ELM-CN sandboxes disabled by PFRX_SPEC_NO_ELMCN"
         # the generated code uses dtotal = delta_ij * den/1000
@@ -262,6 +270,14 @@ class _Gen:
             used.update(int(v) for v in (nt.nh4_id, nt.no3_id, nt.n2o_id) if v >= 0)
             if nt.ngasnit_id >= 0:
                 used.add(naq + int(nt.ngasnit_id))
+        if self.c.plantn:
+            pn = cfg.plantn
+            used.update(int(v) for v in (pn.nh4_id, pn.no3_id) if v >= 0)
+            used.update(naq + int(v) for v in (pn.plantn_id, pn.plantndemand_id, pn.plantnh4uptake_id,
+                                               pn.plantno3uptake_id) if v >= 0)
+        if self.c.langmuir:
+            used.add(int(cfg.langmuir.aq_id))
+            used.add(naq + int(cfg.langmuir.sorb_id))
         if self.c.denitr:
             dn = cfg.denitr
             used.update(int(v) for v in (dn.no3_id, dn.n2_id) if v >= 0)
@@ -567,7 +583,7 @@ class _Gen:
         """RSandboxEvaluate (reaction_sandbox.F90:294-330): the sandboxes in the deck's order, each as
         straight-line code with the network's ids and constants as literals"""
         c = self.c
-        order = [int(v) for v in self.a["sandbox_list"]] if c.nsandbox else [1, 2, 3, 4]
+        order = [int(v) for v in self.a["sandbox_list"]] if c.nsandbox else [1, 2, 3, 4, 5, 6]
         self.w("__device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],")
         self.w("    const double (&tot)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W, double dt) {")
         self.w("  const double denL = s.den_kg * 1.e-3;  // dtotal(i,i) of a network without complexes")
@@ -588,6 +604,14 @@ class _Gen:
             elif kind == abi.SANDBOX_DENITR and c.denitr:
                 self.w("  do {  // DENITRIFICATION")
                 self._emit_denitr()
+                self.w("  } while (0);")
+            elif kind == abi.SANDBOX_PLANTN and c.plantn:
+                self.w("  do {  // PLANTN")
+                self._emit_plantn()
+                self.w("  } while (0);")
+            elif kind == abi.SANDBOX_LANGMUIR and c.langmuir:
+                self.w("  do {  // LANGMUIR")
+                self._emit_langmuir()
                 self.w("  } while (0);")
         self.w("}")
         self.w()
@@ -1070,6 +1094,120 @@ class _Gen:
             self._Jsub(naq + int(dn.ngasdeni_id), no3, "drate")
         w("    }")
 
+    def _emit_plantn(self) -> None:
+        """PlantNReact (reaction_sandbox_plantn.F90:222-640)"""
+        naq, w = self.naq, self.w
+        pn = self.cfg.plantn
+        nh4, no3, pl = int(pn.nh4_id), int(pn.no3_id), naq + int(pn.plantn_id)
+        both = nh4 >= 0 and no3 >= 0
+        w("    if (s.sat < 0.01) break;")
+        w("    const double L_water = s.sat * s.por * 1.0e3;")
+        w("    if (s.temp < -0.1) break;")
+        w("    double c_nh4 = 0.0, c_no3 = 0.0, fnh4 = 1.0, dfnh4 = 0.0, fno3 = 1.0, dfno3 = 0.0, finh = 1.0;")
+        if both:
+            w(f"    c_nh4 = tot[{nh4}] * L_water; c_no3 = tot[{no3}] * L_water;")
+            x4, x3 = _lit(pn.x0eps_nh4), _lit(pn.x0eps_no3)
+            if pn.inhibition_nh4_no3 > 0.0:
+                w(f"    if (c_nh4 > {x4} && c_no3 > {x3}) finh = sx_monod(c_nh4 / c_no3, {_lit(1.0 / pn.inhibition_nh4_no3)});")
+                w(f"    else if (c_nh4 > {x4} && c_no3 <= {x3}) finh = 1.0;")
+            else:
+                w(f"    if (c_nh4 > {x4} && c_no3 <= {x3}) finh = 1.0;")
+            w(f"    else if (c_nh4 <= {x4} && c_no3 > {x3}) finh = 0.0;")
+            w("    else break;")
+        w("    double feps0, dfeps0;")
+        for sp, nm, hs, x0 in ((nh4, "nh4", pn.half_saturation_nh4, pn.x0eps_nh4),
+                               (no3, "no3", pn.half_saturation_no3, pn.x0eps_no3)):
+            if sp < 0:
+                continue
+            w(f"    c_{nm} = tot[{sp}] * L_water;")
+            w(f"    f{nm} = sx_monod(c_{nm}, {_lit(hs)}); df{nm} = sx_dmonod(c_{nm}, {_lit(hs)});")
+            if x0 > 0.0:
+                w(f"    pfrx_sbx::hsmooth(c_{nm}, {_lit(x0 * 10.0)}, {_lit(x0)}, feps0, dfeps0);")
+            else:
+                w("    feps0 = 1.0; dfeps0 = 0.0;")
+            w(f"    df{nm} = df{nm} * feps0 + f{nm} * dfeps0; f{nm} = f{nm} * feps0;")
+        if self.c.elm_pflotran:
+            w("    const double demand = fmax(0.0, s.elm_plantndemand * s.vol);")
+            w("    if (demand <= 0.0) break;")
+        else:
+            w("    const double demand = 1.e-2 * s.vol;")
+        if pn.plantndemand_id >= 0:
+            w(f"    res[{naq + int(pn.plantndemand_id)}] -= demand;")
+        w("    if (demand > 0.0) {")
+        for sp, nm, fac in ((nh4, "nh4", "finh"), (no3, "no3", "(1.0 - finh)")):
+            if sp < 0:
+                continue
+            cap = f"demand * {fac} * dt" if both else "demand * dt"
+            w(f"    {{ const double cap = {cap}; double fcap = 1.0, dfcap = 0.0;")
+            w(f"      if (cap > c_{nm} * s.vol) {{ fcap = sx_monod(c_{nm} * s.vol, cap - c_{nm} * s.vol); "
+              f"dfcap = sx_dmonod(c_{nm} * s.vol, cap - c_{nm} * s.vol); }}")
+            w(f"      df{nm} = df{nm} * fcap + f{nm} * dfcap; f{nm} = f{nm} * fcap; }}")
+        w("    }")
+        if nh4 >= 0:
+            w("    { const double nrate = " + ("demand * fnh4 * finh;" if both else "demand * fnh4;"))
+            w(f"      res[{nh4}] = res[{nh4}] + nrate; res[{pl}] = res[{pl}] - nrate;")
+            if pn.plantnh4uptake_id >= 0:
+                w(f"      res[{naq + int(pn.plantnh4uptake_id)}] -= nrate;")
+            w("      const double dn = " + ("demand * (fnh4 * 0.0 + finh * dfnh4);" if both else "demand * dfnh4;"))
+            self._Jadd(nh4, nh4, "dn * denL")
+            self._Jsub(pl, nh4, "dn")
+            if pn.plantnh4uptake_id >= 0:
+                self._Jsub(naq + int(pn.plantnh4uptake_id), nh4, "dn")
+            w("    }")
+        if no3 >= 0:
+            w("    { const double nrate = " + ("demand * fno3 * (1.0 - finh);" if both else "demand * fno3;"))
+            w(f"      res[{no3}] = res[{no3}] + nrate; res[{pl}] = res[{pl}] - nrate;")
+            if pn.plantno3uptake_id >= 0:
+                w(f"      res[{naq + int(pn.plantno3uptake_id)}] -= nrate;")
+            w("      const double dn = " + ("demand * (dfno3 * (1.0 - finh) + fno3 * (-1.0 * 0.0));" if both
+                                            else "demand * dfno3;"))
+            self._Jadd(no3, no3, "dn * denL")
+            self._Jsub(pl, no3, "dn")
+            if pn.plantno3uptake_id >= 0:
+                self._Jsub(naq + int(pn.plantno3uptake_id), no3, "dn")
+            w("    }")
+
+    def _emit_langmuir(self) -> None:
+        """LangmuirReact (reaction_sandbox_langmu.F90:183-330)"""
+        naq, w = self.naq, self.w
+        lg = self.cfg.langmuir
+        aq, sb = int(lg.aq_id), naq + int(lg.sorb_id)
+        smax, keq, kk = _lit(lg.s_max), _lit(lg.k_equilibrium), _lit(lg.k_kinetic)
+        w("    const double Lwater = s.vol * 1000.0 * s.por * s.sat;")
+        w(f"    const double c_aq = tot[{aq}], c_sorb = c[{sb}];")
+        w("    double rate, drate_daq, drate_dsorb;")
+        w(f"    if ({smax} < c_sorb) {{")
+        w(f"      rate = ({smax} - c_sorb) * s.vol / dt; drate_dsorb = -1.0 / dt; drate_daq = 0.0;")
+        w("    } else {")
+        w(f"      const double c_aq_eq = 0.999 * c_sorb / ({smax} - 0.999 * c_sorb) / {keq};")
+        w(f"      rate = {kk} * (c_aq - c_aq_eq) * Lwater;")
+        w(f"      double t = -{kk} / {keq} * Lwater / s.vol;")
+        w(f"      drate_dsorb = t * {smax} / ({smax} - 0.999 * c_sorb) / ({smax} - 0.999 * c_sorb);")
+        w(f"      drate_daq = {kk};")
+        w("      if (rate > 0.0) {")
+        w(f"        double ratecap = 0.999 * ({smax} - c_sorb) * s.vol / dt;")
+        w("        if (ratecap < rate) {")
+        w("          const double fcap = ratecap / rate; t = -0.999 / dt;")
+        w("          const double dfcap = (ratecap * drate_dsorb - rate * t) / rate / rate;")
+        w("          drate_dsorb = fcap * drate_dsorb + rate * dfcap; rate = rate * fcap;")
+        w("        }")
+        w("        ratecap = 0.999 * (c_aq - c_aq_eq) * Lwater / dt;")
+        w("        if (ratecap < rate) {")
+        w(f"          const double fcap = ratecap / rate; t = -0.999 / {keq} * Lwater / s.vol / dt;")
+        w(f"          t = t * {smax} / ({smax} - 0.999 * c_sorb) / ({smax} - 0.999 * c_sorb);")
+        w("          double dfcap = (ratecap * drate_dsorb - rate * t) / rate / rate;")
+        w("          drate_dsorb = fcap * drate_dsorb + rate * dfcap;")
+        w("          t = 0.999 / dt; dfcap = (ratecap * drate_daq - rate * t) / rate / rate;")
+        w("          drate_daq = fcap * drate_daq + rate * dfcap; rate = rate * fcap;")
+        w("        }")
+        w("      }")
+        w("    }")
+        w(f"    res[{aq}] = res[{aq}] + rate; res[{sb}] = res[{sb}] - rate;")
+        self._Jadd(aq, aq, "drate_daq * denL")
+        self._Jsub(sb, aq, "drate_daq")
+        self._Jadd(aq, sb, "drate_dsorb")
+        self._Jsub(sb, sb, "drate_dsorb")
+
     def _emit_clm_cn(self) -> None:
         """CLM_CN_React (reaction_sandbox_clm_cn.F90:468-787), one straight-line block per reaction"""
         c, a, naq = self.c, self.a, self.naq
@@ -1182,7 +1320,8 @@ class _Gen:
         self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
         self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
         self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
-        nsbx = int(c.clmcn_nrxn > 0) + int(bool(c.somdec)) + int(bool(c.nitrif)) + int(bool(c.denitr))
+        nsbx = (int(c.clmcn_nrxn > 0) + int(bool(c.somdec)) + int(bool(c.nitrif)) + int(bool(c.denitr))
+                + int(bool(c.plantn)) + int(bool(c.langmuir)))
         nnc = (len(self.a["somdec_upstream_nc"]) + len(self.a["somdec_downstream_nc"])) if c.somdec else 0
         self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
         self.w(f"#define SPEC_NSBX {nsbx}")
@@ -1702,7 +1841,7 @@ def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]
             used.update(int(v) for v in cfg.arrays[ids])
     if warps not in (2, 4, 8):
         return False, "2, 4 or 8 warps"
-    if c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr:
+    if c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         return False, "reaction sandbox"
     if len(used) < 2 * warps:
         return False, "too few coupled species for that many warps"

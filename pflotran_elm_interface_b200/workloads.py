@@ -394,7 +394,8 @@ END
 """
 
 
-def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False) -> Workload:
+def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False,
+           full: bool = False) -> Workload:
     """C4(b): SOMDECOMP + NITRIFICATION + DENITRIFICATION on 6 aqueous + 10
     immobile species.  ``elm=True`` is the ELM_PFLOTRAN build in BGC-only
     coupling: the moisture / oxygen / temperature scalars, soil depth,
@@ -410,7 +411,21 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
           LOGTHETA
         /
       /"""
-    dk, net = chem.load_network(C4S_DECK.replace("__ABIOTIC__", abiotic), _read("clmcnplus_CLM-CN_database.dat"))
+    deck = C4S_DECK.replace("__ABIOTIC__", abiotic)
+    if full:
+        # the whole ELM-CN network: + plant N uptake and kinetic NH4+ sorption, with their
+        # tracking species (ngee/CLMCNplus/clm_nuptake3.in, clm_nh4absorption.in)
+        deck = deck.replace("    Lit3N\n  /", "    Lit3N\n    PlantN\n    Plantnh4uptake\n    Plantno3uptake\n"
+                            "    NH4sorb\n  /")
+        deck = deck.replace("    DENITRIFICATION\n", "    PLANTN\n      AMMONIUM_HALF_SATURATION 1.0d-5\n"
+                            "      NITRATE_HALF_SATURATION 1.0d-5\n      AMMONIUM_INHIBITION_NITRATE 1.0d0\n    /\n"
+                            "    LANGMUIR\n      NAME_AQ NH4+\n      NAME_SORB NH4sorb\n"
+                            "      EQUILIBRIUM_CONSTANT 1.0d4\n      KINETIC_CONSTANT 1.0d-5\n      S_MAX 1.0d-1\n    /\n"
+                            "    DENITRIFICATION\n")
+        deck = deck.replace("    Lit3N 0.00731553d-0\n", "    Lit3N 0.00731553d-0\n    PlantN 1.d-20\n"
+                            "    Plantnh4uptake 1.d-20\n    Plantno3uptake 1.d-20\n"
+                            "    NH4sorb 1.d-3\n")
+    dk, net = chem.load_network(deck, _read("clmcnplus_CLM-CN_database.dat"))
     assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
     net.elm_pflotran = bool(elm)
     cfg = abi.ReactionConfig(net)
@@ -418,6 +433,10 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
     st = abi.HostState(cfg, ncell)
     constraint.fill_cells(st, sp)
     st["immobile"][...] = sp.immobile[:, None] * np.exp(rng.standard_normal((net.nimcomp, ncell)))
+    if full:
+        for nm in ("PlantN", "Plantnh4uptake", "Plantno3uptake"):
+            st["immobile"][net.immobile_names.index(nm)] = 1.0e-20   # trackers are reset by ELM every step
+        st["immobile"][net.immobile_names.index("NH4sorb")] = 10.0 ** rng.uniform(-4.0, -1.2, ncell)
     # mineral N from depleted to fertilised, independent of the pH
     scale = np.ones((net.naqcomp, ncell))
     for nm, lo, hi in (("NH4+", -7.0, -2.3), ("NO3-", -8.0, -3.5), ("CO2(aq)", -10.0, -4.0)):
@@ -439,9 +458,13 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
         st["elm_kscalar_decomp_c"][...] = 1.0
         st["elm_bulkdensity_dry"][...] = rng.uniform(900.0, 1600.0, ncell)
         st["elm_bsw"][...] = rng.uniform(2.0, 10.0, ncell)
-    name = "c4s_elm_cn_elmscalars" if elm else "c4s_elm_cn"
-    return Workload(name, cfg, st, tran_dt, net,
-                    "SOMDECOMP (7 rxns, N immobilisation from NH4+/NO3-) + NITRIFICATION + DENITRIFICATION, 16 dof")
+        # plant N demand: zero at night / in winter for a third of the cells
+        st["elm_rate_plantndemand"][...] = np.where(rng.random(ncell) < 0.33, 0.0, 10.0 ** rng.uniform(-9.0, -6.5, ncell))
+    name = ("c4f_elm_cn_full" if full else "c4s_elm_cn") + ("_elmscalars" if elm else "")
+    note = "SOMDECOMP (7 rxns, N immobilisation from NH4+/NO3-) + NITRIFICATION + DENITRIFICATION"
+    if full:
+        note += " + PLANTN + LANGMUIR"
+    return Workload(name, cfg, st, tran_dt, net, note + f", {net.ncomp} dof")
 
 
 def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
@@ -456,6 +479,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4": (clm_cn, {}),
         "c4s": (elm_cn, {}),
         "c4se": (elm_cn, {"elm": True}),
+        "c4fe": (elm_cn, {"full": True, "elm": True}),
         "c5": (hanford, {"variant": "minerals"}),
     }
     fn, kw = table[name]
@@ -499,6 +523,10 @@ def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
         f += 60.0 + 20.0 * 7
     if getattr(net, "denitr", None) is not None:
         f += 40.0 + 20.0 * 2
+    if getattr(net, "plantn", None) is not None:
+        f += 90.0
+    if getattr(net, "langmuir", None) is not None:
+        f += 50.0
     f += 10.0 * n
     solve = (2.0 / 3.0) * n ** 3 + 5.0 * n * n + 20.0 * n
     return f, solve

@@ -115,7 +115,8 @@ def test_c4_clm_cn(dt):
 
 
 @pytest.mark.parametrize("variant,dt,host", [("c4s", 1800.0, False), ("c4s", 86400.0, False), ("c4s", 1800.0, True),
-                                             ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True)])
+                                             ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True),
+                                             ("c4fe", 1800.0, True), ("c4fe", 86400.0, False)])
 def test_c4s_elm_cn_sandboxes(variant, dt, host):
     """SOMDECOMP + NITRIFICATION + DENITRIFICATION (SomDecReact/React1/React2/Nemission,
     NitrifReact, DenitrReact) in the thread-per-cell kernel, stand-alone and ELM builds;
@@ -143,11 +144,12 @@ def test_hanford(variant, dt):
                                              ("c3", 3600.0, False), ("c3", 30 * 86400.0, True),
                                              ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True),
                                              ("c4s", 1800.0, False), ("c4s", 86400.0, True), ("c4se", 1800.0, False),
-                                             ("c4se", 6 * 3600.0, True)])
+                                             ("c4se", 6 * 3600.0, True), ("c4fe", 1800.0, True),
+                                             ("c4fe", 86400.0, False)])
 def test_specialized_kernel(variant, dt, host):
     """the code-generated kernel (specialize.py + pfrx_spec.cuh) against the oracle"""
-    wl = W.by_name(variant, ncell=1 if variant == "c1" else (6000 if variant.startswith("c4s") else 1500), tran_dt=dt)
-    if variant.startswith("c4s"):
+    wl = W.by_name(variant, ncell=1 if variant == "c1" else (6000 if variant[:3] in ("c4s", "c4f") else 1500), tran_dt=dt)
+    if variant[:3] in ("c4s", "c4f"):
         wl.state.a["imat"][0, 11] = 0
         wl.state.a["sat"][0, 17] = 1.0e-50   # dry cell
         wl.state.a["temp"][0, 19] = -60.0    # below the CLM-CN temperature cut-off
@@ -157,7 +159,7 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se"])
+@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se", "c4fe"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
