@@ -321,6 +321,11 @@ struct pfrx_handle {
   int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
   size_t spec_smem = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host
+  // kernel seconds per cell and link seconds per cell seen by the latest pfrx_rstep_host: a step
+  // whose kernel outweighs its transfers gains nothing from many chunks and, with the refill
+  // skeleton, pays the slowest cell of every chunk
+  double host_kernel_s_per_cell = 0.0, host_link_s_per_cell = 0.0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   // batched RReaction (pfrx_reaction): always the thread-per-cell layout
   DevCfg rx_cfg;
   void (*rx_kernel)(DevCfg, DevState, int64_t, int, double *, double *, double) = nullptr;
@@ -996,6 +1001,8 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->arena) cudaFree(h->arena);
   if (h->d_summ) cudaFree(h->d_summ);
   if (h->h_summ) cudaFreeHost(h->h_summ);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->d_red) cudaFree(h->d_red);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1315,7 +1322,12 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   }
   int nchunk = 1;
   if (const char *ev = getenv("PFRX_CHUNKS")) nchunk = atoi(ev);
-  else nchunk = (int)std::min<int64_t>(PFRX_MAX_CHUNKS, std::max<int64_t>(1, ncell / 131072));
+  else {
+    nchunk = (int)std::min<int64_t>(PFRX_MAX_CHUNKS, std::max<int64_t>(1, ncell / 131072));
+    if (h->host_kernel_s_per_cell > 0.0 && h->host_link_s_per_cell > 0.0 &&
+        h->host_kernel_s_per_cell > 2.0 * h->host_link_s_per_cell)
+      nchunk = (int)std::max(1.0, floor(nchunk * 2.0 * h->host_link_s_per_cell / h->host_kernel_s_per_cell));
+  }
   if (nchunk < 1) nchunk = 1;
   if (nchunk > PFRX_MAX_CHUNKS) nchunk = PFRX_MAX_CHUNKS;
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
@@ -1353,6 +1365,12 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
       if (skip_in[f] && rows[f]) CUDA_OK(cudaMemsetAsync(dptr[f], 0xff, (size_t)rows[f] * ncell * w8, s_in));
   }
   h->last_h2d = h->last_d2h = 0;
+  if (!h->ev_t0) {
+    CUDA_OK(cudaEventCreate(&h->ev_t0));
+    CUDA_OK(cudaEventCreate(&h->ev_t1));
+  }
+  float kernel_ms_sum = 0.f;
+  (void)kernel_ms_sum;
   for (int ch = 0; ch < nchunk; ch++) {
     int64_t c0 = ncell * ch / nchunk, c1 = ncell * (ch + 1) / nchunk, nc = c1 - c0;
     if (nc <= 0) continue;
@@ -1407,8 +1425,10 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     PFRX_OFF(num_kinetic_state_updates);
     PFRX_OFF(ierror);
 #undef PFRX_OFF
+    if (ch == 0) CUDA_OK(cudaEventRecord(h->ev_t0, s_k));
     rc = launch_kernel(h, dc, nc, tran_dt, s_k);
     if (rc) return rc;
+    if (ch == nchunk - 1) CUDA_OK(cudaEventRecord(h->ev_t1, s_k));
     CUDA_OK(cudaEventRecord(h->ev_k[ch], s_k));
     CUDA_OK(cudaStreamWaitEvent(s_out, h->ev_k[ch], 0));
     for (int f : io) {
@@ -1429,6 +1449,15 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   CUDA_OK(cudaStreamSynchronize(s_out));
   h->pending = false;
   summary_out(h, out);
+  if (nchunk == 1 || h->host_kernel_s_per_cell == 0.0) {
+    // with one chunk the span between the events is the kernel alone; with several it also
+    // holds the waits for uploads, so it is only taken as the first estimate
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) == cudaSuccess && ms > 0.f)
+      h->host_kernel_s_per_cell = 1.e-3 * ms / (double)ncell;
+  }
+  // host link at ~45 GB/s per direction (PCIe gen5 x16, measured through this path), full duplex
+  h->host_link_s_per_cell = (double)std::max(h->last_h2d, h->last_d2h) / 45.e9 / (double)ncell;
   // first_failed_cell of chunked launches is chunk-local; recover the shard index
   if (out->first_failed_cell >= 0 && nchunk > 1) {
     out->first_failed_cell = -1;
