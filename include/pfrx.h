@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 3
+#define PFRX_ABI_VERSION 4
 
 /* error classes */
 #define PFRX_OK 0
@@ -53,6 +53,11 @@ extern "C" {
 #define PFRX_NULL_SURFACE 0
 #define PFRX_ROCK_SURFACE 1
 #define PFRX_MINERAL_SURFACE 2
+
+/* reaction_isotherm_aux.F90: isotherm types */
+#define PFRX_SORPTION_LINEAR 1
+#define PFRX_SORPTION_LANGMUIR 2
+#define PFRX_SORPTION_FREUNDLICH 3
 
 /* compiled-in limits of the CUDA path (oracle has none beyond memory) */
 #define PFRX_MAX_NCOMP 32
@@ -285,6 +290,31 @@ typedef struct pfrx_config {
   const double *kinmr_rate;              /* [.] 1/s */
   const double *kinmr_frac;              /* [.] */
 
+  /* ---- ion exchange (RTotalSorbEqIonx, reaction.F90:4906-5140) ------------ */
+  int32_t neqionxrxn;
+  const int32_t *eqionx_ptr;             /* [neqionxrxn+1] -> cations; the first
+                                            cation of a reaction is its REFERENCE */
+  const int32_t *eqionx_cationid;        /* [.] primary ids */
+  const double *eqionx_k;                /* [.] selectivity coefficients (1 for the reference) */
+  const double *eqionx_CEC;              /* [neqionxrxn] eq/m^3 bulk (or per mineral volume) */
+  const int32_t *eqionx_to_surf;         /* [neqionxrxn] kinetic-mineral id, -1: CEC is absolute */
+  const int32_t *eqionx_Z_flag;          /* [neqionxrxn] 1: valences differ => inner Newton */
+  /* ---- KD isotherms (RTotalSorbKD, reaction_isotherm.F90:273-359) ---------- */
+  int32_t neqkdrxn;
+  int32_t ikd_units;                     /* 0 kg water/m^3 bulk, 1 mL water/g soil */
+  const int32_t *eqkd_specid;            /* [neqkdrxn] primary ids */
+  const int32_t *eqkd_type;              /* [neqkdrxn] PFRX_SORPTION_* */
+  const int32_t *eqkd_mineral;           /* [neqkdrxn] kinetic-mineral id scaling the KD, -1 none */
+  const double *eqkd_coeff;              /* [neqkdrxn] KD */
+  const double *eqkd_langmuir_b;         /* [neqkdrxn] */
+  const double *eqkd_freundlich_n;       /* [neqkdrxn] */
+  /* ---- dynamic KD (RTotalSorbDynamicKD, reaction.F90:4836-4902) ------------ */
+  int32_t neqdynamickdrxn;
+  const int32_t *eqdynamickd_specid;     /* [.] sorbing species */
+  const int32_t *eqdynamickd_refspecid;  /* [.] species the KD depends on */
+  const double *eqdynamickd_refspechigh; /* [.] */
+  const double *eqdynamickd_low, *eqdynamickd_high, *eqdynamickd_power;
+
   /* ---- CLM-CN reaction sandbox (reaction_sandbox_clm_cn.F90:468-787) ----- */
   int32_t clmcn_nrxn;                    /* 0 => sandbox absent */
   int32_t clmcn_npool;
@@ -341,7 +371,9 @@ typedef struct pfrx_state {
   double *mnrl_rate;           /* io [nkinmnrl] mol/m^3/s                     */
   double *srfcplxrxn_free_site_conc; /* io [nsrfcplxrxn]                      */
   double *eqsrfcplx_conc;      /* io [nsrfcplx]                               */
-  double *total_sorb_eq;       /* io [naqcomp]                                */
+  double *total_sorb_eq;       /* io [naqcomp] when any equilibrium sorption reaction
+                                  (surface complexation, ion exchange, KD) exists  */
+  /* (the two ion-exchange fields are declared after the ELM scalars below) */
   double *kinmr_total_sorb;    /* io [sum_r naqcomp*(nrate_r+1)]: rxn r, rate
                                   slot q (0 = equilibrium target), comp i at
                                   row  naqcomp*(kinmr_rate_ptr[r]+r+q) + i    */
@@ -376,6 +408,12 @@ typedef struct pfrx_state {
    * value: pfrx_somdec.upstream_nc / downstream_nc.  NULL => every evaluation
    * starts from those set-up values. */
   double *somdec_nc;
+  /* ion exchange: sorbed concentration of every reaction's reference cation, the starting
+   * point of its inner Newton (rt_auxvar%eqionx_ref_cation_sorbed_conc, initial value 1e-9,
+   * reactive_transport_aux.F90:281-285), io [neqionxrxn]; and the sorbed concentration of
+   * every cation (rt_auxvar%eqionx_conc), io [eqionx_ptr[neqionxrxn]], may be NULL */
+  double *eqionx_ref_cation_sorbed_conc;
+  double *eqionx_conc;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

@@ -54,6 +54,8 @@ typedef struct {
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
   int nsomdec_nc;
+  double *eqionx_ref, *eqionx_conc; /* ion exchange: reference-cation sorbed conc, cation concs */
+  int nionx, nionxcat;
   /* per-cell copies of the temperature dependent tables
    * (the reference overwrites the shared ones, reaction.F90:6003-6031) */
   double *eqcplx_logK, *kinmnrl_logK, *srfcplx_logK;
@@ -73,7 +75,7 @@ static size_t cell_doubles(const pfrx_config *cfg) {
   size_t nk = cfg->nkinmnrl, nr = cfg->nsrfcplxrxn, ns = cfg->nsrfcplx;
   size_t nsd = cfg->somdec ? (size_t)(cfg->somdec->nrxn + cfg->somdec->downstream_ptr[cfg->somdec->nrxn]) : 0;
   return 4 * naq + nim + 3 * nc + 4 * nk + nr + 2 * ns + naq + 2 * naq * naq +
-         mr_rows(cfg) + nsd + 64;
+         mr_rows(cfg) + nsd + (cfg->neqionxrxn > 0 ? cfg->neqionxrxn + cfg->eqionx_ptr[cfg->neqionxrxn] : 0) + 64;
 }
 
 static void cell_init(cell_t *c, const pfrx_config *cfg) {
@@ -111,6 +113,10 @@ static void cell_init(cell_t *c, const pfrx_config *cfg) {
   TAKE(srfcplx_logK, c->nsrfcplx);
   c->nsomdec_nc = cfg->somdec ? cfg->somdec->nrxn + cfg->somdec->downstream_ptr[cfg->somdec->nrxn] : 0;
   TAKE(somdec_nc, c->nsomdec_nc);
+  c->nionx = cfg->neqionxrxn;
+  c->nionxcat = cfg->neqionxrxn > 0 ? cfg->eqionx_ptr[cfg->neqionxrxn] : 0;
+  TAKE(eqionx_ref, c->nionx);
+  TAKE(eqionx_conc, c->nionxcat);
 #undef TAKE
   if (c->ncplx) memcpy(c->eqcplx_logK, cfg->eqcplx_logK, sizeof(double) * c->ncplx);
   if (c->nkin) memcpy(c->kinmnrl_logK, cfg->kinmnrl_logK, sizeof(double) * c->nkin);
@@ -131,6 +137,9 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
     else
       c->somdec_nc[k] = k < sd->nrxn ? sd->upstream_nc[k] : sd->downstream_nc[k - sd->nrxn];
   }
+  for (k = 0; k < c->nionx; k++)
+    c->eqionx_ref[k] = st->eqionx_ref_cation_sorbed_conc ? LD(st->eqionx_ref_cation_sorbed_conc, k) : 1.e-9;
+  for (k = 0; k < c->nionxcat; k++) c->eqionx_conc[k] = st->eqionx_conc ? LD(st->eqionx_conc, k) : 0.0;
   for (k = 0; k < c->naq; k++) {
     c->total[k] = LD(st->total, k);
     c->pri_molal[k] = LD(st->pri_molal, k);
@@ -193,6 +202,10 @@ static void cell_scatter(const cell_t *c, const pfrx_state *st, int64_t ic) {
   for (k = 0; k < c->nmrrows; k++) LD(st->kinmr_total_sorb, k) = c->kinmr_total_sorb[k];
   if (st->somdec_nc)
     for (k = 0; k < c->nsomdec_nc; k++) LD(st->somdec_nc, k) = c->somdec_nc[k];
+  if (st->eqionx_ref_cation_sorbed_conc)
+    for (k = 0; k < c->nionx; k++) LD(st->eqionx_ref_cation_sorbed_conc, k) = c->eqionx_ref[k];
+  if (st->eqionx_conc)
+    for (k = 0; k < c->nionxcat; k++) LD(st->eqionx_conc, k) = c->eqionx_conc[k];
 }
 
 /* ------------------------------------------------------------------------ */
@@ -620,7 +633,150 @@ static void r_total_sorb_eq_surf_cplx1(cell_t *c, const pfrx_config *cfg, int ir
   }
 }
 
-static int neqsorb(const pfrx_config *cfg) { return cfg->neqsrfcplxrxn; }
+/* reaction.F90:881: neqsorb = neqionxrxn + neqkdrxn + neqsrfcplxrxn (+ neqdynamickdrxn) */
+static int neqsorb(const pfrx_config *cfg) {
+  return cfg->neqsrfcplxrxn + cfg->neqionxrxn + cfg->neqkdrxn + cfg->neqdynamickdrxn;
+}
+
+/* reaction.F90:4906-5140  RTotalSorbEqIonx; returns 1 where the reference sets ierror
+ * (more than 20000 iterations of the inner Newton) */
+static int r_total_sorb_eq_ionx(cell_t *c, const pfrx_config *cfg) {
+  const double tol = 1.e-12;
+  int naq = c->naq, irxn, i, j;
+  double cation_X[PFRX_MAX_NCOMP];
+  for (i = 0; i < c->nionxcat; i++) c->eqionx_conc[i] = 0.0;
+  for (irxn = 0; irxn < cfg->neqionxrxn; irxn++) {
+    int p0 = cfg->eqionx_ptr[irxn], ncomp = cfg->eqionx_ptr[irxn + 1] - p0;
+    const int *cat = cfg->eqionx_cationid + p0;
+    const double *kk = cfg->eqionx_k + p0;
+    double omega, sumZX;
+    if (cfg->eqionx_to_surf[irxn] >= 0)
+      omega = fmax(cfg->eqionx_CEC[irxn] * c->mnrl_volfrac[cfg->eqionx_to_surf[irxn]], 1.e-40);
+    else
+      omega = cfg->eqionx_CEC[irxn];
+    if (cfg->eqionx_Z_flag[irxn]) {
+      int icomp = cat[0], one_more = 0, it = 0;
+      double ref_cation_conc = c->pri_molal[icomp] * c->pri_act_coef[icomp];
+      double ref_cation_Z = cfg->primary_spec_Z[icomp];
+      double ref_cation_k = kk[0];
+      double ref_cation_X = ref_cation_Z * c->eqionx_ref[irxn] / omega;
+      double KDj, total, dres_dKDj, res, delta_KDj;
+      for (j = 0; j < ncomp; j++) cation_X[j] = 0.0;
+      KDj = ref_cation_X / (ref_cation_k * ref_cation_conc);
+      for (;;) {
+        it++;
+        if (it > 20000) return 1;
+        ref_cation_X = KDj * (ref_cation_k * ref_cation_conc);
+        cation_X[0] = ref_cation_X;
+        total = ref_cation_X;
+        dres_dKDj = 0.0;
+        for (j = 1; j < ncomp; j++) {
+          icomp = cat[j];
+          cation_X[j] = kk[j] * c->pri_molal[icomp] * c->pri_act_coef[icomp] *
+                        pow(KDj, cfg->primary_spec_Z[icomp] / ref_cation_Z);
+          total = total + cation_X[j];
+          dres_dKDj = dres_dKDj + cation_X[j] / KDj * cfg->primary_spec_Z[icomp];
+        }
+        dres_dKDj = dres_dKDj / ref_cation_Z + (ref_cation_k * ref_cation_conc);
+        res = 1.0 - total;
+        if (one_more) break;
+        delta_KDj = res / dres_dKDj;
+        KDj = KDj + delta_KDj;
+        KDj = fmax(KDj, 1.e-40);
+        if (fabs(delta_KDj / KDj) < tol) one_more = 1;
+      }
+      c->eqionx_ref[irxn] = ref_cation_X * omega / ref_cation_Z;
+    } else {
+      double sumkm = 0.0;
+      for (j = 0; j < ncomp; j++) {
+        int icomp = cat[j];
+        cation_X[j] = c->pri_molal[icomp] * c->pri_act_coef[icomp] * kk[j];
+        sumkm = sumkm + cation_X[j];
+      }
+      for (j = 0; j < ncomp; j++) cation_X[j] = cation_X[j] / sumkm;
+    }
+    sumZX = 0.0;
+    for (i = 0; i < ncomp; i++) sumZX = sumZX + cfg->primary_spec_Z[cat[i]] * cation_X[i];
+    for (i = 0; i < ncomp; i++) {
+      int icomp = cat[i];
+      double tempreal1 = cation_X[i] * omega / cfg->primary_spec_Z[icomp];
+      double tempreal2;
+      c->eqionx_conc[p0 + i] = c->eqionx_conc[p0 + i] + tempreal1;
+      c->total_sorb_eq[icomp] = c->total_sorb_eq[icomp] + tempreal1;
+      tempreal2 = cfg->primary_spec_Z[icomp] / sumZX;
+      for (j = 0; j < ncomp; j++) {
+        int jcomp = cat[j];
+        if (i == j)
+          c->dtotal_sorb_eq[icomp + jcomp * naq] =
+              c->dtotal_sorb_eq[icomp + jcomp * naq] + tempreal1 * (1.0 - (tempreal2 * cation_X[j])) / c->pri_molal[jcomp];
+        else
+          c->dtotal_sorb_eq[icomp + jcomp * naq] =
+              c->dtotal_sorb_eq[icomp + jcomp * naq] + (-tempreal1) * tempreal2 * cation_X[j] / c->pri_molal[jcomp];
+      }
+    }
+  }
+  return 0;
+}
+
+/* reaction.F90:4836-4902  RTotalSorbDynamicKD */
+static void r_total_sorb_dynamic_kd(cell_t *c, const pfrx_config *cfg) {
+  const double Lwater_m3bulk = 250.0;
+  int naq = c->naq, irxn;
+  for (irxn = 0; irxn < cfg->neqdynamickdrxn; irxn++) {
+    int ikd = cfg->eqdynamickd_specid[irxn], iref = cfg->eqdynamickd_refspecid[irxn];
+    double kd_species_molality = c->pri_molal[ikd];
+    double ref_high = cfg->eqdynamickd_refspechigh[irxn];
+    double ref_species_molality = c->pri_molal[iref];
+    double KD_power = cfg->eqdynamickd_power[irxn];
+    double KD_low = cfg->eqdynamickd_low[irxn];
+    double KD_high_minus_low = cfg->eqdynamickd_high[irxn] - KD_low;
+    double tempreal = pow(ref_species_molality / ref_high, KD_power);
+    double KD = KD_low + tempreal * KD_high_minus_low;
+    double dKD_dref = KD_power * tempreal / ref_species_molality * KD_high_minus_low;
+    double total_sorb = KD * kd_species_molality * Lwater_m3bulk;
+    double dtotal_sorb_dckd = KD * Lwater_m3bulk;
+    double dtotal_sorb_dcref = dKD_dref * kd_species_molality * Lwater_m3bulk;
+    c->total_sorb_eq[ikd] = c->total_sorb_eq[ikd] + total_sorb;
+    c->dtotal_sorb_eq[ikd + ikd * naq] = c->dtotal_sorb_eq[ikd + ikd * naq] + dtotal_sorb_dckd;
+    c->dtotal_sorb_eq[ikd + iref * naq] = c->dtotal_sorb_eq[ikd + iref * naq] + dtotal_sorb_dcref;
+  }
+}
+
+/* reaction_isotherm.F90:273-359  RTotalSorbKD */
+static void r_total_sorb_kd(cell_t *c, const pfrx_config *cfg) {
+  int naq = c->naq, irxn;
+  for (irxn = 0; irxn < cfg->neqkdrxn; irxn++) {
+    int icomp = cfg->eqkd_specid[irxn];
+    double molality = c->pri_molal[icomp];
+    double kd_kgw_m3b, res, dres_dc, tempreal, one_over_n;
+    if (cfg->ikd_units == 1)
+      kd_kgw_m3b = cfg->eqkd_coeff[irxn] * c->den_kg * (1.0 - c->porosity) * c->soil_particle_density * 1.e-3;
+    else
+      kd_kgw_m3b = cfg->eqkd_coeff[irxn];
+    if (cfg->eqkd_mineral[irxn] >= 0) kd_kgw_m3b = kd_kgw_m3b * (c->mnrl_volfrac[cfg->eqkd_mineral[irxn]]);
+    switch (cfg->eqkd_type[irxn]) {
+      case PFRX_SORPTION_LINEAR:
+        res = kd_kgw_m3b * molality;
+        dres_dc = kd_kgw_m3b;
+        break;
+      case PFRX_SORPTION_LANGMUIR:
+        tempreal = kd_kgw_m3b * molality;
+        res = tempreal * cfg->eqkd_langmuir_b[irxn] / (1.0 + tempreal);
+        dres_dc = res / molality - res / (1.0 + tempreal) * tempreal / molality;
+        break;
+      case PFRX_SORPTION_FREUNDLICH:
+        one_over_n = 1.0 / cfg->eqkd_freundlich_n[irxn];
+        res = kd_kgw_m3b * pow(molality, one_over_n);
+        dres_dc = res / molality * one_over_n;
+        break;
+      default:
+        res = 0.0;
+        dres_dc = 0.0;
+    }
+    c->total_sorb_eq[icomp] = c->total_sorb_eq[icomp] + res;
+    c->dtotal_sorb_eq[icomp + icomp * naq] = c->dtotal_sorb_eq[icomp + icomp * naq] + dres_dc;
+  }
+}
 
 /* reaction.F90:4783-4832 RTotalSorb (+RZeroSorb :4765); surface complexation
  * branch reaction_surf_complex.F90:446-487 */
@@ -634,6 +790,10 @@ static void r_total_sorb(cell_t *c, const pfrx_config *cfg) {
     r_total_sorb_eq_surf_cplx1(c, cfg, irxn, &c->free_site[irxn], c->eqsrfcplx_conc, c->total_sorb_eq,
                                c->dtotal_sorb_eq);
   }
+  /* RTotalSorb order (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD */
+  if (cfg->neqionxrxn > 0 && r_total_sorb_eq_ionx(c, cfg)) c->option_ierror = 1;
+  if (cfg->neqdynamickdrxn > 0) r_total_sorb_dynamic_kd(c, cfg);
+  if (cfg->neqkdrxn > 0) r_total_sorb_kd(c, cfg);
 }
 
 /* reaction.F90:4618-4661 RTotal == reaction.F90:5606 RTAuxVarCompute */

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 3
+PFRX_ABI_VERSION = 4
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -101,6 +101,28 @@ class PfrxConfig(C.Structure):
         ("kinmr_rate_ptr", c_int32_p),
         ("kinmr_rate", c_double_p),
         ("kinmr_frac", c_double_p),
+        ("neqionxrxn", C.c_int32),
+        ("eqionx_ptr", c_int32_p),
+        ("eqionx_cationid", c_int32_p),
+        ("eqionx_k", c_double_p),
+        ("eqionx_CEC", c_double_p),
+        ("eqionx_to_surf", c_int32_p),
+        ("eqionx_Z_flag", c_int32_p),
+        ("neqkdrxn", C.c_int32),
+        ("ikd_units", C.c_int32),
+        ("eqkd_specid", c_int32_p),
+        ("eqkd_type", c_int32_p),
+        ("eqkd_mineral", c_int32_p),
+        ("eqkd_coeff", c_double_p),
+        ("eqkd_langmuir_b", c_double_p),
+        ("eqkd_freundlich_n", c_double_p),
+        ("neqdynamickdrxn", C.c_int32),
+        ("eqdynamickd_specid", c_int32_p),
+        ("eqdynamickd_refspecid", c_int32_p),
+        ("eqdynamickd_refspechigh", c_double_p),
+        ("eqdynamickd_low", c_double_p),
+        ("eqdynamickd_high", c_double_p),
+        ("eqdynamickd_power", c_double_p),
         ("clmcn_nrxn", C.c_int32),
         ("clmcn_npool", C.c_int32),
         ("clmcn_C_species_id", C.c_int32),
@@ -184,13 +206,14 @@ STATE_DOUBLE_FIELDS = [
 # ELM per-cell scalars (pfrx_state.elm_*): present when the configuration sets
 # elm_pflotran, NULL otherwise
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
-                    "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc"]
+                    "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc",
+                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
     "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
     "mnrl_volfrac", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "total_sorb_eq",
-    "kinmr_total_sorb", "somdec_nc",
+    "kinmr_total_sorb", "somdec_nc", "eqionx_ref_cation_sorbed_conc", "eqionx_conc",
 ]
 STATE_RESULT_FIELDS = ["num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 
@@ -419,6 +442,32 @@ class ReactionConfig:
                 c.kinmr_rate = _dp(self._keep("kinmr_rate", _f64(rates)))
                 c.kinmr_frac = _dp(self._keep("kinmr_frac", _f64(fracs)))
 
+        # ion exchange, KD isotherms, dynamic KD
+        ix = getattr(net, "ionx", None)
+        if ix:
+            c.neqionxrxn = len(ix["CEC"])
+            c.eqionx_ptr = _ip(self._keep("eqionx_ptr", _i32(ix["ptr"])))
+            c.eqionx_cationid = _ip(self._keep("eqionx_cationid", _i32(ix["cationid"])))
+            c.eqionx_k = _dp(self._keep("eqionx_k", _f64(ix["k"])))
+            c.eqionx_CEC = _dp(self._keep("eqionx_CEC", _f64(ix["CEC"])))
+            c.eqionx_to_surf = _ip(self._keep("eqionx_to_surf", _i32(ix["to_surf"])))
+            c.eqionx_Z_flag = _ip(self._keep("eqionx_Z_flag", _i32(ix["Z_flag"])))
+        kd = getattr(net, "kd", None)
+        if kd:
+            c.neqkdrxn = len(kd["specid"])
+            c.ikd_units = kd["ikd_units"]
+            for k in ("specid", "type", "mineral"):
+                setattr(c, "eqkd_" + k, _ip(self._keep("eqkd_" + k, _i32(kd[k]))))
+            for k in ("coeff", "langmuir_b", "freundlich_n"):
+                setattr(c, "eqkd_" + k, _dp(self._keep("eqkd_" + k, _f64(kd[k]))))
+        dk = getattr(net, "dynkd", None)
+        if dk:
+            c.neqdynamickdrxn = len(dk["specid"])
+            for k in ("specid", "refspecid"):
+                setattr(c, "eqdynamickd_" + k, _ip(self._keep("eqdynamickd_" + k, _i32(dk[k]))))
+            for k in ("refspechigh", "low", "high", "power"):
+                setattr(c, "eqdynamickd_" + k, _dp(self._keep("eqdynamickd_" + k, _f64(dk[k]))))
+
         # CLM-CN
         cc = net.clmcn
         if cc is not None:
@@ -507,10 +556,13 @@ class ReactionConfig:
             "pri_act_coef": c.naqcomp, "sec_act_coef": c.neqcplx, "sec_molal": c.neqcplx,
             "ln_act_h2o": 1, "mnrl_volfrac": c.nkinmnrl, "mnrl_area": c.nkinmnrl, "mnrl_rate": c.nkinmnrl,
             "srfcplxrxn_free_site_conc": c.nsrfcplxrxn, "eqsrfcplx_conc": c.nsrfcplx,
-            "total_sorb_eq": c.naqcomp if c.neqsrfcplxrxn > 0 else 0,
+            "total_sorb_eq": (c.naqcomp if (c.neqsrfcplxrxn + c.neqionxrxn + c.neqkdrxn + c.neqdynamickdrxn) > 0
+                              else 0),
             "kinmr_total_sorb": mr_rows,
             "den_kg": 1, "sat": 1, "temp": 1, "porosity": 1, "volume": 1, "soil_particle_density": 1,
             **{f: (1 if c.elm_pflotran else 0) for f in STATE_ELM_FIELDS},
+            "eqionx_ref_cation_sorbed_conc": c.neqionxrxn,
+            "eqionx_conc": int(self.arrays["eqionx_ptr"][c.neqionxrxn]) if c.neqionxrxn else 0,
             "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
                           if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,
@@ -540,6 +592,8 @@ class HostState:
         self.a["soil_particle_density"][:] = 2650.0
         self.a["imat"][:] = 1
         self.a["srfcplxrxn_free_site_conc"][:] = 1.0e-9
+        self.a["eqionx_ref_cation_sorbed_conc"][:] = 1.0e-9   # reactive_transport_aux.F90:282
+        self.a["eqionx_conc"][:] = 1.0e-9
         self.a["elm_rate_plantndemand"][:] = 1.0e-2
         for f in ("elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_kscalar_decomp_c", "elm_bsw"):
             self.a[f][:] = 1.0

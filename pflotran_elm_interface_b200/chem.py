@@ -347,6 +347,9 @@ class Chemistry:
     minerals: List[str] = field(default_factory=list)
     mineral_kinetics: List[MineralKinetics] = field(default_factory=list)
     srfcplx_rxns: List[SrfCplxRxn] = field(default_factory=list)
+    ionx_rxns: List[dict] = field(default_factory=list)
+    isotherm_rxns: List[dict] = field(default_factory=list)
+    dynamic_kd_rxns: List[dict] = field(default_factory=list)
     clm_cn: Optional[ClmCnSandbox] = None
     somdec: Optional[SomDecSandbox] = None
     nitrif: Optional[dict] = None
@@ -481,6 +484,82 @@ def _read_srfcplx_rxn(cur: _Cursor) -> SrfCplxRxn:
             rx.site_fractions = [1.0 / float(len(rx.rates))] * len(rx.rates)
         rx.rates = [r * rx.kinmr_scale_factor for r in rx.rates]
     return rx
+
+
+def _read_ionx_rxn(cur: _Cursor) -> dict:
+    # reaction.F90:625-730: the REFERENCE cation (k = 1) moves to the front of the list
+    rx = {"mineral": "", "CEC": None, "cations": []}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "MINERAL":
+            rx["mineral"] = t[1]
+        elif key == "CEC":
+            rx["CEC"] = _fnum(t[1])
+        elif key == "CATIONS":
+            ref = None
+            for u in cur.block():
+                rx["cations"].append((u[0], _fnum(u[1])))
+                if len(u) > 2 and u[2].upper() == "REFERENCE":
+                    ref = u[0]
+            if ref is None:
+                raise ValueError("Reference cation missing in Ion Exchange reaction.")
+            i = [n for n, _ in rx["cations"]].index(ref)
+            if abs(rx["cations"][i][1] - 1.0) > 1.0e-40:
+                raise ValueError(f'Reference cation "{ref}" must have k = 1.d0.')
+            rx["cations"].insert(0, rx["cations"].pop(i))
+        else:
+            raise ValueError(f"ION_EXCHANGE_RXN keyword {key}")
+    if rx["CEC"] is None:
+        raise ValueError("A CEC must be defined for all ion exchange reactions.")
+    return rx
+
+
+def _read_isotherm_rxns(cur: _Cursor) -> List[dict]:
+    # IsothermRead, reaction_isotherm.F90:30-228
+    out = []
+    for t in cur.block():
+        rx = {"species": t[0], "type": 1, "kd": None, "kd_units": "", "langmuir_b": 0.0, "freundlich_n": 0.0,
+              "mineral": ""}
+        for u in cur.block():
+            key = u[0].upper()
+            if key == "TYPE":
+                rx["type"] = {"LINEAR": 1, "LANGMUIR": 2, "FREUNDLICH": 3}[u[1].upper()]
+            elif key in ("DISTRIBUTION_COEFFICIENT", "KD"):
+                rx["kd"] = _fnum(u[1])
+                if len(u) > 2:
+                    rx["kd_units"] = u[2]
+            elif key == "LANGMUIR_B":
+                rx["langmuir_b"] = _fnum(u[1])
+                rx["type"] = 2
+            elif key == "FREUNDLICH_N":
+                rx["freundlich_n"] = _fnum(u[1])
+                rx["type"] = 3
+            elif key == "KD_MINERAL_NAME":
+                rx["mineral"] = u[1]
+            else:
+                raise ValueError(f"ISOTHERM_REACTIONS keyword {key}")
+        if rx["kd"] is None:
+            raise ValueError("DISTRIBUTION_COEFFICIENT missing in ISOTHERM_REACTIONS")
+        out.append(rx)
+    return out
+
+
+def _read_dynamic_kd_rxns(cur: _Cursor) -> List[dict]:
+    # reaction.F90:540-612
+    out = []
+    for t in cur.block():
+        rx = {"species": t[0], "ref": "", "ref_high": 0.0, "low": 0.0, "high": 0.0, "power": 0.0}
+        keys = {"REFERENCE_SPECIES_HIGH": "ref_high", "KD_LOW": "low", "KD_HIGH": "high", "KD_POWER": "power"}
+        for u in cur.block():
+            key = u[0].upper()
+            if key == "REFERENCE_SPECIES":
+                rx["ref"] = u[1]
+            elif key in keys:
+                rx[keys[key]] = _fnum(u[1])
+            else:
+                raise ValueError(f"DYNAMIC_KD_REACTIONS keyword {key}")
+        out.append(rx)
+    return out
 
 
 def _read_clm_cn(cur: _Cursor) -> ClmCnSandbox:
@@ -769,6 +848,12 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                 k2 = u[0].upper()
                 if k2 == "SURFACE_COMPLEXATION_RXN":
                     ch.srfcplx_rxns.append(_read_srfcplx_rxn(cur))
+                elif k2 == "ION_EXCHANGE_RXN":
+                    ch.ionx_rxns.append(_read_ionx_rxn(cur))
+                elif k2 == "ISOTHERM_REACTIONS":
+                    ch.isotherm_rxns += _read_isotherm_rxns(cur)
+                elif k2 == "DYNAMIC_KD_REACTIONS":
+                    ch.dynamic_kd_rxns += _read_dynamic_kd_rxns(cur)
                 else:
                     ch.unsupported.append("SORPTION," + k2)
                     _skip_nested(cur)
@@ -1036,6 +1121,7 @@ class ReactionNetwork:
         self._minerals()
         self._surface_complexation()
         self._clm_cn()
+        self._sorption_isotherms()
         self.sandbox_order = list(chem.sandbox_order)
         self.elm_pflotran = False
         self._somdec()
@@ -1246,6 +1332,51 @@ class ReactionNetwork:
             resp=np.array([r["resp"] for r in sb.reactions], dtype=np.float64),
             inhib=np.array([r["inhib"] for r in sb.reactions], dtype=np.float64),
         )
+
+    # -- ion exchange / KD isotherms / dynamic KD (reaction_database.F90:2800-2925) -------- #
+    def _sorption_isotherms(self):
+        pri = {n: i for i, n in enumerate(self.primary_names)}
+        kin = {n: i for i, n in enumerate(self.kinmnrl_names)}
+        self.ionx = self.kd = self.dynkd = None
+        if self.chem.ionx_rxns:
+            ptr, ids, ks, cec, surf, zf = [0], [], [], [], [], []
+            for rx in self.chem.ionx_rxns:
+                for nm, k in rx["cations"]:
+                    ids.append(pri[nm])
+                    ks.append(k)
+                ptr.append(len(ids))
+                cec.append(rx["CEC"])
+                surf.append(kin[rx["mineral"]] if rx["mineral"] else -1)
+                z = [self.primary_Z[pri[nm]] for nm, _ in rx["cations"]]
+                zf.append(int(any(abs(a - b) > 0.1 for a in z for b in z)))
+            self.ionx = dict(ptr=ptr, cationid=ids, k=ks, CEC=cec, to_surf=surf, Z_flag=zf)
+        if self.chem.isotherm_rxns:
+            # IsothermConvertKDUnits: kg water / m^3 bulk, or mL water / g soil (L/kg)
+            units = set()
+            coeff = []
+            for rx in self.chem.isotherm_rxns:
+                u = rx["kd_units"].lower()
+                if u in ("", "kg/m^3"):
+                    units.add(0)
+                    coeff.append(rx["kd"])
+                elif u in ("l/kg", "ml/g"):
+                    units.add(1)
+                    coeff.append(rx["kd"])
+                else:
+                    raise ValueError(f"Unrecognized kd_units: {rx['kd_units']}")
+            if len(units) != 1:
+                raise ValueError("all KD isotherms must use the same units")
+            self.kd = dict(specid=[pri[r["species"]] for r in self.chem.isotherm_rxns],
+                           type=[r["type"] for r in self.chem.isotherm_rxns],
+                           mineral=[(kin[r["mineral"]] if r["mineral"] else -1) for r in self.chem.isotherm_rxns],
+                           coeff=coeff, langmuir_b=[r["langmuir_b"] for r in self.chem.isotherm_rxns],
+                           freundlich_n=[r["freundlich_n"] for r in self.chem.isotherm_rxns],
+                           ikd_units=units.pop())
+        if self.chem.dynamic_kd_rxns:
+            d = self.chem.dynamic_kd_rxns
+            self.dynkd = dict(specid=[pri[r["species"]] for r in d], refspecid=[pri[r["ref"]] for r in d],
+                              refspechigh=[r["ref_high"] for r in d], low=[r["low"] for r in d],
+                              high=[r["high"] for r in d], power=[r["power"] for r in d])
 
     # -- SOMDECOMP (SomDecSetup, reaction_sandbox_somdec.F90:987-1501) -------- #
     def _species(self, name: str) -> Tuple[int, int]:

@@ -193,6 +193,11 @@ static uint64_t config_signature(const pfrx_config *c) {
     ADD(c->clmcn_respiration_fraction, c->clmcn_nrxn)
     ADD(c->clmcn_inhibition_constant, c->clmcn_nrxn)
   }
+  if (c->neqionxrxn > 0 || c->neqkdrxn > 0 || c->neqdynamickdrxn > 0) {
+    // not covered by the generator: any cubin signature must differ
+    int32_t hi[4] = {c->neqionxrxn, c->neqkdrxn, c->neqdynamickdrxn, c->ikd_units};
+    h = fnv1a(h, hi, sizeof(hi));
+  }
   // ELM-CN sandboxes: every parameter the generated code bakes in
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
@@ -428,15 +433,17 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 29
+#define PFRX_NUM_D 31
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
   const int e = c->elm_pflotran ? 1 : 0;
   const int nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
+  const int nix = c->neqionxrxn, nixc = c->neqionxrxn > 0 ? c->eqionx_ptr[c->neqionxrxn] : 0;
+  const int nsorb = c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn;
   int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
-                       c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, c->neqsrfcplxrxn > 0 ? c->naqcomp : 0,
-                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e};
+                       c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, nsorb > 0 ? c->naqcomp : 0,
+                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -481,6 +488,7 @@ static void tpc_layout(DevCfg &d, int N) {
   d.off_sec = 0;
   d.off_dt = d.need_dt ? take(d.naq * d.naq) : 0;
   d.off_nc = d.n_nc > 0 ? take(d.n_nc) : 0;
+  d.off_ix = d.nionx > 0 ? take(d.nionx + d.n_ixcat) : 0;
   d.ws_stride = off | 1;
 }
 
@@ -578,6 +586,23 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
                      !c->kinmnrl_pref_activation_energy))
       return set_err(PFRX_E_INVALID, "prefactor arrays missing%s", "");
   }
+  const bool has_sorb2 = c->neqionxrxn > 0 || c->neqkdrxn > 0 || c->neqdynamickdrxn > 0;
+  if (c->neqionxrxn > 0) {
+    if (!c->eqionx_ptr || !c->eqionx_cationid || !c->eqionx_k || !c->eqionx_CEC || !c->eqionx_to_surf ||
+        !c->eqionx_Z_flag)
+      return set_err(PFRX_E_INVALID, "ion exchange tables missing%s", "");
+    for (int r = 0; r < c->neqionxrxn; r++) {
+      if (c->eqionx_ptr[r + 1] - c->eqionx_ptr[r] > PFRX_MAX_NCOMP || c->eqionx_ptr[r + 1] - c->eqionx_ptr[r] < 1)
+        return set_err(PFRX_E_LIMIT, "ion exchange reaction with too many / no cations%s", "");
+      if (c->eqionx_to_surf[r] >= c->nkinmnrl) return set_err(PFRX_E_INVALID, "ion exchange mineral id%s", "");
+    }
+  }
+  if (c->neqkdrxn > 0 && (!c->eqkd_specid || !c->eqkd_type || !c->eqkd_mineral || !c->eqkd_coeff ||
+                          !c->eqkd_langmuir_b || !c->eqkd_freundlich_n))
+    return set_err(PFRX_E_INVALID, "KD isotherm tables missing%s", "");
+  if (c->neqdynamickdrxn > 0 && (!c->eqdynamickd_specid || !c->eqdynamickd_refspecid || !c->eqdynamickd_refspechigh ||
+                                 !c->eqdynamickd_low || !c->eqdynamickd_high || !c->eqdynamickd_power))
+    return set_err(PFRX_E_INVALID, "dynamic KD tables missing%s", "");
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
   const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir;
   if (c->plantn && (c->plantn->plantn_id < 0 || (c->plantn->nh4_id < 0 && c->plantn->no3_id < 0)))
@@ -660,6 +685,12 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.nsrfrxn = c->nsrfcplxrxn;
   d.nsrfcplx = c->nsrfcplx;
   d.neqsr = c->neqsrfcplxrxn;
+  d.nionx = c->neqionxrxn;
+  d.nkd = c->neqkdrxn;
+  d.ndynkd = c->neqdynamickdrxn;
+  d.ikd_units = c->ikd_units;
+  d.nsorb = d.neqsr + d.nionx + d.nkd + d.ndynkd;
+  d.n_ixcat = c->neqionxrxn > 0 ? c->eqionx_ptr[c->neqionxrxn] : 0;
   d.nmr = c->nkinmrsrfcplxrxn;
   d.cn_nrxn = c->clmcn_nrxn;
   d.cn_C = c->clmcn_C_species_id;
@@ -697,7 +728,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
-    if (!rc0 && (has_pref || act_newton || has_sbx3) && !h->tpc) {
+    if (!rc0 && (has_pref || act_newton || has_sbx3 || has_sorb2) && !h->tpc) {
       // mineral prefactors, the iterated ionic strength and the SOMDECOMP / NITRIFICATION /
       // DENITRIFICATION sandboxes live in the thread-per-cell kernel only
       const KernelGetter *gt = nullptr;
@@ -913,6 +944,36 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->clmcn_respiration_fraction, nx, &d.cn_resp);
     A.add(c->clmcn_inhibition_constant, nx, &d.cn_inhib);
   }
+  if (has_sorb2) {
+    A.add(c->primary_spec_Z, naq, &d.pri_Z);
+    if (c->neqionxrxn > 0) {
+      const int nr = c->neqionxrxn, nn = c->eqionx_ptr[nr];
+      A.add(c->eqionx_ptr, nr + 1, &d.ix_ptr);
+      A.add(c->eqionx_cationid, nn, &d.ix_cat);
+      A.add(c->eqionx_k, nn, &d.ix_k);
+      A.add(c->eqionx_CEC, nr, &d.ix_cec);
+      A.add(c->eqionx_to_surf, nr, &d.ix_surf);
+      A.add(c->eqionx_Z_flag, nr, &d.ix_zflag);
+    }
+    if (c->neqkdrxn > 0) {
+      const int nr = c->neqkdrxn;
+      A.add(c->eqkd_specid, nr, &d.kd_spec);
+      A.add(c->eqkd_type, nr, &d.kd_type);
+      A.add(c->eqkd_mineral, nr, &d.kd_mnrl);
+      A.add(c->eqkd_coeff, nr, &d.kd_coeff);
+      A.add(c->eqkd_langmuir_b, nr, &d.kd_lb);
+      A.add(c->eqkd_freundlich_n, nr, &d.kd_fn);
+    }
+    if (c->neqdynamickdrxn > 0) {
+      const int nr = c->neqdynamickdrxn;
+      A.add(c->eqdynamickd_specid, nr, &d.dk_spec);
+      A.add(c->eqdynamickd_refspecid, nr, &d.dk_ref);
+      A.add(c->eqdynamickd_refspechigh, nr, &d.dk_refhigh);
+      A.add(c->eqdynamickd_low, nr, &d.dk_low);
+      A.add(c->eqdynamickd_high, nr, &d.dk_high);
+      A.add(c->eqdynamickd_power, nr, &d.dk_power);
+    }
+  }
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
     d.sd = *sd;  // scalars; every pointer below is re-homed into the arena
@@ -1053,6 +1114,8 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->elm_bsw = s->elm_bsw;
   d->somdec_nc = s->somdec_nc;
   d->elm_plantndemand = s->elm_rate_plantndemand;
+  d->eqionx_ref = s->eqionx_ref_cation_sorbed_conc;
+  d->eqionx_conc = s->eqionx_conc;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -1260,7 +1323,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.elm_w, (double **)&h->own_st.elm_o, (double **)&h->own_st.elm_t,
                            (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
                            (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
-                           (double **)&h->own_st.elm_plantndemand};
+                           (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -1278,14 +1341,15 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->sat,          host->temp,         host->porosity,  host->volume,
                               host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
-                              host->somdec_nc,    host->elm_rate_plantndemand};
+                              host->somdec_nc,    host->elm_rate_plantndemand, host->eqionx_ref_cation_sorbed_conc,
+                              host->eqionx_conc};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
-                         d.somdec_nc,    (double *)d.elm_plantndemand};
+                         d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -1302,6 +1366,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (!host->elm_bsw) d.elm_bsw = nullptr;
   if (!host->somdec_nc) d.somdec_nc = nullptr;
   if (!host->elm_rate_plantndemand) d.elm_plantndemand = nullptr;
+  if (!host->eqionx_ref_cation_sorbed_conc) d.eqionx_ref = nullptr;
+  if (!host->eqionx_conc) d.eqionx_conc = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -1333,7 +1399,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   int rc = summary_reset(h, s_k);
   if (rc) return rc;
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30};
   double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
                          host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
                          host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
@@ -1341,7 +1407,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
-                         host->somdec_nc,    nullptr};
+                         host->somdec_nc,    nullptr,            host->eqionx_ref_cation_sorbed_conc,
+                         host->eqionx_conc};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the
@@ -1419,6 +1486,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     PFRX_OFF(elm_bsw);
     PFRX_OFF(somdec_nc);
     PFRX_OFF(elm_plantndemand);
+    PFRX_OFF(eqionx_ref);
+    PFRX_OFF(eqionx_conc);
     PFRX_OFF(imat);
     PFRX_OFF(num_sub_steps);
     PFRX_OFF(num_iterations);
@@ -1543,7 +1612,7 @@ extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
   // written once, four int32 results
   if (!h) return 0;
   const int *r = h->rows_d.data();
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30};
   int64_t in = 0, outn = 0;
   for (int f = 0; f < kNumD; f++)
     if (f != 11) in += r[f];

@@ -81,6 +81,16 @@ struct DevCfg {
   const double *sc_st, *sc_h2o, *sc_fs, *sc_logK, *sc_logKcoef;
   const int *se_ptr, *se_pp;   // per surface complex: all (p,p2) entry pairs, p | p2<<16
   int neqsr;
+  // ion exchange, KD isotherms, dynamic KD (thread-per-cell kernel); nsorb = all equilibrium sorption
+  int nsorb, nionx, nkd, ndynkd, ikd_units;
+  const int *ix_ptr, *ix_cat, *ix_surf, *ix_zflag;
+  const double *ix_k, *ix_cec, *pri_Z;
+  const int *kd_spec, *kd_type, *kd_mnrl;
+  const double *kd_coeff, *kd_lb, *kd_fn;
+  const int *dk_spec, *dk_ref;
+  const double *dk_refhigh, *dk_low, *dk_high, *dk_power;
+  int n_ixcat;  // cations of all ion-exchange reactions
+  int off_ix;   // workspace: reference-cation sorbed concentrations, then cation concentrations
   const int *eqsr;
   int nmr;
   const int *mr_rxn, *mr_ptr;

@@ -376,13 +376,153 @@ struct CellT {
     }
 #pragma unroll 1
     for (int i = naq; i < n; i++) TOT(i) = C(i);
-    if (cfg.neqsr > 0) {
+    if (cfg.nsorb > 0) {
+      // RTotalSorb (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD
 #pragma unroll 1
       for (int k = 0; k < cfg.nsrfcplx; k++) ws[cfg.off_sc + k] = 0.0;
 #pragma unroll 1
       for (int i = 0; i < naq; i++) TS(i) = 0.0;
 #pragma unroll 1
       for (int e = 0; e < cfg.neqsr; e++) surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, vol / dt, true);
+      if (cfg.nionx > 0) ion_exchange(want_J, vol / dt);
+      if (cfg.ndynkd > 0) dynamic_kd(want_J, vol / dt);
+      if (cfg.nkd > 0) isotherm_kd(want_J, vol / dt);
+    }
+  }
+
+  // ---- RTotalSorbEqIonx (reaction.F90:4906-5140): Gaines-Thomas ion exchange; with mixed
+  // valences the equivalent fraction of the reference cation comes from a scalar Newton on KDj
+  // (tol 1e-12) that starts from the cell's previous answer.  d(total_sorb)/d(free) goes
+  // straight into the Jacobian with the V/dt of RAccumulationSorbDerivative.
+  __device__ __forceinline__ void ion_exchange(bool want_J, double jscale) {
+    const int nix = cfg.nionx;
+    double *ref = ws + cfg.off_ix;
+    double *conc = ws + cfg.off_ix + nix;
+#pragma unroll 1
+    for (int r = 0; r < nix; r++) {
+      const int p0 = cfg.ix_ptr[r], nc = cfg.ix_ptr[r + 1] - p0;
+      double omega;
+      if (cfg.ix_surf[r] >= 0)
+        omega = fmax(cfg.ix_cec[r] * st.mnrl_volfrac[cfg.ix_surf[r] * st.ld + cell], 1.e-40);
+      else
+        omega = cfg.ix_cec[r];
+      double *X = ws + cfg.off_tmp;  // equivalent fractions of this reaction's cations
+      if (cfg.ix_zflag[r]) {
+        int ic = cfg.ix_cat[p0];
+        const double rconc = exp(LNA(ic));  // molality * activity coefficient
+        const double rZ = cfg.pri_Z[ic], rk = cfg.ix_k[p0];
+        double rX = rZ * ref[r] / omega;
+        double KDj = rX / (rk * rconc);
+        bool one_more = false;
+        int it = 0;
+        for (;;) {
+          it++;
+          if (it > 20000) break;  // the reference flags an error here; never reached in practice
+          rX = KDj * (rk * rconc);
+          X[0] = rX;
+          double total = rX, dres = 0.0;
+#pragma unroll 1
+          for (int j = 1; j < nc; j++) {
+            ic = cfg.ix_cat[p0 + j];
+            const double xj = cfg.ix_k[p0 + j] * exp(LNA(ic)) * pow(KDj, cfg.pri_Z[ic] / rZ);
+            X[j] = xj;
+            total = total + xj;
+            dres = dres + xj / KDj * cfg.pri_Z[ic];
+          }
+          dres = dres / rZ + (rk * rconc);
+          const double res = 1.0 - total;
+          if (one_more) break;
+          const double dK = res / dres;
+          KDj = KDj + dK;
+          KDj = fmax(KDj, 1.e-40);
+          if (fabs(dK / KDj) < 1.e-12) one_more = true;
+        }
+        ref[r] = rX * omega / rZ;
+      } else {
+        double sumkm = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < nc; j++) {
+          const int ic = cfg.ix_cat[p0 + j];
+          const double xj = exp(LNA(ic)) * cfg.ix_k[p0 + j];
+          X[j] = xj;
+          sumkm = sumkm + xj;
+        }
+#pragma unroll 1
+        for (int j = 0; j < nc; j++) X[j] = X[j] / sumkm;
+      }
+      double sumZX = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < nc; i++) sumZX = sumZX + cfg.pri_Z[cfg.ix_cat[p0 + i]] * X[i];
+#pragma unroll 1
+      for (int i = 0; i < nc; i++) {
+        const int ic = cfg.ix_cat[p0 + i];
+        const double t1 = X[i] * omega / cfg.pri_Z[ic];
+        conc[p0 + i] = t1;
+        TS(ic) = TS(ic) + t1;
+        if (want_J) {
+          const double t2 = cfg.pri_Z[ic] / sumZX;
+#pragma unroll 1
+          for (int j = 0; j < nc; j++) {
+            const int jc = cfg.ix_cat[p0 + j];
+            double d;
+            if (i == j)
+              d = t1 * (1.0 - (t2 * X[j])) * INVC(jc);
+            else
+              d = (-t1) * t2 * X[j] * INVC(jc);
+            J(ic, jc) += d * jscale;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- RTotalSorbDynamicKD (reaction.F90:4836-4902) ---------------------------------------
+  __device__ __forceinline__ void dynamic_kd(bool want_J, double jscale) {
+    const double Lw = 250.0;
+#pragma unroll 1
+    for (int r = 0; r < cfg.ndynkd; r++) {
+      const int ikd = cfg.dk_spec[r], iref = cfg.dk_ref[r];
+      const double mk = C(ikd), mr = C(iref);
+      const double pw = cfg.dk_power[r], lo = cfg.dk_low[r], hml = cfg.dk_high[r] - lo;
+      const double t = pow(mr / cfg.dk_refhigh[r], pw);
+      const double KD = lo + t * hml;
+      const double dKD = pw * t / mr * hml;
+      TS(ikd) = TS(ikd) + KD * mk * Lw;
+      if (want_J) {
+        J(ikd, ikd) += (KD * Lw) * jscale;
+        J(ikd, iref) += (dKD * mk * Lw) * jscale;
+      }
+    }
+  }
+
+  // ---- RTotalSorbKD (reaction_isotherm.F90:273-359): linear / Langmuir / Freundlich -----------
+  __device__ __forceinline__ void isotherm_kd(bool want_J, double jscale) {
+#pragma unroll 1
+    for (int r = 0; r < cfg.nkd; r++) {
+      const int ic = cfg.kd_spec[r];
+      const double m = C(ic);
+      double kd;
+      if (cfg.ikd_units == 1)
+        kd = cfg.kd_coeff[r] * den_kg * (1.0 - por) * spd * 1.e-3;
+      else
+        kd = cfg.kd_coeff[r];
+      if (cfg.kd_mnrl[r] >= 0) kd = kd * (st.mnrl_volfrac[cfg.kd_mnrl[r] * st.ld + cell]);
+      double res = 0.0, dres = 0.0;
+      const int ty = cfg.kd_type[r];
+      if (ty == PFRX_SORPTION_LINEAR) {
+        res = kd * m;
+        dres = kd;
+      } else if (ty == PFRX_SORPTION_LANGMUIR) {
+        const double t = kd * m;
+        res = t * cfg.kd_lb[r] / (1.0 + t);
+        dres = res / m - res / (1.0 + t) * t / m;
+      } else if (ty == PFRX_SORPTION_FREUNDLICH) {
+        const double on = 1.0 / cfg.kd_fn[r];
+        res = kd * pow(m, on);
+        dres = res / m * on;
+      }
+      TS(ic) = TS(ic) + res;
+      if (want_J) J(ic, ic) += dres * jscale;
     }
   }
 
@@ -882,7 +1022,7 @@ struct CellT {
       double f = 0.0;
       if (i < naq) {
         if (!dry) f = psv * st.total[i * ld + c];
-        if (cfg.neqsr > 0) f = f + st.total_sorb_eq[i * ld + c] * vol;
+        if (cfg.nsorb > 0) f = f + st.total_sorb_eq[i * ld + c] * vol;
         C(i) = guess[i];
       } else if (i < n) {
         if (!dry) f = 0.0 + st.immobile[(i - naq) * ld + c] * vol;
@@ -906,7 +1046,7 @@ struct CellT {
       if (its > cfg.max_its) {
         // total and immobile keep their initial values (never overwritten in
         // HBM); total_sorb_eq is not restored (reaction.F90:3891-3894)
-        if (cfg.neqsr > 0)
+        if (cfg.nsorb > 0)
           for (int i = 0; i < naq; i++) st.total_sorb_eq[i * ld + c] = TS(i);
         its_out = its;
         return 1;
@@ -916,7 +1056,7 @@ struct CellT {
         if (i < n) {
           double a = 0.0;
           if (!dry) a = (i < naq) ? psv * TOT(i) : 0.0 + C(i) * vol;
-          if (cfg.neqsr > 0 && i < naq) a = a + TS(i) * vol;
+          if (cfg.nsorb > 0 && i < naq) a = a + TS(i) * vol;
           RES(i) = (a - fixed[i]) / dt;
         }
       }
@@ -947,7 +1087,7 @@ struct CellT {
         // solve_error branch: no restore (reaction.F90:3964-3967)
         for (int i = 0; i < naq; i++) {
           st.total[i * ld + c] = TOT(i);
-          if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = TS(i);
+          if (cfg.nsorb > 0) st.total_sorb_eq[i * ld + c] = TS(i);
         }
         for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
         its_out = its;
@@ -990,7 +1130,7 @@ struct CellT {
     // RTotal at the same c: TOT / TS / sec_molal already hold those values
     for (int i = 0; i < naq; i++) {
       st.total[i * ld + c] = TOT(i);
-      if (cfg.neqsr > 0) st.total_sorb_eq[i * ld + c] = TS(i);
+      if (cfg.nsorb > 0) st.total_sorb_eq[i * ld + c] = TS(i);
     }
     for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
 #pragma unroll
@@ -1143,6 +1283,9 @@ struct CellT {
       for (int i = 0; i < naq; i++) ws[cfg.off_mr + (2 * q) * N + i] = st.kinmr[(base + i) * ld + c];
     }
     if (cfg.nsbx > 0) sandbox_load(c);
+#pragma unroll 1
+    for (int r = 0; r < cfg.nionx; r++)
+      ws[cfg.off_ix + r] = st.eqionx_ref ? st.eqionx_ref[r * ld + c] : 1.e-9;
     small_mask = 0u;
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -1218,6 +1361,13 @@ struct CellT {
     }
     if (st.ln_act_h2o && cfg.use_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
     if (cfg.n_nc > 0) sandbox_store(c);
+    if (cfg.nionx > 0) {
+      const int ncat = cfg.ix_ptr[cfg.nionx];
+      if (st.eqionx_ref)
+        for (int r = 0; r < cfg.nionx; r++) st.eqionx_ref[r * ld + c] = ws[cfg.off_ix + r];
+      if (st.eqionx_conc)
+        for (int k = 0; k < ncat; k++) st.eqionx_conc[k * ld + c] = ws[cfg.off_ix + cfg.nionx + k];
+    }
   }
 
   // RStep's reaction to the outcome of one RReact (reaction.F90:3660-3716);

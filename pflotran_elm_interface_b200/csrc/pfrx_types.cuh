@@ -15,6 +15,7 @@ struct DevState {
   const double *elm_w, *elm_o, *elm_t, *elm_zsoil, *elm_kscalar, *elm_bd_dry, *elm_bsw;
   double *somdec_nc;
   const double *elm_plantndemand;
+  double *eqionx_ref, *eqionx_conc;
 };
 
 // shard summary accumulated with atomics, one set per warp

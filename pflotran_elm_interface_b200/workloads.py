@@ -467,6 +467,140 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
     return Workload(name, cfg, st, tran_dt, net, note + f", {net.ncomp} dof")
 
 
+# --------------------------------------------------------------------------- #
+C6_DECK = """
+# C6: sorption without surface complexes -- the ion exchange network of
+# ascem/batch/ion-exchange-valocchi.in (Na+ reference, Ca++, Mg++ on a CEC tied to nothing /
+# to Halite), plus one KD isotherm of every type and a dynamic KD
+CHEMISTRY
+  PRIMARY_SPECIES
+    Na+
+    Ca++
+    Mg++
+    Cl-
+    K+
+    Tracer
+    Tracer2
+    NO3-
+  /
+  MINERALS
+    Halite
+  /
+  MINERAL_KINETICS
+    Halite
+      RATE_CONSTANT 1.d-40 mol/cm^2-sec
+    /
+  /
+  SORPTION
+    ION_EXCHANGE_RXN
+      CEC 750. eq/m^3
+      CATIONS
+        Ca++  3.38638672536d0
+        Na+   1.d0 REFERENCE
+        Mg++  6.00240096038d0
+      /
+    /
+    ION_EXCHANGE_RXN
+      MINERAL Halite
+      CEC 5.d4
+      CATIONS
+        Na+   1.d0 REFERENCE
+        K+    2.5d0
+      /
+    /
+    ISOTHERM_REACTIONS
+      Tracer
+        TYPE LINEAR
+        DISTRIBUTION_COEFFICIENT 500.
+      /
+      Tracer2
+        TYPE FREUNDLICH
+        DISTRIBUTION_COEFFICIENT 20.
+        FREUNDLICH_N 1.5
+      /
+      K+
+        TYPE LANGMUIR
+        DISTRIBUTION_COEFFICIENT 3.d3
+        LANGMUIR_B 0.2
+      /
+    /
+    DYNAMIC_KD_REACTIONS
+      NO3-
+        REFERENCE_SPECIES Cl-
+        REFERENCE_SPECIES_HIGH 0.2
+        KD_LOW 0.05
+        KD_HIGH 2.0
+        KD_POWER 1.5
+      /
+    /
+  /
+  DATABASE ./hanford_subset.dat
+  LOG_FORMULATION
+END
+CONSTRAINT initial
+  CONCENTRATIONS
+    Na+     8.65d-2 T
+    Ca++    1.82d-2 T
+    Mg++    1.11d-2 T
+    Cl-     2.d-3   Z
+    K+      1.d-3   T
+    Tracer  1.d-6   T
+    Tracer2 1.d-5   T
+    NO3-    1.d-4   T
+  /
+  MINERALS
+    Halite 1.d-5 1.d0 cm^2/cm^3
+  /
+END
+CONSTRAINT inlet
+  CONCENTRATIONS
+    Na+     9.4d-3  T
+    Ca++    5.d-4   T
+    Mg++    2.13d-3 T
+    Cl-     1.d-2   Z
+    K+      1.d-4   T
+    Tracer  1.d-3   T
+    Tracer2 1.d-3   T
+    NO3-    1.d-3   T
+  /
+  MINERALS
+    Halite 1.d-5 1.d0 cm^2/cm^3
+  /
+END
+"""
+
+
+def ion_exchange(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED) -> Workload:
+    """C6: ion exchange (mixed valences: inner Newton; equal valences: closed form; CEC absolute and
+    tied to a mineral), linear / Langmuir / Freundlich KD isotherms and a dynamic KD.  Cells are mixes
+    of the resident water and the inlet water of the Valocchi problem; the sorbed state is the resident
+    one, so the step re-partitions every cation."""
+    rng = np.random.default_rng(seed)
+    dk, net = chem.load_network(C6_DECK, _read("hanford_subset.dat"))
+    assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67(25.0)
+    waters = [constraint.equilibrate_constraint(net, dk.constraints[k], den_kg=den, porosity=0.25)
+              for k in ("initial", "inlet")]
+    st = abi.HostState(cfg, ncell)
+    f = rng.random(ncell)
+    wts = np.stack([1.0 - f, f])
+    _mix_fill(st, waters, wts, rng, jitter=0.0)
+    st["den_kg"][...] = den
+    st["porosity"][...] = 0.25
+    st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
+    st["sat"][...] = rng.uniform(0.4, 1.0, ncell)
+    st["temp"][...] = 25.0
+    st["mnrl_volfrac"][...] = 10.0 ** rng.uniform(-6.0, -4.0, (net.nkinmnrl, ncell))
+    st["mnrl_area"][...] = 100.0
+    # sorbed totals of the resident water on every cell: one oracle-free estimate is enough, the
+    # step starts from total_sorb_eq as the fixed accumulation and re-equilibrates
+    st["total_sorb_eq"][...] = np.asarray(waters[0].total_sorb_eq)[:, None] * np.ones((1, ncell)) \
+        if getattr(waters[0], "total_sorb_eq", None) is not None and np.any(waters[0].total_sorb_eq) else 0.0
+    return Workload("c6_ion_exchange_kd", cfg, st, tran_dt, net,
+                    "2 ion-exchange reactions (5 cations), 3 KD isotherms, 1 dynamic KD, kinetic Halite")
+
+
 def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
     table = {
         "c1": (calcite_batch, {}),
@@ -481,6 +615,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4se": (elm_cn, {"elm": True}),
         "c4fe": (elm_cn, {"full": True, "elm": True}),
         "c5": (hanford, {"variant": "minerals"}),
+        "c6": (ion_exchange, {}),
     }
     fn, kw = table[name]
     kw = dict(kw)

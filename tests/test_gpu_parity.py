@@ -132,6 +132,20 @@ def test_c4s_elm_cn_sandboxes(variant, dt, host):
     assert rr.num_cut_cells > 0  # the workload exercises the sub-step logic
 
 
+@pytest.mark.parametrize("dt,host", [(3600.0, False), (86400.0, False), (30 * 86400.0, True)])
+def test_c6_ion_exchange_and_isotherms(dt, host):
+    """RTotalSorbEqIonx (inner Newton on mixed valences, closed form on equal ones, absolute and
+    mineral-bound CEC), RTotalSorbKD (linear / Langmuir / Freundlich), RTotalSorbDynamicKD in the
+    thread-per-cell kernel; eqionx_conc and the reference-cation memory are compared too"""
+    wl = W.by_name("c6", ncell=5000, tran_dt=dt)
+    wl.state.a["imat"][0, 5] = 0
+    wl.state.a["sat"][0, 6] = 1.0e-50   # dry: identity + sorption derivative
+    ref, rr, got, rg, info = _run_both(wl, host_path=host)
+    assert info["lanes"] in (0, 1)
+    _compare(ref, got, f"c6 dt={dt}")
+    _check_summary(rr, rg)
+
+
 @pytest.mark.parametrize("variant,dt", [("c3", 3600.0), ("c3", 30 * 86400.0), ("c3mr", 3600.0), ("c5", 86400.0)])
 def test_hanford(variant, dt):
     wl = W.by_name(variant, ncell=3000, tran_dt=dt)

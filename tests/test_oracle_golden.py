@@ -248,3 +248,24 @@ def test_plantn_gold(name):
         elif title.startswith("CONCENTRATION: ") and title[len("CONCENTRATION: "):] in net.immobile_names:
             got = st["immobile"][net.immobile_names.index(title[len("CONCENTRATION: "):]), 0]
             _check_rel(got, sec["1"], 1.0e-7, f"{name} {title}")
+
+
+def test_ion_exchange_gold():
+    """ascem/batch/ion-exchange-valocchi: RTotalSorbEqIonx with mixed valences (Na+ reference,
+    Ca++, Mg++: the inner Newton on KDj), speciation only (MAX_STEPS -1).  batch.cfg: 1e-12."""
+    dk, net, cfg, st = _setup("ion-exchange-valocchi.in", "hanford_subset.dat")
+    assert cfg.c.neqionxrxn == 1 and cfg.arrays["eqionx_Z_flag"][0] == 1
+    assert net.primary_names[cfg.arrays["eqionx_cationid"][0]] == "Na+"   # the REFERENCE cation leads
+    girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold("ion-exchange-valocchi.regression.gold")
+    for nm in ("Na+", "Ca++", "Mg++", "Cl-"):
+        i = net.primary_names.index(nm)
+        _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")
+        want = _val(gold, f"CONCENTRATION: Total Sorbed {nm}")
+        if want == 0.0:
+            assert st["total_sorb_eq"][i, 0] == 0.0
+        else:
+            _check_rel(st["total_sorb_eq"][i, 0], want, 1.0e-12, f"Total Sorbed {nm}")
+    # the sorbed charge adds up to the exchange capacity: sum Z_i S_i = CEC
+    Z = cfg.arrays["primary_spec_Z"]
+    assert abs(float(np.sum(Z * st["total_sorb_eq"][:, 0])) - 750.0) < 1.0e-9

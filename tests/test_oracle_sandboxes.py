@@ -127,3 +127,33 @@ def test_rstep_on_elm_cn_workload(name, dt):
 
     n0, n1 = total_n(before), total_n(st)
     assert np.all(np.abs(n1 - n0) <= 1e-5 * np.abs(n0))  # Newton stops at 1e-6 relative change
+
+
+def test_sorption_jacobian_vs_finite_differences():
+    """ion exchange (inner Newton and closed form, absolute and mineral-bound CEC), linear /
+    Langmuir / Freundlich KD and dynamic KD: d(total_sorb_eq)/d(free) of the oracle against
+    central differences of its own residual (reaction.F90:41 perturbation_tolerance scale)"""
+    wl = W.by_name("c6", ncell=12)
+    cfg, dt = wl.cfg, wl.tran_dt
+    naq = cfg.c.naqcomp
+    for cell in range(12):
+        st0 = wl.state.copy()
+        e, R0, J, _ = orc.girt_residual(cfg, st0, cell, dt)
+        assert e == 0
+        for j in range(naq):
+            cols = []
+            for sgn in (1.0, -1.0):
+                st = wl.state.copy()
+                st.a["pri_molal"][j, cell] *= 1.0 + sgn * 1.0e-6
+                _, R, _, _ = orc.girt_residual(cfg, st, cell, dt)
+                cols.append((R, st.a["pri_molal"][j, cell]))
+            fd = (cols[0][0] - cols[1][0]) / (cols[0][1] - cols[1][1])
+            scale = np.abs(J[:, j]).max()
+            assert np.abs(J[:, j] - fd).max() <= 2.0e-5 * scale, (cell, j, J[:, j], fd)
+    # the exchanger is full: sum Z_i S_i = CEC for the absolute-CEC reaction
+    st = wl.state.copy()
+    orc.auxvar_compute(cfg, st, 0)
+    z = cfg.arrays["primary_spec_Z"]
+    ptr, cat = cfg.arrays["eqionx_ptr"], cfg.arrays["eqionx_cationid"]
+    s0 = sum(z[cat[k]] * st["eqionx_conc"][k, 0] for k in range(ptr[0], ptr[1]))
+    assert abs(s0 - 750.0) < 1e-9

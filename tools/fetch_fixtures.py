@@ -37,6 +37,8 @@ COPY = [
     ("regression_tests/ascem/batch/surface-complexation-1.in", None),
     ("regression_tests/ascem/batch/surface-complexation-1.regression.gold", None),
     ("regression_tests/ascem/batch/surface-complexation.dat", None),
+    ("regression_tests/ascem/batch/ion-exchange-valocchi.in", None),
+    ("regression_tests/ascem/batch/ion-exchange-valocchi.regression.gold", None),
     ("regression_tests/ngee/CLM-CN.in", None),
     ("regression_tests/ngee/CLM-CN.regression.gold", None),
     ("regression_tests/ngee/CLM-CN_database.dat", None),
@@ -114,7 +116,7 @@ def main():
     ch = dk.chemistry
     names = (["H2O"] + ch.primary + ch.secondary + ch.gases + ch.minerals
              + [c for r in ch.srfcplx_rxns for c in r.complexes]
-             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)"])
+             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite"])
     db = chem.Database.from_file(os.path.join(REF, "database/hanford.dat"))
     with open(os.path.join(OUT, "hanford_subset.dat"), "w") as f:
         f.write(db.subset_text(names))
