@@ -570,6 +570,57 @@ END
 """
 
 
+def _sorbed_totals(net: chem.ReactionNetwork, water, volfrac: float, den_kg: float, porosity: float,
+                   particle_density: float = 2650.0) -> np.ndarray:
+    """total_sorb_eq of one speciated water (ion exchange by bisection on the exchanger's
+    charge balance, KD isotherms, dynamic KD): the resident sorbed state the C6 cells start from.
+    Set-up helper with its own arithmetic -- the step re-equilibrates anyway."""
+    m = np.asarray(water.pri_molal, dtype=np.float64)
+    act = m * np.asarray(water.pri_act_coef, dtype=np.float64)
+    Z = np.asarray(net.primary_Z, dtype=np.float64)
+    out = np.zeros(net.naqcomp)
+    ix = net.ionx
+    if ix:
+        for r in range(len(ix["CEC"])):
+            ids = ix["cationid"][ix["ptr"][r]:ix["ptr"][r + 1]]
+            ks = np.asarray(ix["k"][ix["ptr"][r]:ix["ptr"][r + 1]])
+            omega = ix["CEC"][r] * (volfrac if ix["to_surf"][r] >= 0 else 1.0)
+            zr = Z[ids[0]]
+
+            def total(kd):
+                return sum(ks[j] * act[ids[j]] * kd ** (Z[ids[j]] / zr) for j in range(len(ids)))
+
+            lo, hi = 1.0e-30, 1.0e30
+            for _ in range(400):
+                mid = np.sqrt(lo * hi)
+                if total(mid) > 1.0:
+                    hi = mid
+                else:
+                    lo = mid
+            kd = np.sqrt(lo * hi)
+            for j in range(len(ids)):
+                out[ids[j]] += ks[j] * act[ids[j]] * kd ** (Z[ids[j]] / zr) * omega / Z[ids[j]]
+    if net.dynkd:
+        d = net.dynkd
+        for r in range(len(d["specid"])):
+            kd = d["low"][r] + (m[d["refspecid"][r]] / d["refspechigh"][r]) ** d["power"][r] * (d["high"][r] - d["low"][r])
+            out[d["specid"][r]] += kd * m[d["specid"][r]] * 250.0
+    if net.kd:
+        k = net.kd
+        for r in range(len(k["specid"])):
+            i = k["specid"][r]
+            kd = k["coeff"][r]
+            if k["ikd_units"] == 1:
+                kd = kd * den_kg * (1.0 - porosity) * particle_density * 1.0e-3
+            if k["type"][r] == 1:
+                out[i] += kd * m[i]
+            elif k["type"][r] == 2:
+                out[i] += kd * m[i] * k["langmuir_b"][r] / (1.0 + kd * m[i])
+            else:
+                out[i] += kd * m[i] ** (1.0 / k["freundlich_n"][r])
+    return out
+
+
 def ion_exchange(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED) -> Workload:
     """C6: ion exchange (mixed valences: inner Newton; equal valences: closed form; CEC absolute and
     tied to a mineral), linear / Langmuir / Freundlich KD isotherms and a dynamic KD.  Cells are mixes
@@ -591,12 +642,14 @@ def ion_exchange(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEE
     st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
     st["sat"][...] = rng.uniform(0.4, 1.0, ncell)
     st["temp"][...] = 25.0
-    st["mnrl_volfrac"][...] = 10.0 ** rng.uniform(-6.0, -4.0, (net.nkinmnrl, ncell))
+    vf = 10.0 ** rng.uniform(-6.0, -4.0, ncell)
+    st["mnrl_volfrac"][...] = vf[None, :]
     st["mnrl_area"][...] = 100.0
-    # sorbed totals of the resident water on every cell: one oracle-free estimate is enough, the
-    # step starts from total_sorb_eq as the fixed accumulation and re-equilibrates
-    st["total_sorb_eq"][...] = np.asarray(waters[0].total_sorb_eq)[:, None] * np.ones((1, ncell)) \
-        if getattr(waters[0], "total_sorb_eq", None) is not None and np.any(waters[0].total_sorb_eq) else 0.0
+    # the exchanger and the KD sites hold what the resident water left there; the mixed water of
+    # the cell then re-partitions every cation (sorbed totals are linear in the mineral-bound CEC)
+    s_lo = _sorbed_totals(net, waters[0], 1.0e-6, den, 0.25)
+    s_hi = _sorbed_totals(net, waters[0], 1.0e-4, den, 0.25)
+    st["total_sorb_eq"][...] = s_lo[:, None] + (s_hi - s_lo)[:, None] * ((vf - 1.0e-6) / (1.0e-4 - 1.0e-6))[None, :]
     return Workload("c6_ion_exchange_kd", cfg, st, tran_dt, net,
                     "2 ion-exchange reactions (5 cations), 3 KD isotherms, 1 dynamic KD, kinetic Halite")
 
