@@ -346,6 +346,34 @@ def main():
                  "kernel": _kernel_name(info), "kernel_ms": 1000.0 * t_launch,
                  "fp64_peak_sm_mhz": mhz})
 
+    # ---- the block-vector transposes either side of the cell loop (HBM-bound) ------
+    osv = None
+    if world == 1 and not a.no_e2e:
+        naq, ncomp = int(wl.cfg.c.naqcomp), int(wl.cfg.ncomp)
+        vec = torch.zeros((ncell, ncomp), dtype=torch.float64, device=dev)
+        vec2 = torch.rand((ncell, ncomp), dtype=torch.float64, device=dev)
+        restore()
+        algo = {"fixed_accum": 8 * (2 * naq + 3), "load": 16 * ncomp, "store": 16 * ncomp}
+        calls = {"fixed_accum": lambda: step.os_fixed_accum(vec), "load": lambda: step.os_load(vec2, vec2),
+                 "store": lambda: step.os_store(vec)}
+        osv = {}
+        for nm in ("fixed_accum", "store", "load"):
+            calls[nm]()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(kstream)
+                calls[nm]()
+                e1.record(kstream)
+                torch.cuda.synchronize(dev)
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+            t = float(np.median(ts))
+            gbs = algo[nm] * ncell / t / 1e9
+            osv[nm] = {"ms": 1e3 * t, "algorithmic_bytes_per_cell": algo[nm], "GB/s": gbs, "frac_hbm": gbs / hbm_gbs}
+        osv["note"] = ("pfrx_os_fixed_accum / pfrx_os_store / pfrx_os_load: PETSc block vectors <-> SoA "
+                       "(pmc_subsurface_osrt.F90:260-274, 303-376), vectors larger than L2")
+        del vec, vec2
+
     cpu = None
     if not a.no_cpu:
         cpu = cpu_baseline(wl, a.cpu_seconds, os.cpu_count() or 1)
@@ -356,6 +384,7 @@ def main():
            "config": dict(cfg_json, name=wl.name, ncomp=wl.cfg.ncomp, neqcplx=int(wl.cfg.c.neqcplx),
                           kernel=info, kernel_variant=step.variant, autotune_s=tuned, note=wl.note),
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+           "os_block_vectors": osv,
            "result": res.as_dict(), "wall_s_timed_region": wall}
     print(json.dumps(out))
     if world > 1:

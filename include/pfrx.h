@@ -514,6 +514,27 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * Multirate sorption is not covered yet (PFRX_E_INVALID).                     */
 int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
+/* ---- the steps either side of the cell loop ---------------------
+ * PETSc keeps the transport unknowns and right-hand sides as BLOCK vectors, ncomp
+ * values per cell: v[cell*ncomp + i].  The chemistry state here is cell-major SoA,
+ * so the reference's per-component VecStrideGather / scatter loops around KSPSolve
+ * (pmc_subsurface_osrt.F90:303-333) disappear -- component i of a SoA field IS the
+ * contiguous work vector -- and what remains are three transposes of the bound
+ * device state against block vectors in device memory (cells with imat <= 0 are
+ * skipped like in the reference; entries the reference does not write stay
+ * untouched):
+ *   pfrx_os_fixed_accum   fixed_accum(cell, i) = porosity*sat*1000*volume*total(i), i < naqcomp
+ *                         (:260-274; immobile entries untouched)
+ *   pfrx_os_load          total(i) <- solved(cell, i) for i < naqcomp (:322-327, all
+ *                         components at once) and immobile(k) <- tran_xx(cell, naqcomp+k)
+ *                         (:356-359); either vector may be NULL
+ *   pfrx_os_store         tran_xx(cell, i) <- pri_molal(i), tran_xx(cell, naqcomp+k) <-
+ *                         immobile(k) after the step (:371-376)
+ * All three are HBM-bound; they run on the handle's stream and return when done. */
+int pfrx_os_fixed_accum(pfrx_handle *h, double *fixed_accum);
+int pfrx_os_load(pfrx_handle *h, const double *solved_total, const double *tran_xx);
+int pfrx_os_store(pfrx_handle *h, double *tran_xx);
+
 /* ---- network-specialised kernels -------------------------------------------
  * The generic kernels read the reaction network from tables, the way the
  * reference's RTotalAqueous / RKineticMineral loops read reaction%eqcplxspecid

@@ -1284,6 +1284,110 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
   return PFRX_OK;
 }
 
+// ---- block vectors <-> SoA around the cell loop (pmc_subsurface_osrt.F90:260-274, 303-333, 356-376) ----
+// One block moves a tile of OS_CELLS cells x ncomp components through shared memory, so that both
+// sides are coalesced: the block vector is read / written as one contiguous run of OS_CELLS*ncomp
+// doubles, the SoA fields as runs of OS_CELLS consecutive cells per component.  The tile is padded
+// (ncomp | 1 doubles per cell) so that the cell-wise accesses are bank-conflict free.
+#define OS_CELLS 256
+enum { OS_FIXED_ACCUM = 0, OS_LOAD = 1, OS_STORE = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t ncell, int naq, int nim,
+                                                            const double *in_a, const double *in_b, double *out) {
+  extern __shared__ double tile[];
+  const int n = naq + nim, ldt = n | 1;
+  const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
+  for (int64_t t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const int64_t c0 = t * OS_CELLS;
+    const int nc = (int)min((int64_t)OS_CELLS, ncell - c0);
+    const int64_t c = c0 + threadIdx.x;
+    const bool mine = threadIdx.x < nc;
+    const bool active = mine && !(st.imat && st.imat[c] <= 0);
+    if (MODE == OS_FIXED_ACCUM) {
+      // SoA -> tile (per cell), tile -> block vector (contiguous); only aqueous entries of active
+      // cells are written, the rest of the vector is left as it is
+      if (active) {
+        const double f = st.porosity[c] * st.sat[c] * 1000.0 * st.volume[c];
+        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = f * st.total[i * st.ld + c];
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+        const int cc = e / n, i = e - cc * n;
+        const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
+        if (i < naq && act) out[c0 * n + e] = tile[cc * ldt + i];
+      }
+      __syncthreads();
+    } else if (MODE == OS_LOAD) {
+      // block vectors -> tile (contiguous), tile -> SoA (per cell)
+      if (in_a) {
+        for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+          const int cc = e / n, i = e - cc * n;
+          if (i < naq) tile[cc * ldt + i] = in_a[c0 * n + e];
+        }
+      }
+      if (in_b && nim > 0) {
+        for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+          const int cc = e / n, i = e - cc * n;
+          if (i >= naq) tile[cc * ldt + i] = in_b[c0 * n + e];
+        }
+      }
+      __syncthreads();
+      if (active) {
+        if (in_a)
+          for (int i = 0; i < naq; i++) st.total[i * st.ld + c] = tile[threadIdx.x * ldt + i];
+        if (in_b)
+          for (int k = 0; k < nim; k++) st.immobile[k * st.ld + c] = tile[threadIdx.x * ldt + naq + k];
+      }
+      __syncthreads();
+    } else {
+      if (active) {
+        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = st.pri_molal[i * st.ld + c];
+        for (int k = 0; k < nim; k++) tile[threadIdx.x * ldt + naq + k] = st.immobile[k * st.ld + c];
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+        const int cc = e / n, i = e - cc * n;
+        const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
+        if (act) out[c0 * n + e] = tile[cc * ldt + i];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int MODE>
+static int os_launch(pfrx_handle *h, const double *a, const double *b, double *out) {
+  if (!h) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->ncell <= 0) return PFRX_OK;
+  const int naq = h->cfg.naq, nim = h->cfg.nim;
+  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double) + sizeof(double) * OS_CELLS;
+  const int64_t ntile = (h->ncell + OS_CELLS - 1) / OS_CELLS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * 8));
+  CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  pfrx_os_kernel<MODE><<<grid, OS_CELLS, smem, h->stream>>>(h->st, h->ncell, naq, nim, a, b, out);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_os_fixed_accum(pfrx_handle *h, double *fixed_accum) {
+  if (!fixed_accum) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  return os_launch<OS_FIXED_ACCUM>(h, nullptr, nullptr, fixed_accum);
+}
+extern "C" int pfrx_os_load(pfrx_handle *h, const double *solved_total, const double *tran_xx) {
+  if (!solved_total && !tran_xx) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  return os_launch<OS_LOAD>(h, solved_total, tran_xx, nullptr);
+}
+extern "C" int pfrx_os_store(pfrx_handle *h, double *tran_xx) {
+  if (!tran_xx) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  return os_launch<OS_STORE>(h, nullptr, nullptr, tran_xx);
+}
+
 // ---- host-resident state: H2D, kernel, D2H ------------------------------------
 static const int kNumD = PFRX_NUM_D;
 static size_t field_off(const int *rows, int64_t ld, int f) {

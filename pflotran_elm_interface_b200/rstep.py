@@ -62,6 +62,9 @@ def lib():
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
     L.pfrx_reaction.argtypes = [hp, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfrx_os_fixed_accum.argtypes = [hp, C.c_void_p]
+    L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
+    L.pfrx_os_store.argtypes = [hp, C.c_void_p]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
@@ -215,6 +218,21 @@ class ChemistryStep:
         _check(lib().pfrx_reaction(self._h, float(tran_dt), int(bool(want_jacobian)), res.data_ptr(),
                                    jac.data_ptr() if jac is not None else None), "pfrx_reaction")
         return res, jac
+
+    # -- block vectors either side of the cell loop (pmc_subsurface_osrt.F90:260-274, 303-376) -- #
+    def os_fixed_accum(self, fixed_accum) -> None:
+        """fixed_accum[cell, i] = porosity*sat*1000*volume*total(i) for the aqueous components of
+        the active cells; ``fixed_accum`` is a device tensor [ncell, ncomp] (PETSc block layout)"""
+        _check(lib().pfrx_os_fixed_accum(self._h, fixed_accum.data_ptr()), "pfrx_os_fixed_accum")
+
+    def os_load(self, solved_total=None, tran_xx=None) -> None:
+        """total <- solved_total[:, :naq], immobile <- tran_xx[:, naq:] (block vectors [ncell, ncomp])"""
+        _check(lib().pfrx_os_load(self._h, solved_total.data_ptr() if solved_total is not None else None,
+                                  tran_xx.data_ptr() if tran_xx is not None else None), "pfrx_os_load")
+
+    def os_store(self, tran_xx) -> None:
+        """tran_xx[cell, :] <- (pri_molal, immobile) of the active cells"""
+        _check(lib().pfrx_os_store(self._h, tran_xx.data_ptr()), "pfrx_os_store")
 
     # -- host-resident path (H2D + kernel + D2H inside the call) ---------------- #
     def rstep_host(self, host: abi.HostState, tran_dt: float) -> abi.PfrxStepResult:

@@ -264,6 +264,54 @@ def test_refill_skeleton(name, n, dt, host, style):
     step.close()
 
 
+@pytest.mark.parametrize("name,n", [("c3", 70001), ("c4", 5000), ("c2", 3), ("c4fe", 777)])
+def test_os_block_vector_transposes(name, n):
+    """pfrx_os_fixed_accum / pfrx_os_load / pfrx_os_store against numpy restatements of
+    pmc_subsurface_osrt.F90:260-274, :322-327 + :356-359, :371-376 -- bit for bit, inactive cells
+    and entries the reference does not write left untouched"""
+    import torch
+
+    rstep = _gpu()
+    wl = W.by_name(name, ncell=n)
+    rng = np.random.default_rng(7)
+    a = wl.state.a
+    a["imat"][0, rng.random(n) < 0.1] = 0
+    naq, nim = wl.cfg.c.naqcomp, wl.cfg.c.nimcomp
+    ncomp = naq + nim
+    act = a["imat"][0] > 0
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    # fixed accumulation
+    sentinel = rng.standard_normal((n, ncomp))
+    fa = torch.from_numpy(sentinel.copy()).cuda()
+    step.os_fixed_accum(fa)
+    want = sentinel.copy()
+    f = a["porosity"][0] * a["sat"][0] * 1000.0 * a["volume"][0]
+    want[act, :naq] = (f[None, :] * a["total"]).T[act]
+    assert np.array_equal(fa.cpu().numpy(), want)
+    # load: totals from the transport solve, immobile from tran_xx
+    solved = rng.random((n, ncomp))
+    xx = rng.random((n, ncomp))
+    step.os_load(torch.from_numpy(solved).cuda(), torch.from_numpy(xx).cuda())
+    got = dev.to_host()
+    wt, wi = a["total"].copy(), a["immobile"].copy()
+    wt[:, act] = solved[act, :naq].T
+    if nim:
+        wi[:, act] = xx[act, naq:].T
+    assert np.array_equal(got["total"], wt) and np.array_equal(got["immobile"], wi)
+    step.os_load(torch.from_numpy(solved).cuda(), None)      # either vector may be absent
+    # store
+    out = torch.from_numpy(sentinel.copy()).cuda()
+    step.os_store(out)
+    want = sentinel.copy()
+    want[act, :naq] = got["pri_molal"].T[act]
+    if nim:
+        want[act, naq:] = got["immobile"].T[act]
+    assert np.array_equal(out.cpu().numpy(), want)
+    step.close()
+
+
 def test_autotune_picks_a_variant_and_leaves_state_alone():
     rstep = _gpu()
     from pflotran_elm_interface_b200 import specialize
