@@ -1309,9 +1309,11 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
       // cells are written, the rest of the vector is left as it is
       if (active) {
         const double f = st.porosity[c] * st.sat[c] * 1000.0 * st.volume[c];
-        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = f * st.total[i * st.ld + c];
+#pragma unroll 8
+        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = f * __ldcs(st.total + i * st.ld + c);
       }
       __syncthreads();
+#pragma unroll 4
       for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
         const int cc = e / n, i = e - cc * n;
         const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
@@ -1321,13 +1323,15 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
     } else if (MODE == OS_LOAD) {
       // block vectors -> tile (contiguous), tile -> SoA (per cell)
       if (in_a) {
-        for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+  #pragma unroll 4
+      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
           const int cc = e / n, i = e - cc * n;
           if (i < naq) tile[cc * ldt + i] = in_a[c0 * n + e];
         }
       }
       if (in_b && nim > 0) {
-        for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
+  #pragma unroll 4
+      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
           const int cc = e / n, i = e - cc * n;
           if (i >= naq) tile[cc * ldt + i] = in_b[c0 * n + e];
         }
@@ -1335,17 +1339,22 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
       __syncthreads();
       if (active) {
         if (in_a)
+#pragma unroll 8
           for (int i = 0; i < naq; i++) st.total[i * st.ld + c] = tile[threadIdx.x * ldt + i];
         if (in_b)
+#pragma unroll 8
           for (int k = 0; k < nim; k++) st.immobile[k * st.ld + c] = tile[threadIdx.x * ldt + naq + k];
       }
       __syncthreads();
     } else {
       if (active) {
-        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = st.pri_molal[i * st.ld + c];
-        for (int k = 0; k < nim; k++) tile[threadIdx.x * ldt + naq + k] = st.immobile[k * st.ld + c];
+#pragma unroll 8
+        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = __ldcs(st.pri_molal + i * st.ld + c);
+#pragma unroll 8
+        for (int k = 0; k < nim; k++) tile[threadIdx.x * ldt + naq + k] = __ldcs(st.immobile + k * st.ld + c);
       }
       __syncthreads();
+#pragma unroll 4
       for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
         const int cc = e / n, i = e - cc * n;
         const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
