@@ -91,7 +91,12 @@ __device__ __forceinline__ double sx_dmonod(double c, double k) { return sx_div(
 #define SPEC_FIXED(i) SW(SPEC_OFF_FIXED + (i))  // read once per iteration, constant over a sub-step
 #define SPEC_SMALL(i) SW(SPEC_OFF_SMALL + (i))  // totals <= 1e-40 to put back at the end (rare)
 #endif
-#define SPEC_SLOTS (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
+#ifndef SPEC_NRO
+#define SPEC_NRO 0      // Jacobian entries of the row-only species (kept outside the dense matrix)
+#define SPEC_NROSPEC 0
+#endif
+#define SPEC_OFF_RO (SPEC_OFF_LNGSEC + (SPEC_ACT_UPD ? 0 : SPEC_NCX))
+#define SPEC_SLOTS (SPEC_OFF_RO + SPEC_NRO)
 // slot -> index relative to the thread's base pointer
 #define SW(e) W[(e) * 32]
 #define JX(ci, cj) (((ci) * SPEC_JS + (cj)) * 32)
@@ -173,14 +178,17 @@ __device__ __forceinline__ void spec_sandbox_store(const SpecCell &s, const DevS
 // ro[i] is the slice offset of the row at logical position i, an interchange
 // swaps two offsets, and the scaling factor / right-hand side travel with the
 // row in its extra column.  Every register array is indexed by literals.
-__device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
-                                           const SpecCell &s, double dt) {
+__device__ __forceinline__ bool spec_rowonly(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
+                                             const SpecCell &s, double dt);
+
+__device__ __forceinline__ bool spec_solve_core(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
+                                                const SpecCell &s, double dt) {
   constexpr int N = SPEC_N, NC = SPEC_NC, NCA = NC > 0 ? NC : 1;
   bool bad = false;
   // species outside the matrix: J is diagonal (RTAccumulationDerivative only)
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    if (spec_cmap(i) < 0) {
+    if (spec_cmap(i) < 0 && !spec_is_rowonly(i)) {
       double Jd = (i < SPEC_NAQ) ? (1.0 * (s.den_kg * 1.e-3)) * (s.por * s.sat * 1000.0 * s.vol / dt) : s.vol / dt;
       if (s.dry) Jd = 1.0;
       double nm = sx_rcp(fmax(1.0, fabs(Jd)));
@@ -403,6 +411,17 @@ __device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], con
   return true;
 }
 #endif
+
+// RSolve for the whole system: the dense core, then the row-only species whose update follows
+// from the core's (their columns are diagonal, so nothing in the core depends on them)
+__device__ __forceinline__ bool spec_solve(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
+                                           const SpecCell &s, double dt) {
+  bool ok = spec_solve_core(W, res, c, s, dt);
+#if SPEC_NROSPEC > 0
+  ok = spec_rowonly(W, res, c, s, dt) && ok;
+#endif
+  return ok;
+}
 
 #ifndef SPEC_LOCKSTEP
 #define SPEC_LOCKSTEP 0
@@ -921,8 +940,13 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       if (!done) its++;
       s.store = !done;
 
-      // ---- one Newton iteration (reaction.F90:3860-4041), every lane of the block
+      // ---- one Newton iteration (reaction.F90:3860-4041), every lane of the block -- except
+      // that a warp whose 32 cells are all finished skips the arithmetic (it still votes): at
+      // the ragged end of a launch the live warps then have the instruction supply to themselves
       double lna[N], ic[N], tot[N], res[N], ts[N];
+      bool conv = false, need_solve = false, fail = false;
+      const bool warp_live = __any_sync(0xffffffffu, !done);
+      if (warp_live) {
       if (SPEC_ACT_UPD) spec_activity(c, s);
       spec_rtotal(c, lna, ic, tot, s, W, st.sec_molal + cell, ld, dt);
 #pragma unroll
@@ -949,12 +973,13 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       const double nrm = sqrt(ss);
       if (its == 1) norm0 = nrm;
       const double rel = nrm / norm0;
-      bool conv = (mabs < prm.tol_res) || (rel < prm.tol_relres);
-      const bool need_solve = !done && !over && !conv;
-      bool fail = !done && over;
+      conv = (mabs < prm.tol_res) || (rel < prm.tol_relres);
+      need_solve = !done && !over && !conv;
+      fail = !done && over;
+      }  // warp_live
       bool solve_error = false;
 
-      if (__syncthreads_or(need_solve ? 1 : 0)) {
+      if (__syncthreads_or(need_solve ? 1 : 0) && warp_live) {
         const bool ok = spec_solve(W, res, c, s, dt);
         if (need_solve) {
           if (!ok) {

@@ -285,11 +285,30 @@ class _Gen:
             used.update(int(v) for v in (dn.no3_id, dn.n2_id) if v >= 0)
             if dn.ngasdeni_id >= 0:
                 used.add(naq + int(dn.ngasdeni_id))
-        self.coupled = sorted(used)
+        self.used = sorted(used)
+        self._recording = False
+        self._pairs = set()
+        self._layout([])
+
+    def _layout(self, rowonly) -> None:
+        """core species form the dense matrix; ROW-ONLY species (their Jacobian column is the
+        diagonal alone: reaction products and tracking species such as CO2(aq), N2O(aq), PlantN,
+        Nmin) keep their few row entries in separate slots and are eliminated after the solve"""
+        self.rowonly = list(rowonly)
+        self.roset = set(rowonly)
+        self.ropairs = {}
+        self.coupled = [sp for sp in self.used if sp not in self.roset]
         self.cpos = {sp: ci for ci, sp in enumerate(self.coupled)}
         self.nc = len(self.coupled)
 
     def J(self, i: int, j: int) -> str:
+        if self._recording:
+            self._pairs.add((i, j))
+        if i in self.roset:
+            assert j == i or j not in self.roset, (i, j)
+            k = self.ropairs.setdefault((i, j), len(self.ropairs))
+            return f"SW(SPEC_OFF_RO + {k})"
+        assert j not in self.roset, (i, j)
         return f"W[JX({self.cpos[i]}, {self.cpos[j]})]"
 
     def _class_of(self, z: float, a0: float) -> int:
@@ -421,6 +440,9 @@ class _Gen:
             self.w(f"  tot[{i}] *= denL;")
         # finalise d(total)/d(free) * denL * psvd (RTAccumulationDerivative); only
         # aqueous species can be coupled (immobile ones need a sandbox)
+        self.w("#pragma unroll")
+        self.w("  for (int k = 0; k < SPEC_NRO; k++) SW(SPEC_OFF_RO + k) = 0.0;")
+        rec, self._recording = self._recording, False   # the loop below touches every pair: not structure
         for i in self.coupled:
             for j in self.coupled:
                 e = self.J(i, j)
@@ -435,6 +457,7 @@ class _Gen:
                     self.w(f"  {e} = (1.0 * denL) * psvd;")
                 else:
                     self.w(f"  {e} = 0.0;")
+        self._recording = rec
         if self.nc:
             self.w("  if (s.dry) {")
             self.w("#pragma unroll 1")
@@ -1285,14 +1308,76 @@ class _Gen:
             self.w("  }")
 
     # ------------------------------------------------------------------ whole file
+    def _gen_body(self, nsbx: int) -> List[str]:
+        self.out = []
+        self.gen_tables()
+        self.gen_activity()
+        self.gen_rtotal()
+        self.gen_sorption()
+        self.gen_minerals()
+        if nsbx > 0:
+            self.gen_sandbox()
+        return self.out
+
+    def gen_rowonly(self) -> None:
+        """u_t = (res_t - sum_j J_tj u_j) / J_tt for the row-only species, after the dense solve
+        (log formulation: columns scaled by c_j like RSolve does, reaction.F90:5493-5497).  The
+        reference eliminates these rows inside its LU; the result is the same up to rounding."""
+        naq = self.naq
+        self.w("__device__ __forceinline__ bool spec_rowonly(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],")
+        self.w("    const SpecCell &s, double dt) {")
+        self.w("  bool ok = true;")
+        for t in self.rowonly:
+            self.w("  {")
+            if t < naq:
+                self.w("    double Jd = (1.0 * (s.den_kg * 1.e-3)) * (s.por * s.sat * 1000.0 * s.vol / dt);")
+            else:
+                self.w("    double Jd = s.vol / dt;")
+            self.w("    if (s.dry) Jd = 1.0;")
+            if (t, t) in self.ropairs:
+                self.w(f"    Jd = Jd + SW(SPEC_OFF_RO + {self.ropairs[(t, t)]});")
+            self.w(f"    double r = res[{t}];")
+            for (i, j), k in self.ropairs.items():
+                if i == t and j != t:
+                    cj = f" * c[{j}]" if self.c.use_log_formulation else ""
+                    self.w(f"    r = r - (SW(SPEC_OFF_RO + {k}){cj}) * res[{j}];")
+            self.w(f"    const double a = Jd{' * c[%d]' % t if self.c.use_log_formulation else ''};")
+            self.w("    if (!(fabs(a) > 0.0)) ok = false;")
+            self.w(f"    res[{t}] = sx_div(r, a);")
+            self.w("  }")
+        self.w("  (void)W; (void)c; (void)s; (void)dt;")
+        self.w("  return ok;")
+        self.w("}")
+        self.w()
+
     def source(self) -> str:
         c = self.c
         n = self.n
+        nsbx = (int(c.clmcn_nrxn > 0) + int(bool(c.somdec)) + int(bool(c.nitrif)) + int(bool(c.denitr))
+                + int(bool(c.plantn)) + int(bool(c.langmuir)))
+        # pass 1: every species that occurs in a reaction is in the matrix; record which Jacobian
+        # entries the network really has
+        self._layout([])
+        self._pairs = set()
+        self._recording = True
+        self._gen_body(nsbx)
+        self._recording = False
+        rowonly = []
+        if not os.environ.get("PFRX_SPEC_NO_ROWONLY"):
+            cols = {j for (i, j) in self._pairs if i != j}
+            rowonly = [t for t in self.used if t not in cols]
+        # pass 2: the final layout
+        self._layout(rowonly)
+        body = self._gen_body(nsbx)
+        self.out = []
+        self.gen_rowonly()
+        body = body + self.out
+        nro = len(self.ropairs)
         if self.loop_lu:
             slots = self.nc * (self.nc + 2) + self.nc
         else:
             slots = self.nc * (self.nc + 1) + 2 * n
-        slots = max(1, slots + (0 if self.act_upd else self.ncx))
+        slots = max(1, slots + (0 if self.act_upd else self.ncx) + nro)
         per_warp = slots * 32 * 8 + 1024  # + the per-block reservation when a block is one warp
         if slots * 32 * 8 > 160 * 1024:
             threads = 32
@@ -1310,20 +1395,19 @@ class _Gen:
             threads = 32 * minblocks
             minblocks = 1
         self.threads, self.minblocks, self.slots = threads, minblocks, slots
-        o = self.out
-        o.clear()
+        self.out = []
         self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
         self.w(f"#define SPEC_N {n}")
         self.w(f"#define SPEC_NAQ {self.naq}")
         self.w(f"#define SPEC_NC {self.nc}")
+        self.w(f"#define SPEC_NRO {nro}")
+        self.w(f"#define SPEC_NROSPEC {len(self.rowonly)}")
         self.w(f"#define SPEC_NCX {self.ncx}")
         self.w(f"#define SPEC_NCLS {len(self.cls)}")
         self.w(f"#define SPEC_NKIN {c.nkinmnrl}")
         self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
         self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
         self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
-        nsbx = (int(c.clmcn_nrxn > 0) + int(bool(c.somdec)) + int(bool(c.nitrif)) + int(bool(c.denitr))
-                + int(bool(c.plantn)) + int(bool(c.langmuir)))
         nnc = (len(self.a["somdec_upstream_nc"]) + len(self.a["somdec_downstream_nc"])) if c.somdec else 0
         self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
         self.w(f"#define SPEC_NSBX {nsbx}")
@@ -1344,8 +1428,10 @@ class _Gen:
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")
         cm = " : ".join(f"i == {sp} ? {ci}" for sp, ci in self.cpos.items())
         so = " : ".join(f"ci == {ci} ? {sp}" for sp, ci in self.cpos.items())
+        ro = " || ".join(f"i == {t}" for t in self.rowonly)
         self.w("__host__ __device__ constexpr int spec_cmap(int i) { return " + (cm + " : -1" if cm else "-1") + "; }")
         self.w("__host__ __device__ constexpr int spec_sp_of(int ci) { return " + (so + " : 0" if so else "0") + "; }")
+        self.w("__host__ __device__ constexpr bool spec_is_rowonly(int i) { return " + (ro if ro else "false") + "; }")
         pc = " : ".join(f"i == {i} ? {q}" for i, q in enumerate(self.pri_cls) if q >= 0)
         self.w("__host__ __device__ constexpr int spec_pri_cls(int i) { return " + (pc + " : -1" if pc else "-1") + "; }")
         self.w("__device__ __forceinline__ double spec_cx_z2(int k);")
@@ -1353,14 +1439,7 @@ class _Gen:
         self.w("__device__ __forceinline__ double spec_mn_vol(int m);")
         self.w('#include "pfrx_spec.cuh"')
         self.w()
-        self.gen_tables()
-        self.gen_activity()
-        self.gen_rtotal()
-        self.gen_sorption()
-        self.gen_minerals()
-        if nsbx > 0:
-            self.gen_sandbox()
-        return "\n".join(o) + "\n"
+        return "\n".join(self.out + body) + "\n"
 
 
 class _GenW(_Gen):
