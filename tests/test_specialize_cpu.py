@@ -54,8 +54,25 @@ def test_sandbox_network():
     wl = W.by_name("c4", ncell=2)
     src = specialize.generate_source(wl.cfg)
     assert "#define SPEC_NCLM 7" in src and "void spec_sandbox(" in src
-    assert "#define SPEC_NC 12" in src  # the aqueous tracer of the CLM-CN deck stays out of the matrix
+    # the aqueous tracer of the CLM-CN deck stays out of the matrix (no reaction), and so does the
+    # respired C: a product only, its Jacobian column is the diagonal alone ("row-only")
+    assert "#define SPEC_NC 11" in src and "#define SPEC_NROSPEC 1" in src
     assert not specialize.supported_multiwarp(wl.cfg, 4)[0]
+
+
+def test_row_only_species_leave_the_matrix(monkeypatch):
+    """products and tracking species of the ELM-CN network: CO2, N2O, N2, PlantN, the uptake
+    trackers and the litter N pools (the reference's Jacobian has no column for them)"""
+    wl = W.by_name("c4fe", ncell=2)
+    src = specialize.generate_source(wl.cfg)
+    assert "#define SPEC_N 20" in src and "#define SPEC_NC 10" in src and "#define SPEC_NROSPEC 9" in src
+    assert "bool spec_rowonly(" in src
+    monkeypatch.setenv("PFRX_SPEC_NO_ROWONLY", "1")
+    full = specialize.generate_source(wl.cfg)
+    assert "#define SPEC_NC 19" in full and "#define SPEC_NROSPEC 0" in full
+    # Hanford: every species sits in some complex, nothing is row-only
+    src3 = specialize.generate_source(W.by_name("c3", ncell=2).cfg)
+    assert "#define SPEC_NC 13" in src3 and "#define SPEC_NROSPEC 0" in src3
 
 
 def test_variants_generate():
