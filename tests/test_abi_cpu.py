@@ -64,3 +64,50 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle_lib" not in txt and "pfrx_oracle" not in txt, fn
+
+
+def _create_rc(cfg):
+    """pfrx_create return code and message; configuration checks run before any CUDA call"""
+    L = _lib()
+    L.pfrx_create.argtypes = [C.POINTER(abi.PfrxConfig), C.c_int, C.POINTER(C.c_void_p)]
+    L.pfrx_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    rc = L.pfrx_create(C.byref(cfg.c), 0, C.byref(h))
+    return rc, L.pfrx_last_error().decode()
+
+
+def test_unsupported_configurations_are_refused_not_approximated():
+    """what the CUDA path does not cover comes back as PFRX_E_INVALID (1) with a reason --
+    also on a machine without a GPU, because the checks precede device selection"""
+    from pflotran_elm_interface_b200 import workloads
+
+    # SOMDECOMP with its CO2 as a gas species (ITYPE_GAS = 1)
+    cfg = workloads.by_name("c4s", ncell=1).cfg
+    cfg.somdec.co2_itype = 1
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "gas" in msg
+    # ELM build that asks for the flow-coupled moisture response
+    cfg = workloads.by_name("c4se", ncell=1).cfg
+    cfg.arrays["somdec_moisture_response_function"][:] = 1
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "MOISTURE_RESPONSE_FUNCTION" in msg
+    # PLANTN without its PlantN pool
+    cfg = workloads.by_name("c4fe", ncell=1).cfg
+    cfg.plantn.plantn_id = -1
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "PLANTN" in msg
+    # ion exchange with a table missing
+    cfg = workloads.by_name("c6", ncell=1).cfg
+    cfg.c.eqionx_k = C.cast(None, abi.c_double_p)
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "ion exchange" in msg
+    # a sandbox list naming a sandbox that does not exist
+    cfg = workloads.by_name("c4s", ncell=1).cfg
+    cfg.arrays["sandbox_list"][0] = 99
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "sandbox_list" in msg
+    # ABI mismatch
+    cfg = workloads.by_name("c2", ncell=1).cfg
+    cfg.c.abi_version = 1
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "abi_version" in msg
