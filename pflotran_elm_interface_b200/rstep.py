@@ -312,7 +312,7 @@ class ChemistryStep:
         _check(lib().pfrx_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "pfrx_last_transfer_bytes")
         return a.value, b.value
 
-    def autotune(self, state: DeviceState, tran_dt: float, variants=("s1", "k1", "q1", "p1"), sample: int = 303104,
+    def autotune(self, state: DeviceState, tran_dt: float, variants=("s1", "k1", "q1", "p1", "w1"), sample: int = 303104,
                  repeats: int = 2) -> Dict[str, float]:
         """Pick the specialised-kernel variant that is fastest on THIS state.
 

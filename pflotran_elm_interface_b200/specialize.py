@@ -38,7 +38,7 @@ LOG_TO_LN = chem.LOG_TO_LN
 
 # variant letter -> code style (PFRX_SPEC_VARIANT=<letter><warps per 32 cells>)
 VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled", "q": "refill",
-                  "p": "refill_looplu"}
+                  "p": "refill_looplu", "w": "refill_warp"}
 
 
 def _fnv1a(data: bytes) -> int:
@@ -220,6 +220,7 @@ class _Gen:
     loop_lu = False  # dense solve as rolled loops (style "looplu")
     lockstep = False  # 128-thread blocks whose warps execute the same Newton iteration (style "lockstep")
     refill = False  # lock-step blocks whose finished lanes fetch the next cell (style "refill")
+    onewarp = False  # refill in one-warp blocks: no block barriers, the warps of an SM drift (style "refill_warp")
 
     def __init__(self, cfg: abi.ReactionConfig):
         ok, why = supported(cfg)
@@ -1390,7 +1391,7 @@ class _Gen:
         else:
             threads = 128
             minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
-        if self.lockstep and threads == 32:
+        if self.lockstep and threads == 32 and not self.onewarp:
             # the warps that shared an SM as separate blocks become one block that votes
             threads = 32 * minblocks
             minblocks = 1
@@ -1957,8 +1958,9 @@ def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style:
         return _GenW(cfg, warps).source()
     g = _Gen(cfg)
     g.loop_lu = style in ("looplu", "klooplu", "refill_looplu")
-    g.lockstep = style in ("lockstep", "klooplu", "refill", "refill_looplu")
-    g.refill = style in ("refill", "refill_looplu")
+    g.lockstep = style in ("lockstep", "klooplu", "refill", "refill_looplu", "refill_warp")
+    g.refill = style in ("refill", "refill_looplu", "refill_warp")
+    g.onewarp = style == "refill_warp"
     return g.source()
 
 

@@ -233,7 +233,7 @@ def test_specialized_skeletons_agree_with_oracle(variant):
     step.close()
 
 
-@pytest.mark.parametrize("style", ["refill", "refill_looplu"])
+@pytest.mark.parametrize("style", ["refill", "refill_looplu", "refill_warp"])
 @pytest.mark.parametrize("name,n,dt,host", [("c4s", 20000, 1800.0, False), ("c4s", 300000, 1800.0, True),
                                             ("c3", 5000, 3600.0, False), ("c2", 50, 3600.0, False)])
 def test_refill_skeleton(name, n, dt, host, style):
