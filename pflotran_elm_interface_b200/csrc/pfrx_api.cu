@@ -179,6 +179,13 @@ static uint64_t config_signature(const pfrx_config *c) {
     ADD(c->srfcplx_free_site_stoich, c->nsrfcplx)
     ADD(c->srfcplx_logK, c->nsrfcplx)
     ADD(c->eqsrfcplxrxn_to_srfcplxrxn, c->neqsrfcplxrxn)
+    if (c->nkinmrsrfcplxrxn > 0 && c->kinmr_rate_ptr) {
+      const int nm = c->nkinmrsrfcplxrxn;
+      ADD(c->kinmrsrfcplxrxn_to_srfcplxrxn, nm)
+      ADD(c->kinmr_rate_ptr, nm + 1)
+      ADD(c->kinmr_rate, c->kinmr_rate_ptr[nm])
+      ADD(c->kinmr_frac, c->kinmr_rate_ptr[nm])
+    }
   }
   if (c->clmcn_nrxn > 0) {
     int32_t ch[3] = {c->clmcn_npool, c->clmcn_C_species_id, c->clmcn_N_species_id};

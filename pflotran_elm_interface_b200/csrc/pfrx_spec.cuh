@@ -38,6 +38,9 @@
 #ifndef SPEC_NSBX
 #define SPEC_NSBX 0  // reaction sandboxes of any kind
 #endif
+#ifndef SPEC_NMR
+#define SPEC_NMR 0     // multirate kinetic surface-complexation reactions (one-warp skeleton "s" only)
+#endif
 #ifndef SPEC_REFILL
 #define SPEC_REFILL 0  // lock-step skeleton: finished lanes fetch the next cell (variant "q")
 #endif
@@ -116,6 +119,10 @@ struct SpecCell {
   double fsite[SPEC_NSRFRXN > 0 ? SPEC_NSRFRXN : 1];
   double scconc[SPEC_NSRFCPLX > 0 ? SPEC_NSRFCPLX : 1];
   double mrate[SPEC_NKIN > 0 ? SPEC_NKIN : 1];
+  // multirate sorption (RMultiRateSorption): per reaction the equilibrium target S_eq (what
+  // kinmr_total_sorb(:,0,irxn) holds), B = sum_k k_k/(1+k_k dt) S_k of the sub-step, A = sum_k k_k f_k/(1+k_k dt)
+  double mr_seq[SPEC_NMR > 0 ? SPEC_NMR * SPEC_NAQ : 1], mr_B[SPEC_NMR > 0 ? SPEC_NMR * SPEC_NAQ : 1];
+  double mr_A[SPEC_NMR > 0 ? SPEC_NMR : 1];
   double nc[SPEC_NNC > 0 ? SPEC_NNC : 1];  // N:C ratios that persist between evaluations
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   bool dry;
@@ -144,6 +151,53 @@ __device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const
 __device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],
                                              const double (&tot)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W,
                                              double dt);
+
+#if SPEC_NMR > 0
+// generated: S_eq of every multirate reaction into s.mr_seq and V * A * dS_eq into the Jacobian
+__device__ __forceinline__ void spec_mr_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N], SpecCell &s,
+                                                 double *W, const DevState &st, long long cell);
+// RMultiRateSorption, start of a sub-step (reaction_surf_complex.F90:552-637): A and B for this dt.
+// The rate loop is rolled (tables), the species loop unrolled; the sum over the rates runs in the
+// reference's order for every species.
+__device__ __forceinline__ void spec_mr_begin(SpecCell &s, const DevState &st, long long cell, double dt) {
+#pragma unroll
+  for (int q = 0; q < SPEC_NMR; q++) {
+    const int r0 = spec_mr_ptr(q), r1 = spec_mr_ptr(q + 1);
+    const long long base = (long long)SPEC_NAQ * (r0 + q);
+    double A = 0.0, B[SPEC_NAQ];
+#pragma unroll
+    for (int i = 0; i < SPEC_NAQ; i++) B[i] = 0.0;
+#pragma unroll 1
+    for (int k = r0; k < r1; k++) {
+      const double rk = spec_mr_rate_tab[k];
+      const double kk = rk / (1.0 + rk * dt);
+      A += kk * spec_mr_frac_tab[k];
+      const double *S = st.kinmr + (base + (long long)SPEC_NAQ * (k - r0 + 1)) * st.ld + cell;
+#pragma unroll
+      for (int i = 0; i < SPEC_NAQ; i++) B[i] += kk * S[i * st.ld];
+    }
+    s.mr_A[q] = A;
+#pragma unroll
+    for (int i = 0; i < SPEC_NAQ; i++) s.mr_B[q * SPEC_NAQ + i] = B[i];
+  }
+}
+// RSrfCplxMRUpdateKinState (reaction_surf_complex.F90:1107-1145) after an accepted sub-step
+__device__ __forceinline__ void spec_mr_update(const SpecCell &s, const DevState &st, long long cell, double dt) {
+#pragma unroll
+  for (int q = 0; q < SPEC_NMR; q++) {
+    const int r0 = spec_mr_ptr(q), r1 = spec_mr_ptr(q + 1);
+    const long long base = (long long)SPEC_NAQ * (r0 + q);
+#pragma unroll 1
+    for (int k = r0; k < r1; k++) {
+      const double kdt = spec_mr_rate_tab[k] * dt, fk = spec_mr_frac_tab[k];
+      double *S = st.kinmr + (base + (long long)SPEC_NAQ * (k - r0 + 1)) * st.ld + cell;
+#pragma unroll
+      for (int i = 0; i < SPEC_NAQ; i++)
+        S[i * st.ld] = (S[i * st.ld] + kdt * fk * s.mr_seq[q * SPEC_NAQ + i]) / (1.0 + kdt);
+    }
+  }
+}
+#endif
 
 // per-cell inputs of the ELM-CN sandboxes
 __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &st, long long cell) {
@@ -450,6 +504,9 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     SPEC_FIXED(i) = f;
     c[i] = guess[i];
   }
+#if SPEC_NMR > 0
+  spec_mr_begin(s, st, cell, dt);
+#endif
   int its = 0;
   double norm0 = 0.0;
   double lna[N], ic[N], tot[N], res[N], ts[N];
@@ -477,6 +534,17 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       res[i] = sx_div(a - SPEC_FIXED(i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
+#if SPEC_NMR > 0
+    if (!s.dry) {  // RMultiRateSorption: Res += V (A S_eq - B), Jac += V A dS_eq
+      spec_mr_sorption(lna, ic, s, W, st, cell);
+#pragma unroll
+      for (int q = 0; q < SPEC_NMR; q++) {
+#pragma unroll
+        for (int i = 0; i < NAQ; i++)
+          res[i] += s.vol * (s.mr_A[q] * s.mr_seq[q * NAQ + i] - s.mr_B[q * NAQ + i]);
+      }
+    }
+#endif
 #if SPEC_NSBX > 0
     if (!s.dry) spec_sandbox(c, lna, tot, res, s, W, dt);  // RReaction returns before the sandboxes in a dry cell
 #endif
@@ -565,6 +633,14 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   s.spd = st.soil_particle_density ? st.soil_particle_density[cell] : 0.0;
   s.ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[cell] : 0.0;
   spec_sandbox_load(s, st, cell);
+#if SPEC_NMR > 0
+#pragma unroll
+  for (int q = 0; q < SPEC_NMR; q++) {
+    const long long base = (long long)NAQ * (spec_mr_ptr(q) + q);
+#pragma unroll
+    for (int i = 0; i < NAQ; i++) s.mr_seq[q * NAQ + i] = st.kinmr[(base + i) * ld + cell];
+  }
+#endif
   nss = nit = nku = ierr = 0;
   had_cut = false;
   double Is = 0.0, ms = 0.0;
@@ -650,6 +726,10 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
           st.mnrl_volfrac[m * ld + cell] = vf;
         }
       }
+#if SPEC_NMR > 0
+      upd = true;
+      spec_mr_update(s, st, cell, dt);
+#endif
       cumulative += dt;
       nss++;
       nconst++;
@@ -694,6 +774,14 @@ __device__ __forceinline__ void spec_run(const DevState &st, const SpecParams &p
   for (int k = 0; k < SPEC_NKIN; k++) st.mnrl_rate[k * ld + cell] = s.mrate[k];
   if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = s.ln_act_h2o;
   spec_sandbox_store(s, st, cell);
+#if SPEC_NMR > 0
+#pragma unroll
+  for (int q = 0; q < SPEC_NMR; q++) {
+    const long long base = (long long)NAQ * (spec_mr_ptr(q) + q);
+#pragma unroll
+    for (int i = 0; i < NAQ; i++) st.kinmr[(base + i) * ld + cell] = s.mr_seq[q * NAQ + i];
+  }
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
@@ -754,6 +842,9 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
 }
 #else
 
+#if SPEC_NMR > 0
+#error "multirate sorption is generated for the one-warp skeleton (style s) only"
+#endif
 // ======================================================================================
 // Lock-step skeleton (SPEC_LOCKSTEP 1): the four warps of a 128-thread block execute the
 // SAME Newton iteration at the same time.

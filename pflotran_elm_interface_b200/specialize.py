@@ -96,6 +96,12 @@ def signature(cfg: abi.ReactionConfig) -> int:
         for k in ("srfcplx_h2ostoich", "srfcplx_free_site_stoich", "srfcplx_logK"):
             add(k, ns, f8)
         add("eqsrfcplxrxn_to_srfcplxrxn", c.neqsrfcplxrxn, i4)
+        if c.nkinmrsrfcplxrxn > 0:
+            nm = c.nkinmrsrfcplxrxn
+            add("kinmrsrfcplxrxn_to_srfcplxrxn", nm, i4)
+            add("kinmr_rate_ptr", nm + 1, i4)
+            add("kinmr_rate", int(a["kinmr_rate_ptr"][nm]), f8)
+            add("kinmr_frac", int(a["kinmr_rate_ptr"][nm]), f8)
     if c.clmcn_nrxn > 0:
         parts.append(struct.pack("<3i", c.clmcn_npool, c.clmcn_C_species_id, c.clmcn_N_species_id))
         add("clmcn_CN_ratio", c.clmcn_npool, f8)
@@ -158,10 +164,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "anisothermal logK"
     if c.act_coef_update_algorithm != abi._chem.ACT_COEF_ALGORITHM_LAG:
         return False, "activity algorithm NEWTON"
-    if c.nkinmrsrfcplxrxn > 0:
-        return False, "multirate sorption"
-    if c.nsrfcplxrxn != c.neqsrfcplxrxn:
-        return False, "non-equilibrium surface complexation"
+    if c.nsrfcplxrxn != c.neqsrfcplxrxn + c.nkinmrsrfcplxrxn:
+        return False, "kinetic surface complexation"
     if c.nsrfcplxrxn and np.any(a["srfcplxrxn_stoich_flag"] != 0):
         return False, "free-site stoichiometry other than 1"
     for k in ("kinmnrl_Temkin_const", "kinmnrl_min_scale_factor", "kinmnrl_affinity_power",
@@ -476,7 +480,31 @@ class _Gen:
         for k in range(c.nsrfcplx):
             self.w(f"  if (s.store) s.scconc[{k}] = 0.0;")
         for e in range(c.neqsrfcplxrxn):
-            r = int(a["eqsrfcplxrxn_to_srfcplxrxn"][e])
+            self._emit_srfcplx_rxn(int(a["eqsrfcplxrxn_to_srfcplxrxn"][e]), "ts[%d]", True)
+        self.w("}")
+        self.w()
+        if c.nkinmrsrfcplxrxn > 0:
+            # multirate reactions: the same equilibrium calculation per reaction, into s.mr_seq, with
+            # V * A as the Jacobian scale (RMultiRateSorption, reaction_surf_complex.F90:552-637)
+            nm, naq = c.nkinmrsrfcplxrxn, self.naq
+            ptr = a["kinmr_rate_ptr"]
+            self.w("__device__ __forceinline__ void spec_mr_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],")
+            self.w("    SpecCell &s, double *W, const DevState &st, long long cell) {")
+            for q in range(nm):
+                self.w("  {")
+                self.w(f"    const double jscale = s.vol * s.mr_A[{q}];")
+                for i in range(naq):
+                    self.w(f"    s.mr_seq[{q * naq + i}] = 0.0;")
+                self._emit_srfcplx_rxn(int(a["kinmrsrfcplxrxn_to_srfcplxrxn"][q]), f"s.mr_seq[{q * naq} + %d]", False)
+                self.w("  }")
+            self.w("}")
+            self.w()
+
+    def _emit_srfcplx_rxn(self, r: int, ts_fmt: str, store_conc: bool) -> None:
+        """RTotalSorbEqSurfCplx1 for reaction r with unit free-site stoichiometry (closed form):
+        sorbed totals into ts_fmt % species, jscale * d(total_sorb)/d(free) into the Jacobian"""
+        c, a = self.c, self.a
+        if True:
             cx = [int(v) for v in a["srfcplxrxn_to_complex"][a["srfcplxrxn_ptr"][r]:a["srfcplxrxn_ptr"][r + 1]]]
             ty = int(a["srfcplxrxn_surf_type"][r])
             dens = _lit(float(a["srfcplxrxn_site_density"][r]))
@@ -506,7 +534,8 @@ class _Gen:
             self.w(f"      if (s.store) s.fsite[{r}] = fs;")
             for q, k in enumerate(cx):
                 self.w(f"      const double S{q} = e{q} * fs;")
-                self.w(f"      if (s.store) s.scconc[{k}] += S{q};")
+                if store_conc:
+                    self.w(f"      if (s.store) s.scconc[{k}] += S{q};")
             self.w("      double den = 0.0;")
             for q in range(len(cx)):
                 self.w(f"      den += S{q};")
@@ -518,7 +547,7 @@ class _Gen:
                 for p in range(ptr[k], ptr[k + 1]):
                     i, nu = int(ids[p]), float(st_[p])
                     v = f"S{q}" if nu == 1.0 else f"{_lit(nu)} * S{q}"
-                    self.w(f"      tmp{i} += {v}; ts[{i}] += {v};")
+                    self.w(f"      tmp{i} += {v}; {ts_fmt % i} += {v};")
             for i in species:
                 self.w(f"      const double dsx{i} = (-tmp{i} / den) * ic[{i}];")
             for q, k in enumerate(cx):
@@ -536,8 +565,6 @@ class _Gen:
                 self.w("      }")
             self.w("    }")
             self.w("  }")
-        self.w("}")
-        self.w()
 
     def gen_minerals(self) -> None:
         c, a, n = self.c, self.a, self.n
@@ -1409,6 +1436,14 @@ class _Gen:
         self.w(f"#define SPEC_NSRFRXN {c.nsrfcplxrxn}")
         self.w(f"#define SPEC_NSRFCPLX {c.nsrfcplx}")
         self.w(f"#define SPEC_NEQSR {c.neqsrfcplxrxn}")
+        self.w(f"#define SPEC_NMR {c.nkinmrsrfcplxrxn}")
+        if c.nkinmrsrfcplxrxn > 0:
+            if self.lockstep:
+                raise ValueError("multirate sorption is generated for the one-warp skeleton (style straight) only")
+            mp = " : ".join(f"q == {q} ? {int(v)}" for q, v in enumerate(self.a["kinmr_rate_ptr"]))
+            self.w("__host__ __device__ constexpr int spec_mr_ptr(int q) { return " + mp + " : 0; }")
+            self.w("static __device__ const double spec_mr_rate_tab[] = {" + ", ".join(_lit(float(v)) for v in self.a["kinmr_rate"]) + "};")
+            self.w("static __device__ const double spec_mr_frac_tab[] = {" + ", ".join(_lit(float(v)) for v in self.a["kinmr_frac"]) + "};")
         nnc = (len(self.a["somdec_upstream_nc"]) + len(self.a["somdec_downstream_nc"])) if c.somdec else 0
         self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
         self.w(f"#define SPEC_NSBX {nsbx}")

@@ -159,6 +159,7 @@ def test_hanford(variant, dt):
                                              ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True),
                                              ("c4s", 1800.0, False), ("c4s", 86400.0, True), ("c4se", 1800.0, False),
                                              ("c4se", 6 * 3600.0, True), ("c4fe", 1800.0, True),
+                                             ("c3mr", 3600.0, False), ("c3mr", 30 * 86400.0, True),
                                              ("c4fe", 86400.0, False)])
 def test_specialized_kernel(variant, dt, host):
     """the code-generated kernel (specialize.py + pfrx_spec.cuh) against the oracle"""

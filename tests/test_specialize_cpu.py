@@ -12,7 +12,8 @@ from pflotran_elm_interface_b200 import specialize, workloads as W
 
 
 def test_supported_networks():
-    for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", False), ("c4", True)):
+    for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", True), ("c4", True),
+                     ("c4fe", True), ("c6", False), ("c2pf", False), ("c3an", False)):
         wl = W.by_name(name, ncell=2)
         got, why = specialize.supported(wl.cfg)
         assert got is ok, (name, why)
@@ -20,6 +21,14 @@ def test_supported_networks():
             assert why
             with pytest.raises(ValueError):
                 specialize.generate_source(wl.cfg)
+
+
+def test_multirate_is_generated_for_the_one_warp_skeleton_only():
+    wl = W.by_name("c3mr", ncell=2)
+    src = specialize.generate_source(wl.cfg)
+    assert "#define SPEC_NMR 1" in src and "void spec_mr_sorption(" in src and "spec_mr_rate_tab" in src
+    with pytest.raises(ValueError):
+        specialize.generate_source(wl.cfg, warps=1, style="refill")
 
 
 def test_source_is_deterministic_and_covers_the_network():
