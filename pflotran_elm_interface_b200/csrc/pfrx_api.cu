@@ -1774,8 +1774,8 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   if (!cubin_path) return PFRX_OK;
   // features outside what specialize.py generates (its supported() is the twin of this test)
   const DevCfg &d = h->cfg;
-  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess || d.nmr > 0 ||
-      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG)
+  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
+      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();
   if (rc) return rc;
