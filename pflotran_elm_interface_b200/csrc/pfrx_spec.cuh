@@ -190,10 +190,15 @@ __device__ __forceinline__ void spec_mr_update(const SpecCell &s, const DevState
 #pragma unroll 1
     for (int k = r0; k < r1; k++) {
       const double kdt = spec_mr_rate_tab[k] * dt, fk = spec_mr_frac_tab[k];
+      // one reciprocal per rate instead of one division per species (the reference divides
+      // 15 times by the same 1 + k dt): at most one ulp apart, 700 divisions per cell fewer
+      const double inv = 1.0 / (1.0 + kdt);
       double *S = st.kinmr + (base + (long long)SPEC_NAQ * (k - r0 + 1)) * st.ld + cell;
+      double v[SPEC_NAQ];
 #pragma unroll
-      for (int i = 0; i < SPEC_NAQ; i++)
-        S[i * st.ld] = (S[i * st.ld] + kdt * fk * s.mr_seq[q * SPEC_NAQ + i]) / (1.0 + kdt);
+      for (int i = 0; i < SPEC_NAQ; i++) v[i] = S[i * st.ld];
+#pragma unroll
+      for (int i = 0; i < SPEC_NAQ; i++) S[i * st.ld] = (v[i] + kdt * fk * s.mr_seq[q * SPEC_NAQ + i]) * inv;
     }
   }
 }

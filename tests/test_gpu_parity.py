@@ -345,7 +345,7 @@ def test_specialized_kernel_refuses_other_network():
     assert step.signature == specialize.signature(c2.cfg)
     with pytest.raises(rstep.PfrxError, match="another network"):
         step.load_specialized(specialize.build(c3.cfg))
-    unsupported = W.by_name("c3mr", ncell=4)
+    unsupported = W.by_name("c6", ncell=4)  # ion exchange / KD isotherms: generic kernel only
     assert not specialize.supported(unsupported.cfg)[0]
     step4 = rstep.ChemistryStep(unsupported.cfg, 0)
     assert step4.specialize() is False
