@@ -535,6 +535,21 @@ int pfrx_os_fixed_accum(pfrx_handle *h, double *fixed_accum);
 int pfrx_os_load(pfrx_handle *h, const double *solved_total, const double *tran_xx);
 int pfrx_os_store(pfrx_handle *h, double *tran_xx);
 
+/* The whole operator-split chemistry step of PMCSubsurfaceOSRTStepDT
+ * (pmc_subsurface_osrt.F90:303-378) for a caller whose block vectors live in HOST
+ * memory (PETSc Vecs) while the chemistry state stays bound in device memory from
+ * step to step, the way rt_auxvars persist in the reference:
+ *   upload solved_total (may be NULL: totals already in the state) and -- when the
+ *   network has immobile species or the state has imat -- tran_xx;
+ *   pfrx_os_load, RStep over tran_dt on every cell, pfrx_os_store;
+ *   download tran_xx.
+ * ncomp doubles per cell cross the link in each direction instead of the whole
+ * state (pfrx_rstep_host).  Chunks of cells are pipelined over three streams; pass
+ * page-locked vectors (cudaHostRegister) for the copies to overlap the kernel.
+ * Per-cell counts and flags stay in the bound state.                              */
+int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
+                      pfrx_step_result *out);
+
 /* ---- network-specialised kernels -------------------------------------------
  * The generic kernels read the reaction network from tables, the way the
  * reference's RTotalAqueous / RKineticMineral loops read reaction%eqcplxspecid

@@ -332,7 +332,10 @@ struct pfrx_handle {
   void *spec_module = nullptr, *spec_func = nullptr;
   int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
   size_t spec_smem = 0;
-  int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host
+  int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host / pfrx_os_step_host
+  // device staging of the two block vectors of pfrx_os_step_host
+  double *os_a = nullptr, *os_b = nullptr;
+  int64_t os_cap = 0;
   // kernel seconds per cell and link seconds per cell seen by the latest pfrx_rstep_host: a step
   // whose kernel outweighs its transfers gains nothing from many chunks and, with the refill
   // skeleton, pays the slowest cell of every chunk
@@ -1074,6 +1077,8 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->d_red) cudaFree(h->d_red);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->os_a) cudaFree(h->os_a);
+  if (h->os_b) cudaFree(h->os_b);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
   if (h->ev_ready)
@@ -1152,6 +1157,13 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
 
 extern "C" int pfrx_bind_state(pfrx_handle *h, int64_t ncell, const pfrx_state *dev) {
   if (!h || !dev || ncell < 0 || dev->ld < ncell) return set_err(PFRX_E_INVALID, "bad bind_state arguments%s", "");
+  if (ncell == 0) {
+    // a rank that owns no cells: nothing to point at, every call on the shard is a no-op
+    h->st = DevState();
+    h->ncell = 0;
+    h->bound = true;
+    return PFRX_OK;
+  }
   int rc = to_dev_state(h, dev, &h->st);
   if (rc) return rc;
   h->ncell = ncell;
@@ -1372,21 +1384,31 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
   }
 }
 
+// enqueue one transpose of `ncell` cells of `st` (already offset to the first cell) on `s`
+template <int MODE>
+static int os_enqueue(pfrx_handle *h, const DevState &st, int64_t ncell, const double *a, const double *b,
+                      double *out, cudaStream_t s) {
+  if (ncell <= 0) return PFRX_OK;
+  const int naq = h->cfg.naq, nim = h->cfg.nim;
+  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double) + sizeof(double) * OS_CELLS;
+  const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * 8));
+  CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  pfrx_os_kernel<MODE><<<grid, OS_CELLS, smem, s>>>(st, ncell, naq, nim, a, b, out);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return PFRX_OK;
+}
+
 template <int MODE>
 static int os_launch(pfrx_handle *h, const double *a, const double *b, double *out) {
   if (!h) return set_err(PFRX_E_INVALID, "null argument%s", "");
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   CUDA_OK(cudaSetDevice(h->device));
   if (h->ncell <= 0) return PFRX_OK;
-  const int naq = h->cfg.naq, nim = h->cfg.nim;
-  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double) + sizeof(double) * OS_CELLS;
-  const int64_t ntile = (h->ncell + OS_CELLS - 1) / OS_CELLS;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * 8));
-  CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  pfrx_os_kernel<MODE><<<grid, OS_CELLS, smem, h->stream>>>(h->st, h->ncell, naq, nim, a, b, out);
-  CUDA_OK(cudaGetLastError());
-  h->launches++;
+  int rc = os_enqueue<MODE>(h, h->st, h->ncell, a, b, out, h->stream);
+  if (rc) return rc;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return PFRX_OK;
 }
@@ -1402,6 +1424,151 @@ extern "C" int pfrx_os_load(pfrx_handle *h, const double *solved_total, const do
 extern "C" int pfrx_os_store(pfrx_handle *h, double *tran_xx) {
   if (!tran_xx) return set_err(PFRX_E_INVALID, "null argument%s", "");
   return os_launch<OS_STORE>(h, nullptr, nullptr, tran_xx);
+}
+
+// the views of `d` starting at cell c0 (same leading dimension)
+static DevState dev_state_at(const DevState &d, int64_t c0) {
+  DevState dc = d;
+#define PFRX_OFF(field) \
+  if (dc.field) dc.field = dc.field + c0
+  PFRX_OFF(total);
+  PFRX_OFF(pri_molal);
+  PFRX_OFF(immobile);
+  PFRX_OFF(pri_act_coef);
+  PFRX_OFF(sec_act_coef);
+  PFRX_OFF(sec_molal);
+  PFRX_OFF(ln_act_h2o);
+  PFRX_OFF(mnrl_volfrac);
+  PFRX_OFF(mnrl_area);
+  PFRX_OFF(mnrl_rate);
+  PFRX_OFF(free_site);
+  PFRX_OFF(eqsrfcplx_conc);
+  PFRX_OFF(total_sorb_eq);
+  PFRX_OFF(kinmr);
+  PFRX_OFF(den_kg);
+  PFRX_OFF(sat);
+  PFRX_OFF(temp);
+  PFRX_OFF(porosity);
+  PFRX_OFF(volume);
+  PFRX_OFF(soil_particle_density);
+  PFRX_OFF(elm_w);
+  PFRX_OFF(elm_o);
+  PFRX_OFF(elm_t);
+  PFRX_OFF(elm_zsoil);
+  PFRX_OFF(elm_kscalar);
+  PFRX_OFF(elm_bd_dry);
+  PFRX_OFF(elm_bsw);
+  PFRX_OFF(somdec_nc);
+  PFRX_OFF(elm_plantndemand);
+  PFRX_OFF(eqionx_ref);
+  PFRX_OFF(eqionx_conc);
+  PFRX_OFF(imat);
+  PFRX_OFF(num_sub_steps);
+  PFRX_OFF(num_iterations);
+  PFRX_OFF(num_kinetic_state_updates);
+  PFRX_OFF(ierror);
+#undef PFRX_OFF
+  return dc;
+}
+
+static int pipeline_events(pfrx_handle *h) {
+  if (!h->ev_ready) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < PFRX_MAX_CHUNKS; i++) {
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+    }
+    h->ev_ready = true;
+  }
+  return PFRX_OK;
+}
+
+// ---- the operator-split step with the chemistry state resident in HBM --------------
+// pmc_subsurface_osrt.F90:303-378 as one call: what crosses the host link per step is what PETSc
+// holds -- the solved totals and tran_xx, ncomp doubles per cell each -- while rt_auxvars live in the
+// bound device state from step to step.  Chunks of cells are pipelined over three streams: upload of
+// chunk i+1, {load transpose, RStep kernel, store transpose} of chunk i, download of chunk i-1.
+extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
+                                 pfrx_step_result *out) {
+  if (!h || !tran_xx || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int64_t ncell = h->ncell;
+  if (ncell == 0) {
+    memset(out, 0, sizeof(*out));
+    out->first_failed_cell = -1;
+    return PFRX_OK;
+  }
+  const int n = h->cfg.naq + h->cfg.nim;
+  if (h->os_cap < ncell) {
+    if (h->os_a) CUDA_OK(cudaFree(h->os_a));
+    if (h->os_b) CUDA_OK(cudaFree(h->os_b));
+    h->os_a = h->os_b = nullptr;
+    h->os_cap = 0;
+    CUDA_OK(cudaMalloc(&h->os_a, (size_t)ncell * n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&h->os_b, (size_t)ncell * n * sizeof(double)));
+    h->os_cap = ncell;
+  }
+  int rc = pipeline_events(h);
+  if (rc) return rc;
+  // the transfers are a few per cent of the kernel: a handful of chunks hides all but the first
+  // upload and the last download
+  int nchunk = (int)std::min<int64_t>(8, std::max<int64_t>(1, ncell / 262144));
+  if (const char *ev = getenv("PFRX_OS_CHUNKS")) nchunk = std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(ev)));
+  cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
+  rc = summary_reset(h, s_k);
+  if (rc) return rc;
+  // tran_xx goes up when the step reads it (immobile entries) or when inactive cells must keep
+  // their entries through the download
+  const bool up_xx = h->cfg.nim > 0 || h->st.imat != nullptr;
+  h->last_h2d = h->last_d2h = 0;
+  const size_t w8 = sizeof(double);
+  for (int ch = 0; ch < nchunk; ch++) {
+    const int64_t c0 = ncell * ch / nchunk, c1 = ncell * (ch + 1) / nchunk, nc = c1 - c0;
+    if (nc <= 0) continue;
+    const size_t off = (size_t)c0 * n, cnt = (size_t)nc * n;
+    if (solved_total) {
+      CUDA_OK(cudaMemcpyAsync(h->os_a + off, solved_total + off, cnt * w8, cudaMemcpyHostToDevice, s_in));
+      h->last_h2d += (int64_t)(cnt * w8);
+    }
+    if (up_xx) {
+      CUDA_OK(cudaMemcpyAsync(h->os_b + off, tran_xx + off, cnt * w8, cudaMemcpyHostToDevice, s_in));
+      h->last_h2d += (int64_t)(cnt * w8);
+    }
+    CUDA_OK(cudaEventRecord(h->ev_in[ch], s_in));
+    CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_in[ch], 0));
+    const DevState dc = dev_state_at(h->st, c0);
+    if (solved_total || h->cfg.nim > 0) {
+      rc = os_enqueue<OS_LOAD>(h, dc, nc, solved_total ? h->os_a + off : nullptr,
+                               h->cfg.nim > 0 ? h->os_b + off : nullptr, nullptr, s_k);
+      if (rc) return rc;
+    }
+    rc = launch_kernel(h, dc, nc, tran_dt, s_k);
+    if (rc) return rc;
+    rc = os_enqueue<OS_STORE>(h, dc, nc, nullptr, nullptr, h->os_b + off, s_k);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(h->ev_k[ch], s_k));
+    CUDA_OK(cudaStreamWaitEvent(s_out, h->ev_k[ch], 0));
+    CUDA_OK(cudaMemcpyAsync(tran_xx + off, h->os_b + off, cnt * w8, cudaMemcpyDeviceToHost, s_out));
+    h->last_d2h += (int64_t)(cnt * w8);
+  }
+  CUDA_OK(cudaMemcpyAsync(h->h_summ, h->d_summ, sizeof(DevSummary), cudaMemcpyDeviceToHost, s_k));
+  CUDA_OK(cudaStreamSynchronize(s_k));
+  CUDA_OK(cudaStreamSynchronize(s_out));
+  h->pending = false;
+  summary_out(h, out);
+  if (out->first_failed_cell >= 0 && nchunk > 1) {
+    // chunk-local index: recover the shard index from the per-cell error flags
+    std::vector<int> ie((size_t)ncell);
+    CUDA_OK(cudaMemcpy(ie.data(), h->st.ierror, (size_t)ncell * sizeof(int), cudaMemcpyDeviceToHost));
+    out->first_failed_cell = -1;
+    for (int64_t c = 0; c < ncell; c++)
+      if (ie[c] != 0) {
+        out->first_failed_cell = c;
+        break;
+      }
+  }
+  return PFRX_OK;
 }
 
 // ---- host-resident state: H2D, kernel, D2H ------------------------------------
@@ -1498,13 +1665,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   // while chunk i computes (kernel stream) and chunk i-1 downloads (copy-out
   // stream).  PCIe is full duplex, so the step costs about
   // max(H2D, kernel, D2H) instead of their sum.
-  if (!h->ev_ready) {
-    CUDA_OK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < PFRX_MAX_CHUNKS; i++) {
-      CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-      CUDA_OK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
-    }
-    h->ev_ready = true;
+  {
+    int rce = pipeline_events(h);
+    if (rce) return rce;
   }
   int nchunk = 1;
   if (const char *ev = getenv("PFRX_CHUNKS")) nchunk = atoi(ev);
@@ -1574,46 +1737,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     }
     CUDA_OK(cudaEventRecord(h->ev_in[ch], s_in));
     CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_in[ch], 0));
-    DevState dc = d;
-#define PFRX_OFF(field) \
-  if (dc.field) dc.field = dc.field + c0
-    PFRX_OFF(total);
-    PFRX_OFF(pri_molal);
-    PFRX_OFF(immobile);
-    PFRX_OFF(pri_act_coef);
-    PFRX_OFF(sec_act_coef);
-    PFRX_OFF(sec_molal);
-    PFRX_OFF(ln_act_h2o);
-    PFRX_OFF(mnrl_volfrac);
-    PFRX_OFF(mnrl_area);
-    PFRX_OFF(mnrl_rate);
-    PFRX_OFF(free_site);
-    PFRX_OFF(eqsrfcplx_conc);
-    PFRX_OFF(total_sorb_eq);
-    PFRX_OFF(kinmr);
-    PFRX_OFF(den_kg);
-    PFRX_OFF(sat);
-    PFRX_OFF(temp);
-    PFRX_OFF(porosity);
-    PFRX_OFF(volume);
-    PFRX_OFF(soil_particle_density);
-    PFRX_OFF(elm_w);
-    PFRX_OFF(elm_o);
-    PFRX_OFF(elm_t);
-    PFRX_OFF(elm_zsoil);
-    PFRX_OFF(elm_kscalar);
-    PFRX_OFF(elm_bd_dry);
-    PFRX_OFF(elm_bsw);
-    PFRX_OFF(somdec_nc);
-    PFRX_OFF(elm_plantndemand);
-    PFRX_OFF(eqionx_ref);
-    PFRX_OFF(eqionx_conc);
-    PFRX_OFF(imat);
-    PFRX_OFF(num_sub_steps);
-    PFRX_OFF(num_iterations);
-    PFRX_OFF(num_kinetic_state_updates);
-    PFRX_OFF(ierror);
-#undef PFRX_OFF
+    DevState dc = dev_state_at(d, c0);
     if (ch == 0) CUDA_OK(cudaEventRecord(h->ev_t0, s_k));
     rc = launch_kernel(h, dc, nc, tran_dt, s_k);
     if (rc) return rc;

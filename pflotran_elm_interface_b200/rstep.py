@@ -65,6 +65,7 @@ def lib():
     L.pfrx_os_fixed_accum.argtypes = [hp, C.c_void_p]
     L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
     L.pfrx_os_store.argtypes = [hp, C.c_void_p]
+    L.pfrx_os_step_host.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_double, resp]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
@@ -233,6 +234,18 @@ class ChemistryStep:
     def os_store(self, tran_xx) -> None:
         """tran_xx[cell, :] <- (pri_molal, immobile) of the active cells"""
         _check(lib().pfrx_os_store(self._h, tran_xx.data_ptr()), "pfrx_os_store")
+
+    def os_step_host(self, solved_total, tran_xx, tran_dt: float) -> abi.PfrxStepResult:
+        """the operator-split step on the bound (device-resident) state with HOST block vectors
+        [ncell, ncomp] (torch CPU tensors, pinned for overlap): upload, os_load, RStep, os_store,
+        download of ``tran_xx`` (pmc_subsurface_osrt.F90:303-378)"""
+        res = abi.PfrxStepResult()
+        for t in (solved_total, tran_xx):
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise PfrxError("os_step_host takes contiguous host tensors")
+        _check(lib().pfrx_os_step_host(self._h, solved_total.data_ptr() if solved_total is not None else None,
+                                       tran_xx.data_ptr(), float(tran_dt), C.byref(res)), "pfrx_os_step_host")
+        return res
 
     # -- host-resident path (H2D + kernel + D2H inside the call) ---------------- #
     def rstep_host(self, host: abi.HostState, tran_dt: float) -> abi.PfrxStepResult:

@@ -313,6 +313,68 @@ def test_os_block_vector_transposes(name, n):
     step.close()
 
 
+@pytest.mark.parametrize("name,n,chunks,spec", [("c3", 3001, "3", True), ("c4fe", 777, "2", False),
+                                                ("c2", 600001, None, True), ("c2", 0, None, False)])
+def test_os_step_host_against_oracle(name, n, chunks, spec, monkeypatch):
+    """pfrx_os_step_host = pmc_subsurface_osrt.F90:303-378 with host block vectors and the
+    chemistry state resident on the device: the oracle runs RStep on the state whose totals /
+    immobile concentrations were replaced by the vectors; tran_xx must come back as the new
+    free-ion / immobile concentrations (1e-10), inactive cells untouched, counts identical"""
+    import torch
+
+    rstep = _gpu()
+    if chunks:
+        monkeypatch.setenv("PFRX_OS_CHUNKS", chunks)
+    wl = W.by_name(name, ncell=n)
+    rng = np.random.default_rng(11)
+    a = wl.state.a
+    if n:
+        a["imat"][0, rng.random(n) < 0.1] = 0
+    naq, nim = wl.cfg.c.naqcomp, wl.cfg.c.nimcomp
+    ncomp = naq + nim
+    act = a["imat"][0] > 0
+    solved = np.ascontiguousarray((a["total"] * (1.0 + 0.02 * rng.random(a["total"].shape))).T)
+    solved = np.concatenate([solved, rng.random((n, nim))], axis=1) if nim else solved
+    xx = rng.random((n, ncomp))
+    if nim:
+        xx[:, naq:] = (a["immobile"] * (1.0 + 0.02 * rng.random(a["immobile"].shape))).T
+    # oracle: what the reference's loop does cell by cell
+    ref = wl.state.copy()
+    ref.a["total"][:, act] = solved[act, :naq].T
+    if nim:
+        ref.a["immobile"][:, act] = xx[act, naq:].T
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
+    want = xx.copy()
+    want[act, :naq] = ref.a["pri_molal"].T[act]
+    if nim:
+        want[act, naq:] = ref.a["immobile"].T[act]
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    if spec:
+        from pflotran_elm_interface_b200 import specialize
+
+        specialize.build(wl.cfg)
+        assert step.specialize(required=True)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    t_solved = torch.from_numpy(solved.copy()).pin_memory()
+    t_xx = torch.from_numpy(xx.copy()).pin_memory()
+    res = step.os_step_host(t_solved, t_xx, wl.tran_dt)
+    got_xx = t_xx.numpy()
+    if n:
+        ok = (ref.a["ierror"][0] == 0)
+        assert np.array_equal(got_xx[~act], xx[~act])
+        g, w = got_xx[act & ok], want[act & ok]
+        scale = np.maximum(np.abs(g), np.abs(w))
+        err = np.where(scale < 1e-30, 0.0, np.abs(g - w) / np.where(scale > 0, scale, 1.0))
+        assert err.max() <= RTOL, err.max()
+        got = dev.to_host()
+        _compare(ref, got, f"os_step_host {name}")
+        h2d, d2h = step.last_transfer_bytes()
+        assert d2h == n * ncomp * 8 and h2d == 2 * n * ncomp * 8
+    _check_summary(res_ref, res)
+    step.close()
+
+
 def test_autotune_picks_a_variant_and_leaves_state_alone():
     rstep = _gpu()
     from pflotran_elm_interface_b200 import specialize
