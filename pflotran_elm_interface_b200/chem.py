@@ -1024,6 +1024,15 @@ def read_deck(text: str) -> Deck:
             dk.reference_liquid_density = _fnum(t[1])
         elif key == "REFERENCE_TEMPERATURE":
             dk.reference_temperature = _fnum(t[1])
+        elif key == "EOS" and len(t) > 1 and t[1].upper() == "WATER":
+            # EOS WATER / DENSITY CONSTANT rho: without a flow mode the liquid density of every
+            # cell is this constant (eos_water.F90 EOSWaterSetDensity('CONSTANT'))
+            while True:
+                u = cur.next()
+                if u is None or u[0].upper() in ("END", "/"):
+                    break
+                if u[0].upper() == "DENSITY" and len(u) > 2 and u[1].upper() == "CONSTANT":
+                    dk.reference_liquid_density = _fnum(u[2])
         elif key == "MODE" and len(t) > 1 and t[1].upper() == "OSRT":
             dk.osrt = True
         elif key == "FINAL_TIME":

@@ -534,3 +534,30 @@ def test_full_size_properties_c2():
     assert np.abs(mol - gained).max() < 1e-4 * np.abs(gained).max()
     assert (a["pri_molal"] > 0).all()
     step.close()
+
+
+def test_dynamic_kd_gold_on_the_gpu():
+    """The reference's one single-cell OSRT gold (default/batch/dynamic_KD: MODE OSRT, one step of
+    1 y) through the CUDA path: RStep with RTotalSorbDynamicKD must land on the gold's totals,
+    sorbed total and KD to batch.cfg's 1e-12, like the oracle (test_oracle_golden.test_dynamic_kd_gold)."""
+    import test_oracle_golden as tg
+
+    rstep = _gpu()
+    dk, net, cfg, st = tg._setup("dynamic_KD.in", "hanford_subset.dat", cons="U_source")
+    gold = tg._gold("dynamic_KD.regression.gold")
+    ref = st.copy()
+    res_ref = orc.rstep(cfg, ref, dk.initial_dt)
+    step = rstep.ChemistryStep(cfg, 0)
+    dev = rstep.DeviceState.from_host(st, "cuda:0")
+    step.bind(dev)
+    res = step.rstep(dk.initial_dt)
+    got = dev.to_host()
+    step.close()
+    _check_summary(res_ref, res)
+    _compare(ref, got, "dynamic_KD")
+    i = net.primary_names.index("UO2++")
+    to_molal = 1000.0 / got.a["den_kg"][0, 0]
+    tg._check_rel(got.a["total"][i, 0] * to_molal, tg._val(gold, "CONCENTRATION: Total UO2++"), 1.0e-12, "Total UO2++")
+    tg._check_rel(got.a["total_sorb_eq"][i, 0], tg._val(gold, "CONCENTRATION: Total Sorbed UO2++"), 1.0e-12, "sorbed")
+    kd = got.a["total_sorb_eq"][i, 0] / (got.a["porosity"][0, 0] * got.a["sat"][0, 0] * 1000.0) / got.a["total"][i, 0]
+    tg._check_rel(kd, tg._val(gold, "CONCENTRATION: UO2++ KD"), 1.0e-12, "KD")

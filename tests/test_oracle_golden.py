@@ -269,3 +269,51 @@ def test_ion_exchange_gold():
     # the sorbed charge adds up to the exchange capacity: sum Z_i S_i = CEC
     Z = cfg.arrays["primary_spec_Z"]
     assert abs(float(np.sum(Z * st["total_sorb_eq"][:, 0])) - 750.0) < 1.0e-9
+
+
+def test_dynamic_kd_gold():
+    """default/batch/dynamic_KD: RTotalSorbDynamicKD (reaction.F90:4836-4902) -- KD of UO2++
+    interpolated between KD_LOW and KD_HIGH by the Tracer concentration; one step of 1 y under
+    LOG_FORMULATION.  batch.cfg: concentrations 1e-12 relative.  The printed "KD" is
+    ReactionComputeKd (reaction.F90:5520-5565): total sorbed / (porosity*sat*1000) / total."""
+    dk, net, cfg, st = _setup("dynamic_KD.in", "hanford_subset.dat", cons="U_source")
+    assert cfg.c.neqdynamickdrxn == 1 and dk.osrt and st["den_kg"][0, 0] == 1000.0   # EOS WATER DENSITY CONSTANT
+    gold = _gold("dynamic_KD.regression.gold")
+    # MODE OSRT: this gold pins RStep itself.  One cell, no flow: the transport solve returns the
+    # totals unchanged (pmc_subsurface_osrt.F90:303-333), then the cell loop (:346-383)
+    assert dk.final_time == dk.initial_dt and int(gold["SOLUTION: Transport"]["Time Steps"]) == 1
+    res = orc.rstep(cfg, st, dk.initial_dt)
+    assert res.rstep_error == 0 and res.num_cut_cells == 0
+    # MOLAL in the deck: totals are printed as molalities (reaction.F90:896-900)
+    assert dk.chemistry.initialize_with_molality
+    to_molal = 1000.0 / st["den_kg"][0, 0]
+    for nm in ("UO2++", "Tracer"):
+        i = net.primary_names.index(nm)
+        _check_rel(st["total"][i, 0] * to_molal, _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")
+        want = _val(gold, f"CONCENTRATION: Total Sorbed {nm}")
+        kd = st["total_sorb_eq"][i, 0] / (st["porosity"][0, 0] * st["sat"][0, 0] * 1000.0) / st["total"][i, 0]
+        if want == 0.0:
+            assert st["total_sorb_eq"][i, 0] == 0.0 and kd == 0.0
+        else:
+            _check_rel(st["total_sorb_eq"][i, 0], want, 1.0e-12, f"Total Sorbed {nm}")
+            _check_rel(kd, _val(gold, f"CONCENTRATION: {nm} KD"), 1.0e-12, f"{nm} KD")
+
+
+@pytest.mark.parametrize("deck", ["solute_KD_wo_mineral", "solute_KD_w_mineral"])
+def test_linear_kd_gold(deck):
+    """default/batch/solute_KD_{wo,w}_mineral: RTotalSorbKD, linear isotherm, KD in kg water / m^3 bulk
+    and in mL/g of a mineral (KD_MINERAL_NAME, reaction_isotherm.F90:273-359); two steps of 1 h.
+    The batch system is closed, so the aqueous total must stay at its constraint value to 1e-12
+    while the sorbed total follows the retardation R = 2 the deck is written for."""
+    dk, net, cfg, st = _setup(deck + ".in", "hanford_subset.dat")
+    assert cfg.c.neqkdrxn == 1
+    run = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold(deck + ".regression.gold")
+    assert run.steps == int(gold["SOLUTION: Transport"]["Time Steps"]) and run.cuts == 0
+    _check_rel(st["total"][0, 0], _val(gold, "CONCENTRATION: Total A(aq)"), 1.0e-12, "Total A(aq)")
+    # R = 1 + sorbed / (porosity*sat*1000*total) = 2
+    R = 1.0 + st["total_sorb_eq"][0, 0] / (st["porosity"][0, 0] * st["sat"][0, 0] * 1000.0 * st["total"][0, 0])
+    _check_rel(R, 2.0, 1.0e-9, "retardation")
+    if deck.endswith("w_mineral"):
+        _check_abs(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: A(s) VF"), 1.0e-12, "A(s) VF")
+        assert st["mnrl_rate"][0, 0] == 0.0
