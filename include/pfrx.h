@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 4
+#define PFRX_ABI_VERSION 5
 
 /* error classes */
 #define PFRX_OK 0
@@ -346,6 +346,36 @@ typedef struct pfrx_config {
    * come per cell from ELM (pfrx_state.elm_*) instead of the response
    * functions / constants of the stand-alone build */
   int32_t elm_pflotran;
+
+  /* ---- other kinetic terms of RReaction (ABI v5; counts 0 => absent) -------- */
+  /* general kinetic reactions, RGeneral (reaction.F90:5316-5460), tables as built at
+   * reaction_database.F90:3060-3145: every species of reaction k with its signed
+   * stoichiometry (reactants negative), the reactants again with |stoich| for the
+   * forward rate law, the products for the backward one.  Aqueous species only.   */
+  int32_t ngeneral_rxn;
+  const int32_t *general_ptr;        /* [n+1] CSR into general_specid / general_stoich */
+  const int32_t *general_specid;
+  const double *general_stoich;
+  const int32_t *general_fwd_ptr;    /* [n+1] */
+  const int32_t *general_fwd_specid;
+  const double *general_fwd_stoich;  /* > 0 */
+  const int32_t *general_bwd_ptr;    /* [n+1] */
+  const int32_t *general_bwd_specid;
+  const double *general_bwd_stoich;
+  const double *general_kf;          /* [n] kg^(m-1)/mol^(m-1)-sec; <= 0 => no forward term */
+  const double *general_kr;          /* [n] */
+  /* radioactive decay of one parent (aqueous + sorbed inventory) into any number
+   * of daughters, RRadioactiveDecay (reaction.F90:5211-5311; tables :2940-3017) */
+  int32_t nradiodecay_rxn;
+  const int32_t *radiodecay_ptr;     /* [n+1] CSR into radiodecay_specid / _stoich */
+  const int32_t *radiodecay_specid;
+  const double *radiodecay_stoich;   /* parent negative */
+  const int32_t *radiodecay_forward_specid; /* [n] the parent */
+  const double *radiodecay_kf;       /* [n] 1/s */
+  /* first-order decay of immobile species, RImmobileDecay (reaction_immobile.F90:244-296) */
+  int32_t nimmobile_decay_rxn;
+  const int32_t *immobile_decay_specid;   /* [n] immobile index */
+  const double *immobile_decay_constant;  /* [n] 1/s */
 } pfrx_config;
 
 /*

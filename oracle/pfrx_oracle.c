@@ -2329,11 +2329,125 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
   }
 }
 
-/* reaction.F90:4059-4130  RReaction (dispatch order preserved) */
+/* reaction.F90:5211-5311  RRadioactiveDecay: one parent, aqueous + sorbed inventory, any
+ * number of daughters (no active gas phase here) */
+static void r_radioactive_decay(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
+  int naq = c->naq, n = c->n, irxn, i, j;
+  double L_pore = c->porosity * c->volume * 1.e3;
+  double L_water = L_pore * c->sat;
+  int have_sorb = neqsorb(cfg) > 0;
+  for (irxn = 0; irxn < cfg->nradiodecay_rxn; irxn++) {
+    int p0 = cfg->radiodecay_ptr[irxn], p1 = cfg->radiodecay_ptr[irxn + 1];
+    int icomp = cfg->radiodecay_forward_specid[irxn], jcomp;
+    double sum = c->total[icomp] * L_water, rate, tempreal;
+    if (have_sorb) sum = sum + c->total_sorb_eq[icomp] * c->volume;
+    rate = sum * cfg->radiodecay_kf[irxn];
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->radiodecay_specid[i];
+      Res[icomp] = Res[icomp] - cfg->radiodecay_stoich[i] * rate;
+    }
+    if (!compute_derivative) continue;
+    tempreal = -1.0 * cfg->radiodecay_kf[irxn];
+    jcomp = cfg->radiodecay_forward_specid[irxn];
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->radiodecay_specid[i];
+      for (j = 0; j < naq; j++)
+        Jac[icomp + j * n] =
+            Jac[icomp + j * n] + tempreal * cfg->radiodecay_stoich[i] * c->dtotal[jcomp + j * naq] * L_water;
+    }
+    if (have_sorb) {
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->radiodecay_specid[i];
+        for (j = 0; j < naq; j++)
+          Jac[icomp + j * n] = Jac[icomp + j * n] +
+                               tempreal * cfg->radiodecay_stoich[i] * c->dtotal_sorb_eq[jcomp + j * naq] * c->volume;
+      }
+    }
+  }
+}
+
+/* reaction.F90:5316-5460  RGeneral: forward / backward mass-action rates in activities */
+static void r_general(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
+  int naq = c->naq, n = c->n, irxn, i, j;
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  for (i = 0; i < naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+  }
+  for (irxn = 0; irxn < cfg->ngeneral_rxn; irxn++) {
+    double kf = cfg->general_kf[irxn], kr = cfg->general_kr[irxn];
+    double lnQkf = 0.0, lnQkr = 0.0, Qkf, Qkr, por_den_sat_vol, tempreal;
+    int f0 = cfg->general_fwd_ptr[irxn], f1 = cfg->general_fwd_ptr[irxn + 1];
+    int b0 = cfg->general_bwd_ptr[irxn], b1 = cfg->general_bwd_ptr[irxn + 1];
+    int p0 = cfg->general_ptr[irxn], p1 = cfg->general_ptr[irxn + 1];
+    if (kf > 0.0) {
+      lnQkf = log(kf);
+      for (i = f0; i < f1; i++) lnQkf = lnQkf + cfg->general_fwd_stoich[i] * ln_act[cfg->general_fwd_specid[i]];
+      Qkf = exp(lnQkf);
+    } else {
+      Qkf = 0.0;
+    }
+    if (kr > 0.0) {
+      lnQkr = log(kr);
+      for (i = b0; i < b1; i++) lnQkr = lnQkr + cfg->general_bwd_stoich[i] * ln_act[cfg->general_bwd_specid[i]];
+      Qkr = exp(lnQkr);
+    } else {
+      Qkr = 0.0;
+    }
+    por_den_sat_vol = c->porosity * c->den_kg * c->sat * c->volume;
+    for (i = p0; i < p1; i++) {
+      int icomp = cfg->general_specid[i];
+      Res[icomp] = Res[icomp] - cfg->general_stoich[i] * (Qkf - Qkr) * por_den_sat_vol;
+    }
+    if (!compute_derivative) continue;
+    if (kf > 0.0) {
+      for (j = f0; j < f1; j++) {
+        int jcomp = cfg->general_fwd_specid[j];
+        tempreal = -1.0 * cfg->general_fwd_stoich[j] * exp(lnQkf - ln_conc[jcomp]) * por_den_sat_vol;
+        for (i = p0; i < p1; i++) {
+          int icomp = cfg->general_specid[i];
+          Jac[icomp + jcomp * n] = Jac[icomp + jcomp * n] + cfg->general_stoich[i] * tempreal;
+        }
+      }
+    }
+    if (kr > 0.0) {
+      for (j = b0; j < b1; j++) {
+        int jcomp = cfg->general_bwd_specid[j];
+        tempreal = cfg->general_bwd_stoich[j] * exp(lnQkr - ln_conc[jcomp]) * por_den_sat_vol;
+        for (i = p0; i < p1; i++) {
+          int icomp = cfg->general_specid[i];
+          Jac[icomp + jcomp * n] = Jac[icomp + jcomp * n] + cfg->general_stoich[i] * tempreal;
+        }
+      }
+    }
+  }
+}
+
+/* reaction_immobile.F90:244-296  RImmobileDecay */
+static void r_immobile_decay(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
+  int n = c->n, irxn;
+  double volume = c->volume;
+  for (irxn = 0; irxn < cfg->nimmobile_decay_rxn; irxn++) {
+    int icomp = cfg->immobile_decay_specid[irxn];
+    double rate_constant = cfg->immobile_decay_constant[irxn] * volume;
+    double rate = rate_constant * c->immobile[icomp];
+    int immobile_id = c->naq + icomp;
+    Res[immobile_id] = Res[immobile_id] + rate;
+    if (!compute_derivative) continue;
+    Jac[immobile_id + immobile_id * n] = Jac[immobile_id + immobile_id * n] + rate_constant;
+  }
+}
+
+/* reaction.F90:4059-4130  RReaction (dispatch order preserved: mineral, multirate sorption,
+ * [kinetic surface complexation], radioactive decay, general, [microbial], immobile decay,
+ * sandboxes) */
 static void r_reaction(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac, int derivative) {
   if (c->sat < cfg->rt_min_saturation) return;
   if (c->nkin > 0) r_kinetic_mineral(c, cfg, Res, Jac, derivative);
   if (cfg->nkinmrsrfcplxrxn > 0) r_multirate_sorption(c, cfg, tran_dt, Res, Jac, derivative);
+  if (cfg->nradiodecay_rxn > 0) r_radioactive_decay(c, cfg, Res, Jac, derivative);
+  if (cfg->ngeneral_rxn > 0) r_general(c, cfg, Res, Jac, derivative);
+  if (cfg->nimmobile_decay_rxn > 0) r_immobile_decay(c, cfg, Res, Jac, derivative);
   if (n_sandboxes(cfg) > 0) r_sandbox_evaluate(c, cfg, tran_dt, Res, Jac, derivative);
 }
 
@@ -2773,7 +2887,8 @@ int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   for (i = 0; i < n * n; i++) Jac[i] = 0.0;
   /* the GIRT caller has just run RTAuxVarCompute (reactive_transport.F90:2599-2642):
    * the sandboxes that read rt_auxvar%aqueous%dtotal need it here too */
-  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir) rt_auxvar_compute(&c, cfg);
+  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir || cfg->nradiodecay_rxn > 0)
+    rt_auxvar_compute(&c, cfg);
   r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
   for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];
   if (st->somdec_nc)

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 4
+PFRX_ABI_VERSION = 5
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -144,6 +144,27 @@ class PfrxConfig(C.Structure):
         ("nsandbox", C.c_int32),
         ("sandbox_list", c_int32_p),
         ("elm_pflotran", C.c_int32),
+        ("ngeneral_rxn", C.c_int32),
+        ("general_ptr", c_int32_p),
+        ("general_specid", c_int32_p),
+        ("general_stoich", c_double_p),
+        ("general_fwd_ptr", c_int32_p),
+        ("general_fwd_specid", c_int32_p),
+        ("general_fwd_stoich", c_double_p),
+        ("general_bwd_ptr", c_int32_p),
+        ("general_bwd_specid", c_int32_p),
+        ("general_bwd_stoich", c_double_p),
+        ("general_kf", c_double_p),
+        ("general_kr", c_double_p),
+        ("nradiodecay_rxn", C.c_int32),
+        ("radiodecay_ptr", c_int32_p),
+        ("radiodecay_specid", c_int32_p),
+        ("radiodecay_stoich", c_double_p),
+        ("radiodecay_forward_specid", c_int32_p),
+        ("radiodecay_kf", c_double_p),
+        ("nimmobile_decay_rxn", C.c_int32),
+        ("immobile_decay_specid", c_int32_p),
+        ("immobile_decay_constant", c_double_p),
     ]
 
 
@@ -467,6 +488,27 @@ class ReactionConfig:
                 setattr(c, "eqdynamickd_" + k, _ip(self._keep("eqdynamickd_" + k, _i32(dk[k]))))
             for k in ("refspechigh", "low", "high", "power"):
                 setattr(c, "eqdynamickd_" + k, _dp(self._keep("eqdynamickd_" + k, _f64(dk[k]))))
+
+        # general / radioactive decay / immobile decay
+        g = getattr(net, "general", None)
+        if g:
+            c.ngeneral_rxn = len(g["kf"])
+            for k in ("ptr", "specid", "fwd_ptr", "fwd_specid", "bwd_ptr", "bwd_specid"):
+                setattr(c, "general_" + k, _ip(self._keep("general_" + k, _i32(g[k]))))
+            for k in ("stoich", "fwd_stoich", "bwd_stoich", "kf", "kr"):
+                setattr(c, "general_" + k, _dp(self._keep("general_" + k, _f64(g[k]))))
+        rd = getattr(net, "radiodecay", None)
+        if rd:
+            c.nradiodecay_rxn = len(rd["kf"])
+            for k in ("ptr", "specid", "forward_specid"):
+                setattr(c, "radiodecay_" + k, _ip(self._keep("radiodecay_" + k, _i32(rd[k]))))
+            for k in ("stoich", "kf"):
+                setattr(c, "radiodecay_" + k, _dp(self._keep("radiodecay_" + k, _f64(rd[k]))))
+        idc = getattr(net, "immdecay", None)
+        if idc:
+            c.nimmobile_decay_rxn = len(idc["k"])
+            c.immobile_decay_specid = _ip(self._keep("immobile_decay_specid", _i32(idc["specid"])))
+            c.immobile_decay_constant = _dp(self._keep("immobile_decay_constant", _f64(idc["k"])))
 
         # CLM-CN
         cc = net.clmcn

@@ -372,6 +372,10 @@ class Chemistry:
     max_rel_residual_tolerance: float = 1.0e-8
     maximum_reaction_iterations: int = 20
     maximum_reaction_cuts: int = 10
+    # GENERAL_REACTION / RADIOACTIVE_DECAY_REACTION / IMMOBILE_DECAY_REACTION blocks, deck order
+    general_rxns: List[dict] = field(default_factory=list)       # {reaction, kf, kr}
+    radiodecay_rxns: List[dict] = field(default_factory=list)    # {reaction, k}
+    immobile_decay_rxns: List[dict] = field(default_factory=list)  # {species, k}
     unsupported: List[str] = field(default_factory=list)
 
 
@@ -381,6 +385,7 @@ _RATE_UNITS = {  # -> mol/m^2-sec
     "mol/dm^2-sec": 1.0e2, "mol/dm^2-s": 1.0e2,
 }
 
+_AREA_PER_MASS_UNITS = {"m^2/kg": 1.0, "m^2/g": 1.0e3, "cm^2/g": 1.0e-1, "cm^2/kg": 1.0e-4}  # -> m^2/kg
 _AREA_UNITS = {  # -> m^2/m^3
     "m^2/m^3": 1.0, "cm^2/cm^3": 100.0, "dm^2/dm^3": 10.0, "m^2/g": None,
 }
@@ -822,6 +827,61 @@ def _read_langmuir(cur: _Cursor) -> dict:
     return d
 
 
+def _per_time(tokens, i) -> float:
+    """value at tokens[i] with an optional 1/<time> unit behind it -> 1/s"""
+    v = _fnum(tokens[i])
+    if len(tokens) > i + 1 and not tokens[i + 1].startswith(("!", "#")):
+        u = tokens[i + 1].lower()
+        if not u.startswith("1/") or u[2:] not in _TIME_UNITS:
+            raise ValueError(f"rate unit {tokens[i + 1]} not supported")
+        v /= _TIME_UNITS[u[2:]]
+    return v
+
+
+def _read_kinetic_rxn_block(cur: "_Cursor", kind: str) -> dict:
+    """GENERAL_REACTION (reaction.F90:357-460), RADIOACTIVE_DECAY_REACTION (:294-356) and
+    IMMOBILE_DECAY_REACTION (reaction_immobile.F90:94-160) blocks"""
+    r = {"reaction": "", "kf": 0.0, "kr": 0.0, "k": None, "species": ""}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "REACTION":
+            r["reaction"] = " ".join(x for x in t[1:])
+        elif key == "SPECIES_NAME":
+            r["species"] = t[1]
+        elif key == "FORWARD_RATE":
+            r["kf"] = _fnum(t[1])      # kg^(n-1)/mol^(n-1)-sec; other units are not converted here
+        elif key == "BACKWARD_RATE":
+            r["kr"] = _fnum(t[1])
+        elif key == "RATE_CONSTANT":
+            r["k"] = _per_time(t, 1)
+        elif key == "HALF_LIFE":
+            r["k"] = -1.0 * math.log(0.5) / time_to_sec(_fnum(t[1]), t[2] if len(t) > 2 else "s")
+        else:
+            raise ValueError(f"{kind}: keyword {key} not supported")
+    return r
+
+
+def parse_reaction_string(text: str):
+    """'A(aq) + 2 B(aq) <-> C(aq)' -> [(name, stoich)], reactants negative
+    (DatabaseRxnCreateFromRxnString, reaction_database_aux.F90:91-316)"""
+    if "<->" not in text:
+        raise ValueError(f"reaction '{text}' has no <->")
+    out = []
+    for side, sign in zip(text.split("<->", 1), (-1.0, 1.0)):
+        coef = None
+        for tok in side.split():
+            if tok == "+":
+                continue
+            if tok.startswith(("!", "#")):
+                break
+            if coef is None and _is_num(tok):
+                coef = _fnum(tok)
+                continue
+            out.append((tok, sign * (1.0 if coef is None else coef)))
+            coef = None
+    return out
+
+
 def read_chemistry(cur: _Cursor) -> Chemistry:
     """CHEMISTRY block (ReactionReadPass1, reaction.F90:121-936)."""
     ch = Chemistry()
@@ -843,6 +903,18 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
             ch.minerals = _read_names(cur)
         elif key == "MINERAL_KINETICS":
             ch.mineral_kinetics = _read_mineral_kinetics(cur)
+        elif key == "GENERAL_REACTION":
+            ch.general_rxns.append(_read_kinetic_rxn_block(cur, key))
+        elif key == "RADIOACTIVE_DECAY_REACTION":
+            r = _read_kinetic_rxn_block(cur, key)
+            if r["k"] is None:
+                raise ValueError("RATE_CONSTANT or HALF_LIFE must be set in RADIOACTIVE_DECAY_REACTION")
+            ch.radiodecay_rxns.append(r)
+        elif key == "IMMOBILE_DECAY_REACTION":
+            r = _read_kinetic_rxn_block(cur, key)
+            if r["k"] is None:
+                raise ValueError("RATE_CONSTANT or HALF_LIFE must be set in IMMOBILE_DECAY_REACTION")
+            ch.immobile_decay_rxns.append(r)
         elif key == "SORPTION":
             for u in cur.block():
                 k2 = u[0].upper()
@@ -950,6 +1022,9 @@ class Constraint:
     name: str
     conc: List[Tuple[str, float, str, str]] = field(default_factory=list)  # (species, value, type, aux name)
     minerals: Dict[str, Tuple[float, float]] = field(default_factory=dict)  # name -> (vol frac, area m^2/m^3)
+    # name -> (vol frac, specific surface area per mass as written, its factor to m^2/kg): resolved
+    # into `minerals` by load_network once molar weight and volume are known (MineralProcessConstraint)
+    minerals_per_mass: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)
     immobile: Dict[str, float] = field(default_factory=dict)
     free_site_guess: Dict[str, float] = field(default_factory=dict)
 
@@ -969,6 +1044,10 @@ def read_constraint(cur: _Cursor, name: str) -> Constraint:
                 vf = _fnum(u[1])
                 area = _fnum(u[2])
                 unit = u[3].lower() if len(u) > 3 else "m^2/m^3"
+                if unit in _AREA_PER_MASS_UNITS:
+                    cn.minerals_per_mass[u[0]] = (vf, area, _AREA_PER_MASS_UNITS[unit])
+                    cn.minerals[u[0]] = (vf, float("nan"))
+                    continue
                 fac = _AREA_UNITS.get(unit)
                 if fac is None:
                     raise ValueError(f"mineral area unit {unit} not supported")
@@ -1131,6 +1210,7 @@ class ReactionNetwork:
         self._surface_complexation()
         self._clm_cn()
         self._sorption_isotherms()
+        self._kinetic_rxns()
         self.sandbox_order = list(chem.sandbox_order)
         self.elm_pflotran = False
         self._somdec()
@@ -1341,6 +1421,47 @@ class ReactionNetwork:
             resp=np.array([r["resp"] for r in sb.reactions], dtype=np.float64),
             inhib=np.array([r["inhib"] for r in sb.reactions], dtype=np.float64),
         )
+
+    # -- general / radioactive decay / immobile decay (reaction_database.F90:2940-3145) -------- #
+    def _kinetic_rxns(self):
+        pri = {n: i for i, n in enumerate(self.primary_names)}
+        imm = {n: i for i, n in enumerate(self.immobile_names)}
+        self.general = self.radiodecay = self.immdecay = None
+        if self.chem.general_rxns:
+            ptr, ids, st, fptr, fids, fst, bptr, bids, bst = [0], [], [], [0], [], [], [0], [], []
+            for r in self.chem.general_rxns:
+                for nm, v in parse_reaction_string(r["reaction"]):
+                    ids.append(pri[nm])
+                    st.append(v)
+                    if v < 0.0:       # forward stoichiometries are stored positive (:3119-3126)
+                        fids.append(pri[nm])
+                        fst.append(abs(v))
+                    elif v > 0.0:
+                        bids.append(pri[nm])
+                        bst.append(v)
+                ptr.append(len(ids)); fptr.append(len(fids)); bptr.append(len(bids))
+            self.general = dict(ptr=ptr, specid=ids, stoich=st, fwd_ptr=fptr, fwd_specid=fids, fwd_stoich=fst,
+                                bwd_ptr=bptr, bwd_specid=bids, bwd_stoich=bst,
+                                kf=[r["kf"] for r in self.chem.general_rxns],
+                                kr=[r["kr"] for r in self.chem.general_rxns])
+        if self.chem.radiodecay_rxns:
+            ptr, ids, st, fwd = [0], [], [], []
+            for r in self.chem.radiodecay_rxns:
+                parent = None
+                for nm, v in parse_reaction_string(r["reaction"]):
+                    ids.append(pri[nm])
+                    st.append(v)
+                    if v < 0.0:
+                        parent = pri[nm]      # the last negative one, like :3006-3010
+                if parent is None:
+                    raise ValueError("RADIOACTIVE_DECAY_REACTION without a parent species")
+                fwd.append(parent)
+                ptr.append(len(ids))
+            self.radiodecay = dict(ptr=ptr, specid=ids, stoich=st, forward_specid=fwd,
+                                   kf=[r["k"] for r in self.chem.radiodecay_rxns])
+        if self.chem.immobile_decay_rxns:
+            self.immdecay = dict(specid=[imm[r["species"]] for r in self.chem.immobile_decay_rxns],
+                                 k=[r["k"] for r in self.chem.immobile_decay_rxns])
 
     # -- ion exchange / KD isotherms / dynamic KD (reaction_database.F90:2800-2925) -------- #
     def _sorption_isotherms(self):
@@ -1597,5 +1718,17 @@ def load_network(deck_text: str, db_text: str, use_isothermal: bool = True) -> T
     dk = read_deck(deck_text)
     if dk.chemistry is None:
         raise ValueError("deck has no CHEMISTRY block")
-    net = ReactionNetwork(dk.chemistry, Database(db_text), dk.reference_temperature, use_isothermal)
+    db = Database(db_text)
+    net = ReactionNetwork(dk.chemistry, db, dk.reference_temperature, use_isothermal)
+    for cn in dk.constraints.values():
+        # specific surface area per mass of mineral (reaction_mineral.F90:588-641):
+        # m^2/kg * 1e-3 kg/g * g/mol / (m^3/mol) = m^2 per m^3 mineral, times the volume fraction
+        for nm, (vf, ssa, to_m2_kg) in cn.minerals_per_mass.items():
+            m = db.mineral[nm]
+            if not (m.mw > 0.0 and m.molar_volume > 0.0) or vf <= 0.0:
+                raise ValueError(f"mineral {nm}: a mass-based surface area needs molar weight, molar volume "
+                                 "and a non-zero volume fraction")
+            conv = to_m2_kg * 1.0e-3 * m.mw / m.molar_volume      # same order of operations as :621-640
+            conv = conv * vf
+            cn.minerals[nm] = (vf, conv * ssa)
     return dk, net

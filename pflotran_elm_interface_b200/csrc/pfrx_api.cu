@@ -205,6 +205,11 @@ static uint64_t config_signature(const pfrx_config *c) {
     int32_t hi[4] = {c->neqionxrxn, c->neqkdrxn, c->neqdynamickdrxn, c->ikd_units};
     h = fnv1a(h, hi, sizeof(hi));
   }
+  if (c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0) {
+    // not covered by the generator either
+    int32_t hi[3] = {c->ngeneral_rxn, c->nradiodecay_rxn, c->nimmobile_decay_rxn};
+    h = fnv1a(h, hi, sizeof(hi));
+  }
   // ELM-CN sandboxes: every parameter the generated code bakes in
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
@@ -613,6 +618,48 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->neqdynamickdrxn > 0 && (!c->eqdynamickd_specid || !c->eqdynamickd_refspecid || !c->eqdynamickd_refspechigh ||
                                  !c->eqdynamickd_low || !c->eqdynamickd_high || !c->eqdynamickd_power))
     return set_err(PFRX_E_INVALID, "dynamic KD tables missing%s", "");
+  // general kinetic reactions, radioactive decay, immobile decay
+  const bool has_kin3 = c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0;
+  if (c->ngeneral_rxn < 0 || c->nradiodecay_rxn < 0 || c->nimmobile_decay_rxn < 0)
+    return set_err(PFRX_E_INVALID, "negative reaction count%s", "");
+  if (c->ngeneral_rxn > 0) {
+    if (!c->general_ptr || !c->general_specid || !c->general_stoich || !c->general_fwd_ptr || !c->general_fwd_specid ||
+        !c->general_fwd_stoich || !c->general_bwd_ptr || !c->general_bwd_specid || !c->general_bwd_stoich ||
+        !c->general_kf || !c->general_kr)
+      return set_err(PFRX_E_INVALID, "general reaction tables missing%s", "");
+    for (int k = 0; k < c->general_ptr[c->ngeneral_rxn]; k++)
+      if (c->general_specid[k] < 0 || c->general_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "general reaction species id out of range%s", "");
+    for (int k = 0; k < c->general_fwd_ptr[c->ngeneral_rxn]; k++)
+      if (c->general_fwd_specid[k] < 0 || c->general_fwd_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "general reaction species id out of range%s", "");
+    for (int k = 0; k < c->general_bwd_ptr[c->ngeneral_rxn]; k++)
+      if (c->general_bwd_specid[k] < 0 || c->general_bwd_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "general reaction species id out of range%s", "");
+  }
+  if (c->nradiodecay_rxn > 0) {
+    if (!c->radiodecay_ptr || !c->radiodecay_specid || !c->radiodecay_stoich || !c->radiodecay_forward_specid ||
+        !c->radiodecay_kf)
+      return set_err(PFRX_E_INVALID, "radioactive decay tables missing%s", "");
+    for (int k = 0; k < c->radiodecay_ptr[c->nradiodecay_rxn]; k++)
+      if (c->radiodecay_specid[k] < 0 || c->radiodecay_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "radioactive decay species id out of range%s", "");
+    for (int r = 0; r < c->nradiodecay_rxn; r++)
+      if (c->radiodecay_forward_specid[r] < 0 || c->radiodecay_forward_specid[r] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "radioactive decay parent id out of range%s", "");
+    // the Jacobian of the sorbed inventory needs rt_auxvar%dtotal_sorb_eq as a matrix of its own,
+    // which the CUDA path does not keep (sorption derivatives go straight into the Jacobian)
+    if (c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0)
+      return set_err(PFRX_E_INVALID,
+                     "radioactive decay together with equilibrium sorption is not covered by the CUDA path yet%s", "");
+  }
+  if (c->nimmobile_decay_rxn > 0) {
+    if (!c->immobile_decay_specid || !c->immobile_decay_constant)
+      return set_err(PFRX_E_INVALID, "immobile decay tables missing%s", "");
+    for (int r = 0; r < c->nimmobile_decay_rxn; r++)
+      if (c->immobile_decay_specid[r] < 0 || c->immobile_decay_specid[r] >= c->nimcomp)
+        return set_err(PFRX_E_INVALID, "immobile decay species id out of range%s", "");
+  }
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
   const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir;
   if (c->plantn && (c->plantn->plantn_id < 0 || (c->plantn->nh4_id < 0 && c->plantn->no3_id < 0)))
@@ -711,7 +758,10 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_pn = c->plantn ? 1 : 0;
   d.has_lg = c->langmuir ? 1 : 0;
   d.elm = c->elm_pflotran ? 1 : 0;
-  d.need_dt = has_sbx3 ? 1 : 0;
+  d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
+  d.ngen = c->ngeneral_rxn;
+  d.nrd = c->nradiodecay_rxn;
+  d.nidc = c->nimmobile_decay_rxn;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
     static const int def_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
@@ -738,7 +788,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
-    if (!rc0 && (has_pref || act_newton || has_sbx3 || has_sorb2) && !h->tpc) {
+    if (!rc0 && (has_pref || act_newton || has_sbx3 || has_sorb2 || has_kin3) && !h->tpc) {
       // mineral prefactors, the iterated ionic strength and the SOMDECOMP / NITRIFICATION /
       // DENITRIFICATION sandboxes live in the thread-per-cell kernel only
       const KernelGetter *gt = nullptr;
@@ -983,6 +1033,32 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
       A.add(c->eqdynamickd_high, nr, &d.dk_high);
       A.add(c->eqdynamickd_power, nr, &d.dk_power);
     }
+  }
+  if (c->ngeneral_rxn > 0) {
+    const int nr = c->ngeneral_rxn;
+    A.add(c->general_ptr, nr + 1, &d.gn_ptr);
+    A.add(c->general_specid, c->general_ptr[nr], &d.gn_id);
+    A.add(c->general_stoich, c->general_ptr[nr], &d.gn_st);
+    A.add(c->general_fwd_ptr, nr + 1, &d.gn_fptr);
+    A.add(c->general_fwd_specid, c->general_fwd_ptr[nr], &d.gn_fid);
+    A.add(c->general_fwd_stoich, c->general_fwd_ptr[nr], &d.gn_fst);
+    A.add(c->general_bwd_ptr, nr + 1, &d.gn_bptr);
+    A.add(c->general_bwd_specid, c->general_bwd_ptr[nr], &d.gn_bid);
+    A.add(c->general_bwd_stoich, c->general_bwd_ptr[nr], &d.gn_bst);
+    A.add(c->general_kf, nr, &d.gn_kf);
+    A.add(c->general_kr, nr, &d.gn_kr);
+  }
+  if (c->nradiodecay_rxn > 0) {
+    const int nr = c->nradiodecay_rxn;
+    A.add(c->radiodecay_ptr, nr + 1, &d.rd_ptr);
+    A.add(c->radiodecay_specid, c->radiodecay_ptr[nr], &d.rd_id);
+    A.add(c->radiodecay_stoich, c->radiodecay_ptr[nr], &d.rd_st);
+    A.add(c->radiodecay_forward_specid, nr, &d.rd_fwd);
+    A.add(c->radiodecay_kf, nr, &d.rd_kf);
+  }
+  if (c->nimmobile_decay_rxn > 0) {
+    A.add(c->immobile_decay_specid, c->nimmobile_decay_rxn, &d.idc_id);
+    A.add(c->immobile_decay_constant, c->nimmobile_decay_rxn, &d.idc_k);
   }
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
@@ -1899,7 +1975,8 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   // features outside what specialize.py generates (its supported() is the twin of this test)
   const DevCfg &d = h->cfg;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
-      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref)
+      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();
   if (rc) return rc;

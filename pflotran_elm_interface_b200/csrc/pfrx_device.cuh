@@ -89,6 +89,14 @@ struct DevCfg {
   const double *kd_coeff, *kd_lb, *kd_fn;
   const int *dk_spec, *dk_ref;
   const double *dk_refhigh, *dk_low, *dk_high, *dk_power;
+  // general kinetic reactions, radioactive decay, immobile decay (thread-per-cell kernel)
+  int ngen, nrd, nidc;
+  const int *gn_ptr, *gn_id, *gn_fptr, *gn_fid, *gn_bptr, *gn_bid;
+  const double *gn_st, *gn_fst, *gn_bst, *gn_kf, *gn_kr;
+  const int *rd_ptr, *rd_id, *rd_fwd;
+  const double *rd_st, *rd_kf;
+  const int *idc_id;
+  const double *idc_k;
   int n_ixcat;  // cations of all ion-exchange reactions
   int off_ix;   // workspace: reference-cation sorbed concentrations, then cation concentrations
   const int *eqsr;

@@ -476,6 +476,87 @@ struct CellT {
     }
   }
 
+  // ---- RRadioactiveDecay (reaction.F90:5211-5311): aqueous inventory of one parent decays into
+  // its daughters; d(total)/d(free) is the DT copy of this iteration.  (With equilibrium sorption
+  // the sorbed inventory decays too: pfrx_create refuses that combination for now.)
+  __device__ __forceinline__ void radioactive_decay() {
+    const int naq = cfg.naq;
+    const double L_pore = por * vol * 1.e3;
+    const double L_water = L_pore * sat;
+#pragma unroll 1
+    for (int r = 0; r < cfg.nrd; r++) {
+      const int p0 = cfg.rd_ptr[r], p1 = cfg.rd_ptr[r + 1], jc = cfg.rd_fwd[r];
+      const double kf = cfg.rd_kf[r];
+      const double sum = TOT(jc) * L_water;
+      const double rate = sum * kf;
+      const double t = -1.0 * kf;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) {
+        const int ic = cfg.rd_id[p];
+        const double nu = cfg.rd_st[p];
+        RES(ic) = RES(ic) - nu * rate;
+#pragma unroll 1
+        for (int j = 0; j < naq; j++) J(ic, j) = J(ic, j) + t * nu * DT(jc, j) * L_water;
+      }
+    }
+  }
+
+  // ---- RGeneral (reaction.F90:5316-5460): forward / backward mass-action rates in activities ----
+  __device__ __forceinline__ void general_reactions() {
+    const double pdsv = por * den_kg * sat * vol;
+#pragma unroll 1
+    for (int r = 0; r < cfg.ngen; r++) {
+      const double kf = cfg.gn_kf[r], kr = cfg.gn_kr[r];
+      const int f0 = cfg.gn_fptr[r], f1 = cfg.gn_fptr[r + 1], b0 = cfg.gn_bptr[r], b1 = cfg.gn_bptr[r + 1];
+      const int p0 = cfg.gn_ptr[r], p1 = cfg.gn_ptr[r + 1];
+      double lnQkf = 0.0, lnQkr = 0.0, Qkf = 0.0, Qkr = 0.0;
+      if (kf > 0.0) {
+        lnQkf = log(kf);
+#pragma unroll 1
+        for (int p = f0; p < f1; p++) lnQkf = lnQkf + cfg.gn_fst[p] * LNA(cfg.gn_fid[p]);
+        Qkf = exp(lnQkf);
+      }
+      if (kr > 0.0) {
+        lnQkr = log(kr);
+#pragma unroll 1
+        for (int p = b0; p < b1; p++) lnQkr = lnQkr + cfg.gn_bst[p] * LNA(cfg.gn_bid[p]);
+        Qkr = exp(lnQkr);
+      }
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) RES(cfg.gn_id[p]) = RES(cfg.gn_id[p]) - cfg.gn_st[p] * (Qkf - Qkr) * pdsv;
+      if (kf > 0.0) {
+#pragma unroll 1
+        for (int q = f0; q < f1; q++) {
+          const int jc = cfg.gn_fid[q];
+          const double t = -1.0 * cfg.gn_fst[q] * exp(lnQkf - log(C(jc))) * pdsv;
+#pragma unroll 1
+          for (int p = p0; p < p1; p++) J(cfg.gn_id[p], jc) = J(cfg.gn_id[p], jc) + cfg.gn_st[p] * t;
+        }
+      }
+      if (kr > 0.0) {
+#pragma unroll 1
+        for (int q = b0; q < b1; q++) {
+          const int jc = cfg.gn_bid[q];
+          const double t = cfg.gn_bst[q] * exp(lnQkr - log(C(jc))) * pdsv;
+#pragma unroll 1
+          for (int p = p0; p < p1; p++) J(cfg.gn_id[p], jc) = J(cfg.gn_id[p], jc) + cfg.gn_st[p] * t;
+        }
+      }
+    }
+  }
+
+  // ---- RImmobileDecay (reaction_immobile.F90:244-296) ------------------------------------------
+  __device__ __forceinline__ void immobile_decay() {
+    const int naq = cfg.naq;
+#pragma unroll 1
+    for (int r = 0; r < cfg.nidc; r++) {
+      const int id = naq + cfg.idc_id[r];
+      const double rc = cfg.idc_k[r] * vol;
+      RES(id) = RES(id) + rc * C(id);
+      J(id, id) = J(id, id) + rc;
+    }
+  }
+
   // ---- RTotalSorbDynamicKD (reaction.F90:4836-4902) ---------------------------------------
   __device__ __forceinline__ void dynamic_kd(bool want_J, double jscale) {
     const double Lw = 250.0;
@@ -1062,7 +1143,11 @@ struct CellT {
       }
       if (cfg.nkin > 0) kinetic_mineral(!dry);
       if (!dry) {
+        // RReaction's order (reaction.F90:4095-4127)
         if (cfg.nmr > 0) multirate(dt);
+        if (cfg.nrd > 0) radioactive_decay();
+        if (cfg.ngen > 0) general_reactions();
+        if (cfg.nidc > 0) immobile_decay();
         if (cfg.nsbx > 0) sandboxes(dt);
       }
       if (!act_ok) {
@@ -1211,12 +1296,15 @@ struct CellT {
 #pragma unroll 1
         for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
       }
-      if (cfg.nsbx > 0) {
-        if (cfg.need_dt) {
+      if (cfg.need_dt) {
 #pragma unroll 1
-          for (int i = 0; i < naq; i++) TOT(i) = st.total[i * ld + c];
-          dtotal_from_state();
-        }
+        for (int i = 0; i < naq; i++) TOT(i) = st.total[i * ld + c];
+        dtotal_from_state();
+      }
+      if (cfg.nrd > 0) radioactive_decay();
+      if (cfg.ngen > 0) general_reactions();
+      if (cfg.nidc > 0) immobile_decay();
+      if (cfg.nsbx > 0) {
         sandbox_load(c);
         sandboxes(tran_dt);
         sandbox_store(c);

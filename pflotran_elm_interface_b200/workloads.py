@@ -654,6 +654,89 @@ def ion_exchange(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEE
                     "2 ion-exchange reactions (5 cations), 3 KD isotherms, 1 dynamic KD, kinetic Halite")
 
 
+C7_DECK = """
+# C7: the other kinetic terms of RReaction -- two general reactions (a third-order forward /
+# first-order backward pair and an irreversible one), a radioactive decay with a daughter, an immobile
+# decay -- next to a secondary complex, so that d(total)/d(free) is not the identity
+CHEMISTRY
+  PRIMARY_SPECIES
+    A(aq)
+    B(aq)
+    C(aq)
+  /
+  SECONDARY_SPECIES
+    AB(aq)
+  /
+  IMMOBILE_SPECIES
+    Xim
+  /
+  GENERAL_REACTION
+    REACTION A(aq) + 2 B(aq) <-> C(aq)
+    FORWARD_RATE 4.d1
+    BACKWARD_RATE 2.d-7
+  /
+  GENERAL_REACTION
+    REACTION C(aq) <-> 0.5 A(aq)
+    FORWARD_RATE 1.d-7
+    BACKWARD_RATE 0.d0
+  /
+  RADIOACTIVE_DECAY_REACTION
+    REACTION B(aq) <-> 0.5 C(aq)
+    HALF_LIFE 30. d
+  /
+  IMMOBILE_DECAY_REACTION
+    SPECIES_NAME Xim
+    HALF_LIFE 10. d
+  /
+  DATABASE ./hanford_subset.dat
+  LOG_FORMULATION
+  ACTIVITY_COEFFICIENTS TIMESTEP
+END
+CONSTRAINT initial
+  CONCENTRATIONS
+    A(aq)  1.d-3 T
+    B(aq)  2.d-3 T
+    C(aq)  1.d-5 T
+  /
+  IMMOBILE
+    Xim 1.d-2
+  /
+END
+CONSTRAINT inlet
+  CONCENTRATIONS
+    A(aq)  1.d-5 T
+    B(aq)  5.d-4 T
+    C(aq)  3.d-3 T
+  /
+  IMMOBILE
+    Xim 1.d-4
+  /
+END
+"""
+
+
+def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED) -> Workload:
+    """C7: RGeneral, RRadioactiveDecay and RImmobileDecay on mixes of two waters"""
+    rng = np.random.default_rng(seed)
+    dk, net = chem.load_network(C7_DECK, _read("hanford_subset.dat"))
+    assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67(25.0)
+    waters = [constraint.equilibrate_constraint(net, dk.constraints[k], den_kg=den, porosity=0.3)
+              for k in ("initial", "inlet")]
+    st = abi.HostState(cfg, ncell)
+    f = rng.random(ncell)
+    _mix_fill(st, waters, np.stack([1.0 - f, f]), rng, jitter=0.0)
+    st["immobile"][...] = (10.0 ** rng.uniform(-4.0, -2.0, ncell))[None, :]
+    st["den_kg"][...] = den
+    st["porosity"][...] = 0.3
+    st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
+    st["sat"][...] = rng.uniform(0.4, 1.0, ncell)
+    st["temp"][...] = 25.0
+    return Workload("c7_general_decay", cfg, st, tran_dt, net,
+                    "2 general reactions, 1 radioactive decay with daughter, 1 immobile decay, 1 complex")
+
+
 def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
     table = {
         "c1": (calcite_batch, {}),
@@ -669,6 +752,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4fe": (elm_cn, {"full": True, "elm": True}),
         "c5": (hanford, {"variant": "minerals"}),
         "c6": (ion_exchange, {}),
+        "c7": (general_decay, {}),
     }
     fn, kw = table[name]
     kw = dict(kw)
@@ -715,6 +799,17 @@ def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
         f += 90.0
     if getattr(net, "langmuir", None) is not None:
         f += 50.0
+    g = getattr(net, "general", None)
+    if g:
+        # two exponentials (~25 flops each) and a log per rate law, residual and Jacobian updates
+        f += sum(80.0 + 4.0 * (g["ptr"][k + 1] - g["ptr"][k]) * (g["fwd_ptr"][k + 1] - g["fwd_ptr"][k] +
+                                                                g["bwd_ptr"][k + 1] - g["bwd_ptr"][k] + 1)
+                 for k in range(len(g["kf"])))
+    rd = getattr(net, "radiodecay", None)
+    if rd:
+        f += sum(4.0 + (rd["ptr"][k + 1] - rd["ptr"][k]) * (2.0 + 4.0 * naq) for k in range(len(rd["kf"])))
+    if getattr(net, "immdecay", None):
+        f += 4.0 * len(net.immdecay["k"])
     f += 10.0 * n
     solve = (2.0 / 3.0) * n ** 3 + 5.0 * n * n + 20.0 * n
     return f, solve

@@ -156,6 +156,9 @@ class GirtBatch:
             its = self.step(dt_step)
             dt_step = self.last_dt          # smaller than requested after a cut
             # PMRTUpdateTimestep "original implementation", pm_rt.F90:760-775
+            if dk.ts_acceleration == 0:
+                dt = dt_step              # iacceleration == 0: the step size is left alone (:734)
+                continue
             if its <= dk.ts_acceleration:
                 # its == 0 (residual below ATOL at once): the reference indexes tfac(0); growth
                 # like a one-iteration step is the benign reading

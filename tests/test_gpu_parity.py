@@ -146,6 +146,21 @@ def test_c6_ion_exchange_and_isotherms(dt, host):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("dt,host", [(3600.0, False), (86400.0, True), (30 * 86400.0, False)])
+def test_c7_general_decay_reactions(dt, host):
+    """RGeneral (third-order forward / first-order backward, and an irreversible one),
+    RRadioactiveDecay with a daughter (through dtotal of a network with a complex) and
+    RImmobileDecay in the thread-per-cell kernel"""
+    wl = W.by_name("c7", ncell=5000, tran_dt=dt)
+    wl.state.a["imat"][0, 5] = 0
+    wl.state.a["sat"][0, 6] = 1.0e-50
+    ref, rr, got, rg, info = _run_both(wl, host_path=host)
+    assert info["lanes"] in (0, 1)
+    assert rr.sum_newton_iterations > 3 * 4998
+    _compare(ref, got, f"c7 dt={dt}")
+    _check_summary(rr, rg)
+
+
 @pytest.mark.parametrize("variant,dt", [("c3", 3600.0), ("c3", 30 * 86400.0), ("c3mr", 3600.0), ("c5", 86400.0)])
 def test_hanford(variant, dt):
     wl = W.by_name(variant, ncell=3000, tran_dt=dt)
@@ -174,14 +189,14 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se", "c4fe"])
+@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se", "c4fe", "c7"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
 
     rstep = _gpu()
     wl = W.by_name(variant, ncell=300)
-    if variant.startswith("c4"):
+    if variant.startswith("c4") or variant == "c7":
         wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
         wl.state.a["sat"][0, 9] = 1.0e-50
     ref = wl.state.copy()

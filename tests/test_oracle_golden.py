@@ -68,7 +68,7 @@ def test_density_ifc67():
     assert abs(eos.water_density_ifc67() - 997.16) < 0.01
 
 
-@pytest.mark.parametrize("deck", ["calcite-kinetics", "calcite-kinetics-volume-fractions"])
+@pytest.mark.parametrize("deck", ["calcite-kinetics", "calcite-kinetics-volume-fractions", "calcite-area-per-mass"])
 def test_calcite_kinetics_gold(deck):
     dk, net, cfg, st = _setup(deck + ".in", "calcite.dat")
     b = girt.GirtBatch(cfg, st, dk).run()
@@ -86,7 +86,7 @@ def test_calcite_kinetics_gold(deck):
     for i, nm in enumerate(net.primary_names):
         _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm} (rel)")
     _check_rel(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: Calcite VF"), 1.0e-12, "Calcite VF (rel)")
-    if deck == "calcite-kinetics":  # the other deck sits at equilibrium: rate = rounding noise of 1-QK
+    if deck != "calcite-kinetics-volume-fractions":  # that deck sits at equilibrium: rate = rounding noise of 1-QK
         _check_rel(st["mnrl_rate"][0, 0], _val(gold, "RATE: Calcite Rate"), 1.0e-11, "Calcite rate (rel)")
 
 
@@ -317,3 +317,17 @@ def test_linear_kd_gold(deck):
     if deck.endswith("w_mineral"):
         _check_abs(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: A(s) VF"), 1.0e-12, "A(s) VF")
         assert st["mnrl_rate"][0, 0] == 0.0
+
+
+def test_general_reaction_gold():
+    """ascem/batch/general-reaction: RGeneral (reaction.F90:5316-5460), A(aq) <-> B(aq) with a forward
+    rate of 0.1/d over 50 d in 500 steps, linear formulation.  batch.cfg: 1e-12."""
+    dk, net, cfg, st = _setup("general-reaction.in", "hanford_subset.dat", cons="Initial")
+    assert cfg.c.ngeneral_rxn == 1
+    run = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold("general-reaction.regression.gold")
+    sol = gold["SOLUTION: Transport"]
+    assert run.steps == int(sol["Time Steps"]) and run.newton_its == int(sol["Newton Iterations"]) and run.cuts == 0
+    for nm in ("A(aq)", "B(aq)"):
+        i = net.primary_names.index(nm)
+        _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")

@@ -157,3 +157,39 @@ def test_sorption_jacobian_vs_finite_differences():
     ptr, cat = cfg.arrays["eqionx_ptr"], cfg.arrays["eqionx_cationid"]
     s0 = sum(z[cat[k]] * st["eqionx_conc"][k, 0] for k in range(ptr[0], ptr[1]))
     assert abs(s0 - 750.0) < 1e-9
+
+
+def test_general_decay_jacobian_vs_finite_differences():
+    """RGeneral, RRadioactiveDecay (through dtotal of a network with a complex) and RImmobileDecay:
+    the oracle's analytic Jacobian against central differences of its own residual, all unknowns"""
+    wl = W.by_name("c7", ncell=8)
+    cfg, dt = wl.cfg, wl.tran_dt
+    naq, n = cfg.c.naqcomp, cfg.ncomp
+    assert cfg.c.ngeneral_rxn == 2 and cfg.c.nradiodecay_rxn == 1 and cfg.c.nimmobile_decay_rxn == 1
+    for cell in range(8):
+        st0 = wl.state.copy()
+        e, R0, J, _ = orc.girt_residual(cfg, st0, cell, dt)
+        assert e == 0
+        for j in range(n):
+            fld, k = ("pri_molal", j) if j < naq else ("immobile", j - naq)
+            cols = []
+            for sgn in (1.0, -1.0):
+                st = wl.state.copy()
+                st.a[fld][k, cell] *= 1.0 + sgn * 1.0e-6
+                _, R, _, _ = orc.girt_residual(cfg, st, cell, dt)
+                cols.append((R, st.a[fld][k, cell]))
+            fd = (cols[0][0] - cols[1][0]) / (cols[0][1] - cols[1][1])
+            scale = np.abs(J[:, j]).max()
+            assert np.abs(J[:, j] - fd).max() <= 2.0e-5 * scale, (cell, j, J[:, j], fd)
+
+
+def test_general_decay_rstep_mass_balance():
+    """C7 through RStep: every cell converges without cuts, and the immobile species decays by the
+    backward-Euler factor 1/(1 + k dt) of its half-life"""
+    wl = W.by_name("c7", ncell=500)
+    st = wl.state.copy()
+    res = orc.rstep(wl.cfg, st, wl.tran_dt, 2)
+    assert res.rstep_error == 0 and res.num_cut_cells == 0
+    k = -np.log(0.5) / (10.0 * 86400.0)
+    want = wl.state["immobile"][0] / (1.0 + k * wl.tran_dt)
+    assert np.allclose(st["immobile"][0], want, rtol=1.0e-9)

@@ -94,6 +94,10 @@ COPY = [
     ("regression_tests/ngee/CLMCNplus/clm_nh4desorption.in", "clmcnplus_clm_nh4desorption.in"),
     ("regression_tests/ngee/CLMCNplus/clm_nh4desorption.regression.gold", "clmcnplus_clm_nh4desorption.regression.gold"),
     ("regression_tests/ngee/CLMCNplus/CLM-CN_database.dat", "clmcnplus_CLM-CN_database.dat"),
+    ("regression_tests/ascem/batch/calcite-area-per-mass.in", None),
+    ("regression_tests/ascem/batch/calcite-area-per-mass.regression.gold", None),
+    ("regression_tests/ascem/batch/general-reaction.in", None),
+    ("regression_tests/ascem/batch/general-reaction.regression.gold", None),
     # KD isotherms and dynamic KD (default/batch)
     ("regression_tests/default/batch/dynamic_KD.in", None),
     ("regression_tests/default/batch/dynamic_KD.regression.gold", None),
@@ -123,7 +127,7 @@ def main():
     ch = dk.chemistry
     names = (["H2O"] + ch.primary + ch.secondary + ch.gases + ch.minerals
              + [c for r in ch.srfcplx_rxns for c in r.complexes]
-             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)"])
+             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)", "B(aq)", "C(aq)", "AB(aq)"])
     db = chem.Database.from_file(os.path.join(REF, "database/hanford.dat"))
     with open(os.path.join(OUT, "hanford_subset.dat"), "w") as f:
         f.write(db.subset_text(names))
