@@ -970,6 +970,10 @@ struct CellT {
     const double denL = den_kg * 1.e-3;
 #pragma unroll 1
     for (int e = 0; e < naq * naq; e++) ws[cfg.off_dt + e] = 0.0;
+    // the totals too, from the free-ion concentrations, like RTAuxVarCompute before RReaction in
+    // the GIRT residual (reactive_transport.F90:2590-2626)
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) TOT(i) = C(i);
 #pragma unroll 1
     for (int k = 0; k < ncx; k++) {
       const int p0 = cfg.cx_ptr[k], p1 = cfg.cx_ptr[k + 1];
@@ -980,6 +984,8 @@ struct CellT {
       for (int p = p0; p < p1; p++) lnQK += cfg.cx_st[p] * LNA(cfg.cx_id[p]);
       const double sk = exp(lnQK) / st.sec_act_coef[k * st.ld + cell];
 #pragma unroll 1
+      for (int p = p0; p < p1; p++) TOT(cfg.cx_id[p]) += cfg.cx_st[p] * sk;
+#pragma unroll 1
       for (int p2 = p0; p2 < p1; p2++) {
         const int j = cfg.cx_id[p2];
         const double t = (cfg.cx_st[p2] * sk) * INVC(j);
@@ -989,6 +995,7 @@ struct CellT {
     }
 #pragma unroll 1
     for (int i = 0; i < naq; i++) {
+      TOT(i) *= denL;
       DT(i, i) += 1.0;
 #pragma unroll 1
       for (int j = 0; j < naq; j++) DT(i, j) *= denL;
@@ -1296,11 +1303,7 @@ struct CellT {
 #pragma unroll 1
         for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
       }
-      if (cfg.need_dt) {
-#pragma unroll 1
-        for (int i = 0; i < naq; i++) TOT(i) = st.total[i * ld + c];
-        dtotal_from_state();
-      }
+      if (cfg.need_dt) dtotal_from_state();
       if (cfg.nrd > 0) radioactive_decay();
       if (cfg.ngen > 0) general_reactions();
       if (cfg.nidc > 0) immobile_decay();
