@@ -31,9 +31,9 @@ import numpy as np  # noqa: E402
 
 DEFAULT_CELLS = {"c2": 10000, "c3": 256 * 256 * 64, "c3mr": 1 << 20, "c4": 2 * 1024 * 1024, "c4s": 2 * 1024 * 1024,
                  "c4se": 2 * 1024 * 1024, "c4fe": 2 * 1024 * 1024, "c5": 256 * 256 * 64, "c6": 1 << 20,
-                 "c7": 1 << 20}
+                 "c7": 1 << 20, "c8": 1 << 20}
 DEFAULT_DT = {"c2": 3600.0, "c3": 3600.0, "c3mr": 3600.0, "c4": 1800.0, "c4s": 1800.0, "c4se": 1800.0, "c4fe": 1800.0,
-              "c5": 86400.0, "c6": 86400.0, "c7": 86400.0}
+              "c5": 86400.0, "c6": 86400.0, "c7": 86400.0, "c8": 86400.0}
 
 
 def _kernel_name(info) -> str:

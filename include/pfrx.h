@@ -95,6 +95,15 @@ extern "C" {
 #define PFRX_SANDBOX_PLANTN 5
 #define PFRX_SANDBOX_LANGMUIR 6
 #define PFRX_MAX_SANDBOXES 8
+/* reaction_microbial_aux.F90:14-22 */
+#define PFRX_MICROBIAL_MOLALITY 1
+#define PFRX_MICROBIAL_ACTIVITY 2
+#define PFRX_MICROBIAL_MOLARITY 3
+#define PFRX_INHIBITION_THRESHOLD 1
+#define PFRX_INHIBITION_MONOD 3
+#define PFRX_INHIBITION_INVERSE_MONOD 4
+#define PFRX_INHIBITION_SMOOTHSTEP 5
+#define PFRX_MAX_MONOD_TERMS 8
 
 /*
  * SOMDECOMP sandbox: reaction_sandbox_somdec_type after SomDecSetup
@@ -376,6 +385,27 @@ typedef struct pfrx_config {
   int32_t nimmobile_decay_rxn;
   const int32_t *immobile_decay_specid;   /* [n] immobile index */
   const double *immobile_decay_constant;  /* [n] 1/s */
+  /* Monod-type microbial reactions, RMicrobial (reaction_microbial.F90:287-602; tables
+   * reaction_database.F90:3150-3400).  Monod and inhibition terms are CSR lists per
+   * reaction (at most PFRX_MAX_MONOD_TERMS each).                                    */
+  int32_t nmicrobial_rxn;
+  int32_t microbial_concentration_units;     /* PFRX_MICROBIAL_* */
+  const int32_t *microbial_ptr;              /* [n+1] CSR into microbial_specid / _stoich */
+  const int32_t *microbial_specid;           /* aqueous species */
+  const double *microbial_stoich;            /* reactants negative */
+  const double *microbial_rate_constant;     /* [n] */
+  const double *microbial_activation_energy; /* [n] J/mol, or NULL when no reaction has one */
+  const int32_t *microbial_monod_ptr;        /* [n+1] */
+  const int32_t *microbial_monod_specid;
+  const double *microbial_monod_K;
+  const double *microbial_monod_Cth;
+  const int32_t *microbial_inhibition_ptr;   /* [n+1] */
+  const int32_t *microbial_inhibition_specid;
+  const int32_t *microbial_inhibition_type;  /* PFRX_INHIBITION_* */
+  const double *microbial_inhibition_C;
+  const double *microbial_inhibition_C2;
+  const int32_t *microbial_biomassid;        /* [n] 0 none, k+1 aqueous species k, -(k+1) immobile species k */
+  const double *microbial_biomass_yield;     /* [n] */
 } pfrx_config;
 
 /*

@@ -2423,6 +2423,169 @@ static void r_general(cell_t *c, const pfrx_config *cfg, double *Res, double *Ja
   }
 }
 
+/* reaction_microbial.F90:287-602  RMicrobial: rate = k * prod(Monod) * prod(inhibition) * biomass.
+ * The biomass derivative is kept as written (:578-583: without the L_water / volume factor). */
+static void r_microbial(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
+  const double PI = 3.14159265359; /* pflotran_constants.F90:92, truncated as there */
+  int naq = c->naq, n = c->n, irxn, i, ii, jj;
+  double concentration[PFRX_MAX_NCOMP * 4], dconcentration_dmolal[PFRX_MAX_NCOMP * 4];
+  double monod[PFRX_MAX_MONOD_TERMS], inhibition[PFRX_MAX_MONOD_TERMS];
+  double L_water;
+  for (i = 0; i < naq; i++) {
+    switch (cfg->microbial_concentration_units) {
+      case PFRX_MICROBIAL_MOLALITY:
+        dconcentration_dmolal[i] = 1.0;
+        break;
+      case PFRX_MICROBIAL_ACTIVITY:
+        dconcentration_dmolal[i] = c->pri_act_coef[i];
+        break;
+      default:
+        dconcentration_dmolal[i] = c->den_kg * 1.e-3;
+        break;
+    }
+    concentration[i] = c->pri_molal[i] * dconcentration_dmolal[i];
+  }
+  L_water = c->porosity * c->sat * c->volume * 1.e3;
+  for (irxn = 0; irxn < cfg->nmicrobial_rxn; irxn++) {
+    int p0 = cfg->microbial_ptr[irxn], p1 = cfg->microbial_ptr[irxn + 1];
+    int m0 = cfg->microbial_monod_ptr[irxn], nmonod = cfg->microbial_monod_ptr[irxn + 1] - m0;
+    int h0 = cfg->microbial_inhibition_ptr[irxn], ninh = cfg->microbial_inhibition_ptr[irxn + 1] - h0;
+    double effective_rate_constant = cfg->microbial_rate_constant[irxn];
+    double yield = 0.0, biomass_conc = 0.0, dbiomass_conc_dconc = 0.0;
+    double monod_terms = 1.0, inhibition_terms = 1.0, biomass_term = 1.0, rate;
+    int ibiomass = cfg->microbial_biomassid[irxn]; /* 1-based like the reference, 0 none */
+    int ibio_row = -1;                              /* 0-based row of the biomass unknown */
+    if (cfg->microbial_activation_energy) {
+      effective_rate_constant = effective_rate_constant * exp(cfg->microbial_activation_energy[irxn] / IDEAL_GAS_CONSTANT *
+                                                              (1.0 / 298.15 - 1.0 / (c->temp + 273.15)));
+    }
+    for (ii = 0; ii < nmonod; ii++) {
+      int imonod = m0 + ii;
+      double conc = concentration[cfg->microbial_monod_specid[imonod]];
+      monod[ii] = (conc - cfg->microbial_monod_Cth[imonod]) /
+                  (cfg->microbial_monod_K[imonod] + conc - cfg->microbial_monod_Cth[imonod]);
+      monod_terms = monod_terms * monod[ii];
+    }
+    for (ii = 0; ii < ninh; ii++) {
+      int iinh = h0 + ii;
+      double conc = concentration[cfg->microbial_inhibition_specid[iinh]];
+      double C1 = cfg->microbial_inhibition_C[iinh], C2 = cfg->microbial_inhibition_C2[iinh];
+      switch (cfg->microbial_inhibition_type[iinh]) {
+        case PFRX_INHIBITION_MONOD:
+          inhibition[ii] = C1 / (C1 + conc);
+          break;
+        case PFRX_INHIBITION_INVERSE_MONOD:
+          inhibition[ii] = conc / (C1 + conc);
+          break;
+        case PFRX_INHIBITION_THRESHOLD:
+          inhibition[ii] = 0.5 + copysign(1.0, C1) * atan((conc - fabs(C1)) * C2) / PI;
+          break;
+        default: { /* SMOOTHSTEP */
+          double log10_conc = log10(conc), log10_C = log10(C1), log10_interval = C2;
+          double lower = log10_C - 0.5 * log10_interval;
+          double z = (log10_conc - lower) / log10_interval, v;
+          if (z < 0.0)
+            v = 0.0;
+          else if (z > 1.0)
+            v = 1.0;
+          else
+            v = 3.0 * (z * z) - 2.0 * (z * z * z);
+          inhibition[ii] = v;
+        } break;
+      }
+      inhibition_terms = inhibition_terms * inhibition[ii];
+    }
+    if (ibiomass != 0) {
+      if (ibiomass > 0) {
+        biomass_conc = concentration[ibiomass - 1];
+        biomass_term = biomass_term * biomass_conc * L_water;
+        dbiomass_conc_dconc = dconcentration_dmolal[ibiomass - 1];
+        ibio_row = ibiomass - 1;
+      } else {
+        int k = -ibiomass - 1;
+        biomass_conc = c->immobile[k];
+        ibio_row = naq + k;
+        biomass_term = biomass_term * biomass_conc * c->volume;
+        dbiomass_conc_dconc = 1.0;
+      }
+      yield = cfg->microbial_biomass_yield[irxn];
+    } else {
+      biomass_term = biomass_term * L_water;
+    }
+    rate = effective_rate_constant * monod_terms * inhibition_terms * biomass_term;
+    for (i = p0; i < p1; i++) {
+      int icomp = cfg->microbial_specid[i];
+      Res[icomp] = Res[icomp] - cfg->microbial_stoich[i] * rate;
+    }
+    if (ibio_row >= 0) Res[ibio_row] = Res[ibio_row] - yield * rate;
+    if (!compute_derivative) continue;
+    for (ii = 0; ii < nmonod; ii++) {
+      int imonod = m0 + ii;
+      int jcomp = cfg->microbial_monod_specid[imonod];
+      double conc = concentration[jcomp], dconc_dmolal = dconcentration_dmolal[jcomp];
+      double dR_dX = effective_rate_constant * inhibition_terms * biomass_term, denominator, dX_dc, dR_dc;
+      for (jj = 0; jj < ii; jj++) dR_dX = dR_dX * monod[jj];
+      for (jj = ii + 1; jj < nmonod; jj++) dR_dX = dR_dX * monod[jj];
+      denominator = cfg->microbial_monod_K[imonod] + conc - cfg->microbial_monod_Cth[imonod];
+      dX_dc = dconc_dmolal / denominator -
+              dconc_dmolal * (conc - cfg->microbial_monod_Cth[imonod]) / (denominator * denominator);
+      dR_dc = -1.0 * dR_dX * dX_dc;
+      for (i = p0; i < p1; i++) {
+        int icomp = cfg->microbial_specid[i];
+        Jac[icomp + jcomp * n] = Jac[icomp + jcomp * n] + cfg->microbial_stoich[i] * dR_dc;
+      }
+      if (ibio_row >= 0) Jac[ibio_row + jcomp * n] = Jac[ibio_row + jcomp * n] + yield * dR_dc;
+    }
+    for (ii = 0; ii < ninh; ii++) {
+      int iinh = h0 + ii;
+      int jcomp = cfg->microbial_inhibition_specid[iinh];
+      double conc = concentration[jcomp], dconc_dmolal = dconcentration_dmolal[jcomp];
+      double C1 = cfg->microbial_inhibition_C[iinh], C2 = cfg->microbial_inhibition_C2[iinh];
+      double dR_dX = effective_rate_constant * monod_terms * biomass_term, denominator, dX_dc, dR_dc, tempreal;
+      for (jj = 0; jj < ii; jj++) dR_dX = dR_dX * inhibition[jj];
+      for (jj = ii + 1; jj < ninh; jj++) dR_dX = dR_dX * inhibition[jj];
+      switch (cfg->microbial_inhibition_type[iinh]) {
+        case PFRX_INHIBITION_MONOD:
+          denominator = C1 + conc;
+          dX_dc = -1.0 * dconc_dmolal * C1 / (denominator * denominator);
+          break;
+        case PFRX_INHIBITION_INVERSE_MONOD:
+          denominator = C1 + conc;
+          dX_dc = dconc_dmolal / denominator - dconc_dmolal * conc / (denominator * denominator);
+          break;
+        case PFRX_INHIBITION_THRESHOLD:
+          tempreal = (conc - fabs(C1)) * C2;
+          dX_dc = copysign(1.0, C1) * (C2 * dconc_dmolal / (1.0 + tempreal * tempreal)) / PI;
+          break;
+        default: {
+          double log10_conc = log10(conc), log10_C = log10(C1), log10_interval = C2;
+          double lower = log10_C - 0.5 * log10_interval;
+          double z = (log10_conc - lower) / log10_interval;
+          if (z < 0.0 || z > 1.0)
+            dX_dc = 0.0;
+          else
+            dX_dc = (6.0 * z - 6.0 * (z * z)) / (log10_interval * conc * LOG_TO_LN) * dconc_dmolal;
+        } break;
+      }
+      dR_dc = -1.0 * dR_dX * dX_dc;
+      for (i = p0; i < p1; i++) {
+        int icomp = cfg->microbial_specid[i];
+        Jac[icomp + jcomp * n] = Jac[icomp + jcomp * n] + cfg->microbial_stoich[i] * dR_dc;
+      }
+      if (ibio_row >= 0) Jac[ibio_row + jcomp * n] = Jac[ibio_row + jcomp * n] + yield * dR_dc;
+    }
+    if (ibio_row >= 0) {
+      double dR_dbiomass = effective_rate_constant * monod_terms * inhibition_terms;
+      dR_dbiomass = -1.0 * dR_dbiomass * dbiomass_conc_dconc;
+      for (i = p0; i < p1; i++) {
+        int icomp = cfg->microbial_specid[i];
+        Jac[icomp + ibio_row * n] = Jac[icomp + ibio_row * n] + cfg->microbial_stoich[i] * dR_dbiomass;
+      }
+      Jac[ibio_row + ibio_row * n] = Jac[ibio_row + ibio_row * n] + yield * dR_dbiomass;
+    }
+  }
+}
+
 /* reaction_immobile.F90:244-296  RImmobileDecay */
 static void r_immobile_decay(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
   int n = c->n, irxn;
@@ -2439,7 +2602,7 @@ static void r_immobile_decay(cell_t *c, const pfrx_config *cfg, double *Res, dou
 }
 
 /* reaction.F90:4059-4130  RReaction (dispatch order preserved: mineral, multirate sorption,
- * [kinetic surface complexation], radioactive decay, general, [microbial], immobile decay,
+ * [kinetic surface complexation], radioactive decay, general, microbial, immobile decay,
  * sandboxes) */
 static void r_reaction(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac, int derivative) {
   if (c->sat < cfg->rt_min_saturation) return;
@@ -2447,6 +2610,7 @@ static void r_reaction(cell_t *c, const pfrx_config *cfg, double tran_dt, double
   if (cfg->nkinmrsrfcplxrxn > 0) r_multirate_sorption(c, cfg, tran_dt, Res, Jac, derivative);
   if (cfg->nradiodecay_rxn > 0) r_radioactive_decay(c, cfg, Res, Jac, derivative);
   if (cfg->ngeneral_rxn > 0) r_general(c, cfg, Res, Jac, derivative);
+  if (cfg->nmicrobial_rxn > 0) r_microbial(c, cfg, Res, Jac, derivative);
   if (cfg->nimmobile_decay_rxn > 0) r_immobile_decay(c, cfg, Res, Jac, derivative);
   if (n_sandboxes(cfg) > 0) r_sandbox_evaluate(c, cfg, tran_dt, Res, Jac, derivative);
 }

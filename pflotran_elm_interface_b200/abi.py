@@ -165,6 +165,24 @@ class PfrxConfig(C.Structure):
         ("nimmobile_decay_rxn", C.c_int32),
         ("immobile_decay_specid", c_int32_p),
         ("immobile_decay_constant", c_double_p),
+        ("nmicrobial_rxn", C.c_int32),
+        ("microbial_concentration_units", C.c_int32),
+        ("microbial_ptr", c_int32_p),
+        ("microbial_specid", c_int32_p),
+        ("microbial_stoich", c_double_p),
+        ("microbial_rate_constant", c_double_p),
+        ("microbial_activation_energy", c_double_p),
+        ("microbial_monod_ptr", c_int32_p),
+        ("microbial_monod_specid", c_int32_p),
+        ("microbial_monod_K", c_double_p),
+        ("microbial_monod_Cth", c_double_p),
+        ("microbial_inhibition_ptr", c_int32_p),
+        ("microbial_inhibition_specid", c_int32_p),
+        ("microbial_inhibition_type", c_int32_p),
+        ("microbial_inhibition_C", c_double_p),
+        ("microbial_inhibition_C2", c_double_p),
+        ("microbial_biomassid", c_int32_p),
+        ("microbial_biomass_yield", c_double_p),
     ]
 
 
@@ -509,6 +527,20 @@ class ReactionConfig:
             c.nimmobile_decay_rxn = len(idc["k"])
             c.immobile_decay_specid = _ip(self._keep("immobile_decay_specid", _i32(idc["specid"])))
             c.immobile_decay_constant = _dp(self._keep("immobile_decay_constant", _f64(idc["k"])))
+
+        mb = getattr(net, "microbial", None)
+        if mb:
+            c.nmicrobial_rxn = len(mb["rate_constant"])
+            c.microbial_concentration_units = mb["units"]
+            for k in ("ptr", "specid", "monod_ptr", "monod_specid", "inhibition_ptr", "inhibition_specid",
+                      "inhibition_type", "biomassid"):
+                setattr(c, "microbial_" + k, _ip(self._keep("microbial_" + k, _i32(mb[k]))))
+            for k in ("stoich", "rate_constant", "monod_K", "monod_Cth", "inhibition_C", "inhibition_C2",
+                      "biomass_yield"):
+                setattr(c, "microbial_" + k, _dp(self._keep("microbial_" + k, _f64(mb[k]))))
+            if any(e > 0.0 for e in mb["activation_energy"]):
+                c.microbial_activation_energy = _dp(self._keep("microbial_activation_energy",
+                                                               _f64(mb["activation_energy"])))
 
         # CLM-CN
         cc = net.clmcn

@@ -376,6 +376,8 @@ class Chemistry:
     general_rxns: List[dict] = field(default_factory=list)       # {reaction, kf, kr}
     radiodecay_rxns: List[dict] = field(default_factory=list)    # {reaction, k}
     immobile_decay_rxns: List[dict] = field(default_factory=list)  # {species, k}
+    microbial_rxns: List[dict] = field(default_factory=list)
+    microbial_units: int = 0        # 0 = not set -> MOLARITY (reaction_microbial.F90:233)
     unsupported: List[str] = field(default_factory=list)
 
 
@@ -849,15 +851,82 @@ def _read_kinetic_rxn_block(cur: "_Cursor", kind: str) -> dict:
         elif key == "SPECIES_NAME":
             r["species"] = t[1]
         elif key == "FORWARD_RATE":
-            r["kf"] = _fnum(t[1])      # kg^(n-1)/mol^(n-1)-sec; other units are not converted here
+            r["kf"] = _per_time(t, 1)  # kg^(n-1)/mol^(n-1)-sec; only 1/<time> units are converted here
         elif key == "BACKWARD_RATE":
-            r["kr"] = _fnum(t[1])
+            r["kr"] = _per_time(t, 1)
         elif key == "RATE_CONSTANT":
             r["k"] = _per_time(t, 1)
         elif key == "HALF_LIFE":
             r["k"] = -1.0 * math.log(0.5) / time_to_sec(_fnum(t[1]), t[2] if len(t) > 2 else "s")
         else:
             raise ValueError(f"{kind}: keyword {key} not supported")
+    return r
+
+
+MICROBIAL_UNITS = {"MOLALITY": 1, "ACTIVITY": 2, "MOLARITY": 3}
+INHIBITION_TYPES = {"THRESHOLD": 1, "MONOD": 3, "INVERSE_MONOD": 4, "SMOOTHSTEP": 5}
+_ENERGY_UNITS = {"j/mol": 1.0, "kj/mol": 1.0e3, "cal/mol": 4.184, "kcal/mol": 4184.0}
+
+
+def _read_microbial_rxn(cur: "_Cursor", ch: "Chemistry") -> dict:
+    """MICROBIAL_REACTION block (MicrobialRead, reaction_microbial.F90:40-282)"""
+    r = {"reaction": "", "rate_constant": 0.0, "activation_energy": 0.0, "monod": [], "inhibition": [],
+         "biomass": None, "yield": 0.0}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "REACTION":
+            r["reaction"] = " ".join(t[1:])
+        elif key == "CONCENTRATION_UNITS":
+            u = MICROBIAL_UNITS[t[1].upper()]
+            if ch.microbial_units and ch.microbial_units != u:
+                raise ValueError("Concentration units must be consistent for all microbial reactions")
+            ch.microbial_units = u
+        elif key == "RATE_CONSTANT":
+            if len(t) > 2 and not t[2].startswith(("!", "#")):
+                raise ValueError("MICROBIAL_REACTION RATE_CONSTANT with units is not supported")
+            r["rate_constant"] = _fnum(t[1])
+        elif key == "ACTIVATION_ENERGY":
+            u = t[2].lower() if len(t) > 2 and not t[2].startswith(("!", "#")) else "j/mol"
+            r["activation_energy"] = _fnum(t[1]) * _ENERGY_UNITS[u]
+        elif key == "MONOD":
+            m = {"species": "", "K": 0.0, "Cth": 0.0}
+            for u in cur.block():
+                k2 = u[0].upper()
+                if k2 == "SPECIES_NAME":
+                    m["species"] = u[1]
+                elif k2 == "HALF_SATURATION_CONSTANT":
+                    m["K"] = _fnum(u[1])
+                elif k2 == "THRESHOLD_CONCENTRATION":
+                    m["Cth"] = _fnum(u[1])
+                else:
+                    raise ValueError(f"MICROBIAL_REACTION,MONOD: keyword {k2} not supported")
+            r["monod"].append(m)
+        elif key == "INHIBITION":
+            h = {"species": "", "type": 0, "C": 0.0, "C2": 0.0}
+            for u in cur.block():
+                k2 = u[0].upper()
+                if k2 == "SPECIES_NAME":
+                    h["species"] = u[1]
+                elif k2 == "TYPE":
+                    h["type"] = INHIBITION_TYPES[u[1].upper()]
+                    if h["type"] in (1, 5):
+                        h["C2"] = _fnum(u[2])
+                elif k2 == "INHIBITION_CONSTANT":
+                    h["C"] = _fnum(u[1])
+                else:
+                    raise ValueError(f"MICROBIAL_REACTION,INHIBITION: keyword {k2} not supported")
+            if not h["type"]:
+                raise ValueError("MICROBIAL_REACTION,INHIBITION needs a TYPE")
+            r["inhibition"].append(h)
+        elif key == "BIOMASS":
+            for u in cur.block():
+                k2 = u[0].upper()
+                if k2 == "SPECIES_NAME":
+                    r["biomass"] = u[1]
+                elif k2 == "YIELD":
+                    r["yield"] = _fnum(u[1])
+        else:
+            raise ValueError(f"MICROBIAL_REACTION: keyword {key} not supported")
     return r
 
 
@@ -905,6 +974,8 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
             ch.mineral_kinetics = _read_mineral_kinetics(cur)
         elif key == "GENERAL_REACTION":
             ch.general_rxns.append(_read_kinetic_rxn_block(cur, key))
+        elif key == "MICROBIAL_REACTION":
+            ch.microbial_rxns.append(_read_microbial_rxn(cur, ch))
         elif key == "RADIOACTIVE_DECAY_REACTION":
             r = _read_kinetic_rxn_block(cur, key)
             if r["k"] is None:
@@ -1459,6 +1530,41 @@ class ReactionNetwork:
                 ptr.append(len(ids))
             self.radiodecay = dict(ptr=ptr, specid=ids, stoich=st, forward_specid=fwd,
                                    kf=[r["k"] for r in self.chem.radiodecay_rxns])
+        self.microbial = None
+        if self.chem.microbial_rxns:
+            ptr, ids, st, mptr, mid, mK, mC = [0], [], [], [0], [], [], []
+            iptr, iid, ityp, iC, iC2, bio, yld = [0], [], [], [], [], [], []
+            for r in self.chem.microbial_rxns:
+                names = []
+                for nm, v in parse_reaction_string(r["reaction"]):
+                    ids.append(pri[nm]); st.append(v); names.append(nm)
+                ptr.append(len(ids))
+                for m in r["monod"]:
+                    if m["species"] not in names:
+                        raise ValueError(f"Monod species {m['species']} not found in microbial reaction")
+                    mid.append(pri[m["species"]]); mK.append(m["K"]); mC.append(m["Cth"])
+                mptr.append(len(mid))
+                for h in r["inhibition"]:
+                    iid.append(pri[h["species"]]); ityp.append(h["type"]); iC.append(h["C"]); iC2.append(h["C2"])
+                iptr.append(len(iid))
+                b = r["biomass"]
+                if b is None:
+                    bio.append(0)
+                elif b in pri:
+                    bio.append(pri[b] + 1)
+                elif b in imm:
+                    bio.append(-(imm[b] + 1))
+                else:
+                    raise ValueError(f"Biomass species {b} not found among the primary aqueous or immobile species")
+                if b is not None and b in names:
+                    raise ValueError(f"Biomass species {b} should not be included in the microbial reaction")
+                yld.append(r["yield"])
+            self.microbial = dict(units=self.chem.microbial_units or 3, ptr=ptr, specid=ids, stoich=st,
+                                  rate_constant=[r["rate_constant"] for r in self.chem.microbial_rxns],
+                                  activation_energy=[r["activation_energy"] for r in self.chem.microbial_rxns],
+                                  monod_ptr=mptr, monod_specid=mid, monod_K=mK, monod_Cth=mC,
+                                  inhibition_ptr=iptr, inhibition_specid=iid, inhibition_type=ityp,
+                                  inhibition_C=iC, inhibition_C2=iC2, biomassid=bio, biomass_yield=yld)
         if self.chem.immobile_decay_rxns:
             self.immdecay = dict(specid=[imm[r["species"]] for r in self.chem.immobile_decay_rxns],
                                  k=[r["k"] for r in self.chem.immobile_decay_rxns])

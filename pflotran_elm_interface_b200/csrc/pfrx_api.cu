@@ -205,9 +205,9 @@ static uint64_t config_signature(const pfrx_config *c) {
     int32_t hi[4] = {c->neqionxrxn, c->neqkdrxn, c->neqdynamickdrxn, c->ikd_units};
     h = fnv1a(h, hi, sizeof(hi));
   }
-  if (c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0) {
+  if (c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0 || c->nmicrobial_rxn > 0) {
     // not covered by the generator either
-    int32_t hi[3] = {c->ngeneral_rxn, c->nradiodecay_rxn, c->nimmobile_decay_rxn};
+    int32_t hi[4] = {c->ngeneral_rxn, c->nradiodecay_rxn, c->nimmobile_decay_rxn, c->nmicrobial_rxn};
     h = fnv1a(h, hi, sizeof(hi));
   }
   // ELM-CN sandboxes: every parameter the generated code bakes in
@@ -619,9 +619,46 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
                                  !c->eqdynamickd_low || !c->eqdynamickd_high || !c->eqdynamickd_power))
     return set_err(PFRX_E_INVALID, "dynamic KD tables missing%s", "");
   // general kinetic reactions, radioactive decay, immobile decay
-  const bool has_kin3 = c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0;
-  if (c->ngeneral_rxn < 0 || c->nradiodecay_rxn < 0 || c->nimmobile_decay_rxn < 0)
+  const bool has_kin3 =
+      c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0 || c->nmicrobial_rxn > 0;
+  if (c->ngeneral_rxn < 0 || c->nradiodecay_rxn < 0 || c->nimmobile_decay_rxn < 0 || c->nmicrobial_rxn < 0)
     return set_err(PFRX_E_INVALID, "negative reaction count%s", "");
+  if (c->nmicrobial_rxn > 0) {
+    const int nr = c->nmicrobial_rxn;
+    if (!c->microbial_ptr || !c->microbial_specid || !c->microbial_stoich || !c->microbial_rate_constant ||
+        !c->microbial_monod_ptr || !c->microbial_inhibition_ptr || !c->microbial_biomassid ||
+        !c->microbial_biomass_yield)
+      return set_err(PFRX_E_INVALID, "microbial reaction tables missing%s", "");
+    if (c->microbial_monod_ptr[nr] > 0 && (!c->microbial_monod_specid || !c->microbial_monod_K || !c->microbial_monod_Cth))
+      return set_err(PFRX_E_INVALID, "microbial reaction Monod tables missing%s", "");
+    if (c->microbial_inhibition_ptr[nr] > 0 && (!c->microbial_inhibition_specid || !c->microbial_inhibition_type ||
+                                                !c->microbial_inhibition_C || !c->microbial_inhibition_C2))
+      return set_err(PFRX_E_INVALID, "microbial reaction inhibition tables missing%s", "");
+    if (c->microbial_concentration_units < PFRX_MICROBIAL_MOLALITY ||
+        c->microbial_concentration_units > PFRX_MICROBIAL_MOLARITY)
+      return set_err(PFRX_E_INVALID, "microbial_concentration_units%s", "");
+    for (int k = 0; k < c->microbial_ptr[nr]; k++)
+      if (c->microbial_specid[k] < 0 || c->microbial_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "microbial reaction species id out of range%s", "");
+    for (int k = 0; k < c->microbial_monod_ptr[nr]; k++)
+      if (c->microbial_monod_specid[k] < 0 || c->microbial_monod_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "microbial reaction species id out of range%s", "");
+    for (int k = 0; k < c->microbial_inhibition_ptr[nr]; k++) {
+      if (c->microbial_inhibition_specid[k] < 0 || c->microbial_inhibition_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "microbial reaction species id out of range%s", "");
+      const int t = c->microbial_inhibition_type[k];
+      if (t != PFRX_INHIBITION_THRESHOLD && t != PFRX_INHIBITION_MONOD && t != PFRX_INHIBITION_INVERSE_MONOD &&
+          t != PFRX_INHIBITION_SMOOTHSTEP)
+        return set_err(PFRX_E_INVALID, "microbial reaction inhibition type%s", "");
+    }
+    for (int r = 0; r < nr; r++) {
+      if (c->microbial_monod_ptr[r + 1] - c->microbial_monod_ptr[r] > PFRX_MAX_MONOD_TERMS ||
+          c->microbial_inhibition_ptr[r + 1] - c->microbial_inhibition_ptr[r] > PFRX_MAX_MONOD_TERMS)
+        return set_err(PFRX_E_LIMIT, "more than 8 Monod / inhibition terms in a microbial reaction%s", "");
+      const int b = c->microbial_biomassid[r];
+      if (b > c->naqcomp || -b > c->nimcomp) return set_err(PFRX_E_INVALID, "microbial biomass species id%s", "");
+    }
+  }
   if (c->ngeneral_rxn > 0) {
     if (!c->general_ptr || !c->general_specid || !c->general_stoich || !c->general_fwd_ptr || !c->general_fwd_specid ||
         !c->general_fwd_stoich || !c->general_bwd_ptr || !c->general_bwd_specid || !c->general_bwd_stoich ||
@@ -762,6 +799,8 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.ngen = c->ngeneral_rxn;
   d.nrd = c->nradiodecay_rxn;
   d.nidc = c->nimmobile_decay_rxn;
+  d.nmb = c->nmicrobial_rxn;
+  d.mb_units = c->microbial_concentration_units;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
     static const int def_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
@@ -1055,6 +1094,26 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->radiodecay_stoich, c->radiodecay_ptr[nr], &d.rd_st);
     A.add(c->radiodecay_forward_specid, nr, &d.rd_fwd);
     A.add(c->radiodecay_kf, nr, &d.rd_kf);
+  }
+  if (c->nmicrobial_rxn > 0) {
+    const int nr = c->nmicrobial_rxn, ns = c->microbial_ptr[nr], nm = c->microbial_monod_ptr[nr],
+              nh = c->microbial_inhibition_ptr[nr];
+    A.add(c->microbial_ptr, nr + 1, &d.mb_ptr);
+    A.add(c->microbial_specid, ns, &d.mb_id);
+    A.add(c->microbial_stoich, ns, &d.mb_st);
+    A.add(c->microbial_rate_constant, nr, &d.mb_k);
+    A.add(c->microbial_activation_energy, c->microbial_activation_energy ? nr : 0, &d.mb_ea);
+    A.add(c->microbial_monod_ptr, nr + 1, &d.mb_mptr);
+    A.add(c->microbial_monod_specid, nm, &d.mb_mid);
+    A.add(c->microbial_monod_K, nm, &d.mb_mK);
+    A.add(c->microbial_monod_Cth, nm, &d.mb_mC);
+    A.add(c->microbial_inhibition_ptr, nr + 1, &d.mb_hptr);
+    A.add(c->microbial_inhibition_specid, nh, &d.mb_hid);
+    A.add(c->microbial_inhibition_type, nh, &d.mb_htype);
+    A.add(c->microbial_inhibition_C, nh, &d.mb_hC);
+    A.add(c->microbial_inhibition_C2, nh, &d.mb_hC2);
+    A.add(c->microbial_biomassid, nr, &d.mb_bio);
+    A.add(c->microbial_biomass_yield, nr, &d.mb_yield);
   }
   if (c->nimmobile_decay_rxn > 0) {
     A.add(c->immobile_decay_specid, c->nimmobile_decay_rxn, &d.idc_id);
@@ -1976,7 +2035,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   const DevCfg &d = h->cfg;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0)
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();
   if (rc) return rc;

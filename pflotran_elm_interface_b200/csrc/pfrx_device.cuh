@@ -97,6 +97,10 @@ struct DevCfg {
   const double *rd_st, *rd_kf;
   const int *idc_id;
   const double *idc_k;
+  // Monod-type microbial reactions (thread-per-cell kernel)
+  int nmb, mb_units;
+  const int *mb_ptr, *mb_id, *mb_mptr, *mb_mid, *mb_hptr, *mb_hid, *mb_htype, *mb_bio;
+  const double *mb_st, *mb_k, *mb_ea, *mb_mK, *mb_mC, *mb_hC, *mb_hC2, *mb_yield;
   int n_ixcat;  // cations of all ion-exchange reactions
   int off_ix;   // workspace: reference-cation sorbed concentrations, then cation concentrations
   const int *eqsr;

@@ -545,6 +545,132 @@ struct CellT {
     }
   }
 
+  // ---- RMicrobial (reaction_microbial.F90:287-602): rate = k * prod(Monod) * prod(inhibition) *
+  // biomass; the biomass column of the Jacobian as written there (:578-583, no L_water / volume) ----
+  __device__ __forceinline__ double mb_conc(int i, double &dcdm) {
+    dcdm = cfg.mb_units == PFRX_MICROBIAL_MOLALITY ? 1.0
+           : cfg.mb_units == PFRX_MICROBIAL_ACTIVITY ? pref_act_coef(i)
+                                                     : den_kg * 1.e-3;
+    return C(i) * dcdm;
+  }
+  __device__ __forceinline__ double mb_inhibition(int h, double conc, double dcdm, double &dX) {
+    const double PI = 3.14159265359;  // pflotran_constants.F90:92, truncated as there
+    const double C1 = cfg.mb_hC[h], C2 = cfg.mb_hC2[h];
+    const int type = cfg.mb_htype[h];
+    if (type == PFRX_INHIBITION_MONOD) {
+      const double den = C1 + conc;
+      dX = -1.0 * dcdm * C1 / (den * den);
+      return C1 / (C1 + conc);
+    }
+    if (type == PFRX_INHIBITION_INVERSE_MONOD) {
+      const double den = C1 + conc;
+      dX = dcdm / den - dcdm * conc / (den * den);
+      return conc / (C1 + conc);
+    }
+    if (type == PFRX_INHIBITION_THRESHOLD) {
+      const double t = (conc - fabs(C1)) * C2;
+      dX = copysign(1.0, C1) * (C2 * dcdm / (1.0 + t * t)) / PI;
+      return 0.5 + copysign(1.0, C1) * atan(t) / PI;
+    }
+    const double lower = log10(C1) - 0.5 * C2;
+    const double z = (log10(conc) - lower) / C2;
+    if (z < 0.0) {
+      dX = 0.0;
+      return 0.0;
+    }
+    if (z > 1.0) {
+      dX = 0.0;
+      return 1.0;
+    }
+    dX = (6.0 * z - 6.0 * (z * z)) / (C2 * conc * 2.30258509299) * dcdm;
+    return 3.0 * (z * z) - 2.0 * (z * z * z);
+  }
+  __device__ __forceinline__ void microbial() {
+    const int naq = cfg.naq;
+    const double L_water = por * sat * vol * 1.e3;
+#pragma unroll 1
+    for (int r = 0; r < cfg.nmb; r++) {
+      const int p0 = cfg.mb_ptr[r], p1 = cfg.mb_ptr[r + 1];
+      const int m0 = cfg.mb_mptr[r], nm = cfg.mb_mptr[r + 1] - m0;
+      const int h0 = cfg.mb_hptr[r], nh = cfg.mb_hptr[r + 1] - h0;
+      double k_eff = cfg.mb_k[r];
+      if (cfg.mb_ea) k_eff = k_eff * exp(cfg.mb_ea[r] / 8.31446 * (1.0 / 298.15 - 1.0 / (temp + 273.15)));
+      double monod[PFRX_MAX_MONOD_TERMS], inhib[PFRX_MAX_MONOD_TERMS];
+      double monod_terms = 1.0, inhib_terms = 1.0, d;
+#pragma unroll 1
+      for (int ii = 0; ii < nm; ii++) {
+        const double conc = mb_conc(cfg.mb_mid[m0 + ii], d);
+        const double cth = cfg.mb_mC[m0 + ii];
+        monod[ii] = (conc - cth) / (cfg.mb_mK[m0 + ii] + conc - cth);
+        monod_terms = monod_terms * monod[ii];
+      }
+#pragma unroll 1
+      for (int ii = 0; ii < nh; ii++) {
+        double dcdm, dX;
+        const double conc = mb_conc(cfg.mb_hid[h0 + ii], dcdm);
+        inhib[ii] = mb_inhibition(h0 + ii, conc, dcdm, dX);
+        inhib_terms = inhib_terms * inhib[ii];
+      }
+      const int ib = cfg.mb_bio[r];
+      int brow = -1;
+      double biomass_term = 1.0, yield = 0.0, dbio = 0.0;
+      if (ib > 0) {
+        const double bc = mb_conc(ib - 1, dbio);
+        biomass_term = biomass_term * bc * L_water;
+        brow = ib - 1;
+        yield = cfg.mb_yield[r];
+      } else if (ib < 0) {
+        brow = naq + (-ib - 1);
+        biomass_term = biomass_term * C(brow) * vol;
+        dbio = 1.0;
+        yield = cfg.mb_yield[r];
+      } else {
+        biomass_term = biomass_term * L_water;
+      }
+      const double rate = k_eff * monod_terms * inhib_terms * biomass_term;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) RES(cfg.mb_id[p]) = RES(cfg.mb_id[p]) - cfg.mb_st[p] * rate;
+      if (brow >= 0) RES(brow) = RES(brow) - yield * rate;
+#pragma unroll 1
+      for (int ii = 0; ii < nm; ii++) {
+        const int jc = cfg.mb_mid[m0 + ii];
+        double dcdm;
+        const double conc = mb_conc(jc, dcdm);
+        double dR_dX = k_eff * inhib_terms * biomass_term;
+        for (int jj = 0; jj < ii; jj++) dR_dX = dR_dX * monod[jj];
+        for (int jj = ii + 1; jj < nm; jj++) dR_dX = dR_dX * monod[jj];
+        const double cth = cfg.mb_mC[m0 + ii];
+        const double den = cfg.mb_mK[m0 + ii] + conc - cth;
+        const double dX = dcdm / den - dcdm * (conc - cth) / (den * den);
+        const double dR_dc = -1.0 * dR_dX * dX;
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) J(cfg.mb_id[p], jc) = J(cfg.mb_id[p], jc) + cfg.mb_st[p] * dR_dc;
+        if (brow >= 0) J(brow, jc) = J(brow, jc) + yield * dR_dc;
+      }
+#pragma unroll 1
+      for (int ii = 0; ii < nh; ii++) {
+        const int jc = cfg.mb_hid[h0 + ii];
+        double dcdm, dX;
+        const double conc = mb_conc(jc, dcdm);
+        double dR_dX = k_eff * monod_terms * biomass_term;
+        for (int jj = 0; jj < ii; jj++) dR_dX = dR_dX * inhib[jj];
+        for (int jj = ii + 1; jj < nh; jj++) dR_dX = dR_dX * inhib[jj];
+        (void)mb_inhibition(h0 + ii, conc, dcdm, dX);
+        const double dR_dc = -1.0 * dR_dX * dX;
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) J(cfg.mb_id[p], jc) = J(cfg.mb_id[p], jc) + cfg.mb_st[p] * dR_dc;
+        if (brow >= 0) J(brow, jc) = J(brow, jc) + yield * dR_dc;
+      }
+      if (brow >= 0) {
+        double dRb = k_eff * monod_terms * inhib_terms;
+        dRb = -1.0 * dRb * dbio;
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) J(cfg.mb_id[p], brow) = J(cfg.mb_id[p], brow) + cfg.mb_st[p] * dRb;
+        J(brow, brow) = J(brow, brow) + yield * dRb;
+      }
+    }
+  }
+
   // ---- RImmobileDecay (reaction_immobile.F90:244-296) ------------------------------------------
   __device__ __forceinline__ void immobile_decay() {
     const int naq = cfg.naq;
@@ -1154,6 +1280,7 @@ struct CellT {
         if (cfg.nmr > 0) multirate(dt);
         if (cfg.nrd > 0) radioactive_decay();
         if (cfg.ngen > 0) general_reactions();
+        if (cfg.nmb > 0) microbial();
         if (cfg.nidc > 0) immobile_decay();
         if (cfg.nsbx > 0) sandboxes(dt);
       }
@@ -1288,7 +1415,8 @@ struct CellT {
       if (i < naq) {
         double cc = st.pri_molal[i * ld + c];
         C(i) = cc;
-        LNA(i) = log(cc) + log(st.pri_act_coef[i * ld + c]);
+        lngam[i] = log(st.pri_act_coef[i * ld + c]);
+        LNA(i) = log(cc) + lngam[i];
         INVC(i) = 1.0 / cc;
       } else if (i < n) {
         C(i) = st.immobile[(i - naq) * ld + c];
@@ -1306,6 +1434,7 @@ struct CellT {
       if (cfg.need_dt) dtotal_from_state();
       if (cfg.nrd > 0) radioactive_decay();
       if (cfg.ngen > 0) general_reactions();
+      if (cfg.nmb > 0) microbial();
       if (cfg.nidc > 0) immobile_decay();
       if (cfg.nsbx > 0) {
         sandbox_load(c);

@@ -176,8 +176,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
     if c.neqionxrxn > 0 or c.neqkdrxn > 0 or c.neqdynamickdrxn > 0:
         return False, "ion exchange / KD isotherms"
-    if c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0:
-        return False, "general / radioactive decay / immobile decay reactions"
+    if c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0 or c.nmicrobial_rxn > 0:
+        return False, "general / radioactive decay / immobile decay / microbial reactions"
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         if os.environ.get("PFRX_SPEC_NO_ELMCN"):
             return False, "ELM-CN sandboxes disabled by PFRX_SPEC_NO_ELMCN"

@@ -737,6 +737,140 @@ def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SE
                     "2 general reactions, 1 radioactive decay with daughter, 1 immobile decay, 1 complex")
 
 
+C8_DECK = """
+# C8: Monod-type microbial reactions (the ABCD network of default/batch/ABCD_microbial*.in):
+# immobile biomass with yield and decay, a second reaction on aqueous biomass, all four inhibition
+# types, activation energy, concentrations as activities with Debye-Hueckel coefficients
+CHEMISTRY
+  PRIMARY_SPECIES
+    A(aq)
+    B(aq)
+    C(aq)
+    D(aq)
+    Na+
+    Cl-
+  /
+  IMMOBILE_SPECIES
+    D(im)
+  /
+  MICROBIAL_REACTION
+    CONCENTRATION_UNITS ACTIVITY
+    REACTION A(aq) + 2 B(aq) <-> 1.5 C(aq)
+    RATE_CONSTANT 1.d-6
+    ACTIVATION_ENERGY 6.5d0 kJ/mol
+    MONOD
+      SPECIES_NAME A(aq)
+      HALF_SATURATION_CONSTANT 1.d-5
+      THRESHOLD_CONCENTRATION 1.d-20
+    /
+    MONOD
+      SPECIES_NAME B(aq)
+      HALF_SATURATION_CONSTANT 1.d-4
+      THRESHOLD_CONCENTRATION 1.d-11
+    /
+    INHIBITION
+      SPECIES_NAME C(aq)
+      TYPE THRESHOLD 1.d5
+      INHIBITION_CONSTANT -1.d-4
+    /
+    INHIBITION
+      SPECIES_NAME Cl-
+      TYPE MONOD
+      INHIBITION_CONSTANT 5.d-2
+    /
+    BIOMASS
+      SPECIES_NAME D(im)
+      YIELD 0.01d0
+    /
+  /
+  MICROBIAL_REACTION
+    CONCENTRATION_UNITS ACTIVITY
+    REACTION C(aq) <-> 0.5 A(aq)
+    RATE_CONSTANT 2.d-4
+    MONOD
+      SPECIES_NAME C(aq)
+      HALF_SATURATION_CONSTANT 2.d-4
+    /
+    INHIBITION
+      SPECIES_NAME A(aq)
+      TYPE INVERSE_MONOD
+      INHIBITION_CONSTANT 6.d-4
+    /
+    INHIBITION
+      SPECIES_NAME B(aq)
+      TYPE SMOOTHSTEP 1.5
+      INHIBITION_CONSTANT 3.d-4
+    /
+    BIOMASS
+      SPECIES_NAME D(aq)
+      YIELD 0.05d0
+    /
+  /
+  GENERAL_REACTION
+    REACTION D(aq) <->
+    FORWARD_RATE 60.d-9 1/min
+    BACKWARD_RATE 0.d0
+  /
+  IMMOBILE_DECAY_REACTION
+    SPECIES_NAME D(im)
+    RATE_CONSTANT 1.d-9
+  /
+  DATABASE ./hanford_subset.dat
+  LOG_FORMULATION
+  ACTIVITY_COEFFICIENTS TIMESTEP
+END
+CONSTRAINT initial
+  CONCENTRATIONS
+    A(aq)  1.d-4 T
+    B(aq)  1.d-3 T
+    C(aq)  1.d-7 T
+    D(aq)  1.d-5 T
+    Na+    5.d-2 T
+    Cl-    5.d-2 Z
+  /
+  IMMOBILE
+    D(im) 1.d-4
+  /
+END
+CONSTRAINT inlet
+  CONCENTRATIONS
+    A(aq)  2.d-3 T
+    B(aq)  3.d-4 T
+    C(aq)  4.d-4 T
+    D(aq)  1.d-7 T
+    Na+    1.d-3 T
+    Cl-    1.d-3 Z
+  /
+  IMMOBILE
+    D(im) 1.d-6
+  /
+END
+"""
+
+
+def microbial(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED) -> Workload:
+    """C8: RMicrobial with every option, next to a general reaction and an immobile decay"""
+    rng = np.random.default_rng(seed)
+    dk, net = chem.load_network(C8_DECK, _read("hanford_subset.dat"))
+    assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67(25.0)
+    waters = [constraint.equilibrate_constraint(net, dk.constraints[k], den_kg=den, porosity=0.3)
+              for k in ("initial", "inlet")]
+    st = abi.HostState(cfg, ncell)
+    f = rng.random(ncell)
+    _mix_fill(st, waters, np.stack([1.0 - f, f]), rng, jitter=0.0)
+    st["immobile"][...] = (10.0 ** rng.uniform(-6.0, -3.0, ncell))[None, :]
+    st["den_kg"][...] = den
+    st["porosity"][...] = 0.3
+    st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
+    st["sat"][...] = rng.uniform(0.4, 1.0, ncell)
+    st["temp"][...] = rng.uniform(5.0, 35.0, ncell)
+    return Workload("c8_microbial", cfg, st, tran_dt, net,
+                    "2 microbial reactions (4 inhibition types, immobile and aqueous biomass, activation energy), "
+                    "1 general reaction, 1 immobile decay")
+
+
 def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = None) -> Workload:
     table = {
         "c1": (calcite_batch, {}),
@@ -753,6 +887,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c5": (hanford, {"variant": "minerals"}),
         "c6": (ion_exchange, {}),
         "c7": (general_decay, {}),
+        "c8": (microbial, {}),
     }
     fn, kw = table[name]
     kw = dict(kw)
@@ -810,6 +945,13 @@ def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
         f += sum(4.0 + (rd["ptr"][k + 1] - rd["ptr"][k]) * (2.0 + 4.0 * naq) for k in range(len(rd["kf"])))
     if getattr(net, "immdecay", None):
         f += 4.0 * len(net.immdecay["k"])
+    mb = getattr(net, "microbial", None)
+    if mb:
+        for k in range(len(mb["rate_constant"])):
+            nm = mb["monod_ptr"][k + 1] - mb["monod_ptr"][k]
+            nh = mb["inhibition_ptr"][k + 1] - mb["inhibition_ptr"][k]
+            ns = mb["ptr"][k + 1] - mb["ptr"][k]
+            f += 30.0 + 12.0 * nm + 40.0 * nh + (nm + nh + 1) * (2.0 * ns + 12.0)
     f += 10.0 * n
     solve = (2.0 / 3.0) * n ** 3 + 5.0 * n * n + 20.0 * n
     return f, solve

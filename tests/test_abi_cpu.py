@@ -115,6 +115,11 @@ def test_unsupported_configurations_are_refused_not_approximated():
     cfg.arrays["general_fwd_specid"][0] = 17
     rc, msg = _create_rc(cfg)
     assert rc == 1 and "general reaction" in msg
+    # a microbial reaction with an inhibition type that does not exist
+    cfg = workloads.by_name("c8", ncell=1).cfg
+    cfg.arrays["microbial_inhibition_type"][0] = 2
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "inhibition type" in msg
     # a sandbox list naming a sandbox that does not exist
     cfg = workloads.by_name("c4s", ncell=1).cfg
     cfg.arrays["sandbox_list"][0] = 99

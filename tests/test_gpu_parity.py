@@ -161,6 +161,41 @@ def test_c7_general_decay_reactions(dt, host):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("dt,host", [(3600.0, True), (86400.0, False), (10 * 86400.0, False)])
+def test_c8_microbial_reactions(dt, host):
+    """RMicrobial in the thread-per-cell kernel: Monod terms with thresholds, THRESHOLD / MONOD /
+    INVERSE_MONOD / SMOOTHSTEP inhibition, immobile and aqueous biomass, activation energy over a range
+    of cell temperatures, activities as concentrations (the network of the ABCD_microbial golds)"""
+    wl = W.by_name("c8", ncell=5000, tran_dt=dt)
+    wl.state.a["imat"][0, 5] = 0
+    wl.state.a["sat"][0, 6] = 1.0e-50
+    ref, rr, got, rg, info = _run_both(wl, host_path=host)
+    assert info["lanes"] in (0, 1)
+    _compare(ref, got, f"c8 dt={dt}")
+    _check_summary(rr, rg)
+
+
+@pytest.mark.parametrize("name", ["ABCD_microbial", "ABCD_microbial_aq_biomass", "ABCD_microbial_activation_high"])
+def test_microbial_gold_decks_one_step_on_the_gpu(name):
+    """the reference's own ABCD_microbial decks as single-cell RStep inputs: the CUDA path against the
+    oracle (which test_oracle_golden pins to the golds over the whole 25 y run)"""
+    import test_oracle_golden as tg
+
+    rstep = _gpu()
+    dk, net, cfg, st = tg._setup(name + ".in", "hanford_subset.dat")
+    for dt in (3600.0, 0.25 * 365 * 86400.0):
+        ref = st.copy()
+        res_ref = orc.rstep(cfg, ref, dt)
+        step = rstep.ChemistryStep(cfg, 0)
+        dev = rstep.DeviceState.from_host(st, "cuda:0")
+        step.bind(dev)
+        res = step.rstep(dt)
+        got = dev.to_host()
+        step.close()
+        _check_summary(res_ref, res)
+        _compare(ref, got, f"{name} dt={dt}")
+
+
 @pytest.mark.parametrize("variant,dt", [("c3", 3600.0), ("c3", 30 * 86400.0), ("c3mr", 3600.0), ("c5", 86400.0)])
 def test_hanford(variant, dt):
     wl = W.by_name(variant, ncell=3000, tran_dt=dt)
@@ -189,14 +224,14 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se", "c4fe", "c7"])
+@pytest.mark.parametrize("variant", ["c2", "c5", "c4", "c4s", "c4se", "c4fe", "c7", "c8"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
 
     rstep = _gpu()
     wl = W.by_name(variant, ncell=300)
-    if variant.startswith("c4") or variant == "c7":
+    if variant.startswith("c4") or variant in ("c7", "c8"):
         wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
         wl.state.a["sat"][0, 9] = 1.0e-50
     ref = wl.state.copy()

@@ -29,6 +29,7 @@ def _setup(deck, db, cons="initial"):
     constraint.fill_cells(st, sp)
     st["den_kg"][:] = den
     st["porosity"][:] = por
+    st["temp"][:] = dk.reference_temperature
     # CondControlAssignRTTranInitCond (condition_control.F90:1636-1650): cells
     # start from the constraint's free-ion molalities with activity
     # coefficients = 1, then RTotal, then two (act. coef., RTotal) sweeps
@@ -331,3 +332,34 @@ def test_general_reaction_gold():
     for nm in ("A(aq)", "B(aq)"):
         i = net.primary_names.index(nm)
         _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")
+
+
+MICROBIAL_GOLDS = ["ABCD_microbial", "ABCD_microbial_activation_high", "ABCD_microbial_activation_low",
+                   "ABCD_microbial_activity", "ABCD_microbial_aq_biomass", "ABCD_microbial_molality",
+                   "ABCD_microbial_molarity"]
+
+
+@pytest.mark.parametrize("name", MICROBIAL_GOLDS)
+def test_microbial_gold(name):
+    """default/batch/AB*_microbial*: RMicrobial (reaction_microbial.F90:287-602) -- Monod terms with
+    thresholds, THRESHOLD / INVERSE_MONOD inhibition, immobile and aqueous biomass with yield, activation
+    energy at 35 C, the three concentration units -- next to RImmobileDecay or a first-order
+    GENERAL_REACTION for the biomass decay; 25 y in ~110 steps.  batch.cfg: 1e-12 relative; step and
+    Newton iteration counts must match too.  (AB_microbial_linear_scaling / _truncation exercise the
+    GIRT solver's ITOL_RELATIVE_UPDATE test and update truncation, not the chemistry: not replayed.)"""
+    dk, net, cfg, st = _setup(name + ".in", "hanford_subset.dat")
+    assert cfg.c.nmicrobial_rxn == 1
+    run = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold(name + ".regression.gold")
+    sol = gold["SOLUTION: Transport"]
+    assert run.cuts == 0
+    assert run.steps == int(sol["Time Steps"]), (run.steps, sol["Time Steps"])
+    assert run.newton_its == int(sol["Newton Iterations"]), (run.newton_its, sol["Newton Iterations"])
+    to_print = 1000.0 / st["den_kg"][0, 0] if dk.chemistry.initialize_with_molality else 1.0
+    for title, sec in gold.items():
+        if title.startswith("CONCENTRATION: Total "):
+            i = net.primary_names.index(title[len("CONCENTRATION: Total "):])
+            _check_rel(st["total"][i, 0] * to_print, sec["1"], 1.0e-12, f"{name} {title}")
+        elif title.startswith("CONCENTRATION: "):
+            i = net.immobile_names.index(title[len("CONCENTRATION: "):])
+            _check_rel(st["immobile"][i, 0], sec["1"], 1.0e-12, f"{name} {title}")

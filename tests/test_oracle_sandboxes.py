@@ -193,3 +193,33 @@ def test_general_decay_rstep_mass_balance():
     k = -np.log(0.5) / (10.0 * 86400.0)
     want = wl.state["immobile"][0] / (1.0 + k * wl.tran_dt)
     assert np.allclose(st["immobile"][0], want, rtol=1.0e-9)
+
+
+def test_microbial_jacobian_vs_finite_differences():
+    """RMicrobial: Monod terms with thresholds, the four inhibition types, activation energy,
+    activities as concentrations -- the oracle's Jacobian against central differences of its own
+    residual.  The biomass columns are left out: the reference's d(rate)/d(biomass) omits the
+    L_water / volume factor (reaction_microbial.F90:578-583), restated as written and pinned by the
+    seven ABCD_microbial golds through the Newton iteration counts."""
+    wl = W.by_name("c8", ncell=10)
+    cfg, dt = wl.cfg, wl.tran_dt
+    naq, n = cfg.c.naqcomp, cfg.ncomp
+    assert cfg.c.nmicrobial_rxn == 2 and set(cfg.arrays["microbial_inhibition_type"]) == {1, 3, 4, 5}
+    bio = {wl.net.primary_names.index("D(aq)"), naq + wl.net.immobile_names.index("D(im)")}
+    for cell in range(10):
+        st0 = wl.state.copy()
+        e, R0, J, _ = orc.girt_residual(cfg, st0, cell, dt)
+        assert e == 0
+        for j in range(n):
+            if j in bio:
+                continue
+            fld, k = ("pri_molal", j) if j < naq else ("immobile", j - naq)
+            cols = []
+            for sgn in (1.0, -1.0):
+                st = wl.state.copy()
+                st.a[fld][k, cell] *= 1.0 + sgn * 1.0e-6
+                _, R, _, _ = orc.girt_residual(cfg, st, cell, dt)
+                cols.append((R, st.a[fld][k, cell]))
+            fd = (cols[0][0] - cols[1][0]) / (cols[0][1] - cols[1][1])
+            scale = np.abs(J[:, j]).max()
+            assert np.abs(J[:, j] - fd).max() <= 5.0e-5 * scale, (cell, j, J[:, j], fd)

@@ -98,6 +98,21 @@ COPY = [
     ("regression_tests/ascem/batch/calcite-area-per-mass.regression.gold", None),
     ("regression_tests/ascem/batch/general-reaction.in", None),
     ("regression_tests/ascem/batch/general-reaction.regression.gold", None),
+    # RMicrobial (+ RImmobileDecay, RGeneral) batch golds
+    ("regression_tests/default/batch/ABCD_microbial.in", None),
+    ("regression_tests/default/batch/ABCD_microbial.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_activation_high.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_activation_high.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_activation_low.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_activation_low.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_activity.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_activity.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_aq_biomass.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_aq_biomass.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_molality.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_molality.regression.gold", None),
+    ("regression_tests/default/batch/ABCD_microbial_molarity.in", None),
+    ("regression_tests/default/batch/ABCD_microbial_molarity.regression.gold", None),
     # KD isotherms and dynamic KD (default/batch)
     ("regression_tests/default/batch/dynamic_KD.in", None),
     ("regression_tests/default/batch/dynamic_KD.regression.gold", None),
@@ -127,7 +142,7 @@ def main():
     ch = dk.chemistry
     names = (["H2O"] + ch.primary + ch.secondary + ch.gases + ch.minerals
              + [c for r in ch.srfcplx_rxns for c in r.complexes]
-             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)", "B(aq)", "C(aq)", "AB(aq)"])
+             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)", "B(aq)", "C(aq)", "AB(aq)", "D(aq)"])
     db = chem.Database.from_file(os.path.join(REF, "database/hanford.dat"))
     with open(os.path.join(OUT, "hanford_subset.dat"), "w") as f:
         f.write(db.subset_text(names))
