@@ -660,9 +660,12 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     }
   }
   if (c->ngeneral_rxn > 0) {
-    if (!c->general_ptr || !c->general_specid || !c->general_stoich || !c->general_fwd_ptr || !c->general_fwd_specid ||
-        !c->general_fwd_stoich || !c->general_bwd_ptr || !c->general_bwd_specid || !c->general_bwd_stoich ||
+    if (!c->general_ptr || !c->general_specid || !c->general_stoich || !c->general_fwd_ptr || !c->general_bwd_ptr ||
         !c->general_kf || !c->general_kr)
+      return set_err(PFRX_E_INVALID, "general reaction tables missing%s", "");
+    // a side of a reaction may be empty ("D(aq) <->")
+    if ((c->general_fwd_ptr[c->ngeneral_rxn] > 0 && (!c->general_fwd_specid || !c->general_fwd_stoich)) ||
+        (c->general_bwd_ptr[c->ngeneral_rxn] > 0 && (!c->general_bwd_specid || !c->general_bwd_stoich)))
       return set_err(PFRX_E_INVALID, "general reaction tables missing%s", "");
     for (int k = 0; k < c->general_ptr[c->ngeneral_rxn]; k++)
       if (c->general_specid[k] < 0 || c->general_specid[k] >= c->naqcomp)
