@@ -502,6 +502,7 @@ static void tpc_layout(DevCfg &d, int N) {
   d.off_lng = act_upd ? 0 : take(d.ncplx);
   d.off_sec = 0;
   d.off_dt = d.need_dt ? take(d.naq * d.naq) : 0;
+  d.off_ds = d.need_ds ? take(d.naq * d.naq) : 0;
   d.off_nc = d.n_nc > 0 ? take(d.n_nc) : 0;
   d.off_ix = d.nionx > 0 ? take(d.nionx + d.n_ixcat) : 0;
   d.ws_stride = off | 1;
@@ -687,11 +688,9 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     for (int r = 0; r < c->nradiodecay_rxn; r++)
       if (c->radiodecay_forward_specid[r] < 0 || c->radiodecay_forward_specid[r] >= c->naqcomp)
         return set_err(PFRX_E_INVALID, "radioactive decay parent id out of range%s", "");
-    // the Jacobian of the sorbed inventory needs rt_auxvar%dtotal_sorb_eq as a matrix of its own,
-    // which the CUDA path does not keep (sorption derivatives go straight into the Jacobian)
-    if (c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0)
-      return set_err(PFRX_E_INVALID,
-                     "radioactive decay together with equilibrium sorption is not covered by the CUDA path yet%s", "");
+    // the Jacobian of the sorbed inventory needs rt_auxvar%dtotal_sorb_eq as a matrix of its own
+    // (DevCfg.need_ds); multirate sorption keeps its sorbed totals elsewhere (kinmr_total_sorb), like
+    // in the reference, and does not take part
   }
   if (c->nimmobile_decay_rxn > 0) {
     if (!c->immobile_decay_specid || !c->immobile_decay_constant)
@@ -799,6 +798,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_lg = c->langmuir ? 1 : 0;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
+  d.need_ds = (c->nradiodecay_rxn > 0 && c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0) ? 1 : 0;
   d.ngen = c->ngeneral_rxn;
   d.nrd = c->nradiodecay_rxn;
   d.nidc = c->nimmobile_decay_rxn;
@@ -1403,6 +1403,8 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   if (h->cfg.nmr > 0)
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover multirate sorption yet%s", "");
+  if (h->cfg.need_ds)
+    return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover radioactive decay of a sorbing species yet%s", "");
   if (h->cfg.mn_npref)
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover mineral prefactors yet%s", "");
   CUDA_OK(cudaSetDevice(h->device));

@@ -91,6 +91,7 @@ struct DevCfg {
   const double *dk_refhigh, *dk_low, *dk_high, *dk_power;
   // general kinetic reactions, radioactive decay, immobile decay (thread-per-cell kernel)
   int ngen, nrd, nidc;
+  int need_ds, off_ds;  // rt_auxvar%dtotal_sorb_eq as a matrix of its own (decay of a sorbing parent)
   const int *gn_ptr, *gn_id, *gn_fptr, *gn_fid, *gn_bptr, *gn_bid;
   const double *gn_st, *gn_fst, *gn_bst, *gn_kf, *gn_kr;
   const int *rd_ptr, *rd_id, *rd_fwd;

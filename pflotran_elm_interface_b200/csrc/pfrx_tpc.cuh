@@ -56,6 +56,7 @@ struct CellT {
   __device__ __forceinline__ double TOTc(int i) const { return ws[cfg.off_acc + i]; }
   __device__ __forceinline__ double LNAc(int i) const { return ws[cfg.off_lnact + i]; }
   __device__ __forceinline__ double &DT(int i, int j) { return ws[cfg.off_dt + i * cfg.naq + j]; }
+  __device__ __forceinline__ double &DS(int i, int j) { return ws[cfg.off_ds + i * cfg.naq + j]; }
   __device__ __forceinline__ double &NC(int k) { return ws[cfg.off_nc + k]; }
 
   __device__ __forceinline__ double cx_logK(int k) const {
@@ -186,7 +187,8 @@ struct CellT {
 
   // ---- RTotalSorbEqSurfCplx1 (reaction_surf_complex.F90:641-900) -------------
   // adds nu*S to ws.ts and (add_J) jscale * dtotal_sorb to the Jacobian
-  __device__ __forceinline__ void surf_cplx1(int irxn, double *tsacc, bool add_J, double jscale, bool store_conc) {
+  __device__ __forceinline__ void surf_cplx1(int irxn, double *tsacc, bool add_J, double jscale, bool store_conc,
+                                             bool add_ds = false) {
     const int naq = cfg.naq;
     const int r0 = cfg.sr_ptr[irxn], r1 = cfg.sr_ptr[irxn + 1];
     double fs = fmax(ws[cfg.off_fs + irxn], 1.e-40);
@@ -288,9 +290,14 @@ struct CellT {
 #pragma unroll 1
       for (int p2 = p0; p2 < p1; p2++) {
         int j = cfg.sc_id[p2];
-        double t = jscale * (cfg.sc_st[p2] * Sk * INVC(j) + nuiSx * TMP(j));
+        const double t0 = cfg.sc_st[p2] * Sk * INVC(j) + nuiSx * TMP(j);
+        double t = jscale * t0;
 #pragma unroll 1
         for (int p = p0; p < p1; p++) J(cfg.sc_id[p], j) += cfg.sc_st[p] * t;
+        if (add_ds) {
+#pragma unroll 1
+          for (int p = p0; p < p1; p++) DS(cfg.sc_id[p], j) += cfg.sc_st[p] * t0;
+        }
       }
     }
   }
@@ -383,7 +390,13 @@ struct CellT {
 #pragma unroll 1
       for (int i = 0; i < naq; i++) TS(i) = 0.0;
 #pragma unroll 1
-      for (int e = 0; e < cfg.neqsr; e++) surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, vol / dt, true);
+      if (want_J && cfg.need_ds) {
+#pragma unroll 1
+        for (int e = 0; e < naq * naq; e++) ws[cfg.off_ds + e] = 0.0;
+      }
+#pragma unroll 1
+      for (int e = 0; e < cfg.neqsr; e++)
+        surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, vol / dt, true, cfg.need_ds != 0);
       if (cfg.nionx > 0) ion_exchange(want_J, vol / dt);
       if (cfg.ndynkd > 0) dynamic_kd(want_J, vol / dt);
       if (cfg.nkd > 0) isotherm_kd(want_J, vol / dt);
@@ -470,6 +483,7 @@ struct CellT {
             else
               d = (-t1) * t2 * X[j] * INVC(jc);
             J(ic, jc) += d * jscale;
+            if (cfg.need_ds) DS(ic, jc) += d;
           }
         }
       }
@@ -477,8 +491,8 @@ struct CellT {
   }
 
   // ---- RRadioactiveDecay (reaction.F90:5211-5311): aqueous inventory of one parent decays into
-  // its daughters; d(total)/d(free) is the DT copy of this iteration.  (With equilibrium sorption
-  // the sorbed inventory decays too: pfrx_create refuses that combination for now.)
+  // its daughters; d(total)/d(free) is the DT copy of this iteration.  With equilibrium sorption the
+  // sorbed inventory decays too, through total_sorb_eq and the DS copy of d(total_sorb)/d(free).
   __device__ __forceinline__ void radioactive_decay() {
     const int naq = cfg.naq;
     const double L_pore = por * vol * 1.e3;
@@ -487,7 +501,8 @@ struct CellT {
     for (int r = 0; r < cfg.nrd; r++) {
       const int p0 = cfg.rd_ptr[r], p1 = cfg.rd_ptr[r + 1], jc = cfg.rd_fwd[r];
       const double kf = cfg.rd_kf[r];
-      const double sum = TOT(jc) * L_water;
+      double sum = TOT(jc) * L_water;
+      if (cfg.nsorb > 0) sum = sum + TS(jc) * vol;
       const double rate = sum * kf;
       const double t = -1.0 * kf;
 #pragma unroll 1
@@ -497,6 +512,15 @@ struct CellT {
         RES(ic) = RES(ic) - nu * rate;
 #pragma unroll 1
         for (int j = 0; j < naq; j++) J(ic, j) = J(ic, j) + t * nu * DT(jc, j) * L_water;
+      }
+      if (cfg.need_ds) {
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) {
+          const int ic = cfg.rd_id[p];
+          const double nu = cfg.rd_st[p];
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) J(ic, j) = J(ic, j) + t * nu * DS(jc, j) * vol;
+        }
       }
     }
   }
@@ -698,6 +722,10 @@ struct CellT {
       if (want_J) {
         J(ikd, ikd) += (KD * Lw) * jscale;
         J(ikd, iref) += (dKD * mk * Lw) * jscale;
+        if (cfg.need_ds) {
+          DS(ikd, ikd) += KD * Lw;
+          DS(ikd, iref) += dKD * mk * Lw;
+        }
       }
     }
   }
@@ -729,7 +757,10 @@ struct CellT {
         dres = res / m * on;
       }
       TS(ic) = TS(ic) + res;
-      if (want_J) J(ic, ic) += dres * jscale;
+      if (want_J) {
+        J(ic, ic) += dres * jscale;
+        if (cfg.need_ds) DS(ic, ic) += dres;
+      }
     }
   }
 

@@ -715,10 +715,39 @@ END
 """
 
 
-def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED) -> Workload:
-    """C7: RGeneral, RRadioactiveDecay and RImmobileDecay on mixes of two waters"""
+C7_SORPTION = """  SORPTION
+    ISOTHERM_REACTIONS
+      B(aq)
+        TYPE FREUNDLICH
+        DISTRIBUTION_COEFFICIENT 40.
+        FREUNDLICH_N 1.3
+      /
+      C(aq)
+        TYPE LINEAR
+        DISTRIBUTION_COEFFICIENT 150.
+      /
+    /
+    DYNAMIC_KD_REACTIONS
+      B(aq)
+        REFERENCE_SPECIES A(aq)
+        REFERENCE_SPECIES_HIGH 3.d-3
+        KD_LOW 0.2
+        KD_HIGH 1.5
+        KD_POWER 1.2
+      /
+    /
+  /
+"""
+
+
+def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED, sorbing: bool = False) -> Workload:
+    """C7: RGeneral, RRadioactiveDecay and RImmobileDecay on mixes of two waters.  ``sorbing``: the
+    decaying parent B(aq) and its daughter also sorb (Freundlich + dynamic KD, linear KD), so the sorbed
+    inventory decays too and the Jacobian needs d(total_sorb)/d(free) (reaction.F90:5257-5305)"""
     rng = np.random.default_rng(seed)
-    dk, net = chem.load_network(C7_DECK, _read("hanford_subset.dat"))
+    deck = C7_DECK.replace("  DATABASE ./hanford_subset.dat", C7_SORPTION + "  DATABASE ./hanford_subset.dat") if sorbing \
+        else C7_DECK
+    dk, net = chem.load_network(deck, _read("hanford_subset.dat"))
     assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
     cfg = abi.ReactionConfig(net)
     den = eos.water_density_ifc67(25.0)
@@ -733,8 +762,13 @@ def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SE
     st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
     st["sat"][...] = rng.uniform(0.4, 1.0, ncell)
     st["temp"][...] = 25.0
-    return Workload("c7_general_decay", cfg, st, tran_dt, net,
-                    "2 general reactions, 1 radioactive decay with daughter, 1 immobile decay, 1 complex")
+    if sorbing:
+        # sorbed totals in equilibrium with the first water, so the step re-partitions towards the mix
+        s0 = _sorbed_totals(net, waters[0], 0.0, den, 0.3)
+        st["total_sorb_eq"][...] = s0[:, None]
+    return Workload("c7s_general_decay_sorbing" if sorbing else "c7_general_decay", cfg, st, tran_dt, net,
+                    "2 general reactions, 1 radioactive decay with daughter, 1 immobile decay, 1 complex"
+                    + (", parent and daughter sorbing (2 KD isotherms, 1 dynamic KD)" if sorbing else ""))
 
 
 C8_DECK = """
@@ -887,6 +921,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c5": (hanford, {"variant": "minerals"}),
         "c6": (ion_exchange, {}),
         "c7": (general_decay, {}),
+        "c7s": (general_decay, {"sorbing": True}),
         "c8": (microbial, {}),
     }
     fn, kw = table[name]

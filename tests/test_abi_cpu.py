@@ -101,15 +101,6 @@ def test_unsupported_configurations_are_refused_not_approximated():
     cfg.c.eqionx_k = C.cast(None, abi.c_double_p)
     rc, msg = _create_rc(cfg)
     assert rc == 1 and "ion exchange" in msg
-    # radioactive decay next to equilibrium sorption (needs dtotal_sorb_eq as a matrix)
-    cfg = workloads.by_name("c7", ncell=1).cfg
-    cfg.c.neqkdrxn = 1
-    for k, v in (("specid", [0]), ("type", [1]), ("mineral", [-1])):
-        setattr(cfg.c, "eqkd_" + k, abi._ip(cfg._keep("eqkd_" + k, abi._i32(v))))
-    for k in ("coeff", "langmuir_b", "freundlich_n"):
-        setattr(cfg.c, "eqkd_" + k, abi._dp(cfg._keep("eqkd_" + k, abi._f64([1.0]))))
-    rc, msg = _create_rc(cfg)
-    assert rc == 1 and "radioactive decay" in msg
     # a general reaction naming a species that does not exist
     cfg = workloads.by_name("c7", ncell=1).cfg
     cfg.arrays["general_fwd_specid"][0] = 17

@@ -146,18 +146,20 @@ def test_c6_ion_exchange_and_isotherms(dt, host):
     _check_summary(rr, rg)
 
 
-@pytest.mark.parametrize("dt,host", [(3600.0, False), (86400.0, True), (30 * 86400.0, False)])
-def test_c7_general_decay_reactions(dt, host):
+@pytest.mark.parametrize("name,dt,host", [("c7", 3600.0, False), ("c7", 86400.0, True), ("c7", 30 * 86400.0, False),
+                                          ("c7s", 3600.0, True), ("c7s", 86400.0, False), ("c7s", 30 * 86400.0, False)])
+def test_c7_general_decay_reactions(name, dt, host):
     """RGeneral (third-order forward / first-order backward, and an irreversible one),
     RRadioactiveDecay with a daughter (through dtotal of a network with a complex) and
-    RImmobileDecay in the thread-per-cell kernel"""
-    wl = W.by_name("c7", ncell=5000, tran_dt=dt)
+    RImmobileDecay in the thread-per-cell kernel; c7s: parent and daughter sorb (Freundlich, linear
+    and dynamic KD), so the sorbed inventory decays through total_sorb_eq and dtotal_sorb_eq"""
+    wl = W.by_name(name, ncell=5000, tran_dt=dt)
     wl.state.a["imat"][0, 5] = 0
     wl.state.a["sat"][0, 6] = 1.0e-50
     ref, rr, got, rg, info = _run_both(wl, host_path=host)
     assert info["lanes"] in (0, 1)
     assert rr.sum_newton_iterations > 3 * 4998
-    _compare(ref, got, f"c7 dt={dt}")
+    _compare(ref, got, f"{name} dt={dt}")
     _check_summary(rr, rg)
 
 

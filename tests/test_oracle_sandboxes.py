@@ -159,10 +159,12 @@ def test_sorption_jacobian_vs_finite_differences():
     assert abs(s0 - 750.0) < 1e-9
 
 
-def test_general_decay_jacobian_vs_finite_differences():
-    """RGeneral, RRadioactiveDecay (through dtotal of a network with a complex) and RImmobileDecay:
-    the oracle's analytic Jacobian against central differences of its own residual, all unknowns"""
-    wl = W.by_name("c7", ncell=8)
+@pytest.mark.parametrize("name", ["c7", "c7s"])
+def test_general_decay_jacobian_vs_finite_differences(name):
+    """RGeneral, RRadioactiveDecay (through dtotal of a network with a complex; c7s: of a sorbing
+    parent, through dtotal_sorb_eq too) and RImmobileDecay: the oracle's analytic Jacobian against
+    central differences of its own residual, all unknowns"""
+    wl = W.by_name(name, ncell=8)
     cfg, dt = wl.cfg, wl.tran_dt
     naq, n = cfg.c.naqcomp, cfg.ncomp
     assert cfg.c.ngeneral_rxn == 2 and cfg.c.nradiodecay_rxn == 1 and cfg.c.nimmobile_decay_rxn == 1
