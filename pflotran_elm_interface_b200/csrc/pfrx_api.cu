@@ -1405,8 +1405,6 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover multirate sorption yet%s", "");
   if (h->cfg.need_ds)
     return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover radioactive decay of a sorbing species yet%s", "");
-  if (h->cfg.mn_npref)
-    return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover mineral prefactors yet%s", "");
   CUDA_OK(cudaSetDevice(h->device));
   if (!h->rx_kernel) {
     const KernelGetter *gt = nullptr;

@@ -1456,6 +1456,20 @@ struct CellT {
     }
 #pragma unroll 1
     for (int e = 0; e < n * cfg.js; e++) ws[cfg.off_J + e] = 0.0;
+    if (cfg.mn_npref) {
+      // prefactors on secondary species read ln(gamma) of the complexes the way RReact keeps them
+      if (cfg.act_freq != PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER) {
+#pragma unroll 1
+        for (int k = 0; k < cfg.ncplx; k++) ws[cfg.off_lng + k] = log(st.sec_act_coef[k * ld + c]);
+      } else {
+#pragma unroll 1
+        for (int k = 0; k < cfg.ncplx; k++)
+          if (cfg.cx_cls[k] >= 0) ws[cfg.off_cls + cfg.cx_cls[k]] = log(st.sec_act_coef[k * ld + c]);
+#pragma unroll 1
+        for (int i = 0; i < naq; i++)
+          if (cfg.pri_cls[i] >= 0) ws[cfg.off_cls + cfg.pri_cls[i]] = log(st.pri_act_coef[i * ld + c]);
+      }
+    }
     if (!dry) {  // RReaction returns at once in a dry cell (reaction.F90:4085)
       if (cfg.nkin > 0) {
         kinetic_mineral(true);
