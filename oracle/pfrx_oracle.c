@@ -3050,8 +3050,10 @@ int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   for (i = 0; i < n; i++) Res[i] = 0.0;
   for (i = 0; i < n * n; i++) Jac[i] = 0.0;
   /* the GIRT caller has just run RTAuxVarCompute (reactive_transport.F90:2599-2642):
-   * the sandboxes that read rt_auxvar%aqueous%dtotal need it here too */
-  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir || cfg->nradiodecay_rxn > 0)
+   * the sandboxes that read rt_auxvar%aqueous%dtotal need it here too, radioactive decay reads
+   * total and dtotal, mineral prefactors on secondary species read sec_molal */
+  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir || cfg->nradiodecay_rxn > 0 ||
+      cfg->kinmnrl_num_prefactors)
     rt_auxvar_compute(&c, cfg);
   r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
   for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];
