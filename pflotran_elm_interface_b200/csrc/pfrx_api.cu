@@ -1628,15 +1628,16 @@ static int pipeline_events(pfrx_handle *h) {
 // chunk i+1, {load transpose, RStep kernel, store transpose} of chunk i, download of chunk i-1.
 extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
                                  pfrx_step_result *out) {
-  if (!h || !tran_xx || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   CUDA_OK(cudaSetDevice(h->device));
   const int64_t ncell = h->ncell;
-  if (ncell == 0) {
+  if (ncell == 0) {  // a rank without cells: its vectors are empty (and may be NULL)
     memset(out, 0, sizeof(*out));
     out->first_failed_cell = -1;
     return PFRX_OK;
   }
+  if (!tran_xx) return set_err(PFRX_E_INVALID, "null argument%s", "");
   const int n = h->cfg.naq + h->cfg.nim;
   if (h->os_cap < ncell) {
     if (h->os_a) CUDA_OK(cudaFree(h->os_a));
