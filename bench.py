@@ -152,8 +152,27 @@ def cpu_baseline(wl, seconds, threads):
             "per_core": n / dt / threads, "seconds": dt}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # libraries write to fd 1 (NCCL prints its version banner there at communicator set-up): point
+    # fd 1 at stderr for the run and keep the real stdout for the JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -188,7 +207,7 @@ def main():
                "e2e": {"value": v, "unit": "cell-solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "note": "reference Fortran cannot be built in this image (no Fortran compiler/PETSc/MPI); this arm "
                        "times the C oracle port of the same path with back-substitution enabled (SURVEY 0.2)"}
-        print(json.dumps(out))
+        emit(out)
         return 0
 
     # ------------------------------------------------------------------ GPU arm
@@ -423,7 +442,7 @@ def main():
            "roofline": roof, "cpu_baseline": cpu,
            "os_block_vectors": osv,
            "result": res.as_dict(), "wall_s_timed_region": wall}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
