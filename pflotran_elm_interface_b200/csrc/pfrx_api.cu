@@ -1460,14 +1460,15 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
 }
 
 // ---- block vectors <-> SoA around the cell loop (pmc_subsurface_osrt.F90:260-274, 303-333, 356-376) ----
-// One block moves a tile of OS_CELLS cells x ncomp components through shared memory, so that both
+// One block moves a tile of OS_CELLS cells (64 by default: 0.56 / 0.55 / 0.62 of the HBM peak on C3
+// against 0.53 / 0.52 / 0.58 with 256) x ncomp components through shared memory, so that both
 // sides are coalesced: the block vector is read / written as one contiguous run of OS_CELLS*ncomp
 // doubles, the SoA fields as runs of OS_CELLS consecutive cells per component.  The tile is padded
 // (ncomp | 1 doubles per cell) so that the cell-wise accesses are bank-conflict free.
-#define OS_CELLS 256
+#define PFRX_OS_CELLS_DEFAULT 64
 enum { OS_FIXED_ACCUM = 0, OS_LOAD = 1, OS_STORE = 2 };
 
-template <int MODE>
+template <int MODE, int OS_CELLS>
 __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t ncell, int naq, int nim,
                                                             const double *in_a, const double *in_b, double *out) {
   extern __shared__ double tile[];
@@ -1541,20 +1542,34 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
 }
 
 // enqueue one transpose of `ncell` cells of `st` (already offset to the first cell) on `s`
+template <int MODE, int OS_CELLS>
+static int os_enqueue_t(pfrx_handle *h, const DevState &st, int64_t ncell, const double *a, const double *b,
+                        double *out, cudaStream_t s) {
+  const int naq = h->cfg.naq, nim = h->cfg.nim;
+  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double);
+  const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * (2048 / OS_CELLS)));
+  CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE, OS_CELLS>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pfrx_os_kernel<MODE, OS_CELLS><<<grid, OS_CELLS, smem, s>>>(st, ncell, naq, nim, a, b, out);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return PFRX_OK;
+}
+
 template <int MODE>
 static int os_enqueue(pfrx_handle *h, const DevState &st, int64_t ncell, const double *a, const double *b,
                       double *out, cudaStream_t s) {
   if (ncell <= 0) return PFRX_OK;
-  const int naq = h->cfg.naq, nim = h->cfg.nim;
-  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double) + sizeof(double) * OS_CELLS;
-  const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * 8));
-  CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  pfrx_os_kernel<MODE><<<grid, OS_CELLS, smem, s>>>(st, ncell, naq, nim, a, b, out);
-  CUDA_OK(cudaGetLastError());
-  h->launches++;
-  return PFRX_OK;
+  // tile height: smaller tiles keep more blocks per SM in different phases (load / store) of the
+  // load -> barrier -> store cycle; PFRX_OS_CELLS overrides for measurements
+  static const int cells = [] {
+    const char *ev = getenv("PFRX_OS_CELLS");
+    return ev ? atoi(ev) : PFRX_OS_CELLS_DEFAULT;
+  }();
+  if (cells == 64) return os_enqueue_t<MODE, 64>(h, st, ncell, a, b, out, s);
+  if (cells == 128) return os_enqueue_t<MODE, 128>(h, st, ncell, a, b, out, s);
+  return os_enqueue_t<MODE, 256>(h, st, ncell, a, b, out, s);
 }
 
 template <int MODE>
