@@ -1460,12 +1460,11 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
 }
 
 // ---- block vectors <-> SoA around the cell loop (pmc_subsurface_osrt.F90:260-274, 303-333, 356-376) ----
-// One block moves a tile of OS_CELLS cells (64 by default: 0.56 / 0.55 / 0.62 of the HBM peak on C3
-// against 0.53 / 0.52 / 0.58 with 256) x ncomp components through shared memory, so that both
+// One block moves a tile of OS_CELLS cells (128 by default) x ncomp components through shared memory, so that both
 // sides are coalesced: the block vector is read / written as one contiguous run of OS_CELLS*ncomp
 // doubles, the SoA fields as runs of OS_CELLS consecutive cells per component.  The tile is padded
 // (ncomp | 1 doubles per cell) so that the cell-wise accesses are bank-conflict free.
-#define PFRX_OS_CELLS_DEFAULT 64
+#define PFRX_OS_CELLS_DEFAULT 128
 enum { OS_FIXED_ACCUM = 0, OS_LOAD = 1, OS_STORE = 2 };
 
 template <int MODE, int OS_CELLS>
@@ -1473,72 +1472,78 @@ __global__ void __launch_bounds__(OS_CELLS) pfrx_os_kernel(DevState st, int64_t 
                                                             const double *in_a, const double *in_b, double *out) {
   extern __shared__ double tile[];
   const int n = naq + nim, ldt = n | 1;
+  unsigned char *act_s = reinterpret_cast<unsigned char *>(tile + OS_CELLS * ldt);  // activity of the tile's cells
   const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
+  // element e = threadIdx.x + k * OS_CELLS of the tile's block-vector run is (cell e / n, component
+  // e % n): one division per thread, then increments
+  const int cc0 = threadIdx.x / n, i0 = threadIdx.x - cc0 * n;
+  const int qs = OS_CELLS / n, rs = OS_CELLS - qs * n;
+#define PFRX_OS_FOR_ELEMENTS(body)                                        \
+  {                                                                       \
+    int cc = cc0, i = i0;                                                 \
+    _Pragma("unroll 4") for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) { \
+      body;                                                               \
+      cc += qs;                                                           \
+      i += rs;                                                            \
+      if (i >= n) {                                                       \
+        i -= n;                                                           \
+        cc++;                                                             \
+      }                                                                   \
+    }                                                                     \
+  }
   for (int64_t t = blockIdx.x; t < ntile; t += gridDim.x) {
     const int64_t c0 = t * OS_CELLS;
     const int nc = (int)min((int64_t)OS_CELLS, ncell - c0);
     const int64_t c = c0 + threadIdx.x;
     const bool mine = threadIdx.x < nc;
     const bool active = mine && !(st.imat && st.imat[c] <= 0);
+    act_s[threadIdx.x] = active ? 1 : 0;
+    double *row = tile + threadIdx.x * ldt;
+    double *vout = out ? out + c0 * n : nullptr;
     if (MODE == OS_FIXED_ACCUM) {
       // SoA -> tile (per cell), tile -> block vector (contiguous); only aqueous entries of active
       // cells are written, the rest of the vector is left as it is
       if (active) {
         const double f = st.porosity[c] * st.sat[c] * 1000.0 * st.volume[c];
 #pragma unroll 8
-        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = f * __ldcs(st.total + i * st.ld + c);
+        for (int k = 0; k < naq; k++) row[k] = f * __ldcs(st.total + k * st.ld + c);
       }
       __syncthreads();
-#pragma unroll 4
-      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
-        const int cc = e / n, i = e - cc * n;
-        const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
-        if (i < naq && act) out[c0 * n + e] = tile[cc * ldt + i];
-      }
+      PFRX_OS_FOR_ELEMENTS(if (i < naq && act_s[cc]) vout[e] = tile[cc * ldt + i]);
       __syncthreads();
     } else if (MODE == OS_LOAD) {
       // block vectors -> tile (contiguous), tile -> SoA (per cell)
       if (in_a) {
-  #pragma unroll 4
-      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
-          const int cc = e / n, i = e - cc * n;
-          if (i < naq) tile[cc * ldt + i] = in_a[c0 * n + e];
-        }
+        const double *va = in_a + c0 * n;
+        PFRX_OS_FOR_ELEMENTS(if (i < naq) tile[cc * ldt + i] = __ldcs(va + e));
       }
       if (in_b && nim > 0) {
-  #pragma unroll 4
-      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
-          const int cc = e / n, i = e - cc * n;
-          if (i >= naq) tile[cc * ldt + i] = in_b[c0 * n + e];
-        }
+        const double *vb = in_b + c0 * n;
+        PFRX_OS_FOR_ELEMENTS(if (i >= naq) tile[cc * ldt + i] = __ldcs(vb + e));
       }
       __syncthreads();
       if (active) {
         if (in_a)
 #pragma unroll 8
-          for (int i = 0; i < naq; i++) st.total[i * st.ld + c] = tile[threadIdx.x * ldt + i];
+          for (int k = 0; k < naq; k++) st.total[k * st.ld + c] = row[k];
         if (in_b)
 #pragma unroll 8
-          for (int k = 0; k < nim; k++) st.immobile[k * st.ld + c] = tile[threadIdx.x * ldt + naq + k];
+          for (int k = 0; k < nim; k++) st.immobile[k * st.ld + c] = row[naq + k];
       }
       __syncthreads();
     } else {
       if (active) {
 #pragma unroll 8
-        for (int i = 0; i < naq; i++) tile[threadIdx.x * ldt + i] = __ldcs(st.pri_molal + i * st.ld + c);
+        for (int k = 0; k < naq; k++) row[k] = __ldcs(st.pri_molal + k * st.ld + c);
 #pragma unroll 8
-        for (int k = 0; k < nim; k++) tile[threadIdx.x * ldt + naq + k] = __ldcs(st.immobile + k * st.ld + c);
+        for (int k = 0; k < nim; k++) row[naq + k] = __ldcs(st.immobile + k * st.ld + c);
       }
       __syncthreads();
-#pragma unroll 4
-      for (int e = threadIdx.x; e < nc * n; e += OS_CELLS) {
-        const int cc = e / n, i = e - cc * n;
-        const bool act = !(st.imat && st.imat[c0 + cc] <= 0);
-        if (act) out[c0 * n + e] = tile[cc * ldt + i];
-      }
+      PFRX_OS_FOR_ELEMENTS(if (act_s[cc]) vout[e] = tile[cc * ldt + i]);
       __syncthreads();
     }
   }
+#undef PFRX_OS_FOR_ELEMENTS
 }
 
 // enqueue one transpose of `ncell` cells of `st` (already offset to the first cell) on `s`
@@ -1546,7 +1551,7 @@ template <int MODE, int OS_CELLS>
 static int os_enqueue_t(pfrx_handle *h, const DevState &st, int64_t ncell, const double *a, const double *b,
                         double *out, cudaStream_t s) {
   const int naq = h->cfg.naq, nim = h->cfg.nim;
-  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double);
+  const size_t smem = (size_t)OS_CELLS * ((naq + nim) | 1) * sizeof(double) + OS_CELLS;  // tile + activity flags
   const int64_t ntile = (ncell + OS_CELLS - 1) / OS_CELLS;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (int64_t)h->sm_count * (2048 / OS_CELLS)));
   CUDA_OK(cudaFuncSetAttribute((const void *)pfrx_os_kernel<MODE, OS_CELLS>,
