@@ -569,9 +569,10 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * Side effect as in the reference: mnrl_rate of the bound state is updated.
  * Inactive cells (imat <= 0) get zeros; dry cells get zeros (reaction.F90:4085).
  * tran_dt is option%tran_dt, which the SOMDECOMP sandbox reads (rate caps,
- * reaction_sandbox_somdec.F90:1762,2853); the aqueous totals the sandboxes
- * read are pfrx_state.total, d(total)/d(free) is recomputed from the state.
- * Multirate sorption is not covered yet (PFRX_E_INVALID).                     */
+ * reaction_sandbox_somdec.F90:1762,2853) and RMultiRateSorption uses; the
+ * aqueous totals and d(total)/d(free) that the sandboxes and radioactive decay
+ * read are recomputed from the free-ion concentrations of the state.
+ * Radioactive decay of a sorbing species is not covered yet (PFRX_E_INVALID). */
 int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
 /* ---- the steps either side of the cell loop ---------------------

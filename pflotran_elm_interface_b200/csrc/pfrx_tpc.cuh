@@ -1476,6 +1476,13 @@ struct CellT {
 #pragma unroll 1
         for (int k = 0; k < cfg.nkin; k++) st.mnrl_rate[k * ld + c] = ws[cfg.off_mn + k];
       }
+      if (cfg.nmr > 0) {
+        // RMultiRateSorption: free-site guesses and the sorbed totals of every rate from the state
+#pragma unroll 1
+        for (int k = 0; k < cfg.nsrfrxn; k++) ws[cfg.off_fs + k] = st.free_site[k * ld + c];
+        multirate_begin(tran_dt);
+        multirate(tran_dt);
+      }
       if (cfg.need_dt) dtotal_from_state();
       if (cfg.nrd > 0) radioactive_decay();
       if (cfg.ngen > 0) general_reactions();

@@ -226,7 +226,7 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c4", "c4s", "c4se", "c4fe", "c7", "c8"])
+@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c7", "c8"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
