@@ -1419,8 +1419,6 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
   if (!h || !res || (want_jacobian && !jac)) return set_err(PFRX_E_INVALID, "null argument%s", "");
   if (!(tran_dt > 0.0)) return set_err(PFRX_E_INVALID, "tran_dt must be positive%s", "");
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
-  if (h->cfg.need_ds)
-    return set_err(PFRX_E_INVALID, "pfrx_reaction does not cover radioactive decay of a sorbing species yet%s", "");
   CUDA_OK(cudaSetDevice(h->device));
   if (!h->rx_kernel) {
     const KernelGetter *gt = nullptr;

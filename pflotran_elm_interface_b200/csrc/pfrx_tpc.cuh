@@ -383,24 +383,28 @@ struct CellT {
     }
 #pragma unroll 1
     for (int i = naq; i < n; i++) TOT(i) = C(i);
-    if (cfg.nsorb > 0) {
-      // RTotalSorb (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD
+    if (cfg.nsorb > 0) total_sorb(want_J, vol / dt);
+  }
+
+  // ---- RTotalSorb (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD;
+  // jscale * d(total_sorb)/d(free) goes into the Jacobian (RAccumulationSorbDerivative), and into DS
+  // unscaled when the decay of a sorbing species needs it
+  __device__ __forceinline__ void total_sorb(bool want_J, double jscale) {
+    const int naq = cfg.naq;
 #pragma unroll 1
-      for (int k = 0; k < cfg.nsrfcplx; k++) ws[cfg.off_sc + k] = 0.0;
+    for (int k = 0; k < cfg.nsrfcplx; k++) ws[cfg.off_sc + k] = 0.0;
 #pragma unroll 1
-      for (int i = 0; i < naq; i++) TS(i) = 0.0;
+    for (int i = 0; i < naq; i++) TS(i) = 0.0;
+    if (want_J && cfg.need_ds) {
 #pragma unroll 1
-      if (want_J && cfg.need_ds) {
-#pragma unroll 1
-        for (int e = 0; e < naq * naq; e++) ws[cfg.off_ds + e] = 0.0;
-      }
-#pragma unroll 1
-      for (int e = 0; e < cfg.neqsr; e++)
-        surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, vol / dt, true, cfg.need_ds != 0);
-      if (cfg.nionx > 0) ion_exchange(want_J, vol / dt);
-      if (cfg.ndynkd > 0) dynamic_kd(want_J, vol / dt);
-      if (cfg.nkd > 0) isotherm_kd(want_J, vol / dt);
+      for (int e = 0; e < naq * naq; e++) ws[cfg.off_ds + e] = 0.0;
     }
+#pragma unroll 1
+    for (int e = 0; e < cfg.neqsr; e++)
+      surf_cplx1(cfg.eqsr[e], ws + cfg.off_ts, want_J, jscale, true, cfg.need_ds != 0);
+    if (cfg.nionx > 0) ion_exchange(want_J, jscale);
+    if (cfg.ndynkd > 0) dynamic_kd(want_J, jscale);
+    if (cfg.nkd > 0) isotherm_kd(want_J, jscale);
   }
 
   // ---- RTotalSorbEqIonx (reaction.F90:4906-5140): Gaines-Thomas ion exchange; with mixed
@@ -1484,6 +1488,17 @@ struct CellT {
         multirate(tran_dt);
       }
       if (cfg.need_dt) dtotal_from_state();
+      if (cfg.need_ds) {
+        // the sorbed inventory and d(total_sorb)/d(free) of RTAuxVarCompute; jscale 0 keeps the
+        // accumulation derivative out of RReaction's Jacobian
+        if (cfg.nmr == 0) {
+#pragma unroll 1
+          for (int k = 0; k < cfg.nsrfrxn; k++) ws[cfg.off_fs + k] = st.free_site[k * ld + c];
+        }
+#pragma unroll 1
+        for (int r = 0; r < cfg.nionx; r++) ws[cfg.off_ix + r] = st.eqionx_ref ? st.eqionx_ref[r * ld + c] : 1.e-9;
+        total_sorb(true, 0.0);
+      }
       if (cfg.nrd > 0) radioactive_decay();
       if (cfg.ngen > 0) general_reactions();
       if (cfg.nmb > 0) microbial();

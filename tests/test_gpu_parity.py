@@ -226,14 +226,14 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c7", "c8"])
+@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c7", "c7s", "c8"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
 
     rstep = _gpu()
     wl = W.by_name(variant, ncell=300)
-    if variant.startswith("c4") or variant in ("c7", "c8"):
+    if variant.startswith("c4") or variant in ("c7", "c7s", "c8"):
         wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
         wl.state.a["sat"][0, 9] = 1.0e-50
     ref = wl.state.copy()
