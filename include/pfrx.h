@@ -571,8 +571,8 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * tran_dt is option%tran_dt, which the SOMDECOMP sandbox reads (rate caps,
  * reaction_sandbox_somdec.F90:1762,2853) and RMultiRateSorption uses; the
  * aqueous totals and d(total)/d(free) that the sandboxes and radioactive decay
- * read are recomputed from the free-ion concentrations of the state.
- * Radioactive decay of a sorbing species is not covered yet (PFRX_E_INVALID). */
+ * read are recomputed from the free-ion concentrations of the state, and so
+ * are the sorbed totals when a sorbing species decays.                         */
 int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
 /* ---- the steps either side of the cell loop ---------------------
