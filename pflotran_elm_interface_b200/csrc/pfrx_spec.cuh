@@ -360,22 +360,28 @@ __device__ __forceinline__ bool spec_solve_core(double *W, double (&res)[SPEC_N]
   for (int i = 0; i < NC; i++) {
     double row[NCA];
     double m = 0.0;
+    // entries outside the network's structure (spec_jnz) hold exact zeros here: they take no part
+    // in the maxima and scaling them is a no-op
 #pragma unroll
     for (int j = 0; j < NC; j++) {
-      row[j] = W[JX(i, j)];
-      const double av = fabs(row[j]);
-      m = av > m ? av : m;  // maxval(abs()) without fmax's NaN plumbing
+      if (spec_jnz(i, j)) {
+        row[j] = W[JX(i, j)];
+        const double av = fabs(row[j]);
+        m = av > m ? av : m;  // maxval(abs()) without fmax's NaN plumbing
+      }
     }
     double nm = sx_rcp(fmax(1.0, m));
     b[i] = res[spec_sp_of(i)] * nm;
     double m2 = 0.0;
 #pragma unroll
     for (int j = 0; j < NC; j++) {
-      double v = row[j] * nm;
-      if (SPEC_USE_LOG) v *= c[spec_sp_of(j)];
-      W[JX(i, j)] = v;
-      const double av = fabs(v);
-      m2 = av > m2 ? av : m2;
+      if (spec_jnz(i, j)) {
+        double v = row[j] * nm;
+        if (SPEC_USE_LOG) v *= c[spec_sp_of(j)];
+        W[JX(i, j)] = v;
+        const double av = fabs(v);
+        m2 = av > m2 ? av : m2;
+      }
     }
     if (!(m2 > 0.0)) bad = true;
     W[JX(i, NC)] = sx_rcp(m2);

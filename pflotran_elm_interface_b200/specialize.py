@@ -295,6 +295,8 @@ class _Gen:
         self.used = sorted(used)
         self._recording = False
         self._pairs = set()
+        self._nz = set()          # every (i, j) the generated code ever assigns something non-zero
+        self._touch_all = False
         self._layout([])
 
     def _layout(self, rowonly) -> None:
@@ -311,6 +313,8 @@ class _Gen:
     def J(self, i: int, j: int) -> str:
         if self._recording:
             self._pairs.add((i, j))
+        if not self._touch_all:
+            self._nz.add((i, j))
         if i in self.roset:
             assert j == i or j not in self.roset, (i, j)
             k = self.ropairs.setdefault((i, j), len(self.ropairs))
@@ -394,6 +398,7 @@ class _Gen:
         budget = int(os.environ.get("PFRX_SPEC_HOT", 20 if n > 8 else 9))
         hot = sorted(hits, key=lambda e: -hits[e])[:budget]
         hot = [e for e in hot if hits[e] >= 4]
+        self._nz |= set(hot)
         for (i, j) in hot:
             self.w(f"  double jh_{i}_{j} = {'1.0' if i == j else '0.0'};")
         written = set()
@@ -450,6 +455,7 @@ class _Gen:
         self.w("#pragma unroll")
         self.w("  for (int k = 0; k < SPEC_NRO; k++) SW(SPEC_OFF_RO + k) = 0.0;")
         rec, self._recording = self._recording, False   # the loop below touches every pair: not structure
+        self._touch_all = True
         for i in self.coupled:
             for j in self.coupled:
                 e = self.J(i, j)
@@ -465,6 +471,7 @@ class _Gen:
                 else:
                     self.w(f"  {e} = 0.0;")
         self._recording = rec
+        self._touch_all = False
         if self.nc:
             self.w("  if (s.dry) {")
             self.w("#pragma unroll 1")
@@ -1470,6 +1477,23 @@ class _Gen:
         self.w("__host__ __device__ constexpr int spec_cmap(int i) { return " + (cm + " : -1" if cm else "-1") + "; }")
         self.w("__host__ __device__ constexpr int spec_sp_of(int ci) { return " + (so + " : 0" if so else "0") + "; }")
         self.w("__host__ __device__ constexpr bool spec_is_rowonly(int i) { return " + (ro if ro else "false") + "; }")
+        # structure of the dense core: bit cj of row ci is set when the generated code can make J(ci, cj)
+        # non-zero (the diagonal always: accumulation, and the identity of a dry cell); RSolve's row
+        # scaling skips the others, which hold exact zeros until the decomposition fills them in
+        masks = []
+        for sp_i, ci in self.cpos.items():
+            m = 1 << ci
+            for sp_j, cj in self.cpos.items():
+                if (sp_i, sp_j) in self._nz:
+                    m |= 1 << cj
+            masks.append((ci, m))
+        if os.environ.get("PFRX_SPEC_DENSE_SCALING") or self.nc > 60:
+            masks = [(ci, (1 << max(self.nc, 1)) - 1) for ci, _ in masks]
+        jm = " : ".join(f"ci == {ci} ? {m}ull" for ci, m in masks)
+        self.w("__host__ __device__ constexpr unsigned long long spec_jrow_mask(int ci) { return "
+               + (jm + " : 0ull" if jm else "0ull") + "; }")
+        self.w("__host__ __device__ constexpr bool spec_jnz(int ci, int cj) { return (spec_jrow_mask(ci) >> cj) & 1ull; }")
+        self.jnz_density = (sum(bin(m).count("1") for _, m in masks) / float(max(1, self.nc * self.nc)))
         pc = " : ".join(f"i == {i} ? {q}" for i, q in enumerate(self.pri_cls) if q >= 0)
         self.w("__host__ __device__ constexpr int spec_pri_cls(int i) { return " + (pc + " : -1" if pc else "-1") + "; }")
         self.w("__device__ __forceinline__ double spec_cx_z2(int k);")
