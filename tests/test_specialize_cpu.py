@@ -106,3 +106,27 @@ def test_build_is_cached(tmp_path, monkeypatch):
     assert specialize.build(wl.cfg) == p and os.path.getmtime(p) == t0  # stamp hit, no recompile
     log = open(p[:-6] + ".log").read()
     assert "sm_100a" in log and re.search(r"Used \d+ registers", log)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c3mr", "c5", "c4", "c4s", "c4se", "c4fe"])
+def test_structural_mask_covers_the_oracle_jacobian(name):
+    """RSolve's row scaling in the generated kernels skips the entries outside spec_jrow_mask: every
+    entry the oracle's Jacobian (accumulation + RReaction, reaction.F90:3868-3925) has on real cells
+    must be inside it"""
+    import oracle_lib as orc
+    from pflotran_elm_interface_b200 import workloads
+
+    wl = workloads.by_name(name, ncell=24)
+    g = specialize._Gen(wl.cfg)
+    g.source()
+    assert 0.0 < g.jnz_density <= 1.0
+    allowed = set(g._nz) | {(i, i) for i in range(wl.cfg.ncomp)}
+    for cell in range(24):
+        st = wl.state.copy()
+        e, R, J, _ = orc.girt_residual(wl.cfg, st, cell, wl.tran_dt)
+        assert e == 0
+        nzi, nzj = np.nonzero(J)
+        missing = {(int(i), int(j)) for i, j in zip(nzi, nzj)} - allowed
+        # row-only species sit outside the dense core; their rows are not scaled by the mask
+        missing = {(i, j) for (i, j) in missing if i not in g.roset}
+        assert not missing, (name, cell, sorted(missing)[:8])
