@@ -605,8 +605,10 @@ int pfrx_os_store(pfrx_handle *h, double *tran_xx);
  *   pfrx_os_load, RStep over tran_dt on every cell, pfrx_os_store;
  *   download tran_xx.
  * ncomp doubles per cell cross the link in each direction instead of the whole
- * state (pfrx_rstep_host).  Chunks of cells are pipelined over three streams; pass
- * page-locked vectors (cudaHostRegister) for the copies to overlap the kernel.
+ * state (pfrx_rstep_host).  Chunks of cells are pipelined over three streams (the
+ * first call on a shard runs in one chunk, the second in eight, later ones in
+ * whichever was faster); pass page-locked vectors (cudaHostRegister) for the
+ * copies to overlap the kernel.
  * Per-cell counts and flags stay in the bound state.                              */
 int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
                       pfrx_step_result *out);

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "pfrx_device.cuh"
@@ -341,6 +342,11 @@ struct pfrx_handle {
   // device staging of the two block vectors of pfrx_os_step_host
   double *os_a = nullptr, *os_b = nullptr;
   int64_t os_cap = 0;
+  // pfrx_os_step_host tries one chunk on its first call and eight on its second, then keeps the
+  // faster: a ragged workload pays the slowest cell of every chunk, a uniform one gains the overlap
+  double os_trial_s[2] = {0.0, 0.0};
+  int64_t os_trial_ncell = -1;
+  int os_calls = 0;
   // kernel seconds per cell and link seconds per cell seen by the latest pfrx_rstep_host: a step
   // whose kernel outweighs its transfers gains nothing from many chunks and, with the refill
   // skeleton, pays the slowest cell of every chunk
@@ -1686,8 +1692,16 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   if (rc) return rc;
   // the transfers are a few per cent of the kernel: a handful of chunks hides all but the first
   // upload and the last download
-  int nchunk = (int)std::min<int64_t>(8, std::max<int64_t>(1, ncell / 262144));
-  if (const char *ev = getenv("PFRX_OS_CHUNKS")) nchunk = std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(ev)));
+  const int many = (int)std::min<int64_t>(8, std::max<int64_t>(1, ncell / 262144));
+  if (h->os_trial_ncell != ncell) {
+    h->os_trial_ncell = ncell;
+    h->os_calls = 0;
+    h->os_trial_s[0] = h->os_trial_s[1] = 0.0;
+  }
+  int nchunk = h->os_calls == 0 ? 1 : h->os_calls == 1 ? many : (h->os_trial_s[1] < h->os_trial_s[0] ? many : 1);
+  const bool forced = getenv("PFRX_OS_CHUNKS") != nullptr;
+  if (forced) nchunk = std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(getenv("PFRX_OS_CHUNKS"))));
+  const auto wall0 = std::chrono::steady_clock::now();
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   rc = summary_reset(h, s_k);
   if (rc) return rc;
@@ -1730,6 +1744,9 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   CUDA_OK(cudaStreamSynchronize(s_out));
   h->pending = false;
   summary_out(h, out);
+  if (!forced && h->os_calls < 2)
+    h->os_trial_s[h->os_calls] = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  if (!forced) h->os_calls++;
   if (out->first_failed_cell >= 0 && nchunk > 1) {
     // chunk-local index: recover the shard index from the per-cell error flags
     std::vector<int> ie((size_t)ncell);
