@@ -296,6 +296,18 @@ static uint64_t config_signature(const pfrx_config *c) {
     h = fnv1a(h, &e, sizeof(e));
     if (c->sandbox_list) ADD(c->sandbox_list, c->nsandbox)
   }
+  // what the generator bakes in or refuses beyond the tables above: a cubin cached by signature
+  // must not survive a change of any of these (presence and contents)
+  {
+    int32_t feat[5] = {c->h2o_aq_id, c->use_isothermal, c->act_coef_update_algorithm, c->use_total_as_guess,
+                       c->use_full_geochemistry};
+    h = fnv1a(h, feat, sizeof(feat));
+    ADD(c->kinmnrl_Temkin_const, c->nkinmnrl)
+    ADD(c->kinmnrl_min_scale_factor, c->nkinmnrl)
+    ADD(c->kinmnrl_affinity_power, c->nkinmnrl)
+    ADD(c->kinmnrl_num_prefactors, c->nkinmnrl)
+    ADD(c->srfcplxrxn_stoich_flag, c->nsrfcplxrxn)
+  }
 #undef ADD
   return h;
 }
@@ -328,6 +340,7 @@ struct pfrx_handle {
   int64_t launches = 0;
   // row counts of every field, in pfrx_state order
   std::vector<int> rows_d;  // 20 double fields
+  std::vector<int> sr_flag_host;  // srfcplxrxn_stoich_flag (host copy: pfrx_load_specialized refuses inner-Newton sites)
   // owned device state for pfrx_rstep_host
   void *own = nullptr;
   int64_t own_ncell = 0;
@@ -606,6 +619,7 @@ static int layout_and_launch_params(pfrx_handle *h) {
   return PFRX_OK;
 }
 
+extern "C" void pfrx_destroy(pfrx_handle *h);
 extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) {
   if (!c || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
   if (c->abi_version != PFRX_ABI_VERSION) return set_err(PFRX_E_INVALID, "abi_version mismatch%s", "");
@@ -1199,7 +1213,14 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     delete h;
     return set_err(PFRX_E_CUDA, "cudaMalloc(tables): %s", cudaGetErrorString(e));
   }
-  if (!A.bytes.empty()) cudaMemcpy(h->arena, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice);
+  if (!A.bytes.empty()) {
+    e = cudaMemcpy(h->arena, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(h->arena);
+      delete h;
+      return set_err(PFRX_E_CUDA, "cudaMemcpy(tables): %s", cudaGetErrorString(e));
+    }
+  }
   for (auto &f : A.fix) *f.second = (unsigned char *)h->arena + f.first;
 
   h->rows_d.resize(PFRX_NUM_D);
@@ -1216,10 +1237,16 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     delete h;
     return rc;
   }
-  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-  cudaMalloc(&h->d_summ, sizeof(DevSummary));
-  cudaMallocHost(&h->h_summ, sizeof(DevSummary));
+  // nothing half-built is handed out: a handle whose streams or summary buffers are missing would
+  // fault at its first step
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_summ, sizeof(DevSummary));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_summ, sizeof(DevSummary));
+  if (e != cudaSuccess) {
+    pfrx_destroy(h);
+    return set_err(PFRX_E_CUDA, "pfrx_create (streams / summary buffers): %s", cudaGetErrorString(e));
+  }
   *out = h;
   return PFRX_OK;
 }
@@ -1342,8 +1369,9 @@ static int summary_reset(pfrx_handle *h, cudaStream_t s) {
   return PFRX_OK;
 }
 
-// one kernel launch over cells [0, ncell) of `st`; `cell0` is added to the
-// first-failed-cell index so that chunked launches report shard-local indices
+// one kernel launch over cells [0, ncell) of `st`.  Chunked callers pass a view that starts at
+// their first cell; the chunk-local first-failed-cell index is turned into a shard-local one on the
+// host when the chunks are merged
 static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
   if (ncell <= 0) return PFRX_OK;
   int cpw = 32 / h->lanes;
@@ -2088,9 +2116,13 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   if (!cubin_path) return PFRX_OK;
   // features outside what specialize.py generates (its supported() is the twin of this test)
   const DevCfg &d = h->cfg;
+  bool inner_newton = false;
+  for (int r = 0; r < d.nsrfrxn && h->sr_flag_host.size() == (size_t)d.nsrfrxn; r++)
+    inner_newton = inner_newton || h->sr_flag_host[r] != 0;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0)
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton ||
+      d.nsrfrxn != d.neqsr + d.nmr)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();
   if (rc) return rc;

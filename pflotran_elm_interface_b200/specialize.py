@@ -37,7 +37,7 @@ OUT = os.path.join(CSRC, "_spec")
 LOG_TO_LN = chem.LOG_TO_LN
 
 # variant letter -> code style (PFRX_SPEC_VARIANT=<letter><warps per 32 cells>)
-VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "r": "rolled", "q": "refill",
+VARIANT_STYLES = {"s": "straight", "k": "lockstep", "l": "looplu", "m": "klooplu", "q": "refill",
                   "p": "refill_looplu", "w": "refill_warp"}
 
 
@@ -140,6 +140,16 @@ def signature(cfg: abi.ReactionConfig) -> int:
         parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
         if c.nsandbox:
             parts.append(np.ascontiguousarray(a["sandbox_list"], dtype=i4).tobytes())
+    # what the generator bakes in or refuses beyond the tables above (same bytes as config_signature())
+    parts.append(struct.pack("<5i", c.h2o_aq_id, c.use_isothermal, c.act_coef_update_algorithm, c.use_total_as_guess,
+                             c.use_full_geochemistry))
+    for k in ("kinmnrl_Temkin_const", "kinmnrl_min_scale_factor", "kinmnrl_affinity_power"):
+        if k in a:
+            add(k, c.nkinmnrl, f8)
+    if "kinmnrl_num_prefactors" in a:
+        add("kinmnrl_num_prefactors", c.nkinmnrl, i4)
+    if c.nsrfcplxrxn > 0 and "srfcplxrxn_stoich_flag" in a:
+        add("srfcplxrxn_stoich_flag", c.nsrfcplxrxn, i4)
     return _fnv1a(b"".join(parts))
 
 
@@ -149,10 +159,21 @@ def _variant(cfg: abi.ReactionConfig, warps: Optional[int], style: Optional[str]
     return (dw if warps is None else warps), (ds if style is None else style)
 
 
+def uses_form2(cfg: abi.ReactionConfig, warps: int, style: str) -> bool:
+    """form 2 (specialize2.py / csrc/pfrx_spec2.cuh: product-form speciation, symmetric ln-space
+    Jacobian, sparse L D L^T) serves the one-warp-per-32-cells styles of the networks it covers"""
+    from . import specialize2
+
+    if warps != 1 or style not in specialize2.FORM2_STYLES:
+        return False
+    return supported(cfg)[0] and specialize2.supported2(cfg)[0]
+
+
 def cubin_path(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
     warps, style = _variant(cfg, warps, style)
     tag = {v: k for k, v in VARIANT_STYLES.items()}[style]
-    return os.path.join(OUT, f"spec_{signature(cfg):016x}_{tag}{warps}.cubin")
+    form = "f2" if uses_form2(cfg, warps, style) else ""
+    return os.path.join(OUT, f"spec_{signature(cfg):016x}_{tag}{warps}{form}.cubin")
 
 
 def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
@@ -1504,519 +1525,29 @@ class _Gen:
         return "\n".join(self.out + body) + "\n"
 
 
-class _GenW(_Gen):
-    """SPEC_W warps per group of 32 cells (csrc/pfrx_specw.cuh)"""
-
-    def __init__(self, cfg: abi.ReactionConfig, warps: int):
-        super().__init__(cfg)
-        self.W = warps
-        ok, why = supported_multiwarp(cfg, warps)
-        if not ok:
-            raise ValueError("multi-warp specialisation: " + why)
-        # species owner: coupled species by matrix position (the LU's row ownership),
-        # the others round-robin
-        self.owner = {}
-        dec = 0
-        for i in range(self.n):
-            if i in self.cpos:
-                self.owner[i] = self.cpos[i] % warps
-            else:
-                self.owner[i] = dec % warps
-                dec += 1
-        self.cx_owner = [k % warps for k in range(self.ncx)]
-
-    def lna(self, i: int) -> str:
-        return f"SW(EXS({self.cpos[i]}))"
-
-    def ic(self, i: int) -> str:
-        return f"SW(SW_OFF_IC + {self.cpos[i]})"
-
-    def lnqk(self, logk: float, h2o: float, ptr, ids, st, k: int) -> str:
-        expr = _lit(-float(logk) * LOG_TO_LN)
-        if h2o != 0.0:
-            expr += _term(h2o, "s.ln_act_h2o")
-        for p in range(ptr[k], ptr[k + 1]):
-            expr += _term(float(st[p]), self.lna(int(ids[p])))
-        return expr
-
-    def gen_maps(self) -> None:
-        def chain(pairs, var, default):
-            body = " : ".join(f"{var} == {a} ? {b}" for a, b in pairs)
-            return (body + f" : {default}") if body else str(default)
-
-        self.w("__host__ __device__ constexpr int spec_cmap(int i) { return " +
-               chain(self.cpos.items(), "i", -1) + "; }")
-        self.w("__host__ __device__ constexpr int spec_sp_of(int ci) { return " +
-               chain([(ci, sp) for sp, ci in self.cpos.items()], "ci", 0) + "; }")
-        self.w("__host__ __device__ constexpr int spec_owner(int i) { return " +
-               chain(self.owner.items(), "i", 0) + "; }")
-        self.w("__host__ __device__ constexpr int spec_cx_owner(int k) { return k % SPEC_W; }")
-        z2 = [(i, _lit(float(self.a["primary_spec_Z"][i]) ** 2)) for i in range(self.naq)]
-        self.w("__host__ __device__ constexpr double spec_z2(int i) { return " + chain(z2, "i", "0.0") + "; }")
-
-    def gen_activity_w(self, w: int) -> None:
-        c = self.c
-        self.w(f"template <> __device__ __forceinline__ void specw_activity<{w}>(double I, CellW &s) {{")
-        need = set()
-        for i in range(self.naq):
-            if self.owner[i] == w and self.pri_cls[i] >= 0:
-                need.add(self.pri_cls[i])
-        for k in range(self.ncx):
-            if self.cx_owner[k] == w and self.cx_cls[k] >= 0:
-                need.add(self.cx_cls[k])
-        self.w("  const double sq = sqrt(I);")
-        A, B, Bd = _lit(c.debyeA), _lit(c.debyeB), _lit(c.debyeBdot)
-        for q in sorted(need):
-            negz2, a0 = self.cls[q]
-            self.w(f"  s.lgcls[{q}] = ({_lit(negz2)} * sq * {A} / (1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN;")
-        for i in range(self.naq):
-            if self.owner[i] == w:
-                q = self.pri_cls[i]
-                self.w(f"  s.lngam[{i}] = {'0.0' if q < 0 else f's.lgcls[{q}]'};")
-        self.w("}")
-        self.w()
-
-    def gen_complexes_w(self, w: int) -> None:
-        a = self.a
-        self.w(f"template <> __device__ __forceinline__ void specw_complexes<{w}>(CellW &s, const double *W,")
-        self.w("    double *sec_out, long long ld, bool store) {")
-        self.w("  double Is = 0.0;")
-        if self.ncx:
-            ptr, ids, st = a["eqcplx_ptr"], a["eqcplx_specid"], a["eqcplx_stoich"]
-            for k in range(self.ncx):
-                if self.cx_owner[k] != w:
-                    continue
-                expr = self.lnqk(a["eqcplx_logK"][k], float(a["eqcplx_h2ostoich"][k]), ptr, ids, st, k)
-                q = self.cx_cls[k]
-                arg = f"({expr})" if q < 0 else f"({expr}) - s.lgcls[{q}]"
-                self.w("  {")
-                self.w(f"    const double sk = exp({arg});")
-                self.w(f"    if (store) sec_out[{k} * ld] = sk;")
-                z2 = float(a["eqcplx_Z"][k]) ** 2
-                if z2 != 0.0:
-                    self.w(f"    Is += sk * {_lit(z2)};")
-                self.w("  }")
-        self.w("  s.Is_part = Is;")
-        self.w("}")
-        self.w()
-
-    def gen_rows_w(self, w: int) -> None:
-        a = self.a
-        own = [i for i in self.coupled if self.owner[i] == w]
-        self.w(f"template <> __device__ __forceinline__ void specw_rows<{w}>(const CellW &s, double *W,")
-        self.w("    const double *sec_in, long long ld, double dt, double (&tot)[SPEC_N]) {")
-        self.w("  const double denL = s.den_kg * 1.e-3;")
-        self.w("  const double psvd = s.por * s.sat * 1000.0 * s.vol / dt;")
-        for i in own:
-            self.w(f"  tot[{i}] = SW(SW_OFF_C + {self.cpos[i]});")
-        hits = {}
-        if self.ncx:
-            ptr, ids, st = a["eqcplx_ptr"], a["eqcplx_specid"], a["eqcplx_stoich"]
-            for k in range(self.ncx):
-                sp = range(ptr[k], ptr[k + 1])
-                for p2 in sp:
-                    for p in sp:
-                        if int(ids[p]) in own:
-                            e = (int(ids[p]), int(ids[p2]))
-                            hits[e] = hits.get(e, 0) + 1
-        hot = [e for e in sorted(hits, key=lambda e: -hits[e])[:8] if hits[e] >= 4]
-        for (i, j) in hot:
-            self.w(f"  double jh_{i}_{j} = {'1.0' if i == j else '0.0'};")
-        written = set()
-        if self.ncx:
-            for k in range(self.ncx):
-                sp = list(range(ptr[k], ptr[k + 1]))
-                mine = [p for p in sp if int(ids[p]) in own]
-                if not mine:
-                    continue
-                self.w("  {")
-                self.w(f"    const double sk = __ldcg(sec_in + {k} * ld);")
-                for p in mine:
-                    i, s_i = int(ids[p]), float(st[p])
-                    if s_i == 1.0:
-                        self.w(f"    tot[{i}] += sk;")
-                    elif s_i == -1.0:
-                        self.w(f"    tot[{i}] -= sk;")
-                    else:
-                        self.w(f"    tot[{i}] += {_lit(s_i)} * sk;")
-                for p2 in sp:
-                    j, s_j = int(ids[p2]), float(st[p2])
-                    tj = f"(sk * {self.ic(j)})" if s_j == 1.0 else f"(({_lit(s_j)} * sk) * {self.ic(j)})"
-                    self.w(f"    {{ const double t = {tj};")
-                    for p in mine:
-                        i, s_i = int(ids[p]), float(st[p])
-                        val = "t" if s_i == 1.0 else f"{_lit(s_i)} * t"
-                        if (i, j) in hot:
-                            self.w(f"      jh_{i}_{j} += {val};")
-                        else:
-                            e = self.J(i, j)
-                            if (i, j) in written:
-                                self.w(f"      {e} += {val};")
-                            else:
-                                init = "1.0 + " if i == j else ""
-                                self.w(f"      {e} = {init}{val};")
-                                written.add((i, j))
-                    self.w("    }")
-                self.w("  }")
-        for i in own:
-            self.w(f"  tot[{i}] *= denL;")
-        for i in own:
-            for j in self.coupled:
-                e = self.J(i, j)
-                if (i, j) in hot:
-                    self.w(f"  {e} = (jh_{i}_{j} * denL) * psvd;")
-                elif (i, j) in written:
-                    self.w(f"  {e} = ({e} * denL) * psvd;")
-                elif i == j:
-                    self.w(f"  {e} = (1.0 * denL) * psvd;")
-                else:
-                    self.w(f"  {e} = 0.0;")
-        if own:
-            self.w("  if (s.dry) {")
-            for i in own:
-                ci = self.cpos[i]
-                self.w("#pragma unroll 1")
-                self.w(f"    for (int j = 0; j < SPEC_NC; j++) W[JX({ci}, j)] = (j == {ci}) ? 1.0 : 0.0;")
-            self.w("  }")
-        self.w("}")
-        self.w()
-
-    def gen_eval(self) -> None:
-        c, a = self.c, self.a
-        self.w("__device__ __noinline__ void specw_eval(const double *W, const DevState &st, long long cell,")
-        self.w("    double den_kg, double por, double vol, double spd, double temp, double ln_act_h2o, bool apply,")
-        self.w("    EvalOut *out) {")
-        self.w("  struct { double ln_act_h2o; } s = {ln_act_h2o};")
-        for e in range(c.neqsrfcplxrxn):
-            r = int(a["eqsrfcplxrxn_to_srfcplxrxn"][e])
-            cx = [int(v) for v in a["srfcplxrxn_to_complex"][a["srfcplxrxn_ptr"][r]:a["srfcplxrxn_ptr"][r + 1]]]
-            ty = int(a["srfcplxrxn_surf_type"][r])
-            dens = _lit(float(a["srfcplxrxn_site_density"][r]))
-            ptr, ids, st_ = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
-            species = sorted({int(ids[p]) for k in cx for p in range(ptr[k], ptr[k + 1])})
-            self.w("  {")
-            if ty == chem.MINERAL_SURFACE:
-                self.w(f"    const double dens = {dens} * __ldcg(st.mnrl_volfrac + {int(a['srfcplxrxn_to_surf'][r])} * st.ld + cell);")
-            elif ty == chem.ROCK_SURFACE:
-                self.w(f"    const double dens = {dens} * spd * (1.0 - por);")
-            else:
-                self.w(f"    const double dens = {dens};")
-            self.w("    if (dens < 1.e-40) {")
-            self.w(f"      out->fsite[{r}] = 0.0;")
-            for k in cx:
-                self.w(f"      out->S[{k}] = 0.0; out->nuis[{k}] = 0.0;")
-            for i in species:
-                self.w(f"      out->dsx[{r} * SPEC_NC + {self.cpos[i]}] = 0.0;")
-            self.w("    } else {")
-            for q, k in enumerate(cx):
-                expr = self.lnqk(a["srfcplx_logK"][k], float(a["srfcplx_h2ostoich"][k]), ptr, ids, st_, k)
-                self.w(f"      const double e{q} = exp({expr});")
-            self.w("      double esum = 0.0;")
-            for q in range(len(cx)):
-                self.w(f"      esum += e{q};")
-            self.w("      const double fs = dens / (1.0 + esum);")
-            self.w(f"      out->fsite[{r}] = fs;")
-            for q, k in enumerate(cx):
-                self.w(f"      const double S{q} = e{q} * fs;")
-                self.w(f"      out->S[{k}] = S{q}; out->nuis[{k}] = S{q} / fs;")
-            self.w("      double den = 0.0;")
-            for q in range(len(cx)):
-                self.w(f"      den += S{q};")
-            self.w("      den = den / fs + 1.0;")
-            for i in species:
-                self.w(f"      double tmp{i} = 0.0;")
-            for q, k in enumerate(cx):
-                for p in range(ptr[k], ptr[k + 1]):
-                    i, nu = int(ids[p]), float(st_[p])
-                    v = f"S{q}" if nu == 1.0 else f"{_lit(nu)} * S{q}"
-                    self.w(f"      tmp{i} += {v};")
-            for i in species:
-                self.w(f"      out->dsx[{r} * SPEC_NC + {self.cpos[i]}] = (-tmp{i} / den) * {self.ic(i)};")
-            self.w("    }")
-            self.w("  }")
-        for m in range(c.nkinmnrl):
-            ptr, ids, st_ = a["kinmnrl_ptr"], a["kinmnrl_specid"], a["kinmnrl_stoich"]
-            expr = self.lnqk(a["kinmnrl_logK"][m], float(a["kinmnrl_h2ostoich"][m]), ptr, ids, st_, m)
-            thr = float(a["kinmnrl_affinity_threshold"][m])
-            lim = float(a["kinmnrl_rate_limiter"][m])
-            eact = float(a["kinmnrl_activation_energy"][m])
-            irr = int(a["kinmnrl_irreversible"][m])
-            rate = _lit(float(a["kinmnrl_rate_constant"][m]))
-            self.w("  {")
-            self.w(f"    const double QK = exp({expr});")
-            self.w("    double aff = 1.0 - QK;")
-            self.w("    const double sgn = copysign(1.0, aff);")
-            self.w(f"    bool active = (__ldcg(st.mnrl_volfrac + {m} * st.ld + cell) > 0.0 || sgn < 0.0);")
-            if irr == 1:
-                self.w("    if (sgn < 0.0) active = false;")
-            if thr > 0.0:
-                self.w(f"    if (sgn < 0.0 && QK < {_lit(thr)}) active = false;")
-            self.w("    double rate_vol = 0.0, Imv = 0.0, dfac = 0.0;")
-            self.w("    if (active) {")
-            if lim > 0.0:
-                self.w(f"      aff = aff / (1.0 + (1.0 - aff) / {_lit(lim)});")
-            if eact > 0.0:
-                self.w(f"      const double spr = {rate} * exp({_lit(eact)} / 8.31446 * "
-                       "(1.0 / (25.0 + 273.15) - 1.0 / (temp + 273.15)));")
-            else:
-                self.w(f"      const double spr = {rate} * 1.0;")
-            self.w(f"      double Im_const = -st.mnrl_area[{m} * st.ld + cell];")
-            self.w("      double Im = Im_const * sgn * fabs(aff) * spr;")
-            self.w("      rate_vol = Im;")
-            self.w("      if (apply) {")
-            self.w("        Im_const = Im_const * vol;")
-            self.w("        Imv = Im * vol;")
-            self.w("        const double dIm_dQK = -Im_const * spr;")
-            if lim > 0.0:
-                self.w(f"        const double den = 1.0 + (1.0 - aff) / {_lit(lim)};")
-                self.w(f"        dfac = dIm_dQK * (1.0 + QK / {_lit(lim)} / den) * QK * (den_kg * 1.e-3) / den;")
-            else:
-                self.w("        dfac = dIm_dQK * QK * (den_kg * 1.e-3);")
-            self.w("      }")
-            self.w("    }")
-            self.w(f"    out->Im[{m}] = Imv; out->dfac[{m}] = dfac; out->mrate[{m}] = rate_vol;")
-            self.w("  }")
-        self.w("}")
-        self.w()
-
-    def gen_apply_w(self, w: int) -> None:
-        c, a = self.c, self.a
-        self.w(f"template <> __device__ __forceinline__ void specw_apply<{w}>(const CellW &s, const EvalOut &e,")
-        self.w("    double *W, double jscale, double (&ts)[SPEC_N], double (&res)[SPEC_N], bool minerals) {")
-        self.w("  if (!minerals) {")
-        for eq in range(c.neqsrfcplxrxn):
-            r = int(a["eqsrfcplxrxn_to_srfcplxrxn"][eq])
-            cx = [int(v) for v in a["srfcplxrxn_to_complex"][a["srfcplxrxn_ptr"][r]:a["srfcplxrxn_ptr"][r + 1]]]
-            ptr, ids, st_ = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
-            for k in cx:
-                sp = list(range(ptr[k], ptr[k + 1]))
-                mine = [p for p in sp if self.owner[int(ids[p])] == w]
-                if not mine:
-                    continue
-                for p in mine:
-                    i, nu = int(ids[p]), float(st_[p])
-                    v = f"e.S[{k}]" if nu == 1.0 else f"{_lit(nu)} * e.S[{k}]"
-                    self.w(f"    ts[{i}] += {v};")
-                for p2 in sp:
-                    j, nu_j = int(ids[p2]), float(st_[p2])
-                    a1 = (f"e.S[{k}] * {self.ic(j)}" if nu_j == 1.0 else f"{_lit(nu_j)} * e.S[{k}] * {self.ic(j)}")
-                    self.w(f"    {{ const double t = {a1} + e.nuis[{k}] * e.dsx[{r} * SPEC_NC + {self.cpos[j]}];")
-                    for p in mine:
-                        i, nu_i = int(ids[p]), float(st_[p])
-                        v = "t" if nu_i == 1.0 else f"({_lit(nu_i)} * t)"
-                        self.w(f"      {self.J(i, j)} += jscale * {v};")
-                    self.w("    }")
-        self.w("  } else {")
-        for m in range(c.nkinmnrl):
-            ptr, ids, st_ = a["kinmnrl_ptr"], a["kinmnrl_specid"], a["kinmnrl_stoich"]
-            sp = list(range(ptr[m], ptr[m + 1]))
-            mine = [p for p in sp if self.owner[int(ids[p])] == w]
-            if not mine:
-                continue
-            for p in mine:
-                i, nu = int(ids[p]), float(st_[p])
-                self.w(f"    res[{i}] +={' ' if nu == 1.0 else f' {_lit(nu)} *'} e.Im[{m}];")
-            for p2 in sp:
-                j, nu_j = int(ids[p2]), float(st_[p2])
-                self.w(f"    {{ const double t = e.dfac[{m}] * ({_lit(nu_j)} * {self.ic(j)});")
-                for p in mine:
-                    i, nu_i = int(ids[p]), float(st_[p])
-                    v = "t" if nu_i == 1.0 else f"{_lit(nu_i)} * t"
-                    self.w(f"      {self.J(i, j)} += {v};")
-                self.w("    }")
-        self.w("  }")
-        self.w("}")
-        self.w()
-
-    def source(self) -> str:
-        c, n, W = self.c, self.n, self.W
-        slots = self.nc * (self.nc + 1) + 2 * self.nc + 3 * W
-        per_block = slots * 32 * 8 + 1024
-        groups = max(1, min(16 // W, (227 * 1024) // per_block))  # <= 16 warps/SM keeps 128 registers per thread
-        self.threads, self.minblocks, self.slots = 32 * W, groups, slots
-        self.out.clear()
-        self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
-        for k, v in (("SPEC_N", n), ("SPEC_NAQ", self.naq), ("SPEC_NC", self.nc), ("SPEC_NCX", self.ncx),
-                     ("SPEC_NCLS", len(self.cls)), ("SPEC_NKIN", c.nkinmnrl), ("SPEC_NSRFRXN", c.nsrfcplxrxn),
-                     ("SPEC_NSRFCPLX", c.nsrfcplx), ("SPEC_NEQSR", c.neqsrfcplxrxn),
-                     ("SPEC_USE_LOG", int(c.use_log_formulation)), ("SPEC_ACT_UPD", int(self.act_upd)),
-                     ("SPEC_USE_ACT_H2O", int(c.use_activity_h2o)), ("SPEC_W", W), ("SPEC_MINBLOCKS", groups)):
-            self.w(f"#define {k} {v}")
-        self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
-        self.gen_maps()
-        self.w("__device__ __forceinline__ double spec_cx_z2(int k);")
-        self.w("__device__ __forceinline__ int spec_cx_cls(int k);")
-        self.w("__device__ __forceinline__ double spec_mn_vol(int m);")
-        self.w('#include "pfrx_specw.cuh"')
-        self.w()
-        self.gen_tables()
-        self.gen_eval()
-        for w in range(W):
-            self.gen_activity_w(w)
-            self.gen_complexes_w(w)
-            self.gen_rows_w(w)
-            self.gen_apply_w(w)
-        self.w('#include "pfrx_specw_kernel.cuh"')
-        return "\n".join(self.out) + "\n"
-
-
-class _GenR(_GenW):
-    """rolled variant (csrc/pfrx_specr.cuh): the network as __constant__ tables, sizes
-    as macros, one instruction stream for the SPEC_W warps of a group"""
-
-    def table(self, ctype: str, name: str, vals, fmt) -> None:
-        vals = list(vals)
-        body = ", ".join(fmt(v) for v in vals) if vals else ("0" if ctype == "int" else "0.0")
-        self.w(f"__constant__ {ctype} {name}[{max(1, len(vals))}] = {{{body}}};")
-
-    def source(self) -> str:
-        c, a, n, W = self.c, self.a, self.n, self.W
-        I = lambda v: str(int(v))
-        D = lambda v: _lit(float(v))
-        slots = self.nc * (self.nc + 1) + 2 * self.nc + 3 * W
-        per_block = slots * 32 * 8 + 1024
-        groups = max(1, min(16 // W, (227 * 1024) // per_block))
-        self.threads, self.minblocks, self.slots = 32 * W, groups, slots
-        nr = c.nsrfcplxrxn
-        maxq = 1
-        if nr:
-            rp = a["srfcplxrxn_ptr"]
-            maxq = max(int(rp[r + 1] - rp[r]) for r in range(nr))
-            cxs = [int(v) for v in a["srfcplxrxn_to_complex"]]
-            if len(set(cxs)) != len(cxs):
-                raise ValueError("a surface complex that belongs to two reactions")
-        self.out.clear()
-        self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
-        for k, v in (("SPEC_N", n), ("SPEC_NAQ", self.naq), ("SPEC_NC", self.nc), ("SPEC_NCX", self.ncx),
-                     ("SPEC_NCLS", len(self.cls)), ("SPEC_NKIN", c.nkinmnrl), ("SPEC_NSRFRXN", nr),
-                     ("SPEC_NSRFCPLX", c.nsrfcplx), ("SPEC_NEQSR", c.neqsrfcplxrxn), ("SPEC_MAXQ", maxq),
-                     ("SPEC_USE_LOG", int(c.use_log_formulation)), ("SPEC_ACT_UPD", int(self.act_upd)),
-                     ("SPEC_W", W), ("SPEC_MINBLOCKS", groups), ("SPEC_DEBYE_A", _lit(c.debyeA)),
-                     ("SPEC_DEBYE_B", _lit(c.debyeB)), ("SPEC_DEBYE_BDOT", _lit(c.debyeBdot))):
-            self.w(f"#define {k} {v}")
-        self.w(f"#define SPEC_SIG {signature(self.cfg)}ull")
-        self.w("#include <cuda_runtime.h>")
-        cp = self.cpos
-        self.table("int", "T_cmap", [cp.get(i, -1) for i in range(n)], I)
-        self.table("double", "T_z2", [float(a["primary_spec_Z"][i]) ** 2 if i < self.naq else 0.0 for i in range(n)], D)
-        self.table("int", "T_pcls", [self.pri_cls[i] if i < self.naq else -1 for i in range(n)], I)
-        self.table("double", "T_cls_negz2", [q[0] for q in self.cls], D)
-        self.table("double", "T_cls_a0", [q[1] for q in self.cls], D)
-        # secondary complexes and their transpose (species -> complexes, ascending k)
-        if self.ncx:
-            ptr, ids, st = a["eqcplx_ptr"], a["eqcplx_specid"], a["eqcplx_stoich"]
-        else:
-            ptr, ids, st = [0], [], []
-        self.table("int", "T_cx_ptr", ptr, I)
-        self.table("int", "T_cx_id", [cp[int(v)] for v in ids], I)
-        self.table("double", "T_cx_nu", st, D)
-        self.table("double", "T_cx_lnk", [-float(v) * LOG_TO_LN for v in (a["eqcplx_logK"] if self.ncx else [])], D)
-        self.table("double", "T_cx_h2o", a["eqcplx_h2ostoich"] if self.ncx else [], D)
-        self.table("double", "T_cx_z2", [float(v) ** 2 for v in (a["eqcplx_Z"] if self.ncx else [])], D)
-        self.table("int", "T_cx_cls", self.cx_cls, I)
-        sp_ptr, sp_cx, sp_nu = [0], [], []
-        for ci, sp in enumerate(self.coupled):
-            for k in range(self.ncx):
-                for p in range(ptr[k], ptr[k + 1]):
-                    if int(ids[p]) == sp:
-                        sp_cx.append(k)
-                        sp_nu.append(float(st[p]))
-            sp_ptr.append(len(sp_cx))
-        self.table("int", "T_sp_ptr", sp_ptr, I)
-        self.table("int", "T_sp_cx", sp_cx, I)
-        self.table("double", "T_sp_nu", sp_nu, D)
-        # kinetic minerals
-        nk = c.nkinmnrl
-        if nk:
-            mptr, mids, mst = a["kinmnrl_ptr"], a["kinmnrl_specid"], a["kinmnrl_stoich"]
-        else:
-            mptr, mids, mst = [0], [], []
-        self.table("int", "T_mn_ptr", mptr, I)
-        self.table("int", "T_mn_id", [cp[int(v)] for v in mids], I)
-        self.table("int", "T_mn_sp", mids, I)
-        self.table("double", "T_mn_nu", mst, D)
-        self.table("double", "T_mn_lnk", [-float(v) * LOG_TO_LN for v in (a["kinmnrl_logK"] if nk else [])], D)
-        for nm, key in (("T_mn_h2o", "kinmnrl_h2ostoich"), ("T_mn_vol", "kinmnrl_molar_vol"),
-                        ("T_mn_rate", "kinmnrl_rate_constant"), ("T_mn_eact", "kinmnrl_activation_energy"),
-                        ("T_mn_thr", "kinmnrl_affinity_threshold"), ("T_mn_lim", "kinmnrl_rate_limiter")):
-            self.table("double", nm, a[key] if nk else [], D)
-        self.table("int", "T_mn_irr", a["kinmnrl_irreversible"] if nk else [], I)
-        # equilibrium surface complexation
-        if nr:
-            kinds = {chem.MINERAL_SURFACE: 1, chem.ROCK_SURFACE: 2}
-            self.table("int", "T_sr_ptr", a["srfcplxrxn_ptr"], I)
-            self.table("int", "T_sr_cx", a["srfcplxrxn_to_complex"], I)
-            self.table("int", "T_sr_type", [kinds.get(int(v), 0) for v in a["srfcplxrxn_surf_type"]], I)
-            self.table("int", "T_sr_surf", [max(0, int(v)) for v in a["srfcplxrxn_to_surf"]], I)
-            self.table("double", "T_sr_dens", a["srfcplxrxn_site_density"], D)
-            sptr, sids, sst = a["srfcplx_ptr"], a["srfcplx_specid"], a["srfcplx_stoich"]
-            self.table("int", "T_sc_ptr", sptr, I)
-            self.table("int", "T_sc_id", [cp[int(v)] for v in sids], I)
-            self.table("int", "T_sc_sp", sids, I)
-            self.table("double", "T_sc_nu", sst, D)
-            self.table("double", "T_sc_lnk", [-float(v) * LOG_TO_LN for v in a["srfcplx_logK"]], D)
-            self.table("double", "T_sc_h2o", a["srfcplx_h2ostoich"], D)
-            self.table("int", "T_eq", a["eqsrfcplxrxn_to_srfcplxrxn"], I)
-            dnu = [0.0] * (nr * maxq * self.nc)
-            rp = a["srfcplxrxn_ptr"]
-            for r in range(nr):
-                for qq, k in enumerate(a["srfcplxrxn_to_complex"][rp[r]:rp[r + 1]]):
-                    for p in range(sptr[k], sptr[k + 1]):
-                        dnu[(r * maxq + qq) * self.nc + cp[int(sids[p])]] = float(sst[p])
-            self.table("double", "T_sr_dnu", dnu, D)
-        else:
-            for nm in ("T_sr_ptr", "T_sr_cx", "T_sr_type", "T_sr_surf", "T_sc_ptr", "T_sc_id", "T_sc_sp", "T_eq"):
-                self.table("int", nm, [0, 0] if nm.endswith("ptr") else [], I)
-            for nm in ("T_sr_dens", "T_sc_nu", "T_sc_lnk", "T_sc_h2o", "T_sr_dnu"):
-                self.table("double", nm, [], D)
-        self.w('#include "pfrx_specr.cuh"')
-        return "\n".join(self.out) + "\n"
-
-
-def supported_multiwarp(cfg: abi.ReactionConfig, warps: int) -> Tuple[bool, str]:
-    ok, why = supported(cfg)
-    if not ok:
-        return ok, why
-    c = cfg.c
-    used = set()
-    for ids in ("eqcplx_specid", "kinmnrl_specid", "srfcplx_specid"):
-        if ids in cfg.arrays:
-            used.update(int(v) for v in cfg.arrays[ids])
-    if warps not in (2, 4, 8):
-        return False, "2, 4 or 8 warps"
-    if c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
-        return False, "reaction sandbox"
-    if len(used) < 2 * warps:
-        return False, "too few coupled species for that many warps"
-    if not c.use_log_formulation:
-        return False, "linear update needs a global minimum ratio"
-    if c.act_coef_update_frequency != chem.ACT_COEF_FREQUENCY_NEWTON_ITER:
-        return False, "frozen activity coefficients of the complexes would need NCX more slots"
-    if c.use_activity_h2o:
-        return False, "activity of water"
-    return True, ""
-
-
 def default_variant(cfg: abi.ReactionConfig) -> Tuple[int, str]:
-    """(warps per 32 cells, style).  Measured on B200 with the Hanford 15/88 network
-    (profiles/r01_spec_variants.md): straight-line code with one warp per 32 cells
-    135 ms, rolled tables with four warps 396 ms, straight-line with four warps
-    635 ms per 4.19 M cells -- so the first is the default for every network; the
-    other two stay selectable for experiments:
-    PFRX_SPEC_VARIANT=<style><warps> with style s (straight), r (rolled) or l (straight-line
-    assembly, dense solve as rolled loops; one warp only)."""
+    """(warps per 32 cells, style): PFRX_SPEC_VARIANT=<style letter>1 selects a skeleton by hand
+    (s straight, k lock-step, q refill, w refill in independent warps, l / m / p with the rolled
+    dense solve of form 1); the default is the lock-step skeleton for the networks of form 2 (two
+    warps per scheduler share one instruction stream) and the nested-loop one otherwise.
+    ChemistryStep.autotune times the built variants on the actual state."""
     env = os.environ.get("PFRX_SPEC_VARIANT")
     if env:
         return int(env[1:]), VARIANT_STYLES[env[0]]
+    if uses_form2(cfg, 1, "lockstep"):
+        return 1, "lockstep"
     return 1, "straight"
 
 
 def generate_source(cfg: abi.ReactionConfig, warps: Optional[int] = None, style: Optional[str] = None) -> str:
     warps, style = _variant(cfg, warps, style)
-    if style == "rolled":
-        return _GenR(cfg, warps).source()
-    if warps > 1:
-        return _GenW(cfg, warps).source()
+    if uses_form2(cfg, warps, style):
+        from . import specialize2
+
+        return specialize2.generate_source2(cfg, style)
+    if warps != 1:
+        raise ValueError("one warp per 32 cells is the only layout (the multi-warp variants of round 1 measured "
+                         "4-7x slower and were removed)")
     g = _Gen(cfg)
     g.loop_lu = style in ("looplu", "klooplu", "refill_looplu")
     g.lockstep = style in ("lockstep", "klooplu", "refill", "refill_looplu", "refill_warp")
@@ -2029,7 +1560,7 @@ def _stamp(src: str) -> str:
     import hashlib
 
     h = hashlib.sha1(src.encode())
-    for d in ("pfrx_fastmath.cuh", "pfrx_spec.cuh", "pfrx_specw.cuh", "pfrx_specw_kernel.cuh", "pfrx_specr.cuh", "pfrx_types.cuh",
+    for d in ("pfrx_fastmath.cuh", "pfrx_spec.cuh", "pfrx_spec2.cuh", "pfrx_types.cuh",
               "pfrx_sandbox.cuh"):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(f.read())

@@ -37,16 +37,20 @@ def test_source_is_deterministic_and_covers_the_network():
     b = specialize.generate_source(W.by_name("c3", ncell=2).cfg)
     assert a == b
     c = wl.cfg.c
-    # one exp per secondary complex, streamed to rt_auxvar%sec_molal
-    assert len(re.findall(r"sec_out\[\d+ \* ld\] = sk;", a)) == c.neqcplx
+    # one product per secondary complex, streamed to rt_auxvar%sec_molal
+    assert len(re.findall(r"if \(s.store\) \*sp_ = sk;", a)) == c.neqcplx
     # tracers stay out of the matrix (two of the 15 Hanford primaries occur in no reaction)
     assert f"#define SPEC_N {c.naqcomp + c.nimcomp}" in a
     assert "#define SPEC_NC 13" in a
     assert f"#define SPEC_SIG {specialize.signature(wl.cfg)}ull" in a
     # every literal is an exact hexadecimal float or a small integer constant
     assert "0x1." in a and "nan" not in a.lower().replace("isnan", "")
+    for routine in ("void spec2_eval(", "bool spec2_solve_sym(", "void spec2_store_totals(", "void spec2_store_act("):
+        assert routine in a
+    # form 1 of the same network (multirate variant): the reference's exp-of-sums formulation
+    b1 = specialize.generate_source(W.by_name("c3mr", ncell=2).cfg)
     for routine in ("spec_activity", "spec_rtotal", "spec_sorption", "spec_minerals"):
-        assert f"void {routine}(" in a
+        assert f"void {routine}(" in b1
 
 
 def test_signature_tracks_tables():
@@ -66,7 +70,6 @@ def test_sandbox_network():
     # the aqueous tracer of the CLM-CN deck stays out of the matrix (no reaction), and so does the
     # respired C: a product only, its Jacobian column is the diagonal alone ("row-only")
     assert "#define SPEC_NC 11" in src and "#define SPEC_NROSPEC 1" in src
-    assert not specialize.supported_multiwarp(wl.cfg, 4)[0]
 
 
 def test_row_only_species_leave_the_matrix(monkeypatch):
@@ -80,18 +83,45 @@ def test_row_only_species_leave_the_matrix(monkeypatch):
     full = specialize.generate_source(wl.cfg)
     assert "#define SPEC_NC 19" in full and "#define SPEC_NROSPEC 0" in full
     # Hanford: every species sits in some complex, nothing is row-only
-    src3 = specialize.generate_source(W.by_name("c3", ncell=2).cfg)
+    src3 = specialize.generate_source(W.by_name("c3mr", ncell=2).cfg)
     assert "#define SPEC_NC 13" in src3 and "#define SPEC_NROSPEC 0" in src3
 
 
-def test_variants_generate():
+def test_variants_generate(monkeypatch):
     wl = W.by_name("c3", ncell=2)
-    straight4 = specialize.generate_source(wl.cfg, warps=4, style="straight")
-    rolled4 = specialize.generate_source(wl.cfg, warps=4, style="rolled")
-    assert '#include "pfrx_specw.cuh"' in straight4 and "specw_rows<3>" in straight4
-    assert '#include "pfrx_specr.cuh"' in rolled4 and "__constant__ double T_cx_lnk" in rolled4
-    ok, why = specialize.supported_multiwarp(W.by_name("c2", ncell=2).cfg, 4)
-    assert not ok and "coupled" in why
+    with pytest.raises(ValueError):
+        specialize.generate_source(wl.cfg, warps=4, style="straight")
+    # form 2 serves the one-warp styles of the Hanford / calcite class; the rolled dense solve and
+    # everything with a sandbox or multirate sorption stay on form 1
+    for style in ("straight", "lockstep", "refill", "refill_warp"):
+        src = specialize.generate_source(wl.cfg, warps=1, style=style)
+        assert "#define SPEC_FORM 2" in src and '#include "pfrx_spec2.cuh"' in src
+        assert specialize.cubin_path(wl.cfg, 1, style).endswith("f2.cubin")
+    assert '#include "pfrx_spec.cuh"' in specialize.generate_source(wl.cfg, warps=1, style="refill_looplu")
+    assert '#include "pfrx_spec.cuh"' in specialize.generate_source(W.by_name("c4", ncell=2).cfg)
+    assert '#include "pfrx_spec.cuh"' in specialize.generate_source(W.by_name("c3mr", ncell=2).cfg)
+    monkeypatch.setenv("PFRX_SPEC_FORM", "1")
+    assert '#include "pfrx_spec.cuh"' in specialize.generate_source(wl.cfg, warps=1, style="lockstep")
+
+
+def test_form2_symbolic_factorisation():
+    """the sparse L D L^T of form 2: elimination order, fill and the columns the reference's
+    surface-complexation Jacobian leaves incomplete"""
+    from pflotran_elm_interface_b200 import specialize2
+
+    g = specialize2._Gen2(W.by_name("c3", ncell=2).cfg)
+    assert g.nc == 13 and sorted(g.order) == g.coupled
+    assert g.nl == 69                       # 58 structural entries of the lower triangle + 11 fill
+    assert len(g.lslot) == g.nl and sorted(g.lslot.values()) == list(range(g.nl))
+    # UO2++ / H+ / HCO3- share the surface site; only HCO3- (species 7) is missing from a complex
+    assert g.sorb_species == [0, 4, 7] and g.ecols == [7]
+    assert sorted(i for (i, j) in g.evar) == [0, 4]
+    src = g.source()
+    assert "#define SPEC_SYM 1" in src and "#define SPEC_NL 69" in src and "#define SPEC_THREADS 256" in src
+    g5 = specialize2._Gen2(W.by_name("c5", ncell=2).cfg)
+    assert g5.ecols == [] and g5.nl == 69
+    lu = specialize2._Gen2(W.by_name("c3", ncell=2).cfg, solver="lu").source()
+    assert "#define SPEC_SYM 0" in lu and "#define SPEC_THREADS 128" in lu
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc")
@@ -99,7 +129,7 @@ def test_build_is_cached(tmp_path, monkeypatch):
     monkeypatch.setattr(specialize, "OUT", str(tmp_path))
     wl = W.by_name("c2", ncell=2)
     p = specialize.build(wl.cfg)
-    assert p.endswith("_s1.cubin")
+    assert p.endswith("_k1f2.cubin")
     import os
 
     t0 = os.path.getmtime(p)
