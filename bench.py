@@ -13,8 +13,16 @@ a parity-test case; `--workload c2` benches it anyway.
 
 Multi-GPU: one rank per GPU (torchrun), cells sharded by contiguous ownership
 ranges with no data-path collective; the only communication is the NCCL
-allreduce of the step flags (pfrx_allreduce).  Scaling is WEAK: every rank
-steps a full-size shard.
+allreduce of the step flags, enqueued by pfrx_rstep_async on the kernel stream
+behind the kernel and therefore inside the timed region.  Scaling is WEAK: every
+rank steps a full-size C3 shard.  At N >= 2 the line also carries `c5_baseline`:
+BASELINE.json's 512 x 512 x 256 multi-mineral grid split over the N ranks
+(STRONG scaling of a fixed 67 108 864-cell grid).
+
+`e2e` is the call that replaces the cell loop of PMCSubsurfaceOSRTStepDT
+(pmc_subsurface_osrt.F90:303-378): pfrx_os_step_host with HOST block vectors,
+the chemistry state resident in device memory from step to step as rt_auxvars
+are in the reference.  `e2e_full_state` moves the whole state (pfrx_rstep_host).
 """
 import argparse
 import json
@@ -123,6 +131,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_numa(local_rank: int) -> str:
+    """pin this rank (and the pinned host buffers it allocates afterwards) to the CPUs next to its GPU"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (int(mask[i // 64]) >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu {local_rank}"
+    except Exception as e:  # diagnostics only
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
+class _Sample:
+    """what cpu_baseline needs of a workload: cfg, tran_dt, name and a host state"""
+
+    def __init__(self, wl, n):
+        from pflotran_elm_interface_b200 import abi
+
+        self.cfg, self.tran_dt, self.name = wl.cfg, wl.tran_dt, wl.name
+        n = int(min(n, wl.state.ncell))
+        self.state = abi.HostState(wl.cfg, n)
+        for k, v in wl.state.a.items():
+            self.state.a[k][...] = v[:, :n]
+
+
 def cpu_baseline(wl, seconds, threads):
     """the oracle (a CPU port of the reference path: `kind` = port) on a bounded
     sample of the same workload, all host threads"""
@@ -149,7 +188,96 @@ def cpu_baseline(wl, seconds, threads):
     return {"value": n / dt, "unit": "cell-solves/s", "cores": threads, "kind": "port",
             "sample": f"first {n} cells of {wl.name} (same seeded states), {dt:.1f} s wall, "
                       f"{res.sum_newton_iterations / max(1, res.ncell_active):.2f} Newton its/cell",
-            "per_core": n / dt / threads, "seconds": dt}
+            "per_core": n / dt / threads, "seconds": dt, "cells_stepped": n}
+
+
+def parity_sample(wl_cfg, pristine, work, tran_dt, nsample=8192, seed=20261018):
+    """the launch that was just timed against the oracle on a random sample of its cells: inputs
+    from the pristine copy, outputs from the stepped state"""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    from pflotran_elm_interface_b200 import abi
+
+    n = pristine.ncell
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    idx = torch.randperm(n, generator=g)[: min(nsample, n)].sort().values.to(pristine.device)
+    ref = abi.HostState(wl_cfg, idx.numel())
+    got = abi.HostState(wl_cfg, idx.numel())
+    for k in ref.a:
+        ref.a[k][...] = pristine.t[k][:, idx].cpu().numpy()
+        got.a[k][...] = work.t[k][:, idx].cpu().numpy()
+    orc.rstep(wl_cfg, ref, tran_dt, os.cpu_count() or 1)
+    counts_equal = all(bool(np.array_equal(ref.a[f], got.a[f])) for f in abi.STATE_RESULT_FIELDS)
+    worst, where = 0.0, None
+    for f in ("total", "pri_molal", "immobile", "mnrl_volfrac", "total_sorb_eq", "sec_molal"):
+        a, b = ref.a[f], got.a[f]
+        if a.size == 0:
+            continue
+        scale = np.maximum(np.abs(a), np.abs(b))
+        err = np.where(scale < 1e-30, 0.0, np.abs(a - b) / np.maximum(scale, 1e-300))
+        if err.max() > worst:
+            worst, where = float(err.max()), f
+    return {"cells": int(idx.numel()), "max_rel_err": worst, "field": where, "counts_equal": bool(counts_equal),
+            "note": "random cells of the last timed launch vs the CPU oracle on the same inputs (tolerance 1e-10)"}
+
+
+def c5_baseline(step_c3, work_c3, pristine_c3, rank, world, local_rank, dev, total_cells=512 * 512 * 256, small=1 << 20,
+                steps=2, warmup=1):
+    import torch
+    import torch.distributed as dist
+    from pflotran_elm_interface_b200 import rstep, workloads
+
+    # free the C3 shard first
+    step_c3.close()
+    for d in (work_c3, pristine_c3):
+        d.t.clear()
+    torch.cuda.empty_cache()
+    n_rank = total_cells // world
+    dt = DEFAULT_DT["c5"]
+    wl = workloads.by_name("c5", ncell=small, tran_dt=dt)
+    step = rstep.ChemistryStep(wl.cfg, local_rank)
+    step.init_comm()
+    step.specialize(required=True)
+    tile = rstep.DeviceState.from_host(wl.state, dev)
+    shard = rstep.DeviceState(wl.cfg, n_rank, dev)
+
+    def retile():
+        for k, t in shard.t.items():
+            src = tile.t[k]
+            for c0 in range(0, n_rank, small):
+                c1 = min(n_rank, c0 + small)
+                t[:, c0:c1].copy_(src[:, : c1 - c0])
+        torch.cuda.synchronize(dev)
+
+    step.bind(shard)
+    ks = torch.cuda.ExternalStream(step.stream_ptr, device=dev)
+    ms = []
+    res = None
+    for i in range(warmup + steps):
+        retile()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ks)
+        step.rstep_async(dt)
+        e1.record(ks)
+        res = step.allreduce(step.rstep_finish())
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([float(np.sum(ms)) * 1e-3], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max = float(t.item())
+    out = {"workload": "c5", "grid": "512x512x256", "cells": int(res.ncell_active), "cells_per_gpu": n_rank,
+           "scaling": "strong", "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * t_max / steps,
+           "value": int(res.ncell_active) * steps / t_max, "unit": "cell-solves/s", "tran_dt_s": dt,
+           "kernel_variant": step.variant, "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
+           "inputs": f"shard tiled on the device from {small} seeded cells, re-tiled between steps",
+           "timing": "CUDA events on the kernel stream around kernel + NCCL reduction, max over ranks"}
+    step.close()
+    return out
 
 
 _REAL_STDOUT = None
@@ -191,6 +319,9 @@ def main():
         threads = os.cpu_count() or 1
         wl = workloads.by_name(a.workload, ncell=min(ncell, 1 << 18), tran_dt=dt)
         wl.name = workloads.by_name(a.workload, ncell=8, tran_dt=dt).name
+        cfg_json["cells_generated"] = int(wl.state.ncell)
+        cfg_json["note"] = ("the CPU arm steps a bounded sample per step (cells_stepped_per_step) of states drawn "
+                            "like the GPU arm's; throughput is per cell, the grid size is nominal")
         per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
         vals = []
         for i in range(a.warmup + a.steps):
@@ -203,7 +334,8 @@ def main():
                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_json,
                "cpu_baseline": {"value": v, "unit": "cell-solves/s", "cores": threads, "kind": "port",
-                                "sample": vals[-1]["sample"]},
+                                "sample": vals[-1]["sample"], "cells_stepped": vals[-1]["cells_stepped"]},
+               "cells_stepped_per_step": vals[-1]["cells_stepped"],
                "e2e": {"value": v, "unit": "cell-solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "note": "reference Fortran cannot be built in this image (no Fortran compiler/PETSc/MPI); this arm "
                        "times the C oracle port of the same path with back-substitution enabled (SURVEY 0.2)"}
@@ -220,7 +352,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    numa = bind_numa(local_rank)
     wl = workloads.by_name(a.workload, ncell=ncell, tran_dt=dt)
+    cpu_sample = _Sample(wl, 1 << 18) if (rank == 0 and not a.no_cpu) else None
     step = rstep.ChemistryStep(wl.cfg, local_rank)
     step.init_comm()
     if a.kernel != "generic":
@@ -264,10 +398,10 @@ def main():
         restore()
         barrier()
         ev[i][0].record(kstream)
-        step.rstep_async(dt)
+        step.rstep_async(dt)     # kernel + (N > 1) the NCCL reduction of the shard summaries, same stream
         ev[i][1].record(kstream)
         res = step.rstep_finish()
-        res = step.allreduce(res)
+        res = step.allreduce(res)  # N > 1: reads back what the stream already reduced
         kern_ms.append(ev[i][0].elapsed_time(ev[i][1]))
     barrier()
     wall = time.perf_counter() - wall0
@@ -283,6 +417,9 @@ def main():
     total_cells = int(res.ncell_active) * a.steps
     value = total_cells / t_max
     ms_per_step = 1000.0 * t_max / a.steps
+    parity = None
+    if rank == 0 and not a.no_cpu:
+        parity = parity_sample(wl.cfg, pristine, work, dt)
 
     # ---- e2e through the C ABI with host buffers (H2D + kernel + D2H) ----------
     e2e = None
@@ -303,6 +440,11 @@ def main():
                     torch.from_numpy(v).copy_(pristine.t[k])
             torch.cuda.synchronize(dev)
 
+        # what the step derives and only the next step reads stays in the device mirror
+        resident = [f for f in ("sec_molal", "sec_act_coef", "pri_act_coef") if rows[f]]
+        if wl.cfg.c.act_coef_update_frequency != 2:   # frozen coefficients are inputs the caller owns
+            resident = [f for f in resident if f == "sec_molal"]
+        step.rstep_host_resident(resident)
         refresh()
         step.rstep_host(host, dt)  # warm-up (allocates the device mirror)
         tt = []
@@ -321,8 +463,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             te = float(t.item())
         e2e = {"value": int(r2.ncell_active) / te, "unit": "cell-solves/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000.0 * te,
-               "api": "pfrx_rstep_host (C ABI, pinned host SoA buffers)"}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000.0 * te, "resident_fields": resident,
+               "api": "pfrx_rstep_host (C ABI, pinned host SoA buffers: the whole rt_auxvar state crosses the link; "
+                      "derived fields resident on the device via pfrx_rstep_host_resident)"}
+        step.rstep_host_resident([])
 
     # ---- the same step as PMCSubsurfaceOSRT sees it: chemistry state resident in HBM, only the
     # PETSc block vectors (solved totals in, tran_xx in/out) cross the host link every step ------
@@ -361,6 +505,17 @@ def main():
                          "rt_auxvar state bound in device memory between steps (pmc_subsurface_osrt.F90:303-378)"}
         del h_solved, h_xx
 
+    # ---- BASELINE.json's fifth configuration at its full size: 512 x 512 x 256 cells of the Hanford
+    # basis with six kinetic minerals, split over the ranks (STRONG scaling).  The shard is tiled on the
+    # device from a 2^20-cell host state and re-tiled between steps: no pristine copy of the shard.
+    bytes_per_cell, variant_name = step.bytes_per_cell, step.variant
+    c5 = None
+    if world >= 2 and a.workload == "c3" and not os.environ.get("PFRX_BENCH_NO_C5"):
+        try:
+            c5 = c5_baseline(step, work, pristine, rank, world, local_rank, dev)
+        except Exception as e:  # the headline line must survive a failure here
+            c5 = {"error": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,7 +529,7 @@ def main():
     its_local = res.sum_newton_iterations / max(1, world)        # per rank (weak scaling: equal shards)
     subs = cells_local                                          # >= one sub-step per cell
     flops_launch = its_local * f_eval + max(0.0, its_local - subs) * f_solve
-    bytes_launch = step.bytes_per_cell * cells_local
+    bytes_launch = bytes_per_cell * cells_local
     t_launch = t_max / a.steps
     ach_tf = flops_launch / t_launch / 1e12
     ach_gbs = bytes_launch / t_launch / 1e9
@@ -398,7 +553,7 @@ def main():
         pass
     roof.update({"traffic": traffic, "traffic_source": traffic_src, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
                  "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
-                 "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": step.bytes_per_cell,
+                 "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": bytes_per_cell,
                  "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
                  "kernel": _kernel_name(info), "kernel_ms": 1000.0 * t_launch,
                  "fp64_peak_sm_mhz": mhz})
@@ -433,14 +588,15 @@ def main():
 
     cpu = None
     if not a.no_cpu:
-        cpu = cpu_baseline(wl, a.cpu_seconds, os.cpu_count() or 1)
+        cpu = cpu_baseline(cpu_sample, a.cpu_seconds, os.cpu_count() or 1)
 
     out = {"metric": "rstep_cell_solves_per_sec", "value": value, "unit": "cell-solves/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": dict(cfg_json, name=wl.name, ncomp=wl.cfg.ncomp, neqcplx=int(wl.cfg.c.neqcplx),
-                          kernel=info, kernel_variant=step.variant, autotune_s=tuned, note=wl.note),
-           "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_os_step": e2e_os,
+                          kernel=info, kernel_variant=variant_name, autotune_s=tuned, note=wl.note),
+           "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e_os if e2e_os is not None else e2e,
+           "e2e_full_state": e2e, "parity_sample": parity, "c5_baseline": c5, "numa": numa,
            "roofline": roof, "cpu_baseline": cpu,
            "os_block_vectors": osv,
            "result": res.as_dict(), "wall_s_timed_region": wall}

@@ -526,10 +526,38 @@ int pfrx_rstep(pfrx_handle *h, double tran_dt, pfrx_step_result *out);
 int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *host,
                     double tran_dt, pfrx_step_result *out);
 
+/* Fields that pfrx_rstep_host keeps RESIDENT in its device mirror (bit f of
+ * field_mask = the f-th `double *` member of pfrx_state in declaration order,
+ * PFRX_FIELD_*): uploaded when the mirror is (re)allocated, not downloaded.
+ * For what the step derives and only the next step reads: rt_auxvar%sec_molal
+ * and the activity coefficients are 1.4 of the 1.97 KB per cell a Hanford step
+ * sends back (reactive_transport_aux.F90:21-74 keeps them per cell for output
+ * only).  pfrx_rstep_host_fetch copies the resident fields to the host arrays
+ * on request (output / checkpoint times).  Default mask: 0 (everything moves). */
+#define PFRX_FIELD_TOTAL 0
+#define PFRX_FIELD_PRI_MOLAL 1
+#define PFRX_FIELD_IMMOBILE 2
+#define PFRX_FIELD_PRI_ACT_COEF 3
+#define PFRX_FIELD_SEC_ACT_COEF 4
+#define PFRX_FIELD_SEC_MOLAL 5
+#define PFRX_FIELD_LN_ACT_H2O 6
+#define PFRX_FIELD_MNRL_VOLFRAC 7
+#define PFRX_FIELD_MNRL_AREA 8
+#define PFRX_FIELD_MNRL_RATE 9
+#define PFRX_FIELD_FREE_SITE 10
+#define PFRX_FIELD_EQSRFCPLX_CONC 11
+#define PFRX_FIELD_TOTAL_SORB_EQ 12
+#define PFRX_FIELD_KINMR_TOTAL_SORB 13
+int pfrx_rstep_host_resident(pfrx_handle *h, uint64_t field_mask);
+int pfrx_rstep_host_fetch(pfrx_handle *h, int64_t ncell, const pfrx_state *host);
+
 /* Multi-GPU: one rank per GPU, cells sharded by ownership range, no halo.
  * pfrx_allreduce() replaces MPI_Allreduce(rstep_error,MAX)+MPI_Barrier at
  * pmc_subsurface_osrt.F90:381-383 (MAX of error / iteration / update counts,
- * SUM of iterations and cell counts) with one NCCL call over NVLink.
+ * SUM of iterations and cell counts) with one NCCL call over NVLink.  Once a
+ * communicator is attached, pfrx_rstep_async enqueues that reduction on the
+ * kernel stream straight from the device summary (no host staging), and
+ * pfrx_allreduce of the result pfrx_rstep_finish returned only reads it back.
  * The 128-byte id comes from rank 0 (pfrx_comm_unique_id) and is distributed
  * by the host (MPI_Bcast in the Fortran caller).                            */
 int pfrx_comm_unique_id(void *id128);
@@ -601,14 +629,14 @@ int pfrx_os_store(pfrx_handle *h, double *tran_xx);
  * memory (PETSc Vecs) while the chemistry state stays bound in device memory from
  * step to step, the way rt_auxvars persist in the reference:
  *   upload solved_total (may be NULL: totals already in the state) and -- when the
- *   network has immobile species or the state has imat -- tran_xx;
+ *   network has immobile species or the shard has inactive cells (imat <= 0) -- tran_xx;
  *   pfrx_os_load, RStep over tran_dt on every cell, pfrx_os_store;
  *   download tran_xx.
  * ncomp doubles per cell cross the link in each direction instead of the whole
- * state (pfrx_rstep_host).  Chunks of cells are pipelined over three streams (the
- * first call on a shard runs in one chunk, the second in eight, later ones in
- * whichever was faster); pass page-locked vectors (cudaHostRegister) for the
- * copies to overlap the kernel.
+ * state (pfrx_rstep_host).  Chunks of cells are pipelined over three streams (after
+ * a warm-up call the library times one chunk against eight, keeps the faster and
+ * repeats the trial every 64 calls; PFRX_OS_CHUNKS pins the count); pass page-locked
+ * vectors (cudaHostRegister) for the copies to overlap the kernel.
  * Per-cell counts and flags stay in the bound state.                              */
 int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
                       pfrx_step_result *out);

@@ -1248,9 +1248,23 @@ def fit_logK_coefs(temps: Sequence[float], logK: Sequence[float]) -> np.ndarray:
     vec = np.stack([np.log(tk), np.ones_like(tk), tk, 1.0 / tk, 1.0 / (tk * tk)])
     lk = np.asarray(logK, dtype=np.float64)
     ok = np.abs(lk - 500.0) >= 1.0e-10
-    rhs = (vec[:, ok] * lk[ok]).sum(axis=1)
-    a = vec[:, ok] @ vec[:, ok].T
-    return np.linalg.solve(a, rhs)
+    nok = int(ok.sum())
+    if nok >= 5:
+        rhs = (vec[:, ok] * lk[ok]).sum(axis=1)
+        a = vec[:, ok] @ vec[:, ok].T
+        return np.linalg.solve(a, rhs)
+    # Fewer valid temperatures than coefficients (most Hanford complexes carry one value, at 25 C):
+    # the reference's normal equations are singular there and its LU only survives through the
+    # 1e-20 pivot substitution, so what it returns is rounding noise.  The set-up is not the path
+    # this package accelerates; give such species the lowest-order fit their data supports
+    # (constant for one point) so that an anisothermal run stays meaningful.
+    coefs = np.zeros(5)
+    if nok == 0:
+        return coefs
+    order = [1, 2, 0, 3, 4][:nok]            # 1, T, ln T, 1/T, 1/T^2
+    sol, *_ = np.linalg.lstsq(vec[order][:, ok].T, lk[ok], rcond=None)
+    coefs[order] = sol
+    return coefs
 
 
 @dataclass

@@ -340,6 +340,10 @@ struct pfrx_handle {
   int64_t launches = 0;
   // row counts of every field, in pfrx_state order
   std::vector<int> rows_d;  // 20 double fields
+  // device-side reduction of the shard summary, enqueued by pfrx_rstep_async behind the kernel
+  long long *d_red_step = nullptr, *h_red_step = nullptr;
+  bool red_inflight = false, red_valid = false;
+  pfrx_step_result red_local;
   std::vector<int> sr_flag_host;  // srfcplxrxn_stoich_flag (host copy: pfrx_load_specialized refuses inner-Newton sites)
   // owned device state for pfrx_rstep_host
   void *own = nullptr;
@@ -359,7 +363,11 @@ struct pfrx_handle {
   // faster: a ragged workload pays the slowest cell of every chunk, a uniform one gains the overlap
   double os_trial_s[2] = {0.0, 0.0};
   int64_t os_trial_ncell = -1;
-  int os_calls = 0;
+  int os_calls = 0;       // position in the trial cycle of pfrx_os_step_host (see there)
+  int os_choice = 1;      // chunk count in use
+  int os_env_chunks = -1; // PFRX_OS_CHUNKS, read once (0: not set)
+  int os_inactive = -1;   // inactive cells of the bound shard (-1: not counted yet)
+  uint64_t host_resident_mask = 0;  // pfrx_rstep_host_resident
   // kernel seconds per cell and link seconds per cell seen by the latest pfrx_rstep_host: a step
   // whose kernel outweighs its transfers gains nothing from many chunks and, with the refill
   // skeleton, pays the slowest cell of every chunk
@@ -1265,6 +1273,8 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->d_red) cudaFree(h->d_red);
   if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->d_red_step) cudaFree(h->d_red_step);
+  if (h->h_red_step) cudaFreeHost(h->h_red_step);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->os_a) cudaFree(h->os_a);
   if (h->os_b) cudaFree(h->os_b);
@@ -1357,6 +1367,7 @@ extern "C" int pfrx_bind_state(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (rc) return rc;
   h->ncell = ncell;
   h->bound = true;
+  h->os_inactive = -1;
   return PFRX_OK;
 }
 
@@ -1426,11 +1437,42 @@ static void summary_out(const pfrx_handle *h, pfrx_step_result *out) {
   out->first_failed_cell = s.first_failed == LLONG_MAX ? -1 : s.first_failed;
 }
 
+// shard summary -> the eight int64 of the step's collective (SUM of counts, MAX of maxima)
+__global__ void pfrx_pack_summary_kernel(const DevSummary *s, long long *red) {
+  red[0] = (long long)s->ncell_active;
+  red[1] = (long long)s->sum_its;
+  red[2] = (long long)s->num_cut_cells;
+  red[3] = 0;
+  red[4] = s->max_its;
+  red[5] = s->max_kin;
+  red[6] = s->max_err;
+  red[7] = s->max_sub;
+}
+
 extern "C" int pfrx_rstep_async(pfrx_handle *h, double tran_dt) {
   if (!h) return set_err(PFRX_E_INVALID, "null handle%s", "");
   if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
   CUDA_OK(cudaSetDevice(h->device));
-  return launch(h, h->st, h->ncell, tran_dt, h->stream);
+  int rc = launch(h, h->st, h->ncell, tran_dt, h->stream);
+  if (rc) return rc;
+  h->red_inflight = false;
+  h->red_valid = false;
+  if (h->comm && h->d_red_step) {
+    // the step's one exchange (MPI_Allreduce(rstep_error, MAX), pmc_subsurface_osrt.F90:381) on the
+    // kernel stream, straight from the device summary: no host staging, no extra synchronisation
+    pfrx_pack_summary_kernel<<<1, 1, 0, h->stream>>>(h->d_summ, h->d_red_step);
+    CUDA_OK(cudaGetLastError());
+    const int ncclInt64 = 4, ncclSum = 0, ncclMax = 2;
+    g_nccl.GroupStart();
+    int e1 = g_nccl.AllReduce(h->d_red_step, h->d_red_step, 4, ncclInt64, ncclSum, h->comm, h->stream);
+    int e2 = g_nccl.AllReduce(h->d_red_step + 4, h->d_red_step + 4, 4, ncclInt64, ncclMax, h->comm, h->stream);
+    int e3 = g_nccl.GroupEnd();
+    if (e1 || e2 || e3)
+      return set_err(PFRX_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(e1 ? e1 : (e2 ? e2 : e3)));
+    CUDA_OK(cudaMemcpyAsync(h->h_red_step, h->d_red_step, 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    h->red_inflight = true;
+  }
+  return PFRX_OK;
 }
 
 extern "C" int pfrx_rstep_finish(pfrx_handle *h, pfrx_step_result *out) {
@@ -1439,6 +1481,11 @@ extern "C" int pfrx_rstep_finish(pfrx_handle *h, pfrx_step_result *out) {
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->pending = false;
   summary_out(h, out);
+  if (h->red_inflight) {
+    h->red_inflight = false;
+    h->red_valid = true;
+    h->red_local = *out;
+  }
   return PFRX_OK;
 }
 
@@ -1694,6 +1741,14 @@ static int pipeline_events(pfrx_handle *h) {
 // holds -- the solved totals and tran_xx, ncomp doubles per cell each -- while rt_auxvars live in the
 // bound device state from step to step.  Chunks of cells are pipelined over three streams: upload of
 // chunk i+1, {load transpose, RStep kernel, store transpose} of chunk i, download of chunk i-1.
+__global__ void pfrx_count_inactive_kernel(const int *imat, long long ncell, int *count) {
+  int local = 0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x)
+    local += imat[c] <= 0 ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
 extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_xx, double tran_dt,
                                  pfrx_step_result *out) {
   if (!h || !out) return set_err(PFRX_E_INVALID, "null argument%s", "");
@@ -1718,24 +1773,42 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   }
   int rc = pipeline_events(h);
   if (rc) return rc;
-  // the transfers are a few per cent of the kernel: a handful of chunks hides all but the first
-  // upload and the last download
+  // Chunks: a handful hides all but the first upload and the last download behind the kernel, but
+  // every chunk of a ragged workload ends with its own slowest cell.  Which wins is measured: call 0
+  // on a shard runs in one chunk and is not timed (module load, first touch of the staging
+  // buffers), calls 1 and 2 time one chunk and `many`, the faster is kept; the trial is repeated
+  // every 64 calls because raggedness changes over a run.  PFRX_OS_CHUNKS (read once) pins the count.
   const int many = (int)std::min<int64_t>(8, std::max<int64_t>(1, ncell / 262144));
+  if (h->os_env_chunks < 0) {
+    const char *ev = getenv("PFRX_OS_CHUNKS");
+    h->os_env_chunks = ev ? std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(ev))) : 0;
+  }
   if (h->os_trial_ncell != ncell) {
     h->os_trial_ncell = ncell;
     h->os_calls = 0;
-    h->os_trial_s[0] = h->os_trial_s[1] = 0.0;
+    h->os_choice = 1;
   }
-  int nchunk = h->os_calls == 0 ? 1 : h->os_calls == 1 ? many : (h->os_trial_s[1] < h->os_trial_s[0] ? many : 1);
-  const bool forced = getenv("PFRX_OS_CHUNKS") != nullptr;
-  if (forced) nchunk = std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(getenv("PFRX_OS_CHUNKS"))));
+  const bool forced = h->os_env_chunks > 0;
+  const int phase = h->os_calls;  // 0 warm-up, 1 trial (one chunk), 2 trial (many), >= 3 steady
+  int nchunk = forced ? h->os_env_chunks : (phase <= 1 ? 1 : phase == 2 ? many : h->os_choice);
+  if (h->os_inactive < 0 && h->st.imat) {
+    int *cnt = nullptr;
+    CUDA_OK(cudaMalloc(&cnt, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int), h->stream));
+    pfrx_count_inactive_kernel<<<296, 256, 0, h->stream>>>(h->st.imat, (long long)ncell, cnt);
+    int host_cnt = 0;
+    CUDA_OK(cudaMemcpyAsync(&host_cnt, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaFree(cnt));
+    h->os_inactive = host_cnt;
+  }
   const auto wall0 = std::chrono::steady_clock::now();
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   rc = summary_reset(h, s_k);
   if (rc) return rc;
-  // tran_xx goes up when the step reads it (immobile entries) or when inactive cells must keep
-  // their entries through the download
-  const bool up_xx = h->cfg.nim > 0 || h->st.imat != nullptr;
+  // tran_xx goes up when the step reads it (immobile entries) or when the shard has inactive cells,
+  // which must keep their entries through the download
+  const bool up_xx = h->cfg.nim > 0 || (h->st.imat != nullptr && h->os_inactive != 0);
   h->last_h2d = h->last_d2h = 0;
   const size_t w8 = sizeof(double);
   for (int ch = 0; ch < nchunk; ch++) {
@@ -1772,9 +1845,15 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   CUDA_OK(cudaStreamSynchronize(s_out));
   h->pending = false;
   summary_out(h, out);
-  if (!forced && h->os_calls < 2)
-    h->os_trial_s[h->os_calls] = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
-  if (!forced) h->os_calls++;
+  if (!forced) {
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    if (phase == 1) h->os_trial_s[0] = el;
+    if (phase == 2) {
+      h->os_trial_s[1] = el;
+      h->os_choice = h->os_trial_s[1] < h->os_trial_s[0] ? many : 1;
+    }
+    h->os_calls = phase >= 66 ? 1 : phase + 1;  // steady for 64 calls, then the two trials again
+  }
   if (out->first_failed_cell >= 0 && nchunk > 1) {
     // chunk-local index: recover the shard index from the per-cell error flags
     std::vector<int> ie((size_t)ncell);
@@ -1945,6 +2024,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     for (int f = 0; f < kNumD; f++) {
       if (!rows[f] || !src[f] || f == 11) continue;  // eqsrfcplx_conc is output only
       if (skip_in[f]) continue;
+      if (!fresh_alloc && ((h->host_resident_mask >> f) & 1ull)) continue;  // the device copy is the current one
       CUDA_OK(cudaMemcpy2DAsync(dptr[f] + c0, ncell * w8, src[f] + c0, host->ld * w8, nc * w8, rows[f],
                                 cudaMemcpyHostToDevice, s_in));
       h->last_h2d += (int64_t)(nc * w8) * rows[f];
@@ -1964,6 +2044,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
     CUDA_OK(cudaStreamWaitEvent(s_out, h->ev_k[ch], 0));
     for (int f : io) {
       if (!rows[f] || !hdst[f]) continue;
+      if ((h->host_resident_mask >> f) & 1ull) continue;
       CUDA_OK(cudaMemcpy2DAsync(hdst[f] + c0, host->ld * w8, dptr[f] + c0, ncell * w8, nc * w8, rows[f],
                                 cudaMemcpyDeviceToHost, s_out));
       h->last_d2h += (int64_t)(nc * w8) * rows[f];
@@ -2001,6 +2082,41 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   return PFRX_OK;
 }
 
+// Fields of pfrx_state (bit f = the f-th double field in declaration order) that pfrx_rstep_host
+// keeps RESIDENT in its device mirror: uploaded when the mirror is (re)allocated, never downloaded.
+// Meant for what the step derives and only the next step reads -- rt_auxvar%sec_molal and the
+// activity coefficients are 1.4 of the 1.97 KB per cell that a Hanford step sends back.  The host
+// copies of resident fields go stale; pfrx_rstep_host_fetch brings them up to date on request
+// (output, checkpoint).
+extern "C" int pfrx_rstep_host_resident(pfrx_handle *h, uint64_t field_mask) {
+  if (!h) return set_err(PFRX_E_INVALID, "null handle%s", "");
+  if (field_mask >> 14) return set_err(PFRX_E_INVALID, "field mask has bits beyond the 14 state fields%s", "");
+  h->host_resident_mask = field_mask;
+  return PFRX_OK;
+}
+
+extern "C" int pfrx_rstep_host_fetch(pfrx_handle *h, int64_t ncell, const pfrx_state *host) {
+  if (!h || !host) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->own || h->own_ncell != ncell) return set_err(PFRX_E_NOTBOUND, "no device mirror of that many cells%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int *rows = h->rows_d.data();
+  double *hdst[PFRX_NUM_D] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
+                              host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
+                              host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
+                              host->eqsrfcplx_conc, host->total_sorb_eq, host->kinmr_total_sorb};
+  double *dptr[14] = {h->own_st.total,        h->own_st.pri_molal,    h->own_st.immobile,  h->own_st.pri_act_coef,
+                      h->own_st.sec_act_coef, h->own_st.sec_molal,    h->own_st.ln_act_h2o, h->own_st.mnrl_volfrac,
+                      h->own_st.mnrl_area,    h->own_st.mnrl_rate,    h->own_st.free_site,
+                      h->own_st.eqsrfcplx_conc, h->own_st.total_sorb_eq, h->own_st.kinmr};
+  for (int f = 0; f < 14; f++) {
+    if (!((h->host_resident_mask >> f) & 1ull) || !rows[f] || !hdst[f] || !dptr[f]) continue;
+    CUDA_OK(cudaMemcpy2DAsync(hdst[f], host->ld * sizeof(double), dptr[f], ncell * sizeof(double), ncell * sizeof(double),
+                              rows[f], cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PFRX_OK;
+}
+
 // ---- multi-GPU -----------------------------------------------------------------
 extern "C" int pfrx_comm_unique_id(void *id128) {
   int rc = load_nccl();
@@ -2024,6 +2140,8 @@ extern "C" int pfrx_comm_init(pfrx_handle *h, int nranks, int rank, const void *
   h->nranks = nranks;
   CUDA_OK(cudaMalloc(&h->d_red, 8 * sizeof(long long)));
   CUDA_OK(cudaMallocHost(&h->h_red, 8 * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&h->d_red_step, 8 * sizeof(long long)));
+  CUDA_OK(cudaMallocHost(&h->h_red_step, 8 * sizeof(long long)));
   return PFRX_OK;
 }
 
@@ -2031,6 +2149,24 @@ extern "C" int pfrx_allreduce(pfrx_handle *h, pfrx_step_result *r) {
   if (!h || !r) return set_err(PFRX_E_INVALID, "null argument%s", "");
   if (!h->comm) return PFRX_OK;  // single rank: nothing to reduce
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->red_valid && r->ncell_active == h->red_local.ncell_active &&
+      r->sum_newton_iterations == h->red_local.sum_newton_iterations && r->num_cut_cells == h->red_local.num_cut_cells &&
+      r->max_newton_iterations == h->red_local.max_newton_iterations &&
+      r->max_num_kinetic_state_updates == h->red_local.max_num_kinetic_state_updates &&
+      r->rstep_error == h->red_local.rstep_error && r->max_sub_steps == h->red_local.max_sub_steps) {
+    // the result of the latest pfrx_rstep[_async/_finish]: its reduction ran on the device behind the kernel
+    const long long *b = h->h_red_step;
+    h->red_valid = false;
+    r->ncell_active = b[0];
+    r->sum_newton_iterations = b[1];
+    r->num_cut_cells = b[2];
+    r->max_newton_iterations = (int)b[4];
+    r->max_num_kinetic_state_updates = (int)b[5];
+    r->rstep_error = (int)b[6];
+    r->max_sub_steps = (int)b[7];
+    return PFRX_OK;
+  }
+  h->red_valid = false;
   long long *b = h->h_red;
   b[0] = r->ncell_active;
   b[1] = r->sum_newton_iterations;

@@ -92,7 +92,9 @@ S2_FN double sx_div(double a, double b) { return SPEC_FASTMATH ? pfrx_div(a, b) 
 #define S2_JS (SPEC_NC + 1)                       // full matrix: + one column (scaling factor, then right-hand side)
 #define S2_NJ (SPEC_SYM ? SPEC_NL : SPEC_NC * S2_JS)  // matrix slots: the entries of L, or the full matrix
 #define S2_OFF_C S2_NJ                            // the iterate c (N)
-#define S2_OFF_FRZ (S2_OFF_C + SPEC_N)            // frozen coefficients: gamma_i (NAQ), then 1 / gamma_k (NCX)
+#define S2_OFF_FIX (S2_OFF_C + SPEC_N)            // fixed accumulation of the sub-step (N)
+#define S2_OFF_MN (S2_OFF_FIX + SPEC_N)           // kinetic minerals: volume fraction, specific area (2 NKIN)
+#define S2_OFF_FRZ (S2_OFF_MN + 2 * SPEC_NKIN)    // frozen coefficients: gamma_i (NAQ), then 1 / gamma_k (NCX)
 #define S2_SLOTS (S2_OFF_FRZ + (SPEC_ACT_UPD ? 0 : SPEC_NAQ + SPEC_NCX))
 #define S2_NTV (SPEC_NSTASH > 0 ? SPEC_NSTASH : 1)
 #ifndef SPEC_NEV
@@ -145,6 +147,10 @@ S2_FN void spec2_store_totals(const double (&tv)[S2_NTV], const double *W, const
 S2_FN void spec2_store_act(const Spec2Cell &s, const DevState &st, long long cell);
 // frozen coefficients into the slice at cell entry
 S2_FN void spec2_load_frozen(double *W, const DevState &st, long long cell);
+// sub-step entry: fixed accumulation and the mineral inputs into the slice
+S2_FN void spec2_begin(double *W, const Spec2Cell &s, const DevState &st, long long cell);
+// RStep entry: sum z^2 m and sum m over the state's secondary species
+S2_FN void spec2_isec(Spec2Cell &s, const DevState &st, long long cell);
 #if SPEC_SYM
 // sparse L D L^T of Jt in the slice and the solve for the coupled species: res <- update; false
 // when a pivot is not positive (Jt numerically not positive definite)
@@ -424,17 +430,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       s.dry = sat < prm.min_sat;
       s.psv = por * sat * 1000.0 * s.vol;
       s.rock = spd * (1.0 - por);
-      {
-        double Is = 0.0, ms = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < SPEC_NCX; k++) {
-          const double m = st.sec_molal[k * ld + cell];
-          Is += m * spec_cx_z2(k);
-          ms += m;
-        }
-        s.Isec = Is;
-        s.msec = ms;
-      }
+      spec2_isec(s, st, cell);
       if (!SPEC_ACT_UPD) spec2_load_frozen(W, st, cell);
       small_mask = 0u;
 #pragma unroll
@@ -471,6 +467,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
     if (need_begin && (!done || fresh)) {
 #pragma unroll
       for (int i = 0; i < N; i++) SW(S2_OFF_C + i) = (i < NAQ) ? st.pri_molal[i * ld + cell] : gimm[i >= NAQ ? i - NAQ : 0];
+      spec2_begin(W, s, st, cell);
       s.rdt = 1.0 / dt;
       its = 0;
       need_begin = false;

@@ -66,6 +66,8 @@ def lib():
     L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
     L.pfrx_os_store.argtypes = [hp, C.c_void_p]
     L.pfrx_os_step_host.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_double, resp]
+    L.pfrx_rstep_host_resident.argtypes = [hp, C.c_uint64]
+    L.pfrx_rstep_host_fetch.argtypes = [hp, C.c_int64, stp]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pfrx_load_specialized.argtypes = [hp, C.c_char_p]
     L.pfrx_config_signature.argtypes = [hp]
@@ -254,6 +256,18 @@ class ChemistryStep:
         _check(lib().pfrx_rstep_host(self._h, host.ncell, C.byref(st), float(tran_dt), C.byref(res)),
                "pfrx_rstep_host")
         return res
+
+    def rstep_host_resident(self, fields) -> None:
+        """keep these state fields (names of ``abi.STATE_DOUBLE_FIELDS``) resident in the device
+        mirror of ``rstep_host``: uploaded once, not downloaded (``rstep_host_fetch`` on request)"""
+        mask = 0
+        for f in fields:
+            mask |= 1 << abi.STATE_DOUBLE_FIELDS.index(f)
+        _check(lib().pfrx_rstep_host_resident(self._h, mask), "pfrx_rstep_host_resident")
+
+    def rstep_host_fetch(self, host: abi.HostState) -> None:
+        st = host.struct()
+        _check(lib().pfrx_rstep_host_fetch(self._h, host.ncell, C.byref(st)), "pfrx_rstep_host_fetch")
 
     # -- multi-GPU --------------------------------------------------------------- #
     def init_comm(self) -> None:

@@ -181,6 +181,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
     n = c.naqcomp + c.nimcomp
     if n > 20:
         return False, "more than 20 unknowns"
+    if not c.use_full_geochemistry:
+        return False, "use_full_geochemistry = 0 (RStep's tracer short cut)"
     if not c.use_isothermal:
         return False, "anisothermal logK"
     if c.act_coef_update_algorithm != abi._chem.ACT_COEF_ALGORITHM_LAG:

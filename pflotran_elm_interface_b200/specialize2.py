@@ -450,7 +450,7 @@ class _Gen2:
                     xs.setdefault((i, j), []).append(f"x{r}_{i}_{j}")
             w("  {")
             if ty == chem.MINERAL_SURFACE:
-                w(f"    const double dens = {dens} * st.mnrl_volfrac[{int(a['srfcplxrxn_to_surf'][r])} * ld + cell];")
+                w(f"    const double dens = {dens} * SW(S2_OFF_MN + {2 * int(a['srfcplxrxn_to_surf'][r])});")
             elif ty == chem.ROCK_SURFACE:
                 w(f"    const double dens = {dens} * s.rock;")
             else:
@@ -511,15 +511,13 @@ class _Gen2:
         # ---- residual: (accumulation - fixed accumulation) / dt (RReact, reaction.F90:3880-3900)
         for i in range(n):
             if i < naq:
-                tot = f"tot{i}" if i in self.cpos else f"(c{i} * s.denL)"
+                tot = f"tot{i}" if i in self.cpos else f"(SW(S2_OFF_C + {i}) * s.denL)"
                 acc = f"psv * {tot}"
-                fix = f"psv * st.total[{i} * ld + cell]"
                 if self.eqsr:
                     acc = f"{acc} + {'ts%d' % i if i in self.sorb_species else '0.0'} * s.vol"
-                    fix = f"{fix} + st.total_sorb_eq[{i} * ld + cell] * s.vol"
-                w(f"  res[{i}] = (({acc}) - ({fix})) * s.rdt;")
+                w(f"  res[{i}] = (({acc}) - SW(S2_OFF_FIX + {i})) * s.rdt;")
             else:
-                w(f"  res[{i}] = s.dry ? 0.0 : ((0.0 + c{i} * s.vol) - (0.0 + st.immobile[{i - naq} * ld + cell] * s.vol)) * s.rdt;")
+                w(f"  res[{i}] = s.dry ? 0.0 : ((0.0 + SW(S2_OFF_C + {i}) * s.vol) - SW(S2_OFF_FIX + {i})) * s.rdt;")
         # ---- kinetic minerals (TST)
         for m in range(c.nkinmnrl):
             sp, h2o = self.mn[m]
@@ -535,7 +533,7 @@ class _Gen2:
             w("    const double QK = s2_scale(p, e, emax);")
             w("    double aff = 1.0 - QK;")
             w("    const double sgn = copysign(1.0, aff);")
-            w(f"    bool active = (st.mnrl_volfrac[{m} * ld + cell] > 0.0 || sgn < 0.0);")
+            w(f"    bool active = (SW(S2_OFF_MN + {2 * m}) > 0.0 || sgn < 0.0);")
             if irr == 1:
                 w("    if (sgn < 0.0) active = false;")
             if thr > 0.0:
@@ -546,7 +544,7 @@ class _Gen2:
                 w(f"    const double spr = {rate} * exp({_lit(eact)} / 8.31446 * (1.0 / (25.0 + 273.15) - 1.0 / (s.temp + 273.15)));")
             else:
                 w(f"    const double spr = {rate} * 1.0;")
-            w(f"    const double Im_const = -st.mnrl_area[{m} * ld + cell];")
+            w(f"    const double Im_const = -SW(S2_OFF_MN + {2 * m + 1});")
             w("    const double rate_vol = active ? Im_const * sgn * fabs(aff) * spr : 0.0;")
             w(f"    if (s.store && s.rates) st.mnrl_rate[{m} * ld + cell] = rate_vol;")
             w("    const bool apply = active && !s.dry;")
@@ -582,7 +580,7 @@ class _Gen2:
                     src = f"h_{i}_{j}" if (i, j) in hot else self.slot(i, j)
                     terms.append(f"K1 * {src}")
                 if i == j:
-                    terms.append(f"dg * c{i}")
+                    terms.append(f"dg * SW(S2_OFF_C + {i})")
                 terms += xs.get((i, j), [])
                 expr = " + ".join(terms) if terms else "0.0"
                 if self.sym:
@@ -690,6 +688,46 @@ class _Gen2:
         w("}")
         w()
 
+    def gen_begin(self) -> None:
+        """RReact entry (reaction.F90:3829-3850): the fixed accumulation of the sub-step and what the
+        kinetic minerals / mineral-bound sites read, into the slice; and, at RStep entry, the ionic
+        strength sums of the state's secondary species"""
+        c, a, n, naq = self.c, self.a, self.n, self.naq
+        w = self.w
+        w("S2_FN void spec2_begin(double *W, const Spec2Cell &s, const DevState &st, long long cell) {")
+        w("  const long long ld = st.ld;")
+        w("  const double psv = s.dry ? 0.0 : s.psv;")
+        for i in range(n):
+            if i < naq:
+                fix = f"psv * st.total[{i} * ld + cell]"
+                if self.eqsr:
+                    fix = f"{fix} + st.total_sorb_eq[{i} * ld + cell] * s.vol"
+                w(f"  SW(S2_OFF_FIX + {i}) = {fix};")
+            else:
+                w(f"  SW(S2_OFF_FIX + {i}) = 0.0 + st.immobile[{i - naq} * ld + cell] * s.vol;")
+        for m in range(c.nkinmnrl):
+            w(f"  SW(S2_OFF_MN + {2 * m}) = st.mnrl_volfrac[{m} * ld + cell];")
+            w(f"  SW(S2_OFF_MN + {2 * m + 1}) = st.mnrl_area[{m} * ld + cell];")
+        w("  (void)psv;")
+        w("}")
+        w()
+        w("S2_FN void spec2_isec(Spec2Cell &s, const DevState &st, long long cell) {")
+        w("  const long long ld = st.ld;")
+        w("  const double *sp_ = st.sec_molal + cell;")
+        for k in range(self.ncx):
+            w(f"  const double m{k} = sp_[{k} * ld];")
+        w("  double Is = 0.0, ms = 0.0;")
+        for k in range(self.ncx):
+            z2 = float(a["eqcplx_Z"][k]) ** 2
+            if z2 == 1.0:
+                w(f"  Is += m{k};")
+            elif z2 != 0.0:
+                w(f"  Is += m{k} * {_lit(z2)};")
+            w(f"  ms += m{k};")
+        w("  s.Isec = Is; s.msec = ms;")
+        w("}")
+        w()
+
     def gen_stores(self) -> None:
         c, a, naq = self.c, self.a, self.naq
         w = self.w
@@ -747,7 +785,7 @@ class _Gen2:
         """(slots per thread, threads per block, min blocks per SM)"""
         self.nstash = self.nc + len(self.sorb_species)
         nj = self.nl if self.sym else self.nc * (self.nc + 1)
-        slots = nj + self.n + (0 if self.act_upd else self.naq + self.ncx)
+        slots = nj + 2 * self.n + 2 * self.c.nkinmnrl + (0 if self.act_upd else self.naq + self.ncx)
         smem_max = 227 * 1024
         if self.n <= 8:
             threads = 128
@@ -771,6 +809,7 @@ class _Gen2:
         self.gen_eval()
         if self.sym:
             self.gen_solve_sym()
+        self.gen_begin()
         self.gen_stores()
         body = self.out
         self.out = []

@@ -115,7 +115,8 @@ def _mix_fill(state: abi.HostState, waters, weights: np.ndarray, rng, jitter: fl
     assert ncell == tot.shape[1]
 
 
-def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED, prefactors: bool = False) -> Workload:
+def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED, prefactors: bool = False,
+                   anisothermal: bool = False, no_geochemistry: bool = False) -> Workload:
     """C2: 10k-cell calcite column, post-transport totals on a logistic front.
 
     ``prefactors``: the calcite rate as the sum of three parallel mechanisms in the
@@ -137,8 +138,10 @@ def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED
                          {"name": "Ca++", "alpha": 0.25, "beta": 1.0, "atten": 3.0}]},
             {"rate": 6.5e-7 * 1.0e-4, "activation_energy": 23500.0, "species": []},
         ]
-    net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("calcite.dat")))
+    net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("calcite.dat")), use_isothermal=not anisothermal)
     cfg = abi.ReactionConfig(net)
+    if no_geochemistry:
+        cfg.c.use_full_geochemistry = 0   # RStep's tracer short cut: pri_molal = total / den * 1000 (reaction.F90:3600)
     den = eos.water_density_ifc67()
     bg = constraint.equilibrate_constraint(net, dk.constraints["background"], den_kg=den)
     inl = constraint.equilibrate_constraint(net, dk.constraints["inlet"], den_kg=den)
@@ -154,6 +157,11 @@ def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED
         st["temp"][...] = rng.uniform(10.0, 40.0, ncell)
         return Workload("c2_calcite_prefactors", cfg, st, tran_dt, net,
                         "C2 with a three-mechanism PREFACTOR rate law for Calcite")
+    if anisothermal:
+        st["temp"][...] = rng.uniform(5.0, 60.0, ncell)
+        return Workload("c2_calcite_anisothermal", cfg, st, tran_dt, net, "C2 with logK(T), cells at 5-60 C")
+    if no_geochemistry:
+        return Workload("c2_calcite_no_geochemistry", cfg, st, tran_dt, net, "C2 with use_full_geochemistry = 0")
     return Workload("c2_calcite_column", cfg, st, tran_dt, net,
                     "H+/HCO3-/Ca++ + 6 complexes + kinetic Calcite, logistic inlet/background front")
 
@@ -172,10 +180,13 @@ def calcite_batch() -> Workload:
 
 
 # --------------------------------------------------------------------------- #
-def _hanford_network(variant: str = "base", activity_newton: bool = False):
+def _hanford_network(variant: str = "base", activity_newton: bool = False, anisothermal: bool = False,
+                     activity_h2o: bool = False, total_as_guess: bool = False):
     deck = _read("543_hanford_srfcplx_base.in")
     dk = chem.read_deck(deck)
     ch = dk.chemistry
+    ch.use_activity_h2o = ch.use_activity_h2o or activity_h2o          # ACTIVITY_WATER
+    ch.use_total_as_guess = ch.use_total_as_guess or total_as_guess    # reaction.F90:3640 (guess = total)
     if activity_newton:
         # ACTIVITY_COEFFICIENTS NEWTON NEWTON_ITERATION: ionic strength iterated to 1e-6
         ch.act_coef_update_algorithm = chem.ACT_COEF_ALGORITHM_NEWTON
@@ -190,17 +201,26 @@ def _hanford_network(variant: str = "base", activity_newton: bool = False):
         rates = {"Calcite": 1.0e-8, "Metatorbernite": 2.0e-13, "Dolomite": 1.0e-9, "Gypsum": 1.0e-7,
                  "Fluorite": 1.0e-9, "Schoepite": 1.0e-10}
         ch.mineral_kinetics = [chem.MineralKinetics(n, rate_constant=r) for n, r in rates.items()]
-    net = chem.ReactionNetwork(ch, chem.Database(_read("hanford_subset.dat")))
+    net = chem.ReactionNetwork(ch, chem.Database(_read("hanford_subset.dat")), use_isothermal=not anisothermal)
     return dk, net
 
 
 def hanford(ncell: int = 256 * 256 * 64, tran_dt: float = 3600.0, variant: str = "base",
-            seed: int = SEED, activity_newton: bool = False) -> Workload:
+            seed: int = SEED, activity_newton: bool = False, anisothermal: bool = False, activity_h2o: bool = False,
+            total_as_guess: bool = False, inner_newton_sites: bool = False) -> Workload:
     """C3 (variant base|mr) and C5 (variant minerals): Hanford 15 primary / 88
-    secondary; cells are Dirichlet(1) mixes of the three deck waters."""
+    secondary; cells are Dirichlet(1) mixes of the three deck waters.
+
+    Options for the parity tests of the less-travelled branches: ``anisothermal`` (logK(T) from the
+    database's temperature fit, cells at 5-60 C: RUpdateTempDependentCoefs, reaction.F90:5976-6067),
+    ``activity_h2o`` (ACTIVITY_WATER, reaction.F90:4580-4612), ``total_as_guess``
+    (reaction.F90:3640) and ``inner_newton_sites`` (the free-site Newton iteration of
+    RTotalSorbEqSurfCplx1, reaction_surf_complex.F90:700-800, forced through srfcplxrxn_stoich_flag)."""
     rng = np.random.default_rng(seed)
-    dk, net = _hanford_network(variant, activity_newton)
+    dk, net = _hanford_network(variant, activity_newton, anisothermal, activity_h2o, total_as_guess)
     cfg = abi.ReactionConfig(net)
+    if inner_newton_sites and cfg.c.nsrfcplxrxn > 0:
+        cfg.arrays["srfcplxrxn_stoich_flag"][...] = 1   # in place: the ctypes struct points at this buffer
     den = eos.water_density_ifc67()
     waters = []
     for nm in ("groundwater", "U_source", "river_water"):
@@ -235,7 +255,13 @@ def hanford(ncell: int = 256 * 256 * 64, tran_dt: float = 3600.0, variant: str =
         if net.mr_rxn_ids:
             vals = [w.kinmr_total_sorb for w in waters]
             st["kinmr_total_sorb"][...] = sum(v[:, None] * wts[i][None, :] for i, v in enumerate(vals))
+    if anisothermal:
+        st["temp"][...] = rng.uniform(5.0, 60.0, ncell)
     name = {"base": "c3_hanford_srfcplx", "mr": "c3_hanford_multirate", "minerals": "c5_hanford_minerals"}[variant]
+    for flag, tag in ((anisothermal, "_anisothermal"), (activity_h2o, "_activity_h2o"), (total_as_guess, "_total_guess"),
+                      (inner_newton_sites, "_inner_newton")):
+        if flag:
+            name += tag
     return Workload(name, cfg, st, tran_dt, net, f"Hanford 15/88, variant {variant}, Dirichlet mix of 3 deck waters")
 
 
@@ -914,6 +940,12 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c3": (hanford, {"variant": "base"}),
         "c3mr": (hanford, {"variant": "mr"}),
         "c3an": (hanford, {"variant": "base", "activity_newton": True}),
+        "c3t": (hanford, {"variant": "base", "anisothermal": True}),
+        "c3aw": (hanford, {"variant": "base", "activity_h2o": True}),
+        "c3tg": (hanford, {"variant": "base", "total_as_guess": True}),
+        "c3sf": (hanford, {"variant": "base", "inner_newton_sites": True}),
+        "c2t": (calcite_column, {"anisothermal": True}),
+        "c2ng": (calcite_column, {"no_geochemistry": True}),
         "c4": (clm_cn, {}),
         "c4s": (elm_cn, {}),
         "c4se": (elm_cn, {"elm": True}),

@@ -45,14 +45,7 @@ extern "C" int s2_host_rstep(const pfrx_state *ps, long long ncell, double tran_
       s.rock = spd * (1.0 - por);
       s.Iact = 0.0;
       s.store = true;
-      double Is = 0.0, ms = 0.0;
-      for (int k = 0; k < SPEC_NCX; k++) {
-        const double m = st.sec_molal[k * ld + cell];
-        Is += m * spec_cx_z2(k);
-        ms += m;
-      }
-      s.Isec = Is;
-      s.msec = ms;
+      spec2_isec(s, st, cell);
       if (!SPEC_ACT_UPD) spec2_load_frozen(W, st, cell);
       unsigned small_mask = 0u;
       double small_val[N], gimm[NIM > 0 ? NIM : 1];
@@ -69,6 +62,7 @@ extern "C" int s2_host_rstep(const pfrx_state *ps, long long ncell, double tran_
       int ncuts = 0, nconst = 0;
       while (cumulative < tran_dt) {
         for (int i = 0; i < N; i++) SW(S2_OFF_C + i) = (i < NAQ) ? st.pri_molal[i * ld + cell] : gimm[i >= NAQ ? i - NAQ : 0];
+        spec2_begin(W, s, st, cell);
         s.rdt = 1.0 / dt;
         int its = 0;
         bool conv = false, fail = false, solve_error = false;
@@ -198,16 +192,10 @@ extern "C" int s2_host_eval(const pfrx_state *ps, long long cell, double dt, dou
   s.store = false;
   s.rates = false;
   s.rdt = 1.0 / dt;
-  double Is = 0.0, ms = 0.0;
-  for (int k = 0; k < SPEC_NCX; k++) {
-    const double m = st.sec_molal[k * ld + cell];
-    Is += m * spec_cx_z2(k);
-    ms += m;
-  }
-  s.Isec = Is;
-  s.msec = ms;
+  spec2_isec(s, st, cell);
   if (!SPEC_ACT_UPD) spec2_load_frozen(W, st, cell);
   for (int i = 0; i < N; i++) SW(S2_OFF_C + i) = (i < NAQ) ? st.pri_molal[i * ld + cell] : st.immobile[(i - NAQ) * ld + cell];
+  spec2_begin(W, s, st, cell);
   double res[N], tv[S2_NTV], ev[S2_NEV];
   spec2_eval(res, tv, ev, s, W, st, cell);
   for (int i = 0; i < N; i++) res_out[i] = res[i];

@@ -50,7 +50,7 @@ def _compare(name, ref, got, tol=1e-10):
     for f in ("num_sub_steps", "num_kinetic_state_updates", "ierror"):
         assert np.array_equal(ref[f], got[f]), (name, f)
     for f in ("total", "pri_molal", "immobile", "mnrl_volfrac", "sec_molal", "pri_act_coef", "sec_act_coef",
-              "total_sorb_eq", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc"):
+              "total_sorb_eq", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "ln_act_h2o"):
         a, b = ref[f], got[f]
         if a.size == 0:
             continue
@@ -66,7 +66,7 @@ def _compare(name, ref, got, tol=1e-10):
 
 @pytest.mark.parametrize("solver", ["sym", "lu"])
 @pytest.mark.parametrize("name,ncell,dts", [("c2", 300, (3600.0, 86400.0)), ("c3", 160, (3600.0, 30 * 86400.0)),
-                                            ("c5", 120, (86400.0,))])
+                                            ("c5", 120, (86400.0,)), ("c3aw", 96, (3600.0,))])
 def test_generated_code_on_the_host_matches_the_oracle(name, ncell, dts, solver):
     wl = W.by_name(name, ncell=ncell)
     ok, why = specialize2.supported2(wl.cfg)
