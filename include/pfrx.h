@@ -654,6 +654,17 @@ int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, double *tran_x
  * cubin_path == NULL detaches (back to the generic kernel).                  */
 int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path);
 uint64_t pfrx_config_signature(pfrx_handle *h);
+/* The configuration of the handle as a text file with exact bit patterns, for
+ *   python -m pflotran_elm_interface_b200.specialize <file>
+ * which generates and compiles the specialised cubins for it (set-up time; nvcc
+ * needed there, not at run time): a host that flattened reaction_rt_type into
+ * pfrx_config reaches the fast kernels without the Python deck reader.  The
+ * signature computed from the file equals pfrx_config_signature(h).          */
+int pfrx_config_dump(pfrx_handle *h, const char *path);
+/* the same file and signature straight from a pfrx_config: no device needed
+ * (set-up on a build or login node) */
+int pfrx_config_write(const pfrx_config *cfg, const char *path);
+uint64_t pfrx_config_signature_of(const pfrx_config *cfg);
 
 /* diagnostics: measured FP64 FMA peak of `device` in TFLOP/s (the FP64
  * roofline denominator; MEASURED_PEAKS.json only carries HBM and bf16), and

@@ -614,6 +614,67 @@ class ReactionConfig:
             c.langmuir = C.cast(C.pointer(o), C.c_void_p)
 
     # ------------------------------------------------------------------ #
+    @classmethod
+    def from_dump(cls, path: str) -> "ReactionConfig":
+        """a configuration written by ``pfrx_config_dump`` / ``pfrx_config_write`` (the C side of the
+        boundary): the scalars of the structs and every table the code generator reads, with exact bit
+        patterns.  What set-up needs beyond the generator (names, the reaction network object) is not
+        in the file: the result serves :mod:`.specialize`, not the deck-level helpers."""
+        self = cls.__new__(cls)
+        self.net = None
+        self.arrays = {}
+        structs = {"config": PfrxConfig, "somdec": PfrxSomdec, "nitrif": PfrxNitrif, "denitr": PfrxDenitr,
+                   "plantn": PfrxPlantn, "langmuir": PfrxLangmuir}
+        prefix = {"c": ("", None), "sd": ("somdec_", "somdec"), "nt": ("nitrif_", "nitrif"), "dn": ("denitr_", "denitr"),
+                  "pn": ("plantn_", "plantn"), "lg": ("langmuir_", "langmuir")}
+        objs = {}
+        sig = None
+        with open(path) as f:
+            head = f.readline().split()
+            if head[:2] != ["pfrx_config_dump", "1"] or int(head[3]) != PFRX_ABI_VERSION:
+                raise ValueError(f"{path}: not a pfrx_config_dump of ABI {PFRX_ABI_VERSION}")
+            tables = []
+            for ln in f:
+                w = ln.split()
+                if not w:
+                    continue
+                if w[0] == "S":
+                    ty = structs[w[1]]
+                    raw = bytes.fromhex(w[3])
+                    if len(raw) != int(w[2]) or len(raw) != C.sizeof(ty):
+                        raise ValueError(f"{path}: struct {w[1]} has {len(raw)} bytes, this build expects {C.sizeof(ty)}")
+                    o = ty.from_buffer_copy(raw)
+                    for name, ct in ty._fields_:          # pointers of the writer's address space mean nothing here
+                        if ct in (c_double_p, c_int32_p, C.c_void_p):
+                            setattr(o, name, None)
+                    objs[w[1]] = o
+                elif w[0] == "T":
+                    tables.append((w[1], int(w[2]), int(w[3]), w[4]))
+                elif w[0] == "signature":
+                    sig = int(w[1], 16)
+        self.c = objs["config"]
+        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir"):
+            if k in objs:
+                setattr(self, k, objs[k])
+                setattr(self.c, k, C.cast(C.pointer(objs[k]), C.c_void_p))
+        for name, elem, count, hx in tables:
+            owner, field = name.split("->")
+            pre, attr = prefix[owner]
+            obj = self.c if attr is None else getattr(self, attr)
+            ct = dict(type(obj)._fields_)[field]
+            dt = np.float64 if ct is c_double_p else np.int32
+            arr = np.frombuffer(bytes.fromhex(hx), dtype=dt).copy()
+            if arr.size != count or arr.itemsize != elem:
+                raise ValueError(f"{path}: table {name} is malformed")
+            self._keep(pre + field, arr)
+            setattr(obj, field, _dp(arr) if ct is c_double_p else _ip(arr))
+        if "somdec" in objs:   # empty tables (e.g. no inhibition terms) are not written: the generator expects the keys
+            for field, ct in PfrxSomdec._fields_:
+                if ct in (c_double_p, c_int32_p) and "somdec_" + field not in self.arrays:
+                    self.arrays["somdec_" + field] = np.zeros(0, dtype=np.float64 if ct is c_double_p else np.int32)
+        self.dump_signature = sig
+        return self
+
     @property
     def ncomp(self) -> int:
         return self.c.naqcomp + self.c.nimcomp

@@ -126,8 +126,30 @@ static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
   }
   return h;
 }
-static uint64_t config_signature(const pfrx_config *c) {
+// One traversal serves the signature and pfrx_config_dump: `sink` sees every scalar group and
+// every table the generator bakes in, in a fixed order.  name == NULL: anonymous scalar bytes.
+struct CfgSink {
   uint64_t h = 0xCBF29CE484222325ull;
+  std::string *dump = nullptr;  // when set: "T <name> <elem size> <count> <hex bytes>" per named table
+  void bytes(const char *name, const void *p, size_t elem, size_t count) {
+    h = fnv1a(h, p, elem * count);
+    if (dump && name) {
+      char head[160];
+      snprintf(head, sizeof(head), "T %s %zu %zu ", name, elem, count);
+      dump->append(head);
+      static const char hx[] = "0123456789abcdef";
+      const unsigned char *b = (const unsigned char *)p;
+      for (size_t i = 0; i < elem * count; i++) {
+        dump->push_back(hx[b[i] >> 4]);
+        dump->push_back(hx[b[i] & 15]);
+      }
+      dump->push_back('\n');
+    }
+  }
+};
+
+static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
+  uint64_t &h = sink.h;
 
   int32_t head[12] = {c->naqcomp,          c->nimcomp,
                       c->neqcplx,          c->nkinmnrl,
@@ -139,7 +161,7 @@ static uint64_t config_signature(const pfrx_config *c) {
   h = fnv1a(h, head, sizeof(head));
   h = fnv1a(h, dh, sizeof(dh));
 #define ADD(ptr, count)                                                  \
-  if ((ptr) && (count) > 0) h = fnv1a(h, (ptr), sizeof(*(ptr)) * (size_t)(count));
+  if ((ptr) && (count) > 0) sink.bytes(#ptr, (ptr), sizeof(*(ptr)), (size_t)(count));
   ADD(c->primary_spec_Z, c->naqcomp)
   ADD(c->primary_spec_a0, c->naqcomp)
   if (c->neqcplx > 0 && c->eqcplx_ptr) {
@@ -312,6 +334,51 @@ static uint64_t config_signature(const pfrx_config *c) {
   return h;
 }
 
+static uint64_t config_signature(const pfrx_config *c) {
+  CfgSink sink;
+  return config_walk(c, sink);
+}
+
+static void hex_struct(std::string &out, const char *tag, const void *p, size_t n) {
+  char head[64];
+  snprintf(head, sizeof(head), "S %s %zu ", tag, n);
+  out.append(head);
+  static const char hx[] = "0123456789abcdef";
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; i++) {
+    out.push_back(hx[b[i] >> 4]);
+    out.push_back(hx[b[i] & 15]);
+  }
+  out.push_back('\n');
+}
+
+// text form of a configuration for `python -m pflotran_elm_interface_b200.specialize <file>`:
+// the structs as raw bytes (scalars; pointer members are ignored by the reader) and every table the
+// generator reads, with exact bit patterns -- the signature computed from the file is the handle's
+static std::string config_dump_text(const pfrx_config *c) {
+  std::string out;
+  char head[96];
+  snprintf(head, sizeof(head), "pfrx_config_dump 1 abi %d\n", PFRX_ABI_VERSION);
+  out.append(head);
+  hex_struct(out, "config", c, sizeof(*c));
+  if (c->somdec) hex_struct(out, "somdec", c->somdec, sizeof(*c->somdec));
+  if (c->nitrif) hex_struct(out, "nitrif", c->nitrif, sizeof(*c->nitrif));
+  if (c->denitr) hex_struct(out, "denitr", c->denitr, sizeof(*c->denitr));
+  if (c->plantn) hex_struct(out, "plantn", c->plantn, sizeof(*c->plantn));
+  if (c->langmuir) hex_struct(out, "langmuir", c->langmuir, sizeof(*c->langmuir));
+  CfgSink sink;
+  sink.dump = &out;
+  const uint64_t sig = config_walk(c, sink);
+  if (c->sandbox_list && c->nsandbox > 0 && !(c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir)) {
+    CfgSink extra;  // the order of a CLM-CN-only list is read by the generator but is not part of the signature
+    extra.dump = &out;
+    extra.bytes("c->sandbox_list", c->sandbox_list, sizeof(*c->sandbox_list), (size_t)c->nsandbox);
+  }
+  snprintf(head, sizeof(head), "signature %016llx\n", (unsigned long long)sig);
+  out.append(head);
+  return out;
+}
+
 #define PFRX_MAX_CHUNKS 32
 
 // ---- handle -----------------------------------------------------------------
@@ -344,6 +411,7 @@ struct pfrx_handle {
   long long *d_red_step = nullptr, *h_red_step = nullptr;
   bool red_inflight = false, red_valid = false;
   pfrx_step_result red_local;
+  std::string dump_text;          // pfrx_config_dump
   std::vector<int> sr_flag_host;  // srfcplxrxn_stoich_flag (host copy: pfrx_load_specialized refuses inner-Newton sites)
   // owned device state for pfrx_rstep_host
   void *own = nullptr;
@@ -1778,7 +1846,7 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   // on a shard runs in one chunk and is not timed (module load, first touch of the staging
   // buffers), calls 1 and 2 time one chunk and `many`, the faster is kept; the trial is repeated
   // every 64 calls because raggedness changes over a run.  PFRX_OS_CHUNKS (read once) pins the count.
-  const int many = (int)std::min<int64_t>(8, std::max<int64_t>(1, ncell / 262144));
+  const int many = (int)std::min<int64_t>(10, std::max<int64_t>(1, ncell / 262144));
   if (h->os_env_chunks < 0) {
     const char *ev = getenv("PFRX_OS_CHUNKS");
     h->os_env_chunks = ev ? std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(ev))) : 0;
@@ -1811,8 +1879,32 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   const bool up_xx = h->cfg.nim > 0 || (h->st.imat != nullptr && h->os_inactive != 0);
   h->last_h2d = h->last_d2h = 0;
   const size_t w8 = sizeof(double);
+  // Chunk boundaries.  The first upload and the last download are the only transfers the kernel
+  // cannot hide, so the chunks grow from the ends towards the middle (1 : 2 : 4 : ... : 4 : 2 : 1),
+  // and every boundary sits on a whole number of kernel waves (resident blocks x cells per block)
+  // so that no chunk ends in a partly filled wave.
+  int64_t bnd[PFRX_MAX_CHUNKS + 1];
+  {
+    const int64_t wave = h->spec_func ? (int64_t)h->sm_count * h->spec_blocks_per_sm * h->spec_cells
+                                      : (int64_t)h->sm_count * h->blocks_per_sm * h->threads;
+    double wsum = 0.0, wgt[PFRX_MAX_CHUNKS];
+    for (int ch = 0; ch < nchunk; ch++) {
+      const int e = std::min(std::min(ch, nchunk - 1 - ch), 3);
+      wgt[ch] = (nchunk >= 4 && !getenv("PFRX_OS_EQUAL_CHUNKS")) ? (double)(1 << e) : 1.0;
+      wsum += wgt[ch];
+    }
+    double acc = 0.0;
+    bnd[0] = 0;
+    for (int ch = 0; ch < nchunk; ch++) {
+      acc += wgt[ch];
+      int64_t b = (int64_t)((double)ncell * acc / wsum);
+      if (wave > 0 && ncell >= 4 * wave * nchunk) b = (b + wave / 2) / wave * wave;
+      bnd[ch + 1] = std::max(bnd[ch], std::min(ncell, b));
+    }
+    bnd[nchunk] = ncell;
+  }
   for (int ch = 0; ch < nchunk; ch++) {
-    const int64_t c0 = ncell * ch / nchunk, c1 = ncell * (ch + 1) / nchunk, nc = c1 - c0;
+    const int64_t c0 = bnd[ch], c1 = bnd[ch + 1], nc = c1 - c0;
     if (nc <= 0) continue;
     const size_t off = (size_t)c0 * n, cnt = (size_t)nc * n;
     if (solved_total) {
@@ -2237,6 +2329,30 @@ extern "C" int pfrx_kernel_info(pfrx_handle *h, int *info5) {
 }
 
 extern "C" uint64_t pfrx_config_signature(pfrx_handle *h) { return h ? h->sig : 0; }
+
+// Writes the configuration the handle was created from in the text form the code generator reads
+// (python -m pflotran_elm_interface_b200.specialize <path> builds the specialised cubins for it):
+// the route from a Fortran / C host that flattened reaction_rt_type into pfrx_config to the fast
+// kernels, without the Python deck reader.
+static int write_text(const std::string &text, const char *path) {
+  FILE *f = fopen(path, "w");
+  if (!f) return set_err(PFRX_E_INVALID, "cannot open %s for writing", path);
+  const size_t n = fwrite(text.data(), 1, text.size(), f);
+  const int rc = fclose(f);
+  if (n != text.size() || rc != 0) return set_err(PFRX_E_INVALID, "short write to %s", path);
+  return PFRX_OK;
+}
+extern "C" int pfrx_config_dump(pfrx_handle *h, const char *path) {
+  if (!h || !path) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  return write_text(h->dump_text, path);
+}
+// the same file straight from a pfrx_config: needs no device (set-up on a build or login node)
+extern "C" int pfrx_config_write(const pfrx_config *cfg, const char *path) {
+  if (!cfg || !path) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (cfg->abi_version != PFRX_ABI_VERSION) return set_err(PFRX_E_INVALID, "pfrx_config.abi_version mismatch%s", "");
+  return write_text(config_dump_text(cfg), path);
+}
+extern "C" uint64_t pfrx_config_signature_of(const pfrx_config *cfg) { return cfg ? config_signature(cfg) : 0; }
 
 // Attach a network-specialised kernel (cubin written by specialize.py / nvcc).
 // The cubin carries the signature of the tables it was generated from; a cubin

@@ -66,6 +66,10 @@ def lib():
     L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
     L.pfrx_os_store.argtypes = [hp, C.c_void_p]
     L.pfrx_os_step_host.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_double, resp]
+    L.pfrx_config_dump.argtypes = [hp, C.c_char_p]
+    L.pfrx_config_write.argtypes = [cfgp, C.c_char_p]
+    L.pfrx_config_signature_of.argtypes = [cfgp]
+    L.pfrx_config_signature_of.restype = C.c_uint64
     L.pfrx_rstep_host_resident.argtypes = [hp, C.c_uint64]
     L.pfrx_rstep_host_fetch.argtypes = [hp, C.c_int64, stp]
     L.pfrx_last_transfer_bytes.argtypes = [hp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -1597,3 +1597,40 @@ def build(cfg: abi.ReactionConfig, force: bool = False, verbose: bool = False, w
     if verbose:
         print(p.stdout)
     return cubin
+
+
+def main(argv=None) -> int:
+    """``python -m pflotran_elm_interface_b200.specialize <dump> [--styles s,k,q,w] [--out DIR]``:
+    generate and compile the specialised cubins for a configuration written by ``pfrx_config_dump`` /
+    ``pfrx_config_write`` (include/pfrx.h).  Prints one cubin path per line; the host attaches one
+    with ``pfrx_load_specialized``."""
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="python -m pflotran_elm_interface_b200.specialize")
+    ap.add_argument("dump")
+    ap.add_argument("--styles", default="default", help="comma-separated: default, straight, lockstep, refill, refill_warp")
+    ap.add_argument("--out", default=None, help="directory for the cubins (default: csrc/_spec of the package)")
+    ap.add_argument("--force", action="store_true")
+    a = ap.parse_args(argv)
+    cfg = abi.ReactionConfig.from_dump(a.dump)
+    ok, why = supported(cfg)
+    if not ok:
+        print("not covered by the code generator: " + why)
+        return 2
+    sig = signature(cfg)
+    if cfg.dump_signature is not None and cfg.dump_signature != sig:
+        print(f"signature mismatch: file {cfg.dump_signature:016x}, computed {sig:016x}")
+        return 3
+    global OUT
+    if a.out:
+        OUT = os.path.abspath(a.out)
+    for st in a.styles.split(","):
+        path = build(cfg, force=a.force) if st == "default" else build(cfg, force=a.force, warps=1, style=st)
+        print(path)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+
+    sys.exit(main())

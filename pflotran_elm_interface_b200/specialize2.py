@@ -387,7 +387,7 @@ class _Gen2:
                 for y in ids:
                     if x <= y:
                         hits[(x, y)] = hits.get((x, y), 0) + 1
-        budget = int(os.environ.get("PFRX_SPEC2_HOT", "28"))
+        budget = int(os.environ.get("PFRX_SPEC2_HOT", "32"))
         hot = set(sorted(hits, key=lambda e: (-hits[e], e))[:budget])
         for (i, j) in sorted(hot):
             w(f"  double h_{i}_{j} = 0.0;")

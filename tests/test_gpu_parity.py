@@ -427,6 +427,110 @@ def test_os_step_host_against_oracle(name, n, chunks, spec, monkeypatch):
     step.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,spec", [("c3", 4001, True), ("c5", 2500, True), ("c4s", 3000, True)])
+def test_os_step_host_state_resident_over_several_steps(name, n, spec):
+    """the chemistry state stays bound in device memory from step to step, the way rt_auxvars persist
+    in the reference: four consecutive pfrx_os_step_host calls, each with new solved totals from a
+    mock transport step, against the oracle stepping ONE host state the same way; all-active shard,
+    so only solved_total goes up (no immobile species) and tran_xx comes down"""
+    import torch
+
+    rstep = _gpu()
+    wl = W.by_name(name, ncell=n)
+    naq, nim = wl.cfg.c.naqcomp, wl.cfg.c.nimcomp
+    ncomp = naq + nim
+    rng = np.random.default_rng(5)
+    ref = wl.state.copy()
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    if spec:
+        from pflotran_elm_interface_b200 import specialize
+
+        specialize.build(wl.cfg)
+        assert step.specialize(required=True)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    t_solved = torch.zeros((n, ncomp), dtype=torch.float64).pin_memory()
+    t_xx = torch.zeros((n, ncomp), dtype=torch.float64).pin_memory()
+    for k in range(4):
+        # mock transport: the totals drift by up to 3 % per step; immobile entries pass through tran_xx
+        f = 1.0 + 0.03 * (rng.random((naq, n)) - 0.4)
+        solved = ref.a["total"] * f
+        ref.a["total"][...] = solved
+        t_solved[:, :naq] = torch.from_numpy(np.ascontiguousarray(solved.T))
+        if nim:
+            t_xx[:, naq:] = torch.from_numpy(np.ascontiguousarray(ref.a["immobile"].T))
+        res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
+        res = step.os_step_host(t_solved, t_xx, wl.tran_dt)
+        _check_summary(res_ref, res)
+        want = np.concatenate([ref.a["pri_molal"].T, ref.a["immobile"].T], axis=1)
+        g = t_xx.numpy()
+        ok = ref.a["ierror"][0] == 0
+        scale = np.maximum(np.abs(g), np.abs(want))
+        err = np.where(scale < 1e-30, 0.0, np.abs(g - want) / np.where(scale > 0, scale, 1.0))
+        assert err[ok].max() <= RTOL, (k, err[ok].max())
+        h2d, d2h = step.last_transfer_bytes()
+        assert d2h == n * ncomp * 8 and h2d == (2 if nim else 1) * n * ncomp * 8, (h2d, d2h)
+    _compare(ref, dev.to_host(), f"os_step_host x4 {name}")
+    step.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dt,spec", [("c3t", 3600.0, False), ("c3t", 30 * 86400.0, False), ("c2t", 86400.0, False),
+                                          ("c3aw", 3600.0, False), ("c3aw", 3600.0, True), ("c3aw", 30 * 86400.0, True),
+                                          ("c3tg", 3600.0, False), ("c3sf", 3600.0, False), ("c3sf", 30 * 86400.0, False),
+                                          ("c2ng", 3600.0, False)])
+def test_less_travelled_branches(name, dt, spec):
+    """anisothermal logK(T) at 5-60 C (RUpdateTempDependentCoefs, reaction.F90:5976-6067), ACTIVITY_WATER
+    (also through the specialised kernel), USE_TOTAL_CONCENTRATION_AS_GUESS (reaction.F90:3640), the
+    free-site Newton iteration of RTotalSorbEqSurfCplx1 (reaction_surf_complex.F90:700-800) and
+    use_full_geochemistry = 0 (reaction.F90:3600) against the oracle"""
+    wl = W.by_name(name, ncell=1500, tran_dt=dt)
+    ref, res_ref, got, res, info = _run_both(wl, spec=spec)
+    assert (info["lanes"] == -1) == spec, info
+    _compare(ref, got, f"{name} dt={dt} spec={spec}")
+    _check_summary(res_ref, res)
+    if name in ("c3t", "c2t"):
+        assert wl.cfg.c.use_isothermal == 0 and np.ptp(wl.state.a["temp"]) > 40.0
+    if name == "c3aw":
+        assert np.abs(got.a["ln_act_h2o"]).max() > 0.0   # the activity of water was really updated
+
+
+@pytest.mark.gpu
+def test_rstep_host_resident_fields():
+    """pfrx_rstep_host_resident: derived fields stay in the device mirror (no download, no re-upload);
+    two consecutive steps give the same state as two steps with everything crossing the link, and
+    pfrx_rstep_host_fetch brings the resident fields back on request"""
+    rstep = _gpu()
+    wl = W.by_name("c3", ncell=5000)
+    full = wl.state.copy()
+    lean = wl.state.copy()
+    s_full = rstep.ChemistryStep(wl.cfg, 0)
+    s_lean = rstep.ChemistryStep(wl.cfg, 0)
+    resident = ["sec_molal", "sec_act_coef", "pri_act_coef"]
+    s_lean.rstep_host_resident(resident)
+    moved = []
+    for k in range(2):
+        for st in (full, lean):
+            st.a["total"] *= 1.01
+        r_full = s_full.rstep_host(full, wl.tran_dt)
+        r_lean = s_lean.rstep_host(lean, wl.tran_dt)
+        assert r_full.as_dict() == r_lean.as_dict()
+        moved.append((s_full.last_transfer_bytes(), s_lean.last_transfer_bytes()))
+    (f1, l1), (f2, l2) = moved
+    n, ncx, naq = 5000, wl.cfg.c.neqcplx, wl.cfg.c.naqcomp
+    assert f2[1] - l2[1] == 8 * n * (2 * ncx + naq)      # less down: sec_molal, sec_act_coef, pri_act_coef
+    assert f2[0] - l2[0] == 8 * n * ncx                  # less up: sec_molal (the coefficients never go up here)
+    for f in ("total", "pri_molal", "mnrl_volfrac", "total_sorb_eq"):
+        assert np.array_equal(full.a[f], lean.a[f]), f
+    assert not np.array_equal(full.a["sec_molal"], lean.a["sec_molal"])   # the host copy went stale ...
+    s_lean.rstep_host_fetch(lean)
+    for f in resident:
+        assert np.array_equal(full.a[f], lean.a[f]), f                    # ... until it is fetched
+    s_full.close()
+    s_lean.close()
+
+
 def test_autotune_picks_a_variant_and_leaves_state_alone():
     rstep = _gpu()
     from pflotran_elm_interface_b200 import specialize
