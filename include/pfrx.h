@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 5
+#define PFRX_ABI_VERSION 6
 
 /* error classes */
 #define PFRX_OK 0
@@ -94,6 +94,7 @@ extern "C" {
 #define PFRX_SANDBOX_DENITR 4
 #define PFRX_SANDBOX_PLANTN 5
 #define PFRX_SANDBOX_LANGMUIR 6
+#define PFRX_SANDBOX_CNDEGAS 7
 #define PFRX_MAX_SANDBOXES 8
 /* reaction_microbial_aux.F90:14-22 */
 #define PFRX_MICROBIAL_MOLALITY 1
@@ -194,6 +195,30 @@ typedef struct pfrx_langmuir {
   double k_equilibrium;                   /* 2.5e3 */
   double s_max;                           /* 1e-3 mol/m^3 */
 } pfrx_langmuir;
+
+/* CNDEGAS sandbox: first-order exchange of dissolved CO2 / N2O / N2 with a gas reservoir at the
+ * Weiss (1974) / Weiss & Price (1980) solubilities, and an optional pH-stat
+ * (reaction_sandbox_cndegas.F90:14-29, 216-546; solubilities :548-787).
+ * A pair is active when both ids are >= 0.  *_g_id is the index the reference adds to
+ * reaction%offset_immobile for the residual row of the gas reservoir (a primary-species id of
+ * 'CO2(g)*' or a gas id of 'CO2(g)', CNdegasSetup :160-190 -- used as an immobile index either way). */
+typedef struct pfrx_cndegas {
+  int32_t co2a_id, n2oa_id, n2a_id;       /* primary ids of CO2(aq), N2O(aq), N2(aq); -1 absent */
+  int32_t co2g_id, n2og_id, n2g_id;       /* reservoir rows: naqcomp + id; -1 absent */
+  int32_t proton_id, himm_id;             /* pH-stat: H+ (primary), Himm (immobile) */
+  int32_t fixph_on;                       /* FIXPH given */
+  int32_t initialize_with_molality;       /* reaction%initialize_with_molality: c_h in mol/L */
+  /* 0: stand-alone transport (tc, air pressure = the reference values, liquid saturation 0.5);
+   * 1: RICHARDS flow (pressure and saturation of the cell); 2: TH flow or an ELM_PFLOTRAN build
+   * (also the cell's temperature).  In an ELM_PFLOTRAN build (pfrx_config.elm_pflotran) the partial
+   * pressures come from the reservoir concentrations instead of the atmospheric defaults. */
+  int32_t cell_state_mode;
+  int32_t pad_;
+  double k_kinetic_co2, k_kinetic_n2o, k_kinetic_n2, k_kinetic_h;   /* 1e-5 1/s each */
+  double fixph;                           /* 6.5 */
+  double reference_temperature;           /* option%flow%reference_temperature, C */
+  double reference_pressure;              /* option%flow%reference_pressure, Pa */
+} pfrx_cndegas;
 
 /*
  * Flattened, read-only reaction description: the subset of
@@ -345,8 +370,9 @@ typedef struct pfrx_config {
   const pfrx_denitr *denitr;     /* reaction_sandbox_denitr.F90:212-404   */
   const pfrx_plantn *plantn;     /* reaction_sandbox_plantn.F90:222-640   */
   const pfrx_langmuir *langmuir; /* reaction_sandbox_langmu.F90:183-330   */
+  const pfrx_cndegas *cndegas;   /* reaction_sandbox_cndegas.F90:216-546  */
   /* evaluation order of the sandboxes (PFRX_SANDBOX_*); NULL => the order
-   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR */
+   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR, CNDEGAS */
   int32_t nsandbox;
   const int32_t *sandbox_list;
   /* 1 => the behaviour of a reference built with -DELM_PFLOTRAN in BGC-only
@@ -474,6 +500,9 @@ typedef struct pfrx_state {
    * every cation (rt_auxvar%eqionx_conc), io [eqionx_ptr[neqionxrxn]], may be NULL */
   double *eqionx_ref_cation_sorbed_conc;
   double *eqionx_conc;
+  /* in, optional: liquid pressure [Pa] (global_auxvar%pres(1)); read by the CNDEGAS sandbox when
+   * its cell_state_mode is 1 or 2 */
+  const double *pres;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

@@ -50,6 +50,7 @@ typedef struct {
   double *dtotal;      /* dtotal(i,j) at [i + j*naq] */
   double ln_act_h2o;
   double den_kg, sat, temp, porosity, volume, soil_particle_density;
+  double pres; /* liquid pressure, CNDEGAS only */
   /* ELM per-cell scalars (elm_pflotran builds) */
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
@@ -167,6 +168,7 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->porosity = LD(st->porosity, 0);
   c->volume = LD(st->volume, 0);
   c->soil_particle_density = st->soil_particle_density ? LD(st->soil_particle_density, 0) : 0.0;
+  c->pres = st->pres ? LD(st->pres, 0) : 101325.0;
   c->elm_w = st->elm_w_scalar ? LD(st->elm_w_scalar, 0) : 1.0;
   c->elm_o = st->elm_o_scalar ? LD(st->elm_o_scalar, 0) : 1.0;
   c->elm_t = st->elm_t_scalar ? LD(st->elm_t_scalar, 0) : 1.0;
@@ -2291,18 +2293,183 @@ static void langmuir_react(cell_t *c, const pfrx_config *cfg, double tran_dt, do
 #undef DTOT
 }
 
+/* reaction_sandbox_cndegas.F90:548-787: Weiss (1974) CO2, Weiss & Price (1980) N2O, Weiss (1970) N2
+ * solubilities.  rgas is a default-real literal in the reference (0.08205601 without d0): its value
+ * is the single-precision one. */
+#define CND_RGAS ((double)0.08205601f)
+static double weiss_co2_xmole(double tt, double tp, double ts, double pco2) {
+  const double atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double a1 = -58.0931, a2 = 90.5069, a3 = 22.2940, b1 = 0.027766, b2 = -0.025888, b3 = 0.0050578;
+  double tk = tt + 273.15, tk2 = tk * tk, tk3 = tk2 * tk, tk_100k = tk / 100.0;
+  double p_rt = (tp / atm) / CND_RGAS / tk, x1, x2, epsilon, bt, fg, k0, vbar, cco2;
+  p_rt = p_rt / 1000.0;
+  x1 = pco2 / tp;
+  x2 = 1.0 - x1;
+  epsilon = 57.7 - 0.118 * tk;
+  bt = -1636.75 + 12.0408 * tk - 3.27957e-2 * tk2 + 3.16528e-5 * tk3;
+  fg = pco2 * exp((bt + 2.0 * x2 * x2 * epsilon) * p_rt);
+  k0 = a1 + a2 / tk_100k + a3 * log(tk_100k) + ts * (b1 + b2 * tk_100k + b3 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = k0 / atm;
+  vbar = exp((1.0 - tp / atm) * 30.0e-3 / CND_RGAS / tk);
+  cco2 = k0 * fg * vbar;
+  return cco2 / (1.0 / xmwh2o);
+}
+static double weiss_price_n2o_xmole(double tt, double tp, double ts, double pn2o) {
+  const double atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double a1 = -62.7076, a2 = 97.3066, a3 = 24.1406, b1 = -0.058420, b2 = 0.033193, b3 = -0.0051313;
+  double tk = tt + 273.15, tk2 = tk * tk, tk_100k = tk / 100.0;
+  double p_rt = (tp / atm) / CND_RGAS / tk, x1, x2, epsilon, bt, fg, k0, vbar, cn2o;
+  p_rt = p_rt / 1000.0;
+  x1 = pn2o / tp;
+  x2 = 1.0 - x1;
+  epsilon = 65.0 - 0.1338 * tk;
+  bt = -905.95 + 4.1685 * tk - 0.0052734 * tk2;
+  fg = pn2o * exp((bt + 2.0 * x2 * x2 * epsilon) * p_rt);
+  k0 = a1 + a2 / tk_100k + a3 * log(tk_100k) + ts * (b1 + b2 * tk_100k + b3 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = k0 / atm;
+  vbar = exp((1.0 - tp / atm) * 32.3e-3 / CND_RGAS / tk);
+  cn2o = k0 * fg * vbar;
+  return cn2o / (1.0 / xmwh2o);
+}
+static double weiss_n2_xmole(double tt, double ts, double pn2) {
+  const double atmn2 = 0.78084, atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double a1 = -172.4965, a2 = 248.4262, a3 = 143.3483, a4 = -21.7120, b1 = -0.049781, b2 = -0.025018,
+               b3 = -0.0034861;
+  double tk = tt + 273.15, tk_100k = tk / 100.0, k0, kh, cn2;
+  k0 = a1 + a2 / tk_100k + a3 * log(tk_100k) + a4 * tk_100k + ts * (b1 + b2 * tk_100k + b3 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = (k0 * 1.e-3) / CND_RGAS / 298.15;
+  kh = (atmn2 * atm) / k0;
+  kh = kh * (1.0 / xmwh2o); /* the reference divides by this kh although it is per mole fraction by now */
+  cn2 = (pn2 * 1.0) / kh;
+  return cn2 / (1.0 / xmwh2o);
+}
+
+/* reaction_sandbox_cndegas.F90:216-546  CNdegasReact */
+static void cndegas_react(cell_t *c, const pfrx_config *cfg, double *Residual, double *Jacobian,
+                          int compute_derivative) {
+  const pfrx_cndegas *cd = cfg->cndegas;
+  const double H2O_kg_mol = 18.01534e-3, rgas = 8.3144621;
+  int off = c->naq, n = c->n, elm = cfg->elm_pflotran ? 1 : 0;
+  double convert_molal_to_molar = cd->initialize_with_molality ? c->den_kg * 1.0 / 1000.0 : 1.0;
+  double tc = cd->reference_temperature, air_press = cd->reference_pressure, lsat = 0.50;
+  double porosity, volume, air_vol, air_molar, temp_real, total_sal, rate, drate;
+#define JAC(i, j) Jacobian[(i) + (size_t)(j) * n]
+#define DTOT(i, j) c->dtotal[(i) + (size_t)(j) * c->naq]
+  if (cd->cell_state_mode >= 1) {
+    air_press = fmax(air_press, c->pres);
+    lsat = c->sat;
+    if (cd->cell_state_mode >= 2) tc = c->temp;
+  }
+  porosity = c->porosity;
+  volume = c->volume;
+  air_vol = 1.0;
+  air_molar = air_press / rgas / (tc + 273.15);
+  if (cd->co2a_id >= 0 && cd->co2g_id >= 0) {
+    int ia = cd->co2a_id, ig = cd->co2g_id + off;
+    double c_aq = c->total[cd->co2a_id], c_eq;
+    double co2_p = 350.0e-6 * cd->reference_pressure;
+    if (elm) {
+      double co2_molar = c->immobile[cd->co2g_id] / air_vol;
+      co2_p = co2_molar / air_molar * air_press;
+    }
+    temp_real = fmax(fmin(tc, 40.0), -1.0);
+    total_sal = 1.e-20;
+    c_eq = weiss_co2_xmole(temp_real, air_press, total_sal, co2_p) / H2O_kg_mol;
+    temp_real = volume * 1000.0 * porosity * lsat;
+    rate = cd->k_kinetic_co2 * (c_aq - c_eq) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      Residual[ia] = Residual[ia] + rate;
+      Residual[ig] = Residual[ig] - rate;
+      if (compute_derivative) {
+        drate = cd->k_kinetic_co2 * temp_real;
+        JAC(ia, ia) = JAC(ia, ia) + drate * DTOT(cd->co2a_id, cd->co2a_id);
+        JAC(ig, ia) = JAC(ig, ia) - drate;
+      }
+    }
+  }
+  if (cd->n2oa_id >= 0 && cd->n2og_id >= 0) {
+    int ia = cd->n2oa_id, ig = cd->n2og_id + off;
+    double c_aq = c->total[cd->n2oa_id], c_eq;
+    double n2o_p = 310.0e-9 * cd->reference_pressure;
+    if (elm) {
+      double n2o_molar = c->immobile[cd->n2og_id] / air_vol;
+      n2o_p = n2o_molar / air_molar * air_press;
+    }
+    temp_real = fmax(fmin(tc, 40.0), 1.e-20);
+    total_sal = 1.0e-20;
+    c_eq = weiss_price_n2o_xmole(temp_real, air_press, total_sal, n2o_p) / H2O_kg_mol;
+    temp_real = volume * 1000.0 * porosity * lsat;
+    rate = cd->k_kinetic_n2o * (c_aq - c_eq) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      Residual[ia] = Residual[ia] + rate;
+      Residual[ig] = Residual[ig] - rate;
+      if (compute_derivative) {
+        drate = cd->k_kinetic_n2o * temp_real;
+        JAC(ia, ia) = JAC(ia, ia) + drate * DTOT(cd->n2oa_id, cd->n2oa_id);
+        JAC(ig, ia) = JAC(ig, ia) - drate;
+      }
+    }
+  }
+  if (cd->n2a_id >= 0 && cd->n2g_id >= 0) {
+    int ia = cd->n2a_id, ig = cd->n2g_id + off;
+    double c_aq = c->total[cd->n2a_id], c_eq;
+    double n2_p = 0.78084 * cd->reference_pressure;
+    if (elm) {
+      double n2_molar = c->immobile[cd->n2g_id] / air_vol;
+      n2_p = n2_molar / air_molar * air_press;
+    }
+    temp_real = fmax(fmin(tc, 40.0), -2.0);
+    total_sal = 1.0e-20;
+    c_eq = weiss_n2_xmole(temp_real, total_sal, n2_p) / H2O_kg_mol;
+    temp_real = volume * porosity * lsat * 1.e3;
+    rate = cd->k_kinetic_n2 * (c_aq - c_eq) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      Residual[ia] = Residual[ia] + rate;
+      Residual[ig] = Residual[ig] - rate;
+      if (compute_derivative) {
+        drate = cd->k_kinetic_n2 * temp_real;
+        JAC(ia, ia) = JAC(ia, ia) + drate * DTOT(cd->n2a_id, cd->n2a_id);
+        JAC(ig, ia) = JAC(ig, ia) - drate;
+      }
+    }
+  }
+  if (cd->fixph_on) {
+    int ip = cd->proton_id, ih = cd->himm_id + off;
+    double c_h = c->pri_molal[cd->proton_id] * convert_molal_to_molar;
+    double c_h_fix = pow(10.0, -1.0 * cd->fixph) / c->pri_act_coef[cd->proton_id];
+    temp_real = volume * 1000.0 * porosity * lsat;
+    rate = cd->k_kinetic_h * (c_h - c_h_fix) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      Residual[ip] = Residual[ip] + rate;
+      Residual[ih] = Residual[ih] - rate;
+      if (compute_derivative) {
+        drate = cd->k_kinetic_h * convert_molal_to_molar * temp_real;
+        JAC(ip, ip) = JAC(ip, ip) + drate;
+        /* as written (:501): the Himm row takes the TRANSPOSED entry as its starting value */
+        JAC(ih, ip) = JAC(ip, ih) - drate;
+      }
+    }
+  }
+#undef JAC
+#undef DTOT
+}
+
 static int n_sandboxes(const pfrx_config *cfg) {
   return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL) +
-         (cfg->plantn != NULL) + (cfg->langmuir != NULL);
+         (cfg->plantn != NULL) + (cfg->langmuir != NULL) + (cfg->cndegas != NULL);
 }
 
 /* reaction_sandbox.F90:294-330  RSandboxEvaluate: walk the list in deck order */
 static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
                                int derivative) {
-  static const int32_t default_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
-                                           PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR};
+  static const int32_t default_order[7] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
+                                           PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
+                                           PFRX_SANDBOX_CNDEGAS};
   const int32_t *order = cfg->sandbox_list ? cfg->sandbox_list : default_order;
-  int ns = cfg->sandbox_list ? cfg->nsandbox : 6, k;
+  int ns = cfg->sandbox_list ? cfg->nsandbox : 7, k;
   for (k = 0; k < ns; k++) {
     switch (order[k]) {
       case PFRX_SANDBOX_CLM_CN:
@@ -2322,6 +2489,9 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
         break;
       case PFRX_SANDBOX_LANGMUIR:
         if (cfg->langmuir) langmuir_react(c, cfg, tran_dt, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_CNDEGAS:
+        if (cfg->cndegas) cndegas_react(c, cfg, Res, Jac, derivative);
         break;
       default:
         break;
@@ -3052,8 +3222,8 @@ int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   /* the GIRT caller has just run RTAuxVarCompute (reactive_transport.F90:2599-2642):
    * the sandboxes that read rt_auxvar%aqueous%dtotal need it here too, radioactive decay reads
    * total and dtotal, mineral prefactors on secondary species read sec_molal */
-  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir || cfg->nradiodecay_rxn > 0 ||
-      cfg->kinmnrl_num_prefactors)
+  if (cfg->somdec || cfg->nitrif || cfg->denitr || cfg->plantn || cfg->langmuir || cfg->cndegas ||
+      cfg->nradiodecay_rxn > 0 || cfg->kinmnrl_num_prefactors)
     rt_auxvar_compute(&c, cfg);
   r_reaction(&c, cfg, tran_dt, Res, Jac, 1);
   for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];

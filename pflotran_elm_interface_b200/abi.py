@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 5
+PFRX_ABI_VERSION = 6
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -141,6 +141,7 @@ class PfrxConfig(C.Structure):
         ("denitr", C.c_void_p),
         ("plantn", C.c_void_p),
         ("langmuir", C.c_void_p),
+        ("cndegas", C.c_void_p),
         ("nsandbox", C.c_int32),
         ("sandbox_list", c_int32_p),
         ("elm_pflotran", C.c_int32),
@@ -187,6 +188,7 @@ class PfrxConfig(C.Structure):
 
 
 SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR, SANDBOX_PLANTN, SANDBOX_LANGMUIR = 1, 2, 3, 4, 5, 6
+SANDBOX_CNDEGAS = 7
 SPEC_AQUEOUS, SPEC_IMMOBILE = 0, 2
 
 
@@ -231,6 +233,13 @@ class PfrxLangmuir(C.Structure):
                 + [(f, C.c_double) for f in ("k_kinetic", "k_equilibrium", "s_max")])
 
 
+class PfrxCndegas(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("co2a_id", "n2oa_id", "n2a_id", "co2g_id", "n2og_id", "n2g_id", "proton_id",
+                                           "himm_id", "fixph_on", "initialize_with_molality", "cell_state_mode", "pad_")]
+                + [(f, C.c_double) for f in ("k_kinetic_co2", "k_kinetic_n2o", "k_kinetic_n2", "k_kinetic_h", "fixph",
+                                             "reference_temperature", "reference_pressure")])
+
+
 class PfrxDenitr(C.Structure):
     _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
                 + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])
@@ -246,7 +255,7 @@ STATE_DOUBLE_FIELDS = [
 # elm_pflotran, NULL otherwise
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
                     "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc",
-                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc"]
+                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
@@ -568,7 +577,7 @@ class ReactionConfig:
         for kind in getattr(net, "sandbox_order", []):
             order.append({"CLM-CN": SANDBOX_CLM_CN, "SOMDECOMP": SANDBOX_SOMDEC, "NITRIFICATION": SANDBOX_NITRIF,
                           "DENITRIFICATION": SANDBOX_DENITR, "PLANTN": SANDBOX_PLANTN,
-                          "LANGMUIR": SANDBOX_LANGMUIR}[kind])
+                          "LANGMUIR": SANDBOX_LANGMUIR, "CNDEGAS": SANDBOX_CNDEGAS}[kind])
         if order:
             c.nsandbox = len(order)
             c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
@@ -612,6 +621,13 @@ class ReactionConfig:
                 setattr(o, k, v)
             self.langmuir = o
             c.langmuir = C.cast(C.pointer(o), C.c_void_p)
+        cd = getattr(net, "cndegas", None)
+        if cd is not None:
+            o = PfrxCndegas()
+            for k, v in cd.items():
+                setattr(o, k, v)
+            self.cndegas = o
+            c.cndegas = C.cast(C.pointer(o), C.c_void_p)
 
     # ------------------------------------------------------------------ #
     @classmethod
@@ -624,7 +640,7 @@ class ReactionConfig:
         self.net = None
         self.arrays = {}
         structs = {"config": PfrxConfig, "somdec": PfrxSomdec, "nitrif": PfrxNitrif, "denitr": PfrxDenitr,
-                   "plantn": PfrxPlantn, "langmuir": PfrxLangmuir}
+                   "plantn": PfrxPlantn, "langmuir": PfrxLangmuir, "cndegas": PfrxCndegas}
         prefix = {"c": ("", None), "sd": ("somdec_", "somdec"), "nt": ("nitrif_", "nitrif"), "dn": ("denitr_", "denitr"),
                   "pn": ("plantn_", "plantn"), "lg": ("langmuir_", "langmuir")}
         objs = {}
@@ -653,7 +669,7 @@ class ReactionConfig:
                 elif w[0] == "signature":
                     sig = int(w[1], 16)
         self.c = objs["config"]
-        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir"):
+        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir", "cndegas"):
             if k in objs:
                 setattr(self, k, objs[k])
                 setattr(self.c, k, C.cast(C.pointer(objs[k]), C.c_void_p))
@@ -698,6 +714,7 @@ class ReactionConfig:
             **{f: (1 if c.elm_pflotran else 0) for f in STATE_ELM_FIELDS},
             "eqionx_ref_cation_sorbed_conc": c.neqionxrxn,
             "eqionx_conc": int(self.arrays["eqionx_ptr"][c.neqionxrxn]) if c.neqionxrxn else 0,
+            "pres": 1 if (getattr(self, "cndegas", None) is not None and self.cndegas.cell_state_mode >= 1) else 0,
             "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
                           if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,
@@ -733,6 +750,7 @@ class HostState:
         for f in ("elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_kscalar_decomp_c", "elm_bsw"):
             self.a[f][:] = 1.0
         self.a["elm_bulkdensity_dry"][:] = 1.25e3
+        self.a["pres"][:] = 101325.0
         if rows["somdec_nc"]:
             nc0 = np.concatenate([cfg.arrays["somdec_upstream_nc"],
                                   cfg.arrays.get("somdec_downstream_nc", np.zeros(0))])

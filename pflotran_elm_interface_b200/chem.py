@@ -356,6 +356,7 @@ class Chemistry:
     denitr: Optional[dict] = None
     plantn: Optional[dict] = None
     langmuir: Optional[dict] = None
+    cndegas: Optional[dict] = None
     sandbox_order: List[str] = field(default_factory=list)
     database: str = ""
     use_log_formulation: bool = False
@@ -829,6 +830,24 @@ def _read_langmuir(cur: _Cursor) -> dict:
     return d
 
 
+def _read_cndegas(cur: _Cursor) -> dict:
+    # CNdegasCreate / CNdegasRead, reaction_sandbox_cndegas.F90:44-130
+    d = {"k_kinetic_co2": 1.0e-5, "k_kinetic_n2o": 1.0e-5, "k_kinetic_n2": 1.0e-5, "k_kinetic_h": 1.0e-5,
+         "fixph": 6.5, "fixph_on": 0}
+    keys = {"KINETIC_CONSTANT_CO2": "k_kinetic_co2", "KINETIC_CONSTANT_N2O": "k_kinetic_n2o",
+            "KINETIC_CONSTANT_N2": "k_kinetic_n2", "KINETIC_CONSTANT_H+": "k_kinetic_h"}
+    for t in cur.block():
+        key = t[0].upper()
+        if key in keys:
+            d[keys[key]] = _fnum(t[1])
+        elif key == "FIXPH":
+            d["fixph"] = _fnum(t[1])
+            d["fixph_on"] = 1
+        else:
+            raise ValueError(f"CNDEGAS keyword {key}")
+    return d
+
+
 def _per_time(tokens, i) -> float:
     """value at tokens[i] with an optional 1/<time> unit behind it -> 1/s"""
     v = _fnum(tokens[i])
@@ -1020,6 +1039,9 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                     ch.sandbox_order.append(k2)
                 elif k2 == "LANGMUIR" and ch.langmuir is None:
                     ch.langmuir = _read_langmuir(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "CNDEGAS" and ch.cndegas is None:
+                    ch.cndegas = _read_cndegas(cur)
                     ch.sandbox_order.append(k2)
                 else:
                     ch.unsupported.append("REACTION_SANDBOX," + k2)
@@ -1813,6 +1835,37 @@ class ReactionNetwork:
             g = self.chem.langmuir
             self.langmuir = {"aq_id": pri[g["name_aq"]], "sorb_id": imm[g["name_sorb"]],
                              "k_kinetic": g["k_kinetic"], "k_equilibrium": g["k_equilibrium"], "s_max": g["s_max"]}
+
+        self.cndegas = None
+        if self.chem.cndegas is not None:
+            # CNdegasSetup, reaction_sandbox_cndegas.F90:140-206.  The reservoir of a gas is looked up as
+            # the PRIMARY species 'X(g)*' and, failing that, as the gas species 'X(g)'; either id is then
+            # added to reaction%offset_immobile (:317, :367, :415), i.e. read as an immobile index.
+            g = dict(self.chem.cndegas)
+
+            def gas_id(name):
+                if name + "*" in pri:
+                    return pri[name + "*"]
+                if name in self.chem.gases:
+                    return self.chem.gases.index(name)
+                return g.get("gas_ids", {}).get(name, -1)
+
+            d = {"co2a_id": pri.get("CO2(aq)", -1), "n2oa_id": pri.get("N2O(aq)", -1), "n2a_id": pri.get("N2(aq)", -1),
+                 "co2g_id": gas_id("CO2(g)"), "n2og_id": gas_id("N2O(g)"), "n2g_id": gas_id("N2(g)"),
+                 "proton_id": -1, "himm_id": -1, "fixph_on": int(g["fixph_on"]),
+                 "initialize_with_molality": int(g.get("initialize_with_molality", 0)),
+                 "cell_state_mode": int(g.get("cell_state_mode", 0)), "pad_": 0,
+                 "k_kinetic_co2": g["k_kinetic_co2"], "k_kinetic_n2o": g["k_kinetic_n2o"],
+                 "k_kinetic_n2": g["k_kinetic_n2"], "k_kinetic_h": g["k_kinetic_h"], "fixph": g["fixph"],
+                 "reference_temperature": float(g.get("reference_temperature", self.tref)),
+                 "reference_pressure": float(g.get("reference_pressure", 101325.0))}
+            if d["fixph_on"]:
+                if "H+" not in pri:
+                    raise KeyError("CNDEGAS: H+ is not defined even though pH needs to be fixed")
+                if "Himm" not in imm:
+                    raise KeyError("CNDEGAS: Himm is not defined even though pH needs to be fixed")
+                d["proton_id"], d["himm_id"] = pri["H+"], imm["Himm"]
+            self.cndegas = d
 
     # -- helpers -------------------------------------------------------------- #
     def csr(self, rxns: Sequence[Rxn]):

@@ -313,6 +313,9 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
     h = fnv1a(h, hi, sizeof(hi));
     h = fnv1a(h, hd, sizeof(hd));
   }
+  if (c->cndegas) {  // not covered by the generator: any cubin signature must differ
+    h = fnv1a(h, c->cndegas, sizeof(*c->cndegas));
+  }
   if (c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir) {
     int32_t e = c->elm_pflotran ? 1 : 0;
     h = fnv1a(h, &e, sizeof(e));
@@ -366,6 +369,7 @@ static std::string config_dump_text(const pfrx_config *c) {
   if (c->denitr) hex_struct(out, "denitr", c->denitr, sizeof(*c->denitr));
   if (c->plantn) hex_struct(out, "plantn", c->plantn, sizeof(*c->plantn));
   if (c->langmuir) hex_struct(out, "langmuir", c->langmuir, sizeof(*c->langmuir));
+  if (c->cndegas) hex_struct(out, "cndegas", c->cndegas, sizeof(*c->cndegas));
   CfgSink sink;
   sink.dump = &out;
   const uint64_t sig = config_walk(c, sink);
@@ -543,7 +547,7 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 31
+#define PFRX_NUM_D 32
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
@@ -553,7 +557,8 @@ static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   const int nsorb = c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn;
   int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
                        c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, nsorb > 0 ? c->naqcomp : 0,
-                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc};
+                       mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc,
+                       (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -814,7 +819,17 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
         return set_err(PFRX_E_INVALID, "immobile decay species id out of range%s", "");
   }
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
-  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir;
+  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir || c->cndegas;
+  if (c->cndegas) {
+    const pfrx_cndegas *cd = c->cndegas;
+    const int gid[3] = {cd->co2g_id, cd->n2og_id, cd->n2g_id}, aid[3] = {cd->co2a_id, cd->n2oa_id, cd->n2a_id};
+    for (int k = 0; k < 3; k++)
+      if ((aid[k] >= c->naqcomp) || (aid[k] >= 0 && gid[k] >= c->nimcomp))
+        return set_err(PFRX_E_INVALID, "CNDEGAS species id out of range%s", "");
+    if (cd->fixph_on && (cd->proton_id < 0 || cd->proton_id >= c->naqcomp || cd->himm_id < 0 || cd->himm_id >= c->nimcomp))
+      return set_err(PFRX_E_INVALID, "CNDEGAS FIXPH needs H+ and the immobile species Himm%s", "");
+    if (cd->cell_state_mode < 0 || cd->cell_state_mode > 2) return set_err(PFRX_E_INVALID, "CNDEGAS cell_state_mode%s", "");
+  }
   if (c->plantn && (c->plantn->plantn_id < 0 || (c->plantn->nh4_id < 0 && c->plantn->no3_id < 0)))
     return set_err(PFRX_E_INVALID, "PLANTN needs PlantN and NH4+ or NO3-%s", "");
   if (c->langmuir && (c->langmuir->aq_id < 0 || c->langmuir->sorb_id < 0))
@@ -844,7 +859,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
   if (c->sandbox_list)
     for (int k = 0; k < c->nsandbox; k++)
-      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_LANGMUIR ||
+      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_CNDEGAS ||
           c->nsandbox > PFRX_MAX_SANDBOXES)
         return set_err(PFRX_E_INVALID, "bad sandbox_list%s", "");
   int ndev = 0;
@@ -910,6 +925,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_dn = c->denitr ? 1 : 0;
   d.has_pn = c->plantn ? 1 : 0;
   d.has_lg = c->langmuir ? 1 : 0;
+  d.has_cd = c->cndegas ? 1 : 0;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
   d.need_ds = (c->nradiodecay_rxn > 0 && c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0) ? 1 : 0;
@@ -920,17 +936,18 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.mb_units = c->microbial_concentration_units;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
-    static const int def_order[6] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
-                                     PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR};
+    static const int def_order[7] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
+                                     PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
+                                     PFRX_SANDBOX_CNDEGAS};
     const int32_t *ord = c->sandbox_list ? c->sandbox_list : def_order;
-    const int no = c->sandbox_list ? c->nsandbox : 6;
+    const int no = c->sandbox_list ? c->nsandbox : 7;
     d.nsbx = 0;
     for (int k = 0; k < no; k++) {
       const int kind = ord[k];
       const bool present = (kind == PFRX_SANDBOX_CLM_CN && c->clmcn_nrxn > 0) ||
                            (kind == PFRX_SANDBOX_SOMDEC && c->somdec) || (kind == PFRX_SANDBOX_NITRIF && c->nitrif) ||
                            (kind == PFRX_SANDBOX_DENITR && c->denitr) || (kind == PFRX_SANDBOX_PLANTN && c->plantn) ||
-                           (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir);
+                           (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir) || (kind == PFRX_SANDBOX_CNDEGAS && c->cndegas);
       if (present) d.sbx[d.nsbx++] = kind;
     }
   }
@@ -938,6 +955,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->denitr) d.dn = *c->denitr;
   if (c->plantn) d.pn = *c->plantn;
   if (c->langmuir) d.lg = *c->langmuir;
+  if (c->cndegas) d.cd = *c->cndegas;
 
   // kernel variant first: the task partition depends on the lane count
   {
@@ -1395,6 +1413,7 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->elm_plantndemand = s->elm_rate_plantndemand;
   d->eqionx_ref = s->eqionx_ref_cation_sorbed_conc;
   d->eqionx_conc = s->eqionx_conc;
+  d->pres = s->pres;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -1999,7 +2018,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.elm_w, (double **)&h->own_st.elm_o, (double **)&h->own_st.elm_t,
                            (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
                            (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
-                           (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc};
+                           (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc,
+                           (double **)&h->own_st.pres};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -2018,14 +2038,14 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
                               host->somdec_nc,    host->elm_rate_plantndemand, host->eqionx_ref_cation_sorbed_conc,
-                              host->eqionx_conc};
+                              host->eqionx_conc,  host->pres};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
-                         d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc};
+                         d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc, (double *)d.pres};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -2373,7 +2393,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
     inner_newton = inner_newton || h->sr_flag_host[r] != 0;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton ||
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd ||
       d.nsrfrxn != d.neqsr + d.nmr)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();

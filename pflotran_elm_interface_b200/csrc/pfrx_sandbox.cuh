@@ -913,4 +913,127 @@ __device__ __forceinline__ void langmuir_react(Cell &s, double tran_dt) {
   s.J(ires_sorb, ires_sorb) = s.J(ires_sorb, ires_sorb) - drate_dsorb;
 }
 
+// ---- CNDEGAS (reaction_sandbox_cndegas.F90:216-546; solubilities :548-787) -------------
+// rgas of the solubility routines is a default-real literal in the reference (0.08205601
+// without d0): the single-precision value
+#define PFRX_CND_RGAS ((double)0.08205601f)
+__device__ __forceinline__ double weiss_co2_xmole(double tt, double tp, double ts, double pco2) {
+  const double atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double tk = tt + 273.15, tk2 = tk * tk, tk3 = tk2 * tk, tk_100k = tk / 100.0;
+  double p_rt = (tp / atm) / PFRX_CND_RGAS / tk;
+  p_rt = p_rt / 1000.0;
+  const double x1 = pco2 / tp, x2 = 1.0 - x1;
+  const double epsilon = 57.7 - 0.118 * tk;
+  const double bt = -1636.75 + 12.0408 * tk - 3.27957e-2 * tk2 + 3.16528e-5 * tk3;
+  const double fg = pco2 * exp((bt + 2.0 * x2 * x2 * epsilon) * p_rt);
+  double k0 = -58.0931 + 90.5069 / tk_100k + 22.2940 * log(tk_100k) +
+              ts * (0.027766 + -0.025888 * tk_100k + 0.0050578 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = k0 / atm;
+  const double vbar = exp((1.0 - tp / atm) * 30.0e-3 / PFRX_CND_RGAS / tk);
+  const double cco2 = k0 * fg * vbar;
+  return cco2 / (1.0 / xmwh2o);
+}
+__device__ __forceinline__ double weiss_price_n2o_xmole(double tt, double tp, double ts, double pn2o) {
+  const double atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double tk = tt + 273.15, tk2 = tk * tk, tk_100k = tk / 100.0;
+  double p_rt = (tp / atm) / PFRX_CND_RGAS / tk;
+  p_rt = p_rt / 1000.0;
+  const double x1 = pn2o / tp, x2 = 1.0 - x1;
+  const double epsilon = 65.0 - 0.1338 * tk;
+  const double bt = -905.95 + 4.1685 * tk - 0.0052734 * tk2;
+  const double fg = pn2o * exp((bt + 2.0 * x2 * x2 * epsilon) * p_rt);
+  double k0 = -62.7076 + 97.3066 / tk_100k + 24.1406 * log(tk_100k) +
+              ts * (-0.058420 + 0.033193 * tk_100k + -0.0051313 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = k0 / atm;
+  const double vbar = exp((1.0 - tp / atm) * 32.3e-3 / PFRX_CND_RGAS / tk);
+  const double cn2o = k0 * fg * vbar;
+  return cn2o / (1.0 / xmwh2o);
+}
+__device__ __forceinline__ double weiss_n2_xmole(double tt, double ts, double pn2) {
+  const double atmn2 = 0.78084, atm = 1.01325e5, xmwh2o = 18.01534e-3;
+  const double tk = tt + 273.15, tk_100k = tk / 100.0;
+  double k0 = -172.4965 + 248.4262 / tk_100k + 143.3483 * log(tk_100k) + -21.7120 * tk_100k +
+              ts * (-0.049781 + -0.025018 * tk_100k + -0.0034861 * tk_100k * tk_100k);
+  k0 = exp(k0);
+  k0 = (k0 * 1.e-3) / PFRX_CND_RGAS / 298.15;
+  double kh = (atmn2 * atm) / k0;
+  kh = kh * (1.0 / xmwh2o);
+  const double cn2 = (pn2 * 1.0) / kh;
+  return cn2 / (1.0 / xmwh2o);
+}
+
+// lngam_proton: ln of rt_auxvar%pri_act_coef(H+) (only read by the pH-stat)
+template <class Cell>
+__device__ __forceinline__ void cndegas_react(Cell &s, double lngam_proton) {
+  const pfrx_cndegas &cd = s.cfg.cd;
+  const double H2O_kg_mol = 18.01534e-3, rgas = 8.3144621;
+  const int off = s.cfg.naq;
+  const bool elm = s.cfg.elm != 0;
+  const double convert_molal_to_molar = cd.initialize_with_molality ? s.den_kg * 1.0 / 1000.0 : 1.0;
+  double tc = cd.reference_temperature, air_press = cd.reference_pressure, lsat = 0.50;
+  if (cd.cell_state_mode >= 1) {
+    air_press = fmax(air_press, s.st.pres ? s.st.pres[s.cell] : 101325.0);
+    lsat = s.sat;
+    if (cd.cell_state_mode >= 2) tc = s.temp;
+  }
+  const double porosity = s.por, volume = s.vol, air_vol = 1.0;
+  const double air_molar = air_press / rgas / (tc + 273.15);
+#pragma unroll 1
+  for (int g = 0; g < 3; g++) {
+    const int aq = g == 0 ? cd.co2a_id : g == 1 ? cd.n2oa_id : cd.n2a_id;
+    const int gs = g == 0 ? cd.co2g_id : g == 1 ? cd.n2og_id : cd.n2g_id;
+    if (aq < 0 || gs < 0) continue;
+    const int ia = aq, ig = gs + off;
+    const double c_aq = s.TOTc(aq);
+    double p = (g == 0 ? 350.0e-6 : g == 1 ? 310.0e-9 : 0.78084) * cd.reference_pressure;
+    if (elm) {
+      const double molar = s.Cc(ig) / air_vol;
+      p = molar / air_molar * air_press;
+    }
+    const double total_sal = 1.e-20;
+    double c_eq, temp_real, kk;
+    if (g == 0) {
+      temp_real = fmax(fmin(tc, 40.0), -1.0);
+      c_eq = weiss_co2_xmole(temp_real, air_press, total_sal, p) / H2O_kg_mol;
+      temp_real = volume * 1000.0 * porosity * lsat;
+      kk = cd.k_kinetic_co2;
+    } else if (g == 1) {
+      temp_real = fmax(fmin(tc, 40.0), 1.e-20);
+      c_eq = weiss_price_n2o_xmole(temp_real, air_press, total_sal, p) / H2O_kg_mol;
+      temp_real = volume * 1000.0 * porosity * lsat;
+      kk = cd.k_kinetic_n2o;
+    } else {
+      temp_real = fmax(fmin(tc, 40.0), -2.0);
+      c_eq = weiss_n2_xmole(temp_real, total_sal, p) / H2O_kg_mol;
+      temp_real = volume * porosity * lsat * 1.e3;
+      kk = cd.k_kinetic_n2;
+    }
+    const double rate = kk * (c_aq - c_eq) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      s.RES(ia) = s.RES(ia) + rate;
+      s.RES(ig) = s.RES(ig) - rate;
+      const double drate = kk * temp_real;
+      s.J(ia, ia) = s.J(ia, ia) + drate * s.DT(aq, aq);
+      s.J(ig, ia) = s.J(ig, ia) - drate;
+    }
+  }
+  if (cd.fixph_on) {
+    const int ip = cd.proton_id, ih = cd.himm_id + off;
+    const double c_h = s.Cc(ip) * convert_molal_to_molar;
+    const double c_h_fix = pow(10.0, -1.0 * cd.fixph) / exp(lngam_proton);
+    const double temp_real = volume * 1000.0 * porosity * lsat;
+    const double rate = cd.k_kinetic_h * (c_h - c_h_fix) * temp_real;
+    if (fabs(rate) > 1.0e-20) {
+      s.RES(ip) = s.RES(ip) + rate;
+      s.RES(ih) = s.RES(ih) - rate;
+      const double drate = cd.k_kinetic_h * convert_molal_to_molar * temp_real;
+      s.J(ip, ip) = s.J(ip, ip) + drate;
+      // as written (:501): the Himm row takes the TRANSPOSED entry as its starting value
+      s.J(ih, ip) = s.J(ip, ih) - drate;
+    }
+  }
+}
+
 }  // namespace pfrx_sbx

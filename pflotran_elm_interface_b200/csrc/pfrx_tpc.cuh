@@ -1091,6 +1091,14 @@ struct CellT {
         if (cfg.has_pn) pfrx_sbx::plantn_react(*this, dt);
       } else if (kind == PFRX_SANDBOX_LANGMUIR) {
         if (cfg.has_lg) pfrx_sbx::langmuir_react(*this, dt);
+      } else if (kind == PFRX_SANDBOX_CNDEGAS) {
+        if (cfg.has_cd) {
+          double lgp = 0.0;  // ln gamma of H+ (register array: literal indices only)
+#pragma unroll
+          for (int i = 0; i < N; i++)
+            if (i == cfg.cd.proton_id) lgp = lngam[i];
+          pfrx_sbx::cndegas_react(*this, lgp);
+        }
       }
     }
   }

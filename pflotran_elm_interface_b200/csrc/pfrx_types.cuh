@@ -16,6 +16,7 @@ struct DevState {
   double *somdec_nc;
   const double *elm_plantndemand;
   double *eqionx_ref, *eqionx_conc;
+  const double *pres;  // liquid pressure (CNDEGAS sandbox, optional)
 };
 
 // shard summary accumulated with atomics, one set per warp

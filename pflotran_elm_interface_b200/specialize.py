@@ -136,6 +136,8 @@ def signature(cfg: abi.ReactionConfig) -> int:
     if c.langmuir:
         lg = cfg.langmuir
         parts.append(struct.pack("<2i3d", lg.aq_id, lg.sorb_id, lg.k_kinetic, lg.k_equilibrium, lg.s_max))
+    if c.cndegas:
+        parts.append(bytes(cfg.cndegas))
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
         if c.nsandbox:
@@ -201,6 +203,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "ion exchange / KD isotherms"
     if c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0 or c.nmicrobial_rxn > 0:
         return False, "general / radioactive decay / immobile decay / microbial reactions"
+    if c.cndegas:
+        return False, "CNDEGAS sandbox"
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         if os.environ.get("PFRX_SPEC_NO_ELMCN"):
             return False, "ELM-CN sandboxes disabled by PFRX_SPEC_NO_ELMCN"

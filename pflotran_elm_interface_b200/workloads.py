@@ -421,7 +421,7 @@ END
 
 
 def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False,
-           full: bool = False) -> Workload:
+           full: bool = False, degas: bool = False) -> Workload:
     """C4(b): SOMDECOMP + NITRIFICATION + DENITRIFICATION on 6 aqueous + 10
     immobile species.  ``elm=True`` is the ELM_PFLOTRAN build in BGC-only
     coupling: the moisture / oxygen / temperature scalars, soil depth,
@@ -451,7 +451,23 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
         deck = deck.replace("    Lit3N 0.00731553d-0\n", "    Lit3N 0.00731553d-0\n    PlantN 1.d-20\n"
                             "    Plantnh4uptake 1.d-20\n    Plantno3uptake 1.d-20\n"
                             "    NH4sorb 1.d-3\n")
-    dk, net = chem.load_network(deck, _read("clmcnplus_CLM-CN_database.dat"))
+    if degas:
+        # + the CNDEGAS sandbox (reaction_sandbox_cndegas.F90): CO2 / N2O / N2 exchange with gas reservoirs
+        # kept as immobile species, and the pH-stat.  No deck of the reference's test suite runs it.
+        deck = deck.replace("    Lit3N\n  /", "    Lit3N\n    CO2imm\n    N2Oimm\n    N2imm\n    Himm\n  /")
+        deck = deck.replace("    DENITRIFICATION\n", "    CNDEGAS\n      KINETIC_CONSTANT_CO2 2.0d-5\n"
+                            "      KINETIC_CONSTANT_N2O 1.0d-5\n      KINETIC_CONSTANT_N2 5.0d-6\n"
+                            "      KINETIC_CONSTANT_H+ 1.0d-5\n      FIXPH 6.5\n    /\n    DENITRIFICATION\n", 1)
+        deck = deck.replace("    Lit3N 0.00731553d-0\n", "    Lit3N 0.00731553d-0\n    CO2imm 1.66d-2\n"
+                            "    N2Oimm 1.3d-5\n    N2imm 32.5d0\n    Himm 1.d-20\n")
+    dk = chem.read_deck(deck)
+    if degas:
+        names = list(dk.chemistry.immobile)
+        dk.chemistry.cndegas["gas_ids"] = {"CO2(g)": names.index("CO2imm"), "N2O(g)": names.index("N2Oimm"),
+                                           "N2(g)": names.index("N2imm")}
+        dk.chemistry.cndegas["cell_state_mode"] = 2 if elm else 0
+    net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("clmcnplus_CLM-CN_database.dat")),
+                               dk.reference_temperature, True)
     assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
     net.elm_pflotran = bool(elm)
     cfg = abi.ReactionConfig(net)
@@ -486,10 +502,18 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
         st["elm_bsw"][...] = rng.uniform(2.0, 10.0, ncell)
         # plant N demand: zero at night / in winter for a third of the cells
         st["elm_rate_plantndemand"][...] = np.where(rng.random(ncell) < 0.33, 0.0, 10.0 ** rng.uniform(-9.0, -6.5, ncell))
-    name = ("c4f_elm_cn_full" if full else "c4s_elm_cn") + ("_elmscalars" if elm else "")
+    if degas:
+        for nm, lo, hi in (("CO2imm", 1.0e-2, 8.0e-2), ("N2Oimm", 5.0e-6, 1.0e-4), ("N2imm", 30.0, 35.0)):
+            st["immobile"][net.immobile_names.index(nm)] = rng.uniform(lo, hi, ncell)
+        st["immobile"][net.immobile_names.index("Himm")] = 1.0e-20
+        if elm:
+            st["pres"][...] = rng.uniform(0.9e5, 1.3e5, ncell)
+    name = ("c4f_elm_cn_full" if full else "c4s_elm_cn") + ("_elmscalars" if elm else "") + ("_degas" if degas else "")
     note = "SOMDECOMP (7 rxns, N immobilisation from NH4+/NO3-) + NITRIFICATION + DENITRIFICATION"
     if full:
         note += " + PLANTN + LANGMUIR"
+    if degas:
+        note += " + CNDEGAS"
     return Workload(name, cfg, st, tran_dt, net, note + f", {net.ncomp} dof")
 
 
@@ -950,6 +974,8 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4s": (elm_cn, {}),
         "c4se": (elm_cn, {"elm": True}),
         "c4fe": (elm_cn, {"full": True, "elm": True}),
+        "c4g": (elm_cn, {"degas": True}),
+        "c4ge": (elm_cn, {"degas": True, "elm": True}),
         "c5": (hanford, {"variant": "minerals"}),
         "c6": (ion_exchange, {}),
         "c7": (general_decay, {}),
@@ -1001,6 +1027,8 @@ def flops_model(net: chem.ReactionNetwork) -> Tuple[float, float]:
         f += 90.0
     if getattr(net, "langmuir", None) is not None:
         f += 50.0
+    if getattr(net, "cndegas", None) is not None:
+        f += 3.0 * (40.0 + 20.0 * 4) + 30.0
     g = getattr(net, "general", None)
     if g:
         # two exponentials (~25 flops each) and a log per rate law, residual and Jacobian updates

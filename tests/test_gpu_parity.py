@@ -226,7 +226,8 @@ def test_specialized_kernel(variant, dt, host):
     _check_summary(res_ref, res)
 
 
-@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c7", "c7s", "c8"])
+@pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c4g", "c4ge", "c7",
+                                     "c7s", "c8"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
@@ -494,6 +495,26 @@ def test_less_travelled_branches(name, dt, spec):
         assert wl.cfg.c.use_isothermal == 0 and np.ptp(wl.state.a["temp"]) > 40.0
     if name == "c3aw":
         assert np.abs(got.a["ln_act_h2o"]).max() > 0.0   # the activity of water was really updated
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dt,host", [("c4g", 1800.0, False), ("c4g", 86400.0, True), ("c4ge", 1800.0, False),
+                                          ("c4ge", 6 * 3600.0, True)])
+def test_cndegas_sandbox(name, dt, host):
+    """CNDEGAS (reaction_sandbox_cndegas.F90:216-546) next to SOMDECOMP / NITRIFICATION / DENITRIFICATION:
+    CO2 / N2O / N2 exchange at the Weiss solubilities and the pH-stat, stand-alone build (atmospheric
+    partial pressures, reference T and P) and ELM build (reservoir concentrations, the cell's pressure,
+    saturation and temperature through pfrx_state.pres / sat / temp)"""
+    wl = W.by_name(name, ncell=4000, tran_dt=dt)
+    wl.state.a["imat"][0, 11] = 0
+    wl.state.a["sat"][0, 17] = 1.0e-50   # dry cell: RReaction returns before the sandboxes
+    ref, res_ref, got, res, info = _run_both(wl, host_path=host)
+    _compare(ref, got, f"{name} dt={dt}")
+    _check_summary(res_ref, res)
+    him = wl.net.immobile_names.index("Himm")
+    assert np.abs(got.a["immobile"][him]).max() > 1e-9      # the pH-stat moved protons
+    gas = wl.net.immobile_names.index("CO2imm")
+    assert np.abs(got.a["immobile"][gas] - wl.state.a["immobile"][gas]).max() > 1e-7
 
 
 @pytest.mark.gpu

