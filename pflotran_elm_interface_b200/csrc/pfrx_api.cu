@@ -895,6 +895,10 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.tol_relres = c->max_rel_residual_tolerance;
   d.min_sat = c->rt_min_saturation;
   h->sig = config_signature(c);
+  h->dump_text = config_dump_text(c);
+  h->sr_flag_host.clear();
+  if (c->nsrfcplxrxn > 0 && c->srfcplxrxn_stoich_flag)
+    h->sr_flag_host.assign(c->srfcplxrxn_stoich_flag, c->srfcplxrxn_stoich_flag + c->nsrfcplxrxn);
   h->spec_prm.max_its = d.max_its;
   h->spec_prm.max_cuts = d.max_cuts;
   h->spec_prm.max_dlnC = d.max_dlnC;

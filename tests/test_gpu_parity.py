@@ -518,6 +518,26 @@ def test_cndegas_sandbox(name, dt, host):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2pf", "c3sf", "c3t", "c3tg", "c2ng", "c4g", "c6", "c7", "c8", "c3an"])
+def test_library_refuses_a_cubin_where_the_generator_refuses_the_network(name):
+    """pfrx_load_specialized is the twin of specialize.supported(): a host that loads cubins by hand
+    (cached by signature) must not be able to attach one to a configuration whose features the generated
+    code does not implement -- prefactor / inner-Newton / anisothermal / total-as-guess / tracer-only /
+    CNDEGAS / ion exchange / general / microbial / NEWTON activity"""
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    wl = W.by_name(name, ncell=8)
+    ok, why = specialize.supported(wl.cfg)
+    assert not ok and why
+    any_cubin = specialize.build(W.by_name("c2", ncell=2).cfg)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    with pytest.raises(rstep.PfrxError, match="features the specialised kernels do not cover"):
+        step.load_specialized(any_cubin)
+    step.close()
+
+
+@pytest.mark.gpu
 def test_rstep_host_resident_fields():
     """pfrx_rstep_host_resident: derived fields stay in the device mirror (no download, no re-upload);
     two consecutive steps give the same state as two steps with everything crossing the link, and

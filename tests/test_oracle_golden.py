@@ -363,3 +363,44 @@ def test_microbial_gold(name):
         elif title.startswith("CONCENTRATION: "):
             i = net.immobile_names.index(title[len("CONCENTRATION: "):])
             _check_rel(st["immobile"][i, 0], sec["1"], 1.0e-12, f"{name} {title}")
+
+
+def test_hanford_gold_pins_the_88_complex_speciation():
+    """default/543/543_hanford_srfcplx_base (the chemistry of the headline benchmark: Hanford 15 primary /
+    88 secondary species, hanford.dat): the gold is a flow + transport run of 86 s, so the cells the river
+    and the source have not reached still hold the equilibrated `groundwater` constraint.  Its non-trivial
+    outputs -- pH from Calcite equilibrium, total H+, Na+ from the charge balance -- come out of the 88
+    complexes and the Debye-Hueckel activity model; they are the gold's extreme values (pH Min, totals Max,
+    printed as molalities) and the oracle's RTotal reproduces them from the constraint's free-ion
+    concentrations.  This pins database reader, basis switching, activity coefficients and
+    RTotalAqueous on the benchmark network; the transport part of the gold is out of scope."""
+    import re
+
+    from pflotran_elm_interface_b200 import constraint, eos, workloads as W
+
+    dk, net = W._hanford_network("base")
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67()
+    w = constraint.equilibrate_constraint(net, dk.constraints["groundwater"], den_kg=den, porosity=0.25,
+                                          soil_particle_density=2500.0)
+    st = abi.HostState(cfg, 1)
+    constraint.fill_cells(st, w)
+    st["den_kg"][...] = den
+    st["total"][...] = 0.0            # to be recomputed by the oracle
+    st["sec_molal"][...] = 0.0
+    for _ in range(40):               # activity coefficients and RTotal to self-consistency, oracle only
+        orc.activity(cfg, st, 0)
+        orc.auxvar_compute(cfg, st, 0)
+    gold = open(os.path.join(G, "543_hanford_srfcplx_base.regression.gold")).read()
+
+    def section(title):
+        m = re.search(r"-- %s --\n\s+Max:\s+(\S+)\n\s+Min:\s+(\S+)" % re.escape(title), gold)
+        return float(m.group(1)), float(m.group(2))
+
+    ph = -np.log10(st["pri_molal"][0, 0] * st["pri_act_coef"][0, 0])
+    assert abs(ph - section("GENERIC: pH")[1]) < 5e-9
+    molal = st["total"][:, 0] / den * 1000.0
+    names = net.primary_names
+    for nm in ("H+", "Na+", "Ca++", "HCO3-", "SO4--", "Cl-"):
+        got, want = molal[names.index(nm)], section(f"CONCENTRATION: Total {nm}")[0]
+        assert abs(got - want) / want < 2e-8, (nm, got, want)
