@@ -528,7 +528,27 @@ def main():
     cells_local = ncell
     its_local = res.sum_newton_iterations / max(1, world)        # per rank (weak scaling: equal shards)
     subs = cells_local                                          # >= one sub-step per cell
-    flops_launch = its_local * f_eval + max(0.0, its_local - subs) * f_solve
+    flops_closed = its_local * f_eval + max(0.0, its_local - subs) * f_solve
+    # algorithmic flops: COUNTED by the op-counting build of the oracle on a sample of the same cells
+    # (add/sub/mul/div/compare = 1, transcendental = 20), scaled by the launch's Newton iterations;
+    # the closed form of SURVEY 8(d) is kept beside it
+    flops_launch, flops_src = flops_closed, "closed form (workloads.flops_model)"
+    if cpu_sample is not None:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as orc
+
+            ns = min(4096, cpu_sample.state.ncell)
+            smp = abi.HostState(wl.cfg, ns)
+            for k, v in cpu_sample.state.a.items():
+                smp.a[k][...] = v[:, :ns]
+            rc, ops = orc.count_ops(wl.cfg, smp, dt, os.cpu_count() or 1)
+            ops_per_it = ops / max(1, rc.sum_newton_iterations)
+            flops_launch = ops_per_it * its_local
+            flops_src = (f"oracle op-counter (oracle/pfrx_oracle_count.cpp) on the first {ns} cells: "
+                         f"{ops_per_it:.0f} flop per Newton iteration incl. its share of the solves")
+        except Exception as e:  # the closed form stays
+            flops_src += f" (op-counter unavailable: {type(e).__name__})"
     bytes_launch = bytes_per_cell * cells_local
     t_launch = t_max / a.steps
     ach_tf = flops_launch / t_launch / 1e12
@@ -544,7 +564,7 @@ def main():
     # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tr = json.load(f).get(a.workload)
         if tr and tr["kernel"] == _kernel_name(info):
             traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / tr["cells"] * cells_local
@@ -552,7 +572,9 @@ def main():
     except (OSError, ValueError, KeyError):
         pass
     roof.update({"traffic": traffic, "traffic_source": traffic_src, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
-                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
+                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_flops_source": flops_src,
+                 "algorithmic_flops_closed_form": flops_closed, "counted_over_closed_form": flops_launch / flops_closed,
+                 "algorithmic_bytes_per_launch": bytes_launch,
                  "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": bytes_per_cell,
                  "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
                  "kernel": _kernel_name(info), "kernel_ms": 1000.0 * t_launch,

@@ -31,6 +31,15 @@
 
 #include "../include/pfrx.h"
 
+/* tables of pfrx_config read through a pointer: the identity here; in the op-counting build
+ * (pfrx_oracle_count.cpp compiles this file as C++ with `double` replaced by a counting scalar of the
+ * same layout) the cast that makes the pointer types agree */
+#ifdef PFRX_ORACLE_COUNTING
+#define CFGP(p) ((const double *)(const void *)(p))
+#else
+#define CFGP(p) (p)
+#endif
+
 /* pflotran_constants.F90:84-92 (truncated on purpose, as in the reference) */
 #define LOG_TO_LN 2.30258509299
 #define IDEAL_GAS_CONSTANT 8.31446
@@ -304,9 +313,9 @@ static void interpolate_logK(const double *coefs, double *logKs, double temp, in
 
 /* reaction.F90:5976-6067  RUpdateTempDependentCoefs (non-hpt branch) */
 static void update_temp_dependent_coefs(cell_t *c, const pfrx_config *cfg) {
-  if (cfg->eqcplx_logKcoef) interpolate_logK(cfg->eqcplx_logKcoef, c->eqcplx_logK, c->temp, c->ncplx);
-  if (cfg->kinmnrl_logKcoef) interpolate_logK(cfg->kinmnrl_logKcoef, c->kinmnrl_logK, c->temp, c->nkin);
-  if (cfg->srfcplx_logKcoef) interpolate_logK(cfg->srfcplx_logKcoef, c->srfcplx_logK, c->temp, c->nsrfcplx);
+  if (cfg->eqcplx_logKcoef) interpolate_logK(CFGP(cfg->eqcplx_logKcoef), c->eqcplx_logK, c->temp, c->ncplx);
+  if (cfg->kinmnrl_logKcoef) interpolate_logK(CFGP(cfg->kinmnrl_logKcoef), c->kinmnrl_logK, c->temp, c->nkin);
+  if (cfg->srfcplx_logKcoef) interpolate_logK(CFGP(cfg->srfcplx_logKcoef), c->srfcplx_logK, c->temp, c->nsrfcplx);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -315,8 +324,8 @@ static void r_activity_coefficients(cell_t *c, const pfrx_config *cfg) {
   int icplx, icomp, it, j, jcomp, i;
   double I, sqrt_I, II, f, fpri, didi, dcdi = 0, den, dgamdi, lnQK, sum;
   double sum_pri_molal = 0.0, sum_sec_molal;
-  const double *Z = cfg->primary_spec_Z, *a0 = cfg->primary_spec_a0;
-  const double *cZ = cfg->eqcplx_Z, *ca0 = cfg->eqcplx_a0;
+  const double *Z = CFGP(cfg->primary_spec_Z), *a0 = CFGP(cfg->primary_spec_a0);
+  const double *cZ = CFGP(cfg->eqcplx_Z), *ca0 = CFGP(cfg->eqcplx_a0);
 
   if (cfg->use_activity_h2o) {
     sum_pri_molal = 0.0;
@@ -650,7 +659,7 @@ static int r_total_sorb_eq_ionx(cell_t *c, const pfrx_config *cfg) {
   for (irxn = 0; irxn < cfg->neqionxrxn; irxn++) {
     int p0 = cfg->eqionx_ptr[irxn], ncomp = cfg->eqionx_ptr[irxn + 1] - p0;
     const int *cat = cfg->eqionx_cationid + p0;
-    const double *kk = cfg->eqionx_k + p0;
+    const double *kk = CFGP(cfg->eqionx_k) + p0;
     double omega, sumZX;
     if (cfg->eqionx_to_surf[irxn] >= 0)
       omega = fmax(cfg->eqionx_CEC[irxn] * c->mnrl_volfrac[cfg->eqionx_to_surf[irxn]], 1.e-40);
@@ -1875,7 +1884,7 @@ static void somdec_react(cell_t *c, const pfrx_config *cfg, double tran_dt, doub
         f_t = get_temperature_response(tc, sd->temperature_response_function[cur], sd->q10[cur]);
         break;
       default:
-        f_t = cfg->elm_pflotran ? c->elm_t : 1.0;
+        f_t = cfg->elm_pflotran ? c->elm_t : (double)1.0;
     }
     if (cfg->elm_pflotran) {
       if (sd->decomp_depth_efolding[cur] > 0.0) {
@@ -2010,7 +2019,7 @@ static void nitrif_react(cell_t *c, const pfrx_config *cfg, double *Residual, do
       JAC(ires_no3, ires_nh4) = JAC(ires_no3, ires_nh4) - drate_nitri_dnh4 * DTOT(nt->no3_id, nt->nh4_id);
     }
   }
-  rho_b = cfg->elm_pflotran ? c->elm_bd_dry : 1.25e3;
+  rho_b = cfg->elm_pflotran ? c->elm_bd_dry : (double)1.25e3;
   temp_real = N_molecular_weight * 1.0e6;
   M_2_ug_per_g = temp_real / (volume * rho_b * 1.e3);
   c_nh4_ugg = c_nh4 * volume * M_2_ug_per_g;
@@ -2052,7 +2061,7 @@ static void denitr_react(cell_t *c, const pfrx_config *cfg, double *Residual, do
   int ires_no3 = dn->no3_id, ires_n2 = dn->n2_id;
   double temp_real, f_t, s_min, f_w, c_no3, feps0, dfeps0_dx, fno3, dfno3_dno3, rate_deni, drate_deni_dno3;
   if (dn->n2_id < 0) return;
-  temp_real = cfg->elm_pflotran ? c->elm_bsw : 1.0;
+  temp_real = cfg->elm_pflotran ? c->elm_bsw : (double)1.0;
   f_t = exp(0.08 * (tc - 25.0));
   s_min = 0.6;
   f_w = 0.0;
@@ -2353,7 +2362,7 @@ static void cndegas_react(cell_t *c, const pfrx_config *cfg, double *Residual, d
   const pfrx_cndegas *cd = cfg->cndegas;
   const double H2O_kg_mol = 18.01534e-3, rgas = 8.3144621;
   int off = c->naq, n = c->n, elm = cfg->elm_pflotran ? 1 : 0;
-  double convert_molal_to_molar = cd->initialize_with_molality ? c->den_kg * 1.0 / 1000.0 : 1.0;
+  double convert_molal_to_molar = cd->initialize_with_molality ? c->den_kg * 1.0 / 1000.0 : (double)1.0;
   double tc = cd->reference_temperature, air_press = cd->reference_pressure, lsat = 0.50;
   double porosity, volume, air_vol, air_molar, temp_real, total_sal, rate, drate;
 #define JAC(i, j) Jacobian[(i) + (size_t)(j) * n]
@@ -2919,7 +2928,7 @@ static int r_react(cell_t *c, const pfrx_config *cfg, const double *guess, doubl
           any = 1;
         }
       }
-      maximum_relative_change = any ? m : NAN;
+      maximum_relative_change = any ? m : (double)NAN;
     }
     if (maximum_relative_change < cfg->max_relative_change_tolerance) break;
 
@@ -3098,6 +3107,9 @@ static void *job_run(void *arg) {
     if (ierr != 0 && r->first_failed_cell < 0) r->first_failed_cell = ic;
   }
   cell_free(&c);
+  #ifdef PFRX_ORACLE_COUNTING
+  pfrx_oracle_ops_flush(); /* this thread's operation count into the total */
+#endif
   return NULL;
 }
 

@@ -105,3 +105,29 @@ def rsolve(Res, Jac, conc, use_log):
     u = np.zeros_like(r)
     e = lib().pfrx_oracle_rsolve(_dp(r), _dp(J), _dp(c), _dp(u), len(r), int(use_log))
     return e, u
+
+
+# ---- op-counting build (oracle/pfrx_oracle_count.cpp): the same source with a counting scalar ----
+SO_COUNT = os.path.join(ROOT, "oracle", "_build", "libpfrx_oracle_count.so")
+_lib_count = None
+
+
+def count_ops(cfg: abi.ReactionConfig, state: abi.HostState, tran_dt: float, nthreads: int = 1):
+    """RStep over the cells of `state` (updated in place) with the operation counter on: returns
+    (result, counted operations) -- add / sub / mul / div / compare = 1, exp / log / pow / sqrt / atan = 20,
+    the convention of SURVEY.md section 8(d)"""
+    global _lib_count
+    if _lib_count is None:
+        if not os.path.exists(SO_COUNT):
+            build()
+        L = C.CDLL(SO_COUNT)
+        L.pfrx_oracle_rstep.argtypes = [C.POINTER(abi.PfrxConfig), C.c_int64, C.POINTER(abi.PfrxState), C.c_double,
+                                        C.POINTER(abi.PfrxStepResult), C.c_int]
+        L.pfrx_oracle_ops_get.restype = C.c_ulonglong
+        _lib_count = L
+    res = abi.PfrxStepResult()
+    st = state.struct()
+    _lib_count.pfrx_oracle_ops_reset()
+    rc = _lib_count.pfrx_oracle_rstep(C.byref(cfg.c), state.ncell, C.byref(st), float(tran_dt), C.byref(res), nthreads)
+    assert rc == 0, rc
+    return res, int(_lib_count.pfrx_oracle_ops_get())

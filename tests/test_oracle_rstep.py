@@ -164,3 +164,24 @@ def test_threads_do_not_change_results():
     assert ra.as_dict() == rb.as_dict()
     for k in a.a:
         assert np.array_equal(a.a[k], b.a[k])
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c4s"])
+def test_op_counting_build_is_the_same_oracle(name):
+    """oracle/pfrx_oracle_count.cpp compiles pfrx_oracle.c with a counting scalar in place of double: the
+    results are bit-identical to the plain build, and the count per Newton iteration brackets the closed
+    form of SURVEY 8(d) that round 1 used as the roofline numerator (the closed form misses the
+    convergence tests, the update and part of the sorption arithmetic: 9-42 % low)"""
+    from pflotran_elm_interface_b200 import workloads as W
+
+    wl = W.by_name(name, ncell=256)
+    a, b = wl.state.copy(), wl.state.copy()
+    r0 = orc.rstep(wl.cfg, a, wl.tran_dt, 2)
+    r1, ops = orc.count_ops(wl.cfg, b, wl.tran_dt, 2)
+    assert r0.as_dict() == r1.as_dict()
+    for f in a.a:
+        assert np.array_equal(a.a[f], b.a[f], equal_nan=True), f
+    f_eval, f_solve = W.flops_model(wl.net)
+    its = r0.sum_newton_iterations
+    closed = its * f_eval + max(0, its - r0.ncell_active) * f_solve
+    assert 1.0 < ops / closed < 1.6, ops / closed
