@@ -137,7 +137,7 @@ S2_FN double s2_split(double a, int &e) {
 // one evaluation at the iterate in the slice: activity coefficients, RTotal, sorption, residual,
 // kinetic minerals; Jt into the slice (SPEC_SYM: the lower triangle in elimination order;
 // otherwise both triangles and the structural zeros); the totals of this evaluation into tv;
-// rt_auxvar%sec_molal, free-site / surface-complex concentrations and mineral rates stored through
+// free-site / surface-complex concentrations and mineral rates stored through
 S2_FN void spec2_eval(double (&res)[SPEC_N], double (&tv)[S2_NTV], double (&ev)[S2_NEV], Spec2Cell &s, double *W,
                       const DevState &st, long long cell);
 // rt_auxvar%total (and %total_sorb_eq) <- tv
@@ -145,6 +145,8 @@ S2_FN void spec2_store_totals(const double (&tv)[S2_NTV], const double *W, const
                               long long cell, bool tot, bool sorb);
 // activity coefficients of the cell, recomputed from the ionic strength of the latest evaluation
 S2_FN void spec2_store_act(const Spec2Cell &s, const DevState &st, long long cell);
+// rt_auxvar%sec_molal of the cell's last evaluation (iterate and activity of water in the slice / s, ionic strength s.Iact)
+S2_FN void spec2_store_sec(const double *W, const Spec2Cell &s, const DevState &st, long long cell);
 // frozen coefficients into the slice at cell entry
 S2_FN void spec2_load_frozen(double *W, const DevState &st, long long cell);
 // sub-step entry: fixed accumulation and the mineral inputs into the slice
@@ -595,6 +597,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
             }
           }
         }
+        spec2_store_sec(W, s, st, cell);
         if (SPEC_ACT_UPD) spec2_store_act(s, st, cell);
         if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = (s.aw == 1.0) ? 0.0 : log(s.aw);
       }

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -295,7 +296,7 @@ class _Gen2:
         if extra:
             fac.append(extra)
         # (f_a * f_b) * (K * f_c) ...: a shallow product tree instead of a chain
-        terms = [_lit(kf)] + fac
+        terms = [self.kc(kf)] + fac
         while len(terms) > 1:
             nxt = []
             for x in range(0, len(terms) - 1, 2):
@@ -317,6 +318,16 @@ class _Gen2:
             s = s[2:]
         self.w(f"{indent}const int {evar} = {s};")
 
+    def kc(self, v: float) -> str:
+        """a double constant as an operand from the constant bank (DMUL R, R, c[3][..]) instead of an
+        immediate, which costs two UMOVs per use when its low word is not zero"""
+        if not int(os.environ.get("PFRX_SPEC2_KTAB", "1")):
+            return _lit(v)
+        key = float(v).hex()
+        if key not in self.ktab:
+            self.ktab[key] = len(self.ktab)
+        return f"SK({self.ktab[key]})"
+
     def H(self, i: int, j: int) -> Tuple[int, int]:
         return (i, j) if i <= j else (j, i)
 
@@ -332,34 +343,17 @@ class _Gen2:
             ci, cj = cj, ci
         return f"W[JX({ci}, {cj})]"
 
-    # ------------------------------------------------------------------ spec2_eval
-    def gen_eval(self) -> None:
-        c, a, n, naq = self.c, self.a, self.n, self.naq
-        w = self.w
-        w("S2_FN void spec2_eval(double (&res)[SPEC_N], double (&tv)[S2_NTV], double (&ev)[S2_NEV], Spec2Cell &s, double *W,")
-        w("                      const DevState &st, long long cell) {")
-        for x in range(max(1, len(self.evar))):
-            w(f"  ev[{x}] = 0.0;")
-        w("  const long long ld = st.ld;")
-        w("  const double psv = s.dry ? 0.0 : s.psv;")
-        w("  double *sp_ = st.sec_molal + cell;")
-        w("  int emax = 0;")
-        for i in range(n):
-            w(f"  const double c{i} = SW(S2_OFF_C + {i});")
-        # ---- activity coefficients (RActivityCoefficients, LAG branch)
+    def _gen_activities(self, update_aw: bool) -> None:
+        """activity coefficients at the ionic strength I (LAG: RActivityCoefficients) or the frozen
+        ones of the slice; mantissa / exponent of the activities and the powers the products need.
+        Emitted twice with identical arithmetic: in spec2_eval and in spec2_store_sec."""
+        c, a, naq, w = self.c, self.a, self.naq, self.w
         if self.act_upd:
-            terms = [f"c{i} * {_lit(float(a['primary_spec_Z'][i]) ** 2)}" for i in range(naq)
-                     if float(a["primary_spec_Z"][i]) != 0.0]
-            w("  double Ip = 0.0;")
-            for t in terms:
-                w(f"  Ip += {t};")
-            w("  const double I = 0.5 * (Ip + s.Isec);")
-            w("  if (s.store) s.Iact = I;")
             w("  const double sq = sqrt(I);")
             A, B, Bd = _lit(c.debyeA), _lit(c.debyeB), _lit(c.debyeBdot)
             for q, (negz2, a0) in enumerate(self.cls):
                 w(f"  const double g{q} = sx_exp((sx_div({_lit(negz2)} * sq * {A}, 1.0 + {_lit(a0)} * {B} * sq) + {Bd} * I) * SPEC_LN);")
-            if c.use_activity_h2o:
+            if c.use_activity_h2o and update_aw:
                 mp = " + ".join(f"c{i}" for i in range(naq) if i != c.h2o_aq_id) or "0.0"
                 w(f"  if (s.store) {{ const double t = 1.0 - 0.017 * (({mp}) + s.msec); s.aw = t > 0.0 ? t : 1.0; }}")
             used_rg = sorted({q for q in self.cx_cls if q >= 0})
@@ -376,6 +370,43 @@ class _Gen2:
         if self.wpw:
             w("  int ew; const double fwp1 = s2_split(s.aw, ew);")
             self._emit_powers("fw", self.wpw)
+
+    def _gen_complex(self, k: int) -> None:
+        """sk = molality of aqueous complex k (RTotalAqueous, reaction_aux / reaction.F90 product form)"""
+        a, naq = self.a, self.naq
+        sp, h2o = self.cx[k]
+        kf, ke = _kinv(float(a["eqcplx_logK"][k]))
+        if self.act_upd:
+            extra = f"rg{self.cx_cls[k]}" if self.cx_cls[k] >= 0 else None
+        else:
+            extra = f"SW(S2_OFF_FRZ + {naq + k})"
+        self._product(kf, ke, sp, h2o, extra, "p", "e")
+        self.w("    const double sk = s2_scale(p, e, emax);")
+
+    # ------------------------------------------------------------------ spec2_eval
+    def gen_eval(self) -> None:
+        c, a, n, naq = self.c, self.a, self.n, self.naq
+        w = self.w
+        start = len(self.out)
+        w("S2_FN void spec2_eval(double (&res)[SPEC_N], double (&tv)[S2_NTV], double (&ev)[S2_NEV], Spec2Cell &s, double *W,")
+        w("                      const DevState &st, long long cell) {")
+        for x in range(max(1, len(self.evar))):
+            w(f"  ev[{x}] = 0.0;")
+        w("  const long long ld = st.ld;")
+        w("  const double psv = s.dry ? 0.0 : s.psv;")
+        w("  int emax = 0;")
+        for i in range(n):
+            w(f"  const double c{i} = SW(S2_OFF_C + {i});")
+        # ---- activity coefficients (RActivityCoefficients, LAG branch)
+        if self.act_upd:
+            terms = [f"c{i} * {_lit(float(a['primary_spec_Z'][i]) ** 2)}" for i in range(naq)
+                     if float(a["primary_spec_Z"][i]) != 0.0]
+            w("  double Ip = 0.0;")
+            for t in terms:
+                w(f"  Ip += {t};")
+            w("  const double I = 0.5 * (Ip + s.Isec);")
+            w("  if (s.store) s.Iact = I;")
+        self._gen_activities(update_aw=True)
         # ---- RTotalAqueous
         for i in self.coupled:
             w(f"  double tot{i} = c{i};")
@@ -395,16 +426,8 @@ class _Gen2:
         self.aq_struct = set(hits)
         for k in range(self.ncx):
             sp, h2o = self.cx[k]
-            kf, ke = _kinv(float(a["eqcplx_logK"][k]))
-            if self.act_upd:
-                extra = f"rg{self.cx_cls[k]}" if self.cx_cls[k] >= 0 else None
-            else:
-                extra = f"SW(S2_OFF_FRZ + {naq + k})"
             w("  {")
-            self._product(kf, ke, sp, h2o, extra, "p", "e")
-            w("    const double sk = s2_scale(p, e, emax);")
-            w("    if (s.store) *sp_ = sk;")
-            w("    sp_ += ld;")
+            self._gen_complex(k)
             z2 = float(a["eqcplx_Z"][k]) ** 2
             if z2 == 1.0:
                 w("    Is += sk;")
@@ -595,6 +618,33 @@ class _Gen2:
                     w(f"  {{ const double v = {expr}; W[JX({ci}, {cj})] = v{eu}; W[JX({cj}, {ci})] = v{el}; }}")
         w("}")
         w()
+        self._inline_rare_powers(start)
+
+    def _inline_rare_powers(self, start: int) -> None:
+        """a power f<i>[pm]<n> that spec2_eval uses at most PFRX_SPEC2_INLINE times is multiplied out
+        where it is used instead of being held in a register pair from the top of the routine
+        (255 registers per thread: every pair that stays live through the 88 complexes is a spill)"""
+        thresh = int(os.environ.get("PFRX_SPEC2_INLINE", "2"))
+        if thresh <= 0:
+            return
+        body = self.out[start:]
+        pat = re.compile(r"^\s*const double (f\w+[pm]\d+) = (f\w+[pm]\d+ \* f\w+[pm]\d+);$")
+        changed = True
+        while changed:
+            changed = False
+            for x in range(len(body) - 1, -1, -1):
+                m = pat.match(body[x])
+                if not m:
+                    continue
+                name, expr = m.group(1), m.group(2)
+                word = re.compile(r"\b" + name + r"\b")
+                uses = sum(len(word.findall(l)) for l in body[x + 1:])
+                if 0 < uses <= thresh:
+                    body[x + 1:] = [word.sub(f"({expr})", l) for l in body[x + 1:]]
+                    del body[x]
+                    changed = True
+                    break
+        self.out[start:] = body
 
     # ------------------------------------------------------------------ sparse L D L^T
     def gen_solve_sym(self) -> None:
@@ -752,6 +802,28 @@ class _Gen2:
         w("  (void)sorb; (void)s; (void)W;")
         w("}")
         w()
+        # rt_auxvar%sec_molal of the cell's last evaluation, recomputed once when the cell is published
+        # (same source text as spec2_eval's products: products of the same operands in the same
+        # order, no additions to contract, so the values are the ones that evaluation had)
+        w("S2_FN void spec2_store_sec(const double *W, const Spec2Cell &s, const DevState &st, long long cell) {")
+        if self.ncx:
+            w("  const long long ld = st.ld;")
+            w("  int emax = 0;")
+            for i in sorted(self.pw):
+                w(f"  const double c{i} = SW(S2_OFF_C + {i});")
+            if self.act_upd:
+                w("  const double I = s.Iact;")
+            self._gen_activities(update_aw=False)
+            w("  double *sp_ = st.sec_molal + cell;")
+            for k in range(self.ncx):
+                w("  {")
+                self._gen_complex(k)
+                w(f"    sp_[{k} * ld] = sk;")
+                w("  }")
+            w("  (void)emax;")
+        w("  (void)W; (void)s; (void)st; (void)cell;")
+        w("}")
+        w()
         w("S2_FN void spec2_store_act(const Spec2Cell &s, const DevState &st, long long cell) {")
         if self.act_upd:
             w("  const long long ld = st.ld;")
@@ -806,6 +878,7 @@ class _Gen2:
         c = self.c
         slots, threads, minblocks = self.layout()
         self.out = []
+        self.ktab: Dict[str, int] = {}
         self.gen_eval()
         if self.sym:
             self.gen_solve_sym()
@@ -868,6 +941,13 @@ class _Gen2:
         w("#endif")
         mv = " : ".join(f"m == {m} ? {_lit(v)}" for m, v in enumerate(vol))
         w("S2_CE double spec_mn_vol(int m) { return " + mv + " : 0.0; }")
+        kt = ", ".join(_lit(float.fromhex(k)) for k in self.ktab) or "0.0"
+        w("#ifndef S2_HOST")
+        w("static __constant__ double spec_k_tab[] = {" + kt + "};")
+        w("#else")
+        w("static const double spec_k_tab[] = {" + kt + "};")
+        w("#endif")
+        w("#define SK(i) spec_k_tab[i]")
         w('#include "pfrx_spec2.cuh"')
         w()
         self.slots, self.threads, self.minblocks = slots, threads, minblocks

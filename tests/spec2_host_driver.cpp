@@ -145,6 +145,7 @@ extern "C" int s2_host_rstep(const pfrx_state *ps, long long ncell, double tran_
             *p = small_val[i];
           }
       }
+      spec2_store_sec(W, s, st, cell);
       if (SPEC_ACT_UPD) spec2_store_act(s, st, cell);
       if (st.ln_act_h2o && SPEC_USE_ACT_H2O) st.ln_act_h2o[cell] = (s.aw == 1.0) ? 0.0 : log(s.aw);
     }

@@ -37,8 +37,10 @@ def test_source_is_deterministic_and_covers_the_network():
     b = specialize.generate_source(W.by_name("c3", ncell=2).cfg)
     assert a == b
     c = wl.cfg.c
-    # one product per secondary complex, streamed to rt_auxvar%sec_molal
-    assert len(re.findall(r"if \(s.store\) \*sp_ = sk;", a)) == c.neqcplx
+    # one product per secondary complex in the evaluation, and once more in the routine that
+    # writes rt_auxvar%sec_molal when the cell is published
+    assert len(re.findall(r"sp_\[\d+ \* ld\] = sk;", a)) == c.neqcplx
+    assert len(re.findall(r"const double sk = s2_scale\(p, e, emax\);", a)) == 2 * c.neqcplx
     # tracers stay out of the matrix (two of the 15 Hanford primaries occur in no reaction)
     assert f"#define SPEC_N {c.naqcomp + c.nimcomp}" in a
     assert "#define SPEC_NC 13" in a
