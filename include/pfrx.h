@@ -632,6 +632,60 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * are the sorbed totals when a sorbing species decays.                         */
 int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
+/* ---- batched ReactionEquilibrateConstraint -----------------------------------
+ * The set-up step that turns a CONSTRAINT block into a speciated rt_auxvar
+ * (reaction.F90:1328-2117, called per condition by
+ * condition_control.F90 / transport_constraint_rt.F90): Newton on the free-ion
+ * molalities with one equation per primary species chosen by its constraint
+ * type; activity coefficients are switched on after a first convergence and
+ * the loop ends at the second.  Here every cell of the bound state is
+ * equilibrated at once with its own constraint values (an initial condition
+ * that varies from cell to cell) and the same constraint types.
+ * Constraint types carry the reference's values (transport_constraint_rt.F90:22-34). */
+#define PFRX_CONSTRAINT_NULL 0       /* treated as TOTAL (reaction.F90:1619)                  */
+#define PFRX_CONSTRAINT_FREE 1       /* free-ion concentration                                */
+#define PFRX_CONSTRAINT_TOTAL 2      /* total aqueous component concentration                 */
+#define PFRX_CONSTRAINT_LOG 3        /* log10 of the free-ion concentration                   */
+#define PFRX_CONSTRAINT_PH 4         /* pH, on the primary species H+                         */
+#define PFRX_CONSTRAINT_MINERAL 7    /* equilibrium with a mineral (tables below)             */
+#define PFRX_CONSTRAINT_GAS 8        /* equilibrium with a gas at a partial pressure [bar];
+                                        a value <= 0 is log10 of the pressure                 */
+#define PFRX_CONSTRAINT_CHARGE_BAL 9 /* charge balance                                        */
+/* not built: PE (5), EH (6), TOTAL_SORB (10), SUPERCRIT_CO2 (11), TOTAL_AQ_PLUS_SORB (12):
+ * pfrx_equilibrate_constraint returns PFRX_E_INVALID                                         */
+
+typedef struct pfrx_constraint {
+  int32_t naqcomp;                   /* = the configuration's                                  */
+  int32_t initialize_with_molality;  /* reaction%initialize_with_molality: values are molalities */
+  int32_t max_iterations;            /* the reference gives up at 10000 (0 = that)             */
+  int32_t reserved;
+  const int32_t *type;               /* [naqcomp] PFRX_CONSTRAINT_*                            */
+  /* the mineral / gas reaction of a MINERAL / GAS constraint on species i (mnrl_logK, mnrlspecid,
+   * mnrlstoich, mnrlh2ostoich / paseq* of the reference): ln Q/K = -logK ln10 + h2o ln a_w +
+   * sum_p stoich[p] ln(m gamma)[spec[p]], p in [eq_ptr[i], eq_ptr[i+1]); NULL when no species
+   * has such a constraint */
+  const double *eq_logK;             /* [naqcomp]                                              */
+  const double *eq_logK_coef;        /* [naqcomp][5] or NULL: used when !use_isothermal        */
+  const double *eq_h2o_stoich;       /* [naqcomp]                                              */
+  const int32_t *eq_ptr;             /* [naqcomp + 1]                                          */
+  const int32_t *eq_spec;            /* 0-based primary species                                */
+  const double *eq_stoich;
+} pfrx_constraint;
+
+/* conc: device pointer, conc[i*ld + cell] = constraint value of species i in the cell (ld of the
+ * bound state; the units of the CONSTRAINT block: mol/L or mol/kg, pH, bar, ...).
+ * In: den_kg, temp, porosity, saturation, volume, mnrl_volfrac, soil particle density of the
+ * bound state.  Out (bound state): pri_molal, total, sec_molal, pri_act_coef, sec_act_coef,
+ * ln_act_h2o and, once equilibrated, the sorbed state (total_sorb_eq, free-site and
+ * surface-complex concentrations, kinmr_total_sorb filled as at equilibrium, ion-exchange
+ * state).  total and sec_molal are those of the last RTotal of the loop, as in the reference.
+ * num_iterations / ierror: device int32 [ncell] or NULL.  ierror: 0 converged, 1 singular
+ * Jacobian, 2 a non-positive (or NaN) free-ion concentration, 3 max_iterations reached -- the
+ * three conditions under which the reference stops the run.  Inactive cells are skipped.
+ * With use_full_geochemistry = 0: pri_molal and total from the values (reaction.F90:1472-1480). */
+int pfrx_equilibrate_constraint(pfrx_handle *h, const pfrx_constraint *cons, const double *conc,
+                                int32_t *num_iterations, int32_t *ierror);
+
 /* ---- the steps either side of the cell loop ---------------------
  * PETSc keeps the transport unknowns and right-hand sides as BLOCK vectors, ncomp
  * values per cell: v[cell*ncomp + i].  The chemistry state here is cell-major SoA,

@@ -3177,6 +3177,209 @@ int pfrx_oracle_activity(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   return e;
 }
 
+/* reaction.F90:1328-2117  ReactionEquilibrateConstraint for the constraint values conc[i*ldc + ic] of
+ * cell ic (types / reaction tables in pfrx_constraint, include/pfrx.h).  The state of the cell supplies
+ * den_kg, temp, porosity ... and receives the speciation.  Returns 0, or 1 singular Jacobian, 2 non-positive
+ * concentration, 3 iteration limit (the reference stops the run in each of the three). */
+int pfrx_oracle_equilibrate_constraint(const pfrx_config *cfg, const pfrx_constraint *k, const pfrx_state *st,
+                                       int64_t ic, const double *conc_in, int64_t ldc, int *num_iterations_out) {
+  cell_t c;
+  int naq = cfg->naqcomp, icomp, jcomp, kcomp, p, ierror = 0;
+  int num_iterations = 0, num_it_act_coef_turned_on = 0, compute_activity_coefs = 0, use_log_formulation;
+  int max_it = k->max_iterations > 0 ? k->max_iterations : 10000;
+  double conc[PFRX_MAX_NCOMP * 4], free_conc[PFRX_MAX_NCOMP * 4], total_conc[PFRX_MAX_NCOMP * 4];
+  double Res[PFRX_MAX_NCOMP * 4], update[PFRX_MAX_NCOMP * 4], prev_molal[PFRX_MAX_NCOMP * 4];
+  double *Jac;
+  double convert_molal_to_molar, convert_molar_to_molal, maximum_residual, maximum_relative_change, lnQK;
+  cell_init(&c, cfg);
+  cell_gather(&c, cfg, st, ic);
+  Jac = (double *)malloc(sizeof(double) * (naq * naq + 1));
+  if (k->initialize_with_molality) {
+    convert_molal_to_molar = c.den_kg / 1000.0;
+    convert_molar_to_molal = 1.0;
+  } else {
+    convert_molal_to_molar = 1.0;
+    convert_molar_to_molal = 1000.0 / c.den_kg;
+  }
+  for (icomp = 0; icomp < naq; icomp++) conc[icomp] = conc_in[icomp * ldc + ic];
+  if (num_iterations_out) *num_iterations_out = 0;
+  if (!cfg->use_full_geochemistry) { /* :1472-1480 */
+    for (icomp = 0; icomp < naq; icomp++) {
+      c.pri_molal[icomp] = conc[icomp] * convert_molar_to_molal;
+      c.total[icomp] = conc[icomp] * convert_molal_to_molar;
+    }
+    cell_scatter(&c, st, ic);
+    free(Jac);
+    cell_free(&c);
+    return 0;
+  }
+  if (!cfg->use_isothermal) update_temp_dependent_coefs(&c, cfg);
+  /* a fresh rt_auxvar (RTAuxVarInit): unit activity coefficients, no complexes */
+  c.ln_act_h2o = 0.0;
+  for (icomp = 0; icomp < naq; icomp++) c.pri_act_coef[icomp] = 1.0;
+  for (p = 0; p < c.ncplx; p++) {
+    c.sec_act_coef[p] = 1.0;
+    c.sec_molal[p] = 0.0;
+  }
+  for (icomp = 0; icomp < naq; icomp++) {
+    free_conc[icomp] = 1.e-9;
+    total_conc[icomp] = 0.0;
+    switch (k->type[icomp]) {
+      case PFRX_CONSTRAINT_NULL:
+      case PFRX_CONSTRAINT_TOTAL: total_conc[icomp] = conc[icomp] * convert_molal_to_molar; break;
+      case PFRX_CONSTRAINT_FREE: free_conc[icomp] = conc[icomp] * convert_molar_to_molal; break;
+      case PFRX_CONSTRAINT_LOG: free_conc[icomp] = pow(10.0, conc[icomp]) * convert_molar_to_molal; break;
+      case PFRX_CONSTRAINT_CHARGE_BAL: free_conc[icomp] = conc[icomp] * convert_molar_to_molal; break;
+      case PFRX_CONSTRAINT_PH: free_conc[icomp] = pow(10.0, -conc[icomp]); break;
+      case PFRX_CONSTRAINT_MINERAL: free_conc[icomp] = conc[icomp] * convert_molar_to_molal; break;
+      case PFRX_CONSTRAINT_GAS:
+        if (conc[icomp] <= 0.0) conc[icomp] = pow(10.0, conc[icomp]);
+        break;
+      default: break;
+    }
+  }
+  for (icomp = 0; icomp < naq; icomp++) c.pri_molal[icomp] = free_conc[icomp];
+  for (;;) {
+    for (icomp = 0; icomp < naq; icomp++)
+      if (k->type[icomp] == PFRX_CONSTRAINT_FREE || k->type[icomp] == PFRX_CONSTRAINT_LOG)
+        c.pri_molal[icomp] = free_conc[icomp];
+    if (cfg->act_coef_update_frequency != PFRX_ACT_COEF_FREQUENCY_OFF && compute_activity_coefs)
+      r_activity_coefficients(&c, cfg);
+    rt_auxvar_compute(&c, cfg); /* RTotal */
+    for (icomp = 0; icomp < naq * naq; icomp++) Jac[icomp] = 0.0;
+    for (icomp = 0; icomp < naq; icomp++) {
+      switch (k->type[icomp]) {
+        case PFRX_CONSTRAINT_NULL:
+        case PFRX_CONSTRAINT_TOTAL:
+          Res[icomp] = c.total[icomp] - total_conc[icomp];
+          for (jcomp = 0; jcomp < naq; jcomp++) Jac[icomp + jcomp * naq] = c.dtotal[icomp + jcomp * naq];
+          break;
+        case PFRX_CONSTRAINT_FREE:
+        case PFRX_CONSTRAINT_LOG:
+          Res[icomp] = 0.0;
+          Jac[icomp + icomp * naq] = 1.0;
+          break;
+        case PFRX_CONSTRAINT_CHARGE_BAL:
+          Res[icomp] = 0.0;
+          for (jcomp = 0; jcomp < naq; jcomp++) {
+            Res[icomp] = Res[icomp] + cfg->primary_spec_Z[jcomp] * c.total[jcomp];
+            for (kcomp = 0; kcomp < naq; kcomp++)
+              Jac[icomp + jcomp * naq] =
+                  Jac[icomp + jcomp * naq] + cfg->primary_spec_Z[kcomp] * c.dtotal[kcomp + jcomp * naq];
+          }
+          break;
+        case PFRX_CONSTRAINT_PH:
+          Res[icomp] = 0.0;
+          c.pri_molal[icomp] = pow(10.0, -conc[icomp]) / c.pri_act_coef[icomp];
+          Jac[icomp + icomp * naq] = 1.0;
+          break;
+        case PFRX_CONSTRAINT_MINERAL:
+        case PFRX_CONSTRAINT_GAS: {
+          double logK = k->eq_logK[icomp];
+          if (!cfg->use_isothermal && k->eq_logK_coef) interpolate_logK(CFGP(k->eq_logK_coef) + 5 * icomp, &logK, c.temp, 1);
+          lnQK = -logK * LOG_TO_LN;
+          if (k->eq_h2o_stoich[icomp] != 0.0) lnQK = lnQK + k->eq_h2o_stoich[icomp] * c.ln_act_h2o;
+          for (p = k->eq_ptr[icomp]; p < k->eq_ptr[icomp + 1]; p++) {
+            int comp_id = k->eq_spec[p];
+            lnQK = lnQK + k->eq_stoich[p] * log(c.pri_molal[comp_id] * c.pri_act_coef[comp_id]);
+          }
+          Res[icomp] = k->type[icomp] == PFRX_CONSTRAINT_GAS ? lnQK - log(conc[icomp]) : lnQK;
+          for (p = k->eq_ptr[icomp]; p < k->eq_ptr[icomp + 1]; p++) {
+            int comp_id = k->eq_spec[p];
+            Jac[icomp + comp_id * naq] = k->eq_stoich[p] / c.pri_molal[comp_id];
+          }
+          break;
+        }
+        default: break;
+      }
+    }
+    maximum_residual = 0.0;
+    for (icomp = 0; icomp < naq; icomp++) maximum_residual = fmax(maximum_residual, fabs(Res[icomp]));
+    if (cfg->use_log_formulation) {
+      if (num_iterations > 3 && num_iterations < 9)
+        use_log_formulation = (num_iterations % 2 == 0);
+      else
+        use_log_formulation = 1;
+    } else {
+      use_log_formulation = 0;
+    }
+    if (r_solve(Res, Jac, c.pri_molal, update, naq, use_log_formulation) != 0) {
+      ierror = 1;
+      break;
+    }
+    for (icomp = 0; icomp < naq; icomp++) prev_molal[icomp] = c.pri_molal[icomp];
+    if (use_log_formulation) {
+      for (icomp = 0; icomp < naq; icomp++) {
+        update[icomp] = copysign(1.0, update[icomp]) * fmin(fabs(update[icomp]), cfg->max_dlnC_rreact);
+        c.pri_molal[icomp] = c.pri_molal[icomp] * exp(-update[icomp]);
+      }
+    } else {
+      double min_ratio = 1.7976931348623157e308, ratio;
+      for (icomp = 0; icomp < naq; icomp++) {
+        if (prev_molal[icomp] <= update[icomp]) {
+          ratio = fabs(prev_molal[icomp] / update[icomp]);
+          if (ratio < min_ratio) min_ratio = ratio;
+        }
+      }
+      if (min_ratio <= 1.0)
+        for (icomp = 0; icomp < naq; icomp++) update[icomp] = update[icomp] * min_ratio * 0.99;
+      for (icomp = 0; icomp < naq; icomp++) c.pri_molal[icomp] = prev_molal[icomp] - update[icomp];
+    }
+    num_iterations = num_iterations + 1;
+    {
+      int bad = 0;
+      for (icomp = 0; icomp < naq; icomp++)
+        if (!(c.pri_molal[icomp] > 0.0)) bad = 1;
+      if (bad) {
+        ierror = 2;
+        break;
+      }
+    }
+    maximum_relative_change = 0.0;
+    for (icomp = 0; icomp < naq; icomp++)
+      maximum_relative_change =
+          fmax(maximum_relative_change, fabs((c.pri_molal[icomp] - prev_molal[icomp]) / prev_molal[icomp]));
+    if (num_iterations >= max_it) {
+      ierror = 3;
+      break;
+    }
+    if (maximum_residual < cfg->max_residual_tolerance &&
+        maximum_relative_change < cfg->max_relative_change_tolerance) {
+      if (compute_activity_coefs && num_iterations - num_it_act_coef_turned_on > 1) break;
+      if (!compute_activity_coefs) num_it_act_coef_turned_on = num_iterations;
+      compute_activity_coefs = 1;
+    }
+  }
+  if (num_iterations_out) *num_iterations_out = num_iterations;
+  if (ierror == 0) {
+    /* once equilibrated, the sorbed concentrations (:2036-2071) */
+    if (neqsorb(cfg) > 0) r_total_sorb(&c, cfg);
+    if (cfg->nkinmrsrfcplxrxn > 0) {
+      double total_sorb_eq[PFRX_MAX_NCOMP * 4];
+      double *dts = (double *)malloc(sizeof(double) * (naq * naq + 1));
+      int q, irate;
+      for (q = 0; q < cfg->nkinmrsrfcplxrxn; q++) { /* RTotalSorbMultiRateAsEQ */
+        int irxn = cfg->kinmrsrfcplxrxn_to_srfcplxrxn[q];
+        int r0 = cfg->kinmr_rate_ptr[q], r1 = cfg->kinmr_rate_ptr[q + 1];
+        int base = naq * (r0 + q);
+        for (icomp = 0; icomp < naq; icomp++) total_sorb_eq[icomp] = 0.0;
+        for (icomp = 0; icomp < naq * naq; icomp++) dts[icomp] = 0.0;
+        r_total_sorb_eq_surf_cplx1(&c, cfg, irxn, &c.free_site[irxn], NULL, total_sorb_eq, dts);
+        for (icomp = 0; icomp < naq; icomp++) {
+          c.kinmr_total_sorb[base + icomp] = total_sorb_eq[icomp];
+          for (irate = r0; irate < r1; irate++)
+            c.kinmr_total_sorb[base + naq * (irate - r0 + 1) + icomp] = cfg->kinmr_frac[irate] * total_sorb_eq[icomp];
+        }
+      }
+      free(dts);
+    }
+    cell_scatter(&c, st, ic);
+  }
+  free(Jac);
+  cell_free(&c);
+  return ierror;
+}
+
 /* RTAuxVarCompute on cell ic (totals, sec_molal, sorbed totals) */
 int pfrx_oracle_auxvar_compute(const pfrx_config *cfg, const pfrx_state *st, int64_t ic) {
   cell_t c;

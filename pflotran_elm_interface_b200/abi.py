@@ -240,6 +240,50 @@ class PfrxCndegas(C.Structure):
                                              "reference_temperature", "reference_pressure")])
 
 
+# constraint types of pfrx_equilibrate_constraint (transport_constraint_rt.F90:22-34)
+CONSTRAINT_NULL, CONSTRAINT_FREE, CONSTRAINT_TOTAL, CONSTRAINT_LOG, CONSTRAINT_PH = 0, 1, 2, 3, 4
+CONSTRAINT_MINERAL, CONSTRAINT_GAS, CONSTRAINT_CHARGE_BAL = 7, 8, 9
+
+
+class PfrxConstraint(C.Structure):
+    _fields_ = [("naqcomp", C.c_int32), ("initialize_with_molality", C.c_int32), ("max_iterations", C.c_int32),
+                ("reserved", C.c_int32),
+                ("type", C.POINTER(C.c_int32)),
+                ("eq_logK", C.POINTER(C.c_double)), ("eq_logK_coef", C.POINTER(C.c_double)),
+                ("eq_h2o_stoich", C.POINTER(C.c_double)),
+                ("eq_ptr", C.POINTER(C.c_int32)), ("eq_spec", C.POINTER(C.c_int32)),
+                ("eq_stoich", C.POINTER(C.c_double))]
+
+
+class Constraint:
+    """pfrx_constraint with the numpy arrays its pointers refer to kept alive"""
+
+    def __init__(self, naqcomp: int, types, eq_logK=None, eq_h2o_stoich=None, eq_ptr=None, eq_spec=None,
+                 eq_stoich=None, eq_logK_coef=None, initialize_with_molality: bool = False, max_iterations: int = 0):
+        self.c = PfrxConstraint()
+        self.c.naqcomp = int(naqcomp)
+        self.c.initialize_with_molality = int(bool(initialize_with_molality))
+        self.c.max_iterations = int(max_iterations)
+        self.a = {}
+
+        def put(name, arr, dt, ct):
+            if arr is None:
+                return
+            v = np.ascontiguousarray(arr, dtype=dt)
+            self.a[name] = v
+            setattr(self.c, name, v.ctypes.data_as(C.POINTER(ct)))
+
+        put("type", types, np.int32, C.c_int32)
+        put("eq_logK", eq_logK, np.float64, C.c_double)
+        put("eq_logK_coef", eq_logK_coef, np.float64, C.c_double)
+        put("eq_h2o_stoich", eq_h2o_stoich, np.float64, C.c_double)
+        put("eq_ptr", eq_ptr, np.int32, C.c_int32)
+        put("eq_spec", eq_spec if eq_spec is not None and len(eq_spec) else (None if eq_spec is None else [0]),
+            np.int32, C.c_int32)
+        put("eq_stoich", eq_stoich if eq_stoich is not None and len(eq_stoich) else (None if eq_stoich is None else [0.0]),
+            np.float64, C.c_double)
+
+
 class PfrxDenitr(C.Structure):
     _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
                 + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])

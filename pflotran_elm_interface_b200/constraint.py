@@ -18,6 +18,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
+from . import abi as _abi
 from . import chem as _chem
 from .chem import LOG_TO_LN
 
@@ -331,3 +332,45 @@ def fill_cells(state, sp: Speciation, cells=slice(None)) -> None:
     put("eqsrfcplx_conc", sp.eqsrfcplx_conc)
     put("total_sorb_eq", sp.total_sorb_eq)
     put("kinmr_total_sorb", sp.kinmr_total_sorb)
+
+
+_TYPE_CODES = {"T": _abi.CONSTRAINT_TOTAL, "TOTAL": _abi.CONSTRAINT_TOTAL, "F": _abi.CONSTRAINT_FREE,
+               "FREE": _abi.CONSTRAINT_FREE, "L": _abi.CONSTRAINT_LOG, "LOG": _abi.CONSTRAINT_LOG,
+               "P": _abi.CONSTRAINT_PH, "PH": _abi.CONSTRAINT_PH, "Z": _abi.CONSTRAINT_CHARGE_BAL,
+               "CHG": _abi.CONSTRAINT_CHARGE_BAL, "M": _abi.CONSTRAINT_MINERAL, "MINERAL": _abi.CONSTRAINT_MINERAL,
+               "MNRL": _abi.CONSTRAINT_MINERAL, "G": _abi.CONSTRAINT_GAS, "GAS": _abi.CONSTRAINT_GAS}
+
+
+def to_abi(net: _chem.ReactionNetwork, cons: _chem.Constraint):
+    """the CONSTRAINT block as ``pfrx_equilibrate_constraint`` takes it: (abi.Constraint with the types and the
+    mineral / gas reactions in the network's basis, values[naqcomp] in the units of the block)"""
+    naq = net.naqcomp
+    by_name = {c[0]: c for c in cons.conc}
+    types = np.zeros(naq, dtype=np.int32)
+    vals = np.zeros(naq)
+    logK = np.zeros(naq)
+    coef = np.zeros((naq, 5))
+    h2o = np.zeros(naq)
+    ptr = [0]
+    spec: List[int] = []
+    st: List[float] = []
+    for i, nm in enumerate(net.primary_names):
+        if nm not in by_name:
+            raise KeyError(f"constraint {cons.name}: no concentration for {nm}")
+        _, v, t, aux = by_name[nm]
+        code = _TYPE_CODES.get(t.upper())
+        if code is None:
+            raise ValueError(f"constraint type {t} not supported")
+        types[i] = code
+        vals[i] = v
+        if code in (_abi.CONSTRAINT_MINERAL, _abi.CONSTRAINT_GAS):
+            rx = net.mnrl_rxn[aux] if code == _abi.CONSTRAINT_MINERAL else net.gas_rxn[aux]
+            logK[i] = net.logK_at_tref(rx.logK_T)
+            coef[i] = _chem.fit_logK_coefs(net.db.temperatures, rx.logK_T)
+            h2o[i] = rx.h2o_stoich
+            spec += [int(j) for j in rx.ids]
+            st += [float(x) for x in rx.stoich]
+        ptr.append(len(spec))
+    k = _abi.Constraint(naq, types, logK, h2o, ptr, spec, st, eq_logK_coef=coef,
+                        initialize_with_molality=net.chem.initialize_with_molality)
+    return k, vals

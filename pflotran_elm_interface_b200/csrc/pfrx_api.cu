@@ -416,6 +416,7 @@ struct pfrx_handle {
   bool red_inflight = false, red_valid = false;
   pfrx_step_result red_local;
   std::string dump_text;          // pfrx_config_dump
+  std::vector<double> pri_Z_host;  // primary_spec_Z (charge-balance constraints)
   std::vector<int> sr_flag_host;  // srfcplxrxn_stoich_flag (host copy: pfrx_load_specialized refuses inner-Newton sites)
   // owned device state for pfrx_rstep_host
   void *own = nullptr;
@@ -481,16 +482,20 @@ PFRX_DECL(3) PFRX_DECL(4) PFRX_DECL(8) PFRX_DECL(13) PFRX_DECL(15) PFRX_DECL(16)
 typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *, double);
 #define PFRX_DECLR(N) extern "C" pfrx_reaction_fn pfrx_reaction_kernel_##N(void);
 PFRX_DECLR(3) PFRX_DECLR(4) PFRX_DECLR(8) PFRX_DECLR(13) PFRX_DECLR(15) PFRX_DECLR(16) PFRX_DECLR(32)
+typedef void (*pfrx_constraint_fn)(DevCfg, DevState, int64_t, DevCons, int *, int *);
+#define PFRX_DECLC(N) extern "C" pfrx_constraint_fn pfrx_constraint_kernel_##N(void);
+PFRX_DECLC(3) PFRX_DECLC(4) PFRX_DECLC(8) PFRX_DECLC(13) PFRX_DECLC(15) PFRX_DECLC(16) PFRX_DECLC(32)
 struct KernelGetter {
   int n;
   pfrx_kernel_fn (*get)(int);
   pfrx_reaction_fn (*get_rx)(void);
+  pfrx_constraint_fn (*get_cons)(void);
 };
 static const KernelGetter g_getters[] = {
-    {3, pfrx_kernel_3, pfrx_reaction_kernel_3},    {4, pfrx_kernel_4, pfrx_reaction_kernel_4},
-    {8, pfrx_kernel_8, pfrx_reaction_kernel_8},    {13, pfrx_kernel_13, pfrx_reaction_kernel_13},
-    {15, pfrx_kernel_15, pfrx_reaction_kernel_15}, {16, pfrx_kernel_16, pfrx_reaction_kernel_16},
-    {32, pfrx_kernel_32, pfrx_reaction_kernel_32}};
+    {3, pfrx_kernel_3, pfrx_reaction_kernel_3, pfrx_constraint_kernel_3},    {4, pfrx_kernel_4, pfrx_reaction_kernel_4, pfrx_constraint_kernel_4},
+    {8, pfrx_kernel_8, pfrx_reaction_kernel_8, pfrx_constraint_kernel_8},    {13, pfrx_kernel_13, pfrx_reaction_kernel_13, pfrx_constraint_kernel_13},
+    {15, pfrx_kernel_15, pfrx_reaction_kernel_15, pfrx_constraint_kernel_15}, {16, pfrx_kernel_16, pfrx_reaction_kernel_16, pfrx_constraint_kernel_16},
+    {32, pfrx_kernel_32, pfrx_reaction_kernel_32, pfrx_constraint_kernel_32}};
 
 static bool default_tpc(int npad) {
   // measured on B200: the thread-per-cell kernel wins for small networks (C2: 2.6x);
@@ -896,6 +901,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.min_sat = c->rt_min_saturation;
   h->sig = config_signature(c);
   h->dump_text = config_dump_text(c);
+  h->pri_Z_host.assign(c->primary_spec_Z, c->primary_spec_Z + c->naqcomp);
   h->sr_flag_host.clear();
   if (c->nsrfcplxrxn > 0 && c->srfcplxrxn_stoich_flag)
     h->sr_flag_host.assign(c->srfcplxrxn_stoich_flag, c->srfcplxrxn_stoich_flag + c->nsrfcplxrxn);
@@ -1624,6 +1630,102 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
   CUDA_OK(cudaGetLastError());
   h->launches++;
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PFRX_OK;
+}
+
+// ---- batched ReactionEquilibrateConstraint (reaction.F90:1328-2117) ----
+extern "C" int pfrx_equilibrate_constraint(pfrx_handle *h, const pfrx_constraint *k, const double *conc,
+                                           int32_t *num_iterations, int32_t *ierror) {
+  if (!h || !k || !conc || !k->type) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  const DevCfg &d = h->cfg;
+  const int naq = d.naq;
+  if (k->naqcomp != naq) return set_err(PFRX_E_INVALID, "pfrx_constraint.naqcomp differs from the configuration%s", "");
+  if (naq < 1) return set_err(PFRX_E_INVALID, "no aqueous species to equilibrate%s", "");
+  if (d.act_freq != PFRX_ACT_COEF_FREQUENCY_OFF && d.act_alg == PFRX_ACT_COEF_ALGORITHM_NEWTON)
+    return set_err(PFRX_E_INVALID, "constraint equilibration with the NEWTON activity algorithm is not built%s", "");
+  bool any_eq = false;
+  for (int i = 0; i < naq; i++) {
+    switch (k->type[i]) {
+      case PFRX_CONSTRAINT_NULL:
+      case PFRX_CONSTRAINT_FREE:
+      case PFRX_CONSTRAINT_TOTAL:
+      case PFRX_CONSTRAINT_LOG:
+      case PFRX_CONSTRAINT_CHARGE_BAL: break;
+      case PFRX_CONSTRAINT_PH:
+        // the reference allows pH on H+ (or on OH-, or with H+ as a complex): only the first is built
+        if (h->pri_Z_host.size() != (size_t)naq || h->pri_Z_host[i] != 1.0)
+          return set_err(PFRX_E_INVALID, "a pH constraint must be on the primary species H+%s", "");
+        break;
+      case PFRX_CONSTRAINT_MINERAL:
+      case PFRX_CONSTRAINT_GAS: any_eq = true; break;
+      default: return set_err(PFRX_E_INVALID, "constraint type not built (PE, EH, TOTAL_SORB, SUPERCRIT_CO2, TOTAL_AQ_PLUS_SORB)%s", "");
+    }
+  }
+  if (any_eq) {
+    if (!k->eq_logK || !k->eq_h2o_stoich || !k->eq_ptr || !k->eq_spec || !k->eq_stoich)
+      return set_err(PFRX_E_INVALID, "MINERAL / GAS constraint without its reaction tables%s", "");
+    for (int i = 0; i < naq; i++) {
+      if (k->eq_ptr[i] > k->eq_ptr[i + 1] || k->eq_ptr[i] < 0) return set_err(PFRX_E_INVALID, "pfrx_constraint.eq_ptr is not a CSR row pointer%s", "");
+      for (int p = k->eq_ptr[i]; p < k->eq_ptr[i + 1]; p++)
+        if (k->eq_spec[p] < 0 || k->eq_spec[p] >= naq) return set_err(PFRX_E_INVALID, "pfrx_constraint.eq_spec out of range%s", "");
+    }
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  const KernelGetter *gt = nullptr;
+  for (const auto &g : g_getters)
+    if (g.n == h->npad) gt = &g;
+  if (!gt) return set_err(PFRX_E_LIMIT, "no kernel variant for this size%s", "");
+  DevCfg cfg = h->cfg;
+  tpc_layout(cfg, h->npad);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  const size_t per_thread = (size_t)cfg.ws_stride * sizeof(double);
+  int t = 128;
+  while (t > 32 && per_thread * t > (size_t)prop.sharedMemPerBlockOptin) t /= 2;
+  if (per_thread * t > (size_t)prop.sharedMemPerBlockOptin)
+    return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
+  pfrx_constraint_fn fn = gt->get_cons();
+  CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_thread * t)));
+  int nb = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, t, per_thread * t));
+  if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+  if (h->ncell <= 0) return PFRX_OK;
+  // the constraint's tables: one small device block per call (set-up path, not the time loop)
+  const int nnz = any_eq ? k->eq_ptr[naq] : 0;
+  std::vector<double> zero(naq, 0.0);
+  std::vector<int> ptr0(naq + 1, 0);
+  Arena A;
+  DevCons dc;
+  memset(&dc, 0, sizeof(dc));
+  dc.init_molality = k->initialize_with_molality != 0;
+  dc.max_iterations = k->max_iterations;
+  A.add(k->type, naq, &dc.type);
+  A.add(h->pri_Z_host.data(), naq, &dc.Z);
+  A.add(any_eq ? k->eq_logK : zero.data(), naq, &dc.eq_logK);
+  if (any_eq && k->eq_logK_coef) A.add(k->eq_logK_coef, 5 * naq, &dc.eq_logKcoef);
+  A.add(any_eq ? k->eq_h2o_stoich : zero.data(), naq, &dc.eq_h2o);
+  A.add(any_eq ? k->eq_ptr : ptr0.data(), naq + 1, &dc.eq_ptr);
+  if (nnz > 0) {
+    A.add(k->eq_spec, nnz, &dc.eq_spec);
+    A.add(k->eq_stoich, nnz, &dc.eq_st);
+  }
+  void *blk = nullptr;
+  CUDA_OK(cudaMalloc(&blk, std::max<size_t>(A.bytes.size(), 16)));
+  int rc = PFRX_OK;
+  if (cudaMemcpy(blk, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = PFRX_E_CUDA;
+  if (rc == PFRX_OK) {
+    for (auto &f : A.fix) *f.second = (unsigned char *)blk + f.first;
+    dc.conc = conc;
+    int64_t need = (h->ncell + t - 1) / t;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * nb));
+    fn<<<grid, t, per_thread * t, h->stream>>>(cfg, h->st, h->ncell, dc, num_iterations, ierror);
+    if (cudaGetLastError() != cudaSuccess) rc = PFRX_E_CUDA;
+    h->launches++;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = PFRX_E_CUDA;
+  }
+  cudaFree(blk);
+  if (rc != PFRX_OK) return set_err(rc, "CUDA error in pfrx_equilibrate_constraint%s", "");
   return PFRX_OK;
 }
 

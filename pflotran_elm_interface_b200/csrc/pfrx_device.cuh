@@ -37,6 +37,17 @@
 #define PFRX_LOG_TO_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 #define PFRX_IDEAL_GAS_CONSTANT 8.31446
 
+// constraint of pfrx_equilibrate_constraint (include/pfrx.h): device copies of the tables
+struct DevCons {
+  int init_molality, max_iterations;
+  const int *type;
+  const double *Z;  // primary_spec_Z
+  const double *eq_logK, *eq_logKcoef, *eq_h2o;
+  const int *eq_ptr, *eq_spec;
+  const double *eq_st;
+  const double *conc;  // [naq][ld]
+};
+
 struct DevCfg {
   int naq, nim, n;
   int use_full_geochemistry, use_log, use_total_as_guess, use_isothermal;

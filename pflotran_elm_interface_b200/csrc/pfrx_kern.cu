@@ -28,3 +28,6 @@ extern "C" pfrx_kernel_fn PFRX_CAT(pfrx_kernel_, PFRX_N)(int lanes) {
 
 typedef void (*pfrx_reaction_fn)(DevCfg, DevState, int64_t, int, double *, double *, double);
 extern "C" pfrx_reaction_fn PFRX_CAT(pfrx_reaction_kernel_, PFRX_N)(void) { return pfrx_reaction_tpc_kernel<PFRX_N>; }
+
+typedef void (*pfrx_constraint_fn)(DevCfg, DevState, int64_t, DevCons, int *, int *);
+extern "C" pfrx_constraint_fn PFRX_CAT(pfrx_constraint_kernel_, PFRX_N)(void) { return pfrx_constraint_tpc_kernel<PFRX_N>; }

@@ -338,7 +338,6 @@ __device__ const unsigned long long pfrx_spec_sig = SPEC_SIG;
 __device__ const int pfrx_spec_info[5] = {SPEC_N, S2_SLOTS * SPEC_THREADS, SPEC_THREADS, SPEC_MINBLOCKS, SPEC_THREADS};
 }
 
-__device__ __forceinline__ int s2_vote_or(int p) { return SPEC_SYNC ? __syncthreads_or(p) : __any_sync(0xffffffffu, p); }
 __device__ __forceinline__ int s2_vote_and(int p) { return SPEC_SYNC ? __syncthreads_and(p) : __all_sync(0xffffffffu, p); }
 
 // ======================================================================================
@@ -499,7 +498,8 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       need_solve = !done && !over && !conv;
       fail = !done && over;
     }
-    if (s2_vote_or(need_solve ? 1 : 0) && warp_live) {
+    // a warp none of whose cells needs the solve goes straight to the vote that ends the pass
+    if (__any_sync(0xffffffffu, need_solve)) {
       const bool ok = spec2_solve(W, res, ev, s);
       if (need_solve) {
         if (!ok) {

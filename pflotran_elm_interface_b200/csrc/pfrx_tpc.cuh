@@ -304,11 +304,13 @@ struct CellT {
 
   // ---- RTAuxVarCompute = RTotal (reaction.F90:4618-4759) + accumulation terms --
   // want_J: also d(accumulation)/dc/dt into the Jacobian (reaction.F90:5775-5848)
-  __device__ __forceinline__ void auxvar_compute(bool want_J, double dt) {
+  // aq_only (ReactionEquilibrateConstraint): the Jacobian is rt_auxvar%aqueous%dtotal itself, the
+  // complexes take the class coefficients of the latest activity(), no sorbed totals
+  __device__ __forceinline__ void auxvar_compute(bool want_J, double dt, bool aq_only = false) {
     const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
     const double denL = den_kg * 1.e-3;
-    const double f = denL * (por * sat * 1000.0 * vol / dt);  // dtotal -> Jacobian
-    const bool act_upd = cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+    const double f = aq_only ? denL : denL * (por * sat * 1000.0 * vol / dt);  // dtotal -> Jacobian
+    const bool act_upd = aq_only || cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
 #pragma unroll
     for (int i = 0; i < N; i++)
       if (i < naq) {
@@ -370,7 +372,7 @@ struct CellT {
 #pragma unroll 1
         for (int i = 0; i < naq; i++) {
           J(i, i) += 1.0;
-          if (cfg.need_dt) {  // rt_auxvar%aqueous%dtotal for the sandboxes (reaction.F90:4757)
+          if (cfg.need_dt && !aq_only) {  // rt_auxvar%aqueous%dtotal for the sandboxes (reaction.F90:4757)
 #pragma unroll 1
             for (int j = 0; j < naq; j++) DT(i, j) = J(i, j) * denL;
           }
@@ -383,7 +385,7 @@ struct CellT {
     }
 #pragma unroll 1
     for (int i = naq; i < n; i++) TOT(i) = C(i);
-    if (cfg.nsorb > 0) total_sorb(want_J, vol / dt);
+    if (cfg.nsorb > 0 && !aq_only) total_sorb(want_J, vol / dt);
   }
 
   // ---- RTotalSorb (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD;
@@ -1174,8 +1176,9 @@ struct CellT {
   // ---- RSolve (reaction.F90:5457-5516) + LU (utility.F90:597-735) in shared ---
   // Jacobian rows are addressed through logical row offsets ro[] (ints kept in
   // ws.x), so a row interchange swaps two offsets.  The update lands in RES.
-  __device__ __forceinline__ bool solve() {
-    const int n = cfg.n, js = cfg.js;
+  __device__ __forceinline__ bool solve() { return solve(cfg.n, cfg.use_log != 0); }
+  __device__ __forceinline__ bool solve(const int n, const bool use_log) {
+    const int js = cfg.js;
     double *A = ws + cfg.off_J;
     int *ro = reinterpret_cast<int *>(ws + cfg.off_x);  // n row offsets
     double *vv = ws + cfg.off_xs;                        // implicit scaling
@@ -1193,7 +1196,7 @@ struct CellT {
 #pragma unroll 1
       for (int j = 0; j < n; j++) {
         double v = row[j] * nm;
-        if (cfg.use_log) v *= C(j);
+        if (use_log) v *= C(j);
         row[j] = v;
         m2 = fmax(m2, fabs(v));
       }
@@ -1665,6 +1668,242 @@ struct CellT {
     }
   }
 
+  // ---- ReactionEquilibrateConstraint (reaction.F90:1328-2117) for the cell's own constraint values.
+  // Returns ierror (0 converged, 1 singular Jacobian, 2 non-positive concentration, 3 iteration limit).
+  __device__ __forceinline__ int equilibrate(int64_t c, const DevCons &k, int &its_out) {
+    cell = c;
+    const int naq = cfg.naq, ncx = cfg.ncplx;
+    const int64_t ld = st.ld;
+    den_kg = st.den_kg[c];
+    sat = st.sat[c];
+    temp = st.temp[c];
+    por = st.porosity[c];
+    vol = st.volume[c];
+    spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
+    ln_act_h2o = 0.0;
+    dry = false;
+    its_out = 0;
+    const double to_molar = k.init_molality ? den_kg / 1000.0 : 1.0;
+    const double to_molal = k.init_molality ? 1.0 : 1000.0 / den_kg;
+    if (!cfg.use_full_geochemistry) {  // reaction.F90:1472-1480
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) {
+        const double v = k.conc[i * ld + c];
+        st.pri_molal[i * ld + c] = v * to_molal;
+        st.total[i * ld + c] = v * to_molar;
+      }
+      return 0;
+    }
+    // guesses (reaction.F90:1489-1576)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      lngam[i] = 0.0;
+      if (i < naq) {
+        const double v = k.conc[i * ld + c];
+        double g = 1.e-9;
+        switch (k.type[i]) {
+          case PFRX_CONSTRAINT_FREE:
+          case PFRX_CONSTRAINT_CHARGE_BAL:
+          case PFRX_CONSTRAINT_MINERAL: g = v * to_molal; break;
+          case PFRX_CONSTRAINT_LOG: g = pow(10.0, v) * to_molal; break;
+          case PFRX_CONSTRAINT_PH: g = pow(10.0, -v); break;
+          default: break;
+        }
+        C(i) = g;
+      }
+    }
+#pragma unroll 1
+    for (int q = 0; q < cfg.ncls; q++) ws[cfg.off_cls + q] = 0.0;
+    Isum = 0.0;
+    msum = 0.0;
+    int it = 0, it_act_on = 0;
+    bool compute_act = false;
+    const int max_it = k.max_iterations > 0 ? k.max_iterations : 10000;
+    for (;;) {
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) {  // reaction.F90:1592-1598
+        const int t = k.type[i];
+        if (t == PFRX_CONSTRAINT_FREE) C(i) = k.conc[i * ld + c] * to_molal;
+        if (t == PFRX_CONSTRAINT_LOG) C(i) = pow(10.0, k.conc[i * ld + c]) * to_molal;
+      }
+      if (cfg.act_freq != PFRX_ACT_COEF_FREQUENCY_OFF && compute_act) activity();
+      auxvar_compute(true, 1.0, true);  // RTotal: TOT = total, J = dtotal
+      // charge-balance row before any row is replaced
+      double zres = 0.0;
+      bool any_z = false;
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) any_z = any_z || k.type[i] == PFRX_CONSTRAINT_CHARGE_BAL;
+      if (any_z) {
+#pragma unroll 1
+        for (int j = 0; j < naq; j++) {
+          zres += k.Z[j] * TOT(j);
+          double a = 0.0;
+#pragma unroll 1
+          for (int kk = 0; kk < naq; kk++) a += k.Z[kk] * J(kk, j);
+          TMP(j) = a;
+        }
+      }
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) {
+        const int t = k.type[i];
+        const double v = k.conc[i * ld + c];
+        if (t == PFRX_CONSTRAINT_NULL || t == PFRX_CONSTRAINT_TOTAL) {
+          RES(i) = TOT(i) - v * to_molar;
+        } else if (t == PFRX_CONSTRAINT_CHARGE_BAL) {
+          RES(i) = zres;
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) J(i, j) = TMP(j);
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) J(i, j) = 0.0;
+          if (t == PFRX_CONSTRAINT_FREE || t == PFRX_CONSTRAINT_LOG) {
+            RES(i) = 0.0;
+            J(i, i) = 1.0;
+          } else if (t == PFRX_CONSTRAINT_PH) {
+            RES(i) = 0.0;
+            C(i) = pow(10.0, -v) / exp(lngam_at(i));
+            J(i, i) = 1.0;
+          } else {  // MINERAL, GAS
+            double logK = (cfg.use_isothermal || !k.eq_logKcoef) ? k.eq_logK[i] : interp_logK(k.eq_logKcoef + 5 * i, temp);
+            double lnQK = -logK * PFRX_LOG_TO_LN;
+            if (k.eq_h2o[i] != 0.0) lnQK += k.eq_h2o[i] * ln_act_h2o;
+#pragma unroll 1
+            for (int p = k.eq_ptr[i]; p < k.eq_ptr[i + 1]; p++) {
+              const int j = k.eq_spec[p];
+              lnQK += k.eq_st[p] * log(C(j) * exp(lngam_at(j)));
+              J(i, j) = k.eq_st[p] / C(j);
+            }
+            if (t == PFRX_CONSTRAINT_GAS) {
+              const double pp = v <= 0.0 ? pow(10.0, v) : v;
+              lnQK -= log(pp);
+            }
+            RES(i) = lnQK;
+          }
+        }
+      }
+      double max_res = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < naq; i++) max_res = fmax(max_res, fabs(RES(i)));
+      const bool use_log = cfg.use_log ? ((it > 3 && it < 9) ? (it % 2 == 0) : true) : false;
+      if (!solve(naq, use_log)) {
+        its_out = it;
+        return 1;
+      }
+      double max_rel = 0.0, minc = 1.e300;
+      bool nonpos = false;
+      if (use_log) {
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) {
+          double u = RES(i);
+          u = copysign(1.0, u) * fmin(fabs(u), cfg.max_dlnC);
+          const double cc = C(i), cn = cc * exp(-u);
+          C(i) = cn;
+          max_rel = fmax(max_rel, fabs((cn - cc) / cc));
+          if (!(cn > 0.0)) nonpos = true;
+        }
+      } else {
+        double minr = 1.7976931348623157e308;
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) {
+          const double u = RES(i), cc = C(i);
+          if (cc <= u) minr = fmin(minr, fabs(cc / u));
+        }
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) {
+          double u = RES(i);
+          const double cc = C(i);
+          if (minr <= 1.0) u = u * minr * 0.99;
+          const double cn = cc - u;
+          C(i) = cn;
+          max_rel = fmax(max_rel, fabs((cn - cc) / cc));
+          if (!(cn > 0.0)) nonpos = true;
+        }
+      }
+      (void)minc;
+      it++;
+      if (nonpos) {
+        its_out = it;
+        return 2;
+      }
+      if (it >= max_it) {
+        its_out = it;
+        return 3;
+      }
+      if (max_res < cfg.tol_res && max_rel < cfg.tol_relchange) {
+        if (compute_act && it - it_act_on > 1) break;
+        if (!compute_act) it_act_on = it;
+        compute_act = true;
+      }
+    }
+    its_out = it;
+    // ---- the speciated state; total / sec_molal are the last RTotal's (before the final update)
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) {
+        st.pri_molal[i * ld + c] = C(i);
+        st.total[i * ld + c] = TOT(i);
+        st.pri_act_coef[i * ld + c] = exp(lngam[i]);
+        LNA(i) = log(C(i)) + lngam[i];
+        INVC(i) = 1.0 / C(i);
+      }
+#pragma unroll 1
+    for (int kx = 0; kx < ncx; kx++) {
+      const int q = cfg.cx_cls[kx];
+      st.sec_act_coef[kx * ld + c] = q < 0 ? 1.0 : exp(ws[cfg.off_cls + q]);
+    }
+    if (st.ln_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
+    // ---- once equilibrated, the sorbed concentrations (reaction.F90:2036-2060)
+    if (cfg.nsorb > 0 || cfg.nmr > 0) {
+#pragma unroll 1
+      for (int r = 0; r < cfg.nsrfrxn; r++) ws[cfg.off_fs + r] = st.free_site[r * ld + c];
+#pragma unroll 1
+      for (int r = 0; r < cfg.nionx; r++) ws[cfg.off_ix + r] = st.eqionx_ref ? st.eqionx_ref[r * ld + c] : 1.e-9;
+      if (cfg.nsorb > 0) {
+        total_sorb(false, 0.0);
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) st.total_sorb_eq[i * ld + c] = TS(i);
+      }
+      if (cfg.neqsr > 0 && st.eqsrfcplx_conc)
+        for (int r = 0; r < cfg.nsrfcplx; r++) st.eqsrfcplx_conc[r * ld + c] = ws[cfg.off_sc + r];
+      // RTotalSorbMultiRateAsEQ + the site fractions (reaction.F90:2062-2071)
+#pragma unroll 1
+      for (int q = 0; q < cfg.nmr; q++) {
+        const int r0 = cfg.mr_ptr[q], r1 = cfg.mr_ptr[q + 1];
+        double *seq = ws + cfg.off_mr + (2 * q) * N;
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) seq[i] = 0.0;
+        surf_cplx1(cfg.mr_rxn[q], seq, false, 0.0, false);
+        const int64_t base = (int64_t)naq * (r0 + q);
+#pragma unroll 1
+        for (int i = 0; i < naq; i++) {
+          st.kinmr[(base + i) * ld + c] = seq[i];
+#pragma unroll 1
+          for (int r = r0; r < r1; r++)
+            st.kinmr[(base + (int64_t)naq * (r - r0 + 1) + i) * ld + c] = cfg.mr_frac[r] * seq[i];
+        }
+      }
+#pragma unroll 1
+      for (int r = 0; r < cfg.nsrfrxn; r++) st.free_site[r * ld + c] = ws[cfg.off_fs + r];
+      if (cfg.nionx > 0) {
+        const int ncat = cfg.ix_ptr[cfg.nionx];
+        if (st.eqionx_ref)
+          for (int r = 0; r < cfg.nionx; r++) st.eqionx_ref[r * ld + c] = ws[cfg.off_ix + r];
+        if (st.eqionx_conc)
+          for (int r = 0; r < ncat; r++) st.eqionx_conc[r * ld + c] = ws[cfg.off_ix + cfg.nionx + r];
+      }
+    }
+    return 0;
+  }
+
+  // ln gamma of primary species i with a run-time index (lngam[] lives in registers)
+  __device__ __forceinline__ double lngam_at(int i) const {
+    double g = 0.0;
+#pragma unroll
+    for (int x = 0; x < N; x++)
+      if (x == i) g = lngam[x];
+    return g;
+  }
+
   // RStep's reaction to the outcome of one RReact (reaction.F90:3660-3716);
   // returns false when the cell is finished
   __device__ __forceinline__ bool step_bookkeeping(int e, double &dt, double &cumulative, double target, int &ncuts,
@@ -1749,6 +1988,23 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1))) pfrx_rst
     atomicMax(&summ->max_kin, l_maxkin);
     atomicMax(&summ->max_err, l_maxerr);
     atomicMax(&summ->max_sub, l_maxsub);
+  }
+}
+
+// batched ReactionEquilibrateConstraint: one thread per cell
+template <int N>
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1)))
+    pfrx_constraint_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, DevCons k, int *num_its, int *ierror) {
+  extern __shared__ double smem[];
+  double *ws = smem + (size_t)threadIdx.x * cfg.ws_stride;
+  CellT<N> sol(cfg, st, ws);
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = gthread; c < ncell; c += nthreads) {
+    int its = 0, e = 0;
+    if (!(st.imat && st.imat[c] <= 0)) e = sol.equilibrate(c, k, its);
+    if (num_its) num_its[c] = its;
+    if (ierror) ierror[c] = e;
   }
 }
 

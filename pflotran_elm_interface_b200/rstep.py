@@ -62,6 +62,7 @@ def lib():
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
     L.pfrx_reaction.argtypes = [hp, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfrx_equilibrate_constraint.argtypes = [hp, C.POINTER(abi.PfrxConstraint), C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfrx_os_fixed_accum.argtypes = [hp, C.c_void_p]
     L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
     L.pfrx_os_store.argtypes = [hp, C.c_void_p]
@@ -225,6 +226,24 @@ class ChemistryStep:
         _check(lib().pfrx_reaction(self._h, float(tran_dt), int(bool(want_jacobian)), res.data_ptr(),
                                    jac.data_ptr() if jac is not None else None), "pfrx_reaction")
         return res, jac
+
+    def equilibrate_constraint(self, cons: abi.Constraint, conc):
+        """batched ReactionEquilibrateConstraint on the bound state: ``conc[naqcomp, ncell]`` (device tensor)
+        holds each cell's constraint values; the speciated rt_auxvar fields of the state are overwritten.
+        Returns (num_iterations, ierror) as int32 device tensors"""
+        import torch
+
+        st = self._state
+        if st is None:
+            raise PfrxError("bind() a DeviceState first")
+        if not conc.is_cuda or conc.dtype != torch.float64 or not conc.is_contiguous() or \
+                tuple(conc.shape) != (self.cfg.c.naqcomp, st.ncell):
+            raise PfrxError("conc must be a contiguous float64 device tensor [naqcomp, ncell]")
+        its = torch.zeros(st.ncell, dtype=torch.int32, device=st.device)
+        err = torch.zeros(st.ncell, dtype=torch.int32, device=st.device)
+        _check(lib().pfrx_equilibrate_constraint(self._h, C.byref(cons.c), conc.data_ptr(), its.data_ptr(),
+                                                 err.data_ptr()), "pfrx_equilibrate_constraint")
+        return its, err
 
     # -- block vectors either side of the cell loop (pmc_subsurface_osrt.F90:260-274, 303-376) -- #
     def os_fixed_accum(self, fixed_accum) -> None:

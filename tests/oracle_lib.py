@@ -38,6 +38,8 @@ def lib():
     L.pfrx_oracle_rsolve.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int]
     L.pfrx_oracle_lu_solve.argtypes = [dp, C.c_int, dp]
     L.pfrx_oracle_set_ref_bug_compat.argtypes = [C.c_int]
+    L.pfrx_oracle_equilibrate_constraint.argtypes = [cfgp, C.POINTER(abi.PfrxConstraint), stp, C.c_int64, dp, C.c_int64,
+                                                     C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -131,3 +133,19 @@ def count_ops(cfg: abi.ReactionConfig, state: abi.HostState, tran_dt: float, nth
     rc = _lib_count.pfrx_oracle_rstep(C.byref(cfg.c), state.ncell, C.byref(st), float(tran_dt), C.byref(res), nthreads)
     assert rc == 0, rc
     return res, int(_lib_count.pfrx_oracle_ops_get())
+
+
+def equilibrate_constraint(cfg: abi.ReactionConfig, cons: abi.Constraint, state: abi.HostState, conc):
+    """ReactionEquilibrateConstraint on every cell of ``state`` with conc[naqcomp, ncell]; returns (its, ierror)"""
+    L = lib()
+    conc = np.ascontiguousarray(conc, dtype=np.float64)
+    n = state.ncell
+    its = np.zeros(n, dtype=np.int32)
+    err = np.zeros(n, dtype=np.int32)
+    st = state.struct()
+    for ic in range(n):
+        it = C.c_int(0)
+        err[ic] = L.pfrx_oracle_equilibrate_constraint(C.byref(cfg.c), C.byref(cons.c), C.byref(st), ic, _dp(conc), n,
+                                                       C.byref(it))
+        its[ic] = it.value
+    return its, err
