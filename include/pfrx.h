@@ -632,6 +632,25 @@ int pfrx_kernel_info(pfrx_handle *h, int *info5);
  * are the sorbed totals when a sorbing species decays.                         */
 int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, double *res, double *jac);
 
+/* ---- checkpoint layout of the kinetically sorbed concentrations ---------------
+ * RTCheckpointKineticSorptionBinary / HDF5 (reactive_transport.F90:3968-4182) write the explicitly
+ * stored sorbed concentrations as a sequence of per-cell vectors: components that take part in a
+ * multirate reaction outermost, then the multirate reactions, then their rates
+ * (kinmr_total_sorb(icomp, irate, irxn), irate >= 1; the equilibrium target of slot 0 is not
+ * checkpointed).  Every such vector is one row of pfrx_state.kinmr_total_sorb -- cell-major, i.e.
+ * already the array VecView writes -- and rows[k] is the row of the k-th vector of the checkpoint;
+ * *nrows receives their number (rows may be NULL to ask for it).  Host-only, no device needed. */
+int pfrx_kinmr_checkpoint_rows(const pfrx_config *cfg, int32_t *rows, int32_t *nrows);
+
+/* ---- RTUpdateAuxVars over the bound state ------------------------------------
+ * The refresh the reference runs after a restart, after the initial condition and after every
+ * accepted GIRT step (reactive_transport.F90:3525-3660, cells branch): for every active cell,
+ * pri_molal / immobile <- tran_xx (device block vector [ncell][ncomp], or NULL: keep the state's),
+ * RActivityCoefficients when update_activity_coefs != 0 (and the update frequency is not OFF),
+ * then RTAuxVarCompute: total, sec_molal, and the equilibrium-sorbed state (total_sorb_eq,
+ * free-site / surface-complex concentrations, ion-exchange state). */
+int pfrx_update_auxvars(pfrx_handle *h, const double *tran_xx, int update_activity_coefs);
+
 /* ---- batched ReactionEquilibrateConstraint -----------------------------------
  * The set-up step that turns a CONSTRAINT block into a speciated rt_auxvar
  * (reaction.F90:1328-2117, called per condition by

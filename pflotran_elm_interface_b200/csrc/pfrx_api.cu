@@ -485,17 +485,21 @@ PFRX_DECLR(3) PFRX_DECLR(4) PFRX_DECLR(8) PFRX_DECLR(13) PFRX_DECLR(15) PFRX_DEC
 typedef void (*pfrx_constraint_fn)(DevCfg, DevState, int64_t, DevCons, int *, int *);
 #define PFRX_DECLC(N) extern "C" pfrx_constraint_fn pfrx_constraint_kernel_##N(void);
 PFRX_DECLC(3) PFRX_DECLC(4) PFRX_DECLC(8) PFRX_DECLC(13) PFRX_DECLC(15) PFRX_DECLC(16) PFRX_DECLC(32)
+typedef void (*pfrx_auxvars_fn)(DevCfg, DevState, int64_t, const double *, int);
+#define PFRX_DECLA(N) extern "C" pfrx_auxvars_fn pfrx_auxvars_kernel_##N(void);
+PFRX_DECLA(3) PFRX_DECLA(4) PFRX_DECLA(8) PFRX_DECLA(13) PFRX_DECLA(15) PFRX_DECLA(16) PFRX_DECLA(32)
 struct KernelGetter {
   int n;
   pfrx_kernel_fn (*get)(int);
   pfrx_reaction_fn (*get_rx)(void);
   pfrx_constraint_fn (*get_cons)(void);
+  pfrx_auxvars_fn (*get_aux)(void);
 };
 static const KernelGetter g_getters[] = {
-    {3, pfrx_kernel_3, pfrx_reaction_kernel_3, pfrx_constraint_kernel_3},    {4, pfrx_kernel_4, pfrx_reaction_kernel_4, pfrx_constraint_kernel_4},
-    {8, pfrx_kernel_8, pfrx_reaction_kernel_8, pfrx_constraint_kernel_8},    {13, pfrx_kernel_13, pfrx_reaction_kernel_13, pfrx_constraint_kernel_13},
-    {15, pfrx_kernel_15, pfrx_reaction_kernel_15, pfrx_constraint_kernel_15}, {16, pfrx_kernel_16, pfrx_reaction_kernel_16, pfrx_constraint_kernel_16},
-    {32, pfrx_kernel_32, pfrx_reaction_kernel_32, pfrx_constraint_kernel_32}};
+    {3, pfrx_kernel_3, pfrx_reaction_kernel_3, pfrx_constraint_kernel_3, pfrx_auxvars_kernel_3},    {4, pfrx_kernel_4, pfrx_reaction_kernel_4, pfrx_constraint_kernel_4, pfrx_auxvars_kernel_4},
+    {8, pfrx_kernel_8, pfrx_reaction_kernel_8, pfrx_constraint_kernel_8, pfrx_auxvars_kernel_8},    {13, pfrx_kernel_13, pfrx_reaction_kernel_13, pfrx_constraint_kernel_13, pfrx_auxvars_kernel_13},
+    {15, pfrx_kernel_15, pfrx_reaction_kernel_15, pfrx_constraint_kernel_15, pfrx_auxvars_kernel_15}, {16, pfrx_kernel_16, pfrx_reaction_kernel_16, pfrx_constraint_kernel_16, pfrx_auxvars_kernel_16},
+    {32, pfrx_kernel_32, pfrx_reaction_kernel_32, pfrx_constraint_kernel_32, pfrx_auxvars_kernel_32}};
 
 static bool default_tpc(int npad) {
   // measured on B200: the thread-per-cell kernel wins for small networks (C2: 2.6x);
@@ -1633,6 +1637,89 @@ extern "C" int pfrx_reaction(pfrx_handle *h, double tran_dt, int want_jacobian, 
   return PFRX_OK;
 }
 
+// ---- order of the kinetic-sorption checkpoint vectors (reactive_transport.F90:3968-4060) ----
+extern "C" int pfrx_kinmr_checkpoint_rows(const pfrx_config *c, int32_t *rows, int32_t *nrows) {
+  if (!c || !nrows) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  const int naq = c->naqcomp, nmr = c->nkinmrsrfcplxrxn;
+  if (naq < 0 || naq > PFRX_MAX_NCOMP) return set_err(PFRX_E_LIMIT, "ncomp out of range%s", "");
+  int n = 0;
+  if (nmr > 0) {
+    if (!c->kinmrsrfcplxrxn_to_srfcplxrxn || !c->kinmr_rate_ptr || !c->srfcplxrxn_ptr || !c->srfcplxrxn_to_complex ||
+        !c->srfcplx_ptr || !c->srfcplx_specid)
+      return set_err(PFRX_E_INVALID, "multirate surface complexation tables missing%s", "");
+    std::vector<char> flag(naq, 0);
+    for (int q = 0; q < nmr; q++) {
+      const int irxn = c->kinmrsrfcplxrxn_to_srfcplxrxn[q];
+      for (int j = c->srfcplxrxn_ptr[irxn]; j < c->srfcplxrxn_ptr[irxn + 1]; j++) {
+        const int icplx = c->srfcplxrxn_to_complex[j];
+        for (int p = c->srfcplx_ptr[icplx]; p < c->srfcplx_ptr[icplx + 1]; p++) {
+          const int icomp = c->srfcplx_specid[p];
+          if (icomp < 0 || icomp >= naq) return set_err(PFRX_E_INVALID, "srfcplx_specid out of range%s", "");
+          flag[icomp] = 1;
+        }
+      }
+    }
+    for (int icomp = 0; icomp < naq; icomp++) {
+      if (!flag[icomp]) continue;
+      for (int q = 0; q < nmr; q++) {
+        const int r0 = c->kinmr_rate_ptr[q], r1 = c->kinmr_rate_ptr[q + 1];
+        for (int irate = 1; irate <= r1 - r0; irate++) {
+          if (rows) rows[n] = naq * (r0 + q + irate) + icomp;
+          n++;
+        }
+      }
+    }
+  }
+  *nrows = n;
+  return PFRX_OK;
+}
+
+// launch shape of a thread-per-cell set-up kernel (workspace in shared memory)
+static int tpc_launch_shape(pfrx_handle *h, const void *fn, DevCfg *cfg, int *threads, size_t *smem, int *blocks_per_sm) {
+  *cfg = h->cfg;
+  tpc_layout(*cfg, h->npad);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  const size_t per_thread = (size_t)cfg->ws_stride * sizeof(double);
+  int t = 128;
+  while (t > 32 && per_thread * t > (size_t)prop.sharedMemPerBlockOptin) t /= 2;
+  if (per_thread * t > (size_t)prop.sharedMemPerBlockOptin)
+    return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
+  CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_thread * t)));
+  int nb = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, t, per_thread * t));
+  if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+  *threads = t;
+  *smem = per_thread * t;
+  *blocks_per_sm = nb;
+  return PFRX_OK;
+}
+
+// ---- RTUpdateAuxVars (reactive_transport.F90:3525-3660) over the bound state ----
+extern "C" int pfrx_update_auxvars(pfrx_handle *h, const double *tran_xx, int update_activity_coefs) {
+  if (!h) return set_err(PFRX_E_INVALID, "null argument%s", "");
+  if (!h->bound) return set_err(PFRX_E_NOTBOUND, "pfrx_bind_state has not been called%s", "");
+  CUDA_OK(cudaSetDevice(h->device));
+  const KernelGetter *gt = nullptr;
+  for (const auto &g : g_getters)
+    if (g.n == h->npad) gt = &g;
+  if (!gt) return set_err(PFRX_E_LIMIT, "no kernel variant for this size%s", "");
+  pfrx_auxvars_fn fn = gt->get_aux();
+  DevCfg cfg;
+  int t = 0, nb = 0;
+  size_t smem = 0;
+  int rc = tpc_launch_shape(h, (const void *)fn, &cfg, &t, &smem, &nb);
+  if (rc) return rc;
+  if (h->ncell <= 0) return PFRX_OK;
+  int64_t need = (h->ncell + t - 1) / t;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * nb));
+  fn<<<grid, t, smem, h->stream>>>(cfg, h->st, h->ncell, tran_xx, update_activity_coefs);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PFRX_OK;
+}
+
 // ---- batched ReactionEquilibrateConstraint (reaction.F90:1328-2117) ----
 extern "C" int pfrx_equilibrate_constraint(pfrx_handle *h, const pfrx_constraint *k, const double *conc,
                                            int32_t *num_iterations, int32_t *ierror) {
@@ -1676,20 +1763,14 @@ extern "C" int pfrx_equilibrate_constraint(pfrx_handle *h, const pfrx_constraint
   for (const auto &g : g_getters)
     if (g.n == h->npad) gt = &g;
   if (!gt) return set_err(PFRX_E_LIMIT, "no kernel variant for this size%s", "");
-  DevCfg cfg = h->cfg;
-  tpc_layout(cfg, h->npad);
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
-  const size_t per_thread = (size_t)cfg.ws_stride * sizeof(double);
-  int t = 128;
-  while (t > 32 && per_thread * t > (size_t)prop.sharedMemPerBlockOptin) t /= 2;
-  if (per_thread * t > (size_t)prop.sharedMemPerBlockOptin)
-    return set_err(PFRX_E_LIMIT, "per-cell workspace does not fit shared memory%s", "");
   pfrx_constraint_fn fn = gt->get_cons();
-  CUDA_OK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_thread * t)));
-  int nb = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, t, per_thread * t));
-  if (nb < 1) return set_err(PFRX_E_LIMIT, "kernel does not fit on an SM%s", "");
+  DevCfg cfg;
+  int t = 0, nb = 0;
+  size_t smem_bytes = 0;
+  {
+    int rc0 = tpc_launch_shape(h, (const void *)fn, &cfg, &t, &smem_bytes, &nb);
+    if (rc0) return rc0;
+  }
   if (h->ncell <= 0) return PFRX_OK;
   // the constraint's tables: one small device block per call (set-up path, not the time loop)
   const int nnz = any_eq ? k->eq_ptr[naq] : 0;
@@ -1719,7 +1800,7 @@ extern "C" int pfrx_equilibrate_constraint(pfrx_handle *h, const pfrx_constraint
     dc.conc = conc;
     int64_t need = (h->ncell + t - 1) / t;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * nb));
-    fn<<<grid, t, per_thread * t, h->stream>>>(cfg, h->st, h->ncell, dc, num_iterations, ierror);
+    fn<<<grid, t, smem_bytes, h->stream>>>(cfg, h->st, h->ncell, dc, num_iterations, ierror);
     if (cudaGetLastError() != cudaSuccess) rc = PFRX_E_CUDA;
     h->launches++;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = PFRX_E_CUDA;
@@ -1971,7 +2052,7 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   // on a shard runs in one chunk and is not timed (module load, first touch of the staging
   // buffers), calls 1 and 2 time one chunk and `many`, the faster is kept; the trial is repeated
   // every 64 calls because raggedness changes over a run.  PFRX_OS_CHUNKS (read once) pins the count.
-  const int many = (int)std::min<int64_t>(10, std::max<int64_t>(1, ncell / 262144));
+  const int many = (int)std::min<int64_t>(16, std::max<int64_t>(1, ncell / 262144));
   if (h->os_env_chunks < 0) {
     const char *ev = getenv("PFRX_OS_CHUNKS");
     h->os_env_chunks = ev ? std::max(1, std::min(PFRX_MAX_CHUNKS, atoi(ev))) : 0;

@@ -31,3 +31,6 @@ extern "C" pfrx_reaction_fn PFRX_CAT(pfrx_reaction_kernel_, PFRX_N)(void) { retu
 
 typedef void (*pfrx_constraint_fn)(DevCfg, DevState, int64_t, DevCons, int *, int *);
 extern "C" pfrx_constraint_fn PFRX_CAT(pfrx_constraint_kernel_, PFRX_N)(void) { return pfrx_constraint_tpc_kernel<PFRX_N>; }
+
+typedef void (*pfrx_auxvars_fn)(DevCfg, DevState, int64_t, const double *, int);
+extern "C" pfrx_auxvars_fn PFRX_CAT(pfrx_auxvars_kernel_, PFRX_N)(void) { return pfrx_auxvars_tpc_kernel<PFRX_N>; }

@@ -602,6 +602,8 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
           cn[i] = c[i] - u;
         }
         double v = fabs(sx_div(cn[i] - c[i], c[i]));
+        // IEEE: x / 0 = Inf (no convergence from an exactly-zero iterate), 0 / 0 = NaN (skipped)
+        if (fabs(c[i]) < 2.2250738585072014e-308) v = (cn[i] == c[i]) ? v : (double)INFINITY;
         if (!isnan(v)) maxrel = fmax(maxrel, v);
       }
       conv = (maxrel >= 0.0) && (maxrel < prm.tol_relchange);
@@ -1105,6 +1107,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
                 cn[i] = c[i] - u;
               }
               double v = fabs(sx_div(cn[i] - c[i], c[i]));
+              if (fabs(c[i]) < 2.2250738585072014e-308) v = (cn[i] == c[i]) ? v : (double)INFINITY;
               if (!isnan(v)) maxrel = fmax(maxrel, v);
             }
             if ((maxrel >= 0.0) && (maxrel < prm.tol_relchange)) {

@@ -306,11 +306,12 @@ struct CellT {
   // want_J: also d(accumulation)/dc/dt into the Jacobian (reaction.F90:5775-5848)
   // aq_only (ReactionEquilibrateConstraint): the Jacobian is rt_auxvar%aqueous%dtotal itself, the
   // complexes take the class coefficients of the latest activity(), no sorbed totals
-  __device__ __forceinline__ void auxvar_compute(bool want_J, double dt, bool aq_only = false) {
+  // cls: the complexes take the class coefficients of the latest activity() whatever the update frequency
+  __device__ __forceinline__ void auxvar_compute(bool want_J, double dt, bool aq_only = false, bool cls = false) {
     const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
     const double denL = den_kg * 1.e-3;
     const double f = aq_only ? denL : denL * (por * sat * 1000.0 * vol / dt);  // dtotal -> Jacobian
-    const bool act_upd = aq_only || cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
+    const bool act_upd = aq_only || cls || cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
 #pragma unroll
     for (int i = 0; i < N; i++)
       if (i < naq) {
@@ -1895,6 +1896,101 @@ struct CellT {
     return 0;
   }
 
+  // ---- one cell of RTUpdateAuxVars (reactive_transport.F90:3525-3660): [RActivityCoefficients,] RTAuxVarCompute
+  // at the free-ion concentrations of the state (or of the block vector xx when given)
+  __device__ __forceinline__ bool update_auxvars(int64_t c, const double *xx, bool update_act) {
+    cell = c;
+    const int naq = cfg.naq, n = cfg.n, ncx = cfg.ncplx;
+    const int64_t ld = st.ld;
+    den_kg = st.den_kg[c];
+    sat = st.sat[c];
+    temp = st.temp[c];
+    por = st.porosity[c];
+    vol = st.volume[c];
+    spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
+    ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
+    dry = false;
+    if (xx) {
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        const double v = xx[c * n + i];
+        if (i < naq)
+          st.pri_molal[i * ld + c] = v;
+        else
+          st.immobile[(i - naq) * ld + c] = v;
+      }
+    }
+    double Is = 0.0, ms = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < ncx; k++) {
+      const double sk = st.sec_molal[k * ld + c];
+      Is += sk * cfg.cx_Z2[k];
+      ms += sk;
+      ws[cfg.off_lng + k] = log(st.sec_act_coef[k * ld + c]);
+    }
+    Isum = Is;
+    msum = ms;
+    const bool newton = cfg.act_alg == PFRX_ACT_COEF_ALGORITHM_NEWTON;
+    if (update_act && newton) {
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++)
+        if (cfg.cx_cls[k] >= 0) ws[cfg.off_cls + cfg.cx_cls[k]] = log(st.sec_act_coef[k * ld + c]);
+#pragma unroll 1
+      for (int i = 0; i < naq; i++)
+        if (cfg.pri_cls[i] >= 0) ws[cfg.off_cls + cfg.pri_cls[i]] = log(st.pri_act_coef[i * ld + c]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsrfrxn; k++) ws[cfg.off_fs + k] = st.free_site[k * ld + c];
+#pragma unroll 1
+    for (int r = 0; r < cfg.nionx; r++) ws[cfg.off_ix + r] = st.eqionx_ref ? st.eqionx_ref[r * ld + c] : 1.e-9;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      lngam[i] = 0.0;
+      if (i < naq) {
+        lngam[i] = log(st.pri_act_coef[i * ld + c]);
+        C(i) = st.pri_molal[i * ld + c];
+      } else if (i < n) {
+        C(i) = st.immobile[(i - naq) * ld + c];
+      }
+    }
+    bool ok = true;
+    const bool act = update_act && cfg.act_freq != PFRX_ACT_COEF_FREQUENCY_OFF;
+    if (act) {
+      if (newton)
+        ok = activity_newton();
+      else
+        activity();
+    }
+    auxvar_compute(false, 1.0, false, act);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < naq) {
+        st.total[i * ld + c] = TOT(i);
+        if (act) st.pri_act_coef[i * ld + c] = exp(lngam[i]);
+        if (cfg.nsorb > 0) st.total_sorb_eq[i * ld + c] = TS(i);
+      }
+    if (act) {
+#pragma unroll 1
+      for (int k = 0; k < ncx; k++) {
+        const int q = cfg.cx_cls[k];
+        st.sec_act_coef[k * ld + c] = q < 0 ? 1.0 : exp(ws[cfg.off_cls + q]);
+      }
+      if (st.ln_act_h2o && cfg.use_act_h2o) st.ln_act_h2o[c] = ln_act_h2o;
+    }
+#pragma unroll 1
+    for (int k = 0; k < cfg.nsrfrxn; k++) st.free_site[k * ld + c] = ws[cfg.off_fs + k];
+    if (cfg.neqsr > 0 && st.eqsrfcplx_conc)
+      for (int k = 0; k < cfg.nsrfcplx; k++) st.eqsrfcplx_conc[k * ld + c] = ws[cfg.off_sc + k];
+    if (cfg.nionx > 0) {
+      const int ncat = cfg.ix_ptr[cfg.nionx];
+      if (st.eqionx_ref)
+        for (int r = 0; r < cfg.nionx; r++) st.eqionx_ref[r * ld + c] = ws[cfg.off_ix + r];
+      if (st.eqionx_conc)
+        for (int k = 0; k < ncat; k++) st.eqionx_conc[k * ld + c] = ws[cfg.off_ix + cfg.nionx + k];
+    }
+    return ok;
+  }
+
   // ln gamma of primary species i with a run-time index (lngam[] lives in registers)
   __device__ __forceinline__ double lngam_at(int i) const {
     double g = 0.0;
@@ -1989,6 +2085,19 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1))) pfrx_rst
     atomicMax(&summ->max_err, l_maxerr);
     atomicMax(&summ->max_sub, l_maxsub);
   }
+}
+
+// RTUpdateAuxVars over the active cells: one thread per cell
+template <int N>
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 8 ? 2 : 1)))
+    pfrx_auxvars_tpc_kernel(DevCfg cfg, DevState st, int64_t ncell, const double *xx, int update_act) {
+  extern __shared__ double smem[];
+  double *ws = smem + (size_t)threadIdx.x * cfg.ws_stride;
+  CellT<N> sol(cfg, st, ws);
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = gthread; c < ncell; c += nthreads)
+    if (!(st.imat && st.imat[c] <= 0)) sol.update_auxvars(c, xx, update_act != 0);
 }
 
 // batched ReactionEquilibrateConstraint: one thread per cell

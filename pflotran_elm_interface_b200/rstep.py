@@ -62,6 +62,8 @@ def lib():
     L.pfrx_bytes_per_cell.restype = C.c_int64
     L.pfrx_kernel_info.argtypes = [hp, C.POINTER(C.c_int)]
     L.pfrx_reaction.argtypes = [hp, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfrx_update_auxvars.argtypes = [hp, C.c_void_p, C.c_int]
+    L.pfrx_kinmr_checkpoint_rows.argtypes = [C.POINTER(abi.PfrxConfig), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.pfrx_equilibrate_constraint.argtypes = [hp, C.POINTER(abi.PfrxConstraint), C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfrx_os_fixed_accum.argtypes = [hp, C.c_void_p]
     L.pfrx_os_load.argtypes = [hp, C.c_void_p, C.c_void_p]
@@ -226,6 +228,13 @@ class ChemistryStep:
         _check(lib().pfrx_reaction(self._h, float(tran_dt), int(bool(want_jacobian)), res.data_ptr(),
                                    jac.data_ptr() if jac is not None else None), "pfrx_reaction")
         return res, jac
+
+    def update_auxvars(self, tran_xx=None, update_activity_coefs: bool = True) -> None:
+        """RTUpdateAuxVars on the bound state (reactive_transport.F90:3525-3660): free-ion concentrations from
+        the device block vector ``tran_xx`` [ncell, ncomp] (or the state's own), activity coefficients,
+        RTAuxVarCompute"""
+        _check(lib().pfrx_update_auxvars(self._h, tran_xx.data_ptr() if tran_xx is not None else None,
+                                         int(bool(update_activity_coefs))), "pfrx_update_auxvars")
 
     def equilibrate_constraint(self, cons: abi.Constraint, conc):
         """batched ReactionEquilibrateConstraint on the bound state: ``conc[naqcomp, ncell]`` (device tensor)
@@ -456,3 +465,16 @@ def shard_range(ncell: int, rank: int, world: int):
     lo = ncell * rank // world
     hi = ncell * (rank + 1) // world
     return lo, hi
+
+
+def kinmr_checkpoint_rows(cfg: abi.ReactionConfig):
+    """rows of ``kinmr_total_sorb`` in the order RTCheckpointKineticSorption* writes them
+    (reactive_transport.F90:3968-4182); host-only"""
+    import numpy as np
+
+    n = C.c_int32(0)
+    _check(lib().pfrx_kinmr_checkpoint_rows(C.byref(cfg.c), None, C.byref(n)), "pfrx_kinmr_checkpoint_rows")
+    rows = np.zeros(max(n.value, 1), dtype=np.int32)
+    _check(lib().pfrx_kinmr_checkpoint_rows(C.byref(cfg.c), rows.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)),
+           "pfrx_kinmr_checkpoint_rows")
+    return rows[:n.value]

@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from pflotran_elm_interface_b200 import abi
@@ -121,3 +122,35 @@ def test_unsupported_configurations_are_refused_not_approximated():
     cfg.c.abi_version = 1
     rc, msg = _create_rc(cfg)
     assert rc == 1 and "abi_version" in msg
+
+
+def test_kinetic_sorption_checkpoint_order():
+    """pfrx_kinmr_checkpoint_rows against the loops of RTCheckpointKineticSorptionBinary
+    (reactive_transport.F90:4006-4056) restated here on the multirate Hanford network: flagged components
+    outermost, then reactions, then rates 1..nrate; every vector is a row of kinmr_total_sorb"""
+    from pflotran_elm_interface_b200 import rstep, workloads as W
+
+    wl = W.by_name("c3mr", ncell=2)
+    c, a = wl.cfg.c, wl.cfg.arrays
+    naq, nmr = c.naqcomp, c.nkinmrsrfcplxrxn
+    assert nmr > 0
+    flag = np.zeros(naq, dtype=bool)
+    for q in range(nmr):
+        irxn = int(a["kinmrsrfcplxrxn_to_srfcplxrxn"][q])
+        for j in range(int(a["srfcplxrxn_ptr"][irxn]), int(a["srfcplxrxn_ptr"][irxn + 1])):
+            icplx = int(a["srfcplxrxn_to_complex"][j])
+            for p in range(int(a["srfcplx_ptr"][icplx]), int(a["srfcplx_ptr"][icplx + 1])):
+                flag[int(a["srfcplx_specid"][p])] = True
+    want = []
+    for icomp in range(naq):
+        if not flag[icomp]:
+            continue
+        for q in range(nmr):
+            nrate = int(a["kinmr_rate_ptr"][q + 1] - a["kinmr_rate_ptr"][q])
+            for irate in range(1, nrate + 1):
+                want.append(naq * (int(a["kinmr_rate_ptr"][q]) + q + irate) + icomp)
+    got = rstep.kinmr_checkpoint_rows(wl.cfg)
+    assert list(got) == want and len(want) == int(flag.sum()) * int(a["kinmr_rate_ptr"][nmr])
+    assert max(want) < wl.state.a["kinmr_total_sorb"].shape[0] and len(set(want)) == len(want)
+    # a network without multirate sorption has nothing to checkpoint
+    assert len(rstep.kinmr_checkpoint_rows(W.by_name("c2", ncell=2).cfg)) == 0

@@ -114,6 +114,24 @@ def test_c4_clm_cn(dt):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("spec", [False, True])
+def test_exactly_zero_immobile_guess_in_the_linear_formulation(spec):
+    """an immobile pool that is exactly 0: the guess keeps the 0 (pmc_subsurface_osrt.F90:356-362), so the
+    first relative change is x / 0 = +Inf and the cell cannot converge in that iteration
+    (reaction.F90:4030-4041) -- on every kernel, the generated ones with their own divide included"""
+    wl = W.by_name("c4", ncell=4000, tran_dt=1800.0)
+    base = orc.rstep(wl.cfg, wl.state.copy(), wl.tran_dt, 4).sum_newton_iterations
+    wl.state.a["immobile"][0, ::7] = 0.0       # mineral N: the pools mineralise into it
+    wl.state.a["immobile"][10, 3::11] = 0.0    # litter N
+    ref, rr, got, rg, info = _run_both(wl, spec=spec)
+    assert rr.sum_newton_iterations > base   # the zero guesses cost iterations
+    # counts are compared exactly; the concentrations to 1e-9: with no mineral N the decomposition of a cell is
+    # N-limited to the last digit of the Newton tolerance (the round-off of the two codes shows up as 1.3e-10
+    # in one SOM pool of 4000 cells, every other field is inside 1e-10)
+    _compare(ref, got, "c4 with zero pools", rtol=1e-9)
+    _check_summary(rr, rg)
+
+
 @pytest.mark.parametrize("variant,dt,host", [("c4s", 1800.0, False), ("c4s", 86400.0, False), ("c4s", 1800.0, True),
                                              ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True),
                                              ("c4fe", 1800.0, True), ("c4fe", 86400.0, False)])
@@ -856,4 +874,51 @@ def test_batched_constraint_equilibration(case):
         assert sub.size == 0 or sub.max() <= 1e-9, (f, sub.max())
     # an inactive cell keeps what it had
     assert (got.a["pri_molal"][:, 3] == st["pri_molal"][:, 3]).all()
+    step.close()
+
+
+@pytest.mark.parametrize("name,act", [("c3", True), ("c3", False), ("c3mr", True), ("c6", True), ("c4s", False), ("c3an", True)])
+def test_update_auxvars_matches_oracle(name, act):
+    """pfrx_update_auxvars: RTUpdateAuxVars over the cells -- free-ion concentrations from the
+    block vector, RActivityCoefficients, RTAuxVarCompute (totals, complexes, sorbed state) -- against the
+    oracle's per-cell routines (reactive_transport.F90:3525-3660; reaction.F90:4368-4759)"""
+    import torch
+
+    rstep = _gpu()
+    n = 500
+    wl = W.by_name(name, ncell=n)
+    rng = np.random.default_rng(3)
+    cfg, st = wl.cfg, wl.state
+    st.a["imat"][0, 5] = 0
+    nc = cfg.ncomp
+    naq = cfg.c.naqcomp
+    xx = np.concatenate([st.a["pri_molal"], st.a["immobile"]], axis=0).T.copy()   # [ncell, ncomp]
+    xx *= np.exp(rng.uniform(-0.3, 0.3, xx.shape))
+    ref = st.copy()
+    off = cfg.c.act_coef_update_frequency == 0   # ACT_COEF_FREQUENCY_OFF: the reference's callers skip the update
+    for c in range(n):
+        if ref.a["imat"][0, c] <= 0:
+            continue
+        ref.a["pri_molal"][:, c] = xx[c, :naq]
+        if nc > naq:
+            ref.a["immobile"][:, c] = xx[c, naq:]
+        if act and not off:
+            orc.activity(cfg, ref, c)
+        orc.auxvar_compute(cfg, ref, c)
+    step = rstep.ChemistryStep(cfg, 0)
+    dev = rstep.DeviceState.from_host(st, "cuda:0")
+    step.bind(dev)
+    step.update_auxvars(torch.from_numpy(xx).to("cuda:0"), act)
+    torch.cuda.synchronize()
+    got = dev.to_host()
+    for f in abi.STATE_IO_FIELDS:
+        a, b = ref.a[f], got.a[f]
+        if a.size == 0:
+            continue
+        scale = np.maximum(np.abs(a), np.abs(b))
+        err = np.where(scale < 1e-30, 0.0, np.abs(a - b) / np.where(scale > 0, scale, 1.0))
+        assert err.max() <= 1e-10, (f, err.max(), np.unravel_index(err.argmax(), err.shape))
+    assert np.abs(ref.a["total"] - st.a["total"]).max() > 0     # the refresh did something
+    # without a block vector the state's own free-ion concentrations are used
+    step.update_auxvars(None, False)
     step.close()
