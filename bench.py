@@ -480,8 +480,8 @@ def main():
         if ncomp_ > naq_:
             h_xx[:, naq_:].copy_(pristine.t["immobile"].t())
         restore()
-        for _ in range(2):                          # warm-up: device staging, and the library's two
-            restore()                               # chunking trials (one chunk, then eight)
+        for _ in range(4):                          # warm-up: device staging (one chunk, many chunks) and the
+            restore()                               # library's two timed chunking trials
             step.os_step_host(h_solved, h_xx, dt)
         tt = []
         for _ in range(max(2, min(a.steps, 3))):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 6
+#define PFRX_ABI_VERSION 7
 
 /* error classes */
 #define PFRX_OK 0
@@ -95,6 +95,7 @@ extern "C" {
 #define PFRX_SANDBOX_PLANTN 5
 #define PFRX_SANDBOX_LANGMUIR 6
 #define PFRX_SANDBOX_CNDEGAS 7
+#define PFRX_SANDBOX_CALCITE 8
 #define PFRX_MAX_SANDBOXES 8
 /* reaction_microbial_aux.F90:14-22 */
 #define PFRX_MICROBIAL_MOLALITY 1
@@ -219,6 +220,18 @@ typedef struct pfrx_cndegas {
   double reference_temperature;           /* option%flow%reference_temperature, C */
   double reference_pressure;              /* option%flow%reference_pressure, Pa */
 } pfrx_cndegas;
+
+/* CALCITE sandbox (reaction_sandbox_calcite.F90:177-365): two parallel TST pathways for one kinetic
+ * mineral whose RATE_CONSTANT in MINERAL_KINETICS is zero -- the first takes stoichiometry and logK of
+ * the mineral from the kinmnrl tables, the second is written out for Calcite = Ca++ + HCO3- - H+ with
+ * pKeq 1.8487.  The sum of the two rates [mol/m^3 bulk/s] is kept per cell
+ * (rt_auxvar%auxiliary_data -> pfrx_state.sandbox_aux) and moves the mineral's volume fraction when
+ * the step is accepted (CalciteUpdateKineticState :369-410). */
+typedef struct pfrx_calcite_sandbox {
+  int32_t mineral_id;                     /* kinetic-mineral index */
+  int32_t h_ion_id, calcium_id, bicarbonate_id; /* primary ids */
+  double rate_constant1, rate_constant2;  /* mol/m^2/s */
+} pfrx_calcite_sandbox;
 
 /*
  * Flattened, read-only reaction description: the subset of
@@ -371,8 +384,9 @@ typedef struct pfrx_config {
   const pfrx_plantn *plantn;     /* reaction_sandbox_plantn.F90:222-640   */
   const pfrx_langmuir *langmuir; /* reaction_sandbox_langmu.F90:183-330   */
   const pfrx_cndegas *cndegas;   /* reaction_sandbox_cndegas.F90:216-546  */
+  const pfrx_calcite_sandbox *calcite; /* reaction_sandbox_calcite.F90:177-410 */
   /* evaluation order of the sandboxes (PFRX_SANDBOX_*); NULL => the order
-   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR, CNDEGAS */
+   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR, CNDEGAS, CALCITE */
   int32_t nsandbox;
   const int32_t *sandbox_list;
   /* 1 => the behaviour of a reference built with -DELM_PFLOTRAN in BGC-only
@@ -503,6 +517,9 @@ typedef struct pfrx_state {
   /* in, optional: liquid pressure [Pa] (global_auxvar%pres(1)); read by the CNDEGAS sandbox when
    * its cell_state_mode is 1 or 2 */
   const double *pres;
+  /* io [1] when the CALCITE sandbox is configured: rt_auxvar%auxiliary_data, the sandbox's rate of the
+   * latest evaluation [mol/m^3 bulk/s] (read by its kinetic-state update) */
+  double *sandbox_aux;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

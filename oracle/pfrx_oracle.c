@@ -60,6 +60,7 @@ typedef struct {
   double ln_act_h2o;
   double den_kg, sat, temp, porosity, volume, soil_particle_density;
   double pres; /* liquid pressure, CNDEGAS only */
+  double sandbox_aux; /* rt_auxvar%auxiliary_data of the CALCITE sandbox */
   /* ELM per-cell scalars (elm_pflotran builds) */
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
@@ -178,6 +179,7 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->volume = LD(st->volume, 0);
   c->soil_particle_density = st->soil_particle_density ? LD(st->soil_particle_density, 0) : 0.0;
   c->pres = st->pres ? LD(st->pres, 0) : 101325.0;
+  c->sandbox_aux = st->sandbox_aux ? LD(st->sandbox_aux, 0) : 0.0;
   c->elm_w = st->elm_w_scalar ? LD(st->elm_w_scalar, 0) : 1.0;
   c->elm_o = st->elm_o_scalar ? LD(st->elm_o_scalar, 0) : 1.0;
   c->elm_t = st->elm_t_scalar ? LD(st->elm_t_scalar, 0) : 1.0;
@@ -217,6 +219,7 @@ static void cell_scatter(const cell_t *c, const pfrx_state *st, int64_t ic) {
     for (k = 0; k < c->nionx; k++) LD(st->eqionx_ref_cation_sorbed_conc, k) = c->eqionx_ref[k];
   if (st->eqionx_conc)
     for (k = 0; k < c->nionxcat; k++) LD(st->eqionx_conc, k) = c->eqionx_conc[k];
+  if (st->sandbox_aux) LD(st->sandbox_aux, 0) = c->sandbox_aux;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -2466,19 +2469,98 @@ static void cndegas_react(cell_t *c, const pfrx_config *cfg, double *Residual, d
 #undef DTOT
 }
 
+/* reaction_sandbox_calcite.F90:177-365  CalciteEvaluate */
+static void calcite_evaluate(cell_t *c, const pfrx_config *cfg, double *Residual, double *Jacobian,
+                             int compute_derivative) {
+  const pfrx_calcite_sandbox *this_ = cfg->calcite;
+  int n = c->n, i, j, icomp, jcomp, imnrl = this_->mineral_id;
+  int p0 = cfg->kinmnrl_ptr[imnrl], p1 = cfg->kinmnrl_ptr[imnrl + 1];
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  double rate, drate_dQK, lnQK, QK, affinity_factor, dQK_dmj, sign_, molality_to_molarity;
+  int calculate_rate;
+  molality_to_molarity = c->den_kg * 1.e-3;
+  /* reaction path #1: stoichiometry and logK of the mineral from the database */
+  for (i = 0; i < c->naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+  }
+  lnQK = -c->kinmnrl_logK[imnrl] * LOG_TO_LN;
+  if (cfg->kinmnrl_h2ostoich[imnrl] != 0.0) lnQK = lnQK + cfg->kinmnrl_h2ostoich[imnrl] * c->ln_act_h2o;
+  for (i = p0; i < p1; i++) {
+    icomp = cfg->kinmnrl_specid[i];
+    lnQK = lnQK + cfg->kinmnrl_stoich[i] * ln_act[icomp];
+  }
+  QK = exp(lnQK);
+  affinity_factor = 1.0 - QK;
+  sign_ = copysign(1.0, affinity_factor);
+  rate = 0.0;
+  calculate_rate = c->mnrl_volfrac[imnrl] > 0 || sign_ < 0.0;
+  if (calculate_rate) rate = -c->mnrl_area[imnrl] * sign_ * fabs(affinity_factor) * this_->rate_constant1;
+  c->sandbox_aux = rate;
+  rate = rate * c->volume;
+  for (i = p0; i < p1; i++) {
+    icomp = cfg->kinmnrl_specid[i];
+    Residual[icomp] = Residual[icomp] + cfg->kinmnrl_stoich[i] * rate;
+  }
+  if (compute_derivative && calculate_rate) {
+    drate_dQK = c->mnrl_area[imnrl] * this_->rate_constant1 * c->volume;
+    for (j = p0; j < p1; j++) {
+      jcomp = cfg->kinmnrl_specid[j];
+      dQK_dmj = cfg->kinmnrl_stoich[j] * QK * exp(-ln_conc[jcomp]) * molality_to_molarity;
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->kinmnrl_specid[i];
+        Jacobian[icomp + jcomp * n] = Jacobian[icomp + jcomp * n] + cfg->kinmnrl_stoich[i] * drate_dQK * dQK_dmj;
+      }
+    }
+  }
+  /* reaction path #2: QK = {Ca++}{HCO3-}/(Keq {H+}), pKeq 1.8487 */
+  {
+    int ih = this_->h_ion_id, ica = this_->calcium_id, ib = this_->bicarbonate_id;
+    lnQK = -1.8487 * LOG_TO_LN - ln_act[ih] + ln_act[ica] + ln_act[ib];
+    affinity_factor = 1.0 - exp(lnQK);
+    sign_ = copysign(1.0, affinity_factor);
+    rate = 0.0;
+    calculate_rate = c->mnrl_volfrac[imnrl] > 0 || sign_ < 0.0;
+    if (calculate_rate) rate = -c->mnrl_area[imnrl] * sign_ * fabs(affinity_factor) * this_->rate_constant2;
+    c->sandbox_aux = c->sandbox_aux + rate;
+    rate = rate * c->volume;
+    Residual[ih] = Residual[ih] - rate;
+    Residual[ica] = Residual[ica] + rate;
+    Residual[ib] = Residual[ib] + rate;
+    if (compute_derivative && calculate_rate) {
+      drate_dQK = c->mnrl_area[imnrl] * this_->rate_constant2 * c->volume;
+      jcomp = ih;
+      dQK_dmj = -1.0 * exp(lnQK - ln_conc[jcomp]) * molality_to_molarity;
+      Jacobian[ih + jcomp * n] = Jacobian[ih + jcomp * n] - drate_dQK * dQK_dmj;
+      Jacobian[ica + jcomp * n] = Jacobian[ica + jcomp * n] + drate_dQK * dQK_dmj;
+      Jacobian[ib + jcomp * n] = Jacobian[ib + jcomp * n] + drate_dQK * dQK_dmj;
+      jcomp = ica;
+      dQK_dmj = 1.0 * exp(lnQK - ln_conc[jcomp]) * molality_to_molarity;
+      Jacobian[ih + jcomp * n] = Jacobian[ih + jcomp * n] - drate_dQK * dQK_dmj;
+      Jacobian[ica + jcomp * n] = Jacobian[ica + jcomp * n] + drate_dQK * dQK_dmj;
+      Jacobian[ib + jcomp * n] = Jacobian[ib + jcomp * n] + drate_dQK * dQK_dmj;
+      jcomp = ib;
+      dQK_dmj = 1.0 * exp(lnQK - ln_conc[jcomp]) * molality_to_molarity;
+      Jacobian[ih + jcomp * n] = Jacobian[ih + jcomp * n] - drate_dQK * dQK_dmj;
+      Jacobian[ica + jcomp * n] = Jacobian[ica + jcomp * n] + drate_dQK * dQK_dmj;
+      Jacobian[ib + jcomp * n] = Jacobian[ib + jcomp * n] + drate_dQK * dQK_dmj;
+    }
+  }
+}
+
 static int n_sandboxes(const pfrx_config *cfg) {
   return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL) +
-         (cfg->plantn != NULL) + (cfg->langmuir != NULL) + (cfg->cndegas != NULL);
+         (cfg->plantn != NULL) + (cfg->langmuir != NULL) + (cfg->cndegas != NULL) + (cfg->calcite != NULL);
 }
 
 /* reaction_sandbox.F90:294-330  RSandboxEvaluate: walk the list in deck order */
 static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
                                int derivative) {
-  static const int32_t default_order[7] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
+  static const int32_t default_order[8] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
                                            PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
-                                           PFRX_SANDBOX_CNDEGAS};
+                                           PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE};
   const int32_t *order = cfg->sandbox_list ? cfg->sandbox_list : default_order;
-  int ns = cfg->sandbox_list ? cfg->nsandbox : 7, k;
+  int ns = cfg->sandbox_list ? cfg->nsandbox : 8, k;
   for (k = 0; k < ns; k++) {
     switch (order[k]) {
       case PFRX_SANDBOX_CLM_CN:
@@ -2501,6 +2583,9 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
         break;
       case PFRX_SANDBOX_CNDEGAS:
         if (cfg->cndegas) cndegas_react(c, cfg, Res, Jac, derivative);
+        break;
+      case PFRX_SANDBOX_CALCITE:
+        if (cfg->calcite) calcite_evaluate(c, cfg, Res, Jac, derivative);
         break;
       default:
         break;
@@ -2973,6 +3058,12 @@ static int r_update_kinetic_state(cell_t *c, const pfrx_config *cfg, double tran
       for (i = 0; i < c->naq; i++)
         S[i] = (S[i] + kdt * cfg->kinmr_frac[irate] * c->kinmr_total_sorb[base + i]) / one_plus_kdt;
     }
+  }
+  if (cfg->calcite) { /* CalciteUpdateKineticState, reaction_sandbox_calcite.F90:369-410 */
+    int imnrl = cfg->calcite->mineral_id;
+    double delta_volfrac = c->sandbox_aux * cfg->kinmnrl_molar_vol[imnrl] * tran_dt;
+    c->mnrl_volfrac[imnrl] = c->mnrl_volfrac[imnrl] + delta_volfrac;
+    if (c->mnrl_volfrac[imnrl] < 0.0) c->mnrl_volfrac[imnrl] = 0.0;
   }
   if (n_sandboxes(cfg) > 0) kinetic_state_updated = 1; /* any sandbox => true, reaction.F90:5965 */
   return kinetic_state_updated;

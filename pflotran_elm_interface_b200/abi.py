@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 6
+PFRX_ABI_VERSION = 7
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -142,6 +142,7 @@ class PfrxConfig(C.Structure):
         ("plantn", C.c_void_p),
         ("langmuir", C.c_void_p),
         ("cndegas", C.c_void_p),
+        ("calcite", C.c_void_p),
         ("nsandbox", C.c_int32),
         ("sandbox_list", c_int32_p),
         ("elm_pflotran", C.c_int32),
@@ -189,6 +190,7 @@ class PfrxConfig(C.Structure):
 
 SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR, SANDBOX_PLANTN, SANDBOX_LANGMUIR = 1, 2, 3, 4, 5, 6
 SANDBOX_CNDEGAS = 7
+SANDBOX_CALCITE = 8
 SPEC_AQUEOUS, SPEC_IMMOBILE = 0, 2
 
 
@@ -284,6 +286,11 @@ class Constraint:
             np.float64, C.c_double)
 
 
+class PfrxCalciteSandbox(C.Structure):
+    _fields_ = ([(f, C.c_int32) for f in ("mineral_id", "h_ion_id", "calcium_id", "bicarbonate_id")]
+                + [(f, C.c_double) for f in ("rate_constant1", "rate_constant2")])
+
+
 class PfrxDenitr(C.Structure):
     _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
                 + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])
@@ -299,13 +306,13 @@ STATE_DOUBLE_FIELDS = [
 # elm_pflotran, NULL otherwise
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
                     "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc",
-                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres"]
+                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres", "sandbox_aux"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
     "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
     "mnrl_volfrac", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "total_sorb_eq",
-    "kinmr_total_sorb", "somdec_nc", "eqionx_ref_cation_sorbed_conc", "eqionx_conc",
+    "kinmr_total_sorb", "somdec_nc", "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "sandbox_aux",
 ]
 STATE_RESULT_FIELDS = ["num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 
@@ -621,7 +628,7 @@ class ReactionConfig:
         for kind in getattr(net, "sandbox_order", []):
             order.append({"CLM-CN": SANDBOX_CLM_CN, "SOMDECOMP": SANDBOX_SOMDEC, "NITRIFICATION": SANDBOX_NITRIF,
                           "DENITRIFICATION": SANDBOX_DENITR, "PLANTN": SANDBOX_PLANTN,
-                          "LANGMUIR": SANDBOX_LANGMUIR, "CNDEGAS": SANDBOX_CNDEGAS}[kind])
+                          "LANGMUIR": SANDBOX_LANGMUIR, "CNDEGAS": SANDBOX_CNDEGAS, "CALCITE": SANDBOX_CALCITE}[kind])
         if order:
             c.nsandbox = len(order)
             c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
@@ -672,6 +679,13 @@ class ReactionConfig:
                 setattr(o, k, v)
             self.cndegas = o
             c.cndegas = C.cast(C.pointer(o), C.c_void_p)
+        cs = getattr(net, "calcite_sandbox", None)
+        if cs is not None:
+            o = PfrxCalciteSandbox()
+            for k, v in cs.items():
+                setattr(o, k, v)
+            self.calcite = o
+            c.calcite = C.cast(C.pointer(o), C.c_void_p)
 
     # ------------------------------------------------------------------ #
     @classmethod
@@ -684,7 +698,8 @@ class ReactionConfig:
         self.net = None
         self.arrays = {}
         structs = {"config": PfrxConfig, "somdec": PfrxSomdec, "nitrif": PfrxNitrif, "denitr": PfrxDenitr,
-                   "plantn": PfrxPlantn, "langmuir": PfrxLangmuir, "cndegas": PfrxCndegas}
+                   "plantn": PfrxPlantn, "langmuir": PfrxLangmuir, "cndegas": PfrxCndegas,
+                   "calcite": PfrxCalciteSandbox}
         prefix = {"c": ("", None), "sd": ("somdec_", "somdec"), "nt": ("nitrif_", "nitrif"), "dn": ("denitr_", "denitr"),
                   "pn": ("plantn_", "plantn"), "lg": ("langmuir_", "langmuir")}
         objs = {}
@@ -713,7 +728,7 @@ class ReactionConfig:
                 elif w[0] == "signature":
                     sig = int(w[1], 16)
         self.c = objs["config"]
-        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir", "cndegas"):
+        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir", "cndegas", "calcite"):
             if k in objs:
                 setattr(self, k, objs[k])
                 setattr(self.c, k, C.cast(C.pointer(objs[k]), C.c_void_p))
@@ -759,6 +774,7 @@ class ReactionConfig:
             "eqionx_ref_cation_sorbed_conc": c.neqionxrxn,
             "eqionx_conc": int(self.arrays["eqionx_ptr"][c.neqionxrxn]) if c.neqionxrxn else 0,
             "pres": 1 if (getattr(self, "cndegas", None) is not None and self.cndegas.cell_state_mode >= 1) else 0,
+            "sandbox_aux": 1 if getattr(self, "calcite", None) is not None else 0,
             "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
                           if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,

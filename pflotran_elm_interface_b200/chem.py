@@ -357,6 +357,7 @@ class Chemistry:
     plantn: Optional[dict] = None
     langmuir: Optional[dict] = None
     cndegas: Optional[dict] = None
+    calcite_sandbox: Optional[dict] = None
     sandbox_order: List[str] = field(default_factory=list)
     database: str = ""
     use_log_formulation: bool = False
@@ -830,6 +831,20 @@ def _read_langmuir(cur: _Cursor) -> dict:
     return d
 
 
+def _read_calcite_sandbox(cur: _Cursor) -> dict:
+    # CalciteReadInput, reaction_sandbox_calcite.F90:52-104
+    d: Dict[str, float] = {}
+    for t in cur.block():
+        key = t[0].upper()
+        if key in ("RATE_CONSTANT1", "RATE_CONSTANT2"):
+            d[key.lower()] = _fnum(t[1])
+        else:
+            raise ValueError(f"CALCITE sandbox keyword {key}")
+    if len(d) != 2:
+        raise ValueError("RATE_CONSTANT1 and RATE_CONSTANT2 must be set for REACTION_SANDBOX,CALCITE")
+    return d
+
+
 def _read_cndegas(cur: _Cursor) -> dict:
     # CNdegasCreate / CNdegasRead, reaction_sandbox_cndegas.F90:44-130
     d = {"k_kinetic_co2": 1.0e-5, "k_kinetic_n2o": 1.0e-5, "k_kinetic_n2": 1.0e-5, "k_kinetic_h": 1.0e-5,
@@ -1042,6 +1057,9 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                     ch.sandbox_order.append(k2)
                 elif k2 == "CNDEGAS" and ch.cndegas is None:
                     ch.cndegas = _read_cndegas(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "CALCITE" and ch.calcite_sandbox is None:
+                    ch.calcite_sandbox = _read_calcite_sandbox(cur)
                     ch.sandbox_order.append(k2)
                 else:
                     ch.unsupported.append("REACTION_SANDBOX," + k2)
@@ -1866,6 +1884,19 @@ class ReactionNetwork:
                     raise KeyError("CNDEGAS: Himm is not defined even though pH needs to be fixed")
                 d["proton_id"], d["himm_id"] = pri["H+"], imm["Himm"]
             self.cndegas = d
+
+        self.calcite_sandbox = None
+        if self.chem.calcite_sandbox is not None:
+            # CalciteSetup, reaction_sandbox_calcite.F90:108-146
+            g = self.chem.calcite_sandbox
+            for nm in ("H+", "Ca++", "HCO3-"):
+                if nm not in pri:
+                    raise KeyError(f"CALCITE sandbox: primary species {nm} not found")
+            if "Calcite" not in self.kinmnrl_names:
+                raise KeyError("CALCITE sandbox: Calcite is not among the kinetic minerals")
+            self.calcite_sandbox = {"mineral_id": self.kinmnrl_names.index("Calcite"), "h_ion_id": pri["H+"],
+                                    "calcium_id": pri["Ca++"], "bicarbonate_id": pri["HCO3-"],
+                                    "rate_constant1": g["rate_constant1"], "rate_constant2": g["rate_constant2"]}
 
     # -- helpers -------------------------------------------------------------- #
     def csr(self, rxns: Sequence[Rxn]):

@@ -316,6 +316,7 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
   if (c->cndegas) {  // not covered by the generator: any cubin signature must differ
     h = fnv1a(h, c->cndegas, sizeof(*c->cndegas));
   }
+  if (c->calcite) h = fnv1a(h, c->calcite, sizeof(*c->calcite));
   if (c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir) {
     int32_t e = c->elm_pflotran ? 1 : 0;
     h = fnv1a(h, &e, sizeof(e));
@@ -370,6 +371,7 @@ static std::string config_dump_text(const pfrx_config *c) {
   if (c->plantn) hex_struct(out, "plantn", c->plantn, sizeof(*c->plantn));
   if (c->langmuir) hex_struct(out, "langmuir", c->langmuir, sizeof(*c->langmuir));
   if (c->cndegas) hex_struct(out, "cndegas", c->cndegas, sizeof(*c->cndegas));
+  if (c->calcite) hex_struct(out, "calcite", c->calcite, sizeof(*c->calcite));
   CfgSink sink;
   sink.dump = &out;
   const uint64_t sig = config_walk(c, sink);
@@ -556,7 +558,7 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 32
+#define PFRX_NUM_D 33
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
@@ -567,7 +569,7 @@ static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
                        c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, nsorb > 0 ? c->naqcomp : 0,
                        mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc,
-                       (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0};
+                       (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0, c->calcite ? 1 : 0};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -828,7 +830,18 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
         return set_err(PFRX_E_INVALID, "immobile decay species id out of range%s", "");
   }
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
-  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir || c->cndegas;
+  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir || c->cndegas || c->calcite;
+  if (c->calcite) {
+    const pfrx_calcite_sandbox *cs = c->calcite;
+    const int ids[3] = {cs->h_ion_id, cs->calcium_id, cs->bicarbonate_id};
+    for (int k = 0; k < 3; k++)
+      if (ids[k] < 0 || ids[k] >= c->naqcomp) return set_err(PFRX_E_INVALID, "CALCITE sandbox species id out of range%s", "");
+    if (cs->mineral_id < 0 || cs->mineral_id >= c->nkinmnrl)
+      return set_err(PFRX_E_INVALID, "CALCITE sandbox needs its mineral among the kinetic minerals%s", "");
+    // "the RATE_CONSTANT in the default MINERAL_KINETICS block must be set to zero" (reaction_sandbox_calcite.F90:238-243)
+    if (c->kinmnrl_rate_constant[cs->mineral_id] != 0.0)
+      return set_err(PFRX_E_INVALID, "CALCITE sandbox: the mineral's RATE_CONSTANT must be zero%s", "");
+  }
   if (c->cndegas) {
     const pfrx_cndegas *cd = c->cndegas;
     const int gid[3] = {cd->co2g_id, cd->n2og_id, cd->n2g_id}, aid[3] = {cd->co2a_id, cd->n2oa_id, cd->n2a_id};
@@ -868,7 +881,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
   if (c->sandbox_list)
     for (int k = 0; k < c->nsandbox; k++)
-      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_CNDEGAS ||
+      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_CALCITE ||
           c->nsandbox > PFRX_MAX_SANDBOXES)
         return set_err(PFRX_E_INVALID, "bad sandbox_list%s", "");
   int ndev = 0;
@@ -940,6 +953,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_pn = c->plantn ? 1 : 0;
   d.has_lg = c->langmuir ? 1 : 0;
   d.has_cd = c->cndegas ? 1 : 0;
+  d.has_cs = c->calcite ? 1 : 0;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
   d.need_ds = (c->nradiodecay_rxn > 0 && c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0) ? 1 : 0;
@@ -950,18 +964,19 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.mb_units = c->microbial_concentration_units;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
-    static const int def_order[7] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
+    static const int def_order[8] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
                                      PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
-                                     PFRX_SANDBOX_CNDEGAS};
+                                     PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE};
     const int32_t *ord = c->sandbox_list ? c->sandbox_list : def_order;
-    const int no = c->sandbox_list ? c->nsandbox : 7;
+    const int no = c->sandbox_list ? c->nsandbox : 8;
     d.nsbx = 0;
     for (int k = 0; k < no; k++) {
       const int kind = ord[k];
       const bool present = (kind == PFRX_SANDBOX_CLM_CN && c->clmcn_nrxn > 0) ||
                            (kind == PFRX_SANDBOX_SOMDEC && c->somdec) || (kind == PFRX_SANDBOX_NITRIF && c->nitrif) ||
                            (kind == PFRX_SANDBOX_DENITR && c->denitr) || (kind == PFRX_SANDBOX_PLANTN && c->plantn) ||
-                           (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir) || (kind == PFRX_SANDBOX_CNDEGAS && c->cndegas);
+                           (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir) || (kind == PFRX_SANDBOX_CNDEGAS && c->cndegas) ||
+                           (kind == PFRX_SANDBOX_CALCITE && c->calcite);
       if (present) d.sbx[d.nsbx++] = kind;
     }
   }
@@ -970,6 +985,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->plantn) d.pn = *c->plantn;
   if (c->langmuir) d.lg = *c->langmuir;
   if (c->cndegas) d.cd = *c->cndegas;
+  if (c->calcite) d.cs = *c->calcite;
 
   // kernel variant first: the task partition depends on the lane count
   {
@@ -1428,6 +1444,7 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->eqionx_ref = s->eqionx_ref_cation_sorbed_conc;
   d->eqionx_conc = s->eqionx_conc;
   d->pres = s->pres;
+  d->sandbox_aux = s->sandbox_aux;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -1989,6 +2006,8 @@ static DevState dev_state_at(const DevState &d, int64_t c0) {
   PFRX_OFF(elm_plantndemand);
   PFRX_OFF(eqionx_ref);
   PFRX_OFF(eqionx_conc);
+  PFRX_OFF(pres);
+  PFRX_OFF(sandbox_aux);
   PFRX_OFF(imat);
   PFRX_OFF(num_sub_steps);
   PFRX_OFF(num_iterations);
@@ -2048,9 +2067,9 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   int rc = pipeline_events(h);
   if (rc) return rc;
   // Chunks: a handful hides all but the first upload and the last download behind the kernel, but
-  // every chunk of a ragged workload ends with its own slowest cell.  Which wins is measured: call 0
-  // on a shard runs in one chunk and is not timed (module load, first touch of the staging
-  // buffers), calls 1 and 2 time one chunk and `many`, the faster is kept; the trial is repeated
+  // every chunk of a ragged workload ends with its own slowest cell.  Which wins is measured: calls 0
+  // and 1 on a shard run in one chunk and in `many` and are not timed (module load, first touch of
+  // the staging buffers), calls 2 and 3 time the two shapes, the faster is kept; the trial is repeated
   // every 64 calls because raggedness changes over a run.  PFRX_OS_CHUNKS (read once) pins the count.
   const int many = (int)std::min<int64_t>(16, std::max<int64_t>(1, ncell / 262144));
   if (h->os_env_chunks < 0) {
@@ -2063,8 +2082,10 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
     h->os_choice = 1;
   }
   const bool forced = h->os_env_chunks > 0;
-  const int phase = h->os_calls;  // 0 warm-up, 1 trial (one chunk), 2 trial (many), >= 3 steady
-  int nchunk = forced ? h->os_env_chunks : (phase <= 1 ? 1 : phase == 2 ? many : h->os_choice);
+  // 0, 1 warm-up (one chunk, many: first touch of the staging buffers and events of either shape),
+  // 2 trial (one chunk), 3 trial (many), >= 4 steady
+  const int phase = h->os_calls;
+  int nchunk = forced ? h->os_env_chunks : (phase == 0 || phase == 2) ? 1 : (phase == 1 || phase == 3) ? many : h->os_choice;
   if (h->os_inactive < 0 && h->st.imat) {
     int *cnt = nullptr;
     CUDA_OK(cudaMalloc(&cnt, sizeof(int)));
@@ -2145,12 +2166,12 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   summary_out(h, out);
   if (!forced) {
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
-    if (phase == 1) h->os_trial_s[0] = el;
-    if (phase == 2) {
+    if (phase == 2) h->os_trial_s[0] = el;
+    if (phase == 3) {
       h->os_trial_s[1] = el;
       h->os_choice = h->os_trial_s[1] < h->os_trial_s[0] ? many : 1;
     }
-    h->os_calls = phase >= 66 ? 1 : phase + 1;  // steady for 64 calls, then the two trials again
+    h->os_calls = phase >= 67 ? 2 : phase + 1;  // steady for 64 calls, then the two trials again
   }
   if (out->first_failed_cell >= 0 && nchunk > 1) {
     // chunk-local index: recover the shard index from the per-cell error flags
@@ -2206,7 +2227,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
                            (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
                            (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc,
-                           (double **)&h->own_st.pres};
+                           (double **)&h->own_st.pres, &h->own_st.sandbox_aux};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -2225,14 +2246,15 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
                               host->somdec_nc,    host->elm_rate_plantndemand, host->eqionx_ref_cation_sorbed_conc,
-                              host->eqionx_conc,  host->pres};
+                              host->eqionx_conc,  host->pres,         host->sandbox_aux};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
                          (double *)d.sat, (double *)d.temp, (double *)d.porosity, (double *)d.volume,
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
-                         d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc, (double *)d.pres};
+                         d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc, (double *)d.pres,
+                         d.sandbox_aux};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -2251,6 +2273,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (!host->elm_rate_plantndemand) d.elm_plantndemand = nullptr;
   if (!host->eqionx_ref_cation_sorbed_conc) d.eqionx_ref = nullptr;
   if (!host->eqionx_conc) d.eqionx_conc = nullptr;
+  if (!host->sandbox_aux) d.sandbox_aux = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -2278,7 +2301,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   int rc = summary_reset(h, s_k);
   if (rc) return rc;
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32};
   double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
                          host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
                          host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
@@ -2287,7 +2310,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
                          host->somdec_nc,    nullptr,            host->eqionx_ref_cation_sorbed_conc,
-                         host->eqionx_conc};
+                         host->eqionx_conc,  nullptr,            host->sandbox_aux};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the
@@ -2509,7 +2532,7 @@ extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
   // written once, four int32 results
   if (!h) return 0;
   const int *r = h->rows_d.data();
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32};
   int64_t in = 0, outn = 0;
   for (int f = 0; f < kNumD; f++)
     if (f != 11) in += r[f];
@@ -2580,7 +2603,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
     inner_newton = inner_newton || h->sr_flag_host[r] != 0;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd ||
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd || d.has_cs ||
       d.nsrfrxn != d.neqsr + d.nmr)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();

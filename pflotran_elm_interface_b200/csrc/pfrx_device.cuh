@@ -122,7 +122,7 @@ struct DevCfg {
   // CLM-CN
   // ELM-CN sandboxes (pfrx_sandbox.cuh): tables as in include/pfrx.h with device pointers
   int nsbx, sbx[PFRX_MAX_SANDBOXES];  // evaluation order, PFRX_SANDBOX_*
-  int has_sd, has_nt, has_dn, has_pn, has_lg, has_cd, elm;
+  int has_sd, has_nt, has_dn, has_pn, has_lg, has_cd, has_cs, elm;
   int need_dt;           // a sandbox reads d(total)/d(free): keep a copy next to the Jacobian
   int off_dt, off_nc, n_nc;
   pfrx_somdec sd;
@@ -131,6 +131,7 @@ struct DevCfg {
   pfrx_plantn pn;
   pfrx_langmuir lg;
   pfrx_cndegas cd;
+  pfrx_calcite_sandbox cs;
   int cn_nrxn, cn_C, cn_N;
   const double *cn_CN, *cn_k, *cn_resp, *cn_inhib;
   const int *cn_nspec, *cn_cid, *cn_nid, *cn_up, *cn_down;

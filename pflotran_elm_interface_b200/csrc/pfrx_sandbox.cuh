@@ -913,6 +913,72 @@ __device__ __forceinline__ void langmuir_react(Cell &s, double tran_dt) {
   s.J(ires_sorb, ires_sorb) = s.J(ires_sorb, ires_sorb) - drate_dsorb;
 }
 
+// ---- CALCITE (reaction_sandbox_calcite.F90:177-365) --------------------------------------
+// two parallel TST pathways: #1 with the mineral's stoichiometry and logK from the kinmnrl tables,
+// #2 written out for Ca++ + HCO3- - H+ with pKeq 1.8487; returns the sum of the two rates
+// [mol/m^3 bulk/s] (rt_auxvar%auxiliary_data)
+template <class Cell>
+__device__ __forceinline__ double calcite_react(Cell &s) {
+  const pfrx_calcite_sandbox &cs = s.cfg.cs;
+  const int m = cs.mineral_id;
+  const double volume = s.vol, molality_to_molarity = s.den_kg * 1.e-3;
+  const double area = s.st.mnrl_area[m * s.st.ld + s.cell], volfrac = s.st.mnrl_volfrac[m * s.st.ld + s.cell];
+  const int p0 = s.cfg.mn_ptr[m], p1 = s.cfg.mn_ptr[m + 1];
+  // reaction path #1
+  double lnQK = -s.mn_logK(m) * PFRX_LOG_TO_LN;
+  if (s.cfg.mn_h2o[m] != 0.0) lnQK = lnQK + s.cfg.mn_h2o[m] * s.ln_act_h2o;
+#pragma unroll 1
+  for (int p = p0; p < p1; p++) lnQK = lnQK + s.cfg.mn_st[p] * s.LNAc(s.cfg.mn_id[p]);
+  double QK = exp(lnQK);
+  double affinity_factor = 1.0 - QK;
+  double sign_ = copysign(1.0, affinity_factor);
+  double rate = 0.0;
+  bool calculate_rate = volfrac > 0.0 || sign_ < 0.0;
+  if (calculate_rate) rate = -area * sign_ * fabs(affinity_factor) * cs.rate_constant1;
+  double aux = rate;
+  rate = rate * volume;
+#pragma unroll 1
+  for (int p = p0; p < p1; p++) s.RES(s.cfg.mn_id[p]) = s.RES(s.cfg.mn_id[p]) + s.cfg.mn_st[p] * rate;
+  if (calculate_rate) {
+    const double drate_dQK = area * cs.rate_constant1 * volume;
+#pragma unroll 1
+    for (int q = p0; q < p1; q++) {
+      const int jcomp = s.cfg.mn_id[q];
+      const double dQK_dmj = s.cfg.mn_st[q] * QK * exp(-log(s.Cc(jcomp))) * molality_to_molarity;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++)
+        s.J(s.cfg.mn_id[p], jcomp) = s.J(s.cfg.mn_id[p], jcomp) + s.cfg.mn_st[p] * drate_dQK * dQK_dmj;
+    }
+  }
+  // reaction path #2
+  const int ih = cs.h_ion_id, ica = cs.calcium_id, ib = cs.bicarbonate_id;
+  lnQK = -1.8487 * PFRX_LOG_TO_LN - s.LNAc(ih) + s.LNAc(ica) + s.LNAc(ib);
+  affinity_factor = 1.0 - exp(lnQK);
+  sign_ = copysign(1.0, affinity_factor);
+  rate = 0.0;
+  calculate_rate = volfrac > 0.0 || sign_ < 0.0;
+  if (calculate_rate) rate = -area * sign_ * fabs(affinity_factor) * cs.rate_constant2;
+  aux = aux + rate;
+  rate = rate * volume;
+  s.RES(ih) = s.RES(ih) - rate;
+  s.RES(ica) = s.RES(ica) + rate;
+  s.RES(ib) = s.RES(ib) + rate;
+  if (calculate_rate) {
+    const double drate_dQK = area * cs.rate_constant2 * volume;
+    const int jc[3] = {ih, ica, ib};
+    const double sj[3] = {-1.0, 1.0, 1.0};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const int jcomp = jc[q];
+      const double dQK_dmj = sj[q] * exp(lnQK - log(s.Cc(jcomp))) * molality_to_molarity;
+      s.J(ih, jcomp) = s.J(ih, jcomp) - drate_dQK * dQK_dmj;
+      s.J(ica, jcomp) = s.J(ica, jcomp) + drate_dQK * dQK_dmj;
+      s.J(ib, jcomp) = s.J(ib, jcomp) + drate_dQK * dQK_dmj;
+    }
+  }
+  return aux;
+}
+
 // ---- CNDEGAS (reaction_sandbox_cndegas.F90:216-546; solubilities :548-787) -------------
 // rgas of the solubility routines is a default-real literal in the reference (0.08205601
 // without d0): the single-precision value

@@ -1102,6 +1102,11 @@ struct CellT {
             if (i == cfg.cd.proton_id) lgp = lngam[i];
           pfrx_sbx::cndegas_react(*this, lgp);
         }
+      } else if (kind == PFRX_SANDBOX_CALCITE) {
+        if (cfg.has_cs) {
+          const double aux = pfrx_sbx::calcite_react(*this);
+          if (st.sandbox_aux) st.sandbox_aux[cell] = aux;
+        }
       }
     }
   }
@@ -1436,6 +1441,12 @@ struct CellT {
           st.kinmr[ix] = (st.kinmr[ix] + kdt * cfg.mr_frac[k] * seq) / (1.0 + kdt);
         }
       }
+    }
+    if (cfg.has_cs && st.sandbox_aux) {  // CalciteUpdateKineticState (reaction_sandbox_calcite.F90:369-410)
+      const int m = cfg.cs.mineral_id;
+      double vf = st.mnrl_volfrac[m * st.ld + cell] + st.sandbox_aux[cell] * cfg.mn_vol[m] * dt;
+      if (vf < 0.0) vf = 0.0;
+      st.mnrl_volfrac[m * st.ld + cell] = vf;
     }
     if (cfg.nsbx > 0) upd = true;  // any sandbox => true (reaction.F90:5965)
     return upd;

@@ -17,6 +17,7 @@ struct DevState {
   const double *elm_plantndemand;
   double *eqionx_ref, *eqionx_conc;
   const double *pres;  // liquid pressure (CNDEGAS sandbox, optional)
+  double *sandbox_aux; // rt_auxvar%auxiliary_data of the CALCITE sandbox
 };
 
 // shard summary accumulated with atomics, one set per warp

@@ -138,6 +138,8 @@ def signature(cfg: abi.ReactionConfig) -> int:
         parts.append(struct.pack("<2i3d", lg.aq_id, lg.sorb_id, lg.k_kinetic, lg.k_equilibrium, lg.s_max))
     if c.cndegas:
         parts.append(bytes(cfg.cndegas))
+    if c.calcite:
+        parts.append(bytes(cfg.calcite))
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
         if c.nsandbox:
@@ -205,6 +207,8 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "general / radioactive decay / immobile decay / microbial reactions"
     if c.cndegas:
         return False, "CNDEGAS sandbox"
+    if c.calcite:
+        return False, "CALCITE sandbox"
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         if os.environ.get("PFRX_SPEC_NO_ELMCN"):
             return False, "ELM-CN sandboxes disabled by PFRX_SPEC_NO_ELMCN"

@@ -116,7 +116,7 @@ def _mix_fill(state: abi.HostState, waters, weights: np.ndarray, rng, jitter: fl
 
 
 def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED, prefactors: bool = False,
-                   anisothermal: bool = False, no_geochemistry: bool = False) -> Workload:
+                   anisothermal: bool = False, no_geochemistry: bool = False, sandbox: bool = False) -> Workload:
     """C2: 10k-cell calcite column, post-transport totals on a logistic front.
 
     ``prefactors``: the calcite rate as the sum of three parallel mechanisms in the
@@ -125,7 +125,15 @@ def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED
     CO2(aq) with an attenuation denominator, and a species-free term with an activation
     energy."""
     rng = np.random.default_rng(seed)
-    dk = chem.read_deck(C2_DECK)
+    deck = C2_DECK
+    if sandbox:
+        # the chemistry of regression_tests/default/reaction_sandbox/reaction_sandbox_calcite.in: the mineral's
+        # own rate constant zero, the CALCITE sandbox's two parallel pathways in its place
+        deck = deck.replace("      RATE_CONSTANT 1.d-6 mol/m^2-sec\n", "      RATE_CONSTANT 0.d0\n")
+        deck = deck.replace("  DATABASE ./calcite.dat\n", "  REACTION_SANDBOX\n    CALCITE\n      RATE_CONSTANT1 5.d-7\n"
+                            "      RATE_CONSTANT2 5.d-7\n    /\n  /\n  DATABASE ./calcite.dat\n")
+        assert "CALCITE" in deck and "RATE_CONSTANT 0.d0" in deck
+    dk = chem.read_deck(deck)
     if prefactors:
         # prefactors == "primary": the second mechanism in primary species only (its analytic
         # Jacobian is then a true derivative and can be checked by finite differences)
@@ -162,6 +170,9 @@ def calcite_column(ncell: int = 10000, tran_dt: float = 3600.0, seed: int = SEED
         return Workload("c2_calcite_anisothermal", cfg, st, tran_dt, net, "C2 with logK(T), cells at 5-60 C")
     if no_geochemistry:
         return Workload("c2_calcite_no_geochemistry", cfg, st, tran_dt, net, "C2 with use_full_geochemistry = 0")
+    if sandbox:
+        st["mnrl_volfrac"][0, ::5] = 0.0      # cells without the mineral: dissolution switched off, precipitation not
+        return Workload("c2_calcite_sandbox", cfg, st, tran_dt, net, "C2 with the CALCITE reaction sandbox")
     return Workload("c2_calcite_column", cfg, st, tran_dt, net,
                     "H+/HCO3-/Ca++ + 6 complexes + kinetic Calcite, logistic inlet/background front")
 
@@ -970,6 +981,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c3sf": (hanford, {"variant": "base", "inner_newton_sites": True}),
         "c2t": (calcite_column, {"anisothermal": True}),
         "c2ng": (calcite_column, {"no_geochemistry": True}),
+        "c2sb": (calcite_column, {"sandbox": True}),
         "c4": (clm_cn, {}),
         "c4s": (elm_cn, {}),
         "c4se": (elm_cn, {"elm": True}),

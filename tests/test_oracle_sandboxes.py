@@ -300,3 +300,43 @@ def test_cndegas_equilibrium_is_a_fixed_point(name):
         st = wl.state.copy()
         r2, _ = orc.reaction(wl.cfg, st, cell, wl.tran_dt)
         assert r2[ih] != 0.0
+
+
+def test_calcite_sandbox_is_the_mineral_rate_law_it_splits():
+    """CalciteEvaluate (reaction_sandbox_calcite.F90:177-365): the deck of the reference's regression test
+    (default/reaction_sandbox/reaction_sandbox_calcite.in) sets RATE_CONSTANT1 = RATE_CONSTANT2 = 5e-7 "so that
+    the parallel rate pathways sum to 1.d-6", the rate constant of the mineral in the calcite decks whose golds
+    pin RKineticMineral (test_oracle_golden.py::test_calcite_kinetics_gold).  With pathway 2's hard-wired
+    pKeq 1.8487 equal to the database's, a step through the sandbox must land where the step through
+    MINERAL_KINETICS lands -- concentrations, volume fractions (CalciteUpdateKineticState vs
+    MineralUpdateKineticState) and iteration counts -- and the rate it leaves in rt_auxvar%auxiliary_data
+    must be the mineral rate of the other run."""
+    n = 1500
+    for dt in (3600.0, 30 * 86400.0):
+        sb, mk = W.by_name("c2sb", ncell=n, tran_dt=dt), W.by_name("c2", ncell=n, tran_dt=dt)
+        assert sb.cfg.c.calcite and sb.cfg.arrays["kinmnrl_rate_constant"][0] == 0.0
+        mk.state.a["mnrl_volfrac"][...] = sb.state.a["mnrl_volfrac"]      # every fifth cell has no mineral
+        ra, rb = orc.rstep(sb.cfg, sb.state, dt, 4), orc.rstep(mk.cfg, mk.state, dt, 4)
+        assert ra.as_dict() == rb.as_dict()
+        for f in ("pri_molal", "total", "sec_molal"):
+            np.testing.assert_allclose(sb.state.a[f], mk.state.a[f], rtol=1e-12, atol=1e-300, err_msg=f)
+        # (a volume fraction that has all but dissolved is a difference of nearly equal numbers)
+        np.testing.assert_allclose(sb.state.a["mnrl_volfrac"], mk.state.a["mnrl_volfrac"], rtol=1e-12, atol=1e-18)
+        np.testing.assert_allclose(sb.state.a["sandbox_aux"][0], mk.state.a["mnrl_rate"][0], rtol=1e-9, atol=1e-22)
+        assert np.abs(sb.state.a["mnrl_rate"]).max() == 0.0 and np.abs(sb.state.a["sandbox_aux"]).max() > 0.0
+
+
+def test_calcite_sandbox_jacobian_vs_finite_differences():
+    wl = W.by_name("c2sb", ncell=16)
+    cfg, dt = wl.cfg, wl.tran_dt
+    n = cfg.ncomp
+    for cell in range(16):
+        r0, J = orc.reaction(cfg, wl.state.copy(), cell, dt)
+        # the reference's derivative carries the factor kg water / L water (dQK_dmj * molality_to_molarity,
+        # reaction_sandbox_calcite.F90:262-264, as RKineticMineral's does): d Res / d molality times den_kg * 1e-3
+        fd = _fd_jacobian(wl, cell, dt, np.arange(n), np.arange(n)) * (wl.state.a["den_kg"][0, cell] * 1.0e-3)
+        scale = np.abs(J).max()
+        if scale == 0.0:       # no mineral and undersaturated: the sandbox is switched off
+            assert np.abs(fd).max() == 0.0
+            continue
+        assert np.abs(J - fd).max() <= 2.0e-5 * scale, (cell, J, fd)
