@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 7
+#define PFRX_ABI_VERSION 8
 
 /* error classes */
 #define PFRX_OK 0
@@ -96,7 +96,8 @@ extern "C" {
 #define PFRX_SANDBOX_LANGMUIR 6
 #define PFRX_SANDBOX_CNDEGAS 7
 #define PFRX_SANDBOX_CALCITE 8
-#define PFRX_MAX_SANDBOXES 8
+#define PFRX_SANDBOX_RADON 9
+#define PFRX_MAX_SANDBOXES 10
 /* reaction_microbial_aux.F90:14-22 */
 #define PFRX_MICROBIAL_MOLALITY 1
 #define PFRX_MICROBIAL_ACTIVITY 2
@@ -232,6 +233,14 @@ typedef struct pfrx_calcite_sandbox {
   int32_t h_ion_id, calcium_id, bicarbonate_id; /* primary ids */
   double rate_constant1, rate_constant2;  /* mol/m^2/s */
 } pfrx_calcite_sandbox;
+
+/* RADON sandbox (reaction_sandbox_radon.F90:150-188): zero-order generation of a species in proportion
+ * to the volume fraction of a mineral */
+typedef struct pfrx_radon {
+  int32_t species_id;                     /* primary id (Rn(aq)) */
+  int32_t mineral_id;                     /* kinetic-mineral index */
+  double radon_generation_rate;           /* mol/m^3 mineral/s */
+} pfrx_radon;
 
 /*
  * Flattened, read-only reaction description: the subset of
@@ -385,8 +394,9 @@ typedef struct pfrx_config {
   const pfrx_langmuir *langmuir; /* reaction_sandbox_langmu.F90:183-330   */
   const pfrx_cndegas *cndegas;   /* reaction_sandbox_cndegas.F90:216-546  */
   const pfrx_calcite_sandbox *calcite; /* reaction_sandbox_calcite.F90:177-410 */
+  const pfrx_radon *radon;       /* reaction_sandbox_radon.F90:150-188    */
   /* evaluation order of the sandboxes (PFRX_SANDBOX_*); NULL => the order
-   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR, CNDEGAS, CALCITE */
+   * CLM-CN, SOMDEC, NITRIF, DENITR, PLANTN, LANGMUIR, CNDEGAS, CALCITE, RADON */
   int32_t nsandbox;
   const int32_t *sandbox_list;
   /* 1 => the behaviour of a reference built with -DELM_PFLOTRAN in BGC-only
@@ -446,6 +456,18 @@ typedef struct pfrx_config {
   const double *microbial_inhibition_C2;
   const int32_t *microbial_biomassid;        /* [n] 0 none, k+1 aqueous species k, -(k+1) immobile species k */
   const double *microbial_biomass_yield;     /* [n] */
+  /* active gas species, RTotalGas (reaction_gas.F90:87-174): a gas phase that holds the components in
+   * equilibrium with the water -- partial pressure [bar] = exp(-logK ln10 + h2o ln a_w + sum nu ln a_i),
+   * ideal-gas concentration added to rt_auxvar%total(:,2); its accumulation (reaction.F90:5761-5769,
+   * 5838-5846) and its share of a decaying inventory (:5243-5296) follow.  Thread-per-cell kernel only. */
+  int32_t nactive_gas;
+  int32_t pad_gas_;
+  const int32_t *acteq_ptr;          /* [nactive_gas+1] CSR into acteq_specid / _stoich          */
+  const int32_t *acteq_specid;       /* primary ids                                             */
+  const double *acteq_stoich;
+  const double *acteq_h2ostoich;     /* [nactive_gas]                                           */
+  const double *acteq_logK;          /* [nactive_gas] at the reference temperature              */
+  const double *acteq_logK_coef;     /* [nactive_gas][5] or NULL                                */
 } pfrx_config;
 
 /*
@@ -520,6 +542,13 @@ typedef struct pfrx_state {
   /* io [1] when the CALCITE sandbox is configured: rt_auxvar%auxiliary_data, the sandbox's rate of the
    * latest evaluation [mol/m^3 bulk/s] (read by its kinetic-state update) */
   double *sandbox_aux;
+  /* active gas phase (pfrx_config.nactive_gas > 0, else NULL): gas saturation global_auxvar%sat(2), in [1];
+   * rt_auxvar%total(:,2) [mol/L gas], io [naqcomp] -- the fixed accumulation of a step reads the value the
+   * latest RTotal left, as in the reference ("still need code to overwrite other phases",
+   * reaction.F90:3832); rt_auxvar%gas_pp [bar], out [nactive_gas] */
+  const double *sat_gas;
+  double *total_gas;
+  double *gas_pp;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

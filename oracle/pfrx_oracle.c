@@ -61,6 +61,10 @@ typedef struct {
   double den_kg, sat, temp, porosity, volume, soil_particle_density;
   double pres; /* liquid pressure, CNDEGAS only */
   double sandbox_aux; /* rt_auxvar%auxiliary_data of the CALCITE sandbox */
+  /* active gas phase */
+  int ngas;
+  double sat_gas;
+  double *total_gas, *dtotal_gas, *gas_pp, *acteq_logK;
   /* ELM per-cell scalars (elm_pflotran builds) */
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
@@ -85,7 +89,8 @@ static size_t cell_doubles(const pfrx_config *cfg) {
   size_t naq = cfg->naqcomp, nim = cfg->nimcomp, nc = cfg->neqcplx;
   size_t nk = cfg->nkinmnrl, nr = cfg->nsrfcplxrxn, ns = cfg->nsrfcplx;
   size_t nsd = cfg->somdec ? (size_t)(cfg->somdec->nrxn + cfg->somdec->downstream_ptr[cfg->somdec->nrxn]) : 0;
-  return 4 * naq + nim + 3 * nc + 4 * nk + nr + 2 * ns + naq + 2 * naq * naq +
+  return 4 * naq + nim + 3 * nc + 4 * nk + nr + 2 * ns + naq + 2 * naq * naq + naq + naq * naq +
+         2 * (size_t)(cfg->nactive_gas > 0 ? cfg->nactive_gas : 0) +
          mr_rows(cfg) + nsd + (cfg->neqionxrxn > 0 ? cfg->neqionxrxn + cfg->eqionx_ptr[cfg->neqionxrxn] : 0) + 64;
 }
 
@@ -128,7 +133,13 @@ static void cell_init(cell_t *c, const pfrx_config *cfg) {
   c->nionxcat = cfg->neqionxrxn > 0 ? cfg->eqionx_ptr[cfg->neqionxrxn] : 0;
   TAKE(eqionx_ref, c->nionx);
   TAKE(eqionx_conc, c->nionxcat);
+  c->ngas = cfg->nactive_gas > 0 ? cfg->nactive_gas : 0;
+  TAKE(total_gas, c->naq);
+  TAKE(dtotal_gas, c->naq * c->naq);
+  TAKE(gas_pp, c->ngas);
+  TAKE(acteq_logK, c->ngas);
 #undef TAKE
+  if (c->ngas) memcpy(c->acteq_logK, cfg->acteq_logK, sizeof(double) * c->ngas);
   if (c->ncplx) memcpy(c->eqcplx_logK, cfg->eqcplx_logK, sizeof(double) * c->ncplx);
   if (c->nkin) memcpy(c->kinmnrl_logK, cfg->kinmnrl_logK, sizeof(double) * c->nkin);
   if (c->nsrfcplx) memcpy(c->srfcplx_logK, cfg->srfcplx_logK, sizeof(double) * c->nsrfcplx);
@@ -180,6 +191,11 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->soil_particle_density = st->soil_particle_density ? LD(st->soil_particle_density, 0) : 0.0;
   c->pres = st->pres ? LD(st->pres, 0) : 101325.0;
   c->sandbox_aux = st->sandbox_aux ? LD(st->sandbox_aux, 0) : 0.0;
+  c->sat_gas = st->sat_gas ? LD(st->sat_gas, 0) : 0.0;
+  if (c->ngas) {
+    for (k = 0; k < c->naq; k++) c->total_gas[k] = st->total_gas ? LD(st->total_gas, k) : 0.0;
+    for (k = 0; k < c->ngas; k++) c->gas_pp[k] = st->gas_pp ? LD(st->gas_pp, k) : 0.0;
+  }
   c->elm_w = st->elm_w_scalar ? LD(st->elm_w_scalar, 0) : 1.0;
   c->elm_o = st->elm_o_scalar ? LD(st->elm_o_scalar, 0) : 1.0;
   c->elm_t = st->elm_t_scalar ? LD(st->elm_t_scalar, 0) : 1.0;
@@ -220,6 +236,12 @@ static void cell_scatter(const cell_t *c, const pfrx_state *st, int64_t ic) {
   if (st->eqionx_conc)
     for (k = 0; k < c->nionxcat; k++) LD(st->eqionx_conc, k) = c->eqionx_conc[k];
   if (st->sandbox_aux) LD(st->sandbox_aux, 0) = c->sandbox_aux;
+  if (c->ngas) {
+    if (st->total_gas)
+      for (k = 0; k < c->naq; k++) LD(st->total_gas, k) = c->total_gas[k];
+    if (st->gas_pp)
+      for (k = 0; k < c->ngas; k++) LD(st->gas_pp, k) = c->gas_pp[k];
+  }
 }
 
 /* ------------------------------------------------------------------------ */
@@ -319,6 +341,7 @@ static void update_temp_dependent_coefs(cell_t *c, const pfrx_config *cfg) {
   if (cfg->eqcplx_logKcoef) interpolate_logK(CFGP(cfg->eqcplx_logKcoef), c->eqcplx_logK, c->temp, c->ncplx);
   if (cfg->kinmnrl_logKcoef) interpolate_logK(CFGP(cfg->kinmnrl_logKcoef), c->kinmnrl_logK, c->temp, c->nkin);
   if (cfg->srfcplx_logKcoef) interpolate_logK(CFGP(cfg->srfcplx_logKcoef), c->srfcplx_logK, c->temp, c->nsrfcplx);
+  if (c->ngas && cfg->acteq_logK_coef) interpolate_logK(CFGP(cfg->acteq_logK_coef), c->acteq_logK, c->temp, c->ngas);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -810,12 +833,54 @@ static void r_total_sorb(cell_t *c, const pfrx_config *cfg) {
   if (cfg->neqkdrxn > 0) r_total_sorb_kd(c, cfg);
 }
 
+/* reaction_gas.F90:304-323 RGasConcentration [mol/m^3] */
+static double r_gas_concentration(double gas_pp, double temperature) {
+  return gas_pp * 1.e5 / (IDEAL_GAS_CONSTANT * (temperature + 273.15));
+}
+
+/* reaction_gas.F90:87-174 RTotalGas */
+static void r_total_gas(cell_t *c, const pfrx_config *cfg) {
+  int i, j, igas, icomp, jcomp, naq = c->naq;
+  double ln_conc[PFRX_MAX_NCOMP * 4], ln_act[PFRX_MAX_NCOMP * 4];
+  double lnQK, tempreal, gas_concentration;
+  for (i = 0; i < naq; i++) c->total_gas[i] = 0.0;
+  for (i = 0; i < naq; i++) {
+    ln_conc[i] = log(c->pri_molal[i]);
+    ln_act[i] = ln_conc[i] + log(c->pri_act_coef[i]);
+  }
+  for (i = 0; i < naq * naq; i++) c->dtotal_gas[i] = 0.0;
+  for (igas = 0; igas < c->ngas; igas++) {
+    int p0 = cfg->acteq_ptr[igas], p1 = cfg->acteq_ptr[igas + 1];
+    lnQK = -c->acteq_logK[igas] * LOG_TO_LN;
+    if (cfg->acteq_h2ostoich[igas] != 0.0) lnQK = lnQK + cfg->acteq_h2ostoich[igas] * c->ln_act_h2o;
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->acteq_specid[i];
+      lnQK = lnQK + cfg->acteq_stoich[i] * ln_act[icomp];
+    }
+    c->gas_pp[igas] = exp(lnQK);
+    gas_concentration = r_gas_concentration(c->gas_pp[igas], c->temp) * 1.e-3;
+    for (i = p0; i < p1; i++) {
+      icomp = cfg->acteq_specid[i];
+      c->total_gas[icomp] = c->total_gas[icomp] + cfg->acteq_stoich[i] * gas_concentration;
+    }
+    for (j = p0; j < p1; j++) {
+      jcomp = cfg->acteq_specid[j];
+      tempreal = cfg->acteq_stoich[j] * r_gas_concentration(exp(lnQK - ln_conc[jcomp]), c->temp) * 1.e-3;
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->acteq_specid[i];
+        c->dtotal_gas[icomp + jcomp * naq] = c->dtotal_gas[icomp + jcomp * naq] + cfg->acteq_stoich[i] * tempreal;
+      }
+    }
+  }
+}
+
 /* reaction.F90:4618-4661 RTotal == reaction.F90:5606 RTAuxVarCompute */
 static void rt_auxvar_compute(cell_t *c, const pfrx_config *cfg) {
   int i;
   for (i = 0; i < c->naq; i++) c->total[i] = 0.0;
   if (c->naq > 0) r_total_aqueous(c, cfg);
   if (neqsorb(cfg) > 0) r_total_sorb(c, cfg);
+  if (c->ngas > 0) r_total_gas(c, cfg);
 }
 
 /* reaction.F90:5710-5771 RTAccumulation */
@@ -827,6 +892,10 @@ static void rt_accumulation(const cell_t *c, const pfrx_config *cfg, double *Res
   psv_t = c->porosity * c->sat * 1000.0 * c->volume;
   for (i = 0; i < c->naq; i++) Res[i] = psv_t * c->total[i];
   for (i = 0; i < c->nim; i++) Res[c->naq + i] = Res[c->naq + i] + c->immobile[i] * c->volume;
+  if (c->ngas > 0) { /* :5761-5769 */
+    psv_t = c->porosity * c->sat_gas * 1000.0 * c->volume;
+    for (i = 0; i < c->naq; i++) Res[i] = Res[i] + psv_t * c->total_gas[i];
+  }
 }
 
 /* reaction.F90:5775-5848 RTAccumulationDerivative; J(i,j) at [i + j*n] */
@@ -842,6 +911,11 @@ static void rt_accumulation_derivative(const cell_t *c, const pfrx_config *cfg, 
   for (j = 0; j < naq; j++)
     for (i = 0; i < naq; i++) J[i + j * n] = c->dtotal[i + j * naq] * psvd_t;
   for (i = 0; i < c->nim; i++) J[(naq + i) + (naq + i) * n] = c->volume / tran_dt;
+  if (c->ngas > 0) { /* :5838-5846 */
+    psvd_t = c->porosity * c->sat_gas * 1000.0 * c->volume / tran_dt;
+    for (j = 0; j < naq; j++)
+      for (i = 0; i < naq; i++) J[i + j * n] = J[i + j * n] + c->dtotal_gas[i + j * naq] * psvd_t;
+  }
 }
 
 /* reaction.F90:5144-5172 / :5177-5207 */
@@ -2550,17 +2624,18 @@ static void calcite_evaluate(cell_t *c, const pfrx_config *cfg, double *Residual
 
 static int n_sandboxes(const pfrx_config *cfg) {
   return (cfg->clmcn_nrxn > 0) + (cfg->somdec != NULL) + (cfg->nitrif != NULL) + (cfg->denitr != NULL) +
-         (cfg->plantn != NULL) + (cfg->langmuir != NULL) + (cfg->cndegas != NULL) + (cfg->calcite != NULL);
+         (cfg->plantn != NULL) + (cfg->langmuir != NULL) + (cfg->cndegas != NULL) + (cfg->calcite != NULL) +
+         (cfg->radon != NULL);
 }
 
 /* reaction_sandbox.F90:294-330  RSandboxEvaluate: walk the list in deck order */
 static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt, double *Res, double *Jac,
                                int derivative) {
-  static const int32_t default_order[8] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
+  static const int32_t default_order[9] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC,  PFRX_SANDBOX_NITRIF,
                                            PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
-                                           PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE};
+                                           PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE, PFRX_SANDBOX_RADON};
   const int32_t *order = cfg->sandbox_list ? cfg->sandbox_list : default_order;
-  int ns = cfg->sandbox_list ? cfg->nsandbox : 8, k;
+  int ns = cfg->sandbox_list ? cfg->nsandbox : 9, k;
   for (k = 0; k < ns; k++) {
     switch (order[k]) {
       case PFRX_SANDBOX_CLM_CN:
@@ -2587,6 +2662,12 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
       case PFRX_SANDBOX_CALCITE:
         if (cfg->calcite) calcite_evaluate(c, cfg, Res, Jac, derivative);
         break;
+      case PFRX_SANDBOX_RADON: /* reaction_sandbox_radon.F90:150-188 RadonEvaluate: no derivative */
+        if (cfg->radon)
+          Res[cfg->radon->species_id] = Res[cfg->radon->species_id] -
+                                        (1.0) * cfg->radon->radon_generation_rate *
+                                            c->mnrl_volfrac[cfg->radon->mineral_id] * c->volume;
+        break;
       default:
         break;
     }
@@ -2594,16 +2675,18 @@ static void r_sandbox_evaluate(cell_t *c, const pfrx_config *cfg, double tran_dt
 }
 
 /* reaction.F90:5211-5311  RRadioactiveDecay: one parent, aqueous + sorbed inventory, any
- * number of daughters (no active gas phase here) */
+ * number of daughters */
 static void r_radioactive_decay(cell_t *c, const pfrx_config *cfg, double *Res, double *Jac, int compute_derivative) {
   int naq = c->naq, n = c->n, irxn, i, j;
   double L_pore = c->porosity * c->volume * 1.e3;
   double L_water = L_pore * c->sat;
+  double L_gas = L_pore * c->sat_gas;
   int have_sorb = neqsorb(cfg) > 0;
   for (irxn = 0; irxn < cfg->nradiodecay_rxn; irxn++) {
     int p0 = cfg->radiodecay_ptr[irxn], p1 = cfg->radiodecay_ptr[irxn + 1];
     int icomp = cfg->radiodecay_forward_specid[irxn], jcomp;
     double sum = c->total[icomp] * L_water, rate, tempreal;
+    if (c->ngas > 0) sum = sum + c->total_gas[icomp] * L_gas;
     if (have_sorb) sum = sum + c->total_sorb_eq[icomp] * c->volume;
     rate = sum * cfg->radiodecay_kf[irxn];
     for (i = p0; i < p1; i++) {
@@ -2618,6 +2701,14 @@ static void r_radioactive_decay(cell_t *c, const pfrx_config *cfg, double *Res, 
       for (j = 0; j < naq; j++)
         Jac[icomp + j * n] =
             Jac[icomp + j * n] + tempreal * cfg->radiodecay_stoich[i] * c->dtotal[jcomp + j * naq] * L_water;
+    }
+    if (c->ngas > 0) {
+      for (i = p0; i < p1; i++) {
+        icomp = cfg->radiodecay_specid[i];
+        for (j = 0; j < naq; j++)
+          Jac[icomp + j * n] =
+              Jac[icomp + j * n] + tempreal * cfg->radiodecay_stoich[i] * c->dtotal_gas[jcomp + j * naq] * L_gas;
+      }
     }
     if (have_sorb) {
       for (i = p0; i < p1; i++) {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 7
+PFRX_ABI_VERSION = 8
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -143,6 +143,7 @@ class PfrxConfig(C.Structure):
         ("langmuir", C.c_void_p),
         ("cndegas", C.c_void_p),
         ("calcite", C.c_void_p),
+        ("radon", C.c_void_p),
         ("nsandbox", C.c_int32),
         ("sandbox_list", c_int32_p),
         ("elm_pflotran", C.c_int32),
@@ -185,12 +186,21 @@ class PfrxConfig(C.Structure):
         ("microbial_inhibition_C2", c_double_p),
         ("microbial_biomassid", c_int32_p),
         ("microbial_biomass_yield", c_double_p),
+        ("nactive_gas", C.c_int32),
+        ("pad_gas_", C.c_int32),
+        ("acteq_ptr", c_int32_p),
+        ("acteq_specid", c_int32_p),
+        ("acteq_stoich", c_double_p),
+        ("acteq_h2ostoich", c_double_p),
+        ("acteq_logK", c_double_p),
+        ("acteq_logK_coef", c_double_p),
     ]
 
 
 SANDBOX_CLM_CN, SANDBOX_SOMDEC, SANDBOX_NITRIF, SANDBOX_DENITR, SANDBOX_PLANTN, SANDBOX_LANGMUIR = 1, 2, 3, 4, 5, 6
 SANDBOX_CNDEGAS = 7
 SANDBOX_CALCITE = 8
+SANDBOX_RADON = 9
 SPEC_AQUEOUS, SPEC_IMMOBILE = 0, 2
 
 
@@ -291,6 +301,10 @@ class PfrxCalciteSandbox(C.Structure):
                 + [(f, C.c_double) for f in ("rate_constant1", "rate_constant2")])
 
 
+class PfrxRadon(C.Structure):
+    _fields_ = [("species_id", C.c_int32), ("mineral_id", C.c_int32), ("radon_generation_rate", C.c_double)]
+
+
 class PfrxDenitr(C.Structure):
     _fields_ = ([(f, C.c_int32) for f in ("no3_id", "n2_id", "n2o_id", "ngasdeni_id")]
                 + [(f, C.c_double) for f in ("half_saturation", "k_deni_max", "x0eps")])
@@ -306,13 +320,15 @@ STATE_DOUBLE_FIELDS = [
 # elm_pflotran, NULL otherwise
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
                     "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc",
-                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres", "sandbox_aux"]
+                    "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres", "sandbox_aux",
+                    "sat_gas", "total_gas", "gas_pp"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
     "total", "pri_molal", "immobile", "pri_act_coef", "sec_act_coef", "sec_molal", "ln_act_h2o",
     "mnrl_volfrac", "mnrl_rate", "srfcplxrxn_free_site_conc", "eqsrfcplx_conc", "total_sorb_eq",
     "kinmr_total_sorb", "somdec_nc", "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "sandbox_aux",
+    "total_gas", "gas_pp",
 ]
 STATE_RESULT_FIELDS = ["num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 
@@ -602,6 +618,18 @@ class ReactionConfig:
                 c.microbial_activation_energy = _dp(self._keep("microbial_activation_energy",
                                                                _f64(mb["activation_energy"])))
 
+        # active gas species (RTotalGas)
+        ag = getattr(net, "active_gas", None)
+        if ag:
+            c.nactive_gas = len(ag["logK"])
+            c.acteq_ptr = _ip(self._keep("acteq_ptr", _i32(ag["ptr"])))
+            c.acteq_specid = _ip(self._keep("acteq_specid", _i32(ag["specid"])))
+            c.acteq_stoich = _dp(self._keep("acteq_stoich", _f64(ag["stoich"])))
+            c.acteq_h2ostoich = _dp(self._keep("acteq_h2ostoich", _f64(ag["h2ostoich"])))
+            c.acteq_logK = _dp(self._keep("acteq_logK", _f64(ag["logK"])))
+            if not net.use_isothermal:
+                c.acteq_logK_coef = _dp(self._keep("acteq_logK_coef", _f64(ag["logK_coef"])))
+
         # CLM-CN
         cc = net.clmcn
         if cc is not None:
@@ -628,7 +656,8 @@ class ReactionConfig:
         for kind in getattr(net, "sandbox_order", []):
             order.append({"CLM-CN": SANDBOX_CLM_CN, "SOMDECOMP": SANDBOX_SOMDEC, "NITRIFICATION": SANDBOX_NITRIF,
                           "DENITRIFICATION": SANDBOX_DENITR, "PLANTN": SANDBOX_PLANTN,
-                          "LANGMUIR": SANDBOX_LANGMUIR, "CNDEGAS": SANDBOX_CNDEGAS, "CALCITE": SANDBOX_CALCITE}[kind])
+                          "LANGMUIR": SANDBOX_LANGMUIR, "CNDEGAS": SANDBOX_CNDEGAS, "CALCITE": SANDBOX_CALCITE,
+                          "RADON": SANDBOX_RADON}[kind])
         if order:
             c.nsandbox = len(order)
             c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
@@ -686,6 +715,13 @@ class ReactionConfig:
                 setattr(o, k, v)
             self.calcite = o
             c.calcite = C.cast(C.pointer(o), C.c_void_p)
+        rn = getattr(net, "radon", None)
+        if rn is not None:
+            o = PfrxRadon()
+            for k, v in rn.items():
+                setattr(o, k, v)
+            self.radon = o
+            c.radon = C.cast(C.pointer(o), C.c_void_p)
 
     # ------------------------------------------------------------------ #
     @classmethod
@@ -699,7 +735,7 @@ class ReactionConfig:
         self.arrays = {}
         structs = {"config": PfrxConfig, "somdec": PfrxSomdec, "nitrif": PfrxNitrif, "denitr": PfrxDenitr,
                    "plantn": PfrxPlantn, "langmuir": PfrxLangmuir, "cndegas": PfrxCndegas,
-                   "calcite": PfrxCalciteSandbox}
+                   "calcite": PfrxCalciteSandbox, "radon": PfrxRadon}
         prefix = {"c": ("", None), "sd": ("somdec_", "somdec"), "nt": ("nitrif_", "nitrif"), "dn": ("denitr_", "denitr"),
                   "pn": ("plantn_", "plantn"), "lg": ("langmuir_", "langmuir")}
         objs = {}
@@ -728,7 +764,7 @@ class ReactionConfig:
                 elif w[0] == "signature":
                     sig = int(w[1], 16)
         self.c = objs["config"]
-        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir", "cndegas", "calcite"):
+        for k in ("somdec", "nitrif", "denitr", "plantn", "langmuir", "cndegas", "calcite", "radon"):
             if k in objs:
                 setattr(self, k, objs[k])
                 setattr(self.c, k, C.cast(C.pointer(objs[k]), C.c_void_p))
@@ -775,6 +811,9 @@ class ReactionConfig:
             "eqionx_conc": int(self.arrays["eqionx_ptr"][c.neqionxrxn]) if c.neqionxrxn else 0,
             "pres": 1 if (getattr(self, "cndegas", None) is not None and self.cndegas.cell_state_mode >= 1) else 0,
             "sandbox_aux": 1 if getattr(self, "calcite", None) is not None else 0,
+            "sat_gas": 1 if c.nactive_gas > 0 else 0,
+            "total_gas": c.naqcomp if c.nactive_gas > 0 else 0,
+            "gas_pp": max(c.nactive_gas, 0),
             "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
                           if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,

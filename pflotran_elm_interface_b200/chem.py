@@ -343,6 +343,8 @@ class Chemistry:
     secondary: List[str] = field(default_factory=list)
     immobile: List[str] = field(default_factory=list)
     gases: List[str] = field(default_factory=list)
+    active_gases: List[str] = field(default_factory=list)   # ACTIVE_GAS_SPECIES (RTotalGas)
+    radon: Optional[dict] = None
     decoupled: List[str] = field(default_factory=list)
     minerals: List[str] = field(default_factory=list)
     mineral_kinetics: List[MineralKinetics] = field(default_factory=list)
@@ -831,6 +833,24 @@ def _read_langmuir(cur: _Cursor) -> dict:
     return d
 
 
+def _read_radon(cur: _Cursor) -> dict:
+    # RadonReadInput, reaction_sandbox_radon.F90:54-100
+    d: Dict[str, object] = {}
+    for t in cur.block():
+        key = t[0].upper()
+        if key == "SPECIES_NAME":
+            d["species_name"] = t[1]
+        elif key == "MINERAL_NAME":
+            d["mineral_name"] = t[1]
+        elif key == "RADON_GENERATION_RATE":
+            d["radon_generation_rate"] = _fnum(t[1])
+        else:
+            raise ValueError(f"RADON sandbox keyword {key}")
+    if len(d) != 3:
+        raise ValueError("SPECIES_NAME, MINERAL_NAME and RADON_GENERATION_RATE must be set for REACTION_SANDBOX,RADON")
+    return d
+
+
 def _read_calcite_sandbox(cur: _Cursor) -> dict:
     # CalciteReadInput, reaction_sandbox_calcite.F90:52-104
     d: Dict[str, float] = {}
@@ -997,9 +1017,10 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
         elif key == "IMMOBILE_SPECIES":
             ch.immobile = _read_names(cur)
         elif key in ("GAS_SPECIES", "PASSIVE_GAS_SPECIES", "ACTIVE_GAS_SPECIES"):
+            names = [n for n in _read_names(cur) if n.upper() != "GAS_TRANSPORT_IS_UNVETTED"]
             if key == "ACTIVE_GAS_SPECIES":
-                ch.unsupported.append(key)
-            ch.gases += [n for n in _read_names(cur) if n.upper() != "GAS_TRANSPORT_IS_UNVETTED"]
+                ch.active_gases += names
+            ch.gases += [n for n in names if n not in ch.gases]
         elif key == "DECOUPLED_EQUILIBRIUM_REACTIONS":
             ch.decoupled = _read_names(cur)
         elif key == "MINERALS":
@@ -1060,6 +1081,9 @@ def read_chemistry(cur: _Cursor) -> Chemistry:
                     ch.sandbox_order.append(k2)
                 elif k2 == "CALCITE" and ch.calcite_sandbox is None:
                     ch.calcite_sandbox = _read_calcite_sandbox(cur)
+                    ch.sandbox_order.append(k2)
+                elif k2 == "RADON" and ch.radon is None:
+                    ch.radon = _read_radon(cur)
                     ch.sandbox_order.append(k2)
                 else:
                     ch.unsupported.append("REACTION_SANDBOX," + k2)
@@ -1181,6 +1205,7 @@ class Deck:
     rock_density: List[float] = field(default_factory=list)
     reference_liquid_density: Optional[float] = None
     reference_temperature: float = 25.0
+    reference_saturation: float = 1.0     # option_flow.F90:141
     final_time: float = 0.0
     initial_dt: float = 1.0
     maximum_dt: float = 1.0e20
@@ -1214,6 +1239,8 @@ def read_deck(text: str) -> Deck:
             dk.reference_liquid_density = _fnum(t[1])
         elif key == "REFERENCE_TEMPERATURE":
             dk.reference_temperature = _fnum(t[1])
+        elif key == "REFERENCE_SATURATION":
+            dk.reference_saturation = _fnum(t[1])
         elif key == "EOS" and len(t) > 1 and t[1].upper() == "WATER":
             # EOS WATER / DENSITY CONSTANT rho: without a flow mode the liquid density of every
             # cell is this constant (eos_water.F90 EOSWaterSetDensity('CONSTANT'))
@@ -1897,6 +1924,28 @@ class ReactionNetwork:
             self.calcite_sandbox = {"mineral_id": self.kinmnrl_names.index("Calcite"), "h_ion_id": pri["H+"],
                                     "calcium_id": pri["Ca++"], "bicarbonate_id": pri["HCO3-"],
                                     "rate_constant1": g["rate_constant1"], "rate_constant2": g["rate_constant2"]}
+
+        self.radon = None
+        if self.chem.radon is not None:
+            # RadonSetup, reaction_sandbox_radon.F90:104-146
+            g = self.chem.radon
+            if g["species_name"] not in pri:
+                raise KeyError(f"RADON sandbox: primary species {g['species_name']} not found")
+            if g["mineral_name"] not in self.kinmnrl_names:
+                raise KeyError(f"RADON sandbox: {g['mineral_name']} is not among the kinetic minerals")
+            self.radon = {"species_id": pri[g["species_name"]],
+                          "mineral_id": self.kinmnrl_names.index(g["mineral_name"]),
+                          "radon_generation_rate": g["radon_generation_rate"]}
+
+        # active gas species: the reactions of the chosen gases in the basis of the primaries
+        # (reaction_database.F90: gas%acteq*), read by RTotalGas
+        self.active_gas = None
+        if self.chem.active_gases:
+            rx = [self.gas_rxn[n] for n in self.chem.active_gases]
+            ptr, ids, st = self.csr(rx)
+            self.active_gas = {"names": list(self.chem.active_gases), "ptr": ptr, "specid": ids, "stoich": st,
+                               "h2ostoich": [r.h2o_stoich for r in rx], "logK": self.logKs(rx),
+                               "logK_coef": self.logK_coefs(rx)}
 
     # -- helpers -------------------------------------------------------------- #
     def csr(self, rxns: Sequence[Rxn]):

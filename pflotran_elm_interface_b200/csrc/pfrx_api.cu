@@ -317,6 +317,15 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
     h = fnv1a(h, c->cndegas, sizeof(*c->cndegas));
   }
   if (c->calcite) h = fnv1a(h, c->calcite, sizeof(*c->calcite));
+  if (c->radon) h = fnv1a(h, c->radon, sizeof(*c->radon));
+  if (c->nactive_gas > 0 && c->acteq_ptr) {  // not covered by the generator either
+    const int ng = c->nactive_gas, nnz = c->acteq_ptr[ng];
+    ADD(c->acteq_ptr, ng + 1)
+    ADD(c->acteq_specid, nnz)
+    ADD(c->acteq_stoich, nnz)
+    ADD(c->acteq_h2ostoich, ng)
+    ADD(c->acteq_logK, ng)
+  }
   if (c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir) {
     int32_t e = c->elm_pflotran ? 1 : 0;
     h = fnv1a(h, &e, sizeof(e));
@@ -372,6 +381,7 @@ static std::string config_dump_text(const pfrx_config *c) {
   if (c->langmuir) hex_struct(out, "langmuir", c->langmuir, sizeof(*c->langmuir));
   if (c->cndegas) hex_struct(out, "cndegas", c->cndegas, sizeof(*c->cndegas));
   if (c->calcite) hex_struct(out, "calcite", c->calcite, sizeof(*c->calcite));
+  if (c->radon) hex_struct(out, "radon", c->radon, sizeof(*c->radon));
   CfgSink sink;
   sink.dump = &out;
   const uint64_t sig = config_walk(c, sink);
@@ -558,7 +568,7 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 33
+#define PFRX_NUM_D 36
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
@@ -569,7 +579,8 @@ static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int r[PFRX_NUM_D] = {c->naqcomp, c->naqcomp, c->nimcomp, c->naqcomp, c->neqcplx, c->neqcplx, 1, c->nkinmnrl,
                        c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, nsorb > 0 ? c->naqcomp : 0,
                        mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc,
-                       (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0, c->calcite ? 1 : 0};
+                       (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0, c->calcite ? 1 : 0,
+                       c->nactive_gas > 0 ? 1 : 0, c->nactive_gas > 0 ? c->naqcomp : 0, c->nactive_gas > 0 ? c->nactive_gas : 0};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -616,6 +627,8 @@ static void tpc_layout(DevCfg &d, int N) {
   d.off_ds = d.need_ds ? take(d.naq * d.naq) : 0;
   d.off_nc = d.n_nc > 0 ? take(d.n_nc) : 0;
   d.off_ix = d.nionx > 0 ? take(d.nionx + d.n_ixcat) : 0;
+  d.off_tg = d.ngas > 0 ? take(d.naq) : 0;
+  d.off_dg = d.ngas > 0 ? take(d.naq * d.naq) : 0;
   d.ws_stride = off | 1;
 }
 
@@ -830,7 +843,21 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
         return set_err(PFRX_E_INVALID, "immobile decay species id out of range%s", "");
   }
   // ELM-CN sandboxes: what the CUDA path covers (everything else is refused, not approximated)
-  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir || c->cndegas || c->calcite;
+  const bool has_sbx3 = c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir || c->cndegas || c->calcite || c->radon;
+  if (c->radon) {
+    if (c->radon->species_id < 0 || c->radon->species_id >= c->naqcomp)
+      return set_err(PFRX_E_INVALID, "RADON sandbox species id out of range%s", "");
+    if (c->radon->mineral_id < 0 || c->radon->mineral_id >= c->nkinmnrl)
+      return set_err(PFRX_E_INVALID, "RADON sandbox needs its mineral among the kinetic minerals%s", "");
+  }
+  if (c->nactive_gas < 0) return set_err(PFRX_E_INVALID, "negative nactive_gas%s", "");
+  if (c->nactive_gas > 0) {
+    if (!c->acteq_ptr || !c->acteq_specid || !c->acteq_stoich || !c->acteq_h2ostoich || !c->acteq_logK)
+      return set_err(PFRX_E_INVALID, "active gas tables missing%s", "");
+    for (int k = 0; k < c->acteq_ptr[c->nactive_gas]; k++)
+      if (c->acteq_specid[k] < 0 || c->acteq_specid[k] >= c->naqcomp)
+        return set_err(PFRX_E_INVALID, "active gas species id out of range%s", "");
+  }
   if (c->calcite) {
     const pfrx_calcite_sandbox *cs = c->calcite;
     const int ids[3] = {cs->h_ion_id, cs->calcium_id, cs->bicarbonate_id};
@@ -881,7 +908,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
   if (c->sandbox_list)
     for (int k = 0; k < c->nsandbox; k++)
-      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_CALCITE ||
+      if (c->sandbox_list[k] < PFRX_SANDBOX_CLM_CN || c->sandbox_list[k] > PFRX_SANDBOX_RADON ||
           c->nsandbox > PFRX_MAX_SANDBOXES)
         return set_err(PFRX_E_INVALID, "bad sandbox_list%s", "");
   int ndev = 0;
@@ -954,6 +981,8 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_lg = c->langmuir ? 1 : 0;
   d.has_cd = c->cndegas ? 1 : 0;
   d.has_cs = c->calcite ? 1 : 0;
+  d.has_rn = c->radon ? 1 : 0;
+  d.ngas = c->nactive_gas;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
   d.need_ds = (c->nradiodecay_rxn > 0 && c->neqsrfcplxrxn + c->neqionxrxn + c->neqkdrxn + c->neqdynamickdrxn > 0) ? 1 : 0;
@@ -964,11 +993,11 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.mb_units = c->microbial_concentration_units;
   d.n_nc = c->somdec ? c->somdec->nrxn + c->somdec->downstream_ptr[c->somdec->nrxn] : 0;
   {
-    static const int def_order[8] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
+    static const int def_order[9] = {PFRX_SANDBOX_CLM_CN, PFRX_SANDBOX_SOMDEC, PFRX_SANDBOX_NITRIF,
                                      PFRX_SANDBOX_DENITR, PFRX_SANDBOX_PLANTN, PFRX_SANDBOX_LANGMUIR,
-                                     PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE};
+                                     PFRX_SANDBOX_CNDEGAS, PFRX_SANDBOX_CALCITE, PFRX_SANDBOX_RADON};
     const int32_t *ord = c->sandbox_list ? c->sandbox_list : def_order;
-    const int no = c->sandbox_list ? c->nsandbox : 8;
+    const int no = c->sandbox_list ? c->nsandbox : 9;
     d.nsbx = 0;
     for (int k = 0; k < no; k++) {
       const int kind = ord[k];
@@ -976,7 +1005,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
                            (kind == PFRX_SANDBOX_SOMDEC && c->somdec) || (kind == PFRX_SANDBOX_NITRIF && c->nitrif) ||
                            (kind == PFRX_SANDBOX_DENITR && c->denitr) || (kind == PFRX_SANDBOX_PLANTN && c->plantn) ||
                            (kind == PFRX_SANDBOX_LANGMUIR && c->langmuir) || (kind == PFRX_SANDBOX_CNDEGAS && c->cndegas) ||
-                           (kind == PFRX_SANDBOX_CALCITE && c->calcite);
+                           (kind == PFRX_SANDBOX_CALCITE && c->calcite) || (kind == PFRX_SANDBOX_RADON && c->radon);
       if (present) d.sbx[d.nsbx++] = kind;
     }
   }
@@ -986,13 +1015,14 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   if (c->langmuir) d.lg = *c->langmuir;
   if (c->cndegas) d.cd = *c->cndegas;
   if (c->calcite) d.cs = *c->calcite;
+  if (c->radon) d.rn = *c->radon;
 
   // kernel variant first: the task partition depends on the lane count
   {
     int want = 0;
     if (const char *ev = getenv("PFRX_LANES")) want = atoi(ev);
     int rc0 = pick_kernel(h, want);  // PFRX_TPC=1 selects the thread-per-cell kernel
-    if (!rc0 && (has_pref || act_newton || has_sbx3 || has_sorb2 || has_kin3) && !h->tpc) {
+    if (!rc0 && (has_pref || act_newton || has_sbx3 || has_sorb2 || has_kin3 || c->nactive_gas > 0) && !h->tpc) {
       // mineral prefactors, the iterated ionic strength and the SOMDECOMP / NITRIFICATION /
       // DENITRIFICATION sandboxes live in the thread-per-cell kernel only
       const KernelGetter *gt = nullptr;
@@ -1280,6 +1310,15 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     A.add(c->microbial_biomassid, nr, &d.mb_bio);
     A.add(c->microbial_biomass_yield, nr, &d.mb_yield);
   }
+  if (c->nactive_gas > 0) {
+    const int ng = c->nactive_gas, nnz = c->acteq_ptr[ng];
+    A.add(c->acteq_ptr, ng + 1, &d.gs_ptr);
+    A.add(c->acteq_specid, nnz, &d.gs_id);
+    A.add(c->acteq_stoich, nnz, &d.gs_st);
+    A.add(c->acteq_h2ostoich, ng, &d.gs_h2o);
+    A.add(c->acteq_logK, ng, &d.gs_logK);
+    A.add(c->acteq_logK_coef, (c->acteq_logK_coef && !c->use_isothermal) ? 5 * ng : 0, &d.gs_logKcoef);
+  }
   if (c->nimmobile_decay_rxn > 0) {
     A.add(c->immobile_decay_specid, c->nimmobile_decay_rxn, &d.idc_id);
     A.add(c->immobile_decay_constant, c->nimmobile_decay_rxn, &d.idc_k);
@@ -1445,6 +1484,9 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->eqionx_conc = s->eqionx_conc;
   d->pres = s->pres;
   d->sandbox_aux = s->sandbox_aux;
+  d->sat_gas = s->sat_gas;
+  d->total_gas = s->total_gas;
+  d->gas_pp = s->gas_pp;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -2008,6 +2050,9 @@ static DevState dev_state_at(const DevState &d, int64_t c0) {
   PFRX_OFF(eqionx_conc);
   PFRX_OFF(pres);
   PFRX_OFF(sandbox_aux);
+  PFRX_OFF(sat_gas);
+  PFRX_OFF(total_gas);
+  PFRX_OFF(gas_pp);
   PFRX_OFF(imat);
   PFRX_OFF(num_sub_steps);
   PFRX_OFF(num_iterations);
@@ -2227,7 +2272,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.elm_zsoil, (double **)&h->own_st.elm_kscalar,
                            (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
                            (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc,
-                           (double **)&h->own_st.pres, &h->own_st.sandbox_aux};
+                           (double **)&h->own_st.pres, &h->own_st.sandbox_aux,
+                           (double **)&h->own_st.sat_gas, &h->own_st.total_gas, &h->own_st.gas_pp};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -2246,7 +2292,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->soil_particle_density, host->elm_w_scalar, host->elm_o_scalar, host->elm_t_scalar,
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
                               host->somdec_nc,    host->elm_rate_plantndemand, host->eqionx_ref_cation_sorbed_conc,
-                              host->eqionx_conc,  host->pres,         host->sandbox_aux};
+                              host->eqionx_conc,  host->pres,         host->sandbox_aux,
+                              host->sat_gas,      host->total_gas,    host->gas_pp};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
@@ -2254,7 +2301,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
                          d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc, (double *)d.pres,
-                         d.sandbox_aux};
+                         d.sandbox_aux,  (double *)d.sat_gas, d.total_gas, d.gas_pp};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -2274,6 +2321,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (!host->eqionx_ref_cation_sorbed_conc) d.eqionx_ref = nullptr;
   if (!host->eqionx_conc) d.eqionx_conc = nullptr;
   if (!host->sandbox_aux) d.sandbox_aux = nullptr;
+  if (!host->sat_gas) d.sat_gas = nullptr;
+  if (!host->total_gas) d.total_gas = nullptr;
+  if (!host->gas_pp) d.gas_pp = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -2301,7 +2351,7 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   int rc = summary_reset(h, s_k);
   if (rc) return rc;
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32, 34, 35};
   double *hdst[kNumD] = {host->total,        host->pri_molal,    host->immobile,  host->pri_act_coef,
                          host->sec_act_coef, host->sec_molal,    host->ln_act_h2o, host->mnrl_volfrac,
                          host->mnrl_area,    host->mnrl_rate,    host->srfcplxrxn_free_site_conc,
@@ -2310,7 +2360,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          nullptr,            nullptr,            nullptr,         nullptr,
                          host->somdec_nc,    nullptr,            host->eqionx_ref_cation_sorbed_conc,
-                         host->eqionx_conc,  nullptr,            host->sandbox_aux};
+                         host->eqionx_conc,  nullptr,            host->sandbox_aux,
+                         nullptr,            host->total_gas,    host->gas_pp};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the
@@ -2532,7 +2583,7 @@ extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
   // written once, four int32 results
   if (!h) return 0;
   const int *r = h->rows_d.data();
-  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32};
+  const int io[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 27, 29, 30, 32, 34, 35};
   int64_t in = 0, outn = 0;
   for (int f = 0; f < kNumD; f++)
     if (f != 11) in += r[f];
@@ -2603,7 +2654,7 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
     inner_newton = inner_newton || h->sr_flag_host[r] != 0;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd || d.has_cs ||
+      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd || d.has_cs || d.has_rn || d.ngas > 0 ||
       d.nsrfrxn != d.neqsr + d.nmr)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();

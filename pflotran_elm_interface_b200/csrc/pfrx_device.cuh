@@ -132,6 +132,12 @@ struct DevCfg {
   pfrx_langmuir lg;
   pfrx_cndegas cd;
   pfrx_calcite_sandbox cs;
+  int has_rn;
+  pfrx_radon rn;
+  // active gas species (reaction_gas.F90:87-174), CSR; thread-per-cell kernel only
+  int ngas, off_tg, off_dg;
+  const int *gs_ptr, *gs_id;
+  const double *gs_st, *gs_h2o, *gs_logK, *gs_logKcoef;
   int cn_nrxn, cn_C, cn_N;
   const double *cn_CN, *cn_k, *cn_resp, *cn_inhib;
   const int *cn_nspec, *cn_cid, *cn_nid, *cn_up, *cn_down;

@@ -58,6 +58,12 @@ struct CellT {
   __device__ __forceinline__ double &DT(int i, int j) { return ws[cfg.off_dt + i * cfg.naq + j]; }
   __device__ __forceinline__ double &DS(int i, int j) { return ws[cfg.off_ds + i * cfg.naq + j]; }
   __device__ __forceinline__ double &NC(int k) { return ws[cfg.off_nc + k]; }
+  __device__ __forceinline__ double &TG(int i) { return ws[cfg.off_tg + i]; }
+  __device__ __forceinline__ double &DG(int i, int j) { return ws[cfg.off_dg + i * cfg.naq + j]; }
+  __device__ __forceinline__ double sat_gas() const { return st.sat_gas ? st.sat_gas[cell] : 0.0; }
+  __device__ __forceinline__ double gs_logK(int g) const {
+    return (cfg.use_isothermal || !cfg.gs_logKcoef) ? cfg.gs_logK[g] : interp_logK(cfg.gs_logKcoef + 5 * g, temp);
+  }
 
   __device__ __forceinline__ double cx_logK(int k) const {
     return cfg.use_isothermal ? cfg.cx_logK[k] : interp_logK(cfg.cx_logKcoef + 5 * k, temp);
@@ -387,6 +393,53 @@ struct CellT {
 #pragma unroll 1
     for (int i = naq; i < n; i++) TOT(i) = C(i);
     if (cfg.nsorb > 0 && !aq_only) total_sorb(want_J, vol / dt);
+    if (cfg.ngas > 0 && !aq_only) total_gas(want_J, want_J, dt);
+  }
+
+  // ---- RTotalGas (reaction_gas.F90:87-174): partial pressures of the active gas species in
+  // equilibrium with the water, their ideal-gas concentrations as rt_auxvar%total(:,2) and its
+  // derivative; the gas share of RTAccumulationDerivative (reaction.F90:5838-5846) goes into the Jacobian
+  __device__ __forceinline__ double gas_concentration(double pp) const {  // reaction_gas.F90:304-323, mol/m^3
+    return pp * 1.e5 / (PFRX_IDEAL_GAS_CONSTANT * (temp + 273.15));
+  }
+  __device__ __forceinline__ void total_gas(bool want_J, bool add_J, double dt) {
+    const int naq = cfg.naq;
+#pragma unroll 1
+    for (int i = 0; i < naq; i++) TG(i) = 0.0;
+    if (want_J) {
+#pragma unroll 1
+      for (int e = 0; e < naq * naq; e++) ws[cfg.off_dg + e] = 0.0;
+    }
+#pragma unroll 1
+    for (int g = 0; g < cfg.ngas; g++) {
+      const int p0 = cfg.gs_ptr[g], p1 = cfg.gs_ptr[g + 1];
+      double lnQK = -gs_logK(g) * PFRX_LOG_TO_LN;
+      const double h = cfg.gs_h2o[g];
+      if (h != 0.0) lnQK = lnQK + h * ln_act_h2o;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) lnQK = lnQK + cfg.gs_st[p] * LNA(cfg.gs_id[p]);
+      const double pp = exp(lnQK);
+      if (st.gas_pp) st.gas_pp[g * st.ld + cell] = pp;
+      const double gc = gas_concentration(pp) * 1.e-3;
+#pragma unroll 1
+      for (int p = p0; p < p1; p++) TG(cfg.gs_id[p]) = TG(cfg.gs_id[p]) + cfg.gs_st[p] * gc;
+      if (want_J) {
+#pragma unroll 1
+        for (int q = p0; q < p1; q++) {
+          const int jc = cfg.gs_id[q];
+          const double t = cfg.gs_st[q] * gas_concentration(exp(lnQK - log(C(jc)))) * 1.e-3;
+#pragma unroll 1
+          for (int p = p0; p < p1; p++) DG(cfg.gs_id[p], jc) = DG(cfg.gs_id[p], jc) + cfg.gs_st[p] * t;
+        }
+      }
+    }
+    if (add_J && !dry) {
+      const double fg = por * sat_gas() * 1000.0 * vol / dt;
+#pragma unroll 1
+      for (int i = 0; i < naq; i++)
+#pragma unroll 1
+        for (int j = 0; j < naq; j++) J(i, j) = J(i, j) + DG(i, j) * fg;
+    }
   }
 
   // ---- RTotalSorb (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD;
@@ -504,11 +557,13 @@ struct CellT {
     const int naq = cfg.naq;
     const double L_pore = por * vol * 1.e3;
     const double L_water = L_pore * sat;
+    const double L_gas = cfg.ngas > 0 ? L_pore * sat_gas() : 0.0;
 #pragma unroll 1
     for (int r = 0; r < cfg.nrd; r++) {
       const int p0 = cfg.rd_ptr[r], p1 = cfg.rd_ptr[r + 1], jc = cfg.rd_fwd[r];
       const double kf = cfg.rd_kf[r];
       double sum = TOT(jc) * L_water;
+      if (cfg.ngas > 0) sum = sum + TG(jc) * L_gas;
       if (cfg.nsorb > 0) sum = sum + TS(jc) * vol;
       const double rate = sum * kf;
       const double t = -1.0 * kf;
@@ -519,6 +574,15 @@ struct CellT {
         RES(ic) = RES(ic) - nu * rate;
 #pragma unroll 1
         for (int j = 0; j < naq; j++) J(ic, j) = J(ic, j) + t * nu * DT(jc, j) * L_water;
+      }
+      if (cfg.ngas > 0) {
+#pragma unroll 1
+        for (int p = p0; p < p1; p++) {
+          const int ic = cfg.rd_id[p];
+          const double nu = cfg.rd_st[p];
+#pragma unroll 1
+          for (int j = 0; j < naq; j++) J(ic, j) = J(ic, j) + t * nu * DG(jc, j) * L_gas;
+        }
       }
       if (cfg.need_ds) {
 #pragma unroll 1
@@ -1107,6 +1171,11 @@ struct CellT {
           const double aux = pfrx_sbx::calcite_react(*this);
           if (st.sandbox_aux) st.sandbox_aux[cell] = aux;
         }
+      } else if (kind == PFRX_SANDBOX_RADON) {
+        // RadonEvaluate (reaction_sandbox_radon.F90:150-188): zero-order generation, no derivative
+        if (cfg.has_rn)
+          RES(cfg.rn.species_id) = RES(cfg.rn.species_id) - (1.0) * cfg.rn.radon_generation_rate *
+                                                                st.mnrl_volfrac[cfg.rn.mineral_id * st.ld + cell] * vol;
       }
     }
   }
@@ -1274,6 +1343,14 @@ struct CellT {
     return true;
   }
 
+  // rt_auxvar%total(:,2) of the latest RTotal: every way out of RReact leaves it in the state
+  __device__ __forceinline__ void store_total_gas() {
+    if (cfg.ngas > 0 && st.total_gas) {
+#pragma unroll 1
+      for (int i = 0; i < cfg.naq; i++) st.total_gas[i * st.ld + cell] = TG(i);
+    }
+  }
+
   // ---- RReact (reaction.F90:3742-4055) -------------------------------------------
   // state in: st.total / st.immobile / st.total_sorb_eq hold total*, the guess is
   // in st.pri_molal / st.immobile.  Returns ierror; on success the converged state
@@ -1282,12 +1359,14 @@ struct CellT {
     const int naq = cfg.naq, n = cfg.n;
     const int64_t ld = st.ld, c = cell;
     const double psv = por * sat * 1000.0 * vol;
+    const double psv_g = cfg.ngas > 0 ? por * sat_gas() * 1000.0 * vol : 0.0;
     dry = sat < cfg.min_sat;
 #pragma unroll
     for (int i = 0; i < N; i++) {
       double f = 0.0;
       if (i < naq) {
         if (!dry) f = psv * st.total[i * ld + c];
+        if (!dry && cfg.ngas > 0 && st.total_gas) f = f + psv_g * st.total_gas[i * ld + c];
         if (cfg.nsorb > 0) f = f + st.total_sorb_eq[i * ld + c] * vol;
         C(i) = guess[i];
       } else if (i < n) {
@@ -1314,6 +1393,7 @@ struct CellT {
         // HBM); total_sorb_eq is not restored (reaction.F90:3891-3894)
         if (cfg.nsorb > 0)
           for (int i = 0; i < naq; i++) st.total_sorb_eq[i * ld + c] = TS(i);
+        store_total_gas();
         its_out = its;
         return 1;
       }
@@ -1322,6 +1402,7 @@ struct CellT {
         if (i < n) {
           double a = 0.0;
           if (!dry) a = (i < naq) ? psv * TOT(i) : 0.0 + C(i) * vol;
+          if (!dry && cfg.ngas > 0 && i < naq) a = a + psv_g * TG(i);
           if (cfg.nsorb > 0 && i < naq) a = a + TS(i) * vol;
           RES(i) = (a - fixed[i]) / dt;
         }
@@ -1339,6 +1420,7 @@ struct CellT {
       if (!act_ok) {
         // the reference has filled the state with NaN by now and leaves RReact with
         // option%ierror set after RReaction (reaction.F90:3921); no restore
+        store_total_gas();
         its_out = its;
         return 1;
       }
@@ -1361,6 +1443,7 @@ struct CellT {
           if (cfg.nsorb > 0) st.total_sorb_eq[i * ld + c] = TS(i);
         }
         for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
+        store_total_gas();
         its_out = its;
         return 1;
       }
@@ -1404,6 +1487,7 @@ struct CellT {
       if (cfg.nsorb > 0) st.total_sorb_eq[i * ld + c] = TS(i);
     }
     for (int i = naq; i < n; i++) st.immobile[(i - naq) * ld + c] = C(i);
+    store_total_gas();
 #pragma unroll
     for (int i = 0; i < N; i++)
       if (i < n) guess[i] = C(i);
@@ -1522,6 +1606,7 @@ struct CellT {
         for (int r = 0; r < cfg.nionx; r++) ws[cfg.off_ix + r] = st.eqionx_ref ? st.eqionx_ref[r * ld + c] : 1.e-9;
         total_sorb(true, 0.0);
       }
+      if (cfg.ngas > 0 && cfg.nrd > 0) total_gas(true, false, tran_dt);  // the decaying inventory in the gas phase
       if (cfg.nrd > 0) radioactive_decay();
       if (cfg.ngen > 0) general_reactions();
       if (cfg.nmb > 0) microbial();
@@ -1973,6 +2058,7 @@ struct CellT {
         activity();
     }
     auxvar_compute(false, 1.0, false, act);
+    store_total_gas();
 #pragma unroll
     for (int i = 0; i < N; i++)
       if (i < naq) {

@@ -18,6 +18,9 @@ struct DevState {
   double *eqionx_ref, *eqionx_conc;
   const double *pres;  // liquid pressure (CNDEGAS sandbox, optional)
   double *sandbox_aux; // rt_auxvar%auxiliary_data of the CALCITE sandbox
+  // active gas phase (RTotalGas): global_auxvar%sat(2), rt_auxvar%total(:,2), rt_auxvar%gas_pp
+  const double *sat_gas;
+  double *total_gas, *gas_pp;
 };
 
 // shard summary accumulated with atomics, one set per warp

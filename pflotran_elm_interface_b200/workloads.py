@@ -832,6 +832,114 @@ def general_decay(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SE
                     + (", parent and daughter sorbing (2 KD isotherms, 1 dynamic KD)" if sorbing else ""))
 
 
+C7G_DECK = """
+# C7g: an ACTIVE gas phase (RTotalGas) -- the chemistry of default/batch/radon.in (Rn(g) over Rn(aq), zero-order
+# generation by the RADON sandbox, radioactive decay of the aqueous + gaseous inventory) next to the
+# carbonate system with CO2(g) active, so that one gas couples two components and carries water
+CHEMISTRY
+  PRIMARY_SPECIES
+    Rn(aq)
+    SiO2(aq)
+    H+
+    HCO3-
+  /
+  SECONDARY_SPECIES
+    OH-
+    CO3--
+    CO2(aq)
+  /
+  ACTIVE_GAS_SPECIES
+    GAS_TRANSPORT_IS_UNVETTED
+    Rn(g)
+    CO2(g)
+  /
+  MINERALS
+    Quartz
+  /
+  MINERAL_KINETICS
+    Quartz
+      RATE_CONSTANT 1.d-13
+    /
+  /
+  REACTION_SANDBOX
+    RADON
+      SPECIES_NAME Rn(aq)
+      MINERAL_NAME Quartz
+      RADON_GENERATION_RATE 1.1627850420873736e-19
+    /
+  /
+  RADIOACTIVE_DECAY_REACTION
+    REACTION Rn(aq) <->
+    HALF_LIFE 3.8235 d
+  /
+  DATABASE ./hanford_subset.dat
+  LOG_FORMULATION
+  ACTIVITY_COEFFICIENTS TIMESTEP
+END
+CONSTRAINT initial
+  CONCENTRATIONS
+    Rn(aq)    1.d-18  T
+    SiO2(aq)  1.d-4   T
+    H+        7.5     P
+    HCO3-     2.d-3   T
+  /
+  MINERALS
+    Quartz  0.5d0 1.d2 m^2/m^3
+  /
+END
+CONSTRAINT inlet
+  CONCENTRATIONS
+    Rn(aq)    1.d-15  T
+    SiO2(aq)  3.d-5   T
+    H+        5.5     P
+    HCO3-     1.d-4   T
+  /
+  MINERALS
+    Quartz  0.5d0 1.d2 m^2/m^3
+  /
+END
+"""
+
+
+def active_gas(ncell: int = 1 << 20, tran_dt: float = 86400.0, seed: int = SEED, anisothermal: bool = False) -> Workload:
+    """C7g: two active gas species (reaction_gas.F90:87-174), the RADON sandbox and radioactive decay of an
+    inventory that sits mostly in the gas phase; liquid saturations from 1e-5 (the radon deck) to 0.9"""
+    rng = np.random.default_rng(seed)
+    dk = chem.read_deck(C7G_DECK)
+    net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("hanford_subset.dat")), use_isothermal=not anisothermal)
+    assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
+    cfg = abi.ReactionConfig(net)
+    den = eos.water_density_ifc67(25.0)
+    waters = [constraint.equilibrate_constraint(net, dk.constraints[k], den_kg=den, porosity=0.3)
+              for k in ("initial", "inlet")]
+    st = abi.HostState(cfg, ncell)
+    f = rng.random(ncell)
+    _mix_fill(st, waters, np.stack([1.0 - f, f]), rng, jitter=0.0)
+    st["den_kg"][...] = den
+    st["porosity"][...] = rng.uniform(0.2, 1.0, ncell)
+    st["volume"][...] = rng.uniform(0.5, 2.0, ncell)
+    sat = np.where(rng.random(ncell) < 0.25, 1.0e-5, rng.uniform(0.05, 0.9, ncell))
+    st["sat"][...] = sat
+    st["sat_gas"][...] = 1.0 - sat
+    st["temp"][...] = rng.uniform(5.0, 60.0, ncell) if anisothermal else 25.0
+    st["mnrl_volfrac"][0, :] = rng.uniform(0.1, 1.0, ncell)
+    st["mnrl_area"][0, :] = 1.0e2
+    # gas-phase totals of the previous step: in equilibrium with the first water
+    # (the fixed accumulation reads them, reaction.F90:5761-5769)
+    pp_rn = 10.0 ** rng.uniform(-22.0, -16.0, ncell)
+    pp_co2 = 10.0 ** rng.uniform(-4.0, -2.0, ncell)
+    rt = 8.31446 * (st["temp"][0] + 273.15)
+    names = net.primary_names
+    st["total_gas"][names.index("Rn(aq)"), :] = pp_rn * 1.0e5 / rt * 1.0e-3
+    st["total_gas"][names.index("H+"), :] = pp_co2 * 1.0e5 / rt * 1.0e-3
+    st["total_gas"][names.index("HCO3-"), :] = pp_co2 * 1.0e5 / rt * 1.0e-3
+    st["gas_pp"][0, :] = pp_rn
+    st["gas_pp"][1, :] = pp_co2
+    return Workload("c7gt_active_gas_anisothermal" if anisothermal else "c7g_active_gas", cfg, st, tran_dt, net,
+                    "2 active gas species (Rn, CO2), RADON sandbox, radioactive decay of the aqueous + gaseous "
+                    "inventory, 3 complexes, kinetic Quartz")
+
+
 C8_DECK = """
 # C8: Monod-type microbial reactions (the ABCD network of default/batch/ABCD_microbial*.in):
 # immobile biomass with yield and decay, a second reaction on aqueous biomass, all four inhibition
@@ -992,6 +1100,8 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c6": (ion_exchange, {}),
         "c7": (general_decay, {}),
         "c7s": (general_decay, {"sorbing": True}),
+        "c7g": (active_gas, {}),
+        "c7gt": (active_gas, {"anisothermal": True}),
         "c8": (microbial, {}),
     }
     fn, kw = table[name]

@@ -181,6 +181,22 @@ def test_c7_general_decay_reactions(name, dt, host):
     _check_summary(rr, rg)
 
 
+@pytest.mark.parametrize("name,dt,host", [("c7g", 3600.0, False), ("c7g", 86400.0, True), ("c7g", 30 * 86400.0, False),
+                                          ("c7gt", 86400.0, False), ("c7gt", 10 * 86400.0, True)])
+def test_c7g_active_gas_phase(name, dt, host):
+    """RTotalGas (reaction_gas.F90:87-174: Rn(g), and CO2(g) over H+ / HCO3- / H2O), its share of the
+    accumulation and of the decaying inventory, the RADON sandbox; c7gt: gas logK(T) at 5-60 C.  The
+    gas-phase totals and partial pressures are part of the compared state"""
+    wl = W.by_name(name, ncell=5000, tran_dt=dt)
+    wl.state.a["imat"][0, 5] = 0
+    wl.state.a["sat"][0, 6] = 1.0e-50
+    ref, rr, got, rg, info = _run_both(wl, host_path=host)
+    assert info["lanes"] in (0, 1)
+    assert np.abs(ref.a["total_gas"] - wl.state.a["total_gas"]).max() > 0 and np.abs(ref.a["gas_pp"]).min() > 0
+    _compare(ref, got, f"{name} dt={dt}")
+    _check_summary(rr, rg)
+
+
 @pytest.mark.parametrize("dt,host", [(3600.0, True), (86400.0, False), (10 * 86400.0, False)])
 def test_c8_microbial_reactions(dt, host):
     """RMicrobial in the thread-per-cell kernel: Monod terms with thresholds, THRESHOLD / MONOD /
@@ -245,14 +261,14 @@ def test_specialized_kernel(variant, dt, host):
 
 
 @pytest.mark.parametrize("variant", ["c2", "c2pf", "c2pfp", "c2sb", "c5", "c3mr", "c4", "c4s", "c4se", "c4fe", "c4g", "c4ge",
-                                     "c7", "c7s", "c8"])
+                                     "c7", "c7s", "c7g", "c8"])
 def test_batched_reaction_matches_oracle(variant):
     """pfrx_reaction: RReaction + RReactionDerivative of every cell (GIRT / ELM caller)"""
     import torch
 
     rstep = _gpu()
     wl = W.by_name(variant, ncell=300)
-    if variant.startswith("c4") or variant in ("c7", "c7s", "c8"):
+    if variant.startswith("c4") or variant in ("c7", "c7s", "c7g", "c8"):
         wl.state.a["imat"][0, 7] = 0  # one inactive and one dry cell
         wl.state.a["sat"][0, 9] = 1.0e-50
     ref = wl.state.copy()
@@ -556,7 +572,7 @@ def test_calcite_sandbox(dt, host):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c2pf", "c3sf", "c3t", "c3tg", "c2ng", "c2sb", "c4g", "c6", "c7", "c8", "c3an"])
+@pytest.mark.parametrize("name", ["c2pf", "c3sf", "c3t", "c3tg", "c2ng", "c2sb", "c4g", "c6", "c7", "c7g", "c8", "c3an"])
 def test_library_refuses_a_cubin_where_the_generator_refuses_the_network(name):
     """pfrx_load_specialized is the twin of specialize.supported(): a host that loads cubins by hand
     (cached by signature) must not be able to attach one to a configuration whose features the generated

@@ -30,6 +30,9 @@ def _setup(deck, db, cons="initial"):
     st["den_kg"][:] = den
     st["porosity"][:] = por
     st["temp"][:] = dk.reference_temperature
+    st["sat"][:] = dk.reference_saturation
+    if cfg.c.nactive_gas > 0:   # init_subsurface_transport.F90:84-88
+        st["sat_gas"][:] = 1.0 - dk.reference_saturation
     # CondControlAssignRTTranInitCond (condition_control.F90:1636-1650): cells
     # start from the constraint's free-ion molalities with activity
     # coefficients = 1, then RTotal, then two (act. coef., RTotal) sweeps
@@ -332,6 +335,31 @@ def test_general_reaction_gold():
     for nm in ("A(aq)", "B(aq)"):
         i = net.primary_names.index(nm)
         _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")
+
+
+def test_radon_gold():
+    """default/batch/radon: an ACTIVE gas phase (RTotalGas, reaction_gas.F90:87-174: Rn(g) in equilibrium with
+    Rn(aq), liquid saturation 1e-5), the RADON sandbox (zero-order generation from the Quartz volume fraction,
+    reaction_sandbox_radon.F90:150-188) and RADIOACTIVE_DECAY_REACTION of the aqueous + gaseous inventory
+    (reaction.F90:5211-5311): secular equilibrium after one year.  batch.cfg: 1e-12 relative."""
+    dk, net, cfg, st = _setup("radon.in", "hanford_subset.dat")
+    assert cfg.c.nactive_gas == 1 and cfg.c.nradiodecay_rxn == 1 and cfg.c.radon
+    run = girt.GirtBatch(cfg, st, dk).run()
+    gold = _gold("radon.regression.gold")
+    sol = gold["SOLUTION: Transport"]
+    assert run.cuts == 0
+    assert run.steps == int(sol["Time Steps"]), (run.steps, sol["Time Steps"])
+    assert run.newton_its == int(sol["Newton Iterations"]), (run.newton_its, sol["Newton Iterations"])
+    for nm in ("Rn(aq)", "SiO2(aq)"):
+        i = net.primary_names.index(nm)
+        _check_rel(st["total"][i, 0], _val(gold, f"CONCENTRATION: Total {nm}"), 1.0e-12, f"Total {nm}")
+    # OUTPUT GAS_CONCENTRATION prints RGasConcentration(gas_pp, T) [mol/m^3 gas]; rt_auxvar%total(:,2) is that
+    # in mol/L gas (reaction_gas.F90:144-146), and Rn(g) holds one Rn(aq)
+    irn = net.primary_names.index("Rn(aq)")
+    _check_rel(st["total_gas"][irn, 0] * 1.0e3, _val(gold, "CONCENTRATION: Active Gas Rn(g)"), 1.0e-12, "Active Gas Rn(g)")
+    _check_rel(st["gas_pp"][0, 0] * 1.0e5 / (8.31446 * (dk.reference_temperature + 273.15)),
+               _val(gold, "CONCENTRATION: Active Gas Rn(g)"), 1.0e-12, "Rn(g) from its partial pressure")
+    _check_abs(st["mnrl_volfrac"][0, 0], _val(gold, "VOLUME_FRACTION: Quartz VF"), 1.0e-12, "Quartz VF")
 
 
 MICROBIAL_GOLDS = ["ABCD_microbial", "ABCD_microbial_activation_high", "ABCD_microbial_activation_low",

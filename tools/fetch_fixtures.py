@@ -45,6 +45,8 @@ COPY = [
     ("regression_tests/default/543/543_hanford_srfcplx_base.in", None),
     ("regression_tests/default/543/543_hanford_srfcplx_base.regression.gold", None),
     ("regression_tests/default/543/543_hanford_srfcplx_mr.in", None),
+    ("regression_tests/default/batch/radon.in", None),
+    ("regression_tests/default/batch/radon.regression.gold", None),
     ("regression_tests/default/column/surface_complexation_mr_os.in", None),
     ("regression_tests/default/column/tracer_os.in", None),
     ("regression_tests/default/column/tracer_os.regression.gold", None),
@@ -142,7 +144,8 @@ def main():
     ch = dk.chemistry
     names = (["H2O"] + ch.primary + ch.secondary + ch.gases + ch.minerals
              + [c for r in ch.srfcplx_rxns for c in r.complexes]
-             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)", "B(aq)", "C(aq)", "AB(aq)", "D(aq)"])
+             + ["Dolomite", "Gypsum", "Fluorite", "Schoepite", "O2(aq)", "O2(g)", "Halite", "A(aq)", "A(s)", "B(aq)", "C(aq)", "AB(aq)", "D(aq)",
+                "Rn(aq)", "Rn(g)", "Quartz", "SiO2(aq)"])
     db = chem.Database.from_file(os.path.join(REF, "database/hanford.dat"))
     with open(os.path.join(OUT, "hanford_subset.dat"), "w") as f:
         f.write(db.subset_text(names))
