@@ -3626,6 +3626,7 @@ int pfrx_oracle_reaction(const pfrx_config *cfg, const pfrx_state *st, int64_t i
   for (i = 0; i < c.nkin; i++) st->mnrl_rate[i * st->ld + ic] = c.mnrl_rate[i];
   if (st->somdec_nc)
     for (i = 0; i < c.nsomdec_nc; i++) st->somdec_nc[i * st->ld + ic] = c.somdec_nc[i];
+  if (st->sandbox_aux) st->sandbox_aux[ic] = c.sandbox_aux; /* CalciteEvaluate leaves its rate in auxiliary_data */
   cell_free(&c);
   return 0;
 }

@@ -223,16 +223,6 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
     ADD(c->clmcn_respiration_fraction, c->clmcn_nrxn)
     ADD(c->clmcn_inhibition_constant, c->clmcn_nrxn)
   }
-  if (c->neqionxrxn > 0 || c->neqkdrxn > 0 || c->neqdynamickdrxn > 0) {
-    // not covered by the generator: any cubin signature must differ
-    int32_t hi[4] = {c->neqionxrxn, c->neqkdrxn, c->neqdynamickdrxn, c->ikd_units};
-    h = fnv1a(h, hi, sizeof(hi));
-  }
-  if (c->ngeneral_rxn > 0 || c->nradiodecay_rxn > 0 || c->nimmobile_decay_rxn > 0 || c->nmicrobial_rxn > 0) {
-    // not covered by the generator either
-    int32_t hi[4] = {c->ngeneral_rxn, c->nradiodecay_rxn, c->nimmobile_decay_rxn, c->nmicrobial_rxn};
-    h = fnv1a(h, hi, sizeof(hi));
-  }
   // ELM-CN sandboxes: every parameter the generated code bakes in
   if (c->somdec) {
     const pfrx_somdec *sd = c->somdec;
@@ -342,6 +332,89 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
     ADD(c->kinmnrl_affinity_power, c->nkinmnrl)
     ADD(c->kinmnrl_num_prefactors, c->nkinmnrl)
     ADD(c->srfcplxrxn_stoich_flag, c->nsrfcplxrxn)
+  }
+  // ion exchange, KD isotherms, dynamic KD (generated by specialize.gen_sorption)
+  {
+    int32_t sb[4] = {c->neqionxrxn, c->neqkdrxn, c->neqdynamickdrxn, c->neqkdrxn > 0 ? c->ikd_units : 0};
+    h = fnv1a(h, sb, sizeof(sb));
+    if (c->neqionxrxn > 0 && c->eqionx_ptr) {
+      const int n = c->neqionxrxn, nnz = c->eqionx_ptr[n];
+      ADD(c->eqionx_ptr, n + 1)
+      ADD(c->eqionx_cationid, nnz)
+      ADD(c->eqionx_k, nnz)
+      ADD(c->eqionx_CEC, n)
+      ADD(c->eqionx_to_surf, n)
+      ADD(c->eqionx_Z_flag, n)
+    }
+    if (c->neqkdrxn > 0) {
+      const int n = c->neqkdrxn;
+      ADD(c->eqkd_specid, n)
+      ADD(c->eqkd_type, n)
+      ADD(c->eqkd_mineral, n)
+      ADD(c->eqkd_coeff, n)
+      ADD(c->eqkd_langmuir_b, n)
+      ADD(c->eqkd_freundlich_n, n)
+    }
+    if (c->neqdynamickdrxn > 0) {
+      const int n = c->neqdynamickdrxn;
+      ADD(c->eqdynamickd_specid, n)
+      ADD(c->eqdynamickd_refspecid, n)
+      ADD(c->eqdynamickd_refspechigh, n)
+      ADD(c->eqdynamickd_low, n)
+      ADD(c->eqdynamickd_high, n)
+      ADD(c->eqdynamickd_power, n)
+    }
+  }
+  // general / radioactive-decay / immobile-decay / microbial reactions (generated by specialize.gen_kinetic)
+  {
+    int32_t k3[5] = {c->ngeneral_rxn, c->nradiodecay_rxn, c->nimmobile_decay_rxn, c->nmicrobial_rxn,
+                     c->nmicrobial_rxn > 0 ? c->microbial_concentration_units : 0};
+    h = fnv1a(h, k3, sizeof(k3));
+    if (c->ngeneral_rxn > 0 && c->general_ptr && c->general_fwd_ptr && c->general_bwd_ptr) {
+      const int n = c->ngeneral_rxn;
+      ADD(c->general_ptr, n + 1)
+      ADD(c->general_specid, c->general_ptr[n])
+      ADD(c->general_stoich, c->general_ptr[n])
+      ADD(c->general_fwd_ptr, n + 1)
+      ADD(c->general_fwd_specid, c->general_fwd_ptr[n])
+      ADD(c->general_fwd_stoich, c->general_fwd_ptr[n])
+      ADD(c->general_bwd_ptr, n + 1)
+      ADD(c->general_bwd_specid, c->general_bwd_ptr[n])
+      ADD(c->general_bwd_stoich, c->general_bwd_ptr[n])
+      ADD(c->general_kf, n)
+      ADD(c->general_kr, n)
+    }
+    if (c->nradiodecay_rxn > 0 && c->radiodecay_ptr) {
+      const int n = c->nradiodecay_rxn;
+      ADD(c->radiodecay_ptr, n + 1)
+      ADD(c->radiodecay_specid, c->radiodecay_ptr[n])
+      ADD(c->radiodecay_stoich, c->radiodecay_ptr[n])
+      ADD(c->radiodecay_forward_specid, n)
+      ADD(c->radiodecay_kf, n)
+    }
+    if (c->nimmobile_decay_rxn > 0) {
+      ADD(c->immobile_decay_specid, c->nimmobile_decay_rxn)
+      ADD(c->immobile_decay_constant, c->nimmobile_decay_rxn)
+    }
+    if (c->nmicrobial_rxn > 0 && c->microbial_ptr && c->microbial_monod_ptr && c->microbial_inhibition_ptr) {
+      const int n = c->nmicrobial_rxn;
+      ADD(c->microbial_ptr, n + 1)
+      ADD(c->microbial_specid, c->microbial_ptr[n])
+      ADD(c->microbial_stoich, c->microbial_ptr[n])
+      ADD(c->microbial_rate_constant, n)
+      ADD(c->microbial_activation_energy, n)
+      ADD(c->microbial_monod_ptr, n + 1)
+      ADD(c->microbial_monod_specid, c->microbial_monod_ptr[n])
+      ADD(c->microbial_monod_K, c->microbial_monod_ptr[n])
+      ADD(c->microbial_monod_Cth, c->microbial_monod_ptr[n])
+      ADD(c->microbial_inhibition_ptr, n + 1)
+      ADD(c->microbial_inhibition_specid, c->microbial_inhibition_ptr[n])
+      ADD(c->microbial_inhibition_type, c->microbial_inhibition_ptr[n])
+      ADD(c->microbial_inhibition_C, c->microbial_inhibition_ptr[n])
+      ADD(c->microbial_inhibition_C2, c->microbial_inhibition_ptr[n])
+      ADD(c->microbial_biomassid, n)
+      ADD(c->microbial_biomass_yield, n)
+    }
   }
 #undef ADD
   return h;
@@ -2653,8 +2726,10 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   for (int r = 0; r < d.nsrfrxn && h->sr_flag_host.size() == (size_t)d.nsrfrxn; r++)
     inner_newton = inner_newton || h->sr_flag_host[r] != 0;
   if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
-      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0 || d.mn_npref ||
-      d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0 || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd || d.has_cs || d.has_rn || d.ngas > 0 ||
+      d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.mn_npref ||
+      ((d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0) && (d.nmr > 0 || d.nsbx > 0)) || (d.nrd > 0 && d.nionx > 0) ||
+      (d.nrd > 0 && d.nsrfrxn > 0) ||
+      ((d.ngen > 0 || d.nrd > 0 || d.nidc > 0 || d.nmb > 0) && (d.nmr > 0 || d.nsbx > 0)) || d.mn_temkin || d.mn_scale || d.mn_power || inner_newton || d.has_cd || d.has_cs || d.has_rn || d.ngas > 0 ||
       d.nsrfrxn != d.neqsr + d.nmr)
     return set_err(PFRX_E_INVALID, "configuration uses features the specialised kernels do not cover%s", "");
   int rc = load_driver();

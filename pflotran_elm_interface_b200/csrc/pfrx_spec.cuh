@@ -35,6 +35,22 @@
 #endif
 #include "pfrx_sandbox.cuh"  // response functions shared with the generic kernels
 
+#ifndef SPEC_NKIN3
+#define SPEC_NKIN3 0  // general / radioactive-decay / immobile-decay / microbial reactions (spec_kinetic)
+#endif
+#ifndef SPEC_NDTP
+#define SPEC_NDTP 0  // entries of d(total)/d(free) that RRadioactiveDecay reads
+#endif
+#ifndef SPEC_NDSP
+#define SPEC_NDSP 0  // entries of d(total_sorb_eq)/d(free) that RRadioactiveDecay reads
+#endif
+#ifndef SPEC_NIONX
+#define SPEC_NIONX 0  // ion-exchange reactions
+#define SPEC_NIXCAT 0
+#endif
+#ifndef SPEC_NSORB
+#define SPEC_NSORB SPEC_NEQSR  // equilibrium sorption of any kind (surface complexation, ion exchange, KD)
+#endif
 #ifndef SPEC_NSBX
 #define SPEC_NSBX 0  // reaction sandboxes of any kind
 #endif
@@ -124,6 +140,10 @@ struct SpecCell {
   double mr_seq[SPEC_NMR > 0 ? SPEC_NMR * SPEC_NAQ : 1], mr_B[SPEC_NMR > 0 ? SPEC_NMR * SPEC_NAQ : 1];
   double mr_A[SPEC_NMR > 0 ? SPEC_NMR : 1];
   double nc[SPEC_NNC > 0 ? SPEC_NNC : 1];  // N:C ratios that persist between evaluations
+  double dtp[SPEC_NDTP > 0 ? SPEC_NDTP : 1];  // rt_auxvar%aqueous%dtotal(parent, j) of the latest RTotal
+  double dsp[SPEC_NDSP > 0 ? SPEC_NDSP : 1];  // rt_auxvar%dtotal_sorb_eq(parent, j)
+  double ixref[SPEC_NIONX > 0 ? SPEC_NIONX : 1];    // eqionx_ref_cation_sorbed_conc (guess of the next evaluation)
+  double ixconc[SPEC_NIXCAT > 0 ? SPEC_NIXCAT : 1];  // eqionx_conc
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
   bool dry;
   bool store;  // false: the lane has finished its cell, rt_auxvar%sec_molal must not be touched
@@ -138,9 +158,9 @@ __device__ __forceinline__ void spec_activity(const double (&c)[SPEC_N], SpecCel
 __device__ __forceinline__ void spec_rtotal(const double (&c)[SPEC_N], double (&lna)[SPEC_N], double (&ic)[SPEC_N],
                                             double (&tot)[SPEC_N], SpecCell &s, double *W, double *sec_out, long long ld,
                                             double dt);
-__device__ __forceinline__ void spec_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],
-                                              double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st,
-                                              long long cell, double jscale);
+__device__ __forceinline__ void spec_sorption(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],
+                                              const double (&ic)[SPEC_N], double (&ts)[SPEC_N], SpecCell &s, double *W,
+                                              const DevState &st, long long cell, double jscale);
 __device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],
                                               double (&res)[SPEC_N], SpecCell &s, double *W, const DevState &st,
                                               long long cell, bool apply);
@@ -150,6 +170,11 @@ __device__ __forceinline__ void spec_minerals(const double (&lna)[SPEC_N], const
 #endif
 __device__ __forceinline__ void spec_sandbox(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],
                                              const double (&tot)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W,
+                                             double dt);
+// generated: RRadioactiveDecay, RGeneral, RMicrobial, RImmobileDecay (RReaction's order, reaction.F90:4095-4127)
+__device__ __forceinline__ void spec_kinetic(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],
+                                             const double (&ic)[SPEC_N], const double (&tot)[SPEC_N],
+                                             const double (&ts)[SPEC_N], double (&res)[SPEC_N], SpecCell &s, double *W,
                                              double dt);
 
 #if SPEC_NMR > 0
@@ -206,6 +231,12 @@ __device__ __forceinline__ void spec_mr_update(const SpecCell &s, const DevState
 
 // per-cell inputs of the ELM-CN sandboxes
 __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &st, long long cell) {
+#if SPEC_NIONX > 0
+#pragma unroll
+  for (int r = 0; r < SPEC_NIONX; r++) s.ixref[r] = st.eqionx_ref ? st.eqionx_ref[r * st.ld + cell] : 1.e-9;
+#pragma unroll
+  for (int k = 0; k < SPEC_NIXCAT; k++) s.ixconc[k] = 0.0;
+#endif
 #if SPEC_ELM
   s.elm_w = st.elm_w ? st.elm_w[cell] : 1.0;
   s.elm_o = st.elm_o ? st.elm_o[cell] : 1.0;
@@ -222,6 +253,16 @@ __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &s
 #endif
 }
 __device__ __forceinline__ void spec_sandbox_store(const SpecCell &s, const DevState &st, long long cell) {
+#if SPEC_NIONX > 0
+  if (st.eqionx_ref) {
+#pragma unroll
+    for (int r = 0; r < SPEC_NIONX; r++) st.eqionx_ref[r * st.ld + cell] = s.ixref[r];
+  }
+  if (st.eqionx_conc) {
+#pragma unroll
+    for (int k = 0; k < SPEC_NIXCAT; k++) st.eqionx_conc[k * st.ld + cell] = s.ixconc[k];
+  }
+#endif
 #if SPEC_NNC > 0
   if (st.somdec_nc) {
 #pragma unroll
@@ -508,7 +549,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     double f = 0.0;
     if (i < NAQ) {
       if (!s.dry) f = psv * st.total[i * ld + cell];
-      if (SPEC_NEQSR > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
+      if (SPEC_NSORB > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
     } else {
       if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
     }
@@ -527,10 +568,10 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     spec_rtotal(c, lna, ic, tot, s, W, st.sec_molal + cell, ld, dt);
 #pragma unroll
     for (int i = 0; i < N; i++) ts[i] = 0.0;
-    if (SPEC_NEQSR > 0) spec_sorption(lna, ic, ts, s, W, st, cell, s.vol / dt);
+    if (SPEC_NSORB > 0) spec_sorption(c, lna, ic, ts, s, W, st, cell, s.vol / dt);
     if (its > prm.max_its) {
       // total / immobile keep their initial values in HBM; total_sorb_eq does not
-      if (SPEC_NEQSR > 0) {
+      if (SPEC_NSORB > 0) {
 #pragma unroll
         for (int i = 0; i < NAQ; i++) st.total_sorb_eq[i * ld + cell] = ts[i];
       }
@@ -541,7 +582,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     for (int i = 0; i < N; i++) {
       double a = 0.0;
       if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
-      if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
+      if (SPEC_NSORB > 0 && i < NAQ) a = a + ts[i] * s.vol;
       res[i] = sx_div(a - SPEC_FIXED(i), dt);
     }
     if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
@@ -555,6 +596,9 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
           res[i] += s.vol * (s.mr_A[q] * s.mr_seq[q * NAQ + i] - s.mr_B[q * NAQ + i]);
       }
     }
+#endif
+#if SPEC_NKIN3 > 0
+    if (!s.dry) spec_kinetic(c, lna, ic, tot, ts, res, s, W, dt);
 #endif
 #if SPEC_NSBX > 0
     if (!s.dry) spec_sandbox(c, lna, tot, res, s, W, dt);  // RReaction returns before the sandboxes in a dry cell
@@ -576,7 +620,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
         for (int i = 0; i < N; i++) {
           if (i < NAQ) {
             st.total[i * ld + cell] = tot[i];
-            if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+            if (SPEC_NSORB > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
           } else {
             st.immobile[(i - NAQ) * ld + cell] = c[i];
           }
@@ -621,7 +665,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
   for (int i = 0; i < N; i++) {
     if (i < NAQ) {
       st.total[i * ld + cell] = tot[i];
-      if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+      if (SPEC_NSORB > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
     } else {
       st.immobile[(i - NAQ) * ld + cell] = c[i];
     }
@@ -1031,7 +1075,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
           double f = 0.0;
           if (i < NAQ) {
             if (!s.dry) f = psv * st.total[i * ld + cell];
-            if (SPEC_NEQSR > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
+            if (SPEC_NSORB > 0) f = f + st.total_sorb_eq[i * ld + cell] * s.vol;
           } else {
             if (!s.dry) f = 0.0 + st.immobile[(i - NAQ) * ld + cell] * s.vol;
           }
@@ -1055,16 +1099,19 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       spec_rtotal(c, lna, ic, tot, s, W, st.sec_molal + cell, ld, dt);
 #pragma unroll
       for (int i = 0; i < N; i++) ts[i] = 0.0;
-      if (SPEC_NEQSR > 0) spec_sorption(lna, ic, ts, s, W, st, cell, s.vol / dt);
+      if (SPEC_NSORB > 0) spec_sorption(c, lna, ic, ts, s, W, st, cell, s.vol / dt);
       const bool over = its > prm.max_its;
 #pragma unroll
       for (int i = 0; i < N; i++) {
         double a = 0.0;
         if (!s.dry) a = (i < NAQ) ? psv * tot[i] : 0.0 + c[i] * s.vol;
-        if (SPEC_NEQSR > 0 && i < NAQ) a = a + ts[i] * s.vol;
+        if (SPEC_NSORB > 0 && i < NAQ) a = a + ts[i] * s.vol;
         res[i] = sx_div(a - SPEC_FIXED(i), dt);
       }
       if (SPEC_NKIN > 0) spec_minerals(lna, ic, res, s, W, st, cell, !s.dry);
+#if SPEC_NKIN3 > 0
+      if (!s.dry) spec_kinetic(c, lna, ic, tot, ts, res, s, W, dt);
+#endif
 #if SPEC_NSBX > 0
       if (!s.dry) spec_sandbox(c, lna, tot, res, s, W, dt);
 #endif
@@ -1129,7 +1176,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
 #pragma unroll
           for (int i = 0; i < N; i++) {
             if (i < NAQ) {
-              if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+              if (SPEC_NSORB > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
               if (solve_error) st.total[i * ld + cell] = tot[i];
             } else if (solve_error) {
               st.immobile[(i - NAQ) * ld + cell] = c[i];
@@ -1151,7 +1198,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
           for (int i = 0; i < N; i++) {
             if (i < NAQ) {
               st.total[i * ld + cell] = tot[i];
-              if (SPEC_NEQSR > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
+              if (SPEC_NSORB > 0) st.total_sorb_eq[i * ld + cell] = ts[i];
               st.pri_molal[i * ld + cell] = c[i];
             } else {
               st.immobile[(i - NAQ) * ld + cell] = c[i];

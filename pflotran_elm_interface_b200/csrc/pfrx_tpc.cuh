@@ -2006,6 +2006,7 @@ struct CellT {
     spd = st.soil_particle_density ? st.soil_particle_density[c] : 0.0;
     ln_act_h2o = st.ln_act_h2o ? st.ln_act_h2o[c] : 0.0;
     dry = false;
+    const bool per_iter = cfg.act_freq == PFRX_ACT_COEF_FREQUENCY_NEWTON_ITER;
     if (xx) {
 #pragma unroll 1
       for (int i = 0; i < n; i++) {
@@ -2022,12 +2023,14 @@ struct CellT {
       const double sk = st.sec_molal[k * ld + c];
       Is += sk * cfg.cx_Z2[k];
       ms += sk;
-      ws[cfg.off_lng + k] = log(st.sec_act_coef[k * ld + c]);
+      if (!per_iter) ws[cfg.off_lng + k] = log(st.sec_act_coef[k * ld + c]);
     }
     Isum = Is;
     msum = ms;
     const bool newton = cfg.act_alg == PFRX_ACT_COEF_ALGORITHM_NEWTON;
-    if (update_act && newton) {
+    if (per_iter || (update_act && newton)) {
+      // coefficients per (Z, a0) class: the state's own when they are not refreshed here (with the
+      // per-iteration update frequency the workspace has no per-complex slots)
 #pragma unroll 1
       for (int k = 0; k < ncx; k++)
         if (cfg.cx_cls[k] >= 0) ws[cfg.off_cls + cfg.cx_cls[k]] = log(st.sec_act_coef[k * ld + c]);

@@ -21,6 +21,7 @@ running on the generic kernels.
 """
 from __future__ import annotations
 
+import math
 import os
 import struct
 import subprocess
@@ -154,6 +155,71 @@ def signature(cfg: abi.ReactionConfig) -> int:
         add("kinmnrl_num_prefactors", c.nkinmnrl, i4)
     if c.nsrfcplxrxn > 0 and "srfcplxrxn_stoich_flag" in a:
         add("srfcplxrxn_stoich_flag", c.nsrfcplxrxn, i4)
+    # ion exchange, KD isotherms, dynamic KD (gen_sorption)
+    parts.append(struct.pack("<4i", c.neqionxrxn, c.neqkdrxn, c.neqdynamickdrxn, c.ikd_units if c.neqkdrxn > 0 else 0))
+    if c.neqionxrxn > 0:
+        n, nnz = c.neqionxrxn, int(a["eqionx_ptr"][c.neqionxrxn])
+        add("eqionx_ptr", n + 1, i4)
+        add("eqionx_cationid", nnz, i4)
+        add("eqionx_k", nnz, f8)
+        add("eqionx_CEC", n, f8)
+        add("eqionx_to_surf", n, i4)
+        add("eqionx_Z_flag", n, i4)
+    if c.neqkdrxn > 0:
+        n = c.neqkdrxn
+        for k in ("eqkd_specid", "eqkd_type", "eqkd_mineral"):
+            add(k, n, i4)
+        for k in ("eqkd_coeff", "eqkd_langmuir_b", "eqkd_freundlich_n"):
+            add(k, n, f8)
+    if c.neqdynamickdrxn > 0:
+        n = c.neqdynamickdrxn
+        for k in ("eqdynamickd_specid", "eqdynamickd_refspecid"):
+            add(k, n, i4)
+        for k in ("eqdynamickd_refspechigh", "eqdynamickd_low", "eqdynamickd_high", "eqdynamickd_power"):
+            add(k, n, f8)
+    # general / radioactive-decay / immobile-decay / microbial reactions (gen_kinetic)
+    parts.append(struct.pack("<5i", c.ngeneral_rxn, c.nradiodecay_rxn, c.nimmobile_decay_rxn, c.nmicrobial_rxn,
+                             c.microbial_concentration_units if c.nmicrobial_rxn > 0 else 0))
+    if c.ngeneral_rxn > 0:
+        n = c.ngeneral_rxn
+        for pre in ("", "fwd_", "bwd_"):
+            nnz = int(a[f"general_{pre}ptr"][n])
+            add(f"general_{pre}ptr", n + 1, i4)
+            add(f"general_{pre}specid", nnz, i4)
+            add(f"general_{pre}stoich", nnz, f8)
+        add("general_kf", n, f8)
+        add("general_kr", n, f8)
+    if c.nradiodecay_rxn > 0:
+        n = c.nradiodecay_rxn
+        nnz = int(a["radiodecay_ptr"][n])
+        add("radiodecay_ptr", n + 1, i4)
+        add("radiodecay_specid", nnz, i4)
+        add("radiodecay_stoich", nnz, f8)
+        add("radiodecay_forward_specid", n, i4)
+        add("radiodecay_kf", n, f8)
+    if c.nimmobile_decay_rxn > 0:
+        add("immobile_decay_specid", c.nimmobile_decay_rxn, i4)
+        add("immobile_decay_constant", c.nimmobile_decay_rxn, f8)
+    if c.nmicrobial_rxn > 0:
+        n = c.nmicrobial_rxn
+        nnz, nm, nh = int(a["microbial_ptr"][n]), int(a["microbial_monod_ptr"][n]), int(a["microbial_inhibition_ptr"][n])
+        add("microbial_ptr", n + 1, i4)
+        add("microbial_specid", nnz, i4)
+        add("microbial_stoich", nnz, f8)
+        add("microbial_rate_constant", n, f8)
+        if "microbial_activation_energy" in a:
+            add("microbial_activation_energy", n, f8)
+        add("microbial_monod_ptr", n + 1, i4)
+        add("microbial_monod_specid", nm, i4)
+        add("microbial_monod_K", nm, f8)
+        add("microbial_monod_Cth", nm, f8)
+        add("microbial_inhibition_ptr", n + 1, i4)
+        add("microbial_inhibition_specid", nh, i4)
+        add("microbial_inhibition_type", nh, i4)
+        add("microbial_inhibition_C", nh, f8)
+        add("microbial_inhibition_C2", nh, f8)
+        add("microbial_biomassid", n, i4)
+        add("microbial_biomass_yield", n, f8)
     return _fnv1a(b"".join(parts))
 
 
@@ -201,10 +267,18 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
             return False, k
     if c.use_total_as_guess:
         return False, "USE_TOTAL_CONCENTRATION_AS_GUESS"
-    if c.neqionxrxn > 0 or c.neqkdrxn > 0 or c.neqdynamickdrxn > 0:
-        return False, "ion exchange / KD isotherms"
-    if c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0 or c.nmicrobial_rxn > 0:
-        return False, "general / radioactive decay / immobile decay / microbial reactions"
+    if (c.neqionxrxn > 0 or c.neqkdrxn > 0 or c.neqdynamickdrxn > 0) and (
+            c.nkinmrsrfcplxrxn > 0 or c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir):
+        return False, "ion exchange / KD isotherms next to multirate sorption or reaction sandboxes"
+    if c.nradiodecay_rxn > 0 and (c.nsrfcplxrxn > 0 or c.neqionxrxn > 0):
+        return False, "radioactive decay of an inventory sorbed by surface complexation or ion exchange"
+    if has_kinetic3(cfg) and (c.nkinmrsrfcplxrxn > 0 or c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr
+                              or c.plantn or c.langmuir):
+        return False, "general / decay / microbial reactions next to multirate sorption or reaction sandboxes"
+    if c.nactive_gas > 0:
+        return False, "active gas species"
+    if c.radon:
+        return False, "RADON sandbox"
     if c.cndegas:
         return False, "CNDEGAS sandbox"
     if c.calcite:
@@ -232,6 +306,12 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         if c.elm_pflotran and int(sa["moisture_response_function"][0]) != 0:
             return False, "ELM build with a moisture response function"
     return True, ""
+
+
+def has_kinetic3(cfg: abi.ReactionConfig) -> bool:
+    """RGeneral / RRadioactiveDecay / RImmobileDecay / RMicrobial present (generated by gen_kinetic)"""
+    c = cfg.c
+    return c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0 or c.nmicrobial_rxn > 0
 
 
 def _lit(x: float) -> str:
@@ -323,6 +403,25 @@ class _Gen:
             used.update(int(v) for v in (dn.no3_id, dn.n2_id) if v >= 0)
             if dn.ngasdeni_id >= 0:
                 used.add(naq + int(dn.ngasdeni_id))
+        for ids in ("eqionx_cationid", "eqkd_specid", "eqdynamickd_specid", "eqdynamickd_refspecid"):
+            if ids in self.a:
+                used.update(int(v) for v in self.a[ids])
+        self.dsp = {}
+        for ids in ("general_specid", "general_fwd_specid", "general_bwd_specid", "radiodecay_specid",
+                    "radiodecay_forward_specid", "microbial_specid", "microbial_monod_specid",
+                    "microbial_inhibition_specid"):
+            if ids in self.a:
+                used.update(int(v) for v in self.a[ids])
+        if self.c.nimmobile_decay_rxn > 0:
+            used.update(naq + int(v) for v in self.a["immobile_decay_specid"])
+        if self.c.nmicrobial_rxn > 0:
+            for b in self.a["microbial_biomassid"]:
+                if int(b) > 0:
+                    used.add(int(b) - 1)
+                elif int(b) < 0:
+                    used.add(naq + (-int(b) - 1))
+        # rows of d(total)/d(free) that RRadioactiveDecay reads: (parent, j) pairs kept beside the Jacobian
+        self.dtp = {}
         self.used = sorted(used)
         self._recording = False
         self._pairs = set()
@@ -485,6 +584,21 @@ class _Gen:
         # aqueous species can be coupled (immobile ones need a sandbox)
         self.w("#pragma unroll")
         self.w("  for (int k = 0; k < SPEC_NRO; k++) SW(SPEC_OFF_RO + k) = 0.0;")
+        if self.c.nradiodecay_rxn > 0:
+            # rt_auxvar%aqueous%dtotal(parent, :) for RRadioactiveDecay (reaction.F90:5280-5290)
+            self.dtp = {}
+            for jc in sorted({int(v) for v in a["radiodecay_forward_specid"]}):
+                for j in range(naq):
+                    if (jc, j) in hot:
+                        src = f"jh_{jc}_{j}"
+                    elif (jc, j) in written:
+                        src = self.J(jc, j)
+                    elif jc == j:
+                        src = "1.0"
+                    else:
+                        continue
+                    k = self.dtp.setdefault((jc, j), len(self.dtp))
+                    self.w(f"  s.dtp[{k}] = {src} * denL;")
         rec, self._recording = self._recording, False   # the loop below touches every pair: not structure
         self._touch_all = True
         for i in self.coupled:
@@ -515,12 +629,68 @@ class _Gen:
 
     def gen_sorption(self) -> None:
         c, a, n = self.c, self.a, self.n
-        self.w("__device__ __forceinline__ void spec_sorption(const double (&lna)[SPEC_N], const double (&ic)[SPEC_N],")
-        self.w("    double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st, long long cell, double jscale) {")
+        self.w("__device__ __forceinline__ void spec_sorption(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],")
+        self.w("    const double (&ic)[SPEC_N], double (&ts)[SPEC_N], SpecCell &s, double *W, const DevState &st,")
+        self.w("    long long cell, double jscale) {")
+        self.w("  (void)c;")
         for k in range(c.nsrfcplx):
             self.w(f"  if (s.store) s.scconc[{k}] = 0.0;")
         for e in range(c.neqsrfcplxrxn):
             self._emit_srfcplx_rxn(int(a["eqsrfcplxrxn_to_srfcplxrxn"][e]), "ts[%d]", True)
+        # RTotalSorb's order (reaction.F90:4783-4835): surface complexation, ion exchange, dynamic KD, KD
+        parents = sorted({int(v) for v in a["radiodecay_forward_specid"]}) if c.nradiodecay_rxn > 0 else []
+        self.dsp = {}
+
+        def ds_add(i: int, j: int, expr: str) -> None:
+            # rt_auxvar%dtotal_sorb_eq(parent, j) for RRadioactiveDecay (reaction.F90:5257-5305)
+            if i in parents:
+                k = self.dsp.setdefault((i, j), len(self.dsp))
+                self.w(f"    s.dsp[{k}] += {expr};")
+
+        if parents and (c.neqkdrxn > 0 or c.neqdynamickdrxn > 0):
+            self.w("#pragma unroll")
+            self.w("  for (int k = 0; k < SPEC_NDSP; k++) s.dsp[k] = 0.0;")
+        for r in range(c.neqionxrxn):
+            self._emit_ionx(r)
+        for r in range(c.neqdynamickdrxn):
+            ikd, iref = int(a["eqdynamickd_specid"][r]), int(a["eqdynamickd_refspecid"][r])
+            pw, lo = float(a["eqdynamickd_power"][r]), float(a["eqdynamickd_low"][r])
+            hml = float(a["eqdynamickd_high"][r]) - lo
+            self.w("  {  // RTotalSorbDynamicKD")
+            self.w(f"    const double t = pow(c[{iref}] / {_lit(float(a['eqdynamickd_refspechigh'][r]))}, {_lit(pw)});")
+            self.w(f"    const double KD = {_lit(lo)} + t * {_lit(hml)};")
+            self.w(f"    const double dKD = {_lit(pw)} * t / c[{iref}] * {_lit(hml)};")
+            self.w(f"    ts[{ikd}] = ts[{ikd}] + KD * c[{ikd}] * 250.0;")
+            self.w(f"    {self.J(ikd, ikd)} += (KD * 250.0) * jscale;")
+            self.w(f"    {self.J(ikd, iref)} += (dKD * c[{ikd}] * 250.0) * jscale;")
+            ds_add(ikd, ikd, "KD * 250.0")
+            ds_add(ikd, iref, f"dKD * c[{ikd}] * 250.0")
+            self.w("  }")
+        for r in range(c.neqkdrxn):
+            ic_, ty, mn = int(a["eqkd_specid"][r]), int(a["eqkd_type"][r]), int(a["eqkd_mineral"][r])
+            co = _lit(float(a["eqkd_coeff"][r]))
+            self.w("  {  // RTotalSorbKD")
+            if int(c.ikd_units) == 1:
+                self.w(f"    double kd = {co} * s.den_kg * (1.0 - s.por) * s.spd * 1.e-3;")
+            else:
+                self.w(f"    double kd = {co};")
+            if mn >= 0:
+                self.w(f"    kd = kd * (st.mnrl_volfrac[{mn} * st.ld + cell]);")
+            self.w(f"    const double m = c[{ic_}];")
+            if ty == 1:      # PFRX_SORPTION_LINEAR
+                self.w("    const double res = kd * m, dres = kd;")
+            elif ty == 2:    # PFRX_SORPTION_LANGMUIR
+                self.w("    const double t = kd * m;")
+                self.w(f"    const double res = t * {_lit(float(a['eqkd_langmuir_b'][r]))} / (1.0 + t);")
+                self.w("    const double dres = res / m - res / (1.0 + t) * t / m;")
+            else:
+                on = 1.0 / float(a["eqkd_freundlich_n"][r])
+                self.w(f"    const double res = kd * pow(m, {_lit(on)});")
+                self.w(f"    const double dres = res / m * {_lit(on)};")
+            self.w(f"    ts[{ic_}] = ts[{ic_}] + res;")
+            self.w(f"    {self.J(ic_, ic_)} += dres * jscale;")
+            ds_add(ic_, ic_, "dres")
+            self.w("  }")
         self.w("}")
         self.w()
         if c.nkinmrsrfcplxrxn > 0:
@@ -539,6 +709,77 @@ class _Gen:
                 self.w("  }")
             self.w("}")
             self.w()
+
+    def _emit_ionx(self, r: int) -> None:
+        """RTotalSorbEqIonx (reaction.F90:4906-5140) for exchange reaction r: Gaines-Thomas equivalent fractions
+        (mixed valences: the scalar Newton iteration on KDj from the cell's previous answer), sorbed
+        concentrations, jscale * d(total_sorb)/d(free) into the Jacobian.  The arithmetic of pfrx_tpc.cuh."""
+        c, a = self.c, self.a
+        p0, p1 = int(a["eqionx_ptr"][r]), int(a["eqionx_ptr"][r + 1])
+        cats = [int(a["eqionx_cationid"][p]) for p in range(p0, p1)]
+        ks = [float(a["eqionx_k"][p]) for p in range(p0, p1)]
+        Z = [float(a["primary_spec_Z"][i]) for i in cats]
+        nc = len(cats)
+        surf = int(a["eqionx_to_surf"][r])
+        cec = _lit(float(a["eqionx_CEC"][r]))
+        self.w("  {  // RTotalSorbEqIonx")
+        if surf >= 0:
+            self.w(f"    const double omega = fmax({cec} * st.mnrl_volfrac[{surf} * st.ld + cell], 1.e-40);")
+        else:
+            self.w(f"    const double omega = {cec};")
+        for j in range(nc):
+            self.w(f"    double X{j};")
+        if int(a["eqionx_Z_flag"][r]):
+            self.w(f"    const double rkc = {_lit(ks[0])} * exp(lna[{cats[0]}]);")
+            for j in range(1, nc):
+                self.w(f"    const double ka{j} = {_lit(ks[j])} * exp(lna[{cats[j]}]);")
+            self.w(f"    double rX = {_lit(Z[0])} * s.ixref[{r}] / omega;")
+            self.w("    double KDj = rX / rkc;")
+            self.w("    bool one_more = false;")
+            self.w("    int it = 0;")
+            self.w("    for (;;) {")
+            self.w("      it++;")
+            self.w("      if (it > 20000) break;")
+            self.w("      rX = KDj * rkc;")
+            self.w("      X0 = rX;")
+            self.w("      double total = rX, dres = 0.0;")
+            for j in range(1, nc):
+                ratio = Z[j] / Z[0]
+                self.w(f"      X{j} = ka{j} * pow(KDj, {_lit(ratio)});")
+                self.w(f"      total = total + X{j};")
+                self.w(f"      dres = dres + X{j} / KDj * {_lit(Z[j])};")
+            self.w(f"      dres = dres / {_lit(Z[0])} + rkc;")
+            self.w("      const double res = 1.0 - total;")
+            self.w("      if (one_more) break;")
+            self.w("      const double dK = res / dres;")
+            self.w("      KDj = KDj + dK;")
+            self.w("      KDj = fmax(KDj, 1.e-40);")
+            self.w("      if (fabs(dK / KDj) < 1.e-12) one_more = true;")
+            self.w("    }")
+            self.w(f"    if (s.store) s.ixref[{r}] = rX * omega / {_lit(Z[0])};")
+        else:
+            self.w("    double sumkm = 0.0;")
+            for j in range(nc):
+                self.w(f"    X{j} = exp(lna[{cats[j]}]) * {_lit(ks[j])};")
+                self.w(f"    sumkm = sumkm + X{j};")
+            for j in range(nc):
+                self.w(f"    X{j} = X{j} / sumkm;")
+        self.w("    double sumZX = 0.0;")
+        for j in range(nc):
+            self.w(f"    sumZX = sumZX + {_lit(Z[j])} * X{j};")
+        for i in range(nc):
+            self.w(f"    {{ const double t1 = X{i} * omega / {_lit(Z[i])};")
+            self.w(f"      if (s.store) s.ixconc[{p0 + i}] = t1;")
+            self.w(f"      ts[{cats[i]}] = ts[{cats[i]}] + t1;")
+            self.w(f"      const double t2 = {_lit(Z[i])} / sumZX;")
+            for j in range(nc):
+                if i == j:
+                    d = f"t1 * (1.0 - (t2 * X{j})) * ic[{cats[j]}]"
+                else:
+                    d = f"(-t1) * t2 * X{j} * ic[{cats[j]}]"
+                self.w(f"      {self.J(cats[i], cats[j])} += ({d}) * jscale;")
+            self.w("    }")
+        self.w("  }")
 
     def _emit_srfcplx_rxn(self, r: int, ts_fmt: str, store_conc: bool) -> None:
         """RTotalSorbEqSurfCplx1 for reaction r with unit free-site stoichiometry (closed form):
@@ -668,6 +909,212 @@ class _Gen:
             self.w("      }")
             self.w("    }")
             self.w(f"    if (s.store) s.mrate[{m}] = rate_vol;")
+            self.w("  }")
+        self.w("}")
+        self.w()
+
+    def _lngam_expr(self, i: int) -> str:
+        if self.act_upd:
+            return "0.0" if self.pri_cls[i] < 0 else f"s.lgcls[{self.pri_cls[i]}]"
+        return f"s.lngam[{i}]"
+
+    def gen_kinetic(self) -> None:
+        """RRadioactiveDecay, RGeneral, RMicrobial, RImmobileDecay in RReaction's order (reaction.F90:4095-4127) as
+        straight-line code: species ids, stoichiometries, rate constants, Monod / inhibition constants as literals.
+        Same arithmetic as the table-driven pfrx_tpc.cuh (which follows reaction.F90:5211-5460,
+        reaction_microbial.F90:287-602, reaction_immobile.F90:244-296)."""
+        c, a, naq = self.c, self.a, self.naq
+        self.w("__device__ __forceinline__ void spec_kinetic(const double (&c)[SPEC_N], const double (&lna)[SPEC_N],")
+        self.w("    const double (&ic)[SPEC_N], const double (&tot)[SPEC_N], const double (&ts)[SPEC_N], double (&res)[SPEC_N],")
+        self.w("    SpecCell &s, double *W, double dt) {")
+        self.w("  (void)lna; (void)ic; (void)tot; (void)ts; (void)dt; (void)W;")
+        self.w("  const double L_water = s.por * s.vol * 1.e3 * s.sat;")
+        self.w("  (void)L_water;")
+        # ---- RRadioactiveDecay
+        for r in range(c.nradiodecay_rxn):
+            ptr, ids, st = a["radiodecay_ptr"], a["radiodecay_specid"], a["radiodecay_stoich"]
+            jc = int(a["radiodecay_forward_specid"][r])
+            kf = _lit(float(a["radiodecay_kf"][r]))
+            self.w("  {  // RRadioactiveDecay")
+            if c.neqkdrxn > 0 or c.neqdynamickdrxn > 0:
+                self.w(f"    const double sum = tot[{jc}] * L_water + ts[{jc}] * s.vol;")
+            else:
+                self.w(f"    const double sum = tot[{jc}] * L_water;")
+            self.w(f"    const double rate = sum * {kf};")
+            self.w(f"    const double t = -1.0 * {kf};")
+            for p in range(ptr[r], ptr[r + 1]):
+                i, nu = int(ids[p]), float(st[p])
+                self.w(f"    res[{i}] = res[{i}] - {_lit(nu)} * rate;")
+                for (pj, j), k in self.dtp.items():
+                    if pj == jc:
+                        self._Jadd(i, j, f"t * {_lit(nu)} * s.dtp[{k}] * L_water")
+            for p in range(ptr[r], ptr[r + 1]):
+                i, nu = int(ids[p]), float(st[p])
+                for (pj, j), k in self.dsp.items():
+                    if pj == jc:
+                        self._Jadd(i, j, f"t * {_lit(nu)} * s.dsp[{k}] * s.vol")
+            self.w("  }")
+        # ---- RGeneral
+        if c.ngeneral_rxn > 0:
+            self.w("  const double pdsv = s.por * s.den_kg * s.sat * s.vol;")
+        for r in range(c.ngeneral_rxn):
+            ptr, ids, st = a["general_ptr"], a["general_specid"], a["general_stoich"]
+            fp, fi, fs = a["general_fwd_ptr"], a.get("general_fwd_specid"), a.get("general_fwd_stoich")
+            bp, bi, bs = a["general_bwd_ptr"], a.get("general_bwd_specid"), a.get("general_bwd_stoich")
+            kf, kr = float(a["general_kf"][r]), float(a["general_kr"][r])
+            self.w("  {  // RGeneral")
+            for side, kk, pp, ii, ss in (("f", kf, fp, fi, fs), ("r", kr, bp, bi, bs)):
+                if kk > 0.0:
+                    expr = _lit(math.log(kk))
+                    for p in range(pp[r], pp[r + 1]):
+                        expr += _term(float(ss[p]), f"lna[{int(ii[p])}]")
+                    self.w(f"    const double lnQk{side} = {expr};")
+                    self.w(f"    const double Qk{side} = sx_exp(lnQk{side});")
+                else:
+                    self.w(f"    const double Qk{side} = 0.0;")
+            for p in range(ptr[r], ptr[r + 1]):
+                i, nu = int(ids[p]), float(st[p])
+                self.w(f"    res[{i}] = res[{i}] - {_lit(nu)} * (Qkf - Qkr) * pdsv;")
+            if kf > 0.0:
+                for q in range(fp[r], fp[r + 1]):
+                    jc = int(fi[q])
+                    self.w(f"    {{ const double t = -1.0 * {_lit(float(fs[q]))} * sx_exp(lnQkf - sx_log(c[{jc}])) * pdsv;")
+                    for p in range(ptr[r], ptr[r + 1]):
+                        self._Jadd(int(ids[p]), jc, f"{_lit(float(st[p]))} * t")
+                    self.w("    }")
+            if kr > 0.0:
+                for q in range(bp[r], bp[r + 1]):
+                    jc = int(bi[q])
+                    self.w(f"    {{ const double t = {_lit(float(bs[q]))} * sx_exp(lnQkr - sx_log(c[{jc}])) * pdsv;")
+                    for p in range(ptr[r], ptr[r + 1]):
+                        self._Jadd(int(ids[p]), jc, f"{_lit(float(st[p]))} * t")
+                    self.w("    }")
+            self.w("  }")
+        # ---- RMicrobial
+        units = int(c.microbial_concentration_units) if c.nmicrobial_rxn > 0 else 0
+
+        def dcdm(i: int) -> str:
+            if units == 1:     # PFRX_MICROBIAL_MOLALITY / _ACTIVITY / _MOLARITY = 1 / 2 / 3
+                return "1.0"
+            if units == 2:
+                lg = self._lngam_expr(i)
+                return "1.0" if lg == "0.0" else f"exp({lg})"
+            return "(s.den_kg * 1.e-3)"
+
+        for r in range(c.nmicrobial_rxn):
+            ptr, ids, st = a["microbial_ptr"], a["microbial_specid"], a["microbial_stoich"]
+            mp, hp = a["microbial_monod_ptr"], a["microbial_inhibition_ptr"]
+            m0, nm = int(mp[r]), int(mp[r + 1] - mp[r])
+            h0, nh = int(hp[r]), int(hp[r + 1] - hp[r])
+            self.w("  {  // RMicrobial")
+            k = _lit(float(a["microbial_rate_constant"][r]))
+            ea = float(a["microbial_activation_energy"][r]) if "microbial_activation_energy" in a else None
+            if ea is not None:
+                self.w(f"    const double k_eff = {k} * exp({_lit(ea)} / 8.31446 * (1.0 / 298.15 - 1.0 / (s.temp + 273.15)));")
+            else:
+                self.w(f"    const double k_eff = {k};")
+            # concentrations in the reaction's units, once per distinct species
+            spec = []
+            for ii in range(nm):
+                spec.append(int(a["microbial_monod_specid"][m0 + ii]))
+            for ii in range(nh):
+                spec.append(int(a["microbial_inhibition_specid"][h0 + ii]))
+            ib = int(a["microbial_biomassid"][r])
+            if ib > 0:
+                spec.append(ib - 1)
+            for i in sorted(set(spec)):
+                self.w(f"    const double dc{i} = {dcdm(i)};")
+                self.w(f"    const double cc{i} = c[{i}] * dc{i};")
+            for ii in range(nm):
+                i = int(a["microbial_monod_specid"][m0 + ii])
+                K, cth = _lit(float(a["microbial_monod_K"][m0 + ii])), _lit(float(a["microbial_monod_Cth"][m0 + ii]))
+                self.w(f"    const double mden{ii} = {K} + cc{i} - {cth};")
+                self.w(f"    const double monod{ii} = (cc{i} - {cth}) / mden{ii};")
+                self.w(f"    const double dmon{ii} = dc{i} / mden{ii} - dc{i} * (cc{i} - {cth}) / (mden{ii} * mden{ii});")
+            for ii in range(nh):
+                i = int(a["microbial_inhibition_specid"][h0 + ii])
+                ty = int(a["microbial_inhibition_type"][h0 + ii])
+                C1, C2 = float(a["microbial_inhibition_C"][h0 + ii]), float(a["microbial_inhibition_C2"][h0 + ii])
+                if ty == 3:       # PFRX_INHIBITION_MONOD
+                    self.w(f"    const double hden{ii} = {_lit(C1)} + cc{i};")
+                    self.w(f"    const double dinh{ii} = -1.0 * dc{i} * {_lit(C1)} / (hden{ii} * hden{ii});")
+                    self.w(f"    const double inhib{ii} = {_lit(C1)} / ({_lit(C1)} + cc{i});")
+                elif ty == 4:     # PFRX_INHIBITION_INVERSE_MONOD
+                    self.w(f"    const double hden{ii} = {_lit(C1)} + cc{i};")
+                    self.w(f"    const double dinh{ii} = dc{i} / hden{ii} - dc{i} * cc{i} / (hden{ii} * hden{ii});")
+                    self.w(f"    const double inhib{ii} = cc{i} / ({_lit(C1)} + cc{i});")
+                elif ty == 1:     # PFRX_INHIBITION_THRESHOLD
+                    sg = "1.0" if math.copysign(1.0, C1) > 0 else "-1.0"
+                    self.w(f"    const double ht{ii} = (cc{i} - {_lit(abs(C1))}) * {_lit(C2)};")
+                    self.w(f"    const double dinh{ii} = {sg} * ({_lit(C2)} * dc{i} / (1.0 + ht{ii} * ht{ii})) / 3.14159265359;")
+                    self.w(f"    const double inhib{ii} = 0.5 + {sg} * atan(ht{ii}) / 3.14159265359;")
+                else:  # SMOOTHSTEP
+                    lower = math.log10(C1) - 0.5 * C2
+                    self.w(f"    const double hz{ii} = (log10(cc{i}) - {_lit(lower)}) / {_lit(C2)};")
+                    self.w(f"    const double dinh{ii} = (hz{ii} < 0.0 || hz{ii} > 1.0) ? 0.0 : "
+                           f"(6.0 * hz{ii} - 6.0 * (hz{ii} * hz{ii})) / ({_lit(C2)} * cc{i} * 2.30258509299) * dc{i};")
+                    self.w(f"    const double inhib{ii} = hz{ii} < 0.0 ? 0.0 : (hz{ii} > 1.0 ? 1.0 : "
+                           f"3.0 * (hz{ii} * hz{ii}) - 2.0 * (hz{ii} * hz{ii} * hz{ii}));")
+            self.w("    double monod_terms = 1.0, inhib_terms = 1.0;")
+            for ii in range(nm):
+                self.w(f"    monod_terms = monod_terms * monod{ii};")
+            for ii in range(nh):
+                self.w(f"    inhib_terms = inhib_terms * inhib{ii};")
+            brow, yld = -1, 0.0
+            if ib > 0:
+                brow, yld = ib - 1, float(a["microbial_biomass_yield"][r])
+                self.w(f"    const double biomass_term = 1.0 * cc{brow} * L_water;")
+                self.w(f"    const double dbio = dc{brow};")
+            elif ib < 0:
+                brow, yld = naq + (-ib - 1), float(a["microbial_biomass_yield"][r])
+                self.w(f"    const double biomass_term = 1.0 * c[{brow}] * s.vol;")
+                self.w("    const double dbio = 1.0;")
+            else:
+                self.w("    const double biomass_term = 1.0 * L_water;")
+            self.w("    const double rate = k_eff * monod_terms * inhib_terms * biomass_term;")
+            rows = [(int(ids[p]), float(st[p])) for p in range(ptr[r], ptr[r + 1])]
+            for i, nu in rows:
+                self.w(f"    res[{i}] = res[{i}] - {_lit(nu)} * rate;")
+            if brow >= 0:
+                self.w(f"    res[{brow}] = res[{brow}] - {_lit(yld)} * rate;")
+            for ii in range(nm):
+                jc = int(a["microbial_monod_specid"][m0 + ii])
+                expr = "k_eff * inhib_terms * biomass_term"
+                for jj in range(nm):
+                    if jj != ii:
+                        expr = f"({expr}) * monod{jj}"
+                self.w(f"    {{ const double dR_dc = -1.0 * ({expr}) * dmon{ii};")
+                for i, nu in rows:
+                    self._Jadd(i, jc, f"{_lit(nu)} * dR_dc")
+                if brow >= 0:
+                    self._Jadd(brow, jc, f"{_lit(yld)} * dR_dc")
+                self.w("    }")
+            for ii in range(nh):
+                jc = int(a["microbial_inhibition_specid"][h0 + ii])
+                expr = "k_eff * monod_terms * biomass_term"
+                for jj in range(nh):
+                    if jj != ii:
+                        expr = f"({expr}) * inhib{jj}"
+                self.w(f"    {{ const double dR_dc = -1.0 * ({expr}) * dinh{ii};")
+                for i, nu in rows:
+                    self._Jadd(i, jc, f"{_lit(nu)} * dR_dc")
+                if brow >= 0:
+                    self._Jadd(brow, jc, f"{_lit(yld)} * dR_dc")
+                self.w("    }")
+            if brow >= 0:
+                self.w("    { const double dRb = -1.0 * (k_eff * monod_terms * inhib_terms) * dbio;")
+                for i, nu in rows:
+                    self._Jadd(i, brow, f"{_lit(nu)} * dRb")
+                self._Jadd(brow, brow, f"{_lit(yld)} * dRb")
+                self.w("    }")
+            self.w("  }")
+        # ---- RImmobileDecay
+        for r in range(c.nimmobile_decay_rxn):
+            i = naq + int(a["immobile_decay_specid"][r])
+            self.w("  {  // RImmobileDecay")
+            self.w(f"    const double rc = {_lit(float(a['immobile_decay_constant'][r]))} * s.vol;")
+            self.w(f"    res[{i}] = res[{i}] + rc * c[{i}];")
+            self._Jadd(i, i, "rc")
             self.w("  }")
         self.w("}")
         self.w()
@@ -1383,6 +1830,8 @@ class _Gen:
         self.gen_rtotal()
         self.gen_sorption()
         self.gen_minerals()
+        if has_kinetic3(self.cfg):
+            self.gen_kinetic()
         if nsbx > 0:
             self.gen_sandbox()
         return self.out
@@ -1487,6 +1936,12 @@ class _Gen:
         nnc = (len(self.a["somdec_upstream_nc"]) + len(self.a["somdec_downstream_nc"])) if c.somdec else 0
         self.w(f"#define SPEC_NCLM {c.clmcn_nrxn}")
         self.w(f"#define SPEC_NSBX {nsbx}")
+        self.w(f"#define SPEC_NKIN3 {int(has_kinetic3(self.cfg))}")
+        self.w(f"#define SPEC_NDTP {len(self.dtp)}")
+        self.w(f"#define SPEC_NDSP {len(self.dsp)}")
+        self.w(f"#define SPEC_NIONX {c.neqionxrxn}")
+        self.w(f"#define SPEC_NIXCAT {int(self.a['eqionx_ptr'][c.neqionxrxn]) if c.neqionxrxn else 0}")
+        self.w(f"#define SPEC_NSORB {c.neqsrfcplxrxn + c.neqionxrxn + c.neqkdrxn + c.neqdynamickdrxn}")
         self.w(f"#define SPEC_NNC {nnc}")
         self.w(f"#define SPEC_ELM {int(bool(c.elm_pflotran))}")
         if nnc:

@@ -55,6 +55,8 @@ def supported2(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "multirate sorption"
     if c.clmcn_nrxn > 0 or c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
         return False, "reaction sandbox"
+    if c.ngeneral_rxn > 0 or c.nradiodecay_rxn > 0 or c.nimmobile_decay_rxn > 0 or c.nmicrobial_rxn > 0:
+        return False, "general / decay / microbial reactions (non-symmetric Jacobian)"
     for name in ("eqcplx_stoich", "eqcplx_h2ostoich", "kinmnrl_stoich", "kinmnrl_h2ostoich", "srfcplx_stoich",
                  "srfcplx_h2ostoich"):
         if name in a and not all(_is_int(v) for v in a[name]):

@@ -13,7 +13,8 @@ from pflotran_elm_interface_b200 import specialize, workloads as W
 
 def test_supported_networks():
     for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", True), ("c4", True),
-                     ("c4fe", True), ("c6", False), ("c2pf", False), ("c3an", False)):
+                     ("c4fe", True), ("c6", True), ("c7", True), ("c7s", True), ("c8", True), ("c7g", False), ("c2pf", False),
+                     ("c3an", False)):
         wl = W.by_name(name, ncell=2)
         got, why = specialize.supported(wl.cfg)
         assert got is ok, (name, why)
@@ -53,6 +54,26 @@ def test_source_is_deterministic_and_covers_the_network():
     b1 = specialize.generate_source(W.by_name("c3mr", ncell=2).cfg)
     for routine in ("spec_activity", "spec_rtotal", "spec_sorption", "spec_minerals"):
         assert f"void {routine}(" in b1
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c3mr", "c5", "c4", "c4s", "c4se", "c4fe", "c6", "c7", "c7s", "c8"])
+def test_library_and_generator_agree_on_the_signature(name, tmp_path):
+    """config_signature() in csrc/pfrx_api.cu and specialize.signature() hash the same bytes, and the
+    configuration written by pfrx_config_write generates the same kernel as the deck-built one"""
+    import ctypes as C
+
+    from pflotran_elm_interface_b200 import abi, rstep
+
+    L = rstep.lib()
+    cfg = W.by_name(name, ncell=2).cfg
+    assert specialize.supported(cfg)[0]
+    sig = specialize.signature(cfg)
+    assert L.pfrx_config_signature_of(C.byref(cfg.c)) == sig
+    f = str(tmp_path / "cfg.dump")
+    assert L.pfrx_config_write(C.byref(cfg.c), f.encode()) == 0
+    back = abi.ReactionConfig.from_dump(f)
+    assert back.dump_signature == sig == specialize.signature(back)
+    assert specialize.generate_source(back) == specialize.generate_source(cfg)
 
 
 def test_signature_tracks_tables():
@@ -140,7 +161,7 @@ def test_build_is_cached(tmp_path, monkeypatch):
     assert "sm_100a" in log and re.search(r"Used \d+ registers", log)
 
 
-@pytest.mark.parametrize("name", ["c2", "c3", "c3mr", "c5", "c4", "c4s", "c4se", "c4fe"])
+@pytest.mark.parametrize("name", ["c2", "c3", "c3mr", "c5", "c4", "c4s", "c4se", "c4fe", "c6", "c7", "c7s", "c8"])
 def test_structural_mask_covers_the_oracle_jacobian(name):
     """RSolve's row scaling in the generated kernels skips the entries outside spec_jrow_mask: every
     entry the oracle's Jacobian (accumulation + RReaction, reaction.F90:3868-3925) has on real cells
