@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PFRX_ABI_VERSION 8
+#define PFRX_ABI_VERSION 9
 
 /* error classes */
 #define PFRX_OK 0
@@ -468,6 +468,13 @@ typedef struct pfrx_config {
   const double *acteq_h2ostoich;     /* [nactive_gas]                                           */
   const double *acteq_logK;          /* [nactive_gas] at the reference temperature              */
   const double *acteq_logK_coef;     /* [nactive_gas][5] or NULL                                */
+  /* ELM build WITH a flow mode (option%nflowspec > 0, reaction_sandbox_somdec.F90:1640-1644): SOMDECOMP
+   * reactions whose MOISTURE_RESPONSE_FUNCTION is CLMCN or DLEM take f_w from GetMoistureResponse
+   * (elm_rspfuncs.F90:124-237: Clapp-Hornberger matric potential from sucsat / bsw / dry bulk density, or
+   * the DLEM curve between field capacity and effective porosity) instead of ELM's w_scalar.  0: BGC-only
+   * coupling, the function is ignored as in the reference.  Only read when elm_pflotran != 0. */
+  int32_t elm_flow_coupled;
+  int32_t pad_elm_;
 } pfrx_config;
 
 /*
@@ -549,6 +556,11 @@ typedef struct pfrx_state {
   const double *sat_gas;
   double *total_gas;
   double *gas_pp;
+  /* ELM soil hydraulic properties for GetMoistureResponse (elm_pf_idata%sucsat_pfs [mm H2O], watfc_pfs,
+   * effporosity_pfs), in [1] each; needed only when pfrx_config.elm_flow_coupled != 0, else NULL */
+  const double *elm_sucsat;
+  const double *elm_watfc;
+  const double *elm_effporosity;
   /* per-cell results of RStep (reaction.F90:3564-3566) */
   int32_t *num_sub_steps;
   int32_t *num_iterations;

@@ -67,6 +67,7 @@ typedef struct {
   double *total_gas, *dtotal_gas, *gas_pp, *acteq_logK;
   /* ELM per-cell scalars (elm_pflotran builds) */
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
+  double elm_sucsat, elm_watfc, elm_effpor; /* GetMoistureResponse inputs (elm_flow_coupled) */
   double *somdec_nc; /* persisted N:C ratios, see pfrx_state.somdec_nc */
   int nsomdec_nc;
   double *eqionx_ref, *eqionx_conc; /* ion exchange: reference-cation sorbed conc, cation concs */
@@ -203,6 +204,9 @@ static void cell_gather(cell_t *c, const pfrx_config *cfg, const pfrx_state *st,
   c->elm_kscalar = st->elm_kscalar_decomp_c ? LD(st->elm_kscalar_decomp_c, 0) : 1.0;
   c->elm_bd_dry = st->elm_bulkdensity_dry ? LD(st->elm_bulkdensity_dry, 0) : 1.25e3;
   c->elm_bsw = st->elm_bsw ? LD(st->elm_bsw, 0) : 1.0;
+  c->elm_sucsat = st->elm_sucsat ? LD(st->elm_sucsat, 0) : 200.0;
+  c->elm_watfc = st->elm_watfc ? LD(st->elm_watfc, 0) : 0.1;
+  c->elm_effpor = st->elm_effporosity ? LD(st->elm_effporosity, 0) : 0.4;
   c->elm_plantndemand = st->elm_rate_plantndemand ? LD(st->elm_rate_plantndemand, 0) : 0.0;
   c->option_ierror = 0;
 }
@@ -1387,6 +1391,45 @@ static double get_temperature_response(double tc, int itype, double Q10orEA) {
   return Ft;
 }
 
+/* elm_rspfuncs.F90:124-237  GetMoistureResponse, ELM_PFLOTRAN build: theta is the volumetric water content */
+static double elm_moisture_response(const cell_t *c, double theta, int itype) {
+  const double minpsi = -10.0e6; /* Pa */
+  const double EARTH_GRAVITY = 9.8068; /* pflotran_constants.F90:94 */
+  double F_theta, maxpsi, psi, lsat, thetar, thetas, se;
+  switch (itype) {
+    case PFRX_MOISTURE_RESPONSE_CLMCN:
+      maxpsi = c->elm_sucsat * (-EARTH_GRAVITY);
+      lsat = theta / fmin(1.0, 1.0 - fmin(0.9999, c->elm_bd_dry / 2.70e3));
+      psi = c->elm_sucsat * (-EARTH_GRAVITY) * pow(lsat, -c->elm_bsw);
+      psi = fmin(psi, maxpsi);
+      if (psi > minpsi) {
+        F_theta = log(minpsi / psi) / log(minpsi / maxpsi);
+        if (psi > (maxpsi - 1.0e02)) F_theta = F_theta * 0.10;
+      } else {
+        F_theta = 0.0;
+      }
+      break;
+    case PFRX_MOISTURE_RESPONSE_DLEM:
+      thetas = c->elm_effpor;
+      thetar = c->elm_watfc;
+      if (theta >= thetas) {
+        F_theta = 1.0;
+      } else if (theta <= thetar) {
+        F_theta = 0.0;
+      } else {
+        se = (theta - thetar) / (thetas - thetar);
+        /* "1.0 - se * se * 0.368 * exp(se)": default-kind literals, single precision */
+        F_theta = (double)1.0f - se * se * (double)0.368f * exp(se);
+        if (F_theta < 0.0) F_theta = 0.0;
+        if (F_theta > 1.0) F_theta = 1.0;
+      }
+      break;
+    default:
+      F_theta = 1.0;
+  }
+  return F_theta;
+}
+
 /* elm_rspfuncs.F90:287-317  GetAerobicCondition */
 static double get_aerobic_condition(double OXorWFPS, double K_Ox, int itype, int compute_derivative) {
   double F_Ox;
@@ -1929,8 +1972,12 @@ static void somdec_react(cell_t *c, const pfrx_config *cfg, double tran_dt, doub
     double crate_uc, dcrate_uc_duc;
     int ispec_uc, nd = sd->downstream_ptr[irxn + 1] - sd->downstream_ptr[irxn];
     somdec_scratch_t w;
-    if (cfg->elm_pflotran) {
-      /* BGC-only coupling (option%nflowspec == 0): factors from ELM, :1634-1641 */
+    if (cfg->elm_pflotran && cfg->elm_flow_coupled &&
+        sd->moisture_response_function[cur] != PFRX_MOISTURE_RESPONSE_OFF) {
+      /* a flow mode is active (option%nflowspec > 0), :1640-1643 */
+      f_w = elm_moisture_response(c, theta, sd->moisture_response_function[cur]);
+    } else if (cfg->elm_pflotran) {
+      /* BGC-only coupling (option%nflowspec == 0): factors from ELM, :1645-1650 */
       f_w = c->elm_w;
     } else {
       if (sd->moisture_response_function[cur] == PFRX_MOISTURE_RESPONSE_LOGTHETA) {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import chem as _chem
 
-PFRX_ABI_VERSION = 8
+PFRX_ABI_VERSION = 9
 PFRX_MAX_NCOMP = 32
 
 c_double_p = C.POINTER(C.c_double)
@@ -194,6 +194,8 @@ class PfrxConfig(C.Structure):
         ("acteq_h2ostoich", c_double_p),
         ("acteq_logK", c_double_p),
         ("acteq_logK_coef", c_double_p),
+        ("elm_flow_coupled", C.c_int32),
+        ("pad_elm_", C.c_int32),
     ]
 
 
@@ -321,7 +323,7 @@ STATE_DOUBLE_FIELDS = [
 STATE_ELM_FIELDS = ["elm_w_scalar", "elm_o_scalar", "elm_t_scalar", "elm_zsoil", "elm_kscalar_decomp_c",
                     "elm_bulkdensity_dry", "elm_bsw", "elm_rate_plantndemand", "somdec_nc",
                     "eqionx_ref_cation_sorbed_conc", "eqionx_conc", "pres", "sandbox_aux",
-                    "sat_gas", "total_gas", "gas_pp"]
+                    "sat_gas", "total_gas", "gas_pp", "elm_sucsat", "elm_watfc", "elm_effporosity"]
 STATE_INT_FIELDS = ["imat", "num_sub_steps", "num_iterations", "num_kinetic_state_updates", "ierror"]
 # fields the step updates ("io" in pfrx.h) and per-cell results
 STATE_IO_FIELDS = [
@@ -662,6 +664,7 @@ class ReactionConfig:
             c.nsandbox = len(order)
             c.sandbox_list = _ip(self._keep("sandbox_list", _i32(order)))
         c.elm_pflotran = int(getattr(net, "elm_pflotran", False))
+        c.elm_flow_coupled = int(getattr(net, "elm_flow_coupled", False))
         sd = getattr(net, "somdec", None)
         if sd is not None:
             o = PfrxSomdec()
@@ -814,6 +817,8 @@ class ReactionConfig:
             "sat_gas": 1 if c.nactive_gas > 0 else 0,
             "total_gas": c.naqcomp if c.nactive_gas > 0 else 0,
             "gas_pp": max(c.nactive_gas, 0),
+            "elm_sucsat": 1 if c.elm_flow_coupled else 0, "elm_watfc": 1 if c.elm_flow_coupled else 0,
+            "elm_effporosity": 1 if c.elm_flow_coupled else 0,
             "somdec_nc": (len(self.arrays["somdec_upstream_nc"]) + len(self.arrays.get("somdec_downstream_nc", []))
                           if c.somdec else 0),
             "imat": 1, "num_sub_steps": 1, "num_iterations": 1, "num_kinetic_state_updates": 1, "ierror": 1,
@@ -850,6 +855,9 @@ class HostState:
             self.a[f][:] = 1.0
         self.a["elm_bulkdensity_dry"][:] = 1.25e3
         self.a["pres"][:] = 101325.0
+        self.a["elm_sucsat"][:] = 200.0
+        self.a["elm_watfc"][:] = 0.1
+        self.a["elm_effporosity"][:] = 0.4
         if rows["somdec_nc"]:
             nc0 = np.concatenate([cfg.arrays["somdec_upstream_nc"],
                                   cfg.arrays.get("somdec_downstream_nc", np.zeros(0))])

@@ -317,7 +317,7 @@ static uint64_t config_walk(const pfrx_config *c, CfgSink &sink) {
     ADD(c->acteq_logK, ng)
   }
   if (c->somdec || c->nitrif || c->denitr || c->plantn || c->langmuir) {
-    int32_t e = c->elm_pflotran ? 1 : 0;
+    int32_t e = c->elm_pflotran ? (c->elm_flow_coupled ? 3 : 1) : 0;
     h = fnv1a(h, &e, sizeof(e));
     if (c->sandbox_list) ADD(c->sandbox_list, c->nsandbox)
   }
@@ -641,7 +641,7 @@ static int pick_kernel(pfrx_handle *h, int want_lanes) {
 
 // double fields of pfrx_state in header order: 20 of ABI v1, then the seven ELM
 // scalars and the SOMDECOMP N:C memory
-#define PFRX_NUM_D 36
+#define PFRX_NUM_D 39
 static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
   int mr = 0;
   if (c->nkinmrsrfcplxrxn > 0) mr = c->naqcomp * (c->kinmr_rate_ptr[c->nkinmrsrfcplxrxn] + c->nkinmrsrfcplxrxn);
@@ -653,7 +653,9 @@ static int field_rows(const pfrx_config *c, int *rows /*PFRX_NUM_D*/) {
                        c->nkinmnrl, c->nkinmnrl, c->nsrfcplxrxn, c->nsrfcplx, nsorb > 0 ? c->naqcomp : 0,
                        mr, 1, 1, 1, 1, 1, 1, e, e, e, e, e, e, e, nc, e, nix, nixc,
                        (c->cndegas && c->cndegas->cell_state_mode >= 1) ? 1 : 0, c->calcite ? 1 : 0,
-                       c->nactive_gas > 0 ? 1 : 0, c->nactive_gas > 0 ? c->naqcomp : 0, c->nactive_gas > 0 ? c->nactive_gas : 0};
+                       c->nactive_gas > 0 ? 1 : 0, c->nactive_gas > 0 ? c->naqcomp : 0, c->nactive_gas > 0 ? c->nactive_gas : 0,
+                       (c->elm_pflotran && c->elm_flow_coupled) ? 1 : 0, (c->elm_pflotran && c->elm_flow_coupled) ? 1 : 0,
+                       (c->elm_pflotran && c->elm_flow_coupled) ? 1 : 0};
   memcpy(rows, r, sizeof(r));
   return 0;
 }
@@ -971,11 +973,6 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
     for (int r = 0; r < sd->nrxn; r++)
       if (sd->ox_specid[r] >= 0 && !kind_ok(sd->ox_specitype[r]))
         return set_err(PFRX_E_INVALID, "SOMDECOMP Ox species must be primary or immobile%s", "");
-    if (c->elm_pflotran)
-      for (int r = 0; r < sd->nrxn; r++)
-        if (sd->moisture_response_function[r] != PFRX_MOISTURE_RESPONSE_OFF)
-          return set_err(PFRX_E_INVALID,
-                         "ELM build with a MOISTURE_RESPONSE_FUNCTION (flow-coupled mode) is not covered%s", "");
   }
   if (c->nitrif && c->nitrif->nh4_id < 0) return set_err(PFRX_E_INVALID, "NITRIFICATION needs NH4+%s", "");
   if (c->denitr && c->denitr->no3_id < 0) return set_err(PFRX_E_INVALID, "DENITRIFICATION needs NO3-%s", "");
@@ -1055,6 +1052,7 @@ extern "C" int pfrx_create(const pfrx_config *c, int device, pfrx_handle **out) 
   d.has_cd = c->cndegas ? 1 : 0;
   d.has_cs = c->calcite ? 1 : 0;
   d.has_rn = c->radon ? 1 : 0;
+  d.elm_flow = (c->elm_pflotran && c->elm_flow_coupled) ? 1 : 0;
   d.ngas = c->nactive_gas;
   d.elm = c->elm_pflotran ? 1 : 0;
   d.need_dt = (has_sbx3 || c->nradiodecay_rxn > 0) ? 1 : 0;
@@ -1560,6 +1558,9 @@ static int to_dev_state(const pfrx_handle *h, const pfrx_state *s, DevState *d) 
   d->sat_gas = s->sat_gas;
   d->total_gas = s->total_gas;
   d->gas_pp = s->gas_pp;
+  d->elm_sucsat = s->elm_sucsat;
+  d->elm_watfc = s->elm_watfc;
+  d->elm_effpor = s->elm_effporosity;
   // required pointers
   const void *req[] = {r[0] ? s->total : (void *)1,
                        r[1] ? s->pri_molal : (void *)1,
@@ -2126,6 +2127,9 @@ static DevState dev_state_at(const DevState &d, int64_t c0) {
   PFRX_OFF(sat_gas);
   PFRX_OFF(total_gas);
   PFRX_OFF(gas_pp);
+  PFRX_OFF(elm_sucsat);
+  PFRX_OFF(elm_watfc);
+  PFRX_OFF(elm_effpor);
   PFRX_OFF(imat);
   PFRX_OFF(num_sub_steps);
   PFRX_OFF(num_iterations);
@@ -2346,7 +2350,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                            (double **)&h->own_st.elm_bd_dry, (double **)&h->own_st.elm_bsw, &h->own_st.somdec_nc,
                            (double **)&h->own_st.elm_plantndemand, &h->own_st.eqionx_ref, &h->own_st.eqionx_conc,
                            (double **)&h->own_st.pres, &h->own_st.sandbox_aux,
-                           (double **)&h->own_st.sat_gas, &h->own_st.total_gas, &h->own_st.gas_pp};
+                           (double **)&h->own_st.sat_gas, &h->own_st.total_gas, &h->own_st.gas_pp,
+                           (double **)&h->own_st.elm_sucsat, (double **)&h->own_st.elm_watfc,
+                           (double **)&h->own_st.elm_effpor};
     for (int f = 0; f < kNumD; f++) *dst[f] = rows[f] ? base + field_off(rows, ncell, f) : nullptr;
     int *ib = (int *)(base + ndbl);
     h->own_st.imat = ib;
@@ -2366,7 +2372,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                               host->elm_zsoil,    host->elm_kscalar_decomp_c, host->elm_bulkdensity_dry, host->elm_bsw,
                               host->somdec_nc,    host->elm_rate_plantndemand, host->eqionx_ref_cation_sorbed_conc,
                               host->eqionx_conc,  host->pres,         host->sandbox_aux,
-                              host->sat_gas,      host->total_gas,    host->gas_pp};
+                              host->sat_gas,      host->total_gas,    host->gas_pp,
+                              host->elm_sucsat,   host->elm_watfc,    host->elm_effporosity};
   double *dptr[kNumD] = {d.total,        d.pri_molal,    d.immobile,  d.pri_act_coef, d.sec_act_coef,
                          d.sec_molal,    d.ln_act_h2o,   d.mnrl_volfrac, d.mnrl_area, d.mnrl_rate,
                          d.free_site,    d.eqsrfcplx_conc, d.total_sorb_eq, d.kinmr,  (double *)d.den_kg,
@@ -2374,7 +2381,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          (double *)d.soil_particle_density, (double *)d.elm_w, (double *)d.elm_o, (double *)d.elm_t,
                          (double *)d.elm_zsoil, (double *)d.elm_kscalar, (double *)d.elm_bd_dry, (double *)d.elm_bsw,
                          d.somdec_nc,    (double *)d.elm_plantndemand, d.eqionx_ref, d.eqionx_conc, (double *)d.pres,
-                         d.sandbox_aux,  (double *)d.sat_gas, d.total_gas, d.gas_pp};
+                         d.sandbox_aux,  (double *)d.sat_gas, d.total_gas, d.gas_pp,
+                         (double *)d.elm_sucsat, (double *)d.elm_watfc, (double *)d.elm_effpor};
   bool have_spd = host->soil_particle_density != nullptr;
   if (!have_spd) d.soil_particle_density = nullptr;
   bool have_lnw = host->ln_act_h2o != nullptr;
@@ -2397,6 +2405,9 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
   if (!host->sat_gas) d.sat_gas = nullptr;
   if (!host->total_gas) d.total_gas = nullptr;
   if (!host->gas_pp) d.gas_pp = nullptr;
+  if (!host->elm_sucsat) d.elm_sucsat = nullptr;
+  if (!host->elm_watfc) d.elm_watfc = nullptr;
+  if (!host->elm_effporosity) d.elm_effpor = nullptr;
   {
     DevState chk;
     pfrx_state probe = *host;
@@ -2434,7 +2445,8 @@ extern "C" int pfrx_rstep_host(pfrx_handle *h, int64_t ncell, const pfrx_state *
                          nullptr,            nullptr,            nullptr,         nullptr,
                          host->somdec_nc,    nullptr,            host->eqionx_ref_cation_sorbed_conc,
                          host->eqionx_conc,  nullptr,            host->sandbox_aux,
-                         nullptr,            host->total_gas,    host->gas_pp};
+                         nullptr,            host->total_gas,    host->gas_pp,
+                         nullptr,            nullptr,            nullptr};
   const size_t w8 = sizeof(double);
   // Fields every active cell overwrites before it reads them need no upload -- as
   // long as every cell is active (imat absent or all positive), otherwise the download would hand the

@@ -133,6 +133,7 @@ struct DevCfg {
   pfrx_cndegas cd;
   pfrx_calcite_sandbox cs;
   int has_rn;
+  int elm_flow;  // elm_flow_coupled: SOMDECOMP's f_w from GetMoistureResponse
   pfrx_radon rn;
   // active gas species (reaction_gas.F90:87-174), CSR; thread-per-cell kernel only
   int ngas, off_tg, off_dg;

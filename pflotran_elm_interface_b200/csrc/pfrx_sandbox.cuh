@@ -22,6 +22,35 @@
 
 namespace pfrx_sbx {
 
+// GetMoistureResponse of the ELM_PFLOTRAN build (elm_rspfuncs.F90:124-237): f_w of a SOMDECOMP reaction when a flow
+// mode is active.  CLMCN: Clapp-Hornberger matric potential on a log scale between -10 MPa and the air-entry
+// suction; DLEM: Tian et al. 2010 between field capacity and the effective porosity.
+__device__ __forceinline__ double elm_moisture_response(double theta, int itype, double sucsat, double bd_dry, double bsw,
+                                                        double watfc, double effpor) {
+  const double minpsi = -10.0e6, g = 9.8068;
+  if (itype == PFRX_MOISTURE_RESPONSE_CLMCN) {
+    const double maxpsi = sucsat * (-g);
+    const double lsat = theta / fmin(1.0, 1.0 - fmin(0.9999, bd_dry / 2.70e3));
+    double psi = sucsat * (-g) * pow(lsat, -bsw);
+    psi = fmin(psi, maxpsi);
+    if (!(psi > minpsi)) return 0.0;
+    double F = log(minpsi / psi) / log(minpsi / maxpsi);
+    if (psi > (maxpsi - 1.0e02)) F = F * 0.10;
+    return F;
+  }
+  if (itype == PFRX_MOISTURE_RESPONSE_DLEM) {
+    if (theta >= effpor) return 1.0;
+    if (theta <= watfc) return 0.0;
+    const double se = (theta - watfc) / (effpor - watfc);
+    double F = (double)1.0f - se * se * (double)0.368f * exp(se);
+    if (F < 0.0) F = 0.0;
+    if (F > 1.0) F = 1.0;
+    return F;
+  }
+  return 1.0;
+}
+
+
 __device__ __forceinline__ void hsmooth(double x, double x_1, double x_0, double &H, double &dH) {
   if (fabs(x_1 - x_0) < 1.e-50) {
     H = copysign(0.5, (x - x_1)) + 0.5;
@@ -542,7 +571,10 @@ struct SomDec {
 #pragma unroll 1
     for (int irxn = 0; irxn < sd.nrxn; irxn++) {
       double f_w, f_t, f_depth = 1.0, kd_scalar = 1.0;
-      if (elm) {
+      if (elm && s.cfg.elm_flow && sd.moisture_response_function[cur] != PFRX_MOISTURE_RESPONSE_OFF) {
+        f_w = elm_moisture_response(theta, sd.moisture_response_function[cur], s.elm_sucsat, s.elm_bd_dry, s.elm_bsw,
+                                    s.elm_watfc, s.elm_effpor);
+      } else if (elm) {
         f_w = s.elm_w;
       } else if (sd.moisture_response_function[cur] == PFRX_MOISTURE_RESPONSE_LOGTHETA) {
         // single-precision literals of the reference (:1645-1649)

@@ -145,6 +145,7 @@ struct SpecCell {
   double ixref[SPEC_NIONX > 0 ? SPEC_NIONX : 1];    // eqionx_ref_cation_sorbed_conc (guess of the next evaluation)
   double ixconc[SPEC_NIXCAT > 0 ? SPEC_NIXCAT : 1];  // eqionx_conc
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
+  double elm_sucsat, elm_watfc, elm_effpor;  // GetMoistureResponse (flow-coupled ELM build)
   bool dry;
   bool store;  // false: the lane has finished its cell, rt_auxvar%sec_molal must not be touched
 };
@@ -246,6 +247,9 @@ __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &s
   s.elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[cell] : 1.25e3;
   s.elm_bsw = st.elm_bsw ? st.elm_bsw[cell] : 1.0;
   s.elm_plantndemand = st.elm_plantndemand ? st.elm_plantndemand[cell] : 0.0;
+  s.elm_sucsat = st.elm_sucsat ? st.elm_sucsat[cell] : 200.0;
+  s.elm_watfc = st.elm_watfc ? st.elm_watfc[cell] : 0.1;
+  s.elm_effpor = st.elm_effpor ? st.elm_effpor[cell] : 0.4;
 #endif
 #if SPEC_NNC > 0
 #pragma unroll
@@ -280,6 +284,10 @@ __device__ __forceinline__ void spec_sandbox_store(const SpecCell &s, const DevS
 // row in its extra column.  Every register array is indexed by literals.
 __device__ __forceinline__ bool spec_rowonly(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
                                              const SpecCell &s, double dt);
+
+#if !SPEC_LOOP_LU
+__device__ __forceinline__ bool spec_solve_sparse(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N]);
+#endif
 
 __device__ __forceinline__ bool spec_solve_core(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N],
                                                 const SpecCell &s, double dt) {
@@ -396,6 +404,11 @@ __device__ __forceinline__ bool spec_solve_core(double *W, double (&res)[SPEC_N]
 }
 #else
   if (NC == 0) return !bad;
+#ifdef SPEC_SPARSE_LU
+  // sparse elimination in the static order the generator chose; false: a multiplier failed the
+  // threshold test, the Jacobian is as assembled again and the reference's algorithm below takes over
+  if (spec_solve_sparse(W, res, c)) return !bad;
+#endif
   double b[NCA];
 #pragma unroll
   for (int i = 0; i < NC; i++) {

@@ -35,6 +35,7 @@ struct CellT {
   // per-cell scalars
   double den_kg, sat, temp, por, vol, spd, ln_act_h2o;
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;  // ELM scalars
+  double elm_sucsat, elm_watfc, elm_effpor;  // GetMoistureResponse (flow-coupled ELM build)
   double Isum, msum;  // sum z^2 m and sum m over the secondary species of the latest RTotal
   bool dry;
   // register-resident per-component arrays (compile-time indices only)
@@ -1191,6 +1192,9 @@ struct CellT {
       elm_bd_dry = st.elm_bd_dry ? st.elm_bd_dry[c] : 1.25e3;
       elm_bsw = st.elm_bsw ? st.elm_bsw[c] : 1.0;
       elm_plantndemand = st.elm_plantndemand ? st.elm_plantndemand[c] : 0.0;
+      elm_sucsat = st.elm_sucsat ? st.elm_sucsat[c] : 200.0;
+      elm_watfc = st.elm_watfc ? st.elm_watfc[c] : 0.1;
+      elm_effpor = st.elm_effpor ? st.elm_effpor[c] : 0.4;
     }
 #pragma unroll 1
     for (int k = 0; k < cfg.n_nc; k++) {

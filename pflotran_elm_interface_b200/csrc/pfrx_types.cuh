@@ -21,6 +21,7 @@ struct DevState {
   // active gas phase (RTotalGas): global_auxvar%sat(2), rt_auxvar%total(:,2), rt_auxvar%gas_pp
   const double *sat_gas;
   double *total_gas, *gas_pp;
+  const double *elm_sucsat, *elm_watfc, *elm_effpor;  // GetMoistureResponse inputs (elm_flow_coupled)
 };
 
 // shard summary accumulated with atomics, one set per warp

@@ -142,7 +142,7 @@ def signature(cfg: abi.ReactionConfig) -> int:
     if c.calcite:
         parts.append(bytes(cfg.calcite))
     if c.somdec or c.nitrif or c.denitr or c.plantn or c.langmuir:
-        parts.append(struct.pack("<i", 1 if c.elm_pflotran else 0))
+        parts.append(struct.pack("<i", (3 if c.elm_flow_coupled else 1) if c.elm_pflotran else 0))
         if c.nsandbox:
             parts.append(np.ascontiguousarray(a["sandbox_list"], dtype=i4).tobytes())
     # what the generator bakes in or refuses beyond the tables above (same bytes as config_signature())
@@ -303,8 +303,6 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
                 return False, "SOMDECOMP reactions with different ABIOTIC_FACTORS"
         if np.any(sa["ox_specid"] >= 0):
             return False, "SOMDECOMP Ox species"
-        if c.elm_pflotran and int(sa["moisture_response_function"][0]) != 0:
-            return False, "ELM build with a moisture response function"
     return True, ""
 
 
@@ -1188,7 +1186,10 @@ class _Gen:
         # abiotic factors: identical for every reaction (supported())
         mf, of, tf = (int(sa[k][0]) for k in ("moisture_response_function", "ox_response_function",
                                               "temperature_response_function"))
-        if elm:
+        if elm and self.c.elm_flow_coupled and mf != 0:
+            w(f"    double f_w = pfrx_sbx::elm_moisture_response(theta, {mf}, s.elm_sucsat, s.elm_bd_dry, s.elm_bsw, "
+              "s.elm_watfc, s.elm_effpor);")
+        elif elm:
             w("    double f_w = s.elm_w;")
         elif mf == 3:
             w("    double f_w;")
@@ -1867,6 +1868,97 @@ class _Gen:
         self.w("}")
         self.w()
 
+    def gen_sparse_solve(self) -> None:
+        """The Newton system of the dense core by SPARSE elimination in a STATIC order: the network's
+        structure (self._nz) is known when the kernel is generated, so the pivot order is chosen here
+        (diagonal pivots, least fill first), every multiply-add is emitted with literal addresses and
+        entries that are structurally zero cost nothing.  RSolve's row scaling and the implicit-scaled
+        partial pivoting of LUDecomposition (reaction.F90:5485-5498, utility.F90:597-688) exist to make
+        elimination safe for an arbitrary matrix; here safety is CHECKED instead: every multiplier must
+        satisfy |l| <= 64 (threshold pivoting).  If one does not -- or is NaN -- the non-zeros are put
+        back and the caller runs the reference's dense algorithm.  The solution is the same up to
+        rounding (row scaling does not change it; the log formulation's column scaling by c_j is the
+        substitution y = c * delta, undone at the end)."""
+        nc = self.nc
+        self.w("__device__ __forceinline__ bool spec_solve_sparse(double *W, double (&res)[SPEC_N], const double (&c)[SPEC_N]) {")
+        if nc == 0:
+            self.w("  (void)W; (void)res; (void)c; return true;\n}\n")
+            return
+        sp = {ci: s_ for s_, ci in self.cpos.items()}
+        nz = {(self.cpos[i], self.cpos[j]) for (i, j) in self._nz if i in self.cpos and j in self.cpos}
+        nz |= {(k, k) for k in range(nc)}
+        cur = set(nz)
+        left = list(range(nc))
+        order = []
+        fills = []
+        while left:
+            best = None
+            for k in left:
+                row = [j for j in left if j != k and (k, j) in cur]
+                col = [i for i in left if i != k and (i, k) in cur]
+                f = sum(1 for i in col for j in row if (i, j) not in cur)
+                cost = (f, len(row) * len(col), k)
+                if best is None or cost < best[0]:
+                    best = (cost, k, row, col)
+            _, k, row, col = best
+            for i in col:
+                for j in row:
+                    if (i, j) not in cur:
+                        cur.add((i, j))
+                        fills.append((i, j))
+            order.append((k, row, col))
+            left.remove(k)
+        self.sparse_order = [k for k, _, _ in order]
+        self.sparse_fill = len(fills)
+        nzl = sorted(nz)
+        self.w(f"  double sav[{len(nzl)}];  // the non-zeros as assembled, for the dense fall-back")
+        for q, (i, j) in enumerate(nzl):
+            self.w(f"  sav[{q}] = W[JX({i}, {j})];")
+        for ci in range(nc):
+            self.w(f"  double b{ci} = res[{sp[ci]}];")
+        self.w("  bool ok = true;")
+        fillset = set(fills)
+        touched = set()
+        nmul = 0
+        for k, row, col in order:
+            self.w(f"  const double ip{k} = 1.0 / W[JX({k}, {k})];")
+            for j in row:
+                self.w(f"  const double u{k}_{j} = W[JX({k}, {j})];")
+            for i in col:
+                self.w(f"  {{ const double l = W[JX({i}, {k})] * ip{k};")
+                self.w("    ok = ok && (fabs(l) <= 64.0);")
+                for j in row:
+                    if (i, j) in fillset and (i, j) not in touched:
+                        self.w(f"    W[JX({i}, {j})] = -(l * u{k}_{j});")
+                        touched.add((i, j))
+                    else:
+                        self.w(f"    W[JX({i}, {j})] -= l * u{k}_{j};")
+                    nmul += 1
+                self.w(f"    b{i} -= l * b{k};")
+                self.w("  }")
+        self.sparse_muladds = nmul
+        self.w("  if (!ok) {")
+        for q, (i, j) in enumerate(nzl):
+            self.w(f"    W[JX({i}, {j})] = sav[{q}];")
+        for (i, j) in fills:
+            self.w(f"    W[JX({i}, {j})] = 0.0;")
+        self.w("    return false;")
+        self.w("  }")
+        for k, row, col in reversed(order):
+            expr = f"b{k}"
+            for j in row:
+                expr += f" - u{k}_{j} * y{j}"
+            self.w(f"  const double y{k} = ({expr}) * ip{k};")
+        for ci in range(nc):
+            if self.c.use_log_formulation:
+                self.w(f"  res[{sp[ci]}] = y{ci} / c[{sp[ci]}];")
+            else:
+                self.w(f"  res[{sp[ci]}] = y{ci};")
+        self.w("  (void)c;")
+        self.w("  return true;")
+        self.w("}")
+        self.w()
+
     def source(self) -> str:
         c = self.c
         n = self.n
@@ -1888,6 +1980,9 @@ class _Gen:
         body = self._gen_body(nsbx)
         self.out = []
         self.gen_rowonly()
+        sparse = not self.loop_lu and os.environ.get("PFRX_SPEC_SOLVER", "sparse") != "dense"
+        if sparse:
+            self.gen_sparse_solve()
         body = body + self.out
         nro = len(self.ropairs)
         if self.loop_lu:
@@ -1954,6 +2049,8 @@ class _Gen:
         self.w(f"#define SPEC_THREADS {threads}")
         self.w(f"#define SPEC_FASTMATH {int(os.environ.get('PFRX_SPEC_FASTMATH', '1'))}")
         self.w(f"#define SPEC_LOOP_LU {int(self.loop_lu)}")
+        if sparse:
+            self.w("#define SPEC_SPARSE_LU 1")
         self.w(f"#define SPEC_LOCKSTEP {int(self.lockstep)}")
         self.w(f"#define SPEC_REFILL {int(self.refill)}")
         self.w(f"#define SPEC_MINBLOCKS {minblocks}")

@@ -432,15 +432,24 @@ END
 
 
 def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False,
-           full: bool = False, degas: bool = False) -> Workload:
+           full: bool = False, degas: bool = False, flow: Optional[str] = None) -> Workload:
     """C4(b): SOMDECOMP + NITRIFICATION + DENITRIFICATION on 6 aqueous + 10
     immobile species.  ``elm=True`` is the ELM_PFLOTRAN build in BGC-only
     coupling: the moisture / oxygen / temperature scalars, soil depth,
     decomposition scalar, dry bulk density and Clapp-Hornberger b are per-cell
     ELM inputs; otherwise the CLM-CN temperature response and the log-theta
-    moisture response of the stand-alone build are evaluated from T and theta."""
+    moisture response of the stand-alone build are evaluated from T and theta.
+    ``flow`` ("CLMCN" or "DLEM", with ``elm``): the ELM build next to a flow mode -- SOMDECOMP's moisture factor
+    comes from GetMoistureResponse (elm_rspfuncs.F90:124-237) on the cell's sucsat / bsw / bulk density or field
+    capacity / effective porosity instead of ELM's w_scalar."""
     rng = np.random.default_rng(seed)
-    abiotic = "" if elm else """ABIOTIC_FACTORS
+    if flow:
+        assert elm and flow in ("CLMCN", "DLEM")
+    abiotic = ("""ABIOTIC_FACTORS
+        MOISTURE_RESPONSE_FUNCTION
+          %s
+        /
+      /""" % flow) if flow else "" if elm else """ABIOTIC_FACTORS
         TEMPERATURE_RESPONSE_FUNCTION
           CLMCN
         /
@@ -481,6 +490,7 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
                                dk.reference_temperature, True)
     assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
     net.elm_pflotran = bool(elm)
+    net.elm_flow_coupled = bool(flow)
     cfg = abi.ReactionConfig(net)
     sp = constraint.equilibrate_constraint(net, dk.constraints["initial"], den_kg=1000.0)
     st = abi.HostState(cfg, ncell)
@@ -513,13 +523,18 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
         st["elm_bsw"][...] = rng.uniform(2.0, 10.0, ncell)
         # plant N demand: zero at night / in winter for a third of the cells
         st["elm_rate_plantndemand"][...] = np.where(rng.random(ncell) < 0.33, 0.0, 10.0 ** rng.uniform(-9.0, -6.5, ncell))
+    if flow:
+        st["elm_sucsat"][...] = rng.uniform(50.0, 600.0, ncell)          # mm H2O (ELM's Clapp-Hornberger table)
+        st["elm_effporosity"][...] = st["porosity"] * rng.uniform(0.8, 1.0, ncell)
+        st["elm_watfc"][...] = st["elm_effporosity"] * rng.uniform(0.2, 0.6, ncell)
     if degas:
         for nm, lo, hi in (("CO2imm", 1.0e-2, 8.0e-2), ("N2Oimm", 5.0e-6, 1.0e-4), ("N2imm", 30.0, 35.0)):
             st["immobile"][net.immobile_names.index(nm)] = rng.uniform(lo, hi, ncell)
         st["immobile"][net.immobile_names.index("Himm")] = 1.0e-20
         if elm:
             st["pres"][...] = rng.uniform(0.9e5, 1.3e5, ncell)
-    name = ("c4f_elm_cn_full" if full else "c4s_elm_cn") + ("_elmscalars" if elm else "") + ("_degas" if degas else "")
+    name = (("c4f_elm_cn_full" if full else "c4s_elm_cn") + ("_elmscalars" if elm else "") + ("_degas" if degas else "")
+            + (f"_flow_{flow.lower()}" if flow else ""))
     note = "SOMDECOMP (7 rxns, N immobilisation from NH4+/NO3-) + NITRIFICATION + DENITRIFICATION"
     if full:
         note += " + PLANTN + LANGMUIR"
@@ -1099,6 +1114,9 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4fe": (elm_cn, {"full": True, "elm": True}),
         "c4g": (elm_cn, {"degas": True}),
         "c4ge": (elm_cn, {"degas": True, "elm": True}),
+        "c4sw": (elm_cn, {"elm": True, "flow": "CLMCN"}),
+        "c4sd": (elm_cn, {"elm": True, "flow": "DLEM"}),
+        "c4fw": (elm_cn, {"full": True, "elm": True, "flow": "CLMCN"}),
         "c5": (hanford, {"variant": "minerals"}),
         "c6": (ion_exchange, {}),
         "c7": (general_decay, {}),

@@ -87,11 +87,16 @@ def test_unsupported_configurations_are_refused_not_approximated():
     cfg.somdec.co2_itype = 1
     rc, msg = _create_rc(cfg)
     assert rc == 1 and "gas" in msg
-    # ELM build that asks for the flow-coupled moisture response
-    cfg = workloads.by_name("c4se", ncell=1).cfg
-    cfg.arrays["somdec_moisture_response_function"][:] = 1
+    # an active gas species naming a component that does not exist
+    cfg = workloads.by_name("c7g", ncell=1).cfg
+    cfg.arrays["acteq_specid"][0] = 9
     rc, msg = _create_rc(cfg)
-    assert rc == 1 and "MOISTURE_RESPONSE_FUNCTION" in msg
+    assert rc == 1 and "active gas" in msg
+    # the RADON sandbox without its mineral
+    cfg = workloads.by_name("c7g", ncell=1).cfg
+    cfg.radon.mineral_id = 3
+    rc, msg = _create_rc(cfg)
+    assert rc == 1 and "RADON" in msg
     # PLANTN without its PlantN pool
     cfg = workloads.by_name("c4fe", ncell=1).cfg
     cfg.plantn.plantn_id = -1

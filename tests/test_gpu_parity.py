@@ -27,7 +27,8 @@ def _gpu():
     return rstep
 
 
-def _compare(ref: abi.HostState, got: abi.HostState, what: str, rtol=RTOL, counts_exact=True, vf_scale=None):
+def _compare(ref: abi.HostState, got: abi.HostState, what: str, rtol=RTOL, counts_exact=True, vf_scale=None,
+             total_by_terms=False):
     for f in ("num_iterations", "num_sub_steps", "num_kinetic_state_updates", "ierror"):
         a, b = ref.a[f], got.a[f]
         bad = np.flatnonzero(a != b)
@@ -49,11 +50,38 @@ def _compare(ref: abi.HostState, got: abi.HostState, what: str, rtol=RTOL, count
             # (possibly cancelling) value.
             kA = ref.cfg.arrays["kinmnrl_rate_constant"][:, None] * ref.a["mnrl_area"][:, ok]
             err = np.abs(a - b) / np.maximum(np.maximum(scale, kA), 1.0e-300)
+        if f == "total" and total_by_terms:
+            # a total that is a cancelling sum (total H+ = H+ + CO2(aq) - CO3-- - OH-) is pinned to 1e-10 of the
+            # sum of the magnitudes of its terms, the scale its rounding and convergence errors live on
+            cfg = ref.cfg
+            ptr, ids, nu = cfg.arrays["eqcplx_ptr"], cfg.arrays["eqcplx_specid"], cfg.arrays["eqcplx_stoich"]
+            terms = np.abs(ref.a["pri_molal"][:, ok]).copy()
+            for k in range(cfg.c.neqcplx):
+                for p in range(ptr[k], ptr[k + 1]):
+                    terms[ids[p]] += abs(nu[p]) * np.abs(ref.a["sec_molal"][k, ok])
+            terms *= ref.a["den_kg"][0, ok] * 1.0e-3
+            err = np.abs(a - b) / np.maximum(np.maximum(scale, terms), 1.0e-300)
         if f == "mnrl_volfrac" and vf_scale is not None:
             # a mineral that dissolves completely ends at vf0 + rate * V_m * dt ~ 0: pinned to 1e-10 of vf0
-            err = np.abs(a - b) / np.maximum(scale, vf_scale[:, ok])
+            err = np.abs(a - b) / np.maximum(np.maximum(scale, vf_scale[:, ok]), 1.0e-300)
         worst = float(err.max()) if err.size else 0.0
         assert worst <= rtol, f"{what}: field {f} max rel err {worst:.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def _oracle_noise(wl, ref, eps=1.0e-15):
+    """largest relative change of the oracle's answer when its inputs move by eps (relative, random)"""
+    rng = np.random.default_rng(7)
+    pert = wl.state.copy()
+    for f in ("total", "immobile"):
+        pert.a[f] *= 1.0 + eps * rng.standard_normal(pert.a[f].shape)
+    orc.rstep(wl.cfg, pert, wl.tran_dt, 4)
+    worst = 0.0
+    for f in ("total", "immobile", "pri_molal"):
+        a, b = ref.a[f], pert.a[f]
+        scale = np.maximum(np.abs(a), np.abs(b))
+        err = np.where(scale < 1.0e-30, 0.0, np.abs(a - b) / np.where(scale > 0, scale, 1.0))
+        worst = max(worst, float(err.max()) if err.size else 0.0)
+    return worst
 
 
 def _run_both(wl, host_path=False, spec=False):
@@ -137,11 +165,13 @@ def test_exactly_zero_immobile_guess_in_the_linear_formulation(spec):
 
 @pytest.mark.parametrize("variant,dt,host", [("c4s", 1800.0, False), ("c4s", 86400.0, False), ("c4s", 1800.0, True),
                                              ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True),
-                                             ("c4fe", 1800.0, True), ("c4fe", 86400.0, False)])
+                                             ("c4fe", 1800.0, True), ("c4fe", 86400.0, False),
+                                             ("c4sw", 1800.0, False), ("c4sd", 1800.0, True), ("c4fw", 1800.0, False)])
 def test_c4s_elm_cn_sandboxes(variant, dt, host):
     """SOMDECOMP + NITRIFICATION + DENITRIFICATION (SomDecReact/React1/React2/Nemission,
     NitrifReact, DenitrReact) in the thread-per-cell kernel, stand-alone and ELM builds;
-    the persisted N:C ratios (pfrx_state.somdec_nc) are part of the compared state"""
+    the persisted N:C ratios (pfrx_state.somdec_nc) are part of the compared state.  c4sw / c4sd / c4fw: the ELM
+    build next to a flow mode -- f_w from GetMoistureResponse (CLMCN / DLEM curve) on per-cell soil properties"""
     wl = W.by_name(variant, ncell=6000, tran_dt=dt)
     wl.state.a["imat"][0, 11] = 0
     wl.state.a["sat"][0, 17] = 1.0e-50   # dry cell: RReaction skipped
@@ -196,7 +226,7 @@ def test_c7g_active_gas_phase(name, dt, host):
     ref, rr, got, rg, info = _run_both(wl, host_path=host)
     assert info["lanes"] in (0, 1)
     assert np.abs(ref.a["total_gas"] - wl.state.a["total_gas"]).max() > 0 and np.abs(ref.a["gas_pp"]).min() > 0
-    _compare(ref, got, f"{name} dt={dt}")
+    _compare(ref, got, f"{name} dt={dt}", total_by_terms=True)
     _check_summary(rr, rg)
 
 
@@ -207,6 +237,9 @@ def test_radon_gold_deck_one_step_on_the_gpu():
 
     rstep = _gpu()
     dk, net, cfg, st = tg._setup("radon.in", "hanford_subset.dat")
+    # RReact's absolute residual test (1e-12 mol/s) would accept the deck's 1 m^3 cell at once -- the generation
+    # term is 1e-19 mol/s; a 1e10 m^3 cell makes the operator-split solve iterate (16, 6 and 5 Newton iterations)
+    st.a["volume"][:] = 1.0e10
     for dt in (3600.0, 3.8235 * 86400.0, 0.25 * 365 * 86400.0):
         ref = st.copy()
         res_ref = orc.rstep(cfg, ref, dt)
@@ -218,6 +251,7 @@ def test_radon_gold_deck_one_step_on_the_gpu():
         step.close()
         _check_summary(res_ref, res)
         _compare(ref, got, f"radon dt={dt}")
+        assert res_ref.sum_newton_iterations >= 5
         assert ref.a["total_gas"][0, 0] > 0 and ref.a["total_gas"][0, 0] != st.a["total_gas"][0, 0]
         st = ref   # the next, longer step starts from this one's state
 
@@ -270,6 +304,7 @@ def test_hanford(variant, dt):
                                              ("c5", 86400.0, False), ("c4", 1800.0, False), ("c4", 86400.0, True),
                                              ("c4s", 1800.0, False), ("c4s", 86400.0, True), ("c4se", 1800.0, False),
                                              ("c4se", 6 * 3600.0, True), ("c4fe", 1800.0, True),
+                                             ("c4sw", 1800.0, True), ("c4sd", 3600.0, False), ("c4fw", 1800.0, False),
                                              ("c3mr", 3600.0, False), ("c3mr", 30 * 86400.0, True),
                                              ("c4fe", 86400.0, False),
                                              ("c7", 3600.0, False), ("c7", 30 * 86400.0, True),
@@ -285,7 +320,14 @@ def test_specialized_kernel(variant, dt, host):
         wl.state.a["temp"][0, 19] = -60.0    # below the CLM-CN temperature cut-off
     ref, res_ref, got, res, info = _run_both(wl, host_path=host, spec=True)
     assert info["lanes"] == -1, info
-    _compare(ref, got, f"specialised {variant} dt={dt}")
+    rtol = RTOL
+    if variant[:3] in ("c4s", "c4f") and dt > 3600.0:
+        # cells that cut their step dozens of times amplify rounding: the tolerance is the larger of 1e-10 and
+        # four times what the ORACLE itself answers to a 1e-15 relative perturbation of its inputs (7e-11 on
+        # the c4s state at dt = 1 d)
+        rtol = max(RTOL, 4.0 * _oracle_noise(wl, ref))
+        assert rtol < 1.0e-8
+    _compare(ref, got, f"specialised {variant} dt={dt}", rtol=rtol)
     _check_summary(res_ref, res)
 
 
@@ -621,7 +663,11 @@ def test_calcite_sandbox(dt, host):
     wl.state.a["sat"][0, 9] = 1.0e-50
     ref, rr, got, rg, info = _run_both(wl, host_path=host)
     assert info["lanes"] in (0, 1)
-    _compare(ref, got, f"c2sb dt={dt}", vf_scale=wl.state.a["mnrl_volfrac"])
+    # the volume fraction moves by rate * V_m * dt and the rate k A (1 - QK) is pinned to 1e-10 of k A (a
+    # cancelling difference near equilibrium): the same scale for what it is integrated into
+    kA = (wl.cfg.calcite.rate_constant1 + wl.cfg.calcite.rate_constant2) * wl.state.a["mnrl_area"]
+    vf_scale = np.maximum(wl.state.a["mnrl_volfrac"], kA * wl.cfg.arrays["kinmnrl_molar_vol"][:, None] * dt)
+    _compare(ref, got, f"c2sb dt={dt}", vf_scale=vf_scale)
     _check_summary(rr, rg)
     assert np.abs(ref.a["sandbox_aux"]).max() > 0.0
     assert np.abs(ref.a["mnrl_volfrac"] - wl.state.a["mnrl_volfrac"]).max() > 0.0
@@ -714,7 +760,7 @@ def test_specialized_kernel_refuses_other_network():
     assert step.signature == specialize.signature(c2.cfg)
     with pytest.raises(rstep.PfrxError, match="another network"):
         step.load_specialized(specialize.build(c3.cfg))
-    unsupported = W.by_name("c6", ncell=4)  # ion exchange / KD isotherms: generic kernel only
+    unsupported = W.by_name("c7g", ncell=4)  # an active gas phase: generic kernel only
     assert not specialize.supported(unsupported.cfg)[0]
     step4 = rstep.ChemistryStep(unsupported.cfg, 0)
     assert step4.specialize() is False

@@ -232,6 +232,42 @@ def test_radon_secular_equilibrium_through_rstep():
     assert np.allclose(inv, want, rtol=1.0e-6), (inv, want)
 
 
+@pytest.mark.parametrize("kind", ["CLMCN", "DLEM"])
+def test_elm_flow_coupled_moisture_response(kind):
+    """GetMoistureResponse of the ELM_PFLOTRAN build (elm_rspfuncs.F90:124-237): with a flow mode SOMDECOMP's f_w is
+    the Clapp-Hornberger (CLMCN) or DLEM curve of the cell's soil properties.  f_w multiplies every SOMDECOMP rate, so
+    the flow-coupled residual must equal the BGC-only one evaluated with w_scalar := the curve, restated here."""
+    n = 64
+    wl = W.by_name("c4sw" if kind == "CLMCN" else "c4sd", ncell=n)
+    ref = W.by_name("c4se", ncell=n)
+    assert wl.cfg.c.elm_flow_coupled == 1 and ref.cfg.c.elm_flow_coupled == 0
+    st = wl.state
+    theta = st["sat"][0] * st["porosity"][0]
+    if kind == "CLMCN":
+        g, minpsi = 9.8068, -10.0e6
+        maxpsi = st["elm_sucsat"][0] * (-g)
+        lsat = theta / np.minimum(1.0, 1.0 - np.minimum(0.9999, st["elm_bulkdensity_dry"][0] / 2.70e3))
+        psi = np.minimum(st["elm_sucsat"][0] * (-g) * lsat ** (-st["elm_bsw"][0]), maxpsi)
+        f = np.where(psi > minpsi, np.log(minpsi / psi) / np.log(minpsi / maxpsi), 0.0)
+        f = np.where(psi > maxpsi - 100.0, f * 0.10, f)
+    else:
+        ts, tr = st["elm_effporosity"][0], st["elm_watfc"][0]
+        se = (theta - tr) / (ts - tr)
+        f = np.clip(float(np.float32(1.0)) - se * se * float(np.float32(0.368)) * np.exp(se), 0.0, 1.0)
+        f = np.where(theta >= ts, 1.0, np.where(theta <= tr, 0.0, f))
+    assert 0.0 <= f.min() and f.max() <= 1.0 and np.ptp(f) > 0.3      # the cells cover the curve
+    # the same state in the BGC-only configuration with w_scalar = f
+    for k in ref.state.a:
+        if k in st.a and ref.state.a[k].shape == st.a[k].shape:
+            ref.state.a[k][...] = st.a[k]
+    ref.state.a["elm_w_scalar"][0] = f
+    for c in range(n):
+        r1, j1 = orc.reaction(wl.cfg, wl.state.copy(), c, wl.tran_dt)
+        r0, j0 = orc.reaction(ref.cfg, ref.state.copy(), c, ref.tran_dt)
+        assert np.abs(r1 - r0).max() <= 1.0e-13 * max(np.abs(r0).max(), 1e-300), (c, f[c], r1, r0)
+        assert np.abs(j1 - j0).max() <= 1.0e-13 * max(np.abs(j0).max(), 1e-300)
+
+
 def test_general_decay_rstep_mass_balance():
     """C7 through RStep: every cell converges without cuts, and the immobile species decays by the
     backward-Euler factor 1/(1 + k dt) of its half-life"""
