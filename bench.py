@@ -616,7 +616,12 @@ def main():
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": dict(cfg_json, name=wl.name, ncomp=wl.cfg.ncomp, neqcplx=int(wl.cfg.c.neqcplx),
-                          kernel=info, kernel_variant=variant_name, autotune_s=tuned, note=wl.note),
+                          kernel=info, kernel_variant=variant_name, autotune_s=tuned, note=wl.note,
+                          cell_order=(None if not (variant_name or "").startswith(("q", "w", "p"))
+                                      or os.environ.get("PFRX_CELL_ORDER") == "0" else
+                                      "refill kernel: cells handed out by the previous launch's Newton counts, longest "
+                                      "first (pfrx_cell_order); every timed step solves the same restored state, so "
+                                      "here the prediction is exact; the sort runs inside the timed region")),
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e_os if e2e_os is not None else e2e,
            "e2e_full_state": e2e, "parity_sample": parity, "c5_baseline": c5, "numa": numa,
            "roofline": roof, "cpu_baseline": cpu,

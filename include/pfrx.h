@@ -656,6 +656,12 @@ int pfrx_allreduce(pfrx_handle *h, pfrx_step_result *inout);
 void *pfrx_stream(pfrx_handle *h);
 /* number of kernel launches issued by this handle so far */
 int64_t pfrx_launch_count(pfrx_handle *h);
+/* Refill kernels (the generated variants for ragged workloads) hand out cells longest-first: after a launch over
+ * the whole shard the library sorts the cells by the Newton iterations they just needed, and the next launch on
+ * that shard starts with the slowest ones -- chemistry hot spots persist from one transport step to the next,
+ * so the cells that cut their step dozens of times no longer trail the launch.  Results do not depend on the
+ * order (a cell is computed from its own state).  mode 0 switches it off, 1 (default; PFRX_CELL_ORDER) on. */
+int pfrx_cell_order(pfrx_handle *h, int mode);
 /* bytes of state read+written per cell-solve by the bound configuration
  * (the algorithmic HBM traffic of SURVEY.md section 8(d))                    */
 int64_t pfrx_bytes_per_cell(pfrx_handle *h);

@@ -11,6 +11,8 @@
 #include <chrono>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pfrx_device.cuh"
 
 static thread_local char g_err[512] = "";
@@ -512,6 +514,16 @@ struct pfrx_handle {
   SpecParams spec_prm;
   void *spec_module = nullptr, *spec_func = nullptr;
   int spec_threads = 0, spec_blocks_per_sm = 0, spec_cells = 0;
+  // longest-first hand-out of the refill skeleton: after a whole-shard launch the cells are sorted by the
+  // Newton iterations they just needed (descending), the next launch on the same shard starts with the slowest
+  int spec_refill = 0;
+  int order_mode = 1;  // PFRX_CELL_ORDER=0 / pfrx_cell_order(h, 0) switch it off
+  int *d_order = nullptr, *d_iota = nullptr, *d_keys_out = nullptr;
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int64_t order_cap = 0, order_ncell = 0;
+  const int *order_key = nullptr;  // the num_iterations array the order was built from
+  bool order_valid = false;
   size_t spec_smem = 0;
   int64_t last_h2d = 0, last_d2h = 0;  // bytes moved by the latest pfrx_rstep_host / pfrx_os_step_host
   // device staging of the two block vectors of pfrx_os_step_host
@@ -1502,6 +1514,10 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->d_red_step) cudaFree(h->d_red_step);
   if (h->h_red_step) cudaFreeHost(h->h_red_step);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->d_order) cudaFree(h->d_order);
+  if (h->d_iota) cudaFree(h->d_iota);
+  if (h->d_keys_out) cudaFree(h->d_keys_out);
+  if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
   if (h->os_a) cudaFree(h->os_a);
   if (h->os_b) cudaFree(h->os_b);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1617,6 +1633,44 @@ static int summary_reset(pfrx_handle *h, cudaStream_t s) {
 // one kernel launch over cells [0, ncell) of `st`.  Chunked callers pass a view that starts at
 // their first cell; the chunk-local first-failed-cell index is turned into a shard-local one on the
 // host when the chunks are merged
+__global__ void pfrx_iota_kernel(int *v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (int)i;
+}
+
+// order of the NEXT launch on this shard: cells by the Newton iterations of the launch just enqueued, descending
+// (stable: equal counts keep index order).  A ragged workload ends with the few cells that cut their step dozens
+// of times; handed out first, their serial chains overlap the bulk instead of trailing it.
+static int build_cell_order(pfrx_handle *h, const DevState &st, int64_t ncell, cudaStream_t s) {
+  if (ncell > h->order_cap) {
+    if (h->d_order) cudaFree(h->d_order);
+    if (h->d_iota) cudaFree(h->d_iota);
+    if (h->d_keys_out) cudaFree(h->d_keys_out);
+    if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
+    h->d_order = h->d_iota = h->d_keys_out = nullptr;
+    h->d_sort_tmp = nullptr;
+    h->order_cap = 0;
+    h->order_valid = false;
+    CUDA_OK(cudaMalloc(&h->d_order, ncell * sizeof(int)));
+    CUDA_OK(cudaMalloc(&h->d_iota, ncell * sizeof(int)));
+    CUDA_OK(cudaMalloc(&h->d_keys_out, ncell * sizeof(int)));
+    size_t bytes = 0;
+    CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int *)nullptr, (int *)nullptr,
+                                                      (const int *)nullptr, (int *)nullptr, (int)ncell, 0, 31, s));
+    CUDA_OK(cudaMalloc(&h->d_sort_tmp, std::max<size_t>(bytes, 16)));
+    h->sort_tmp_bytes = bytes;
+    h->order_cap = ncell;
+    pfrx_iota_kernel<<<256, 256, 0, s>>>(h->d_iota, ncell);
+    CUDA_OK(cudaGetLastError());
+  }
+  size_t bytes = h->sort_tmp_bytes;
+  CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, bytes, (const int *)st.num_iterations, h->d_keys_out,
+                                                    (const int *)h->d_iota, h->d_order, (int)ncell, 0, 31, s));
+  h->order_valid = true;
+  h->order_key = st.num_iterations;
+  h->order_ncell = ncell;
+  return PFRX_OK;
+}
+
 static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, double tran_dt, cudaStream_t s) {
   if (ncell <= 0) return PFRX_OK;
   int cpw = 32 / h->lanes;
@@ -1629,6 +1683,11 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
     cap = (int64_t)h->sm_count * h->spec_blocks_per_sm;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, cap));
     DevState st_arg = st;
+    const bool ordered = h->spec_refill && h->order_mode && ncell >= 65536 && ncell < (int64_t)INT_MAX &&
+                         (ncell == h->ncell || ncell == h->own_ncell);
+    st_arg.order = (ordered && h->order_valid && h->order_key == st.num_iterations && h->order_ncell == ncell)
+                       ? h->d_order
+                       : nullptr;
     long long n_arg = ncell;
     double dt_arg = tran_dt;
     SpecParams prm = h->spec_prm;
@@ -1639,6 +1698,7 @@ static int launch_kernel(pfrx_handle *h, const DevState &st, int64_t ncell, doub
     DRV_OK(g_drv.LaunchKernel(h->spec_func, (unsigned)grid, 1, 1, (unsigned)h->spec_threads, 1, 1,
                               (unsigned)h->spec_smem, s, args, nullptr));
     h->launches++;
+    if (ordered) return build_cell_order(h, st, ncell, s);
     return PFRX_OK;
   }
   int grid = (int)std::min<int64_t>(need, cap);
@@ -2663,6 +2723,13 @@ extern "C" int pfrx_last_transfer_bytes(pfrx_handle *h, int64_t *h2d, int64_t *d
 extern "C" void *pfrx_stream(pfrx_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int64_t pfrx_launch_count(pfrx_handle *h) { return h ? h->launches : 0; }
 
+extern "C" int pfrx_cell_order(pfrx_handle *h, int mode) {
+  if (!h) return set_err(PFRX_E_INVALID, "null handle%s", "");
+  h->order_mode = mode != 0;
+  h->order_valid = false;
+  return PFRX_OK;
+}
+
 extern "C" int64_t pfrx_bytes_per_cell(pfrx_handle *h) {
   // every in/io field read once, every io field
   // written once, four int32 results
@@ -2802,6 +2869,16 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   }
   h->spec_module = mod;
   h->spec_func = fn;
+  {
+    int flags = 0;
+    unsigned long long fptr = 0;
+    size_t fbytes = 0;
+    if (!g_drv.ModuleGetGlobal(&fptr, &fbytes, mod, "pfrx_spec_flags") && fbytes == sizeof(flags))
+      g_drv.MemcpyDtoH(&flags, fptr, sizeof(flags));
+    h->spec_refill = flags & 1;
+    h->order_valid = false;
+    if (const char *ev = getenv("PFRX_CELL_ORDER")) h->order_mode = atoi(ev) != 0;
+  }
   h->spec_threads = threads;
   h->spec_cells = info[4];
   h->spec_smem = smem;

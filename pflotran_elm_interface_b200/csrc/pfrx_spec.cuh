@@ -124,6 +124,8 @@ extern "C" {
 __device__ const unsigned long long pfrx_spec_sig = SPEC_SIG;
 // {N, shared doubles per block, threads per block, min blocks per SM, cells per block}
 __device__ const int pfrx_spec_info[5] = {SPEC_N, SPEC_SLOTS * SPEC_THREADS, SPEC_THREADS, SPEC_MINBLOCKS, SPEC_THREADS};
+// bit 0: the refill skeleton, which hands out cells through DevState.order
+__device__ const int pfrx_spec_flags = SPEC_REFILL ? 1 : 0;
 }
 
 struct SpecCell {
@@ -977,7 +979,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
         first = __shfl_sync(want, first, leader);
         const long long mine = (long long)first + __popc(want & ((1u << lane32) - 1u));
         if (mine < ncell) {
-          cell = mine;
+          cell = st.order ? (long long)st.order[mine] : mine;
           inrange = true;
           live = !(st.imat && st.imat[cell] <= 0);
           fresh = true;

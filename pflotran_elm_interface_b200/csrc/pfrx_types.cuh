@@ -22,6 +22,9 @@ struct DevState {
   const double *sat_gas;
   double *total_gas, *gas_pp;
   const double *elm_sucsat, *elm_watfc, *elm_effpor;  // GetMoistureResponse inputs (elm_flow_coupled)
+  // refill skeleton: the k-th cell handed out is order[k] (a permutation of the shard: the cells that needed the
+  // most Newton iterations in the previous step first); NULL: index order.  Set by the library, not by the caller.
+  const int *order;
 };
 
 // shard summary accumulated with atomics, one set per warp

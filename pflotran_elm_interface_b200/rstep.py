@@ -56,6 +56,7 @@ def lib():
     L.pfrx_allreduce.argtypes = [hp, resp]
     L.pfrx_stream.argtypes = [hp]
     L.pfrx_stream.restype = C.c_void_p
+    L.pfrx_cell_order.argtypes = [hp, C.c_int]
     L.pfrx_launch_count.argtypes = [hp]
     L.pfrx_launch_count.restype = C.c_int64
     L.pfrx_bytes_per_cell.argtypes = [hp]
@@ -325,6 +326,10 @@ class ChemistryStep:
     @property
     def stream_ptr(self) -> int:
         return int(lib().pfrx_stream(self._h))
+
+    def cell_order(self, on: bool) -> None:
+        """longest-first hand-out of the refill kernels (pfrx_cell_order); on by default"""
+        _check(lib().pfrx_cell_order(self._h, int(bool(on))), "pfrx_cell_order")
 
     @property
     def launch_count(self) -> int:
