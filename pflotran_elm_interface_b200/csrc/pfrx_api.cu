@@ -2804,7 +2804,8 @@ extern "C" int pfrx_load_specialized(pfrx_handle *h, const char *cubin_path) {
   bool inner_newton = false;
   for (int r = 0; r < d.nsrfrxn && h->sr_flag_host.size() == (size_t)d.nsrfrxn; r++)
     inner_newton = inner_newton || h->sr_flag_host[r] != 0;
-  if (!d.use_full_geochemistry || !d.use_isothermal || d.use_total_as_guess ||
+  if (!d.use_full_geochemistry || (!d.use_isothermal && (d.ncplx > 0 || d.nkin > 0 || d.nsrfcplx > 0)) ||
+      d.use_total_as_guess ||
       d.act_alg != PFRX_ACT_COEF_ALGORITHM_LAG || d.mn_npref ||
       ((d.nionx > 0 || d.nkd > 0 || d.ndynkd > 0) && (d.nmr > 0 || d.nsbx > 0)) || (d.nrd > 0 && d.nionx > 0) ||
       (d.nrd > 0 && d.nsrfrxn > 0) ||

@@ -253,7 +253,9 @@ def supported(cfg: abi.ReactionConfig) -> Tuple[bool, str]:
         return False, "more than 20 unknowns"
     if not c.use_full_geochemistry:
         return False, "use_full_geochemistry = 0 (RStep's tracer short cut)"
-    if not c.use_isothermal:
+    if not c.use_isothermal and (c.neqcplx > 0 or c.nkinmnrl > 0 or c.nsrfcplx > 0):
+        # without complexes, minerals and surface complexes nothing has a logK(T): the ELM-CN networks next to a
+        # thermal flow mode run the same generated kernel
         return False, "anisothermal logK"
     if c.act_coef_update_algorithm != abi._chem.ACT_COEF_ALGORITHM_LAG:
         return False, "activity algorithm NEWTON"

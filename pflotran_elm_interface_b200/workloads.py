@@ -432,7 +432,7 @@ END
 
 
 def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SEED, elm: bool = False,
-           full: bool = False, degas: bool = False, flow: Optional[str] = None) -> Workload:
+           full: bool = False, degas: bool = False, flow: Optional[str] = None, anisothermal: bool = False) -> Workload:
     """C4(b): SOMDECOMP + NITRIFICATION + DENITRIFICATION on 6 aqueous + 10
     immobile species.  ``elm=True`` is the ELM_PFLOTRAN build in BGC-only
     coupling: the moisture / oxygen / temperature scalars, soil depth,
@@ -487,7 +487,7 @@ def elm_cn(ncell: int = 2 * 1024 * 1024, tran_dt: float = 1800.0, seed: int = SE
                                            "N2(g)": names.index("N2imm")}
         dk.chemistry.cndegas["cell_state_mode"] = 2 if elm else 0
     net = chem.ReactionNetwork(dk.chemistry, chem.Database(_read("clmcnplus_CLM-CN_database.dat")),
-                               dk.reference_temperature, True)
+                               dk.reference_temperature, not anisothermal)
     assert dk.chemistry.unsupported == [], dk.chemistry.unsupported
     net.elm_pflotran = bool(elm)
     net.elm_flow_coupled = bool(flow)
@@ -1114,6 +1114,7 @@ def by_name(name: str, ncell: Optional[int] = None, tran_dt: Optional[float] = N
         "c4fe": (elm_cn, {"full": True, "elm": True}),
         "c4g": (elm_cn, {"degas": True}),
         "c4ge": (elm_cn, {"degas": True, "elm": True}),
+        "c4st": (elm_cn, {"elm": True, "flow": "DLEM", "anisothermal": True}),   # next to a thermal flow mode
         "c4sw": (elm_cn, {"elm": True, "flow": "CLMCN"}),
         "c4sd": (elm_cn, {"elm": True, "flow": "DLEM"}),
         "c4fw": (elm_cn, {"full": True, "elm": True, "flow": "CLMCN"}),

@@ -166,7 +166,8 @@ def test_exactly_zero_immobile_guess_in_the_linear_formulation(spec):
 @pytest.mark.parametrize("variant,dt,host", [("c4s", 1800.0, False), ("c4s", 86400.0, False), ("c4s", 1800.0, True),
                                              ("c4se", 1800.0, False), ("c4se", 6 * 3600.0, True),
                                              ("c4fe", 1800.0, True), ("c4fe", 86400.0, False),
-                                             ("c4sw", 1800.0, False), ("c4sd", 1800.0, True), ("c4fw", 1800.0, False)])
+                                             ("c4sw", 1800.0, False), ("c4sd", 1800.0, True), ("c4fw", 1800.0, False),
+                                             ("c4st", 1800.0, False)])
 def test_c4s_elm_cn_sandboxes(variant, dt, host):
     """SOMDECOMP + NITRIFICATION + DENITRIFICATION (SomDecReact/React1/React2/Nemission,
     NitrifReact, DenitrReact) in the thread-per-cell kernel, stand-alone and ELM builds;
@@ -305,6 +306,7 @@ def test_hanford(variant, dt):
                                              ("c4s", 1800.0, False), ("c4s", 86400.0, True), ("c4se", 1800.0, False),
                                              ("c4se", 6 * 3600.0, True), ("c4fe", 1800.0, True),
                                              ("c4sw", 1800.0, True), ("c4sd", 3600.0, False), ("c4fw", 1800.0, False),
+                                             ("c4st", 1800.0, False),
                                              ("c3mr", 3600.0, False), ("c3mr", 30 * 86400.0, True),
                                              ("c4fe", 86400.0, False),
                                              ("c7", 3600.0, False), ("c7", 30 * 86400.0, True),

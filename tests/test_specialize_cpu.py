@@ -13,7 +13,7 @@ from pflotran_elm_interface_b200 import specialize, workloads as W
 
 def test_supported_networks():
     for name, ok in (("c1", True), ("c2", True), ("c3", True), ("c5", True), ("c3mr", True), ("c4", True),
-                     ("c4fe", True), ("c6", True), ("c7", True), ("c7s", True), ("c8", True), ("c7g", False), ("c2pf", False),
+                     ("c4fe", True), ("c6", True), ("c7", True), ("c7s", True), ("c8", True), ("c4sw", True), ("c4st", True), ("c3t", False), ("c7g", False), ("c2pf", False),
                      ("c3an", False)):
         wl = W.by_name(name, ncell=2)
         got, why = specialize.supported(wl.cfg)
