@@ -336,6 +336,9 @@ extern "C" {
 __device__ const unsigned long long pfrx_spec_sig = SPEC_SIG;
 // {N, shared doubles per block, threads per block, min blocks per SM, cells per block}
 __device__ const int pfrx_spec_info[5] = {SPEC_N, S2_SLOTS * SPEC_THREADS, SPEC_THREADS, SPEC_MINBLOCKS, SPEC_THREADS};
+// bit 0 would announce a kernel that hands out cells through DevState.order (pfrx_spec.cuh's refill skeleton);
+// form 2 serves uniform workloads and takes cells in index order
+__device__ const int pfrx_spec_flags = 0;
 }
 
 __device__ __forceinline__ int s2_vote_and(int p) { return SPEC_SYNC ? __syncthreads_and(p) : __all_sync(0xffffffffu, p); }

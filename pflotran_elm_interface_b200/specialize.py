@@ -2000,7 +2000,8 @@ class _Gen:
             threads = 32
             # measured (profiles/r01_occupancy_sweep_spec.txt): one warp per scheduler is the
             # optimum for these 255-register kernels; a fifth warp per SM costs 12 %
-            minblocks = max(1, min(4, (228 * 1024) // per_warp))
+            maxw = int(os.environ.get("PFRX_SPEC_MAXWARPS", "4"))
+            minblocks = max(1, min(maxw, (228 * 1024) // per_warp))
         else:
             threads = 128
             minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
