@@ -41,6 +41,9 @@
 #ifndef SPEC_NDTP
 #define SPEC_NDTP 0  // entries of d(total)/d(free) that RRadioactiveDecay reads
 #endif
+#ifndef SPEC_NKC
+#define SPEC_NKC 0  // per-cell constants of the generated code (spec_cell_constants)
+#endif
 #ifndef SPEC_NDSP
 #define SPEC_NDSP 0  // entries of d(total_sorb_eq)/d(free) that RRadioactiveDecay reads
 #endif
@@ -86,6 +89,24 @@ __device__ __forceinline__ double sx_div(double a, double b) { return SPEC_FASTM
 // FuncMonod and its derivative (elm_rspfuncs.F90:321-338) for the generated sandbox code
 __device__ __forceinline__ double sx_monod(double c, double k) { return sx_div(c, c + k); }
 __device__ __forceinline__ double sx_dmonod(double c, double k) { return sx_div(sx_div(k, c + k), c + k); }
+
+// Linear formulation, the update's scaling factor (reaction.F90:4010-4023): min over the components with
+// c_i <= u_i of |c_i / u_i|, starting from 1e20.  The reference divides inside a branch per component; here the
+// smallest ratio is found by cross-multiplication (|c_i| |u_b| < |c_b| |u_i|, all factors non-negative) and ONE
+// division of the selected pair follows -- the same quotient the reference forms for that pair.  u_i = 0 never
+// wins (the reference's Inf / NaN does not either).
+template <int NN>
+__device__ __forceinline__ double spec_min_ratio(const double (&c)[NN], const double (&u)[NN]) {
+  double bc = 1.e20, bu = 1.0;
+#pragma unroll
+  for (int i = 0; i < NN; i++) {
+    const double ac = fabs(c[i]), au = fabs(u[i]);
+    const bool cand = (c[i] <= u[i]) && (ac * bu < bc * au);
+    bc = cand ? ac : bc;
+    bu = cand ? au : bu;
+  }
+  return bc / bu;
+}
 
 #define SPEC_LN 2.30258509299  // pflotran_constants.F90:84 (truncated there)
 
@@ -144,6 +165,7 @@ struct SpecCell {
   double nc[SPEC_NNC > 0 ? SPEC_NNC : 1];  // N:C ratios that persist between evaluations
   double dtp[SPEC_NDTP > 0 ? SPEC_NDTP : 1];  // rt_auxvar%aqueous%dtotal(parent, j) of the latest RTotal
   double dsp[SPEC_NDSP > 0 ? SPEC_NDSP : 1];  // rt_auxvar%dtotal_sorb_eq(parent, j)
+  double kc[SPEC_NKC > 0 ? SPEC_NKC : 1];     // sub-expressions of per-cell scalars, evaluated once per cell
   double ixref[SPEC_NIONX > 0 ? SPEC_NIONX : 1];    // eqionx_ref_cation_sorbed_conc (guess of the next evaluation)
   double ixconc[SPEC_NIXCAT > 0 ? SPEC_NIXCAT : 1];  // eqionx_conc
   double elm_w, elm_o, elm_t, elm_zsoil, elm_kscalar, elm_bd_dry, elm_bsw, elm_plantndemand;
@@ -232,6 +254,8 @@ __device__ __forceinline__ void spec_mr_update(const SpecCell &s, const DevState
 }
 #endif
 
+__device__ __forceinline__ void spec_cell_constants(SpecCell &s);  // generated
+
 // per-cell inputs of the ELM-CN sandboxes
 __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &st, long long cell) {
 #if SPEC_NIONX > 0
@@ -256,6 +280,9 @@ __device__ __forceinline__ void spec_sandbox_load(SpecCell &s, const DevState &s
 #if SPEC_NNC > 0
 #pragma unroll
   for (int k = 0; k < SPEC_NNC; k++) s.nc[k] = st.somdec_nc ? st.somdec_nc[k * st.ld + cell] : spec_nc0_tab[k];
+#endif
+#if SPEC_NKC > 0
+  spec_cell_constants(s);
 #endif
 }
 __device__ __forceinline__ void spec_sandbox_store(const SpecCell &s, const DevState &st, long long cell) {
@@ -621,7 +648,10 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
     double mabs = 0.0, ss = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      mabs = fmax(mabs, fabs(res[i]));
+      {
+          const double av = fabs(res[i]);  // maxval(abs(residual)): a NaN never wins, as with fmax
+          mabs = av > mabs ? av : mabs;
+        }
       ss += res[i] * res[i];
     }
     double nrm = sqrt(ss);
@@ -646,9 +676,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
       double cn[N], maxrel = -1.0;
       double minr = 1.e20;
       if (!SPEC_USE_LOG) {
-#pragma unroll
-        for (int i = 0; i < N; i++)
-          if (c[i] <= res[i]) minr = fmin(minr, fabs(c[i] / res[i]));
+        minr = spec_min_ratio(c, res);
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -663,7 +691,7 @@ __device__ __forceinline__ int spec_react(const DevState &st, const SpecParams &
         double v = fabs(sx_div(cn[i] - c[i], c[i]));
         // IEEE: x / 0 = Inf (no convergence from an exactly-zero iterate), 0 / 0 = NaN (skipped)
         if (fabs(c[i]) < 2.2250738585072014e-308) v = (cn[i] == c[i]) ? v : (double)INFINITY;
-        if (!isnan(v)) maxrel = fmax(maxrel, v);
+        maxrel = v > maxrel ? v : maxrel;  // a NaN is skipped (false), as by MAXVAL
       }
       conv = (maxrel >= 0.0) && (maxrel < prm.tol_relchange);
       if (!conv) {
@@ -1133,7 +1161,10 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
       double mabs = 0.0, ss = 0.0;
 #pragma unroll
       for (int i = 0; i < N; i++) {
-        mabs = fmax(mabs, fabs(res[i]));
+        {
+          const double av = fabs(res[i]);  // maxval(abs(residual)): a NaN never wins, as with fmax
+          mabs = av > mabs ? av : mabs;
+        }
         ss += res[i] * res[i];
       }
       const double nrm = sqrt(ss);
@@ -1154,9 +1185,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
           } else {
             double cn[N], maxrel = -1.0, minr = 1.e20;
             if (!SPEC_USE_LOG) {
-#pragma unroll
-              for (int i = 0; i < N; i++)
-                if (c[i] <= res[i]) minr = fmin(minr, fabs(c[i] / res[i]));
+              minr = spec_min_ratio(c, res);
             }
 #pragma unroll
             for (int i = 0; i < N; i++) {
@@ -1170,7 +1199,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINBLOCKS)
               }
               double v = fabs(sx_div(cn[i] - c[i], c[i]));
               if (fabs(c[i]) < 2.2250738585072014e-308) v = (cn[i] == c[i]) ? v : (double)INFINITY;
-              if (!isnan(v)) maxrel = fmax(maxrel, v);
+              maxrel = v > maxrel ? v : maxrel;  // a NaN is skipped (false), as by MAXVAL
             }
             if ((maxrel >= 0.0) && (maxrel < prm.tol_relchange)) {
               conv = true;

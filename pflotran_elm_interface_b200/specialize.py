@@ -1010,7 +1010,7 @@ class _Gen:
             k = _lit(float(a["microbial_rate_constant"][r]))
             ea = float(a["microbial_activation_energy"][r]) if "microbial_activation_energy" in a else None
             if ea is not None:
-                self.w(f"    const double k_eff = {k} * exp({_lit(ea)} / 8.31446 * (1.0 / 298.15 - 1.0 / (s.temp + 273.15)));")
+                self.w(f"    const double k_eff = {k} * " + self.cellconst(f"exp({_lit(ea)} / 8.31446 * (1.0 / 298.15 - 1.0 / (s.temp + 273.15)))") + ";")
             else:
                 self.w(f"    const double k_eff = {k};")
             # concentrations in the reaction's units, once per distinct species
@@ -1157,6 +1157,23 @@ class _Gen:
         self.w()
 
     # -- helpers of the ELM-CN emitters: dtotal = delta_ij * denL (no complexes) ------------
+    def cellconst(self, expr: str) -> str:
+        """a sub-expression of per-cell scalars only (temperature, saturation, ELM soil properties): evaluated once
+        when the cell is loaded (spec_cell_constants) instead of in every Newton iteration of every sub-step"""
+        if os.environ.get("PFRX_SPEC_NO_CELLCONST"):
+            return "(" + expr + ")"
+        if expr not in self.kc:
+            self.kc.append(expr)
+        return f"s.kc[{self.kc.index(expr)}]"
+
+    def gen_cell_constants(self) -> None:
+        self.w("__device__ __forceinline__ void spec_cell_constants(SpecCell &s) {")
+        for k, e in enumerate(self.kc):
+            self.w(f"  s.kc[{k}] = {e};")
+        self.w("  (void)s;")
+        self.w("}")
+        self.w()
+
     def _Jsub(self, i: int, j: int, expr: str) -> None:
         self.w(f"    {self.J(i, j)} = {self.J(i, j)} - {expr};")
 
@@ -1200,20 +1217,20 @@ class _Gen:
         else:
             w("    double f_w = 1.0;")
         if of == 2:
-            w("    f_w = f_w * pfrx_sbx::wfps(s.sat);")
+            w(f"    f_w = f_w * {self.cellconst('pfrx_sbx::wfps(s.sat)')};")
         elif elm:
             w("    f_w = f_w * s.elm_o;")
         if tf == 4:
-            w(f"    const double f_t = pfrx_sbx::temperature_response(s.temp, 4, {_lit(float(sa['ea'][0]))});")
+            w("    const double f_t = " + self.cellconst(f"pfrx_sbx::temperature_response(s.temp, 4, {_lit(float(sa['ea'][0]))})") + ";")
         elif tf == 1:
-            w("    const double f_t = pfrx_sbx::temperature_response(s.temp, 1, 0.0);")
+            w("    const double f_t = " + self.cellconst("pfrx_sbx::temperature_response(s.temp, 1, 0.0)") + ";")
         elif tf in (2, 3):
-            w(f"    const double f_t = pfrx_sbx::temperature_response(s.temp, {tf}, {_lit(float(sa['q10'][0]))});")
+            w("    const double f_t = " + self.cellconst(f"pfrx_sbx::temperature_response(s.temp, {tf}, {_lit(float(sa['q10'][0]))})") + ";")
         else:
             w("    const double f_t = " + ("s.elm_t;" if elm else "1.0;"))
         ef = float(sa["decomp_depth_efolding"][0])
         if elm and ef > 0.0:
-            w(f"    const double f_depth = fmin(1.0, fmax(1.e-20, exp(-s.elm_zsoil / {_lit(ef)})));")
+            w("    const double f_depth = " + self.cellconst(f"fmin(1.0, fmax(1.e-20, exp(-s.elm_zsoil / {_lit(ef)})))") + ";")
         else:
             w("    const double f_depth = 1.0;")
         w("    if (f_t < 1.0e-20 || f_w < 1.0e-20 || f_depth < 1.0e-20) break;")
@@ -1289,8 +1306,8 @@ class _Gen:
             n2o = int(sd.n2o_id)
             w(f"    if (net_nmin_rate > {x0}) {{")
             w(f"    const double c_nh4 = tot[{nh4}] * theta * 1000.0;")
-            w("    double f_t2 = -0.06 + 0.13 * exp(0.07 * s.temp);")
-            w("    double f_w2 = pfrx_sbx::wfps(s.sat);")
+            w(f"    double f_t2 = {self.cellconst('-0.06 + 0.13 * exp(0.07 * s.temp)')};")
+            w(f"    double f_w2 = {self.cellconst('pfrx_sbx::wfps(s.sat)')};")
             self._emit_ph(int(sd.proton_id))
             w(f"    if (f_t2 > {x0} && f_w2 > {x0} && f_ph > {x0}) {{")
             w("    f_t2 = fmin(f_t2, 1.0); f_w2 = fmin(f_w2, 1.0); f_ph = fmin(f_ph, 1.0);")
@@ -1563,7 +1580,7 @@ class _Gen:
             w(f"    if (c_nh4 < {_lit(nt.x0eps)}) break;")
         if nh4 >= 0 and no3 >= 0:
             w("    {")
-            w("    const double f_t = exp(0.08 * (s.temp - 25.0));")
+            w(f"    const double f_t = {self.cellconst('exp(0.08 * (s.temp - 25.0))')};")
             w("    saturation = fmax(0.0, fmin(saturation, 1.0));")
             w("    const double f_w = saturation * (1.0 - saturation) / 0.25;")
             w(f"    double t = fmin({_lit(nt.k_nitr_max)} * f_t * f_w * s.vol, 1.0);")
@@ -1574,13 +1591,15 @@ class _Gen:
             w(f"    const double drate = {_lit(nt.k_nitr_max)} * f_t * f_w * s.vol * t;")
             self._Jadd(nh4, nh4, "drate * denL")
             w("    }")
-        w("    const double rho_b = " + ("s.elm_bd_dry;" if self.c.elm_pflotran else "1.25e3;"))
-        w("    const double M_2_ug_per_g = (14.0067 * 1.0e6) / (s.vol * rho_b * 1.e3);")
+        rho_b = "s.elm_bd_dry" if self.c.elm_pflotran else "1.25e3"
+        w(f"    const double rho_b = {rho_b};")
+        w("    const double M_2_ug_per_g = " + self.cellconst(f"(14.0067 * 1.0e6) / (s.vol * {rho_b} * 1.e3)") + ";")
         w("    const double c_nh4_ugg = c_nh4 * s.vol * M_2_ug_per_g;")
         if n2o >= 0:
             w("    if (c_nh4_ugg > 3.0) {")
-            w("    double f_t = -0.06 + 0.13 * exp(0.07 * s.temp);")
-            w("    double f_w = pfrx_sbx::wfps(saturation);")
+            w(f"    double f_t = {self.cellconst('-0.06 + 0.13 * exp(0.07 * s.temp)')};")
+            sat_e = "fmax(0.0, fmin(s.sat, 1.0))" if (nh4 >= 0 and no3 >= 0) else "s.sat"   # `saturation` at this point
+            w("    double f_w = " + self.cellconst(f"pfrx_sbx::wfps({sat_e})") + ";")
             self._emit_ph(int(nt.proton_id))
             w("    if (f_t > 0.0 && f_w > 0.0 && f_ph > 0.0) {")
             w("    f_t = fmin(f_t, 1.0); f_w = fmin(f_w, 1.0); f_ph = fmin(f_ph, 1.0);")
@@ -1608,10 +1627,9 @@ class _Gen:
         if n2 < 0:
             return
         w("    const double L_water = s.por * s.sat * 1.e3;")
-        w("    const double bsw = " + ("s.elm_bsw;" if self.c.elm_pflotran else "1.0;"))
-        w("    const double f_t = exp(0.08 * (s.temp - 25.0));")
-        w("    double f_w = 0.0;")
-        w("    if (s.sat > 0.6) { f_w = (s.sat - 0.6) / (1.0 - 0.6); f_w = pow(f_w, bsw); }")
+        bsw = "s.elm_bsw" if self.c.elm_pflotran else "1.0"
+        w(f"    const double f_t = {self.cellconst('exp(0.08 * (s.temp - 25.0))')};")
+        w("    const double f_w = " + self.cellconst(f"((s.sat > 0.6) ? pow((s.sat - 0.6) / (1.0 - 0.6), {bsw}) : 0.0)") + ";")
         w(f"    const double c_no3 = tot[{no3}] * L_water;")
         w("    double feps0, dfeps0;")
         if dn.x0eps > 0.0:
@@ -1756,8 +1774,8 @@ class _Gen:
         c, a, naq = self.c, self.a, self.naq
         self.w("  const double temp_K = s.temp + 273.15;")
         self.w("  if (!(temp_K > 227.15)) break;")
-        self.w("  const double F_t = exp(308.56 * (1.408054069e-2 - 1.0 / (temp_K - 227.13)));")
-        self.w("  const double F_theta = log(0.01 / fmax(0.01, s.sat)) * -2.17147241e-1;")
+        self.w("  const double F_t = " + self.cellconst("exp(308.56 * (1.408054069e-2 - 1.0 / ((s.temp + 273.15) - 227.13)))") + ";")
+        self.w("  const double F_theta = " + self.cellconst("log(0.01 / fmax(0.01, s.sat)) * -2.17147241e-1") + ";")
         self.w("  const double cinh = F_t * F_theta;")
         iC = naq + int(c.clmcn_C_species_id)
         iN = naq + int(c.clmcn_N_species_id)
@@ -1828,6 +1846,7 @@ class _Gen:
     # ------------------------------------------------------------------ whole file
     def _gen_body(self, nsbx: int) -> List[str]:
         self.out = []
+        self.kc = []
         self.gen_tables()
         self.gen_activity()
         self.gen_rtotal()
@@ -1837,6 +1856,7 @@ class _Gen:
             self.gen_kinetic()
         if nsbx > 0:
             self.gen_sandbox()
+        self.gen_cell_constants()
         return self.out
 
     def gen_rowonly(self) -> None:
@@ -2037,6 +2057,7 @@ class _Gen:
         self.w(f"#define SPEC_NKIN3 {int(has_kinetic3(self.cfg))}")
         self.w(f"#define SPEC_NDTP {len(self.dtp)}")
         self.w(f"#define SPEC_NDSP {len(self.dsp)}")
+        self.w(f"#define SPEC_NKC {len(self.kc)}")
         self.w(f"#define SPEC_NIONX {c.neqionxrxn}")
         self.w(f"#define SPEC_NIXCAT {int(self.a['eqionx_ptr'][c.neqionxrxn]) if c.neqionxrxn else 0}")
         self.w(f"#define SPEC_NSORB {c.neqsrfcplxrxn + c.neqionxrxn + c.neqkdrxn + c.neqdynamickdrxn}")
