@@ -562,13 +562,20 @@ def main():
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": frac_hbm,
                 "peak_source": f"MEASURED_PEAKS.json ({which})"}
     # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_counters = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tr = json.load(f).get(a.workload)
         if tr and tr["kernel"] == _kernel_name(info):
             traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / tr["cells"] * cells_local
             traffic_src = tr["source"]
+            if "fp64_pipe_busy_pct" in tr:
+                # what the hardware did in that capture, next to the algorithmic numerator above: the share of
+                # cycles the FP64 pipe was busy and the issue slots used (a frac above 1 means the kernel reaches
+                # the reference's result with fewer operations than the reference algorithm counts)
+                ncu_counters = {"fp64_pipe_busy_pct": tr["fp64_pipe_busy_pct"], "issue_active_pct": tr["issue_active_pct"],
+                                "warp_instructions_per_cell_iteration": tr["warp_instructions"] / tr["newton_iterations"],
+                                "source": tr["source"]}
     except (OSError, ValueError, KeyError):
         pass
     roof.update({"traffic": traffic, "traffic_source": traffic_src, "frac_fp64": frac_fp64, "frac_hbm": frac_hbm,
@@ -578,7 +585,7 @@ def main():
                  "flops_per_newton_iteration": f_eval + f_solve, "bytes_per_cell": bytes_per_cell,
                  "newton_its_per_cell": res.sum_newton_iterations / max(1, res.ncell_active),
                  "kernel": _kernel_name(info), "kernel_ms": 1000.0 * t_launch,
-                 "fp64_peak_sm_mhz": mhz})
+                 "fp64_peak_sm_mhz": mhz, "ncu": ncu_counters})
 
     # ---- the block-vector transposes either side of the cell loop (HBM-bound) ------
     osv = None
