@@ -479,6 +479,34 @@ def main():
         h_solved[:, :naq_].copy_(pristine.t["total"].t())
         if ncomp_ > naq_:
             h_xx[:, naq_:].copy_(pristine.t["immobile"].t())
+        # what the host link gives THIS rank while every rank uses it: 256 MiB up and 256 MiB down at the same
+        # time from pinned memory, all ranks between the same barriers (the floor of any host-vector e2e)
+        link = None
+        try:
+            nb = 1 << 28
+            hp_u, hp_d = torch.empty(nb, dtype=torch.uint8).pin_memory(), torch.empty(nb, dtype=torch.uint8).pin_memory()
+            dv_u, dv_d = torch.empty(nb, dtype=torch.uint8, device=dev), torch.zeros(nb, dtype=torch.uint8, device=dev)
+            s_u, s_d = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            best = None
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_u):
+                    dv_u.copy_(hp_u, non_blocking=True)
+                with torch.cuda.stream(s_d):
+                    hp_d.copy_(dv_d, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                tl = time.perf_counter() - t0
+                best = tl if best is None else min(best, tl)
+            if world > 1:
+                t = torch.tensor([best], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item())
+            link = {"GBps_each_direction_per_rank": nb / best / 1e9, "ranks_at_once": world,
+                    "note": "256 MiB up and 256 MiB down concurrently from pinned host memory on every rank, slowest rank"}
+            del hp_u, hp_d, dv_u, dv_d
+        except RuntimeError:
+            link = None
         restore()
         for _ in range(4):                          # warm-up: device staging (one chunk, many chunks) and the
             restore()                               # library's two timed chunking trials
@@ -501,6 +529,9 @@ def main():
         e2e_os = {"value": int(r3.ncell_active) / te, "unit": "cell-solves/s", "h2d_bytes_per_step": int(h2d3),
                   "d2h_bytes_per_step": int(d2h3), "ms_per_step": 1000.0 * te,
                   "sum_newton_iterations": int(r3.sum_newton_iterations),
+                  "host_link": link,
+                  "link_floor_ms": (None if not link else
+                                    1000.0 * max(int(h2d3), int(d2h3)) / (link["GBps_each_direction_per_rank"] * 1e9)),
                   "api": "pfrx_os_step_host (C ABI): pinned host block vectors solved_total / tran_xx, "
                          "rt_auxvar state bound in device memory between steps (pmc_subsurface_osrt.F90:303-378)"}
         del h_solved, h_xx
