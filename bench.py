@@ -534,6 +534,33 @@ def main():
                                     1000.0 * max(int(h2d3), int(d2h3)) / (link["GBps_each_direction_per_rank"] * 1e9)),
                   "api": "pfrx_os_step_host (C ABI): pinned host block vectors solved_total / tran_xx, "
                          "rt_auxvar state bound in device memory between steps (pmc_subsurface_osrt.F90:303-378)"}
+        # the same step for a host whose PETSc vectors live in device memory (VECCUDA): pfrx_os_load, pfrx_rstep,
+        # pfrx_os_store on device pointers -- the C-ABI path without the host link (not the contract's e2e: no copies)
+        try:
+            d_solved, d_xx = h_solved.to(dev), h_xx.to(dev)
+            td = []
+            for k in range(2 + max(2, min(a.steps, 3))):
+                restore()
+                barrier()
+                t0 = time.perf_counter()
+                step.os_load(d_solved, d_xx if ncomp_ > naq_ else None)
+                r4 = step.rstep(dt)
+                step.os_store(d_xx)
+                r4 = step.allreduce(r4)
+                torch.cuda.synchronize(dev)
+                if k >= 2:
+                    td.append(time.perf_counter() - t0)
+            tdm = float(np.mean(td))
+            if world > 1:
+                t = torch.tensor([tdm], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tdm = float(t.item())
+            e2e_os["device_vectors"] = {"ms_per_step": 1000.0 * tdm, "value": int(r4.ncell_active) / tdm,
+                                        "api": "pfrx_os_load + pfrx_rstep + pfrx_os_store on device block vectors "
+                                               "(wall clock around the three C-ABI calls and the reduction)"}
+            del d_solved, d_xx
+        except RuntimeError:
+            pass
         del h_solved, h_xx
 
     # ---- BASELINE.json's fifth configuration at its full size: 512 x 512 x 256 cells of the Hanford
