@@ -477,6 +477,8 @@ struct pfrx_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second kernel stream of pfrx_os_step_host (odd chunks), created on first use
+  cudaEvent_t ev_reset = nullptr;
   cudaStream_t out_stream = nullptr;
   cudaEvent_t ev_in[PFRX_MAX_CHUNKS], ev_k[PFRX_MAX_CHUNKS];
   bool ev_ready = false;
@@ -1521,6 +1523,8 @@ extern "C" void pfrx_destroy(pfrx_handle *h) {
   if (h->os_a) cudaFree(h->os_a);
   if (h->os_b) cudaFree(h->os_b);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_reset) cudaEventDestroy(h->ev_reset);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
   if (h->ev_ready)
     for (int i = 0; i < PFRX_MAX_CHUNKS; i++) {
@@ -2283,6 +2287,19 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
   cudaStream_t s_in = h->copy_stream, s_k = h->stream, s_out = h->out_stream;
   rc = summary_reset(h, s_k);
   if (rc) return rc;
+  // Even and odd chunks run on two kernel streams: a chunk's kernel is a persistent grid of one block per SM,
+  // and the blocks of the next chunk start on the SMs the current one has already left instead of waiting for
+  // its slowest block.  Not for the refill kernels (one work counter per launch; ragged shards run in one chunk).
+  const bool dual = nchunk > 1 && !(h->spec_func && h->spec_refill) && !getenv("PFRX_OS_ONE_KERNEL_STREAM");
+  if (dual) {
+    if (!h->stream2) {
+      CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_reset, cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventRecord(h->ev_reset, s_k));  // the summary is zeroed before either stream adds to it
+    CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_reset, 0));
+  }
+  int last_odd = -1;
   // tran_xx goes up when the step reads it (immobile entries) or when the shard has inactive cells,
   // which must keep their entries through the download
   const bool up_xx = h->cfg.nim > 0 || (h->st.imat != nullptr && h->os_inactive != 0);
@@ -2325,22 +2342,25 @@ extern "C" int pfrx_os_step_host(pfrx_handle *h, const double *solved_total, dou
       h->last_h2d += (int64_t)(cnt * w8);
     }
     CUDA_OK(cudaEventRecord(h->ev_in[ch], s_in));
-    CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_in[ch], 0));
+    cudaStream_t s_c = (dual && (ch & 1)) ? h->stream2 : s_k;  // this chunk's kernel stream
+    if (dual && (ch & 1)) last_odd = ch;
+    CUDA_OK(cudaStreamWaitEvent(s_c, h->ev_in[ch], 0));
     const DevState dc = dev_state_at(h->st, c0);
     if (solved_total || h->cfg.nim > 0) {
       rc = os_enqueue<OS_LOAD>(h, dc, nc, solved_total ? h->os_a + off : nullptr,
-                               h->cfg.nim > 0 ? h->os_b + off : nullptr, nullptr, s_k);
+                               h->cfg.nim > 0 ? h->os_b + off : nullptr, nullptr, s_c);
       if (rc) return rc;
     }
-    rc = launch_kernel(h, dc, nc, tran_dt, s_k);
+    rc = launch_kernel(h, dc, nc, tran_dt, s_c);
     if (rc) return rc;
-    rc = os_enqueue<OS_STORE>(h, dc, nc, nullptr, nullptr, h->os_b + off, s_k);
+    rc = os_enqueue<OS_STORE>(h, dc, nc, nullptr, nullptr, h->os_b + off, s_c);
     if (rc) return rc;
-    CUDA_OK(cudaEventRecord(h->ev_k[ch], s_k));
+    CUDA_OK(cudaEventRecord(h->ev_k[ch], s_c));
     CUDA_OK(cudaStreamWaitEvent(s_out, h->ev_k[ch], 0));
     CUDA_OK(cudaMemcpyAsync(tran_xx + off, h->os_b + off, cnt * w8, cudaMemcpyDeviceToHost, s_out));
     h->last_d2h += (int64_t)(cnt * w8);
   }
+  if (last_odd >= 0) CUDA_OK(cudaStreamWaitEvent(s_k, h->ev_k[last_odd], 0));  // the summary of both streams
   CUDA_OK(cudaMemcpyAsync(h->h_summ, h->d_summ, sizeof(DevSummary), cudaMemcpyDeviceToHost, s_k));
   CUDA_OK(cudaStreamSynchronize(s_k));
   CUDA_OK(cudaStreamSynchronize(s_out));
