@@ -2027,8 +2027,11 @@ class _Gen:
             minblocks = max(1, min(4, (228 * 1024) // (slots * 128 * 8 + 1024)))
         if self.lockstep and threads == 32 and not self.onewarp:
             # the warps that shared an SM as separate blocks become one block that votes
-            threads = 32 * minblocks
-            minblocks = 1
+            # (PFRX_SPEC_LOCKSTEP_WARPS = 2: two blocks of two warps, for measurements)
+            lw = int(os.environ.get("PFRX_SPEC_LOCKSTEP_WARPS", "0")) or minblocks
+            lw = max(1, min(lw, minblocks))
+            threads = 32 * lw
+            minblocks = max(1, minblocks // lw)
         self.threads, self.minblocks, self.slots = threads, minblocks, slots
         self.out = []
         self.w("// generated by pflotran_elm_interface_b200/specialize.py -- do not edit")
