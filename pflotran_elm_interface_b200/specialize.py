@@ -1933,6 +1933,8 @@ class _Gen:
         self.sparse_order = [k for k, _, _ in order]
         self.sparse_fill = len(fills)
         nzl = sorted(nz)
+        # PFRX_SPEC_SPARSE_THRESHOLD=0 makes every solve fall back: how the tests keep the dense path exercised
+        thr = _lit(float(os.environ.get("PFRX_SPEC_SPARSE_THRESHOLD", "64.0")))
         self.w(f"  double sav[{len(nzl)}];  // the non-zeros as assembled, for the dense fall-back")
         for q, (i, j) in enumerate(nzl):
             self.w(f"  sav[{q}] = W[JX({i}, {j})];")
@@ -1948,7 +1950,7 @@ class _Gen:
                 self.w(f"  const double u{k}_{j} = W[JX({k}, {j})];")
             for i in col:
                 self.w(f"  {{ const double l = W[JX({i}, {k})] * ip{k};")
-                self.w("    ok = ok && (fabs(l) <= 64.0);")
+                self.w(f"    ok = ok && (fabs(l) <= {thr});")
                 for j in row:
                     if (i, j) in fillset and (i, j) not in touched:
                         self.w(f"    W[JX({i}, {j})] = -(l * u{k}_{j});")

@@ -404,6 +404,34 @@ def test_specialized_kinetic_reactions_in_every_skeleton(name, variant):
     _check_summary(res_ref, res)
 
 
+@pytest.mark.parametrize("name,style", [("c4s", "straight"), ("c4fe", "refill"), ("c8", "lockstep")])
+def test_sparse_solve_falls_back_to_the_dense_lu(name, style, tmp_path, monkeypatch):
+    """the generated sparse solve with its threshold at zero: every Newton solve fails the multiplier test, puts
+    the Jacobian back and runs the reference's dense algorithm (row scaling, implicit-scaled partial pivoting) --
+    same results against the oracle, so the fall-back path stays exercised although real states never take it"""
+    rstep = _gpu()
+    from pflotran_elm_interface_b200 import specialize
+
+    monkeypatch.setenv("PFRX_SPEC_SPARSE_THRESHOLD", "0")
+    monkeypatch.setattr(specialize, "OUT", str(tmp_path))   # do not touch the cached cubins
+    wl = W.by_name(name, ncell=1500, tran_dt=3600.0)
+    wl.state.a["imat"][0, 13] = 0
+    wl.state.a["sat"][0, 14] = 1.0e-50
+    path = specialize.build(wl.cfg, warps=1, style=style)
+    assert "<= 0.0)" in open(path[:-6] + ".cu").read()
+    ref = wl.state.copy()
+    res_ref = orc.rstep(wl.cfg, ref, wl.tran_dt, 4)
+    step = rstep.ChemistryStep(wl.cfg, 0)
+    step.load_specialized(path)
+    dev = rstep.DeviceState.from_host(wl.state, "cuda:0")
+    step.bind(dev)
+    res = step.rstep(wl.tran_dt)
+    got = dev.to_host()
+    step.close()
+    _compare(ref, got, f"{name} {style} dense fall-back")
+    _check_summary(res_ref, res)
+
+
 @pytest.mark.parametrize("variant", ["q1", "w1"])
 def test_refill_kernels_hand_out_the_slowest_cells_first(variant):
     """pfrx_cell_order: from the second launch on a shard the refill kernels take the cells in the order of the
