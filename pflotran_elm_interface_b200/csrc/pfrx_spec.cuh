@@ -217,12 +217,13 @@ __device__ __forceinline__ void spec_mr_begin(SpecCell &s, const DevState &st, l
     double A = 0.0, B[SPEC_NAQ];
 #pragma unroll
     for (int i = 0; i < SPEC_NAQ; i++) B[i] = 0.0;
-#pragma unroll 1
-    for (int k = r0; k < r1; k++) {
+    const long long row = (long long)SPEC_NAQ * st.ld;
+    const double *S = st.kinmr + (base + (long long)SPEC_NAQ) * st.ld + cell;
+#pragma unroll 2
+    for (int k = r0; k < r1; k++, S += row) {
       const double rk = spec_mr_rate_tab[k];
       const double kk = rk / (1.0 + rk * dt);
       A += kk * spec_mr_frac_tab[k];
-      const double *S = st.kinmr + (base + (long long)SPEC_NAQ * (k - r0 + 1)) * st.ld + cell;
 #pragma unroll
       for (int i = 0; i < SPEC_NAQ; i++) B[i] += kk * S[i * st.ld];
     }
@@ -237,18 +238,25 @@ __device__ __forceinline__ void spec_mr_update(const SpecCell &s, const DevState
   for (int q = 0; q < SPEC_NMR; q++) {
     const int r0 = spec_mr_ptr(q), r1 = spec_mr_ptr(q + 1);
     const long long base = (long long)SPEC_NAQ * (r0 + q);
-#pragma unroll 1
-    for (int k = r0; k < r1; k++) {
+    // the equilibrium targets in registers for the whole loop, the row pointer stepped instead of recomputed, two
+    // rates per trip so that 30 loads are in flight (the loop is latency-bound: ncu, r02_ncu_c3mr_s1_s3.txt)
+    double seq[SPEC_NAQ];
+#pragma unroll
+    for (int i = 0; i < SPEC_NAQ; i++) seq[i] = s.mr_seq[q * SPEC_NAQ + i];
+    const long long row = (long long)SPEC_NAQ * st.ld;
+    double *S = st.kinmr + (base + (long long)SPEC_NAQ) * st.ld + cell;
+#pragma unroll 2
+    for (int k = r0; k < r1; k++, S += row) {
       const double kdt = spec_mr_rate_tab[k] * dt, fk = spec_mr_frac_tab[k];
       // one reciprocal per rate instead of one division per species (the reference divides
       // 15 times by the same 1 + k dt): at most one ulp apart, 700 divisions per cell fewer
       const double inv = 1.0 / (1.0 + kdt);
-      double *S = st.kinmr + (base + (long long)SPEC_NAQ * (k - r0 + 1)) * st.ld + cell;
+      const double w = kdt * fk;
       double v[SPEC_NAQ];
 #pragma unroll
       for (int i = 0; i < SPEC_NAQ; i++) v[i] = S[i * st.ld];
 #pragma unroll
-      for (int i = 0; i < SPEC_NAQ; i++) S[i * st.ld] = (v[i] + kdt * fk * s.mr_seq[q * SPEC_NAQ + i]) * inv;
+      for (int i = 0; i < SPEC_NAQ; i++) S[i * st.ld] = (v[i] + w * seq[i]) * inv;
     }
   }
 }
